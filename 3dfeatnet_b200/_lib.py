@@ -1,0 +1,82 @@
+"""ctypes binding of lib3dfeatnet_b200.so (include/feat3dnet_b200.h).  There is NO fallback: if the CUDA library
+is missing or a call fails, this raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib3dfeatnet_b200.so")
+
+_c = ctypes
+_vp, _i, _f, _sz, _ll = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_longlong
+
+# name -> (restype, argtypes); mirrors include/feat3dnet_b200.h one to one
+SIGNATURES = {
+    "f3d_version": (_i, []),
+    "f3d_last_error_string": (_c.c_char_p, []),
+    "f3d_launch_count": (_ll, []),
+    "f3d_reset_launch_count": (None, []),
+    "f3d_farthest_point_sample": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "f3d_gather_point": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "f3d_gather_point_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "f3d_query_ball_point": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "f3d_query_ball_point2": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "f3d_selection_sort": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "f3d_knn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "f3d_knn_point": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "f3d_group_point": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "f3d_scatter_workspace_bytes": (_sz, [_ll]),
+    "f3d_group_point_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "f3d_packed_weights_floats": (_sz, [_i]),
+    "f3d_packed_weights_num_blocks": (_i, []),
+    "f3d_packed_weights_offsets": (_i, [_i, _vp, _vp]),
+    "f3d_forward_workspace_bytes": (_sz, [_i, _i, _i]),
+    "f3d_detector_forward": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "f3d_descriptor_forward": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+}
+
+_LIB = None
+
+
+class F3DError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the C-ABI library (once).  Raises if it has not been built -- there is no CPU path."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise F3DError(
+                "lib3dfeatnet_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "This package has no CPU or PyTorch fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().f3d_last_error_string().decode("utf-8", "replace")
+        if rc in (-1,):
+            raise ValueError("%s: %s" % (what, msg))
+        raise F3DError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise F3DError("3dfeatnet_b200 ops need CUDA tensors (got a %s tensor): there is no CPU path" % t.device)

@@ -1,0 +1,58 @@
+// forward.cu -- C ABI of the fused detector / descriptor forward; dispatches on `precision`.
+#include "common.cuh"
+#include "weights_layout.h"
+
+namespace f3d {
+int detector_forward_fp32(int b, int n, int m, int S, float radius, const float *xyz, const float *new_xyz, const int *idx,
+                          const float *packed, float *pooled_ws, float *attention, float *orientation, cudaStream_t st);
+int descriptor_forward_fp32(int b, int n, int m, int S, float radius, int feature_dim, const float *xyz,
+                            const float *new_xyz, const int *idx, const float *orientation, const float *packed,
+                            float *pooled_ws, float *features, cudaStream_t st);
+}  // namespace f3d
+
+using namespace f3d;
+
+F3D_API size_t f3d_packed_weights_floats(int feature_dim) { return static_cast<size_t>(make_weight_layout(feature_dim).total); }
+F3D_API int f3d_packed_weights_num_blocks(void) { return kNumWeightSlots; }
+F3D_API int f3d_packed_weights_offsets(int feature_dim, int *offsets, int *sizes) {
+    if (!offsets || !sizes) return fail(F3D_ERR_INVALID_ARGUMENT, "packed_weights_offsets: null output");
+    const WeightLayout L = make_weight_layout(feature_dim);
+    for (int i = 0; i < kNumWeightSlots; ++i) {
+        offsets[i] = L.off[i];
+        sizes[i] = L.size[i];
+    }
+    return 0;
+}
+
+F3D_API size_t f3d_forward_workspace_bytes(int b, int m, int feature_dim) {
+    (void)feature_dim;
+    return static_cast<size_t>(b) * m * 256 * sizeof(float) + 256;
+}
+
+F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const float *xyz, const float *new_xyz,
+                                 const int *idx, const float *packed, float *attention, float *orientation,
+                                 int precision, void *workspace, size_t workspace_bytes, void *stream) {
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f) || !xyz || !new_xyz || !idx || !packed || !attention ||
+        !orientation)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "detector_forward: bad arguments");
+    if (!workspace || workspace_bytes < f3d_forward_workspace_bytes(b, m, 32))
+        return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "detector_forward: workspace too small");
+    if (precision == 0)
+        return detector_forward_fp32(b, n, m, nsample, radius, xyz, new_xyz, idx, packed, static_cast<float *>(workspace),
+                                     attention, orientation, as_stream(stream));
+    return fail(F3D_ERR_UNSUPPORTED, "detector_forward: precision must be 0 (fp32)");
+}
+
+F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radius, int feature_dim, const float *xyz,
+                                   const float *new_xyz, const int *idx, const float *orientation, const float *packed,
+                                   float *features, int precision, void *workspace, size_t workspace_bytes,
+                                   void *stream) {
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f) || !xyz || !new_xyz || !idx || !packed || !features)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "descriptor_forward: bad arguments");
+    if (!workspace || workspace_bytes < f3d_forward_workspace_bytes(b, m, feature_dim))
+        return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "descriptor_forward: workspace too small");
+    if (precision == 0)
+        return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
+                                       static_cast<float *>(workspace), features, as_stream(stream));
+    return fail(F3D_ERR_UNSUPPORTED, "descriptor_forward: precision must be 0 (fp32)");
+}

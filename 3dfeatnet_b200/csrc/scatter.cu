@@ -1,0 +1,224 @@
+// scatter.cu -- deterministic scatter-add (the gradients of gather_point and group_point) for sm_100a.
+//
+// Replaces tf_sampling_g.cu:183-192 (scatteraddpointKernel) and tf_grouping_g.cu:115-132
+// (group_point_grad_gpu).  The reference zero-fills on the host side and then issues one atomicAdd per
+// element: the fp32 sum order -- hence the result -- changes from run to run, and popular points serialise.
+// Here the (slot -> point) map is inverted once with a stable LSD radix sort of (point id, slot id) pairs,
+// and every output element is then produced by exactly one thread that adds its segment in ascending slot
+// order: no atomics, no memset, bit-reproducible, and equal to the reference's CPU statement
+// (tf_ops/grouping/test/query_ball_point.cpp:68-84), which accumulates in the same (j,k) order.
+//
+// The radix sort is hand-written (8-bit digits; per pass: block histograms -> one exclusive scan ->
+// stable scatter with warp match_any ranking).
+#include "common.cuh"
+
+namespace f3d {
+
+constexpr int kRsTile = 4096;     // keys per CTA
+constexpr int kRsThreads = 256;   // 8 warps, 512 consecutive keys each
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsPerWarp = kRsTile / kRsWarps;
+
+__global__ void __launch_bounds__(kRsThreads)
+rs_hist_kernel(const unsigned *__restrict__ keys, long long n, int shift, unsigned *__restrict__ hist, int nblocks) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long t0 = static_cast<long long>(blockIdx.x) * kRsTile;
+    for (int i = threadIdx.x; i < kRsTile; i += kRsThreads) {
+        const long long g = t0 + i;
+        if (g < n) atomicAdd(&h[(keys[g] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[static_cast<size_t>(threadIdx.x) * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
+}
+
+// exclusive scan of `count` unsigned values in place, one CTA of 1024 threads
+__global__ void __launch_bounds__(1024)
+rs_scan_kernel(unsigned *__restrict__ data, long long count) {
+    __shared__ unsigned warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long per = (count + 1023) / 1024;
+    const long long lo = min(per * tid, count), hi = min(lo + per, count);
+    unsigned sum = 0;
+    for (long long i = lo; i < hi; ++i) sum += data[i];
+    unsigned inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = warp_tot[lane];
+        unsigned winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(kFull, winc, o);
+            if (lane >= o) winc += v;
+        }
+        warp_tot[lane] = winc - w;  // exclusive
+    }
+    __syncthreads();
+    unsigned run = warp_tot[warp] + (inc - sum);
+    for (long long i = lo; i < hi; ++i) {
+        const unsigned v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(kRsThreads)
+rs_scatter_kernel(const unsigned *__restrict__ keys_in, const unsigned *__restrict__ vals_in,
+                  unsigned *__restrict__ keys_out, unsigned *__restrict__ vals_out, long long n, int shift,
+                  const unsigned *__restrict__ offsets, int nblocks) {
+    __shared__ unsigned wh[kRsWarps][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kRsWarps * 256; i += kRsThreads) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const long long w0 = static_cast<long long>(blockIdx.x) * kRsTile + static_cast<long long>(warp) * kRsPerWarp;
+    for (int ch = 0; ch < kRsPerWarp; ch += 32) {
+        const long long g = w0 + ch + lane;
+        if (g < n) atomicAdd(&wh[warp][(keys_in[g] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    {  // per digit: turn the per-warp counts into per-warp global start offsets
+        unsigned base = offsets[static_cast<size_t>(tid) * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kRsWarps; ++w) {
+            const unsigned c = wh[w][tid];
+            wh[w][tid] = base;
+            base += c;
+        }
+    }
+    __syncthreads();
+    const unsigned lt = lanemask_lt();
+    for (int ch = 0; ch < kRsPerWarp; ch += 32) {
+        const long long g = w0 + ch + lane;
+        const bool valid = g < n;
+        const unsigned mask = __ballot_sync(kFull, valid);
+        if (valid) {
+            const unsigned key = keys_in[g];
+            const unsigned d = (key >> shift) & 255u;
+            const unsigned peers = __match_any_sync(mask, d);
+            const unsigned pos = wh[warp][d] + __popc(peers & lt);
+            __syncwarp(mask);
+            if ((peers & lt) == 0) wh[warp][d] += __popc(peers);  // lowest lane of each digit group
+            __syncwarp(mask);
+            keys_out[pos] = key;
+            vals_out[pos] = vals_in[g];
+        }
+    }
+}
+
+// keys[i] = global point id (batch*n + idx[i]) or the sentinel b*n for an out-of-range index; vals[i] = i
+__global__ void scatter_keys_kernel(long long total, long long slots_per_batch, int n, unsigned sentinel,
+                                    const int *__restrict__ idx, unsigned *__restrict__ keys,
+                                    unsigned *__restrict__ vals) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long bb = i / slots_per_batch;
+    const int a = idx[i];
+    keys[i] = (a >= 0 && a < n) ? static_cast<unsigned>(bb * n + a) : sentinel;
+    vals[i] = static_cast<unsigned>(i);
+}
+
+// one thread per output float (q, l): segment [lower_bound(q), lower_bound(q+1)) of the sorted keys,
+// summed in ascending slot order (the sort is stable and vals started ascending).
+__global__ void segmented_sum_kernel(long long out_total, int c, long long total,
+                                     const unsigned *__restrict__ keys, const unsigned *__restrict__ vals,
+                                     const float *__restrict__ grad, float *__restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= out_total) return;
+    const unsigned q = static_cast<unsigned>(i / c);
+    const int l = static_cast<int>(i - static_cast<long long>(q) * c);
+    long long lo = 0, hi = total;
+    while (lo < hi) {  // first position with key >= q
+        const long long mid = (lo + hi) >> 1;
+        if (keys[mid] < q) lo = mid + 1; else hi = mid;
+    }
+    float acc = 0.0f;
+    for (long long p = lo; p < total && keys[p] == q; ++p) acc += grad[static_cast<size_t>(vals[p]) * c + l];
+    out[i] = acc;
+}
+
+static inline unsigned blocks_for(long long total, int per_block) {
+    return static_cast<unsigned>((total + per_block - 1) / per_block);
+}
+
+// Sorts (keys, vals) by the low `bits` bits of the keys.  a = input buffers, b = scratch; returns which holds the result.
+static int radix_sort_pairs(unsigned *&ka, unsigned *&va, unsigned *&kb, unsigned *&vb, unsigned *hist, long long n,
+                            int bits, cudaStream_t st) {
+    const int nblocks = static_cast<int>((n + kRsTile - 1) / kRsTile);
+    for (int shift = 0; shift < bits; shift += 8) {
+        rs_hist_kernel<<<nblocks, kRsThreads, 0, st>>>(ka, n, shift, hist, nblocks);
+        int rc = check_launch("rs_hist_kernel");
+        if (rc) return rc;
+        rs_scan_kernel<<<1, 1024, 0, st>>>(hist, 256LL * nblocks);
+        rc = check_launch("rs_scan_kernel");
+        if (rc) return rc;
+        rs_scatter_kernel<<<nblocks, kRsThreads, 0, st>>>(ka, va, kb, vb, n, shift, hist, nblocks);
+        rc = check_launch("rs_scatter_kernel");
+        if (rc) return rc;
+        unsigned *t = ka; ka = kb; kb = t;
+        t = va; va = vb; vb = t;
+    }
+    return 0;
+}
+
+// out (b,n,c) = scatter-add of grad (b,L,c) at idx (b,L)
+static int scatter_add_sorted(int b, int n, int c, long long L, const float *grad, const int *idx, float *out,
+                              void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    const long long total = static_cast<long long>(b) * L;
+    const long long out_total = static_cast<long long>(b) * n * c;
+    if (out_total == 0) return 0;
+    if (static_cast<long long>(b) * n >= 0xffffffffLL || total >= 0xffffffffLL)
+        return fail(F3D_ERR_UNSUPPORTED, "scatter-add: more than 2^32 points or slots");
+    if (total == 0) {
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * out_total, st);
+        return e == cudaSuccess ? 0 : fail(static_cast<int>(e), "scatter-add: memset");
+    }
+    if (!workspace || workspace_bytes < f3d_scatter_workspace_bytes(total))
+        return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "scatter-add: workspace too small");
+    unsigned *ka = static_cast<unsigned *>(workspace);
+    unsigned *va = ka + total;
+    unsigned *kb = va + total;
+    unsigned *vb = kb + total;
+    unsigned *hist = vb + total;
+    const unsigned sentinel = static_cast<unsigned>(static_cast<long long>(b) * n);
+    scatter_keys_kernel<<<blocks_for(total, 256), 256, 0, st>>>(total, L, n, sentinel, idx, ka, va);
+    int rc = check_launch("scatter_keys_kernel");
+    if (rc) return rc;
+    int bits = 1;
+    while ((1ULL << bits) <= sentinel) ++bits;
+    rc = radix_sort_pairs(ka, va, kb, vb, hist, total, bits, st);
+    if (rc) return rc;
+    segmented_sum_kernel<<<blocks_for(out_total, 256), 256, 0, st>>>(out_total, c, total, ka, va, grad, out);
+    return check_launch("segmented_sum_kernel");
+}
+
+}  // namespace f3d
+
+using namespace f3d;
+
+F3D_API size_t f3d_scatter_workspace_bytes(long long num_slots) {
+    if (num_slots < 0) num_slots = 0;
+    const long long nblocks = (num_slots + kRsTile - 1) / kRsTile;
+    return static_cast<size_t>(num_slots) * 16 + static_cast<size_t>(nblocks) * 256 * 4 + 1024;
+}
+
+F3D_API int f3d_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    if (b < 0 || n <= 0 || m < 0 || !out_g || !idx || !inp_g)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "gather_point_grad: bad arguments");
+    return scatter_add_sorted(b, n, 3, m, out_g, idx, inp_g, workspace, workspace_bytes, as_stream(stream));
+}
+
+F3D_API int f3d_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                                 float *grad_points, void *workspace, size_t workspace_bytes, void *stream) {
+    if (b < 0 || n <= 0 || c <= 0 || m < 0 || nsample <= 0 || !grad_out || !idx || !grad_points)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "group_point_grad: bad arguments");
+    return scatter_add_sorted(b, n, c, static_cast<long long>(m) * nsample, grad_out, idx, grad_points, workspace,
+                              workspace_bytes, as_stream(stream));
+}

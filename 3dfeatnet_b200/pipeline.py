@@ -1,0 +1,130 @@
+"""Detect-and-describe pipeline: the north-star hot path as one call.
+
+    FPS(num_clusters) -> gather_point -> query_ball_point (once) -> detector forward -> descriptor forward
+
+All buffers are allocated once (180 GB of HBM: nothing is sized dynamically per call), every stage is one C-ABI
+call on the caller's stream, and the whole sequence can be replayed from a CUDA graph (`use_graph=True`) so a
+batch costs one launch from the host.  Mirrors Feat3dNet.get_inference_model (models/feat3dnet.py:258-313) in eval
+mode; results are identical to calling the operators one by one.
+"""
+import importlib
+
+import torch
+
+_ROOT = __name__.split(".")[0]
+_pfx = "3dfeatnet_b200." if _ROOT == "3dfeatnet_b200" else ""
+_lib = importlib.import_module(_pfx + "_lib")
+_f3d = importlib.import_module(_pfx + "models.feat3dnet")
+
+STAGES = ("fps", "gather", "ball_query", "detector", "descriptor")
+
+
+class DetectDescribePipeline:
+    def __init__(self, batch, num_points, weights=None, num_clusters=512, radius=2.0, nsample=64, feature_dim=32,
+                 no_regress=False, precision="fp32", device="cuda", use_graph=False, seed=0):
+        self.B, self.N, self.M, self.S, self.F = batch, num_points, num_clusters, nsample, feature_dim
+        self.radius, self.no_regress, self.precision = float(radius), no_regress, precision
+        self.device = torch.device(device)
+        self.L = _lib.lib()
+        params = _f3d.init_params(seed, feature_dim, self.device) if weights is None else \
+            _f3d.params_to_device(weights, self.device)
+        self.packed = _f3d.fold_params(params, feature_dim)
+        dev, B, N, M, S, F = self.device, batch, num_points, num_clusters, nsample, feature_dim
+        self.xyz = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        self.fps_idx = torch.empty((B, M), dtype=torch.int32, device=dev)
+        self.keypoints = torch.empty((B, M, 3), dtype=torch.float32, device=dev)
+        self.idx = torch.empty((B, M, S), dtype=torch.int32, device=dev)
+        self.pts_cnt = torch.empty((B, M), dtype=torch.int32, device=dev)
+        self.attention = torch.empty((B, M), dtype=torch.float32, device=dev)
+        self.orientation = torch.empty((B, M), dtype=torch.float32, device=dev)
+        self.features = torch.empty((B, M, F), dtype=torch.float32, device=dev)
+        self.fps_temp = torch.empty((B, N), dtype=torch.float32, device=dev) if N > 16384 else None
+        self.ws_bytes = self.L.f3d_forward_workspace_bytes(B, M, F)
+        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
+        # pinned host mirrors for the end-to-end (host buffers in, host buffers out) entry point
+        self.h_xyz = torch.empty((B, N, 3), dtype=torch.float32).pin_memory()
+        self.h_out = torch.empty((B, M, 3 + 1 + 1 + F), dtype=torch.float32).pin_memory()
+        self.d_out = torch.empty((B, M, 3 + 1 + 1 + F), dtype=torch.float32, device=dev)
+        self.h2d_bytes = self.h_xyz.numel() * 4
+        self.d2h_bytes = self.h_out.numel() * 4
+        self.launches_per_step = None
+        self._graph = None
+        self.use_graph = use_graph
+
+    # one stage = one C-ABI call; `events` (optional list) receives a CUDA event after each stage
+    def _enqueue(self, events=None):
+        L, p, st = self.L, _lib.ptr, _lib.stream()
+        B, N, M, S, F = self.B, self.N, self.M, self.S, self.F
+        prec = _f3d.PRECISIONS[self.precision]
+
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+
+        mark()
+        _lib.check(L.f3d_farthest_point_sample(B, N, M, p(self.xyz), p(self.fps_temp), p(self.fps_idx), st), "fps")
+        mark()
+        _lib.check(L.f3d_gather_point(B, N, M, p(self.xyz), p(self.fps_idx), p(self.keypoints), st), "gather_point")
+        mark()
+        _lib.check(L.f3d_query_ball_point(B, N, M, self.radius, S, p(self.xyz), p(self.keypoints), p(self.idx),
+                                          p(self.pts_cnt), st), "query_ball_point")
+        mark()
+        _lib.check(L.f3d_detector_forward(B, N, M, S, self.radius, p(self.xyz), p(self.keypoints), p(self.idx),
+                                          p(self.packed), p(self.attention), p(self.orientation), prec, p(self.ws),
+                                          self.ws_bytes, st), "detector_forward")
+        mark()
+        ori = None if self.no_regress else self.orientation
+        _lib.check(L.f3d_descriptor_forward(B, N, M, S, self.radius, F, p(self.xyz), p(self.keypoints), p(self.idx),
+                                            p(ori), p(self.packed), p(self.features), prec, p(self.ws), self.ws_bytes, st),
+                   "descriptor_forward")
+        mark()
+
+    def step(self, events=None):
+        """One pass over the batch already resident in self.xyz (device).  Results stay on the device."""
+        if self.launches_per_step is None:
+            self.L.f3d_reset_launch_count()
+            self._enqueue()
+            self.launches_per_step = int(self.L.f3d_launch_count())
+            return
+        if self.use_graph and events is None:
+            if self._graph is None:
+                torch.cuda.synchronize()
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._enqueue()
+                    self._graph = g
+                except Exception as exc:  # capture is an optimisation only: run eagerly, loudly
+                    import warnings
+
+                    warnings.warn("CUDA graph capture failed (%s); running the stages eagerly" % exc)
+                    self.use_graph = False
+                    torch.cuda.synchronize()
+                    self._enqueue()
+                    return
+            self._graph.replay()
+        else:
+            self._enqueue(events)
+
+    def run(self, xyz):
+        """xyz: (B,N,3) CUDA float32 -> dict of device tensors (views of the pipeline's buffers)."""
+        _lib.require_cuda(xyz)
+        self.xyz.copy_(xyz[:, :, :3])
+        self.step()
+        return dict(xyz=self.keypoints, features=self.features, attention=self.attention,
+                    orientation=self.orientation, idx=self.idx, pts_cnt=self.pts_cnt, fps_idx=self.fps_idx)
+
+    def step_host(self):
+        """End to end: pinned host xyz (self.h_xyz) -> device -> pipeline -> packed [xyz|att|ori|desc] rows back in
+        pinned host memory (self.h_out).  Asynchronous on the current stream; the caller synchronises."""
+        self.xyz.copy_(self.h_xyz, non_blocking=True)
+        self.step()
+        F = self.F
+        self.d_out[:, :, 0:3] = self.keypoints
+        self.d_out[:, :, 3] = self.attention
+        self.d_out[:, :, 4] = self.orientation
+        self.d_out[:, :, 5:5 + F] = self.features
+        self.h_out.copy_(self.d_out, non_blocking=True)
+        return self.h_out

@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""bench.py -- keypoints+descriptors per second of the 3DFeat-Net detect-and-describe hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; N>1 under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the path's CPU statement on the host cores)
+
+Workload (BASELINE.json configs[2], "C3"): per GPU a batch of 64 synthetic Oxford-shape clouds of 16384 points;
+FPS to 512 clusters, ball query r=2.0 / 64 samples, detector (attention + orientation) and 32-D descriptor forward,
+eval-mode BN, seed-0 random-init weights.  A step is one pass over one batch; batches shard across ranks with no
+data-path collective (weak scaling).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_DET_ROW, FLOPS_DET_CLUSTER = 2 * 41152, 2 * 41152
+FLOPS_DESC_ROW, FLOPS_DESC_CLUSTER = 2 * 10336, 2 * (8192 + 4096)  # split-weight form
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clouds per GPU per step")
+    ap.add_argument("--points", type=int, default=16384)
+    ap.add_argument("--clusters", type=int, default=512)
+    ap.add_argument("--nsample", type=int, default=64)
+    ap.add_argument("--precision", default=os.environ.get("F3D_PRECISION", "fp32"), choices=["fp32", "tf32", "3xtf32"])
+    ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="clouds in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), bf16=d.get("bf16_tflops", 1590.0),
+                    bf16_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append([x.strip() for x in o])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=reasons,
+                    samples=len(self.samples))
+
+
+def cpu_reference_pass(xyz_np, params, clusters, nsample, radius=2.0):
+    """The path's CPU statement: C oracle ops (OpenMP) + PyTorch-CPU fp32 network, all host threads."""
+    import torch
+    from oracle import net as onet
+
+    t0 = time.perf_counter()
+    onet.inference_model(xyz_np, params, num_clusters=clusters, radius=radius, nsample=nsample)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference registers GPU-only kernels
+    (tf_sampling.cpp:92, tf_grouping.cpp:125) and TF 1.15 is not installable here, so this is the oracle port
+    (kind "port"): oracle/ops_oracle.c + oracle/net.py on all host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    from oracle import net as onet, ops as oops
+
+    synth = importlib.import_module("3dfeatnet_b200.synth")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = max(1, args.cpu_sample)
+    xyz = synth.make_batch(sample, args.points, seed0=1000)
+    params = onet.to_torch(onet.init_params(seed=0))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_pass(xyz, params, args.clusters, args.nsample)
+    steps = max(1, min(args.steps, 5))
+    t = [cpu_reference_pass(xyz, params, args.clusters, args.nsample) for _ in range(steps)]
+    sec = sum(t) / len(t)
+    value = sample * args.clusters / sec
+    line = dict(metric="keypoints+descriptors/sec", value=value, unit="keypoints/s", n_gpus=args.gpus, steps=steps,
+                warmup=min(args.warmup, 1), ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="C3: Oxford-shape clouds, %d pts, %d clusters x %d nsample, detector+descriptor fwd"
+                            % (args.points, args.clusters, args.nsample), clouds_per_step=sample),
+                cpu_baseline=dict(value=value, unit="keypoints/s", cores=max(cores, oops.num_threads()), kind="port",
+                                  sample="%d clouds of %d points per step (of the 64-cloud batch)" % (sample, args.points)),
+                e2e=dict(value=value, unit="keypoints/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    dist = importlib.import_module("3dfeatnet_b200.dist")
+    synth = importlib.import_module("3dfeatnet_b200.synth")
+    pipe_mod = importlib.import_module("3dfeatnet_b200.pipeline")
+    rank, local_rank, world = dist.init("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, N, M, S = args.batch, args.points, args.clusters, args.nsample
+
+    xyz = synth.make_batch(B, N, seed0=1000 + rank * B)
+    pipe = pipe_mod.DetectDescribePipeline(B, N, num_clusters=M, nsample=S, precision=args.precision, device=dev,
+                                           use_graph=bool(args.graph), seed=0)
+    pipe.h_xyz.copy_(torch.as_tensor(xyz))
+    pipe.xyz.copy_(pipe.h_xyz)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def l2_flush():
+        flush.fill_(1)
+
+    pipe.step()  # counts launches
+    for _ in range(max(args.warmup, 3)):
+        pipe.step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident timing: K steps, each bracketed by events, L2 flushed between steps -------------------
+    L = pipe.L
+    dist.barrier()
+    torch.cuda.synchronize()
+    L.f3d_reset_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s, e in ev:
+        l2_flush()
+        s.record()
+        pipe.step()
+        e.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    launches = pipe.launches_per_step * args.steps
+    dev_ms = dist.max_over_ranks(dev_ms, dev)
+
+    # ---- per-stage breakdown (eager, events between the C-ABI calls) -------------------------------------------
+    stage_ms = {k: 0.0 for k in pipe_mod.STAGES}
+    reps = min(args.steps, 10)
+    for _ in range(reps):
+        l2_flush()
+        evs = []
+        pipe.step(events=evs)
+        torch.cuda.synchronize()
+        for i, k in enumerate(pipe_mod.STAGES):
+            stage_ms[k] += evs[i].elapsed_time(evs[i + 1]) / reps
+
+    # ---- end to end through the public call: pinned host in, pinned host out --------------------------------
+    for _ in range(2):
+        pipe.step_host()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s, e in ev2:
+        l2_flush()
+        s.record()
+        pipe.step_host()
+        e.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_ms = dist.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev2), dev)
+
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    units = B * M * world * args.steps
+    value = units / (dev_ms * 1e-3)
+    e2e_value = units / (e2e_ms * 1e-3)
+    rows = B * M * S
+    det_flops = rows * FLOPS_DET_ROW + B * M * FLOPS_DET_CLUSTER
+    det_ms = stage_ms["detector"]
+    achieved = det_flops / (det_ms * 1e-3) / 1e12
+    tensor_peak = peaks["bf16"] / 2.0  # kind::tf32 runs at half the bf16 rate; no separate TF32 measurement exists
+    roofline = dict(bound="tensor", kernel="f3d_detector_forward (%s)" % args.precision, achieved=achieved, peak=tensor_peak,
+                    unit="TFLOP/s", frac=achieved / tensor_peak, traffic=None,
+                    peak_source="%s bf16 burst / 2 (TF32 rate)" % peaks["source"], flops_per_launch=det_flops,
+                    ms_per_launch=det_ms)
+    line = dict(metric="keypoints+descriptors/sec", value=value, unit="keypoints/s", n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32" if args.precision == "fp32" else args.precision, data="synthetic",
+                config=dict(workload="C3: %d Oxford-shape clouds/GPU, %d pts, %d clusters x %d nsample, FPS+ballquery+detector+descriptor fwd"
+                            % (B, N, M, S), l2="flushed between timed steps (256 MiB write)", cuda_graph=bool(args.graph),
+                            precision=args.precision, parallelism="batch-sharded dp%d, no collective" % world),
+                e2e=dict(value=e2e_value, unit="keypoints/s", h2d_bytes_per_step=pipe.h2d_bytes, d2h_bytes_per_step=pipe.d2h_bytes,
+                         ms_per_step=e2e_ms / args.steps),
+                gpu_launches=launches, stage_ms=stage_ms, roofline=roofline, clocks=sampler.summary())
+    if not args.no_cpu_baseline:
+        from oracle import net as onet, ops as oops
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sample = max(1, args.cpu_sample)
+        cpu_params = onet.to_torch(onet.init_params(seed=0))
+        cpu_xyz = xyz[:sample]
+        cpu_reference_pass(cpu_xyz, cpu_params, M, S)
+        sec = min(cpu_reference_pass(cpu_xyz, cpu_params, M, S) for _ in range(3))
+        line["cpu_baseline"] = dict(value=sample * M / sec, unit="keypoints/s", cores=max(cores, oops.num_threads()), kind="port",
+                                    sample="%d of the %d clouds of one step (oracle C ops + PyTorch-CPU fp32 net)" % (sample, B))
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

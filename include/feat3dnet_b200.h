@@ -1,0 +1,128 @@
+/*
+ * feat3dnet_b200.h -- C ABI of the B200-native 3DFeat-Net sample-and-group + set-abstraction path.
+ *
+ * This is the drop-in boundary.  Every entry point below replaces one launcher (or one group of
+ * TensorFlow graph ops) of cwlroda/3DFeatNet; the reference interface it replaces is cited as
+ * file:line relative to the reference tree.  Conventions (all functions):
+ *   - plain C: raw DEVICE pointers + int sizes, row-major contiguous fp32 / int32 tensors with the
+ *     reference's shapes; no torch / TF types;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); the callee only
+ *     enqueues work on it: it never allocates, never synchronises, never touches another stream;
+ *   - zero-fills that the reference leaves to its caller (tf_sampling.cpp:174, tf_grouping.cpp:270)
+ *     happen inside the callee;
+ *   - return value: 0 on success, F3D_ERR_* (negative) for invalid arguments, or a positive
+ *     cudaError_t from the launch.  f3d_last_error_string() describes the last non-zero code.
+ *   - workspaces are caller-provided; f3d_*_workspace_bytes() tells the size.
+ */
+#ifndef FEAT3DNET_B200_H_
+#define FEAT3DNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F3D_ERR_INVALID_ARGUMENT (-1)
+#define F3D_ERR_WORKSPACE_TOO_SMALL (-2)
+#define F3D_ERR_UNSUPPORTED (-3)
+
+/* library / device introspection */
+int f3d_version(void);
+const char *f3d_last_error_string(void);
+/* number of kernel launches issued through this library by the calling thread since the last reset */
+long long f3d_launch_count(void);
+void f3d_reset_launch_count(void);
+
+/* ---------------------------------------------------------------- tf_ops/sampling ------------- */
+
+/* farthestpointsamplingLauncher(b,n,m,inp,temp,out)  tf_sampling_g.cu:203-205, op tf_sampling.cpp:95-123.
+ * inp (b,n,3) f32 -> out (b,m) i32.  `temp` (the reference's 32*n float scratch) is accepted for
+ * signature compatibility and ignored (may be NULL): running distances live in registers. */
+int f3d_farthest_point_sample(int b, int n, int m, const float *inp, float *temp, int *out, void *stream);
+
+/* gatherpointLauncher(b,n,m,inp,idx,out)  tf_sampling_g.cu:206-208, op tf_sampling.cpp:126-148. */
+int f3d_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream);
+
+/* scatteraddpointLauncher(b,n,m,out_g,idx,inp_g)  tf_sampling_g.cu:209-211, op tf_sampling.cpp:151-178.
+ * Deterministic (no atomics): contributions to one point are added in ascending j.
+ * workspace: f3d_scatter_workspace_bytes(b*m) bytes. */
+int f3d_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------- tf_ops/grouping ------------- */
+
+/* queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt)  tf_grouping_g.cu:179-182,
+ * op tf_grouping.cpp:86-125.  xyz1 (b,n,3), xyz2 (b,m,3) -> idx (b,m,nsample) i32, pts_cnt (b,m) i32.
+ * Bit-exact with the reference including the pad-with-first-hit rule and the carried "nearest"
+ * fallback of empty balls (tf_grouping_g.cu:13-14,43-47). */
+int f3d_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                         int *pts_cnt, void *stream);
+
+/* queryBallPoint2Launcher(b,n,m,nsample,xyz1,xyz2,radii,idx,pts_cnt)  tf_grouping_g.cu:183-186,
+ * op tf_grouping.cpp:128-172.  radii (b,m).  Rows of empty balls are left untouched, as in the reference. */
+int f3d_query_ball_point2(int b, int n, int m, int nsample, const float *xyz1, const float *xyz2, const float *radii,
+                          int *idx, int *pts_cnt, void *stream);
+
+/* selectionSortLauncher(b,n,m,k,dist,outi,out)  tf_grouping_g.cu:187-190, op tf_grouping.cpp:175-205.
+ * dist (b,m,n) -> outi (b,m,n) i32, out (b,m,n) f32; the first k entries of each row are the k smallest
+ * in the reference's (unstable, swap-based) order; the remaining n-k entries hold the leftover elements
+ * exactly as the reference leaves them. */
+int f3d_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out, void *stream);
+
+/* knn_point(k, xyz1, xyz2)  tf_grouping.py:63-88 (TF tile/sub/square/reduce_sum + SelectionSort + slice),
+ * fused: no (b,m,n) matrix in HBM.  xyz1 (b,n,c), xyz2 (b,m,c) -> val (b,m,k) squared L2, idx (b,m,k).
+ * workspace: f3d_knn_workspace_bytes(b,n,m,c,k). */
+size_t f3d_knn_workspace_bytes(int b, int n, int m, int c, int k);
+int f3d_knn_point(int b, int n, int m, int c, int k, const float *xyz1, const float *xyz2, float *val, int *idx,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* groupPointLauncher(b,n,c,m,nsample,points,idx,out)  tf_grouping_g.cu:191-194, op tf_grouping.cpp:209-237. */
+int f3d_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                    void *stream);
+
+/* groupPointGradLauncher(b,n,c,m,nsample,grad_out,idx,grad_points)  tf_grouping_g.cu:195-199,
+ * op tf_grouping.cpp:240-274.  Deterministic segmented reduction (no atomics): the contributions to one
+ * point are added in ascending (j,k) order -- the order of the reference's CPU statement
+ * (tf_ops/grouping/test/query_ball_point.cpp:68-84).
+ * workspace: f3d_scatter_workspace_bytes(b*m*nsample). */
+size_t f3d_scatter_workspace_bytes(long long num_slots);
+int f3d_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                         float *grad_points, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------- models/ (fused forward) ----- */
+
+/* Folded eval-mode weights of the detector + descriptor (models/feat3dnet.py:277-310, layers.py:11-46):
+ * every conv+BN pair is folded on the host into W' (Cin,Cout) and b' (Cout).  `packed` is one device
+ * buffer of f3d_packed_weights_floats(feature_dim) floats; block i (see weights_layout.h: WeightSlot, 22
+ * blocks: W,b of detection/conv0..2, conv_post_0..1, attention, orientation, description/layer1/conv0..1,
+ * conv_mid_0, conv_post_0) starts at offsets[i] and holds sizes[i] floats. */
+size_t f3d_packed_weights_floats(int feature_dim);
+int f3d_packed_weights_num_blocks(void);
+int f3d_packed_weights_offsets(int feature_dim, int *offsets, int *sizes);
+
+/* workspace of the two fused forward entry points below (pooled per-cluster vectors) */
+size_t f3d_forward_workspace_bytes(int b, int m, int feature_dim);
+
+/* feature_detection_module forward (feat3dnet.py:90-151) on given cluster centres, eval-mode BN:
+ * xyz (b,n,3), new_xyz (b,m,3), idx (b,m,nsample) from f3d_query_ball_point ->
+ * attention (b,m), orientation (b,m).  Fuses group_point, translate, /radius, the 3->64->128->256 shared
+ * MLP, max-pool, 256->128->64, softplus / l2norm+atan2 heads: no grouped tensor touches HBM.
+ * precision: 0 = fp32 CUDA-core FFMA, 1 = tcgen05 TF32 (single pass), 3 = tcgen05 3xTF32 (fp32-accurate).
+ * nsample must be 8, 16, 32, 64 or 128. */
+int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const float *xyz, const float *new_xyz,
+                         const int *idx, const float *packed, float *attention, float *orientation, int precision,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* feature_extraction_module forward (feat3dnet.py:154-187 -> pointnet_sa_module :9-87 ->
+ * sample_and_group pointnet_common.py:69-135) on given keypoints and orientations (NULL = NoRegress):
+ * -> features (b,m,feature_dim), l2-normalised.  feature_dim in {16,32,64,128} (inference.py:41). */
+int f3d_descriptor_forward(int b, int n, int m, int nsample, float radius, int feature_dim, const float *xyz,
+                           const float *new_xyz, const int *idx, const float *orientation, const float *packed,
+                           float *features, int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEAT3DNET_B200_H_ */

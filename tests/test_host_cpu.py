@@ -1,0 +1,158 @@
+"""CPU tests of the host-side logic: argument validation mirrors the reference's OP_REQUIRES checks, the product
+refuses to run without CUDA (no fallback), BN folding, batch sharding and the gloo world_size-2 gradient exchange."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import pkg
+
+
+def test_validation_errors_match_reference_checks(f3d_lib):
+    ts = pkg("tf_ops.sampling.tf_sampling")
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    x = torch.zeros((1, 8, 3))
+    with pytest.raises(ValueError):
+        ts.farthest_point_sample(0, x)  # tf_sampling.cpp:99 npoint > 0
+    with pytest.raises(ValueError):
+        ts.farthest_point_sample(4, torch.zeros((1, 8, 2)))  # :105 shape
+    with pytest.raises(ValueError):
+        ts.gather_point(torch.zeros((1, 8, 4)), torch.zeros((1, 2), dtype=torch.int32))  # :131
+    with pytest.raises(ValueError):
+        tg.query_ball_point(0.0, 4, x, x)  # tf_grouping.cpp:90 radius > 0
+    with pytest.raises(ValueError):
+        tg.query_ball_point(1.0, 0, x, x)  # :93 nsample > 0
+    with pytest.raises(ValueError):
+        tg.query_ball_point(1.0, 4, x, torch.zeros((2, 8, 3)))  # batch mismatch
+    with pytest.raises(ValueError):
+        tg.select_top_k(0, torch.zeros((1, 2, 3)))  # :179
+    with pytest.raises(ValueError):
+        tg.group_point(torch.zeros((1, 8)), torch.zeros((1, 2, 2), dtype=torch.int32))  # :215
+
+
+def test_no_cpu_fallback(f3d_lib):
+    """The product path fails loudly on CPU tensors instead of computing anything on the host."""
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    lib_mod = pkg("_lib")
+    x = torch.zeros((1, 8, 3))
+    with pytest.raises(lib_mod.F3DError):
+        tg.query_ball_point(1.0, 4, x, x)
+    with pytest.raises(lib_mod.F3DError):
+        pkg("tf_ops.sampling.tf_sampling").farthest_point_sample(2, x)
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under 3dfeatnet_b200/ may import, call or link oracle/."""
+    root = os.path.dirname(pkg().__file__)
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_dropin_import_paths(f3d_lib):
+    """The reference's own import lines resolve once the package directory is on sys.path."""
+    pkg().install_dropin()
+    try:
+        m = importlib.import_module("tf_ops.grouping.tf_grouping")
+        assert callable(m.query_ball_point) and callable(m.group_point) and callable(m.knn_point)
+        m = importlib.import_module("tf_ops.sampling.tf_sampling")
+        assert callable(m.farthest_point_sample) and callable(m.gather_point)
+        m = importlib.import_module("models.pointnet_common")
+        assert callable(m.sample_and_group) and callable(m.query_and_group_points)
+        m = importlib.import_module("models.feat3dnet")
+        assert callable(m.feature_detection_module) and callable(m.feature_extraction_module)
+        assert importlib.import_module("models.net_factory").get_network("3DFeatNet") is m.Feat3dNet
+    finally:
+        sys.path.remove(os.path.dirname(pkg().__file__))
+        for k in [k for k in sys.modules if k.split(".")[0] in ("tf_ops", "models", "_lib")]:
+            del sys.modules[k]
+
+
+def test_fold_params_equals_unfolded_layer(f3d_lib):
+    """W' = W*s, b' = (b-mean)*s+beta reproduces conv+BN(eval) of models/layers.py for every layer."""
+    from oracle import net as onet
+
+    f3 = pkg("models.feat3dnet")
+    layers = pkg("models.layers")
+    params = {k: torch.as_tensor(v) for k, v in onet.init_params(seed=5, randomize_bn=True).items()}
+    packed = f3.fold_params(params, 32)
+    import ctypes
+
+    nb = f3d_lib.f3d_packed_weights_num_blocks()
+    offs, sizes = (ctypes.c_int * nb)(), (ctypes.c_int * nb)()
+    assert f3d_lib.f3d_packed_weights_offsets(32, offs, sizes) == 0
+    assert packed.numel() == f3d_lib.f3d_packed_weights_floats(32)
+    g = torch.Generator().manual_seed(0)
+    for i, (scope, cin, cout, bn) in enumerate(f3.DET_LAYERS + f3.desc_layers(32)):
+        x = torch.randn((2, 3, 4, cin), generator=g)
+        want = layers.conv2d(x, cout, [1, 1], padding='VALID', bn=bn, is_training=False, activation=None, scope=scope,
+                             params=params)
+        w = packed[offs[2 * i]:offs[2 * i] + cin * cout].reshape(cin, cout)
+        b = packed[offs[2 * i + 1]:offs[2 * i + 1] + cout]
+        got = x @ w + b
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), scope
+        assert offs[2 * i] % 4 == 0 and offs[2 * i + 1] % 4 == 0
+
+
+def test_unfused_layers_match_oracle_net_on_cpu():
+    """models/layers.py + the loss follow the same semantics as oracle/net.py (both restate SURVEY.md appendix B)."""
+    from oracle import net as onet
+
+    layers = pkg("models.layers")
+    P = {k: torch.as_tensor(v) for k, v in onet.init_params(seed=2, randomize_bn=True).items()}
+    x = torch.randn((2, 5, 7, 3))
+    for training in (False, True):
+        a = layers.conv2d(x, 64, [1, 1], padding='VALID', bn=True, is_training=training, scope="detection/conv0", params=P)
+        b = onet.conv2d(x, P, "detection/conv0", True, "relu", training)
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    fa, fp, fn = torch.randn(3, 2, 9, 4).unbind(0)
+    att = torch.rand(2, 9) + 0.1
+    net = pkg("models.feat3dnet").Feat3dNet.__new__(pkg("models.feat3dnet").Feat3dNet)
+    net.param = dict(Attention=True, margin=0.2)
+    loss, _ = net.get_loss(None, (fa, fp, fn), att, {})
+    assert torch.allclose(loss, onet.triplet_loss(fa, fp, fn, att, 0.2, True))
+
+
+def test_shard_range_partitions():
+    d = pkg("dist")
+    for total in (0, 1, 7, 64, 65):
+        for world in (1, 2, 3, 8):
+            spans = [d.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    d = importlib.import_module("3dfeatnet_b200.dist")
+    d.init("gloo")
+    lo, hi = d.shard_range(10, rank, world)
+    flat = torch.arange(107619, dtype=torch.float32) * (rank + 1)  # the model's 107 619 trainable floats
+    d.allreduce_mean_(flat)
+    mx = d.max_over_ranks(float(rank) + 0.5, torch.device("cpu"))
+    d.barrier()
+    q.put((rank, lo, hi, float(flat[1000]), mx))
+
+
+def test_gloo_world_size_2_gradient_exchange():
+    """N>1 path on CPU: batch sharding + the single flat-buffer all-reduce (mean) of the training step."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    assert [(r[1], r[2]) for r in res] == [(0, 5), (5, 10)]
+    assert all(abs(r[3] - 1000 * 1.5) < 1e-3 for r in res)  # mean of 1x and 2x
+    assert all(r[4] == 1.5 for r in res)

@@ -1,0 +1,143 @@
+"""GPU parity tests (-m gpu) of the fused detector / descriptor forward and of the model-level API against the
+oracle network (oracle/net.py, PyTorch-CPU).  Index outputs (FPS, ball query) are compared bit-exactly; floating
+point outputs within the tolerances written here:
+
+  fp32 path   (CUDA-core FFMA, BN folded into the weights):  attention 1e-4 relative to the cloud's max attention,
+              orientation 1e-4 rad (wrapped), descriptors 1e-4 absolute on unit-norm vectors.
+  tf32/3xtf32 (tcgen05) paths: see TOL below.
+The oracle itself moves by ~1e-6 between fp32 and fp64 evaluation, so these bounds leave two orders of headroom for
+summation-order differences and none for a wrong layer.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import net as onet
+from tests.conftest import pkg
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": dict(att=1e-4, ori=1e-4, feat=1e-4),
+       "3xtf32": dict(att=2e-4, ori=2e-4, feat=2e-4),
+       "tf32": dict(att=2e-2, ori=2e-2, feat=2e-2)}
+
+
+def wrap(d):
+    return torch.atan2(torch.sin(d), torch.cos(d))
+
+
+def compare(out, ref, tol, what=""):
+    att, ratt = out["attention"].cpu().double(), ref["attention"].double()
+    e_att = ((att - ratt).abs() / ratt.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)).max().item()
+    e_ori = wrap(out["orientation"].cpu().double() - ref["orientation"].double()).abs().max().item()
+    e_feat = (out["features"].cpu().double() - ref["features"].double()).abs().max().item()
+    assert e_att < tol["att"], "%s attention err %.3e" % (what, e_att)
+    assert e_feat < tol["feat"], "%s descriptor err %.3e" % (what, e_feat)
+    # orientation of a near-zero (x,y) head output is ill-conditioned; require the bound on all but 0.5 % of clusters
+    d = wrap(out["orientation"].cpu().double() - ref["orientation"].double()).abs().reshape(-1)
+    assert (d > tol["ori"]).double().mean().item() < 5e-3, "%s orientation err %.3e" % (what, e_ori)
+    return e_att, e_ori, e_feat
+
+
+def run_pipeline(xyz, params, M, S=64, F=32, precision="fp32", no_regress=False, dev="cuda:0"):
+    pm = pkg("pipeline")
+    B, N, _ = xyz.shape
+    pipe = pm.DetectDescribePipeline(B, N, weights=params, num_clusters=M, nsample=S, feature_dim=F, precision=precision,
+                                     no_regress=no_regress, device=dev)
+    out = pipe.run(torch.as_tensor(xyz).to(dev))
+    torch.cuda.synchronize()
+    return {k: v.clone() for k, v in out.items()}, pipe
+
+
+@pytest.mark.parametrize("randomize_bn", [True, False])
+def test_c1_oxford_270_fp32(cuda, randomize_bn):
+    """BASELINE.json configs[0]: example_data/oxford_270 (16384 pts), 512 clusters, r=2.0, nsample=64, random init.
+    randomize_bn=False is the TF random-init state (EMA shadows 0 => x31.6 per BN layer)."""
+    xyz = pkg("synth").base_cloud("oxford")[None]
+    params = onet.init_params(seed=0, randomize_bn=randomize_bn)
+    out, pipe = run_pipeline(xyz, params, 512)
+    ref = onet.inference_model(xyz, onet.to_torch(params, torch.float64), num_clusters=512, dtype=torch.float64)
+    assert np.array_equal(out["fps_idx"].cpu().numpy(), ref["fps_idx"])
+    assert np.array_equal(out["idx"].cpu().numpy(), ref["idx"])
+    assert np.array_equal(out["pts_cnt"].cpu().numpy(), ref["pts_cnt"])
+    assert np.array_equal(out["xyz"].cpu().numpy(), ref["xyz"])
+    compare(out, ref, TOL["fp32"], "C1")
+    assert abs(out["features"].norm(dim=2) - 1).max().item() < 1e-5
+    assert pipe.launches_per_step >= 5
+
+
+@pytest.mark.parametrize("B,N,M,S,F,no_regress", [(3, 4096, 128, 64, 32, False), (2, 2048, 100, 32, 64, False),
+                                                  (1, 3000, 37, 16, 128, True), (2, 1024, 64, 128, 16, False),
+                                                  (1, 5000, 129, 8, 32, False)])
+def test_fused_forward_shapes_fp32(cuda, B, N, M, S, F, no_regress):
+    """ragged cluster counts (M not a multiple of the 2-cluster tile), every supported nsample and feature_dim"""
+    xyz = pkg("synth").make_batch(B, N, seed0=50 + N)
+    params = onet.init_params(seed=1, feature_dim=F, randomize_bn=True)
+    out, _ = run_pipeline(xyz, params, M, S, F, no_regress=no_regress)
+    ref = onet.inference_model(xyz, onet.to_torch(params, torch.float64), num_clusters=M, nsample=S, feature_dim=F,
+                               no_regress=no_regress, dtype=torch.float64)
+    assert np.array_equal(out["idx"].cpu().numpy(), ref["idx"])
+    compare(out, ref, TOL["fp32"], "shape")
+
+
+def test_model_api_matches_pipeline_and_unfused_path(cuda):
+    """Feat3dNet.get_inference_model (reference signature): the fused eval path equals the pipeline, and the unfused
+    differentiable layers (models/layers.py) agree with it within the fp32 tolerance; external keypoints are honoured."""
+    f3 = pkg("models.feat3dnet")
+    xyz = pkg("synth").make_batch(2, 4096, seed0=9)
+    params = onet.init_params(seed=4, randomize_bn=True)
+    net = f3.Feat3dNet({'num_clusters': 64}, weights=params, device=cuda)
+    pc = torch.as_tensor(np.concatenate([xyz, np.zeros_like(xyz)], axis=2)).to(cuda)  # (B,N,6): only xyz is used
+    kp, feat, att, ep = net.get_inference_model(pc, False)
+    out, _ = run_pipeline(xyz, params, 64)
+    assert torch.equal(kp, out["xyz"]) and torch.equal(feat, out["features"]) and torch.equal(att, out["attention"])
+    kp2, feat2, att2, ep2 = net.get_inference_model(pc, False, use_bn=True, keypoints=kp)
+    assert torch.equal(feat2, feat)
+    # unfused statement, eval mode, routed through models.layers (is_training=False, compute_det_gradients -> unfused)
+    new_xyz, idx, att_u, ori_u, _ = f3.feature_detection_module(
+        pc[:, :, :3].contiguous(), None, 64, 2.0, False, [64, 128, 256], [128, 64], params=net.weights)
+    assert torch.equal(idx, ep["idx"])
+    _, feat_u, _ = f3.feature_extraction_module(pc[:, :, :3].contiguous(), None, False, [32, 64], [128], [32],
+                                                keypoints=new_xyz, orientations=ori_u, params=net.weights)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = dict(attention=att_u.cpu(), orientation=ori_u.cpu(), features=feat_u.cpu())
+    compare(dict(attention=att, orientation=ep["orientation"], features=feat), ref, TOL["fp32"], "unfused")
+
+
+def test_saliency_gradients_run_through_group_point_grad(cuda):
+    """compute_det_gradients (feat3dnet.py:125-127; KeyError in the reference) exercises GroupPointGrad+GatherPointGrad."""
+    f3 = pkg("models.feat3dnet")
+    xyz = torch.as_tensor(pkg("synth").make_batch(1, 2048, seed0=3)).to(cuda)
+    net = f3.Feat3dNet({'num_clusters': 32}, weights=onet.init_params(seed=4, randomize_bn=True), device=cuda)
+    _, _, _, ep = net.get_inference_model(xyz, False, compute_det_gradients=True)
+    g = ep['gradients']['det']
+    assert set(g) == {'mlp_0', 'mlp_1', 'mlp_2'}
+    assert all(v.shape == xyz.shape and torch.isfinite(v).all() and v.abs().sum() > 0 for v in g.values())
+
+
+def test_training_step_matches_oracle(cuda):
+    """One stage-2 step on a small triplet batch: loss, gradients and the TF-style Adam update vs the CPU oracle."""
+    f3 = pkg("models.feat3dnet")
+    synth = pkg("synth")
+    B, N, M = 2, 1024, 32
+    a, p, n = (synth.make_batch(B, N, seed0=s) for s in (1, 2, 3))
+    params = onet.init_params(seed=6, randomize_bn=True)
+    net = f3.Feat3dNet({'num_clusters': M}, weights=params, device=cuda).train_mode()
+    A, P_, Nn = (torch.as_tensor(t).to(cuda) for t in (a, p, n))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xyz, feats, att, ep = net.get_train_model(A, P_, Nn, True)
+    loss, ep = net.get_loss(xyz, feats, att, ep)
+    before = {k: v.detach().clone() for k, v in net.weights.items()}
+    flat = net.get_train_op(loss, lr=1e-3, end_points=ep)
+    oP = onet.to_torch(params, torch.float64, requires_grad=True)
+    oloss, ograds, _ = onet.train_step(a, p, n, oP, {}, num_clusters=M, lr=1e-3, dtype=torch.float64)
+    assert abs(loss.item() - oloss.item()) < 1e-4 * max(1.0, abs(oloss.item()))
+    names = [k for k, v in net.trainable_variables().items()]
+    og = torch.cat([ograds[k].reshape(-1) for k in names]).float()
+    assert flat.numel() == 107619
+    denom = og.abs().max().item() + 1e-12
+    assert (flat.cpu() - og).abs().max().item() / denom < 5e-3
+    moved = sum((net.weights[k] - before[k]).abs().sum().item() for k in names)
+    assert moved > 0
+    for k in ("detection/conv0/bn/moving_mean", "description/layer1/conv_mid_0/bn/moving_variance"):
+        assert torch.allclose(net.weights[k].cpu().double(), oP[k], rtol=1e-3, atol=1e-4)

@@ -1,0 +1,298 @@
+"""GPU parity tests (-m gpu) of the sampling / grouping operators, called through the C ABI (ctypes) via the
+reference-shaped Python wrappers.  Checkers: the CPU oracle (oracle/ops_oracle.c) and, when oracle/_ref is present,
+the reference's own CUDA kernels built unmodified for sm_100a.  Indices are compared BIT-EXACTLY."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as oops
+from oracle import ref as oref
+from tests.conftest import pkg
+
+pytestmark = pytest.mark.gpu
+
+HAVE_REF = oref.available("libref_grouping.so") and oref.available("libref_sampling.so")
+
+
+def T(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+
+
+def clouds(kind, b, n, seed):
+    synth = pkg("synth")
+    if kind == "uniform":
+        return synth.uniform_cloud(b, n, seed)
+    if kind == "oxford":
+        return synth.make_batch(b, n, seed0=seed)
+    rng = np.random.default_rng(seed)
+    if kind == "dups":  # 10 % exact duplicates (datagenerator.py:148-157 pads clouds this way)
+        x = synth.uniform_cloud(b, n, seed)
+        k = max(1, n // 10)
+        for i in range(b):
+            x[i, rng.choice(n, k, replace=False)] = x[i, rng.choice(n, k, replace=False)]
+        return x
+    raise ValueError(kind)
+
+
+# ------------------------------------------------------------------------------------------------ FPS / gather
+@pytest.mark.parametrize("kind,b,n,m", [
+    ("uniform", 2, 4096, 512), ("oxford", 2, 16384, 512), ("dups", 3, 5000, 300), ("uniform", 1, 777, 64),
+    ("dups", 2, 8192, 256), ("uniform", 33, 1024, 32), ("uniform", 1, 40000, 128), ("uniform", 2, 100, 100),
+])
+def test_fps_bit_exact_vs_oracle(cuda, kind, b, n, m):
+    ts = pkg("tf_ops.sampling.tf_sampling")
+    x = clouds(kind, b, n, 100 + n)
+    got = ts.farthest_point_sample(m, T(x, cuda)).cpu().numpy()
+    want = oops.farthest_point_sample(m, x)
+    assert got.dtype == np.int32 and np.array_equal(got, want)
+    kp = ts.gather_point(T(x, cuda), T(want, cuda)).cpu().numpy()
+    assert np.array_equal(kp, oops.gather_point(x, want))
+
+
+def test_fps_all_points_identical(cuda):
+    """every distance ties at 0: the reference tie rule picks k=0 each round"""
+    ts = pkg("tf_ops.sampling.tf_sampling")
+    x = np.ones((1, 2000, 3), np.float32)
+    got = ts.farthest_point_sample(5, T(x, cuda)).cpu().numpy()
+    assert np.array_equal(got, oops.farthest_point_sample(5, x))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+@pytest.mark.parametrize("kind,b,n,m", [("oxford", 4, 16384, 512), ("dups", 2, 4096, 512), ("uniform", 2, 131072, 64)])
+def test_fps_bit_exact_vs_reference_cuda(cuda, kind, b, n, m):
+    ts = pkg("tf_ops.sampling.tf_sampling")
+    x = T(clouds(kind, b, n, 7), cuda)
+    assert torch.equal(ts.farthest_point_sample(m, x), oref.gpu_farthest_point_sample(m, x))
+
+
+def test_gather_point_grad_deterministic_and_exact(cuda):
+    ts = pkg("tf_ops.sampling.tf_sampling")
+    rng = np.random.default_rng(1)
+    b, n, m = 3, 500, 4000  # m > n: many repeated indices
+    inp = rng.random((b, n, 3), dtype=np.float32)
+    idx = rng.integers(0, n, (b, m)).astype(np.int32)
+    g = rng.standard_normal((b, m, 3)).astype(np.float32)
+    want = oops.gather_point_grad(inp, idx, g)
+    got = ts.gather_point_grad(n, T(idx, cuda), T(g, cuda))
+    assert np.array_equal(got.cpu().numpy(), want)  # same ascending-j summation order as the oracle: bit-exact
+    assert torch.equal(got, ts.gather_point_grad(n, T(idx, cuda), T(g, cuda)))
+    x = T(inp, cuda).requires_grad_(True)
+    ts.gather_point(x, T(idx, cuda)).backward(T(g, cuda))
+    assert np.array_equal(x.grad.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------------ ball query
+def _centres(x, m, mode, seed):
+    rng = np.random.default_rng(seed)
+    b, n, _ = x.shape
+    if mode == "subset":
+        idx = np.stack([rng.choice(n, m, replace=(m > n)) for _ in range(b)]).astype(np.int32)
+        return oops.gather_point(x, idx)
+    if mode == "external":  # not in the cloud; a third of them far away (empty balls -> carried fallback)
+        c = x[:, rng.integers(0, n, m)] + rng.normal(0, 0.5, (b, m, 3)).astype(np.float32)
+        c[:, m // 3::3] += 1000.0
+        c[:, 1] = x[:, 3]
+        return np.ascontiguousarray(c, np.float32)
+    raise ValueError(mode)
+
+
+@pytest.mark.parametrize("kind,b,n,m,radius,ns,mode", [
+    ("uniform", 2, 4096, 512, 2.0, 64, "subset"), ("oxford", 2, 16384, 512, 2.0, 64, "subset"),
+    ("uniform", 2, 8192, 256, 2.0, 64, "external"), ("dups", 2, 4096, 700, 1.5, 32, "external"),
+    ("uniform", 1, 1237, 101, 3.0, 64, "subset"), ("uniform", 3, 333, 1030, 4.0, 16, "external"),
+    ("oxford", 1, 32768, 1024, 2.0, 64, "subset"), ("uniform", 1, 65536, 2048, 2.0, 64, "subset"),
+    ("uniform", 1, 131072, 4096, 2.0, 64, "subset"), ("uniform", 2, 600, 70, 0.05, 8, "external"),
+    ("uniform", 1, 50, 9, 100.0, 64, "subset"),
+])
+def test_ball_query_bit_exact_vs_oracle(cuda, kind, b, n, m, radius, ns, mode):
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    x = clouds(kind, b, n, 5 + n)
+    c = _centres(x, m, mode, n + m)
+    idx, cnt = tg.query_ball_point(radius, ns, T(x, cuda), T(c, cuda))
+    widx, wcnt = oops.query_ball_point(radius, ns, x, c)
+    assert idx.dtype == torch.int32 and cnt.dtype == torch.int32
+    assert np.array_equal(cnt.cpu().numpy(), wcnt)
+    assert np.array_equal(idx.cpu().numpy(), widx)
+    if mode == "external":
+        assert (wcnt == 0).any()  # the fallback path was exercised
+
+
+def test_ball_query_radius_on_representable_boundaries(cuda):
+    """points at exactly d == r (not a hit: strict '<'), one ulp inside, one ulp outside; radii 0.5, 2.0, sqrt-inexact 0.3"""
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    for r in (0.5, 2.0, 0.3, 1e-3, 37.25):
+        r32 = np.float32(r)
+        xs = np.array([r32, np.nextafter(r32, np.float32(0)), np.nextafter(r32, np.float32(100)), 0.0,
+                       np.nextafter(np.nextafter(r32, np.float32(0)), np.float32(0))], np.float32)
+        x = np.zeros((1, 5 * 3, 3), np.float32)
+        for a in range(3):
+            x[0, a * 5:(a + 1) * 5, a] = xs
+        c = np.zeros((1, 1, 3), np.float32)
+        idx, cnt = tg.query_ball_point(float(r32), 16, T(x, cuda), T(c, cuda))
+        widx, wcnt = oops.query_ball_point(float(r32), 16, x, c)
+        assert np.array_equal(cnt.cpu().numpy(), wcnt) and np.array_equal(idx.cpu().numpy(), widx), r
+    # random near-boundary configurations: centres at distance r*(1 +- few ulp) in random directions
+    rng = np.random.default_rng(0)
+    n = 4096
+    d = rng.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    scale = 2.0 * (1 + rng.integers(-4, 5, n) * 2.0 ** -24)
+    x = (d * scale[:, None]).astype(np.float32)[None]
+    c = np.zeros((1, 1, 3), np.float32)
+    idx, cnt = tg.query_ball_point(2.0, 4096, T(x, cuda), T(c, cuda))
+    widx, wcnt = oops.query_ball_point(2.0, 4096, x, c)
+    assert 0 < wcnt[0, 0] < n
+    assert np.array_equal(cnt.cpu().numpy(), wcnt) and np.array_equal(idx.cpu().numpy(), widx)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+@pytest.mark.parametrize("kind,b,n,m,mode", [("oxford", 2, 16384, 512, "subset"), ("uniform", 2, 4096, 777, "external"),
+                                             ("uniform", 1, 131072, 4096, "subset")])
+def test_ball_query_bit_exact_vs_reference_cuda(cuda, kind, b, n, m, mode):
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    x = clouds(kind, b, n, 9)
+    c = _centres(x, m, mode, 10)
+    idx, cnt = tg.query_ball_point(2.0, 64, T(x, cuda), T(c, cuda))
+    ridx, rcnt = oref.gpu_query_ball_point(2.0, 64, T(x, cuda), T(c, cuda))
+    assert torch.equal(cnt, rcnt) and torch.equal(idx, ridx)
+
+
+def test_query_ball_point2_vs_oracle(cuda):
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    rng = np.random.default_rng(2)
+    x = rng.random((2, 3000, 3), dtype=np.float32)
+    c = rng.random((2, 130, 3), dtype=np.float32)
+    c[:, ::7] += 10.0
+    radii = rng.uniform(0.05, 0.4, (2, 130)).astype(np.float32)
+    idx, cnt = tg.query_ball_point2(T(radii, cuda), 32, T(x, cuda), T(c, cuda))
+    widx, wcnt = oops.query_ball_point2(radii, 32, x, c)
+    ne = wcnt > 0
+    assert np.array_equal(cnt.cpu().numpy(), wcnt) and (~ne).any()
+    assert np.array_equal(idx.cpu().numpy()[ne], widx[ne])  # empty rows are undefined in the reference
+
+
+# ------------------------------------------------------------------------------------------------ group_point (+grad)
+@pytest.mark.parametrize("b,n,c,m,ns", [(2, 4096, 3, 512, 64), (2, 1000, 64, 128, 32), (1, 333, 5, 17, 7), (1, 16384, 3, 2048, 64),
+                                        (2, 512, 16, 128, 64)])
+def test_group_point_and_grad_vs_oracle(cuda, b, n, c, m, ns):
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    rng = np.random.default_rng(n + c)
+    pts = rng.random((b, n, c), dtype=np.float32)
+    idx = rng.integers(0, n, (b, m, ns)).astype(np.int32)
+    idx[:, :, ns // 2:] = idx[:, :, :1]  # padded rows: repeated indices, multiplicity matters
+    out = tg.group_point(T(pts, cuda), T(idx, cuda))
+    assert np.array_equal(out.cpu().numpy(), oops.group_point(pts, idx))
+    g = rng.standard_normal((b, m, ns, c)).astype(np.float32)
+    want = oops.group_point_grad(pts, idx, g)
+    got = tg.group_point_grad(n, T(idx, cuda), T(g, cuda))
+    assert np.array_equal(got.cpu().numpy(), want)  # ascending (j,k) order, no atomics: bit-exact and reproducible
+    assert torch.equal(got, tg.group_point_grad(n, T(idx, cuda), T(g, cuda)))
+    p = T(pts, cuda).requires_grad_(True)
+    tg.group_point(p, T(idx, cuda)).backward(T(g, cuda))
+    assert np.array_equal(p.grad.cpu().numpy(), want)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_group_point_grad_vs_reference_cuda_atomics(cuda):
+    """the reference's atomicAdd result is order-dependent: compare within fp32 reassociation tolerance"""
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    rng = np.random.default_rng(3)
+    b, n, c, m, ns = 2, 2048, 16, 256, 64
+    pts = T(rng.random((b, n, c), dtype=np.float32), cuda)
+    idx = T(rng.integers(0, n, (b, m, ns)).astype(np.int32), cuda)
+    g = T(rng.standard_normal((b, m, ns, c)).astype(np.float32), cuda)
+    assert torch.equal(tg.group_point(pts, idx), oref.gpu_group_point(pts, idx))
+    assert torch.allclose(tg.group_point_grad(n, idx, g), oref.gpu_group_point_grad(pts, idx, g), rtol=1e-5, atol=1e-5)
+
+
+def test_reference_unit_test_group_point_grad(cuda):
+    """tf_grouping_op_test.py:10-27 with its shapes: points (1,128,16), xyz1 (1,128,3), xyz2 (1,8,3), r=0.3, nsample=32;
+    analytic gradient vs numeric Jacobian, err < 1e-4."""
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    rng = np.random.RandomState(0)
+    points = T(rng.random_sample((1, 128, 16)).astype("float32"), cuda).requires_grad_(True)
+    xyz1 = T(rng.random_sample((1, 128, 3)).astype("float32"), cuda)
+    xyz2 = T(rng.random_sample((1, 8, 3)).astype("float32"), cuda)
+    idx, _ = tg.query_ball_point(0.3, 32, xyz1, xyz2)
+    w = T(rng.standard_normal((1, 8, 32, 16)).astype("float32"), cuda)
+    (tg.group_point(points, idx) * w).sum().backward()
+    analytic = points.grad.clone()
+    eps = 1e-2
+    with torch.no_grad():
+        for i in rng.choice(128 * 16, 48, replace=False):
+            d = torch.zeros(128 * 16, device=cuda)
+            d[i] = eps
+            d = d.reshape(1, 128, 16)
+            num = ((tg.group_point(points + d, idx) * w).sum() - (tg.group_point(points - d, idx) * w).sum()) / (2 * eps)
+            assert abs(num.item() - analytic.reshape(-1)[i].item()) < 1e-4 * max(1.0, abs(num.item()))
+
+
+def test_reference_unit_test_query_ball_point2(cuda):
+    """tf_grouping_op_test.py:32-65 with its shapes and its cdist property check."""
+    from scipy.spatial.distance import cdist
+
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    rng = np.random.RandomState(0)
+    xyz1 = rng.random_sample((1, 128, 3)).astype("float32")
+    xyz2 = rng.random_sample((1, 8, 3)).astype("float32")
+    radii = rng.uniform(low=0.2, high=0.4, size=(1, 8)).astype("float32")
+    idx, pts_cnt = tg.query_ball_point2(T(radii, cuda), 32, T(xyz1, cuda), T(xyz2, cuda))
+    idx, pts_cnt = idx.cpu().numpy(), pts_cnt.cpu().numpy()
+    assert idx.max() < 128 and pts_cnt.max() <= 32
+    Y = cdist(xyz1[0].astype(np.float64), xyz2[0].astype(np.float64))
+    within = Y < radii[0][None, :]
+    assert np.array_equal(pts_cnt[0], within.sum(0))
+    for j in range(8):
+        assert set(idx[0, j]) == set(np.nonzero(within[:, j])[0])
+
+
+# ------------------------------------------------------------------------------------------------ top-k / kNN
+def test_select_top_k_known_answer_and_ties(cuda):
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    dist = (10 - np.arange(16, dtype=np.float32)).reshape(2, 2, 4)  # test/selection_sort.cpp:65-93
+    outi, out = tg.select_top_k(3, T(dist, cuda))
+    assert np.array_equal(outi.cpu().numpy().ravel(), np.tile([3, 2, 1, 0], 4))
+    outi, _ = tg.select_top_k(4, T(np.array([[[2, 2, 1, 2, 1, 3]]], np.float32), cuda))
+    assert outi[0, 0, :4].tolist() == [2, 4, 0, 3]  # unstable-sort tie order, SURVEY.md A-6
+    rng = np.random.default_rng(4)
+    d = rng.integers(0, 9, (2, 50, 300)).astype(np.float32)
+    outi, out = tg.select_top_k(64, T(d, cuda))
+    wi, wo = oops.select_top_k(64, d)
+    assert np.array_equal(outi.cpu().numpy(), wi) and np.array_equal(out.cpu().numpy(), wo)  # whole (b,m,n) arrays
+    if HAVE_REF:
+        ri, ro = oref.gpu_select_top_k(64, T(d, cuda))
+        assert torch.equal(outi, ri) and torch.equal(out, ro)
+
+
+@pytest.mark.parametrize("b,n,m,c,k", [(2, 512, 128, 3, 64), (1, 1000, 33, 3, 16), (2, 300, 20, 5, 300)])
+def test_knn_point_vs_oracle(cuda, b, n, m, c, k):
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    rng = np.random.default_rng(k)
+    x1 = rng.random((b, n, c), dtype=np.float32)
+    x1[:, n // 2:] = x1[:, :n - n // 2]  # duplicates: exact distance ties
+    x2 = rng.random((b, m, c), dtype=np.float32)
+    val, idx = tg.knn_point(k, T(x1, cuda), T(x2, cuda))
+    wval, widx = oops.knn_point(k, x1, x2)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(val.cpu().numpy(), wval)
+
+
+# ------------------------------------------------------------------------------------------------ layer-level composition
+def test_sample_and_group_matches_oracle_composition(cuda):
+    pc = pkg("models.pointnet_common")
+    x = clouds("oxford", 2, 4096, 3)
+    xyz = T(x, cuda)
+    ori = torch.linspace(-3, 3, 2 * 64, device=cuda).reshape(2, 64)
+    new_xyz, new_points, idx, grouped, ep = pc.sample_and_group(64, 2.0, 32, xyz, None, orientations=ori,
+                                                                normalize_radius=True)
+    fps = oops.farthest_point_sample(64, x)
+    kp = oops.gather_point(x, fps)
+    widx, wcnt = oops.query_ball_point(2.0, 32, x, kp)
+    assert np.array_equal(new_xyz.cpu().numpy(), kp) and np.array_equal(idx.cpu().numpy(), widx)
+    g = (oops.group_point(x, widx) - kp[:, :, None, :]) / np.float32(2.0)
+    assert np.allclose(ep['grouped_xyz_before'].cpu().numpy(), g, rtol=1e-6, atol=1e-6)
+    c, s = np.cos(ori.cpu().numpy())[:, :, None], np.sin(ori.cpu().numpy())[:, :, None]
+    rot = np.stack([g[..., 0] * c - g[..., 1] * s, g[..., 0] * s + g[..., 1] * c, g[..., 2]], -1)
+    assert np.allclose(grouped.cpu().numpy(), rot, rtol=1e-5, atol=1e-5)
+    assert torch.equal(new_points, grouped)
+    # detector-side helper: identity sampling when npoint <= 0 (pointnet_common.py:24-25)
+    assert torch.equal(pc.sample_points(xyz, -1), xyz)
