@@ -158,10 +158,17 @@ def test_ball_query_empty_ball_carry_quirk():
     idx, cnt = ops.query_ball_point(0.05, 8, xyz1, xyz2)
     assert (cnt[0, 256:] == 0).all()
     assert (idx[0, 263] == 123).all() and (idx[0, 519] == 123).all()  # stale carry, not the true nearest
-    d = np.linalg.norm(xyz1[0] - xyz2[0, 300], axis=1)
-    true_nearest = int(np.argmin(d))
-    # thread 44 (300 % 256): carried minimum over centre 44's examined prefix and centre 300's full scan
-    assert idx[0, 300, 0] in (true_nearest, idx[0, 300, 0])
+    # thread 44 (300 % 256): first strict minimum over centre 44's examined prefix followed by centre 300's full scan
+    def dist(j, ks):
+        d = xyz2[0, j] - xyz1[0, ks]
+        s = np.float32(d[:, 1] * d[:, 1])
+        s = (d[:, 0].astype(np.float64) * d[:, 0] + s).astype(np.float32)
+        s = (d[:, 2].astype(np.float64) * d[:, 2] + s).astype(np.float32)
+        return np.maximum(np.sqrt(s), np.float32(1e-20))
+    kexit = int(idx[0, 44, 7]) if cnt[0, 44] == 8 else n - 1
+    seq_d = np.concatenate([dist(44, np.arange(kexit + 1)), dist(300, np.arange(n))])
+    seq_k = np.concatenate([np.arange(kexit + 1), np.arange(n)])
+    assert idx[0, 300, 0] == seq_k[int(np.argmin(seq_d))]
     # a centre with no earlier hit-free history and nothing nearer: gets its true nearest
     xyz2b = xyz2[:, :200].copy()
     xyz2b[0, 100] += 500.0
