@@ -32,6 +32,8 @@ SIGNATURES = {
     "f3d_forward_workspace_bytes": (_sz, [_i, _i, _i]),
     "f3d_detector_forward": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "f3d_descriptor_forward": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "f3d_debug_umma_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "f3d_detector_tc_weight_bytes": (_sz, []),
 }
 
 _LIB = None

@@ -8,9 +8,16 @@ int detector_forward_fp32(int b, int n, int m, int S, float radius, const float 
 int descriptor_forward_fp32(int b, int n, int m, int S, float radius, int feature_dim, const float *xyz,
                             const float *new_xyz, const int *idx, const float *orientation, const float *packed,
                             float *pooled_ws, float *features, cudaStream_t st);
+int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
+                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, cudaStream_t st);
+int detector_post_fp32(long long num_clusters, const float *pooled, const float *packed, float *attention,
+                       float *orientation, cudaStream_t st);
 }  // namespace f3d
+extern "C" size_t f3d_detector_tc_weight_bytes(void);
 
 using namespace f3d;
+
+static size_t pooled_bytes(int b, int m) { return (static_cast<size_t>(b) * m * 256 * sizeof(float) + 255) & ~static_cast<size_t>(255); }
 
 F3D_API size_t f3d_packed_weights_floats(int feature_dim) { return static_cast<size_t>(make_weight_layout(feature_dim).total); }
 F3D_API int f3d_packed_weights_num_blocks(void) { return kNumWeightSlots; }
@@ -26,7 +33,7 @@ F3D_API int f3d_packed_weights_offsets(int feature_dim, int *offsets, int *sizes
 
 F3D_API size_t f3d_forward_workspace_bytes(int b, int m, int feature_dim) {
     (void)feature_dim;
-    return static_cast<size_t>(b) * m * 256 * sizeof(float) + 256;
+    return pooled_bytes(b, m) + f3d_detector_tc_weight_bytes() + 256;
 }
 
 F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const float *xyz, const float *new_xyz,
@@ -40,7 +47,15 @@ F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius,
     if (precision == 0)
         return detector_forward_fp32(b, n, m, nsample, radius, xyz, new_xyz, idx, packed, static_cast<float *>(workspace),
                                      attention, orientation, as_stream(stream));
-    return fail(F3D_ERR_UNSUPPORTED, "detector_forward: precision must be 0 (fp32)");
+    if (precision == 2) {  // tcgen05, bf16x3 split
+        if (nsample != 64) return fail(F3D_ERR_UNSUPPORTED, "detector_forward: the tensor-core path needs nsample == 64");
+        float *pooled = static_cast<float *>(workspace);
+        uint8_t *wimg = static_cast<uint8_t *>(workspace) + pooled_bytes(b, m);
+        int rc = detector_rows_tc(static_cast<long long>(b) * m, n, m, radius, xyz, new_xyz, idx, packed, wimg, pooled, as_stream(stream));
+        if (rc) return rc;
+        return detector_post_fp32(static_cast<long long>(b) * m, pooled, packed, attention, orientation, as_stream(stream));
+    }
+    return fail(F3D_ERR_UNSUPPORTED, "detector_forward: precision must be 0 (fp32) or 2 (bf16x3 tensor cores)");
 }
 
 F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radius, int feature_dim, const float *xyz,
@@ -54,5 +69,8 @@ F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radiu
     if (precision == 0)
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
                                        static_cast<float *>(workspace), features, as_stream(stream));
-    return fail(F3D_ERR_UNSUPPORTED, "descriptor_forward: precision must be 0 (fp32)");
+    if (precision == 2)  // the descriptor's tensor-core kernel is not written yet: its fp32 kernel is exact
+        return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
+                                       static_cast<float *>(workspace), features, as_stream(stream));
+    return fail(F3D_ERR_UNSUPPORTED, "descriptor_forward: precision must be 0 (fp32) or 2 (bf16x3 tensor cores)");
 }

@@ -347,6 +347,17 @@ int detector_forward_fp32(int b, int n, int m, int S, float radius, const float 
     return check_launch("det_post_fp32_kernel");
 }
 
+int detector_post_fp32(long long nc, const float *pooled, const float *packed, float *attention, float *orientation,
+                       cudaStream_t st) {
+    if (nc == 0) return 0;
+    const WeightLayout L = make_weight_layout(32);
+    const size_t smem_post = sizeof(float) * (256 + 128) * kTileRows;
+    cudaFuncSetAttribute(det_post_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_post));
+    det_post_fp32_kernel<<<static_cast<unsigned>((nc + kTileRows - 1) / kTileRows), kMlpThreads, smem_post, st>>>(
+        nc, pooled, packed, L, attention, orientation);
+    return check_launch("det_post_fp32_kernel");
+}
+
 int descriptor_forward_fp32(int b, int n, int m, int S, float radius, int feature_dim, const float *xyz,
                             const float *new_xyz, const int *idx, const float *orientation, const float *packed,
                             float *pooled_ws, float *features, cudaStream_t st) {

@@ -1,0 +1,403 @@
+// mlp_tc.cu -- fused detector forward on the Blackwell tensor cores (tcgen05.mma, TMEM accumulators, bulk-TMA
+// weight staging), precision "bf16x3".
+//
+// Replaces the same TensorFlow graph as mlp_fp32.cu (models/feat3dnet.py:112-130: group, translate, /radius,
+// conv 3->64->128->256 + BN + ReLU, reduce_max).  The two dense contractions (64->128 and 128->256, 97 % of the
+// detector's flops) run on tcgen05; the K=3 first layer, bias/ReLU, the max-pool and the operand repacking stay on
+// CUDA cores in the same kernel.  Nothing but the pooled (B*M,256) vectors reaches HBM.
+//
+// Numerics: every fp32 operand x is split as x = hi + lo with hi = bf16(x), lo = bf16(x - hi); a product is
+// evaluated as hi*hi + hi*lo + lo*hi on kind::f16 MMAs with fp32 accumulation in TMEM.  The dropped terms are
+// O(2^-16) relative, i.e. ~1e-5 -- two orders tighter than single-pass TF32 at 1.5x its tensor time and with the
+// same shared-memory footprint (2 x 2 bytes per element), which is what lets all weights stay SM-resident.
+//
+// Formulation: D^T = W^T X^T -- the M (TMEM lane) axis is the OUTPUT CHANNEL, the N (TMEM column) axis is the
+// sample.  One thread of the epilogue therefore owns one channel of every sample of a cluster: the max-pool over
+// the 64 samples is a register reduction, the bias is a per-thread scalar, and the next layer's operand is written
+// K-major with one 2-byte store per value.
+//
+// Persistent kernel, one CTA per SM, one cluster (64 samples) per tile, 13 warps:
+//   warp 0      : TMEM allocation, bulk-TMA of the packed weights, then ONE lane issues every tcgen05.mma
+//   warps 1-4   : producers -- gather + normalise + layer 0 (3->64, FFMA) -> operand X1 (bf16 hi/lo, K-major)
+//   warps 5-8   : epilogue of even tiles, warps 9-12: epilogue of odd tiles
+//                 E1: D1 (TMEM) -> +bias, ReLU -> operand X2 ;  E2: D2 (TMEM) -> max over samples, +bias, ReLU -> HBM
+// Tensor-pipe order in steady state:  ... MMA2(t-1) | MMA1(t+1) | MMA2(t) | MMA1(t+2) ...  so E1(t) runs under
+// MMA2(t-1), its X2 stores land under MMA1(t+1), and E2(t-1) runs under MMA2(t).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "weights_layout.h"
+
+#include <cuda_bf16.h>
+
+namespace f3d {
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------ self test
+// One CTA: D[128 x N] = A[128 x K] * B[N x K]^T with operands given as canonical K-major no-swizzle bf16 images.
+// Validates the descriptor encodings (LBO/SBO semantics, idesc, TMEM addressing) in isolation on the device.
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restrict__ b_img, float *__restrict__ D, int N, int K,
+                     uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t a_bytes, uint32_t b_bytes) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_load, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *sa = smem;
+    uint8_t *sb = smem + ((a_bytes + 127) & ~127u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_load, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_base_s, 256);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bar_load, a_bytes + b_bytes);
+        bulk_g2s(sa, a_img, a_bytes, &bar_load);
+        bulk_g2s(sb, b_img, b_bytes, &bar_load);
+        mbar_wait(&bar_load, 0);
+        tcgen05_fence_after();
+        const uint32_t idesc = make_idesc(1, 128, static_cast<uint32_t>(N));
+        for (int k = 0; k < K / 16; ++k) {
+            const uint64_t da = make_smem_desc(smem_u32(sa) + k * 2 * lbo_a, lbo_a, sbo_a);
+            const uint64_t db = make_smem_desc(smem_u32(sb) + k * 2 * lbo_b, lbo_b, sbo_b);
+            umma_f16(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tcgen05_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (c0 + j < N) D[static_cast<size_t>(warp * 32 + lane) * N + c0 + j] = __uint_as_float(r[j]);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ detector rows
+namespace det {
+constexpr int kSamples = 64;                 // samples per cluster = MMA N
+constexpr int kThreads = 13 * 32;
+constexpr uint32_t kSbo = 128;               // 8 rows x 16 B
+constexpr uint32_t kLboW = 128 * 16;         // weights: 128 rows per K chunk
+constexpr uint32_t kLboX1 = kSamples * 16;   // X1: written 16 B per thread, no padding needed
+constexpr uint32_t kLboX2 = kSamples * 16 + 16;  // X2: +16 B so the 2-byte epilogue stores of a warp hit 32 distinct banks
+// shared-memory image (bytes).  The first kWeightBytes are copied verbatim from the packed global buffer.
+constexpr uint32_t kW1Split = 128 * 64 * 2;            // 16 KB per split
+constexpr uint32_t kW2Blk = 128 * 128 * 2;             // 32 KB per (split, M block)
+constexpr uint32_t kOffW1 = 0;                          // [split 2][chunk 8][row 128][8] bf16
+constexpr uint32_t kOffW2 = kOffW1 + 2 * kW1Split;      // [split 2][mblk 2][chunk 16][row 128][8] bf16
+constexpr uint32_t kOffW0 = kOffW2 + 4 * kW2Blk;        // fp32 [3][64]
+constexpr uint32_t kOffB0 = kOffW0 + 3 * 64 * 4;        // fp32 [64]
+constexpr uint32_t kOffB1 = kOffB0 + 64 * 4;            // fp32 [128]
+constexpr uint32_t kOffB2 = kOffB1 + 128 * 4;           // fp32 [256]
+constexpr uint32_t kWeightBytes = kOffB2 + 256 * 4;     // 166 400
+constexpr uint32_t kX1Split = 8 * kLboX1;               // 8 KB
+constexpr uint32_t kOffX1 = kWeightBytes;               // [split 2][chunk 8][row 64][8] bf16
+constexpr uint32_t kX2Split = 16 * kLboX2;              // 16 640
+constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Split;      // [split 2][chunk 16] stride kLboX2
+constexpr uint32_t kOffBars = kOffX2 + 2 * kX2Split;
+constexpr uint32_t kSmemBytes = kOffBars + 16 * 8 + 16;
+static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffBars % 8 == 0, "alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+// TMEM columns: D1[2] at 0 / 64, D2[2] at 128 / 256 (two M blocks of 64 columns each)
+constexpr uint32_t kTmemCols = 512;
+
+enum Bar { W_FULL = 0, X1_FULL, X1_FREE, X2_FULL, X2_FREE, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1, D2_FULL0, D2_FULL1,
+           D2_FREE0, D2_FREE1, kNumBars };
+}  // namespace det
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+__global__ void __launch_bounds__(det::kThreads, 1)
+det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const float *__restrict__ xyz,
+                   const float *__restrict__ new_xyz, const int *__restrict__ idx, const uint8_t *__restrict__ wimg,
+                   float *__restrict__ pooled) {
+    using namespace det;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBars);
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(smem + kOffBars + kNumBars * 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[W_FULL], 1);
+        mbar_init(&bars[X1_FULL], 128);
+        mbar_init(&bars[X1_FREE], 1);
+        mbar_init(&bars[X2_FULL], 128);
+        mbar_init(&bars[X2_FREE], 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars[D1_FULL0 + b], 1);
+            mbar_init(&bars[D1_FREE0 + b], 128);
+            mbar_init(&bars[D2_FULL0 + b], 1);
+            mbar_init(&bars[D2_FREE0 + b], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_base_s, kTmemCols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    // tiles of this CTA: cluster c = blockIdx.x + t * gridDim.x
+    const long long first = blockIdx.x;
+    const int T = first < num_clusters ? static_cast<int>((num_clusters - first + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- weights: one bulk-TMA burst, resident for the whole kernel ---------------------------------
+            mbar_arrive_expect_tx(&bars[W_FULL], kWeightBytes);
+            for (uint32_t off = 0; off < kWeightBytes; off += 16384) {
+                const uint32_t sz = min(16384u, kWeightBytes - off);
+                bulk_g2s(smem + off, wimg + off, sz, &bars[W_FULL]);
+            }
+            mbar_wait(&bars[W_FULL], 0);
+            // ---- MMA issue loop ---------------------------------------------------------------------------
+            const uint32_t idesc = make_idesc(1, 128, kSamples);
+            const uint32_t sbase = smem_u32(smem);
+            auto mma1 = [&](int t) {
+                mbar_wait(&bars[X1_FULL], t & 1);
+                mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d = tmem_base + (t & 1) * 64;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {  // (Whi,Xhi) (Whi,Xlo) (Wlo,Xhi)
+                    const uint32_t wa = sbase + kOffW1 + (pass == 2 ? kW1Split : 0);
+                    const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_f16(d, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
+                                 make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(&bars[X1_FREE]);
+                umma_commit(&bars[D1_FULL0 + (t & 1)]);
+            };
+            auto mma2 = [&](int t) {
+                mbar_wait(&bars[X2_FULL], t & 1);
+                mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    const uint32_t d = tmem_base + 128 + (t & 1) * 128 + mb * 64;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t wa = sbase + kOffW2 + ((pass == 2 ? 2 : 0) + mb) * kW2Blk;
+                        const uint32_t xb = sbase + kOffX2 + (pass == 1 ? kX2Split : 0);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            umma_f16(d, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
+                                     make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSbo), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                }
+                umma_commit(&bars[X2_FREE]);
+                umma_commit(&bars[D2_FULL0 + (t & 1)]);
+            };
+            if (T > 0) mma1(0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) mma1(t + 1);
+                mma2(t);
+            }
+        }
+    } else if (warp <= 4) {
+        // ---- producers: gather + normalise + layer 0 -> X1 ------------------------------------------------------
+        mbar_wait(&bars[W_FULL], 0);  // W0 / b0 live in the weight image
+        const float *W0 = reinterpret_cast<const float *>(smem + kOffW0);
+        const float *B0 = reinterpret_cast<const float *>(smem + kOffB0);
+        const int pt = threadIdx.x - 32;      // 0..127
+        const int s = pt & 63, h = pt >> 6;   // sample, channel half
+        uint8_t *x1 = smem + kOffX1 + s * 16;
+        for (int t = 0; t < T; ++t) {
+            const long long cl = first + static_cast<long long>(t) * gridDim.x;
+            int ii = __ldg(idx + cl * kSamples + s);
+            ii = min(max(ii, 0), n - 1);
+            const float *p = xyz + ((cl / m) * n + ii) * 3;
+            const float *c = new_xyz + cl * 3;
+            const float gx = (__ldg(p) - __ldg(c)) / radius;
+            const float gy = (__ldg(p + 1) - __ldg(c + 1)) / radius;
+            const float gz = (__ldg(p + 2) - __ldg(c + 2)) / radius;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = h * 32 + j * 2 + e;
+                    float a = B0[k];
+                    a = fmaf(gx, W0[k], a);
+                    a = fmaf(gy, W0[64 + k], a);
+                    a = fmaf(gz, W0[128 + k], a);
+                    v[e] = fmaxf(a, 0.0f);
+                }
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+                hi[j] = pack_bf16x2(h0, h1);
+                lo[j] = pack_bf16x2(__float2bfloat16_rn(v[0] - __bfloat162float(h0)),
+                                    __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
+            }
+            mbar_wait(&bars[X1_FREE], (t & 1) ^ 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // K chunk h*4+q holds channels h*32 + q*8 .. +7
+                *reinterpret_cast<uint4 *>(x1 + (h * 4 + q) * kLboX1) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+                *reinterpret_cast<uint4 *>(x1 + kX1Split + (h * 4 + q) * kLboX1) =
+                    make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[X1_FULL]);
+        }
+    } else {
+        // ---- epilogue warpgroups: g = 0 (warps 5-8) even tiles, g = 1 (warps 9-12) odd tiles ----------------------
+        mbar_wait(&bars[W_FULL], 0);  // biases live in the weight image
+        const int g = (warp - 5) >> 2;
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int ch = q * 32 + lane;        // output channel (TMEM lane) owned by this thread
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const float b1 = reinterpret_cast<const float *>(smem + kOffB1)[ch];
+        const float *B2 = reinterpret_cast<const float *>(smem + kOffB2);
+        uint8_t *x2 = smem + kOffX2 + (ch >> 3) * kLboX2 + (ch & 7) * 2;
+        for (int t = g; t < T; t += 2) {
+            const int b = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            // E1: D1 -> +bias, ReLU, split -> X2
+            mbar_wait(&bars[D1_FULL0 + b], ph);
+            tcgen05_fence_after();
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tmem_base + lane_addr + b * 64, r0);
+            tmem_ld32(tmem_base + lane_addr + b * 64 + 32, r1);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&bars[D1_FREE0 + b]);
+            mbar_wait(&bars[X2_FREE], (t & 1) ^ 1);
+#pragma unroll
+            for (int sidx = 0; sidx < 64; ++sidx) {
+                const float v = fmaxf(__uint_as_float(sidx < 32 ? r0[sidx & 31] : r1[sidx & 31]) + b1, 0.0f);
+                const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+                const __nv_bfloat16 lv = __float2bfloat16_rn(v - __bfloat162float(hv));
+                *reinterpret_cast<__nv_bfloat16 *>(x2 + sidx * 16) = hv;
+                *reinterpret_cast<__nv_bfloat16 *>(x2 + kX2Split + sidx * 16) = lv;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[X2_FULL]);
+            // E2: D2 -> max over the 64 samples, +bias, ReLU -> pooled (ReLU and +bias commute with max)
+            mbar_wait(&bars[D2_FULL0 + b], ph);
+            tcgen05_fence_after();
+            float mx[2];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                tmem_ld32(tmem_base + lane_addr + 128 + b * 128 + mb * 64, r0);
+                tmem_ld32(tmem_base + lane_addr + 128 + b * 128 + mb * 64 + 32, r1);
+                tmem_ld_wait();
+                float mv = __uint_as_float(r0[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r0[j]));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r1[j]));
+                mx[mb] = mv;
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&bars[D2_FREE0 + b]);
+            const long long cl = first + static_cast<long long>(t) * gridDim.x;
+            pooled[cl * 256 + ch] = fmaxf(mx[0] + B2[ch], 0.0f);
+            pooled[cl * 256 + 128 + ch] = fmaxf(mx[1] + B2[128 + ch], 0.0f);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Builds the kernel's shared-memory weight image from the packed fp32 (BN-folded) weights: bf16 hi/lo splits of
+// W1^T [128 x 64] and W2^T [256 x 128] in the canonical K-major core-matrix order, then W0, b0, b1, b2 in fp32.
+__global__ void det_tc_prep_kernel(const float *__restrict__ P, WeightLayout L, uint8_t *__restrict__ wimg) {
+    using namespace det;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 128 * 64) {  // W1: A[r][k] = W[k][r]
+        const int r = i & 127, k = i >> 7;
+        const float w = P[L.off[W_DET1] + k * 128 + r];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        const uint32_t o = (k >> 3) * kLboW + r * 16 + (k & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(wimg + kOffW1 + o) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(wimg + kOffW1 + kW1Split + o) = lo;
+    } else if (i < 128 * 64 + 256 * 128) {  // W2: A[r][k] = W[k][r], r = mb*128 + rr
+        const int e = i - 128 * 64;
+        const int r = e & 255, k = e >> 8;
+        const float w = P[L.off[W_DET2] + k * 256 + r];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        const int mb = r >> 7, rr = r & 127;
+        const uint32_t o = (k >> 3) * kLboW + rr * 16 + (k & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(wimg + kOffW2 + mb * kW2Blk + o) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(wimg + kOffW2 + (2 + mb) * kW2Blk + o) = lo;
+    } else {
+        const int e = i - 128 * 64 - 256 * 128;
+        float *f = reinterpret_cast<float *>(wimg + kOffW0);
+        if (e < 192) f[e] = P[L.off[W_DET0] + e];
+        else if (e < 256) f[e] = P[L.off[B_DET0] + e - 192];
+        else if (e < 384) f[e] = P[L.off[B_DET1] + e - 256];
+        else if (e < 640) f[e] = P[L.off[B_DET2] + e - 384];
+    }
+}
+
+int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
+                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, cudaStream_t st) {
+    if (num_clusters == 0) return 0;
+    {
+        const int total = 128 * 64 + 256 * 128 + 640;
+        det_tc_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(32), wimg);
+        const int rc = check_launch("det_tc_prep_kernel");
+        if (rc) return rc;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    cudaError_t e = cudaFuncSetAttribute(det_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(det::kSmemBytes));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "det_rows_tc: cudaFuncSetAttribute");
+    const unsigned grid = static_cast<unsigned>(num_clusters < num_sms ? num_clusters : num_sms);
+    det_rows_tc_kernel<<<grid, det::kThreads, det::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, wimg, pooled);
+    return check_launch("det_rows_tc_kernel");
+}
+
+}  // namespace f3d
+
+using namespace f3d;
+
+// Debug / bring-up entry point (not part of the reference surface): runs the single-CTA UMMA self test.
+F3D_API int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int N, int K, int lbo_a, int sbo_a, int lbo_b,
+                                    int sbo_b, int a_bytes, int b_bytes, void *stream) {
+    if (!a_img || !b_img || !D || N < 8 || N > 256 || N % 8 || K < 16 || K % 16) return fail(F3D_ERR_INVALID_ARGUMENT, "umma_selftest: bad arguments");
+    const size_t smem = ((static_cast<size_t>(a_bytes) + 127) & ~static_cast<size_t>(127)) + b_bytes + 128;
+    cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(static_cast<const uint8_t *>(a_img), static_cast<const uint8_t *>(b_img), D, N, K,
+                                                             lbo_a, sbo_a, lbo_b, sbo_b, a_bytes, b_bytes);
+    return check_launch("umma_selftest_kernel");
+}
+
+F3D_API size_t f3d_detector_tc_weight_bytes(void) { return det::kWeightBytes; }

@@ -27,7 +27,7 @@ conv2d, pairwise_dist = _layers.conv2d, _layers.pairwise_dist
 sample_points, sample_and_group = _pc.sample_points, _pc.sample_and_group
 sample_and_group_all, query_and_group_points = _pc.sample_and_group_all, _pc.query_and_group_points
 
-PRECISIONS = {"fp32": 0, "tf32": 1, "3xtf32": 3}
+PRECISIONS = {"fp32": 0, "bf16x3": 2}
 
 # (scope, Cin, Cout, has_bn) -- feat3dnet.py:277-284 (detector) and :297-310 (descriptor)
 DET_LAYERS = [
@@ -248,7 +248,7 @@ class Feat3dNet:
         param: dict with the reference's keys ('NoRegress', 'BaseScale', 'Attention', 'num_clusters',
                'num_samples', 'margin', 'feature_dim', 'freeze_scopes').
         weights: flat {TF variable name: array}; random-init state when None.
-        precision: 'fp32' (CUDA-core FFMA), 'tf32' or '3xtf32' (tcgen05) for the fused eval-mode kernels.
+        precision: 'fp32' (CUDA-core FFMA) or 'bf16x3' (tcgen05 tensor cores, split-bf16) for the fused eval-mode kernels.
         """
         self.logger = logging.getLogger(self.__class__.__name__)
         self.param = dict(self.DEFAULT_PARAM)

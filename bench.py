@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--points", type=int, default=16384)
     ap.add_argument("--clusters", type=int, default=512)
     ap.add_argument("--nsample", type=int, default=64)
-    ap.add_argument("--precision", default=os.environ.get("F3D_PRECISION", "fp32"), choices=["fp32", "tf32", "3xtf32"])
+    ap.add_argument("--precision", default=os.environ.get("F3D_PRECISION", "fp32"), choices=["fp32", "bf16x3"])
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=2, help="clouds in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -109,7 +109,9 @@ size_t f3d_forward_workspace_bytes(int b, int m, int feature_dim);
  * xyz (b,n,3), new_xyz (b,m,3), idx (b,m,nsample) from f3d_query_ball_point ->
  * attention (b,m), orientation (b,m).  Fuses group_point, translate, /radius, the 3->64->128->256 shared
  * MLP, max-pool, 256->128->64, softplus / l2norm+atan2 heads: no grouped tensor touches HBM.
- * precision: 0 = fp32 CUDA-core FFMA, 1 = tcgen05 TF32 (single pass), 3 = tcgen05 3xTF32 (fp32-accurate).
+ * precision: 0 = fp32 CUDA-core FFMA (exact fp32 reference path);
+ *            2 = tcgen05 tensor cores, "bf16x3": operands split x = hi + lo in bf16, hi*hi + hi*lo + lo*hi accumulated
+ *                in fp32 (TMEM) -- ~1e-5 relative, needs nsample == 64.
  * nsample must be 8, 16, 32, 64 or 128. */
 int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const float *xyz, const float *new_xyz,
                          const int *idx, const float *packed, float *attention, float *orientation, int precision,
@@ -121,6 +123,14 @@ int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const f
 int f3d_descriptor_forward(int b, int n, int m, int nsample, float radius, int feature_dim, const float *xyz,
                            const float *new_xyz, const int *idx, const float *orientation, const float *packed,
                            float *features, int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------- bring-up / debugging ---------- */
+
+/* Single-CTA tcgen05 self test: D[128 x N] = A[128 x K] * B[N x K]^T from canonical K-major no-swizzle bf16 operand
+ * images (element (r,k) at (k/8)*lbo + (r/8)*sbo + (r%8)*16 + (k%8)*2 bytes).  Not part of the reference surface. */
+int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int N, int K, int lbo_a, int sbo_a, int lbo_b,
+                            int sbo_b, int a_bytes, int b_bytes, void *stream);
+size_t f3d_detector_tc_weight_bytes(void);
 
 #ifdef __cplusplus
 }

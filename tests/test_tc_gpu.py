@@ -1,0 +1,69 @@
+"""GPU tests (-m gpu) of the tcgen05 tensor-core path: the single-CTA UMMA self test (descriptor / layout semantics in
+isolation) and the fused detector kernel (precision "bf16x3") against the fp32 kernel and the fp64 oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net as onet
+from tests.conftest import pkg
+from tests.test_model_gpu import compare, run_pipeline
+
+pytestmark = pytest.mark.gpu
+
+# bf16x3 drops terms of relative size 2^-16 per product: 1e-5-level errors, bounded here with one order of headroom
+TOL_BF16X3 = dict(att=2e-4, ori=2e-4, feat=2e-4)
+
+
+def make_image(A, lbo, sbo):
+    """canonical K-major no-swizzle bf16 operand image: element (r,k) at (k/8)*lbo + (r/8)*sbo + (r%8)*16 + (k%8)*2"""
+    rows, K = A.shape
+    r = torch.arange(rows).view(-1, 1)
+    k = torch.arange(K).view(1, -1)
+    off = (k // 8) * lbo + (r // 8) * sbo + (r % 8) * 16 + (k % 8) * 2
+    nbytes = int(off.max()) + 2
+    nbytes = (nbytes + 15) // 16 * 16
+    img = torch.zeros(nbytes // 2, dtype=torch.int16)
+    img[(off // 2).reshape(-1)] = A.to(torch.bfloat16).view(torch.int16).reshape(-1)
+    return img, nbytes
+
+
+@pytest.mark.parametrize("N,K,lbo_b", [(64, 64, 1024), (64, 128, 1040), (8, 16, 128), (256, 32, 4096), (64, 16, 1040)])
+def test_umma_selftest(cuda, N, K, lbo_b):
+    lib_mod = pkg("_lib")
+    L = lib_mod.lib()
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    A = torch.randn((128, K), generator=g).to(torch.bfloat16).float()
+    B = torch.randn((N, K), generator=g).to(torch.bfloat16).float()
+    a_img, a_bytes = make_image(A, 2048, 128)
+    b_img, b_bytes = make_image(B, lbo_b, 128)
+    a_d, b_d = a_img.to(cuda), b_img.to(cuda)
+    D = torch.full((128, N), float("nan"), device=cuda)
+    rc = L.f3d_debug_umma_selftest(lib_mod.ptr(a_d), lib_mod.ptr(b_d), lib_mod.ptr(D), N, K, 2048, 128, lbo_b, 128, a_bytes, b_bytes,
+                                   lib_mod.stream())
+    lib_mod.check(rc, "umma_selftest")
+    torch.cuda.synchronize()
+    want = A.double() @ B.double().t()
+    err = (D.cpu().double() - want).abs().max().item()
+    assert err < 1e-3 * max(1.0, want.abs().max().item()), "UMMA self test: max err %.3e" % err
+
+
+def test_detector_bf16x3_vs_fp32_and_oracle(cuda):
+    xyz = pkg("synth").make_batch(3, 4096, seed0=21)
+    for rb in (True, False):
+        params = onet.init_params(seed=2, randomize_bn=rb)
+        out_tc, _ = run_pipeline(xyz, params, 200, precision="bf16x3")
+        out_32, _ = run_pipeline(xyz, params, 200, precision="fp32")
+        ref = onet.inference_model(xyz, onet.to_torch(params, torch.float64), num_clusters=200, dtype=torch.float64)
+        assert torch.equal(out_tc["idx"], out_32["idx"])
+        e = compare(out_tc, ref, TOL_BF16X3, "bf16x3 rb=%s" % rb)
+        print("bf16x3 errors (att rel, ori rad, feat abs):", e)
+
+
+def test_detector_bf16x3_c1(cuda):
+    xyz = pkg("synth").base_cloud("oxford")[None]
+    params = onet.init_params(seed=0, randomize_bn=True)
+    out, _ = run_pipeline(xyz, params, 512, precision="bf16x3")
+    ref = onet.inference_model(xyz, onet.to_torch(params, torch.float64), num_clusters=512, dtype=torch.float64)
+    compare(out, ref, TOL_BF16X3, "C1 bf16x3")
