@@ -10,6 +10,11 @@ int descriptor_forward_fp32(int b, int n, int m, int S, float radius, int featur
                             float *pooled_ws, float *features, cudaStream_t st);
 int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
                      const int *idx, const float *packed, uint8_t *wimg, float *pooled, cudaStream_t st);
+int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
+                       const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
+                       float *pooled2, cudaStream_t st);
+int descriptor_post_fp32(long long nc, const float *pooled2, const float *packed, int feature_dim, float *features,
+                         cudaStream_t st);
 int detector_post_fp32(long long num_clusters, const float *pooled, const float *packed, float *attention,
                        float *orientation, cudaStream_t st);
 }  // namespace f3d
@@ -69,7 +74,15 @@ F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radiu
     if (precision == 0)
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
                                        static_cast<float *>(workspace), features, as_stream(stream));
-    if (precision == 2)  // the descriptor's tensor-core kernel is not written yet: its fp32 kernel is exact
+    if (precision == 2 && nsample == 64 && feature_dim <= 64) {  // tcgen05, bf16x3 split
+        float *pooled2 = static_cast<float *>(workspace);
+        uint8_t *wimg = static_cast<uint8_t *>(workspace) + pooled_bytes(b, m);
+        int rc = descriptor_rows_tc(static_cast<long long>(b) * m, n, m, radius, feature_dim, xyz, new_xyz, idx, orientation,
+                                    packed, wimg, pooled2, as_stream(stream));
+        if (rc) return rc;
+        return descriptor_post_fp32(static_cast<long long>(b) * m, pooled2, packed, feature_dim, features, as_stream(stream));
+    }
+    if (precision == 2)  // shapes the tensor-core kernel does not cover (nsample != 64, feature_dim 128): exact fp32 kernel
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
                                        static_cast<float *>(workspace), features, as_stream(stream));
     return fail(F3D_ERR_UNSUPPORTED, "descriptor_forward: precision must be 0 (fp32) or 2 (bf16x3 tensor cores)");

@@ -358,6 +358,26 @@ int detector_post_fp32(long long nc, const float *pooled, const float *packed, f
     return check_launch("det_post_fp32_kernel");
 }
 
+int descriptor_post_fp32(long long nc, const float *pooled2, const float *packed, int feature_dim, float *features,
+                         cudaStream_t st) {
+    if (nc == 0) return 0;
+    const WeightLayout L = make_weight_layout(feature_dim);
+    const size_t smem_post = sizeof(float) * (256 + 128) * kTileRows;
+    const unsigned gp = static_cast<unsigned>((nc + kTileRows - 1) / kTileRows);
+#define F3D_POST2(CT)                                                                                                 \
+    cudaFuncSetAttribute(desc_post_fp32_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                         static_cast<int>(smem_post));                                                                \
+    desc_post_fp32_kernel<CT><<<gp, kMlpThreads, smem_post, st>>>(nc, pooled2, packed, L, features)
+    switch (feature_dim) {
+        case 16: F3D_POST2(1); break;
+        case 32: F3D_POST2(2); break;
+        case 64: F3D_POST2(4); break;
+        default: F3D_POST2(8); break;
+    }
+#undef F3D_POST2
+    return check_launch("desc_post_fp32_kernel");
+}
+
 int descriptor_forward_fp32(int b, int n, int m, int S, float radius, int feature_dim, const float *xyz,
                             const float *new_xyz, const int *idx, const float *orientation, const float *packed,
                             float *pooled_ws, float *features, cudaStream_t st) {

@@ -1,0 +1,350 @@
+// mlp_tc_desc.cu -- fused descriptor forward (per-row part) on the Blackwell tensor cores, precision "bf16x3".
+//
+// Replaces the TensorFlow graph of pointnet_sa_module (models/feat3dnet.py:54-75) on top of sample_and_group
+// (models/pointnet_common.py:104-120): group, translate, /radius, rotate by the detector's orientation,
+// conv 3->32->64 (+BN+ReLU), reduce_max, tile+concat, conv_mid_0 128->128 (+BN, no ReLU), reduce_max.
+// Same machinery and the same D^T = W^T X^T formulation as mlp_tc.cu (TMEM lane = output channel, column = sample).
+//
+//   MMA1 : D1[128(64 real) x 64] = W1^T[128 x 32]  X1^T          (conv1, 32 -> 64; the M axis is zero-padded to 128)
+//   E1   : relu(D1 + b1) -> X2 (K-major operand of conv_mid_0) and, per channel, its max over the 64 samples -> P
+//   MMA2 : D2[128 x 64]  = Wa^T[128 x 64]  X2^T                   (conv_mid_0, rows 0..63 of its weight: the per-point part)
+//   MMA3 : D3[128 x 8]   = Wb^T[128 x 64]  P^T                    (rows 64..127: the tiled max-pool part, ONE column per
+//                                                                   cluster instead of 64 -- the split-weight identity)
+//   E2   : pooled2 = max_s D2[:, s] + D3[:, 0] + b_mid            (no ReLU: final_relu=False, feat3dnet.py:71)
+//
+// conv_post_0 + l2-normalise run afterwards over 128 clusters per CTA (desc_post_fp32_kernel).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "weights_layout.h"
+
+#include <cuda_bf16.h>
+
+namespace f3d {
+
+using namespace tc;
+
+namespace dsc {
+constexpr int kSamples = 64;
+constexpr int kThreads = 13 * 32;
+constexpr uint32_t kSbo = 128;
+constexpr uint32_t kLboW = 128 * 16;
+constexpr uint32_t kLboX1 = kSamples * 16;
+constexpr uint32_t kLboX2 = kSamples * 16 + 16;
+constexpr uint32_t kLboP = 8 * 16;                      // P: one 8-row group per K chunk
+constexpr uint32_t kW1Split = 128 * 32 * 2;             // 8 KB
+constexpr uint32_t kWmSplit = 128 * 64 * 2;             // 16 KB
+constexpr uint32_t kOffW1 = 0;                           // [split 2][chunk 4][row 128][8]
+constexpr uint32_t kOffWa = kOffW1 + 2 * kW1Split;       // [split 2][chunk 8][row 128][8]
+constexpr uint32_t kOffWb = kOffWa + 2 * kWmSplit;
+constexpr uint32_t kOffW0 = kOffWb + 2 * kWmSplit;       // fp32 [3][32]
+constexpr uint32_t kOffB0 = kOffW0 + 3 * 32 * 4;         // fp32 [32]
+constexpr uint32_t kOffB1 = kOffB0 + 32 * 4;             // fp32 [64]
+constexpr uint32_t kOffBm = kOffB1 + 64 * 4;             // fp32 [128]
+constexpr uint32_t kWeightBytes = kOffBm + 128 * 4;      // 83 200
+constexpr uint32_t kX1Split = 4 * kLboX1;                // 4 KB
+constexpr uint32_t kOffX1 = kWeightBytes;
+constexpr uint32_t kX2Split = 8 * kLboX2;                // 8 320
+constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Split;
+constexpr uint32_t kPSplit = 8 * kLboP;                  // 1 KB
+constexpr uint32_t kOffP = kOffX2 + 2 * kX2Split;
+constexpr uint32_t kOffBars = kOffP + 2 * kPSplit;
+constexpr uint32_t kSmemBytes = kOffBars + 16 * 8 + 16;
+static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffP % 128 == 0 && kOffBars % 8 == 0, "alignment");
+// TMEM columns: D1[2] at 0 / 64, D2[2] at 128 / 192, D3[2] at 256 / 288
+constexpr uint32_t kTmemCols = 512;
+enum Bar { W_FULL = 0, X1_FULL, X1_FREE, X2_FULL, X2_FREE, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1, D2_FULL0, D2_FULL1,
+           D2_FREE0, D2_FREE1, kNumBars };
+}  // namespace dsc
+
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+__global__ void __launch_bounds__(dsc::kThreads, 1)
+desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const float *__restrict__ xyz,
+                    const float *__restrict__ new_xyz, const int *__restrict__ idx, const float *__restrict__ orientation,
+                    const uint8_t *__restrict__ wimg, float *__restrict__ pooled2) {
+    using namespace dsc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBars);
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(smem + kOffBars + kNumBars * 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[W_FULL], 1);
+        mbar_init(&bars[X1_FULL], 128);
+        mbar_init(&bars[X1_FREE], 1);
+        mbar_init(&bars[X2_FULL], 128);
+        mbar_init(&bars[X2_FREE], 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars[D1_FULL0 + b], 1);
+            mbar_init(&bars[D1_FREE0 + b], 128);
+            mbar_init(&bars[D2_FULL0 + b], 1);
+            mbar_init(&bars[D2_FREE0 + b], 128);
+        }
+        fence_barrier_init();
+    }
+    // rows 1..7 of the pooled operand P are never written: zero them once (their D3 columns are never read either)
+    for (uint32_t i = threadIdx.x; i < 2 * kPSplit / 4; i += kThreads) reinterpret_cast<uint32_t *>(smem + kOffP)[i] = 0;
+    fence_proxy_async_smem();
+    if (warp == 0) {
+        tmem_alloc(tmem_base_s, kTmemCols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    const long long first = blockIdx.x;
+    const int T = first < num_clusters ? static_cast<int>((num_clusters - first + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars[W_FULL], kWeightBytes);
+            for (uint32_t off = 0; off < kWeightBytes; off += 16384) {
+                const uint32_t sz = min(16384u, kWeightBytes - off);
+                bulk_g2s(smem + off, wimg + off, sz, &bars[W_FULL]);
+            }
+            mbar_wait(&bars[W_FULL], 0);
+            const uint32_t idesc64 = make_idesc(1, 128, kSamples);
+            const uint32_t idesc8 = make_idesc(1, 128, 8);
+            const uint32_t sbase = smem_u32(smem);
+            auto mma1 = [&](int t) {
+                mbar_wait(&bars[X1_FULL], t & 1);
+                mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d = tmem_base + (t & 1) * 64;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t wa = sbase + kOffW1 + (pass == 2 ? kW1Split : 0);
+                    const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        umma_f16(d, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
+                                 make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc64, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(&bars[X1_FREE]);
+                umma_commit(&bars[D1_FULL0 + (t & 1)]);
+            };
+            auto mma23 = [&](int t) {
+                mbar_wait(&bars[X2_FULL], t & 1);
+                mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d2 = tmem_base + 128 + (t & 1) * 64;
+                const uint32_t d3 = tmem_base + 256 + (t & 1) * 32;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t wa = sbase + kOffWa + (pass == 2 ? kWmSplit : 0);
+                    const uint32_t xb = sbase + kOffX2 + (pass == 1 ? kX2Split : 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_f16(d2, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
+                                 make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSbo), idesc64, acc);
+                        acc = 1;
+                    }
+                }
+                acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t wa = sbase + kOffWb + (pass == 2 ? kWmSplit : 0);
+                    const uint32_t xb = sbase + kOffP + (pass == 1 ? kPSplit : 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_f16(d3, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
+                                 make_smem_desc(xb + k * 2 * kLboP, kLboP, kSbo), idesc8, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(&bars[X2_FREE]);
+                umma_commit(&bars[D2_FULL0 + (t & 1)]);
+            };
+            if (T > 0) mma1(0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) mma1(t + 1);
+                mma23(t);
+            }
+        }
+    } else if (warp <= 4) {
+        // ---- producers: gather + normalise + rotate + layer 0 (3 -> 32) -> X1 ------------------------------------
+        mbar_wait(&bars[W_FULL], 0);
+        const float *W0 = reinterpret_cast<const float *>(smem + kOffW0);
+        const float *B0 = reinterpret_cast<const float *>(smem + kOffB0);
+        const int pt = threadIdx.x - 32;
+        const int s = pt & 63, h = pt >> 6;  // sample, channel half (16 channels = 2 K chunks)
+        uint8_t *x1 = smem + kOffX1 + s * 16;
+        for (int t = 0; t < T; ++t) {
+            const long long cl = first + static_cast<long long>(t) * gridDim.x;
+            int ii = __ldg(idx + cl * kSamples + s);
+            ii = min(max(ii, 0), n - 1);
+            const float *p = xyz + ((cl / m) * n + ii) * 3;
+            const float *c = new_xyz + cl * 3;
+            float gx = (__ldg(p) - __ldg(c)) / radius;
+            float gy = (__ldg(p + 1) - __ldg(c + 1)) / radius;
+            const float gz = (__ldg(p + 2) - __ldg(c + 2)) / radius;
+            if (orientation) {  // pointnet_common.py:110-120: x' = x c - y s ; y' = x s + y c
+                const float th = __ldg(orientation + cl);
+                const float cs = cosf(th), sn = sinf(th);
+                const float xr = gx * cs - gy * sn;
+                const float yr = gx * sn + gy * cs;
+                gx = xr;
+                gy = yr;
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = h * 16 + j * 2 + e;
+                    float a = B0[k];
+                    a = fmaf(gx, W0[k], a);
+                    a = fmaf(gy, W0[32 + k], a);
+                    a = fmaf(gz, W0[64 + k], a);
+                    v[e] = fmaxf(a, 0.0f);
+                }
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+                hi[j] = pack2(h0, h1);
+                lo[j] = pack2(__float2bfloat16_rn(v[0] - __bfloat162float(h0)), __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
+            }
+            mbar_wait(&bars[X1_FREE], (t & 1) ^ 1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                *reinterpret_cast<uint4 *>(x1 + (h * 2 + q) * kLboX1) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+                *reinterpret_cast<uint4 *>(x1 + kX1Split + (h * 2 + q) * kLboX1) =
+                    make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[X1_FULL]);
+        }
+    } else {
+        // ---- epilogue warpgroups ---------------------------------------------------------------------------------
+        mbar_wait(&bars[W_FULL], 0);
+        const int g = (warp - 5) >> 2;
+        const int q = warp & 3;
+        const int ch = q * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const float b1 = ch < 64 ? reinterpret_cast<const float *>(smem + kOffB1)[ch] : 0.0f;
+        const float bm = reinterpret_cast<const float *>(smem + kOffBm)[ch];
+        uint8_t *x2 = smem + kOffX2 + (ch >> 3) * kLboX2 + (ch & 7) * 2;
+        uint8_t *pp = smem + kOffP + (ch >> 3) * kLboP + (ch & 7) * 2;  // row 0 of the pooled operand
+        for (int t = g; t < T; t += 2) {
+            const int b = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            // E1 (channels 0..63 are real; 64..127 are the zero padding of the M axis)
+            mbar_wait(&bars[D1_FULL0 + b], ph);
+            tcgen05_fence_after();
+            uint32_t r0[32], r1[32];
+            if (q < 2) {
+                tmem_ld32(tmem_base + lane_addr + b * 64, r0);
+                tmem_ld32(tmem_base + lane_addr + b * 64 + 32, r1);
+                tmem_ld_wait();
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&bars[D1_FREE0 + b]);
+            mbar_wait(&bars[X2_FREE], (t & 1) ^ 1);
+            if (q < 2) {
+                float pmax = 0.0f;  // values are post-ReLU (>= 0)
+#pragma unroll
+                for (int sidx = 0; sidx < 64; ++sidx) {
+                    const float v = fmaxf(__uint_as_float(sidx < 32 ? r0[sidx & 31] : r1[sidx & 31]) + b1, 0.0f);
+                    pmax = fmaxf(pmax, v);
+                    const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+                    const __nv_bfloat16 lv = __float2bfloat16_rn(v - __bfloat162float(hv));
+                    *reinterpret_cast<__nv_bfloat16 *>(x2 + sidx * 16) = hv;
+                    *reinterpret_cast<__nv_bfloat16 *>(x2 + kX2Split + sidx * 16) = lv;
+                }
+                const __nv_bfloat16 hp = __float2bfloat16_rn(pmax);
+                *reinterpret_cast<__nv_bfloat16 *>(pp) = hp;
+                *reinterpret_cast<__nv_bfloat16 *>(pp + kPSplit) = __float2bfloat16_rn(pmax - __bfloat162float(hp));
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[X2_FULL]);
+            // E2
+            mbar_wait(&bars[D2_FULL0 + b], ph);
+            tcgen05_fence_after();
+            tmem_ld32(tmem_base + lane_addr + 128 + b * 64, r0);
+            tmem_ld32(tmem_base + lane_addr + 128 + b * 64 + 32, r1);
+            tmem_ld_wait();
+            float mv = __uint_as_float(r0[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r0[j]));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r1[j]));
+            tmem_ld32(tmem_base + lane_addr + 256 + b * 32, r0);  // only column 0 (the pooled row) is meaningful
+            tmem_ld_wait();
+            const float cterm = __uint_as_float(r0[0]);
+            tcgen05_fence_before();
+            mbar_arrive(&bars[D2_FREE0 + b]);
+            const long long cl = first + static_cast<long long>(t) * gridDim.x;
+            pooled2[cl * 128 + ch] = mv + cterm + bm;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// shared-memory weight image of the descriptor kernel from the packed fp32 (BN-folded) weights (MID = 128)
+__global__ void desc_tc_prep_kernel(const float *__restrict__ P, WeightLayout L, uint8_t *__restrict__ wimg) {
+    using namespace dsc;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    auto put = [&](uint32_t base, uint32_t split, uint32_t o, float w) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        *reinterpret_cast<__nv_bfloat16 *>(wimg + base + o) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(wimg + base + split + o) = __float2bfloat16_rn(w - __bfloat162float(hi));
+    };
+    if (i < 128 * 32) {  // W1^T, rows 64..127 zero
+        const int r = i & 127, k = i >> 7;
+        put(kOffW1, kW1Split, (k >> 3) * kLboW + r * 16 + (k & 7) * 2, r < 64 ? P[L.off[W_DESC1] + k * 64 + r] : 0.0f);
+    } else if (i < 128 * 32 + 128 * 64) {  // Wa^T = W_mid[0:64, :]^T
+        const int e = i - 128 * 32;
+        const int r = e & 127, k = e >> 7;
+        put(kOffWa, kWmSplit, (k >> 3) * kLboW + r * 16 + (k & 7) * 2, P[L.off[W_MID] + k * 128 + r]);
+    } else if (i < 128 * 32 + 2 * 128 * 64) {  // Wb^T = W_mid[64:128, :]^T
+        const int e = i - 128 * 32 - 128 * 64;
+        const int r = e & 127, k = e >> 7;
+        put(kOffWb, kWmSplit, (k >> 3) * kLboW + r * 16 + (k & 7) * 2, P[L.off[W_MID] + (64 + k) * 128 + r]);
+    } else {
+        const int e = i - 128 * 32 - 2 * 128 * 64;
+        float *f = reinterpret_cast<float *>(wimg + kOffW0);
+        if (e < 96) f[e] = P[L.off[W_DESC0] + e];
+        else if (e < 128) f[e] = P[L.off[B_DESC0] + e - 96];
+        else if (e < 192) f[e] = P[L.off[B_DESC1] + e - 128];
+        else if (e < 320) f[e] = P[L.off[B_MID] + e - 192];
+    }
+}
+
+int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
+                       const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
+                       float *pooled2, cudaStream_t st) {
+    if (num_clusters == 0) return 0;
+    {
+        const int total = 128 * 32 + 2 * 128 * 64 + 320;
+        desc_tc_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(feature_dim), wimg);
+        const int rc = check_launch("desc_tc_prep_kernel");
+        if (rc) return rc;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    cudaError_t e = cudaFuncSetAttribute(desc_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(dsc::kSmemBytes));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "desc_rows_tc: cudaFuncSetAttribute");
+    const unsigned grid = static_cast<unsigned>(num_clusters < num_sms ? num_clusters : num_sms);
+    desc_rows_tc_kernel<<<grid, dsc::kThreads, dsc::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, orientation, wimg,
+                                                                      pooled2);
+    return check_launch("desc_rows_tc_kernel");
+}
+
+size_t descriptor_tc_weight_bytes() { return dsc::kWeightBytes; }
+
+}  // namespace f3d

@@ -61,6 +61,18 @@ def test_detector_bf16x3_vs_fp32_and_oracle(cuda):
         print("bf16x3 errors (att rel, ori rad, feat abs):", e)
 
 
+@pytest.mark.parametrize("F,no_regress", [(32, False), (64, False), (16, True), (128, False)])
+def test_bf16x3_feature_dims(cuda, F, no_regress):
+    """descriptor tensor kernel for feature_dim <= 64 (MID = 128); feature_dim 128 routes to the exact fp32 kernel"""
+    xyz = pkg("synth").make_batch(2, 4096, seed0=31 + F)
+    params = onet.init_params(seed=5, feature_dim=F, randomize_bn=True)
+    out, _ = run_pipeline(xyz, params, 150, F=F, precision="bf16x3", no_regress=no_regress)
+    ref = onet.inference_model(xyz, onet.to_torch(params, torch.float64), num_clusters=150, feature_dim=F,
+                               no_regress=no_regress, dtype=torch.float64)
+    e = compare(out, ref, TOL_BF16X3, "bf16x3 F=%d" % F)
+    print("bf16x3 F=%d errors:" % F, e)
+
+
 def test_detector_bf16x3_c1(cuda):
     xyz = pkg("synth").base_cloud("oxford")[None]
     params = onet.init_params(seed=0, randomize_bn=True)
