@@ -8,7 +8,9 @@
 //   * coordinates are staged once into shared memory as SoA (12 B/point, <= 196 KB at n = 16384),
 //   * the running distances live in REGISTERS (PPT per thread) for the whole kernel,
 //   * the arg-max is two redux.sync per warp + one 32-entry shared-memory hop: ONE __syncthreads per round,
-//   * the winner's coordinates travel with the arg-max, so no dependent global load per round.
+//   * the winner's coordinates travel with the arg-max, so no dependent global load per round,
+//   * points are binned spatially once, and a warp whose bounding box is provably too far from the new sample
+//     to change any of its running distances skips the round (exact: see fps_cull_kernel).
 // The reference's tie rule is reproduced exactly: its thread t owns k = t (mod 512) and keeps its first
 // strict maximum, the tree keeps the lower thread => the winner is the maximum distance with the lowest
 // (k mod 512, k).  That pair is packed into one 32-bit tie key so it rides through redux.sync.min.
@@ -63,73 +65,200 @@ __device__ __forceinline__ int fps_block_argmax(FpsSlots &S, int par, float best
     return fps_tie_key_inv(bmin);
 }
 
-// ---- main path: n <= 1024*PPT, coordinates in shared memory, distances in registers ----------------------
-// Thread t owns the points k = 4*(t + 1024*g) + q, g < PPT/4, q < 4 (float4 shared-memory loads).  Within a
-// thread, k mod 512 grows with q and k grows with g, so walking (q major, g minor) with a strict '>' keeps
-// the thread's lowest (k mod 512, k) among equal maxima.
+// ---- main path: n <= 1024*PPT, coordinates in shared memory, distances in registers, exact spatial culling ------
+//
+// Each round only the points near the newly selected sample can lower their running distance.  The kernel therefore
+// first BINS the cloud (16 x 16 xy grid in Morton order, counting sort in shared memory) so that a warp owns 32*PPT
+// spatially neighbouring points, and keeps per warp an axis-aligned box and the maximum running distance `wmx`.
+// A round skips a warp when the squared distance from the new sample to the warp's box (with a 1e-4 safety margin
+// against fp32 rounding, the arithmetic error being < 1e-6) is >= wmx: then fmin(d, td) == td for every point of the
+// warp, so its cached arg-max is still exact.  Skipping changes no value, hence no result.  Binning permutes the
+// points, so the reference tie rule is applied on the ORIGINAL index (kept as u16 per point): thread, warp and block
+// levels all select the maximum distance with the lowest tie key of that index -- a total order, independent of the
+// (non-deterministic) order in which the counting sort places points inside a cell.
+// Warp w owns sorted positions [w*32*PPT, (w+1)*32*PPT); lane l reads float4 #(l + 32 g) of that range (conflict-free).
 template <int PPT>
 __global__ void __launch_bounds__(kFpsThreads, 1)
-fps_smem_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
     constexpr int G = PPT / 4;
     constexpr int NP = kFpsThreads * PPT;
+    constexpr int kCells = 256;
     extern __shared__ float4 fps_smem[];
     float *xs = reinterpret_cast<float *>(fps_smem);
     float *ys = xs + NP;
     float *zs = ys + NP;
+    unsigned short *oi = reinterpret_cast<unsigned short *>(zs + NP);  // original index of each sorted position
     __shared__ FpsSlots slots;
+    __shared__ int cell_cursor[kCells];
+    __shared__ float red[4][32];
+    __shared__ float bbox[4];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *p = inp + static_cast<size_t>(blockIdx.x) * n * 3;
     int *o = out + static_cast<size_t>(blockIdx.x) * m;
 
-    for (int i = tid; i < n * 3; i += kFpsThreads) {  // coalesced AoS read -> SoA
-        const float v = __ldg(p + i);
-        const int k = i / 3, c = i - 3 * k;
-        (c == 0 ? xs : (c == 1 ? ys : zs))[k] = v;
+    // ---- 1. xy bounding box of the cloud
+    float mnx = 3.0e38f, mxx = -3.0e38f, mny = 3.0e38f, mxy = -3.0e38f;
+    for (int k = tid; k < n; k += kFpsThreads) {
+        const float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1);
+        mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y);
     }
-    for (int k = n + tid; k < NP; k += kFpsThreads) xs[k] = ys[k] = zs[k] = 0.0f;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(kFull, mnx, s)); mxx = fmaxf(mxx, __shfl_xor_sync(kFull, mxx, s));
+        mny = fminf(mny, __shfl_xor_sync(kFull, mny, s)); mxy = fmaxf(mxy, __shfl_xor_sync(kFull, mxy, s));
+    }
+    if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mxx; red[2][warp] = mny; red[3][warp] = mxy; }
+    if (tid < kCells) cell_cursor[tid] = 0;
+    __syncthreads();
+    if (warp == 0) {
+        mnx = red[0][lane]; mxx = red[1][lane]; mny = red[2][lane]; mxy = red[3][lane];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(kFull, mnx, s)); mxx = fmaxf(mxx, __shfl_xor_sync(kFull, mxx, s));
+            mny = fminf(mny, __shfl_xor_sync(kFull, mny, s)); mxy = fmaxf(mxy, __shfl_xor_sync(kFull, mxy, s));
+        }
+        if (lane == 0) { bbox[0] = mnx; bbox[1] = mxx; bbox[2] = mny; bbox[3] = mxy; }
+    }
+    __syncthreads();
+    const float x0 = bbox[0], y0 = bbox[2];
+    const float ex = bbox[1] - bbox[0], ey = bbox[3] - bbox[2];
+    const float sx = (ex > 0.0f && ex < 3.0e38f) ? 16.0f / ex : 0.0f;  // degenerate / non-finite extents: one cell
+    const float sy = (ey > 0.0f && ey < 3.0e38f) ? 16.0f / ey : 0.0f;
+    auto cell_of = [&](float x, float y) -> int {
+        int ix = static_cast<int>((x - x0) * sx), iy = static_cast<int>((y - y0) * sy);
+        ix = min(max(ix, 0), 15);
+        iy = min(max(iy, 0), 15);
+        // Morton interleave of two 4-bit numbers
+        ix = (ix | (ix << 2)) & 0x33; ix = (ix | (ix << 1)) & 0x55;
+        iy = (iy | (iy << 2)) & 0x33; iy = (iy | (iy << 1)) & 0x55;
+        return ix | (iy << 1);
+    };
+    // ---- 2. counting sort by cell: histogram, exclusive scan, scatter
+    for (int k = tid; k < n; k += kFpsThreads) atomicAdd(&cell_cursor[cell_of(__ldg(p + 3 * k), __ldg(p + 3 * k + 1))], 1);
+    __syncthreads();
+    if (warp == 0) {
+        int c[8], tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { c[i] = cell_cursor[lane * 8 + i]; tot += c[i]; }
+        int inc = tot;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, inc, s); if (lane >= s) inc += v; }
+        int run = inc - tot;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { cell_cursor[lane * 8 + i] = run; run += c[i]; }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += kFpsThreads) {
+        const float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1), z = __ldg(p + 3 * k + 2);
+        const int pos = atomicAdd(&cell_cursor[cell_of(x, y)], 1);
+        xs[pos] = x; ys[pos] = y; zs[pos] = z;
+        oi[pos] = static_cast<unsigned short>(k);
+    }
+    for (int k = n + tid; k < NP; k += kFpsThreads) { xs[k] = ys[k] = zs[k] = 0.0f; oi[k] = 0; }
     __syncthreads();
 
+    // ---- 3. per-thread state: running distances (registers), per-warp box
+    const int wbase = warp * 32 * PPT;  // first sorted position of this warp
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs + wbase);
+    const float4 *ys4 = reinterpret_cast<const float4 *>(ys + wbase);
+    const float4 *zs4 = reinterpret_cast<const float4 *>(zs + wbase);
     float td[PPT];
+    float lox = 3.0e38f, hix = -3.0e38f, loy = 3.0e38f, hiy = -3.0e38f, loz = 3.0e38f, hiz = -3.0e38f;
 #pragma unroll
-    for (int g = 0; g < G; ++g)
+    for (int g = 0; g < G; ++g) {
+        const float4 X = xs4[lane + 32 * g], Y = ys4[lane + 32 * g], Z = zs4[lane + 32 * g];
+        const float xv[4] = {X.x, X.y, X.z, X.w}, yv[4] = {Y.x, Y.y, Y.z, Y.w}, zv[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) td[g * 4 + q] = (4 * (tid + kFpsThreads * g) + q) < n ? 1e38f : -1.0f;
+        for (int q = 0; q < 4; ++q) {
+            const bool real = wbase + 4 * (lane + 32 * g) + q < n;
+            td[g * 4 + q] = real ? 1e38f : -1.0f;
+            if (real) {
+                lox = fminf(lox, xv[q]); hix = fmaxf(hix, xv[q]);
+                loy = fminf(loy, yv[q]); hiy = fmaxf(hiy, yv[q]);
+                loz = fminf(loz, zv[q]); hiz = fmaxf(hiz, zv[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(kFull, lox, s)); hix = fmaxf(hix, __shfl_xor_sync(kFull, hix, s));
+        loy = fminf(loy, __shfl_xor_sync(kFull, loy, s)); hiy = fmaxf(hiy, __shfl_xor_sync(kFull, hiy, s));
+        loz = fminf(loz, __shfl_xor_sync(kFull, loz, s)); hiz = fmaxf(hiz, __shfl_xor_sync(kFull, hiz, s));
+    }
 
-    float ox = xs[0], oy = ys[0], oz = zs[0];
+    float ox = __ldg(p + 0), oy = __ldg(p + 1), oz = __ldg(p + 2);  // the first sample is point 0 (:114-116)
     if (tid == 0) o[0] = 0;
-
-    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
-    const float4 *ys4 = reinterpret_cast<const float4 *>(ys);
-    const float4 *zs4 = reinterpret_cast<const float4 *>(zs);
+    // cached arg-max of this warp (uniform across its lanes)
+    int cw_d = __float_as_int(-1.0f);
+    unsigned cw_key = 0xffffffffu;
+    float cw_x = 0.f, cw_y = 0.f, cw_z = 0.f, wmx = 3.0e38f;
 
     for (int j = 1; j < m; ++j) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const float4 X = xs4[tid + kFpsThreads * g];
-            const float4 Y = ys4[tid + kFpsThreads * g];
-            const float4 Z = zs4[tid + kFpsThreads * g];
-            td[g * 4 + 0] = fminf(sqdist_ref(X.x - ox, Y.x - oy, Z.x - oz), td[g * 4 + 0]);
-            td[g * 4 + 1] = fminf(sqdist_ref(X.y - ox, Y.y - oy, Z.y - oz), td[g * 4 + 1]);
-            td[g * 4 + 2] = fminf(sqdist_ref(X.z - ox, Y.z - oy, Z.z - oz), td[g * 4 + 2]);
-            td[g * 4 + 3] = fminf(sqdist_ref(X.w - ox, Y.w - oy, Z.w - oz), td[g * 4 + 3]);
-        }
-        float best = -1.0f;
-        int besti = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
+        const float bx = fmaxf(fmaxf(lox - ox, ox - hix), 0.0f);
+        const float by = fmaxf(fmaxf(loy - oy, oy - hiy), 0.0f);
+        const float bz = fmaxf(fmaxf(loz - oz, oz - hiz), 0.0f);
+        const float lbd = (bx * bx + by * by + bz * bz) * 0.9999f;
+        if (j == 1 || !(lbd >= wmx)) {  // warp-uniform
+            float vmax = -1.0f;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const float v = td[g * 4 + q];
-                if (v > best) {
-                    best = v;
-                    besti = 4 * (tid + kFpsThreads * g) + q;
-                }
+                const float4 X = xs4[lane + 32 * g], Y = ys4[lane + 32 * g], Z = zs4[lane + 32 * g];
+                td[g * 4 + 0] = fminf(sqdist_ref(X.x - ox, Y.x - oy, Z.x - oz), td[g * 4 + 0]);
+                td[g * 4 + 1] = fminf(sqdist_ref(X.y - ox, Y.y - oy, Z.y - oz), td[g * 4 + 1]);
+                td[g * 4 + 2] = fminf(sqdist_ref(X.z - ox, Y.z - oy, Z.z - oz), td[g * 4 + 2]);
+                td[g * 4 + 3] = fminf(sqdist_ref(X.w - ox, Y.w - oy, Z.w - oz), td[g * 4 + 3]);
+                vmax = fmaxf(fmaxf(fmaxf(td[g * 4 + 0], td[g * 4 + 1]), fmaxf(td[g * 4 + 2], td[g * 4 + 3])), vmax);
             }
-        const int old = fps_block_argmax(
-            slots, j & 1, best, besti,
-            [&](int k, float &x, float &y, float &z) { x = xs[k]; y = ys[k]; z = zs[k]; }, ox, oy, oz);
-        if (tid == 0) o[j] = old;
+            const int bi = __float_as_int(vmax);
+            const int wmax = __reduce_max_sync(kFull, bi);
+            // tie key only where it matters: lanes holding the warp maximum
+            unsigned tk = 0xffffffffu;
+            int bpos = 0;
+            if (bi == wmax) {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (td[g * 4 + q] == vmax) {
+                            const int pos = wbase + 4 * (lane + 32 * g) + q;
+                            const unsigned k2 = fps_tie_key(vmax < 0.0f ? 0 : oi[pos]);
+                            if (k2 < tk) { tk = k2; bpos = pos; }
+                        }
+            }
+            const unsigned wmin = __reduce_min_sync(kFull, tk);
+            const int src = __ffs(__ballot_sync(kFull, tk == wmin)) - 1;
+            cw_d = wmax;
+            cw_key = wmin;
+            float vx = 0.f, vy = 0.f, vz = 0.f;
+            if (lane == src) {  // only the winner touches shared memory
+                vx = xs[bpos];
+                vy = ys[bpos];
+                vz = zs[bpos];
+            }
+            cw_x = __shfl_sync(kFull, vx, src);
+            cw_y = __shfl_sync(kFull, vy, src);
+            cw_z = __shfl_sync(kFull, vz, src);
+            wmx = __int_as_float(wmax);
+        }
+        const int par = j & 1;
+        if (lane == 0) {
+            slots.d[par][warp] = cw_d;
+            slots.key[par][warp] = cw_key;
+            slots.x[par][warp] = cw_x;
+            slots.y[par][warp] = cw_y;
+            slots.z[par][warp] = cw_z;
+        }
+        __syncthreads();
+        const int d2 = slots.d[par][lane];
+        const unsigned k2 = slots.key[par][lane];
+        const int bmax = __reduce_max_sync(kFull, d2);
+        const unsigned bmin = __reduce_min_sync(kFull, d2 == bmax ? k2 : 0xffffffffu);
+        const int src = __ffs(__ballot_sync(kFull, d2 == bmax && k2 == bmin)) - 1;
+        ox = slots.x[par][src];
+        oy = slots.y[par][src];
+        oz = slots.z[par][src];
+        if (tid == 0) o[j] = fps_tie_key_inv(bmin);
     }
 }
 
@@ -186,12 +315,12 @@ __global__ void gather_point_kernel(int n, int m, long long total, const float *
 
 template <int PPT>
 static int launch_fps_smem(int b, int n, int m, const float *inp, int *out, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(kFpsThreads) * PPT * 3 * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(fps_smem_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = static_cast<size_t>(kFpsThreads) * PPT * (3 * sizeof(float) + sizeof(unsigned short));
+    cudaError_t e = cudaFuncSetAttribute(fps_cull_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "fps: cudaFuncSetAttribute");
-    fps_smem_kernel<PPT><<<b, kFpsThreads, smem, st>>>(n, m, inp, out);
-    return check_launch("fps_smem_kernel");
+    fps_cull_kernel<PPT><<<b, kFpsThreads, smem, st>>>(n, m, inp, out);
+    return check_launch("fps_cull_kernel");
 }
 
 }  // namespace f3d
