@@ -149,6 +149,199 @@ bq_fallback_kernel(int b, int n, int m, int nsample, const float *__restrict__ x
     for (int s = lane; s < nsample; s += 32) idxb[static_cast<size_t>(j) * nsample + s] = fill;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Grid-accelerated ball query (uniform radius).  The brute-force scan above tests every (centre, point) pair up to the
+// nsample-th hit; on LiDAR clouds 95 % of those tests are against points tens of metres away.  Here the cloud is
+// binned once per call into an xy grid of cell size c >= 1.002 r (counting sort in shared memory, one CTA per cloud);
+// a centre then tests only the points of its 3x3 cell neighbourhood -- three contiguous runs of the sorted array --
+// with the SAME distance expression and threshold as the scan, so the hit set is identical.  (A point that tests as a
+// hit has |dx|,|dy| <= r (1 + 2^-22); the 0.2 % slack in c is two orders above the rounding of the cell coordinates,
+// so it can never lie two cells away.)  The reference's contract is the first nsample hits in ASCENDING INDEX order:
+// hits are recorded in a per-warp bitmap over the point indices (shared memory, n/8 bytes) and read back in index
+// order with popc prefix sums, which also yields the first hit for padding.  Empty balls go to bq_fallback_kernel.
+constexpr int kBqMaxCells = 4096;
+constexpr int kBqBuildThreads = 1024;
+
+struct BqGridInfo {
+    float x0, y0, inv_c;
+    int ncx, ncy;
+    int pad[3];
+};
+
+__device__ __forceinline__ int bq_cell_coord(float v, float v0, float inv_c, int nc) {
+    const float t = floorf((v - v0) * inv_c);
+    return static_cast<int>(fminf(fmaxf(t, -2.0f), static_cast<float>(nc + 1)));
+}
+
+__global__ void __launch_bounds__(kBqBuildThreads, 1)
+bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4 *__restrict__ sorted,
+                     int *__restrict__ cell_start, BqGridInfo *__restrict__ info) {
+    __shared__ int cursor[kBqMaxCells];
+    __shared__ float red[4][32];
+    __shared__ int wsum[32];
+    __shared__ BqGridInfo gi;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *p = xyz1 + static_cast<size_t>(blockIdx.x) * n * 3;
+    float4 *out = sorted + static_cast<size_t>(blockIdx.x) * n;
+    int *cs = cell_start + static_cast<size_t>(blockIdx.x) * (kBqMaxCells + 1);
+
+    float mnx = 3.0e38f, mxx = -3.0e38f, mny = 3.0e38f, mxy = -3.0e38f;
+    for (int k = tid; k < n; k += kBqBuildThreads) {
+        const float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1);
+        mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(kFull, mnx, s)); mxx = fmaxf(mxx, __shfl_xor_sync(kFull, mxx, s));
+        mny = fminf(mny, __shfl_xor_sync(kFull, mny, s)); mxy = fmaxf(mxy, __shfl_xor_sync(kFull, mxy, s));
+    }
+    if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mxx; red[2][warp] = mny; red[3][warp] = mxy; }
+    for (int i = tid; i < kBqMaxCells; i += kBqBuildThreads) cursor[i] = 0;
+    __syncthreads();
+    if (warp == 0) {
+        mnx = red[0][lane]; mxx = red[1][lane]; mny = red[2][lane]; mxy = red[3][lane];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(kFull, mnx, s)); mxx = fmaxf(mxx, __shfl_xor_sync(kFull, mxx, s));
+            mny = fminf(mny, __shfl_xor_sync(kFull, mny, s)); mxy = fmaxf(mxy, __shfl_xor_sync(kFull, mxy, s));
+        }
+        if (lane == 0) {
+            const float ex = fmaxf(mxx - mnx, 0.0f), ey = fmaxf(mxy - mny, 0.0f);
+            float c = radius * 1.002f;
+            int ncx = 1, ncy = 1;
+            for (int it = 0; it < 64; ++it) {  // grow the cell until the grid fits the shared-memory histogram
+                const float inv = 1.0f / c;
+                const float fx = floorf(ex * inv), fy = floorf(ey * inv);
+                if (fx < 4000.0f && fy < 4000.0f) {
+                    ncx = static_cast<int>(fx) + 1;
+                    ncy = static_cast<int>(fy) + 1;
+                    if (ncx * ncy <= kBqMaxCells) break;
+                }
+                c *= 1.25f;
+            }
+            if (!(ncx * ncy <= kBqMaxCells)) { ncx = 1; ncy = 1; c = 3.0e38f; }  // non-finite extents: a single cell
+            gi.x0 = mnx; gi.y0 = mny; gi.inv_c = 1.0f / c; gi.ncx = ncx; gi.ncy = ncy;
+            info[blockIdx.x] = gi;
+        }
+    }
+    __syncthreads();
+    const float x0 = gi.x0, y0 = gi.y0, inv_c = gi.inv_c;
+    const int ncx = gi.ncx, ncy = gi.ncy, ncells = ncx * ncy;
+    auto cell_of = [&](float x, float y) {
+        const int cx = min(max(bq_cell_coord(x, x0, inv_c, ncx), 0), ncx - 1);
+        const int cy = min(max(bq_cell_coord(y, y0, inv_c, ncy), 0), ncy - 1);
+        return cy * ncx + cx;
+    };
+    for (int k = tid; k < n; k += kBqBuildThreads) atomicAdd(&cursor[cell_of(__ldg(p + 3 * k), __ldg(p + 3 * k + 1))], 1);
+    __syncthreads();
+    {  // exclusive scan of kBqMaxCells counters: 4 per thread, warp shuffle scan, 32 warp totals
+        constexpr int PER = kBqMaxCells / kBqBuildThreads;
+        int c[PER], tot = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { c[i] = cursor[tid * PER + i]; tot += c[i]; }
+        int inc = tot;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, inc, s); if (lane >= s) inc += v; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = wsum[lane];
+            int winc = w;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, winc, s); if (lane >= s) winc += v; }
+            wsum[lane] = winc - w;
+        }
+        __syncthreads();
+        int run = wsum[warp] + inc - tot;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            cursor[tid * PER + i] = run;
+            if (tid * PER + i <= ncells) cs[tid * PER + i] = run;
+            run += c[i];
+        }
+        if (tid == kBqBuildThreads - 1 && ncells == kBqMaxCells) cs[kBqMaxCells] = run;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += kBqBuildThreads) {
+        const float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1), z = __ldg(p + 3 * k + 2);
+        const int pos = atomicAdd(&cursor[cell_of(x, y)], 1);
+        out[pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+}
+
+// one warp per centre; dynamic shared memory: (warps per CTA) x ceil(n/32) bitmap words
+__global__ void __launch_bounds__(256)
+bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float4 *__restrict__ sorted,
+                     const int *__restrict__ cell_start, const BqGridInfo *__restrict__ info,
+                     const float *__restrict__ xyz2, int *__restrict__ idx, int *__restrict__ pts_cnt) {
+    extern __shared__ unsigned bq_bitmap[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int nwords = (n + 31) >> 5;
+    unsigned *bm = bq_bitmap + static_cast<size_t>(wl) * nwords;
+    const long long w = static_cast<long long>(blockIdx.x) * wpc + wl;
+    if (w >= static_cast<long long>(b) * m) return;
+    const int batch = static_cast<int>(w / m);
+    const int j = static_cast<int>(w - static_cast<long long>(batch) * m);
+    const float *c = xyz2 + (static_cast<size_t>(batch) * m + j) * 3;
+    const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+    const float T = ball_threshold(radius);
+    const BqGridInfo gi = info[batch];
+    const float4 *pts = sorted + static_cast<size_t>(batch) * n;
+    const int *cs = cell_start + static_cast<size_t>(batch) * (kBqMaxCells + 1);
+    int *row = idx + (static_cast<size_t>(batch) * m + j) * nsample;
+
+    for (int i = lane; i < nwords; i += 32) bm[i] = 0;
+    __syncwarp();
+    const int gx = bq_cell_coord(cx, gi.x0, gi.inv_c, gi.ncx), gy = bq_cell_coord(cy, gi.y0, gi.inv_c, gi.ncy);
+    const int c0 = max(gx - 1, 0), c1 = min(gx + 1, gi.ncx - 1);
+    const int r0 = max(gy - 1, 0), r1 = min(gy + 1, gi.ncy - 1);
+    int H = 0;
+    if (c0 <= c1 && T > 0.0f) {
+        for (int r = r0; r <= r1; ++r) {
+            const int s = cs[r * gi.ncx + c0], e = cs[r * gi.ncx + c1 + 1];
+            for (int i0 = s; i0 < e; i0 += 32) {
+                const int i = i0 + lane;
+                bool hit = false;
+                if (i < e) {
+                    const float4 q = __ldg(pts + i);
+                    hit = !(sqdist_ref(cx - q.x, cy - q.y, cz - q.z) >= T);
+                    if (hit) {
+                        const int k = __float_as_int(q.w);
+                        atomicOr(&bm[k >> 5], 1u << (k & 31));
+                    }
+                }
+                H += __popc(__ballot_sync(kFull, hit));
+            }
+        }
+    }
+    __syncwarp();
+    int cnt = 0, first = -1;
+    for (int w0 = 0; w0 < nwords && cnt < nsample && cnt < H; w0 += 32) {
+        unsigned word = (w0 + lane < nwords) ? bm[w0 + lane] : 0u;
+        const int pc = __popc(word);
+        int inc = pc;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, inc, s); if (lane >= s) inc += v; }
+        const int tot = __shfl_sync(kFull, inc, 31);
+        if (first < 0 && tot > 0) {
+            const int fl = __ffs(__ballot_sync(kFull, pc > 0)) - 1;
+            const unsigned fw = __shfl_sync(kFull, word, fl);
+            first = (w0 + fl) * 32 + __ffs(fw) - 1;
+        }
+        int pos = cnt + inc - pc;
+        while (word && pos < nsample) {
+            const int bit = __ffs(word) - 1;
+            row[pos++] = (w0 + lane) * 32 + bit;
+            word &= word - 1;
+        }
+        cnt += tot;
+    }
+    const int cc = min(H, nsample);
+    if (cc > 0)
+        for (int s = cc + lane; s < nsample; s += 32) row[s] = first;
+    if (lane == 0) pts_cnt[static_cast<size_t>(batch) * m + j] = cc;
+}
+
 // group_point: out[b,j,k,:] = points[b,idx[b,j,k],:]  (tf_grouping_g.cu:94-111).
 // One thread per output element of VEC floats: writes are fully coalesced, each gathered row is read as
 // contiguous VEC-wide pieces.  VEC = 4 when c % 4 == 0 and both pointers are 16-byte aligned.
@@ -279,6 +472,41 @@ F3D_API int f3d_query_ball_point(int b, int n, int m, float radius, int nsample,
     if (rc) return rc;
     const long long w = static_cast<long long>(b) * m;
     if (w == 0) return 0;
+    bq_fallback_kernel<<<blocks_for(w, kBqWarps), kBqWarps * 32, 0, st>>>(b, n, m, nsample, xyz1, xyz2, idx, pts_cnt);
+    return check_launch("bq_fallback_kernel");
+}
+
+F3D_API size_t f3d_query_ball_point_workspace_bytes(int b, int n) {
+    if (b <= 0 || n <= 0) return 256;
+    return static_cast<size_t>(b) * n * sizeof(float4) + static_cast<size_t>(b) * (kBqMaxCells + 1) * sizeof(int) +
+           static_cast<size_t>(b) * sizeof(BqGridInfo) + 512;
+}
+
+F3D_API int f3d_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
+                                    int *idx, int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream) {
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f) || !xyz1 || !xyz2 || !idx || !pts_cnt)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "query_ball_point: bad arguments");
+    // the grid path needs a workspace, a finite radius and a per-warp index bitmap that fits shared memory
+    const bool grid_ok = workspace && workspace_bytes >= f3d_query_ball_point_workspace_bytes(b, n) && n <= 262144 &&
+                         radius < 1.0e18f && (reinterpret_cast<uintptr_t>(workspace) % 16 == 0);
+    if (!grid_ok) return f3d_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
+    const long long w = static_cast<long long>(b) * m;
+    if (w == 0 || b == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    float4 *sorted = static_cast<float4 *>(workspace);
+    int *cell_start = reinterpret_cast<int *>(sorted + static_cast<size_t>(b) * n);
+    BqGridInfo *info = reinterpret_cast<BqGridInfo *>(cell_start + static_cast<size_t>(b) * (kBqMaxCells + 1));
+    bq_grid_build_kernel<<<b, kBqBuildThreads, 0, st>>>(n, radius, xyz1, sorted, cell_start, info);
+    int rc = check_launch("bq_grid_build_kernel");
+    if (rc) return rc;
+    const int nwords = (n + 31) / 32;
+    const int wpc = nwords <= 1024 ? 8 : (nwords <= 4096 ? 4 : 2);
+    const size_t smem = static_cast<size_t>(wpc) * nwords * sizeof(unsigned);
+    cudaError_t e = cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "bq_grid_query: cudaFuncSetAttribute");
+    bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, sorted, cell_start, info, xyz2, idx, pts_cnt);
+    rc = check_launch("bq_grid_query_kernel");
+    if (rc) return rc;
     bq_fallback_kernel<<<blocks_for(w, kBqWarps), kBqWarps * 32, 0, st>>>(b, n, m, nsample, xyz1, xyz2, idx, pts_cnt);
     return check_launch("bq_fallback_kernel");
 }

@@ -39,6 +39,8 @@ class DetectDescribePipeline:
         self.orientation = torch.empty((B, M), dtype=torch.float32, device=dev)
         self.features = torch.empty((B, M, F), dtype=torch.float32, device=dev)
         self.fps_temp = torch.empty((B, N), dtype=torch.float32, device=dev) if N > 16384 else None
+        self.bq_ws_bytes = self.L.f3d_query_ball_point_workspace_bytes(B, N)
+        self.bq_ws = torch.empty((self.bq_ws_bytes,), dtype=torch.uint8, device=dev)
         self.ws_bytes = self.L.f3d_forward_workspace_bytes(B, M, F)
         self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
         # pinned host mirrors for the end-to-end (host buffers in, host buffers out) entry point
@@ -50,10 +52,13 @@ class DetectDescribePipeline:
         self.launches_per_step = None
         self._graph = None
         self.use_graph = use_graph
+        # double buffers + side streams of the overlapped host<->device loop (run_host_steps)
+        self._hp = None
 
     # one stage = one C-ABI call; `events` (optional list) receives a CUDA event after each stage
-    def _enqueue(self, events=None):
+    def _enqueue(self, events=None, xyz=None):
         L, p, st = self.L, _lib.ptr, _lib.stream()
+        xyz_buf = self.xyz if xyz is None else xyz
         B, N, M, S, F = self.B, self.N, self.M, self.S, self.F
         prec = _f3d.PRECISIONS[self.precision]
 
@@ -64,19 +69,19 @@ class DetectDescribePipeline:
                 events.append(e)
 
         mark()
-        _lib.check(L.f3d_farthest_point_sample(B, N, M, p(self.xyz), p(self.fps_temp), p(self.fps_idx), st), "fps")
+        _lib.check(L.f3d_farthest_point_sample(B, N, M, p(xyz_buf), p(self.fps_temp), p(self.fps_idx), st), "fps")
         mark()
-        _lib.check(L.f3d_gather_point(B, N, M, p(self.xyz), p(self.fps_idx), p(self.keypoints), st), "gather_point")
+        _lib.check(L.f3d_gather_point(B, N, M, p(xyz_buf), p(self.fps_idx), p(self.keypoints), st), "gather_point")
         mark()
-        _lib.check(L.f3d_query_ball_point(B, N, M, self.radius, S, p(self.xyz), p(self.keypoints), p(self.idx),
-                                          p(self.pts_cnt), st), "query_ball_point")
+        _lib.check(L.f3d_query_ball_point_ws(B, N, M, self.radius, S, p(xyz_buf), p(self.keypoints), p(self.idx),
+                                             p(self.pts_cnt), p(self.bq_ws), self.bq_ws_bytes, st), "query_ball_point")
         mark()
-        _lib.check(L.f3d_detector_forward(B, N, M, S, self.radius, p(self.xyz), p(self.keypoints), p(self.idx),
+        _lib.check(L.f3d_detector_forward(B, N, M, S, self.radius, p(xyz_buf), p(self.keypoints), p(self.idx),
                                           p(self.packed), p(self.attention), p(self.orientation), prec, p(self.ws),
                                           self.ws_bytes, st), "detector_forward")
         mark()
         ori = None if self.no_regress else self.orientation
-        _lib.check(L.f3d_descriptor_forward(B, N, M, S, self.radius, F, p(self.xyz), p(self.keypoints), p(self.idx),
+        _lib.check(L.f3d_descriptor_forward(B, N, M, S, self.radius, F, p(xyz_buf), p(self.keypoints), p(self.idx),
                                             p(ori), p(self.packed), p(self.features), prec, p(self.ws), self.ws_bytes, st),
                    "descriptor_forward")
         mark()
@@ -128,3 +133,102 @@ class DetectDescribePipeline:
         self.d_out[:, :, 5:5 + F] = self.features
         self.h_out.copy_(self.d_out, non_blocking=True)
         return self.h_out
+
+    # ---- overlapped end-to-end loop: H2D of step i+1 and D2H of step i-1 run under the compute of step i ------------
+    def _pack(self, d_out):
+        F = self.F
+        d_out[:, :, 0:3] = self.keypoints
+        d_out[:, :, 3] = self.attention
+        d_out[:, :, 4] = self.orientation
+        d_out[:, :, 5:5 + F] = self.features
+
+    def _host_pipe(self):
+        if self._hp is None:
+            dev, B, N, M, F = self.device, self.B, self.N, self.M, self.F
+            hp = dict(
+                s_h2d=torch.cuda.Stream(device=dev), s_comp=torch.cuda.Stream(device=dev), s_d2h=torch.cuda.Stream(device=dev),
+                xyz=[torch.empty((B, N, 3), dtype=torch.float32, device=dev) for _ in range(2)],
+                d_out=[torch.empty((B, M, 5 + F), dtype=torch.float32, device=dev) for _ in range(2)],
+                h_out=[torch.empty((B, M, 5 + F), dtype=torch.float32).pin_memory() for _ in range(2)],
+                graphs=[None, None])
+            self._hp = hp
+        return self._hp
+
+    def run_host_steps(self, steps, host_batches=None, flush=None):
+        """`steps` end-to-end passes through the public path with HOST buffers: every step copies its input batch from
+        pinned host memory (host_batches[i % len], default self.h_xyz), computes, and copies the packed
+        [xyz | attention | orientation | descriptor] rows back to pinned host memory -- all inside the timed region.
+        Copies and compute of neighbouring steps overlap on three streams (double-buffered input / output).
+        Returns (elapsed_ms by CUDA events from the first H2D to the last D2H, last host output)."""
+        hp = self._host_pipe()
+        host_batches = host_batches or [self.h_xyz]
+        cur = torch.cuda.current_stream()
+        for s in (hp["s_h2d"], hp["s_comp"], hp["s_d2h"]):
+            s.wait_stream(cur)
+        ev_h2d = [None, None]
+        ev_comp = [None, None]
+        ev_d2h = [None, None]
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(hp["s_h2d"]):
+            start.record()
+        for i in range(steps):
+            b = i & 1
+            with torch.cuda.stream(hp["s_h2d"]):
+                if ev_comp[b] is not None:
+                    hp["s_h2d"].wait_event(ev_comp[b])  # compute of step i-2 has consumed this input buffer
+                hp["xyz"][b].copy_(host_batches[i % len(host_batches)], non_blocking=True)
+                ev_h2d[b] = torch.cuda.Event()
+                ev_h2d[b].record()
+            with torch.cuda.stream(hp["s_comp"]):
+                hp["s_comp"].wait_event(ev_h2d[b])
+                if ev_d2h[b] is not None:
+                    hp["s_comp"].wait_event(ev_d2h[b])  # D2H of step i-2 has drained this output buffer
+                if flush is not None:
+                    flush()
+                if self.use_graph:
+                    if hp["graphs"][b] is None:
+                        raise _lib.F3DError("call warm_host_graphs() before timing with use_graph=True")
+                    hp["graphs"][b].replay()
+                else:
+                    self._enqueue(xyz=hp["xyz"][b])
+                    self._pack(hp["d_out"][b])
+                ev_comp[b] = torch.cuda.Event()
+                ev_comp[b].record()
+            with torch.cuda.stream(hp["s_d2h"]):
+                hp["s_d2h"].wait_event(ev_comp[b])
+                hp["h_out"][b].copy_(hp["d_out"][b], non_blocking=True)
+                ev_d2h[b] = torch.cuda.Event()
+                ev_d2h[b].record()
+        with torch.cuda.stream(hp["s_d2h"]):
+            end.record()
+        cur.wait_stream(hp["s_d2h"])
+        cur.wait_stream(hp["s_comp"])
+        cur.wait_stream(hp["s_h2d"])
+        torch.cuda.synchronize()
+        return start.elapsed_time(end), hp["h_out"][(steps - 1) & 1]
+
+    def warm_host_graphs(self):
+        """Capture one CUDA graph per input/output buffer parity for run_host_steps (eager first, to set attributes)."""
+        hp = self._host_pipe()
+        if self.launches_per_step is None:
+            self.step()
+        for b in range(2):
+            hp["xyz"][b].copy_(self.h_xyz)
+            with torch.cuda.stream(hp["s_comp"]):
+                self._enqueue(xyz=hp["xyz"][b])
+                self._pack(hp["d_out"][b])
+            torch.cuda.synchronize()
+            if self.use_graph and hp["graphs"][b] is None:
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=hp["s_comp"]):
+                        self._enqueue(xyz=hp["xyz"][b])
+                        self._pack(hp["d_out"][b])
+                    hp["graphs"][b] = g
+                except Exception as exc:
+                    import warnings
+
+                    warnings.warn("CUDA graph capture failed (%s); running the stages eagerly" % exc)
+                    self.use_graph = False
+                    torch.cuda.synchronize()

@@ -33,7 +33,7 @@ def _check_xyz_pair(op, xyz1, xyz2):
         raise ValueError("%s expects (batch_size, npoint, 3) xyz2 shape." % op)
 
 
-def query_ball_point(radius, nsample, xyz1, xyz2):
+def query_ball_point(radius, nsample, xyz1, xyz2, use_grid=True):
     '''
     Input:
         radius: float32, ball search radius
@@ -56,8 +56,14 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
     L = _lib.lib()
-    _lib.check(L.f3d_query_ball_point(b, n, m, float(radius), nsample, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx),
-                                      _lib.ptr(cnt), _lib.stream()), "query_ball_point")
+    if use_grid:  # grid-accelerated kernel (identical results); use_grid=False forces the plain scan
+        ws_bytes = L.f3d_query_ball_point_workspace_bytes(b, n)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=xyz1.device)
+        _lib.check(L.f3d_query_ball_point_ws(b, n, m, float(radius), nsample, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx),
+                                             _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream()), "query_ball_point")
+    else:
+        _lib.check(L.f3d_query_ball_point(b, n, m, float(radius), nsample, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx),
+                                          _lib.ptr(cnt), _lib.stream()), "query_ball_point")
     return idx, cnt
 
 

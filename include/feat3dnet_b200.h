@@ -60,6 +60,14 @@ int f3d_gather_point_grad(int b, int n, int m, const float *out_g, const int *id
 int f3d_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
                          int *pts_cnt, void *stream);
 
+/* Same operator with a caller-provided workspace of f3d_query_ball_point_workspace_bytes(b,n) bytes: the cloud is
+ * binned into an xy grid of cell size ~radius and each centre only tests its 3x3 cell neighbourhood; identical
+ * results (hits are re-ordered by index through a shared-memory bitmap).  Falls back to the scan above when the
+ * workspace is NULL / too small. */
+size_t f3d_query_ball_point_workspace_bytes(int b, int n);
+int f3d_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                            int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream);
+
 /* queryBallPoint2Launcher(b,n,m,nsample,xyz1,xyz2,radii,idx,pts_cnt)  tf_grouping_g.cu:183-186,
  * op tf_grouping.cpp:128-172.  radii (b,m).  Rows of empty balls are left untouched, as in the reference. */
 int f3d_query_ball_point2(int b, int n, int m, int nsample, const float *xyz1, const float *xyz2, const float *radii,

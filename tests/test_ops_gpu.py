@@ -108,11 +108,12 @@ def test_ball_query_bit_exact_vs_oracle(cuda, kind, b, n, m, radius, ns, mode):
     tg = pkg("tf_ops.grouping.tf_grouping")
     x = clouds(kind, b, n, 5 + n)
     c = _centres(x, m, mode, n + m)
-    idx, cnt = tg.query_ball_point(radius, ns, T(x, cuda), T(c, cuda))
     widx, wcnt = oops.query_ball_point(radius, ns, x, c)
-    assert idx.dtype == torch.int32 and cnt.dtype == torch.int32
-    assert np.array_equal(cnt.cpu().numpy(), wcnt)
-    assert np.array_equal(idx.cpu().numpy(), widx)
+    for use_grid in (True, False):  # grid-accelerated kernel and plain scan: both bit-exact
+        idx, cnt = tg.query_ball_point(radius, ns, T(x, cuda), T(c, cuda), use_grid=use_grid)
+        assert idx.dtype == torch.int32 and cnt.dtype == torch.int32
+        assert np.array_equal(cnt.cpu().numpy(), wcnt), use_grid
+        assert np.array_equal(idx.cpu().numpy(), widx), use_grid
     if mode == "external":
         assert (wcnt == 0).any()  # the fallback path was exercised
 
@@ -128,9 +129,10 @@ def test_ball_query_radius_on_representable_boundaries(cuda):
         for a in range(3):
             x[0, a * 5:(a + 1) * 5, a] = xs
         c = np.zeros((1, 1, 3), np.float32)
-        idx, cnt = tg.query_ball_point(float(r32), 16, T(x, cuda), T(c, cuda))
         widx, wcnt = oops.query_ball_point(float(r32), 16, x, c)
-        assert np.array_equal(cnt.cpu().numpy(), wcnt) and np.array_equal(idx.cpu().numpy(), widx), r
+        for use_grid in (True, False):
+            idx, cnt = tg.query_ball_point(float(r32), 16, T(x, cuda), T(c, cuda), use_grid=use_grid)
+            assert np.array_equal(cnt.cpu().numpy(), wcnt) and np.array_equal(idx.cpu().numpy(), widx), (r, use_grid)
     # random near-boundary configurations: centres at distance r*(1 +- few ulp) in random directions
     rng = np.random.default_rng(0)
     n = 4096
@@ -139,10 +141,11 @@ def test_ball_query_radius_on_representable_boundaries(cuda):
     scale = 2.0 * (1 + rng.integers(-4, 5, n) * 2.0 ** -24)
     x = (d * scale[:, None]).astype(np.float32)[None]
     c = np.zeros((1, 1, 3), np.float32)
-    idx, cnt = tg.query_ball_point(2.0, 4096, T(x, cuda), T(c, cuda))
     widx, wcnt = oops.query_ball_point(2.0, 4096, x, c)
     assert 0 < wcnt[0, 0] < n
-    assert np.array_equal(cnt.cpu().numpy(), wcnt) and np.array_equal(idx.cpu().numpy(), widx)
+    for use_grid in (True, False):
+        idx, cnt = tg.query_ball_point(2.0, 4096, T(x, cuda), T(c, cuda), use_grid=use_grid)
+        assert np.array_equal(cnt.cpu().numpy(), wcnt) and np.array_equal(idx.cpu().numpy(), widx), use_grid
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
