@@ -162,21 +162,25 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
     const int T = first < num_clusters ? static_cast<int>((num_clusters - first + gridDim.x - 1) / gridDim.x) : 0;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             // ---- weights: one bulk-TMA burst, resident for the whole kernel ---------------------------------
-            mbar_arrive_expect_tx(&bars[W_FULL], kWeightBytes);
-            for (uint32_t off = 0; off < kWeightBytes; off += 16384) {
-                const uint32_t sz = min(16384u, kWeightBytes - off);
-                bulk_g2s(smem + off, wimg + off, sz, &bars[W_FULL]);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars[W_FULL], kWeightBytes);
+                for (uint32_t off = 0; off < kWeightBytes; off += 16384) {
+                    const uint32_t sz = min(16384u, kWeightBytes - off);
+                    bulk_g2s(smem + off, wimg + off, sz, &bars[W_FULL]);
+                }
             }
+            __syncwarp();
             mbar_wait(&bars[W_FULL], 0);
-            // ---- MMA issue loop ---------------------------------------------------------------------------
+            // ---- MMA issue loop: the whole warp walks it (uniform control flow), one elected lane issues --------
             const uint32_t idesc = make_idesc(1, 128, kSamples);
             const uint32_t sbase = smem_u32(smem);
             auto mma1 = [&](int t) {
                 mbar_wait(&bars[X1_FULL], t & 1);
                 mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
+                if (elect_one()) {
                 const uint32_t d = tmem_base + (t & 1) * 64;
                 uint32_t acc = 0;
 #pragma unroll
@@ -192,11 +196,14 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 }
                 umma_commit(&bars[X1_FREE]);
                 umma_commit(&bars[D1_FULL0 + (t & 1)]);
+                }
+                __syncwarp();
             };
             auto mma2 = [&](int t) {
                 mbar_wait(&bars[X2_FULL], t & 1);
                 mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
+                if (elect_one()) {
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
                     const uint32_t d = tmem_base + 128 + (t & 1) * 128 + mb * 64;
@@ -215,6 +222,8 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 }
                 umma_commit(&bars[X2_FREE]);
                 umma_commit(&bars[D2_FULL0 + (t & 1)]);
+                }
+                __syncwarp();
             };
             if (T > 0) mma1(0);
             for (int t = 0; t < T; ++t) {
