@@ -100,8 +100,8 @@ constexpr uint32_t kW1Split = 128 * 64 * 2;            // 16 KB per split
 constexpr uint32_t kW2Blk = 128 * 128 * 2;             // 32 KB per (split, M block)
 constexpr uint32_t kOffW1 = 0;                          // [split 2][chunk 8][row 128][8] bf16
 constexpr uint32_t kOffW2 = kOffW1 + 2 * kW1Split;      // [split 2][mblk 2][chunk 16][row 128][8] bf16
-constexpr uint32_t kOffW0 = kOffW2 + 4 * kW2Blk;        // fp32 [3][64]
-constexpr uint32_t kOffB0 = kOffW0 + 3 * 64 * 4;        // fp32 [64]
+constexpr uint32_t kOffW0 = kOffW2 + 4 * kW2Blk;        // float4 [64]: (w_x, w_y, w_z, bias) of layer 0 per channel
+constexpr uint32_t kOffB0 = kOffW0 + 3 * 64 * 4;        // (tail of the float4 table)
 constexpr uint32_t kOffB1 = kOffB0 + 64 * 4;            // fp32 [128]
 constexpr uint32_t kOffB2 = kOffB1 + 128 * 4;           // fp32 [256]
 constexpr uint32_t kWeightBytes = kOffB2 + 256 * 4;     // 166 400
@@ -233,38 +233,56 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         }
     } else if (warp <= 4) {
         // ---- producers: gather + normalise + layer 0 -> X1 ------------------------------------------------------
+        // Software-pipelined: the index of tile t+2 and the coordinates of tile t+1 are in flight while tile t is computed.
         mbar_wait(&bars[W_FULL], 0);  // W0 / b0 live in the weight image
-        const float *W0 = reinterpret_cast<const float *>(smem + kOffW0);
-        const float *B0 = reinterpret_cast<const float *>(smem + kOffB0);
+        const float4 *W0 = reinterpret_cast<const float4 *>(smem + kOffW0);  // per channel: (w_x, w_y, w_z, bias)
         const int pt = threadIdx.x - 32;      // 0..127
         const int s = pt & 63, h = pt >> 6;   // sample, channel half
         uint8_t *x1 = smem + kOffX1 + s * 16;
-        for (int t = 0; t < T; ++t) {
-            const long long cl = first + static_cast<long long>(t) * gridDim.x;
-            int ii = __ldg(idx + cl * kSamples + s);
+        const unsigned stride = gridDim.x;
+        const float inv_guard = radius;  // division by radius is kept exact (TF: grouped_xyz /= radius)
+        auto load_idx = [&](int t) -> int {
+            if (t >= T) return 0;
+            const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
+            return __ldg(idx + static_cast<size_t>(cl) * kSamples + s);
+        };
+        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        auto load_xyz = [&](int t, int ii) {
+            if (t >= T) return;
+            const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
             ii = min(max(ii, 0), n - 1);
-            const float *p = xyz + ((cl / m) * n + ii) * 3;
-            const float *c = new_xyz + cl * 3;
-            const float gx = (__ldg(p) - __ldg(c)) / radius;
-            const float gy = (__ldg(p + 1) - __ldg(c + 1)) / radius;
-            const float gz = (__ldg(p + 2) - __ldg(c + 2)) / radius;
+            const float *p = xyz + (static_cast<size_t>(cl / static_cast<unsigned>(m)) * n + ii) * 3;
+            const float *c = new_xyz + static_cast<size_t>(cl) * 3;
+            px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
+            qx = __ldg(c); qy = __ldg(c + 1); qz = __ldg(c + 2);
+        };
+        int i1 = load_idx(0);
+        load_xyz(0, i1);
+        i1 = load_idx(1);
+        for (int t = 0; t < T; ++t) {
+            const float gx = (px - qx) / inv_guard;
+            const float gy = (py - qy) / inv_guard;
+            const float gz = (pz - qz) / inv_guard;
+            const int i2 = load_idx(t + 2);
+            load_xyz(t + 1, i1);
+            i1 = i2;
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 float v[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int k = h * 32 + j * 2 + e;
-                    float a = B0[k];
-                    a = fmaf(gx, W0[k], a);
-                    a = fmaf(gy, W0[64 + k], a);
-                    a = fmaf(gz, W0[128 + k], a);
+                    const float4 w = W0[h * 32 + j * 2 + e];
+                    float a = w.w;
+                    a = fmaf(gx, w.x, a);
+                    a = fmaf(gy, w.y, a);
+                    a = fmaf(gz, w.z, a);
                     v[e] = fmaxf(a, 0.0f);
                 }
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
-                hi[j] = pack_bf16x2(h0, h1);
-                lo[j] = pack_bf16x2(__float2bfloat16_rn(v[0] - __bfloat162float(h0)),
-                                    __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[0] - __low2float(h2), v[1] - __high2float(h2));
+                hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
+                lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
             }
             mbar_wait(&bars[X1_FREE], (t & 1) ^ 1);
 #pragma unroll
@@ -298,14 +316,24 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(&bars[D1_FREE0 + b]);
+            // bias, ReLU and the hi/lo split happen BEFORE waiting for the operand buffer; r[i] becomes (lo << 16) | hi
+#pragma unroll
+            for (int sidx = 0; sidx < 64; sidx += 2) {
+                uint32_t &ra = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
+                uint32_t &rb = sidx < 32 ? r0[(sidx + 1) & 31] : r1[(sidx + 1) & 31];
+                const float va = fmaxf(__uint_as_float(ra) + b1, 0.0f), vb = fmaxf(__uint_as_float(rb) + b1, 0.0f);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
+                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2), lb = *reinterpret_cast<const uint32_t *>(&l2);
+                ra = (hb & 0xffffu) | (lb << 16);
+                rb = (hb >> 16) | (lb & 0xffff0000u);
+            }
             mbar_wait(&bars[X2_FREE], (t & 1) ^ 1);
 #pragma unroll
             for (int sidx = 0; sidx < 64; ++sidx) {
-                const float v = fmaxf(__uint_as_float(sidx < 32 ? r0[sidx & 31] : r1[sidx & 31]) + b1, 0.0f);
-                const __nv_bfloat16 hv = __float2bfloat16_rn(v);
-                const __nv_bfloat16 lv = __float2bfloat16_rn(v - __bfloat162float(hv));
-                *reinterpret_cast<__nv_bfloat16 *>(x2 + sidx * 16) = hv;
-                *reinterpret_cast<__nv_bfloat16 *>(x2 + kX2Split + sidx * 16) = lv;
+                const uint32_t pk = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
+                *reinterpret_cast<uint16_t *>(x2 + sidx * 16) = static_cast<uint16_t>(pk & 0xffffu);
+                *reinterpret_cast<uint16_t *>(x2 + kX2Split + sidx * 16) = static_cast<uint16_t>(pk >> 16);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[X2_FULL]);
@@ -363,9 +391,10 @@ __global__ void det_tc_prep_kernel(const float *__restrict__ P, WeightLayout L, 
     } else {
         const int e = i - 128 * 64 - 256 * 128;
         float *f = reinterpret_cast<float *>(wimg + kOffW0);
-        if (e < 192) f[e] = P[L.off[W_DET0] + e];
-        else if (e < 256) f[e] = P[L.off[B_DET0] + e - 192];
-        else if (e < 384) f[e] = P[L.off[B_DET1] + e - 256];
+        if (e < 256) {  // per channel k: (W0[0][k], W0[1][k], W0[2][k], b0[k])
+            const int k = e >> 2, c = e & 3;
+            f[e] = c < 3 ? P[L.off[W_DET0] + c * 64 + k] : P[L.off[B_DET0] + k];
+        } else if (e < 384) f[e] = P[L.off[B_DET1] + e - 256];
         else if (e < 640) f[e] = P[L.off[B_DET2] + e - 384];
     }
 }

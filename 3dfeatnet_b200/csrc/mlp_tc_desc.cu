@@ -36,8 +36,8 @@ constexpr uint32_t kWmSplit = 128 * 64 * 2;             // 16 KB
 constexpr uint32_t kOffW1 = 0;                           // [split 2][chunk 4][row 128][8]
 constexpr uint32_t kOffWa = kOffW1 + 2 * kW1Split;       // [split 2][chunk 8][row 128][8]
 constexpr uint32_t kOffWb = kOffWa + 2 * kWmSplit;
-constexpr uint32_t kOffW0 = kOffWb + 2 * kWmSplit;       // fp32 [3][32]
-constexpr uint32_t kOffB0 = kOffW0 + 3 * 32 * 4;         // fp32 [32]
+constexpr uint32_t kOffW0 = kOffWb + 2 * kWmSplit;       // float4 [32]: (w_x, w_y, w_z, bias) of layer 0 per channel
+constexpr uint32_t kOffB0 = kOffW0 + 3 * 32 * 4;         // (tail of the float4 table)
 constexpr uint32_t kOffB1 = kOffB0 + 32 * 4;             // fp32 [64]
 constexpr uint32_t kOffBm = kOffB1 + 64 * 4;             // fp32 [128]
 constexpr uint32_t kWeightBytes = kOffBm + 128 * 4;      // 83 200
@@ -180,45 +180,63 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         }
     } else if (warp <= 4) {
         // ---- producers: gather + normalise + rotate + layer 0 (3 -> 32) -> X1 ------------------------------------
+        // Software-pipelined like the detector's: index of tile t+2 and coordinates / orientation of tile t+1 in flight.
         mbar_wait(&bars[W_FULL], 0);
-        const float *W0 = reinterpret_cast<const float *>(smem + kOffW0);
-        const float *B0 = reinterpret_cast<const float *>(smem + kOffB0);
+        const float4 *W0 = reinterpret_cast<const float4 *>(smem + kOffW0);  // per channel: (w_x, w_y, w_z, bias)
         const int pt = threadIdx.x - 32;
         const int s = pt & 63, h = pt >> 6;  // sample, channel half (16 channels = 2 K chunks)
         uint8_t *x1 = smem + kOffX1 + s * 16;
-        for (int t = 0; t < T; ++t) {
-            const long long cl = first + static_cast<long long>(t) * gridDim.x;
-            int ii = __ldg(idx + cl * kSamples + s);
+        const unsigned stride = gridDim.x;
+        auto load_idx = [&](int t) -> int {
+            if (t >= T) return 0;
+            const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
+            return __ldg(idx + static_cast<size_t>(cl) * kSamples + s);
+        };
+        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, th = 0.f;
+        auto load_xyz = [&](int t, int ii) {
+            if (t >= T) return;
+            const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
             ii = min(max(ii, 0), n - 1);
-            const float *p = xyz + ((cl / m) * n + ii) * 3;
-            const float *c = new_xyz + cl * 3;
-            float gx = (__ldg(p) - __ldg(c)) / radius;
-            float gy = (__ldg(p + 1) - __ldg(c + 1)) / radius;
-            const float gz = (__ldg(p + 2) - __ldg(c + 2)) / radius;
+            const float *p = xyz + (static_cast<size_t>(cl / static_cast<unsigned>(m)) * n + ii) * 3;
+            const float *c = new_xyz + static_cast<size_t>(cl) * 3;
+            px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
+            qx = __ldg(c); qy = __ldg(c + 1); qz = __ldg(c + 2);
+            if (orientation) th = __ldg(orientation + cl);
+        };
+        int i1 = load_idx(0);
+        load_xyz(0, i1);
+        i1 = load_idx(1);
+        for (int t = 0; t < T; ++t) {
+            float gx = (px - qx) / radius;
+            float gy = (py - qy) / radius;
+            const float gz = (pz - qz) / radius;
             if (orientation) {  // pointnet_common.py:110-120: x' = x c - y s ; y' = x s + y c
-                const float th = __ldg(orientation + cl);
                 const float cs = cosf(th), sn = sinf(th);
                 const float xr = gx * cs - gy * sn;
                 const float yr = gx * sn + gy * cs;
                 gx = xr;
                 gy = yr;
             }
+            const int i2 = load_idx(t + 2);
+            load_xyz(t + 1, i1);
+            i1 = i2;
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float v[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int k = h * 16 + j * 2 + e;
-                    float a = B0[k];
-                    a = fmaf(gx, W0[k], a);
-                    a = fmaf(gy, W0[32 + k], a);
-                    a = fmaf(gz, W0[64 + k], a);
+                    const float4 w = W0[h * 16 + j * 2 + e];
+                    float a = w.w;
+                    a = fmaf(gx, w.x, a);
+                    a = fmaf(gy, w.y, a);
+                    a = fmaf(gz, w.z, a);
                     v[e] = fmaxf(a, 0.0f);
                 }
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
-                hi[j] = pack2(h0, h1);
-                lo[j] = pack2(__float2bfloat16_rn(v[0] - __bfloat162float(h0)), __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[0] - __low2float(h2), v[1] - __high2float(h2));
+                hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
+                lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
             }
             mbar_wait(&bars[X1_FREE], (t & 1) ^ 1);
 #pragma unroll
@@ -255,17 +273,28 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             tcgen05_fence_before();
             mbar_arrive(&bars[D1_FREE0 + b]);
+            float pmax = 0.0f;  // values are post-ReLU (>= 0)
+            if (q < 2) {  // bias, ReLU, max-pool and the hi/lo split BEFORE waiting for the operand buffer
+#pragma unroll
+                for (int sidx = 0; sidx < 64; sidx += 2) {
+                    uint32_t &ra = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
+                    uint32_t &rb = sidx < 32 ? r0[(sidx + 1) & 31] : r1[(sidx + 1) & 31];
+                    const float va = fmaxf(__uint_as_float(ra) + b1, 0.0f), vb = fmaxf(__uint_as_float(rb) + b1, 0.0f);
+                    pmax = fmaxf(pmax, fmaxf(va, vb));
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
+                    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2), lb = *reinterpret_cast<const uint32_t *>(&l2);
+                    ra = (hb & 0xffffu) | (lb << 16);
+                    rb = (hb >> 16) | (lb & 0xffff0000u);
+                }
+            }
             mbar_wait(&bars[X2_FREE], (t & 1) ^ 1);
             if (q < 2) {
-                float pmax = 0.0f;  // values are post-ReLU (>= 0)
 #pragma unroll
                 for (int sidx = 0; sidx < 64; ++sidx) {
-                    const float v = fmaxf(__uint_as_float(sidx < 32 ? r0[sidx & 31] : r1[sidx & 31]) + b1, 0.0f);
-                    pmax = fmaxf(pmax, v);
-                    const __nv_bfloat16 hv = __float2bfloat16_rn(v);
-                    const __nv_bfloat16 lv = __float2bfloat16_rn(v - __bfloat162float(hv));
-                    *reinterpret_cast<__nv_bfloat16 *>(x2 + sidx * 16) = hv;
-                    *reinterpret_cast<__nv_bfloat16 *>(x2 + kX2Split + sidx * 16) = lv;
+                    const uint32_t pk = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
+                    *reinterpret_cast<uint16_t *>(x2 + sidx * 16) = static_cast<uint16_t>(pk & 0xffffu);
+                    *reinterpret_cast<uint16_t *>(x2 + kX2Split + sidx * 16) = static_cast<uint16_t>(pk >> 16);
                 }
                 const __nv_bfloat16 hp = __float2bfloat16_rn(pmax);
                 *reinterpret_cast<__nv_bfloat16 *>(pp) = hp;
@@ -321,9 +350,10 @@ __global__ void desc_tc_prep_kernel(const float *__restrict__ P, WeightLayout L,
     } else {
         const int e = i - 128 * 32 - 2 * 128 * 64;
         float *f = reinterpret_cast<float *>(wimg + kOffW0);
-        if (e < 96) f[e] = P[L.off[W_DESC0] + e];
-        else if (e < 128) f[e] = P[L.off[B_DESC0] + e - 96];
-        else if (e < 192) f[e] = P[L.off[B_DESC1] + e - 128];
+        if (e < 128) {  // per channel k: (W0[0][k], W0[1][k], W0[2][k], b0[k])
+            const int k = e >> 2, c = e & 3;
+            f[e] = c < 3 ? P[L.off[W_DESC0] + c * 32 + k] : P[L.off[B_DESC0] + k];
+        } else if (e < 192) f[e] = P[L.off[B_DESC1] + e - 128];
         else if (e < 320) f[e] = P[L.off[B_MID] + e - 192];
     }
 }
