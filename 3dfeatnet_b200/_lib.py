@@ -18,6 +18,8 @@ SIGNATURES = {
     "f3d_farthest_point_sample": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_gather_point": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_gather_point_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "f3d_cumsum": (_i, [_i, _i, _vp, _vp, _vp]),
+    "f3d_prob_sample": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "f3d_query_ball_point": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "f3d_query_ball_point_workspace_bytes": (_sz, [_i, _i]),
     "f3d_query_ball_point_ws": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -34,8 +36,11 @@ SIGNATURES = {
     "f3d_forward_workspace_bytes": (_sz, [_i, _i, _i]),
     "f3d_detector_forward": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "f3d_descriptor_forward": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "f3d_nms_workspace_bytes": (_sz, [_i, _i]),
+    "f3d_nms": (_i, [_i, _i, _vp, _vp, _c.c_double, _c.c_double, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_debug_umma_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "f3d_detector_tc_weight_bytes": (_sz, []),
+    "f3d_debug_set_timeline": (None, [_vp]),
 }
 
 _LIB = None

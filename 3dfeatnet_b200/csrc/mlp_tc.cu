@@ -127,8 +127,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 __global__ void __launch_bounds__(det::kThreads, 1)
 det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const float *__restrict__ xyz,
                    const float *__restrict__ new_xyz, const int *__restrict__ idx, const uint8_t *__restrict__ wimg,
-                   float *__restrict__ pooled) {
+                   float *__restrict__ pooled, long long *__restrict__ dbg) {
     using namespace det;
+    // optional timeline of CTA 0 (bring-up / profiling): dbg[tile*16 + slot] = clock64() at named points
+    auto stamp = [&](int t, int slot) {
+        if (dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) dbg[t * 16 + slot] = clock64();
+    };
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBars);
     uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(smem + kOffBars + kNumBars * 8);
@@ -180,6 +184,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 mbar_wait(&bars[X1_FULL], t & 1);
                 mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
+                stamp(t, 0);
                 if (elect_one()) {
                 const uint32_t d = tmem_base + (t & 1) * 64;
                 uint32_t acc = 0;
@@ -203,6 +208,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 mbar_wait(&bars[X2_FULL], t & 1);
                 mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
+                stamp(t, 1);
                 if (elect_one()) {
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
@@ -224,6 +230,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 umma_commit(&bars[D2_FULL0 + (t & 1)]);
                 }
                 __syncwarp();
+                stamp(t, 2);
             };
             if (T > 0) mma1(0);
             for (int t = 0; t < T; ++t) {
@@ -260,6 +267,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         load_xyz(0, i1);
         i1 = load_idx(1);
         for (int t = 0; t < T; ++t) {
+            if (warp == 1) stamp(t, 4);
             const float gx = (px - qx) / inv_guard;
             const float gy = (py - qy) / inv_guard;
             const float gz = (pz - qz) / inv_guard;
@@ -284,7 +292,9 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
                 lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
             }
+            if (warp == 1) stamp(t, 5);
             mbar_wait(&bars[X1_FREE], (t & 1) ^ 1);
+            if (warp == 1) stamp(t, 6);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // K chunk h*4+q holds channels h*32 + q*8 .. +7
                 *reinterpret_cast<uint4 *>(x1 + (h * 4 + q) * kLboX1) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
@@ -310,6 +320,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             // E1: D1 -> +bias, ReLU, split -> X2
             mbar_wait(&bars[D1_FULL0 + b], ph);
             tcgen05_fence_after();
+            if (q == 1) stamp(t, 8);
             uint32_t r0[32], r1[32];
             tmem_ld32(tmem_base + lane_addr + b * 64, r0);
             tmem_ld32(tmem_base + lane_addr + b * 64 + 32, r1);
@@ -328,7 +339,9 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 ra = (hb & 0xffffu) | (lb << 16);
                 rb = (hb >> 16) | (lb & 0xffff0000u);
             }
+            if (q == 1) stamp(t, 9);
             mbar_wait(&bars[X2_FREE], (t & 1) ^ 1);
+            if (q == 1) stamp(t, 10);
 #pragma unroll
             for (int sidx = 0; sidx < 64; ++sidx) {
                 const uint32_t pk = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
@@ -337,9 +350,11 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[X2_FULL]);
+            if (q == 1) stamp(t, 11);
             // E2: D2 -> max over the 64 samples, +bias, ReLU -> pooled (ReLU and +bias commute with max)
             mbar_wait(&bars[D2_FULL0 + b], ph);
             tcgen05_fence_after();
+            if (q == 1) stamp(t, 12);
             float mx[2];
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
@@ -358,6 +373,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             const long long cl = first + static_cast<long long>(t) * gridDim.x;
             pooled[cl * 256 + ch] = fmaxf(mx[0] + B2[ch], 0.0f);
             pooled[cl * 256 + 128 + ch] = fmaxf(mx[1] + B2[128 + ch], 0.0f);
+            if (q == 1) stamp(t, 13);
         }
     }
     tcgen05_fence_before();
@@ -399,6 +415,8 @@ __global__ void det_tc_prep_kernel(const float *__restrict__ P, WeightLayout L, 
     }
 }
 
+static long long *g_det_dbg = nullptr;  // set through f3d_debug_set_timeline (bring-up only)
+
 int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
                      const int *idx, const float *packed, uint8_t *wimg, float *pooled, cudaStream_t st) {
     if (num_clusters == 0) return 0;
@@ -419,7 +437,8 @@ int detector_rows_tc(long long num_clusters, int n, int m, float radius, const f
                                          static_cast<int>(det::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "det_rows_tc: cudaFuncSetAttribute");
     const unsigned grid = static_cast<unsigned>(num_clusters < num_sms ? num_clusters : num_sms);
-    det_rows_tc_kernel<<<grid, det::kThreads, det::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, wimg, pooled);
+    det_rows_tc_kernel<<<grid, det::kThreads, det::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, wimg, pooled,
+                                                                     g_det_dbg);
     return check_launch("det_rows_tc_kernel");
 }
 
@@ -437,5 +456,8 @@ F3D_API int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float 
                                                              lbo_a, sbo_a, lbo_b, sbo_b, a_bytes, b_bytes);
     return check_launch("umma_selftest_kernel");
 }
+
+// Bring-up: device buffer of (tiles per CTA) x 16 int64 that receives CTA 0's clock64() timeline (NULL disables).
+F3D_API void f3d_debug_set_timeline(void *buf) { f3d::g_det_dbg = static_cast<long long *>(buf); }
 
 F3D_API size_t f3d_detector_tc_weight_bytes(void) { return det::kWeightBytes; }

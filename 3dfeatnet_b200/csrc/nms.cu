@@ -1,0 +1,296 @@
+// nms.cu -- keypoint non-maximum suppression on the device.
+//
+// Replaces nms() of inference.py:226-261, which the reference runs on the CPU with a scikit-learn BallTree:
+//   for every point: its 50 nearest neighbours (itself first, float64 distances); neighbours farther than nms_radius
+//   are ignored; the point survives iff no consulted neighbour has a strictly larger attention (argmax == position 0);
+//   survivors with attention <= max(attention) * min_response_ratio are dropped; the rest are sorted by
+//   (attention, index) descending, the first max_keypoints kept, the tail padded with the best one.
+// Device statement (identical whenever no two neighbours of a point are at exactly the same float64 distance -- the
+// BallTree's order among exact ties is unspecified):
+//   * distances are evaluated like the tree does: float64, d2 = (dx*dx + dy*dy) + dz*dz without FMA, d = sqrt(d2);
+//     "d > radius" is tested as d2 > T with T = max{s : sqrt_rn(s) <= radius} (monotone IEEE sqrt => same predicate);
+//   * a point with at most 49 other points inside the radius consults all of them (they are its nearest ones); only a
+//     point with more than 49 takes the slow path that selects the 49 nearest by (d2, index);
+//   * the threshold is computed in float64 like NumPy 1.19 does for float32_scalar * python_float
+//     (requirements.txt:29);
+//   * the descending (attention, index) order is produced by counting, for every survivor, the survivors that precede
+//     it -- no sort, deterministic.
+#include "common.cuh"
+
+namespace f3d {
+
+constexpr int kNmsTile = 1024;  // points staged per shared-memory tile
+constexpr int kNmsPtsPerWarp = 4;
+constexpr int kNmsWarps = 8;
+
+__device__ __forceinline__ double nms_d2(double ax, double ay, double az, double bx, double by, double bz) {
+    const double dx = ax - bx, dy = ay - by, dz = az - bz;
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// largest double s with sqrt_rn(s) <= r
+__device__ __forceinline__ double nms_threshold(double r) {
+    if (!(r >= 0.0)) return -1.0;
+    double t = __dmul_rn(r, r);
+    for (int it = 0; it < 8; ++it) {
+        if (sqrt(t) > r) t = __longlong_as_double(__double_as_longlong(t) - 1); else break;
+    }
+    for (int it = 0; it < 8; ++it) {
+        const double u = __longlong_as_double(__double_as_longlong(t) + 1);
+        if (sqrt(u) <= r) t = u; else break;
+    }
+    return t;
+}
+
+// keep[b,p] = 1 iff p is a local attention maximum among its (at most num_neighbors-1) nearest in-radius neighbours.
+// One warp handles kNmsPtsPerWarp query points; the cloud streams through shared memory as float64 tiles.
+__global__ void __launch_bounds__(kNmsWarps * 32)
+nms_keep_kernel(int n, double radius, int num_neighbors, const float *__restrict__ xyz, const float *__restrict__ attention,
+                unsigned char *__restrict__ keep, int *__restrict__ dense_list, int *__restrict__ dense_count) {
+    __shared__ double sx[kNmsTile], sy[kNmsTile], sz[kNmsTile];
+    __shared__ float sa[kNmsTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int batch = blockIdx.y;
+    const float *p = xyz + static_cast<size_t>(batch) * n * 3;
+    const float *att = attention + static_cast<size_t>(batch) * n;
+    const int q0 = (blockIdx.x * kNmsWarps + warp) * kNmsPtsPerWarp;
+    const double T = nms_threshold(radius);
+
+    double qx[kNmsPtsPerWarp], qy[kNmsPtsPerWarp], qz[kNmsPtsPerWarp];
+    float qa[kNmsPtsPerWarp], mx[kNmsPtsPerWarp];
+    int cnt[kNmsPtsPerWarp];
+#pragma unroll
+    for (int c = 0; c < kNmsPtsPerWarp; ++c) {
+        const int q = min(q0 + c, n - 1);
+        qx[c] = p[3 * q]; qy[c] = p[3 * q + 1]; qz[c] = p[3 * q + 2];
+        qa[c] = att[q];
+        mx[c] = -3.0e38f;
+        cnt[c] = 0;
+    }
+    for (int base = 0; base < n; base += kNmsTile) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kNmsTile; i += blockDim.x) {
+            const int k = base + i;
+            if (k < n) {
+                sx[i] = p[3 * k]; sy[i] = p[3 * k + 1]; sz[i] = p[3 * k + 2];
+                sa[i] = att[k];
+            }
+        }
+        __syncthreads();
+        const int lim = min(kNmsTile, n - base);
+        for (int i = lane; i < lim; i += 32) {
+            const double x = sx[i], y = sy[i], z = sz[i];
+            const float a = sa[i];
+            const int k = base + i;
+#pragma unroll
+            for (int c = 0; c < kNmsPtsPerWarp; ++c) {
+                const bool in = (k != q0 + c) && !(nms_d2(qx[c], qy[c], qz[c], x, y, z) > T);
+                if (in) {
+                    cnt[c] += 1;
+                    mx[c] = fmaxf(mx[c], a);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kNmsPtsPerWarp; ++c) {
+        int ct = cnt[c];
+        float m = mx[c];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            ct += __shfl_xor_sync(kFull, ct, s);
+            m = fmaxf(m, __shfl_xor_sync(kFull, m, s));
+        }
+        if (lane == 0 && q0 + c < n) {
+            const int q = q0 + c;
+            if (ct <= num_neighbors - 1) {
+                keep[static_cast<size_t>(batch) * n + q] = (m <= qa[c]) ? 1 : 0;  // ties: position 0 (self) wins the argmax
+            } else {  // more in-radius neighbours than the tree returns: resolve with the exact k nearest
+                keep[static_cast<size_t>(batch) * n + q] = 2;
+                const int pos = atomicAdd(dense_count + batch, 1);
+                dense_list[static_cast<size_t>(batch) * n + pos] = q;
+            }
+        }
+    }
+}
+
+// Slow path: one warp per dense point selects its (num_neighbors-1) nearest other points by (d2, index), num_neighbors-1
+// rounds of "smallest key larger than the previous one" over the whole cloud.
+__global__ void __launch_bounds__(kNmsWarps * 32)
+nms_dense_kernel(int n, double radius, int num_neighbors, const float *__restrict__ xyz, const float *__restrict__ attention,
+                 unsigned char *__restrict__ keep, const int *__restrict__ dense_list, const int *__restrict__ dense_count) {
+    const int lane = threadIdx.x & 31;
+    const int batch = blockIdx.y;
+    const int w = blockIdx.x * kNmsWarps + (threadIdx.x >> 5);
+    if (w >= dense_count[batch]) return;
+    const int q = dense_list[static_cast<size_t>(batch) * n + w];
+    const float *p = xyz + static_cast<size_t>(batch) * n * 3;
+    const float *att = attention + static_cast<size_t>(batch) * n;
+    const double T = nms_threshold(radius);
+    const double qx = p[3 * q], qy = p[3 * q + 1], qz = p[3 * q + 2];
+    const float qa = att[q];
+    double last_d = -1.0;
+    int last_k = -1;
+    bool is_max = true;
+    for (int r = 0; r < num_neighbors - 1; ++r) {
+        double bd = 1.0e300;
+        int bk = 0x7fffffff;
+        for (int k = lane; k < n; k += 32) {
+            if (k == q) continue;
+            const double d = nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+            if (d > T) continue;
+            const bool after = d > last_d || (d == last_d && k > last_k);
+            if (after && (d < bd || (d == bd && k < bk))) {
+                bd = d;
+                bk = k;
+            }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const double od = __shfl_xor_sync(kFull, bd, s);
+            const int ok = __shfl_xor_sync(kFull, bk, s);
+            if (od < bd || (od == bd && ok < bk)) {
+                bd = od;
+                bk = ok;
+            }
+        }
+        if (bk == 0x7fffffff) break;
+        if (att[bk] > qa) is_max = false;
+        last_d = bd;
+        last_k = bk;
+    }
+    if (lane == 0) keep[static_cast<size_t>(batch) * n + q] = is_max ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(1024)
+nms_max_kernel(int n, const float *__restrict__ attention, float *__restrict__ maxatt) {
+    __shared__ float red[32];
+    const float *att = attention + static_cast<size_t>(blockIdx.x) * n;
+    float m = -3.4e38f;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) m = fmaxf(m, att[k]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, s));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = red[threadIdx.x];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, s));
+        if (threadIdx.x == 0) maxatt[blockIdx.x] = m;
+    }
+}
+
+__global__ void nms_compact_kernel(int n, double ratio, const float *__restrict__ attention, const unsigned char *__restrict__ keep,
+                                   const float *__restrict__ maxatt, int *__restrict__ list, int *__restrict__ count) {
+    const int batch = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double thresh = static_cast<double>(maxatt[batch]) * ratio;  // float32 scalar * python float -> float64 (NumPy 1.19)
+    if (keep[static_cast<size_t>(batch) * n + k] == 1 && static_cast<double>(attention[static_cast<size_t>(batch) * n + k]) > thresh) {
+        const int pos = atomicAdd(count + batch, 1);
+        list[static_cast<size_t>(batch) * n + pos] = k;
+    }
+}
+
+// rank of a survivor = number of survivors that sort before it in (attention, index) DESCENDING order
+__global__ void __launch_bounds__(256)
+nms_rank_kernel(int n, int max_keypoints, const float *__restrict__ attention, const int *__restrict__ list,
+                const int *__restrict__ count, int *__restrict__ out_idx) {
+    __shared__ float ta[256];
+    __shared__ int ti[256];
+    const int batch = blockIdx.y;
+    const int cnt = count[batch];
+    if (static_cast<int>(blockIdx.x) * 256 >= cnt) return;
+    const int *lst = list + static_cast<size_t>(batch) * n;
+    const float *att = attention + static_cast<size_t>(batch) * n;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int me = e < cnt ? lst[e] : -1;
+    const float ma = e < cnt ? att[me] : 0.0f;
+    int rank = 0;
+    for (int base = 0; base < cnt; base += 256) {
+        __syncthreads();
+        const int j = base + threadIdx.x;
+        if (j < cnt) {
+            ti[threadIdx.x] = lst[j];
+            ta[threadIdx.x] = att[lst[j]];
+        }
+        __syncthreads();
+        const int lim = min(256, cnt - base);
+        for (int i = 0; i < lim; ++i) rank += (ta[i] > ma || (ta[i] == ma && ti[i] > me)) ? 1 : 0;
+    }
+    if (e < cnt && rank < max_keypoints) out_idx[static_cast<size_t>(batch) * max_keypoints + rank] = me;
+}
+
+__global__ void nms_finalize_kernel(int n, int max_keypoints, const float *__restrict__ xyz, const float *__restrict__ attention,
+                                    const int *__restrict__ count, int *__restrict__ out_idx, float *__restrict__ out_xyz,
+                                    float *__restrict__ out_att, int *__restrict__ num_keypoints) {
+    const int batch = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= max_keypoints) return;
+    const int num = min(count[batch], max_keypoints);
+    int *oi = out_idx + static_cast<size_t>(batch) * max_keypoints;
+    const int best = num > 0 ? oi[0] : 0;  // the reference raises when nothing survives; here: index 0, count 0
+    const int k = s < num ? oi[s] : best;
+    if (s >= num) oi[s] = k;  // oi[0] is never rewritten when num > 0, so reading it above races with nothing
+    const float *p = xyz + (static_cast<size_t>(batch) * n + k) * 3;
+    float *o = out_xyz + (static_cast<size_t>(batch) * max_keypoints + s) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    out_att[static_cast<size_t>(batch) * max_keypoints + s] = attention[static_cast<size_t>(batch) * n + k];
+    if (s == 0) num_keypoints[batch] = num;
+}
+
+}  // namespace f3d
+
+using namespace f3d;
+
+F3D_API size_t f3d_nms_workspace_bytes(int b, int n) {
+    if (b <= 0 || n <= 0) return 256;
+    const size_t bn = static_cast<size_t>(b) * n;
+    return bn * (1 + 4 + 4) + static_cast<size_t>(b) * 16 + 1024;
+}
+
+F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_radius, double min_response_ratio,
+                    int max_keypoints, int num_neighbors, int *out_idx, float *out_xyz, float *out_attention,
+                    int *num_keypoints, void *workspace, size_t workspace_bytes, void *stream) {
+    if (b < 0 || n <= 0 || max_keypoints <= 0 || num_neighbors <= 0 || !xyz || !attention || !out_idx || !out_xyz || !out_attention ||
+        !num_keypoints || !(nms_radius >= 0.0))
+        return fail(F3D_ERR_INVALID_ARGUMENT, "nms: bad arguments");
+    if (n < num_neighbors)  // sklearn: "Expected n_neighbors <= n_samples"
+        return fail(F3D_ERR_INVALID_ARGUMENT, "nms: fewer points than num_neighbors (the reference's BallTree query raises)");
+    if (!workspace || workspace_bytes < f3d_nms_workspace_bytes(b, n)) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "nms: workspace too small");
+    if (b == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    const size_t bn = static_cast<size_t>(b) * n;
+    // layout: [counts: 2b ints][maxatt: b floats][pad] [list: bn ints][dense_list: bn ints][keep: bn bytes]
+    char *base = static_cast<char *>(workspace);
+    int *count = reinterpret_cast<int *>(base);
+    int *dense_count = count + b;
+    float *maxatt = reinterpret_cast<float *>(dense_count + b);
+    const size_t head = (static_cast<size_t>(b) * 12 + 255) & ~static_cast<size_t>(255);
+    int *list = reinterpret_cast<int *>(base + head);
+    int *dense_list = list + bn;
+    unsigned char *keep = reinterpret_cast<unsigned char *>(dense_list + bn);
+    cudaError_t e = cudaMemsetAsync(base, 0, head, st);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "nms: memset");
+    const int per_cta = kNmsWarps * kNmsPtsPerWarp;
+    nms_keep_kernel<<<dim3((n + per_cta - 1) / per_cta, b), kNmsWarps * 32, 0, st>>>(n, nms_radius, num_neighbors, xyz, attention, keep,
+                                                                                    dense_list, dense_count);
+    int rc = check_launch("nms_keep_kernel");
+    if (rc) return rc;
+    nms_dense_kernel<<<dim3((n + kNmsWarps - 1) / kNmsWarps, b), kNmsWarps * 32, 0, st>>>(n, nms_radius, num_neighbors, xyz, attention, keep,
+                                                                                         dense_list, dense_count);
+    rc = check_launch("nms_dense_kernel");
+    if (rc) return rc;
+    nms_max_kernel<<<b, 1024, 0, st>>>(n, attention, maxatt);
+    rc = check_launch("nms_max_kernel");
+    if (rc) return rc;
+    nms_compact_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, min_response_ratio, attention, keep, maxatt, list, count);
+    rc = check_launch("nms_compact_kernel");
+    if (rc) return rc;
+    nms_rank_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, max_keypoints, attention, list, count, out_idx);
+    rc = check_launch("nms_rank_kernel");
+    if (rc) return rc;
+    nms_finalize_kernel<<<dim3((max_keypoints + 1023) / 1024, b), min(1024, ((max_keypoints + 31) / 32) * 32), 0, st>>>(
+        n, max_keypoints, xyz, attention, count, out_idx, out_xyz, out_attention, num_keypoints);
+    return check_launch("nms_finalize_kernel");
+}

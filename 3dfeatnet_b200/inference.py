@@ -1,0 +1,57 @@
+"""The device-side pieces of the reference's inference.py: keypoint NMS (inference.py:226-261) and the two-pass
+detect -> NMS -> describe flow of compute_descriptors (inference.py:99-180) on torch CUDA tensors."""
+import importlib
+
+import torch
+
+_ROOT = __name__.split(".")[0]
+_lib = importlib.import_module("3dfeatnet_b200._lib" if _ROOT == "3dfeatnet_b200" else "_lib")
+
+MAX_POINTS = 30000  # inference.py:22: centres per detection pass
+
+
+def nms(xyz, attention, nms_radius=0.5, min_response_ratio=1e-2, max_keypoints=1024, num_neighbors=50, return_indices=False):
+    """nms(xyz, attention) of inference.py:226-261 (args.nms_radius / min_response_ratio / max_keypoints become keywords
+    with the CLI defaults, :40-47).  xyz (B,N,3), attention (B,N) CUDA float32.
+    Returns (xyz_nms (B,K,3), attention_nms (B,K), num_keypoints list[int]) like the reference (+ indices on request)."""
+    if xyz.dim() != 3 or xyz.shape[2] != 3 or attention.dim() != 2 or attention.shape != xyz.shape[:2]:
+        raise ValueError("nms expects xyz (B,N,3) and attention (B,N)")
+    _lib.require_cuda(xyz, attention)
+    if xyz.dtype != torch.float32 or attention.dtype != torch.float32:
+        raise ValueError("nms expects float32 tensors")
+    xyz, attention = xyz.contiguous(), attention.contiguous()
+    b, n, _ = xyz.shape
+    if n < num_neighbors:
+        raise ValueError("Expected n_neighbors <= n_samples (the reference's BallTree query raises too)")
+    dev = xyz.device
+    out_idx = torch.empty((b, max_keypoints), dtype=torch.int32, device=dev)
+    out_xyz = torch.empty((b, max_keypoints, 3), dtype=torch.float32, device=dev)
+    out_att = torch.empty((b, max_keypoints), dtype=torch.float32, device=dev)
+    num = torch.empty((b,), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.f3d_nms_workspace_bytes(b, n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    _lib.check(L.f3d_nms(b, n, _lib.ptr(xyz), _lib.ptr(attention), float(nms_radius), float(min_response_ratio), max_keypoints,
+                         num_neighbors, _lib.ptr(out_idx), _lib.ptr(out_xyz), _lib.ptr(out_att), _lib.ptr(num), _lib.ptr(ws), ws_bytes,
+                         _lib.stream()), "nms")
+    counts = num.cpu().tolist()
+    if return_indices:
+        return out_xyz, out_att, counts, out_idx
+    return out_xyz, out_att, counts
+
+
+def detect_and_describe(model, point_cloud, nms_radius=0.5, min_response_ratio=1e-2, max_keypoints=1024):
+    """compute_descriptors' per-cloud body (inference.py:115-171): attention at EVERY point (centres in chunks of
+    MAX_POINTS, num_clusters=-1 semantics), NMS, then descriptors at the <= max_keypoints survivors.
+    point_cloud: (1,N,>=3) CUDA float32.  Returns (xyz_nms (1,K,3), features (1,K,F), attention_nms (1,K), num_keypoints)."""
+    xyz = point_cloud[:, :, :3].contiguous()
+    n = xyz.shape[1]
+    atts = []
+    for s in range(0, n, MAX_POINTS):
+        kp = xyz[:, s:s + MAX_POINTS, :].contiguous()
+        _, _, att, ep = model.get_inference_model(point_cloud, False, keypoints=kp)
+        atts.append(ep["attention"])
+    attention = torch.cat(atts, dim=1)
+    xyz_nms, att_nms, num = nms(xyz, attention, nms_radius, min_response_ratio, max_keypoints)
+    _, features, _, _ = model.get_inference_model(point_cloud, False, keypoints=xyz_nms)
+    return xyz_nms, features, att_nms, num

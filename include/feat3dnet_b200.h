@@ -51,6 +51,12 @@ int f3d_gather_point(int b, int n, int m, const float *inp, const int *idx, floa
 int f3d_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g, void *workspace,
                           size_t workspace_bytes, void *stream);
 
+/* cumsumLauncher(b,n,inp,out)  tf_sampling_g.cu:194-196.  Bit-exact: same summation DAG as the reference's blocked scan. */
+int f3d_cumsum(int b, int n, const float *inp, float *out, void *stream);
+/* probsampleLauncher(b,n,m,inp_p,inp_r,temp,out)  tf_sampling_g.cu:197-201, op tf_sampling.cpp:66-91.
+ * temp: (b,n) f32 working space (receives the cumsum). */
+int f3d_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out, void *stream);
+
 /* ---------------------------------------------------------------- tf_ops/grouping ------------- */
 
 /* queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt)  tf_grouping_g.cu:179-182,
@@ -132,6 +138,19 @@ int f3d_descriptor_forward(int b, int n, int m, int nsample, float radius, int f
                            const float *new_xyz, const int *idx, const float *orientation, const float *packed,
                            float *features, int precision, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------- inference.py nms ------------ */
+
+/* nms(xyz, attention)  inference.py:226-261 for a batch of clouds, on the device (the reference: CPU, scikit-learn
+ * BallTree).  xyz (b,n,3), attention (b,n) -> out_idx (b,max_keypoints) i32 indices into the cloud, out_xyz
+ * (b,max_keypoints,3), out_attention (b,max_keypoints), num_keypoints (b) i32; rows beyond num_keypoints repeat the
+ * strongest keypoint.  nms_radius / min_response_ratio are doubles like the reference's Python floats
+ * (defaults 0.5 / 1e-2, max_keypoints 1024, num_neighbors 50: inference.py:40-47,236).  n >= num_neighbors.
+ * workspace: f3d_nms_workspace_bytes(b,n). */
+size_t f3d_nms_workspace_bytes(int b, int n);
+int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_radius, double min_response_ratio,
+            int max_keypoints, int num_neighbors, int *out_idx, float *out_xyz, float *out_attention,
+            int *num_keypoints, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------- bring-up / debugging ---------- */
 
 /* Single-CTA tcgen05 self test: D[128 x N] = A[128 x K] * B[N x K]^T from canonical K-major no-swizzle bf16 operand
@@ -139,6 +158,9 @@ int f3d_descriptor_forward(int b, int n, int m, int nsample, float radius, int f
 int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int N, int K, int lbo_a, int sbo_a, int lbo_b,
                             int sbo_b, int a_bytes, int b_bytes, void *stream);
 size_t f3d_detector_tc_weight_bytes(void);
+/* Bring-up: device buffer of (tiles per CTA) x 16 int64 receiving CTA 0's clock64() timeline of the detector tensor
+ * kernel (slots: 0/1/2 MMA warp, 4-6 producer, 8-13 epilogue); NULL disables. */
+void f3d_debug_set_timeline(void *buf);
 
 #ifdef __cplusplus
 }

@@ -29,8 +29,9 @@ def nms(xyz, attention, nms_radius=0.5, min_response_ratio=1e-2, max_keypoints=1
         outside_ball = distances > nms_radius
         knn_attention[outside_ball] = 0.0
         is_max = np.where(np.argmax(knn_attention, axis=1) == 0)[0]
-        attention_thresh = np.max(attention[i, :]) * min_response_ratio
-        is_max_attention = [(attention[i, m], m) for m in is_max if attention[i, m] > attention_thresh]
+        # NumPy 1.19 (requirements.txt:29): float32 scalar * Python float -> float64; stated explicitly so NumPy 2 agrees
+        attention_thresh = float(np.max(attention[i, :])) * min_response_ratio
+        is_max_attention = [(attention[i, m], m) for m in is_max if float(attention[i, m]) > attention_thresh]
         is_max_attention = sorted(is_max_attention, reverse=True)
         max_indices = [m[1] for m in is_max_attention]
         if len(max_indices) >= max_keypoints:
@@ -64,8 +65,8 @@ def nms_bruteforce(xyz, attention, nms_radius=0.5, min_response_ratio=1e-2, max_
         a = attention[i, order].copy()
         a[dist > nms_radius] = 0.0
         is_max = np.where(np.argmax(a, axis=1) == 0)[0]
-        thresh = np.max(attention[i]) * min_response_ratio
-        cand = sorted([(attention[i, m], m) for m in is_max if attention[i, m] > thresh], reverse=True)
+        thresh = float(np.max(attention[i])) * min_response_ratio
+        cand = sorted([(attention[i, m], m) for m in is_max if float(attention[i, m]) > thresh], reverse=True)
         max_indices = [m[1] for m in cand]
         num_keypoints[i] = min(len(max_indices), max_keypoints)
         if len(max_indices) >= max_keypoints:
