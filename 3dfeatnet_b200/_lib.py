@@ -38,9 +38,11 @@ SIGNATURES = {
     "f3d_descriptor_forward": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "f3d_nms_workspace_bytes": (_sz, [_i, _i]),
     "f3d_nms": (_i, [_i, _i, _vp, _vp, _c.c_double, _c.c_double, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "f3d_debug_umma_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "f3d_debug_umma_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "f3d_detector_tc_weight_bytes": (_sz, []),
     "f3d_debug_set_timeline": (None, [_vp]),
+    "f3d_debug_time_detector_rows": (None, [_i]),
+    "f3d_debug_detector_rows_ms": (_c.c_float, []),
 }
 
 _LIB = None

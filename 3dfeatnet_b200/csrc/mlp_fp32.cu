@@ -39,7 +39,7 @@ __device__ __forceinline__ void load_w(const float *__restrict__ p, float (&w)[C
 // acc[i][j] = sum_k in_t[k][rg*8+i] * W[k][col0 + cg*CT + j]   (k ascending, fp32 FMA)
 template <int CT>
 __device__ __forceinline__ void dense_tile(const float *in_t, int cin, const float *__restrict__ W, int ldw, int col0,
-                                           float (&acc)[8][CT]) {
+                                           float (&acc)[8][CT], int ld = kTileRows) {
     const int rg = threadIdx.x & 15, cg = threadIdx.x >> 4;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -49,8 +49,8 @@ __device__ __forceinline__ void dense_tile(const float *in_t, int cin, const flo
     const float *wp = W + col0 + cg * CT;
 #pragma unroll 4
     for (int k = 0; k < cin; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4 *>(ap + k * kTileRows);
-        const float4 a1 = *reinterpret_cast<const float4 *>(ap + k * kTileRows + 4);
+        const float4 a0 = *reinterpret_cast<const float4 *>(ap + k * ld);
+        const float4 a1 = *reinterpret_cast<const float4 *>(ap + k * ld + 4);
         float w[CT];
         load_w<CT>(wp + static_cast<size_t>(k) * ldw, w);
         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -193,18 +193,21 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
 det_post_fp32_kernel(long long num_clusters, const float *__restrict__ pooled, const float *__restrict__ P,
                      WeightLayout L, float *__restrict__ attention, float *__restrict__ orientation) {
     extern __shared__ float4 smem4[];
-    float *in_t = reinterpret_cast<float *>(smem4);  // [256][128]
-    float *a1_t = in_t + 256 * kTileRows;            // [128][128]
+    // the transposed input tile has a leading dimension of 132 floats: the coalesced-read / transposed-store loop below
+    // then spreads a warp's 32 stores over 8 banks instead of 1, and float4 reads stay 16-byte aligned
+    constexpr int kLdIn = kTileRows + 4;
+    float *in_t = reinterpret_cast<float *>(smem4);  // [256][132]
+    float *a1_t = in_t + 256 * kLdIn;                // [128][128]
     float *a2_t = in_t;                              // [64][128], reuses in_t after conv_post_0
     const long long c0 = static_cast<long long>(blockIdx.x) * kTileRows;
     for (int e = threadIdx.x; e < kTileRows * 256; e += kMlpThreads) {  // coalesced read, transposed store
         const int r = e >> 8, k = e & 255;
-        in_t[k * kTileRows + r] = (c0 + r < num_clusters) ? __ldg(pooled + (c0 + r) * 256 + k) : 0.0f;
+        in_t[k * kLdIn + r] = (c0 + r < num_clusters) ? __ldg(pooled + (c0 + r) * 256 + k) : 0.0f;
     }
     __syncthreads();
     {
         float acc[8][8];
-        dense_tile<8>(in_t, 256, P + L.off[W_DETP0], 128, 0, acc);
+        dense_tile<8>(in_t, 256, P + L.off[W_DETP0], 128, 0, acc, kLdIn);
         bias_act_store<8, true>(acc, P + L.off[B_DETP0], 0, a1_t);
     }
     __syncthreads();
@@ -298,18 +301,19 @@ desc_post_fp32_kernel(long long num_clusters, const float *__restrict__ pooled2,
                       WeightLayout L, float *__restrict__ features) {
     extern __shared__ float4 smem4[];
     constexpr int F = 16 * CT;
-    float *in_t = reinterpret_cast<float *>(smem4);  // [MID][128]
-    float *o_t = in_t + 256 * kTileRows;             // [F][128]
+    constexpr int kLdIn = kTileRows + 4;             // see det_post_fp32_kernel
+    float *in_t = reinterpret_cast<float *>(smem4);  // [MID][132]
+    float *o_t = in_t + 256 * kLdIn;                 // [F][128]
     const int MID = L.mid;
     const long long c0 = static_cast<long long>(blockIdx.x) * kTileRows;
     for (int e = threadIdx.x; e < kTileRows * MID; e += kMlpThreads) {
         const int r = e / MID, k = e - r * MID;
-        in_t[k * kTileRows + r] = (c0 + r < num_clusters) ? __ldg(pooled2 + (c0 + r) * MID + k) : 0.0f;
+        in_t[k * kLdIn + r] = (c0 + r < num_clusters) ? __ldg(pooled2 + (c0 + r) * MID + k) : 0.0f;
     }
     __syncthreads();
     {
         float acc[8][CT];
-        dense_tile<CT>(in_t, MID, P + L.off[W_POST], F, 0, acc);
+        dense_tile<CT>(in_t, MID, P + L.off[W_POST], F, 0, acc, kLdIn);
         bias_act_store<CT, false>(acc, P + L.off[B_POST], 0, o_t);
     }
     __syncthreads();
@@ -335,7 +339,7 @@ int detector_forward_fp32(int b, int n, int m, int S, float radius, const float 
     const WeightLayout L = make_weight_layout(32);
     const int cpt = kTileRows / S;
     const size_t smem_rows = sizeof(float) * (4 + 64 + 128 + 16) * kTileRows;
-    const size_t smem_post = sizeof(float) * (256 + 128) * kTileRows;
+    const size_t smem_post = sizeof(float) * (256 * (kTileRows + 4) + 128 * kTileRows);
     cudaFuncSetAttribute(det_rows_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows));
     cudaFuncSetAttribute(det_post_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_post));
     det_rows_fp32_kernel<<<static_cast<unsigned>((nc + cpt - 1) / cpt), kMlpThreads, smem_rows, st>>>(
@@ -351,7 +355,7 @@ int detector_post_fp32(long long nc, const float *pooled, const float *packed, f
                        cudaStream_t st) {
     if (nc == 0) return 0;
     const WeightLayout L = make_weight_layout(32);
-    const size_t smem_post = sizeof(float) * (256 + 128) * kTileRows;
+    const size_t smem_post = sizeof(float) * (256 * (kTileRows + 4) + 128 * kTileRows);
     cudaFuncSetAttribute(det_post_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_post));
     det_post_fp32_kernel<<<static_cast<unsigned>((nc + kTileRows - 1) / kTileRows), kMlpThreads, smem_post, st>>>(
         nc, pooled, packed, L, attention, orientation);
@@ -362,7 +366,7 @@ int descriptor_post_fp32(long long nc, const float *pooled2, const float *packed
                          cudaStream_t st) {
     if (nc == 0) return 0;
     const WeightLayout L = make_weight_layout(feature_dim);
-    const size_t smem_post = sizeof(float) * (256 + 128) * kTileRows;
+    const size_t smem_post = sizeof(float) * (256 * (kTileRows + 4) + 128 * kTileRows);
     const unsigned gp = static_cast<unsigned>((nc + kTileRows - 1) / kTileRows);
 #define F3D_POST2(CT)                                                                                                 \
     cudaFuncSetAttribute(desc_post_fp32_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
@@ -389,7 +393,7 @@ int descriptor_forward_fp32(int b, int n, int m, int S, float radius, int featur
     const WeightLayout L = make_weight_layout(feature_dim);
     const int cpt = kTileRows / S;
     const size_t smem_rows = sizeof(float) * ((4 + 32 + 64 + 16) * kTileRows + 16 * 64 + 16 * 256);
-    const size_t smem_post = sizeof(float) * (256 + 128) * kTileRows;
+    const size_t smem_post = sizeof(float) * (256 * (kTileRows + 4) + 128 * kTileRows);
     cudaFuncSetAttribute(desc_rows_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows));
     desc_rows_fp32_kernel<<<static_cast<unsigned>((nc + cpt - 1) / cpt), kMlpThreads, smem_rows, st>>>(
         nc, n, m, S, radius, xyz, new_xyz, idx, orientation, packed, L, pooled_ws);

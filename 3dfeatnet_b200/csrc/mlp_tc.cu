@@ -38,7 +38,7 @@ using namespace tc;
 // Validates the descriptor encodings (LBO/SBO semantics, idesc, TMEM addressing) in isolation on the device.
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restrict__ b_img, float *__restrict__ D, int N, int K,
-                     uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t a_bytes, uint32_t b_bytes) {
+                     uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t a_bytes, uint32_t b_bytes, int a_in_tmem) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar_load, bar_mma;
     __shared__ uint32_t tmem_base_s;
@@ -51,7 +51,7 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
         fence_barrier_init();
     }
     if (warp == 0) {
-        tmem_alloc(&tmem_base_s, 256);
+        tmem_alloc(&tmem_base_s, 512);
         tmem_relinquish();
     }
     tcgen05_fence_before();
@@ -65,10 +65,16 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
         mbar_wait(&bar_load, 0);
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc(1, 128, static_cast<uint32_t>(N));
+        if (a_in_tmem)  // stage A into TMEM columns 256.. (8 columns = 16 bf16 per K step), then run the MMAs from there
+            for (int k = 0; k < K / 16; ++k)
+                tmem_cp_128x256b(tmem_base + 256 + 8 * k, make_smem_desc(smem_u32(sa) + k * 2 * lbo_a, lbo_a, sbo_a));
         for (int k = 0; k < K / 16; ++k) {
             const uint64_t da = make_smem_desc(smem_u32(sa) + k * 2 * lbo_a, lbo_a, sbo_a);
             const uint64_t db = make_smem_desc(smem_u32(sb) + k * 2 * lbo_b, lbo_b, sbo_b);
-            umma_f16(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
+            if (a_in_tmem)
+                umma_f16_ts(tmem_base, tmem_base + 256 + 8 * k, db, idesc, k > 0 ? 1u : 0u);
+            else
+                umma_f16(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
         }
         umma_commit(&bar_mma);
     }
@@ -416,6 +422,9 @@ __global__ void det_tc_prep_kernel(const float *__restrict__ P, WeightLayout L, 
 }
 
 static long long *g_det_dbg = nullptr;  // set through f3d_debug_set_timeline (bring-up only)
+// optional CUDA-event bracket of the rows kernel on its own launch stream (bench.py's roofline measurement)
+static bool g_det_time = false;
+static cudaEvent_t g_det_ev[2] = {nullptr, nullptr};
 
 int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
                      const int *idx, const float *packed, uint8_t *wimg, float *pooled, cudaStream_t st) {
@@ -437,8 +446,10 @@ int detector_rows_tc(long long num_clusters, int n, int m, float radius, const f
                                          static_cast<int>(det::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "det_rows_tc: cudaFuncSetAttribute");
     const unsigned grid = static_cast<unsigned>(num_clusters < num_sms ? num_clusters : num_sms);
+    if (g_det_time) cudaEventRecord(g_det_ev[0], st);
     det_rows_tc_kernel<<<grid, det::kThreads, det::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, wimg, pooled,
                                                                      g_det_dbg);
+    if (g_det_time) cudaEventRecord(g_det_ev[1], st);
     return check_launch("det_rows_tc_kernel");
 }
 
@@ -448,16 +459,33 @@ using namespace f3d;
 
 // Debug / bring-up entry point (not part of the reference surface): runs the single-CTA UMMA self test.
 F3D_API int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int N, int K, int lbo_a, int sbo_a, int lbo_b,
-                                    int sbo_b, int a_bytes, int b_bytes, void *stream) {
+                                    int sbo_b, int a_bytes, int b_bytes, int a_in_tmem, void *stream) {
     if (!a_img || !b_img || !D || N < 8 || N > 256 || N % 8 || K < 16 || K % 16) return fail(F3D_ERR_INVALID_ARGUMENT, "umma_selftest: bad arguments");
     const size_t smem = ((static_cast<size_t>(a_bytes) + 127) & ~static_cast<size_t>(127)) + b_bytes + 128;
     cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(static_cast<const uint8_t *>(a_img), static_cast<const uint8_t *>(b_img), D, N, K,
-                                                             lbo_a, sbo_a, lbo_b, sbo_b, a_bytes, b_bytes);
+                                                             lbo_a, sbo_a, lbo_b, sbo_b, a_bytes, b_bytes, a_in_tmem);
     return check_launch("umma_selftest_kernel");
 }
 
 // Bring-up: device buffer of (tiles per CTA) x 16 int64 that receives CTA 0's clock64() timeline (NULL disables).
 F3D_API void f3d_debug_set_timeline(void *buf) { f3d::g_det_dbg = static_cast<long long *>(buf); }
+
+// Measurement aid: when enabled, det_rows_tc_kernel is bracketed by CUDA events on the stream it is launched on;
+// f3d_debug_detector_rows_ms() waits for the last bracket and returns its duration (ms), or -1.
+F3D_API void f3d_debug_time_detector_rows(int enable) {
+    if (enable && !f3d::g_det_ev[0]) {
+        cudaEventCreate(&f3d::g_det_ev[0]);
+        cudaEventCreate(&f3d::g_det_ev[1]);
+    }
+    f3d::g_det_time = enable != 0;
+}
+F3D_API float f3d_debug_detector_rows_ms(void) {
+    if (!f3d::g_det_ev[0]) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(f3d::g_det_ev[1]) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, f3d::g_det_ev[0], f3d::g_det_ev[1]) != cudaSuccess) return -1.0f;
+    return ms;
+}
 
 F3D_API size_t f3d_detector_tc_weight_bytes(void) { return det::kWeightBytes; }

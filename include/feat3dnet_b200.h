@@ -154,13 +154,17 @@ int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_r
 /* ---------------------------------------------------------------- bring-up / debugging ---------- */
 
 /* Single-CTA tcgen05 self test: D[128 x N] = A[128 x K] * B[N x K]^T from canonical K-major no-swizzle bf16 operand
- * images (element (r,k) at (k/8)*lbo + (r/8)*sbo + (r%8)*16 + (k%8)*2 bytes).  Not part of the reference surface. */
+ * images (element (r,k) at (k/8)*lbo + (r/8)*sbo + (r%8)*16 + (k%8)*2 bytes).  a_in_tmem != 0 first copies A into
+ * tensor memory (tcgen05.cp) and feeds the MMA from there.  Not part of the reference surface. */
 int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int N, int K, int lbo_a, int sbo_a, int lbo_b,
-                            int sbo_b, int a_bytes, int b_bytes, void *stream);
+                            int sbo_b, int a_bytes, int b_bytes, int a_in_tmem, void *stream);
 size_t f3d_detector_tc_weight_bytes(void);
 /* Bring-up: device buffer of (tiles per CTA) x 16 int64 receiving CTA 0's clock64() timeline of the detector tensor
  * kernel (slots: 0/1/2 MMA warp, 4-6 producer, 8-13 epilogue); NULL disables. */
 void f3d_debug_set_timeline(void *buf);
+/* Measurement aid: bracket det_rows_tc_kernel with CUDA events on its launch stream / read the last duration (ms). */
+void f3d_debug_time_detector_rows(int enable);
+float f3d_debug_detector_rows_ms(void);
 
 #ifdef __cplusplus
 }

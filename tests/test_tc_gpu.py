@@ -29,8 +29,9 @@ def make_image(A, lbo, sbo):
     return img, nbytes
 
 
+@pytest.mark.parametrize("a_in_tmem", [0, 1])
 @pytest.mark.parametrize("N,K,lbo_b", [(64, 64, 1024), (64, 128, 1040), (8, 16, 128), (256, 32, 4096), (64, 16, 1040)])
-def test_umma_selftest(cuda, N, K, lbo_b):
+def test_umma_selftest(cuda, N, K, lbo_b, a_in_tmem):
     lib_mod = pkg("_lib")
     L = lib_mod.lib()
     g = torch.Generator().manual_seed(N * 1000 + K)
@@ -41,7 +42,7 @@ def test_umma_selftest(cuda, N, K, lbo_b):
     a_d, b_d = a_img.to(cuda), b_img.to(cuda)
     D = torch.full((128, N), float("nan"), device=cuda)
     rc = L.f3d_debug_umma_selftest(lib_mod.ptr(a_d), lib_mod.ptr(b_d), lib_mod.ptr(D), N, K, 2048, 128, lbo_b, 128, a_bytes, b_bytes,
-                                   lib_mod.stream())
+                                   a_in_tmem, lib_mod.stream())
     lib_mod.check(rc, "umma_selftest")
     torch.cuda.synchronize()
     want = A.double() @ B.double().t()
