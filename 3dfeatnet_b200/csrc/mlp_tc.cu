@@ -90,7 +90,7 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ detector rows
@@ -114,16 +114,21 @@ constexpr uint32_t kWeightBytes = kOffB2 + 256 * 4;     // 166 400
 constexpr uint32_t kX1Split = 8 * kLboX1;               // 8 KB
 constexpr uint32_t kOffX1 = kWeightBytes;               // [split 2][chunk 8][row 64][8] bf16
 constexpr uint32_t kX2Split = 16 * kLboX2;              // 16 640
-constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Split;      // [split 2][chunk 16] stride kLboX2
-constexpr uint32_t kOffBars = kOffX2 + 2 * kX2Split;
+constexpr uint32_t kX2Buf = 2 * kX2Split;               // one X2 operand (hi + lo)
+// W2 is copied into TENSOR MEMORY once (tcgen05.cp) and its shared-memory staging area is then recycled as the two X2
+// operand buffers, so MMA2 reads only its 2 KB B operand from shared memory and E1(t+1) overlaps MMA2(t).
+constexpr uint32_t kOffX2 = kOffW2;                     // [buf 2][split 2][chunk 16] stride kLboX2 (aliases the W2 staging)
+constexpr uint32_t kOffBars = kOffX1 + 2 * kX1Split;
 constexpr uint32_t kSmemBytes = kOffBars + 16 * 8 + 16;
 static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffBars % 8 == 0, "alignment");
+static_assert(2 * kX2Buf <= 4 * kW2Blk, "X2 buffers must fit the W2 staging area");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-// TMEM columns: D1[2] at 0 / 64, D2[2] at 128 / 256 (two M blocks of 64 columns each)
+// TMEM columns: D1[2] at 0 / 64, D2 (two M blocks) at 128 / 192, W2 at 256 + (split*2 + mblk)*64 (128 K = 64 columns)
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemW2 = 256;
 
-enum Bar { W_FULL = 0, X1_FULL, X1_FREE, X2_FULL, X2_FREE, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1, D2_FULL0, D2_FULL1,
-           D2_FREE0, D2_FREE1, kNumBars };
+enum Bar { W_FULL = 0, W2_TMEM, X1_FULL, X1_FREE, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1,
+           D2_FULL, D2_FREE, kNumBars };
 }  // namespace det
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -146,15 +151,16 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[W_FULL], 1);
+        mbar_init(&bars[W2_TMEM], 1);
         mbar_init(&bars[X1_FULL], 128);
         mbar_init(&bars[X1_FREE], 1);
-        mbar_init(&bars[X2_FULL], 128);
-        mbar_init(&bars[X2_FREE], 1);
+        mbar_init(&bars[D2_FULL], 1);
+        mbar_init(&bars[D2_FREE], 128);
         for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars[X2_FULL0 + b], 128);
+            mbar_init(&bars[X2_FREE0 + b], 1);
             mbar_init(&bars[D1_FULL0 + b], 1);
             mbar_init(&bars[D1_FREE0 + b], 128);
-            mbar_init(&bars[D2_FULL0 + b], 1);
-            mbar_init(&bars[D2_FREE0 + b], 128);
         }
         fence_barrier_init();
     }
@@ -186,6 +192,18 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             // ---- MMA issue loop: the whole warp walks it (uniform control flow), one elected lane issues --------
             const uint32_t idesc = make_idesc(1, 128, kSamples);
             const uint32_t sbase = smem_u32(smem);
+            // ---- W2 (both splits, both M blocks) -> tensor memory, once; its staging area then becomes the X2 buffers
+            tcgen05_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk)  // blk = split*2 + mblk, same order as the shared-memory image
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        tmem_cp_128x256b(tmem_base + kTmemW2 + blk * 64 + k * 8,
+                                         make_smem_desc(sbase + kOffW2 + blk * kW2Blk + k * 2 * kLboW, kLboW, kSbo));
+                umma_commit(&bars[W2_TMEM]);
+            }
+            __syncwarp();
             auto mma1 = [&](int t) {
                 mbar_wait(&bars[X1_FULL], t & 1);
                 mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
@@ -210,38 +228,40 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 }
                 __syncwarp();
             };
-            auto mma2 = [&](int t) {
-                mbar_wait(&bars[X2_FULL], t & 1);
-                mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+            auto mma2 = [&](int t) {  // A operand (W2) from tensor memory, B operand X2[t & 1] from shared memory
+                mbar_wait(&bars[X2_FULL0 + (t & 1)], (t >> 1) & 1);
+                mbar_wait(&bars[D2_FREE], (t & 1) ^ 1);
                 tcgen05_fence_after();
                 stamp(t, 1);
                 if (elect_one()) {
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
-                    const uint32_t d = tmem_base + 128 + (t & 1) * 128 + mb * 64;
+                    const uint32_t d = tmem_base + 128 + mb * 64;
                     uint32_t acc = 0;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t wa = sbase + kOffW2 + ((pass == 2 ? 2 : 0) + mb) * kW2Blk;
-                        const uint32_t xb = sbase + kOffX2 + (pass == 1 ? kX2Split : 0);
+                        const uint32_t wa = tmem_base + kTmemW2 + ((pass == 2 ? 2 : 0) + mb) * 64;
+                        const uint32_t xb = sbase + kOffX2 + (t & 1) * kX2Buf + (pass == 1 ? kX2Split : 0);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            umma_f16(d, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
-                                     make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSbo), idesc, acc);
+                            umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSbo), idesc, acc);
                             acc = 1;
                         }
                     }
                 }
-                umma_commit(&bars[X2_FREE]);
-                umma_commit(&bars[D2_FULL0 + (t & 1)]);
+                umma_commit(&bars[X2_FREE0 + (t & 1)]);
+                umma_commit(&bars[D2_FULL]);
                 }
                 __syncwarp();
                 stamp(t, 2);
             };
+            // tensor-pipe order: MMA1(0) MMA1(1) | MMA2(0) MMA1(2) | MMA2(1) MMA1(3) | ...  (MMA1(t+2) fills the gap in
+            // which E2(t) drains the single D2 accumulator)
             if (T > 0) mma1(0);
+            if (T > 1) mma1(1);
             for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) mma1(t + 1);
                 mma2(t);
+                if (t + 2 < T) mma1(t + 2);
             }
         }
     } else if (warp <= 4) {
@@ -319,11 +339,12 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const float b1 = reinterpret_cast<const float *>(smem + kOffB1)[ch];
         const float *B2 = reinterpret_cast<const float *>(smem + kOffB2);
-        uint8_t *x2 = smem + kOffX2 + (ch >> 3) * kLboX2 + (ch & 7) * 2;
+        uint8_t *x2 = smem + kOffX2 + g * kX2Buf + (ch >> 3) * kLboX2 + (ch & 7) * 2;  // this warpgroup's tiles use X2[g]
+        mbar_wait(&bars[W2_TMEM], 0);  // the X2 buffers alias the W2 staging area: wait until W2 sits in tensor memory
         for (int t = g; t < T; t += 2) {
             const int b = t & 1;
             const uint32_t ph = (t >> 1) & 1;
-            // E1: D1 -> +bias, ReLU, split -> X2
+            // E1: D1 -> +bias, ReLU, split -> X2[b]
             mbar_wait(&bars[D1_FULL0 + b], ph);
             tcgen05_fence_after();
             if (q == 1) stamp(t, 8);
@@ -333,9 +354,8 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(&bars[D1_FREE0 + b]);
-            // bias, ReLU and the hi/lo split happen BEFORE waiting for the operand buffer; r[i] becomes (lo << 16) | hi
 #pragma unroll
-            for (int sidx = 0; sidx < 64; sidx += 2) {
+            for (int sidx = 0; sidx < 64; sidx += 2) {  // r[i] becomes (lo << 16) | hi
                 uint32_t &ra = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
                 uint32_t &rb = sidx < 32 ? r0[(sidx + 1) & 31] : r1[(sidx + 1) & 31];
                 const float va = fmaxf(__uint_as_float(ra) + b1, 0.0f), vb = fmaxf(__uint_as_float(rb) + b1, 0.0f);
@@ -346,7 +366,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 rb = (hb >> 16) | (lb & 0xffff0000u);
             }
             if (q == 1) stamp(t, 9);
-            mbar_wait(&bars[X2_FREE], (t & 1) ^ 1);
+            mbar_wait(&bars[X2_FREE0 + b], ph ^ 1);  // MMA2(t-2) has finished reading this buffer
             if (q == 1) stamp(t, 10);
 #pragma unroll
             for (int sidx = 0; sidx < 64; ++sidx) {
@@ -355,17 +375,17 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 *reinterpret_cast<uint16_t *>(x2 + kX2Split + sidx * 16) = static_cast<uint16_t>(pk >> 16);
             }
             fence_proxy_async_smem();
-            mbar_arrive(&bars[X2_FULL]);
+            mbar_arrive(&bars[X2_FULL0 + b]);
             if (q == 1) stamp(t, 11);
             // E2: D2 -> max over the 64 samples, +bias, ReLU -> pooled (ReLU and +bias commute with max)
-            mbar_wait(&bars[D2_FULL0 + b], ph);
+            mbar_wait(&bars[D2_FULL], t & 1);
             tcgen05_fence_after();
             if (q == 1) stamp(t, 12);
             float mx[2];
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
-                tmem_ld32(tmem_base + lane_addr + 128 + b * 128 + mb * 64, r0);
-                tmem_ld32(tmem_base + lane_addr + 128 + b * 128 + mb * 64 + 32, r1);
+                tmem_ld32(tmem_base + lane_addr + 128 + mb * 64, r0);
+                tmem_ld32(tmem_base + lane_addr + 128 + mb * 64 + 32, r1);
                 tmem_ld_wait();
                 float mv = __uint_as_float(r0[0]);
 #pragma unroll
@@ -375,7 +395,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 mx[mb] = mv;
             }
             tcgen05_fence_before();
-            mbar_arrive(&bars[D2_FREE0 + b]);
+            mbar_arrive(&bars[D2_FREE]);
             const long long cl = first + static_cast<long long>(t) * gridDim.x;
             pooled[cl * 256 + ch] = fmaxf(mx[0] + B2[ch], 0.0f);
             pooled[cl * 256 + 128 + ch] = fmaxf(mx[1] + B2[128 + ch], 0.0f);
