@@ -128,7 +128,11 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemW2 = 256;
 
 enum Bar { W_FULL = 0, W2_TMEM, X1_FULL, X1_FREE, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1,
-           D2_FULL, D2_FREE, kNumBars };
+           D2_FULL0, D2_FULL1, D2_FREE, kNumBars };
+// NOTE on mbarrier parity: a waiter may lag a barrier by at most ONE phase (try_wait.parity(p) is true as soon as the
+// barrier is in the phase after p).  The two epilogue warpgroups alternate tiles, i.e. each sees every SECOND completion of
+// a per-tile event, so every barrier they wait on is per-warpgroup (D1_FULL[2], D2_FULL[2], X2_FREE[2]); only the MMA warp,
+// which consumes every completion in order, waits on shared single barriers (D2_FREE, X1_FULL).
 }  // namespace det
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -154,7 +158,8 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         mbar_init(&bars[W2_TMEM], 1);
         mbar_init(&bars[X1_FULL], 128);
         mbar_init(&bars[X1_FREE], 1);
-        mbar_init(&bars[D2_FULL], 1);
+        mbar_init(&bars[D2_FULL0], 1);
+        mbar_init(&bars[D2_FULL1], 1);
         mbar_init(&bars[D2_FREE], 128);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars[X2_FULL0 + b], 128);
@@ -250,7 +255,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                     }
                 }
                 umma_commit(&bars[X2_FREE0 + (t & 1)]);
-                umma_commit(&bars[D2_FULL]);
+                umma_commit(&bars[D2_FULL0 + (t & 1)]);
                 }
                 __syncwarp();
                 stamp(t, 2);
@@ -378,7 +383,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             mbar_arrive(&bars[X2_FULL0 + b]);
             if (q == 1) stamp(t, 11);
             // E2: D2 -> max over the 64 samples, +bias, ReLU -> pooled (ReLU and +bias commute with max)
-            mbar_wait(&bars[D2_FULL], t & 1);
+            mbar_wait(&bars[D2_FULL0 + b], ph);
             tcgen05_fence_after();
             if (q == 1) stamp(t, 12);
             float mx[2];
