@@ -123,11 +123,13 @@ constexpr uint32_t kSmemBytes = kOffBars + 16 * 8 + 16;
 static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffBars % 8 == 0, "alignment");
 static_assert(2 * kX2Buf <= 4 * kW2Blk, "X2 buffers must fit the W2 staging area");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-// TMEM columns: D1[2] at 0 / 64, D2 (two M blocks) at 128 / 192, W2 at 256 + (split*2 + mblk)*64 (128 K = 64 columns)
+// TMEM columns: D1 at 0 (64), W1 at 64 + split*32 (64 K = 32 columns), D2 (two M blocks) at 128 / 192,
+// W2 at 256 + (split*2 + mblk)*64 (128 K = 64 columns): all 512 columns in use, every MMA reads its A operand from TMEM.
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemW1 = 64;
 constexpr uint32_t kTmemW2 = 256;
 
-enum Bar { W_FULL = 0, W2_TMEM, X1_FULL, X1_FREE, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1,
+enum Bar { W_FULL = 0, W2_TMEM, X1_FULL, X1_FREE, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE,
            D2_FULL0, D2_FULL1, D2_FREE, kNumBars };
 // NOTE on mbarrier parity: a waiter may lag a barrier by at most ONE phase (try_wait.parity(p) is true as soon as the
 // barrier is in the phase after p).  The two epilogue warpgroups alternate tiles, i.e. each sees every SECOND completion of
@@ -165,8 +167,8 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             mbar_init(&bars[X2_FULL0 + b], 128);
             mbar_init(&bars[X2_FREE0 + b], 1);
             mbar_init(&bars[D1_FULL0 + b], 1);
-            mbar_init(&bars[D1_FREE0 + b], 128);
         }
+        mbar_init(&bars[D1_FREE], 128);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -206,25 +208,30 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                     for (int k = 0; k < 8; ++k)
                         tmem_cp_128x256b(tmem_base + kTmemW2 + blk * 64 + k * 8,
                                          make_smem_desc(sbase + kOffW2 + blk * kW2Blk + k * 2 * kLboW, kLboW, kSbo));
+#pragma unroll
+                for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tmem_cp_128x256b(tmem_base + kTmemW1 + sp * 32 + k * 8,
+                                         make_smem_desc(sbase + kOffW1 + sp * kW1Split + k * 2 * kLboW, kLboW, kSbo));
                 umma_commit(&bars[W2_TMEM]);
             }
             __syncwarp();
             auto mma1 = [&](int t) {
                 mbar_wait(&bars[X1_FULL], t & 1);
-                mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+                mbar_wait(&bars[D1_FREE], (t & 1) ^ 1);  // E1(t-1) has moved the single D1 accumulator into registers
                 tcgen05_fence_after();
                 stamp(t, 0);
                 if (elect_one()) {
-                const uint32_t d = tmem_base + (t & 1) * 64;
+                const uint32_t d = tmem_base;
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {  // (Whi,Xhi) (Whi,Xlo) (Wlo,Xhi)
-                    const uint32_t wa = sbase + kOffW1 + (pass == 2 ? kW1Split : 0);
+                    const uint32_t wa = tmem_base + kTmemW1 + (pass == 2 ? 32 : 0);
                     const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        umma_f16(d, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
-                                 make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc, acc);
+                        umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc, acc);
                         acc = 1;
                     }
                 }
@@ -354,11 +361,11 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             tcgen05_fence_after();
             if (q == 1) stamp(t, 8);
             uint32_t r0[32], r1[32];
-            tmem_ld32(tmem_base + lane_addr + b * 64, r0);
-            tmem_ld32(tmem_base + lane_addr + b * 64 + 32, r1);
+            tmem_ld32(tmem_base + lane_addr, r0);
+            tmem_ld32(tmem_base + lane_addr + 32, r1);
             tmem_ld_wait();
             tcgen05_fence_before();
-            mbar_arrive(&bars[D1_FREE0 + b]);
+            mbar_arrive(&bars[D1_FREE]);
 #pragma unroll
             for (int sidx = 0; sidx < 64; sidx += 2) {  // r[i] becomes (lo << 16) | hi
                 uint32_t &ra = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];

@@ -44,16 +44,21 @@ constexpr uint32_t kWeightBytes = kOffBm + 128 * 4;      // 83 200
 constexpr uint32_t kX1Split = 4 * kLboX1;                // 4 KB
 constexpr uint32_t kOffX1 = kWeightBytes;
 constexpr uint32_t kX2Split = 8 * kLboX2;                // 8 320
-constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Split;
+constexpr uint32_t kX2Buf = 2 * kX2Split;                // one X2 operand (hi + lo)
+constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Split;       // [buf 2][split 2][chunk 8] stride kLboX2
 constexpr uint32_t kPSplit = 8 * kLboP;                  // 1 KB
-constexpr uint32_t kOffP = kOffX2 + 2 * kX2Split;
-constexpr uint32_t kOffBars = kOffP + 2 * kPSplit;
-constexpr uint32_t kSmemBytes = kOffBars + 16 * 8 + 16;
+constexpr uint32_t kPBuf = 2 * kPSplit;
+constexpr uint32_t kOffP = kOffX2 + 2 * kX2Buf;          // [buf 2][split 2][chunk 8][row 8][8]
+constexpr uint32_t kOffBars = kOffP + 2 * kPBuf;
+constexpr uint32_t kSmemBytes = kOffBars + 20 * 8 + 16;
 static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffP % 128 == 0 && kOffBars % 8 == 0, "alignment");
-// TMEM columns: D1[2] at 0 / 64, D2[2] at 128 / 192, D3[2] at 256 / 288
+// TMEM columns: D1[2] at 0 / 64, D2[2] at 128 / 192, D3[2] at 256 / 288, then the weights (A operands, copied once with
+// tcgen05.cp): W1 at 320 + split*16 (32 K = 16 columns), Wa at 352 + split*32, Wb at 416 + split*32 (64 K = 32 columns)
 constexpr uint32_t kTmemCols = 512;
-enum Bar { W_FULL = 0, X1_FULL, X1_FREE, X2_FULL, X2_FREE, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1, D2_FULL0, D2_FULL1,
-           D2_FREE0, D2_FREE1, kNumBars };
+constexpr uint32_t kTmemW1 = 320, kTmemWa = 352, kTmemWb = 416;
+// per-warpgroup barriers wherever the two alternating epilogue warpgroups wait (see the note in mlp_tc.cu)
+enum Bar { W_FULL = 0, W_TMEM, X1_FULL, X1_FREE, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1,
+           D2_FULL0, D2_FULL1, D2_FREE0, D2_FREE1, kNumBars };
 }  // namespace dsc
 
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -72,11 +77,12 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[W_FULL], 1);
+        mbar_init(&bars[W_TMEM], 1);
         mbar_init(&bars[X1_FULL], 128);
         mbar_init(&bars[X1_FREE], 1);
-        mbar_init(&bars[X2_FULL], 128);
-        mbar_init(&bars[X2_FREE], 1);
         for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars[X2_FULL0 + b], 128);
+            mbar_init(&bars[X2_FREE0 + b], 1);
             mbar_init(&bars[D1_FULL0 + b], 1);
             mbar_init(&bars[D1_FREE0 + b], 128);
             mbar_init(&bars[D2_FULL0 + b], 1);
@@ -85,7 +91,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         fence_barrier_init();
     }
     // rows 1..7 of the pooled operand P are never written: zero them once (their D3 columns are never read either)
-    for (uint32_t i = threadIdx.x; i < 2 * kPSplit / 4; i += kThreads) reinterpret_cast<uint32_t *>(smem + kOffP)[i] = 0;
+    for (uint32_t i = threadIdx.x; i < 2 * kPBuf / 4; i += kThreads) reinterpret_cast<uint32_t *>(smem + kOffP)[i] = 0;
     fence_proxy_async_smem();
     if (warp == 0) {
         tmem_alloc(tmem_base_s, kTmemCols);
@@ -113,6 +119,27 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             const uint32_t idesc64 = make_idesc(1, 128, kSamples);
             const uint32_t idesc8 = make_idesc(1, 128, 8);
             const uint32_t sbase = smem_u32(smem);
+            // ---- all three weight matrices (hi and lo splits) -> tensor memory, once: every MMA reads A from TMEM
+            tcgen05_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int sp = 0; sp < 2; ++sp) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        tmem_cp_128x256b(tmem_base + kTmemW1 + sp * 16 + k * 8,
+                                         make_smem_desc(sbase + kOffW1 + sp * kW1Split + k * 2 * kLboW, kLboW, kSbo));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tmem_cp_128x256b(tmem_base + kTmemWa + sp * 32 + k * 8,
+                                         make_smem_desc(sbase + kOffWa + sp * kWmSplit + k * 2 * kLboW, kLboW, kSbo));
+                        tmem_cp_128x256b(tmem_base + kTmemWb + sp * 32 + k * 8,
+                                         make_smem_desc(sbase + kOffWb + sp * kWmSplit + k * 2 * kLboW, kLboW, kSbo));
+                    }
+                }
+                umma_commit(&bars[W_TMEM]);
+            }
+            __syncwarp();
+            mbar_wait(&bars[W_TMEM], 0);
             auto mma1 = [&](int t) {
                 mbar_wait(&bars[X1_FULL], t & 1);
                 mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
@@ -122,12 +149,11 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t wa = sbase + kOffW1 + (pass == 2 ? kW1Split : 0);
+                    const uint32_t wa = tmem_base + kTmemW1 + (pass == 2 ? 16 : 0);
                     const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        umma_f16(d, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
-                                 make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc64, acc);
+                        umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc64, acc);
                         acc = 1;
                     }
                 }
@@ -137,7 +163,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 __syncwarp();
             };
             auto mma23 = [&](int t) {
-                mbar_wait(&bars[X2_FULL], t & 1);
+                mbar_wait(&bars[X2_FULL0 + (t & 1)], (t >> 1) & 1);
                 mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
                 if (elect_one()) {
@@ -146,28 +172,26 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t wa = sbase + kOffWa + (pass == 2 ? kWmSplit : 0);
-                    const uint32_t xb = sbase + kOffX2 + (pass == 1 ? kX2Split : 0);
+                    const uint32_t wa = tmem_base + kTmemWa + (pass == 2 ? 32 : 0);
+                    const uint32_t xb = sbase + kOffX2 + (t & 1) * kX2Buf + (pass == 1 ? kX2Split : 0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        umma_f16(d2, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
-                                 make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSbo), idesc64, acc);
+                        umma_f16_ts(d2, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSbo), idesc64, acc);
                         acc = 1;
                     }
                 }
                 acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t wa = sbase + kOffWb + (pass == 2 ? kWmSplit : 0);
-                    const uint32_t xb = sbase + kOffP + (pass == 1 ? kPSplit : 0);
+                    const uint32_t wa = tmem_base + kTmemWb + (pass == 2 ? 32 : 0);
+                    const uint32_t xb = sbase + kOffP + (t & 1) * kPBuf + (pass == 1 ? kPSplit : 0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        umma_f16(d3, make_smem_desc(wa + k * 2 * kLboW, kLboW, kSbo),
-                                 make_smem_desc(xb + k * 2 * kLboP, kLboP, kSbo), idesc8, acc);
+                        umma_f16_ts(d3, wa + k * 8, make_smem_desc(xb + k * 2 * kLboP, kLboP, kSbo), idesc8, acc);
                         acc = 1;
                     }
                 }
-                umma_commit(&bars[X2_FREE]);
+                umma_commit(&bars[X2_FREE0 + (t & 1)]);
                 umma_commit(&bars[D2_FULL0 + (t & 1)]);
                 }
                 __syncwarp();
@@ -257,8 +281,8 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const float b1 = ch < 64 ? reinterpret_cast<const float *>(smem + kOffB1)[ch] : 0.0f;
         const float bm = reinterpret_cast<const float *>(smem + kOffBm)[ch];
-        uint8_t *x2 = smem + kOffX2 + (ch >> 3) * kLboX2 + (ch & 7) * 2;
-        uint8_t *pp = smem + kOffP + (ch >> 3) * kLboP + (ch & 7) * 2;  // row 0 of the pooled operand
+        uint8_t *x2 = smem + kOffX2 + g * kX2Buf + (ch >> 3) * kLboX2 + (ch & 7) * 2;  // this warpgroup's tiles use buffer g
+        uint8_t *pp = smem + kOffP + g * kPBuf + (ch >> 3) * kLboP + (ch & 7) * 2;     // row 0 of the pooled operand
         for (int t = g; t < T; t += 2) {
             const int b = t & 1;
             const uint32_t ph = (t >> 1) & 1;
@@ -288,7 +312,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                     rb = (hb >> 16) | (lb & 0xffff0000u);
                 }
             }
-            mbar_wait(&bars[X2_FREE], (t & 1) ^ 1);
+            mbar_wait(&bars[X2_FREE0 + b], ph ^ 1);  // MMA2/3(t-2) have finished reading this buffer
             if (q < 2) {
 #pragma unroll
                 for (int sidx = 0; sidx < 64; ++sidx) {
@@ -301,7 +325,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 *reinterpret_cast<__nv_bfloat16 *>(pp + kPSplit) = __float2bfloat16_rn(pmax - __bfloat162float(hp));
             }
             fence_proxy_async_smem();
-            mbar_arrive(&bars[X2_FULL]);
+            mbar_arrive(&bars[X2_FULL0 + b]);
             // E2
             mbar_wait(&bars[D2_FULL0 + b], ph);
             tcgen05_fence_after();
