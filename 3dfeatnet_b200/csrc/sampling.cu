@@ -25,6 +25,12 @@ __device__ __forceinline__ unsigned fps_tie_key(int k) {  // orders by (k mod 51
 }
 __device__ __forceinline__ int fps_tie_key_inv(unsigned t) { return static_cast<int>(((t & 0x7fffffu) << 9) | (t >> 23)); }
 
+struct FpsSlots2 {  // double-buffered per-warp winners of fps_cull_kernel: distance bits, sorted position, coordinates
+    int d[2][32];
+    int pos[2][32];
+    float x[2][32], y[2][32], z[2][32];
+};
+
 struct FpsSlots {  // double-buffered per-warp winners
     int d[2][32];
     unsigned key[2][32];
@@ -88,7 +94,7 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
     float *ys = xs + NP;
     float *zs = ys + NP;
     unsigned short *oi = reinterpret_cast<unsigned short *>(zs + NP);  // original index of each sorted position
-    __shared__ FpsSlots slots;
+    __shared__ FpsSlots2 slots2;
     __shared__ int cell_cursor[kCells];
     __shared__ float red[4][32];
     __shared__ float bbox[4];
@@ -189,10 +195,11 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
 
     float ox = __ldg(p + 0), oy = __ldg(p + 1), oz = __ldg(p + 2);  // the first sample is point 0 (:114-116)
     if (tid == 0) o[0] = 0;
-    // cached arg-max of this warp (uniform across its lanes)
+    // cached arg-max of this warp (uniform across its lanes): distance bits, sorted position, coordinates
     int cw_d = __float_as_int(-1.0f);
-    unsigned cw_key = 0xffffffffu;
+    int cw_pos = 0;
     float cw_x = 0.f, cw_y = 0.f, cw_z = 0.f, wmx = 3.0e38f;
+    FpsSlots2 &S2 = slots2;
 
     for (int j = 1; j < m; ++j) {
         const float bx = fmaxf(fmaxf(lox - ox, ox - hix), 0.0f);
@@ -212,30 +219,44 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
             }
             const int bi = __float_as_int(vmax);
             const int wmax = __reduce_max_sync(kFull, bi);
-            // tie key only where it matters: lanes holding the warp maximum
-            unsigned tk = 0xffffffffu;
-            int bpos = 0;
-            if (bi == wmax) {
+            // position of the lane's maximum and how many of its points share it
+            int bpos = 0, neq = 0;
 #pragma unroll
-                for (int g = 0; g < G; ++g)
+            for (int g = G - 1; g >= 0; --g)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (td[g * 4 + q] == vmax) {
-                            const int pos = wbase + 4 * (lane + 32 * g) + q;
-                            const unsigned k2 = fps_tie_key(vmax < 0.0f ? 0 : oi[pos]);
-                            if (k2 < tk) { tk = k2; bpos = pos; }
-                        }
+                for (int q = 3; q >= 0; --q)
+                    if (td[g * 4 + q] == vmax) {
+                        bpos = wbase + 4 * (lane + 32 * g) + q;
+                        ++neq;
+                    }
+            const unsigned cand = __ballot_sync(kFull, bi == wmax);
+            int src = __ffs(cand) - 1;
+            // Ties (several points at exactly the warp maximum -- duplicated points) are the only case that needs the
+            // reference's tie rule, i.e. the original indices; the common case skips those loads and the second redux.
+            if (__any_sync(kFull, bi == wmax && (neq > 1 || (cand & (cand - 1)) != 0))) {
+                unsigned tk = 0xffffffffu;
+                if (bi == wmax) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (td[g * 4 + q] == vmax) {
+                                const int pos = wbase + 4 * (lane + 32 * g) + q;
+                                const unsigned k2 = fps_tie_key(vmax < 0.0f ? 0 : oi[pos]);
+                                if (k2 < tk) { tk = k2; bpos = pos; }
+                            }
+                }
+                const unsigned wmin = __reduce_min_sync(kFull, tk);
+                src = __ffs(__ballot_sync(kFull, tk == wmin)) - 1;
             }
-            const unsigned wmin = __reduce_min_sync(kFull, tk);
-            const int src = __ffs(__ballot_sync(kFull, tk == wmin)) - 1;
-            cw_d = wmax;
-            cw_key = wmin;
             float vx = 0.f, vy = 0.f, vz = 0.f;
             if (lane == src) {  // only the winner touches shared memory
                 vx = xs[bpos];
                 vy = ys[bpos];
                 vz = zs[bpos];
             }
+            cw_d = wmax;
+            cw_pos = __shfl_sync(kFull, bpos, src);
             cw_x = __shfl_sync(kFull, vx, src);
             cw_y = __shfl_sync(kFull, vy, src);
             cw_z = __shfl_sync(kFull, vz, src);
@@ -243,22 +264,26 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
         }
         const int par = j & 1;
         if (lane == 0) {
-            slots.d[par][warp] = cw_d;
-            slots.key[par][warp] = cw_key;
-            slots.x[par][warp] = cw_x;
-            slots.y[par][warp] = cw_y;
-            slots.z[par][warp] = cw_z;
+            S2.d[par][warp] = cw_d;
+            S2.pos[par][warp] = cw_pos;
+            S2.x[par][warp] = cw_x;
+            S2.y[par][warp] = cw_y;
+            S2.z[par][warp] = cw_z;
         }
         __syncthreads();
-        const int d2 = slots.d[par][lane];
-        const unsigned k2 = slots.key[par][lane];
+        const int d2 = S2.d[par][lane];
         const int bmax = __reduce_max_sync(kFull, d2);
-        const unsigned bmin = __reduce_min_sync(kFull, d2 == bmax ? k2 : 0xffffffffu);
-        const int src = __ffs(__ballot_sync(kFull, d2 == bmax && k2 == bmin)) - 1;
-        ox = slots.x[par][src];
-        oy = slots.y[par][src];
-        oz = slots.z[par][src];
-        if (tid == 0) o[j] = fps_tie_key_inv(bmin);
+        const unsigned cand2 = __ballot_sync(kFull, d2 == bmax);
+        int src2 = __ffs(cand2) - 1;
+        if ((cand2 & (cand2 - 1)) != 0) {  // several warps at the block maximum: the reference tie rule decides
+            const unsigned k2 = d2 == bmax ? fps_tie_key(bmax < 0 ? 0 : oi[S2.pos[par][lane]]) : 0xffffffffu;
+            const unsigned bmin = __reduce_min_sync(kFull, k2);
+            src2 = __ffs(__ballot_sync(kFull, k2 == bmin)) - 1;
+        }
+        ox = S2.x[par][src2];
+        oy = S2.y[par][src2];
+        oz = S2.z[par][src2];
+        if (tid == 0) o[j] = oi[S2.pos[par][src2]];
     }
 }
 
