@@ -501,7 +501,9 @@ F3D_API int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float 
 }
 
 // Bring-up: device buffer of (tiles per CTA) x 16 int64 that receives CTA 0's clock64() timeline (NULL disables).
+namespace f3d { extern long long *g_desc_dbg; }
 F3D_API void f3d_debug_set_timeline(void *buf) { f3d::g_det_dbg = static_cast<long long *>(buf); }
+F3D_API void f3d_debug_set_timeline_desc(void *buf) { f3d::g_desc_dbg = static_cast<long long *>(buf); }
 
 // Measurement aid: when enabled, det_rows_tc_kernel is bracketed by CUDA events on the stream it is launched on;
 // f3d_debug_detector_rows_ms() waits for the last bracket and returns its duration (ms), or -1.

@@ -68,8 +68,11 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 __global__ void __launch_bounds__(dsc::kThreads, 1)
 desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const float *__restrict__ xyz,
                     const float *__restrict__ new_xyz, const int *__restrict__ idx, const float *__restrict__ orientation,
-                    const uint8_t *__restrict__ wimg, float *__restrict__ pooled2) {
+                    const uint8_t *__restrict__ wimg, float *__restrict__ pooled2, long long *__restrict__ dbg) {
     using namespace dsc;
+    auto stamp = [&](int t, int slot) {  // optional clock64() timeline of CTA 0 (bring-up)
+        if (dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) dbg[t * 16 + slot] = clock64();
+    };
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBars);
     uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(smem + kOffBars + kNumBars * 8);
@@ -144,6 +147,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 mbar_wait(&bars[X1_FULL], t & 1);
                 mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
+                stamp(t, 0);
                 if (elect_one()) {
                 const uint32_t d = tmem_base + (t & 1) * 64;
                 uint32_t acc = 0;
@@ -166,6 +170,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 mbar_wait(&bars[X2_FULL0 + (t & 1)], (t >> 1) & 1);
                 mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
+                stamp(t, 1);
                 if (elect_one()) {
                 const uint32_t d2 = tmem_base + 128 + (t & 1) * 64;
                 const uint32_t d3 = tmem_base + 256 + (t & 1) * 32;
@@ -195,6 +200,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 umma_commit(&bars[D2_FULL0 + (t & 1)]);
                 }
                 __syncwarp();
+                stamp(t, 2);
             };
             if (T > 0) mma1(0);
             for (int t = 0; t < T; ++t) {
@@ -231,6 +237,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         load_xyz(0, i1);
         i1 = load_idx(1);
         for (int t = 0; t < T; ++t) {
+            if (warp == 1) stamp(t, 4);
             float gx = (px - qx) / radius;
             float gy = (py - qy) / radius;
             const float gz = (pz - qz) / radius;
@@ -262,7 +269,9 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
                 lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
             }
+            if (warp == 1) stamp(t, 5);
             mbar_wait(&bars[X1_FREE], (t & 1) ^ 1);
+            if (warp == 1) stamp(t, 6);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 *reinterpret_cast<uint4 *>(x1 + (h * 2 + q) * kLboX1) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
@@ -289,6 +298,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             // E1 (channels 0..63 are real; 64..127 are the zero padding of the M axis)
             mbar_wait(&bars[D1_FULL0 + b], ph);
             tcgen05_fence_after();
+            if (q == 1) stamp(t, 8);
             uint32_t r0[32], r1[32];
             if (q < 2) {
                 tmem_ld32(tmem_base + lane_addr + b * 64, r0);
@@ -312,7 +322,9 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                     rb = (hb >> 16) | (lb & 0xffff0000u);
                 }
             }
+            if (q == 1) stamp(t, 9);
             mbar_wait(&bars[X2_FREE0 + b], ph ^ 1);  // MMA2/3(t-2) have finished reading this buffer
+            if (q == 1) stamp(t, 10);
             if (q < 2) {
 #pragma unroll
                 for (int sidx = 0; sidx < 64; ++sidx) {
@@ -326,9 +338,11 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[X2_FULL0 + b]);
+            if (q == 1) stamp(t, 11);
             // E2
             mbar_wait(&bars[D2_FULL0 + b], ph);
             tcgen05_fence_after();
+            if (q == 1) stamp(t, 12);
             tmem_ld32(tmem_base + lane_addr + 128 + b * 64, r0);
             tmem_ld32(tmem_base + lane_addr + 128 + b * 64 + 32, r1);
             tmem_ld_wait();
@@ -344,6 +358,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             mbar_arrive(&bars[D2_FREE0 + b]);
             const long long cl = first + static_cast<long long>(t) * gridDim.x;
             pooled2[cl * 128 + ch] = mv + cterm + bm;
+            if (q == 1) stamp(t, 13);
         }
     }
     tcgen05_fence_before();
@@ -382,6 +397,8 @@ __global__ void desc_tc_prep_kernel(const float *__restrict__ P, WeightLayout L,
     }
 }
 
+long long *g_desc_dbg = nullptr;  // bring-up timeline buffer (f3d_debug_set_timeline with which = 1)
+
 int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
                        const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
                        float *pooled2, cudaStream_t st) {
@@ -404,7 +421,7 @@ int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int f
     if (e != cudaSuccess) return fail(static_cast<int>(e), "desc_rows_tc: cudaFuncSetAttribute");
     const unsigned grid = static_cast<unsigned>(num_clusters < num_sms ? num_clusters : num_sms);
     desc_rows_tc_kernel<<<grid, dsc::kThreads, dsc::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, orientation, wimg,
-                                                                      pooled2);
+                                                                      pooled2, g_desc_dbg);
     return check_launch("desc_rows_tc_kernel");
 }
 

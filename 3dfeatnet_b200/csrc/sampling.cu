@@ -83,6 +83,8 @@ __device__ __forceinline__ int fps_block_argmax(FpsSlots &S, int par, float best
 // levels all select the maximum distance with the lowest tie key of that index -- a total order, independent of the
 // (non-deterministic) order in which the counting sort places points inside a cell.
 // Warp w owns sorted positions [w*32*PPT, (w+1)*32*PPT); lane l reads float4 #(l + 32 g) of that range (conflict-free).
+__device__ long long *g_fps_dbg = nullptr;  // bring-up: [round][warp][4] clock64() stamps of CTA 0 (rounds < 256)
+
 template <int PPT>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
@@ -201,7 +203,9 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
     float cw_x = 0.f, cw_y = 0.f, cw_z = 0.f, wmx = 3.0e38f;
     FpsSlots2 &S2 = slots2;
 
+    long long *dbg = (blockIdx.x == 0 && lane == 0) ? g_fps_dbg : nullptr;
     for (int j = 1; j < m; ++j) {
+        if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 0] = clock64();
         const float bx = fmaxf(fmaxf(lox - ox, ox - hix), 0.0f);
         const float by = fmaxf(fmaxf(loy - oy, oy - hiy), 0.0f);
         const float bz = fmaxf(fmaxf(loz - oz, oz - hiz), 0.0f);
@@ -263,6 +267,7 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
             wmx = __int_as_float(wmax);
         }
         const int par = j & 1;
+        if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 1] = clock64();
         if (lane == 0) {
             S2.d[par][warp] = cw_d;
             S2.pos[par][warp] = cw_pos;
@@ -271,6 +276,7 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
             S2.z[par][warp] = cw_z;
         }
         __syncthreads();
+        if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 2] = clock64();
         const int d2 = S2.d[par][lane];
         const int bmax = __reduce_max_sync(kFull, d2);
         const unsigned cand2 = __ballot_sync(kFull, d2 == bmax);
@@ -284,6 +290,7 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
         oy = S2.y[par][src2];
         oz = S2.z[par][src2];
         if (tid == 0) o[j] = oi[S2.pos[par][src2]];
+        if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 3] = clock64() + (ox > 1e30f ? 1 : 0);  // after the new sample is known
     }
 }
 
@@ -362,6 +369,12 @@ F3D_API int f3d_farthest_point_sample(int b, int n, int m, const float *inp, flo
     if (!temp) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "farthest_point_sample: n > 16384 needs temp of b*n floats");
     fps_global_kernel<<<b, kFpsThreads, 0, st>>>(n, m, inp, temp, out);
     return check_launch("fps_global_kernel");
+}
+
+// Bring-up: device buffer of 256*32*4 int64 receiving CTA 0's per-round clock64() stamps of fps_cull_kernel (NULL disables).
+F3D_API void f3d_debug_set_fps_timeline(void *buf) {
+    long long *p = static_cast<long long *>(buf);
+    cudaMemcpyToSymbol(f3d::g_fps_dbg, &p, sizeof(p));
 }
 
 F3D_API int f3d_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream) {
