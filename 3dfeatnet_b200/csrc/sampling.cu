@@ -85,9 +85,32 @@ __device__ __forceinline__ int fps_block_argmax(FpsSlots &S, int par, float best
 // Warp w owns sorted positions [w*32*PPT, (w+1)*32*PPT); lane l reads float4 #(l + 32 g) of that range (conflict-free).
 __device__ long long *g_fps_dbg = nullptr;  // bring-up: [round][warp][4] clock64() stamps of CTA 0 (rounds < 256)
 
-template <int PPT>
+// CL > 1: a thread-block CLUSTER of CL CTAs shares one cloud (n up to CL*1024*PPT): each CTA owns a contiguous chunk of
+// the points and runs the same binned / culled update on it; per round the CL local winners are exchanged through
+// distributed shared memory (one remote store per peer) and a cluster barrier, and every CTA reduces them identically.
+struct FpsPeerSlots {  // double-buffered winners of the CTAs of one cluster
+    int d[2][8];
+    unsigned key[2][8];
+    float x[2][8], y[2][8], z[2][8];
+};
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u32(void *local_ptr, unsigned cta, unsigned v) {
+    unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(local_ptr)), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int PPT, int CL>
 __global__ void __launch_bounds__(kFpsThreads, 1)
-fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+fps_cull_kernel(int n_total, int m, const float *__restrict__ inp, int *__restrict__ out) {
     constexpr int G = PPT / 4;
     constexpr int NP = kFpsThreads * PPT;
     constexpr int kCells = 256;
@@ -100,12 +123,21 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
     __shared__ int cell_cursor[kCells];
     __shared__ float red[4][32];
     __shared__ float bbox[4];
+    // the peer slots reuse the bounding-box scratch (dead after the initial cluster barrier): 227 KB is tight at PPT = 16
+    static_assert(sizeof(FpsPeerSlots) <= sizeof(float) * 4 * 32, "peer slots must fit the reduction scratch");
+    FpsPeerSlots &peers = *reinterpret_cast<FpsPeerSlots *>(&red[0][0]);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float *p = inp + static_cast<size_t>(blockIdx.x) * n * 3;
-    int *o = out + static_cast<size_t>(blockIdx.x) * m;
+    const unsigned rank = CL > 1 ? cluster_ctarank() : 0u;
+    const int cloud = blockIdx.x / CL;
+    const int chunk = CL > 1 ? (n_total + CL - 1) / CL : n_total;  // points per CTA (the last chunk may be shorter)
+    const int k_first = static_cast<int>(rank) * chunk;
+    const int n = max(min(chunk, n_total - k_first), 0);            // points owned by this CTA
+    const float *p0 = inp + static_cast<size_t>(cloud) * n_total * 3;  // the whole cloud (point 0 = first sample)
+    const float *p = p0 + static_cast<size_t>(k_first) * 3;            // this CTA's chunk
+    int *o = out + static_cast<size_t>(cloud) * m;
 
-    // ---- 1. xy bounding box of the cloud
+    // ---- 1. xy bounding box of the chunk
     float mnx = 3.0e38f, mxx = -3.0e38f, mny = 3.0e38f, mxy = -3.0e38f;
     for (int k = tid; k < n; k += kFpsThreads) {
         const float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1);
@@ -195,8 +227,9 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
         loz = fminf(loz, __shfl_xor_sync(kFull, loz, s)); hiz = fmaxf(hiz, __shfl_xor_sync(kFull, hiz, s));
     }
 
-    float ox = __ldg(p + 0), oy = __ldg(p + 1), oz = __ldg(p + 2);  // the first sample is point 0 (:114-116)
-    if (tid == 0) o[0] = 0;
+    float ox = __ldg(p0 + 0), oy = __ldg(p0 + 1), oz = __ldg(p0 + 2);  // the first sample is point 0 (:114-116)
+    if (tid == 0 && rank == 0) o[0] = 0;
+    if (CL > 1) cluster_sync_all();  // every CTA of the cluster is resident before the first remote store
     // cached arg-max of this warp (uniform across its lanes): distance bits, sorted position, coordinates
     int cw_d = __float_as_int(-1.0f);
     int cw_pos = 0;
@@ -286,12 +319,36 @@ fps_cull_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
             const unsigned bmin = __reduce_min_sync(kFull, k2);
             src2 = __ffs(__ballot_sync(kFull, k2 == bmin)) - 1;
         }
-        ox = S2.x[par][src2];
-        oy = S2.y[par][src2];
-        oz = S2.z[par][src2];
-        if (tid == 0) o[j] = oi[S2.pos[par][src2]];
+        if constexpr (CL == 1) {
+            ox = S2.x[par][src2];
+            oy = S2.y[par][src2];
+            oz = S2.z[par][src2];
+            if (tid == 0) o[j] = oi[S2.pos[par][src2]];
+        } else {
+            // publish this CTA's winner (tie key of the GLOBAL original index) to every CTA of the cluster
+            if (warp == 0 && lane < CL) {
+                const int wd = S2.d[par][src2];
+                const unsigned wk = wd < 0 ? 0xffffffffu : fps_tie_key(k_first + oi[S2.pos[par][src2]]);
+                st_cluster_u32(&peers.d[par][rank], lane, static_cast<unsigned>(wd));
+                st_cluster_u32(&peers.key[par][rank], lane, wk);
+                st_cluster_u32(&peers.x[par][rank], lane, __float_as_uint(S2.x[par][src2]));
+                st_cluster_u32(&peers.y[par][rank], lane, __float_as_uint(S2.y[par][src2]));
+                st_cluster_u32(&peers.z[par][rank], lane, __float_as_uint(S2.z[par][src2]));
+            }
+            cluster_sync_all();
+            const int pd = lane < CL ? peers.d[par][lane] : static_cast<int>(0x80000000);
+            const unsigned pk = lane < CL ? peers.key[par][lane] : 0xffffffffu;
+            const int gmax = __reduce_max_sync(kFull, pd);
+            const unsigned gmin = __reduce_min_sync(kFull, pd == gmax ? pk : 0xffffffffu);
+            const int src3 = __ffs(__ballot_sync(kFull, pd == gmax && pk == gmin)) - 1;
+            ox = peers.x[par][src3];
+            oy = peers.y[par][src3];
+            oz = peers.z[par][src3];
+            if (tid == 0 && rank == 0) o[j] = fps_tie_key_inv(gmin);
+        }
         if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 3] = clock64() + (ox > 1e30f ? 1 : 0);  // after the new sample is known
     }
+    if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still write into its shared memory
 }
 
 // ---- fallback for any n: running distances in a caller-provided (b,n) scratch, points from L2 ------------
@@ -345,14 +402,35 @@ __global__ void gather_point_kernel(int n, int m, long long total, const float *
     out[i] = __ldg(inp + (bb * n + a) * 3 + c);
 }
 
-template <int PPT>
+template <int PPT, int CL>
 static int launch_fps_smem(int b, int n, int m, const float *inp, int *out, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(kFpsThreads) * PPT * (3 * sizeof(float) + sizeof(unsigned short));
-    cudaError_t e = cudaFuncSetAttribute(fps_cull_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fps_cull_kernel<PPT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "fps: cudaFuncSetAttribute");
-    fps_cull_kernel<PPT><<<b, kFpsThreads, smem, st>>>(n, m, inp, out);
-    return check_launch("fps_cull_kernel");
+    if (CL == 1) {
+        fps_cull_kernel<PPT, CL><<<b, kFpsThreads, smem, st>>>(n, m, inp, out);
+        return check_launch("fps_cull_kernel");
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(b) * CL);
+    cfg.blockDim = dim3(kFpsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, fps_cull_kernel<PPT, CL>, n, m, inp, out);
+    ++g_launches;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(static_cast<int>(e), "fps_cull_kernel (cluster launch)");
+    }
+    return 0;
 }
 
 }  // namespace f3d
@@ -363,10 +441,14 @@ F3D_API int f3d_farthest_point_sample(int b, int n, int m, const float *inp, flo
     if (b < 0 || n <= 0 || m <= 0 || !inp || !out) return fail(F3D_ERR_INVALID_ARGUMENT, "farthest_point_sample: bad arguments");
     if (b == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    if (n <= 1024 * 4) return launch_fps_smem<4>(b, n, m, inp, out, st);
-    if (n <= 1024 * 8) return launch_fps_smem<8>(b, n, m, inp, out, st);
-    if (n <= 1024 * 16) return launch_fps_smem<16>(b, n, m, inp, out, st);
-    if (!temp) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "farthest_point_sample: n > 16384 needs temp of b*n floats");
+    if (n <= 1024 * 4) return launch_fps_smem<4, 1>(b, n, m, inp, out, st);
+    if (n <= 1024 * 8) return launch_fps_smem<8, 1>(b, n, m, inp, out, st);
+    if (n <= 1024 * 16) return launch_fps_smem<16, 1>(b, n, m, inp, out, st);
+    // larger clouds: a cluster of 2 / 4 / 8 CTAs per cloud, 16384 points each (KITTI-shape scans, 131072 points)
+    if (n <= 2 * 1024 * 16) return launch_fps_smem<16, 2>(b, n, m, inp, out, st);
+    if (n <= 4 * 1024 * 16) return launch_fps_smem<16, 4>(b, n, m, inp, out, st);
+    if (n <= 8 * 1024 * 16) return launch_fps_smem<16, 8>(b, n, m, inp, out, st);
+    if (!temp) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "farthest_point_sample: n > 131072 needs temp of b*n floats");
     fps_global_kernel<<<b, kFpsThreads, 0, st>>>(n, m, inp, temp, out);
     return check_launch("fps_global_kernel");
 }

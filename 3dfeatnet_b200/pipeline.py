@@ -38,7 +38,7 @@ class DetectDescribePipeline:
         self.attention = torch.empty((B, M), dtype=torch.float32, device=dev)
         self.orientation = torch.empty((B, M), dtype=torch.float32, device=dev)
         self.features = torch.empty((B, M, F), dtype=torch.float32, device=dev)
-        self.fps_temp = torch.empty((B, N), dtype=torch.float32, device=dev) if N > 16384 else None
+        self.fps_temp = torch.empty((B, N), dtype=torch.float32, device=dev) if N > 131072 else None
         self.bq_ws_bytes = self.L.f3d_query_ball_point_workspace_bytes(B, N)
         self.bq_ws = torch.empty((self.bq_ws_bytes,), dtype=torch.uint8, device=dev)
         self.ws_bytes = self.L.f3d_forward_workspace_bytes(B, M, F)

@@ -44,7 +44,7 @@ def farthest_point_sample(npoint, inp):
     b, n, _ = inp.shape
     out = torch.empty((b, npoint), dtype=torch.int32, device=inp.device)
     temp = None
-    if n > 16384:
+    if n > 131072:  # beyond the 8-CTA cluster kernel: global-memory fallback needs a (b,n) scratch
         temp = torch.empty((b, n), dtype=torch.float32, device=inp.device)
     L = _lib.lib()
     _lib.check(L.f3d_farthest_point_sample(b, n, npoint, _lib.ptr(inp), _lib.ptr(temp), _lib.ptr(out), _lib.stream()),

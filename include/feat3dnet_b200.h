@@ -38,8 +38,9 @@ void f3d_reset_launch_count(void);
 /* ---------------------------------------------------------------- tf_ops/sampling ------------- */
 
 /* farthestpointsamplingLauncher(b,n,m,inp,temp,out)  tf_sampling_g.cu:203-205, op tf_sampling.cpp:95-123.
- * inp (b,n,3) f32 -> out (b,m) i32.  `temp` (the reference's 32*n float scratch) is accepted for
- * signature compatibility and ignored (may be NULL): running distances live in registers. */
+ * inp (b,n,3) f32 -> out (b,m) i32.  `temp` (the reference's 32*n float scratch) is accepted for signature
+ * compatibility and ignored (may be NULL) for n <= 131072: running distances live in registers (one CTA per cloud up
+ * to 16384 points, a cluster of 2/4/8 CTAs beyond).  Only n > 131072 uses it, as a (b,n) float scratch. */
 int f3d_farthest_point_sample(int b, int n, int m, const float *inp, float *temp, int *out, void *stream);
 
 /* gatherpointLauncher(b,n,m,inp,idx,out)  tf_sampling_g.cu:206-208, op tf_sampling.cpp:126-148. */

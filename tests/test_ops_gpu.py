@@ -38,6 +38,8 @@ def clouds(kind, b, n, seed):
 @pytest.mark.parametrize("kind,b,n,m", [
     ("uniform", 2, 4096, 512), ("oxford", 2, 16384, 512), ("dups", 3, 5000, 300), ("uniform", 1, 777, 64),
     ("dups", 2, 8192, 256), ("uniform", 33, 1024, 32), ("uniform", 1, 40000, 128), ("uniform", 2, 100, 100),
+    ("dups", 2, 20000, 300), ("dups", 1, 100000, 200), ("oxford", 3, 131072, 96), ("uniform", 1, 16385, 40),
+    ("uniform", 1, 140000, 20),
 ])
 def test_fps_bit_exact_vs_oracle(cuda, kind, b, n, m):
     ts = pkg("tf_ops.sampling.tf_sampling")
