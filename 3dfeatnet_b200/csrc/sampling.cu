@@ -279,7 +279,7 @@ fps_cull_kernel(int n_total, int m, const float *__restrict__ inp, int *__restri
                         for (int q = 0; q < 4; ++q)
                             if (td[g * 4 + q] == vmax) {
                                 const int pos = wbase + 4 * (lane + 32 * g) + q;
-                                const unsigned k2 = fps_tie_key(vmax < 0.0f ? 0 : oi[pos]);
+                                const unsigned k2 = fps_tie_key(vmax < 0.0f ? 0 : k_first + oi[pos])  /* tie rule on the GLOBAL index */;
                                 if (k2 < tk) { tk = k2; bpos = pos; }
                             }
                 }
@@ -315,7 +315,7 @@ fps_cull_kernel(int n_total, int m, const float *__restrict__ inp, int *__restri
         const unsigned cand2 = __ballot_sync(kFull, d2 == bmax);
         int src2 = __ffs(cand2) - 1;
         if ((cand2 & (cand2 - 1)) != 0) {  // several warps at the block maximum: the reference tie rule decides
-            const unsigned k2 = d2 == bmax ? fps_tie_key(bmax < 0 ? 0 : oi[S2.pos[par][lane]]) : 0xffffffffu;
+            const unsigned k2 = d2 == bmax ? fps_tie_key(bmax < 0 ? 0 : k_first + oi[S2.pos[par][lane]]) : 0xffffffffu;
             const unsigned bmin = __reduce_min_sync(kFull, k2);
             src2 = __ffs(__ballot_sync(kFull, k2 == bmin)) - 1;
         }
