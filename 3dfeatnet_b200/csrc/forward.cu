@@ -15,6 +15,11 @@ int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int f
                        float *pooled2, cudaStream_t st);
 int descriptor_post_fp32(long long nc, const float *pooled2, const float *packed, int feature_dim, float *features,
                          cudaStream_t st);
+size_t post_tc_weight_bytes();
+int detector_post_tc(long long nc, const float *pooled, const float *packed, uint8_t *wimg, float *attention, float *orientation,
+                     cudaStream_t st);
+int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, const float *packed, uint8_t *wimg, float *features,
+                       cudaStream_t st);
 int detector_post_fp32(long long num_clusters, const float *pooled, const float *packed, float *attention,
                        float *orientation, cudaStream_t st);
 }  // namespace f3d
@@ -38,7 +43,8 @@ F3D_API int f3d_packed_weights_offsets(int feature_dim, int *offsets, int *sizes
 
 F3D_API size_t f3d_forward_workspace_bytes(int b, int m, int feature_dim) {
     (void)feature_dim;
-    return pooled_bytes(b, m) + f3d_detector_tc_weight_bytes() + 256;
+    const size_t img = f3d_detector_tc_weight_bytes() > post_tc_weight_bytes() ? f3d_detector_tc_weight_bytes() : post_tc_weight_bytes();
+    return pooled_bytes(b, m) + img + 256;
 }
 
 F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const float *xyz, const float *new_xyz,
@@ -58,7 +64,8 @@ F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius,
         uint8_t *wimg = static_cast<uint8_t *>(workspace) + pooled_bytes(b, m);
         int rc = detector_rows_tc(static_cast<long long>(b) * m, n, m, radius, xyz, new_xyz, idx, packed, wimg, pooled, as_stream(stream));
         if (rc) return rc;
-        return detector_post_fp32(static_cast<long long>(b) * m, pooled, packed, attention, orientation, as_stream(stream));
+        // the weight-image area of the workspace is recycled: the tail kernel's image is built after the row kernel ran
+        return detector_post_tc(static_cast<long long>(b) * m, pooled, packed, wimg, attention, orientation, as_stream(stream));
     }
     return fail(F3D_ERR_UNSUPPORTED, "detector_forward: precision must be 0 (fp32) or 2 (bf16x3 tensor cores)");
 }
@@ -80,7 +87,7 @@ F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radiu
         int rc = descriptor_rows_tc(static_cast<long long>(b) * m, n, m, radius, feature_dim, xyz, new_xyz, idx, orientation,
                                     packed, wimg, pooled2, as_stream(stream));
         if (rc) return rc;
-        return descriptor_post_fp32(static_cast<long long>(b) * m, pooled2, packed, feature_dim, features, as_stream(stream));
+        return descriptor_post_tc(static_cast<long long>(b) * m, feature_dim, pooled2, packed, wimg, features, as_stream(stream));
     }
     if (precision == 2)  // shapes the tensor-core kernel does not cover (nsample != 64, feature_dim 128): exact fp32 kernel
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
