@@ -236,9 +236,14 @@ fps_cull_kernel(int n_total, int m, const float *__restrict__ inp, int *__restri
     float cw_x = 0.f, cw_y = 0.f, cw_z = 0.f, wmx = 3.0e38f;
     FpsSlots2 &S2 = slots2;
 
+#ifdef F3D_FPS_TIMELINE  // bring-up instrumentation (tools/fps_timeline.py); costs ~25 % of the kernel, off by default
     long long *dbg = (blockIdx.x == 0 && lane == 0) ? g_fps_dbg : nullptr;
+#define F3D_FPS_STAMP(slot) if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + (slot)] = clock64()
+#else
+#define F3D_FPS_STAMP(slot)
+#endif
     for (int j = 1; j < m; ++j) {
-        if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 0] = clock64();
+        F3D_FPS_STAMP(0);
         const float bx = fmaxf(fmaxf(lox - ox, ox - hix), 0.0f);
         const float by = fmaxf(fmaxf(loy - oy, oy - hiy), 0.0f);
         const float bz = fmaxf(fmaxf(loz - oz, oz - hiz), 0.0f);
@@ -300,7 +305,7 @@ fps_cull_kernel(int n_total, int m, const float *__restrict__ inp, int *__restri
             wmx = __int_as_float(wmax);
         }
         const int par = j & 1;
-        if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 1] = clock64();
+        F3D_FPS_STAMP(1);
         if (lane == 0) {
             S2.d[par][warp] = cw_d;
             S2.pos[par][warp] = cw_pos;
@@ -309,7 +314,7 @@ fps_cull_kernel(int n_total, int m, const float *__restrict__ inp, int *__restri
             S2.z[par][warp] = cw_z;
         }
         __syncthreads();
-        if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 2] = clock64();
+        F3D_FPS_STAMP(2);
         const int d2 = S2.d[par][lane];
         const int bmax = __reduce_max_sync(kFull, d2);
         const unsigned cand2 = __ballot_sync(kFull, d2 == bmax);
@@ -346,7 +351,7 @@ fps_cull_kernel(int n_total, int m, const float *__restrict__ inp, int *__restri
             oz = peers.z[par][src3];
             if (tid == 0 && rank == 0) o[j] = fps_tie_key_inv(gmin);
         }
-        if (dbg && j < 256) dbg[(j * 32 + warp) * 4 + 3] = clock64() + (ox > 1e30f ? 1 : 0);  // after the new sample is known
+        F3D_FPS_STAMP(3);
     }
     if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still write into its shared memory
 }

@@ -12,8 +12,10 @@ from tests.test_model_gpu import compare, run_pipeline
 
 pytestmark = pytest.mark.gpu
 
-# bf16x3 drops terms of relative size 2^-16 per product: 1e-5-level errors, bounded here with one order of headroom
-TOL_BF16X3 = dict(att=2e-4, ori=2e-4, feat=2e-4)
+# bf16x3 drops terms of relative size 2^-16 per product: 1e-5-level errors, bounded here with one order of headroom.
+# The orientation is atan2 of an l2-normalised 2-vector whose norm can be small, which amplifies the relative error of the
+# head outputs: 5e-4 rad (0.03 degrees) for all but 0.5 % of the clusters (see test_model_gpu.compare).
+TOL_BF16X3 = dict(att=2e-4, ori=5e-4, feat=2e-4)
 
 
 def make_image(A, lbo, sbo):
