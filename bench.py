@@ -54,31 +54,63 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every ~2 ms (the timed
+    region lasts tens of milliseconds, too short for nvidia-smi subprocesses), nvidia-smi as a fallback."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu, self.samples, self.stop_flag = gpu_index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _reasons(self):
+        n = self.nvml
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        out = []
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20)):
+            if r & bit:
+                out.append(name)
+        return out
 
     def run(self):
+        if self.nvml is not None:
+            while not self.stop_flag:
+                try:
+                    self.samples.append((self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM), self.max_sm, self._reasons()))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag:
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append([x.strip() for x in o])
+                o = [x.strip() for x in o]
+                self.samples.append((int(o[0]), int(o[1]), [n for i, n in enumerate(names) if o[2 + i].lower().startswith("active")]))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({r for s in self.samples for r in s[2]})
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=reasons,
-                    samples=len(self.samples))
+                    samples=len(self.samples), source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def cpu_reference_pass(xyz_np, params, clusters, nsample, radius=2.0):
@@ -223,8 +255,11 @@ def main():
         k_flops = rows * FLOPS_DET_ROW
         achieved = k_flops / (k_ms * 1e-3) / 1e12
         peak = peaks["bf16"]
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        # (profiles/r01_f_det_rows_tc_ncu_summary.txt, same batch): 21.57 MB + 0.43 MB; only valid for the default workload
+        traffic = 21.57e6 + 0.43e6 if (B, N, M, S) == (64, 16384, 512, 64) else None
         roofline = dict(bound="tensor", kernel="det_rows_tc_kernel", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                        traffic=None, peak_source="%s bf16 burst (MEASURED_PEAKS.json)" % peaks["source"], flops_per_launch=k_flops,
+                        traffic=traffic, traffic_unit="bytes of DRAM per launch (ncu)", peak_source="%s bf16 burst (MEASURED_PEAKS.json)" % peaks["source"], flops_per_launch=k_flops,
                         ms_per_launch=k_ms, executed_tensor_tflops=3 * achieved, executed_frac=3 * achieved / peak)
     else:
         det_flops = rows * FLOPS_DET_ROW + B * M * FLOPS_DET_CLUSTER
