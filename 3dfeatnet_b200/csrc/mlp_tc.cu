@@ -96,7 +96,7 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
 // ------------------------------------------------------------------------------------------------ detector rows
 namespace det {
 constexpr int kSamples = 64;                 // samples per cluster = MMA N
-constexpr int kThreads = 13 * 32;
+constexpr int kThreads = 14 * 32;            // warp 0 MMA2 issue, 1-4 producers, 5-12 epilogues, 13 MMA1 issue
 constexpr uint32_t kSbo = 128;               // 8 rows x 16 B
 constexpr uint32_t kLboW = 128 * 16;         // weights: 128 rows per K chunk
 constexpr uint32_t kLboX1 = kSamples * 16;   // X1: written 16 B per thread, no padding needed
@@ -217,29 +217,6 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 umma_commit(&bars[W2_TMEM]);
             }
             __syncwarp();
-            auto mma1 = [&](int t) {
-                mbar_wait(&bars[X1_FULL], t & 1);
-                mbar_wait(&bars[D1_FREE], (t & 1) ^ 1);  // E1(t-1) has moved the single D1 accumulator into registers
-                tcgen05_fence_after();
-                stamp(t, 0);
-                if (elect_one()) {
-                const uint32_t d = tmem_base;
-                uint32_t acc = 0;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {  // (Whi,Xhi) (Whi,Xlo) (Wlo,Xhi)
-                    const uint32_t wa = tmem_base + kTmemW1 + (pass == 2 ? 32 : 0);
-                    const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc, acc);
-                        acc = 1;
-                    }
-                }
-                umma_commit(&bars[X1_FREE]);
-                umma_commit(&bars[D1_FULL0 + (t & 1)]);
-                }
-                __syncwarp();
-            };
             auto mma2 = [&](int t) {  // A operand (W2) from tensor memory, B operand X2[t & 1] from shared memory
                 mbar_wait(&bars[X2_FULL0 + (t & 1)], (t >> 1) & 1);
                 mbar_wait(&bars[D2_FREE], (t & 1) ^ 1);
@@ -267,14 +244,10 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 __syncwarp();
                 stamp(t, 2);
             };
-            // tensor-pipe order: MMA1(0) MMA1(1) | MMA2(0) MMA1(2) | MMA2(1) MMA1(3) | ...  (MMA1(t+2) fills the gap in
-            // which E2(t) drains the single D2 accumulator)
-            if (T > 0) mma1(0);
-            if (T > 1) mma1(1);
-            for (int t = 0; t < T; ++t) {
-                mma2(t);
-                if (t + 2 < T) mma1(t + 2);
-            }
+            // MMA1 (conv1) is issued by warp 13: two issuing warps hide each other's mbarrier-wait latency (~90 cycles per
+            // try_wait, 4 per tile), which a single issuer left as bubbles in the tensor pipe.  Data dependencies are carried by
+            // the barriers alone, so the interleaving of the two instruction streams in the pipe is free.
+            for (int t = 0; t < T; ++t) mma2(t);
         }
     } else if (warp <= 4) {
         // ---- producers: gather + normalise + layer 0 -> X1 ------------------------------------------------------
@@ -285,7 +258,11 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         const int s = pt & 63, h = pt >> 6;   // sample, channel half
         uint8_t *x1 = smem + kOffX1 + s * 16;
         const unsigned stride = gridDim.x;
-        const float inv_guard = radius;  // division by radius is kept exact (TF: grouped_xyz /= radius)
+        // grouped_xyz /= radius (pointnet_common.py:47).  When radius is a power of two (the model's 2.0) multiplying by its
+        // reciprocal is bit-identical to the division and avoids the IEEE-division slow path (taken whenever a lane's
+        // numerator is 0, i.e. for the centre point of every cluster); otherwise the true division is kept.
+        const float inv_r = 1.0f / radius;
+        const bool pow2 = (__float_as_uint(radius) & 0x007fffffu) == 0u && radius > 1e-30f && radius < 1e30f;
         auto load_idx = [&](int t) -> int {
             if (t >= T) return 0;
             const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
@@ -306,9 +283,9 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         i1 = load_idx(1);
         for (int t = 0; t < T; ++t) {
             if (warp == 1) stamp(t, 4);
-            const float gx = (px - qx) / inv_guard;
-            const float gy = (py - qy) / inv_guard;
-            const float gz = (pz - qz) / inv_guard;
+            const float gx = pow2 ? (px - qx) * inv_r : (px - qx) / radius;
+            const float gy = pow2 ? (py - qy) * inv_r : (py - qy) / radius;
+            const float gz = pow2 ? (pz - qz) * inv_r : (pz - qz) / radius;
             const int i2 = load_idx(t + 2);
             load_xyz(t + 1, i1);
             i1 = i2;
@@ -342,6 +319,35 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             fence_proxy_async_smem();
             mbar_arrive(&bars[X1_FULL]);
         }
+    } else if (warp == 13) {
+        // ---- second MMA issuer: conv1 (X1 -> D1), A operand W1 from tensor memory ---------------------------------------
+        const uint32_t idesc = make_idesc(1, 128, kSamples);
+        const uint32_t sbase = smem_u32(smem);
+        mbar_wait(&bars[W2_TMEM], 0);  // W1 / W2 have been copied into tensor memory
+        auto mma1 = [&](int t) {
+            mbar_wait(&bars[X1_FULL], t & 1);
+            mbar_wait(&bars[D1_FREE], (t & 1) ^ 1);  // E1(t-1) has moved the single D1 accumulator into registers
+            tcgen05_fence_after();
+            stamp(t, 0);
+            if (elect_one()) {
+            const uint32_t d = tmem_base;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {  // (Whi,Xhi) (Whi,Xlo) (Wlo,Xhi)
+                const uint32_t wa = tmem_base + kTmemW1 + (pass == 2 ? 32 : 0);
+                const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc, acc);
+                    acc = 1;
+                }
+            }
+            umma_commit(&bars[X1_FREE]);
+            umma_commit(&bars[D1_FULL0 + (t & 1)]);
+            }
+            __syncwarp();
+        };
+        for (int t = 0; t < T; ++t) mma1(t);
     } else {
         // ---- epilogue warpgroups: g = 0 (warps 5-8) even tiles, g = 1 (warps 9-12) odd tiles ----------------------
         mbar_wait(&bars[W_FULL], 0);  // biases live in the weight image

@@ -217,6 +217,8 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         const int s = pt & 63, h = pt >> 6;  // sample, channel half (16 channels = 2 K chunks)
         uint8_t *x1 = smem + kOffX1 + s * 16;
         const unsigned stride = gridDim.x;
+        const float inv_r = 1.0f / radius;  // exact replacement of the division when radius is a power of two (see mlp_tc.cu)
+        const bool pow2 = (__float_as_uint(radius) & 0x007fffffu) == 0u && radius > 1e-30f && radius < 1e30f;
         auto load_idx = [&](int t) -> int {
             if (t >= T) return 0;
             const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
@@ -238,11 +240,12 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         i1 = load_idx(1);
         for (int t = 0; t < T; ++t) {
             if (warp == 1) stamp(t, 4);
-            float gx = (px - qx) / radius;
-            float gy = (py - qy) / radius;
-            const float gz = (pz - qz) / radius;
+            float gx = pow2 ? (px - qx) * inv_r : (px - qx) / radius;
+            float gy = pow2 ? (py - qy) * inv_r : (py - qy) / radius;
+            const float gz = pow2 ? (pz - qz) * inv_r : (pz - qz) / radius;
             if (orientation) {  // pointnet_common.py:110-120: x' = x c - y s ; y' = x s + y c
-                const float cs = cosf(th), sn = sinf(th);
+                float cs, sn;
+                sincosf(th, &sn, &cs);
                 const float xr = gx * cs - gy * sn;
                 const float yr = gx * sn + gy * cs;
                 gx = xr;
