@@ -1,12 +1,12 @@
-"""models/net_factory.py:3-10 of the reference: name -> model class."""
+"""Model registry with the reference's lookup function (models/net_factory.py: get_network(name))."""
 import importlib
 
 _ROOT = __name__.split(".")[0]
-Feat3dNet = importlib.import_module(("3dfeatnet_b200." if _ROOT == "3dfeatnet_b200" else "") + "models.feat3dnet").Feat3dNet
+_feat3dnet = importlib.import_module(("3dfeatnet_b200." if _ROOT == "3dfeatnet_b200" else "") + "models.feat3dnet")
 
-networks_map = {'3DFeatNet': Feat3dNet}
+_REGISTRY = {"3DFeatNet": _feat3dnet.Feat3dNet}
 
 
 def get_network(name):
-    model = networks_map[name]
-    return model
+    """Class registered under `name`; KeyError for unknown names, like the reference's dict lookup."""
+    return _REGISTRY[name]

@@ -1,5 +1,10 @@
-"""PointNet++ sample-and-group compositions -- the reference's models/pointnet_common.py:14-165 on torch CUDA
-tensors, built on the CUDA operators of tf_ops/ (no TF, no CPU path)."""
+"""Sample-and-group compositions on torch CUDA tensors.
+
+Public names, argument order and return arity are those of the reference's models/pointnet_common.py
+(sample_points :14, query_and_group_points :32, sample_and_group :69, sample_and_group_all :138) so that code written
+against that module keeps working; the bodies are built from three private helpers on top of the CUDA operators of
+tf_ops/ (no TF, no CPU path).  Every op here is differentiable through the GatherPoint / GroupPoint gradients.
+"""
 import importlib
 
 import torch
@@ -12,106 +17,88 @@ query_ball_point, group_point, knn_point = _tg.query_ball_point, _tg.group_point
 farthest_point_sample, gather_point = _ts.farthest_point_sample, _ts.gather_point
 
 
+# ------------------------------------------------------------------------------------------------ private helpers
+def _neighbour_indices(xyz, centres, nsample, radius, knn):
+    """(idx (B,M,S) int32, pts_cnt): ball query, or kNN where the reference sets pts_cnt to nsample ("Hack", :37/:99)."""
+    if knn:
+        return knn_point(nsample, xyz, centres)[1], nsample
+    return query_ball_point(radius, nsample, xyz, centres)
+
+
+def _local_frames(xyz, centres, idx, radius, normalize_radius):
+    """Gather the neighbourhoods and express them relative to their centre, optionally in units of the radius."""
+    local = group_point(xyz, idx) - centres.unsqueeze(2)
+    return local / radius if normalize_radius else local
+
+
+def _spin_about_z(local, angles, clockwise):
+    """Rotate every neighbourhood about z by its own angle.
+    clockwise=False: x' = x cos - y sin, y' = x sin + y cos  (sample_and_group: grouped_xyz @ [[c,s,0],[-s,c,0],[0,0,1]], :112-119)
+    clockwise=True : x' = x cos + y sin, y' = -x sin + y cos (query_and_group_points' own convention, :49-54)"""
+    c = torch.cos(angles).unsqueeze(2)
+    s = torch.sin(angles).unsqueeze(2)
+    if clockwise:
+        s = -s
+    x, y, z = local.unbind(dim=3)
+    return torch.stack((x * c - y * s, x * s + y * c, z), dim=3)
+
+
+def _with_features(local_xyz, points, idx, use_xyz):
+    if points is None:
+        return local_xyz
+    feats = group_point(points, idx)
+    return torch.cat((local_xyz, feats), dim=-1) if use_xyz else feats
+
+
+# ------------------------------------------------------------------------------------------------ reference surface
 def sample_points(xyz, npoint):
-    '''
-    :param xyz:
-    :param npoint:
-    :return: new_xyz - Cluster centers   (pointnet_common.py:14-29: identity when npoint <= 0)
-    '''
+    """Cluster centres: `npoint` farthest-point samples of xyz, or every point when npoint <= 0 (reference :24-25)."""
     if npoint <= 0:
-        new_xyz = xyz.clone()
-    else:
-        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
-    return new_xyz
+        return xyz.clone()
+    return gather_point(xyz, farthest_point_sample(npoint, xyz))
 
 
 def query_and_group_points(xyz, points, new_xyz, nsample, radius, knn=False,
                            use_xyz=True, normalize_radius=True, orientations=None):
-    """pointnet_common.py:32-66.  Returns (new_points, idx); `query_and_group_points.last_pts_cnt` keeps the
-    pts_cnt the reference only logs as a histogram (:41)."""
-    if knn:
-        _, idx = knn_point(nsample, xyz, new_xyz)
-        pts_cnt = nsample
-    else:
-        idx, pts_cnt = query_ball_point(radius, nsample, xyz, new_xyz)
+    """Detector-side grouping (reference :32-66): returns (new_points (B,M,S,3[+C]), idx).
+    The pts_cnt the reference only logs as a histogram (:41) is kept in `query_and_group_points.last_pts_cnt`."""
+    idx, pts_cnt = _neighbour_indices(xyz, new_xyz, nsample, radius, knn)
     query_and_group_points.last_pts_cnt = pts_cnt
-
-    grouped_xyz = group_point(xyz, idx)  # (batch_size, npoint, nsample, 3)
-    grouped_xyz = grouped_xyz - new_xyz.unsqueeze(2)  # translation normalization
-    if normalize_radius:
-        grouped_xyz = grouped_xyz / radius  # Scale normalization
-    if orientations is not None:  # :49-54 (note: opposite sign convention to sample_and_group)
-        cosval = torch.cos(orientations).unsqueeze(2)
-        sinval = torch.sin(orientations).unsqueeze(2)
-        grouped_xyz = torch.stack([cosval * grouped_xyz[:, :, :, 0] + sinval * grouped_xyz[:, :, :, 1],
-                                   -sinval * grouped_xyz[:, :, :, 0] + cosval * grouped_xyz[:, :, :, 1],
-                                   grouped_xyz[:, :, :, 2]], dim=3)
-
-    if points is not None:
-        grouped_points = group_point(points, idx)
-        new_points = torch.cat([grouped_xyz, grouped_points], dim=-1) if use_xyz else grouped_points
-    else:
-        new_points = grouped_xyz
-    return new_points, idx
+    local = _local_frames(xyz, new_xyz, idx, radius, normalize_radius)
+    if orientations is not None:
+        local = _spin_about_z(local, orientations, clockwise=True)
+    return _with_features(local, points, idx, use_xyz), idx
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, tnet_spec=None, knn=False, use_xyz=True,
                      keypoints=None, orientations=None, normalize_radius=False):
-    '''pointnet_common.py:69-135.
-    Output:
-        new_xyz: (batch_size, npoint, 3), new_points: (batch_size, npoint, nsample, 3+channel),
-        idx: (batch_size, npoint, nsample), grouped_xyz: (batch_size, npoint, nsample, 3), end_points
-    '''
-    end_points = {}
-    if tnet_spec is not None:
-        raise ValueError("tnet_spec is unused (and undefined) in 3DFeat-Net: pointnet_common.py:122-123")
-    if keypoints is not None:
-        new_xyz = keypoints
-    else:
-        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
-
-    if knn:
-        _, idx = knn_point(nsample, xyz, new_xyz)
-        pts_cnt = nsample
-    else:
-        idx, pts_cnt = query_ball_point(radius, nsample, xyz, new_xyz)
-    end_points['pts_cnt'] = pts_cnt
-
-    grouped_xyz = group_point(xyz, idx)
-    grouped_xyz = grouped_xyz - new_xyz.unsqueeze(2)
-    if normalize_radius:
-        grouped_xyz = grouped_xyz / radius
-    end_points['grouped_xyz_before'] = grouped_xyz
-
-    if orientations is not None:  # :110-120  R = [[c,s,0],[-s,c,0],[0,0,1]];  grouped_xyz @ R
-        cosval = torch.cos(orientations)
-        sinval = torch.sin(orientations)
-        one = torch.ones_like(cosval)
-        zero = torch.zeros_like(cosval)
-        R = torch.stack([torch.stack([cosval, sinval, zero], dim=-1),
-                         torch.stack([-sinval, cosval, zero], dim=-1),
-                         torch.stack([zero, zero, one], dim=-1)], dim=-2)  # (B,M,3,3)
-        grouped_xyz = torch.matmul(grouped_xyz, R)
-        end_points['rotation'] = R
-
-    if points is not None:
-        grouped_points = group_point(points, idx)
-        new_points = torch.cat([grouped_xyz, grouped_points], dim=-1) if use_xyz else grouped_points
-    else:
-        new_points = grouped_xyz
-    end_points['grouped_xyz'] = grouped_xyz
-    return new_xyz, new_points, idx, grouped_xyz, end_points
+    """Descriptor-side sampling + grouping (reference :69-135).
+    Returns (new_xyz (B,M,3), new_points (B,M,S,3[+C]), idx (B,M,S), grouped_xyz (B,M,S,3), end_points) where end_points
+    carries 'grouped_xyz_before', 'rotation' (when orientations are given), 'grouped_xyz' and 'pts_cnt'."""
+    if tnet_spec is not None:  # the reference calls an undefined tnet() here (:122-123); unused by 3DFeat-Net
+        raise ValueError("tnet_spec is not supported")
+    centres = keypoints if keypoints is not None else sample_points(xyz, npoint)
+    idx, pts_cnt = _neighbour_indices(xyz, centres, nsample, radius, knn)
+    before = _local_frames(xyz, centres, idx, radius, normalize_radius)
+    end_points = {'pts_cnt': pts_cnt, 'grouped_xyz_before': before}
+    local = before
+    if orientations is not None:
+        local = _spin_about_z(before, orientations, clockwise=False)
+        c, s = torch.cos(orientations), torch.sin(orientations)
+        o, z = torch.ones_like(c), torch.zeros_like(c)
+        end_points['rotation'] = torch.stack((torch.stack((c, s, z), -1), torch.stack((-s, c, z), -1),
+                                              torch.stack((z, z, o), -1)), dim=-2)  # (B,M,3,3), the reference's R
+    end_points['grouped_xyz'] = local
+    return centres, _with_features(local, points, idx, use_xyz), idx, local, end_points
 
 
 def sample_and_group_all(xyz, points, use_xyz=True):
-    '''pointnet_common.py:138-165: one group holding every point, centroid (0,0,0).'''
-    batch_size, nsample = xyz.shape[0], xyz.shape[1]
-    new_xyz = torch.zeros((batch_size, 1, 3), dtype=torch.float32, device=xyz.device)
-    idx = torch.arange(nsample, dtype=torch.int32, device=xyz.device).reshape(1, 1, nsample).repeat(batch_size, 1, 1)
-    grouped_xyz = xyz.reshape(batch_size, 1, nsample, 3)
-    if points is not None:
-        new_points = torch.cat([xyz, points], dim=2) if use_xyz else points
-        new_points = new_points.unsqueeze(1)
-    else:
-        new_points = grouped_xyz
-    return new_xyz, new_points, idx, grouped_xyz
+    """One group holding the whole cloud, centred on the origin (reference :138-165)."""
+    b, n = xyz.shape[0], xyz.shape[1]
+    centre = xyz.new_zeros((b, 1, 3))
+    idx = torch.arange(n, dtype=torch.int32, device=xyz.device).expand(b, 1, n).contiguous()
+    whole = xyz.reshape(b, 1, n, 3)
+    if points is None:
+        return centre, whole, idx, whole
+    feats = torch.cat((xyz, points), dim=2) if use_xyz else points
+    return centre, feats.unsqueeze(1), idx, whole
