@@ -5,7 +5,7 @@
 // element: the fp32 sum order -- hence the result -- changes from run to run, and popular points serialise.
 // Here the (slot -> point) map is inverted once with a stable LSD radix sort of (point id, slot id) pairs,
 // and every output element is then produced by exactly one thread that adds its segment in ascending slot
-// order: no atomics, no memset, bit-reproducible, and equal to the reference's CPU statement
+// order: no atomics, bit-reproducible, and equal to the reference's CPU statement
 // (tf_ops/grouping/test/query_ball_point.cpp:68-84), which accumulates in the same (j,k) order.
 //
 // The radix sort is hand-written (8-bit digits; per pass: block histograms -> one exclusive scan ->
@@ -14,8 +14,8 @@
 
 namespace f3d {
 
-constexpr int kRsTile = 4096;     // keys per CTA
-constexpr int kRsThreads = 256;   // 8 warps, 512 consecutive keys each
+constexpr int kRsTile = 16384;    // keys per CTA (128 CTAs = one wave for the 2 M slots of a 64 x 512 x 64 batch)
+constexpr int kRsThreads = 256;   // 8 warps, 2048 consecutive keys each
 constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRsPerWarp = kRsTile / kRsWarps;
 
@@ -33,25 +33,22 @@ rs_hist_kernel(const unsigned *__restrict__ keys, long long n, int shift, unsign
     hist[static_cast<size_t>(threadIdx.x) * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
 }
 
-// exclusive scan of `count` unsigned values in place, one CTA of 1024 threads
+// exclusive scan of `count` unsigned values in place, one CTA of 1024 threads.  Each WARP owns a contiguous chunk and walks it
+// 32 values at a time (coalesced), twice: once for the chunk totals, once to write the prefix.
 __global__ void __launch_bounds__(1024)
 rs_scan_kernel(unsigned *__restrict__ data, long long count) {
     __shared__ unsigned warp_tot[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long per = (count + 1023) / 1024;
-    const long long lo = min(per * tid, count), hi = min(lo + per, count);
+    const long long per = ((count + 31) / 32 + 31) / 32 * 32;  // chunk length, multiple of 32
+    const long long lo = min(per * warp, count), hi = min(lo + per, count);
     unsigned sum = 0;
-    for (long long i = lo; i < hi; ++i) sum += data[i];
-    unsigned inc = sum;
+    for (long long i = lo + lane; i < hi; i += 32) sum += data[i];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc += v;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+    if (lane == 0) warp_tot[warp] = sum;
     __syncthreads();
     if (warp == 0) {
-        unsigned w = warp_tot[lane];
+        const unsigned w = warp_tot[lane];
         unsigned winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -61,11 +58,18 @@ rs_scan_kernel(unsigned *__restrict__ data, long long count) {
         warp_tot[lane] = winc - w;  // exclusive
     }
     __syncthreads();
-    unsigned run = warp_tot[warp] + (inc - sum);
-    for (long long i = lo; i < hi; ++i) {
-        const unsigned v = data[i];
-        data[i] = run;
-        run += v;
+    unsigned run = warp_tot[warp];
+    for (long long i0 = lo; i0 < hi; i0 += 32) {
+        const long long i = i0 + lane;
+        const unsigned v = i < hi ? data[i] : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (i < hi) data[i] = run + inc - v;
+        run += __shfl_sync(kFull, inc, 31);
     }
 }
 
@@ -124,23 +128,20 @@ __global__ void scatter_keys_kernel(long long total, long long slots_per_batch, 
     vals[i] = static_cast<unsigned>(i);
 }
 
-// one thread per output float (q, l): segment [lower_bound(q), lower_bound(q+1)) of the sorted keys,
-// summed in ascending slot order (the sort is stable and vals started ascending).
-__global__ void segmented_sum_kernel(long long out_total, int c, long long total,
-                                     const unsigned *__restrict__ keys, const unsigned *__restrict__ vals,
-                                     const float *__restrict__ grad, float *__restrict__ out) {
+// One thread per (sorted position p, channel l).  The thread at the HEAD of a run of equal keys sums the run in ascending
+// slot order (the sort is stable and the values started ascending) and writes the point's output; points that no slot
+// refers to keep the zero of the preceding memset.  No search, no atomics.
+__global__ void segmented_sum_kernel(long long total, int c, unsigned sentinel, const unsigned *__restrict__ keys,
+                                     const unsigned *__restrict__ vals, const float *__restrict__ grad, float *__restrict__ out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= out_total) return;
-    const unsigned q = static_cast<unsigned>(i / c);
-    const int l = static_cast<int>(i - static_cast<long long>(q) * c);
-    long long lo = 0, hi = total;
-    while (lo < hi) {  // first position with key >= q
-        const long long mid = (lo + hi) >> 1;
-        if (keys[mid] < q) lo = mid + 1; else hi = mid;
-    }
+    if (i >= total * c) return;
+    const long long p = i / c;
+    const int l = static_cast<int>(i - p * c);
+    const unsigned q = keys[p];
+    if (q >= sentinel || (p > 0 && keys[p - 1] == q)) return;  // out-of-range index, or not the head of its run
     float acc = 0.0f;
-    for (long long p = lo; p < total && keys[p] == q; ++p) acc += grad[static_cast<size_t>(vals[p]) * c + l];
-    out[i] = acc;
+    for (long long r = p; r < total && keys[r] == q; ++r) acc += grad[static_cast<size_t>(vals[r]) * c + l];
+    out[static_cast<size_t>(q) * c + l] = acc;
 }
 
 static inline unsigned blocks_for(long long total, int per_block) {
@@ -194,7 +195,9 @@ static int scatter_add_sorted(int b, int n, int c, long long L, const float *gra
     while ((1ULL << bits) <= sentinel) ++bits;
     rc = radix_sort_pairs(ka, va, kb, vb, hist, total, bits, st);
     if (rc) return rc;
-    segmented_sum_kernel<<<blocks_for(out_total, 256), 256, 0, st>>>(out_total, c, total, ka, va, grad, out);
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * out_total, st);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "scatter-add: memset");
+    segmented_sum_kernel<<<blocks_for(total * c, 256), 256, 0, st>>>(total, c, sentinel, ka, va, grad, out);
     return check_launch("segmented_sum_kernel");
 }
 
