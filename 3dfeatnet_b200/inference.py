@@ -55,3 +55,40 @@ def detect_and_describe(model, point_cloud, nms_radius=0.5, min_response_ratio=1
     xyz_nms, att_nms, num = nms(xyz, attention, nms_radius, min_response_ratio, max_keypoints)
     _, features, _, _ = model.get_inference_model(point_cloud, False, keypoints=xyz_nms)
     return xyz_nms, features, att_nms, num
+
+
+# ---------------------------------------------------------------------------------------------- file formats
+def load_point_cloud(path, num_cols=6):
+    """data/datagenerator.py:163-182: a raw float32 file of N x num_cols values (xyz + 3 unused columns) -> (N,num_cols)."""
+    import numpy as np
+
+    a = np.fromfile(path, dtype=np.float32)
+    if a.size % num_cols:
+        raise ValueError("%s: %d floats is not a multiple of %d columns" % (path, a.size, num_cols))
+    return a.reshape(-1, num_cols)
+
+
+def save_keypoints_and_descriptors(path, xyz, features):
+    """inference.py:174-177: one float32 row [x y z | descriptor] per keypoint -- the format scripts/Utils.m:56 reads."""
+    import numpy as np
+
+    xyz = xyz.detach().cpu().numpy() if torch.is_tensor(xyz) else np.asarray(xyz)
+    features = features.detach().cpu().numpy() if torch.is_tensor(features) else np.asarray(features)
+    rows = np.concatenate([xyz.reshape(-1, 3), features.reshape(xyz.reshape(-1, 3).shape[0], -1)], axis=1).astype(np.float32)
+    rows.tofile(path)
+    return rows.shape
+
+
+def compute_descriptors_for_file(model, in_path, out_path, randomize_points=False, seed=0, max_keypoints=1024,
+                                 nms_radius=0.5, min_response_ratio=1e-2, device="cuda"):
+    """One iteration of compute_descriptors' file loop (inference.py:99-180): load .bin, (optionally) permute the points,
+    detect at every point, NMS, describe, keep the num_keypoints real rows, write [xyz | descriptor] rows."""
+    import numpy as np
+
+    cloud = load_point_cloud(in_path)
+    if randomize_points:  # inference.py:108-113
+        cloud = cloud[np.random.default_rng(seed).permutation(cloud.shape[0])]
+    pc = torch.as_tensor(np.ascontiguousarray(cloud[None])).to(device)
+    xyz_nms, features, _, num = detect_and_describe(model, pc, nms_radius, min_response_ratio, max_keypoints)
+    k = num[0]
+    return save_keypoints_and_descriptors(out_path, xyz_nms[0, :k], features[0, :k])

@@ -156,3 +156,20 @@ def test_gloo_world_size_2_gradient_exchange():
     assert [(r[1], r[2]) for r in res] == [(0, 5), (5, 10)]
     assert all(abs(r[3] - 1000 * 1.5) < 1e-3 for r in res)  # mean of 1x and 2x
     assert all(r[4] == 1.5 for r in res)
+
+
+def test_bin_formats_roundtrip(tmp_path):
+    """.bin reader (datagenerator.py:163-182) and the [xyz | descriptor] writer (inference.py:174-177)"""
+    inf = pkg("inference")
+    cloud = np.random.default_rng(0).random((100, 6)).astype(np.float32)
+    p = tmp_path / "cloud.bin"
+    cloud.tofile(p)
+    assert np.array_equal(inf.load_point_cloud(str(p)), cloud)
+    with pytest.raises(ValueError):
+        inf.load_point_cloud(str(p), num_cols=7)
+    xyz = torch.rand(17, 3)
+    feat = torch.rand(17, 32)
+    q = tmp_path / "out.bin"
+    assert inf.save_keypoints_and_descriptors(str(q), xyz, feat) == (17, 35)
+    back = np.fromfile(q, dtype=np.float32).reshape(17, 35)
+    assert np.array_equal(back[:, :3], xyz.numpy()) and np.array_equal(back[:, 3:], feat.numpy())

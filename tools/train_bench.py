@@ -1,0 +1,45 @@
+"""Stage-2 training step at BASELINE.json configs[3] (C4): 6 triplets per GPU = 18 clouds x 4096 points, 512 clusters x 64
+samples, attention + rotation, BN batch statistics, triplet loss, backward, ONE flat-gradient all-reduce (NCCL), TF-1 Adam.
+The sampling / grouping operators are the CUDA kernels of this repository; the differentiable MLP layers are the unfused
+statement of models/layers.py (torch matmul + autograd) -- the fused training kernels are the next step.
+
+    python tools/train_bench.py                      (1 GPU)
+    torchrun --nproc-per-node N tools/train_bench.py (N GPUs)
+Prints one JSON line on rank 0 (steps/s, clouds/s; time = max over ranks, CUDA events)."""
+import importlib, json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+dist = importlib.import_module("3dfeatnet_b200.dist"); synth = importlib.import_module("3dfeatnet_b200.synth")
+f3 = importlib.import_module("3dfeatnet_b200.models.feat3dnet")
+
+rank, local_rank, world = dist.init("nccl")
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+B, N, M = 6, 4096, 512
+net = f3.Feat3dNet({'num_clusters': M}, device=dev, seed=0).train_mode()
+a, p, n = (torch.as_tensor(synth.make_batch(B, N, seed0=s + 100 * rank)).to(dev) for s in (1, 2, 3))
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def step():
+    xyz, feats, att, ep = net.get_train_model(a, p, n, True)
+    loss, ep = net.get_loss(xyz, feats, att, ep)
+    net.get_train_op(loss, lr=1e-5, end_points=ep, grad_hook=dist.allreduce_mean_)
+    return loss
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize(); dist.barrier()
+K = 10
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+for _ in range(K):
+    loss = step()
+e.record(); torch.cuda.synchronize(); dist.barrier()
+ms = dist.max_over_ranks(s.elapsed_time(e), dev) / K
+if rank == 0:
+    print(json.dumps(dict(workload="C4 stage-2 train step, 6 triplets/GPU x 4096 pts, 512 clusters x 64", n_gpus=world, ms_per_step=ms,
+                          steps_per_s=1e3 / ms, clouds_per_s=3 * B * world * 1e3 / ms, loss=float(loss),
+                          mlp_backend="torch autograd (unfused layers), CUDA sampling/grouping ops of this repo",
+                          peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)))
