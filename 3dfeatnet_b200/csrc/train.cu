@@ -1,0 +1,269 @@
+// train.cu -- training-step pieces of Feat3dNet: the attention-weighted triplet loss (forward + backward) and TF-1 Adam.
+//
+// Replaces Feat3dNet.get_loss (models/feat3dnet.py:315-357 + models/layers.py:49-62) and get_train_op
+// (models/feat3dnet.py:359-375).  The reference materialises two (B,M,M,F) broadcast tensors (201 MB at B=6, M=512, F=32)
+// for the pairwise distances and runs one ApplyAdam kernel per variable (~40 launches).  Here:
+//   * loss forward  : one warp per anchor descriptor scans the M positive and M negative descriptors of its cloud from
+//                     shared memory, keeps the minima (and how many columns tie for them), nothing (B,M,M) reaches HBM;
+//                     one CTA per cloud then forms the attention-normalised hinge;
+//   * loss backward : the same scan replayed; every anchor i pushes 2 w_i g (f_a - f_p[k*]) to itself and the opposite to
+//                     its arg-min column(s).  Column gradients are accumulated WITHOUT atomics: one thread per column
+//                     gathers, in ascending anchor order, the anchors that selected it (a (B,M) arg-min table is enough
+//                     unless there are exact ties, which take a slower exact path) => bit-reproducible;
+//   * Adam          : one launch over a table of (param, grad, m, v, n) records -- lr_t = lr*sqrt(1-b2^t)/(1-b1^t),
+//                     theta -= lr_t*m/(sqrt(v)+eps) (the TF-1 form, eps outside the bias correction), grad pre-scaled by
+//                     1/world so the data-parallel mean needs no extra pass.
+// tf.reduce_min splits the gradient equally among tied minima; so does this code.
+#include "common.cuh"
+
+namespace f3d {
+
+constexpr int kLossThreads = 256;
+
+// best[b,i] = min_k |fa[b,i]-fo[b,k]|^2 (squared_difference summed over F, layers.py:60), arg[b,i] = first arg-min,
+// ties[b,i] = number of columns attaining the minimum.  One warp per anchor; `other` staged in shared memory.
+__global__ void __launch_bounds__(kLossThreads)
+loss_min_kernel(int m, int f, const float *__restrict__ fa, const float *__restrict__ fo, float *__restrict__ best,
+                int *__restrict__ arg, int *__restrict__ ties) {
+    extern __shared__ float so[];  // [m][f+1]
+    const int b = blockIdx.y;
+    const float *o = fo + static_cast<size_t>(b) * m * f;
+    for (int e = threadIdx.x; e < m * f; e += blockDim.x) so[(e / f) * (f + 1) + e % f] = o[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= m) return;
+    const float *a = fa + (static_cast<size_t>(b) * m + i) * f;
+    float bd = 3.0e38f;
+    int bk = 0x7fffffff, nt = 0;
+    for (int k = lane; k < m; k += 32) {
+        float d = 0.0f;
+        for (int c = 0; c < f; ++c) {
+            const float df = a[c] - so[k * (f + 1) + c];
+            d += df * df;
+        }
+        if (d < bd) { bd = d; bk = k; nt = 1; }
+        else if (d == bd) { ++nt; }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const float od = __shfl_xor_sync(kFull, bd, s);
+        const int ok = __shfl_xor_sync(kFull, bk, s);
+        const int on = __shfl_xor_sync(kFull, nt, s);
+        if (od < bd) { bd = od; bk = ok; nt = on; }
+        else if (od == bd) { nt += on; bk = min(bk, ok); }
+    }
+    if (lane == 0) {
+        best[static_cast<size_t>(b) * m + i] = bd;
+        arg[static_cast<size_t>(b) * m + i] = bk;
+        ties[static_cast<size_t>(b) * m + i] = nt;
+    }
+}
+
+// per cloud: w = att/sum(att) (or 1/M), cost = max(0, sum w*best_p - sum w*best_n + margin); loss = mean over clouds.
+// Also emits what the backward needs: gw[b,i] = dL/d(best_p[b,i]) = w_i * 1[cost>0]/B  and  datt.
+__global__ void __launch_bounds__(kLossThreads)
+loss_reduce_kernel(int nb, int m, float margin, const float *__restrict__ att, const float *__restrict__ best_p,
+                   const float *__restrict__ best_n, float *__restrict__ cost, float *__restrict__ gw, float *__restrict__ datt) {
+    __shared__ float red[3][kLossThreads / 32];
+    __shared__ float tot[3];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *a = att ? att + static_cast<size_t>(b) * m : nullptr;
+    const float *bp = best_p + static_cast<size_t>(b) * m, *bn = best_n + static_cast<size_t>(b) * m;
+    float sa = 0.f, sp = 0.f, sn = 0.f;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const float w = a ? a[i] : 1.0f;
+        sa += w;
+        sp += w * bp[i];
+        sn += w * bn[i];
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        sa += __shfl_xor_sync(kFull, sa, s);
+        sp += __shfl_xor_sync(kFull, sp, s);
+        sn += __shfl_xor_sync(kFull, sn, s);
+    }
+    if (lane == 0) { red[0][warp] = sa; red[1][warp] = sp; red[2][warp] = sn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        for (int w = 0; w < kLossThreads / 32; ++w) { x += red[0][w]; y += red[1][w]; z += red[2][w]; }
+        tot[0] = x; tot[1] = y; tot[2] = z;
+    }
+    __syncthreads();
+    const float S = tot[0];
+    const float sum_p = tot[1] / S, sum_n = tot[2] / S;  // attention_sm * best, summed (feat3dnet.py:341-343); 1/M weights otherwise
+    const float c = sum_p - sum_n + margin;
+    const float g = c > 0.0f ? 1.0f / static_cast<float>(nb) : 0.0f;  // d(mean_b max(0,c_b))/dc_b
+    if (threadIdx.x == 0) cost[b] = fmaxf(c, 0.0f);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const float w = (a ? a[i] : 1.0f) / S;
+        gw[static_cast<size_t>(b) * m + i] = g * w;
+        if (datt) datt[static_cast<size_t>(b) * m + i] = a ? g * ((bp[i] - bn[i]) - (sum_p - sum_n)) / S : 0.0f;
+    }
+}
+
+// d fa[b,i,:] = 2 gw (fa - fp[k*]) / ties_p  summed over the tied k*  -  the same with the negatives
+__global__ void loss_grad_anchor_kernel(int m, int f, long long total, const float *__restrict__ fa, const float *__restrict__ fp,
+                                        const float *__restrict__ fn, const float *__restrict__ gw, const float *__restrict__ best_p,
+                                        const float *__restrict__ best_n, const int *__restrict__ arg_p, const int *__restrict__ arg_n,
+                                        const int *__restrict__ ties_p, const int *__restrict__ ties_n, float *__restrict__ dfa) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long long bi = e / f;
+    const int c = static_cast<int>(e - bi * f);
+    const long long b = bi / m;
+    const float g = gw[bi];
+    const float av = fa[e];
+    float acc = 0.0f;
+    for (int side = 0; side < 2; ++side) {
+        const float *o = (side ? fn : fp) + b * m * f;
+        const int nt = (side ? ties_n : ties_p)[bi];
+        const float sgn = side ? -1.0f : 1.0f;
+        if (nt == 1) {
+            acc += sgn * 2.0f * g * (av - o[static_cast<size_t>((side ? arg_n : arg_p)[bi]) * f + c]);
+        } else {  // exact ties: every tied column gets an equal share (tf.reduce_min gradient)
+            const float bd = (side ? best_n : best_p)[bi];
+            const float *a = fa + bi * f;
+            for (int k = 0; k < m; ++k) {
+                float d = 0.0f;
+                for (int cc = 0; cc < f; ++cc) {
+                    const float df = a[cc] - o[static_cast<size_t>(k) * f + cc];
+                    d += df * df;
+                }
+                if (d == bd) acc += sgn * 2.0f * g * (av - o[static_cast<size_t>(k) * f + c]) / static_cast<float>(nt);
+            }
+        }
+    }
+    dfa[e] = acc;
+}
+
+// d fo[b,k,:] = -sign * sum over anchors i that selected column k (ascending i) of 2 gw_i (fa_i - fo_k) / ties_i
+__global__ void loss_grad_other_kernel(int m, int f, long long total, float sgn, const float *__restrict__ fa, const float *__restrict__ fo,
+                                       const float *__restrict__ gw, const float *__restrict__ best, const int *__restrict__ arg,
+                                       const int *__restrict__ ties, float *__restrict__ dfo) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long long bk = e / f;
+    const int c = static_cast<int>(e - bk * f);
+    const long long b = bk / m;
+    const int k = static_cast<int>(bk - b * m);
+    const float ov = fo[e];
+    const float *ob = fo + bk * f;
+    float acc = 0.0f;
+    for (int i = 0; i < m; ++i) {
+        const long long bi = b * m + i;
+        const int nt = ties[bi];
+        bool sel = false;
+        if (nt == 1) sel = arg[bi] == k;
+        else {
+            const float *a = fa + bi * f;
+            float d = 0.0f;
+            for (int cc = 0; cc < f; ++cc) {
+                const float df = a[cc] - ob[cc];
+                d += df * df;
+            }
+            sel = d == best[bi];
+        }
+        if (sel) acc -= sgn * 2.0f * gw[bi] * (fa[bi * f + c] - ov) / static_cast<float>(nt);
+    }
+    dfo[e] = acc;
+}
+
+__global__ void loss_mean_kernel(int nb, const float *__restrict__ cost, float *__restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float s = 0.0f;
+        for (int b = 0; b < nb; ++b) s += cost[b];
+        loss[0] = s / static_cast<float>(nb);
+    }
+}
+
+struct AdamRecord {
+    float *param;
+    const float *grad;
+    float *m;
+    float *v;
+    long long n;
+};
+
+__global__ void adam_kernel(int num_records, const AdamRecord *__restrict__ recs, float lr_t, float b1, float b2, float eps,
+                            float grad_scale) {
+    for (int r = blockIdx.y; r < num_records; r += gridDim.y) {
+        const AdamRecord R = recs[r];
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < R.n;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const float g = R.grad[i] * grad_scale;
+            const float mm = b1 * R.m[i] + (1.0f - b1) * g;
+            const float vv = b2 * R.v[i] + (1.0f - b2) * g * g;
+            R.m[i] = mm;
+            R.v[i] = vv;
+            R.param[i] -= lr_t * mm / (sqrtf(vv) + eps);
+        }
+    }
+}
+
+}  // namespace f3d
+
+using namespace f3d;
+
+F3D_API size_t f3d_triplet_loss_workspace_bytes(int b, int m) {
+    if (b <= 0 || m <= 0) return 256;
+    return static_cast<size_t>(b) * m * (4 * 2 + 4 * 2 + 4 * 2 + 4) + static_cast<size_t>(b) * 4 + 256;
+}
+
+// Forward: loss (1 float).  Backward pieces are produced in the same call when the d* pointers are non-NULL (they are the
+// gradients of the LOSS, i.e. already multiplied by 1): dfa, dfp, dfn (b,m,f) and datt (b,m; NULL when att is NULL).
+F3D_API int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa, const float *fp, const float *fn, const float *att,
+                             float *loss, float *dfa, float *dfp, float *dfn, float *datt, void *workspace, size_t workspace_bytes,
+                             void *stream) {
+    if (b <= 0 || m <= 0 || f <= 0 || !fa || !fp || !fn || !loss) return fail(F3D_ERR_INVALID_ARGUMENT, "triplet_loss: bad arguments");
+    if (!workspace || workspace_bytes < f3d_triplet_loss_workspace_bytes(b, m)) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "triplet_loss: workspace too small");
+    const size_t smem = static_cast<size_t>(m) * (f + 1) * sizeof(float);
+    if (smem > 200 * 1024) return fail(F3D_ERR_UNSUPPORTED, "triplet_loss: m*(f+1) floats must fit 200 KB of shared memory");
+    cudaStream_t st = as_stream(stream);
+    const size_t bm = static_cast<size_t>(b) * m;
+    float *best_p = static_cast<float *>(workspace), *best_n = best_p + bm, *gw = best_n + bm, *cost = gw + bm;
+    int *arg_p = reinterpret_cast<int *>(cost + b), *arg_n = arg_p + bm, *ties_p = arg_n + bm, *ties_n = ties_p + bm;
+    cudaError_t e = cudaFuncSetAttribute(loss_min_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "triplet_loss: cudaFuncSetAttribute");
+    const dim3 grid((m + kLossThreads / 32 - 1) / (kLossThreads / 32), b);
+    loss_min_kernel<<<grid, kLossThreads, smem, st>>>(m, f, fa, fp, best_p, arg_p, ties_p);
+    int rc = check_launch("loss_min_kernel");
+    if (rc) return rc;
+    loss_min_kernel<<<grid, kLossThreads, smem, st>>>(m, f, fa, fn, best_n, arg_n, ties_n);
+    rc = check_launch("loss_min_kernel");
+    if (rc) return rc;
+    loss_reduce_kernel<<<b, kLossThreads, 0, st>>>(b, m, margin, att, best_p, best_n, cost, gw, datt);
+    rc = check_launch("loss_reduce_kernel");
+    if (rc) return rc;
+    loss_mean_kernel<<<1, 32, 0, st>>>(b, cost, loss);
+    rc = check_launch("loss_mean_kernel");
+    if (rc) return rc;
+    if (dfa && dfp && dfn) {
+        const long long total = static_cast<long long>(bm) * f;
+        const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+        loss_grad_anchor_kernel<<<blocks, 256, 0, st>>>(m, f, total, fa, fp, fn, gw, best_p, best_n, arg_p, arg_n, ties_p, ties_n, dfa);
+        rc = check_launch("loss_grad_anchor_kernel");
+        if (rc) return rc;
+        loss_grad_other_kernel<<<blocks, 256, 0, st>>>(m, f, total, 1.0f, fa, fp, gw, best_p, arg_p, ties_p, dfp);
+        rc = check_launch("loss_grad_other_kernel");
+        if (rc) return rc;
+        loss_grad_other_kernel<<<blocks, 256, 0, st>>>(m, f, total, -1.0f, fa, fn, gw, best_n, arg_n, ties_n, dfn);
+        rc = check_launch("loss_grad_other_kernel");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// records: DEVICE array of {param*, grad*, m*, v*, n} (5 x 8 bytes each).  grad_scale folds the 1/world of the data-parallel mean.
+F3D_API int f3d_adam_step(int num_records, const void *records, long long max_n, float lr, float beta1, float beta2, float eps,
+                          long long step, float grad_scale, void *stream) {
+    if (num_records <= 0 || !records || step <= 0) return fail(F3D_ERR_INVALID_ARGUMENT, "adam_step: bad arguments");
+    const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))) /
+                        (1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
+    const unsigned gx = static_cast<unsigned>(max_n <= 0 ? 1 : (max_n + 255) / 256 > 64 ? 64 : (max_n + 255) / 256);
+    const dim3 grid(gx, static_cast<unsigned>(num_records < 64 ? num_records : 64));
+    adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(num_records, static_cast<const AdamRecord *>(records), static_cast<float>(lr_t),
+                                                     beta1, beta2, eps, grad_scale);
+    return check_launch("adam_kernel");
+}

@@ -341,6 +341,13 @@ class Feat3dNet:
     def get_loss(self, xyz, features, anchor_attention, end_points):
         """ Attention weighted alignment loss (feat3dnet.py:315-357). """
         anchors, positives, negatives = features
+        if self.param.get('fused_loss', True) and anchors.is_cuda:
+            # one CUDA op for the forward and the backward (csrc/train.cu); the per-cloud terms the reference only
+            # logs (sum_positive / sum_negative) are produced by the unfused statement below (fused_loss=False)
+            if self.param['Attention']:
+                end_points['normalized_attention'] = (anchor_attention / anchor_attention.sum(dim=1)[:, None]).detach()
+            return _layers.triplet_loss(anchors, positives, negatives, anchor_attention if self.param['Attention'] else None,
+                                        self.param['margin']), end_points
         best_positive = pairwise_dist(anchors, positives).amin(dim=2)
         best_negative = pairwise_dist(anchors, negatives).amin(dim=2)
         if not self.param['Attention']:
@@ -366,26 +373,31 @@ class Feat3dNet:
         if not names:
             raise _lib.F3DError("get_train_op: no variable requires grad; build the model with train_mode()")
         grads = torch.autograd.grad(loss_op, [var[k] for k in names], allow_unused=True)
-        if self._adam is None:
-            self._adam = {"t": 0, "m": {k: torch.zeros_like(var[k]) for k in names},
-                          "v": {k: torch.zeros_like(var[k]) for k in names}}
         flat = torch.cat([(g if g is not None else torch.zeros_like(var[k])).reshape(-1) for k, g in zip(names, grads)])
+        if self._adam is None or self._adam["names"] != names:
+            # flat first/second moments + a device table of {param*, grad*, m*, v*, n} records: ONE launch per update
+            offs = np.cumsum([0] + [var[k].numel() for k in names])
+            mflat, vflat = torch.zeros_like(flat), torch.zeros_like(flat)
+            gbuf = torch.empty_like(flat)
+            rec = np.zeros((len(names), 5), np.int64)
+            for r, k in enumerate(names):
+                if not var[k].is_contiguous():
+                    raise _lib.F3DError("get_train_op: variable %s is not contiguous" % k)
+                rec[r] = (var[k].data_ptr(), gbuf.data_ptr() + 4 * int(offs[r]), mflat.data_ptr() + 4 * int(offs[r]),
+                          vflat.data_ptr() + 4 * int(offs[r]), var[k].numel())
+            self._adam = {"t": 0, "names": names, "m": mflat, "v": vflat, "g": gbuf, "records": torch.as_tensor(rec).to(flat.device),
+                          "max_n": int(rec[:, 4].max()), "ptrs": [var[k].data_ptr() for k in names]}
+        st = self._adam
+        if st["ptrs"] != [var[k].data_ptr() for k in names]:
+            raise _lib.F3DError("get_train_op: a variable was re-allocated since the optimiser state was built")
         if grad_hook is not None:
             flat = grad_hook(flat)
-        st = self._adam
+        st["g"].copy_(flat)
         st["t"] += 1
-        t = st["t"]
-        b1, b2, eps = 0.9, 0.999, 1e-8
-        lr_t = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
-        off = 0
+        _lib.require_cuda(st["g"])
         with torch.no_grad():
-            for k in names:
-                n = var[k].numel()
-                g = flat[off:off + n].reshape(var[k].shape)
-                off += n
-                st["m"][k].mul_(b1).add_(g, alpha=1 - b1)
-                st["v"][k].mul_(b2).addcmul_(g, g, value=1 - b2)
-                var[k].sub_(lr_t * st["m"][k] / (st["v"][k].sqrt() + eps))
+            _lib.check(_lib.lib().f3d_adam_step(len(names), _lib.ptr(st["records"]), st["max_n"], float(lr), 0.9, 0.999, 1e-8,
+                                                st["t"], 1.0, _lib.stream()), "adam_step")
             if end_points is not None and end_points.get('bn_updates'):
                 for k, v in end_points['bn_updates'].items():
                     self.weights[k].copy_(v)

@@ -79,3 +79,43 @@ def pairwise_dist(A, B):
              and kth descriptor in ith model of B
     '''
     return ((A.unsqueeze(2) - B.unsqueeze(1)) ** 2).sum(3)
+
+
+class _TripletLoss(torch.autograd.Function):
+    """Fused CUDA loss of Feat3dNet.get_loss (csrc/train.cu): the row minima of the two pairwise-distance matrices, the
+    attention-normalised hinge and -- in the same call -- the gradients w.r.t. the three descriptor sets and the
+    attention, so that no (B,M,M[,F]) tensor is ever materialised."""
+
+    @staticmethod
+    def forward(ctx, anchors, positives, negatives, attention, margin):
+        import importlib
+        root = __name__.split(".")[0]
+        _lib = importlib.import_module(("3dfeatnet_b200." if root == "3dfeatnet_b200" else "") + "_lib")
+        fa, fp, fn = (t.detach().contiguous().float() for t in (anchors, positives, negatives))
+        att = attention.detach().contiguous().float() if attention is not None else None
+        _lib.require_cuda(fa, fp, fn)
+        b, m, f = fa.shape
+        L = _lib.lib()
+        nbytes = L.f3d_triplet_loss_workspace_bytes(b, m)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=fa.device)
+        loss = torch.empty(1, dtype=torch.float32, device=fa.device)
+        dfa, dfp, dfn = torch.empty_like(fa), torch.empty_like(fp), torch.empty_like(fn)
+        datt = torch.empty_like(att) if att is not None else None
+        _lib.check(L.f3d_triplet_loss(b, m, f, float(margin), _lib.ptr(fa), _lib.ptr(fp), _lib.ptr(fn),
+                                      _lib.ptr(att) if att is not None else None, _lib.ptr(loss), _lib.ptr(dfa), _lib.ptr(dfp),
+                                      _lib.ptr(dfn), _lib.ptr(datt) if datt is not None else None, _lib.ptr(ws), nbytes,
+                                      _lib.stream()), "triplet_loss")
+        ctx.save_for_backward(dfa, dfp, dfn, datt if datt is not None else torch.empty(0, device=fa.device))
+        ctx.has_att = datt is not None
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dfa, dfp, dfn, datt = ctx.saved_tensors
+        return g * dfa, g * dfp, g * dfn, (g * datt if ctx.has_att else None), None
+
+
+def triplet_loss(anchors, positives, negatives, attention=None, margin=0.2):
+    """mean_b max(0, sum_i w_bi (min_k |a_bi-p_bk|^2 - min_k |a_bi-n_bk|^2) + margin), w = attention / sum(attention)
+    (uniform when attention is None): models/feat3dnet.py:315-357 as one differentiable CUDA op."""
+    return _TripletLoss.apply(anchors, positives, negatives, attention, margin)

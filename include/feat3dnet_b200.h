@@ -152,6 +152,26 @@ int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_r
             int max_keypoints, int num_neighbors, int *out_idx, float *out_xyz, float *out_attention,
             int *num_keypoints, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------- training step --------------- */
+
+/* Feat3dNet.get_loss  models/feat3dnet.py:315-357 (+ pairwise_dist, models/layers.py:49-62): attention-weighted
+ * triplet loss over anchor / positive / negative descriptors fa, fp, fn (b,m,f) and anchor attention att (b,m; NULL =
+ * uniform 1/m weights, the Attention=False branch).  loss: 1 float.  When dfa, dfp, dfn are non-NULL the same call
+ * also writes the gradients of the loss w.r.t. the descriptors (b,m,f) and, if datt is non-NULL, w.r.t. att (b,m);
+ * ties of the row minima share the gradient equally like tf.reduce_min.  Deterministic (no atomics).
+ * workspace: f3d_triplet_loss_workspace_bytes(b,m). */
+size_t f3d_triplet_loss_workspace_bytes(int b, int m);
+int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa, const float *fp, const float *fn,
+                     const float *att, float *loss, float *dfa, float *dfp, float *dfn, float *datt, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* Feat3dNet.get_train_op  models/feat3dnet.py:359-375: tf.train.AdamOptimizer(lr).minimize over all variables in
+ * ONE launch.  records: device array of num_records x {float *param; const float *grad; float *m; float *v;
+ * long long n;} (40 bytes each); max_n = the largest n.  step = 1-based update count; grad_scale multiplies every
+ * gradient first (1/world_size after a sum all-reduce).  theta -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps). */
+int f3d_adam_step(int num_records, const void *records, long long max_n, float lr, float beta1, float beta2, float eps,
+                  long long step, float grad_scale, void *stream);
+
 /* ---------------------------------------------------------------- bring-up / debugging ---------- */
 
 /* Single-CTA tcgen05 self test: D[128 x N] = A[128 x K] * B[N x K]^T from canonical K-major no-swizzle bf16 operand

@@ -1,0 +1,106 @@
+"""Parity of the training-step CUDA ops (csrc/train.cu) with their plain statements: the attention-weighted triplet
+loss of Feat3dNet.get_loss (reference models/feat3dnet.py:315-357) forward + backward, and TF-1 Adam (:359-375)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net as onet
+
+pytestmark = pytest.mark.gpu
+
+
+def pkg(name):
+    return importlib.import_module("3dfeatnet_b200." + name)
+
+
+def plain_loss(fa, fp, fn, att, margin):
+    """The reference's statement, with torch ops (amin splits the gradient equally among ties like tf.reduce_min)."""
+    layers = pkg("models.layers")
+    bp = layers.pairwise_dist(fa, fp).amin(dim=2)
+    bn = layers.pairwise_dist(fa, fn).amin(dim=2)
+    if att is None:
+        sp, sn = bp.mean(1), bn.mean(1)
+    else:
+        w = att / att.sum(dim=1)[:, None]
+        sp, sn = (w * bp).sum(1), (w * bn).sum(1)
+    return torch.clamp(sp - sn + margin, min=0.).mean()
+
+
+@pytest.mark.parametrize("B,M,F,use_att,margin", [(6, 512, 32, True, 0.2), (3, 100, 16, False, 0.2), (2, 33, 128, True, 5.0),
+                                                 (4, 64, 32, True, -10.0), (1, 1, 32, True, 0.2)])
+def test_triplet_loss_forward_backward(cuda, B, M, F, use_att, margin):
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(B * 1000 + M)
+    fa, fp, fn = (torch.nn.functional.normalize(torch.randn(B, M, F, generator=g), dim=-1).to(cuda).requires_grad_(True)
+                  for _ in range(3))
+    att = (torch.rand(B, M, generator=g) + 0.05).to(cuda).requires_grad_(True) if use_att else None
+    ins = [fa, fp, fn] + ([att] if use_att else [])
+    loss = layers.triplet_loss(fa, fp, fn, att, margin)
+    grads = torch.autograd.grad(loss * 3.0, ins)
+    ins64 = [t.detach().double().requires_grad_(True) for t in ins]
+    ref = plain_loss(ins64[0], ins64[1], ins64[2], ins64[3] if use_att else None, margin)
+    rgrads = torch.autograd.grad(ref * 3.0, ins64)
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    for name, a, b in zip(("dfa", "dfp", "dfn", "datt"), grads, rgrads):
+        scale = b.abs().max().item() + 1e-12
+        assert (a.double() - b).abs().max().item() <= 2e-5 * scale + 1e-9, name
+
+
+def test_triplet_loss_ties_split_gradient(cuda):
+    """Duplicate positives make exact ties in the row minima; the gradient is shared equally (tf.reduce_min)."""
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(5)
+    B, M, F = 2, 48, 32
+    fa = torch.randn(B, M, F, generator=g)
+    fp = torch.randn(B, M, F, generator=g)
+    fp[:, 1::2] = fp[:, 0::2]                     # every positive twice -> every minimum is attained twice
+    fn = torch.randn(B, M, F, generator=g)
+    fn[:, 3] = fn[:, 7]
+    att = torch.rand(B, M, generator=g) + 0.1
+    ins = [t.to(cuda).requires_grad_(True) for t in (fa, fp, fn, att)]
+    loss = layers.triplet_loss(*ins, 50.0)
+    grads = torch.autograd.grad(loss, ins)
+    ins64 = [t.detach().double().requires_grad_(True) for t in ins]
+    rgrads = torch.autograd.grad(plain_loss(*ins64, 50.0), ins64)
+    for a, b in zip(grads, rgrads):
+        assert (a.double() - b).abs().max().item() <= 2e-5 * (b.abs().max().item() + 1e-12)
+    assert grads[1][:, 0::2].abs().sum() > 0 and torch.equal(grads[1][:, 0::2], grads[1][:, 1::2])
+
+
+def test_triplet_loss_is_deterministic(cuda):
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(9)
+    fa, fp, fn = (torch.randn(6, 512, 32, generator=g).to(cuda).requires_grad_(True) for _ in range(3))
+    att = torch.rand(6, 512, generator=g).to(cuda).requires_grad_(True)
+    runs = [torch.autograd.grad(layers.triplet_loss(fa, fp, fn, att, 0.2), [fa, fp, fn, att]) for _ in range(3)]
+    for r in runs[1:]:
+        assert all(torch.equal(x, y) for x, y in zip(r, runs[0]))
+
+
+def test_adam_matches_tf_style_oracle(cuda):
+    """Three updates of all 107 619 variables against oracle.net.adam_step (fp64)."""
+    f3 = pkg("models.feat3dnet")
+    params = onet.init_params(seed=2, randomize_bn=True)
+    net = f3.Feat3dNet({'num_clusters': 32}, weights=params, device=cuda).train_mode()
+    var = net.trainable_variables()
+    names = list(var)
+    oP = {k: torch.as_tensor(params[k]).double() for k in names}
+    state = {}
+    g = torch.Generator().manual_seed(1)
+    for step in range(3):
+        grads = {k: torch.randn(var[k].shape, generator=g) * (10.0 ** (step - 2)) for k in names}
+        loss = sum((var[k] * grads[k].to(cuda)).sum() for k in names)      # d loss / d var = grads
+        flat = net.get_train_op(loss, lr=1e-3)
+        assert torch.allclose(flat.cpu(), torch.cat([grads[k].reshape(-1) for k in names]), rtol=1e-6, atol=1e-7)
+        onet.adam_step(oP, {k: v.double() for k, v in grads.items()}, state, lr=1e-3)
+        for k in names:
+            assert torch.allclose(var[k].detach().cpu().double(), oP[k], rtol=1e-5, atol=2e-6), (step, k)
+
+
+def test_triplet_loss_rejects_bad_arguments(cuda):
+    _lib = pkg("_lib")
+    L = _lib.lib()
+    assert L.f3d_triplet_loss(0, 4, 4, 0.2, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert L.f3d_adam_step(0, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
