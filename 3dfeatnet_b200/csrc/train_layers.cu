@@ -1,0 +1,510 @@
+// train_layers.cu -- training-mode 1x1 conv + bias + batch-norm (batch statistics) + ReLU, forward and backward.
+//
+// Replaces, for is_training=True, the op chain of models/layers.py:11-46 (slim.conv2d with bias) + :225-272
+// (tf.nn.moments over [0,1,2], tf.nn.batch_normalization with eps 1e-3, EMA decay 0.9) + the ReLU, and the backward
+// graph TensorFlow derives from it.  All eleven conv layers of the detector / descriptor (models/feat3dnet.py:90-187)
+// are instances: rows = B*M*S grouped points (per-point layers) or B*M clusters (per-cluster layers), channels last.
+//
+//   forward : z = x W + b                         conv_fwd_kernel   (fp32 register tiles, per-tile column sums of z, z^2)
+//             mean, var = moments(z)              bn_stats_finalize (fixed-order fp64 reduction of the tile partials)
+//             y = relu(gamma (z-mean) rsqrt(var+eps) + beta)        bn_apply_kernel
+//   backward: g = gy * [y > 0];  sum g, sum g*zhat                  bn_bwd_reduce_kernel + bn_bwd_finalize
+//             dz = gamma istd (g - mean(g) - zhat mean(g zhat))     bn_bwd_apply_kernel
+//             dW = x^T dz, db = sum dz                              conv_wgrad_kernel (split over rows) + partial_reduce
+//             dx = dz W^T                                           conv_fwd_kernel on the transposed weights / dgrad3
+// Every reduction runs in a fixed order (no atomics): two runs give identical bits.  fp32 FFMA; the tensor-core
+// version of these contractions is future work.
+#include "mlp_tile.cuh"
+
+namespace f3d {
+
+constexpr int kLdT = 132;      // leading dimension of the transposed activation tile (128 rows + 4: 16-byte aligned rows)
+constexpr int kWgKC = 32;      // rows staged per wgrad iteration
+constexpr int kRedBlocks = 592;  // row-chunks of the BN backward reduction (4 per SM)
+
+__device__ __forceinline__ void stage_rows_transposed(float *in_t, const float *__restrict__ x, long long row0, long long rows, int cin) {
+    const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+    const long long row = row0 + r;
+    const bool ok = row < rows;
+    const float *p = x + row * cin;
+    if ((cin & 3) == 0) {
+        for (int k = h * 4; k < cin; k += 8) {
+            const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(p + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            in_t[(k + 0) * kLdT + r] = v.x;
+            in_t[(k + 1) * kLdT + r] = v.y;
+            in_t[(k + 2) * kLdT + r] = v.z;
+            in_t[(k + 3) * kLdT + r] = v.w;
+        }
+    } else {
+        for (int k = h; k < cin; k += 2) in_t[k * kLdT + r] = ok ? __ldg(p + k) : 0.0f;
+    }
+}
+
+// z[rows x cout] = x[rows x cin] * W[cin x cout] (+ bias); optional per-tile column sums of z and z^2 into
+// part[(tile*2+{0,1})*cout + col].  grid = (row tiles, cout / (16*CT)).
+template <int CT>
+__global__ void __launch_bounds__(kMlpThreads)
+conv_fwd_kernel(long long rows, int cin, int cout, const float *__restrict__ x, const float *__restrict__ W,
+                const float *__restrict__ bias, float *__restrict__ z, float *__restrict__ part) {
+    extern __shared__ __align__(16) float sm[];
+    float *in_t = sm;
+    float *red = sm + static_cast<size_t>(cin) * kLdT;  // [2][16][NC]
+    constexpr int NC = 16 * CT;
+    const long long tile = blockIdx.x;
+    const int col0 = blockIdx.y * NC;
+    stage_rows_transposed(in_t, x, tile * kTileRows, rows, cin);
+    __syncthreads();
+    float acc[8][CT];
+    dense_tile<CT>(in_t, cin, W, cout, col0, acc, kLdT);
+    const int rg = threadIdx.x & 15, cg = threadIdx.x >> 4;
+    const int col = col0 + cg * CT;
+    if (bias) {
+#pragma unroll
+        for (int j = 0; j < CT; ++j) {
+            const float bb = __ldg(bias + col + j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i][j] += bb;
+        }
+    }
+    const long long r0 = tile * kTileRows + rg * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (r0 + i < rows) {
+            float *o = z + (r0 + i) * cout + col;
+            if constexpr (CT >= 4) {
+#pragma unroll
+                for (int j = 0; j < CT; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < CT; ++j) o[j] = acc[i][j];
+            }
+        }
+    }
+    if (part) {
+#pragma unroll
+        for (int j = 0; j < CT; ++j) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (r0 + i < rows) { s += acc[i][j]; q = fmaf(acc[i][j], acc[i][j], q); }
+            red[rg * NC + cg * CT + j] = s;
+            red[16 * NC + rg * NC + cg * CT + j] = q;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 2 * NC; e += kMlpThreads) {
+            const int which = e / NC, c = e - which * NC;
+            float s = 0.f;
+            for (int g = 0; g < 16; ++g) s += red[which * 16 * NC + g * NC + c];
+            part[(tile * 2 + which) * cout + col0 + c] = s;
+        }
+    }
+}
+
+// out[w] = sum over parts p (ascending) of part[p*width + w], accumulated in fp64.  One thread per w.
+__global__ void partial_reduce_kernel(int nparts, long long width, const float *__restrict__ part, float *__restrict__ out) {
+    const long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= width) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += static_cast<double>(part[static_cast<size_t>(p) * width + w]);
+    out[w] = static_cast<float>(s);
+}
+
+// sums[2][c] -> mean, var (population), coef = {scale = gamma*rsqrt(var+eps), shift = beta - mean*scale}
+__global__ void bn_stats_finalize_kernel(int c, double inv_rows, float eps, const float *__restrict__ sums, const float *__restrict__ gamma,
+                                         const float *__restrict__ beta, float *__restrict__ mean, float *__restrict__ var, float *__restrict__ coef) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    const double mu = static_cast<double>(sums[ch]) * inv_rows;
+    double v = static_cast<double>(sums[c + ch]) * inv_rows - mu * mu;
+    if (v < 0.0) v = 0.0;
+    mean[ch] = static_cast<float>(mu);
+    var[ch] = static_cast<float>(v);
+    const float sc = gamma[ch] * rsqrtf(static_cast<float>(v) + eps);
+    coef[ch] = sc;
+    coef[c + ch] = beta[ch] - static_cast<float>(mu) * sc;
+}
+
+__global__ void bn_apply_kernel(long long n4, int c, const float *__restrict__ z, const float *__restrict__ coef, int relu, float *__restrict__ y) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n4) return;
+    const int ch = static_cast<int>((e * 4) % c);
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(z) + e);
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(coef + ch));
+    const float4 sh = __ldg(reinterpret_cast<const float4 *>(coef + c + ch));
+    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+    if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+    reinterpret_cast<float4 *>(y)[e] = o;
+}
+
+// per row-chunk partial sums of g and g*zhat, g = gy * [y > 0] (ReLU) or gy.  part[(blk*2+{0,1})*c + ch]
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(long long rows, int c, float eps, const float *__restrict__ gy, const float *__restrict__ y, const float *__restrict__ z,
+                     const float *__restrict__ mean, const float *__restrict__ var, int relu, float *__restrict__ part) {
+    __shared__ float4 red[2][256];
+    const int cvec = c >> 2, rl = 256 / cvec;
+    const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
+    const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const long long rbeg = blockIdx.x * chunk, rend = min(rows, rbeg + chunk);
+    const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean) + cv);
+    const float4 vv = __ldg(reinterpret_cast<const float4 *>(var) + cv);
+    const float4 is = make_float4(rsqrtf(vv.x + eps), rsqrtf(vv.y + eps), rsqrtf(vv.z + eps), rsqrtf(vv.w + eps));
+    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sz = sg;
+    if (rlane < rl) {
+        for (long long r = rbeg + rlane; r < rend; r += rl) {
+            const size_t o = static_cast<size_t>(r) * cvec + cv;
+            float4 g = __ldg(reinterpret_cast<const float4 *>(gy) + o);
+            const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
+            if (relu) {
+                const float4 yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
+                g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+            }
+            sg.x += g.x; sg.y += g.y; sg.z += g.z; sg.w += g.w;
+            sz.x = fmaf(g.x, (zz.x - mu.x) * is.x, sz.x);
+            sz.y = fmaf(g.y, (zz.y - mu.y) * is.y, sz.y);
+            sz.z = fmaf(g.z, (zz.z - mu.z) * is.z, sz.z);
+            sz.w = fmaf(g.w, (zz.w - mu.w) * is.w, sz.w);
+        }
+    }
+    red[0][threadIdx.x] = sg;
+    red[1][threadIdx.x] = sz;
+    __syncthreads();
+    if (threadIdx.x < 2 * cvec) {
+        const int which = threadIdx.x / cvec, v = threadIdx.x - which * cvec;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < rl; ++l) {
+            const float4 t = red[which][l * cvec + v];
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        reinterpret_cast<float4 *>(part + (static_cast<size_t>(blockIdx.x) * 2 + which) * c)[v] = s;
+    }
+}
+
+// sums[2][c] (sum g, sum g*zhat) -> dbeta, dgamma, coef2 = {s = gamma*istd, k1 = mean(g), k2 = mean(g*zhat)}
+__global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const float *__restrict__ sums, const float *__restrict__ gamma,
+                                       const float *__restrict__ var, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef2) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    dbeta[ch] = sums[ch];
+    dgamma[ch] = sums[c + ch];
+    coef2[ch] = gamma[ch] * rsqrtf(var[ch] + eps);
+    coef2[c + ch] = static_cast<float>(static_cast<double>(sums[ch]) * inv_rows);
+    coef2[2 * c + ch] = static_cast<float>(static_cast<double>(sums[c + ch]) * inv_rows);
+}
+
+__global__ void bn_bwd_apply_kernel(long long n4, int c, float eps, const float *__restrict__ gy, const float *__restrict__ y, const float *__restrict__ z,
+                                    const float *__restrict__ mean, const float *__restrict__ var, const float *__restrict__ coef2, int relu,
+                                    float *__restrict__ dz) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n4) return;
+    const int ch = static_cast<int>((e * 4) % c);
+    float4 g = __ldg(reinterpret_cast<const float4 *>(gy) + e);
+    const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + e);
+    if (relu) {
+        const float4 yy = __ldg(reinterpret_cast<const float4 *>(y) + e);
+        g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+    }
+    const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean + ch));
+    const float4 vv = __ldg(reinterpret_cast<const float4 *>(var + ch));
+    const float4 s = __ldg(reinterpret_cast<const float4 *>(coef2 + ch));
+    const float4 k1 = __ldg(reinterpret_cast<const float4 *>(coef2 + c + ch));
+    const float4 k2 = __ldg(reinterpret_cast<const float4 *>(coef2 + 2 * c + ch));
+    float4 o;
+    o.x = s.x * (g.x - k1.x - (zz.x - mu.x) * rsqrtf(vv.x + eps) * k2.x);
+    o.y = s.y * (g.y - k1.y - (zz.y - mu.y) * rsqrtf(vv.y + eps) * k2.y);
+    o.z = s.z * (g.z - k1.z - (zz.z - mu.z) * rsqrtf(vv.z + eps) * k2.z);
+    o.w = s.w * (g.w - k1.w - (zz.w - mu.w) * rsqrtf(vv.w + eps) * k2.w);
+    reinterpret_cast<float4 *>(dz)[e] = o;
+}
+
+// dW partials.  CTA (bx, by): rows [bx*rows_per_cta, ...), weight block (ib, jb) = (by % nib, by / nib) of cin_t x cout_t.
+// 256 threads = TI x TJ x KQ, each holding an 8x8 block (two 4-wide halves per side so that a warp's LDS.128 are
+// contiguous); the KQ groups take alternate staged rows and write separate partials.
+// partW[(bx*KQ+kq)][cin][cout], partB[(bx*KQ+kq)][cout] (column sums of dz, written by the ib == 0, ti == 0 threads).
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(long long rows, int cin, int cout, int cin_t, int cout_t, long long rows_per_cta, const float *__restrict__ x,
+                  const float *__restrict__ dz, float *__restrict__ partW, float *__restrict__ partB) {
+    extern __shared__ __align__(16) float sm[];
+    float *xs = sm;                     // [kWgKC][cin_t]
+    float *ds = sm + kWgKC * cin_t;     // [kWgKC][cout_t]
+    const int nib = (cin + cin_t - 1) / cin_t;
+    const int ib = blockIdx.y % nib, jb = blockIdx.y / nib;
+    const int TI = cin_t >> 3, TJ = cout_t >> 3, KQ = 256 / (TI * TJ);
+    const int ti = threadIdx.x % TI, tj = (threadIdx.x / TI) % TJ, kq = threadIdx.x / (TI * TJ);
+    const long long rbeg = blockIdx.x * rows_per_cta, rend = min(rows, rbeg + rows_per_cta);
+    float acc[8][8];
+    float accb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        accb[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    }
+    const int hi = cin_t >> 1, hj = cout_t >> 1;
+    const bool vec_x = (cin & 3) == 0;
+    for (long long r0 = rbeg; r0 < rend; r0 += kWgKC) {
+        __syncthreads();
+        if (vec_x) {
+            const int v = cin_t >> 2;
+            for (int e = threadIdx.x; e < kWgKC * v; e += 256) {
+                const int r = e / v, cq = e - r * v;
+                const long long row = r0 + r;
+                const int ch = ib * cin_t + cq * 4;
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < rend && ch < cin) val = __ldg(reinterpret_cast<const float4 *>(x + row * cin + ch));
+                reinterpret_cast<float4 *>(xs)[e] = val;
+            }
+        } else {
+            for (int e = threadIdx.x; e < kWgKC * cin_t; e += 256) {
+                const int r = e / cin_t, cq = e - r * cin_t;
+                const long long row = r0 + r;
+                const int ch = ib * cin_t + cq;
+                xs[e] = (row < rend && ch < cin) ? __ldg(x + row * cin + ch) : 0.0f;
+            }
+        }
+        {
+            const int v = cout_t >> 2;
+            for (int e = threadIdx.x; e < kWgKC * v; e += 256) {
+                const int r = e / v, cq = e - r * v;
+                const long long row = r0 + r;
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < rend) val = __ldg(reinterpret_cast<const float4 *>(dz + row * cout + jb * cout_t + cq * 4));
+                reinterpret_cast<float4 *>(ds)[e] = val;
+            }
+        }
+        __syncthreads();
+        if (kq < KQ) {
+            for (int r = kq; r < kWgKC; r += KQ) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(xs + r * cin_t + ti * 4);
+                const float4 a1 = *reinterpret_cast<const float4 *>(xs + r * cin_t + hi + ti * 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(ds + r * cout_t + tj * 4);
+                const float4 b1 = *reinterpret_cast<const float4 *>(ds + r * cout_t + hj + tj * 4);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) accb[j] += b[j];
+            }
+        }
+    }
+    if (kq >= KQ) return;
+    const size_t p = static_cast<size_t>(blockIdx.x) * KQ + kq;
+    float *pw = partW + p * cin * cout;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int ci = ib * cin_t + (i < 4 ? ti * 4 + i : hi + ti * 4 + i - 4);
+        if (ci >= cin) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int cj = jb * cout_t + (half ? hj : 0) + tj * 4;
+            *reinterpret_cast<float4 *>(pw + static_cast<size_t>(ci) * cout + cj) =
+                make_float4(acc[i][half * 4], acc[i][half * 4 + 1], acc[i][half * 4 + 2], acc[i][half * 4 + 3]);
+        }
+    }
+    if (ib == 0 && ti == 0) {
+        float *pb = partB + p * cout;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int cj = jb * cout_t + (half ? hj : 0) + tj * 4;
+            *reinterpret_cast<float4 *>(pb + cj) = make_float4(accb[half * 4], accb[half * 4 + 1], accb[half * 4 + 2], accb[half * 4 + 3]);
+        }
+    }
+}
+
+// dx[rows x 3] = dz[rows x cout] * W[3 x cout]^T  (first layer of the descriptor: the gradient continues into the rotation)
+__global__ void conv_dgrad3_kernel(long long rows, int cout, const float *__restrict__ dz, const float *__restrict__ W, float *__restrict__ dx) {
+    extern __shared__ float ws[];  // [3][cout]
+    for (int e = threadIdx.x; e < 3 * cout; e += blockDim.x) ws[e] = W[e];
+    __syncthreads();
+    const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float4 *p = reinterpret_cast<const float4 *>(dz + r * cout);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = 0; k < cout / 4; ++k) {
+        const float4 v = __ldg(p + k);
+        const float *w0 = ws + 4 * k, *w1 = ws + cout + 4 * k, *w2 = ws + 2 * cout + 4 * k;
+        a0 = fmaf(v.x, w0[0], a0); a0 = fmaf(v.y, w0[1], a0); a0 = fmaf(v.z, w0[2], a0); a0 = fmaf(v.w, w0[3], a0);
+        a1 = fmaf(v.x, w1[0], a1); a1 = fmaf(v.y, w1[1], a1); a1 = fmaf(v.z, w1[2], a1); a1 = fmaf(v.w, w1[3], a1);
+        a2 = fmaf(v.x, w2[0], a2); a2 = fmaf(v.y, w2[1], a2); a2 = fmaf(v.z, w2[2], a2); a2 = fmaf(v.w, w2[3], a2);
+    }
+    dx[r * 3] = a0;
+    dx[r * 3 + 1] = a1;
+    dx[r * 3 + 2] = a2;
+}
+
+__global__ void transpose_kernel(int r, int c, const float *__restrict__ in, float *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r * c) return;
+    const int i = e / c, j = e - i * c;
+    out[j * r + i] = in[e];
+}
+
+static int pick_ct(int cout) { return cout % 128 == 0 ? 8 : cout % 64 == 0 ? 4 : cout % 32 == 0 ? 2 : cout % 16 == 0 ? 1 : 0; }
+
+static int launch_conv_fwd(long long rows, int cin, int cout, const float *x, const float *W, const float *bias, float *z, float *part,
+                           cudaStream_t st) {
+    const int ct = pick_ct(cout);
+    if (!ct) return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train: output channels must be a multiple of 16");
+    const long long tiles = (rows + kTileRows - 1) / kTileRows;
+    const int nc = 16 * ct;
+    const size_t smem = (static_cast<size_t>(cin) * kLdT + 2 * 16 * nc) * sizeof(float);
+    if (smem > 220 * 1024) return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train: input channels exceed the shared-memory tile (max 384)");
+    const dim3 grid(static_cast<unsigned>(tiles), cout / nc);
+    cudaError_t e = cudaSuccess;
+#define F3D_LAUNCH_FWD(CT)                                                                                              \
+    e = cudaFuncSetAttribute(conv_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+    if (e == cudaSuccess) conv_fwd_kernel<CT><<<grid, kMlpThreads, smem, st>>>(rows, cin, cout, x, W, bias, z, part);
+    switch (ct) {
+        case 8: F3D_LAUNCH_FWD(8) break;
+        case 4: F3D_LAUNCH_FWD(4) break;
+        case 2: F3D_LAUNCH_FWD(2) break;
+        default: F3D_LAUNCH_FWD(1) break;
+    }
+#undef F3D_LAUNCH_FWD
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "conv_bn_train: cudaFuncSetAttribute");
+    return check_launch("conv_fwd_kernel");
+}
+
+struct WgradPlan {
+    int cin_t, cout_t, kq, ny, gx;
+    long long rows_per_cta;
+    int nparts;
+};
+
+static WgradPlan plan_wgrad(long long rows, int cin, int cout) {
+    WgradPlan p;
+    p.cin_t = cin >= 128 ? 128 : cin >= 64 ? 64 : cin >= 32 ? 32 : cin >= 16 ? 16 : 8;
+    p.cout_t = cout >= 128 ? 128 : cout;  // cout is a multiple of 16 and, below 128, one of 16/32/64
+    while ((p.cin_t / 8) * (p.cout_t / 8) > 256) p.cout_t /= 2;
+    p.kq = 256 / ((p.cin_t / 8) * (p.cout_t / 8));
+    p.ny = ((cin + p.cin_t - 1) / p.cin_t) * (cout / p.cout_t);
+    long long gx = (rows + 4 * kWgKC - 1) / (4 * kWgKC);
+    const long long cap = (4 * 148 + p.ny - 1) / p.ny;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    p.rows_per_cta = ((rows + gx - 1) / gx + kWgKC - 1) / kWgKC * kWgKC;
+    p.gx = static_cast<int>((rows + p.rows_per_cta - 1) / p.rows_per_cta);
+    p.nparts = p.gx * p.kq;
+    return p;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace f3d
+
+using namespace f3d;
+
+F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int cout) {
+    if (rows <= 0 || cin <= 0 || cout <= 0) return 256;
+    const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
+    const size_t fwd = align256(tiles * 2 * cout * 4) + align256(2 * cout * 4) + align256(2 * cout * 4);
+    const WgradPlan p = plan_wgrad(rows, cin, cout);
+    const size_t bwd = align256(static_cast<size_t>(rows) * cout * 4)                       // dz
+                       + align256(static_cast<size_t>(kRedBlocks) * 2 * cout * 4)           // BN reduction partials
+                       + align256(2 * cout * 4) + align256(3 * cout * 4)                    // sums, coef2
+                       + align256(static_cast<size_t>(p.nparts) * cin * cout * 4)           // dW partials
+                       + align256(static_cast<size_t>(p.nparts) * cout * 4)                 // db partials
+                       + align256(static_cast<size_t>(cin) * cout * 4);                     // W^T
+    return (fwd > bwd ? fwd : bwd) + 256;
+}
+
+// x (rows,cin), W (cin,cout), bias/gamma/beta (cout) -> z (rows,cout) pre-BN, y (rows,cout) post BN(+ReLU), mean/var (cout)
+// = the batch moments (population variance) the caller feeds to the EMA update.
+F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
+                                      const float *gamma, const float *beta, int relu, float eps, float *z, float *y, float *mean,
+                                      float *var, void *workspace, size_t workspace_bytes, void *stream) {
+    if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !y || !mean || !var)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: bad arguments");
+    if (!workspace || workspace_bytes < f3d_conv_bn_train_workspace_bytes(rows, cin, cout))
+        return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "conv_bn_train_forward: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
+    char *w = static_cast<char *>(workspace);
+    float *part = reinterpret_cast<float *>(w);
+    w += align256(tiles * 2 * cout * 4);
+    float *sums = reinterpret_cast<float *>(w);
+    w += align256(2 * cout * 4);
+    float *coef = reinterpret_cast<float *>(w);
+    int rc = launch_conv_fwd(rows, cin, cout, x, W, bias, z, part, st);
+    if (rc) return rc;
+    partial_reduce_kernel<<<(2 * cout + 127) / 128, 128, 0, st>>>(static_cast<int>(tiles), 2 * cout, part, sums);
+    rc = check_launch("partial_reduce_kernel");
+    if (rc) return rc;
+    bn_stats_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, beta, mean, var, coef);
+    rc = check_launch("bn_stats_finalize_kernel");
+    if (rc) return rc;
+    const long long n4 = rows * cout / 4;
+    bn_apply_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(n4, cout, z, coef, relu, y);
+    return check_launch("bn_apply_kernel");
+}
+
+// gy (rows,cout) = dL/dy.  Outputs: dx (rows,cin; NULL to skip), dW (cin,cout), db, dgamma, dbeta (cout).
+F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
+                                       const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
+                                       const float *gy, float *dx, float *dW, float *db, float *dgamma, float *dbeta,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
+    if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !z || !y || !mean || !var || !gy || !dW || !db || !dgamma || !dbeta)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: bad arguments");
+    if (cout % 16 != 0 || 256 % (cout / 4) != 0)
+        return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_backward: output channels must be 16, 32, 64, 128, 256, 512 or 1024");
+    if (dx && cin != 3 && pick_ct(cin) == 0) return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_backward: dx needs cin == 3 or a multiple of 16");
+    if (!workspace || workspace_bytes < f3d_conv_bn_train_workspace_bytes(rows, cin, cout))
+        return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "conv_bn_train_backward: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const WgradPlan p = plan_wgrad(rows, cin, cout);
+    char *w = static_cast<char *>(workspace);
+    float *dz = reinterpret_cast<float *>(w);
+    w += align256(static_cast<size_t>(rows) * cout * 4);
+    float *part = reinterpret_cast<float *>(w);
+    w += align256(static_cast<size_t>(kRedBlocks) * 2 * cout * 4);
+    float *sums = reinterpret_cast<float *>(w);
+    w += align256(2 * cout * 4);
+    float *coef2 = reinterpret_cast<float *>(w);
+    w += align256(3 * cout * 4);
+    float *partW = reinterpret_cast<float *>(w);
+    w += align256(static_cast<size_t>(p.nparts) * cin * cout * 4);
+    float *partB = reinterpret_cast<float *>(w);
+    w += align256(static_cast<size_t>(p.nparts) * cout * 4);
+    float *Wt = reinterpret_cast<float *>(w);
+
+    const int nred = static_cast<int>(rows < kRedBlocks ? rows : kRedBlocks);
+    bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, gy, y, z, mean, var, relu, part);
+    int rc = check_launch("bn_bwd_reduce_kernel");
+    if (rc) return rc;
+    partial_reduce_kernel<<<(2 * cout + 127) / 128, 128, 0, st>>>(nred, 2 * cout, part, sums);
+    rc = check_launch("partial_reduce_kernel");
+    if (rc) return rc;
+    bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2);
+    rc = check_launch("bn_bwd_finalize_kernel");
+    if (rc) return rc;
+    const long long n4 = rows * cout / 4;
+    bn_bwd_apply_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(n4, cout, eps, gy, y, z, mean, var, coef2, relu, dz);
+    rc = check_launch("bn_bwd_apply_kernel");
+    if (rc) return rc;
+
+    const size_t smem = static_cast<size_t>(kWgKC) * (p.cin_t + p.cout_t) * sizeof(float);
+    conv_wgrad_kernel<<<dim3(p.gx, p.ny), 256, smem, st>>>(rows, cin, cout, p.cin_t, p.cout_t, p.rows_per_cta, x, dz, partW, partB);
+    rc = check_launch("conv_wgrad_kernel");
+    if (rc) return rc;
+    const long long nw = static_cast<long long>(cin) * cout;
+    partial_reduce_kernel<<<static_cast<unsigned>((nw + 127) / 128), 128, 0, st>>>(p.nparts, nw, partW, dW);
+    rc = check_launch("partial_reduce_kernel");
+    if (rc) return rc;
+    partial_reduce_kernel<<<(cout + 127) / 128, 128, 0, st>>>(p.nparts, cout, partB, db);
+    rc = check_launch("partial_reduce_kernel");
+    if (rc) return rc;
+    if (dx) {
+        if (cin == 3) {
+            conv_dgrad3_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 3 * cout * sizeof(float), st>>>(rows, cout, dz, W, dx);
+            rc = check_launch("conv_dgrad3_kernel");
+        } else {
+            transpose_kernel<<<(cin * cout + 255) / 256, 256, 0, st>>>(cin, cout, W, Wt);
+            rc = check_launch("transpose_kernel");
+            if (rc) return rc;
+            rc = launch_conv_fwd(rows, cout, cin, dz, Wt, nullptr, dx, nullptr, st);
+        }
+    }
+    return rc;
+}

@@ -14,9 +14,66 @@ import torch.nn.functional as F
 
 BN_EPS = 1e-3   # layers.py:271
 BN_DECAY = 0.9  # layers.py:251 (bn_decay=None everywhere in the model)
+FUSED_TRAINING = True  # training-mode conv+BN(+ReLU) through csrc/train_layers.cu (False: the op-by-op torch statement)
 
 relu = torch.relu
 softplus = F.softplus
+
+
+def _native():
+    import importlib
+    return importlib.import_module(("3dfeatnet_b200." if __name__.split(".")[0] == "3dfeatnet_b200" else "") + "_lib")
+
+
+class _ConvBnTrain(torch.autograd.Function):
+    """conv 1x1 + bias + batch-norm with BATCH statistics + optional ReLU as one differentiable CUDA op
+    (csrc/train_layers.cu).  Returns (y, batch_mean, batch_var); the moments are not differentiable outputs (they only
+    feed the EMA shadows).  Saves x, z (pre-BN) and y for the backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, use_relu):
+        _lib = _native()
+        L = _lib.lib()
+        x2, w2 = x.detach().contiguous().float(), w.detach().contiguous().float()
+        b2, g2, be2 = b.detach().contiguous().float(), gamma.detach().contiguous().float(), beta.detach().contiguous().float()
+        _lib.require_cuda(x2, w2, b2, g2, be2)
+        rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
+        nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
+        z = torch.empty((rows, cout), dtype=torch.float32, device=x2.device)
+        y = torch.empty_like(z)
+        mean = torch.empty(cout, dtype=torch.float32, device=x2.device)
+        var = torch.empty_like(mean)
+        _lib.check(L.f3d_conv_bn_train_forward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g2), _lib.ptr(be2),
+                                               int(use_relu), BN_EPS, _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var),
+                                               _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_forward")
+        ctx.save_for_backward(x2, w2, g2, z, y, mean, var)
+        ctx.use_relu = bool(use_relu)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _gv):
+        _lib = _native()
+        L = _lib.lib()
+        x2, w2, g2, z, y, mean, var = ctx.saved_tensors
+        rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
+        gy = gy.contiguous().float()
+        nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w2)
+        db, dg, dbe = (torch.empty(cout, dtype=torch.float32, device=x2.device) for _ in range(3))
+        _lib.check(L.f3d_conv_bn_train_backward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(z), _lib.ptr(y),
+                                                _lib.ptr(mean), _lib.ptr(var), int(ctx.use_relu), BN_EPS, _lib.ptr(gy),
+                                                _lib.ptr(dx) if dx is not None else None, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dg),
+                                                _lib.ptr(dbe), _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_backward")
+        return dx, dw, db, dg, dbe, None
+
+
+def conv_bn_train(x, w, b, gamma, beta, use_relu=True):
+    """(rows,cin) x (cin,cout) -> (y (rows,cout), batch_mean, batch_var): the training-mode layer as one CUDA op."""
+    return _ConvBnTrain.apply(x, w, b, gamma, beta, use_relu)
 
 
 def batch_norm_template(inputs, is_training, scope, moments_dims, bn_decay, params, new_stats=None):
@@ -62,6 +119,17 @@ def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', acti
     if w.shape[-1] != num_outputs or w.shape[-2] != inputs.shape[-1]:
         raise ValueError("conv2d: weight shape %s does not match (%d -> %d)"
                          % (tuple(w.shape), inputs.shape[-1], num_outputs))
+    if (bn and is_training and inputs.is_cuda and FUSED_TRAINING and (activation is relu or activation is None)
+            and num_outputs % 16 == 0 and num_outputs & (num_outputs - 1) == 0):
+        # training mode on the GPU: conv + bias + batch-statistics BN + ReLU, forward and backward, in csrc/train_layers.cu
+        y, mean, var = conv_bn_train(inputs.reshape(-1, inputs.shape[-1]), w.reshape(w.shape[-2], w.shape[-1]), b,
+                                     params[scope + "/bn/gamma"], params[scope + "/bn/beta"], activation is relu)
+        if new_stats is not None:
+            decay = bn_decay if bn_decay is not None else BN_DECAY
+            mm, mv = params[scope + "/bn/moving_mean"], params[scope + "/bn/moving_variance"]
+            new_stats[scope + "/bn/moving_mean"] = (mm - (1 - decay) * (mm - mean)).detach()
+            new_stats[scope + "/bn/moving_variance"] = (mv - (1 - decay) * (mv - var)).detach()
+        return y.reshape(*inputs.shape[:-1], num_outputs)
     net = torch.matmul(inputs, w.reshape(w.shape[-2], w.shape[-1])) + b
     if bn:
         net = batch_norm_for_conv2d(net, bool(is_training), bn_decay, scope + "/bn", params, new_stats)

@@ -154,6 +154,22 @@ int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_r
 
 /* ---------------------------------------------------------------- training step --------------- */
 
+/* conv2d(..., bn=True, is_training=True)  models/layers.py:11-46 + batch_norm_template :225-272, 1x1 kernels, channels
+ * last: x (rows,cin), W (cin,cout), bias/gamma/beta (cout) -> z = x W + bias (rows,cout), batch moments mean/var (cout,
+ * population variance, what the caller feeds the EMA update), y = [relu](gamma (z-mean) rsqrt(var+eps) + beta).
+ * cout a multiple of 16.  workspace: f3d_conv_bn_train_workspace_bytes(rows,cin,cout) (covers forward and backward). */
+size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int cout);
+int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
+                              const float *gamma, const float *beta, int relu, float eps, float *z, float *y, float *mean,
+                              float *var, void *workspace, size_t workspace_bytes, void *stream);
+/* The gradient TensorFlow derives for the layer above: gy = dL/dy (rows,cout) -> dx (rows,cin; NULL = not needed),
+ * dW (cin,cout), db, dgamma, dbeta (cout), through the batch statistics.  cout a power of two in 16..1024; dx needs
+ * cin == 3 or a multiple of 16.  Fixed-order reductions: bit-reproducible. */
+int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
+                               const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
+                               const float *gy, float *dx, float *dW, float *db, float *dgamma, float *dbeta,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 /* Feat3dNet.get_loss  models/feat3dnet.py:315-357 (+ pairwise_dist, models/layers.py:49-62): attention-weighted
  * triplet loss over anchor / positive / negative descriptors fa, fp, fn (b,m,f) and anchor attention att (b,m; NULL =
  * uniform 1/m weights, the Attention=False branch).  loss: 1 float.  When dfa, dfp, dfn are non-NULL the same call

@@ -104,3 +104,56 @@ def test_triplet_loss_rejects_bad_arguments(cuda):
     L = _lib.lib()
     assert L.f3d_triplet_loss(0, 4, 4, 0.2, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
     assert L.f3d_adam_step(0, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+
+
+def plain_conv_bn(x, w, b, gamma, beta, use_relu):
+    z = x @ w + b
+    mean, var = z.mean(0), z.var(0, unbiased=False)
+    y = (z - mean) * torch.rsqrt(var + 1e-3) * gamma + beta
+    return (torch.relu(y) if use_relu else y), mean, var
+
+
+@pytest.mark.parametrize("rows,cin,cout,use_relu", [(8192 + 37, 3, 64, True), (5000, 64, 128, True), (4096, 128, 256, True),
+                                                    (777, 256, 128, True), (1000, 128, 64, True), (3000, 3, 32, True),
+                                                    (3000, 32, 64, True), (3000, 128, 128, False), (999, 128, 32, False),
+                                                    (1, 64, 16, True), (130, 16, 16, True)])
+def test_conv_bn_train_forward_backward(cuda, rows, cin, cout, use_relu):
+    """The training-mode layer (reference layers.py:11-46,225-272) against its fp64 torch statement + autograd."""
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(rows + cin * 7 + cout)
+    x = torch.randn(rows, cin, generator=g) * 0.7 + 0.1
+    w = torch.randn(cin, cout, generator=g) * (2.0 / cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    gamma = 1.0 + 0.2 * torch.randn(cout, generator=g)
+    beta = 0.1 * torch.randn(cout, generator=g)
+    gy = torch.randn(rows, cout, generator=g)
+    ins = [t.to(cuda).requires_grad_(True) for t in (x, w, b, gamma, beta)]
+    y, mean, var = layers.conv_bn_train(*ins, use_relu)
+    grads = torch.autograd.grad((y * gy.to(cuda)).sum(), ins)
+    ins64 = [t.double().requires_grad_(True) for t in (x, w, b, gamma, beta)]
+    ry, rmean, rvar = plain_conv_bn(*ins64, use_relu)
+    rgrads = torch.autograd.grad((ry * gy.double()).sum(), ins64)
+    assert torch.allclose(mean.cpu().double(), rmean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(var.cpu().double(), rvar, rtol=1e-4, atol=1e-7)
+    if rows > 1:
+        assert (y.detach().cpu().double() - ry).abs().max().item() < 2e-5 * max(1.0, ry.abs().max().item())
+    for name, a, r in zip(("dx", "dW", "db", "dgamma", "dbeta"), grads, rgrads):
+        if name == "db":      # the bias in front of a batch-norm has a mathematically zero gradient: only rounding noise
+            assert a.abs().max().item() < 1e-3 * (rgrads[1].abs().max().item() + 1e-6)
+            continue
+        scale = r.abs().max().item() + 1e-9
+        assert (a.cpu().double() - r).abs().max().item() < 2e-4 * scale + 1e-6, name
+
+
+def test_conv_bn_train_is_deterministic_and_skips_dx(cuda):
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(20000, 64, generator=g).to(cuda)
+    w, b, ga, be = (t.to(cuda).requires_grad_(True) for t in (torch.randn(64, 128, generator=g) * 0.2, torch.zeros(128),
+                                                              torch.ones(128), torch.zeros(128)))
+    gy = torch.randn(20000, 128, generator=g).to(cuda)
+    runs = []
+    for _ in range(2):
+        y, _, _ = layers.conv_bn_train(x, w, b, ga, be, True)
+        runs.append(torch.autograd.grad((y * gy).sum(), [w, b, ga, be]))
+    assert all(torch.equal(a, c) for a, c in zip(*runs))
