@@ -103,69 +103,74 @@ loss_reduce_kernel(int nb, int m, float margin, const float *__restrict__ att, c
     }
 }
 
-// d fa[b,i,:] = 2 gw (fa - fp[k*]) / ties_p  summed over the tied k*  -  the same with the negatives
-__global__ void loss_grad_anchor_kernel(int m, int f, long long total, const float *__restrict__ fa, const float *__restrict__ fp,
-                                        const float *__restrict__ fn, const float *__restrict__ gw, const float *__restrict__ best_p,
-                                        const float *__restrict__ best_n, const int *__restrict__ arg_p, const int *__restrict__ arg_n,
-                                        const int *__restrict__ ties_p, const int *__restrict__ ties_n, float *__restrict__ dfa) {
-    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= total) return;
-    const long long bi = e / f;
-    const int c = static_cast<int>(e - bi * f);
-    const long long b = bi / m;
-    const float g = gw[bi];
-    const float av = fa[e];
-    float acc = 0.0f;
-    for (int side = 0; side < 2; ++side) {
-        const float *o = (side ? fn : fp) + b * m * f;
-        const int nt = (side ? ties_n : ties_p)[bi];
-        const float sgn = side ? -1.0f : 1.0f;
-        if (nt == 1) {
-            acc += sgn * 2.0f * g * (av - o[static_cast<size_t>((side ? arg_n : arg_p)[bi]) * f + c]);
-        } else {  // exact ties: every tied column gets an equal share (tf.reduce_min gradient)
-            const float bd = (side ? best_n : best_p)[bi];
-            const float *a = fa + bi * f;
-            for (int k = 0; k < m; ++k) {
-                float d = 0.0f;
-                for (int cc = 0; cc < f; ++cc) {
-                    const float df = a[cc] - o[static_cast<size_t>(k) * f + cc];
-                    d += df * df;
-                }
-                if (d == bd) acc += sgn * 2.0f * g * (av - o[static_cast<size_t>(k) * f + c]) / static_cast<float>(nt);
+// d fa[b,i,:] (+)= sgn * 2 gw_i / ties_i * sum over the tied arg-min columns k of (fa_i - fo_k).  One warp per anchor replays
+// the scan of loss_min_kernel (same arithmetic => `d == best` is exact) and records the tied columns as a bitmask
+// sel[b,i,k/32] for the column-side kernel.
+__global__ void __launch_bounds__(kLossThreads)
+loss_grad_anchor_kernel(int m, int f, float sgn, int accumulate, const float *__restrict__ fa, const float *__restrict__ fo,
+                        const float *__restrict__ gw, const float *__restrict__ best, const int *__restrict__ ties,
+                        unsigned *__restrict__ sel, float *__restrict__ dfa) {
+    extern __shared__ float so[];  // [m][f+1]
+    const int b = blockIdx.y;
+    const float *o = fo + static_cast<size_t>(b) * m * f;
+    for (int e = threadIdx.x; e < m * f; e += blockDim.x) so[(e / f) * (f + 1) + e % f] = o[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= m) return;
+    const size_t bi = static_cast<size_t>(b) * m + i;
+    const float *a = fa + bi * f;
+    const float bd = best[bi];
+    const int words = (m + 31) >> 5;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < m; k0 += 32) {
+        const int k = k0 + lane;
+        bool tied = false;
+        if (k < m) {
+            float d = 0.0f;
+            for (int c = 0; c < f; ++c) {
+                const float df = a[c] - so[k * (f + 1) + c];
+                d += df * df;
+            }
+            tied = d == bd;
+        }
+        unsigned mask = __ballot_sync(kFull, tied);
+        if (lane == 0) sel[bi * words + (k0 >> 5)] = mask;
+        while (mask) {
+            const int kk = k0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = lane + 32 * q;
+                if (c < f) acc[q] += a[c] - so[kk * (f + 1) + c];
             }
         }
     }
-    dfa[e] = acc;
+    const float scale = sgn * 2.0f * gw[bi] / static_cast<float>(ties[bi]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = lane + 32 * q;
+        if (c < f) dfa[bi * f + c] = accumulate ? dfa[bi * f + c] + scale * acc[q] : scale * acc[q];
+    }
 }
 
-// d fo[b,k,:] = -sign * sum over anchors i that selected column k (ascending i) of 2 gw_i (fa_i - fo_k) / ties_i
+// d fo[b,k,:] = -sgn * sum over the anchors i that selected column k (ascending i) of 2 gw_i (fa_i - fo_k) / ties_i
 __global__ void loss_grad_other_kernel(int m, int f, long long total, float sgn, const float *__restrict__ fa, const float *__restrict__ fo,
-                                       const float *__restrict__ gw, const float *__restrict__ best, const int *__restrict__ arg,
-                                       const int *__restrict__ ties, float *__restrict__ dfo) {
+                                       const float *__restrict__ gw, const int *__restrict__ ties, const unsigned *__restrict__ sel,
+                                       float *__restrict__ dfo) {
     const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const long long bk = e / f;
     const int c = static_cast<int>(e - bk * f);
     const long long b = bk / m;
     const int k = static_cast<int>(bk - b * m);
+    const int words = (m + 31) >> 5;
     const float ov = fo[e];
-    const float *ob = fo + bk * f;
     float acc = 0.0f;
     for (int i = 0; i < m; ++i) {
         const long long bi = b * m + i;
-        const int nt = ties[bi];
-        bool sel = false;
-        if (nt == 1) sel = arg[bi] == k;
-        else {
-            const float *a = fa + bi * f;
-            float d = 0.0f;
-            for (int cc = 0; cc < f; ++cc) {
-                const float df = a[cc] - ob[cc];
-                d += df * df;
-            }
-            sel = d == best[bi];
-        }
-        if (sel) acc -= sgn * 2.0f * gw[bi] * (fa[bi * f + c] - ov) / static_cast<float>(nt);
+        if ((__ldg(sel + bi * words + (k >> 5)) >> (k & 31)) & 1u)
+            acc -= sgn * 2.0f * gw[bi] * (fa[bi * f + c] - ov) / static_cast<float>(ties[bi]);
     }
     dfo[e] = acc;
 }
@@ -208,7 +213,7 @@ using namespace f3d;
 
 F3D_API size_t f3d_triplet_loss_workspace_bytes(int b, int m) {
     if (b <= 0 || m <= 0) return 256;
-    return static_cast<size_t>(b) * m * (4 * 2 + 4 * 2 + 4 * 2 + 4) + static_cast<size_t>(b) * 4 + 256;
+    return static_cast<size_t>(b) * m * (4 * 2 + 4 * 2 + 4 * 2 + 4) + static_cast<size_t>(b) * 4 + 2 * static_cast<size_t>(b) * m * ((m + 31) / 32) * 4 + 256;
 }
 
 // Forward: loss (1 float).  Backward pieces are produced in the same call when the d* pointers are non-NULL (they are the
@@ -240,15 +245,22 @@ F3D_API int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa,
     rc = check_launch("loss_mean_kernel");
     if (rc) return rc;
     if (dfa && dfp && dfn) {
-        const long long total = static_cast<long long>(bm) * f;
-        const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-        loss_grad_anchor_kernel<<<blocks, 256, 0, st>>>(m, f, total, fa, fp, fn, gw, best_p, best_n, arg_p, arg_n, ties_p, ties_n, dfa);
+        if (f > 128) return fail(F3D_ERR_UNSUPPORTED, "triplet_loss: the gradient supports descriptors of up to 128 dimensions");
+        unsigned *sel_p = reinterpret_cast<unsigned *>(ties_n + bm), *sel_n = sel_p + bm * ((m + 31) / 32);
+        e = cudaFuncSetAttribute(loss_grad_anchor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "triplet_loss: cudaFuncSetAttribute");
+        loss_grad_anchor_kernel<<<grid, kLossThreads, smem, st>>>(m, f, 1.0f, 0, fa, fp, gw, best_p, ties_p, sel_p, dfa);
         rc = check_launch("loss_grad_anchor_kernel");
         if (rc) return rc;
-        loss_grad_other_kernel<<<blocks, 256, 0, st>>>(m, f, total, 1.0f, fa, fp, gw, best_p, arg_p, ties_p, dfp);
+        loss_grad_anchor_kernel<<<grid, kLossThreads, smem, st>>>(m, f, -1.0f, 1, fa, fn, gw, best_n, ties_n, sel_n, dfa);
+        rc = check_launch("loss_grad_anchor_kernel");
+        if (rc) return rc;
+        const long long total = static_cast<long long>(bm) * f;
+        const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+        loss_grad_other_kernel<<<blocks, 256, 0, st>>>(m, f, total, 1.0f, fa, fp, gw, ties_p, sel_p, dfp);
         rc = check_launch("loss_grad_other_kernel");
         if (rc) return rc;
-        loss_grad_other_kernel<<<blocks, 256, 0, st>>>(m, f, total, -1.0f, fa, fn, gw, best_n, arg_n, ties_n, dfn);
+        loss_grad_other_kernel<<<blocks, 256, 0, st>>>(m, f, total, -1.0f, fa, fn, gw, ties_n, sel_n, dfn);
         rc = check_launch("loss_grad_other_kernel");
         if (rc) return rc;
     }

@@ -100,13 +100,23 @@ conv_fwd_kernel(long long rows, int cin, int cout, const float *__restrict__ x, 
     }
 }
 
-// out[w] = sum over parts p (ascending) of part[p*width + w], accumulated in fp64.  One thread per w.
-__global__ void partial_reduce_kernel(int nparts, long long width, const float *__restrict__ part, float *__restrict__ out) {
-    const long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (w >= width) return;
+// out[w] = sum over the parts of part[p*width + w] in fp64 and a fixed order: 32 slices (p mod 32) per column, each
+// ascending, then the slices ascending.  Block = 32 columns x 32 slices.
+__global__ void __launch_bounds__(1024)
+partial_reduce_kernel(int nparts, long long width, const float *__restrict__ part, float *__restrict__ out) {
+    __shared__ double red[32][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const long long w = static_cast<long long>(blockIdx.x) * 32 + lane;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += static_cast<double>(part[static_cast<size_t>(p) * width + w]);
-    out[w] = static_cast<float>(s);
+    if (w < width)
+        for (int p = slice; p < nparts; p += 32) s += static_cast<double>(__ldg(part + static_cast<size_t>(p) * width + w));
+    red[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && w < width) {
+        double t = 0.0;
+        for (int k = 0; k < 32; ++k) t += red[k][lane];
+        out[w] = static_cast<float>(t);
+    }
 }
 
 // sums[2][c] -> mean, var (population), coef = {scale = gamma*rsqrt(var+eps), shift = beta - mean*scale}
@@ -334,6 +344,44 @@ __global__ void conv_dgrad3_kernel(long long rows, int cout, const float *__rest
     dx[r * 3 + 2] = a2;
 }
 
+// tf.reduce_max over the sample axis: x (groups, s, c) -> out (groups, c).  One thread per (group, 4 channels).
+__global__ void maxpool_fwd_kernel(long long groups, int s, int c4, const float *__restrict__ x, float *__restrict__ out) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= groups * c4) return;
+    const long long g = e / c4;
+    const int cv = static_cast<int>(e - g * c4);
+    const float4 *p = reinterpret_cast<const float4 *>(x) + g * s * c4 + cv;
+    float4 m = __ldg(p);
+    for (int k = 1; k < s; ++k) {
+        const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    reinterpret_cast<float4 *>(out)[e] = m;
+}
+
+// its gradient: dx = gout / (number of samples attaining the maximum) where x == max, else 0 (TensorFlow's _MinOrMaxGrad)
+__global__ void maxpool_bwd_kernel(long long groups, int s, int c4, const float *__restrict__ x, const float *__restrict__ mx,
+                                   const float *__restrict__ gout, float *__restrict__ dx) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= groups * c4) return;
+    const long long g = e / c4;
+    const int cv = static_cast<int>(e - g * c4);
+    const float4 *p = reinterpret_cast<const float4 *>(x) + g * s * c4 + cv;
+    float4 *q = reinterpret_cast<float4 *>(dx) + g * s * c4 + cv;
+    const float4 m = __ldg(reinterpret_cast<const float4 *>(mx) + e);
+    float4 go = __ldg(reinterpret_cast<const float4 *>(gout) + e);
+    int nx = 0, ny = 0, nz = 0, nw = 0;
+    for (int k = 0; k < s; ++k) {
+        const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
+        nx += v.x == m.x; ny += v.y == m.y; nz += v.z == m.z; nw += v.w == m.w;
+    }
+    go.x /= static_cast<float>(nx); go.y /= static_cast<float>(ny); go.z /= static_cast<float>(nz); go.w /= static_cast<float>(nw);
+    for (int k = 0; k < s; ++k) {
+        const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
+        q[static_cast<size_t>(k) * c4] = make_float4(v.x == m.x ? go.x : 0.f, v.y == m.y ? go.y : 0.f, v.z == m.z ? go.z : 0.f, v.w == m.w ? go.w : 0.f);
+    }
+}
+
 __global__ void transpose_kernel(int r, int c, const float *__restrict__ in, float *__restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= r * c) return;
@@ -429,7 +477,7 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
     float *coef = reinterpret_cast<float *>(w);
     int rc = launch_conv_fwd(rows, cin, cout, x, W, bias, z, part, st);
     if (rc) return rc;
-    partial_reduce_kernel<<<(2 * cout + 127) / 128, 128, 0, st>>>(static_cast<int>(tiles), 2 * cout, part, sums);
+    partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(tiles), 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
     bn_stats_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, beta, mean, var, coef);
@@ -473,7 +521,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, gy, y, z, mean, var, relu, part);
     int rc = check_launch("bn_bwd_reduce_kernel");
     if (rc) return rc;
-    partial_reduce_kernel<<<(2 * cout + 127) / 128, 128, 0, st>>>(nred, 2 * cout, part, sums);
+    partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(nred, 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
     bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2);
@@ -489,10 +537,10 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     rc = check_launch("conv_wgrad_kernel");
     if (rc) return rc;
     const long long nw = static_cast<long long>(cin) * cout;
-    partial_reduce_kernel<<<static_cast<unsigned>((nw + 127) / 128), 128, 0, st>>>(p.nparts, nw, partW, dW);
+    partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(p.nparts, nw, partW, dW);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
-    partial_reduce_kernel<<<(cout + 127) / 128, 128, 0, st>>>(p.nparts, cout, partB, db);
+    partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(p.nparts, cout, partB, db);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
     if (dx) {
@@ -507,4 +555,22 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
         }
     }
     return rc;
+}
+
+// tf.reduce_max(x, axis=[2]) of models/feat3dnet.py:138,147,182 on a channels-last (groups, s, c) tensor, c % 4 == 0.
+F3D_API int f3d_maxpool_samples_forward(long long groups, int s, int c, const float *x, float *out, void *stream) {
+    if (groups <= 0 || s <= 0 || c <= 0 || (c & 3) || !x || !out) return fail(F3D_ERR_INVALID_ARGUMENT, "maxpool_samples_forward: bad arguments");
+    const long long n = groups * (c / 4);
+    maxpool_fwd_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(groups, s, c / 4, x, out);
+    return check_launch("maxpool_fwd_kernel");
+}
+
+// gradient of the above: the samples that attain the maximum share gout equally.
+F3D_API int f3d_maxpool_samples_backward(long long groups, int s, int c, const float *x, const float *out, const float *gout, float *dx,
+                                         void *stream) {
+    if (groups <= 0 || s <= 0 || c <= 0 || (c & 3) || !x || !out || !gout || !dx)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "maxpool_samples_backward: bad arguments");
+    const long long n = groups * (c / 4);
+    maxpool_bwd_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(groups, s, c / 4, x, out, gout, dx);
+    return check_launch("maxpool_bwd_kernel");
 }

@@ -157,7 +157,7 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is
         new_points = conv2d(new_points, num_out_channel, [1, 1], stride=[1, 1], padding='VALID', bn=bn,
                             is_training=is_training, scope=scope + '/conv%d' % i, params=params, new_stats=new_stats)
 
-    pooled = new_points.amax(dim=2, keepdim=True)  # tf.reduce_max; amax shares the gradient among ties like TF
+    pooled = _layers.max_pool_samples(new_points)  # tf.reduce_max; the gradient is shared among ties like TF
     new_points = torch.cat((new_points, pooled.expand(-1, -1, new_points.shape[2], -1)), dim=3)
 
     for i, num_out_channel in enumerate(mlp2 or []):
@@ -166,7 +166,7 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is
                             is_training=is_training, scope=scope + '/conv_mid_%d' % i, bn_decay=bn_decay, activation=act,
                             params=params, new_stats=new_stats)
 
-    new_points = new_points.amax(dim=2, keepdim=True)
+    new_points = _layers.max_pool_samples(new_points)
 
     for i, num_out_channel in enumerate(mlp3 or []):
         act = _layers.relu if (final_relu or i < len(mlp3) - 1) else None
@@ -204,7 +204,7 @@ def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp
             (g,) = torch.autograd.grad(new_points, xyz, grad_outputs=new_points.detach(), retain_graph=True)
             end_points['gradients']['det']['mlp_{}'.format(i)] = g
 
-    new_points = new_points.amax(dim=2, keepdim=True)
+    new_points = _layers.max_pool_samples(new_points)
 
     for i, num_out_channel in enumerate(mlp2 or []):
         new_points = conv2d(new_points, num_out_channel, [1, 1], padding='VALID', stride=[1, 1], bn=use_bn,

@@ -71,6 +71,39 @@ class _ConvBnTrain(torch.autograd.Function):
         return dx, dw, db, dg, dbe, None
 
 
+class _MaxPoolSamples(torch.autograd.Function):
+    """tf.reduce_max over the sample axis of a (B,M,S,C) tensor with TensorFlow's tie-sharing gradient (csrc/train_layers.cu)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _lib = _native()
+        x4 = x.detach().contiguous().float()
+        _lib.require_cuda(x4)
+        b, m, s, c = x4.shape
+        out = torch.empty((b, m, 1, c), dtype=torch.float32, device=x4.device)
+        _lib.check(_lib.lib().f3d_maxpool_samples_forward(b * m, s, c, _lib.ptr(x4), _lib.ptr(out), _lib.stream()), "maxpool_samples_forward")
+        ctx.save_for_backward(x4, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        _lib = _native()
+        x4, out = ctx.saved_tensors
+        b, m, s, c = x4.shape
+        g = g.contiguous().float()
+        dx = torch.empty_like(x4)
+        _lib.check(_lib.lib().f3d_maxpool_samples_backward(b * m, s, c, _lib.ptr(x4), _lib.ptr(out), _lib.ptr(g), _lib.ptr(dx), _lib.stream()),
+                   "maxpool_samples_backward")
+        return dx
+
+
+def max_pool_samples(x):
+    """(B,M,S,C) -> (B,M,1,C): tf.reduce_max(x, axis=[2], keep_dims=True).  CUDA op when x is on the GPU and C % 4 == 0."""
+    if x.is_cuda and x.dim() == 4 and x.shape[3] % 4 == 0:
+        return _MaxPoolSamples.apply(x)
+    return x.amax(dim=2, keepdim=True)  # amax shares the gradient among ties like TF
+
+
 def conv_bn_train(x, w, b, gamma, beta, use_relu=True):
     """(rows,cin) x (cin,cout) -> (y (rows,cout), batch_mean, batch_var): the training-mode layer as one CUDA op."""
     return _ConvBnTrain.apply(x, w, b, gamma, beta, use_relu)

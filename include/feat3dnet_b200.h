@@ -170,6 +170,12 @@ int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x
                                const float *gy, float *dx, float *dW, float *db, float *dgamma, float *dbeta,
                                void *workspace, size_t workspace_bytes, void *stream);
 
+/* tf.reduce_max(new_points, axis=[2])  models/feat3dnet.py:138,147,182 on a channels-last (groups, s, c) tensor
+ * (c % 4 == 0) -> out (groups, c); and its gradient: samples attaining the maximum share gout equally (TF _MinOrMaxGrad). */
+int f3d_maxpool_samples_forward(long long groups, int s, int c, const float *x, float *out, void *stream);
+int f3d_maxpool_samples_backward(long long groups, int s, int c, const float *x, const float *out, const float *gout,
+                                 float *dx, void *stream);
+
 /* Feat3dNet.get_loss  models/feat3dnet.py:315-357 (+ pairwise_dist, models/layers.py:49-62): attention-weighted
  * triplet loss over anchor / positive / negative descriptors fa, fp, fn (b,m,f) and anchor attention att (b,m; NULL =
  * uniform 1/m weights, the Attention=False branch).  loss: 1 float.  When dfa, dfp, dfn are non-NULL the same call

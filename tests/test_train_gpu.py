@@ -157,3 +157,22 @@ def test_conv_bn_train_is_deterministic_and_skips_dx(cuda):
         y, _, _ = layers.conv_bn_train(x, w, b, ga, be, True)
         runs.append(torch.autograd.grad((y * gy).sum(), [w, b, ga, be]))
     assert all(torch.equal(a, c) for a, c in zip(*runs))
+
+
+@pytest.mark.parametrize("shape", [(3, 40, 64, 256), (2, 7, 64, 64), (1, 5, 1, 128), (2, 3, 50, 4)])
+def test_max_pool_samples_matches_reduce_max_and_shares_ties(cuda, shape):
+    """tf.reduce_max over the sample axis (reference feat3dnet.py:138,147,182): value and tie-sharing gradient vs torch.amax."""
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    x = torch.relu(x - 0.8)                       # many exact zeros => ties wherever a whole column is zero
+    x[:, :, 1::2] = x[:, :, 0::2][:, :, :x[:, :, 1::2].shape[2]]  # and duplicated samples (ball-query padding)
+    xc = x.to(cuda).requires_grad_(True)
+    go = torch.randn(shape[0], shape[1], 1, shape[3], generator=g)
+    out = layers.max_pool_samples(xc)
+    (dx,) = torch.autograd.grad((out * go.to(cuda)).sum(), [xc])
+    xr = x.clone().requires_grad_(True)
+    ref = xr.amax(dim=2, keepdim=True)
+    (rdx,) = torch.autograd.grad((ref * go).sum(), [xr])
+    assert torch.equal(out.cpu(), ref.detach())
+    assert torch.allclose(dx.cpu(), rdx, rtol=1e-6, atol=1e-7)

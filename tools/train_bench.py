@@ -1,7 +1,8 @@
 """Stage-2 training step at BASELINE.json configs[3] (C4): 6 triplets per GPU = 18 clouds x 4096 points, 512 clusters x 64
 samples, attention + rotation, BN batch statistics, triplet loss, backward, ONE flat-gradient all-reduce (NCCL), TF-1 Adam.
-The sampling / grouping operators are the CUDA kernels of this repository; the differentiable MLP layers are the unfused
-statement of models/layers.py (torch matmul + autograd) -- the fused training kernels are the next step.
+The sampling / grouping operators, the conv+BN+ReLU layers (forward and backward), the loss and Adam are the CUDA kernels of
+this repository (csrc/train_layers.cu, csrc/train.cu); pooling / concat / rotation glue is torch autograd.
+F3D_TRAIN_UNFUSED=1 times the op-by-op torch statement instead; F3D_TRAIN_PROFILE=1 prints the top kernels of one step.
 
     python tools/train_bench.py                      (1 GPU)
     torchrun --nproc-per-node N tools/train_bench.py (N GPUs)
@@ -19,6 +20,10 @@ B, N, M = 6, 4096, 512
 net = f3.Feat3dNet({'num_clusters': M}, device=dev, seed=0).train_mode()
 a, p, n = (torch.as_tensor(synth.make_batch(B, N, seed0=s + 100 * rank)).to(dev) for s in (1, 2, 3))
 torch.backends.cuda.matmul.allow_tf32 = False
+UNFUSED = os.environ.get("F3D_TRAIN_UNFUSED") == "1"
+if UNFUSED:
+    importlib.import_module("3dfeatnet_b200.models.layers").FUSED_TRAINING = False
+    net.param['fused_loss'] = False
 
 
 def step():
@@ -40,6 +45,11 @@ e.record(); torch.cuda.synchronize(); dist.barrier()
 ms = dist.max_over_ranks(s.elapsed_time(e), dev) / K
 if rank == 0:
     print(json.dumps(dict(workload="C4 stage-2 train step, 6 triplets/GPU x 4096 pts, 512 clusters x 64", n_gpus=world, ms_per_step=ms,
-                          steps_per_s=1e3 / ms, clouds_per_s=3 * B * world * 1e3 / ms, loss=float(loss),
-                          mlp_backend="torch autograd (unfused layers), CUDA sampling/grouping ops of this repo",
+                          steps_per_s=1e3 / ms, clouds_per_s=3 * B * world * 1e3 / ms, loss=float(loss.detach()),
+                          mlp_backend="torch matmul/autograd layers" if UNFUSED else "csrc/train_layers.cu + train.cu, torch glue",
                           peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)))
+if rank == 0 and os.environ.get("F3D_TRAIN_PROFILE") == "1":
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step(); torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
