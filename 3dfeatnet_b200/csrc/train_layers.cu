@@ -12,8 +12,8 @@
 //             dz = gamma istd (g - mean(g) - zhat mean(g zhat))     bn_bwd_apply_kernel
 //             dW = x^T dz, db = sum dz                              conv_wgrad_kernel (split over rows) + partial_reduce
 //             dx = dz W^T                                           conv_fwd_kernel on the transposed weights / dgrad3
-// Every reduction runs in a fixed order (no atomics): two runs give identical bits.  fp32 FFMA; the tensor-core
-// version of these contractions is future work.
+// Every reduction runs in a fixed order (no atomics): two runs give identical bits.  The three contractions run either as
+// the fp32 FFMA kernels of this file (precision 0) or on the tensor cores (precision 2, train_tc.cu).
 #include "mlp_tile.cuh"
 
 namespace f3d {
@@ -201,29 +201,51 @@ __global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const 
     coef2[2 * c + ch] = static_cast<float>(static_cast<double>(sums[c + ch]) * inv_rows);
 }
 
-__global__ void bn_bwd_apply_kernel(long long n4, int c, float eps, const float *__restrict__ gy, const float *__restrict__ y, const float *__restrict__ z,
-                                    const float *__restrict__ mean, const float *__restrict__ var, const float *__restrict__ coef2, int relu,
-                                    float *__restrict__ dz) {
-    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= n4) return;
-    const int ch = static_cast<int>((e * 4) % c);
-    float4 g = __ldg(reinterpret_cast<const float4 *>(gy) + e);
-    const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + e);
-    if (relu) {
-        const float4 yy = __ldg(reinterpret_cast<const float4 *>(y) + e);
-        g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+// dz = s (g - k1 - zhat k2) and, per row chunk, the column sums of dz (= the bias gradient): partB[blk*c + ch]
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(long long rows, int c, float eps, const float *__restrict__ gy, const float *__restrict__ y, const float *__restrict__ z,
+                    const float *__restrict__ mean, const float *__restrict__ var, const float *__restrict__ coef2, int relu,
+                    float *__restrict__ dz, float *__restrict__ partB) {
+    __shared__ float4 red[256];
+    const int cvec = c >> 2, rl = 256 / cvec;
+    const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
+    const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const long long rbeg = blockIdx.x * chunk, rend = min(rows, rbeg + chunk);
+    const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean) + cv);
+    const float4 vv = __ldg(reinterpret_cast<const float4 *>(var) + cv);
+    const float4 is = make_float4(rsqrtf(vv.x + eps), rsqrtf(vv.y + eps), rsqrtf(vv.z + eps), rsqrtf(vv.w + eps));
+    const float4 s = __ldg(reinterpret_cast<const float4 *>(coef2) + cv);
+    const float4 k1 = __ldg(reinterpret_cast<const float4 *>(coef2 + c) + cv);
+    const float4 k2 = __ldg(reinterpret_cast<const float4 *>(coef2 + 2 * c) + cv);
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rlane < rl) {
+        for (long long r = rbeg + rlane; r < rend; r += rl) {
+            const size_t o = static_cast<size_t>(r) * cvec + cv;
+            float4 g = __ldg(reinterpret_cast<const float4 *>(gy) + o);
+            const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
+            if (relu) {
+                const float4 yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
+                g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+            }
+            float4 d;
+            d.x = s.x * (g.x - k1.x - (zz.x - mu.x) * is.x * k2.x);
+            d.y = s.y * (g.y - k1.y - (zz.y - mu.y) * is.y * k2.y);
+            d.z = s.z * (g.z - k1.z - (zz.z - mu.z) * is.z * k2.z);
+            d.w = s.w * (g.w - k1.w - (zz.w - mu.w) * is.w * k2.w);
+            reinterpret_cast<float4 *>(dz)[o] = d;
+            sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
+        }
     }
-    const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean + ch));
-    const float4 vv = __ldg(reinterpret_cast<const float4 *>(var + ch));
-    const float4 s = __ldg(reinterpret_cast<const float4 *>(coef2 + ch));
-    const float4 k1 = __ldg(reinterpret_cast<const float4 *>(coef2 + c + ch));
-    const float4 k2 = __ldg(reinterpret_cast<const float4 *>(coef2 + 2 * c + ch));
-    float4 o;
-    o.x = s.x * (g.x - k1.x - (zz.x - mu.x) * rsqrtf(vv.x + eps) * k2.x);
-    o.y = s.y * (g.y - k1.y - (zz.y - mu.y) * rsqrtf(vv.y + eps) * k2.y);
-    o.z = s.z * (g.z - k1.z - (zz.z - mu.z) * rsqrtf(vv.z + eps) * k2.z);
-    o.w = s.w * (g.w - k1.w - (zz.w - mu.w) * rsqrtf(vv.w + eps) * k2.w);
-    reinterpret_cast<float4 *>(dz)[e] = o;
+    red[threadIdx.x] = sb;
+    __syncthreads();
+    if (threadIdx.x < cvec) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < rl; ++l) {
+            const float4 u = red[l * cvec + threadIdx.x];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        reinterpret_cast<float4 *>(partB + static_cast<size_t>(blockIdx.x) * c)[threadIdx.x] = t;
+    }
 }
 
 // dW partials.  CTA (bx, by): rows [bx*rows_per_cta, ...), weight block (ib, jb) = (by % nib, by / nib) of cin_t x cout_t.
@@ -389,6 +411,17 @@ __global__ void transpose_kernel(int r, int c, const float *__restrict__ in, flo
     out[j * r + i] = in[e];
 }
 
+// tensor-core versions of the three contractions (train_tc.cu)
+int lin_tc_kp(int k_real);
+bool lin_tc_supported(int k_real, int nout);
+size_t lin_tc_weight_bytes(int k_real, int nout);
+int lin_tc_grid(long long rows, int k_real);
+int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias, float *out,
+           float *part, uint8_t *wimg, cudaStream_t st);
+bool wgrad_tc_supported(int cin, int cout);
+void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta);
+int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st);
+
 static int pick_ct(int cout) { return cout % 128 == 0 ? 8 : cout % 64 == 0 ? 4 : cout % 32 == 0 ? 2 : cout % 16 == 0 ? 1 : 0; }
 
 static int launch_conv_fwd(long long rows, int cin, int cout, const float *x, const float *W, const float *bias, float *z, float *part,
@@ -447,14 +480,22 @@ using namespace f3d;
 F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int cout) {
     if (rows <= 0 || cin <= 0 || cout <= 0) return 256;
     const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
-    const size_t fwd = align256(tiles * 2 * cout * 4) + align256(2 * cout * 4) + align256(2 * cout * 4);
+    const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin));
+    const size_t wimg = lin_tc_weight_bytes(cin, cout) > lin_tc_weight_bytes(cout, cin) ? lin_tc_weight_bytes(cin, cout) : lin_tc_weight_bytes(cout, cin);
+    const size_t fwd = align256(stat_parts * 2 * cout * 4) + align256(2 * cout * 4) + align256(2 * cout * 4) + align256(wimg);
     const WgradPlan p = plan_wgrad(rows, cin, cout);
+    int tcg = 0;
+    long long tcper = 0;
+    wgrad_tc_plan(rows, &tcg, &tcper);
+    const size_t wparts = static_cast<size_t>(p.nparts > tcg ? p.nparts : tcg);
     const size_t bwd = align256(static_cast<size_t>(rows) * cout * 4)                       // dz
                        + align256(static_cast<size_t>(kRedBlocks) * 2 * cout * 4)           // BN reduction partials
                        + align256(2 * cout * 4) + align256(3 * cout * 4)                    // sums, coef2
-                       + align256(static_cast<size_t>(p.nparts) * cin * cout * 4)           // dW partials
-                       + align256(static_cast<size_t>(p.nparts) * cout * 4)                 // db partials
-                       + align256(static_cast<size_t>(cin) * cout * 4);                     // W^T
+                       + align256(wparts * cin * cout * 4)                                  // dW partials
+                       + align256(static_cast<size_t>(p.nparts) * cout * 4)                 // db partials (FFMA wgrad scratch)
+                       + align256(static_cast<size_t>(kRedBlocks) * cout * 4)               // db partials
+                       + align256(static_cast<size_t>(cin) * cout * 4)                      // W^T
+                       + align256(wimg);
     return (fwd > bwd ? fwd : bwd) + 256;
 }
 
@@ -462,22 +503,29 @@ F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int co
 // = the batch moments (population variance) the caller feeds to the EMA update.
 F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
                                       const float *gamma, const float *beta, int relu, float eps, float *z, float *y, float *mean,
-                                      float *var, void *workspace, size_t workspace_bytes, void *stream) {
+                                      float *var, int precision, void *workspace, size_t workspace_bytes, void *stream) {
     if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !y || !mean || !var)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: bad arguments");
+    if (precision != 0 && precision != 2) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: precision must be 0 (fp32) or 2 (bf16x3)");
+    if (cout % 4 != 0) return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_forward: output channels must be a multiple of 4");
     if (!workspace || workspace_bytes < f3d_conv_bn_train_workspace_bytes(rows, cin, cout))
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "conv_bn_train_forward: workspace too small");
     cudaStream_t st = as_stream(stream);
     const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
+    const bool tc = precision == 2 && lin_tc_supported(cin, cout);
+    const size_t nparts = tc ? static_cast<size_t>(2 * lin_tc_grid(rows, cin)) : tiles;
+    const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin));
     char *w = static_cast<char *>(workspace);
     float *part = reinterpret_cast<float *>(w);
-    w += align256(tiles * 2 * cout * 4);
+    w += align256(stat_parts * 2 * cout * 4);
     float *sums = reinterpret_cast<float *>(w);
     w += align256(2 * cout * 4);
     float *coef = reinterpret_cast<float *>(w);
-    int rc = launch_conv_fwd(rows, cin, cout, x, W, bias, z, part, st);
+    w += align256(2 * cout * 4);
+    uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
+    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, z, part, wimg, st) : launch_conv_fwd(rows, cin, cout, x, W, bias, z, part, st);
     if (rc) return rc;
-    partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(tiles), 2 * cout, part, sums);
+    partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(nparts), 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
     bn_stats_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, beta, mean, var, coef);
@@ -491,17 +539,26 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
 // gy (rows,cout) = dL/dy.  Outputs: dx (rows,cin; NULL to skip), dW (cin,cout), db, dgamma, dbeta (cout).
 F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
                                        const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
-                                       const float *gy, float *dx, float *dW, float *db, float *dgamma, float *dbeta,
+                                       const float *gy, float *dx, float *dW, float *db, float *dgamma, float *dbeta, int precision,
                                        void *workspace, size_t workspace_bytes, void *stream) {
     if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !z || !y || !mean || !var || !gy || !dW || !db || !dgamma || !dbeta)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: bad arguments");
+    if (precision != 0 && precision != 2) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: precision must be 0 (fp32) or 2 (bf16x3)");
     if (cout % 16 != 0 || 256 % (cout / 4) != 0)
         return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_backward: output channels must be 16, 32, 64, 128, 256, 512 or 1024");
-    if (dx && cin != 3 && pick_ct(cin) == 0) return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_backward: dx needs cin == 3 or a multiple of 16");
+    const bool tc_dgrad = precision == 2 && cin != 3 && lin_tc_supported(cout, cin);
+    if (dx && cin != 3 && !tc_dgrad && pick_ct(cin) == 0)
+        return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_backward: fp32 dx needs cin == 3 or a multiple of 16");
     if (!workspace || workspace_bytes < f3d_conv_bn_train_workspace_bytes(rows, cin, cout))
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "conv_bn_train_backward: workspace too small");
     cudaStream_t st = as_stream(stream);
     const WgradPlan p = plan_wgrad(rows, cin, cout);
+    int tcg = 0;
+    long long tcper = 0;
+    wgrad_tc_plan(rows, &tcg, &tcper);
+    const size_t wparts = static_cast<size_t>(p.nparts > tcg ? p.nparts : tcg);
+    const size_t wimg_bytes = lin_tc_weight_bytes(cin, cout) > lin_tc_weight_bytes(cout, cin) ? lin_tc_weight_bytes(cin, cout) : lin_tc_weight_bytes(cout, cin);
+    (void)wimg_bytes;
     char *w = static_cast<char *>(workspace);
     float *dz = reinterpret_cast<float *>(w);
     w += align256(static_cast<size_t>(rows) * cout * 4);
@@ -512,10 +569,14 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     float *coef2 = reinterpret_cast<float *>(w);
     w += align256(3 * cout * 4);
     float *partW = reinterpret_cast<float *>(w);
-    w += align256(static_cast<size_t>(p.nparts) * cin * cout * 4);
-    float *partB = reinterpret_cast<float *>(w);
+    w += align256(wparts * cin * cout * 4);
+    float *partB_scratch = reinterpret_cast<float *>(w);
     w += align256(static_cast<size_t>(p.nparts) * cout * 4);
+    float *partB = reinterpret_cast<float *>(w);
+    w += align256(static_cast<size_t>(kRedBlocks) * cout * 4);
     float *Wt = reinterpret_cast<float *>(w);
+    w += align256(static_cast<size_t>(cin) * cout * 4);
+    uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
 
     const int nred = static_cast<int>(rows < kRedBlocks ? rows : kRedBlocks);
     bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, gy, y, z, mean, var, relu, part);
@@ -527,26 +588,33 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2);
     rc = check_launch("bn_bwd_finalize_kernel");
     if (rc) return rc;
-    const long long n4 = rows * cout / 4;
-    bn_bwd_apply_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(n4, cout, eps, gy, y, z, mean, var, coef2, relu, dz);
+    bn_bwd_apply_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, gy, y, z, mean, var, coef2, relu, dz, partB);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;
-
-    const size_t smem = static_cast<size_t>(kWgKC) * (p.cin_t + p.cout_t) * sizeof(float);
-    conv_wgrad_kernel<<<dim3(p.gx, p.ny), 256, smem, st>>>(rows, cin, cout, p.cin_t, p.cout_t, p.rows_per_cta, x, dz, partW, partB);
-    rc = check_launch("conv_wgrad_kernel");
-    if (rc) return rc;
-    const long long nw = static_cast<long long>(cin) * cout;
-    partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(p.nparts, nw, partW, dW);
+    partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(nred, cout, partB, db);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
-    partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(p.nparts, cout, partB, db);
+
+    const long long nw = static_cast<long long>(cin) * cout;
+    if (precision == 2 && wgrad_tc_supported(cin, cout)) {
+        rc = wgrad_tc(rows, cin, cout, x, dz, partW, st);
+        if (rc) return rc;
+        partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(tcg, nw, partW, dW);
+    } else {
+        const size_t smem = static_cast<size_t>(kWgKC) * (p.cin_t + p.cout_t) * sizeof(float);
+        conv_wgrad_kernel<<<dim3(p.gx, p.ny), 256, smem, st>>>(rows, cin, cout, p.cin_t, p.cout_t, p.rows_per_cta, x, dz, partW, partB_scratch);
+        rc = check_launch("conv_wgrad_kernel");
+        if (rc) return rc;
+        partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(p.nparts, nw, partW, dW);
+    }
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
     if (dx) {
         if (cin == 3) {
             conv_dgrad3_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 3 * cout * sizeof(float), st>>>(rows, cout, dz, W, dx);
             rc = check_launch("conv_dgrad3_kernel");
+        } else if (tc_dgrad) {
+            rc = lin_tc(rows, cout, cin, dz, W, cout, 1, nullptr, dx, nullptr, wimg, st);  // A[m = ci][k = co] = W[ci][co]
         } else {
             transpose_kernel<<<(cin * cout + 255) / 256, 256, 0, st>>>(cin, cout, W, Wt);
             rc = check_launch("transpose_kernel");

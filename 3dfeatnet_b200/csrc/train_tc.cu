@@ -1,0 +1,393 @@
+// train_tc.cu -- the contractions of the training-mode layers on the tensor cores (tcgen05 + TMEM), "bf16x3" precision.
+//
+// The three products of a 1x1-conv layer over R rows (reference models/layers.py:11-46 and the gradient graph TF derives):
+//     forward  z  = x  W   (R x cin)(cin x cout)      lin_tc_kernel, A = W^T
+//     dgrad    dx = dz W^T (R x cout)(cout x cin)     lin_tc_kernel, A = W
+//     wgrad    dW = x^T dz (cin x R)(R x cout)        wgrad_tc_kernel
+// are HBM-bound streams once the math is on the 5th-gen tensor cores (the fp32 FFMA versions in train_layers.cu ran at
+// ~27 TFLOP/s and were 60 % of the training step).  fp32 operands are split on the fly into bf16 hi + lo and three MMAs
+// (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) reproduce fp32 products to ~1e-5 relative, like the eval kernels.
+//
+// lin_tc_kernel:  D^T[channel x row] = A (TMEM, 128 output channels x K) * X^T (shared memory, 64 rows x K, K-major).
+//   One CTA owns one block of 128 output channels (grid.y) whose hi/lo weight images are copied once into tensor memory
+//   (bulk TMA -> tcgen05.cp) and walks 64-row tiles: all threads build the operand image, one elected lane issues the
+//   3 x K/16 MMAs, the 8 warps read the accumulator back (lane = channel => a warp writes 128 contiguous bytes of a row,
+//   and the BN batch statistics -- sum z, sum z^2 per channel -- are plain per-thread accumulations).  Phases of a tile are
+//   sequential; two to four CTAs share an SM (TMEM columns K + 64 <= 256) and overlap each other.
+// wgrad_tc_kernel: D[cin(128) x cout] += X^T (shared, K = rows) * dZ^T (shared, K = rows) over the CTA's row range, 64 rows
+//   per stage; both operands need K = row contiguous, so a thread transposes 8 rows x 8 channels in registers while
+//   splitting.  Per-CTA partials are reduced in a fixed order afterwards (deterministic).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <cuda_bf16.h>
+
+namespace f3d {
+
+using namespace tc;
+
+namespace ttc {
+constexpr int kTile = 64;                 // rows per tile = MMA N of lin_tc
+constexpr int kThreads = 256;
+constexpr uint32_t kSbo = 128;
+constexpr uint32_t kLboW = 128 * 16;      // weight image: 128 rows per 8-wide K chunk
+constexpr uint32_t kLboX = kTile * 16;    // operand image: 64 rows per K chunk
+constexpr uint32_t kLboA = 128 * 16 + 16; // wgrad A image (padded: the 8 row-chunks a quarter-warp writes hit distinct banks)
+}  // namespace ttc
+
+__device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
+        h[j] = *reinterpret_cast<const uint32_t *>(&h2);
+        l[j] = *reinterpret_cast<const uint32_t *>(&l2);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// weight images: A[m][k] = src[m*sm + k*sk] (0 outside m_real x k_real), per 128-row block [hi | lo], element (r,k) at
+// (k/8)*kLboW + r*16 + (k%8)*2
+__global__ void lin_prep_kernel(const float *__restrict__ src, long long sm, long long sk, int m_real, int k_real, int kp, int mblocks,
+                                uint8_t *__restrict__ img) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long per = 128LL * kp;
+    if (i >= per * mblocks) return;
+    const int mb = static_cast<int>(i / per);
+    const int e = static_cast<int>(i - mb * per);
+    const int r = e & 127, k = e >> 7;
+    const int m = mb * 128 + r;
+    const float w = (m < m_real && k < k_real) ? src[m * sm + k * sk] : 0.0f;
+    uint8_t *base = img + static_cast<size_t>(mb) * kp * 512;
+    const uint32_t o = (k >> 3) * ttc::kLboW + r * 16 + (k & 7) * 2;
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    *reinterpret_cast<__nv_bfloat16 *>(base + o) = h;
+    *reinterpret_cast<__nv_bfloat16 *>(base + static_cast<size_t>(kp) * 256 + o) = __float2bfloat16_rn(w - __bfloat162float(h));
+}
+
+// out[rows x nout] (+bias) = x[rows x k_real] * A^T; optional per-CTA column sums of out and out^2:
+// part[((blockIdx.x*2 + half)*2 + {0,1})*nout + channel]
+__global__ void __launch_bounds__(ttc::kThreads)
+lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
+              const float *__restrict__ bias, float *__restrict__ out, float *__restrict__ part) {
+    using namespace ttc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t xbytes = 256u * kp;  // operand image: 2 splits x (kp/8) chunks x kLboX == one weight split: (kp/8) x kLboW
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + xbytes);
+    uint64_t *bar_m = bar_w + 1;
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_w + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = warp >> 2;
+    const int ch = q * 32 + lane;
+    const int col0 = half * 32;
+    const uint32_t sbase = smem_u32(smem);
+    const int mb = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_m, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_base_s, tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+    uint32_t wpar = 0, mpar = 0;
+
+    // weights -> tensor memory: split hi -> columns [0, kp/2), split lo -> [kp/2, kp)
+    const uint8_t *wsrc = wimg + static_cast<size_t>(mb) * kp * 512;
+    for (int piece = 0; piece < 2; ++piece) {
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(bar_w, xbytes);
+            for (uint32_t off = 0; off < xbytes; off += 16384) {
+                const uint32_t n = xbytes - off < 16384u ? xbytes - off : 16384u;
+                bulk_g2s(smem + off, wsrc + static_cast<size_t>(piece) * xbytes + off, n, bar_w);
+            }
+        }
+        mbar_wait(bar_w, wpar);
+        wpar ^= 1;
+        tcgen05_fence_after();
+        if (warp == 0) {
+            if (elect_one()) {
+                for (int k = 0; k < kp / 16; ++k)
+                    tmem_cp_128x256b(tmem_base + piece * (kp / 2) + k * 8, make_smem_desc(sbase + k * 2 * kLboW, kLboW, kSbo));
+                umma_commit(bar_m);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar_m, mpar);
+        mpar ^= 1;
+        __syncthreads();
+    }
+
+    const uint32_t idesc = make_idesc(1, 128, kTile);
+    const uint32_t split = static_cast<uint32_t>(kp / 8) * kLboX;
+    const uint32_t tmem_d = tmem_base + kp;
+    const int gch = mb * 128 + ch;
+    const bool ch_ok = gch < nout;
+    const float bb = (bias && ch_ok) ? __ldg(bias + gch) : 0.0f;
+    float s1 = 0.0f, s2 = 0.0f;
+    const long long ntiles = (rows + kTile - 1) / kTile;
+    const bool vec = (k_real & 7) == 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long r0 = tile * kTile;
+        {   // fp32 rows -> bf16 hi/lo, K-major
+            const int r = threadIdx.x & 63, cq = threadIdx.x >> 6;
+            const bool valid = r0 + r < rows;
+            const float *row = x + (r0 + r) * k_real;
+            for (int c = cq; c < kp / 8; c += 4) {
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+                    if (vec) {
+                        if (c * 8 < k_real) {
+                            const float4 a = __ldg(reinterpret_cast<const float4 *>(row + c * 8));
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(row + c * 8 + 4));
+                            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (c * 8 + j < k_real) v[j] = __ldg(row + c * 8 + j);
+                    }
+                }
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                uint8_t *dst = smem + c * kLboX + r * 16;
+                *reinterpret_cast<uint4 *>(dst) = hi;
+                *reinterpret_cast<uint4 *>(dst + split) = lo;
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tcgen05_fence_after();
+            if (elect_one()) {
+                uint32_t acc = 0;
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t wa = tmem_base + (pass == 2 ? kp / 2 : 0);
+                    const uint32_t xb = sbase + (pass == 1 ? split : 0);
+                    for (int k = 0; k < kp / 16; ++k) {
+                        umma_f16_ts(tmem_d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX, kLboX, kSbo), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(bar_m);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar_m, mpar);
+        mpar ^= 1;
+        tcgen05_fence_after();
+        uint32_t r[32];
+        tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0, r);
+        tmem_ld_wait();
+        if (ch_ok) {
+            float *o = out + (r0 + col0) * nout + gch;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (r0 + col0 + j < rows) {
+                    const float v = __uint_as_float(r[j]) + bb;
+                    o[static_cast<size_t>(j) * nout] = v;
+                    s1 += v;
+                    s2 = fmaf(v, v, s2);
+                }
+            }
+        }
+        tcgen05_fence_before();
+        __syncthreads();  // the operand image and the accumulator are reused by the next tile
+    }
+    if (part && ch_ok) {
+        float *p = part + (static_cast<size_t>(blockIdx.x) * 2 + half) * 2 * nout;
+        p[gch] = s1;
+        p[nout + gch] = s2;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// 8 rows x 8 channels of a row-major fp32 matrix -> eight 16-byte K(=row)-major chunks, hi and lo
+__device__ __forceinline__ void wgrad_stage_unit(uint8_t *img, uint32_t lbo, uint32_t split, int rc, int cg, const float *__restrict__ src, int ld,
+                                                 long long row0, long long rend) {
+    float v[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long row = row0 + rc * 8 + i;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (row < rend) {
+            a = __ldg(reinterpret_cast<const float4 *>(src + row * ld + cg * 8));
+            b = __ldg(reinterpret_cast<const float4 *>(src + row * ld + cg * 8 + 4));
+        }
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+    }
+    uint8_t *dst = img + rc * lbo + cg * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float col[8] = {v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]};
+        uint4 hi, lo;
+        split8(col, hi, lo);
+        *reinterpret_cast<uint4 *>(dst + j * 16) = hi;
+        *reinterpret_cast<uint4 *>(dst + split + j * 16) = lo;
+    }
+}
+
+// partW[blockIdx.x][cin][cout] = sum over the CTA's rows of x[r][ci] * dz[r][co].  cin % 8 == 0, cin <= 128, cout % 16 == 0, <= 256.
+__global__ void __launch_bounds__(ttc::kThreads)
+wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint32_t tmem_cols, const float *__restrict__ x,
+                const float *__restrict__ dz, float *__restrict__ partW) {
+    using namespace ttc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t lbo_b = static_cast<uint32_t>(cout) * 16 + 16;
+    const uint32_t split_a = 8 * kLboA, split_b = 8 * lbo_b;
+    uint8_t *img_a = smem;
+    uint8_t *img_b = smem + 2 * split_a;
+    uint64_t *bar_m = reinterpret_cast<uint64_t *>(smem + 2 * split_a + ((2 * split_b + 15) & ~15u));
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_m + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_m, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_base_s, tmem_cols);
+        tmem_relinquish();
+    }
+    for (uint32_t o = threadIdx.x * 16; o < 2 * split_a; o += kThreads * 16) *reinterpret_cast<uint4 *>(img_a + o) = make_uint4(0, 0, 0, 0);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+    uint32_t mpar = 0;
+    const uint32_t idesc = make_idesc(1, 128, static_cast<uint32_t>(cout));
+    const long long rbeg = blockIdx.x * rows_per_cta, rend = rbeg + rows_per_cta < rows ? rbeg + rows_per_cta : rows;
+    uint32_t acc = 0;
+    for (long long r0 = rbeg; r0 < rend; r0 += kTile) {
+        for (int u = threadIdx.x; u < cin; u += kThreads) wgrad_stage_unit(img_a, kLboA, split_a, u & 7, u >> 3, x, cin, r0, rend);
+        for (int u = threadIdx.x; u < cout; u += kThreads) wgrad_stage_unit(img_b, lbo_b, split_b, u & 7, u >> 3, dz, cout, r0, rend);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tcgen05_fence_after();
+            if (elect_one()) {
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a = sbase + (pass == 2 ? split_a : 0);
+                    const uint32_t b = sbase + 2 * split_a + (pass == 1 ? split_b : 0);
+                    for (int k = 0; k < kTile / 16; ++k) {
+                        umma_f16(tmem_base, make_smem_desc(a + k * 2 * kLboA, kLboA, kSbo), make_smem_desc(b + k * 2 * lbo_b, lbo_b, kSbo), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(bar_m);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar_m, mpar);  // single-buffered operands: the MMAs must have read them before the next stage overwrites
+        mpar ^= 1;
+        tcgen05_fence_after();
+        __syncthreads();
+    }
+    const int q = warp & 3;
+    const int ci = q * 32 + lane;
+    float *pw = partW + (static_cast<size_t>(blockIdx.x) * cin + ci) * cout;
+    for (int cc = (warp >> 2) * 32; cc < cout; cc += 64) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cc, r);
+        tmem_ld_wait();
+        if (ci < cin) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (cc + j < cout)
+                    *reinterpret_cast<float4 *>(pw + cc + j) =
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static int ttc_num_sms() {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    return num_sms;
+}
+
+static uint32_t pow2_cols(uint32_t need) {
+    uint32_t c = 32;
+    while (c < need) c <<= 1;
+    return c;
+}
+
+int lin_tc_kp(int k_real) { return (k_real + 15) / 16 * 16; }
+bool lin_tc_supported(int k_real, int nout) { return k_real >= 1 && k_real <= 256 && nout >= 1; }
+size_t lin_tc_weight_bytes(int k_real, int nout) { return static_cast<size_t>((nout + 127) / 128) * lin_tc_kp(k_real) * 512; }
+
+// number of row-CTAs lin_tc launches (the stats partials are 2 per CTA)
+int lin_tc_grid(long long rows, int k_real) {
+    const int kp = lin_tc_kp(k_real);
+    const uint32_t cols = pow2_cols(kp + ttc::kTile);
+    int per_sm = static_cast<int>(512 / cols);
+    if (per_sm > 3) per_sm = 3;
+    const long long ntiles = (rows + ttc::kTile - 1) / ttc::kTile;
+    const long long g = static_cast<long long>(ttc_num_sms()) * per_sm;
+    return static_cast<int>(ntiles < g ? ntiles : g);
+}
+
+// out (rows, nout) = x (rows, k_real) * A^T (+ bias) with A[m][k] = src[m*sm + k*sk];  part: 2*lin_tc_grid() partials of
+// {sum, sum of squares} per channel, or NULL.  wimg: lin_tc_weight_bytes() of scratch.
+int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias, float *out,
+           float *part, uint8_t *wimg, cudaStream_t st) {
+    const int kp = lin_tc_kp(k_real);
+    const int mblocks = (nout + 127) / 128;
+    const long long total = 128LL * kp * mblocks;
+    lin_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, sm, sk, nout, k_real, kp, mblocks, wimg);
+    int rc = check_launch("lin_prep_kernel");
+    if (rc) return rc;
+    const uint32_t cols = pow2_cols(kp + ttc::kTile);
+    const size_t smem = 256u * kp + 64;
+    cudaError_t e = cudaFuncSetAttribute(lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
+    const dim3 grid(lin_tc_grid(rows, k_real), mblocks);
+    lin_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, cols, x, wimg, bias, out, part);
+    return check_launch("lin_tc_kernel");
+}
+
+bool wgrad_tc_supported(int cin, int cout) { return cin % 8 == 0 && cin >= 8 && cin <= 128 && cout % 16 == 0 && cout >= 16 && cout <= 256; }
+
+void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta) {
+    const long long ntiles = (rows + ttc::kTile - 1) / ttc::kTile;
+    long long g = 2LL * ttc_num_sms();
+    if (g > ntiles) g = ntiles;
+    const long long per = (ntiles + g - 1) / g;
+    *rows_per_cta = per * ttc::kTile;
+    *grid = static_cast<int>((ntiles + per - 1) / per);
+}
+
+// partW: grid x cin x cout floats
+int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st) {
+    int grid = 0;
+    long long per = 0;
+    wgrad_tc_plan(rows, &grid, &per);
+    const uint32_t cols = pow2_cols(static_cast<uint32_t>(cout));
+    const uint32_t split_a = 8 * ttc::kLboA, split_b = 8 * (static_cast<uint32_t>(cout) * 16 + 16);
+    const size_t smem = 2 * split_a + ((2 * split_b + 15) & ~15u) + 64;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "wgrad_tc: cudaFuncSetAttribute");
+    wgrad_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW);
+    return check_launch("wgrad_tc_kernel");
+}
+
+}  // namespace f3d

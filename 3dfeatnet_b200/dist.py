@@ -38,6 +38,14 @@ def allreduce_mean_(flat):
     return flat
 
 
+def allreduce_sum_(flat):
+    """In-place SUM over ranks; pair it with get_train_op(grad_scale=1/world): the division then happens inside the Adam
+    kernel (f3d_adam_step) instead of as an extra pass over the gradient buffer."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
+
+
 def max_over_ranks(value, device):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -363,10 +363,11 @@ class Feat3dNet:
         triplet_cost = torch.clamp(sum_positive - sum_negative + self.param['margin'], min=0.)
         return triplet_cost.mean(), end_points
 
-    def get_train_op(self, loss_op, lr=1e-5, global_step=None, end_points=None, grad_hook=None):
+    def get_train_op(self, loss_op, lr=1e-5, global_step=None, end_points=None, grad_hook=None, grad_scale=1.0):
         """ One optimiser step (feat3dnet.py:359-375): TF-1 Adam, lr_t = lr*sqrt(1-b2^t)/(1-b1^t),
         theta -= lr_t*m/(sqrt(v)+1e-8), over the trainable variables minus param['freeze_scopes'].
-        grad_hook(flat_grad) runs between backward and the update (the data-parallel all-reduce goes there).
+        grad_hook(flat_grad) runs between backward and the update (the data-parallel all-reduce goes there); grad_scale
+        multiplies the gradient inside the Adam kernel (1/world_size after a SUM all-reduce).
         Also applies the BN EMA updates collected by the forward (end_points['bn_updates'])."""
         var = self.trainable_variables()
         names = [k for k, v in var.items() if v.requires_grad]
@@ -397,7 +398,7 @@ class Feat3dNet:
         _lib.require_cuda(st["g"])
         with torch.no_grad():
             _lib.check(_lib.lib().f3d_adam_step(len(names), _lib.ptr(st["records"]), st["max_n"], float(lr), 0.9, 0.999, 1e-8,
-                                                st["t"], 1.0, _lib.stream()), "adam_step")
+                                                st["t"], float(grad_scale), _lib.stream()), "adam_step")
             if end_points is not None and end_points.get('bn_updates'):
                 for k, v in end_points['bn_updates'].items():
                     self.weights[k].copy_(v)

@@ -15,6 +15,8 @@ import torch.nn.functional as F
 BN_EPS = 1e-3   # layers.py:271
 BN_DECAY = 0.9  # layers.py:251 (bn_decay=None everywhere in the model)
 FUSED_TRAINING = True  # training-mode conv+BN(+ReLU) through csrc/train_layers.cu (False: the op-by-op torch statement)
+TRAIN_PRECISION = "bf16x3"  # contractions of the training layers: "bf16x3" = tcgen05 tensor cores, "fp32" = FFMA kernels
+_PRECISION_CODE = {"fp32": 0, "bf16x3": 2}
 
 relu = torch.relu
 softplus = F.softplus
@@ -33,6 +35,7 @@ class _ConvBnTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, use_relu):
         _lib = _native()
+        ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
         L = _lib.lib()
         x2, w2 = x.detach().contiguous().float(), w.detach().contiguous().float()
         b2, g2, be2 = b.detach().contiguous().float(), gamma.detach().contiguous().float(), beta.detach().contiguous().float()
@@ -46,7 +49,7 @@ class _ConvBnTrain(torch.autograd.Function):
         var = torch.empty_like(mean)
         _lib.check(L.f3d_conv_bn_train_forward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g2), _lib.ptr(be2),
                                                int(use_relu), BN_EPS, _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var),
-                                               _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_forward")
+                                               ctx.precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_forward")
         ctx.save_for_backward(x2, w2, g2, z, y, mean, var)
         ctx.use_relu = bool(use_relu)
         ctx.mark_non_differentiable(mean, var)
@@ -67,7 +70,7 @@ class _ConvBnTrain(torch.autograd.Function):
         _lib.check(L.f3d_conv_bn_train_backward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(z), _lib.ptr(y),
                                                 _lib.ptr(mean), _lib.ptr(var), int(ctx.use_relu), BN_EPS, _lib.ptr(gy),
                                                 _lib.ptr(dx) if dx is not None else None, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dg),
-                                                _lib.ptr(dbe), _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_backward")
+                                                _lib.ptr(dbe), ctx.precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_backward")
         return dx, dw, db, dg, dbe, None
 
 

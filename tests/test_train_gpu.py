@@ -106,20 +106,26 @@ def test_triplet_loss_rejects_bad_arguments(cuda):
     assert L.f3d_adam_step(0, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
 
 
-def plain_conv_bn(x, w, b, gamma, beta, use_relu):
+def plain_conv_bn(x, w, b, gamma, beta, relu_mask):
+    """relu_mask: None (no ReLU) or the 0/1 mask of the device result -- the gradient of a ReLU is discontinuous at 0, so
+    an element whose pre-activation is within rounding of 0 must be routed the same way in both computations."""
     z = x @ w + b
     mean, var = z.mean(0), z.var(0, unbiased=False)
     y = (z - mean) * torch.rsqrt(var + 1e-3) * gamma + beta
-    return (torch.relu(y) if use_relu else y), mean, var
+    return (y * relu_mask if relu_mask is not None else y), mean, var
 
 
 @pytest.mark.parametrize("rows,cin,cout,use_relu", [(8192 + 37, 3, 64, True), (5000, 64, 128, True), (4096, 128, 256, True),
                                                     (777, 256, 128, True), (1000, 128, 64, True), (3000, 3, 32, True),
                                                     (3000, 32, 64, True), (3000, 128, 128, False), (999, 128, 32, False),
-                                                    (1, 64, 16, True), (130, 16, 16, True)])
-def test_conv_bn_train_forward_backward(cuda, rows, cin, cout, use_relu):
-    """The training-mode layer (reference layers.py:11-46,225-272) against its fp64 torch statement + autograd."""
+                                                    (1, 64, 16, True), (130, 16, 16, True), (70000, 128, 256, True),
+                                                    (20011, 64, 64, True)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_conv_bn_train_forward_backward(cuda, rows, cin, cout, use_relu, precision, monkeypatch):
+    """The training-mode layer (reference layers.py:11-46,225-272) against its fp64 torch statement + autograd, for the
+    fp32 FFMA contractions and the tcgen05 ones (bf16 hi/lo split, three MMAs: ~1e-5 relative)."""
     layers = pkg("models.layers")
+    monkeypatch.setattr(layers, "TRAIN_PRECISION", precision)
     g = torch.Generator().manual_seed(rows + cin * 7 + cout)
     x = torch.randn(rows, cin, generator=g) * 0.7 + 0.1
     w = torch.randn(cin, cout, generator=g) * (2.0 / cin) ** 0.5
@@ -131,10 +137,11 @@ def test_conv_bn_train_forward_backward(cuda, rows, cin, cout, use_relu):
     y, mean, var = layers.conv_bn_train(*ins, use_relu)
     grads = torch.autograd.grad((y * gy.to(cuda)).sum(), ins)
     ins64 = [t.double().requires_grad_(True) for t in (x, w, b, gamma, beta)]
-    ry, rmean, rvar = plain_conv_bn(*ins64, use_relu)
+    ry, rmean, rvar = plain_conv_bn(*ins64, (y.detach() > 0).cpu().double() if use_relu else None)
     rgrads = torch.autograd.grad((ry * gy.double()).sum(), ins64)
-    assert torch.allclose(mean.cpu().double(), rmean, rtol=1e-5, atol=1e-6)
-    assert torch.allclose(var.cpu().double(), rvar, rtol=1e-4, atol=1e-7)
+    tc = precision == "bf16x3"      # bf16 hi/lo split: every product carries ~2^-17 relative error
+    assert torch.allclose(mean.cpu().double(), rmean, rtol=1e-4 if tc else 1e-5, atol=2e-5 if tc else 1e-6)
+    assert torch.allclose(var.cpu().double(), rvar, rtol=2e-4 if tc else 1e-4, atol=1e-6 if tc else 1e-7)
     if rows > 1:
         assert (y.detach().cpu().double() - ry).abs().max().item() < 2e-5 * max(1.0, ry.abs().max().item())
     for name, a, r in zip(("dx", "dW", "db", "dgamma", "dbeta"), grads, rgrads):
@@ -145,8 +152,10 @@ def test_conv_bn_train_forward_backward(cuda, rows, cin, cout, use_relu):
         assert (a.cpu().double() - r).abs().max().item() < 2e-4 * scale + 1e-6, name
 
 
-def test_conv_bn_train_is_deterministic_and_skips_dx(cuda):
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_conv_bn_train_is_deterministic_and_skips_dx(cuda, precision, monkeypatch):
     layers = pkg("models.layers")
+    monkeypatch.setattr(layers, "TRAIN_PRECISION", precision)
     g = torch.Generator().manual_seed(3)
     x = torch.randn(20000, 64, generator=g).to(cuda)
     w, b, ga, be = (t.to(cuda).requires_grad_(True) for t in (torch.randn(64, 128, generator=g) * 0.2, torch.zeros(128),

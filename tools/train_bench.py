@@ -29,7 +29,7 @@ if UNFUSED:
 def step():
     xyz, feats, att, ep = net.get_train_model(a, p, n, True)
     loss, ep = net.get_loss(xyz, feats, att, ep)
-    net.get_train_op(loss, lr=1e-5, end_points=ep, grad_hook=dist.allreduce_mean_)
+    net.get_train_op(loss, lr=1e-5, end_points=ep, grad_hook=dist.allreduce_sum_, grad_scale=1.0 / world)
     return loss
 
 
