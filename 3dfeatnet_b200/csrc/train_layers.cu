@@ -205,7 +205,9 @@ __global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const 
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(long long rows, int c, float eps, const float *__restrict__ gy, const float *__restrict__ y, const float *__restrict__ z,
                     const float *__restrict__ mean, const float *__restrict__ var, const float *__restrict__ coef2, int relu,
-                    float *__restrict__ dz, float *__restrict__ partB) {
+                    float *__restrict__ dz, float *__restrict__ partB, const float *__restrict__ x3, float *__restrict__ partW3) {
+    // x3 != NULL: the layer has 3 input channels (the xyz layers); dW (3 x c) = x^T dz is accumulated in the same pass:
+    // partW3[(blk*3 + k)*c + ch]
     __shared__ float4 red[256];
     const int cvec = c >> 2, rl = 256 / cvec;
     const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
@@ -217,7 +219,7 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, const float *__restrict__ 
     const float4 s = __ldg(reinterpret_cast<const float4 *>(coef2) + cv);
     const float4 k1 = __ldg(reinterpret_cast<const float4 *>(coef2 + c) + cv);
     const float4 k2 = __ldg(reinterpret_cast<const float4 *>(coef2 + 2 * c) + cv);
-    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), w0 = sb, w1 = sb, w2 = sb;
     if (rlane < rl) {
         for (long long r = rbeg + rlane; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
@@ -234,17 +236,28 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, const float *__restrict__ 
             d.w = s.w * (g.w - k1.w - (zz.w - mu.w) * is.w * k2.w);
             reinterpret_cast<float4 *>(dz)[o] = d;
             sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
+            if (x3) {
+                const float x0 = __ldg(x3 + r * 3), x1 = __ldg(x3 + r * 3 + 1), x2 = __ldg(x3 + r * 3 + 2);
+                w0.x = fmaf(x0, d.x, w0.x); w0.y = fmaf(x0, d.y, w0.y); w0.z = fmaf(x0, d.z, w0.z); w0.w = fmaf(x0, d.w, w0.w);
+                w1.x = fmaf(x1, d.x, w1.x); w1.y = fmaf(x1, d.y, w1.y); w1.z = fmaf(x1, d.z, w1.z); w1.w = fmaf(x1, d.w, w1.w);
+                w2.x = fmaf(x2, d.x, w2.x); w2.y = fmaf(x2, d.y, w2.y); w2.z = fmaf(x2, d.z, w2.z); w2.w = fmaf(x2, d.w, w2.w);
+            }
         }
     }
-    red[threadIdx.x] = sb;
-    __syncthreads();
-    if (threadIdx.x < cvec) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int l = 0; l < rl; ++l) {
-            const float4 u = red[l * cvec + threadIdx.x];
-            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    const int npass = x3 ? 4 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+        if (pass) __syncthreads();
+        red[threadIdx.x] = pass == 0 ? sb : pass == 1 ? w0 : pass == 2 ? w1 : w2;
+        __syncthreads();
+        if (threadIdx.x < cvec) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int l = 0; l < rl; ++l) {
+                const float4 u = red[l * cvec + threadIdx.x];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            float *dst = pass == 0 ? partB + static_cast<size_t>(blockIdx.x) * c : partW3 + (static_cast<size_t>(blockIdx.x) * 3 + (pass - 1)) * c;
+            reinterpret_cast<float4 *>(dst)[threadIdx.x] = t;
         }
-        reinterpret_cast<float4 *>(partB + static_cast<size_t>(blockIdx.x) * c)[threadIdx.x] = t;
     }
 }
 
@@ -487,7 +500,8 @@ F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int co
     int tcg = 0;
     long long tcper = 0;
     wgrad_tc_plan(rows, &tcg, &tcper);
-    const size_t wparts = static_cast<size_t>(p.nparts > tcg ? p.nparts : tcg);
+    size_t wparts = static_cast<size_t>(p.nparts > tcg ? p.nparts : tcg);
+    if (wparts < static_cast<size_t>(kRedBlocks)) wparts = kRedBlocks;
     const size_t bwd = align256(static_cast<size_t>(rows) * cout * 4)                       // dz
                        + align256(static_cast<size_t>(kRedBlocks) * 2 * cout * 4)           // BN reduction partials
                        + align256(2 * cout * 4) + align256(3 * cout * 4)                    // sums, coef2
@@ -556,7 +570,8 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     int tcg = 0;
     long long tcper = 0;
     wgrad_tc_plan(rows, &tcg, &tcper);
-    const size_t wparts = static_cast<size_t>(p.nparts > tcg ? p.nparts : tcg);
+    size_t wparts = static_cast<size_t>(p.nparts > tcg ? p.nparts : tcg);
+    if (wparts < static_cast<size_t>(kRedBlocks)) wparts = kRedBlocks;
     const size_t wimg_bytes = lin_tc_weight_bytes(cin, cout) > lin_tc_weight_bytes(cout, cin) ? lin_tc_weight_bytes(cin, cout) : lin_tc_weight_bytes(cout, cin);
     (void)wimg_bytes;
     char *w = static_cast<char *>(workspace);
@@ -588,7 +603,8 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2);
     rc = check_launch("bn_bwd_finalize_kernel");
     if (rc) return rc;
-    bn_bwd_apply_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, gy, y, z, mean, var, coef2, relu, dz, partB);
+    const bool w3 = cin == 3;  // the xyz layers: dW rides along with the dz pass (partials in the dW-partials area: 3*cout per chunk)
+    bn_bwd_apply_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, gy, y, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;
     partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(nred, cout, partB, db);
@@ -596,7 +612,9 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     if (rc) return rc;
 
     const long long nw = static_cast<long long>(cin) * cout;
-    if (precision == 2 && wgrad_tc_supported(cin, cout)) {
+    if (w3) {
+        partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(nred, nw, partW, dW);
+    } else if (precision == 2 && wgrad_tc_supported(cin, cout)) {
         rc = wgrad_tc(rows, cin, cout, x, dz, partW, st);
         if (rc) return rc;
         partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(tcg, nw, partW, dW);

@@ -31,7 +31,8 @@ constexpr int kTile = 64;                 // rows per tile = MMA N of lin_tc
 constexpr int kThreads = 256;
 constexpr uint32_t kSbo = 128;
 constexpr uint32_t kLboW = 128 * 16;      // weight image: 128 rows per 8-wide K chunk
-constexpr uint32_t kLboX = kTile * 16;    // operand image: 64 rows per K chunk
+constexpr uint32_t kLboXp = kTile * 16 + 32;  // operand image: 64 rows per K chunk, padded so that the four chunks a
+                                              // quarter-warp writes fall into distinct banks
 constexpr uint32_t kLboA = 128 * 16 + 16; // wgrad A image (padded: the 8 row-chunks a quarter-warp writes hit distinct banks)
 }  // namespace ttc
 
@@ -68,26 +69,41 @@ __global__ void lin_prep_kernel(const float *__restrict__ src, long long sm, lon
 }
 
 // out[rows x nout] (+bias) = x[rows x k_real] * A^T; optional per-CTA column sums of out and out^2:
-// part[((blockIdx.x*2 + half)*2 + {0,1})*nout + channel]
+// part[((cta*2 + half)*2 + {0,1})*nout + channel].  grid = (channel blocks, row CTAs): the CTAs that share a row tile are
+// neighbours in launch order, so the second one finds the tile in L2.
+// The fp32 rows of a tile are one contiguous block of global memory: when k_real % 8 == 0 they are fetched by the TMA
+// engine (bulk copies of up to 16 KB into a ring, kRing tiles ahead, mbarrier completion) so the loads of the next tiles
+// are in flight during the conversion / MMA / epilogue of the current one; the conversion reads the ring with
+// conflict-free LDS.128 and writes the bf16 hi/lo operand image (chunk stride padded by 32 B against bank conflicts).
+constexpr int kRing = 2;
+
 __global__ void __launch_bounds__(ttc::kThreads)
 lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
               const float *__restrict__ bias, float *__restrict__ out, float *__restrict__ part) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t xbytes = 256u * kp;  // operand image: 2 splits x (kp/8) chunks x kLboX == one weight split: (kp/8) x kLboW
-    uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + xbytes);
+    const bool ring = (k_real & 7) == 0;
+    const uint32_t wbytes = 256u * kp;                                  // one weight split: (kp/8) chunks x kLboW
+    const uint32_t split = static_cast<uint32_t>(kp / 8) * kLboXp;      // operand image: 2 splits x (kp/8) chunks x kLboXp
+    const uint32_t opbytes = 2 * split;                                 // >= wbytes
+    const uint32_t stage_bytes = ring ? kTile * static_cast<uint32_t>(k_real) * 4 : 0;
+    uint8_t *ringbuf = smem + opbytes;
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + opbytes + kRing * stage_bytes);
     uint64_t *bar_m = bar_w + 1;
-    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_w + 2);
+    uint64_t *bar_full = bar_w + 2;  // [kRing]
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_w + 2 + kRing);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, half = warp >> 2;
     const int ch = q * 32 + lane;
     const int col0 = half * 32;
     const uint32_t sbase = smem_u32(smem);
-    const int mb = blockIdx.y;
+    const int mb = blockIdx.x;
+    const long long cta = blockIdx.y, ncta = gridDim.y;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_m, 1);
+        for (int s = 0; s < kRing; ++s) mbar_init(bar_full + s, 1);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -104,10 +120,10 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
     const uint8_t *wsrc = wimg + static_cast<size_t>(mb) * kp * 512;
     for (int piece = 0; piece < 2; ++piece) {
         if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(bar_w, xbytes);
-            for (uint32_t off = 0; off < xbytes; off += 16384) {
-                const uint32_t n = xbytes - off < 16384u ? xbytes - off : 16384u;
-                bulk_g2s(smem + off, wsrc + static_cast<size_t>(piece) * xbytes + off, n, bar_w);
+            mbar_arrive_expect_tx(bar_w, wbytes);
+            for (uint32_t off = 0; off < wbytes; off += 16384) {
+                const uint32_t n = wbytes - off < 16384u ? wbytes - off : 16384u;
+                bulk_g2s(smem + off, wsrc + static_cast<size_t>(piece) * wbytes + off, n, bar_w);
             }
         }
         mbar_wait(bar_w, wpar);
@@ -126,45 +142,78 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
         __syncthreads();
     }
 
+    const long long ntiles = (rows + kTile - 1) / kTile;
+    // warp 0: fetch the fp32 rows of `tile` into ring stage s
+    auto fetch = [&](long long tile, int s) {
+        const long long r0 = tile * kTile;
+        const uint32_t valid = static_cast<uint32_t>(rows - r0 < kTile ? rows - r0 : kTile);
+        const uint32_t bytes = valid * static_cast<uint32_t>(k_real) * 4;  // the tile's rows are one contiguous block
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_full + s, bytes);
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(x + r0 * k_real);
+            for (uint32_t off = 0; off < bytes; off += 16384) {
+                const uint32_t n = bytes - off < 16384u ? bytes - off : 16384u;
+                bulk_g2s(ringbuf + s * stage_bytes + off, src + off, n, bar_full + s);
+            }
+        }
+        __syncwarp();
+    };
+    if (ring && warp == 0)
+        for (int s = 0; s < kRing; ++s)
+            if (cta + s * ncta < ntiles) fetch(cta + s * ncta, s);
+
     const uint32_t idesc = make_idesc(1, 128, kTile);
-    const uint32_t split = static_cast<uint32_t>(kp / 8) * kLboX;
     const uint32_t tmem_d = tmem_base + kp;
     const int gch = mb * 128 + ch;
     const bool ch_ok = gch < nout;
     const float bb = (bias && ch_ok) ? __ldg(bias + gch) : 0.0f;
     float s1 = 0.0f, s2 = 0.0f;
-    const long long ntiles = (rows + kTile - 1) / kTile;
-    const bool vec = (k_real & 7) == 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long it = 0;
+    for (long long tile = cta; tile < ntiles; tile += ncta, ++it) {
         const long long r0 = tile * kTile;
-        {   // fp32 rows -> bf16 hi/lo, K-major
+        const int stage = static_cast<int>(it % kRing);
+        if (ring) {
+            mbar_wait(bar_full + stage, static_cast<uint32_t>((it / kRing) & 1));
+            // lane -> (row within a group of 4, chunk c mod 4, 16-byte half of the chunk): a quarter-warp reads 128 contiguous
+            // bytes of one row, a half-warp writes 16 distinct 8-byte slots of the operand image (no bank conflicts)
+            const int rsub = lane >> 3, c4 = (lane >> 1) & 3, h = lane & 1;
+            const uint32_t row_bytes = static_cast<uint32_t>(k_real) * 4;
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int r = p * 32 + warp * 4 + rsub;
+                const bool valid = r0 + r < rows;
+                const uint8_t *src = ringbuf + stage * stage_bytes + r * row_bytes + h * 16;
+                for (int c = c4; c < kp / 8; c += 4) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) a = *reinterpret_cast<const float4 *>(src + c * 32);
+                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - __low2float(h0), a.y - __high2float(h0));
+                    const __nv_bfloat162 l1 = __floats2bfloat162_rn(a.z - __low2float(h1), a.w - __high2float(h1));
+                    uint8_t *dst = smem + c * kLboXp + r * 16 + h * 8;
+                    *reinterpret_cast<uint2 *>(dst) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                    *reinterpret_cast<uint2 *>(dst + split) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+                }
+            }
+        } else {  // few input channels (the xyz layers): straight from global memory
             const int r = threadIdx.x & 63, cq = threadIdx.x >> 6;
             const bool valid = r0 + r < rows;
             const float *row = x + (r0 + r) * k_real;
             for (int c = cq; c < kp / 8; c += 4) {
                 float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (valid) {
-                    if (vec) {
-                        if (c * 8 < k_real) {
-                            const float4 a = __ldg(reinterpret_cast<const float4 *>(row + c * 8));
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(row + c * 8 + 4));
-                            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-                        }
-                    } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (c * 8 + j < k_real) v[j] = __ldg(row + c * 8 + j);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        if (c * 8 + j < k_real) v[j] = __ldg(row + c * 8 + j);
                 }
                 uint4 hi, lo;
                 split8(v, hi, lo);
-                uint8_t *dst = smem + c * kLboX + r * 16;
+                uint8_t *dst = smem + c * kLboXp + r * 16;
                 *reinterpret_cast<uint4 *>(dst) = hi;
                 *reinterpret_cast<uint4 *>(dst + split) = lo;
             }
         }
         fence_proxy_async_smem();
-        __syncthreads();
+        __syncthreads();  // operand image complete; ring stage `stage` fully read
         if (warp == 0) {
             tcgen05_fence_after();
             if (elect_one()) {
@@ -173,13 +222,14 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
                     const uint32_t wa = tmem_base + (pass == 2 ? kp / 2 : 0);
                     const uint32_t xb = sbase + (pass == 1 ? split : 0);
                     for (int k = 0; k < kp / 16; ++k) {
-                        umma_f16_ts(tmem_d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX, kLboX, kSbo), idesc, acc);
+                        umma_f16_ts(tmem_d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboXp, kLboXp, kSbo), idesc, acc);
                         acc = 1;
                     }
                 }
                 umma_commit(bar_m);
             }
             __syncwarp();
+            if (ring && tile + kRing * ncta < ntiles) fetch(tile + kRing * ncta, stage);  // refill the stage just consumed
         }
         mbar_wait(bar_m, mpar);
         mpar ^= 1;
@@ -203,7 +253,7 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
         __syncthreads();  // the operand image and the accumulator are reused by the next tile
     }
     if (part && ch_ok) {
-        float *p = part + (static_cast<size_t>(blockIdx.x) * 2 + half) * 2 * nout;
+        float *p = part + (static_cast<size_t>(cta) * 2 + half) * 2 * nout;
         p[gch] = s1;
         p[nout + gch] = s2;
     }
@@ -335,12 +385,22 @@ int lin_tc_kp(int k_real) { return (k_real + 15) / 16 * 16; }
 bool lin_tc_supported(int k_real, int nout) { return k_real >= 1 && k_real <= 256 && nout >= 1; }
 size_t lin_tc_weight_bytes(int k_real, int nout) { return static_cast<size_t>((nout + 127) / 128) * lin_tc_kp(k_real) * 512; }
 
+static size_t lin_tc_smem(int k_real) {
+    const int kp = lin_tc_kp(k_real);
+    const size_t op = 2 * static_cast<size_t>(kp / 8) * ttc::kLboXp;
+    const size_t ring = (k_real % 8 == 0) ? static_cast<size_t>(kRing) * ttc::kTile * k_real * 4 : 0;
+    return op + ring + 128;
+}
+
 // number of row-CTAs lin_tc launches (the stats partials are 2 per CTA)
 int lin_tc_grid(long long rows, int k_real) {
     const int kp = lin_tc_kp(k_real);
     const uint32_t cols = pow2_cols(kp + ttc::kTile);
     int per_sm = static_cast<int>(512 / cols);
-    if (per_sm > 3) per_sm = 3;
+    const int by_smem = static_cast<int>((220 * 1024) / lin_tc_smem(k_real));
+    if (per_sm > by_smem) per_sm = by_smem;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
     const long long ntiles = (rows + ttc::kTile - 1) / ttc::kTile;
     const long long g = static_cast<long long>(ttc_num_sms()) * per_sm;
     return static_cast<int>(ntiles < g ? ntiles : g);
@@ -357,10 +417,10 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
     int rc = check_launch("lin_prep_kernel");
     if (rc) return rc;
     const uint32_t cols = pow2_cols(kp + ttc::kTile);
-    const size_t smem = 256u * kp + 64;
+    const size_t smem = lin_tc_smem(k_real);
     cudaError_t e = cudaFuncSetAttribute(lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
-    const dim3 grid(lin_tc_grid(rows, k_real), mblocks);
+    const dim3 grid(mblocks, lin_tc_grid(rows, k_real));
     lin_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, cols, x, wimg, bias, out, part);
     return check_launch("lin_tc_kernel");
 }

@@ -53,3 +53,6 @@ if rank == 0 and os.environ.get("F3D_TRAIN_PROFILE") == "1":
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         step(); torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+    seq = [(e.name.split("(")[0][-40:], e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total)
+           for e in prof.events() if ("lin_tc" in e.name or "wgrad" in e.name or "conv_fwd" in e.name) and "Memcpy" not in e.name]
+    print("per-call us:", " ".join("%s=%.0f" % (n.replace("f3d::", "").replace("void ", ""), t) for n, t in seq))
