@@ -7,9 +7,9 @@
 //                     shared memory, keeps the minima (and how many columns tie for them), nothing (B,M,M) reaches HBM;
 //                     one CTA per cloud then forms the attention-normalised hinge;
 //   * loss backward : the same scan replayed; every anchor i pushes 2 w_i g (f_a - f_p[k*]) to itself and the opposite to
-//                     its arg-min column(s).  Column gradients are accumulated WITHOUT atomics: one thread per column
-//                     gathers, in ascending anchor order, the anchors that selected it (a (B,M) arg-min table is enough
-//                     unless there are exact ties, which take a slower exact path) => bit-reproducible;
+//                     its arg-min column(s).  Column gradients are accumulated WITHOUT atomics: one warp per column
+//                     gathers, in ascending anchor order, the anchors that selected it (from a (B,M,M/32) bitmask of the
+//                     tied minima the anchor pass records) => bit-reproducible;
 //   * Adam          : one launch over a table of (param, grad, m, v, n) records -- lr_t = lr*sqrt(1-b2^t)/(1-b1^t),
 //                     theta -= lr_t*m/(sqrt(v)+eps) (the TF-1 form, eps outside the bias correction), grad pre-scaled by
 //                     1/world so the data-parallel mean needs no extra pass.
@@ -154,25 +154,40 @@ loss_grad_anchor_kernel(int m, int f, float sgn, int accumulate, const float *__
     }
 }
 
-// d fo[b,k,:] = -sgn * sum over the anchors i that selected column k (ascending i) of 2 gw_i (fa_i - fo_k) / ties_i
-__global__ void loss_grad_other_kernel(int m, int f, long long total, float sgn, const float *__restrict__ fa, const float *__restrict__ fo,
-                                       const float *__restrict__ gw, const int *__restrict__ ties, const unsigned *__restrict__ sel,
-                                       float *__restrict__ dfo) {
-    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= total) return;
-    const long long bk = e / f;
-    const int c = static_cast<int>(e - bk * f);
+// d fo[b,k,:] = -sgn * sum over the anchors i that selected column k (ascending i) of 2 gw_i (fa_i - fo_k) / ties_i.
+// One warp per column: the lanes test 32 anchors at a time against the tie bitmask and the warp then visits only the
+// anchors that selected the column (about one per column on average), channels across lanes.
+__global__ void __launch_bounds__(kLossThreads)
+loss_grad_other_kernel(int m, int f, long long columns, float sgn, const float *__restrict__ fa, const float *__restrict__ fo,
+                       const float *__restrict__ gw, const int *__restrict__ ties, const unsigned *__restrict__ sel, float *__restrict__ dfo) {
+    const int lane = threadIdx.x & 31;
+    const long long bk = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bk >= columns) return;
     const long long b = bk / m;
     const int k = static_cast<int>(bk - b * m);
     const int words = (m + 31) >> 5;
-    const float ov = fo[e];
-    float acc = 0.0f;
-    for (int i = 0; i < m; ++i) {
-        const long long bi = b * m + i;
-        if ((__ldg(sel + bi * words + (k >> 5)) >> (k & 31)) & 1u)
-            acc -= sgn * 2.0f * gw[bi] * (fa[bi * f + c] - ov) / static_cast<float>(ties[bi]);
+    float ov[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ov[q] = lane + 32 * q < f ? fo[bk * f + lane + 32 * q] : 0.0f;
+    for (int i0 = 0; i0 < m; i0 += 32) {
+        const int i = i0 + lane;
+        bool hit = false;
+        if (i < m) hit = (__ldg(sel + (b * m + i) * words + (k >> 5)) >> (k & 31)) & 1u;
+        unsigned mask = __ballot_sync(kFull, hit);
+        while (mask) {
+            const long long bi = b * m + i0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float w = sgn * 2.0f * gw[bi] / static_cast<float>(ties[bi]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = lane + 32 * q;
+                if (c < f) acc[q] -= w * (fa[bi * f + c] - ov[q]);
+            }
+        }
     }
-    dfo[e] = acc;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (lane + 32 * q < f) dfo[bk * f + lane + 32 * q] = acc[q];
 }
 
 __global__ void loss_mean_kernel(int nb, const float *__restrict__ cost, float *__restrict__ loss) {
@@ -255,12 +270,12 @@ F3D_API int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa,
         loss_grad_anchor_kernel<<<grid, kLossThreads, smem, st>>>(m, f, -1.0f, 1, fa, fn, gw, best_n, ties_n, sel_n, dfa);
         rc = check_launch("loss_grad_anchor_kernel");
         if (rc) return rc;
-        const long long total = static_cast<long long>(bm) * f;
-        const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-        loss_grad_other_kernel<<<blocks, 256, 0, st>>>(m, f, total, 1.0f, fa, fp, gw, ties_p, sel_p, dfp);
+        const long long columns = static_cast<long long>(bm);
+        const unsigned blocks = static_cast<unsigned>((columns + kLossThreads / 32 - 1) / (kLossThreads / 32));
+        loss_grad_other_kernel<<<blocks, kLossThreads, 0, st>>>(m, f, columns, 1.0f, fa, fp, gw, ties_p, sel_p, dfp);
         rc = check_launch("loss_grad_other_kernel");
         if (rc) return rc;
-        loss_grad_other_kernel<<<blocks, 256, 0, st>>>(m, f, total, -1.0f, fa, fn, gw, ties_n, sel_n, dfn);
+        loss_grad_other_kernel<<<blocks, kLossThreads, 0, st>>>(m, f, columns, -1.0f, fa, fn, gw, ties_n, sel_n, dfn);
         rc = check_launch("loss_grad_other_kernel");
         if (rc) return rc;
     }

@@ -146,9 +146,29 @@ __global__ void bn_apply_kernel(long long n4, int c, const float *__restrict__ z
     reinterpret_cast<float4 *>(y)[e] = o;
 }
 
+// Where the upstream gradient of a layer comes from: a dense (rows, c) tensor, or -- when the layer's output only feeds
+// the max-pool over the sample axis -- the pooled maxima, the gradient of the pooled tensor and 1/(number of tied maxima):
+// g[row][ch] = y == max ? gpool/ties : 0 is then formed on the fly and the (rows, c) gradient never exists in HBM.
+struct GradSource {
+    const float *gy;      // dense: (rows, c); pooled: (rows / s, c)
+    const float *pooled;  // (rows / s, c) or NULL
+    const float *inv;     // (rows / s, c) 1 / ties
+    int s;                // samples per group, 0 = dense
+};
+
+__device__ __forceinline__ float4 load_grad(const GradSource &G, size_t o, long long r, int cv, int cvec, const float4 &yy) {
+    if (G.s == 0) return __ldg(reinterpret_cast<const float4 *>(G.gy) + o);
+    const size_t po = static_cast<size_t>(r / G.s) * cvec + cv;
+    const float4 pm = __ldg(reinterpret_cast<const float4 *>(G.pooled) + po);
+    const float4 gp = __ldg(reinterpret_cast<const float4 *>(G.gy) + po);
+    const float4 ic = __ldg(reinterpret_cast<const float4 *>(G.inv) + po);
+    return make_float4(yy.x == pm.x ? gp.x * ic.x : 0.f, yy.y == pm.y ? gp.y * ic.y : 0.f, yy.z == pm.z ? gp.z * ic.z : 0.f,
+                       yy.w == pm.w ? gp.w * ic.w : 0.f);
+}
+
 // per row-chunk partial sums of g and g*zhat, g = gy * [y > 0] (ReLU) or gy.  part[(blk*2+{0,1})*c + ch]
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(long long rows, int c, float eps, const float *__restrict__ gy, const float *__restrict__ y, const float *__restrict__ z,
+bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ y, const float *__restrict__ z,
                      const float *__restrict__ mean, const float *__restrict__ var, int relu, float *__restrict__ part) {
     __shared__ float4 red[2][256];
     const int cvec = c >> 2, rl = 256 / cvec;
@@ -162,10 +182,11 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, const float *__restrict__
     if (rlane < rl) {
         for (long long r = rbeg + rlane; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
-            float4 g = __ldg(reinterpret_cast<const float4 *>(gy) + o);
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
+            float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (relu || G.s) yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
+            float4 g = load_grad(G, o, r, cv, cvec, yy);
             if (relu) {
-                const float4 yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
             sg.x += g.x; sg.y += g.y; sg.z += g.z; sg.w += g.w;
@@ -203,7 +224,7 @@ __global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const 
 
 // dz = s (g - k1 - zhat k2) and, per row chunk, the column sums of dz (= the bias gradient): partB[blk*c + ch]
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(long long rows, int c, float eps, const float *__restrict__ gy, const float *__restrict__ y, const float *__restrict__ z,
+bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ y, const float *__restrict__ z,
                     const float *__restrict__ mean, const float *__restrict__ var, const float *__restrict__ coef2, int relu,
                     float *__restrict__ dz, float *__restrict__ partB, const float *__restrict__ x3, float *__restrict__ partW3) {
     // x3 != NULL: the layer has 3 input channels (the xyz layers); dW (3 x c) = x^T dz is accumulated in the same pass:
@@ -223,10 +244,11 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, const float *__restrict__ 
     if (rlane < rl) {
         for (long long r = rbeg + rlane; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
-            float4 g = __ldg(reinterpret_cast<const float4 *>(gy) + o);
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
+            float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (relu || G.s) yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
+            float4 g = load_grad(G, o, r, cv, cvec, yy);
             if (relu) {
-                const float4 yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
             float4 d;
@@ -379,24 +401,32 @@ __global__ void conv_dgrad3_kernel(long long rows, int cout, const float *__rest
     dx[r * 3 + 2] = a2;
 }
 
-// tf.reduce_max over the sample axis: x (groups, s, c) -> out (groups, c).  One thread per (group, 4 channels).
-__global__ void maxpool_fwd_kernel(long long groups, int s, int c4, const float *__restrict__ x, float *__restrict__ out) {
+// tf.reduce_max over the sample axis: x (groups, s, c) -> out (groups, c), and inv = 1 / (number of samples attaining the
+// maximum) in the same single pass.  One thread per (group, 4 channels).
+__device__ __forceinline__ void max_count(float v, float &m, int &n) {
+    if (v > m) { m = v; n = 1; }
+    else if (v == m) ++n;
+}
+
+__global__ void maxpool_fwd_kernel(long long groups, int s, int c4, const float *__restrict__ x, float *__restrict__ out, float *__restrict__ inv) {
     const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e >= groups * c4) return;
     const long long g = e / c4;
     const int cv = static_cast<int>(e - g * c4);
     const float4 *p = reinterpret_cast<const float4 *>(x) + g * s * c4 + cv;
     float4 m = __ldg(p);
+    int nx = 1, ny = 1, nz = 1, nw = 1;
     for (int k = 1; k < s; ++k) {
         const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        max_count(v.x, m.x, nx); max_count(v.y, m.y, ny); max_count(v.z, m.z, nz); max_count(v.w, m.w, nw);
     }
     reinterpret_cast<float4 *>(out)[e] = m;
+    if (inv) reinterpret_cast<float4 *>(inv)[e] = make_float4(1.0f / nx, 1.0f / ny, 1.0f / nz, 1.0f / nw);
 }
 
 // its gradient: dx = gout / (number of samples attaining the maximum) where x == max, else 0 (TensorFlow's _MinOrMaxGrad)
 __global__ void maxpool_bwd_kernel(long long groups, int s, int c4, const float *__restrict__ x, const float *__restrict__ mx,
-                                   const float *__restrict__ gout, float *__restrict__ dx) {
+                                   const float *__restrict__ inv, const float *__restrict__ gout, float *__restrict__ dx) {
     const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e >= groups * c4) return;
     const long long g = e / c4;
@@ -405,12 +435,8 @@ __global__ void maxpool_bwd_kernel(long long groups, int s, int c4, const float 
     float4 *q = reinterpret_cast<float4 *>(dx) + g * s * c4 + cv;
     const float4 m = __ldg(reinterpret_cast<const float4 *>(mx) + e);
     float4 go = __ldg(reinterpret_cast<const float4 *>(gout) + e);
-    int nx = 0, ny = 0, nz = 0, nw = 0;
-    for (int k = 0; k < s; ++k) {
-        const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
-        nx += v.x == m.x; ny += v.y == m.y; nz += v.z == m.z; nw += v.w == m.w;
-    }
-    go.x /= static_cast<float>(nx); go.y /= static_cast<float>(ny); go.z /= static_cast<float>(nz); go.w /= static_cast<float>(nw);
+    const float4 ic = __ldg(reinterpret_cast<const float4 *>(inv) + e);
+    go.x *= ic.x; go.y *= ic.y; go.z *= ic.z; go.w *= ic.w;
     for (int k = 0; k < s; ++k) {
         const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
         q[static_cast<size_t>(k) * c4] = make_float4(v.x == m.x ? go.x : 0.f, v.y == m.y ? go.y : 0.f, v.z == m.z ? go.z : 0.f, v.w == m.w ? go.w : 0.f);
@@ -433,7 +459,7 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
            float *part, uint8_t *wimg, cudaStream_t st);
 bool wgrad_tc_supported(int cin, int cout);
 void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta);
-int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st);
+int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg = 0);
 
 static int pick_ct(int cout) { return cout % 128 == 0 ? 8 : cout % 64 == 0 ? 4 : cout % 32 == 0 ? 2 : cout % 16 == 0 ? 1 : 0; }
 
@@ -553,10 +579,14 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
 // gy (rows,cout) = dL/dy.  Outputs: dx (rows,cin; NULL to skip), dW (cin,cout), db, dgamma, dbeta (cout).
 F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
                                        const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
-                                       const float *gy, float *dx, float *dW, float *db, float *dgamma, float *dbeta, int precision,
-                                       void *workspace, size_t workspace_bytes, void *stream) {
+                                       const float *gy, int pool_s, const float *pooled, const float *inv_ties, float *dx, float *dW,
+                                       float *db, float *dgamma, float *dbeta, int precision, void *workspace, size_t workspace_bytes,
+                                       void *stream) {
     if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !z || !y || !mean || !var || !gy || !dW || !db || !dgamma || !dbeta)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: bad arguments");
+    if (pool_s < 0 || (pool_s > 0 && (!pooled || !inv_ties || rows % pool_s != 0)))
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: pooled gradient needs pooled, inv_ties and rows % pool_s == 0");
+    const GradSource G{gy, pool_s > 0 ? pooled : nullptr, pool_s > 0 ? inv_ties : nullptr, pool_s};
     if (precision != 0 && precision != 2) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: precision must be 0 (fp32) or 2 (bf16x3)");
     if (cout % 16 != 0 || 256 % (cout / 4) != 0)
         return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_backward: output channels must be 16, 32, 64, 128, 256, 512 or 1024");
@@ -594,7 +624,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
 
     const int nred = static_cast<int>(rows < kRedBlocks ? rows : kRedBlocks);
-    bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, gy, y, z, mean, var, relu, part);
+    bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, y, z, mean, var, relu, part);
     int rc = check_launch("bn_bwd_reduce_kernel");
     if (rc) return rc;
     partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(nred, 2 * cout, part, sums);
@@ -604,7 +634,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     rc = check_launch("bn_bwd_finalize_kernel");
     if (rc) return rc;
     const bool w3 = cin == 3;  // the xyz layers: dW rides along with the dz pass (partials in the dW-partials area: 3*cout per chunk)
-    bn_bwd_apply_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, gy, y, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
+    bn_bwd_apply_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, y, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;
     partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(nred, cout, partB, db);
@@ -644,19 +674,20 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
 }
 
 // tf.reduce_max(x, axis=[2]) of models/feat3dnet.py:138,147,182 on a channels-last (groups, s, c) tensor, c % 4 == 0.
-F3D_API int f3d_maxpool_samples_forward(long long groups, int s, int c, const float *x, float *out, void *stream) {
+// inv_ties (groups, c; may be NULL) receives 1 / (number of samples attaining the maximum), which the gradient needs.
+F3D_API int f3d_maxpool_samples_forward(long long groups, int s, int c, const float *x, float *out, float *inv_ties, void *stream) {
     if (groups <= 0 || s <= 0 || c <= 0 || (c & 3) || !x || !out) return fail(F3D_ERR_INVALID_ARGUMENT, "maxpool_samples_forward: bad arguments");
     const long long n = groups * (c / 4);
-    maxpool_fwd_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(groups, s, c / 4, x, out);
+    maxpool_fwd_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(groups, s, c / 4, x, out, inv_ties);
     return check_launch("maxpool_fwd_kernel");
 }
 
 // gradient of the above: the samples that attain the maximum share gout equally.
-F3D_API int f3d_maxpool_samples_backward(long long groups, int s, int c, const float *x, const float *out, const float *gout, float *dx,
-                                         void *stream) {
-    if (groups <= 0 || s <= 0 || c <= 0 || (c & 3) || !x || !out || !gout || !dx)
+F3D_API int f3d_maxpool_samples_backward(long long groups, int s, int c, const float *x, const float *out, const float *inv_ties,
+                                         const float *gout, float *dx, void *stream) {
+    if (groups <= 0 || s <= 0 || c <= 0 || (c & 3) || !x || !out || !inv_ties || !gout || !dx)
         return fail(F3D_ERR_INVALID_ARGUMENT, "maxpool_samples_backward: bad arguments");
     const long long n = groups * (c / 4);
-    maxpool_bwd_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(groups, s, c / 4, x, out, gout, dx);
+    maxpool_bwd_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(groups, s, c / 4, x, out, inv_ties, gout, dx);
     return check_launch("maxpool_bwd_kernel");
 }

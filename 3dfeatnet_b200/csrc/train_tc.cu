@@ -262,35 +262,49 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// 8 rows x 8 channels of a row-major fp32 matrix -> eight 16-byte K(=row)-major chunks, hi and lo
-__device__ __forceinline__ void wgrad_stage_unit(uint8_t *img, uint32_t lbo, uint32_t split, int rc, int cg, const float *__restrict__ src, int ld,
+// 8 rows x 4 channels of a row-major fp32 matrix -> four 16-byte K(=row)-major chunks, hi and lo.  A warp's 32 units are
+// 8 row-chunks x 4 consecutive channel quads: every load instruction covers whole 32-byte sectors (8 rows x 64 B), and the
+// 8 row-chunks of a quarter-warp land in distinct banks (chunk stride = 16 mod 128 bytes).
+__device__ __forceinline__ void wgrad_stage_unit(uint8_t *img, uint32_t lbo, uint32_t split, int rc, int c4, const float *__restrict__ src, int ld,
                                                  long long row0, long long rend) {
-    float v[8][8];
+    float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const long long row = row0 + rc * 8 + i;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (row < rend) {
-            a = __ldg(reinterpret_cast<const float4 *>(src + row * ld + cg * 8));
-            b = __ldg(reinterpret_cast<const float4 *>(src + row * ld + cg * 8 + 4));
-        }
-        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+        v[i] = row < rend ? __ldg(reinterpret_cast<const float4 *>(src + row * ld + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    uint8_t *dst = img + rc * lbo + cg * 128;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float col[8] = {v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]};
-        uint4 hi, lo;
+    uint8_t *dst = img + rc * lbo + c4 * 64;
+    uint4 hi, lo;
+    {
+        const float col[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
         split8(col, hi, lo);
-        *reinterpret_cast<uint4 *>(dst + j * 16) = hi;
-        *reinterpret_cast<uint4 *>(dst + split + j * 16) = lo;
+        *reinterpret_cast<uint4 *>(dst) = hi;
+        *reinterpret_cast<uint4 *>(dst + split) = lo;
+    }
+    {
+        const float col[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
+        split8(col, hi, lo);
+        *reinterpret_cast<uint4 *>(dst + 16) = hi;
+        *reinterpret_cast<uint4 *>(dst + split + 16) = lo;
+    }
+    {
+        const float col[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
+        split8(col, hi, lo);
+        *reinterpret_cast<uint4 *>(dst + 32) = hi;
+        *reinterpret_cast<uint4 *>(dst + split + 32) = lo;
+    }
+    {
+        const float col[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
+        split8(col, hi, lo);
+        *reinterpret_cast<uint4 *>(dst + 48) = hi;
+        *reinterpret_cast<uint4 *>(dst + split + 48) = lo;
     }
 }
 
 // partW[blockIdx.x][cin][cout] = sum over the CTA's rows of x[r][ci] * dz[r][co].  cin % 8 == 0, cin <= 128, cout % 16 == 0, <= 256.
 __global__ void __launch_bounds__(ttc::kThreads)
 wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint32_t tmem_cols, const float *__restrict__ x,
-                const float *__restrict__ dz, float *__restrict__ partW) {
+                const float *__restrict__ dz, float *__restrict__ partW, int dbg) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lbo_b = static_cast<uint32_t>(cout) * 16 + 16;
@@ -320,14 +334,16 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
     const long long rbeg = blockIdx.x * rows_per_cta, rend = rbeg + rows_per_cta < rows ? rbeg + rows_per_cta : rows;
     uint32_t acc = 0;
     for (long long r0 = rbeg; r0 < rend; r0 += kTile) {
-        for (int u = threadIdx.x; u < cin; u += kThreads) wgrad_stage_unit(img_a, kLboA, split_a, u & 7, u >> 3, x, cin, r0, rend);
-        for (int u = threadIdx.x; u < cout; u += kThreads) wgrad_stage_unit(img_b, lbo_b, split_b, u & 7, u >> 3, dz, cout, r0, rend);
+        if (!(dbg & 1)) {
+            for (int u = threadIdx.x; u < 2 * cin; u += kThreads) wgrad_stage_unit(img_a, kLboA, split_a, u & 7, u >> 3, x, cin, r0, rend);
+            for (int u = threadIdx.x; u < 2 * cout; u += kThreads) wgrad_stage_unit(img_b, lbo_b, split_b, u & 7, u >> 3, dz, cout, r0, rend);
+        }
         fence_proxy_async_smem();
         __syncthreads();
         if (warp == 0) {
             tcgen05_fence_after();
             if (elect_one()) {
-                for (int pass = 0; pass < 3; ++pass) {
+                for (int pass = 0; pass < ((dbg & 2) ? 0 : 3); ++pass) {
                     const uint32_t a = sbase + (pass == 2 ? split_a : 0);
                     const uint32_t b = sbase + 2 * split_a + (pass == 1 ? split_b : 0);
                     for (int k = 0; k < kTile / 16; ++k) {
@@ -437,7 +453,7 @@ void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta) {
 }
 
 // partW: grid x cin x cout floats
-int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st) {
+int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg) {
     int grid = 0;
     long long per = 0;
     wgrad_tc_plan(rows, &grid, &per);
@@ -446,8 +462,14 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
     const size_t smem = 2 * split_a + ((2 * split_b + 15) & ~15u) + 64;
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "wgrad_tc: cudaFuncSetAttribute");
-    wgrad_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW);
+    wgrad_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg);
     return check_launch("wgrad_tc_kernel");
 }
 
 }  // namespace f3d
+
+// Bring-up / micro-benchmark entry: the wgrad contraction alone.  dbg bit 0 skips the operand staging, bit 1 the MMAs.
+F3D_API int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, int dbg, void *stream) {
+    if (!f3d::wgrad_tc_supported(cin, cout)) return f3d::fail(F3D_ERR_UNSUPPORTED, "debug_wgrad_tc: unsupported shape");
+    return f3d::wgrad_tc(rows, cin, cout, x, dz, partW, f3d::as_stream(stream), dbg);
+}

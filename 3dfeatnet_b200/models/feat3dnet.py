@@ -164,9 +164,9 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is
         act = _layers.relu if (final_relu or i < len(mlp2) - 1) else None
         new_points = conv2d(new_points, num_out_channel, [1, 1], padding='VALID', stride=[1, 1], bn=bn,
                             is_training=is_training, scope=scope + '/conv_mid_%d' % i, bn_decay=bn_decay, activation=act,
-                            params=params, new_stats=new_stats)
-
-    new_points = _layers.max_pool_samples(new_points)
+                            params=params, new_stats=new_stats, pool_samples=(i == len(mlp2) - 1))
+    if not mlp2:
+        new_points = _layers.max_pool_samples(new_points)
 
     for i, num_out_channel in enumerate(mlp3 or []):
         act = _layers.relu if (final_relu or i < len(mlp3) - 1) else None
@@ -198,13 +198,16 @@ def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp
     end_points['pts_cnt'] = query_and_group_points.last_pts_cnt
 
     for i, num_out_channel in enumerate(mlp):
+        # the last layer's activation only feeds the max-pool: conv2d(pool_samples=True) pools in the same call
+        pool_here = (i == len(mlp) - 1) and not compute_det_gradients
         new_points = conv2d(new_points, num_out_channel, [1, 1], stride=[1, 1], padding='VALID', bn=use_bn,
-                            is_training=is_training, scope=scope + '/conv%d' % i, params=params, new_stats=new_stats)
+                            is_training=is_training, scope=scope + '/conv%d' % i, params=params, new_stats=new_stats,
+                            pool_samples=pool_here)
         if compute_det_gradients:
             (g,) = torch.autograd.grad(new_points, xyz, grad_outputs=new_points.detach(), retain_graph=True)
             end_points['gradients']['det']['mlp_{}'.format(i)] = g
-
-    new_points = _layers.max_pool_samples(new_points)
+    if compute_det_gradients or not mlp:
+        new_points = _layers.max_pool_samples(new_points)
 
     for i, num_out_channel in enumerate(mlp2 or []):
         new_points = conv2d(new_points, num_out_channel, [1, 1], padding='VALID', stride=[1, 1], bn=use_bn,

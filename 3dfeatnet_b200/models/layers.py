@@ -27,51 +27,96 @@ def _native():
     return importlib.import_module(("3dfeatnet_b200." if __name__.split(".")[0] == "3dfeatnet_b200" else "") + "_lib")
 
 
+def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision):
+    _lib = _native()
+    L = _lib.lib()
+    x2, w2 = x.detach().contiguous().float(), w.detach().contiguous().float()
+    b2, g2, be2 = b.detach().contiguous().float(), gamma.detach().contiguous().float(), beta.detach().contiguous().float()
+    _lib.require_cuda(x2, w2, b2, g2, be2)
+    rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
+    nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
+    z = torch.empty((rows, cout), dtype=torch.float32, device=x2.device)
+    y = torch.empty_like(z)
+    mean = torch.empty(cout, dtype=torch.float32, device=x2.device)
+    var = torch.empty_like(mean)
+    _lib.check(L.f3d_conv_bn_train_forward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g2), _lib.ptr(be2),
+                                           int(use_relu), BN_EPS, _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var),
+                                           precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_forward")
+    return x2, w2, g2, z, y, mean, var
+
+
+def _conv_bn_backward(saved, use_relu, precision, gy, need_dx, pool_s=0, pooled=None, inv=None):
+    _lib = _native()
+    L = _lib.lib()
+    x2, w2, g2, z, y, mean, var = saved
+    rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
+    gy = gy.contiguous().float()
+    nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
+    dx = torch.empty_like(x2) if need_dx else None
+    dw = torch.empty_like(w2)
+    db, dg, dbe = (torch.empty(cout, dtype=torch.float32, device=x2.device) for _ in range(3))
+    _lib.check(L.f3d_conv_bn_train_backward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(z), _lib.ptr(y),
+                                            _lib.ptr(mean), _lib.ptr(var), int(use_relu), BN_EPS, _lib.ptr(gy), int(pool_s),
+                                            _lib.ptr(pooled) if pooled is not None else None, _lib.ptr(inv) if inv is not None else None,
+                                            _lib.ptr(dx) if dx is not None else None, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dg),
+                                            _lib.ptr(dbe), precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_backward")
+    return dx, dw, db, dg, dbe
+
+
+def _max_pool_forward(x3):
+    """x3 (groups, s, c) contiguous fp32 -> pooled (groups, c), 1/ties (groups, c)."""
+    _lib = _native()
+    groups, s, c = x3.shape
+    out = torch.empty((groups, c), dtype=torch.float32, device=x3.device)
+    inv = torch.empty_like(out)
+    _lib.check(_lib.lib().f3d_maxpool_samples_forward(groups, s, c, _lib.ptr(x3), _lib.ptr(out), _lib.ptr(inv), _lib.stream()),
+               "maxpool_samples_forward")
+    return out, inv
+
+
 class _ConvBnTrain(torch.autograd.Function):
     """conv 1x1 + bias + batch-norm with BATCH statistics + optional ReLU as one differentiable CUDA op
-    (csrc/train_layers.cu).  Returns (y, batch_mean, batch_var); the moments are not differentiable outputs (they only
-    feed the EMA shadows).  Saves x, z (pre-BN) and y for the backward."""
+    (csrc/train_layers.cu, contractions in csrc/train_tc.cu).  Returns (y, batch_mean, batch_var); the moments are not
+    differentiable outputs (they only feed the EMA shadows).  Saves x, z (pre-BN) and y for the backward."""
 
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, use_relu):
-        _lib = _native()
         ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
-        L = _lib.lib()
-        x2, w2 = x.detach().contiguous().float(), w.detach().contiguous().float()
-        b2, g2, be2 = b.detach().contiguous().float(), gamma.detach().contiguous().float(), beta.detach().contiguous().float()
-        _lib.require_cuda(x2, w2, b2, g2, be2)
-        rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
-        nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
-        z = torch.empty((rows, cout), dtype=torch.float32, device=x2.device)
-        y = torch.empty_like(z)
-        mean = torch.empty(cout, dtype=torch.float32, device=x2.device)
-        var = torch.empty_like(mean)
-        _lib.check(L.f3d_conv_bn_train_forward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g2), _lib.ptr(be2),
-                                               int(use_relu), BN_EPS, _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var),
-                                               ctx.precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_forward")
-        ctx.save_for_backward(x2, w2, g2, z, y, mean, var)
+        saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision)
+        ctx.save_for_backward(*saved)
         ctx.use_relu = bool(use_relu)
+        y, mean, var = saved[4], saved[5], saved[6]
         ctx.mark_non_differentiable(mean, var)
         return y, mean, var
 
     @staticmethod
     def backward(ctx, gy, _gm, _gv):
-        _lib = _native()
-        L = _lib.lib()
-        x2, w2, g2, z, y, mean, var = ctx.saved_tensors
-        rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
-        gy = gy.contiguous().float()
-        nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
-        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w2)
-        db, dg, dbe = (torch.empty(cout, dtype=torch.float32, device=x2.device) for _ in range(3))
-        _lib.check(L.f3d_conv_bn_train_backward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(z), _lib.ptr(y),
-                                                _lib.ptr(mean), _lib.ptr(var), int(ctx.use_relu), BN_EPS, _lib.ptr(gy),
-                                                _lib.ptr(dx) if dx is not None else None, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dg),
-                                                _lib.ptr(dbe), ctx.precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_backward")
-        return dx, dw, db, dg, dbe, None
+        return _conv_bn_backward(ctx.saved_tensors, ctx.use_relu, ctx.precision, gy, ctx.needs_input_grad[0]) + (None,)
+
+
+class _ConvBnTrainPool(torch.autograd.Function):
+    """The same layer followed by tf.reduce_max over groups of `pool_s` consecutive rows (the sample axis), for layers
+    whose activation only feeds that pool (detector conv2, descriptor conv_mid).  Returns (pooled (rows/pool_s, cout),
+    batch_mean, batch_var).  In the backward the dense (rows, cout) gradient is never materialised: the BN-backward
+    kernels rebuild it on the fly from the pooled maxima, the pooled gradient and the tie counts."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, use_relu, pool_s):
+        ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
+        saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision)
+        y, mean, var = saved[4], saved[5], saved[6]
+        pooled, inv = _max_pool_forward(y.view(y.shape[0] // pool_s, pool_s, y.shape[1]))
+        ctx.save_for_backward(*saved, pooled, inv)
+        ctx.use_relu, ctx.pool_s = bool(use_relu), int(pool_s)
+        ctx.mark_non_differentiable(mean, var)
+        return pooled, mean, var
+
+    @staticmethod
+    def backward(ctx, gpool, _gm, _gv):
+        *saved, pooled, inv = ctx.saved_tensors
+        return _conv_bn_backward(saved, ctx.use_relu, ctx.precision, gpool, ctx.needs_input_grad[0], ctx.pool_s, pooled, inv) + (None, None)
 
 
 class _MaxPoolSamples(torch.autograd.Function):
@@ -83,20 +128,19 @@ class _MaxPoolSamples(torch.autograd.Function):
         x4 = x.detach().contiguous().float()
         _lib.require_cuda(x4)
         b, m, s, c = x4.shape
-        out = torch.empty((b, m, 1, c), dtype=torch.float32, device=x4.device)
-        _lib.check(_lib.lib().f3d_maxpool_samples_forward(b * m, s, c, _lib.ptr(x4), _lib.ptr(out), _lib.stream()), "maxpool_samples_forward")
-        ctx.save_for_backward(x4, out)
-        return out
+        out, inv = _max_pool_forward(x4.view(b * m, s, c))
+        ctx.save_for_backward(x4, out, inv)
+        return out.view(b, m, 1, c)
 
     @staticmethod
     def backward(ctx, g):
         _lib = _native()
-        x4, out = ctx.saved_tensors
+        x4, out, inv = ctx.saved_tensors
         b, m, s, c = x4.shape
         g = g.contiguous().float()
         dx = torch.empty_like(x4)
-        _lib.check(_lib.lib().f3d_maxpool_samples_backward(b * m, s, c, _lib.ptr(x4), _lib.ptr(out), _lib.ptr(g), _lib.ptr(dx), _lib.stream()),
-                   "maxpool_samples_backward")
+        _lib.check(_lib.lib().f3d_maxpool_samples_backward(b * m, s, c, _lib.ptr(x4), _lib.ptr(out), _lib.ptr(inv), _lib.ptr(g), _lib.ptr(dx),
+                                                           _lib.stream()), "maxpool_samples_backward")
         return dx
 
 
@@ -143,10 +187,12 @@ def batch_norm_for_conv2d(inputs, is_training, bn_decay, scope, params, new_stat
 
 
 def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', activation=relu, bn=True, bn_decay=None,
-           is_training=None, scope=None, reuse=None, params=None, new_stats=None):
+           is_training=None, scope=None, reuse=None, params=None, new_stats=None, pool_samples=False):
     """ 2D convolution with non-linear operation (layers.py:11-46): slim.conv2d WITH bias -> BN -> activation.
 
-    inputs: (B,H,W,C).  Only the 1x1 / stride-1 kernels the model uses are implemented."""
+    inputs: (B,H,W,C).  Only the 1x1 / stride-1 kernels the model uses are implemented.
+    pool_samples=True additionally applies tf.reduce_max(axis=[2], keep_dims=True) to the result -- the callers that pool
+    right after the layer say so here, which lets the training path fuse the pool's gradient into the layer's backward."""
     if list(kernel_size) != [1, 1] or list(stride) != [1, 1]:
         raise ValueError("conv2d: only kernel_size=[1,1], stride=[1,1] is supported (all the model uses)")
     if params is None or scope is None:
@@ -158,20 +204,25 @@ def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', acti
     if (bn and is_training and inputs.is_cuda and FUSED_TRAINING and (activation is relu or activation is None)
             and num_outputs % 16 == 0 and num_outputs & (num_outputs - 1) == 0):
         # training mode on the GPU: conv + bias + batch-statistics BN + ReLU, forward and backward, in csrc/train_layers.cu
-        y, mean, var = conv_bn_train(inputs.reshape(-1, inputs.shape[-1]), w.reshape(w.shape[-2], w.shape[-1]), b,
-                                     params[scope + "/bn/gamma"], params[scope + "/bn/beta"], activation is relu)
+        fuse_pool = pool_samples and inputs.dim() == 4
+        args = (inputs.reshape(-1, inputs.shape[-1]), w.reshape(w.shape[-2], w.shape[-1]), b,
+                params[scope + "/bn/gamma"], params[scope + "/bn/beta"], activation is relu)
+        y, mean, var = _ConvBnTrainPool.apply(*args, inputs.shape[2]) if fuse_pool else _ConvBnTrain.apply(*args)
         if new_stats is not None:
             decay = bn_decay if bn_decay is not None else BN_DECAY
             mm, mv = params[scope + "/bn/moving_mean"], params[scope + "/bn/moving_variance"]
             new_stats[scope + "/bn/moving_mean"] = (mm - (1 - decay) * (mm - mean)).detach()
             new_stats[scope + "/bn/moving_variance"] = (mv - (1 - decay) * (mv - var)).detach()
-        return y.reshape(*inputs.shape[:-1], num_outputs)
+        if fuse_pool:
+            return y.reshape(inputs.shape[0], inputs.shape[1], 1, num_outputs)
+        y = y.reshape(*inputs.shape[:-1], num_outputs)
+        return max_pool_samples(y) if pool_samples else y
     net = torch.matmul(inputs, w.reshape(w.shape[-2], w.shape[-1])) + b
     if bn:
         net = batch_norm_for_conv2d(net, bool(is_training), bn_decay, scope + "/bn", params, new_stats)
     if activation is not None:
         net = activation(net)
-    return net
+    return max_pool_samples(net) if pool_samples else net
 
 
 def pairwise_dist(A, B):

@@ -166,17 +166,22 @@ int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x,
                               float *var, int precision, void *workspace, size_t workspace_bytes, void *stream);
 /* The gradient TensorFlow derives for the layer above: gy = dL/dy (rows,cout) -> dx (rows,cin; NULL = not needed),
  * dW (cin,cout), db, dgamma, dbeta (cout), through the batch statistics.  cout a power of two in 16..1024; dx needs
- * cin == 3 or a multiple of 16.  Fixed-order reductions: bit-reproducible. */
+ * cin == 3 or a multiple of 16.  pool_s > 0: the layer's output only feeds the max-pool over groups of pool_s consecutive
+ * rows; gy is then the gradient of the POOLED tensor (rows/pool_s, cout), pooled / inv_ties are the outputs of
+ * f3d_maxpool_samples_forward, and the dense (rows, cout) gradient is formed on the fly instead of passing through HBM.
+ * Fixed-order reductions: bit-reproducible. */
 int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
                                const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
-                               const float *gy, float *dx, float *dW, float *db, float *dgamma, float *dbeta, int precision,
-                               void *workspace, size_t workspace_bytes, void *stream);
+                               const float *gy, int pool_s, const float *pooled, const float *inv_ties, float *dx, float *dW,
+                               float *db, float *dgamma, float *dbeta, int precision, void *workspace, size_t workspace_bytes,
+                               void *stream);
 
 /* tf.reduce_max(new_points, axis=[2])  models/feat3dnet.py:138,147,182 on a channels-last (groups, s, c) tensor
- * (c % 4 == 0) -> out (groups, c); and its gradient: samples attaining the maximum share gout equally (TF _MinOrMaxGrad). */
-int f3d_maxpool_samples_forward(long long groups, int s, int c, const float *x, float *out, void *stream);
-int f3d_maxpool_samples_backward(long long groups, int s, int c, const float *x, const float *out, const float *gout,
-                                 float *dx, void *stream);
+ * (c % 4 == 0) -> out (groups, c) and inv_ties (groups, c; NULL = not wanted) = 1 / (number of samples attaining the
+ * maximum); and its gradient: samples attaining the maximum share gout equally (TF _MinOrMaxGrad). */
+int f3d_maxpool_samples_forward(long long groups, int s, int c, const float *x, float *out, float *inv_ties, void *stream);
+int f3d_maxpool_samples_backward(long long groups, int s, int c, const float *x, const float *out, const float *inv_ties,
+                                 const float *gout, float *dx, void *stream);
 
 /* Feat3dNet.get_loss  models/feat3dnet.py:315-357 (+ pairwise_dist, models/layers.py:49-62): attention-weighted
  * triplet loss over anchor / positive / negative descriptors fa, fp, fn (b,m,f) and anchor attention att (b,m; NULL =
@@ -203,6 +208,9 @@ int f3d_adam_step(int num_records, const void *records, long long max_n, float l
  * tensor memory (tcgen05.cp) and feeds the MMA from there.  Not part of the reference surface. */
 int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int N, int K, int lbo_a, int sbo_a, int lbo_b,
                             int sbo_b, int a_bytes, int b_bytes, int a_in_tmem, void *stream);
+/* Bring-up: the tensor-core weight-gradient contraction alone (partW: 2*SMs x cin x cout floats of per-CTA partials);
+ * dbg bit 0 skips the operand staging, bit 1 the MMAs (micro-benchmarking). */
+int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, int dbg, void *stream);
 size_t f3d_detector_tc_weight_bytes(void);
 /* Bring-up: device buffer of (tiles per CTA) x 16 int64 receiving CTA 0's clock64() timeline of the detector tensor
  * kernel (slots: 0/1/2 MMA warp, 4-6 producer, 8-13 epilogue); NULL disables. */

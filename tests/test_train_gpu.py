@@ -185,3 +185,34 @@ def test_max_pool_samples_matches_reduce_max_and_shares_ties(cuda, shape):
     (rdx,) = torch.autograd.grad((ref * go).sum(), [xr])
     assert torch.equal(out.cpu(), ref.detach())
     assert torch.allclose(dx.cpu(), rdx, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("use_relu", [True, False])
+def test_conv_bn_pool_fused_gradient_matches_unfused(cuda, precision, use_relu, monkeypatch):
+    """conv2d(pool_samples=True) in training mode: pooled output and every gradient equal the unfused composition
+    (layer, then max_pool_samples), which the other tests pin against the fp64 statement."""
+    layers = pkg("models.layers")
+    monkeypatch.setattr(layers, "TRAIN_PRECISION", precision)
+    g = torch.Generator().manual_seed(11)
+    B, M, S, cin, cout = 3, 50, 64, 64, 128
+    x = torch.relu(torch.randn(B, M, S, cin, generator=g))
+    x[:, :, 1::2] = x[:, :, 0::2]          # duplicated samples => tied maxima everywhere
+    params = {"l/conv2d/weights": torch.randn(cin, cout, generator=g) * 0.2, "l/conv2d/biases": torch.zeros(cout),
+              "l/bn/gamma": torch.rand(cout, generator=g) + 0.5, "l/bn/beta": torch.randn(cout, generator=g) * 0.1,
+              "l/bn/moving_mean": torch.zeros(cout), "l/bn/moving_variance": torch.ones(cout)}
+    go = torch.randn(B, M, 1, cout, generator=g).to(cuda)
+    res = []
+    for fused in (True, False):
+        P = {k: v.to(cuda).requires_grad_(k.split("/")[-1] in ("weights", "biases", "gamma", "beta")) for k, v in params.items()}
+        xc = x.to(cuda).requires_grad_(True)
+        act = layers.relu if use_relu else None
+        if fused:
+            out = layers.conv2d(xc, cout, [1, 1], scope="l", is_training=True, activation=act, params=P, pool_samples=True)
+        else:
+            out = layers.max_pool_samples(layers.conv2d(xc, cout, [1, 1], scope="l", is_training=True, activation=act, params=P))
+        leaves = [xc] + [P[k] for k in ("l/conv2d/weights", "l/bn/gamma", "l/bn/beta")]
+        res.append((out.detach(), torch.autograd.grad((out * go).sum(), leaves)))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * (b.abs().max().item() + 1e-9))
