@@ -156,14 +156,24 @@ struct GradSource {
     int s;                // samples per group, 0 = dense
 };
 
-__device__ __forceinline__ float4 load_grad(const GradSource &G, size_t o, long long r, int cv, int cvec, const float4 &yy) {
+// per-thread cache of the pooled maximum and the scaled pooled gradient of the group the thread is walking through
+struct PoolCache {
+    long long grp = -1;
+    float4 pm, gs;
+};
+
+__device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, size_t o, long long r, int cv, int cvec, const float4 &yy) {
     if (G.s == 0) return __ldg(reinterpret_cast<const float4 *>(G.gy) + o);
-    const size_t po = static_cast<size_t>(r / G.s) * cvec + cv;
-    const float4 pm = __ldg(reinterpret_cast<const float4 *>(G.pooled) + po);
-    const float4 gp = __ldg(reinterpret_cast<const float4 *>(G.gy) + po);
-    const float4 ic = __ldg(reinterpret_cast<const float4 *>(G.inv) + po);
-    return make_float4(yy.x == pm.x ? gp.x * ic.x : 0.f, yy.y == pm.y ? gp.y * ic.y : 0.f, yy.z == pm.z ? gp.z * ic.z : 0.f,
-                       yy.w == pm.w ? gp.w * ic.w : 0.f);
+    const long long grp = r / G.s;
+    if (grp != C.grp) {
+        const size_t po = static_cast<size_t>(grp) * cvec + cv;
+        C.grp = grp;
+        C.pm = __ldg(reinterpret_cast<const float4 *>(G.pooled) + po);
+        const float4 gp = __ldg(reinterpret_cast<const float4 *>(G.gy) + po);
+        const float4 ic = __ldg(reinterpret_cast<const float4 *>(G.inv) + po);
+        C.gs = make_float4(gp.x * ic.x, gp.y * ic.y, gp.z * ic.z, gp.w * ic.w);
+    }
+    return make_float4(yy.x == C.pm.x ? C.gs.x : 0.f, yy.y == C.pm.y ? C.gs.y : 0.f, yy.z == C.pm.z ? C.gs.z : 0.f, yy.w == C.pm.w ? C.gs.w : 0.f);
 }
 
 // per row-chunk partial sums of g and g*zhat, g = gy * [y > 0] (ReLU) or gy.  part[(blk*2+{0,1})*c + ch]
@@ -179,13 +189,14 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
     const float4 vv = __ldg(reinterpret_cast<const float4 *>(var) + cv);
     const float4 is = make_float4(rsqrtf(vv.x + eps), rsqrtf(vv.y + eps), rsqrtf(vv.z + eps), rsqrtf(vv.w + eps));
     float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sz = sg;
+    PoolCache pc;
     if (rlane < rl) {
         for (long long r = rbeg + rlane; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
             float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
             if (relu || G.s) yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
-            float4 g = load_grad(G, o, r, cv, cvec, yy);
+            float4 g = load_grad(G, pc, o, r, cv, cvec, yy);
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
@@ -241,13 +252,14 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
     const float4 k1 = __ldg(reinterpret_cast<const float4 *>(coef2 + c) + cv);
     const float4 k2 = __ldg(reinterpret_cast<const float4 *>(coef2 + 2 * c) + cv);
     float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), w0 = sb, w1 = sb, w2 = sb;
+    PoolCache pc;
     if (rlane < rl) {
         for (long long r = rbeg + rlane; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
             float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
             if (relu || G.s) yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
-            float4 g = load_grad(G, o, r, cv, cvec, yy);
+            float4 g = load_grad(G, pc, o, r, cv, cvec, yy);
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
