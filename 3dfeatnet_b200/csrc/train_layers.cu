@@ -45,7 +45,7 @@ __device__ __forceinline__ void stage_rows_transposed(float *in_t, const float *
 template <int CT>
 __global__ void __launch_bounds__(kMlpThreads)
 conv_fwd_kernel(long long rows, int cin, int cout, const float *__restrict__ x, const float *__restrict__ W,
-                const float *__restrict__ bias, float *__restrict__ z, float *__restrict__ part) {
+                const float *__restrict__ bias, const float *__restrict__ gbias, int gs, float *__restrict__ z, float *__restrict__ part) {
     extern __shared__ __align__(16) float sm[];
     float *in_t = sm;
     float *red = sm + static_cast<size_t>(cin) * kLdT;  // [2][16][NC]
@@ -67,6 +67,16 @@ conv_fwd_kernel(long long rows, int cin, int cout, const float *__restrict__ x, 
         }
     }
     const long long r0 = tile * kTileRows + rg * 8;
+    if (gbias) {  // per-group additive term (see lin_tc_kernel)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (r0 + i < rows) {
+                const float *gp = gbias + ((r0 + i) / gs) * cout + col;
+#pragma unroll
+                for (int j = 0; j < CT; ++j) acc[i][j] += __ldg(gp + j);
+            }
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (r0 + i < rows) {
@@ -455,6 +465,21 @@ __global__ void maxpool_bwd_kernel(long long groups, int s, int c4, const float 
     }
 }
 
+// out[g][ch] = sum over the s rows of group g of x[g*s + k][ch] (ascending k): the gradient of a per-group additive term
+__global__ void group_sum_kernel(long long groups, int s, int c4, const float *__restrict__ x, float *__restrict__ out) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= groups * c4) return;
+    const long long g = e / c4;
+    const int cv = static_cast<int>(e - g * c4);
+    const float4 *p = reinterpret_cast<const float4 *>(x) + g * s * c4 + cv;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < s; ++k) {
+        const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4 *>(out)[e] = a;
+}
+
 __global__ void transpose_kernel(int r, int c, const float *__restrict__ in, float *__restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= r * c) return;
@@ -467,16 +492,16 @@ int lin_tc_kp(int k_real);
 bool lin_tc_supported(int k_real, int nout);
 size_t lin_tc_weight_bytes(int k_real, int nout);
 int lin_tc_grid(long long rows, int k_real);
-int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias, float *out,
-           float *part, uint8_t *wimg, cudaStream_t st);
+int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
+           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, cudaStream_t st);
 bool wgrad_tc_supported(int cin, int cout);
 void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta);
 int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg = 0);
 
 static int pick_ct(int cout) { return cout % 128 == 0 ? 8 : cout % 64 == 0 ? 4 : cout % 32 == 0 ? 2 : cout % 16 == 0 ? 1 : 0; }
 
-static int launch_conv_fwd(long long rows, int cin, int cout, const float *x, const float *W, const float *bias, float *z, float *part,
-                           cudaStream_t st) {
+static int launch_conv_fwd(long long rows, int cin, int cout, const float *x, const float *W, const float *bias, const float *gbias, int gs,
+                           float *z, float *part, cudaStream_t st) {
     const int ct = pick_ct(cout);
     if (!ct) return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train: output channels must be a multiple of 16");
     const long long tiles = (rows + kTileRows - 1) / kTileRows;
@@ -487,7 +512,7 @@ static int launch_conv_fwd(long long rows, int cin, int cout, const float *x, co
     cudaError_t e = cudaSuccess;
 #define F3D_LAUNCH_FWD(CT)                                                                                              \
     e = cudaFuncSetAttribute(conv_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-    if (e == cudaSuccess) conv_fwd_kernel<CT><<<grid, kMlpThreads, smem, st>>>(rows, cin, cout, x, W, bias, z, part);
+    if (e == cudaSuccess) conv_fwd_kernel<CT><<<grid, kMlpThreads, smem, st>>>(rows, cin, cout, x, W, bias, gbias, gs, z, part);
     switch (ct) {
         case 8: F3D_LAUNCH_FWD(8) break;
         case 4: F3D_LAUNCH_FWD(4) break;
@@ -554,8 +579,11 @@ F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int co
 // x (rows,cin), W (cin,cout), bias/gamma/beta (cout) -> z (rows,cout) pre-BN, y (rows,cout) post BN(+ReLU), mean/var (cout)
 // = the batch moments (population variance) the caller feeds to the EMA update.
 F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
-                                      const float *gamma, const float *beta, int relu, float eps, float *z, float *y, float *mean,
-                                      float *var, int precision, void *workspace, size_t workspace_bytes, void *stream) {
+                                      const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
+                                      float *z, float *y, float *mean, float *var, int precision, void *workspace, size_t workspace_bytes,
+                                      void *stream) {
+    if (group_bias && (group_s <= 0 || rows % group_s != 0))
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: group_bias needs group_s > 0 dividing rows");
     if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !y || !mean || !var)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: bad arguments");
     if (precision != 0 && precision != 2) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: precision must be 0 (fp32) or 2 (bf16x3)");
@@ -575,7 +603,8 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
     float *coef = reinterpret_cast<float *>(w);
     w += align256(2 * cout * 4);
     uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
-    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, z, part, wimg, st) : launch_conv_fwd(rows, cin, cout, x, W, bias, z, part, st);
+    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, st)
+                : launch_conv_fwd(rows, cin, cout, x, W, bias, group_bias, group_s, z, part, st);
     if (rc) return rc;
     partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(nparts), 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
@@ -592,8 +621,10 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
 F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
                                        const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
                                        const float *gy, int pool_s, const float *pooled, const float *inv_ties, float *dx, float *dW,
-                                       float *db, float *dgamma, float *dbeta, int precision, void *workspace, size_t workspace_bytes,
-                                       void *stream) {
+                                       float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s, int precision,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
+    if (dgroup_bias && (group_s <= 0 || rows % group_s != 0))
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: dgroup_bias needs group_s > 0 dividing rows");
     if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !z || !y || !mean || !var || !gy || !dW || !db || !dgamma || !dbeta)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: bad arguments");
     if (pool_s < 0 || (pool_s > 0 && (!pooled || !inv_ties || rows % pool_s != 0)))
@@ -653,6 +684,12 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
 
+    if (dgroup_bias) {
+        const long long n = (rows / group_s) * (cout / 4);
+        group_sum_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(rows / group_s, group_s, cout / 4, dz, dgroup_bias);
+        rc = check_launch("group_sum_kernel");
+        if (rc) return rc;
+    }
     const long long nw = static_cast<long long>(cin) * cout;
     if (w3) {
         partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(nred, nw, partW, dW);
@@ -674,12 +711,12 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
             conv_dgrad3_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 3 * cout * sizeof(float), st>>>(rows, cout, dz, W, dx);
             rc = check_launch("conv_dgrad3_kernel");
         } else if (tc_dgrad) {
-            rc = lin_tc(rows, cout, cin, dz, W, cout, 1, nullptr, dx, nullptr, wimg, st);  // A[m = ci][k = co] = W[ci][co]
+            rc = lin_tc(rows, cout, cin, dz, W, cout, 1, nullptr, nullptr, 0, dx, nullptr, wimg, st);  // A[m = ci][k = co] = W[ci][co]
         } else {
             transpose_kernel<<<(cin * cout + 255) / 256, 256, 0, st>>>(cin, cout, W, Wt);
             rc = check_launch("transpose_kernel");
             if (rc) return rc;
-            rc = launch_conv_fwd(rows, cout, cin, dz, Wt, nullptr, dx, nullptr, st);
+            rc = launch_conv_fwd(rows, cout, cin, dz, Wt, nullptr, nullptr, 0, dx, nullptr, st);
         }
     }
     return rc;

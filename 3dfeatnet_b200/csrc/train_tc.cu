@@ -77,9 +77,9 @@ __global__ void lin_prep_kernel(const float *__restrict__ src, long long sm, lon
 // conflict-free LDS.128 and writes the bf16 hi/lo operand image (chunk stride padded by 32 B against bank conflicts).
 constexpr int kRing = 2;
 
-__global__ void __launch_bounds__(ttc::kThreads)
+__global__ void __launch_bounds__(ttc::kThreads, 4)
 lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
-              const float *__restrict__ bias, float *__restrict__ out, float *__restrict__ part) {
+              const float *__restrict__ bias, const float *__restrict__ gbias, int gs, float *__restrict__ out, float *__restrict__ part) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const bool ring = (k_real & 7) == 0;
@@ -238,6 +238,24 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
         tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0, r);
         tmem_ld_wait();
         if (ch_ok) {
+            if (gbias) {
+                // optional per-group additive term (rows of a group of gs consecutive rows share it): the pooled half of a
+                // concat([x, tile(pooled)]) input contributes pooled * W_bottom once per group instead of once per row
+                const long long g0 = (r0 + col0) / gs;
+                const int rem0 = static_cast<int>((r0 + col0) - g0 * gs);
+                const long long gmax = (rows - 1) / gs;
+                if (rem0 + 31 < gs) {
+                    const float gb = __ldg(gbias + g0 * nout + gch);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + gb);
+                } else {
+                    for (int j = 0; j < 32; ++j) {
+                        long long grp = g0 + (rem0 + j) / gs;
+                        grp = grp < gmax ? grp : gmax;
+                        r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(gbias + grp * nout + gch));
+                    }
+                }
+            }
             float *o = out + (r0 + col0) * nout + gch;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -422,10 +440,10 @@ int lin_tc_grid(long long rows, int k_real) {
     return static_cast<int>(ntiles < g ? ntiles : g);
 }
 
-// out (rows, nout) = x (rows, k_real) * A^T (+ bias) with A[m][k] = src[m*sm + k*sk];  part: 2*lin_tc_grid() partials of
+// out (rows, nout) = x (rows, k_real) * A^T (+ bias) (+ gbias[row / gs]) with A[m][k] = src[m*sm + k*sk];  part: 2*lin_tc_grid() partials of
 // {sum, sum of squares} per channel, or NULL.  wimg: lin_tc_weight_bytes() of scratch.
-int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias, float *out,
-           float *part, uint8_t *wimg, cudaStream_t st) {
+int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
+           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, cudaStream_t st) {
     const int kp = lin_tc_kp(k_real);
     const int mblocks = (nout + 127) / 128;
     const long long total = 128LL * kp * mblocks;
@@ -437,7 +455,7 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
     cudaError_t e = cudaFuncSetAttribute(lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
     const dim3 grid(mblocks, lin_tc_grid(rows, k_real));
-    lin_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, cols, x, wimg, bias, out, part);
+    lin_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, cols, x, wimg, bias, gbias, gs, out, part);
     return check_launch("lin_tc_kernel");
 }
 

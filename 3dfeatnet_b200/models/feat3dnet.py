@@ -158,14 +158,16 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is
                             is_training=is_training, scope=scope + '/conv%d' % i, params=params, new_stats=new_stats)
 
     pooled = _layers.max_pool_samples(new_points)  # tf.reduce_max; the gradient is shared among ties like TF
-    new_points = torch.cat((new_points, pooled.expand(-1, -1, new_points.shape[2], -1)), dim=3)
-
+    # the reference tiles `pooled` over the samples and concatenates it to new_points (:60-66); conv2d(concat_pooled=) states
+    # the same layer without building the (B,M,S,2C) tensor
     for i, num_out_channel in enumerate(mlp2 or []):
         act = _layers.relu if (final_relu or i < len(mlp2) - 1) else None
         new_points = conv2d(new_points, num_out_channel, [1, 1], padding='VALID', stride=[1, 1], bn=bn,
                             is_training=is_training, scope=scope + '/conv_mid_%d' % i, bn_decay=bn_decay, activation=act,
-                            params=params, new_stats=new_stats, pool_samples=(i == len(mlp2) - 1))
+                            params=params, new_stats=new_stats, pool_samples=(i == len(mlp2) - 1),
+                            concat_pooled=pooled if i == 0 else None)
     if not mlp2:
+        new_points = torch.cat((new_points, pooled.expand(-1, -1, new_points.shape[2], -1)), dim=3)
         new_points = _layers.max_pool_samples(new_points)
 
     for i, num_out_channel in enumerate(mlp3 or []):

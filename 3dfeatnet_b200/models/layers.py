@@ -27,11 +27,12 @@ def _native():
     return importlib.import_module(("3dfeatnet_b200." if __name__.split(".")[0] == "3dfeatnet_b200" else "") + "_lib")
 
 
-def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision):
+def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision, gbias=None, gs=0):
     _lib = _native()
     L = _lib.lib()
     x2, w2 = x.detach().contiguous().float(), w.detach().contiguous().float()
     b2, g2, be2 = b.detach().contiguous().float(), gamma.detach().contiguous().float(), beta.detach().contiguous().float()
+    gb2 = gbias.detach().contiguous().float() if gbias is not None else None
     _lib.require_cuda(x2, w2, b2, g2, be2)
     rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
     nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
@@ -40,13 +41,15 @@ def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision):
     y = torch.empty_like(z)
     mean = torch.empty(cout, dtype=torch.float32, device=x2.device)
     var = torch.empty_like(mean)
-    _lib.check(L.f3d_conv_bn_train_forward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g2), _lib.ptr(be2),
+    _lib.check(L.f3d_conv_bn_train_forward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2),
+                                           _lib.ptr(gb2) if gb2 is not None else None, int(gs), _lib.ptr(g2), _lib.ptr(be2),
                                            int(use_relu), BN_EPS, _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var),
                                            precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_forward")
     return x2, w2, g2, z, y, mean, var
 
 
-def _conv_bn_backward(saved, use_relu, precision, gy, need_dx, pool_s=0, pooled=None, inv=None):
+def _conv_bn_backward(saved, use_relu, precision, gy, need_dx, pool_s=0, pooled=None, inv=None, gs=0):
+    """-> (dx, dW, db, dgamma, dbeta, dgroup_bias); dgroup_bias only when gs > 0."""
     _lib = _native()
     L = _lib.lib()
     x2, w2, g2, z, y, mean, var = saved
@@ -57,12 +60,14 @@ def _conv_bn_backward(saved, use_relu, precision, gy, need_dx, pool_s=0, pooled=
     dx = torch.empty_like(x2) if need_dx else None
     dw = torch.empty_like(w2)
     db, dg, dbe = (torch.empty(cout, dtype=torch.float32, device=x2.device) for _ in range(3))
+    dgb = torch.empty((rows // gs, cout), dtype=torch.float32, device=x2.device) if gs > 0 else None
     _lib.check(L.f3d_conv_bn_train_backward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(z), _lib.ptr(y),
                                             _lib.ptr(mean), _lib.ptr(var), int(use_relu), BN_EPS, _lib.ptr(gy), int(pool_s),
                                             _lib.ptr(pooled) if pooled is not None else None, _lib.ptr(inv) if inv is not None else None,
                                             _lib.ptr(dx) if dx is not None else None, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dg),
-                                            _lib.ptr(dbe), precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_backward")
-    return dx, dw, db, dg, dbe
+                                            _lib.ptr(dbe), _lib.ptr(dgb) if dgb is not None else None, int(gs), precision,
+                                            _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_backward")
+    return dx, dw, db, dg, dbe, dgb
 
 
 def _max_pool_forward(x3):
@@ -78,45 +83,39 @@ def _max_pool_forward(x3):
 
 class _ConvBnTrain(torch.autograd.Function):
     """conv 1x1 + bias + batch-norm with BATCH statistics + optional ReLU as one differentiable CUDA op
-    (csrc/train_layers.cu, contractions in csrc/train_tc.cu).  Returns (y, batch_mean, batch_var); the moments are not
-    differentiable outputs (they only feed the EMA shadows).  Saves x, z (pre-BN) and y for the backward."""
+    (csrc/train_layers.cu, contractions in csrc/train_tc.cu).  Returns (out, batch_mean, batch_var); the moments are not
+    differentiable outputs (they only feed the EMA shadows).  Saves x, z (pre-BN) and y for the backward.
+
+    pool_s > 0: the layer is followed by tf.reduce_max over groups of pool_s consecutive rows (the sample axis) and ONLY
+    feeds that pool (detector conv2, descriptor conv_mid); out is then the pooled (rows/pool_s, cout) tensor and in the
+    backward the dense (rows, cout) gradient is never materialised: the BN-backward kernels rebuild it on the fly from
+    the pooled maxima, the pooled gradient and the tie counts.
+    gbias (rows/gs, cout) or None: a per-group additive term of the pre-BN activation (the pooled half of a
+    concat([x, tile(pooled)]) input, see conv2d_concat_pooled); its gradient is the per-group row sum of dz."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, use_relu):
+    def forward(ctx, x, w, b, gamma, beta, use_relu, pool_s, gbias, gs):
         ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
-        saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision)
-        ctx.save_for_backward(*saved)
-        ctx.use_relu = bool(use_relu)
+        saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision, gbias, gs if gbias is not None else 0)
         y, mean, var = saved[4], saved[5], saved[6]
+        ctx.use_relu, ctx.pool_s, ctx.gs = bool(use_relu), int(pool_s), int(gs) if gbias is not None else 0
         ctx.mark_non_differentiable(mean, var)
+        if pool_s:
+            pooled, inv = _max_pool_forward(y.view(y.shape[0] // pool_s, pool_s, y.shape[1]))
+            ctx.save_for_backward(*saved, pooled, inv)
+            return pooled, mean, var
+        ctx.save_for_backward(*saved)
         return y, mean, var
 
     @staticmethod
-    def backward(ctx, gy, _gm, _gv):
-        return _conv_bn_backward(ctx.saved_tensors, ctx.use_relu, ctx.precision, gy, ctx.needs_input_grad[0]) + (None,)
-
-
-class _ConvBnTrainPool(torch.autograd.Function):
-    """The same layer followed by tf.reduce_max over groups of `pool_s` consecutive rows (the sample axis), for layers
-    whose activation only feeds that pool (detector conv2, descriptor conv_mid).  Returns (pooled (rows/pool_s, cout),
-    batch_mean, batch_var).  In the backward the dense (rows, cout) gradient is never materialised: the BN-backward
-    kernels rebuild it on the fly from the pooled maxima, the pooled gradient and the tie counts."""
-
-    @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, use_relu, pool_s):
-        ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
-        saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision)
-        y, mean, var = saved[4], saved[5], saved[6]
-        pooled, inv = _max_pool_forward(y.view(y.shape[0] // pool_s, pool_s, y.shape[1]))
-        ctx.save_for_backward(*saved, pooled, inv)
-        ctx.use_relu, ctx.pool_s = bool(use_relu), int(pool_s)
-        ctx.mark_non_differentiable(mean, var)
-        return pooled, mean, var
-
-    @staticmethod
-    def backward(ctx, gpool, _gm, _gv):
-        *saved, pooled, inv = ctx.saved_tensors
-        return _conv_bn_backward(saved, ctx.use_relu, ctx.precision, gpool, ctx.needs_input_grad[0], ctx.pool_s, pooled, inv) + (None, None)
+    def backward(ctx, gout, _gm, _gv):
+        if ctx.pool_s:
+            *saved, pooled, inv = ctx.saved_tensors
+        else:
+            saved, pooled, inv = ctx.saved_tensors, None, None
+        dx, dw, db, dg, dbe, dgb = _conv_bn_backward(saved, ctx.use_relu, ctx.precision, gout, ctx.needs_input_grad[0], ctx.pool_s,
+                                                     pooled, inv, ctx.gs)
+        return dx, dw, db, dg, dbe, None, None, dgb, None
 
 
 class _MaxPoolSamples(torch.autograd.Function):
@@ -151,9 +150,9 @@ def max_pool_samples(x):
     return x.amax(dim=2, keepdim=True)  # amax shares the gradient among ties like TF
 
 
-def conv_bn_train(x, w, b, gamma, beta, use_relu=True):
-    """(rows,cin) x (cin,cout) -> (y (rows,cout), batch_mean, batch_var): the training-mode layer as one CUDA op."""
-    return _ConvBnTrain.apply(x, w, b, gamma, beta, use_relu)
+def conv_bn_train(x, w, b, gamma, beta, use_relu=True, pool_s=0, gbias=None, gs=0):
+    """(rows,cin) x (cin,cout) -> (out, batch_mean, batch_var): the training-mode layer as one CUDA op (see _ConvBnTrain)."""
+    return _ConvBnTrain.apply(x, w, b, gamma, beta, use_relu, pool_s, gbias, gs)
 
 
 def batch_norm_template(inputs, is_training, scope, moments_dims, bn_decay, params, new_stats=None):
@@ -187,27 +186,36 @@ def batch_norm_for_conv2d(inputs, is_training, bn_decay, scope, params, new_stat
 
 
 def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', activation=relu, bn=True, bn_decay=None,
-           is_training=None, scope=None, reuse=None, params=None, new_stats=None, pool_samples=False):
+           is_training=None, scope=None, reuse=None, params=None, new_stats=None, pool_samples=False, concat_pooled=None):
     """ 2D convolution with non-linear operation (layers.py:11-46): slim.conv2d WITH bias -> BN -> activation.
 
     inputs: (B,H,W,C).  Only the 1x1 / stride-1 kernels the model uses are implemented.
     pool_samples=True additionally applies tf.reduce_max(axis=[2], keep_dims=True) to the result -- the callers that pool
-    right after the layer say so here, which lets the training path fuse the pool's gradient into the layer's backward."""
+    right after the layer say so here, which lets the training path fuse the pool's gradient into the layer's backward.
+    concat_pooled (B,H,1,C2) or None: the layer's input is concat([inputs, tile(concat_pooled, W)], -1) (the reference's
+    feat3dnet.py:60-66); weights are (C+C2, Cout).  The training path never materialises the concatenation."""
     if list(kernel_size) != [1, 1] or list(stride) != [1, 1]:
         raise ValueError("conv2d: only kernel_size=[1,1], stride=[1,1] is supported (all the model uses)")
     if params is None or scope is None:
         raise ValueError("conv2d needs params= (flat dict keyed by TF scope names) and scope=")
     w, b = params[scope + "/conv2d/weights"], params[scope + "/conv2d/biases"]
-    if w.shape[-1] != num_outputs or w.shape[-2] != inputs.shape[-1]:
-        raise ValueError("conv2d: weight shape %s does not match (%d -> %d)"
-                         % (tuple(w.shape), inputs.shape[-1], num_outputs))
+    cin_total = inputs.shape[-1] + (concat_pooled.shape[-1] if concat_pooled is not None else 0)
+    if w.shape[-1] != num_outputs or w.shape[-2] != cin_total:
+        raise ValueError("conv2d: weight shape %s does not match (%d -> %d)" % (tuple(w.shape), cin_total, num_outputs))
     if (bn and is_training and inputs.is_cuda and FUSED_TRAINING and (activation is relu or activation is None)
             and num_outputs % 16 == 0 and num_outputs & (num_outputs - 1) == 0):
         # training mode on the GPU: conv + bias + batch-statistics BN + ReLU, forward and backward, in csrc/train_layers.cu
         fuse_pool = pool_samples and inputs.dim() == 4
-        args = (inputs.reshape(-1, inputs.shape[-1]), w.reshape(w.shape[-2], w.shape[-1]), b,
-                params[scope + "/bn/gamma"], params[scope + "/bn/beta"], activation is relu)
-        y, mean, var = _ConvBnTrainPool.apply(*args, inputs.shape[2]) if fuse_pool else _ConvBnTrain.apply(*args)
+        w2 = w.reshape(w.shape[-2], w.shape[-1])
+        gbias, gs, x_rows = None, 0, inputs
+        if concat_pooled is not None:
+            # input = concat([inputs, tile(concat_pooled)], -1) without building it: the pooled half contributes
+            # concat_pooled @ W_bottom once per cluster (SURVEY.md appendix C, the split-weight identity)
+            c1 = inputs.shape[-1]
+            gbias = torch.matmul(concat_pooled.reshape(-1, concat_pooled.shape[-1]), w2[c1:])
+            gs, w2 = inputs.shape[2], w2[:c1]
+        y, mean, var = conv_bn_train(x_rows.reshape(-1, x_rows.shape[-1]), w2, b, params[scope + "/bn/gamma"],
+                                     params[scope + "/bn/beta"], activation is relu, inputs.shape[2] if fuse_pool else 0, gbias, gs)
         if new_stats is not None:
             decay = bn_decay if bn_decay is not None else BN_DECAY
             mm, mv = params[scope + "/bn/moving_mean"], params[scope + "/bn/moving_variance"]
@@ -217,6 +225,8 @@ def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', acti
             return y.reshape(inputs.shape[0], inputs.shape[1], 1, num_outputs)
         y = y.reshape(*inputs.shape[:-1], num_outputs)
         return max_pool_samples(y) if pool_samples else y
+    if concat_pooled is not None:
+        inputs = torch.cat((inputs, concat_pooled.expand(-1, -1, inputs.shape[2], -1)), dim=3)
     net = torch.matmul(inputs, w.reshape(w.shape[-2], w.shape[-1])) + b
     if bn:
         net = batch_norm_for_conv2d(net, bool(is_training), bn_decay, scope + "/bn", params, new_stats)

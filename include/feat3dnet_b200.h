@@ -157,13 +157,17 @@ int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_r
 /* conv2d(..., bn=True, is_training=True)  models/layers.py:11-46 + batch_norm_template :225-272, 1x1 kernels, channels
  * last: x (rows,cin), W (cin,cout), bias/gamma/beta (cout) -> z = x W + bias (rows,cout), batch moments mean/var (cout,
  * population variance, what the caller feeds the EMA update), y = [relu](gamma (z-mean) rsqrt(var+eps) + beta).
+ * group_bias (rows/group_s, cout; NULL = none) is added to every row of its group of group_s consecutive rows: with it
+ * the concat([h, tile(pooled)]) input of pointnet_sa_module's conv_mid (feat3dnet.py:60-69) never has to be built --
+ * z = h W_top + (pooled W_bottom)[group] -- and its gradient comes back as dgroup_bias = per-group row sums of dz.
  * cout a multiple of 16.  precision: 0 = fp32 FFMA contractions, 2 = tcgen05 tensor cores with the bf16 hi/lo split
  * ("bf16x3", ~1e-5 relative; cin <= 256).  workspace: f3d_conv_bn_train_workspace_bytes(rows,cin,cout) (covers forward
  * and backward). */
 size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int cout);
 int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
-                              const float *gamma, const float *beta, int relu, float eps, float *z, float *y, float *mean,
-                              float *var, int precision, void *workspace, size_t workspace_bytes, void *stream);
+                              const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
+                              float *z, float *y, float *mean, float *var, int precision, void *workspace,
+                              size_t workspace_bytes, void *stream);
 /* The gradient TensorFlow derives for the layer above: gy = dL/dy (rows,cout) -> dx (rows,cin; NULL = not needed),
  * dW (cin,cout), db, dgamma, dbeta (cout), through the batch statistics.  cout a power of two in 16..1024; dx needs
  * cin == 3 or a multiple of 16.  pool_s > 0: the layer's output only feeds the max-pool over groups of pool_s consecutive
@@ -173,8 +177,8 @@ int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x,
 int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
                                const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
                                const float *gy, int pool_s, const float *pooled, const float *inv_ties, float *dx, float *dW,
-                               float *db, float *dgamma, float *dbeta, int precision, void *workspace, size_t workspace_bytes,
-                               void *stream);
+                               float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s, int precision,
+                               void *workspace, size_t workspace_bytes, void *stream);
 
 /* tf.reduce_max(new_points, axis=[2])  models/feat3dnet.py:138,147,182 on a channels-last (groups, s, c) tensor
  * (c % 4 == 0) -> out (groups, c) and inv_ties (groups, c; NULL = not wanted) = 1 / (number of samples attaining the

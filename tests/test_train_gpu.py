@@ -216,3 +216,35 @@ def test_conv_bn_pool_fused_gradient_matches_unfused(cuda, precision, use_relu, 
     assert torch.equal(res[0][0], res[1][0])
     for a, b in zip(res[0][1], res[1][1]):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * (b.abs().max().item() + 1e-9))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_conv_mid_without_concat_matches_the_concatenated_statement(cuda, precision, monkeypatch):
+    """pointnet_sa_module's conv_mid (reference feat3dnet.py:60-75): concat([h, tile(max_S h)]) -> conv+BN -> max_S.
+    conv2d(concat_pooled=, pool_samples=True) never builds the concat; value and all gradients must equal the literal
+    graph (torch cat + matmul + batch statistics + amax) in fp64."""
+    layers = pkg("models.layers")
+    monkeypatch.setattr(layers, "TRAIN_PRECISION", precision)
+    g = torch.Generator().manual_seed(21)
+    B, M, S, c1, cout = 2, 40, 64, 64, 128
+    h = torch.relu(torch.randn(B, M, S, c1, generator=g))
+    W = torch.randn(2 * c1, cout, generator=g) * 0.15
+    gamma, beta = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    go = torch.randn(B, M, 1, cout, generator=g)
+    P = {"l/conv2d/weights": W.to(cuda).requires_grad_(True), "l/conv2d/biases": torch.zeros(cout, device=cuda, requires_grad=True),
+         "l/bn/gamma": gamma.to(cuda).requires_grad_(True), "l/bn/beta": beta.to(cuda).requires_grad_(True),
+         "l/bn/moving_mean": torch.zeros(cout, device=cuda), "l/bn/moving_variance": torch.ones(cout, device=cuda)}
+    hc = h.to(cuda).requires_grad_(True)
+    pooled = layers.max_pool_samples(hc)
+    out = layers.conv2d(hc, cout, [1, 1], scope="l", is_training=True, activation=None, params=P, pool_samples=True, concat_pooled=pooled)
+    grads = torch.autograd.grad((out * go.to(cuda)).sum(), [hc, P["l/conv2d/weights"], P["l/bn/gamma"], P["l/bn/beta"]])
+    # literal graph in fp64
+    h64, W64, ga64, be64 = (t.double().requires_grad_(True) for t in (h, W, gamma, beta))
+    q = h64.amax(dim=2, keepdim=True)
+    z = torch.cat((h64, q.expand(-1, -1, S, -1)), dim=3) @ W64
+    mean, var = z.mean(dim=(0, 1, 2)), z.var(dim=(0, 1, 2), unbiased=False)
+    ref = ((z - mean) * torch.rsqrt(var + 1e-3) * ga64 + be64).amax(dim=2, keepdim=True)
+    rgrads = torch.autograd.grad((ref * go.double()).sum(), [h64, W64, ga64, be64])
+    assert (out.detach().cpu().double() - ref).abs().max().item() < 5e-5 * max(1.0, ref.abs().max().item())
+    for name, a, r in zip(("dh", "dW", "dgamma", "dbeta"), grads, rgrads):
+        assert (a.cpu().double() - r).abs().max().item() < 3e-4 * (r.abs().max().item() + 1e-9) + 1e-6, name
