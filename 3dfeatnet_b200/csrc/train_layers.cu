@@ -231,6 +231,51 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
     }
 }
 
+// Pooled mode: g is non-zero only where y equals its group maximum, the tied rows share gpool equally and all have the
+// same zhat = (max - beta) / gamma, so  sum g = sum_groups gpool  and  sum g*zhat = sum_groups gpool * zhat_max  (masked by
+// max > 0 under ReLU): the two reductions need the (groups, c) tensors only, not a pass over the rows.
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_pooled_kernel(long long groups, int c, const float *__restrict__ gpool, const float *__restrict__ pooled,
+                            const float *__restrict__ gamma, const float *__restrict__ beta, int relu, float *__restrict__ part) {
+    __shared__ float4 red[2][256];
+    const int cvec = c >> 2, rl = 256 / cvec;
+    const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
+    const long long chunk = (groups + gridDim.x - 1) / gridDim.x;
+    const long long gbeg = blockIdx.x * chunk, gend = min(groups, gbeg + chunk);
+    const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma) + cv);
+    const float4 be = __ldg(reinterpret_cast<const float4 *>(beta) + cv);
+    const float4 ig = make_float4(ga.x != 0.f ? 1.0f / ga.x : 0.f, ga.y != 0.f ? 1.0f / ga.y : 0.f, ga.z != 0.f ? 1.0f / ga.z : 0.f,
+                                  ga.w != 0.f ? 1.0f / ga.w : 0.f);
+    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sz = sg;
+    if (rlane < rl) {
+        for (long long g = gbeg + rlane; g < gend; g += rl) {
+            const size_t o = static_cast<size_t>(g) * cvec + cv;
+            float4 gp = __ldg(reinterpret_cast<const float4 *>(gpool) + o);
+            const float4 pm = __ldg(reinterpret_cast<const float4 *>(pooled) + o);
+            if (relu) {
+                gp.x = pm.x > 0.f ? gp.x : 0.f; gp.y = pm.y > 0.f ? gp.y : 0.f; gp.z = pm.z > 0.f ? gp.z : 0.f; gp.w = pm.w > 0.f ? gp.w : 0.f;
+            }
+            sg.x += gp.x; sg.y += gp.y; sg.z += gp.z; sg.w += gp.w;
+            sz.x = fmaf(gp.x, (pm.x - be.x) * ig.x, sz.x);
+            sz.y = fmaf(gp.y, (pm.y - be.y) * ig.y, sz.y);
+            sz.z = fmaf(gp.z, (pm.z - be.z) * ig.z, sz.z);
+            sz.w = fmaf(gp.w, (pm.w - be.w) * ig.w, sz.w);
+        }
+    }
+    red[0][threadIdx.x] = sg;
+    red[1][threadIdx.x] = sz;
+    __syncthreads();
+    if (threadIdx.x < 2 * cvec) {
+        const int which = threadIdx.x / cvec, v = threadIdx.x - which * cvec;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < rl; ++l) {
+            const float4 t = red[which][l * cvec + v];
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        reinterpret_cast<float4 *>(part + (static_cast<size_t>(blockIdx.x) * 2 + which) * c)[v] = s;
+    }
+}
+
 // sums[2][c] (sum g, sum g*zhat) -> dbeta, dgamma, coef2 = {s = gamma*istd, k1 = mean(g), k2 = mean(g*zhat)}
 __global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const float *__restrict__ sums, const float *__restrict__ gamma,
                                        const float *__restrict__ var, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef2) {
@@ -619,7 +664,7 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
 
 // gy (rows,cout) = dL/dy.  Outputs: dx (rows,cin; NULL to skip), dW (cin,cout), db, dgamma, dbeta (cout).
 F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
-                                       const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
+                                       const float *beta, const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
                                        const float *gy, int pool_s, const float *pooled, const float *inv_ties, float *dx, float *dW,
                                        float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s, int precision,
                                        void *workspace, size_t workspace_bytes, void *stream) {
@@ -667,10 +712,19 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
 
     const int nred = static_cast<int>(rows < kRedBlocks ? rows : kRedBlocks);
-    bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, y, z, mean, var, relu, part);
-    int rc = check_launch("bn_bwd_reduce_kernel");
+    int rc = 0;
+    int nred1 = nred;
+    if (pool_s > 0 && beta) {
+        const long long groups = rows / pool_s;
+        nred1 = static_cast<int>(groups < kRedBlocks ? groups : kRedBlocks);
+        bn_bwd_reduce_pooled_kernel<<<nred1, 256, 0, st>>>(groups, cout, gy, pooled, gamma, beta, relu, part);
+        rc = check_launch("bn_bwd_reduce_pooled_kernel");
+    } else {
+        bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, y, z, mean, var, relu, part);
+        rc = check_launch("bn_bwd_reduce_kernel");
+    }
     if (rc) return rc;
-    partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(nred, 2 * cout, part, sums);
+    partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(nred1, 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
     bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2);

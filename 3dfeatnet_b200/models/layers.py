@@ -45,14 +45,14 @@ def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision, gbias=None, gs=0
                                            _lib.ptr(gb2) if gb2 is not None else None, int(gs), _lib.ptr(g2), _lib.ptr(be2),
                                            int(use_relu), BN_EPS, _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var),
                                            precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_forward")
-    return x2, w2, g2, z, y, mean, var
+    return x2, w2, g2, be2, z, y, mean, var
 
 
 def _conv_bn_backward(saved, use_relu, precision, gy, need_dx, pool_s=0, pooled=None, inv=None, gs=0):
     """-> (dx, dW, db, dgamma, dbeta, dgroup_bias); dgroup_bias only when gs > 0."""
     _lib = _native()
     L = _lib.lib()
-    x2, w2, g2, z, y, mean, var = saved
+    x2, w2, g2, be2, z, y, mean, var = saved
     rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
     gy = gy.contiguous().float()
     nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
@@ -61,7 +61,7 @@ def _conv_bn_backward(saved, use_relu, precision, gy, need_dx, pool_s=0, pooled=
     dw = torch.empty_like(w2)
     db, dg, dbe = (torch.empty(cout, dtype=torch.float32, device=x2.device) for _ in range(3))
     dgb = torch.empty((rows // gs, cout), dtype=torch.float32, device=x2.device) if gs > 0 else None
-    _lib.check(L.f3d_conv_bn_train_backward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(z), _lib.ptr(y),
+    _lib.check(L.f3d_conv_bn_train_backward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(be2), _lib.ptr(z), _lib.ptr(y),
                                             _lib.ptr(mean), _lib.ptr(var), int(use_relu), BN_EPS, _lib.ptr(gy), int(pool_s),
                                             _lib.ptr(pooled) if pooled is not None else None, _lib.ptr(inv) if inv is not None else None,
                                             _lib.ptr(dx) if dx is not None else None, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dg),
@@ -97,7 +97,7 @@ class _ConvBnTrain(torch.autograd.Function):
     def forward(ctx, x, w, b, gamma, beta, use_relu, pool_s, gbias, gs):
         ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
         saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision, gbias, gs if gbias is not None else 0)
-        y, mean, var = saved[4], saved[5], saved[6]
+        y, mean, var = saved[5], saved[6], saved[7]
         ctx.use_relu, ctx.pool_s, ctx.gs = bool(use_relu), int(pool_s), int(gs) if gbias is not None else 0
         ctx.mark_non_differentiable(mean, var)
         if pool_s:

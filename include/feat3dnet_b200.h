@@ -172,10 +172,11 @@ int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x,
  * dW (cin,cout), db, dgamma, dbeta (cout), through the batch statistics.  cout a power of two in 16..1024; dx needs
  * cin == 3 or a multiple of 16.  pool_s > 0: the layer's output only feeds the max-pool over groups of pool_s consecutive
  * rows; gy is then the gradient of the POOLED tensor (rows/pool_s, cout), pooled / inv_ties are the outputs of
- * f3d_maxpool_samples_forward, and the dense (rows, cout) gradient is formed on the fly instead of passing through HBM.
+ * f3d_maxpool_samples_forward, and the dense (rows, cout) gradient is formed on the fly instead of passing through HBM
+ * (beta, which may otherwise be NULL, additionally lets the channel reductions run over the pooled tensors only).
  * Fixed-order reductions: bit-reproducible. */
 int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
-                               const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
+                               const float *beta, const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
                                const float *gy, int pool_s, const float *pooled, const float *inv_ties, float *dx, float *dW,
                                float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s, int precision,
                                void *workspace, size_t workspace_bytes, void *stream);
