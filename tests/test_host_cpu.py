@@ -173,3 +173,56 @@ def test_bin_formats_roundtrip(tmp_path):
     assert inf.save_keypoints_and_descriptors(str(q), xyz, feat) == (17, 35)
     back = np.fromfile(q, dtype=np.float32).reshape(17, 35)
     assert np.array_equal(back[:, :3], xyz.numpy()) and np.array_equal(back[:, 3:], feat.numpy())
+
+
+def test_checkpoint_round_trips_and_restore_rules(tmp_path):
+    """checkpoint.py: npz and TF tensor-bundle round trips, the TF name / layout mapping (1x1 kernels, EMA shadows,
+    optimizer slots ignored) and initialize_model's exclude / ignore-missing rules (reference inference.py:183-217)."""
+    import types
+    from oracle import net as onet
+    ck = importlib.import_module("3dfeatnet_b200.checkpoint")
+    params = onet.init_params(seed=5, randomize_bn=True)
+    tf_names = {}
+    for k, v in params.items():                       # what a TF-1 checkpoint of the reference graph would hold
+        if k.endswith("/conv2d/weights"):
+            tf_names[k] = v.reshape(1, 1, *v.shape)
+        elif k.endswith("/bn/moving_mean"):
+            s = k[:-len("/bn/moving_mean")]
+            tf_names["%s/bn/%s/bn/moments/Squeeze/ExponentialMovingAverage" % (s, s)] = v
+        elif k.endswith("/bn/moving_variance"):
+            s = k[:-len("/bn/moving_variance")]
+            tf_names["%s/bn/%s/bn/moments/Squeeze_1/ExponentialMovingAverage" % (s, s)] = v
+        else:
+            tf_names[k] = v
+    tf_names["detection/conv0/conv2d/weights/Adam"] = np.zeros((1, 1, 3, 64), np.float32)
+    tf_names["beta1_power"] = np.float32(0.9)
+    prefix = str(tmp_path / "model.ckpt-1000")
+    ck.write_tf_bundle(prefix, tf_names)
+    raw = ck.read_tf_bundle(prefix)
+    assert set(raw) == set(tf_names) and all(np.array_equal(raw[k], np.asarray(tf_names[k], np.float32)) for k in tf_names)
+    loaded = ck.load_checkpoint(prefix)
+    assert set(loaded) == set(params) and all(np.array_equal(loaded[k], params[k]) for k in params)
+    ck.save_npz(params, str(tmp_path / "w.npz"))
+    again = ck.load_checkpoint(str(tmp_path / "w.npz"))
+    assert all(np.array_equal(again[k], params[k]) for k in params)
+
+    def fresh():
+        init = onet.init_params(seed=9)
+        m = types.SimpleNamespace(weights={k: torch.as_tensor(v.copy()) for k, v in init.items()}, invalidate=lambda: None)
+        return m, init
+    m, init = fresh()
+    names = ck.initialize_model(m, prefix)
+    assert len(names) == len(params) and all(np.array_equal(m.weights[k].numpy(), params[k]) for k in params)
+    m, init = fresh()                                   # stage 2 of train.sh: restore everything but the detector
+    ck.initialize_model(m, prefix, restore_exclude=["detection"])
+    assert all(np.array_equal(m.weights[k].numpy(), init[k] if k.startswith("detection/") else params[k]) for k in params)
+    partial = {k: v for k, v in params.items() if not k.startswith("description/layer1/conv_post_0")}
+    ck.save_npz(partial, str(tmp_path / "partial.npz"))
+    m, init = fresh()
+    with pytest.raises(KeyError):
+        ck.initialize_model(m, str(tmp_path / "partial.npz"))
+    ck.initialize_model(m, str(tmp_path / "partial.npz"), ignore_missing_vars=True)
+    assert np.array_equal(m.weights["description/layer1/conv_post_0/conv2d/weights"].numpy(), init["description/layer1/conv_post_0/conv2d/weights"])
+    (tmp_path / "bad.index").write_bytes(b"\x00" * 64)
+    with pytest.raises(ValueError):
+        ck.read_tf_bundle(str(tmp_path / "bad"))
