@@ -21,6 +21,7 @@ namespace f3d {
 constexpr int kLdT = 132;      // leading dimension of the transposed activation tile (128 rows + 4: 16-byte aligned rows)
 constexpr int kWgKC = 32;      // rows staged per wgrad iteration
 constexpr int kRedBlocks = 592;  // row-chunks of the BN backward reduction (4 per SM)
+constexpr int kFwdSplit = 3;     // forward contraction on the tensor cores: hi/mid/lo bf16 split, 6 product terms (fp32-grade)
 
 __device__ __forceinline__ void stage_rows_transposed(float *in_t, const float *__restrict__ x, long long row0, long long rows, int cin) {
     const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
@@ -536,9 +537,9 @@ __global__ void transpose_kernel(int r, int c, const float *__restrict__ in, flo
 int lin_tc_kp(int k_real);
 bool lin_tc_supported(int k_real, int nout);
 size_t lin_tc_weight_bytes(int k_real, int nout);
-int lin_tc_grid(long long rows, int k_real);
+int lin_tc_grid(long long rows, int k_real, int nsplit);
 int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
-           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, cudaStream_t st);
+           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st);
 bool wgrad_tc_supported(int cin, int cout);
 void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta);
 int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg = 0);
@@ -601,7 +602,7 @@ using namespace f3d;
 F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int cout) {
     if (rows <= 0 || cin <= 0 || cout <= 0) return 256;
     const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
-    const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin));
+    const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit));
     const size_t wimg = lin_tc_weight_bytes(cin, cout) > lin_tc_weight_bytes(cout, cin) ? lin_tc_weight_bytes(cin, cout) : lin_tc_weight_bytes(cout, cin);
     const size_t fwd = align256(stat_parts * 2 * cout * 4) + align256(2 * cout * 4) + align256(2 * cout * 4) + align256(wimg);
     const WgradPlan p = plan_wgrad(rows, cin, cout);
@@ -638,8 +639,8 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
     cudaStream_t st = as_stream(stream);
     const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
     const bool tc = precision == 2 && lin_tc_supported(cin, cout);
-    const size_t nparts = tc ? static_cast<size_t>(2 * lin_tc_grid(rows, cin)) : tiles;
-    const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin));
+    const size_t nparts = tc ? static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit)) : tiles;
+    const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit));
     char *w = static_cast<char *>(workspace);
     float *part = reinterpret_cast<float *>(w);
     w += align256(stat_parts * 2 * cout * 4);
@@ -648,7 +649,7 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
     float *coef = reinterpret_cast<float *>(w);
     w += align256(2 * cout * 4);
     uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
-    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, st)
+    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, kFwdSplit, st)
                 : launch_conv_fwd(rows, cin, cout, x, W, bias, group_bias, group_s, z, part, st);
     if (rc) return rc;
     partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(nparts), 2 * cout, part, sums);
@@ -765,7 +766,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
             conv_dgrad3_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 3 * cout * sizeof(float), st>>>(rows, cout, dz, W, dx);
             rc = check_launch("conv_dgrad3_kernel");
         } else if (tc_dgrad) {
-            rc = lin_tc(rows, cout, cin, dz, W, cout, 1, nullptr, nullptr, 0, dx, nullptr, wimg, st);  // A[m = ci][k = co] = W[ci][co]
+            rc = lin_tc(rows, cout, cin, dz, W, cout, 1, nullptr, nullptr, 0, dx, nullptr, wimg, 2, st);  // A[m = ci][k = co] = W[ci][co]
         } else {
             transpose_kernel<<<(cin * cout + 255) / 256, 256, 0, st>>>(cin, cout, W, Wt);
             rc = check_launch("transpose_kernel");

@@ -49,10 +49,10 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// weight images: A[m][k] = src[m*sm + k*sk] (0 outside m_real x k_real), per 128-row block [hi | lo], element (r,k) at
-// (k/8)*kLboW + r*16 + (k%8)*2
+// weight images: A[m][k] = src[m*sm + k*sk] (0 outside m_real x k_real), per 128-row block nsplit bf16 images
+// [hi | lo] or [hi | mid | lo] (w = hi + mid + lo to 24 bits), element (r,k) at (k/8)*kLboW + r*16 + (k%8)*2
 __global__ void lin_prep_kernel(const float *__restrict__ src, long long sm, long long sk, int m_real, int k_real, int kp, int mblocks,
-                                uint8_t *__restrict__ img) {
+                                int nsplit, uint8_t *__restrict__ img) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long per = 128LL * kp;
     if (i >= per * mblocks) return;
@@ -60,12 +60,14 @@ __global__ void lin_prep_kernel(const float *__restrict__ src, long long sm, lon
     const int e = static_cast<int>(i - mb * per);
     const int r = e & 127, k = e >> 7;
     const int m = mb * 128 + r;
-    const float w = (m < m_real && k < k_real) ? src[m * sm + k * sk] : 0.0f;
-    uint8_t *base = img + static_cast<size_t>(mb) * kp * 512;
+    float w = (m < m_real && k < k_real) ? src[m * sm + k * sk] : 0.0f;
+    uint8_t *base = img + static_cast<size_t>(mb) * kp * 256 * nsplit;
     const uint32_t o = (k >> 3) * ttc::kLboW + r * 16 + (k & 7) * 2;
-    const __nv_bfloat16 h = __float2bfloat16_rn(w);
-    *reinterpret_cast<__nv_bfloat16 *>(base + o) = h;
-    *reinterpret_cast<__nv_bfloat16 *>(base + static_cast<size_t>(kp) * 256 + o) = __float2bfloat16_rn(w - __bfloat162float(h));
+    for (int sp = 0; sp < nsplit; ++sp) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        *reinterpret_cast<__nv_bfloat16 *>(base + static_cast<size_t>(sp) * kp * 256 + o) = h;
+        w -= __bfloat162float(h);
+    }
 }
 
 // out[rows x nout] (+bias) = x[rows x k_real] * A^T; optional per-CTA column sums of out and out^2:
@@ -75,23 +77,23 @@ __global__ void lin_prep_kernel(const float *__restrict__ src, long long sm, lon
 // engine (bulk copies of up to 16 KB into a ring, kRing tiles ahead, mbarrier completion) so the loads of the next tiles
 // are in flight during the conversion / MMA / epilogue of the current one; the conversion reads the ring with
 // conflict-free LDS.128 and writes the bf16 hi/lo operand image (chunk stride padded by 32 B against bank conflicts).
-constexpr int kRing = 2;
+constexpr int kRingMax = 2;  // ring depth (1 when shared memory cannot hold two stages next to a 3-split operand image)
 
 __global__ void __launch_bounds__(ttc::kThreads, 4)
-lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
+lin_tc_kernel(long long rows, int k_real, int kp, int nout, int nsplit, int kRing, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
               const float *__restrict__ bias, const float *__restrict__ gbias, int gs, float *__restrict__ out, float *__restrict__ part) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const bool ring = (k_real & 7) == 0;
     const uint32_t wbytes = 256u * kp;                                  // one weight split: (kp/8) chunks x kLboW
-    const uint32_t split = static_cast<uint32_t>(kp / 8) * kLboXp;      // operand image: 2 splits x (kp/8) chunks x kLboXp
-    const uint32_t opbytes = 2 * split;                                 // >= wbytes
+    const uint32_t split = static_cast<uint32_t>(kp / 8) * kLboXp;      // operand image: nsplit splits x (kp/8) chunks x kLboXp
+    const uint32_t opbytes = static_cast<uint32_t>(nsplit) * split;     // >= wbytes
     const uint32_t stage_bytes = ring ? kTile * static_cast<uint32_t>(k_real) * 4 : 0;
     uint8_t *ringbuf = smem + opbytes;
     uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + opbytes + kRing * stage_bytes);
     uint64_t *bar_m = bar_w + 1;
     uint64_t *bar_full = bar_w + 2;  // [kRing]
-    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_w + 2 + kRing);
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_w + 2 + kRingMax);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, half = warp >> 2;
     const int ch = q * 32 + lane;
@@ -116,9 +118,9 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
     const uint32_t tmem_base = *tmem_base_s;
     uint32_t wpar = 0, mpar = 0;
 
-    // weights -> tensor memory: split hi -> columns [0, kp/2), split lo -> [kp/2, kp)
-    const uint8_t *wsrc = wimg + static_cast<size_t>(mb) * kp * 512;
-    for (int piece = 0; piece < 2; ++piece) {
+    // weights -> tensor memory: split sp -> columns [sp*kp/2, (sp+1)*kp/2)
+    const uint8_t *wsrc = wimg + static_cast<size_t>(mb) * kp * 256 * nsplit;
+    for (int piece = 0; piece < nsplit; ++piece) {
         if (threadIdx.x == 0) {
             mbar_arrive_expect_tx(bar_w, wbytes);
             for (uint32_t off = 0; off < wbytes; off += 16384) {
@@ -163,7 +165,7 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
             if (cta + s * ncta < ntiles) fetch(cta + s * ncta, s);
 
     const uint32_t idesc = make_idesc(1, 128, kTile);
-    const uint32_t tmem_d = tmem_base + kp;
+    const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(nsplit) * (kp / 2);
     const int gch = mb * 128 + ch;
     const bool ch_ok = gch < nout;
     const float bb = (bias && ch_ok) ? __ldg(bias + gch) : 0.0f;
@@ -186,12 +188,12 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
                 for (int c = c4; c < kp / 8; c += 4) {
                     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid) a = *reinterpret_cast<const float4 *>(src + c * 32);
-                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - __low2float(h0), a.y - __high2float(h0));
-                    const __nv_bfloat162 l1 = __floats2bfloat162_rn(a.z - __low2float(h1), a.w - __high2float(h1));
                     uint8_t *dst = smem + c * kLboXp + r * 16 + h * 8;
-                    *reinterpret_cast<uint2 *>(dst) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                    *reinterpret_cast<uint2 *>(dst + split) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+                    for (int sp = 0; sp < nsplit; ++sp) {  // a = hi (+ mid) + lo, each a bf16
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                        *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                        a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
+                    }
                 }
             }
         } else {  // few input channels (the xyz layers): straight from global memory
@@ -205,11 +207,18 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
                     for (int j = 0; j < 8; ++j)
                         if (c * 8 + j < k_real) v[j] = __ldg(row + c * 8 + j);
                 }
-                uint4 hi, lo;
-                split8(v, hi, lo);
                 uint8_t *dst = smem + c * kLboXp + r * 16;
-                *reinterpret_cast<uint4 *>(dst) = hi;
-                *reinterpret_cast<uint4 *>(dst + split) = lo;
+                for (int sp = 0; sp < nsplit; ++sp) {
+                    uint32_t hw[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        hw[j] = *reinterpret_cast<const uint32_t *>(&h2);
+                        v[2 * j] -= __low2float(h2);
+                        v[2 * j + 1] -= __high2float(h2);
+                    }
+                    *reinterpret_cast<uint4 *>(dst + sp * split) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                }
             }
         }
         fence_proxy_async_smem();
@@ -217,10 +226,16 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, uint32_t tmem_cols, 
         if (warp == 0) {
             tcgen05_fence_after();
             if (elect_one()) {
+                // product terms (weight split, operand split): 2 splits -> hh, hl, lh (error ~2^-17 per product);
+                // 3 splits -> + h*l2, l2*h, m*m (every term down to 2^-24: fp32-grade, used for the forward so that the
+                // ReLU / max-pool routing decisions match an fp32 evaluation)
+                const int nterms = nsplit == 3 ? 6 : 3;
                 uint32_t acc = 0;
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t wa = tmem_base + (pass == 2 ? kp / 2 : 0);
-                    const uint32_t xb = sbase + (pass == 1 ? split : 0);
+                for (int term = 0; term < nterms; ++term) {
+                    const int ws = term == 2 ? 1 : term == 4 ? 2 : term == 5 ? 1 : 0;
+                    const int xs = term == 1 ? 1 : term == 3 ? 2 : term == 5 ? 1 : 0;
+                    const uint32_t wa = tmem_base + ws * (kp / 2);
+                    const uint32_t xb = sbase + xs * split;
                     for (int k = 0; k < kp / 16; ++k) {
                         umma_f16_ts(tmem_d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboXp, kLboXp, kSbo), idesc, acc);
                         acc = 1;
@@ -417,21 +432,27 @@ static uint32_t pow2_cols(uint32_t need) {
 
 int lin_tc_kp(int k_real) { return (k_real + 15) / 16 * 16; }
 bool lin_tc_supported(int k_real, int nout) { return k_real >= 1 && k_real <= 256 && nout >= 1; }
-size_t lin_tc_weight_bytes(int k_real, int nout) { return static_cast<size_t>((nout + 127) / 128) * lin_tc_kp(k_real) * 512; }
+size_t lin_tc_weight_bytes(int k_real, int nout) { return static_cast<size_t>((nout + 127) / 128) * lin_tc_kp(k_real) * 256 * 3; }
 
-static size_t lin_tc_smem(int k_real) {
+static int lin_tc_ring(int k_real, int nsplit) {
+    if (k_real % 8 != 0) return 0;
     const int kp = lin_tc_kp(k_real);
-    const size_t op = 2 * static_cast<size_t>(kp / 8) * ttc::kLboXp;
-    const size_t ring = (k_real % 8 == 0) ? static_cast<size_t>(kRing) * ttc::kTile * k_real * 4 : 0;
-    return op + ring + 128;
+    const size_t op = static_cast<size_t>(nsplit) * (kp / 8) * ttc::kLboXp;
+    return op + static_cast<size_t>(kRingMax) * ttc::kTile * k_real * 4 + 128 <= 226 * 1024 ? kRingMax : 1;
+}
+
+static size_t lin_tc_smem(int k_real, int nsplit) {
+    const int kp = lin_tc_kp(k_real);
+    const size_t op = static_cast<size_t>(nsplit) * (kp / 8) * ttc::kLboXp;
+    return op + static_cast<size_t>(lin_tc_ring(k_real, nsplit)) * ttc::kTile * k_real * 4 + 128;
 }
 
 // number of row-CTAs lin_tc launches (the stats partials are 2 per CTA)
-int lin_tc_grid(long long rows, int k_real) {
+int lin_tc_grid(long long rows, int k_real, int nsplit) {
     const int kp = lin_tc_kp(k_real);
-    const uint32_t cols = pow2_cols(kp + ttc::kTile);
+    const uint32_t cols = pow2_cols(nsplit * (kp / 2) + ttc::kTile);
     int per_sm = static_cast<int>(512 / cols);
-    const int by_smem = static_cast<int>((220 * 1024) / lin_tc_smem(k_real));
+    const int by_smem = static_cast<int>((226 * 1024) / (lin_tc_smem(k_real, nsplit) + 1024));
     if (per_sm > by_smem) per_sm = by_smem;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
@@ -440,22 +461,24 @@ int lin_tc_grid(long long rows, int k_real) {
     return static_cast<int>(ntiles < g ? ntiles : g);
 }
 
-// out (rows, nout) = x (rows, k_real) * A^T (+ bias) (+ gbias[row / gs]) with A[m][k] = src[m*sm + k*sk];  part: 2*lin_tc_grid() partials of
+// out (rows, nout) = x (rows, k_real) * A^T (+ bias) (+ gbias[row / gs]) with A[m][k] = src[m*sm + k*sk]; nsplit = 2 (bf16x3)
+// or 3 (six product terms, fp32-grade);  part: 2*lin_tc_grid() partials of
 // {sum, sum of squares} per channel, or NULL.  wimg: lin_tc_weight_bytes() of scratch.
 int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
-           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, cudaStream_t st) {
+           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st) {
     const int kp = lin_tc_kp(k_real);
     const int mblocks = (nout + 127) / 128;
     const long long total = 128LL * kp * mblocks;
-    lin_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, sm, sk, nout, k_real, kp, mblocks, wimg);
+    lin_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, sm, sk, nout, k_real, kp, mblocks, nsplit, wimg);
     int rc = check_launch("lin_prep_kernel");
     if (rc) return rc;
-    const uint32_t cols = pow2_cols(kp + ttc::kTile);
-    const size_t smem = lin_tc_smem(k_real);
+    const uint32_t cols = pow2_cols(nsplit * (kp / 2) + ttc::kTile);
+    const size_t smem = lin_tc_smem(k_real, nsplit);
     cudaError_t e = cudaFuncSetAttribute(lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
-    const dim3 grid(mblocks, lin_tc_grid(rows, k_real));
-    lin_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, cols, x, wimg, bias, gbias, gs, out, part);
+    const dim3 grid(mblocks, lin_tc_grid(rows, k_real, nsplit));
+    lin_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, nsplit, lin_tc_ring(k_real, nsplit) > 0 ? lin_tc_ring(k_real, nsplit) : 1, cols, x, wimg,
+                                                     bias, gbias, gs, out, part);
     return check_launch("lin_tc_kernel");
 }
 

@@ -248,3 +248,36 @@ def test_conv_mid_without_concat_matches_the_concatenated_statement(cuda, precis
     assert (out.detach().cpu().double() - ref).abs().max().item() < 5e-5 * max(1.0, ref.abs().max().item())
     for name, a, r in zip(("dh", "dW", "dgamma", "dbeta"), grads, rgrads):
         assert (a.cpu().double() - r).abs().max().item() < 3e-4 * (r.abs().max().item() + 1e-9) + 1e-6, name
+
+
+def test_c4_training_step_fused_vs_torch_layers_and_deterministic(cuda):
+    """BASELINE configs[3] size (6 triplets x 4096 points, 512 clusters x 64 samples): the CUDA training layers against the
+    op-by-op torch fp32 statement of the same graph (loss, gradient direction), and bit-reproducibility of the CUDA path."""
+    f3, layers, synth = pkg("models.feat3dnet"), pkg("models.layers"), pkg("synth")
+    B, N, M = 6, 4096, 512
+    a, p, n = (torch.as_tensor(synth.make_batch(B, N, seed0=s)).to(cuda) for s in (11, 12, 13))
+    params = onet.init_params(seed=1, randomize_bn=True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def run(fused, precision="bf16x3"):
+        layers.FUSED_TRAINING, layers.TRAIN_PRECISION = fused, precision
+        try:
+            net = f3.Feat3dNet({'num_clusters': M, 'fused_loss': fused}, weights=params, device=cuda).train_mode()
+            xyz, feats, att, ep = net.get_train_model(a, p, n, True)
+            loss, ep = net.get_loss(xyz, feats, att, ep)
+            flat = net.get_train_op(loss, lr=1e-5, end_points=ep)
+            return loss.detach().item(), flat.detach().clone()
+        finally:
+            layers.FUSED_TRAINING, layers.TRAIN_PRECISION = True, "bf16x3"
+
+    l_ref, g_ref = run(False)
+    l_tc, g_tc = run(True, "bf16x3")
+    l_tc2, g_tc2 = run(True, "bf16x3")
+    l_f32, g_f32 = run(True, "fp32")
+    assert l_tc == l_tc2 and torch.equal(g_tc, g_tc2)                      # no atomics anywhere
+    for l, g in ((l_tc, g_tc), (l_f32, g_f32)):
+        assert abs(l - l_ref) < 2e-4 * max(1.0, abs(l_ref))
+        assert torch.isfinite(g).all() and g.numel() == 107619
+        # ReLU / max-pool routing flips on rounding-level differences, so the comparison is a direction + scale one
+        assert torch.nn.functional.cosine_similarity(g.double(), g_ref.double(), dim=0).item() > 0.999
+        assert abs(g.norm().item() / g_ref.norm().item() - 1.0) < 2e-2

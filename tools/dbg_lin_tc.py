@@ -18,8 +18,10 @@ def run(rows, cin, cout):
         d = (a - r).abs()
         bad = (d > 1e-3 * (r.abs().max() + 1e-9)).nonzero()
         print(rows, cin, cout, name, "max err %.3e scale %.3e nbad %d" % (d.max(), r.abs().max(), len(bad)))
-        if len(bad) and name in ("y", "dx"):
+        if name in ("y", "dx", "dW"):
+            print("      cos %.8f  rel-l2 %.3e" % (torch.nn.functional.cosine_similarity(a.double().flatten(), r.double().flatten(), dim=0), (a.double() - r.double()).norm() / r.double().norm()))
+        if len(bad) and name in ("y", "dx") and len(bad) < 20000:
             rr = bad[:, 0]; cc = bad[:, 1]
             print("   rows%64:", sorted(set((rr % 64).tolist()))[:70], "\n   cols:", sorted(set(cc.tolist()))[:140], "\n   tiles:", sorted(set((rr // 64).tolist()))[:40])
-for shp in ((4096, 128, 256), (4096, 256, 128), (640, 256, 128), (64, 256, 128)):
+for shp in ((589824, 128, 256), (589824, 64, 128), (589824, 3, 64), (589824, 128, 128), (9216, 256, 128)):
     run(*shp)
