@@ -31,8 +31,10 @@ constexpr int kTile = 64;                 // rows per tile = MMA N of lin_tc
 constexpr int kThreads = 256;
 constexpr uint32_t kSbo = 128;
 constexpr uint32_t kLboW = 128 * 16;      // weight image: 128 rows per 8-wide K chunk
-constexpr uint32_t kLboXp = kTile * 16 + 32;  // operand image: 64 rows per K chunk, padded so that the four chunks a
-                                              // quarter-warp writes fall into distinct banks
+// operand image: 64 rows per K chunk, padded so that the chunks a (quarter-)warp writes fall into distinct banks; the
+// 3-split image pads by 16 B only (2-way conflicts on a few stores) so that two CTAs with a 2-deep ring still share an SM
+// at K = 128
+__host__ __device__ constexpr uint32_t lbo_x(int nsplit) { return kTile * 16 + (nsplit == 3 ? 16 : 32); }
 constexpr uint32_t kLboA = 128 * 16 + 16; // wgrad A image (padded: the 8 row-chunks a quarter-warp writes hit distinct banks)
 }  // namespace ttc
 
@@ -79,13 +81,15 @@ __global__ void lin_prep_kernel(const float *__restrict__ src, long long sm, lon
 // conflict-free LDS.128 and writes the bf16 hi/lo operand image (chunk stride padded by 32 B against bank conflicts).
 constexpr int kRingMax = 2;  // ring depth (1 when shared memory cannot hold two stages next to a 3-split operand image)
 
+template <int nsplit>
 __global__ void __launch_bounds__(ttc::kThreads, 4)
-lin_tc_kernel(long long rows, int k_real, int kp, int nout, int nsplit, int kRing, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
+lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
               const float *__restrict__ bias, const float *__restrict__ gbias, int gs, float *__restrict__ out, float *__restrict__ part) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const bool ring = (k_real & 7) == 0;
     const uint32_t wbytes = 256u * kp;                                  // one weight split: (kp/8) chunks x kLboW
+    constexpr uint32_t kLboXp = lbo_x(nsplit);
     const uint32_t split = static_cast<uint32_t>(kp / 8) * kLboXp;      // operand image: nsplit splits x (kp/8) chunks x kLboXp
     const uint32_t opbytes = static_cast<uint32_t>(nsplit) * split;     // >= wbytes
     const uint32_t stage_bytes = ring ? kTile * static_cast<uint32_t>(k_real) * 4 : 0;
@@ -189,6 +193,7 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int nsplit, int kRin
                     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid) a = *reinterpret_cast<const float4 *>(src + c * 32);
                     uint8_t *dst = smem + c * kLboXp + r * 16 + h * 8;
+#pragma unroll
                     for (int sp = 0; sp < nsplit; ++sp) {  // a = hi (+ mid) + lo, each a bf16
                         const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
                         *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
@@ -208,6 +213,7 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int nsplit, int kRin
                         if (c * 8 + j < k_real) v[j] = __ldg(row + c * 8 + j);
                 }
                 uint8_t *dst = smem + c * kLboXp + r * 16;
+#pragma unroll
                 for (int sp = 0; sp < nsplit; ++sp) {
                     uint32_t hw[4];
 #pragma unroll
@@ -229,8 +235,9 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int nsplit, int kRin
                 // product terms (weight split, operand split): 2 splits -> hh, hl, lh (error ~2^-17 per product);
                 // 3 splits -> + h*l2, l2*h, m*m (every term down to 2^-24: fp32-grade, used for the forward so that the
                 // ReLU / max-pool routing decisions match an fp32 evaluation)
-                const int nterms = nsplit == 3 ? 6 : 3;
+                constexpr int nterms = nsplit == 3 ? 6 : 3;
                 uint32_t acc = 0;
+#pragma unroll
                 for (int term = 0; term < nterms; ++term) {
                     const int ws = term == 2 ? 1 : term == 4 ? 2 : term == 5 ? 1 : 0;
                     const int xs = term == 1 ? 1 : term == 3 ? 2 : term == 5 ? 1 : 0;
@@ -437,14 +444,14 @@ size_t lin_tc_weight_bytes(int k_real, int nout) { return static_cast<size_t>((n
 static int lin_tc_ring(int k_real, int nsplit) {
     if (k_real % 8 != 0) return 0;
     const int kp = lin_tc_kp(k_real);
-    const size_t op = static_cast<size_t>(nsplit) * (kp / 8) * ttc::kLboXp;
-    return op + static_cast<size_t>(kRingMax) * ttc::kTile * k_real * 4 + 128 <= 226 * 1024 ? kRingMax : 1;
+    const size_t op = static_cast<size_t>(nsplit) * (kp / 8) * ttc::lbo_x(nsplit);
+    return op + static_cast<size_t>(kRingMax) * ttc::kTile * k_real * 4 + 64 <= 226 * 1024 ? kRingMax : 1;
 }
 
 static size_t lin_tc_smem(int k_real, int nsplit) {
     const int kp = lin_tc_kp(k_real);
-    const size_t op = static_cast<size_t>(nsplit) * (kp / 8) * ttc::kLboXp;
-    return op + static_cast<size_t>(lin_tc_ring(k_real, nsplit)) * ttc::kTile * k_real * 4 + 128;
+    const size_t op = static_cast<size_t>(nsplit) * (kp / 8) * ttc::lbo_x(nsplit);
+    return op + static_cast<size_t>(lin_tc_ring(k_real, nsplit)) * ttc::kTile * k_real * 4 + 64;
 }
 
 // number of row-CTAs lin_tc launches (the stats partials are 2 per CTA)
@@ -452,7 +459,7 @@ int lin_tc_grid(long long rows, int k_real, int nsplit) {
     const int kp = lin_tc_kp(k_real);
     const uint32_t cols = pow2_cols(nsplit * (kp / 2) + ttc::kTile);
     int per_sm = static_cast<int>(512 / cols);
-    const int by_smem = static_cast<int>((226 * 1024) / (lin_tc_smem(k_real, nsplit) + 1024));
+    const int by_smem = static_cast<int>((228 * 1024) / (lin_tc_smem(k_real, nsplit) + 1024));  // 228 KB per SM, 1 KB reserved per CTA
     if (per_sm > by_smem) per_sm = by_smem;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
@@ -474,11 +481,17 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
     if (rc) return rc;
     const uint32_t cols = pow2_cols(nsplit * (kp / 2) + ttc::kTile);
     const size_t smem = lin_tc_smem(k_real, nsplit);
-    cudaError_t e = cudaFuncSetAttribute(lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
     const dim3 grid(mblocks, lin_tc_grid(rows, k_real, nsplit));
-    lin_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, nsplit, lin_tc_ring(k_real, nsplit) > 0 ? lin_tc_ring(k_real, nsplit) : 1, cols, x, wimg,
-                                                     bias, gbias, gs, out, part);
+    const int nring = lin_tc_ring(k_real, nsplit) > 0 ? lin_tc_ring(k_real, nsplit) : 1;
+    cudaError_t e;
+    if (nsplit == 3) {
+        e = cudaFuncSetAttribute(lin_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess) lin_tc_kernel<3><<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, nring, cols, x, wimg, bias, gbias, gs, out, part);
+    } else {
+        e = cudaFuncSetAttribute(lin_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess) lin_tc_kernel<2><<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, nring, cols, x, wimg, bias, gbias, gs, out, part);
+    }
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
     return check_launch("lin_tc_kernel");
 }
 
