@@ -9,6 +9,8 @@
 // BallTree's order among exact ties is unspecified):
 //   * distances are evaluated like the tree does: float64, d2 = (dx*dx + dy*dy) + dz*dz without FMA, d = sqrt(d2);
 //     "d > radius" is tested as d2 > T with T = max{s : sqrt_rn(s) <= radius} (monotone IEEE sqrt => same predicate);
+//   * the cloud is binned into an xy grid of cells >= nms_radius wide (counting sort), so a query only visits the 3 x 3 cells
+//     around it -- O(N) instead of the O(N^2) all-pairs scan (612 ms -> a few ms at N = 131 072);
 //   * a point with at most 49 other points inside the radius consults all of them (they are its nearest ones); only a
 //     point with more than 49 takes the slow path that selects the 49 nearest by (d2, index);
 //   * the threshold is computed in float64 like NumPy 1.19 does for float32_scalar * python_float
@@ -19,8 +21,6 @@
 
 namespace f3d {
 
-constexpr int kNmsTile = 1024;  // points staged per shared-memory tile
-constexpr int kNmsPtsPerWarp = 4;
 constexpr int kNmsWarps = 8;
 
 __device__ __forceinline__ double nms_d2(double ax, double ay, double az, double bx, double by, double bz) {
@@ -42,82 +42,173 @@ __device__ __forceinline__ double nms_threshold(double r) {
     return t;
 }
 
-// keep[b,p] = 1 iff p is a local attention maximum among its (at most num_neighbors-1) nearest in-radius neighbours.
-// One warp handles kNmsPtsPerWarp query points; the cloud streams through shared memory as float64 tiles.
-__global__ void __launch_bounds__(kNmsWarps * 32)
-nms_keep_kernel(int n, double radius, int num_neighbors, const float *__restrict__ xyz, const float *__restrict__ attention,
-                unsigned char *__restrict__ keep, int *__restrict__ dense_list, int *__restrict__ dense_count) {
-    __shared__ double sx[kNmsTile], sy[kNmsTile], sz[kNmsTile];
-    __shared__ float sa[kNmsTile];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// ---- spatial binning: an xy grid of cells >= radius wide, so that every in-radius neighbour of a point lies in the 3 x 3
+// cells around it.  Points are counting-sorted by cell (order inside a cell is irrelevant: the keep rule is a max / count,
+// the slow path orders by (d2, index) itself).
+struct NmsGrid {
+    double x0, y0, inv_h;
+    int nx, ny;
+};
+
+__device__ __forceinline__ NmsGrid nms_grid(const float *__restrict__ bbox, double radius, int max_cells) {
+    NmsGrid g;
+    g.x0 = bbox[0];
+    g.y0 = bbox[1];
+    double h = (radius > 1e-9 ? radius : 1e-9) * 1.000001 + 1e-12;
+    const double ex = static_cast<double>(bbox[2]) - g.x0, ey = static_cast<double>(bbox[3]) - g.y0;
+    for (int it = 0; it < 64; ++it) {
+        const double nx = floor(ex / h) + 1.0, ny = floor(ey / h) + 1.0;
+        if (nx * ny <= static_cast<double>(max_cells)) break;
+        h *= 1.5;  // a cloud too wide for the cell budget: coarser cells (still >= radius), more candidates per query
+    }
+    g.inv_h = 1.0 / h;
+    g.nx = static_cast<int>(floor(ex / h)) + 1;
+    g.ny = static_cast<int>(floor(ey / h)) + 1;
+    return g;
+}
+
+__device__ __forceinline__ int nms_cell_coord(double v, double v0, double inv_h, int n) {
+    const int c = static_cast<int>(floor((v - v0) * inv_h));
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+// bbox[b] = {min x, min y, max x, max y}
+__global__ void __launch_bounds__(1024)
+nms_bbox_kernel(int n, const float *__restrict__ xyz, float *__restrict__ bbox) {
+    __shared__ float red[4][32];
+    const float *p = xyz + static_cast<size_t>(blockIdx.x) * n * 3;
+    float lx = 3.0e38f, ly = 3.0e38f, hx = -3.0e38f, hy = -3.0e38f;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const float x = p[3 * k], y = p[3 * k + 1];
+        lx = fminf(lx, x); ly = fminf(ly, y); hx = fmaxf(hx, x); hy = fmaxf(hy, y);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(kFull, lx, s)); ly = fminf(ly, __shfl_xor_sync(kFull, ly, s));
+        hx = fmaxf(hx, __shfl_xor_sync(kFull, hx, s)); hy = fmaxf(hy, __shfl_xor_sync(kFull, hy, s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = lx; red[1][threadIdx.x >> 5] = ly; red[2][threadIdx.x >> 5] = hx; red[3][threadIdx.x >> 5] = hy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) {
+            lx = fminf(lx, red[0][w]); ly = fminf(ly, red[1][w]); hx = fmaxf(hx, red[2][w]); hy = fmaxf(hy, red[3][w]);
+        }
+        float *o = bbox + blockIdx.x * 4;
+        o[0] = lx; o[1] = ly; o[2] = hx; o[3] = hy;
+    }
+}
+
+__global__ void nms_cell_count_kernel(int n, double radius, int max_cells, const float *__restrict__ xyz, const float *__restrict__ bbox,
+                                      int *__restrict__ cell_count) {
     const int batch = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
+    const float *p = xyz + (static_cast<size_t>(batch) * n + k) * 3;
+    const int cell = nms_cell_coord(p[1], g.y0, g.inv_h, g.ny) * g.nx + nms_cell_coord(p[0], g.x0, g.inv_h, g.nx);
+    atomicAdd(cell_count + static_cast<size_t>(batch) * (max_cells + 1) + cell, 1);
+}
+
+// exclusive scan of the cell counts (in place -> cell starts, entry [cells] = n) and a copy as the fill cursors
+__global__ void __launch_bounds__(1024)
+nms_cell_scan_kernel(int max_cells, int *__restrict__ cell_start, int *__restrict__ cursor) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    int *cs = cell_start + static_cast<size_t>(blockIdx.x) * (max_cells + 1);
+    int *cu = cursor + static_cast<size_t>(blockIdx.x) * (max_cells + 1);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base <= max_cells; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i <= max_cells ? cs[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, s);
+            if (lane >= s) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sum[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(kFull, w, s);
+                if (lane >= s) w += t;
+            }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const int excl = carry + (warp ? warp_sum[warp - 1] : 0) + incl - v;
+        if (i <= max_cells) {
+            cs[i] = excl;
+            cu[i] = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void nms_cell_fill_kernel(int n, double radius, int max_cells, const float *__restrict__ xyz, const float *__restrict__ bbox,
+                                     int *__restrict__ cursor, int *__restrict__ sorted) {
+    const int batch = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
+    const float *p = xyz + (static_cast<size_t>(batch) * n + k) * 3;
+    const int cell = nms_cell_coord(p[1], g.y0, g.inv_h, g.ny) * g.nx + nms_cell_coord(p[0], g.x0, g.inv_h, g.nx);
+    const int pos = atomicAdd(cursor + static_cast<size_t>(batch) * (max_cells + 1) + cell, 1);
+    sorted[static_cast<size_t>(batch) * n + pos] = k;
+}
+
+// keep[b,p] = 1 iff p is a local attention maximum among its (at most num_neighbors-1) nearest in-radius neighbours.
+// One thread per query point scans the 3 x 3 cells around it (float64 distances, the tree's arithmetic).
+__global__ void __launch_bounds__(128)
+nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const float *__restrict__ xyz, const float *__restrict__ attention,
+                const float *__restrict__ bbox, const int *__restrict__ cell_start, const int *__restrict__ sorted,
+                unsigned char *__restrict__ keep, int *__restrict__ dense_list, int *__restrict__ dense_count) {
+    const int batch = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
     const float *p = xyz + static_cast<size_t>(batch) * n * 3;
     const float *att = attention + static_cast<size_t>(batch) * n;
-    const int q0 = (blockIdx.x * kNmsWarps + warp) * kNmsPtsPerWarp;
+    const int *cs = cell_start + static_cast<size_t>(batch) * (max_cells + 1);
+    const int *srt = sorted + static_cast<size_t>(batch) * n;
+    const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
     const double T = nms_threshold(radius);
-
-    double qx[kNmsPtsPerWarp], qy[kNmsPtsPerWarp], qz[kNmsPtsPerWarp];
-    float qa[kNmsPtsPerWarp], mx[kNmsPtsPerWarp];
-    int cnt[kNmsPtsPerWarp];
-#pragma unroll
-    for (int c = 0; c < kNmsPtsPerWarp; ++c) {
-        const int q = min(q0 + c, n - 1);
-        qx[c] = p[3 * q]; qy[c] = p[3 * q + 1]; qz[c] = p[3 * q + 2];
-        qa[c] = att[q];
-        mx[c] = -3.0e38f;
-        cnt[c] = 0;
-    }
-    for (int base = 0; base < n; base += kNmsTile) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < kNmsTile; i += blockDim.x) {
-            const int k = base + i;
-            if (k < n) {
-                sx[i] = p[3 * k]; sy[i] = p[3 * k + 1]; sz[i] = p[3 * k + 2];
-                sa[i] = att[k];
-            }
-        }
-        __syncthreads();
-        const int lim = min(kNmsTile, n - base);
-        for (int i = lane; i < lim; i += 32) {
-            const double x = sx[i], y = sy[i], z = sz[i];
-            const float a = sa[i];
-            const int k = base + i;
-#pragma unroll
-            for (int c = 0; c < kNmsPtsPerWarp; ++c) {
-                const bool in = (k != q0 + c) && !(nms_d2(qx[c], qy[c], qz[c], x, y, z) > T);
-                if (in) {
-                    cnt[c] += 1;
-                    mx[c] = fmaxf(mx[c], a);
-                }
-            }
+    const double qx = p[3 * q], qy = p[3 * q + 1], qz = p[3 * q + 2];
+    const float qa = att[q];
+    const int cx = nms_cell_coord(qx, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(qy, g.y0, g.inv_h, g.ny);
+    int cnt = 0;
+    float mx = -3.0e38f;
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
+        const int c0 = yy * g.nx + max(cx - 1, 0), c1 = yy * g.nx + min(cx + 1, g.nx - 1);
+        for (int e = cs[c0]; e < cs[c1 + 1]; ++e) {  // the cells of one grid row are contiguous in the sorted order
+            const int k = srt[e];
+            if (k == q) continue;
+            if (nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]) > T) continue;
+            ++cnt;
+            mx = fmaxf(mx, att[k]);
         }
     }
-#pragma unroll
-    for (int c = 0; c < kNmsPtsPerWarp; ++c) {
-        int ct = cnt[c];
-        float m = mx[c];
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            ct += __shfl_xor_sync(kFull, ct, s);
-            m = fmaxf(m, __shfl_xor_sync(kFull, m, s));
-        }
-        if (lane == 0 && q0 + c < n) {
-            const int q = q0 + c;
-            if (ct <= num_neighbors - 1) {
-                keep[static_cast<size_t>(batch) * n + q] = (m <= qa[c]) ? 1 : 0;  // ties: position 0 (self) wins the argmax
-            } else {  // more in-radius neighbours than the tree returns: resolve with the exact k nearest
-                keep[static_cast<size_t>(batch) * n + q] = 2;
-                const int pos = atomicAdd(dense_count + batch, 1);
-                dense_list[static_cast<size_t>(batch) * n + pos] = q;
-            }
-        }
+    if (cnt <= num_neighbors - 1) {
+        keep[static_cast<size_t>(batch) * n + q] = (mx <= qa) ? 1 : 0;  // ties: position 0 (self) wins the argmax
+    } else {  // more in-radius neighbours than the tree returns: resolve with the exact k nearest
+        keep[static_cast<size_t>(batch) * n + q] = 2;
+        const int pos = atomicAdd(dense_count + batch, 1);
+        dense_list[static_cast<size_t>(batch) * n + pos] = q;
     }
 }
 
 // Slow path: one warp per dense point selects its (num_neighbors-1) nearest other points by (d2, index), num_neighbors-1
-// rounds of "smallest key larger than the previous one" over the whole cloud.
+// rounds of "smallest key larger than the previous one" over the candidates of the 3 x 3 cells.
 __global__ void __launch_bounds__(kNmsWarps * 32)
-nms_dense_kernel(int n, double radius, int num_neighbors, const float *__restrict__ xyz, const float *__restrict__ attention,
+nms_dense_kernel(int n, double radius, int num_neighbors, int max_cells, const float *__restrict__ xyz, const float *__restrict__ attention,
+                 const float *__restrict__ bbox, const int *__restrict__ cell_start, const int *__restrict__ sorted,
                  unsigned char *__restrict__ keep, const int *__restrict__ dense_list, const int *__restrict__ dense_count) {
     const int lane = threadIdx.x & 31;
     const int batch = blockIdx.y;
@@ -126,23 +217,31 @@ nms_dense_kernel(int n, double radius, int num_neighbors, const float *__restric
     const int q = dense_list[static_cast<size_t>(batch) * n + w];
     const float *p = xyz + static_cast<size_t>(batch) * n * 3;
     const float *att = attention + static_cast<size_t>(batch) * n;
+    const int *cs = cell_start + static_cast<size_t>(batch) * (max_cells + 1);
+    const int *srt = sorted + static_cast<size_t>(batch) * n;
+    const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
     const double T = nms_threshold(radius);
     const double qx = p[3 * q], qy = p[3 * q + 1], qz = p[3 * q + 2];
     const float qa = att[q];
+    const int cx = nms_cell_coord(qx, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(qy, g.y0, g.inv_h, g.ny);
     double last_d = -1.0;
     int last_k = -1;
     bool is_max = true;
     for (int r = 0; r < num_neighbors - 1; ++r) {
         double bd = 1.0e300;
         int bk = 0x7fffffff;
-        for (int k = lane; k < n; k += 32) {
-            if (k == q) continue;
-            const double d = nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
-            if (d > T) continue;
-            const bool after = d > last_d || (d == last_d && k > last_k);
-            if (after && (d < bd || (d == bd && k < bk))) {
-                bd = d;
-                bk = k;
+        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
+            const int c0 = yy * g.nx + max(cx - 1, 0), c1 = yy * g.nx + min(cx + 1, g.nx - 1);
+            for (int e = cs[c0] + lane; e < cs[c1 + 1]; e += 32) {
+                const int k = srt[e];
+                if (k == q) continue;
+                const double d = nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+                if (d > T) continue;
+                const bool after = d > last_d || (d == last_d && k > last_k);
+                if (after && (d < bd || (d == bd && k < bk))) {
+                    bd = d;
+                    bk = k;
+                }
             }
         }
 #pragma unroll
@@ -243,10 +342,18 @@ __global__ void nms_finalize_kernel(int n, int max_keypoints, const float *__res
 
 using namespace f3d;
 
+static int nms_max_cells(int n) {
+    long long c = 4LL * n;
+    if (c < 4096) c = 4096;
+    if (c > (1 << 22)) c = 1 << 22;
+    return static_cast<int>(c);
+}
+
 F3D_API size_t f3d_nms_workspace_bytes(int b, int n) {
     if (b <= 0 || n <= 0) return 256;
     const size_t bn = static_cast<size_t>(b) * n;
-    return bn * (1 + 4 + 4) + static_cast<size_t>(b) * 16 + 1024;
+    const size_t cells = static_cast<size_t>(nms_max_cells(n)) + 1;
+    return bn * (1 + 4 + 4 + 4) + static_cast<size_t>(b) * cells * 8 + static_cast<size_t>(b) * 32 + 2048;
 }
 
 F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_radius, double min_response_ratio,
@@ -261,24 +368,43 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     if (b == 0) return 0;
     cudaStream_t st = as_stream(stream);
     const size_t bn = static_cast<size_t>(b) * n;
-    // layout: [counts: 2b ints][maxatt: b floats][pad] [list: bn ints][dense_list: bn ints][keep: bn bytes]
+    const int max_cells = nms_max_cells(n);
+    const size_t cells = static_cast<size_t>(max_cells) + 1;
+    // layout: [counts: 2b ints][maxatt: b floats][bbox: 4b floats][pad] [cell_start: b*cells ints][cursor: b*cells ints]
+    //         [list: bn ints][dense_list: bn ints][sorted: bn ints][keep: bn bytes]
     char *base = static_cast<char *>(workspace);
     int *count = reinterpret_cast<int *>(base);
     int *dense_count = count + b;
     float *maxatt = reinterpret_cast<float *>(dense_count + b);
-    const size_t head = (static_cast<size_t>(b) * 12 + 255) & ~static_cast<size_t>(255);
-    int *list = reinterpret_cast<int *>(base + head);
+    float *bbox = maxatt + b;
+    const size_t head = (static_cast<size_t>(b) * 28 + 255) & ~static_cast<size_t>(255);
+    int *cell_start = reinterpret_cast<int *>(base + head);
+    int *cursor = cell_start + static_cast<size_t>(b) * cells;
+    int *list = cursor + static_cast<size_t>(b) * cells;
     int *dense_list = list + bn;
-    unsigned char *keep = reinterpret_cast<unsigned char *>(dense_list + bn);
-    cudaError_t e = cudaMemsetAsync(base, 0, head, st);
+    int *sorted = dense_list + bn;
+    unsigned char *keep = reinterpret_cast<unsigned char *>(sorted + bn);
+    cudaError_t e = cudaMemsetAsync(base, 0, head + static_cast<size_t>(b) * cells * sizeof(int), st);  // counters + cell counts
     if (e != cudaSuccess) return fail(static_cast<int>(e), "nms: memset");
-    const int per_cta = kNmsWarps * kNmsPtsPerWarp;
-    nms_keep_kernel<<<dim3((n + per_cta - 1) / per_cta, b), kNmsWarps * 32, 0, st>>>(n, nms_radius, num_neighbors, xyz, attention, keep,
-                                                                                    dense_list, dense_count);
-    int rc = check_launch("nms_keep_kernel");
+    const double grid_radius = nms_radius;
+    nms_bbox_kernel<<<b, 1024, 0, st>>>(n, xyz, bbox);
+    int rc = check_launch("nms_bbox_kernel");
     if (rc) return rc;
-    nms_dense_kernel<<<dim3((n + kNmsWarps - 1) / kNmsWarps, b), kNmsWarps * 32, 0, st>>>(n, nms_radius, num_neighbors, xyz, attention, keep,
-                                                                                         dense_list, dense_count);
+    nms_cell_count_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, grid_radius, max_cells, xyz, bbox, cell_start);
+    rc = check_launch("nms_cell_count_kernel");
+    if (rc) return rc;
+    nms_cell_scan_kernel<<<b, 1024, 0, st>>>(max_cells, cell_start, cursor);
+    rc = check_launch("nms_cell_scan_kernel");
+    if (rc) return rc;
+    nms_cell_fill_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, grid_radius, max_cells, xyz, bbox, cursor, sorted);
+    rc = check_launch("nms_cell_fill_kernel");
+    if (rc) return rc;
+    nms_keep_kernel<<<dim3((n + 127) / 128, b), 128, 0, st>>>(n, nms_radius, num_neighbors, max_cells, xyz, attention, bbox, cell_start, sorted,
+                                                              keep, dense_list, dense_count);
+    rc = check_launch("nms_keep_kernel");
+    if (rc) return rc;
+    nms_dense_kernel<<<dim3((n + kNmsWarps - 1) / kNmsWarps, b), kNmsWarps * 32, 0, st>>>(n, nms_radius, num_neighbors, max_cells, xyz, attention,
+                                                                                         bbox, cell_start, sorted, keep, dense_list, dense_count);
     rc = check_launch("nms_dense_kernel");
     if (rc) return rc;
     nms_max_kernel<<<b, 1024, 0, st>>>(n, attention, maxatt);

@@ -34,6 +34,21 @@ def test_nms_matches_reference_function(cuda, kind, n):
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
 
 
+def test_nms_kitti_scale_batch_matches_reference_function(cuda):
+    """W4 size (131 072 points, KITTI-shape, >49 in-radius neighbours for some points) as a batch of two clouds with
+    different extents: the grid-binned kernel against the reference's nms() on the sklearn BallTree."""
+    synth = pkg("synth")
+    xyz = synth.make_batch(2, 131072, seed0=77, kind="kitti")
+    xyz[1] *= np.float32(0.6)                      # a second, denser cloud: another grid and many truncated neighbourhoods
+    rng = np.random.default_rng(1)
+    att = np.log1p(np.exp(rng.standard_normal(xyz.shape[:2]).astype(np.float32) * 2)).astype(np.float32)
+    want = onms.nms(xyz, att)
+    got = run_nms(xyz, att, cuda)
+    assert got[2] == want[2]
+    assert np.array_equal(got[3], want[3])
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
 def test_nms_dense_cloud_uses_50nn_truncation(cuda):
     """more than 49 neighbours inside the radius: only the 49 nearest are consulted (inference.py:236-237)"""
     rng = np.random.default_rng(5)
