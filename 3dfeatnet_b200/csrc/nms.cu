@@ -11,8 +11,8 @@
 //     "d > radius" is tested as d2 > T with T = max{s : sqrt_rn(s) <= radius} (monotone IEEE sqrt => same predicate);
 //   * the cloud is binned into an xy grid of cells >= nms_radius wide (counting sort), so a query only visits the 3 x 3 cells
 //     around it -- O(N) instead of the O(N^2) all-pairs scan (612 ms -> a few ms at N = 131 072);
-//   * a point with at most 49 other points inside the radius consults all of them (they are its nearest ones); only a
-//     point with more than 49 takes the slow path that selects the 49 nearest by (d2, index);
+//   * a point with at most 49 other points inside the radius consults all of them (they are its nearest ones); a point
+//     with more than 49 dies iff its nearest larger-attention neighbour, in (d2, index) order, is among the first 49;
 //   * the threshold is computed in float64 like NumPy 1.19 does for float32_scalar * python_float
 //     (requirements.txt:29);
 //   * the descending (attention, index) order is produced by counting, for every survivor, the survivors that precede
@@ -21,7 +21,6 @@
 
 namespace f3d {
 
-constexpr int kNmsWarps = 8;
 
 __device__ __forceinline__ double nms_d2(double ax, double ay, double az, double bx, double by, double bz) {
     const double dx = ax - bx, dy = ay - by, dz = az - bz;
@@ -166,11 +165,15 @@ __global__ void nms_cell_fill_kernel(int n, double radius, int max_cells, const 
 }
 
 // keep[b,p] = 1 iff p is a local attention maximum among its (at most num_neighbors-1) nearest in-radius neighbours.
-// One thread per query point scans the 3 x 3 cells around it (float64 distances, the tree's arithmetic).
+// One thread per query point scans the 3 x 3 cells around it (float64 distances, the tree's arithmetic) and records the
+// number of in-radius neighbours and the NEAREST one with a larger attention (the "threat", ordered by (d2, index)).
+// No threat: the point survives.  A threat and at most num_neighbors-1 neighbours: it is consulted, the point dies.
+// Otherwise the tree only returns the num_neighbors-1 nearest: the point dies iff fewer than num_neighbors-1 neighbours
+// precede the nearest threat -- a second scan that counts them (instead of materialising the sorted neighbour list).
 __global__ void __launch_bounds__(128)
 nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const float *__restrict__ xyz, const float *__restrict__ attention,
                 const float *__restrict__ bbox, const int *__restrict__ cell_start, const int *__restrict__ sorted,
-                unsigned char *__restrict__ keep, int *__restrict__ dense_list, int *__restrict__ dense_count) {
+                unsigned char *__restrict__ keep) {
     const int batch = blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
@@ -183,82 +186,41 @@ nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const fl
     const double qx = p[3 * q], qy = p[3 * q + 1], qz = p[3 * q + 2];
     const float qa = att[q];
     const int cx = nms_cell_coord(qx, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(qy, g.y0, g.inv_h, g.ny);
+    const int y_lo = max(cy - 1, 0), y_hi = min(cy + 1, g.ny - 1), x_lo = max(cx - 1, 0), x_hi = min(cx + 1, g.nx - 1);
     int cnt = 0;
-    float mx = -3.0e38f;
-    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
-        const int c0 = yy * g.nx + max(cx - 1, 0), c1 = yy * g.nx + min(cx + 1, g.nx - 1);
-        for (int e = cs[c0]; e < cs[c1 + 1]; ++e) {  // the cells of one grid row are contiguous in the sorted order
+    double td = 1.0e300;  // nearest threat
+    int tk = 0x7fffffff;
+    for (int yy = y_lo; yy <= y_hi; ++yy) {
+        for (int e = cs[yy * g.nx + x_lo]; e < cs[yy * g.nx + x_hi + 1]; ++e) {  // the cells of one grid row are contiguous
             const int k = srt[e];
             if (k == q) continue;
-            if (nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]) > T) continue;
+            const double d = nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+            if (d > T) continue;
             ++cnt;
-            mx = fmaxf(mx, att[k]);
+            if (att[k] > qa && (d < td || (d == td && k < tk))) {  // ties in attention: position 0 (self) wins the argmax
+                td = d;
+                tk = k;
+            }
         }
     }
-    if (cnt <= num_neighbors - 1) {
-        keep[static_cast<size_t>(batch) * n + q] = (mx <= qa) ? 1 : 0;  // ties: position 0 (self) wins the argmax
-    } else {  // more in-radius neighbours than the tree returns: resolve with the exact k nearest
-        keep[static_cast<size_t>(batch) * n + q] = 2;
-        const int pos = atomicAdd(dense_count + batch, 1);
-        dense_list[static_cast<size_t>(batch) * n + pos] = q;
-    }
-}
-
-// Slow path: one warp per dense point selects its (num_neighbors-1) nearest other points by (d2, index), num_neighbors-1
-// rounds of "smallest key larger than the previous one" over the candidates of the 3 x 3 cells.
-__global__ void __launch_bounds__(kNmsWarps * 32)
-nms_dense_kernel(int n, double radius, int num_neighbors, int max_cells, const float *__restrict__ xyz, const float *__restrict__ attention,
-                 const float *__restrict__ bbox, const int *__restrict__ cell_start, const int *__restrict__ sorted,
-                 unsigned char *__restrict__ keep, const int *__restrict__ dense_list, const int *__restrict__ dense_count) {
-    const int lane = threadIdx.x & 31;
-    const int batch = blockIdx.y;
-    const int w = blockIdx.x * kNmsWarps + (threadIdx.x >> 5);
-    if (w >= dense_count[batch]) return;
-    const int q = dense_list[static_cast<size_t>(batch) * n + w];
-    const float *p = xyz + static_cast<size_t>(batch) * n * 3;
-    const float *att = attention + static_cast<size_t>(batch) * n;
-    const int *cs = cell_start + static_cast<size_t>(batch) * (max_cells + 1);
-    const int *srt = sorted + static_cast<size_t>(batch) * n;
-    const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
-    const double T = nms_threshold(radius);
-    const double qx = p[3 * q], qy = p[3 * q + 1], qz = p[3 * q + 2];
-    const float qa = att[q];
-    const int cx = nms_cell_coord(qx, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(qy, g.y0, g.inv_h, g.ny);
-    double last_d = -1.0;
-    int last_k = -1;
-    bool is_max = true;
-    for (int r = 0; r < num_neighbors - 1; ++r) {
-        double bd = 1.0e300;
-        int bk = 0x7fffffff;
-        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
-            const int c0 = yy * g.nx + max(cx - 1, 0), c1 = yy * g.nx + min(cx + 1, g.nx - 1);
-            for (int e = cs[c0] + lane; e < cs[c1 + 1]; e += 32) {
-                const int k = srt[e];
-                if (k == q) continue;
-                const double d = nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
-                if (d > T) continue;
-                const bool after = d > last_d || (d == last_d && k > last_k);
-                if (after && (d < bd || (d == bd && k < bk))) {
-                    bd = d;
-                    bk = k;
+    unsigned char kp = 1;
+    if (tk != 0x7fffffff) {
+        kp = 0;
+        if (cnt > num_neighbors - 1) {
+            int before = 0;
+            for (int yy = y_lo; yy <= y_hi; ++yy) {
+                for (int e = cs[yy * g.nx + x_lo]; e < cs[yy * g.nx + x_hi + 1]; ++e) {
+                    const int k = srt[e];
+                    if (k == q) continue;
+                    const double d = nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+                    if (d > T) continue;
+                    before += (d < td || (d == td && k < tk)) ? 1 : 0;
                 }
             }
+            if (before >= num_neighbors - 1) kp = 1;  // the threat is not among the neighbours the tree returns
         }
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            const double od = __shfl_xor_sync(kFull, bd, s);
-            const int ok = __shfl_xor_sync(kFull, bk, s);
-            if (od < bd || (od == bd && ok < bk)) {
-                bd = od;
-                bk = ok;
-            }
-        }
-        if (bk == 0x7fffffff) break;
-        if (att[bk] > qa) is_max = false;
-        last_d = bd;
-        last_k = bk;
     }
-    if (lane == 0) keep[static_cast<size_t>(batch) * n + q] = is_max ? 1 : 0;
+    keep[static_cast<size_t>(batch) * n + q] = kp;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -400,12 +362,8 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     rc = check_launch("nms_cell_fill_kernel");
     if (rc) return rc;
     nms_keep_kernel<<<dim3((n + 127) / 128, b), 128, 0, st>>>(n, nms_radius, num_neighbors, max_cells, xyz, attention, bbox, cell_start, sorted,
-                                                              keep, dense_list, dense_count);
+                                                              keep);
     rc = check_launch("nms_keep_kernel");
-    if (rc) return rc;
-    nms_dense_kernel<<<dim3((n + kNmsWarps - 1) / kNmsWarps, b), kNmsWarps * 32, 0, st>>>(n, nms_radius, num_neighbors, max_cells, xyz, attention,
-                                                                                         bbox, cell_start, sorted, keep, dense_list, dense_count);
-    rc = check_launch("nms_dense_kernel");
     if (rc) return rc;
     nms_max_kernel<<<b, 1024, 0, st>>>(n, attention, maxatt);
     rc = check_launch("nms_max_kernel");

@@ -49,7 +49,7 @@ def detect_and_describe(model, point_cloud, nms_radius=0.5, min_response_ratio=1
     atts = []
     for s in range(0, n, MAX_POINTS):
         kp = xyz[:, s:s + MAX_POINTS, :].contiguous()
-        _, _, att, ep = model.get_inference_model(point_cloud, False, keypoints=kp)
+        _, _, att, ep = model.get_inference_model(point_cloud, False, keypoints=kp, fetch_features=False)
         atts.append(ep["attention"])
     attention = torch.cat(atts, dim=1)
     xyz_nms, att_nms, num = nms(xyz, attention, nms_radius, min_response_ratio, max_keypoints)

@@ -304,11 +304,14 @@ class Feat3dNet:
         anchor_attention = torch.chunk(attention, 3, dim=0)[0] if attention is not None else None
         return xyz, features, anchor_attention, end_points
 
-    def get_inference_model(self, point_cloud, is_training, use_bn=True, compute_det_gradients=False, keypoints=None):
+    def get_inference_model(self, point_cloud, is_training, use_bn=True, compute_det_gradients=False, keypoints=None,
+                            fetch_features=True):
         """ The core 3DFeat-Net model (feat3dnet.py:258-313).
 
         point_cloud: (B,N,>=3) CUDA float32.  keypoints: optional (B,M,3) cluster centres (what inference.py feeds
         through end_points['keypoints'], :128-131); otherwise FPS picks param['num_clusters'] (or every point when <=0).
+        fetch_features=False is `sess.run([xyz_op, attention_op])` (inference.py:128): TF prunes the descriptor sub-graph
+        when it is not fetched, and so does the fused eval path (features come back as None).
         Returns: xyz, features, attention, end_points
         """
         _lib.require_cuda(point_cloud)
@@ -323,7 +326,7 @@ class Feat3dNet:
                 packed = self.packed_weights()
                 attention, orientation = detector_forward_fused(l0_xyz, kp, idx, radius, packed, self.precision)
                 ori = None if self.param['NoRegress'] else orientation
-                features = descriptor_forward_fused(l0_xyz, kp, idx, ori, radius, packed, fdim, self.precision)
+                features = descriptor_forward_fused(l0_xyz, kp, idx, ori, radius, packed, fdim, self.precision) if fetch_features else None
             end_points.update(keypoints=kp, attention=attention, orientation=orientation, idx=idx, pts_cnt=pts_cnt)
             return kp, features, (attention if self.param['Attention'] else None), end_points
 
