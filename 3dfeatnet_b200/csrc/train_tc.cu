@@ -14,9 +14,9 @@
 //   3 x K/16 MMAs, the 8 warps read the accumulator back (lane = channel => a warp writes 128 contiguous bytes of a row,
 //   and the BN batch statistics -- sum z, sum z^2 per channel -- are plain per-thread accumulations).  Phases of a tile are
 //   sequential; two to four CTAs share an SM (TMEM columns K + 64 <= 256) and overlap each other.
-// wgrad_tc_kernel: D[cin(128) x cout] += X^T (shared, K = rows) * dZ^T (shared, K = rows) over the CTA's row range, 64 rows
-//   per stage; both operands need K = row contiguous, so a thread transposes 8 rows x 8 channels in registers while
-//   splitting.  Per-CTA partials are reduced in a fixed order afterwards (deterministic).
+// wgrad_tc_kernel: D[cin(128) x cout] += X^T (shared, K = rows) * dZ^T (shared, K = rows) over the CTA's row range, 32 rows
+//   per stage (TMA ring, double-buffered operand images; see the kernel).  Per-CTA partials are reduced in a fixed order
+//   afterwards (deterministic).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -35,7 +35,6 @@ constexpr uint32_t kLboW = 128 * 16;      // weight image: 128 rows per 8-wide K
 // 3-split image pads by 16 B only (2-way conflicts on a few stores) so that two CTAs with a 2-deep ring still share an SM
 // at K = 128
 __host__ __device__ constexpr uint32_t lbo_x(int nsplit) { return kTile * 16 + (nsplit == 3 ? 16 : 32); }
-constexpr uint32_t kLboA = 128 * 16 + 16; // wgrad A image (padded: the 8 row-chunks a quarter-warp writes hit distinct banks)
 }  // namespace ttc
 
 __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
@@ -302,108 +301,173 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// 8 rows x 4 channels of a row-major fp32 matrix -> four 16-byte K(=row)-major chunks, hi and lo.  A warp's 32 units are
-// 8 row-chunks x 4 consecutive channel quads: every load instruction covers whole 32-byte sectors (8 rows x 64 B), and the
-// 8 row-chunks of a quarter-warp land in distinct banks (chunk stride = 16 mod 128 bytes).
-__device__ __forceinline__ void wgrad_stage_unit(uint8_t *img, uint32_t lbo, uint32_t split, int rc, int c4, const float *__restrict__ src, int ld,
-                                                 long long row0, long long rend) {
-    float4 v[8];
+// ---------------------------------------------------------------------------------------------------------------------
+// wgrad: partW[cta][cin][cout] = sum over the CTA's rows of x[r][ci] * dz[r][co].
+// D[ci (128, zero-padded) x co] accumulates in tensor memory over the whole row range of the CTA; a stage is 32 rows
+// (two K = 16 MMA steps x 3 split terms).  The fp32 rows of a stage are two contiguous blocks (x and dz): bulk-TMA'd into
+// a 2-deep ring, one stage ahead.  Both operands need K = row contiguous, so the conversion transposes 8 rows x 4 channels
+// per thread: LDS.128 of 32 consecutive channel quads of one row (conflict-free), bf16 hi/lo split, four 16-byte chunks
+// (8 rows of one channel) stored into the operand image whose core-matrix stride is padded to 144 B (conflict-free).
+// The operand images are double-buffered and the roles are split: warp 0 only issues TMA fetches and MMAs, the other 15
+// warps only convert; mbarriers (ring filled / image converted / MMAs done) connect them, so the MMAs and the fetch of
+// stage s overlap the conversion of stage s+1 and nobody waits for the issuer.
+namespace wg {
+constexpr int kRows = 32;            // rows per stage
+constexpr uint32_t kSboP = 144;      // stride between 8-channel core matrices (128 B + 16 B padding)
+constexpr int kChunks = kRows / 8;   // K chunks per stage
+constexpr int kThreads = 512;        // 16 warps: the conversion is the long phase of a stage
+}  // namespace wg
+
+__device__ __forceinline__ void wgrad_convert(uint8_t *img, uint32_t lbo, uint32_t split, const uint8_t *__restrict__ stage, int c, int valid_rows) {
+    // unit u -> (row chunk rc, channel quad c4); a warp handles 32 consecutive quads of one row chunk; converter threads only
+    const int quads = c >> 2;
+    for (int u = threadIdx.x - 32; u < wg::kChunks * quads; u += wg::kThreads - 32) {
+        const int rc = u / quads, c4 = u - rc * quads;
+        float4 v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const long long row = row0 + rc * 8 + i;
-        v[i] = row < rend ? __ldg(reinterpret_cast<const float4 *>(src + row * ld + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    uint8_t *dst = img + rc * lbo + c4 * 64;
-    uint4 hi, lo;
-    {
-        const float col[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
-        split8(col, hi, lo);
-        *reinterpret_cast<uint4 *>(dst) = hi;
-        *reinterpret_cast<uint4 *>(dst + split) = lo;
-    }
-    {
-        const float col[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
-        split8(col, hi, lo);
-        *reinterpret_cast<uint4 *>(dst + 16) = hi;
-        *reinterpret_cast<uint4 *>(dst + split + 16) = lo;
-    }
-    {
-        const float col[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
-        split8(col, hi, lo);
-        *reinterpret_cast<uint4 *>(dst + 32) = hi;
-        *reinterpret_cast<uint4 *>(dst + split + 32) = lo;
-    }
-    {
-        const float col[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
-        split8(col, hi, lo);
-        *reinterpret_cast<uint4 *>(dst + 48) = hi;
-        *reinterpret_cast<uint4 *>(dst + split + 48) = lo;
+        for (int i = 0; i < 8; ++i) {
+            const int r = rc * 8 + i;
+            v[i] = r < valid_rows ? *reinterpret_cast<const float4 *>(stage + (static_cast<size_t>(r) * c + c4 * 4) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint8_t *dst = img + rc * lbo + (c4 >> 1) * wg::kSboP + (c4 & 1) * 64;
+        uint4 hi, lo;
+        {
+            const float col[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
+            split8(col, hi, lo);
+            *reinterpret_cast<uint4 *>(dst) = hi;
+            *reinterpret_cast<uint4 *>(dst + split) = lo;
+        }
+        {
+            const float col[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
+            split8(col, hi, lo);
+            *reinterpret_cast<uint4 *>(dst + 16) = hi;
+            *reinterpret_cast<uint4 *>(dst + split + 16) = lo;
+        }
+        {
+            const float col[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
+            split8(col, hi, lo);
+            *reinterpret_cast<uint4 *>(dst + 32) = hi;
+            *reinterpret_cast<uint4 *>(dst + split + 32) = lo;
+        }
+        {
+            const float col[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
+            split8(col, hi, lo);
+            *reinterpret_cast<uint4 *>(dst + 48) = hi;
+            *reinterpret_cast<uint4 *>(dst + split + 48) = lo;
+        }
     }
 }
 
-// partW[blockIdx.x][cin][cout] = sum over the CTA's rows of x[r][ci] * dz[r][co].  cin % 8 == 0, cin <= 128, cout % 16 == 0, <= 256.
-__global__ void __launch_bounds__(ttc::kThreads)
+// cin % 8 == 0, cin <= 128, cout % 16 == 0, cout <= 256.  One CTA per SM.
+__global__ void __launch_bounds__(wg::kThreads, 1)
 wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint32_t tmem_cols, const float *__restrict__ x,
                 const float *__restrict__ dz, float *__restrict__ partW, int dbg) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t lbo_b = static_cast<uint32_t>(cout) * 16 + 16;
-    const uint32_t split_a = 8 * kLboA, split_b = 8 * lbo_b;
-    uint8_t *img_a = smem;
-    uint8_t *img_b = smem + 2 * split_a;
-    uint64_t *bar_m = reinterpret_cast<uint64_t *>(smem + 2 * split_a + ((2 * split_b + 15) & ~15u));
-    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_m + 1);
+    const uint32_t lbo_a = 16 * wg::kSboP, lbo_b = static_cast<uint32_t>(cout / 8) * wg::kSboP;
+    const uint32_t split_a = wg::kChunks * lbo_a, split_b = wg::kChunks * lbo_b;
+    const uint32_t img_bytes = 2 * split_a + 2 * split_b;                 // one image buffer: [A hi | A lo | B hi | B lo]
+    const uint32_t xs_bytes = wg::kRows * static_cast<uint32_t>(cin) * 4, ds_bytes = wg::kRows * static_cast<uint32_t>(cout) * 4;
+    const uint32_t stage_bytes = xs_bytes + ds_bytes;
+    uint8_t *ring = smem + 2 * img_bytes;
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + 2 * img_bytes + 2 * stage_bytes);  // [2] ring stage filled
+    uint64_t *bar_mma = bar_full + 2;                                                          // [2] MMAs of an image buffer done
+    uint64_t *bar_img = bar_full + 4;                                                          // [2] image buffer converted
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_full + 6);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_m, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_full + i, 1);
+            mbar_init(bar_mma + i, 1);
+            mbar_init(bar_img + i, wg::kThreads / 32 - 1);  // one arrival per converter warp
+        }
         fence_barrier_init();
     }
     if (warp == 0) {
         tmem_alloc(tmem_base_s, tmem_cols);
         tmem_relinquish();
     }
-    for (uint32_t o = threadIdx.x * 16; o < 2 * split_a; o += kThreads * 16) *reinterpret_cast<uint4 *>(img_a + o) = make_uint4(0, 0, 0, 0);
+    // the rows of the A images that belong to channels >= cin stay zero for the whole kernel
+    for (uint32_t o = threadIdx.x * 16; o < 2 * img_bytes; o += wg::kThreads * 16) *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
-    uint32_t mpar = 0;
     const uint32_t idesc = make_idesc(1, 128, static_cast<uint32_t>(cout));
     const long long rbeg = blockIdx.x * rows_per_cta, rend = rbeg + rows_per_cta < rows ? rbeg + rows_per_cta : rows;
-    uint32_t acc = 0;
-    for (long long r0 = rbeg; r0 < rend; r0 += kTile) {
+    const int nstages = static_cast<int>((rend - rbeg + wg::kRows - 1) / wg::kRows);
+
+    if (warp == 0) {
+        // ---- issuer warp: TMA fetches (one stage ahead) and the MMAs; never touches the data itself
+        auto fetch = [&](int s) {  // the fp32 rows of stage s -> ring slot s & 1
+            const long long r0 = rbeg + static_cast<long long>(s) * wg::kRows;
+            const uint32_t valid = static_cast<uint32_t>(rend - r0 < wg::kRows ? rend - r0 : wg::kRows);
+            if (lane == 0) {
+                uint8_t *dst = ring + (s & 1) * stage_bytes;
+                const uint32_t xb = valid * static_cast<uint32_t>(cin) * 4, db = valid * static_cast<uint32_t>(cout) * 4;
+                mbar_arrive_expect_tx(bar_full + (s & 1), xb + db);
+                const uint8_t *xsrc = reinterpret_cast<const uint8_t *>(x + r0 * cin);
+                const uint8_t *dsrc = reinterpret_cast<const uint8_t *>(dz + r0 * cout);
+                for (uint32_t off = 0; off < xb; off += 16384) bulk_g2s(dst + off, xsrc + off, xb - off < 16384u ? xb - off : 16384u, bar_full + (s & 1));
+                for (uint32_t off = 0; off < db; off += 16384)
+                    bulk_g2s(dst + xs_bytes + off, dsrc + off, db - off < 16384u ? db - off : 16384u, bar_full + (s & 1));
+            }
+            __syncwarp();
+        };
         if (!(dbg & 1)) {
-            for (int u = threadIdx.x; u < 2 * cin; u += kThreads) wgrad_stage_unit(img_a, kLboA, split_a, u & 7, u >> 3, x, cin, r0, rend);
-            for (int u = threadIdx.x; u < 2 * cout; u += kThreads) wgrad_stage_unit(img_b, lbo_b, split_b, u & 7, u >> 3, dz, cout, r0, rend);
+            if (nstages > 0) fetch(0);
+            if (nstages > 1) fetch(1);
         }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (warp == 0) {
+        uint32_t acc = 0;
+        for (int s = 0; s < nstages; ++s) {
+            const int b = s & 1;
+            mbar_wait(bar_img + b, static_cast<uint32_t>((s >> 1) & 1));  // image b converted, ring slot b consumed
             tcgen05_fence_after();
+            if (!(dbg & 1) && s + 2 < nstages) fetch(s + 2);
             if (elect_one()) {
+                const uint32_t a0 = sbase + b * img_bytes, b0 = a0 + 2 * split_a;
                 for (int pass = 0; pass < ((dbg & 2) ? 0 : 3); ++pass) {
-                    const uint32_t a = sbase + (pass == 2 ? split_a : 0);
-                    const uint32_t b = sbase + 2 * split_a + (pass == 1 ? split_b : 0);
-                    for (int k = 0; k < kTile / 16; ++k) {
-                        umma_f16(tmem_base, make_smem_desc(a + k * 2 * kLboA, kLboA, kSbo), make_smem_desc(b + k * 2 * lbo_b, lbo_b, kSbo), idesc, acc);
+                    const uint32_t a = a0 + (pass == 2 ? split_a : 0);
+                    const uint32_t bb = b0 + (pass == 1 ? split_b : 0);
+                    for (int k = 0; k < wg::kRows / 16; ++k) {
+                        umma_f16(tmem_base, make_smem_desc(a + k * 2 * lbo_a, lbo_a, wg::kSboP), make_smem_desc(bb + k * 2 * lbo_b, lbo_b, wg::kSboP), idesc, acc);
                         acc = 1;
                     }
                 }
-                umma_commit(bar_m);
+                umma_commit(bar_mma + b);
             }
             __syncwarp();
         }
-        mbar_wait(bar_m, mpar);  // single-buffered operands: the MMAs must have read them before the next stage overwrites
-        mpar ^= 1;
-        tcgen05_fence_after();
-        __syncthreads();
+    } else {
+        // ---- converter warps: ring slot (fp32, row-major) -> operand image (bf16 hi/lo, K = row major)
+        for (int s = 0; s < nstages; ++s) {
+            const int b = s & 1;
+            uint8_t *img = smem + b * img_bytes;
+            if (s >= 2) mbar_wait(bar_mma + b, static_cast<uint32_t>(((s >> 1) - 1) & 1));  // MMAs of stage s-2 have read this image
+            if (!(dbg & 1)) {
+                mbar_wait(bar_full + b, static_cast<uint32_t>((s >> 1) & 1));
+                const long long r0 = rbeg + static_cast<long long>(s) * wg::kRows;
+                const int valid = static_cast<int>(rend - r0 < wg::kRows ? rend - r0 : wg::kRows);
+                const uint8_t *stage = ring + b * stage_bytes;
+                wgrad_convert(img, lbo_a, split_a, stage, cin, valid);
+                wgrad_convert(img + 2 * split_a, lbo_b, split_b, stage + xs_bytes, cout, valid);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_img + b);
+        }
     }
+    // drain: the last MMAs of both image buffers
+    if (nstages >= 1) mbar_wait(bar_mma + ((nstages - 1) & 1), static_cast<uint32_t>(((nstages - 1) >> 1) & 1));
+    if (nstages >= 2) mbar_wait(bar_mma + ((nstages - 2) & 1), static_cast<uint32_t>(((nstages - 2) >> 1) & 1));
+    tcgen05_fence_after();
     const int q = warp & 3;
     const int ci = q * 32 + lane;
     float *pw = partW + (static_cast<size_t>(blockIdx.x) * cin + ci) * cout;
-    for (int cc = (warp >> 2) * 32; cc < cout; cc += 64) {
+    for (int cc = (warp >> 2) * 32; cc < cout; cc += (wg::kThreads / 128) * 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cc, r);
         tmem_ld_wait();
@@ -412,7 +476,7 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
             for (int j = 0; j < 32; j += 4)
                 if (cc + j < cout)
                     *reinterpret_cast<float4 *>(pw + cc + j) =
-                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         }
     }
     tcgen05_fence_before();
@@ -498,12 +562,12 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
 bool wgrad_tc_supported(int cin, int cout) { return cin % 8 == 0 && cin >= 8 && cin <= 128 && cout % 16 == 0 && cout >= 16 && cout <= 256; }
 
 void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta) {
-    const long long ntiles = (rows + ttc::kTile - 1) / ttc::kTile;
-    long long g = 2LL * ttc_num_sms();
-    if (g > ntiles) g = ntiles;
-    const long long per = (ntiles + g - 1) / g;
-    *rows_per_cta = per * ttc::kTile;
-    *grid = static_cast<int>((ntiles + per - 1) / per);
+    const long long nst = (rows + wg::kRows - 1) / wg::kRows;
+    long long g = ttc_num_sms();
+    if (g > nst) g = nst;
+    const long long per = (nst + g - 1) / g;
+    *rows_per_cta = per * wg::kRows;
+    *grid = static_cast<int>((nst + per - 1) / per);
 }
 
 // partW: grid x cin x cout floats
@@ -512,11 +576,11 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
     long long per = 0;
     wgrad_tc_plan(rows, &grid, &per);
     const uint32_t cols = pow2_cols(static_cast<uint32_t>(cout));
-    const uint32_t split_a = 8 * ttc::kLboA, split_b = 8 * (static_cast<uint32_t>(cout) * 16 + 16);
-    const size_t smem = 2 * split_a + ((2 * split_b + 15) & ~15u) + 64;
+    const size_t img = 2 * static_cast<size_t>(wg::kChunks) * 16 * wg::kSboP + 2 * static_cast<size_t>(wg::kChunks) * (cout / 8) * wg::kSboP;
+    const size_t smem = 2 * img + 2 * static_cast<size_t>(wg::kRows) * (cin + cout) * 4 + 64;
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "wgrad_tc: cudaFuncSetAttribute");
-    wgrad_tc_kernel<<<grid, ttc::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg);
+    wgrad_tc_kernel<<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg);
     return check_launch("wgrad_tc_kernel");
 }
 
