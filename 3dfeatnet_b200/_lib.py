@@ -47,7 +47,7 @@ SIGNATURES = {
     "f3d_maxpool_samples_backward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "f3d_triplet_loss_workspace_bytes": (_sz, [_i, _i]),
     "f3d_triplet_loss": (_i, [_i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "f3d_adam_step": (_i, [_i, _vp, _c.c_longlong, _f, _f, _f, _f, _c.c_longlong, _f, _vp]),
+    "f3d_adam_step": (_i, [_i, _vp, _c.c_longlong, _f, _f, _f, _f, _c.c_longlong, _f, _vp, _vp]),
     "f3d_debug_umma_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "f3d_debug_wgrad_tc": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "f3d_detector_tc_weight_bytes": (_sz, []),

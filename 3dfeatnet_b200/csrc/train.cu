@@ -206,8 +206,21 @@ struct AdamRecord {
     long long n;
 };
 
-__global__ void adam_kernel(int num_records, const AdamRecord *__restrict__ recs, float lr_t, float b1, float b2, float eps,
-                            float grad_scale) {
+// step_dev != NULL: the update count lives on the device (a captured CUDA graph replays the same launch every step):
+// t = *step_dev + 1 and the bias-corrected rate is formed here; adam_tick_kernel then advances the counter.
+__global__ void adam_kernel(int num_records, const AdamRecord *__restrict__ recs, float lr_t_host, float lr, float b1, float b2, float eps,
+                            float grad_scale, const long long *__restrict__ step_dev) {
+    __shared__ float lr_s;
+    if (threadIdx.x == 0) {
+        float v = lr_t_host;
+        if (step_dev) {
+            const double t = static_cast<double>(*step_dev + 1);
+            v = static_cast<float>(static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(b2), t)) / (1.0 - pow(static_cast<double>(b1), t)));
+        }
+        lr_s = v;
+    }
+    __syncthreads();
+    const float lr_t = lr_s;
     for (int r = blockIdx.y; r < num_records; r += gridDim.y) {
         const AdamRecord R = recs[r];
         for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < R.n;
@@ -221,6 +234,8 @@ __global__ void adam_kernel(int num_records, const AdamRecord *__restrict__ recs
         }
     }
 }
+
+__global__ void adam_tick_kernel(long long *step_dev) { *step_dev += 1; }
 
 }  // namespace f3d
 
@@ -283,14 +298,21 @@ F3D_API int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa,
 }
 
 // records: DEVICE array of {param*, grad*, m*, v*, n} (5 x 8 bytes each).  grad_scale folds the 1/world of the data-parallel mean.
+// step_dev (device int64, may be NULL): when given, the update count is read from (and then advanced on) the device and
+// `step` is ignored -- the form a CUDA graph of the training step needs.
 F3D_API int f3d_adam_step(int num_records, const void *records, long long max_n, float lr, float beta1, float beta2, float eps,
-                          long long step, float grad_scale, void *stream) {
-    if (num_records <= 0 || !records || step <= 0) return fail(F3D_ERR_INVALID_ARGUMENT, "adam_step: bad arguments");
-    const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))) /
-                        (1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
+                          long long step, float grad_scale, long long *step_dev, void *stream) {
+    if (num_records <= 0 || !records || (!step_dev && step <= 0)) return fail(F3D_ERR_INVALID_ARGUMENT, "adam_step: bad arguments");
+    double lr_t = 0.0;
+    if (!step_dev)
+        lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))) /
+               (1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
     const unsigned gx = static_cast<unsigned>(max_n <= 0 ? 1 : (max_n + 255) / 256 > 64 ? 64 : (max_n + 255) / 256);
     const dim3 grid(gx, static_cast<unsigned>(num_records < 64 ? num_records : 64));
-    adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(num_records, static_cast<const AdamRecord *>(records), static_cast<float>(lr_t),
-                                                     beta1, beta2, eps, grad_scale);
-    return check_launch("adam_kernel");
+    adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(num_records, static_cast<const AdamRecord *>(records), static_cast<float>(lr_t), lr,
+                                                     beta1, beta2, eps, grad_scale, step_dev);
+    int rc = check_launch("adam_kernel");
+    if (rc || !step_dev) return rc;
+    adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
+    return check_launch("adam_tick_kernel");
 }

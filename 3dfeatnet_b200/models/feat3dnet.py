@@ -395,7 +395,8 @@ class Feat3dNet:
                 rec[r] = (var[k].data_ptr(), gbuf.data_ptr() + 4 * int(offs[r]), mflat.data_ptr() + 4 * int(offs[r]),
                           vflat.data_ptr() + 4 * int(offs[r]), var[k].numel())
             self._adam = {"t": 0, "names": names, "m": mflat, "v": vflat, "g": gbuf, "records": torch.as_tensor(rec).to(flat.device),
-                          "max_n": int(rec[:, 4].max()), "ptrs": [var[k].data_ptr() for k in names]}
+                          "max_n": int(rec[:, 4].max()), "ptrs": [var[k].data_ptr() for k in names],
+                          "t_dev": torch.zeros(1, dtype=torch.int64, device=flat.device)}  # the update count lives on the device
         st = self._adam
         if st["ptrs"] != [var[k].data_ptr() for k in names]:
             raise _lib.F3DError("get_train_op: a variable was re-allocated since the optimiser state was built")
@@ -406,12 +407,46 @@ class Feat3dNet:
         _lib.require_cuda(st["g"])
         with torch.no_grad():
             _lib.check(_lib.lib().f3d_adam_step(len(names), _lib.ptr(st["records"]), st["max_n"], float(lr), 0.9, 0.999, 1e-8,
-                                                st["t"], float(grad_scale), _lib.stream()), "adam_step")
+                                                st["t"], float(grad_scale), _lib.ptr(st["t_dev"]), _lib.stream()), "adam_step")
             if end_points is not None and end_points.get('bn_updates'):
                 for k, v in end_points['bn_updates'].items():
                     self.weights[k].copy_(v)
         self.invalidate()
         return flat
+
+    def capture_train_step(self, anchors, positives, negatives, lr=1e-5, grad_hook=None, grad_scale=1.0, warmup=3):
+        """Capture one whole training step (get_train_model -> get_loss -> get_train_op: ~340 launches) into a CUDA graph.
+        Returns replay(anchors=None, positives=None, negatives=None) -> loss tensor (device, updated by every replay); new
+        triplets are copied into the static input buffers first.  The Adam step count lives on the device, so a replay is
+        a real optimiser step.  `warmup` eager steps run first (they are real steps too)."""
+        static = [t.detach().clone() for t in (anchors, positives, negatives)]
+
+        def step():
+            xyz, feats, att, ep = self.get_train_model(static[0], static[1], static[2], True)
+            loss, ep = self.get_loss(xyz, feats, att, ep)
+            self.get_train_op(loss, lr=lr, end_points=ep, grad_hook=grad_hook, grad_scale=grad_scale)
+            return loss.detach()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = step()
+
+        def replay(anchors=None, positives=None, negatives=None):
+            for dst, src in zip(static, (anchors, positives, negatives)):
+                if src is not None:
+                    dst.copy_(src)
+            graph.replay()
+            self._adam["t"] += 1
+            return loss
+
+        replay.graph = graph
+        return replay
 
     def train_mode(self):
         """Mark the trainable variables as requiring grad (TF: GraphKeys.TRAINABLE_VARIABLES)."""

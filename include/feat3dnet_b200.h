@@ -202,9 +202,11 @@ int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa, const f
 /* Feat3dNet.get_train_op  models/feat3dnet.py:359-375: tf.train.AdamOptimizer(lr).minimize over all variables in
  * ONE launch.  records: device array of num_records x {float *param; const float *grad; float *m; float *v;
  * long long n;} (40 bytes each); max_n = the largest n.  step = 1-based update count; grad_scale multiplies every
- * gradient first (1/world_size after a sum all-reduce).  theta -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps). */
+ * gradient first (1/world_size after a sum all-reduce).  theta -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps).
+ * step_dev (device int64 or NULL): when given, t = *step_dev + 1 is read on the device and the counter is advanced
+ * afterwards (`step` is ignored) -- the form a captured CUDA graph of the training step replays. */
 int f3d_adam_step(int num_records, const void *records, long long max_n, float lr, float beta1, float beta2, float eps,
-                  long long step, float grad_scale, void *stream);
+                  long long step, float grad_scale, long long *step_dev, void *stream);
 
 /* ---------------------------------------------------------------- bring-up / debugging ---------- */
 

@@ -103,7 +103,7 @@ def test_triplet_loss_rejects_bad_arguments(cuda):
     _lib = pkg("_lib")
     L = _lib.lib()
     assert L.f3d_triplet_loss(0, 4, 4, 0.2, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
-    assert L.f3d_adam_step(0, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+    assert L.f3d_adam_step(0, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None, None) == -1
 
 
 def plain_conv_bn(x, w, b, gamma, beta, relu_mask):
@@ -281,3 +281,32 @@ def test_c4_training_step_fused_vs_torch_layers_and_deterministic(cuda):
         # ReLU / max-pool routing flips on rounding-level differences, so the comparison is a direction + scale one
         assert torch.nn.functional.cosine_similarity(g.double(), g_ref.double(), dim=0).item() > 0.999
         assert abs(g.norm().item() / g_ref.norm().item() - 1.0) < 2e-2
+
+
+def test_captured_train_step_equals_eager_steps(cuda):
+    """Feat3dNet.capture_train_step: N replays of the CUDA graph == N eager steps, bit for bit (weights, Adam moments, BN
+    shadows) -- the kernels are deterministic and the Adam step count is read on the device."""
+    f3, synth = pkg("models.feat3dnet"), pkg("synth")
+    B, N, M = 2, 2048, 64
+    a, p, n = (torch.as_tensor(synth.make_batch(B, N, seed0=s)).to(cuda) for s in (21, 22, 23))
+    params = onet.init_params(seed=8, randomize_bn=True)
+
+    def eager(steps):
+        net = f3.Feat3dNet({'num_clusters': M}, weights=params, device=cuda).train_mode()
+        for _ in range(steps):
+            xyz, feats, att, ep = net.get_train_model(a, p, n, True)
+            loss, ep = net.get_loss(xyz, feats, att, ep)
+            net.get_train_op(loss, lr=1e-3, end_points=ep)
+        return net, loss.detach().clone()
+
+    net_e, loss_e = eager(5)
+    net_g = f3.Feat3dNet({'num_clusters': M}, weights=params, device=cuda).train_mode()
+    replay = net_g.capture_train_step(a, p, n, lr=1e-3, warmup=2)      # 2 eager + 1 captured-run... capture itself does not execute
+    for _ in range(3):
+        loss_g = replay()
+    torch.cuda.synchronize()
+    assert int(net_g._adam["t_dev"].item()) == 5 == int(net_e._adam["t_dev"].item())
+    assert torch.equal(loss_g, loss_e)
+    for k in net_e.weights:
+        assert torch.equal(net_e.weights[k], net_g.weights[k]), k
+    assert torch.equal(net_e._adam["m"], net_g._adam["m"]) and torch.equal(net_e._adam["v"], net_g._adam["v"])

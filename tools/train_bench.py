@@ -33,6 +33,10 @@ def step():
     return loss
 
 
+GRAPH = os.environ.get("F3D_TRAIN_GRAPH", "1" if world == 1 else "0") == "1" and not UNFUSED
+if GRAPH:   # the whole step (~340 launches) as one CUDA graph: removes the CPU launch gaps (eager: F3D_TRAIN_GRAPH=0)
+    replay = net.capture_train_step(a, p, n, lr=1e-5, grad_hook=dist.allreduce_sum_, grad_scale=1.0 / world)
+    step = replay
 for _ in range(3):
     step()
 torch.cuda.synchronize(); dist.barrier()
@@ -46,9 +50,9 @@ ms = dist.max_over_ranks(s.elapsed_time(e), dev) / K
 if rank == 0:
     print(json.dumps(dict(workload="C4 stage-2 train step, 6 triplets/GPU x 4096 pts, 512 clusters x 64", n_gpus=world, ms_per_step=ms,
                           steps_per_s=1e3 / ms, clouds_per_s=3 * B * world * 1e3 / ms, loss=float(loss.detach()),
-                          mlp_backend="torch matmul/autograd layers" if UNFUSED else "csrc/train_layers.cu + train.cu, torch glue",
+                          mlp_backend="torch matmul/autograd layers" if UNFUSED else "csrc/train_layers.cu + train_tc.cu + train.cu, torch glue", cuda_graph=GRAPH,
                           peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)))
-if rank == 0 and os.environ.get("F3D_TRAIN_PROFILE") == "1":
+if rank == 0 and os.environ.get("F3D_TRAIN_PROFILE") == "1" and not GRAPH:
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         step(); torch.cuda.synchronize()
