@@ -2,7 +2,8 @@
 samples, attention + rotation, BN batch statistics, triplet loss, backward, ONE flat-gradient all-reduce (NCCL), TF-1 Adam.
 The sampling / grouping operators, the conv+BN+ReLU layers (forward and backward), the loss and Adam are the CUDA kernels of
 this repository (csrc/train_layers.cu, csrc/train.cu); pooling / concat / rotation glue is torch autograd.
-F3D_TRAIN_UNFUSED=1 times the op-by-op torch statement instead; F3D_TRAIN_PROFILE=1 prints the top kernels of one step.
+The whole step (incl. the NCCL all-reduce) is replayed as ONE CUDA graph (F3D_TRAIN_GRAPH=0: eager launches).
+F3D_TRAIN_UNFUSED=1 times the op-by-op torch statement instead; F3D_TRAIN_PROFILE=1 prints the top kernels of one eager step.
 
     python tools/train_bench.py                      (1 GPU)
     torchrun --nproc-per-node N tools/train_bench.py (N GPUs)
@@ -33,7 +34,7 @@ def step():
     return loss
 
 
-GRAPH = os.environ.get("F3D_TRAIN_GRAPH", "1" if world == 1 else "0") == "1" and not UNFUSED
+GRAPH = os.environ.get("F3D_TRAIN_GRAPH", "1") == "1" and not UNFUSED and os.environ.get("F3D_TRAIN_PROFILE") != "1"
 if GRAPH:   # the whole step (~340 launches) as one CUDA graph: removes the CPU launch gaps (eager: F3D_TRAIN_GRAPH=0)
     replay = net.capture_train_step(a, p, n, lr=1e-5, grad_hook=dist.allreduce_sum_, grad_scale=1.0 / world)
     step = replay
