@@ -130,6 +130,14 @@ partial_reduce_kernel(int nparts, long long width, const float *__restrict__ par
     }
 }
 
+// scale / shift of the batch-norm affine map y = z*scale + shift, written with explicit roundings so that the forward
+// (bn_stats_finalize -> bn_apply) and the backward kernels, which RECOMPUTE y from z instead of reading it back, agree bit
+// for bit
+__device__ __forceinline__ void bn_scale_shift(float gamma, float beta, float mean, float var, float eps, float &sc, float &sh) {
+    sc = __fmul_rn(gamma, rsqrtf(__fadd_rn(var, eps)));
+    sh = __fmaf_rn(-mean, sc, beta);
+}
+
 // sums[2][c] -> mean, var (population), coef = {scale = gamma*rsqrt(var+eps), shift = beta - mean*scale}
 __global__ void bn_stats_finalize_kernel(int c, double inv_rows, float eps, const float *__restrict__ sums, const float *__restrict__ gamma,
                                          const float *__restrict__ beta, float *__restrict__ mean, float *__restrict__ var, float *__restrict__ coef) {
@@ -140,9 +148,10 @@ __global__ void bn_stats_finalize_kernel(int c, double inv_rows, float eps, cons
     if (v < 0.0) v = 0.0;
     mean[ch] = static_cast<float>(mu);
     var[ch] = static_cast<float>(v);
-    const float sc = gamma[ch] * rsqrtf(static_cast<float>(v) + eps);
+    float sc, sh;
+    bn_scale_shift(gamma[ch], beta[ch], static_cast<float>(mu), static_cast<float>(v), eps, sc, sh);
     coef[ch] = sc;
-    coef[c + ch] = beta[ch] - static_cast<float>(mu) * sc;
+    coef[c + ch] = sh;
 }
 
 __global__ void bn_apply_kernel(long long n4, int c, const float *__restrict__ z, const float *__restrict__ coef, int relu, float *__restrict__ y) {
@@ -152,7 +161,7 @@ __global__ void bn_apply_kernel(long long n4, int c, const float *__restrict__ z
     const float4 v = __ldg(reinterpret_cast<const float4 *>(z) + e);
     const float4 sc = __ldg(reinterpret_cast<const float4 *>(coef + ch));
     const float4 sh = __ldg(reinterpret_cast<const float4 *>(coef + c + ch));
-    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+    float4 o = make_float4(__fmaf_rn(v.x, sc.x, sh.x), __fmaf_rn(v.y, sc.y, sh.y), __fmaf_rn(v.z, sc.z, sh.z), __fmaf_rn(v.w, sc.w, sh.w));
     if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
     reinterpret_cast<float4 *>(y)[e] = o;
 }
@@ -189,8 +198,9 @@ __device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, s
 
 // per row-chunk partial sums of g and g*zhat, g = gy * [y > 0] (ReLU) or gy.  part[(blk*2+{0,1})*c + ch]
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ y, const float *__restrict__ z,
-                     const float *__restrict__ mean, const float *__restrict__ var, int relu, float *__restrict__ part) {
+bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ gamma, const float *__restrict__ beta,
+                     const float *__restrict__ z, const float *__restrict__ mean, const float *__restrict__ var, int relu,
+                     float *__restrict__ part) {
     __shared__ float4 red[2][256];
     const int cvec = c >> 2, rl = 256 / cvec;
     const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
@@ -199,14 +209,21 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
     const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean) + cv);
     const float4 vv = __ldg(reinterpret_cast<const float4 *>(var) + cv);
     const float4 is = make_float4(rsqrtf(vv.x + eps), rsqrtf(vv.y + eps), rsqrtf(vv.z + eps), rsqrtf(vv.w + eps));
+    const float4 bga = __ldg(reinterpret_cast<const float4 *>(gamma) + cv), bbe = __ldg(reinterpret_cast<const float4 *>(beta) + cv);
+    float4 bsc, bsh;
+    bn_scale_shift(bga.x, bbe.x, mu.x, vv.x, eps, bsc.x, bsh.x);
+    bn_scale_shift(bga.y, bbe.y, mu.y, vv.y, eps, bsc.y, bsh.y);
+    bn_scale_shift(bga.z, bbe.z, mu.z, vv.z, eps, bsc.z, bsh.z);
+    bn_scale_shift(bga.w, bbe.w, mu.w, vv.w, eps, bsc.w, bsh.w);
     float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sz = sg;
     PoolCache pc;
     if (rlane < rl) {
         for (long long r = rbeg + rlane; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
-            float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (relu || G.s) yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
+            // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
+            float4 yy = make_float4(__fmaf_rn(zz.x, bsc.x, bsh.x), __fmaf_rn(zz.y, bsc.y, bsh.y), __fmaf_rn(zz.z, bsc.z, bsh.z), __fmaf_rn(zz.w, bsc.w, bsh.w));
+            if (relu) yy = make_float4(fmaxf(yy.x, 0.f), fmaxf(yy.y, 0.f), fmaxf(yy.z, 0.f), fmaxf(yy.w, 0.f));
             float4 g = load_grad(G, pc, o, r, cv, cvec, yy);
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
@@ -291,7 +308,8 @@ __global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const 
 
 // dz = s (g - k1 - zhat k2) and, per row chunk, the column sums of dz (= the bias gradient): partB[blk*c + ch]
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ y, const float *__restrict__ z,
+bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ gamma, const float *__restrict__ beta,
+                    const float *__restrict__ z,
                     const float *__restrict__ mean, const float *__restrict__ var, const float *__restrict__ coef2, int relu,
                     float *__restrict__ dz, float *__restrict__ partB, const float *__restrict__ x3, float *__restrict__ partW3) {
     // x3 != NULL: the layer has 3 input channels (the xyz layers); dW (3 x c) = x^T dz is accumulated in the same pass:
@@ -304,6 +322,12 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
     const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean) + cv);
     const float4 vv = __ldg(reinterpret_cast<const float4 *>(var) + cv);
     const float4 is = make_float4(rsqrtf(vv.x + eps), rsqrtf(vv.y + eps), rsqrtf(vv.z + eps), rsqrtf(vv.w + eps));
+    const float4 bga = __ldg(reinterpret_cast<const float4 *>(gamma) + cv), bbe = __ldg(reinterpret_cast<const float4 *>(beta) + cv);
+    float4 bsc, bsh;
+    bn_scale_shift(bga.x, bbe.x, mu.x, vv.x, eps, bsc.x, bsh.x);
+    bn_scale_shift(bga.y, bbe.y, mu.y, vv.y, eps, bsc.y, bsh.y);
+    bn_scale_shift(bga.z, bbe.z, mu.z, vv.z, eps, bsc.z, bsh.z);
+    bn_scale_shift(bga.w, bbe.w, mu.w, vv.w, eps, bsc.w, bsh.w);
     const float4 s = __ldg(reinterpret_cast<const float4 *>(coef2) + cv);
     const float4 k1 = __ldg(reinterpret_cast<const float4 *>(coef2 + c) + cv);
     const float4 k2 = __ldg(reinterpret_cast<const float4 *>(coef2 + 2 * c) + cv);
@@ -313,8 +337,9 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
         for (long long r = rbeg + rlane; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
-            float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (relu || G.s) yy = __ldg(reinterpret_cast<const float4 *>(y) + o);
+            // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
+            float4 yy = make_float4(__fmaf_rn(zz.x, bsc.x, bsh.x), __fmaf_rn(zz.y, bsc.y, bsh.y), __fmaf_rn(zz.z, bsc.z, bsh.z), __fmaf_rn(zz.w, bsc.w, bsh.w));
+            if (relu) yy = make_float4(fmaxf(yy.x, 0.f), fmaxf(yy.y, 0.f), fmaxf(yy.z, 0.f), fmaxf(yy.w, 0.f));
             float4 g = load_grad(G, pc, o, r, cv, cvec, yy);
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
@@ -671,8 +696,9 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
                                        void *workspace, size_t workspace_bytes, void *stream) {
     if (dgroup_bias && (group_s <= 0 || rows % group_s != 0))
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: dgroup_bias needs group_s > 0 dividing rows");
-    if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !z || !y || !mean || !var || !gy || !dW || !db || !dgamma || !dbeta)
+    if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !mean || !var || !gy || !dW || !db || !dgamma || !dbeta)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: bad arguments");
+    (void)y;  // the activation is recomputed from z (bit-identical), not read back
     if (pool_s < 0 || (pool_s > 0 && (!pooled || !inv_ties || rows % pool_s != 0)))
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: pooled gradient needs pooled, inv_ties and rows % pool_s == 0");
     const GradSource G{gy, pool_s > 0 ? pooled : nullptr, pool_s > 0 ? inv_ties : nullptr, pool_s};
@@ -715,13 +741,13 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     const int nred = static_cast<int>(rows < kRedBlocks ? rows : kRedBlocks);
     int rc = 0;
     int nred1 = nred;
-    if (pool_s > 0 && beta) {
+    if (pool_s > 0) {
         const long long groups = rows / pool_s;
         nred1 = static_cast<int>(groups < kRedBlocks ? groups : kRedBlocks);
         bn_bwd_reduce_pooled_kernel<<<nred1, 256, 0, st>>>(groups, cout, gy, pooled, gamma, beta, relu, part);
         rc = check_launch("bn_bwd_reduce_pooled_kernel");
     } else {
-        bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, y, z, mean, var, relu, part);
+        bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, relu, part);
         rc = check_launch("bn_bwd_reduce_kernel");
     }
     if (rc) return rc;
@@ -732,7 +758,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     rc = check_launch("bn_bwd_finalize_kernel");
     if (rc) return rc;
     const bool w3 = cin == 3;  // the xyz layers: dW rides along with the dz pass (partials in the dW-partials area: 3*cout per chunk)
-    bn_bwd_apply_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, y, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
+    bn_bwd_apply_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;
     partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(nred, cout, partB, db);

@@ -173,7 +173,8 @@ int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x,
  * cin == 3 or a multiple of 16.  pool_s > 0: the layer's output only feeds the max-pool over groups of pool_s consecutive
  * rows; gy is then the gradient of the POOLED tensor (rows/pool_s, cout), pooled / inv_ties are the outputs of
  * f3d_maxpool_samples_forward, and the dense (rows, cout) gradient is formed on the fly instead of passing through HBM
- * (beta, which may otherwise be NULL, additionally lets the channel reductions run over the pooled tensors only).
+ * (the channel reductions then run over the pooled tensors only).  y may be NULL: the activation is recomputed from z
+ * with the forward's exact roundings instead of being read back.
  * Fixed-order reductions: bit-reproducible. */
 int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
                                const float *beta, const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
