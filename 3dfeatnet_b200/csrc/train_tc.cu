@@ -302,6 +302,236 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// lin_tc_pipe_kernel: the same contraction as lin_tc_kernel with the three phases of a tile running CONCURRENTLY on
+// different warps (k_real % 8 == 0): warp 0 issues the TMA fetches (ring, up to 3 tiles ahead) and the MMAs, warps 1-4
+// convert ring slot -> operand image (double-buffered), warps 5-8 drain the accumulator (double-buffered in TMEM) to
+// global memory and keep the BN statistics.  mbarriers: ring_full (TMA bytes), img_full (4 converter warps), mma_done
+// (tcgen05.commit: frees the image AND publishes the accumulator), d_free (4 epilogue warps).
+namespace lp {
+constexpr int kThreads = 288;
+constexpr int kMaxRing = 3;
+__host__ __device__ constexpr uint32_t lbo(int nsplit, int nt) { return static_cast<uint32_t>(nt) * 16 + (nsplit == 3 ? 16 : 32); }
+}  // namespace lp
+
+template <int nsplit, int NT>
+__global__ void __launch_bounds__(lp::kThreads, 1)
+lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint32_t tmem_cols, const float *__restrict__ x,
+                   const uint8_t *__restrict__ wimg, const float *__restrict__ bias, const float *__restrict__ gbias, int gs,
+                   float *__restrict__ out, float *__restrict__ part) {
+    using namespace ttc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t kLbo = lp::lbo(nsplit, NT);
+    const uint32_t wbytes = 256u * kp;
+    const uint32_t split = static_cast<uint32_t>(kp / 8) * kLbo;
+    const uint32_t img_bytes = static_cast<uint32_t>(nsplit) * split;
+    const uint32_t slot_bytes = NT * static_cast<uint32_t>(k_real) * 4;
+    uint8_t *ringbuf = smem + 2 * img_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * img_bytes + nring * slot_bytes);
+    uint64_t *bar_w = bars, *bar_wm = bars + 1, *ring_full = bars + 2, *img_full = bars + 2 + lp::kMaxRing, *mma_done = img_full + 2,
+             *d_free = mma_done + 2;
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(d_free + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const int mb = blockIdx.x;
+    const long long cta = blockIdx.y, ncta = gridDim.y;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_wm, 1);
+        for (int i = 0; i < lp::kMaxRing; ++i) mbar_init(ring_full + i, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(img_full + i, 4);
+            mbar_init(mma_done + i, 1);
+            mbar_init(d_free + i, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_base_s, tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    // weights -> tensor memory: split sp -> columns [sp*kp/2, (sp+1)*kp/2); staged through the (still unused) image area
+    {
+        uint32_t wpar = 0, mpar = 0;
+        const uint8_t *wsrc = wimg + static_cast<size_t>(mb) * kp * 256 * nsplit;
+        for (int piece = 0; piece < nsplit; ++piece) {
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(bar_w, wbytes);
+                for (uint32_t off = 0; off < wbytes; off += 16384) {
+                    const uint32_t n = wbytes - off < 16384u ? wbytes - off : 16384u;
+                    bulk_g2s(smem + off, wsrc + static_cast<size_t>(piece) * wbytes + off, n, bar_w);
+                }
+            }
+            mbar_wait(bar_w, wpar);
+            wpar ^= 1;
+            tcgen05_fence_after();
+            if (warp == 0) {
+                if (elect_one()) {
+                    for (int k = 0; k < kp / 16; ++k)
+                        tmem_cp_128x256b(tmem_base + piece * (kp / 2) + k * 8, make_smem_desc(sbase + k * 2 * kLboW, kLboW, kSbo));
+                    umma_commit(bar_wm);
+                }
+                __syncwarp();
+            }
+            mbar_wait(bar_wm, mpar);
+            mpar ^= 1;
+            __syncthreads();
+        }
+    }
+
+    const long long ntiles = (rows + NT - 1) / NT;
+    const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(nsplit) * (kp / 2);
+    if (warp == 0) {
+        // ------------------------------------------------------------------ issuer: TMA ring + MMAs
+        auto fetch = [&](long long tile, int slot) {
+            const long long r0 = tile * NT;
+            const uint32_t valid = static_cast<uint32_t>(rows - r0 < NT ? rows - r0 : NT);
+            const uint32_t bytes = valid * static_cast<uint32_t>(k_real) * 4;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(ring_full + slot, bytes);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(x + r0 * k_real);
+                for (uint32_t off = 0; off < bytes; off += 16384)
+                    bulk_g2s(ringbuf + slot * slot_bytes + off, src + off, bytes - off < 16384u ? bytes - off : 16384u, ring_full + slot);
+            }
+            __syncwarp();
+        };
+        for (int s = 0; s < nring; ++s)
+            if (cta + s * ncta < ntiles) fetch(cta + s * ncta, s);
+        const uint32_t idesc = make_idesc(1, 128, NT);
+        long long it = 0;
+        for (long long tile = cta; tile < ntiles; tile += ncta, ++it) {
+            const int b = static_cast<int>(it & 1);
+            mbar_wait(img_full + b, static_cast<uint32_t>((it >> 1) & 1));          // image b converted, its ring slot consumed
+            if (it >= 2) mbar_wait(d_free + b, static_cast<uint32_t>(((it >> 1) - 1) & 1));  // accumulator b drained
+            tcgen05_fence_after();
+            if (tile + nring * ncta < ntiles) fetch(tile + nring * ncta, static_cast<int>(it % nring));
+            if (elect_one()) {
+                constexpr int nterms = nsplit == 3 ? 6 : 3;
+                const uint32_t d = tmem_d + b * NT;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int term = 0; term < nterms; ++term) {
+                    const int ws = term == 2 ? 1 : term == 4 ? 2 : term == 5 ? 1 : 0;
+                    const int xs = term == 1 ? 1 : term == 3 ? 2 : term == 5 ? 1 : 0;
+                    const uint32_t wa = tmem_base + ws * (kp / 2);
+                    const uint32_t xb = sbase + b * img_bytes + xs * split;
+                    for (int k = 0; k < kp / 16; ++k) {
+                        umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLbo, kLbo, kSbo), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(mma_done + b);
+            }
+            __syncwarp();
+        }
+    } else if (warp <= 4) {
+        // ------------------------------------------------------------------ converters: ring slot -> operand image
+        const int wc = warp - 1;
+        const int rsub = lane >> 3, c4 = (lane >> 1) & 3, h = lane & 1;
+        const uint32_t row_bytes = static_cast<uint32_t>(k_real) * 4;
+        long long it = 0;
+        for (long long tile = cta; tile < ntiles; tile += ncta, ++it) {
+            const int b = static_cast<int>(it & 1), slot = static_cast<int>(it % nring);
+            const long long r0 = tile * NT;
+            mbar_wait(ring_full + slot, static_cast<uint32_t>((it / nring) & 1));
+            if (it >= 2) mbar_wait(mma_done + b, static_cast<uint32_t>(((it >> 1) - 1) & 1));  // MMAs of tile it-2 have read image b
+            uint8_t *img = smem + b * img_bytes;
+#pragma unroll
+            for (int p = 0; p < NT / 16; ++p) {
+                const int r = p * 16 + wc * 4 + rsub;
+                const bool valid = r0 + r < rows;
+                const uint8_t *src = ringbuf + slot * slot_bytes + r * row_bytes + h * 16;
+                for (int c = c4; c < kp / 8; c += 4) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid && c * 8 < k_real) a = *reinterpret_cast<const float4 *>(src + c * 32);
+                    uint8_t *dst = img + c * kLbo + r * 16 + h * 8;
+#pragma unroll
+                    for (int sp = 0; sp < nsplit; ++sp) {
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                        *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                        a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(img_full + b);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: accumulator -> global, BN statistics
+        const int q = warp & 3;
+        const int ch = q * 32 + lane;
+        const int gch = mb * 128 + ch;
+        const bool ch_ok = gch < nout;
+        const float bb = (bias && ch_ok) ? __ldg(bias + gch) : 0.0f;
+        float s1 = 0.0f, s2 = 0.0f;
+        long long it = 0;
+        for (long long tile = cta; tile < ntiles; tile += ncta, ++it) {
+            const int b = static_cast<int>(it & 1);
+            const long long r0 = tile * NT;
+            mbar_wait(mma_done + b, static_cast<uint32_t>((it >> 1) & 1));
+            tcgen05_fence_after();
+            uint32_t r[NT];
+#pragma unroll
+            for (int hh = 0; hh < NT / 32; ++hh) {
+                uint32_t t[32];
+                tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + b * NT + hh * 32, t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[hh * 32 + j] = t[j];
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d_free + b);
+            if (ch_ok) {
+                if (gbias) {
+                    const long long g0 = r0 / gs;
+                    const int rem0 = static_cast<int>(r0 - g0 * gs);
+                    const long long gmax = (rows - 1) / gs;
+                    if (rem0 + NT - 1 < gs) {
+                        const float gb = __ldg(gbias + g0 * nout + gch);
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + gb);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            long long grp = g0 + (rem0 + j) / gs;
+                            grp = grp < gmax ? grp : gmax;
+                            r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(gbias + grp * nout + gch));
+                        }
+                    }
+                }
+                float *o = out + r0 * nout + gch;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    if (r0 + j < rows) {
+                        const float v = __uint_as_float(r[j]) + bb;
+                        o[static_cast<size_t>(j) * nout] = v;
+                        s1 += v;
+                        s2 = fmaf(v, v, s2);
+                    }
+                }
+            }
+        }
+        if (part && ch_ok) {  // two partial slots per CTA like lin_tc_kernel: this thread owns all rows, the second slot is zero
+            float *p = part + static_cast<size_t>(cta) * 2 * 2 * nout;
+            p[gch] = s1;
+            p[nout + gch] = s2;
+            p[2 * nout + gch] = 0.0f;
+            p[3 * nout + gch] = 0.0f;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // wgrad: partW[cta][cin][cout] = sum over the CTA's rows of x[r][ci] * dz[r][co].
 // D[ci (128, zero-padded) x co] accumulates in tensor memory over the whole row range of the CTA; a stage is 32 rows
 // (two K = 16 MMA steps x 3 split terms).  The fp32 rows of a stage are two contiguous blocks (x and dz): bulk-TMA'd into
@@ -518,19 +748,65 @@ static size_t lin_tc_smem(int k_real, int nsplit) {
     return op + static_cast<size_t>(lin_tc_ring(k_real, nsplit)) * ttc::kTile * k_real * 4 + 64;
 }
 
-// number of row-CTAs lin_tc launches (the stats partials are 2 per CTA)
-int lin_tc_grid(long long rows, int k_real, int nsplit) {
+// launch plan of a lin_tc call
+struct LinPlan {
+    bool pipe;     // warp-specialised kernel
+    int nt;        // rows per tile
+    int nring;     // ring depth
+    uint32_t cols; // TMEM columns
+    size_t smem;
+    int grid;      // row CTAs (the stats partials are 2 per CTA)
+};
+
+static LinPlan lin_tc_plan(long long rows, int k_real, int nsplit) {
+    LinPlan P{};
     const int kp = lin_tc_kp(k_real);
-    const uint32_t cols = pow2_cols(nsplit * (kp / 2) + ttc::kTile);
-    int per_sm = static_cast<int>(512 / cols);
-    const int by_smem = static_cast<int>((228 * 1024) / (lin_tc_smem(k_real, nsplit) + 1024));  // 228 KB per SM, 1 KB reserved per CTA
+    // the warp-specialised kernel pays off when the operand conversion + MMAs are the long phases (K >= 128); for narrow
+    // inputs the tile is store-bound and the all-warps epilogue of lin_tc_kernel at 3-4 CTAs/SM is faster (measured)
+    if (k_real % 8 == 0 && kp >= 128) {
+        for (int nt = 64; nt >= 32 && !P.pipe; nt -= 32) {
+            const size_t img = static_cast<size_t>(nsplit) * (kp / 8) * lp::lbo(nsplit, nt);
+            const size_t slot = static_cast<size_t>(nt) * k_real * 4;
+            for (int nring = lp::kMaxRing; nring >= 2; --nring) {
+                const size_t smem = 2 * img + nring * slot + 128;
+                if (smem <= 226 * 1024 && static_cast<size_t>(256) * kp <= 2 * img + nring * slot) {
+                    P.pipe = true;
+                    P.nt = nt;
+                    P.nring = nring;
+                    P.smem = smem;
+                    P.cols = pow2_cols(nsplit * (kp / 2) + 2 * nt);
+                    break;
+                }
+            }
+        }
+    }
+    if (P.pipe && P.cols <= 512) {
+        int per_sm = static_cast<int>(512 / P.cols);
+        const int by_smem = static_cast<int>((228 * 1024) / (P.smem + 1024));
+        if (per_sm > by_smem) per_sm = by_smem;
+        if (per_sm > 2) per_sm = 2;
+        const long long ntiles = (rows + P.nt - 1) / P.nt;
+        const long long g = static_cast<long long>(ttc_num_sms()) * per_sm;
+        P.grid = static_cast<int>(ntiles < g ? ntiles : g);
+        return P;
+    }
+    P.pipe = false;
+    P.nt = ttc::kTile;
+    P.nring = lin_tc_ring(k_real, nsplit) > 0 ? lin_tc_ring(k_real, nsplit) : 1;
+    P.cols = pow2_cols(nsplit * (kp / 2) + ttc::kTile);
+    P.smem = lin_tc_smem(k_real, nsplit);
+    int per_sm = static_cast<int>(512 / P.cols);
+    const int by_smem = static_cast<int>((228 * 1024) / (P.smem + 1024));  // 228 KB per SM, 1 KB reserved per CTA
     if (per_sm > by_smem) per_sm = by_smem;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     const long long ntiles = (rows + ttc::kTile - 1) / ttc::kTile;
     const long long g = static_cast<long long>(ttc_num_sms()) * per_sm;
-    return static_cast<int>(ntiles < g ? ntiles : g);
+    P.grid = static_cast<int>(ntiles < g ? ntiles : g);
+    return P;
 }
+
+int lin_tc_grid(long long rows, int k_real, int nsplit) { return lin_tc_plan(rows, k_real, nsplit).grid; }
 
 // out (rows, nout) = x (rows, k_real) * A^T (+ bias) (+ gbias[row / gs]) with A[m][k] = src[m*sm + k*sk]; nsplit = 2 (bf16x3)
 // or 3 (six product terms, fp32-grade);  part: 2*lin_tc_grid() partials of
@@ -543,17 +819,28 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
     lin_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, sm, sk, nout, k_real, kp, mblocks, nsplit, wimg);
     int rc = check_launch("lin_prep_kernel");
     if (rc) return rc;
-    const uint32_t cols = pow2_cols(nsplit * (kp / 2) + ttc::kTile);
-    const size_t smem = lin_tc_smem(k_real, nsplit);
-    const dim3 grid(mblocks, lin_tc_grid(rows, k_real, nsplit));
-    const int nring = lin_tc_ring(k_real, nsplit) > 0 ? lin_tc_ring(k_real, nsplit) : 1;
-    cudaError_t e;
+    const LinPlan P = lin_tc_plan(rows, k_real, nsplit);
+    const dim3 grid(mblocks, P.grid);
+    cudaError_t e = cudaSuccess;
+#define F3D_LAUNCH_PIPE(NS, NT)                                                                                                    \
+    e = cudaFuncSetAttribute(lin_tc_pipe_kernel<NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));  \
+    if (e == cudaSuccess)                                                                                                          \
+        lin_tc_pipe_kernel<NS, NT><<<grid, lp::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part);
+    if (P.pipe) {
+        if (nsplit == 3 && P.nt == 64) { F3D_LAUNCH_PIPE(3, 64) }
+        else if (nsplit == 3) { F3D_LAUNCH_PIPE(3, 32) }
+        else if (P.nt == 64) { F3D_LAUNCH_PIPE(2, 64) }
+        else { F3D_LAUNCH_PIPE(2, 32) }
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
+        return check_launch("lin_tc_pipe_kernel");
+    }
+#undef F3D_LAUNCH_PIPE
     if (nsplit == 3) {
-        e = cudaFuncSetAttribute(lin_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess) lin_tc_kernel<3><<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, nring, cols, x, wimg, bias, gbias, gs, out, part);
+        e = cudaFuncSetAttribute(lin_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));
+        if (e == cudaSuccess) lin_tc_kernel<3><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part);
     } else {
-        e = cudaFuncSetAttribute(lin_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess) lin_tc_kernel<2><<<grid, ttc::kThreads, smem, st>>>(rows, k_real, kp, nout, nring, cols, x, wimg, bias, gbias, gs, out, part);
+        e = cudaFuncSetAttribute(lin_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));
+        if (e == cudaSuccess) lin_tc_kernel<2><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part);
     }
     if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
     return check_launch("lin_tc_kernel");
