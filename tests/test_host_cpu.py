@@ -1,6 +1,7 @@
 """CPU tests of the host-side logic: argument validation mirrors the reference's OP_REQUIRES checks, the product
 refuses to run without CUDA (no fallback), BN folding, batch sharding and the gloo world_size-2 gradient exchange."""
 import importlib
+import math
 import os
 import sys
 
@@ -226,3 +227,31 @@ def test_checkpoint_round_trips_and_restore_rules(tmp_path):
     (tmp_path / "bad.index").write_bytes(b"\x00" * 64)
     with pytest.raises(ValueError):
         ck.read_tf_bundle(str(tmp_path / "bad"))
+
+
+def test_augmentations_follow_the_reference_semantics():
+    """3dfeatnet_b200/augment.py vs the statements of the reference's data/augment.py: ranges, per-cloud draws, rigidity."""
+    aug = importlib.import_module("3dfeatnet_b200.augment")
+    g = torch.Generator().manual_seed(3)
+    xyz = torch.randn(5, 200, 3, generator=g) * 10
+    gen = torch.Generator().manual_seed(7)
+    j = aug.jitter(xyz, gen=gen) - xyz
+    assert j.abs().max() <= 0.05 + 1e-6 and 0.005 < j.std() < 0.02                       # N(0, 0.01) clipped at 0.05
+    s = aug.shift(xyz, gen=gen) - xyz
+    assert s.abs().max() <= 0.1 + 1e-6 and torch.allclose(s[:, :1].expand_as(s), s, atol=1e-5)          # one offset per cloud
+    sc = aug.scale(xyz, gen=gen) / xyz
+    assert (sc.min() >= 0.8 - 1e-4) and (sc.max() <= 1.25 + 1e-4) and sc.std(dim=(1, 2)).max() < 1e-4
+    for fn in (aug.rotate_z, aug.rotate_small):
+        r = fn(xyz, gen=gen)
+        assert torch.allclose(r.norm(dim=2), xyz.norm(dim=2), rtol=1e-5, atol=1e-4)      # rigid
+        mode = "donot_use_mm_for_euclid_dist"
+        assert torch.allclose(torch.cdist(r, r, compute_mode=mode), torch.cdist(xyz, xyz, compute_mode=mode), rtol=1e-4, atol=1e-3)
+    rz = aug.rotate_z(xyz, gen=gen)
+    assert torch.allclose(rz[:, :, 2], xyz[:, :, 2])                                      # about the upright axis
+    small = aug.rotate_small(xyz, gen=gen)
+    cosang = torch.nn.functional.cosine_similarity(small.reshape(5, -1), xyz.reshape(5, -1), dim=1)
+    assert (cosang > math.cos(3 * 0.18)).all()                                            # angles clipped at 0.18 rad per axis
+    a = aug.apply_augmentations(xyz, gen=torch.Generator().manual_seed(1))
+    b = aug.apply_augmentations(xyz, gen=torch.Generator().manual_seed(1))
+    assert torch.equal(a, b) and not torch.equal(a, xyz)
+    assert torch.equal(aug.apply_augmentations(xyz, names=()), xyz)
