@@ -21,6 +21,7 @@ namespace f3d {
 constexpr int kLdT = 132;      // leading dimension of the transposed activation tile (128 rows + 4: 16-byte aligned rows)
 constexpr int kWgKC = 32;      // rows staged per wgrad iteration
 constexpr int kRedBlocks = 592;  // row-chunks of the BN backward reduction (4 per SM)
+constexpr int kApplyBlocks = 444;  // row-chunks of the BN backward apply pass (3 resident CTAs per SM at 85 registers)
 constexpr int kFwdSplit = 3;     // forward contraction on the tensor cores: hi/mid/lo bf16 split, 6 product terms (fp32-grade)
 
 __device__ __forceinline__ void stage_rows_transposed(float *in_t, const float *__restrict__ x, long long row0, long long rows, int cin) {
@@ -182,8 +183,8 @@ struct PoolCache {
     float4 pm, gs;
 };
 
-__device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, size_t o, long long r, int cv, int cvec, const float4 &yy) {
-    if (G.s == 0) return __ldg(reinterpret_cast<const float4 *>(G.gy) + o);
+__device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, const float4 &dense, long long r, int cv, int cvec, const float4 &yy) {
+    if (G.s == 0) return dense;  // dense mode: the caller has already loaded gy[row] (one iteration ahead)
     const long long grp = r / G.s;
     if (grp != C.grp) {
         const size_t po = static_cast<size_t>(grp) * cvec + cv;
@@ -224,7 +225,8 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
             // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
             float4 yy = make_float4(__fmaf_rn(zz.x, bsc.x, bsh.x), __fmaf_rn(zz.y, bsc.y, bsh.y), __fmaf_rn(zz.z, bsc.z, bsh.z), __fmaf_rn(zz.w, bsc.w, bsh.w));
             if (relu) yy = make_float4(fmaxf(yy.x, 0.f), fmaxf(yy.y, 0.f), fmaxf(yy.z, 0.f), fmaxf(yy.w, 0.f));
-            float4 g = load_grad(G, pc, o, r, cv, cvec, yy);
+            const float4 gd = G.s == 0 ? __ldg(reinterpret_cast<const float4 *>(G.gy) + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g = load_grad(G, pc, gd, r, cv, cvec, yy);
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
@@ -307,7 +309,7 @@ __global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const 
 }
 
 // dz = s (g - k1 - zhat k2) and, per row chunk, the column sums of dz (= the bias gradient): partB[blk*c + ch]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ z,
                     const float *__restrict__ mean, const float *__restrict__ var, const float *__restrict__ coef2, int relu,
@@ -334,13 +336,27 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
     float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), w0 = sb, w1 = sb, w2 = sb;
     PoolCache pc;
     if (rlane < rl) {
-        for (long long r = rbeg + rlane; r < rend; r += rl) {
+        // the loads of row r + rl are issued before row r is processed (twice the bytes in flight per thread)
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        long long r = rbeg + rlane;
+        float4 zz_n = zero4, gd_n = zero4;
+        if (r < rend) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
-            const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
+            zz_n = __ldg(reinterpret_cast<const float4 *>(z) + o);
+            if (G.s == 0) gd_n = __ldg(reinterpret_cast<const float4 *>(G.gy) + o);
+        }
+        for (; r < rend; r += rl) {
+            const size_t o = static_cast<size_t>(r) * cvec + cv;
+            const float4 zz = zz_n, gd = gd_n;
+            if (r + rl < rend) {
+                const size_t on = static_cast<size_t>(r + rl) * cvec + cv;
+                zz_n = __ldg(reinterpret_cast<const float4 *>(z) + on);
+                if (G.s == 0) gd_n = __ldg(reinterpret_cast<const float4 *>(G.gy) + on);
+            }
             // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
             float4 yy = make_float4(__fmaf_rn(zz.x, bsc.x, bsh.x), __fmaf_rn(zz.y, bsc.y, bsh.y), __fmaf_rn(zz.z, bsc.z, bsh.z), __fmaf_rn(zz.w, bsc.w, bsh.w));
             if (relu) yy = make_float4(fmaxf(yy.x, 0.f), fmaxf(yy.y, 0.f), fmaxf(yy.z, 0.f), fmaxf(yy.w, 0.f));
-            float4 g = load_grad(G, pc, o, r, cv, cvec, yy);
+            float4 g = load_grad(G, pc, gd, r, cv, cvec, yy);
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
@@ -509,7 +525,17 @@ __global__ void maxpool_fwd_kernel(long long groups, int s, int c4, const float 
     const float4 *p = reinterpret_cast<const float4 *>(x) + g * s * c4 + cv;
     float4 m = __ldg(p);
     int nx = 1, ny = 1, nz = 1, nw = 1;
-    for (int k = 1; k < s; ++k) {
+    int k = 1;
+    for (; k + 4 <= s; k += 4) {  // four independent loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(p + static_cast<size_t>(k + u) * c4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            max_count(v[u].x, m.x, nx); max_count(v[u].y, m.y, ny); max_count(v[u].z, m.z, nz); max_count(v[u].w, m.w, nw);
+        }
+    }
+    for (; k < s; ++k) {
         const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
         max_count(v.x, m.x, nx); max_count(v.y, m.y, ny); max_count(v.z, m.z, nz); max_count(v.w, m.w, nw);
     }
@@ -544,6 +570,7 @@ __global__ void group_sum_kernel(long long groups, int s, int c4, const float *_
     const int cv = static_cast<int>(e - g * c4);
     const float4 *p = reinterpret_cast<const float4 *>(x) + g * s * c4 + cv;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int k = 0; k < s; ++k) {
         const float4 v = __ldg(p + static_cast<size_t>(k) * c4);
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
@@ -758,10 +785,11 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     rc = check_launch("bn_bwd_finalize_kernel");
     if (rc) return rc;
     const bool w3 = cin == 3;  // the xyz layers: dW rides along with the dz pass (partials in the dW-partials area: 3*cout per chunk)
-    bn_bwd_apply_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
+    const int napp = static_cast<int>(rows < kApplyBlocks ? rows : kApplyBlocks);
+    bn_bwd_apply_kernel<<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;
-    partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(nred, cout, partB, db);
+    partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(napp, cout, partB, db);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
 
@@ -773,7 +801,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     }
     const long long nw = static_cast<long long>(cin) * cout;
     if (w3) {
-        partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(nred, nw, partW, dW);
+        partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(napp, nw, partW, dW);
     } else if (precision == 2 && wgrad_tc_supported(cin, cout)) {
         rc = wgrad_tc(rows, cin, cout, x, dz, partW, st);
         if (rc) return rc;
