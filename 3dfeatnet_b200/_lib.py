@@ -53,7 +53,6 @@ SIGNATURES = {
     "f3d_detector_tc_weight_bytes": (_sz, []),
     "f3d_debug_set_timeline": (None, [_vp]),
     "f3d_debug_set_timeline_desc": (None, [_vp]),
-    "f3d_debug_set_fps_timeline": (None, [_vp]),
     "f3d_debug_time_detector_rows": (None, [_i]),
     "f3d_debug_detector_rows_ms": (_c.c_float, []),
 }

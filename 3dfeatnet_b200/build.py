@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + os.environ.get("F3D_NVCC_EXTRA", "").split() +
+                        (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -224,8 +224,6 @@ size_t f3d_detector_tc_weight_bytes(void);
  * kernel (slots: 0/1/2 MMA warp, 4-6 producer, 8-13 epilogue); NULL disables. */
 void f3d_debug_set_timeline(void *buf);
 void f3d_debug_set_timeline_desc(void *buf); /* same for the descriptor tensor kernel */
-/* Bring-up: 256*32*4 int64 buffer receiving CTA 0's per-round, per-warp clock64() stamps of the FPS kernel. */
-void f3d_debug_set_fps_timeline(void *buf);
 /* Measurement aid: bracket det_rows_tc_kernel with CUDA events on its launch stream / read the last duration (ms). */
 void f3d_debug_time_detector_rows(int enable);
 float f3d_debug_detector_rows_ms(void);
