@@ -107,6 +107,18 @@ __device__ __forceinline__ void cluster_sync_all() {
 // position; the tie code is 0x7fff - ((k mod 512) << 6 | (k >> 9) - (k_first >> 9)) of the GLOBAL original index k, so a
 // larger key is the reference's preferred point, the winner's coordinates are at xs/ys/zs[key & 0x3fff] and its index is
 // decoded from key >> 14.  No tie detection, no divergent tie path, no original-index loads in the loop.
+template <int LO, int N, class F>
+__device__ __forceinline__ void fps_walk(unsigned act, F &f) {  // f(g) for every set bit g of act in [LO, LO + N)
+    if constexpr (N == 1) {
+        if ((act >> LO) & 1u) f(std::integral_constant<int, LO>{});
+    } else {
+        if (act & (((1u << N) - 1u) << LO)) {
+            fps_walk<LO, N / 2>(act, f);
+            fps_walk<LO + N / 2, N / 2>(act, f);
+        }
+    }
+}
+
 template <int W>
 struct FpsWin {  // double-buffered per-warp winners: (distance bits, tie code << 14 | sorted position)
     int2 dp[2][W];
@@ -118,7 +130,7 @@ fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restr
     constexpr int T = W * 32;
     constexpr int NP = T * 4 * G;
     constexpr int kGrid = 32, kCells = kGrid * kGrid;
-    static_assert(G <= 32 && NP <= 16384, "14-bit sorted positions / one box per lane");
+    static_assert(G <= 16 && (G & (G - 1)) == 0 && NP <= 16384, "14-bit sorted positions / one box per lane / binary walk");
     extern __shared__ float4 fps_smem[];
     float *xs = reinterpret_cast<float *>(fps_smem);
     float *ys = xs + NP;
@@ -276,38 +288,49 @@ fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restr
         const float lbd = (bx * bx + by * by + bz * bz) * 0.9999f;
         const unsigned act = __ballot_sync(kFull, (j == 1 && lane < G) || !(lbd >= gthr));  // bit g: local group g may change
         if (act != 0u) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                if ((act >> g) & 1u) {
-                    const float4 X = xs4[slot4(g)], Y = ys4[slot4(g)], Z = zs4[slot4(g)];
-                    const uint2 kk = tk2[slot4(g)];
-                    const float t0 = fminf(sqdist_ref(X.x - ox, Y.x - oy, Z.x - oz), td[g * 4 + 0]);
-                    const float t1 = fminf(sqdist_ref(X.y - ox, Y.y - oy, Z.y - oz), td[g * 4 + 1]);
-                    const float t2 = fminf(sqdist_ref(X.z - ox, Y.z - oy, Z.z - oz), td[g * 4 + 2]);
-                    const float t3 = fminf(sqdist_ref(X.w - ox, Y.w - oy, Z.w - oz), td[g * 4 + 3]);
-                    td[g * 4 + 0] = t0; td[g * 4 + 1] = t1; td[g * 4 + 2] = t2; td[g * 4 + 3] = t3;
-                    const float mx = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
-                    gm[g] = mx;
-                    const unsigned base = static_cast<unsigned>(4 * slot4(g));
-                    const unsigned k0 = ((kk.x & 0xffffu) << 14) | base, k1 = ((kk.x >> 16) << 14) | (base + 1u);
-                    const unsigned k2 = ((kk.y & 0xffffu) << 14) | (base + 2u), k3 = ((kk.y >> 16) << 14) | (base + 3u);
-                    unsigned gk = t0 == mx ? k0 : 0u;
-                    gk = t1 == mx ? max(gk, k1) : gk;
-                    gk = t2 == mx ? max(gk, k2) : gk;
-                    gk = t3 == mx ? max(gk, k3) : gk;
-                    gkey[g] = gk;
-                    const int gw = __reduce_max_sync(kFull, __float_as_int(mx));
-                    if (lane == g) gthr = __int_as_float(gw);
-                }
+            auto update = [&](auto gc) {
+                constexpr int g = decltype(gc)::value;
+                const float4 X = xs4[slot4(g)], Y = ys4[slot4(g)], Z = zs4[slot4(g)];
+                const uint2 kk = tk2[slot4(g)];
+                const float t0 = fminf(sqdist_ref(X.x - ox, Y.x - oy, Z.x - oz), td[g * 4 + 0]);
+                const float t1 = fminf(sqdist_ref(X.y - ox, Y.y - oy, Z.y - oz), td[g * 4 + 1]);
+                const float t2 = fminf(sqdist_ref(X.z - ox, Y.z - oy, Z.z - oz), td[g * 4 + 2]);
+                const float t3 = fminf(sqdist_ref(X.w - ox, Y.w - oy, Z.w - oz), td[g * 4 + 3]);
+                td[g * 4 + 0] = t0; td[g * 4 + 1] = t1; td[g * 4 + 2] = t2; td[g * 4 + 3] = t3;
+                const float mx = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                gm[g] = mx;
+                const unsigned base = static_cast<unsigned>(4 * slot4(g));
+                const unsigned k0 = ((kk.x & 0xffffu) << 14) | base, k1 = ((kk.x >> 16) << 14) | (base + 1u);
+                const unsigned k2 = ((kk.y & 0xffffu) << 14) | (base + 2u), k3 = ((kk.y >> 16) << 14) | (base + 3u);
+                unsigned gk = t0 == mx ? k0 : 0u;
+                gk = t1 == mx ? max(gk, k1) : gk;
+                gk = t2 == mx ? max(gk, k2) : gk;
+                gk = t3 == mx ? max(gk, k3) : gk;
+                gkey[g] = gk;
+                const int gw = __reduce_max_sync(kFull, __float_as_int(mx));
+                if (lane == g) gthr = __int_as_float(gw);
+            };
+            // binary tree over the bits of `act`: a test-and-skip costs ~28 cycles on the critical path of the round, and
+            // usually one or two of the G groups are active
+            if constexpr (G == 1) {
+                update(std::integral_constant<int, 0>{});
+            } else {
+                fps_walk<0, G / 2>(act, update);
+                fps_walk<G / 2, G / 2>(act, update);
             }
             float vmax = gm[0];
 #pragma unroll
             for (int g = 1; g < G; ++g) vmax = fmaxf(vmax, gm[g]);
             const int bi = __float_as_int(vmax);
             const int wmax = __reduce_max_sync(kFull, bi);
-            unsigned lk = 0u;
+            unsigned ck[G];  // independent selects + a max tree (not a G-long dependent chain)
 #pragma unroll
-            for (int g = 0; g < G; ++g) lk = gm[g] == vmax ? max(lk, gkey[g]) : lk;
+            for (int g = 0; g < G; ++g) ck[g] = gm[g] == vmax ? gkey[g] : 0u;
+#pragma unroll
+            for (int w = 1; w < G; w <<= 1)
+#pragma unroll
+                for (int g = 0; g + w < G; g += 2 * w) ck[g] = max(ck[g], ck[g + w]);
+            const unsigned lk = ck[0];
             cw_key = __reduce_max_sync(kFull, bi == wmax ? lk : 0u);
             cw_d = wmax;
         }
