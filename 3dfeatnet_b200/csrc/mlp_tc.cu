@@ -64,7 +64,9 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
         bulk_g2s(sb, b_img, b_bytes, &bar_load);
         mbar_wait(&bar_load, 0);
         tcgen05_fence_after();
-        const uint32_t idesc = make_idesc(1, 128, static_cast<uint32_t>(N));
+        // a_in_tmem bit 1: the B image is MN-major (canonical no-swizzle: 8 K-rows x 16 B of 8 consecutive N)
+        const uint32_t idesc = make_idesc(1, 128, static_cast<uint32_t>(N)) | ((a_in_tmem & 2) ? kIdescBMnMajor : 0u);
+        a_in_tmem &= 1;
         if (a_in_tmem)  // stage A into TMEM columns 256.. (8 columns = 16 bf16 per K step), then run the MMAs from there
             for (int k = 0; k < K / 16; ++k)
                 tmem_cp_128x256b(tmem_base + 256 + 8 * k, make_smem_desc(smem_u32(sa) + k * 2 * lbo_a, lbo_a, sbo_a));

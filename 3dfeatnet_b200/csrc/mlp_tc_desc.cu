@@ -5,8 +5,11 @@
 // conv 3->32->64 (+BN+ReLU), reduce_max, tile+concat, conv_mid_0 128->128 (+BN, no ReLU), reduce_max.
 // Same machinery and the same D^T = W^T X^T formulation as mlp_tc.cu (TMEM lane = output channel, column = sample).
 //
-//   MMA1 : D1[128(64 real) x 64] = W1^T[128 x 32]  X1^T          (conv1, 32 -> 64; the M axis is zero-padded to 128)
-//   E1   : relu(D1 + b1) -> X2 (K-major operand of conv_mid_0) and, per channel, its max over the 64 samples -> P
+//   MMA1 : D1[128 x 64] = W1^T[128 x 32]  X1^T                   (conv1, 32 -> 64; rows 64..127 of the M axis REPEAT rows
+//                                                                   0..63, so all four epilogue warps of a warpgroup find
+//                                                                   the 64 channels in their own 32 TMEM lanes)
+//   E1   : relu(D1 + b1) -> X2 (operand of conv_mid_0, stored SAMPLE-contiguous = MN-major: one 16-byte store per 8 samples)
+//          and, per channel, its max over the 64 samples -> P; warps 0/1 take samples 0..31, warps 2/3 samples 32..63
 //   MMA2 : D2[128 x 64]  = Wa^T[128 x 64]  X2^T                   (conv_mid_0, rows 0..63 of its weight: the per-point part)
 //   MMA3 : D3[128 x 8]   = Wb^T[128 x 64]  P^T                    (rows 64..127: the tiled max-pool part, ONE column per
 //                                                                   cluster instead of 64 -- the split-weight identity)
@@ -29,7 +32,8 @@ constexpr int kThreads = 13 * 32;
 constexpr uint32_t kSbo = 128;
 constexpr uint32_t kLboW = 128 * 16;
 constexpr uint32_t kLboX1 = kSamples * 16;
-constexpr uint32_t kLboX2 = kSamples * 16 + 16;
+constexpr uint32_t kLboX2 = 128;                        // X2 is MN-major: K groups of 8 channels 128 B apart,
+constexpr uint32_t kSboX2 = 8 * 128;                    // groups of 8 samples 1 KB apart (64 channels)
 constexpr uint32_t kLboP = 8 * 16;                      // P: one 8-row group per K chunk
 constexpr uint32_t kW1Split = 128 * 32 * 2;             // 8 KB
 constexpr uint32_t kWmSplit = 128 * 64 * 2;             // 16 KB
@@ -43,13 +47,14 @@ constexpr uint32_t kOffBm = kOffB1 + 64 * 4;             // fp32 [128]
 constexpr uint32_t kWeightBytes = kOffBm + 128 * 4;      // 83 200
 constexpr uint32_t kX1Split = 4 * kLboX1;                // 4 KB
 constexpr uint32_t kOffX1 = kWeightBytes;
-constexpr uint32_t kX2Split = 8 * kLboX2;                // 8 320
+constexpr uint32_t kX2Split = 8 * kSboX2;                // 8 KB
 constexpr uint32_t kX2Buf = 2 * kX2Split;                // one X2 operand (hi + lo)
 constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Split;       // [buf 2][split 2][chunk 8] stride kLboX2
 constexpr uint32_t kPSplit = 8 * kLboP;                  // 1 KB
 constexpr uint32_t kPBuf = 2 * kPSplit;
 constexpr uint32_t kOffP = kOffX2 + 2 * kX2Buf;          // [buf 2][split 2][chunk 8][row 8][8]
-constexpr uint32_t kOffBars = kOffP + 2 * kPBuf;
+constexpr uint32_t kOffPm = kOffP + 2 * kPBuf;            // fp32 [warpgroup 2][128]: partial channel maxima of the sample halves
+constexpr uint32_t kOffBars = kOffPm + 2 * 128 * 4;
 constexpr uint32_t kSmemBytes = kOffBars + 20 * 8 + 16;
 static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffP % 128 == 0 && kOffBars % 8 == 0, "alignment");
 // TMEM columns: D1[2] at 0 / 64, D2[2] at 128 / 192, D3[2] at 256 / 288, then the weights (A operands, copied once with
@@ -181,7 +186,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                     const uint32_t xb = sbase + kOffX2 + (t & 1) * kX2Buf + (pass == 1 ? kX2Split : 0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        umma_f16_ts(d2, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSbo), idesc64, acc);
+                        umma_f16_ts(d2, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSboX2), idesc64 | kIdescBMnMajor, acc);
                         acc = 1;
                     }
                 }
@@ -224,22 +229,37 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
             return __ldg(idx + static_cast<size_t>(cl) * kSamples + s);
         };
-        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, th = 0.f;
-        auto load_xyz = [&](int t, int ii) {
+        // Software pipeline, depth D: at tile t the coordinates of tile t+D (whose index was loaded D tiles earlier) and the
+        // index of tile t+2D are requested.  With D = 1 the kernel was bound by this dependent L2 gather (clock64 timeline:
+        // ~2100 cycles per producer iteration against ~1000 of MMA + epilogue work); the slots are static (loop unrolled by D).
+        constexpr int D = 3;
+        struct Grp { float px, py, pz, qx, qy, qz, th; };
+        Grp gq[D];
+        int iq[D];
+        auto load_xyz = [&](Grp &g, int t, int ii) {
+            g.px = g.py = g.pz = g.qx = g.qy = g.qz = g.th = 0.f;
             if (t >= T) return;
             const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
             ii = min(max(ii, 0), n - 1);
             const float *p = xyz + (static_cast<size_t>(cl / static_cast<unsigned>(m)) * n + ii) * 3;
             const float *c = new_xyz + static_cast<size_t>(cl) * 3;
-            px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
-            qx = __ldg(c); qy = __ldg(c + 1); qz = __ldg(c + 2);
-            if (orientation) th = __ldg(orientation + cl);
+            g.px = __ldg(p); g.py = __ldg(p + 1); g.pz = __ldg(p + 2);
+            g.qx = __ldg(c); g.qy = __ldg(c + 1); g.qz = __ldg(c + 2);
+            if (orientation) g.th = __ldg(orientation + cl);
         };
-        int i1 = load_idx(0);
-        load_xyz(0, i1);
-        i1 = load_idx(1);
-        for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) iq[d] = load_idx(d);
+#pragma unroll
+        for (int d = 0; d < D; ++d) load_xyz(gq[d], d, iq[d]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) iq[d] = load_idx(D + d);
+        for (int t0 = 0; t0 < T; t0 += D) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const int t = t0 + d;
+            if (t >= T) break;
             if (warp == 1) stamp(t, 4);
+            const float px = gq[d].px, py = gq[d].py, pz = gq[d].pz, qx = gq[d].qx, qy = gq[d].qy, qz = gq[d].qz, th = gq[d].th;
             float gx = pow2 ? (px - qx) * inv_r : (px - qx) / radius;
             float gy = pow2 ? (py - qy) * inv_r : (py - qy) / radius;
             const float gz = pow2 ? (pz - qz) * inv_r : (pz - qz) / radius;
@@ -251,9 +271,8 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 gx = xr;
                 gy = yr;
             }
-            const int i2 = load_idx(t + 2);
-            load_xyz(t + 1, i1);
-            i1 = i2;
+            load_xyz(gq[d], t + D, iq[d]);
+            iq[d] = load_idx(t + 2 * D);
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -283,6 +302,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[X1_FULL]);
+          }
         }
     } else {
         // ---- epilogue warpgroups ---------------------------------------------------------------------------------
@@ -291,53 +311,53 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         const int q = warp & 3;
         const int ch = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        const float b1 = ch < 64 ? reinterpret_cast<const float *>(smem + kOffB1)[ch] : 0.0f;
+        const int hsel = q >> 1;                 // E1: which half of the 64 samples this warp handles
+        const int c1 = (q & 1) * 32 + lane;      // E1: conv1 channel (TMEM lane q*32+lane holds channel (q*32+lane) mod 64)
+        const float b1 = reinterpret_cast<const float *>(smem + kOffB1)[c1];
         const float bm = reinterpret_cast<const float *>(smem + kOffBm)[ch];
-        uint8_t *x2 = smem + kOffX2 + g * kX2Buf + (ch >> 3) * kLboX2 + (ch & 7) * 2;  // this warpgroup's tiles use buffer g
-        uint8_t *pp = smem + kOffP + g * kPBuf + (ch >> 3) * kLboP + (ch & 7) * 2;     // row 0 of the pooled operand
+        // this warpgroup's tiles use operand buffer g; 8 consecutive samples of one channel are 16 contiguous bytes
+        uint8_t *x2 = smem + kOffX2 + g * kX2Buf + hsel * 4 * kSboX2 + (c1 >> 3) * kLboX2 + (c1 & 7) * 16;
+        uint8_t *pp = smem + kOffP + g * kPBuf + (c1 >> 3) * kLboP + (c1 & 7) * 2;     // row 0 of the pooled operand
+        float *pm = reinterpret_cast<float *>(smem + kOffPm) + g * 128;
         for (int t = g; t < T; t += 2) {
             const int b = t & 1;
             const uint32_t ph = (t >> 1) & 1;
-            // E1 (channels 0..63 are real; 64..127 are the zero padding of the M axis)
+            // E1
             mbar_wait(&bars[D1_FULL0 + b], ph);
             tcgen05_fence_after();
             if (q == 1) stamp(t, 8);
             uint32_t r0[32], r1[32];
-            if (q < 2) {
-                tmem_ld32(tmem_base + lane_addr + b * 64, r0);
-                tmem_ld32(tmem_base + lane_addr + b * 64 + 32, r1);
-                tmem_ld_wait();
-            }
+            tmem_ld32(tmem_base + lane_addr + b * 64 + hsel * 32, r0);
+            tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(&bars[D1_FREE0 + b]);
             float pmax = 0.0f;  // values are post-ReLU (>= 0)
-            if (q < 2) {  // bias, ReLU, max-pool and the hi/lo split BEFORE waiting for the operand buffer
+            uint32_t hi[16], lo[16];
+            // bias, ReLU, max-pool and the hi/lo split BEFORE waiting for the operand buffer
 #pragma unroll
-                for (int sidx = 0; sidx < 64; sidx += 2) {
-                    uint32_t &ra = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
-                    uint32_t &rb = sidx < 32 ? r0[(sidx + 1) & 31] : r1[(sidx + 1) & 31];
-                    const float va = fmaxf(__uint_as_float(ra) + b1, 0.0f), vb = fmaxf(__uint_as_float(rb) + b1, 0.0f);
-                    pmax = fmaxf(pmax, fmaxf(va, vb));
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
-                    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2), lb = *reinterpret_cast<const uint32_t *>(&l2);
-                    ra = (hb & 0xffffu) | (lb << 16);
-                    rb = (hb >> 16) | (lb & 0xffff0000u);
-                }
+            for (int sidx = 0; sidx < 32; sidx += 2) {
+                const float va = fmaxf(__uint_as_float(r0[sidx]) + b1, 0.0f), vb = fmaxf(__uint_as_float(r0[sidx + 1]) + b1, 0.0f);
+                pmax = fmaxf(pmax, fmaxf(va, vb));
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
+                hi[sidx >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
+                lo[sidx >> 1] = *reinterpret_cast<const uint32_t *>(&l2);
             }
+            pm[q * 32 + lane] = pmax;
             if (q == 1) stamp(t, 9);
             mbar_wait(&bars[X2_FREE0 + b], ph ^ 1);  // MMA2/3(t-2) have finished reading this buffer
             if (q == 1) stamp(t, 10);
-            if (q < 2) {
 #pragma unroll
-                for (int sidx = 0; sidx < 64; ++sidx) {
-                    const uint32_t pk = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
-                    *reinterpret_cast<uint16_t *>(x2 + sidx * 16) = static_cast<uint16_t>(pk & 0xffffu);
-                    *reinterpret_cast<uint16_t *>(x2 + kX2Split + sidx * 16) = static_cast<uint16_t>(pk >> 16);
-                }
-                const __nv_bfloat16 hp = __float2bfloat16_rn(pmax);
+            for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<uint4 *>(x2 + j * kSboX2) = make_uint4(hi[j * 4], hi[j * 4 + 1], hi[j * 4 + 2], hi[j * 4 + 3]);
+                *reinterpret_cast<uint4 *>(x2 + kX2Split + j * kSboX2) = make_uint4(lo[j * 4], lo[j * 4 + 1], lo[j * 4 + 2], lo[j * 4 + 3]);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");  // both sample halves of every channel maximum are in pm
+            if (q < 2) {
+                const float full = fmaxf(pmax, pm[(q + 2) * 32 + lane]);
+                const __nv_bfloat16 hp = __float2bfloat16_rn(full);
                 *reinterpret_cast<__nv_bfloat16 *>(pp) = hp;
-                *reinterpret_cast<__nv_bfloat16 *>(pp + kPSplit) = __float2bfloat16_rn(pmax - __bfloat162float(hp));
+                *reinterpret_cast<__nv_bfloat16 *>(pp + kPSplit) = __float2bfloat16_rn(full - __bfloat162float(hp));
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[X2_FULL0 + b]);
@@ -378,9 +398,9 @@ __global__ void desc_tc_prep_kernel(const float *__restrict__ P, WeightLayout L,
         *reinterpret_cast<__nv_bfloat16 *>(wimg + base + o) = hi;
         *reinterpret_cast<__nv_bfloat16 *>(wimg + base + split + o) = __float2bfloat16_rn(w - __bfloat162float(hi));
     };
-    if (i < 128 * 32) {  // W1^T, rows 64..127 zero
+    if (i < 128 * 32) {  // W1^T; rows 64..127 repeat rows 0..63
         const int r = i & 127, k = i >> 7;
-        put(kOffW1, kW1Split, (k >> 3) * kLboW + r * 16 + (k & 7) * 2, r < 64 ? P[L.off[W_DESC1] + k * 64 + r] : 0.0f);
+        put(kOffW1, kW1Split, (k >> 3) * kLboW + r * 16 + (k & 7) * 2, P[L.off[W_DESC1] + k * 64 + (r & 63)]);
     } else if (i < 128 * 32 + 128 * 64) {  // Wa^T = W_mid[0:64, :]^T
         const int e = i - 128 * 32;
         const int r = e & 127, k = e >> 7;

@@ -91,6 +91,11 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format, uint32_t M
     return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// OR into the instruction descriptor: B is MN-major.  Canonical no-swizzle MN-major operand in 16-byte units:
+// ((1,n),(8,k)):((X,SBO),(1,LBO)) -- a core matrix is 8 K-rows x 16 B (8 consecutive M/N elements); SBO = byte stride between
+// groups of 8 along M/N, LBO = byte stride between groups of 8 along K (cute/atom/mma_traits_sm100.hpp, make_umma_desc<MN>).
+constexpr uint32_t kIdescBMnMajor = 1u << 16;
+
 // D[tmem] (+)= A[smem] * B[smem]^T, single CTA, bf16/f16 inputs.  Issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

@@ -31,6 +31,39 @@ def make_image(A, lbo, sbo):
     return img, nbytes
 
 
+def make_image_mn(B, lbo, sbo):
+    """canonical MN-major no-swizzle bf16 operand image: element (n,k) at (n/8)*sbo + (k/8)*lbo + (k%8)*16 + (n%8)*2"""
+    rows, K = B.shape
+    n = torch.arange(rows).view(-1, 1)
+    k = torch.arange(K).view(1, -1)
+    off = (n // 8) * sbo + (k // 8) * lbo + (k % 8) * 16 + (n % 8) * 2
+    nbytes = (int(off.max()) + 2 + 15) // 16 * 16
+    img = torch.zeros(nbytes // 2, dtype=torch.int16)
+    img[(off // 2).reshape(-1)] = B.to(torch.bfloat16).view(torch.int16).reshape(-1)
+    return img, nbytes
+
+
+@pytest.mark.parametrize("N,K,lbo_b,sbo_b", [(64, 64, 128, 1024), (64, 128, 128, 2048), (64, 16, 128, 256), (64, 64, 1024, 128)])
+def test_umma_selftest_b_mn_major(cuda, N, K, lbo_b, sbo_b):
+    """B operand stored sample-contiguous (MN-major): the layout the E1 epilogues write with 16-byte stores"""
+    lib_mod = pkg("_lib")
+    L = lib_mod.lib()
+    g = torch.Generator().manual_seed(N * 77 + K)
+    A = torch.randn((128, K), generator=g).to(torch.bfloat16).float()
+    B = torch.randn((N, K), generator=g).to(torch.bfloat16).float()
+    a_img, a_bytes = make_image(A, 2048, 128)
+    b_img, b_bytes = make_image_mn(B, lbo_b, sbo_b)
+    a_d, b_d = a_img.to(cuda), b_img.to(cuda)
+    D = torch.full((128, N), float("nan"), device=cuda)
+    rc = L.f3d_debug_umma_selftest(lib_mod.ptr(a_d), lib_mod.ptr(b_d), lib_mod.ptr(D), N, K, 2048, 128, lbo_b, sbo_b, a_bytes, b_bytes,
+                                   1 | 2, lib_mod.stream())
+    lib_mod.check(rc, "umma_selftest")
+    torch.cuda.synchronize()
+    want = A.double() @ B.double().t()
+    err = (D.cpu().double() - want).abs().max().item()
+    assert err < 1e-3 * max(1.0, want.abs().max().item()), "UMMA self test (B MN-major): max err %.3e" % err
+
+
 @pytest.mark.parametrize("a_in_tmem", [0, 1])
 @pytest.mark.parametrize("N,K,lbo_b", [(64, 64, 1024), (64, 128, 1040), (8, 16, 128), (256, 32, 4096), (64, 16, 1040)])
 def test_umma_selftest(cuda, N, K, lbo_b, a_in_tmem):
