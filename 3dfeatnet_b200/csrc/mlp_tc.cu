@@ -102,7 +102,10 @@ constexpr int kThreads = 14 * 32;            // warp 0 MMA2 issue, 1-4 producers
 constexpr uint32_t kSbo = 128;               // 8 rows x 16 B
 constexpr uint32_t kLboW = 128 * 16;         // weights: 128 rows per K chunk
 constexpr uint32_t kLboX1 = kSamples * 16;   // X1: written 16 B per thread, no padding needed
-constexpr uint32_t kLboX2 = kSamples * 16 + 16;  // X2: +16 B so the 2-byte epilogue stores of a warp hit 32 distinct banks
+// X2 is stored SAMPLE-contiguous (MN-major B operand): a core matrix is 8 channels x 16 B (8 consecutive samples), so an
+// epilogue thread (one channel, 64 samples) writes 8 x 16 B per split instead of 64 x 2 B
+constexpr uint32_t kLboX2 = 128;                 // K groups of 8 channels
+constexpr uint32_t kSboX2 = 16 * 128;            // groups of 8 samples (128 channels)
 // shared-memory image (bytes).  The first kWeightBytes are copied verbatim from the packed global buffer.
 constexpr uint32_t kW1Split = 128 * 64 * 2;            // 16 KB per split
 constexpr uint32_t kW2Blk = 128 * 128 * 2;             // 32 KB per (split, M block)
@@ -115,13 +118,13 @@ constexpr uint32_t kOffB2 = kOffB1 + 128 * 4;           // fp32 [256]
 constexpr uint32_t kWeightBytes = kOffB2 + 256 * 4;     // 166 400
 constexpr uint32_t kX1Split = 8 * kLboX1;               // 8 KB
 constexpr uint32_t kOffX1 = kWeightBytes;               // [split 2][chunk 8][row 64][8] bf16
-constexpr uint32_t kX2Split = 16 * kLboX2;              // 16 640
+constexpr uint32_t kX2Split = 8 * kSboX2;               // 16 KB
 constexpr uint32_t kX2Buf = 2 * kX2Split;               // one X2 operand (hi + lo)
 // W2 is copied into TENSOR MEMORY once (tcgen05.cp) and its shared-memory staging area is then recycled as the two X2
 // operand buffers, so MMA2 reads only its 2 KB B operand from shared memory and E1(t+1) overlaps MMA2(t).
 constexpr uint32_t kOffX2 = kOffW2;                     // [buf 2][split 2][chunk 16] stride kLboX2 (aliases the W2 staging)
 constexpr uint32_t kOffBars = kOffX1 + 2 * kX1Split;
-constexpr uint32_t kSmemBytes = kOffBars + 16 * 8 + 16;
+constexpr uint32_t kSmemBytes = kOffBars + 20 * 8 + 16;
 static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffBars % 8 == 0, "alignment");
 static_assert(2 * kX2Buf <= 4 * kW2Blk, "X2 buffers must fit the W2 staging area");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -131,12 +134,15 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemW1 = 64;
 constexpr uint32_t kTmemW2 = 256;
 
+// D2 (256 channels = two 128-lane M blocks A / B) is single-buffered: its FULL / FREE barriers are per M block, so E2 drains
+// block A while the tensor pipe computes block B, and MMA2(t+1) block A starts as soon as block B of tile t has been issued.
 enum Bar { W_FULL = 0, W2_TMEM, X1_FULL, X1_FREE, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE,
-           D2_FULL0, D2_FULL1, D2_FREE, kNumBars };
+           D2A_FULL0, D2A_FULL1, D2B_FULL0, D2B_FULL1, D2A_FREE, D2B_FREE, kNumBars };
+static_assert(kNumBars <= 20, "barrier area");
 // NOTE on mbarrier parity: a waiter may lag a barrier by at most ONE phase (try_wait.parity(p) is true as soon as the
 // barrier is in the phase after p).  The two epilogue warpgroups alternate tiles, i.e. each sees every SECOND completion of
-// a per-tile event, so every barrier they wait on is per-warpgroup (D1_FULL[2], D2_FULL[2], X2_FREE[2]); only the MMA warp,
-// which consumes every completion in order, waits on shared single barriers (D2_FREE, X1_FULL).
+// a per-tile event, so every barrier they wait on is per-warpgroup (D1_FULL[2], D2A/B_FULL[2], X2_FREE[2]); only the MMA warps,
+// which consume every completion in order, wait on shared single barriers (D2A/B_FREE, X1_FULL).
 }  // namespace det
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -162,9 +168,12 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         mbar_init(&bars[W2_TMEM], 1);
         mbar_init(&bars[X1_FULL], 128);
         mbar_init(&bars[X1_FREE], 1);
-        mbar_init(&bars[D2_FULL0], 1);
-        mbar_init(&bars[D2_FULL1], 1);
-        mbar_init(&bars[D2_FREE], 128);
+        mbar_init(&bars[D2A_FULL0], 1);
+        mbar_init(&bars[D2A_FULL1], 1);
+        mbar_init(&bars[D2B_FULL0], 1);
+        mbar_init(&bars[D2B_FULL1], 1);
+        mbar_init(&bars[D2A_FREE], 128);
+        mbar_init(&bars[D2B_FREE], 128);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars[X2_FULL0 + b], 128);
             mbar_init(&bars[X2_FREE0 + b], 1);
@@ -221,29 +230,30 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             __syncwarp();
             auto mma2 = [&](int t) {  // A operand (W2) from tensor memory, B operand X2[t & 1] from shared memory
                 mbar_wait(&bars[X2_FULL0 + (t & 1)], (t >> 1) & 1);
-                mbar_wait(&bars[D2_FREE], (t & 1) ^ 1);
                 tcgen05_fence_after();
                 stamp(t, 1);
-                if (elect_one()) {
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
-                    const uint32_t d = tmem_base + 128 + mb * 64;
-                    uint32_t acc = 0;
+                    mbar_wait(&bars[D2A_FREE + mb], (t & 1) ^ 1);  // E2(t-1) has moved this M block into registers
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d = tmem_base + 128 + mb * 64;
+                        uint32_t acc = 0;
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t wa = tmem_base + kTmemW2 + ((pass == 2 ? 2 : 0) + mb) * 64;
-                        const uint32_t xb = sbase + kOffX2 + (t & 1) * kX2Buf + (pass == 1 ? kX2Split : 0);
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t wa = tmem_base + kTmemW2 + ((pass == 2 ? 2 : 0) + mb) * 64;
+                            const uint32_t xb = sbase + kOffX2 + (t & 1) * kX2Buf + (pass == 1 ? kX2Split : 0);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSbo), idesc, acc);
-                            acc = 1;
+                            for (int k = 0; k < 8; ++k) {
+                                umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSboX2), idesc | kIdescBMnMajor, acc);
+                                acc = 1;
+                            }
                         }
+                        if (mb == 1) umma_commit(&bars[X2_FREE0 + (t & 1)]);
+                        umma_commit(&bars[(mb == 0 ? D2A_FULL0 : D2B_FULL0) + (t & 1)]);
                     }
+                    __syncwarp();
                 }
-                umma_commit(&bars[X2_FREE0 + (t & 1)]);
-                umma_commit(&bars[D2_FULL0 + (t & 1)]);
-                }
-                __syncwarp();
                 stamp(t, 2);
             };
             // MMA1 (conv1) is issued by warp 13: two issuing warps hide each other's mbarrier-wait latency (~90 cycles per
@@ -359,7 +369,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const float b1 = reinterpret_cast<const float *>(smem + kOffB1)[ch];
         const float *B2 = reinterpret_cast<const float *>(smem + kOffB2);
-        uint8_t *x2 = smem + kOffX2 + g * kX2Buf + (ch >> 3) * kLboX2 + (ch & 7) * 2;  // this warpgroup's tiles use X2[g]
+        uint8_t *x2 = smem + kOffX2 + g * kX2Buf + (ch >> 3) * kLboX2 + (ch & 7) * 16;  // this warpgroup's tiles use X2[g]
         mbar_wait(&bars[W2_TMEM], 0);  // the X2 buffers alias the W2 staging area: wait until W2 sits in tensor memory
         for (int t = g; t < T; t += 2) {
             const int b = t & 1;
@@ -375,50 +385,47 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             tcgen05_fence_before();
             mbar_arrive(&bars[D1_FREE]);
 #pragma unroll
-            for (int sidx = 0; sidx < 64; sidx += 2) {  // r[i] becomes (lo << 16) | hi
+            for (int sidx = 0; sidx < 64; sidx += 2) {  // r[sidx] becomes the hi pair (samples sidx, sidx+1), r[sidx+1] the lo pair
                 uint32_t &ra = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
                 uint32_t &rb = sidx < 32 ? r0[(sidx + 1) & 31] : r1[(sidx + 1) & 31];
                 const float va = fmaxf(__uint_as_float(ra) + b1, 0.0f), vb = fmaxf(__uint_as_float(rb) + b1, 0.0f);
                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
                 const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
-                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2), lb = *reinterpret_cast<const uint32_t *>(&l2);
-                ra = (hb & 0xffffu) | (lb << 16);
-                rb = (hb >> 16) | (lb & 0xffff0000u);
+                ra = *reinterpret_cast<const uint32_t *>(&h2);
+                rb = *reinterpret_cast<const uint32_t *>(&l2);
             }
             if (q == 1) stamp(t, 9);
             mbar_wait(&bars[X2_FREE0 + b], ph ^ 1);  // MMA2(t-2) has finished reading this buffer
             if (q == 1) stamp(t, 10);
 #pragma unroll
-            for (int sidx = 0; sidx < 64; ++sidx) {
-                const uint32_t pk = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
-                *reinterpret_cast<uint16_t *>(x2 + sidx * 16) = static_cast<uint16_t>(pk & 0xffffu);
-                *reinterpret_cast<uint16_t *>(x2 + kX2Split + sidx * 16) = static_cast<uint16_t>(pk >> 16);
+            for (int j = 0; j < 8; ++j) {  // samples 8j .. 8j+7 of this channel: 16 contiguous bytes per split
+                const uint32_t *r = j < 4 ? &r0[(j & 3) * 8] : &r1[(j & 3) * 8];
+                *reinterpret_cast<uint4 *>(x2 + j * kSboX2) = make_uint4(r[0], r[2], r[4], r[6]);
+                *reinterpret_cast<uint4 *>(x2 + kX2Split + j * kSboX2) = make_uint4(r[1], r[3], r[5], r[7]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[X2_FULL0 + b]);
             if (q == 1) stamp(t, 11);
-            // E2: D2 -> max over the 64 samples, +bias, ReLU -> pooled (ReLU and +bias commute with max)
-            mbar_wait(&bars[D2_FULL0 + b], ph);
-            tcgen05_fence_after();
-            if (q == 1) stamp(t, 12);
-            float mx[2];
+            // E2: D2 -> max over the 64 samples, +bias, ReLU -> pooled (ReLU and +bias commute with max); M block A is
+            // released to MMA2(t+1) before block B has even been computed
+            const long long cl = first + static_cast<long long>(t) * gridDim.x;
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
+                mbar_wait(&bars[(mb == 0 ? D2A_FULL0 : D2B_FULL0) + b], ph);
+                tcgen05_fence_after();
+                if (q == 1 && mb == 0) stamp(t, 12);
                 tmem_ld32(tmem_base + lane_addr + 128 + mb * 64, r0);
                 tmem_ld32(tmem_base + lane_addr + 128 + mb * 64 + 32, r1);
                 tmem_ld_wait();
+                tcgen05_fence_before();
+                mbar_arrive(&bars[D2A_FREE + mb]);
                 float mv = __uint_as_float(r0[0]);
 #pragma unroll
                 for (int j = 1; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r0[j]));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r1[j]));
-                mx[mb] = mv;
+                pooled[cl * 256 + mb * 128 + ch] = fmaxf(mv + B2[mb * 128 + ch], 0.0f);
             }
-            tcgen05_fence_before();
-            mbar_arrive(&bars[D2_FREE]);
-            const long long cl = first + static_cast<long long>(t) * gridDim.x;
-            pooled[cl * 256 + ch] = fmaxf(mx[0] + B2[ch], 0.0f);
-            pooled[cl * 256 + 128 + ch] = fmaxf(mx[1] + B2[128 + ch], 0.0f);
             if (q == 1) stamp(t, 13);
         }
     }
