@@ -28,7 +28,7 @@ using namespace tc;
 
 namespace dsc {
 constexpr int kSamples = 64;
-constexpr int kThreads = 13 * 32;
+constexpr int kThreads = 14 * 32;  // warp 0 MMA2/3 issue, 1-4 producers, 5-12 epilogues, 13 MMA1 issue
 constexpr uint32_t kSbo = 128;
 constexpr uint32_t kLboW = 128 * 16;
 constexpr uint32_t kLboX1 = kSamples * 16;
@@ -148,29 +148,6 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             __syncwarp();
             mbar_wait(&bars[W_TMEM], 0);
-            auto mma1 = [&](int t) {
-                mbar_wait(&bars[X1_FULL], t & 1);
-                mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
-                tcgen05_fence_after();
-                stamp(t, 0);
-                if (elect_one()) {
-                const uint32_t d = tmem_base + (t & 1) * 64;
-                uint32_t acc = 0;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t wa = tmem_base + kTmemW1 + (pass == 2 ? 16 : 0);
-                    const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc64, acc);
-                        acc = 1;
-                    }
-                }
-                umma_commit(&bars[X1_FREE]);
-                umma_commit(&bars[D1_FULL0 + (t & 1)]);
-                }
-                __syncwarp();
-            };
             auto mma23 = [&](int t) {
                 mbar_wait(&bars[X2_FULL0 + (t & 1)], (t >> 1) & 1);
                 mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
@@ -207,12 +184,39 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 __syncwarp();
                 stamp(t, 2);
             };
-            if (T > 0) mma1(0);
-            for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) mma1(t + 1);
-                mma23(t);
-            }
+            // MMA1 (conv1) is issued by warp 13: two issuing warps hide each other's mbarrier waits (see mlp_tc.cu)
+            for (int t = 0; t < T; ++t) mma23(t);
         }
+    } else if (warp == 13) {
+        // ---- second MMA issuer: conv1 (X1 -> D1), A operand W1 from tensor memory ---------------------------------------
+        const uint32_t idesc64 = make_idesc(1, 128, kSamples);
+        const uint32_t sbase = smem_u32(smem);
+        mbar_wait(&bars[W_TMEM], 0);  // the weights have been copied into tensor memory
+        tcgen05_fence_after();
+        auto mma1 = [&](int t) {
+            mbar_wait(&bars[X1_FULL], t & 1);
+            mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+            tcgen05_fence_after();
+            stamp(t, 0);
+            if (elect_one()) {
+            const uint32_t d = tmem_base + (t & 1) * 64;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t wa = tmem_base + kTmemW1 + (pass == 2 ? 16 : 0);
+                const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc64, acc);
+                    acc = 1;
+                }
+            }
+            umma_commit(&bars[X1_FREE]);
+            umma_commit(&bars[D1_FULL0 + (t & 1)]);
+            }
+            __syncwarp();
+        };
+        for (int t = 0; t < T; ++t) mma1(t);
     } else if (warp <= 4) {
         // ---- producers: gather + normalise + rotate + layer 0 (3 -> 32) -> X1 ------------------------------------
         // Software-pipelined like the detector's: index of tile t+2 and coordinates / orientation of tile t+1 in flight.
