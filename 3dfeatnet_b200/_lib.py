@@ -23,6 +23,8 @@ SIGNATURES = {
     "f3d_query_ball_point": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "f3d_query_ball_point_workspace_bytes": (_sz, [_i, _i]),
     "f3d_query_ball_point_ws": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "f3d_ball_grid_build": (_i, [_i, _i, _f, _vp, _vp, _sz, _vp]),
+    "f3d_ball_grid_query": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_query_ball_point2": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "f3d_selection_sort": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_knn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -482,33 +482,70 @@ F3D_API size_t f3d_query_ball_point_workspace_bytes(int b, int n) {
            static_cast<size_t>(b) * sizeof(BqGridInfo) + 512;
 }
 
-F3D_API int f3d_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
-                                    int *idx, int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream) {
+// the grid path needs a workspace, a finite radius and a per-warp index bitmap that fits shared memory
+static bool bq_grid_ok(int b, int n, float radius, const void *workspace, size_t workspace_bytes) {
+    return workspace && workspace_bytes >= f3d_query_ball_point_workspace_bytes(b, n) && n <= 262144 && radius < 1.0e18f &&
+           (reinterpret_cast<uintptr_t>(workspace) % 16 == 0);
+}
+struct BqWorkspace {
+    float4 *sorted;
+    int *cell_start;
+    BqGridInfo *info;
+};
+static BqWorkspace bq_workspace(int b, int n, void *workspace) {
+    BqWorkspace w;
+    w.sorted = static_cast<float4 *>(workspace);
+    w.cell_start = reinterpret_cast<int *>(w.sorted + static_cast<size_t>(b) * n);
+    w.info = reinterpret_cast<BqGridInfo *>(w.cell_start + static_cast<size_t>(b) * (kBqMaxCells + 1));
+    return w;
+}
+
+// First half of f3d_query_ball_point_ws: bins xyz1 into the workspace.  It depends on the cloud only (not on the centres),
+// so a caller may run it on a second stream while the centres are still being sampled (3dfeatnet_b200/pipeline.py does).
+F3D_API int f3d_ball_grid_build(int b, int n, float radius, const float *xyz1, void *workspace, size_t workspace_bytes, void *stream) {
+    if (b < 0 || n <= 0 || !(radius > 0.0f) || !xyz1) return fail(F3D_ERR_INVALID_ARGUMENT, "ball_grid_build: bad arguments");
+    if (!bq_grid_ok(b, n, radius, workspace, workspace_bytes))
+        return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "ball_grid_build: workspace missing, too small or misaligned (or n > 262144)");
+    if (b == 0) return 0;
+    const BqWorkspace w = bq_workspace(b, n, workspace);
+    bq_grid_build_kernel<<<b, kBqBuildThreads, 0, as_stream(stream)>>>(n, radius, xyz1, w.sorted, w.cell_start, w.info);
+    return check_launch("bq_grid_build_kernel");
+}
+
+// Second half: query_ball_point over a grid built by f3d_ball_grid_build with the same (b, n, radius, xyz1, workspace).
+F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                                int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream) {
     if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f) || !xyz1 || !xyz2 || !idx || !pts_cnt)
-        return fail(F3D_ERR_INVALID_ARGUMENT, "query_ball_point: bad arguments");
-    // the grid path needs a workspace, a finite radius and a per-warp index bitmap that fits shared memory
-    const bool grid_ok = workspace && workspace_bytes >= f3d_query_ball_point_workspace_bytes(b, n) && n <= 262144 &&
-                         radius < 1.0e18f && (reinterpret_cast<uintptr_t>(workspace) % 16 == 0);
-    if (!grid_ok) return f3d_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
+        return fail(F3D_ERR_INVALID_ARGUMENT, "ball_grid_query: bad arguments");
+    if (!bq_grid_ok(b, n, radius, workspace, workspace_bytes))
+        return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "ball_grid_query: workspace missing, too small or misaligned (or n > 262144)");
     const long long w = static_cast<long long>(b) * m;
     if (w == 0 || b == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    float4 *sorted = static_cast<float4 *>(workspace);
-    int *cell_start = reinterpret_cast<int *>(sorted + static_cast<size_t>(b) * n);
-    BqGridInfo *info = reinterpret_cast<BqGridInfo *>(cell_start + static_cast<size_t>(b) * (kBqMaxCells + 1));
-    bq_grid_build_kernel<<<b, kBqBuildThreads, 0, st>>>(n, radius, xyz1, sorted, cell_start, info);
-    int rc = check_launch("bq_grid_build_kernel");
-    if (rc) return rc;
+    const BqWorkspace ws = bq_workspace(b, n, workspace);
     const int nwords = (n + 31) / 32;
     const int wpc = nwords <= 1024 ? 8 : (nwords <= 4096 ? 4 : 2);
     const size_t smem = static_cast<size_t>(wpc) * nwords * sizeof(unsigned);
     cudaError_t e = cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "bq_grid_query: cudaFuncSetAttribute");
-    bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, sorted, cell_start, info, xyz2, idx, pts_cnt);
-    rc = check_launch("bq_grid_query_kernel");
+    bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, ws.sorted, ws.cell_start, ws.info, xyz2, idx,
+                                                                    pts_cnt);
+    int rc = check_launch("bq_grid_query_kernel");
     if (rc) return rc;
     bq_fallback_kernel<<<blocks_for(w, kBqWarps), kBqWarps * 32, 0, st>>>(b, n, m, nsample, xyz1, xyz2, idx, pts_cnt);
     return check_launch("bq_fallback_kernel");
+}
+
+F3D_API int f3d_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
+                                    int *idx, int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream) {
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f) || !xyz1 || !xyz2 || !idx || !pts_cnt)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "query_ball_point: bad arguments");
+    if (!bq_grid_ok(b, n, radius, workspace, workspace_bytes))
+        return f3d_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
+    if (static_cast<long long>(b) * m == 0) return 0;
+    const int rc = f3d_ball_grid_build(b, n, radius, xyz1, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return f3d_ball_grid_query(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, workspace, workspace_bytes, stream);
 }
 
 F3D_API int f3d_query_ball_point2(int b, int n, int m, int nsample, const float *xyz1, const float *xyz2,

@@ -51,6 +51,7 @@ class DetectDescribePipeline:
         self.d2h_bytes = self.h_out.numel() * 4
         self.launches_per_step = None
         self._graph = None
+        self._side = None  # second stream: ball-query grid build under FPS
         self.use_graph = use_graph
         # double buffers + side streams of the overlapped host<->device loop (run_host_steps)
         self._hp = None
@@ -69,12 +70,29 @@ class DetectDescribePipeline:
                 events.append(e)
 
         mark()
+        # The ball-query grid depends on the cloud only: outside the per-stage timing mode it is built on a side stream
+        # while FPS (one CTA per cloud, 64 of the 148 SMs at the bench batch) selects the centres; inside a CUDA graph this
+        # becomes a parallel branch.
+        fork = events is None and N <= 262144
+        if fork:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                _lib.check(L.f3d_ball_grid_build(B, N, self.radius, p(xyz_buf), p(self.bq_ws), self.bq_ws_bytes, _lib.stream()),
+                           "ball_grid_build")
         _lib.check(L.f3d_farthest_point_sample(B, N, M, p(xyz_buf), p(self.fps_temp), p(self.fps_idx), st), "fps")
         mark()
         _lib.check(L.f3d_gather_point(B, N, M, p(xyz_buf), p(self.fps_idx), p(self.keypoints), st), "gather_point")
         mark()
-        _lib.check(L.f3d_query_ball_point_ws(B, N, M, self.radius, S, p(xyz_buf), p(self.keypoints), p(self.idx),
-                                             p(self.pts_cnt), p(self.bq_ws), self.bq_ws_bytes, st), "query_ball_point")
+        if fork:
+            cur.wait_stream(self._side)
+            _lib.check(L.f3d_ball_grid_query(B, N, M, self.radius, S, p(xyz_buf), p(self.keypoints), p(self.idx),
+                                             p(self.pts_cnt), p(self.bq_ws), self.bq_ws_bytes, st), "ball_grid_query")
+        else:
+            _lib.check(L.f3d_query_ball_point_ws(B, N, M, self.radius, S, p(xyz_buf), p(self.keypoints), p(self.idx),
+                                                 p(self.pts_cnt), p(self.bq_ws), self.bq_ws_bytes, st), "query_ball_point")
         mark()
         _lib.check(L.f3d_detector_forward(B, N, M, S, self.radius, p(xyz_buf), p(self.keypoints), p(self.idx),
                                           p(self.packed), p(self.attention), p(self.orientation), prec, p(self.ws),

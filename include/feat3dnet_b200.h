@@ -74,6 +74,12 @@ int f3d_query_ball_point(int b, int n, int m, float radius, int nsample, const f
 size_t f3d_query_ball_point_workspace_bytes(int b, int n);
 int f3d_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
                             int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream);
+/* The two halves of f3d_query_ball_point_ws as separate calls: the grid build depends on the cloud only, so it can run
+ * on a second stream while the centres (farthest_point_sample + gather_point) are still being computed.  Both need
+ * the workspace (no fallback: F3D_ERR_WORKSPACE_TOO_SMALL); the query must see the same b, n, radius, xyz1, workspace. */
+int f3d_ball_grid_build(int b, int n, float radius, const float *xyz1, void *workspace, size_t workspace_bytes, void *stream);
+int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                        int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream);
 
 /* queryBallPoint2Launcher(b,n,m,nsample,xyz1,xyz2,radii,idx,pts_cnt)  tf_grouping_g.cu:183-186,
  * op tf_grouping.cpp:128-172.  radii (b,m).  Rows of empty balls are left untouched, as in the reference. */
