@@ -26,6 +26,10 @@ FLOPS_DET_ROW, FLOPS_DET_CLUSTER = 2 * 41152, 2 * 41152
 FLOPS_DESC_ROW, FLOPS_DESC_CLUSTER = 2 * 10336, 2 * (8192 + 4096)  # split-weight form
 
 
+def workload_name(B, N, M, S):
+    return ("C3: %d Oxford-shape clouds/GPU, %d pts, %d clusters x %d nsample, FPS+ballquery+detector+descriptor fwd" % (B, N, M, S))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -39,7 +43,8 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("F3D_PRECISION", "bf16x3"), choices=["fp32", "bf16x3"],
                     help="bf16x3 = tcgen05 with split-bf16 fp32 emulation (default); fp32 = exact CUDA-core FFMA path")
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="clouds in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=64,
+                    help="clouds in the bounded CPU-baseline sample (default: the 64 clouds of one step, ~4 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -119,7 +124,8 @@ def cpu_reference_pass(xyz_np, params, clusters, nsample, radius=2.0):
     from oracle import net as onet
 
     t0 = time.perf_counter()
-    onet.inference_model(xyz_np, params, num_clusters=clusters, radius=radius, nsample=nsample)
+    for c0 in range(0, len(xyz_np), 8):  # 8 clouds at a time: the (8,512,64,256) fp32 activations stay at 268 MB
+        onet.inference_model(xyz_np[c0:c0 + 8], params, num_clusters=clusters, radius=radius, nsample=nsample)
     return time.perf_counter() - t0
 
 
@@ -140,7 +146,7 @@ def run_reference(args):
     xyz = synth.make_batch(sample, args.points, seed0=1000)
     params = onet.to_torch(onet.init_params(seed=0))
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_pass(xyz, params, args.clusters, args.nsample)
+        cpu_reference_pass(xyz[:8], params, args.clusters, args.nsample)
     steps = max(1, min(args.steps, 5))
     t = [cpu_reference_pass(xyz, params, args.clusters, args.nsample) for _ in range(steps)]
     sec = sum(t) / len(t)
@@ -148,8 +154,8 @@ def run_reference(args):
     line = dict(metric="keypoints+descriptors/sec", value=value, unit="keypoints/s", n_gpus=args.gpus, steps=steps,
                 warmup=min(args.warmup, 1), ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="C3: Oxford-shape clouds, %d pts, %d clusters x %d nsample, detector+descriptor fwd"
-                            % (args.points, args.clusters, args.nsample), clouds_per_step=sample),
+                config=dict(workload=workload_name(args.batch, args.points, args.clusters, args.nsample), clouds_per_step=sample,
+                            precision="fp32", parallelism="rank 0 only, all host threads"),
                 cpu_baseline=dict(value=value, unit="keypoints/s", cores=max(cores, oops.num_threads()), kind="port",
                                   sample="%d clouds of %d points per step (of the 64-cloud batch)" % (sample, args.points)),
                 e2e=dict(value=value, unit="keypoints/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -273,8 +279,7 @@ def main():
                 warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32" if args.precision == "fp32" else "f32 via bf16x3 tensor-core split (fp32 accumulate)",
                 data="synthetic",
-                config=dict(workload="C3: %d Oxford-shape clouds/GPU, %d pts, %d clusters x %d nsample, FPS+ballquery+detector+descriptor fwd"
-                            % (B, N, M, S), l2="flushed between timed steps (256 MiB write)", cuda_graph=bool(args.graph),
+                config=dict(workload=workload_name(B, N, M, S), l2="flushed between timed steps (256 MiB write)", cuda_graph=bool(args.graph),
                             precision=args.precision, parallelism="batch-sharded dp%d, no collective" % world),
                 e2e=dict(value=e2e_value, unit="keypoints/s", h2d_bytes_per_step=pipe.h2d_bytes, d2h_bytes_per_step=pipe.d2h_bytes,
                          ms_per_step=e2e_ms / args.steps,
@@ -308,9 +313,10 @@ def main():
         torch.set_num_threads(cores)
         sample = max(1, args.cpu_sample)
         cpu_params = onet.to_torch(onet.init_params(seed=0))
+        sample = min(sample, B)
         cpu_xyz = xyz[:sample]
-        cpu_reference_pass(cpu_xyz, cpu_params, M, S)
-        sec = min(cpu_reference_pass(cpu_xyz, cpu_params, M, S) for _ in range(3))
+        cpu_reference_pass(cpu_xyz[:8], cpu_params, M, S)  # warm-up (thread pools, allocator)
+        sec = min(cpu_reference_pass(cpu_xyz, cpu_params, M, S) for _ in range(2))
         line["cpu_baseline"] = dict(value=sample * M / sec, unit="keypoints/s", cores=max(cores, oops.num_threads()), kind="port",
                                     sample="%d of the %d clouds of one step (oracle C ops + PyTorch-CPU fp32 net)" % (sample, B))
     print(json.dumps(line))
