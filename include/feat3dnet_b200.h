@@ -215,6 +215,27 @@ int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa, const f
 int f3d_adam_step(int num_records, const void *records, long long max_n, float lr, float beta1, float beta2, float eps,
                   long long step, float grad_scale, long long *step_dev, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Registration: the MATLAB evaluation step of the reference on the device.
+ *
+ * scripts/computeAndVisualizeMatches.m:43-44  [~, m] = pdist2(desc2, desc1, 'euclidean', 'smallest', 1):
+ * match[i] = index of the row of desc2 (n2 x dim) nearest to row i of desc1 (n1 x dim), lowest index on ties;
+ * dist2 (optional) receives the squared distance. */
+int f3d_match_descriptors(int n1, int n2, int dim, const float *desc1, const float *desc2, int *match, float *dist2, void *stream);
+/* scripts/external/ransacfitRt.m + ransac.m + estimateRigidTransform.m: pts1[k] ~ R pts2[k] + t over npts correspondences
+ * (npts x 3 each).  triples (ntrials x 3) are the 3-point samples of the trials IN ORDER (MATLAB's randsample stream is
+ * not reproducible, so the caller draws them); every trial is scored in parallel and the reference's sequential
+ * bookkeeping (">=" best-score rule, adaptive N at p = 0.99, max_trials, default 10000) is replayed over the scores.
+ * Rt: 12 doubles, row-major 3x4, refit on the inliers (NaN if fewer than 3); inlier_mask: npts bytes;
+ * info: {inliers of the chosen trial, trialcount, chosen trial, status: 1 = triples exhausted before the stop rule}. */
+size_t f3d_ransac_workspace_bytes(int npts, int ntrials);
+int f3d_ransac_fit_rt(int npts, const float *pts1, const float *pts2, int ntrials, const int *triples, float threshold,
+                      int max_trials, double *Rt, unsigned char *inlier_mask, int *info, void *workspace, size_t workspace_bytes,
+                      void *stream);
+/* estimateRt.m / estimateRigidTransform.m on the correspondences with mask[k] != 0 (all when mask is NULL); eps (optional)
+ * receives the smallest singular value S(4,4). */
+int f3d_rigid_fit(int npts, const float *pts1, const float *pts2, const unsigned char *mask, double *Rt, double *eps, void *stream);
+
 /* ---------------------------------------------------------------- bring-up / debugging ---------- */
 
 /* Single-CTA tcgen05 self test: D[128 x N] = A[128 x K] * B[N x K]^T from canonical K-major no-swizzle bf16 operand

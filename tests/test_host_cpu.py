@@ -255,3 +255,84 @@ def test_augmentations_follow_the_reference_semantics():
     b = aug.apply_augmentations(xyz, gen=torch.Generator().manual_seed(1))
     assert torch.equal(a, b) and not torch.equal(a, xyz)
     assert torch.equal(aug.apply_augmentations(xyz, names=()), xyz)
+
+
+def _write_dataset(tmp_path, n_clouds=6, pts=300, seed=0):
+    rng = np.random.default_rng(seed)
+    lines = []
+    for i in range(n_clouds):
+        cloud = np.concatenate([rng.uniform(-25, 25, (pts, 3)), rng.normal(size=(pts, 3))], axis=1).astype(np.float32)
+        cloud.tofile(str(tmp_path / ("c%d.bin" % i)))
+        pos = [(i + 1) % n_clouds]
+        nonneg = [(i + 2) % n_clouds]
+        lines.append("c%d.bin | %s | %s" % (i, " ".join(map(str, pos)), " ".join(map(str, nonneg))))
+    meta = tmp_path / "train.txt"
+    meta.write_text("\n".join(lines) + "\n")
+    return str(meta)
+
+
+def test_datagenerator_follows_the_reference_interface(tmp_path):
+    """data/datagenerator.py:9-182: metadata parsing, epoch bookkeeping, positive / negative rules, crop + resample"""
+    dg_mod = pkg("data.datagenerator")
+    meta = _write_dataset(tmp_path)
+    gen = dg_mod.DataGenerator(meta, num_cols=6, seed=3)
+    assert gen.size == 6 and gen.paths_and_labels[2] == ("c2.bin", {3}, {4})
+    gen.shuffle()
+    order = list(gen.indices)
+    assert sorted(order) == list(range(6))
+    seen = 0
+    while True:
+        a, p, n = gen.next_triplet(k=4, num_points=128)
+        if a is None:
+            break
+        assert a.shape == p.shape == n.shape and a.shape[1:] == (128, 6) and a.dtype == np.float32
+        assert (np.square(a[:, :, :3]).sum(2) <= 400.0 + 1e-3).all()  # 20 m crop (datagenerator.py:149-150)
+        seen += a.shape[0]
+    assert seen == 6  # k=4 then the 2 remaining, then (None, None, None)
+    gen.reset()
+    assert list(gen.indices) == list(range(6))
+    for anchor in range(6):
+        pos, neg = gen.get_positive_negative(anchor)
+        assert pos == (anchor + 1) % 6 and neg not in {(anchor + 1) % 6, (anchor + 2) % 6}
+    # fewer points than requested: every original row is kept and the rest are duplicates (datagenerator.py:153-160)
+    small = np.concatenate([np.random.default_rng(1).uniform(-5, 5, (50, 3)), np.zeros((50, 3))], axis=1).astype(np.float32)
+    out = gen.process_point_cloud(small, num_points=80)
+    assert out.shape == (80, 6) and np.array_equal(out[:50], small)
+    assert all(any(np.array_equal(r, s) for s in small) for r in out[50:])
+    # augmentation objects with the reference's .apply(xyz) interface are applied to all three clouds
+    class Shift1:
+        def apply(self, xyz):
+            return xyz + 1.0
+    gen.reset()
+    a0, _, _ = gen.next_triplet(k=1, num_points=64)
+    gen.reset()
+    gen.rng = np.random.default_rng(3)
+    gen2 = dg_mod.DataGenerator(meta, num_cols=6, seed=11)
+    b0, _, _ = gen2.next_triplet(k=1, num_points=64)
+    gen3 = dg_mod.DataGenerator(meta, num_cols=6, seed=11)
+    b1, _, _ = gen3.next_triplet(k=1, num_points=64, augmentation=[Shift1()])
+    assert np.allclose(b1[:, :, :3], b0[:, :, :3] + 1.0) and np.array_equal(b1[:, :, 3:], b0[:, :, 3:])
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.txt").write_text("c0.bin | 1\n")
+        dg_mod.DataGenerator(str(tmp_path / "bad.txt"))
+
+
+def test_validation_metric_and_cluster_stacking(tmp_path):
+    """train.py:240-315: ground-truth file, 100 m stacking of the validation clusters, FP rate at 95 % recall"""
+    val = pkg("validation")
+    gt = tmp_path / "groundtruths.txt"
+    gt.write_text("idx1 idx2 t match\n" + "\n".join("%d %d 0.5 %d" % (i, i + 7, i % 2) for i in range(10)) + "\n")
+    g = val.load_validation_groundtruths(str(gt))
+    assert g == [(i, i % 2) for i in range(10)]
+    assert val.load_validation_groundtruths(str(gt), proportion=0.5) == [(i, i % 2) for i in range(0, 10, 2)]
+    rng = np.random.default_rng(0)
+    pos, neg = rng.uniform(0, 1, 200), rng.uniform(0.5, 2, 300)
+    thr = np.percentile(pos, 95)
+    assert val.fp_rate_at_95_recall(pos, neg) == np.count_nonzero(neg < thr) / 300
+    assert val.fp_rate_at_95_recall([0.1, 0.2], [0.5, 0.6]) == 0.0 and val.fp_rate_at_95_recall([1.0], [0.5]) == 1.0
+    clouds = [rng.normal(size=(20 + j, 6)).astype(np.float32) for j in range(3)]
+    pc, offsets = val.stack_clusters(clouds)
+    assert pc.shape == (1, 63, 6) and offsets.shape == (1, val.NUM_CLUSTERS, 3)
+    assert np.allclose(pc[0, 20:41, 0], clouds[1][:, 0] + 100.0) and np.array_equal(pc[0, 20:41, 1:], clouds[1][:, 1:])
+    assert offsets[0, :4, 0].tolist() == [0.0, 100.0, 200.0, 0.0] and not offsets[0, :, 1:].any()
+    assert val.validate(None, str(tmp_path), []) == 1  # nothing to validate (train.py:262-263)

@@ -145,3 +145,42 @@ def test_training_step_matches_oracle(cuda):
     assert moved > 0
     for k in ("detection/conv0/bn/moving_mean", "description/layer1/conv_mid_0/bn/moving_variance"):
         assert torch.allclose(net.weights[k].cpu().double(), oP[k], rtol=1e-3, atol=1e-4)
+
+
+def test_validate_fp_rate_matches_oracle(cuda, tmp_path):
+    """train.py:260-315 through the device path: stacked validation clusters described at fed keypoints, descriptor distances
+    and FP rate at 95 % recall against the CPU oracle on the same files"""
+    val = pkg("validation")
+    f3 = pkg("models.feat3dnet")
+    rng = np.random.default_rng(5)
+    n_pairs, gts = 24, []
+    for i in range(n_pairs):
+        base = np.concatenate([rng.normal(0, 1.2, (900, 3)), np.zeros((900, 3))], axis=1).astype(np.float32)
+        match = i % 3 != 0
+        if match:  # same cluster seen again: jitter + a small z rotation
+            a = 0.05 * rng.normal()
+            R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], dtype=np.float32)
+            other = base.copy()
+            other[:, :3] = base[:, :3] @ R.T + rng.normal(0, 0.01, (900, 3)).astype(np.float32)
+        else:
+            other = np.concatenate([rng.normal(0, 1.2, (900, 3)) * [1.5, 0.6, 1.0], np.zeros((900, 3))], axis=1).astype(np.float32)
+        base.tofile(str(tmp_path / ("%d_0.bin" % i)))
+        other.tofile(str(tmp_path / ("%d_1.bin" % i)))
+        gts.append((i, int(match)))
+    params = onet.init_params(seed=6, randomize_bn=True)
+    net = f3.Feat3dNet({'num_clusters': 64}, weights=params, device=cuda)
+    fp = val.validate(net, str(tmp_path), gts, data_dim=6, device=cuda)
+    # oracle: the same stacked clouds through the CPU statement of the network
+    P = onet.to_torch(params)
+    feats = []
+    for side in (0, 1):
+        clouds = [np.fromfile(str(tmp_path / ("%d_%d.bin" % (i, side))), dtype=np.float32).reshape(-1, 6) for i in range(n_pairs)]
+        pc, offsets = val.stack_clusters(clouds)
+        ref = onet.inference_model(pc[:, :, :3].copy(), P, keypoints_np=offsets)
+        feats.append(ref["features"][0, :n_pairs].numpy())
+    d_ref = np.sqrt(np.sum(np.square(feats[0] - feats[1]), axis=1))
+    d_gpu = val.pair_distances(net, [np.fromfile(str(tmp_path / ("%d_0.bin" % i)), dtype=np.float32).reshape(-1, 6) for i in range(n_pairs)],
+                               [np.fromfile(str(tmp_path / ("%d_1.bin" % i)), dtype=np.float32).reshape(-1, 6) for i in range(n_pairs)], cuda)
+    assert np.abs(d_gpu - d_ref).max() < 1e-4, "descriptor distances differ from the oracle: %.3e" % np.abs(d_gpu - d_ref).max()
+    fp_ref = val.fp_rate_at_95_recall([d_ref[i] for i in range(n_pairs) if gts[i][1] == 1], [d_ref[i] for i in range(n_pairs) if gts[i][1] == 0])
+    assert fp == fp_ref and 0.0 <= fp <= 1.0
