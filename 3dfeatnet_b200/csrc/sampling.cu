@@ -464,6 +464,7 @@ F3D_API int f3d_farthest_point_sample(int b, int n, int m, const float *inp, flo
     if (b < 0 || n <= 0 || m <= 0 || !inp || !out) return fail(F3D_ERR_INVALID_ARGUMENT, "farthest_point_sample: bad arguments");
     if (b == 0) return 0;
     cudaStream_t st = as_stream(stream);
+    // 512 threads (measured: 256 threads x 16 groups 0.308 ms, 1024 threads x 4 groups 0.325 ms, 512 x 8 0.266 ms at n = 16384)
     // 512 threads; G = groups of 128 points per warp
     if (n <= 2048) return launch_fps_group<16, 1, 1>(b, n, m, inp, out, st);
     if (n <= 4096) return launch_fps_group<16, 2, 1>(b, n, m, inp, out, st);
