@@ -6,6 +6,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib3dfeatnet_b200.so")
 
+PRECISION_IMAGES_CACHED = 0x100  # F3D_PRECISION_IMAGES_CACHED
+
 _c = ctypes
 _vp, _i, _f, _sz, _ll = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_longlong
 

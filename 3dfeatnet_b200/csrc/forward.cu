@@ -9,17 +9,18 @@ int descriptor_forward_fp32(int b, int n, int m, int S, float radius, int featur
                             const float *new_xyz, const int *idx, const float *orientation, const float *packed,
                             float *pooled_ws, float *features, cudaStream_t st);
 int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
-                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, cudaStream_t st);
+                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, bool build_image, cudaStream_t st);
 int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
                        const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
-                       float *pooled2, cudaStream_t st);
+                       float *pooled2, bool build_image, cudaStream_t st);
+size_t descriptor_tc_weight_bytes();
 int descriptor_post_fp32(long long nc, const float *pooled2, const float *packed, int feature_dim, float *features,
                          cudaStream_t st);
 size_t post_tc_weight_bytes();
 int detector_post_tc(long long nc, const float *pooled, const float *packed, uint8_t *wimg, float *attention, float *orientation,
-                     cudaStream_t st);
+                     bool build_image, cudaStream_t st);
 int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, const float *packed, uint8_t *wimg, float *features,
-                       cudaStream_t st);
+                       bool build_image, cudaStream_t st);
 int detector_post_fp32(long long num_clusters, const float *pooled, const float *packed, float *attention,
                        float *orientation, cudaStream_t st);
 }  // namespace f3d
@@ -41,10 +42,20 @@ F3D_API int f3d_packed_weights_offsets(int feature_dim, int *offsets, int *sizes
     return 0;
 }
 
+// Workspace = pooled vectors | four weight-image slots (detector rows, detector tail, descriptor rows, descriptor tail).  The
+// slots do not alias, so the images survive from call to call and F3D_PRECISION_IMAGES_CACHED can skip rebuilding them.
+static size_t slot_bytes(int slot) {
+    const size_t b = slot == 0 ? f3d_detector_tc_weight_bytes() : (slot == 2 ? descriptor_tc_weight_bytes() : post_tc_weight_bytes());
+    return (b + 255) & ~static_cast<size_t>(255);
+}
+static uint8_t *image_slot(void *workspace, int b, int m, int slot) {
+    uint8_t *p = static_cast<uint8_t *>(workspace) + pooled_bytes(b, m);
+    for (int s = 0; s < slot; ++s) p += slot_bytes(s);
+    return p;
+}
 F3D_API size_t f3d_forward_workspace_bytes(int b, int m, int feature_dim) {
     (void)feature_dim;
-    const size_t img = f3d_detector_tc_weight_bytes() > post_tc_weight_bytes() ? f3d_detector_tc_weight_bytes() : post_tc_weight_bytes();
-    return pooled_bytes(b, m) + img + 256;
+    return pooled_bytes(b, m) + slot_bytes(0) + slot_bytes(1) + slot_bytes(2) + slot_bytes(3) + 256;
 }
 
 F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const float *xyz, const float *new_xyz,
@@ -55,17 +66,19 @@ F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius,
         return fail(F3D_ERR_INVALID_ARGUMENT, "detector_forward: bad arguments");
     if (!workspace || workspace_bytes < f3d_forward_workspace_bytes(b, m, 32))
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "detector_forward: workspace too small");
+    const bool build_images = (precision & F3D_PRECISION_IMAGES_CACHED) == 0;
+    precision &= 0xff;
     if (precision == 0)
         return detector_forward_fp32(b, n, m, nsample, radius, xyz, new_xyz, idx, packed, static_cast<float *>(workspace),
                                      attention, orientation, as_stream(stream));
     if (precision == 2) {  // tcgen05, bf16x3 split
         if (nsample != 64) return fail(F3D_ERR_UNSUPPORTED, "detector_forward: the tensor-core path needs nsample == 64");
         float *pooled = static_cast<float *>(workspace);
-        uint8_t *wimg = static_cast<uint8_t *>(workspace) + pooled_bytes(b, m);
-        int rc = detector_rows_tc(static_cast<long long>(b) * m, n, m, radius, xyz, new_xyz, idx, packed, wimg, pooled, as_stream(stream));
+        int rc = detector_rows_tc(static_cast<long long>(b) * m, n, m, radius, xyz, new_xyz, idx, packed, image_slot(workspace, b, m, 0), pooled,
+                                  build_images, as_stream(stream));
         if (rc) return rc;
-        // the weight-image area of the workspace is recycled: the tail kernel's image is built after the row kernel ran
-        return detector_post_tc(static_cast<long long>(b) * m, pooled, packed, wimg, attention, orientation, as_stream(stream));
+        return detector_post_tc(static_cast<long long>(b) * m, pooled, packed, image_slot(workspace, b, m, 1), attention, orientation,
+                                build_images, as_stream(stream));
     }
     return fail(F3D_ERR_UNSUPPORTED, "detector_forward: precision must be 0 (fp32) or 2 (bf16x3 tensor cores)");
 }
@@ -78,16 +91,18 @@ F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radiu
         return fail(F3D_ERR_INVALID_ARGUMENT, "descriptor_forward: bad arguments");
     if (!workspace || workspace_bytes < f3d_forward_workspace_bytes(b, m, feature_dim))
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "descriptor_forward: workspace too small");
+    const bool build_images = (precision & F3D_PRECISION_IMAGES_CACHED) == 0;
+    precision &= 0xff;
     if (precision == 0)
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
                                        static_cast<float *>(workspace), features, as_stream(stream));
     if (precision == 2 && nsample == 64 && feature_dim <= 64) {  // tcgen05, bf16x3 split
         float *pooled2 = static_cast<float *>(workspace);
-        uint8_t *wimg = static_cast<uint8_t *>(workspace) + pooled_bytes(b, m);
         int rc = descriptor_rows_tc(static_cast<long long>(b) * m, n, m, radius, feature_dim, xyz, new_xyz, idx, orientation,
-                                    packed, wimg, pooled2, as_stream(stream));
+                                    packed, image_slot(workspace, b, m, 2), pooled2, build_images, as_stream(stream));
         if (rc) return rc;
-        return descriptor_post_tc(static_cast<long long>(b) * m, feature_dim, pooled2, packed, wimg, features, as_stream(stream));
+        return descriptor_post_tc(static_cast<long long>(b) * m, feature_dim, pooled2, packed, image_slot(workspace, b, m, 3), features,
+                                  build_images, as_stream(stream));
     }
     if (precision == 2)  // shapes the tensor-core kernel does not cover (nsample != 64, feature_dim 128): exact fp32 kernel
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,

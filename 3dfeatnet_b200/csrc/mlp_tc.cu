@@ -474,9 +474,9 @@ static bool g_det_time = false;
 static cudaEvent_t g_det_ev[2] = {nullptr, nullptr};
 
 int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
-                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, cudaStream_t st) {
+                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, bool build_image, cudaStream_t st) {
     if (num_clusters == 0) return 0;
-    {
+    if (build_image) {
         const int total = 128 * 64 + 256 * 128 + 640;
         det_tc_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(32), wimg);
         const int rc = check_launch("det_tc_prep_kernel");

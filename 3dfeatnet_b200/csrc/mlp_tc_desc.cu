@@ -428,9 +428,9 @@ long long *g_desc_dbg = nullptr;  // bring-up timeline buffer (f3d_debug_set_tim
 
 int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
                        const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
-                       float *pooled2, cudaStream_t st) {
+                       float *pooled2, bool build_image, cudaStream_t st) {
     if (num_clusters == 0) return 0;
-    {
+    if (build_image) {
         const int total = 128 * 32 + 2 * 128 * 64 + 320;
         desc_tc_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(feature_dim), wimg);
         const int rc = check_launch("desc_tc_prep_kernel");

@@ -353,12 +353,15 @@ static int post_num_sms() {
 size_t post_tc_weight_bytes() { return post::kDetImgBytes; }  // >= kDescImgBytes
 
 int detector_post_tc(long long nc, const float *pooled, const float *packed, uint8_t *wimg, float *attention, float *orientation,
-                     cudaStream_t st) {
+                     bool build_image, cudaStream_t st) {
     if (nc == 0) return 0;
-    const int total = 128 * 256 + 128 * 128 + 128 * 64 + 512;
-    post_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(32), 0, wimg);
-    int rc = check_launch("post_prep_kernel");
-    if (rc) return rc;
+    int rc = 0;
+    if (build_image) {
+        const int total = 128 * 256 + 128 * 128 + 128 * 64 + 512;
+        post_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(32), 0, wimg);
+        rc = check_launch("post_prep_kernel");
+        if (rc) return rc;
+    }
     cudaError_t e = cudaFuncSetAttribute(post_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(post::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "post_tc: cudaFuncSetAttribute");
     const long long ntiles = (nc + post::kTile - 1) / post::kTile;
@@ -368,12 +371,15 @@ int detector_post_tc(long long nc, const float *pooled, const float *packed, uin
 }
 
 int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, const float *packed, uint8_t *wimg, float *features,
-                       cudaStream_t st) {
+                       bool build_image, cudaStream_t st) {
     if (nc == 0) return 0;
-    const int total = 128 * 128 + 512;
-    post_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(feature_dim), 1, wimg);
-    int rc = check_launch("post_prep_kernel");
-    if (rc) return rc;
+    int rc = 0;
+    if (build_image) {
+        const int total = 128 * 128 + 512;
+        post_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(feature_dim), 1, wimg);
+        rc = check_launch("post_prep_kernel");
+        if (rc) return rc;
+    }
     cudaError_t e = cudaFuncSetAttribute(post_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(post::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "post_tc: cudaFuncSetAttribute");
     const long long ntiles = (nc + post::kTile - 1) / post::kTile;

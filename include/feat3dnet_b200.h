@@ -133,7 +133,12 @@ size_t f3d_forward_workspace_bytes(int b, int m, int feature_dim);
  * precision: 0 = fp32 CUDA-core FFMA (exact fp32 reference path);
  *            2 = tcgen05 tensor cores, "bf16x3": operands split x = hi + lo in bf16, hi*hi + hi*lo + lo*hi accumulated
  *                in fp32 (TMEM) -- ~1e-5 relative, needs nsample == 64.
- * nsample must be 8, 16, 32, 64 or 128. */
+ * nsample must be 8, 16, 32, 64 or 128.
+ * F3D_PRECISION_IMAGES_CACHED may be OR-ed into `precision`: the tensor-core kernels read the weights as bf16 hi/lo operand
+ * images that each call builds from `packed` into fixed slots of the workspace; with the flag the caller promises that the
+ * workspace still holds the images of an earlier call of the SAME function with unchanged `packed` contents and feature_dim,
+ * and the image-build kernels are skipped (weights are constants between checkpoints; results are bit-identical). */
+#define F3D_PRECISION_IMAGES_CACHED 0x100
 int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const float *xyz, const float *new_xyz,
                          const int *idx, const float *packed, float *attention, float *orientation, int precision,
                          void *workspace, size_t workspace_bytes, void *stream);
