@@ -263,8 +263,8 @@ def main():
         achieved = k_flops / (k_ms * 1e-3) / 1e12
         peak = peaks["bf16"]
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        # (profiles/r01_f_det_rows_tc_ncu_summary.txt, same batch): 21.57 MB + 0.43 MB; only valid for the default workload
-        traffic = 21.57e6 + 0.43e6 if (B, N, M, S) == (64, 16384, 512, 64) else None
+        # (profiles/r01_n_kernels_ncu_summary.md, same batch): 21.56 MB + 0.20 MB; only valid for the default workload
+        traffic = 21.56e6 + 0.20e6 if (B, N, M, S) == (64, 16384, 512, 64) else None
         roofline = dict(bound="tensor", kernel="det_rows_tc_kernel", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
                         traffic=traffic, traffic_unit="bytes of DRAM per launch (ncu)", peak_source="%s bf16 burst (MEASURED_PEAKS.json)" % peaks["source"], flops_per_launch=k_flops,
                         ms_per_launch=k_ms, executed_tensor_tflops=3 * achieved, executed_frac=3 * achieved / peak)

@@ -51,6 +51,28 @@ def test_fps_bit_exact_vs_oracle(cuda, kind, b, n, m):
     assert np.array_equal(kp, oops.gather_point(x, want))
 
 
+@pytest.mark.parametrize("case,n,m", [("more_samples_than_points", 50, 80), ("single_point", 1, 4), ("same_xy", 3000, 200),
+                                      ("outlier", 16384, 128), ("boundary", 2048, 64), ("boundary", 2049, 64), ("boundary", 4096, 64),
+                                      ("boundary", 8193, 64), ("boundary", 16384, 64), ("cluster_ragged", 49999, 96),
+                                      ("two_values", 6000, 300)])
+def test_fps_group_kernel_edge_cases(cuda, case, n, m):
+    """shapes that stress the binned / group-culled kernel: degenerate grid extents, empty groups, padded tails, the
+    2048 / 4096 / 8192 / 16384 template boundaries, a ragged last chunk of a CTA cluster, massive exact ties"""
+    ts = pkg("tf_ops.sampling.tf_sampling")
+    rng = np.random.default_rng(n * 7 + m)
+    x = rng.uniform(-30, 30, (2, n, 3)).astype(np.float32)
+    if case == "same_xy":       # one xy cell, only z differs
+        x[:, :, 0] = 1.5
+        x[:, :, 1] = -2.25
+    elif case == "outlier":     # one far point stretches the grid: almost everything lands in one cell
+        x[:, 17] = (1.0e6, -1.0e6, 3.0)
+    elif case == "two_values":  # every point is one of two locations: every round is a many-way tie
+        x[:, ::2] = x[:, :1]
+        x[:, 1::2] = x[:, 1:2]
+    got = ts.farthest_point_sample(m, T(x, cuda)).cpu().numpy()
+    assert np.array_equal(got, oops.farthest_point_sample(m, x))
+
+
 def test_fps_all_points_identical(cuda):
     """every distance ties at 0: the reference tie rule picks k=0 each round"""
     ts = pkg("tf_ops.sampling.tf_sampling")
