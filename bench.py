@@ -159,11 +159,24 @@ def run_reference(args):
                 cpu_baseline=dict(value=value, unit="keypoints/s", cores=max(cores, oops.num_threads()), kind="port",
                                   sample="%d clouds of %d points per step (of the 64-cloud batch)" % (sample, args.points)),
                 e2e=dict(value=value, unit="keypoints/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else written to fd 1 meanwhile (NCCL's version
+    banner, library chatter) has been diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the run
     if args.impl == "reference":
         return run_reference(args)
 
@@ -248,6 +261,7 @@ def main():
     sampler.join(timeout=2)
 
     if rank != 0:
+        dist.shutdown()
         return
     peaks = load_peaks()
     units = B * M * world * args.steps
@@ -320,7 +334,8 @@ def main():
         sec = min(cpu_reference_pass(cpu_xyz, cpu_params, M, S) for _ in range(2))
         line["cpu_baseline"] = dict(value=sample * M / sec, unit="keypoints/s", cores=max(cores, oops.num_threads()), kind="port",
                                     sample="%d of the %d clouds of one step (oracle C ops + PyTorch-CPU fp32 net)" % (sample, B))
-    print(json.dumps(line))
+    emit(line)
+    dist.shutdown()
 
 
 if __name__ == "__main__":
