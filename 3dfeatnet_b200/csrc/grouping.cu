@@ -269,7 +269,11 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
     }
 }
 
-// one warp per centre; dynamic shared memory: (warps per CTA) x ceil(n/32) bitmap words
+// one warp per centre; dynamic shared memory per warp: ceil(n/32) bitmap words + one SUMMARY bit per bitmap word.
+// Hits land all over the index range (~110 of 16384 at the bench shape), so reading the bitmap back word by word meant
+// 10-16 rounds of load + popc + 5-step warp scan over mostly empty words.  With the summary, lane l owns the contiguous
+// block of bitmap words [l*32*SPL, (l+1)*32*SPL) and walks only its NON-EMPTY words (3-4 of them): one warp scan of the
+// per-lane hit counts gives every lane its output offset, and ascending lane order = ascending index order.
 __global__ void __launch_bounds__(256)
 bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float4 *__restrict__ sorted,
                      const int *__restrict__ cell_start, const BqGridInfo *__restrict__ info,
@@ -277,7 +281,10 @@ bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float
     extern __shared__ unsigned bq_bitmap[];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int nwords = (n + 31) >> 5;
-    unsigned *bm = bq_bitmap + static_cast<size_t>(wl) * nwords;
+    const int spl = (((nwords + 31) >> 5) + 31) >> 5;  // summary words per lane
+    const int per_warp = nwords + 32 * spl;
+    unsigned *bm = bq_bitmap + static_cast<size_t>(wl) * per_warp;
+    unsigned *sm = bm + nwords;                        // summary word s covers bitmap words [32 s, 32 s + 32)
     const long long w = static_cast<long long>(blockIdx.x) * wpc + wl;
     if (w >= static_cast<long long>(b) * m) return;
     const int batch = static_cast<int>(w / m);
@@ -290,51 +297,60 @@ bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float
     const int *cs = cell_start + static_cast<size_t>(batch) * (kBqMaxCells + 1);
     int *row = idx + (static_cast<size_t>(batch) * m + j) * nsample;
 
-    for (int i = lane; i < nwords; i += 32) bm[i] = 0;
+    for (int i = lane; i < per_warp; i += 32) bm[i] = 0;
     __syncwarp();
     const int gx = bq_cell_coord(cx, gi.x0, gi.inv_c, gi.ncx), gy = bq_cell_coord(cy, gi.y0, gi.inv_c, gi.ncy);
     const int c0 = max(gx - 1, 0), c1 = min(gx + 1, gi.ncx - 1);
     const int r0 = max(gy - 1, 0), r1 = min(gy + 1, gi.ncy - 1);
-    int H = 0;
     if (c0 <= c1 && T > 0.0f) {
         for (int r = r0; r <= r1; ++r) {
             const int s = cs[r * gi.ncx + c0], e = cs[r * gi.ncx + c1 + 1];
-            for (int i0 = s; i0 < e; i0 += 32) {
-                const int i = i0 + lane;
-                bool hit = false;
-                if (i < e) {
-                    const float4 q = __ldg(pts + i);
-                    hit = !(sqdist_ref(cx - q.x, cy - q.y, cz - q.z) >= T);
-                    if (hit) {
-                        const int k = __float_as_int(q.w);
-                        atomicOr(&bm[k >> 5], 1u << (k & 31));
-                    }
+            for (int i = s + lane; i < e; i += 32) {
+                const float4 q = __ldg(pts + i);
+                if (!(sqdist_ref(cx - q.x, cy - q.y, cz - q.z) >= T)) {
+                    const int k = __float_as_int(q.w);
+                    atomicOr(&bm[k >> 5], 1u << (k & 31));
+                    atomicOr(&sm[k >> 10], 1u << ((k >> 5) & 31));
                 }
-                H += __popc(__ballot_sync(kFull, hit));
             }
         }
     }
     __syncwarp();
-    int cnt = 0, first = -1;
-    for (int w0 = 0; w0 < nwords && cnt < nsample && cnt < H; w0 += 32) {
-        unsigned word = (w0 + lane < nwords) ? bm[w0 + lane] : 0u;
-        const int pc = __popc(word);
-        int inc = pc;
+    // pass 1: hits owned by this lane, and its lowest hit
+    int mine = 0, low = 0x7fffffff;
+    for (int sp = 0; sp < spl; ++sp) {
+        const int s = lane * spl + sp;
+        unsigned sw = sm[s];
+        while (sw) {
+            const int wi = s * 32 + __ffs(sw) - 1;
+            sw &= sw - 1;
+            const unsigned word = bm[wi];
+            mine += __popc(word);
+            low = min(low, wi * 32 + __ffs(word) - 1);  // words are visited in ascending order: min keeps the first
+        }
+    }
+    int inc = mine;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, inc, s); if (lane >= s) inc += v; }
-        const int tot = __shfl_sync(kFull, inc, 31);
-        if (first < 0 && tot > 0) {
-            const int fl = __ffs(__ballot_sync(kFull, pc > 0)) - 1;
-            const unsigned fw = __shfl_sync(kFull, word, fl);
-            first = (w0 + fl) * 32 + __ffs(fw) - 1;
+    for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, inc, s); if (lane >= s) inc += v; }
+    const int H = __shfl_sync(kFull, inc, 31);
+    const unsigned owners = __ballot_sync(kFull, mine > 0);
+    const int first = owners ? __shfl_sync(kFull, low, __ffs(owners) - 1) : -1;
+    // pass 2: this lane's hits go to row[off ...] in ascending index order, up to nsample
+    int pos = inc - mine;
+    if (mine > 0 && pos < nsample) {
+        for (int sp = 0; sp < spl && pos < nsample; ++sp) {
+            const int s = lane * spl + sp;
+            unsigned sw = sm[s];
+            while (sw && pos < nsample) {
+                const int wi = s * 32 + __ffs(sw) - 1;
+                sw &= sw - 1;
+                unsigned word = bm[wi];
+                while (word && pos < nsample) {
+                    row[pos++] = wi * 32 + __ffs(word) - 1;
+                    word &= word - 1;
+                }
+            }
         }
-        int pos = cnt + inc - pc;
-        while (word && pos < nsample) {
-            const int bit = __ffs(word) - 1;
-            row[pos++] = (w0 + lane) * 32 + bit;
-            word &= word - 1;
-        }
-        cnt += tot;
     }
     const int cc = min(H, nsample);
     if (cc > 0)
@@ -525,7 +541,8 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
     const BqWorkspace ws = bq_workspace(b, n, workspace);
     const int nwords = (n + 31) / 32;
     const int wpc = nwords <= 1024 ? 8 : (nwords <= 4096 ? 4 : 2);
-    const size_t smem = static_cast<size_t>(wpc) * nwords * sizeof(unsigned);
+    const int spl = (((nwords + 31) / 32) + 31) / 32;  // summary words per lane (bq_grid_query_kernel)
+    const size_t smem = static_cast<size_t>(wpc) * (nwords + 32 * spl) * sizeof(unsigned);
     cudaError_t e = cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "bq_grid_query: cudaFuncSetAttribute");
     bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, ws.sorted, ws.cell_start, ws.info, xyz2, idx,
