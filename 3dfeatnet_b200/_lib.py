@@ -18,6 +18,7 @@ SIGNATURES = {
     "f3d_launch_count": (_ll, []),
     "f3d_reset_launch_count": (None, []),
     "f3d_farthest_point_sample": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "f3d_farthest_point_sample_gather": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "f3d_gather_point": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_gather_point_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_cumsum": (_i, [_i, _i, _vp, _vp, _vp]),

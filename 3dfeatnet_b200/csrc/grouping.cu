@@ -20,6 +20,14 @@ constexpr int kCentresPerWarp = 4;
 constexpr int kBqWarps = 8;  // warps per CTA
 constexpr int kRefStride = 256;  // blockDim.x of the reference launch (tf_grouping_g.cu:180): centre j belongs to thread j % 256
 
+// per-cloud header of the grid path's workspace (bq_grid_build_kernel)
+struct BqGridInfo {
+    float x0, y0, inv_c;
+    int ncx, ncy;
+    int has_empty;  // set by the query kernel when a centre of this cloud has no point in its ball (the fallback kernel's cue)
+    int pad[2];
+};
+
 // PER_CENTRE_RADIUS = false: query_ball_point  (radius uniform)    tf_grouping_g.cu:3-52
 // PER_CENTRE_RADIUS = true : query_ball_point2 (radii[b,m])        tf_grouping_g.cu:56-90 (empty rows untouched)
 template <bool PER_CENTRE_RADIUS>
@@ -109,14 +117,17 @@ ball_query_kernel(int b, int n, int m, float radius, const float *__restrict__ r
 // order is the lexicographic minimum of (d, ordinal of j', k).  Runs after ball_query_kernel on the same stream.
 __global__ void __launch_bounds__(kBqWarps * 32)
 bq_fallback_kernel(int b, int n, int m, int nsample, const float *__restrict__ xyz1,
-                   const float *__restrict__ xyz2, int *__restrict__ idx, const int *__restrict__ pts_cnt) {
+                   const float *__restrict__ xyz2, int *__restrict__ idx, const int *__restrict__ pts_cnt,
+                   const BqGridInfo *__restrict__ info) {
     const int lane = threadIdx.x & 31;
-    const long long w = static_cast<long long>(blockIdx.x) * kBqWarps + (threadIdx.x >> 5);
-    if (w >= static_cast<long long>(b) * m) return;
+    // grid-stride over the centres; with the grid path's per-cloud flag a cloud without empty balls costs one load
+    for (long long w = static_cast<long long>(blockIdx.x) * kBqWarps + (threadIdx.x >> 5); w < static_cast<long long>(b) * m;
+         w += static_cast<long long>(gridDim.x) * kBqWarps) {
     const int batch = static_cast<int>(w / m);
+    if (info && info[batch].has_empty == 0) continue;
     const int j = static_cast<int>(w - static_cast<long long>(batch) * m);
     const int *cntb = pts_cnt + static_cast<size_t>(batch) * m;
-    if (cntb[j] != 0) return;
+    if (cntb[j] != 0) continue;
 
     const float *p1 = xyz1 + static_cast<size_t>(batch) * n * 3;
     const float *p2 = xyz2 + static_cast<size_t>(batch) * m * 3;
@@ -147,6 +158,7 @@ bq_fallback_kernel(int b, int n, int m, int nsample, const float *__restrict__ x
     const unsigned kmin = __reduce_min_sync(kFull, (db == dmin && lord == omin) ? static_cast<unsigned>(lk) : 0xffffffffu);
     const int fill = static_cast<int>(kmin);  // -1 (0xffffffff) when nothing was ever nearer than +inf
     for (int s = lane; s < nsample; s += 32) idxb[static_cast<size_t>(j) * nsample + s] = fill;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -162,11 +174,6 @@ bq_fallback_kernel(int b, int n, int m, int nsample, const float *__restrict__ x
 constexpr int kBqMaxCells = 4096;
 constexpr int kBqBuildThreads = 1024;
 
-struct BqGridInfo {
-    float x0, y0, inv_c;
-    int ncx, ncy;
-    int pad[3];
-};
 
 __device__ __forceinline__ int bq_cell_coord(float v, float v0, float inv_c, int nc) {
     const float t = floorf((v - v0) * inv_c);
@@ -220,7 +227,7 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
                 c *= 1.25f;
             }
             if (!(ncx * ncy <= kBqMaxCells)) { ncx = 1; ncy = 1; c = 3.0e38f; }  // non-finite extents: a single cell
-            gi.x0 = mnx; gi.y0 = mny; gi.inv_c = 1.0f / c; gi.ncx = ncx; gi.ncy = ncy;
+            gi.x0 = mnx; gi.y0 = mny; gi.inv_c = 1.0f / c; gi.ncx = ncx; gi.ncy = ncy; gi.has_empty = 0; gi.pad[0] = gi.pad[1] = 0;
             info[blockIdx.x] = gi;
         }
     }
@@ -276,7 +283,7 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
 // per-lane hit counts gives every lane its output offset, and ascending lane order = ascending index order.
 __global__ void __launch_bounds__(256)
 bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float4 *__restrict__ sorted,
-                     const int *__restrict__ cell_start, const BqGridInfo *__restrict__ info,
+                     const int *__restrict__ cell_start, BqGridInfo *info,
                      const float *__restrict__ xyz2, int *__restrict__ idx, int *__restrict__ pts_cnt) {
     extern __shared__ unsigned bq_bitmap[];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wpc = blockDim.x >> 5;
@@ -355,7 +362,10 @@ bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float
     const int cc = min(H, nsample);
     if (cc > 0)
         for (int s = cc + lane; s < nsample; s += 32) row[s] = first;
-    if (lane == 0) pts_cnt[static_cast<size_t>(batch) * m + j] = cc;
+    if (lane == 0) {
+        pts_cnt[static_cast<size_t>(batch) * m + j] = cc;
+        if (cc == 0) info[batch].has_empty = 1;  // every writer stores the same value
+    }
 }
 
 // group_point: out[b,j,k,:] = points[b,idx[b,j,k],:]  (tf_grouping_g.cu:94-111).
@@ -488,7 +498,7 @@ F3D_API int f3d_query_ball_point(int b, int n, int m, float radius, int nsample,
     if (rc) return rc;
     const long long w = static_cast<long long>(b) * m;
     if (w == 0) return 0;
-    bq_fallback_kernel<<<blocks_for(w, kBqWarps), kBqWarps * 32, 0, st>>>(b, n, m, nsample, xyz1, xyz2, idx, pts_cnt);
+    bq_fallback_kernel<<<blocks_for(w, kBqWarps), kBqWarps * 32, 0, st>>>(b, n, m, nsample, xyz1, xyz2, idx, pts_cnt, nullptr);
     return check_launch("bq_fallback_kernel");
 }
 
@@ -549,7 +559,8 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
                                                                     pts_cnt);
     int rc = check_launch("bq_grid_query_kernel");
     if (rc) return rc;
-    bq_fallback_kernel<<<blocks_for(w, kBqWarps), kBqWarps * 32, 0, st>>>(b, n, m, nsample, xyz1, xyz2, idx, pts_cnt);
+    const unsigned fb_blocks = blocks_for(w, kBqWarps);
+    bq_fallback_kernel<<<fb_blocks < 296u ? fb_blocks : 296u, kBqWarps * 32, 0, st>>>(b, n, m, nsample, xyz1, xyz2, idx, pts_cnt, ws.info);
     return check_launch("bq_fallback_kernel");
 }
 

@@ -126,7 +126,7 @@ struct FpsWin {  // double-buffered per-warp winners: (distance bits, tie code <
 
 template <int W, int G, int CL>
 __global__ void __launch_bounds__(W * 32, 1)
-fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restrict__ out) {
+fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restrict__ out, float *__restrict__ out_xyz) {
     constexpr int T = W * 32;
     constexpr int NP = T * 4 * G;
     constexpr int kGrid = 32, kCells = kGrid * kGrid;
@@ -156,6 +156,7 @@ fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restr
     const float *p0 = inp + static_cast<size_t>(cloud) * n_total * 3;
     const float *p = p0 + static_cast<size_t>(k_first) * 3;
     int *o = out + static_cast<size_t>(cloud) * m;
+    float *oc = out_xyz ? out_xyz + static_cast<size_t>(cloud) * m * 3 : nullptr;  // optional fused gather_point of the samples
     const int kbase = k_first >> 9;
 
     // ---- 1. xy bounding box of the chunk
@@ -272,7 +273,10 @@ fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restr
     float gthr = 3.0e38f;  // lane g: maximum running distance inside local group g (the culling threshold of that group)
 
     float ox = __ldg(p0 + 0), oy = __ldg(p0 + 1), oz = __ldg(p0 + 2);  // the first sample is point 0 (:114-116)
-    if (tid == 0 && rank == 0) o[0] = 0;
+    if (tid == 0 && rank == 0) {
+        o[0] = 0;
+        if (oc) { oc[0] = ox; oc[1] = oy; oc[2] = oz; }
+    }
     if (CL > 1) cluster_sync_all();  // every CTA of the cluster is resident before the first remote store
     int cw_d = __float_as_int(-1.0f);  // cached arg-max of this warp (uniform across its lanes): distance bits, key
     unsigned cw_key = 0u;
@@ -348,7 +352,10 @@ fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restr
             ox = wx;
             oy = wy;
             oz = wz;
-            if (tid == 0) o[j] = widx;
+            if (tid == 0) {
+                o[j] = widx;
+                if (oc) { oc[3 * j] = wx; oc[3 * j + 1] = wy; oc[3 * j + 2] = wz; }
+            }
         } else {
             // publish this CTA's winner (tie key of the GLOBAL original index) to every CTA of the cluster
             if (warp == 0 && lane < CL) {
@@ -368,7 +375,10 @@ fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restr
             ox = peers.x[par][src3];
             oy = peers.y[par][src3];
             oz = peers.z[par][src3];
-            if (tid == 0 && rank == 0) o[j] = fps_tie_key_inv(gmin);
+            if (tid == 0 && rank == 0) {
+                o[j] = fps_tie_key_inv(gmin);
+                if (oc) { oc[3 * j] = ox; oc[3 * j + 1] = oy; oc[3 * j + 2] = oz; }
+            }
         }
     }
     if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still write into its shared memory
@@ -426,13 +436,13 @@ __global__ void gather_point_kernel(int n, int m, long long total, const float *
 }
 
 template <int W, int G, int CL>
-static int launch_fps_group(int b, int n, int m, const float *inp, int *out, cudaStream_t st) {
+static int launch_fps_group(int b, int n, int m, const float *inp, int *out, float *out_xyz, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(W) * 32 * 4 * G * (3 * sizeof(float) + sizeof(unsigned short));
     cudaError_t e = cudaFuncSetAttribute(fps_group_kernel<W, G, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "fps: cudaFuncSetAttribute");
     if (CL == 1) {
-        fps_group_kernel<W, G, CL><<<b, W * 32, smem, st>>>(n, m, inp, out);
+        fps_group_kernel<W, G, CL><<<b, W * 32, smem, st>>>(n, m, inp, out, out_xyz);
         return check_launch("fps_group_kernel");
     }
     cudaLaunchConfig_t cfg = {};
@@ -447,7 +457,7 @@ static int launch_fps_group(int b, int n, int m, const float *inp, int *out, cud
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, fps_group_kernel<W, G, CL>, n, m, inp, out);
+    e = cudaLaunchKernelEx(&cfg, fps_group_kernel<W, G, CL>, n, m, inp, out, out_xyz);
     ++g_launches;
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -460,23 +470,37 @@ static int launch_fps_group(int b, int n, int m, const float *inp, int *out, cud
 
 using namespace f3d;
 
-F3D_API int f3d_farthest_point_sample(int b, int n, int m, const float *inp, float *temp, int *out, void *stream) {
+static int fps_dispatch(int b, int n, int m, const float *inp, float *temp, int *out, float *out_xyz, void *stream) {
     if (b < 0 || n <= 0 || m <= 0 || !inp || !out) return fail(F3D_ERR_INVALID_ARGUMENT, "farthest_point_sample: bad arguments");
     if (b == 0) return 0;
     cudaStream_t st = as_stream(stream);
     // 512 threads (measured: 256 threads x 16 groups 0.308 ms, 1024 threads x 4 groups 0.325 ms, 512 x 8 0.266 ms at n = 16384)
-    // 512 threads; G = groups of 128 points per warp
-    if (n <= 2048) return launch_fps_group<16, 1, 1>(b, n, m, inp, out, st);
-    if (n <= 4096) return launch_fps_group<16, 2, 1>(b, n, m, inp, out, st);
-    if (n <= 8192) return launch_fps_group<16, 4, 1>(b, n, m, inp, out, st);
-    if (n <= 16384) return launch_fps_group<16, 8, 1>(b, n, m, inp, out, st);
+    if (n <= 2048) return launch_fps_group<16, 1, 1>(b, n, m, inp, out, out_xyz, st);
+    if (n <= 4096) return launch_fps_group<16, 2, 1>(b, n, m, inp, out, out_xyz, st);
+    if (n <= 8192) return launch_fps_group<16, 4, 1>(b, n, m, inp, out, out_xyz, st);
+    if (n <= 16384) return launch_fps_group<16, 8, 1>(b, n, m, inp, out, out_xyz, st);
     // larger clouds: a cluster of 2 / 4 / 8 CTAs per cloud, 16384 points each (KITTI-shape scans, 131072 points)
-    if (n <= 2 * 16384) return launch_fps_group<16, 8, 2>(b, n, m, inp, out, st);
-    if (n <= 4 * 16384) return launch_fps_group<16, 8, 4>(b, n, m, inp, out, st);
-    if (n <= 8 * 16384) return launch_fps_group<16, 8, 8>(b, n, m, inp, out, st);
+    if (n <= 2 * 16384) return launch_fps_group<16, 8, 2>(b, n, m, inp, out, out_xyz, st);
+    if (n <= 4 * 16384) return launch_fps_group<16, 8, 4>(b, n, m, inp, out, out_xyz, st);
+    if (n <= 8 * 16384) return launch_fps_group<16, 8, 8>(b, n, m, inp, out, out_xyz, st);
     if (!temp) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "farthest_point_sample: n > 131072 needs temp of b*n floats");
     fps_global_kernel<<<b, kFpsThreads, 0, st>>>(n, m, inp, temp, out);
-    return check_launch("fps_global_kernel");
+    int rc = check_launch("fps_global_kernel");
+    if (rc || !out_xyz) return rc;
+    const long long total = 3LL * b * m;
+    gather_point_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(n, m, total, inp, out, out_xyz);
+    return check_launch("gather_point_kernel");
+}
+
+F3D_API int f3d_farthest_point_sample(int b, int n, int m, const float *inp, float *temp, int *out, void *stream) {
+    return fps_dispatch(b, n, m, inp, temp, out, nullptr, stream);
+}
+
+// farthest_point_sample + gather_point of the samples in one launch (sample_points, models/pointnet_common.py:14-29): the
+// kernel already holds the winner's coordinates each round, so new_xyz costs three more stores and no second kernel.
+F3D_API int f3d_farthest_point_sample_gather(int b, int n, int m, const float *inp, float *temp, int *out, float *new_xyz, void *stream) {
+    if (!new_xyz) return fail(F3D_ERR_INVALID_ARGUMENT, "farthest_point_sample_gather: new_xyz is NULL");
+    return fps_dispatch(b, n, m, inp, temp, out, new_xyz, stream);
 }
 
 F3D_API int f3d_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream) {

@@ -85,9 +85,11 @@ class DetectDescribePipeline:
             with torch.cuda.stream(self._side):
                 _lib.check(L.f3d_ball_grid_build(B, N, self.radius, p(xyz_buf), p(self.bq_ws), self.bq_ws_bytes, _lib.stream()),
                            "ball_grid_build")
-        _lib.check(L.f3d_farthest_point_sample(B, N, M, p(xyz_buf), p(self.fps_temp), p(self.fps_idx), st), "fps")
+        # sample_points (pointnet_common.py:14-29) = FPS + gather_point of the samples: one launch (the FPS kernel holds the
+        # winner's coordinates each round); the "gather" stage of the per-stage timing is therefore empty
+        _lib.check(L.f3d_farthest_point_sample_gather(B, N, M, p(xyz_buf), p(self.fps_temp), p(self.fps_idx), p(self.keypoints), st),
+                   "fps+gather")
         mark()
-        _lib.check(L.f3d_gather_point(B, N, M, p(xyz_buf), p(self.fps_idx), p(self.keypoints), st), "gather_point")
         mark()
         if fork:
             cur.wait_stream(self._side)

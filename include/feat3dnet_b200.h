@@ -42,6 +42,9 @@ void f3d_reset_launch_count(void);
  * compatibility and ignored (may be NULL) for n <= 131072: running distances live in registers (one CTA per cloud up
  * to 16384 points, a cluster of 2/4/8 CTAs beyond).  Only n > 131072 uses it, as a (b,n) float scratch. */
 int f3d_farthest_point_sample(int b, int n, int m, const float *inp, float *temp, int *out, void *stream);
+/* The same plus gather_point of the samples (sample_points, models/pointnet_common.py:14-29) in the same launch:
+ * new_xyz (b,m,3) = inp[b, out[b,j], :] -- identical values to f3d_gather_point on the returned indices. */
+int f3d_farthest_point_sample_gather(int b, int n, int m, const float *inp, float *temp, int *out, float *new_xyz, void *stream);
 
 /* gatherpointLauncher(b,n,m,inp,idx,out)  tf_sampling_g.cu:206-208, op tf_sampling.cpp:126-148. */
 int f3d_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream);

@@ -73,6 +73,22 @@ def test_fps_group_kernel_edge_cases(cuda, case, n, m):
     assert np.array_equal(got, oops.farthest_point_sample(m, x))
 
 
+@pytest.mark.parametrize("b,n,m", [(3, 5000, 300), (2, 16384, 512), (2, 40000, 128), (1, 140000, 20)])
+def test_fps_with_fused_gather_equals_the_two_ops(cuda, b, n, m):
+    """f3d_farthest_point_sample_gather (sample_points in one launch): same indices, new_xyz == gather_point(inp, idx) bit for bit"""
+    ts = pkg("tf_ops.sampling.tf_sampling")
+    lib_mod = pkg("_lib")
+    x = T(clouds("dups", b, n, 5 + n), cuda)
+    idx_ref = ts.farthest_point_sample(m, x)
+    kp_ref = ts.gather_point(x, idx_ref)
+    idx = torch.full((b, m), -1, dtype=torch.int32, device=cuda)
+    kp = torch.full((b, m, 3), float("nan"), device=cuda)
+    temp = torch.empty((b, n), device=cuda) if n > 131072 else None
+    lib_mod.check(lib_mod.lib().f3d_farthest_point_sample_gather(b, n, m, lib_mod.ptr(x), lib_mod.ptr(temp), lib_mod.ptr(idx), lib_mod.ptr(kp),
+                                                                 lib_mod.stream()), "fps+gather")
+    assert torch.equal(idx, idx_ref) and torch.equal(kp, kp_ref)
+
+
 def test_fps_all_points_identical(cuda):
     """every distance ties at 0: the reference tie rule picks k=0 each round"""
     ts = pkg("tf_ops.sampling.tf_sampling")
