@@ -109,3 +109,34 @@ F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radiu
                                        static_cast<float *>(workspace), features, as_stream(stream));
     return fail(F3D_ERR_UNSUPPORTED, "descriptor_forward: precision must be 0 (fp32) or 2 (bf16x3 tensor cores)");
 }
+
+// ---- output rows of inference.py ----------------------------------------------------------------------------------------
+namespace f3d {
+__global__ void pack_rows_kernel(long long rows, int feature_dim, const float *__restrict__ xyz, const float *__restrict__ attention,
+                                 const float *__restrict__ orientation, const float *__restrict__ features, float *__restrict__ out) {
+    const int cols = 5 + feature_dim;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    float v;
+    if (c < 3) v = __ldg(xyz + r * 3 + c);
+    else if (c == 3) v = __ldg(attention + r);
+    else if (c == 4) v = __ldg(orientation + r);
+    else v = __ldg(features + r * feature_dim + (c - 5));
+    out[i] = v;
+}
+}  // namespace f3d
+
+// One row [x y z | attention | orientation | descriptor] per keypoint: the layout the host side of the end-to-end path copies
+// back in one transfer (inference.py:174-177 writes [xyz | descriptor] rows from the same fields).
+F3D_API int f3d_pack_rows(long long rows, int feature_dim, const float *xyz, const float *attention, const float *orientation,
+                          const float *features, float *out, void *stream) {
+    if (rows < 0 || feature_dim <= 0 || !xyz || !attention || !orientation || !features || !out)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "pack_rows: bad arguments");
+    const long long total = rows * (5 + feature_dim);
+    if (total == 0) return 0;
+    pack_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(rows, feature_dim, xyz, attention, orientation,
+                                                                                                  features, out);
+    return check_launch("pack_rows_kernel");
+}

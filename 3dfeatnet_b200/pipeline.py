@@ -153,21 +153,15 @@ class DetectDescribePipeline:
         pinned host memory (self.h_out).  Asynchronous on the current stream; the caller synchronises."""
         self.xyz.copy_(self.h_xyz, non_blocking=True)
         self.step()
-        F = self.F
-        self.d_out[:, :, 0:3] = self.keypoints
-        self.d_out[:, :, 3] = self.attention
-        self.d_out[:, :, 4] = self.orientation
-        self.d_out[:, :, 5:5 + F] = self.features
+        self._pack(self.d_out)
         self.h_out.copy_(self.d_out, non_blocking=True)
         return self.h_out
 
     # ---- overlapped end-to-end loop: H2D of step i+1 and D2H of step i-1 run under the compute of step i ------------
     def _pack(self, d_out):
-        F = self.F
-        d_out[:, :, 0:3] = self.keypoints
-        d_out[:, :, 3] = self.attention
-        d_out[:, :, 4] = self.orientation
-        d_out[:, :, 5:5 + F] = self.features
+        p = _lib.ptr
+        _lib.check(self.L.f3d_pack_rows(self.B * self.M, self.F, p(self.keypoints), p(self.attention), p(self.orientation),
+                                        p(self.features), p(d_out), _lib.stream()), "pack_rows")
 
     def _host_pipe(self):
         if self._hp is None:

@@ -223,6 +223,12 @@ int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa, const f
 int f3d_adam_step(int num_records, const void *records, long long max_n, float lr, float beta1, float beta2, float eps,
                   long long step, float grad_scale, long long *step_dev, void *stream);
 
+/* One output row [x y z | attention | orientation | descriptor] per keypoint (rows x (5 + feature_dim) floats): the packed
+ * result the end-to-end path copies to the host in one transfer; inference.py:174-177 writes its [xyz | descriptor] file
+ * rows from the same fields. */
+int f3d_pack_rows(long long rows, int feature_dim, const float *xyz, const float *attention, const float *orientation,
+                  const float *features, float *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Registration: the MATLAB evaluation step of the reference on the device.
  *
