@@ -8,7 +8,7 @@
 // streamed through a 28 KB L1).  Here a tile is 64 clusters = the N axis of every MMA; the weights (bf16 hi/lo) are copied
 // ONCE per CTA into tensor memory (tcgen05.cp) and every layer is D[channel x cluster] = W^T (TMEM) * X^T (shared memory),
 // the same D^T = W^T X^T formulation as the row kernels: an epilogue thread owns one output channel of all 64 clusters,
-// adds its bias, applies ReLU and writes the next operand K-major.  The per-cluster heads (3 rows of a padded 128-row
+// adds its bias, applies ReLU and writes the next operand cluster-contiguous (MN-major, 16-byte stores).  The per-cluster heads (3 rows of a padded 128-row
 // weight) and the l2-normalisation need all channels of one cluster: the accumulator goes through a small shared-memory
 // transpose and one thread per cluster finishes (softplus / atan2 / rsqrt).
 // Phases of a tile are sequential (__syncthreads + one mbarrier for MMA completion): at 3.5 tiles per SM the kernel is
@@ -29,13 +29,18 @@ constexpr int kThreads = 256;
 constexpr uint32_t kSbo = 128;
 constexpr uint32_t kLboW = 128 * 16;       // weight images: 128 rows per K chunk
 constexpr uint32_t kLboIn = kTile * 16;    // first operand: written 16 B per thread
-constexpr uint32_t kLboX = kTile * 16 + 16;  // later operands: 2-byte epilogue stores, padded against bank conflicts
+// later operands are written by the epilogues (thread = channel, 32 clusters) CLUSTER-contiguous = MN-major: 16-byte stores
+constexpr uint32_t kLboX = 128;              // K groups of 8 channels
+constexpr uint32_t kSboX2 = 16 * 128;        // groups of 8 clusters, 128 channels (layer 2 operand)
+constexpr uint32_t kSboX3 = 8 * 128;         // groups of 8 clusters, 64 channels (layer 3 operand)
+constexpr uint32_t kX2Split = (kTile / 8) * kSboX2;  // 16 KB
+constexpr uint32_t kX3Split = (kTile / 8) * kSboX3;  // 8 KB
 constexpr uint32_t kStage = 64 * 1024;     // staging buffer: weight pieces at start-up, then the first operand of each tile
 // shared memory map
 constexpr uint32_t kOffStage = 0;
-constexpr uint32_t kOffX2 = kOffStage + kStage;            // operand of layer 2: [split 2][chunk 16] x kLboX
-constexpr uint32_t kOffX3 = kOffX2 + 2 * 16 * kLboX;       // operand of layer 3: [split 2][chunk 8] x kLboX
-constexpr uint32_t kOffOut = kOffX3 + 2 * 8 * kLboX;       // fp32 [128][kTile + 1] accumulator transpose
+constexpr uint32_t kOffX2 = kOffStage + kStage;            // operand of layer 2: [split 2][cluster group 8][chunk 16][8 ch][8 clusters]
+constexpr uint32_t kOffX3 = kOffX2 + 2 * kX2Split;         // operand of layer 3: [split 2][cluster group 8][chunk 8][8 ch][8 clusters]
+constexpr uint32_t kOffOut = kOffX3 + 2 * kX3Split;        // fp32 [128][kTile + 1] accumulator transpose
 constexpr uint32_t kOffBias = kOffOut + 128 * (kTile + 1) * 4;  // fp32 [512]
 constexpr uint32_t kOffBars = kOffBias + 512 * 4;
 constexpr uint32_t kSmemBytes = kOffBars + 64;
@@ -84,14 +89,14 @@ __device__ __forceinline__ void post_build_operand(uint8_t *img, uint32_t split_
 }
 
 // 3-pass MMA group: D[128 x 64] = (Whi + Wlo) (TMEM) * (Xhi + Xlo)^T (shared), dropping lo*lo.  One elected lane.
-__device__ __forceinline__ void post_mma(uint32_t d, uint32_t w_hi, uint32_t w_lo, uint32_t x_hi, uint32_t x_lo, uint32_t lbo, int ksteps,
-                                         uint32_t idesc) {
+__device__ __forceinline__ void post_mma(uint32_t d, uint32_t w_hi, uint32_t w_lo, uint32_t x_hi, uint32_t x_lo, uint32_t lbo, uint32_t sbo,
+                                         int ksteps, uint32_t idesc) {
     uint32_t acc = 0;
     for (int pass = 0; pass < 3; ++pass) {
         const uint32_t wa = pass == 2 ? w_lo : w_hi;
         const uint32_t xb = pass == 1 ? x_lo : x_hi;
         for (int k = 0; k < ksteps; ++k) {
-            umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * lbo, lbo, post::kSbo), idesc, acc);
+            umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * lbo, lbo, sbo), idesc, acc);
             acc = 1;
         }
     }
@@ -103,17 +108,29 @@ __device__ __forceinline__ void post_load_acc(uint32_t tmem_base, int q, int col
     tmem_ld_wait();
 }
 
-// bias (+ReLU) and hi/lo split of 32 accumulator values, stored K-major as the next layer's operand
+// bias (+ReLU) and hi/lo split of 32 accumulator values (this thread's channel, clusters col0..col0+31), stored
+// cluster-contiguous (MN-major) as the next layer's operand: 8 consecutive clusters of a channel are 16 contiguous bytes
 template <bool RELU>
-__device__ __forceinline__ void post_store_operand(uint8_t *x, uint32_t split_bytes, int ch, int col0, const uint32_t (&r)[32], float bias) {
-    uint8_t *base = x + (ch >> 3) * post::kLboX + (ch & 7) * 2;
+__device__ __forceinline__ void post_store_operand(uint8_t *x, uint32_t split_bytes, uint32_t sbo, int ch, int col0, const uint32_t (&r)[32],
+                                                   float bias) {
+    uint8_t *base = x + (col0 >> 3) * sbo + (ch >> 3) * post::kLboX + (ch & 7) * 16;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float v = __uint_as_float(r[j]) + bias;
-        if (RELU) v = fmaxf(v, 0.0f);
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        *reinterpret_cast<__nv_bfloat16 *>(base + (col0 + j) * 16) = h;
-        *reinterpret_cast<__nv_bfloat16 *>(base + split_bytes + (col0 + j) * 16) = __float2bfloat16_rn(v - __bfloat162float(h));
+    for (int g = 0; g < 4; ++g) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float va = __uint_as_float(r[g * 8 + 2 * j]) + bias, vb = __uint_as_float(r[g * 8 + 2 * j + 1]) + bias;
+            if (RELU) {
+                va = fmaxf(va, 0.0f);
+                vb = fmaxf(vb, 0.0f);
+            }
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
+            hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
+            lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
+        }
+        *reinterpret_cast<uint4 *>(base + g * sbo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(base + split_bytes + g * sbo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -206,7 +223,7 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             tcgen05_fence_after();
             if (elect_one()) {
                 post_mma(tmem_base + kTmemD, tmem_base + 0, tmem_base + (MODE == 0 ? 128 : 64), sbase + kOffStage, sbase + kOffStage + kSplit1,
-                         kLboIn, K1 / 16, idesc);
+                         kLboIn, kSbo, K1 / 16, idesc);
                 umma_commit(bar_m);
             }
             __syncwarp();
@@ -217,7 +234,7 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
         uint32_t r[32];
         post_load_acc(tmem_base, q, col0, r);
         if (MODE == 0) {
-            post_store_operand<true>(smem + kOffX2, 16 * kLboX, ch, col0, r, bias[ch]);  // conv_post_0: 128 channels, ReLU
+            post_store_operand<true>(smem + kOffX2, kX2Split, kSboX2, ch, col0, r, bias[ch]);  // conv_post_0: 128 channels, ReLU
             tcgen05_fence_before();
             fence_proxy_async_smem();
             __syncthreads();
@@ -225,7 +242,8 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             if (warp == 0) {
                 tcgen05_fence_after();
                 if (elect_one()) {
-                    post_mma(tmem_base + kTmemD, tmem_base + 256, tmem_base + 320, sbase + kOffX2, sbase + kOffX2 + 16 * kLboX, kLboX, 8, idesc);
+                    post_mma(tmem_base + kTmemD, tmem_base + 256, tmem_base + 320, sbase + kOffX2, sbase + kOffX2 + kX2Split, kLboX, kSboX2, 8,
+                             idesc | kIdescBMnMajor);
                     umma_commit(bar_m);
                 }
                 __syncwarp();
@@ -234,7 +252,7 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             mpar ^= 1;
             tcgen05_fence_after();
             post_load_acc(tmem_base, q, col0, r);
-            if (q < 2) post_store_operand<true>(smem + kOffX3, 8 * kLboX, ch, col0, r, bias[128 + ch]);
+            if (q < 2) post_store_operand<true>(smem + kOffX3, kX3Split, kSboX3, ch, col0, r, bias[128 + ch]);
             tcgen05_fence_before();
             fence_proxy_async_smem();
             __syncthreads();
@@ -242,7 +260,8 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             if (warp == 0) {
                 tcgen05_fence_after();
                 if (elect_one()) {
-                    post_mma(tmem_base + kTmemD, tmem_base + 384, tmem_base + 416, sbase + kOffX3, sbase + kOffX3 + 8 * kLboX, kLboX, 4, idesc);
+                    post_mma(tmem_base + kTmemD, tmem_base + 384, tmem_base + 416, sbase + kOffX3, sbase + kOffX3 + kX3Split, kLboX, kSboX3, 4,
+                             idesc | kIdescBMnMajor);
                     umma_commit(bar_m);
                 }
                 __syncwarp();
