@@ -184,3 +184,31 @@ def test_validate_fp_rate_matches_oracle(cuda, tmp_path):
     assert np.abs(d_gpu - d_ref).max() < 1e-4, "descriptor distances differ from the oracle: %.3e" % np.abs(d_gpu - d_ref).max()
     fp_ref = val.fp_rate_at_95_recall([d_ref[i] for i in range(n_pairs) if gts[i][1] == 1], [d_ref[i] for i in range(n_pairs) if gts[i][1] == 0])
     assert fp == fp_ref and 0.0 <= fp <= 1.0
+
+
+def test_cached_weight_images_and_packed_rows(cuda):
+    """F3D_PRECISION_IMAGES_CACHED skips the image builds without changing a bit; f3d_pack_rows lays out
+    [xyz | attention | orientation | descriptor] rows; the pipeline's forked grid build equals the single-call ball query"""
+    pm, lib_mod, tg = pkg("pipeline"), pkg("_lib"), pkg("tf_ops.grouping.tf_grouping")
+    xyz = torch.as_tensor(pkg("synth").make_batch(3, 4096, seed0=77)).to(cuda)
+    params = onet.init_params(seed=8, randomize_bn=True)
+    pipe = pm.DetectDescribePipeline(3, 4096, weights=params, num_clusters=160, precision="bf16x3", device=cuda)
+    first = {k: v.clone() for k, v in pipe.run(xyz).items()}       # pass 1: builds the images
+    n_first = pipe.launches_per_step
+    second = {k: v.clone() for k, v in pipe.run(xyz).items()}      # pass 2: images cached
+    assert pipe.launches_per_step == n_first - 4
+    third = pipe.run(xyz)                                          # steady state (graph or eager)
+    for k in first:
+        assert torch.equal(first[k], second[k]) and torch.equal(first[k], third[k]), k
+    idx, cnt = tg.query_ball_point(2.0, 64, xyz, first["xyz"])
+    assert torch.equal(idx, first["idx"]) and torch.equal(cnt, first["pts_cnt"])
+    rows = torch.empty((3, 160, 5 + 32), device=cuda)
+    L = lib_mod.lib()
+    lib_mod.check(L.f3d_pack_rows(3 * 160, 32, lib_mod.ptr(first["xyz"]), lib_mod.ptr(first["attention"]), lib_mod.ptr(first["orientation"]),
+                                  lib_mod.ptr(first["features"]), lib_mod.ptr(rows), lib_mod.stream()), "pack_rows")
+    want = torch.cat([first["xyz"], first["attention"][..., None], first["orientation"][..., None], first["features"]], dim=2)
+    assert torch.equal(rows, want)
+    pipe.h_xyz.copy_(xyz.cpu())
+    host = pipe.step_host()
+    torch.cuda.synchronize()
+    assert torch.equal(host, want.cpu())
