@@ -144,6 +144,142 @@ __global__ void segmented_sum_kernel(long long total, int c, unsigned sentinel, 
     out[static_cast<size_t>(q) * c + l] = acc;
 }
 
+// ---- one CTA per cloud: deterministic scatter-add without a global sort --------------------------------------------------
+// For n <= 16384 points and L <= 65535 slots per cloud everything but the slot list fits one SM's shared memory:
+//   1. count the slots of every point, separately for kScSeg contiguous SEGMENTS of the slot range (shared-memory atomics on
+//      16-bit counters packed two per word; the counts do not depend on the order of the atomics),
+//   2. block scan -> for every (segment, point) the first position of its slots in the cloud's CSR list,
+//   3. placement: warp q walks segment q 32 slots at a time IN ORDER; match_any groups the lanes that hit the same point, the
+//      group leader advances the (segment, point) cursor, lane order gives the rank: the list of every point is in ascending
+//      slot order by construction (a stable counting sort whose only serial part is 4 warps x L/128 steps),
+//   4. (second kernel, whole GPU) one thread per (point, channel) adds its rows in list order = ascending slot order: no atomics on
+//      floats, bit-reproducible, equal to the reference's CPU statement (test/query_ball_point.cpp:68-84); points without slots get
+//      their zero here.
+// Two launches instead of eleven (keys, 3 x {histogram, scan, scatter}, memset, segmented sum).
+constexpr int kScThreads = 512;
+constexpr int kScSeg = 4;  // placement warps = slot segments; two 16-bit counters per 32-bit word
+
+__global__ void __launch_bounds__(kScThreads, 1)
+scatter_cloud_kernel(int n, int L, const int *__restrict__ idx, unsigned short *__restrict__ lists, unsigned short *__restrict__ offs) {
+    extern __shared__ unsigned sc_smem[];
+    unsigned *cnt = sc_smem;                                                  // [kScSeg / 2][n]: (segment 2h | segment 2h+1 << 16)
+    unsigned short *off = reinterpret_cast<unsigned short *>(cnt + (kScSeg / 2) * n);  // [n + 1]
+    __shared__ unsigned warp_tot[kScThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const int *ix = idx + static_cast<size_t>(cloud) * L;
+    unsigned short *list = lists + static_cast<size_t>(cloud) * L;
+    const int seg_len = ((L + kScSeg - 1) / kScSeg + 31) / 32 * 32;  // slots per segment, a multiple of 32
+
+    for (int i = tid; i < (kScSeg / 2) * n; i += kScThreads) cnt[i] = 0u;
+    __syncthreads();
+    // 1. counts
+    for (int s = tid; s < L; s += kScThreads) {
+        const int p = ix[s];
+        if (p >= 0 && p < n) {
+            const int q = s / seg_len;
+            atomicAdd(&cnt[(q >> 1) * n + p], 1u << (16 * (q & 1)));
+        }
+    }
+    __syncthreads();
+    // 2. exclusive scan over the points, counts -> first positions.  Warp w owns a contiguous block of points and reads it 32
+    //    consecutive points at a time (conflict-free); pass A gives the warp totals, pass B the positions.
+    constexpr int kWarps = kScThreads / 32;
+    const int rows = ((n + kWarps - 1) / kWarps + 31) / 32;  // 32-point rows per warp
+    const int wbase = warp * rows * 32;
+    auto total_of = [&](int p) -> unsigned {
+        unsigned t = 0;
+        if (p < n) {
+#pragma unroll
+            for (int h = 0; h < kScSeg / 2; ++h) {
+                const unsigned w = cnt[h * n + p];
+                t += (w & 0xffffu) + (w >> 16);
+            }
+        }
+        return t;
+    };
+    unsigned wsum = 0;
+    for (int r = 0; r < rows; ++r) wsum += total_of(wbase + r * 32 + lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(kFull, wsum, o);
+    if (lane == 0) warp_tot[warp] = wsum;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned w = lane < kWarps ? warp_tot[lane] : 0u;
+        unsigned winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(kFull, winc, o); if (lane >= o) winc += v; }
+        if (lane < kWarps) warp_tot[lane] = winc - w;
+        if (lane == kWarps - 1) off[n] = static_cast<unsigned short>(winc);  // number of valid slots
+    }
+    __syncthreads();
+    unsigned carry = warp_tot[warp];
+    for (int r = 0; r < rows; ++r) {
+        const int p = wbase + r * 32 + lane;
+        const unsigned t = total_of(p);
+        unsigned inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+        unsigned run = carry + inc - t;
+        carry += __shfl_sync(kFull, inc, 31);
+        if (p < n) {
+            off[p] = static_cast<unsigned short>(run);
+#pragma unroll
+            for (int h = 0; h < kScSeg / 2; ++h) {
+                const unsigned w = cnt[h * n + p];
+                const unsigned a = run, b2 = run + (w & 0xffffu);
+                run = b2 + (w >> 16);
+                cnt[h * n + p] = a | (b2 << 16);
+            }
+        }
+    }
+    __syncthreads();
+    // 3. stable placement: warp q walks segment q in slot order
+    if (warp < kScSeg) {
+        const int s_begin = warp * seg_len, s_end = min(s_begin + seg_len, L);
+        const unsigned lt = lanemask_lt();
+        const int sh = 16 * (warp & 1);
+        unsigned *cw = cnt + (warp >> 1) * n;
+        int pnext = s_begin + lane < s_end ? ix[s_begin + lane] : -1;
+        for (int s0 = s_begin; s0 < s_end; s0 += 32) {
+            const int s = s0 + lane;
+            int p = pnext;
+            pnext = s + 32 < s_end ? ix[s + 32] : -1;  // the next chunk's indices are in flight during this chunk's ranking
+            const bool valid = p >= 0 && p < n;
+            if (!valid) p = -1 - lane;  // a private value: no peers
+            const unsigned peers = __match_any_sync(kFull, p);
+            const int leader = __ffs(peers) - 1;
+            const int rank = __popc(peers & lt);
+            unsigned base = 0;
+            if (valid && lane == leader) base = (atomicAdd(&cw[p], static_cast<unsigned>(__popc(peers)) << sh) >> sh) & 0xffffu;
+            base = __shfl_sync(kFull, base, leader);
+            if (valid) list[base + rank] = static_cast<unsigned short>(s);
+        }
+    }
+    // the first positions (off) go to global memory for the summation kernel; `off` was final before the placement started
+    unsigned short *og = offs + static_cast<size_t>(cloud) * (n + 1);
+    for (int i = tid; i <= n; i += kScThreads) og[i] = off[i];
+}
+
+// 4. one thread per (cloud, point, channel): adds the rows of the point's list in list order = ascending slot order
+__global__ void __launch_bounds__(256)
+scatter_sum_kernel(long long total, int n, int c, int L, const unsigned short *__restrict__ lists, const unsigned short *__restrict__ offs,
+                   const float *__restrict__ grad, float *__restrict__ out) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long bp = t / c;  // cloud * n + point
+    const int ch = static_cast<int>(t - bp * c);
+    const long long cloud = bp / n;
+    const int p = static_cast<int>(bp - cloud * n);
+    const unsigned short *o = offs + cloud * (n + 1) + p;
+    const int beg = o[0], end = o[1];
+    const unsigned short *list = lists + cloud * L;
+    const float *g = grad + cloud * L * c + ch;
+    float acc = 0.0f;
+    for (int r = beg; r < end; ++r) acc += __ldg(g + static_cast<size_t>(list[r]) * c);
+    out[t] = acc;
+}
+
 static inline unsigned blocks_for(long long total, int per_block) {
     return static_cast<unsigned>((total + per_block - 1) / per_block);
 }
@@ -182,6 +318,21 @@ static int scatter_add_sorted(int b, int n, int c, long long L, const float *gra
     }
     if (!workspace || workspace_bytes < f3d_scatter_workspace_bytes(total))
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "scatter-add: workspace too small");
+    const size_t cloud_path_bytes = (static_cast<size_t>((total + 7) & ~7LL) + static_cast<size_t>(b) * (n + 1)) * sizeof(unsigned short);
+    if (n <= 16384 && L <= 65535 && workspace_bytes >= cloud_path_bytes) {
+        // one CTA per cloud builds the CSR lists, then a grid-wide ordered sum (see scatter_cloud_kernel); a workspace sized by
+        // f3d_scatter_workspace_bytes always suffices unless the clouds have far more points than slots (then: the sort below)
+        const size_t smem = static_cast<size_t>(kScSeg / 2) * n * sizeof(unsigned) + (static_cast<size_t>(n) + 2) * sizeof(unsigned short);
+        cudaError_t e = cudaFuncSetAttribute(scatter_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "scatter-add: cudaFuncSetAttribute");
+        unsigned short *lists = static_cast<unsigned short *>(workspace);                 // b x L
+        unsigned short *offs = lists + ((total + 7) & ~7LL);                              // b x (n + 1)
+        scatter_cloud_kernel<<<b, kScThreads, smem, st>>>(n, static_cast<int>(L), idx, lists, offs);
+        int rc = check_launch("scatter_cloud_kernel");
+        if (rc) return rc;
+        scatter_sum_kernel<<<blocks_for(out_total, 256), 256, 0, st>>>(out_total, n, c, static_cast<int>(L), lists, offs, grad, out);
+        return check_launch("scatter_sum_kernel");
+    }
     unsigned *ka = static_cast<unsigned *>(workspace);
     unsigned *va = ka + total;
     unsigned *kb = va + total;
@@ -208,7 +359,7 @@ using namespace f3d;
 F3D_API size_t f3d_scatter_workspace_bytes(long long num_slots) {
     if (num_slots < 0) num_slots = 0;
     const long long nblocks = (num_slots + kRsTile - 1) / kRsTile;
-    return static_cast<size_t>(num_slots) * 16 + static_cast<size_t>(nblocks) * 256 * 4 + 1024;
+    return static_cast<size_t>(num_slots) * 16 + static_cast<size_t>(nblocks) * 256 * 4 + 1024;  // the per-cloud path needs 2 B per slot + 2 B per point
 }
 
 F3D_API int f3d_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g,
