@@ -3,10 +3,11 @@
 // Replaces tf_sampling_g.cu:183-192 (scatteraddpointKernel) and tf_grouping_g.cu:115-132
 // (group_point_grad_gpu).  The reference zero-fills on the host side and then issues one atomicAdd per
 // element: the fp32 sum order -- hence the result -- changes from run to run, and popular points serialise.
-// Here the (slot -> point) map is inverted once with a stable LSD radix sort of (point id, slot id) pairs,
-// and every output element is then produced by exactly one thread that adds its segment in ascending slot
-// order: no atomics, bit-reproducible, and equal to the reference's CPU statement
-// (tf_ops/grouping/test/query_ball_point.cpp:68-84), which accumulates in the same (j,k) order.
+// Here the (slot -> point) map is inverted once -- per cloud in shared memory by a stable counting sort
+// (scatter_cloud_kernel, clouds of up to 16384 points / 65535 slots), otherwise with a stable LSD radix sort
+// of (point id, slot id) pairs -- and every output element is then produced by exactly one thread that adds
+// its rows in ascending slot order: no atomics on floats, bit-reproducible, and equal to the reference's CPU
+// statement (tf_ops/grouping/test/query_ball_point.cpp:68-84), which accumulates in the same (j,k) order.
 //
 // The radix sort is hand-written (8-bit digits; per pass: block histograms -> one exclusive scan ->
 // stable scatter with warp match_any ranking).
@@ -157,42 +158,54 @@ __global__ void segmented_sum_kernel(long long total, int c, unsigned sentinel, 
 //      their zero here.
 // Two launches instead of eleven (keys, 3 x {histogram, scan, scatter}, memset, segmented sum).
 constexpr int kScThreads = 512;
-constexpr int kScSeg = 4;  // placement warps = slot segments; two 16-bit counters per 32-bit word
 
+// P CTAs per cloud (P = 1, 2 or 4): CTA `part` owns the points [part * np, (part + 1) * np) and 4 P slot segments, so the shared
+// memory stays 8 n + 2 n / P bytes while the serial part of the placement shrinks to L / (128 P) steps per warp.  Every CTA reads
+// all the indices of its cloud (L2-resident) and ignores the ones outside its point range; the number of valid slots that refer
+// to LOWER points is the base of its slice of the cloud's list.
 __global__ void __launch_bounds__(kScThreads, 1)
-scatter_cloud_kernel(int n, int L, const int *__restrict__ idx, unsigned short *__restrict__ lists, unsigned short *__restrict__ offs) {
+scatter_cloud_kernel(int n, int L, int P, const int *__restrict__ idx, unsigned short *__restrict__ lists, unsigned short *__restrict__ offs) {
     extern __shared__ unsigned sc_smem[];
-    unsigned *cnt = sc_smem;                                                  // [kScSeg / 2][n]: (segment 2h | segment 2h+1 << 16)
-    unsigned short *off = reinterpret_cast<unsigned short *>(cnt + (kScSeg / 2) * n);  // [n + 1]
+    const int seg = 4 * P;                                   // slot segments = placement warps; two 16-bit counters per word
+    const int np = ((n + P - 1) / P + 31) / 32 * 32;         // points per CTA
+    unsigned *cnt = sc_smem;                                 // [seg / 2][np]: (segment 2h | segment 2h+1 << 16)
+    unsigned short *off = reinterpret_cast<unsigned short *>(cnt + (seg / 2) * np);  // [np]
     __shared__ unsigned warp_tot[kScThreads / 32];
+    __shared__ unsigned below_tot[kScThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cloud = blockIdx.x;
+    const int cloud = blockIdx.x / P, part = blockIdx.x - cloud * P;
+    const int pb = part * np, pe = min(pb + np, n);          // this CTA's points
     const int *ix = idx + static_cast<size_t>(cloud) * L;
     unsigned short *list = lists + static_cast<size_t>(cloud) * L;
-    const int seg_len = ((L + kScSeg - 1) / kScSeg + 31) / 32 * 32;  // slots per segment, a multiple of 32
+    const int seg_len = ((L + seg - 1) / seg + 31) / 32 * 32;  // slots per segment, a multiple of 32
 
-    for (int i = tid; i < (kScSeg / 2) * n; i += kScThreads) cnt[i] = 0u;
+    for (int i = tid; i < (seg / 2) * np; i += kScThreads) cnt[i] = 0u;
     __syncthreads();
-    // 1. counts
+    // 1. counts of this CTA's points per segment; valid slots of lower points
+    unsigned below = 0;
     for (int s = tid; s < L; s += kScThreads) {
         const int p = ix[s];
-        if (p >= 0 && p < n) {
+        if (p >= pb && p < pe) {
             const int q = s / seg_len;
-            atomicAdd(&cnt[(q >> 1) * n + p], 1u << (16 * (q & 1)));
+            atomicAdd(&cnt[(q >> 1) * np + (p - pb)], 1u << (16 * (q & 1)));
+        } else if (p >= 0 && p < pb) {
+            ++below;
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(kFull, below, o);
+    if (lane == 0) below_tot[warp] = below;
     __syncthreads();
     // 2. exclusive scan over the points, counts -> first positions.  Warp w owns a contiguous block of points and reads it 32
     //    consecutive points at a time (conflict-free); pass A gives the warp totals, pass B the positions.
     constexpr int kWarps = kScThreads / 32;
-    const int rows = ((n + kWarps - 1) / kWarps + 31) / 32;  // 32-point rows per warp
+    const int rows = ((np + kWarps - 1) / kWarps + 31) / 32;  // 32-point rows per warp
     const int wbase = warp * rows * 32;
-    auto total_of = [&](int p) -> unsigned {
+    auto total_of = [&](int pl) -> unsigned {  // pl: point index local to this CTA
         unsigned t = 0;
-        if (p < n) {
-#pragma unroll
-            for (int h = 0; h < kScSeg / 2; ++h) {
-                const unsigned w = cnt[h * n + p];
+        if (pl < pe - pb) {
+            for (int h = 0; h < seg / 2; ++h) {
+                const unsigned w = cnt[h * np + pl];
                 t += (w & 0xffffu) + (w >> 16);
             }
         }
@@ -204,61 +217,65 @@ scatter_cloud_kernel(int n, int L, const int *__restrict__ idx, unsigned short *
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(kFull, wsum, o);
     if (lane == 0) warp_tot[warp] = wsum;
     __syncthreads();
+    unsigned base0 = 0;  // valid slots of lower points = first list position of this CTA
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) base0 += below_tot[w];
+    __syncthreads();
     if (warp == 0) {
         const unsigned w = lane < kWarps ? warp_tot[lane] : 0u;
         unsigned winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(kFull, winc, o); if (lane >= o) winc += v; }
         if (lane < kWarps) warp_tot[lane] = winc - w;
-        if (lane == kWarps - 1) off[n] = static_cast<unsigned short>(winc);  // number of valid slots
+        if (lane == kWarps - 1 && part == P - 1)  // end of the last point's list = number of valid slots of the cloud
+            offs[static_cast<size_t>(cloud) * (n + 1) + n] = static_cast<unsigned short>(base0 + winc);
     }
     __syncthreads();
-    unsigned carry = warp_tot[warp];
+    unsigned carry = base0 + warp_tot[warp];
     for (int r = 0; r < rows; ++r) {
-        const int p = wbase + r * 32 + lane;
-        const unsigned t = total_of(p);
+        const int pl = wbase + r * 32 + lane;
+        const unsigned t = total_of(pl);
         unsigned inc = t;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
         unsigned run = carry + inc - t;
         carry += __shfl_sync(kFull, inc, 31);
-        if (p < n) {
-            off[p] = static_cast<unsigned short>(run);
-#pragma unroll
-            for (int h = 0; h < kScSeg / 2; ++h) {
-                const unsigned w = cnt[h * n + p];
+        if (pl < pe - pb) {
+            off[pl] = static_cast<unsigned short>(run);
+            for (int h = 0; h < seg / 2; ++h) {
+                const unsigned w = cnt[h * np + pl];
                 const unsigned a = run, b2 = run + (w & 0xffffu);
                 run = b2 + (w >> 16);
-                cnt[h * n + p] = a | (b2 << 16);
+                cnt[h * np + pl] = a | (b2 << 16);
             }
         }
     }
     __syncthreads();
     // 3. stable placement: warp q walks segment q in slot order
-    if (warp < kScSeg) {
+    if (warp < seg) {
         const int s_begin = warp * seg_len, s_end = min(s_begin + seg_len, L);
         const unsigned lt = lanemask_lt();
         const int sh = 16 * (warp & 1);
-        unsigned *cw = cnt + (warp >> 1) * n;
+        unsigned *cw = cnt + (warp >> 1) * np;
         int pnext = s_begin + lane < s_end ? ix[s_begin + lane] : -1;
         for (int s0 = s_begin; s0 < s_end; s0 += 32) {
             const int s = s0 + lane;
             int p = pnext;
             pnext = s + 32 < s_end ? ix[s + 32] : -1;  // the next chunk's indices are in flight during this chunk's ranking
-            const bool valid = p >= 0 && p < n;
+            const bool valid = p >= pb && p < pe;
             if (!valid) p = -1 - lane;  // a private value: no peers
             const unsigned peers = __match_any_sync(kFull, p);
             const int leader = __ffs(peers) - 1;
             const int rank = __popc(peers & lt);
             unsigned base = 0;
-            if (valid && lane == leader) base = (atomicAdd(&cw[p], static_cast<unsigned>(__popc(peers)) << sh) >> sh) & 0xffffu;
+            if (valid && lane == leader) base = (atomicAdd(&cw[p - pb], static_cast<unsigned>(__popc(peers)) << sh) >> sh) & 0xffffu;
             base = __shfl_sync(kFull, base, leader);
             if (valid) list[base + rank] = static_cast<unsigned short>(s);
         }
     }
     // the first positions (off) go to global memory for the summation kernel; `off` was final before the placement started
-    unsigned short *og = offs + static_cast<size_t>(cloud) * (n + 1);
-    for (int i = tid; i <= n; i += kScThreads) og[i] = off[i];
+    unsigned short *og = offs + static_cast<size_t>(cloud) * (n + 1) + pb;
+    for (int i = tid; i < pe - pb; i += kScThreads) og[i] = off[i];
 }
 
 // 4. one thread per (cloud, point, channel): adds the rows of the point's list in list order = ascending slot order
@@ -322,12 +339,21 @@ static int scatter_add_sorted(int b, int n, int c, long long L, const float *gra
     if (n <= 16384 && L <= 65535 && workspace_bytes >= cloud_path_bytes) {
         // one CTA per cloud builds the CSR lists, then a grid-wide ordered sum (see scatter_cloud_kernel); a workspace sized by
         // f3d_scatter_workspace_bytes always suffices unless the clouds have far more points than slots (then: the sort below)
-        const size_t smem = static_cast<size_t>(kScSeg / 2) * n * sizeof(unsigned) + (static_cast<size_t>(n) + 2) * sizeof(unsigned short);
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            if (num_sms <= 0) num_sms = 148;
+        }
+        const int P = (4LL * b <= num_sms && n >= 4 * 1024) ? 4 : ((2LL * b <= num_sms && n >= 2 * 1024) ? 2 : 1);  // CTAs per cloud
+        const int np = ((n + P - 1) / P + 31) / 32 * 32;
+        const size_t smem = static_cast<size_t>(2 * P) * np * sizeof(unsigned) + (static_cast<size_t>(np) + 2) * sizeof(unsigned short);
         cudaError_t e = cudaFuncSetAttribute(scatter_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return fail(static_cast<int>(e), "scatter-add: cudaFuncSetAttribute");
         unsigned short *lists = static_cast<unsigned short *>(workspace);                 // b x L
         unsigned short *offs = lists + ((total + 7) & ~7LL);                              // b x (n + 1)
-        scatter_cloud_kernel<<<b, kScThreads, smem, st>>>(n, static_cast<int>(L), idx, lists, offs);
+        scatter_cloud_kernel<<<b * P, kScThreads, smem, st>>>(n, static_cast<int>(L), P, idx, lists, offs);
         int rc = check_launch("scatter_cloud_kernel");
         if (rc) return rc;
         scatter_sum_kernel<<<blocks_for(out_total, 256), 256, 0, st>>>(out_total, n, c, static_cast<int>(L), lists, offs, grad, out);
