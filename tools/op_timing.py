@@ -65,6 +65,17 @@ def main():
             assert torch.equal(fps, oref.gpu_farthest_point_sample(M, xyz))
             ridx, rcnt = oref.gpu_query_ball_point(2.0, S, xyz, kp)
             assert torch.equal(idx, ridx) and torch.equal(cnt, rcnt)
+        if name in ("C1", "C4"):  # a7: select_top_k / knn_point (unused by the model; (b,m,n) distance matrix)
+            k = 32
+            kb = min(B, 4)
+            x1, x2 = xyz[:kb].contiguous(), kp[:kb].contiguous()
+            dist = ((x2[:, :, None, :] - x1[:, None, :, :]) ** 2).sum(-1).contiguous()
+            r["select_top_k_ms"] = timeit(lambda: tg.select_top_k(k, dist), 3)
+            r["knn_point_ms"] = timeit(lambda: tg.knn_point(k, x1, x2), 3)
+            r["gather_point_grad_ms"] = timeit(lambda: ts.gather_point_grad(N, fps, kp), 3)
+            if have_ref:
+                r["ref_select_top_k_ms"] = timeit(lambda: oref.gpu_select_top_k(k, dist), 2)
+                r["ref_gather_point_grad_ms"] = timeit(lambda: oref.gpu_gather_point_grad(xyz, fps, kp), 3)
         res[name] = r
         print(name, json.dumps(r))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
