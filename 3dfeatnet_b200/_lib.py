@@ -34,6 +34,7 @@ SIGNATURES = {
     "f3d_knn_point": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_group_point": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_scatter_workspace_bytes": (_sz, [_ll]),
+    "f3d_scatter_add_workspace_bytes": (_sz, [_i, _i, _ll]),
     "f3d_group_point_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_packed_weights_floats": (_sz, [_i]),
     "f3d_packed_weights_num_blocks": (_i, []),

@@ -382,6 +382,18 @@ static int scatter_add_sorted(int b, int n, int c, long long L, const float *gra
 
 using namespace f3d;
 
+// Workspace for a scatter-add of b clouds of n points and slots_per_cloud slots: the minimum (f3d_scatter_workspace_bytes) plus,
+// when the clouds have more points than slots, the room the per-cloud path needs for its offset table.
+F3D_API size_t f3d_scatter_add_workspace_bytes(int b, int n, long long slots_per_cloud) {
+    if (b < 0) b = 0;
+    if (n < 0) n = 0;
+    if (slots_per_cloud < 0) slots_per_cloud = 0;
+    const long long total = static_cast<long long>(b) * slots_per_cloud;
+    const size_t base = f3d_scatter_workspace_bytes(total);
+    const size_t cloud = (static_cast<size_t>((total + 7) & ~7LL) + static_cast<size_t>(b) * (static_cast<size_t>(n) + 1)) * sizeof(unsigned short) + 64;
+    return base > cloud ? base : cloud;
+}
+
 F3D_API size_t f3d_scatter_workspace_bytes(long long num_slots) {
     if (num_slots < 0) num_slots = 0;
     const long long nblocks = (num_slots + kRsTile - 1) / kRsTile;

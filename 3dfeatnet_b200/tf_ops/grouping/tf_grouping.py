@@ -164,7 +164,7 @@ def group_point_grad(n, idx, grad_out):
     c = grad_out.shape[3]
     g = torch.empty((b, n, c), dtype=torch.float32, device=grad_out.device)
     L = _lib.lib()
-    ws_bytes = L.f3d_scatter_workspace_bytes(b * m * ns)
+    ws_bytes = L.f3d_scatter_add_workspace_bytes(b, n, m * ns)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=grad_out.device)
     _lib.check(L.f3d_group_point_grad(b, n, c, m, ns, _lib.ptr(grad_out), _lib.ptr(idx), _lib.ptr(g), _lib.ptr(ws),
                                       ws_bytes, _lib.stream()), "group_point_grad")

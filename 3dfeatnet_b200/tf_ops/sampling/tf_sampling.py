@@ -95,7 +95,7 @@ def gather_point_grad(n, idx, out_g):
         raise ValueError("GatherPointGrad expects (batch_size,num_result,3) out_g shape")  # :167
     inp_g = torch.empty((b, n, 3), dtype=torch.float32, device=out_g.device)
     L = _lib.lib()
-    ws_bytes = L.f3d_scatter_workspace_bytes(b * m)
+    ws_bytes = L.f3d_scatter_add_workspace_bytes(b, n, m)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=out_g.device)
     _lib.check(L.f3d_gather_point_grad(b, n, m, _lib.ptr(out_g), _lib.ptr(idx), _lib.ptr(inp_g), _lib.ptr(ws), ws_bytes,
                                        _lib.stream()), "gather_point_grad")

@@ -112,6 +112,9 @@ int f3d_group_point(int b, int n, int c, int m, int nsample, const float *points
  * (tf_ops/grouping/test/query_ball_point.cpp:68-84).
  * workspace: f3d_scatter_workspace_bytes(b*m*nsample). */
 size_t f3d_scatter_workspace_bytes(long long num_slots);
+/* Recommended size for b clouds of n points and slots_per_cloud slots each (>= the minimum above): also holds the offset
+ * table of the per-cloud path (n <= 16384, <= 65535 slots per cloud) when the clouds have more points than slots. */
+size_t f3d_scatter_add_workspace_bytes(int b, int n, long long slots_per_cloud);
 int f3d_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
                          float *grad_points, void *workspace, size_t workspace_bytes, void *stream);
 
