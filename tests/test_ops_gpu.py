@@ -216,7 +216,9 @@ def test_query_ball_point2_vs_oracle(cuda):
 
 # ------------------------------------------------------------------------------------------------ group_point (+grad)
 @pytest.mark.parametrize("b,n,c,m,ns", [(2, 4096, 3, 512, 64), (2, 1000, 64, 128, 32), (1, 333, 5, 17, 7), (1, 16384, 3, 2048, 64),
-                                        (2, 512, 16, 128, 64)])
+                                        (2, 512, 16, 128, 64),
+                                        # per-cloud scatter-add path with 4 / 2 / 1 CTAs per cloud (and the radix path above: 131072 slots)
+                                        (3, 16384, 3, 512, 64), (40, 8192, 3, 256, 64), (64, 16384, 3, 512, 64), (1, 5000, 7, 1000, 64)])
 def test_group_point_and_grad_vs_oracle(cuda, b, n, c, m, ns):
     tg = pkg("tf_ops.grouping.tf_grouping")
     rng = np.random.default_rng(n + c)
