@@ -61,32 +61,46 @@ __device__ __forceinline__ void post_cp_weights(uint32_t tmem_col, uint32_t smem
         tmem_cp_128x256b(tmem_col + k * 8, make_smem_desc(smem_addr + k * 2 * post::kLboW, post::kLboW, post::kSbo));
 }
 
-// fp32 rows (global, row stride `ld` floats) of 64 clusters -> bf16 hi/lo K-major operand image in the staging buffer
-__device__ __forceinline__ void post_build_operand(uint8_t *img, uint32_t split_bytes, const float *__restrict__ src, int ld, int K,
-                                                   long long c0, long long num_clusters) {
-    const int r = threadIdx.x & 63, cq = threadIdx.x >> 6;
-    const bool valid = c0 + r < num_clusters;
-    const float *row = src + (c0 + r) * ld;
-    for (int c = cq; c < K / 8; c += 4) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (valid) {
-            a = __ldg(reinterpret_cast<const float4 *>(row + c * 8));
-            b = __ldg(reinterpret_cast<const float4 *>(row + c * 8 + 4));
-        }
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t hi[4], lo[4];
+// fp32 rows (global, row stride `ld` floats) of 64 clusters -> bf16 hi/lo K-major operand image in the staging buffer, in two
+// halves so that the loads of the NEXT tile can fly while the tensor pipe runs layer 1 of the current one
+template <int K>
+struct PostRows {
+    static constexpr int kIter = K / 32;  // chunks of 8 channels per thread
+    float4 va[kIter], vb[kIter];
+    __device__ __forceinline__ void load(const float *__restrict__ src, int ld, long long c0, long long num_clusters) {
+        const int r = threadIdx.x & 63, cq = threadIdx.x >> 6;
+        const bool valid = c0 + r < num_clusters;
+        const float *row = src + (c0 + r) * ld;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
-            hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
-            lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
+        for (int i = 0; i < kIter; ++i) {  // all loads in flight before the first conversion (L2 latency paid once)
+            va[i] = vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                va[i] = __ldg(reinterpret_cast<const float4 *>(row + (cq + 4 * i) * 8));
+                vb[i] = __ldg(reinterpret_cast<const float4 *>(row + (cq + 4 * i) * 8 + 4));
+            }
         }
-        uint8_t *dst = img + c * post::kLboIn + r * 16;
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4 *>(dst + split_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-}
+    __device__ __forceinline__ void store(uint8_t *img, uint32_t split_bytes) const {
+        const int r = threadIdx.x & 63, cq = threadIdx.x >> 6;
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            const int c = cq + 4 * i;
+            const float4 a = va[i], b = vb[i];
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
+                hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
+                lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
+            }
+            uint8_t *dst = img + c * post::kLboIn + r * 16;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(dst + split_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+};
 
 // 3-pass MMA group: D[128 x 64] = (Whi + Wlo) (TMEM) * (Xhi + Xlo)^T (shared), dropping lo*lo.  One elected lane.
 __device__ __forceinline__ void post_mma(uint32_t d, uint32_t w_hi, uint32_t w_lo, uint32_t x_hi, uint32_t x_lo, uint32_t lbo, uint32_t sbo,
@@ -210,12 +224,17 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
 
     const uint32_t idesc = make_idesc(1, 128, kTile);
     const long long ntiles = (num_clusters + kTile - 1) / kTile;
+    // ---- first operand from HBM/L2: pooled rows -> bf16 hi/lo, K-major.  The rows of tile t+1 are requested right after layer 1 of
+    // tile t has been issued and converted into the staging buffer as soon as that MMA group has completed (its only reader).
+    constexpr int K1 = MODE == 0 ? 256 : 128;
+    constexpr uint32_t kSplit1 = (K1 / 8) * kLboIn;
+    PostRows<K1> rows;
+    if (static_cast<long long>(blockIdx.x) < ntiles) {
+        rows.load(pooled, K1, static_cast<long long>(blockIdx.x) * kTile, num_clusters);
+        rows.store(smem + kOffStage, kSplit1);
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long c0 = tile * kTile;
-        // ---- first operand from HBM/L2: pooled rows -> bf16 hi/lo, K-major
-        constexpr int K1 = MODE == 0 ? 256 : 128;
-        constexpr uint32_t kSplit1 = (K1 / 8) * kLboIn;
-        post_build_operand(smem + kOffStage, kSplit1, pooled, K1, K1, c0, num_clusters);
         fence_proxy_async_smem();
         __syncthreads();
         // ---- layer 1
@@ -228,9 +247,12 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             }
             __syncwarp();
         }
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) rows.load(pooled, K1, next * kTile, num_clusters);
         mbar_wait(bar_m, mpar);
         mpar ^= 1;
         tcgen05_fence_after();
+        if (next < ntiles) rows.store(smem + kOffStage, kSplit1);  // layer 1 was the staging buffer's only reader
         uint32_t r[32];
         post_load_acc(tmem_base, q, col0, r);
         if (MODE == 0) {
