@@ -1,6 +1,7 @@
 """Parity of the training-step CUDA ops (csrc/train.cu) with their plain statements: the attention-weighted triplet
 loss of Feat3dNet.get_loss (reference models/feat3dnet.py:315-357) forward + backward, and TF-1 Adam (:359-375)."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -310,3 +311,37 @@ def test_captured_train_step_equals_eager_steps(cuda):
     for k in net_e.weights:
         assert torch.equal(net_e.weights[k], net_g.weights[k]), k
     assert torch.equal(net_e._adam["m"], net_g._adam["m"]) and torch.equal(net_e._adam["v"], net_g._adam["v"])
+
+
+def test_train_loop_follows_the_reference_schedule(cuda, tmp_path):
+    """train.py:93-184 in miniature on an on-disk dataset: epochs end at the first short batch, checkpoints every n steps,
+    validation at step 1 and every n steps, and the saved checkpoint restores into a fresh model"""
+    trainer, dg, f3, ck = pkg("trainer"), pkg("data.datagenerator"), pkg("models.feat3dnet"), pkg("checkpoint")
+    rng = np.random.default_rng(0)
+    n_clouds, lines = 7, []
+    (tmp_path / "train").mkdir()
+    for i in range(n_clouds):
+        cloud = np.concatenate([rng.uniform(-12, 12, (1500, 3)) * [1, 1, 0.2], np.zeros((1500, 3))], axis=1).astype(np.float32)
+        cloud.tofile(str(tmp_path / "train" / ("%d.bin" % i)))
+        lines.append("%d.bin | %d | %d" % (i, (i + 1) % n_clouds, (i + 2) % n_clouds))
+    (tmp_path / "train" / "train.txt").write_text("\n".join(lines) + "\n")
+    (tmp_path / "clusters").mkdir()
+    gts = []
+    for i in range(6):
+        a = np.concatenate([rng.normal(0, 1.0, (600, 3)), np.zeros((600, 3))], axis=1).astype(np.float32)
+        b = a.copy() if i % 2 else np.concatenate([rng.normal(0, 1.0, (600, 3)) * [2, 0.5, 1], np.zeros((600, 3))], axis=1).astype(np.float32)
+        a.tofile(str(tmp_path / "clusters" / ("%d_0.bin" % i)))
+        b.tofile(str(tmp_path / "clusters" / ("%d_1.bin" % i)))
+        gts.append((i, i % 2))
+    gen = dg.DataGenerator(str(tmp_path / "train" / "train.txt"), num_cols=6, seed=1)
+    net = f3.Feat3dNet({'num_clusters': 64}, device=cuda, seed=0, precision="fp32").train_mode()
+    hist = trainer.train(net, gen, num_epochs=2, batch_size=2, num_points=1024, lr=1e-3, checkpoint_dir=str(tmp_path / "ckpt"),
+                         checkpoint_every_n_steps=3, val_folder=str(tmp_path / "clusters"), val_groundtruths=gts, validate_every_n_steps=4)
+    assert hist["steps"] == 6  # 7 clouds, batch 2: 3 full batches per epoch, the 1-cloud remainder ends the epoch
+    assert len(hist["losses"]) == 6 and all(np.isfinite(hist["losses"]))
+    assert [s for s, _ in hist["fp_rates"]] == [1, 4] and all(0.0 <= r <= 1.0 for _, r in hist["fp_rates"])
+    assert [os.path.basename(p) for p in hist["checkpoints"]] == ["checkpoint.ckpt-3.npz", "checkpoint.ckpt-6.npz"]
+    fresh = f3.Feat3dNet({'num_clusters': 64}, device=cuda, seed=9, precision="fp32")
+    ck.initialize_model(fresh, hist["checkpoints"][-1])
+    for k, v in net.weights.items():
+        assert torch.equal(fresh.weights[k].detach().float().cpu(), v.detach().float().cpu()), k
