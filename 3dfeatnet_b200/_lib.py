@@ -47,6 +47,8 @@ SIGNATURES = {
     "f3d_conv_bn_train_workspace_bytes": (_sz, [_c.c_longlong, _i, _i]),
     "f3d_conv_bn_train_forward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _vp, _sz,
                                        _vp]),
+    "f3d_conv_bn_train_forward_pooled": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _i,
+                                              _vp, _sz, _vp]),
     "f3d_conv_bn_train_backward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "f3d_maxpool_samples_forward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp]),

@@ -543,6 +543,45 @@ __global__ void maxpool_fwd_kernel(long long groups, int s, int c4, const float 
     if (inv) reinterpret_cast<float4 *>(inv)[e] = make_float4(1.0f / nx, 1.0f / ny, 1.0f / nz, 1.0f / nw);
 }
 
+// bn_apply + maxpool_fwd in one pass for a layer whose activation ONLY feeds the max-pool over the sample axis (detector conv2,
+// descriptor conv_mid): y = act(z * scale + shift) is formed on the fly with the roundings of bn_apply_kernel, so the pooled maxima and
+// tie counts are bit-identical to the two-kernel path, and the (rows, c) activation is neither written nor re-read (604 MB each way
+// for the detector's 256-channel layer at C4).  The backward recomputes y from z as well and never needed it.
+__global__ void bn_apply_pool_kernel(long long groups, int s, int c4, const float *__restrict__ z, const float *__restrict__ coef, int relu,
+                                     float *__restrict__ out, float *__restrict__ inv) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= groups * c4) return;
+    const long long g = e / c4;
+    const int cv = static_cast<int>(e - g * c4);
+    const float4 *p = reinterpret_cast<const float4 *>(z) + g * s * c4 + cv;
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(coef) + cv);
+    const float4 sh = __ldg(reinterpret_cast<const float4 *>(coef) + c4 + cv);
+    auto act = [&](float4 v) -> float4 {
+        float4 o = make_float4(__fmaf_rn(v.x, sc.x, sh.x), __fmaf_rn(v.y, sc.y, sh.y), __fmaf_rn(v.z, sc.z, sh.z), __fmaf_rn(v.w, sc.w, sh.w));
+        if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+        return o;
+    };
+    float4 m = act(__ldg(p));
+    int nx = 1, ny = 1, nz = 1, nw = 1;
+    int k = 1;
+    for (; k + 4 <= s; k += 4) {  // four independent loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(p + static_cast<size_t>(k + u) * c4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 y = act(v[u]);
+            max_count(y.x, m.x, nx); max_count(y.y, m.y, ny); max_count(y.z, m.z, nz); max_count(y.w, m.w, nw);
+        }
+    }
+    for (; k < s; ++k) {
+        const float4 y = act(__ldg(p + static_cast<size_t>(k) * c4));
+        max_count(y.x, m.x, nx); max_count(y.y, m.y, ny); max_count(y.z, m.z, nz); max_count(y.w, m.w, nw);
+    }
+    reinterpret_cast<float4 *>(out)[e] = m;
+    reinterpret_cast<float4 *>(inv)[e] = make_float4(1.0f / nx, 1.0f / ny, 1.0f / nz, 1.0f / nw);
+}
+
 // its gradient: dx = gout / (number of samples attaining the maximum) where x == max, else 0 (TensorFlow's _MinOrMaxGrad)
 __global__ void maxpool_bwd_kernel(long long groups, int s, int c4, const float *__restrict__ x, const float *__restrict__ mx,
                                    const float *__restrict__ inv, const float *__restrict__ gout, float *__restrict__ dx) {
@@ -674,16 +713,17 @@ F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int co
     return (fwd > bwd ? fwd : bwd) + 256;
 }
 
-// x (rows,cin), W (cin,cout), bias/gamma/beta (cout) -> z (rows,cout) pre-BN, y (rows,cout) post BN(+ReLU), mean/var (cout)
-// = the batch moments (population variance) the caller feeds to the EMA update.
-F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
-                                      const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
-                                      float *z, float *y, float *mean, float *var, int precision, void *workspace, size_t workspace_bytes,
-                                      void *stream) {
+// y != NULL: the (rows, cout) activation is written.  pool_s > 0 (y == NULL): only its max over groups of pool_s rows is (pooled, inv_ties).
+static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
+                                const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
+                                float *z, float *y, int pool_s, float *pooled, float *inv_ties, float *mean, float *var, int precision,
+                                void *workspace, size_t workspace_bytes, void *stream) {
     if (group_bias && (group_s <= 0 || rows % group_s != 0))
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: group_bias needs group_s > 0 dividing rows");
-    if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !y || !mean || !var)
+    if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !mean || !var)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: bad arguments");
+    if (pool_s > 0 ? (rows % pool_s != 0 || !pooled || !inv_ties) : !y)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: needs y, or pool_s dividing rows with pooled / inv_ties");
     if (precision != 0 && precision != 2) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: precision must be 0 (fp32) or 2 (bf16x3)");
     if (cout % 4 != 0) return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_forward: output channels must be a multiple of 4");
     if (!workspace || workspace_bytes < f3d_conv_bn_train_workspace_bytes(rows, cin, cout))
@@ -710,9 +750,36 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
     bn_stats_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, beta, mean, var, coef);
     rc = check_launch("bn_stats_finalize_kernel");
     if (rc) return rc;
+    if (pool_s > 0) {
+        const long long groups = rows / pool_s, np = groups * (cout / 4);
+        bn_apply_pool_kernel<<<static_cast<unsigned>((np + 127) / 128), 128, 0, st>>>(groups, pool_s, cout / 4, z, coef, relu, pooled, inv_ties);
+        return check_launch("bn_apply_pool_kernel");
+    }
     const long long n4 = rows * cout / 4;
     bn_apply_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(n4, cout, z, coef, relu, y);
     return check_launch("bn_apply_kernel");
+}
+
+// x (rows,cin), W (cin,cout), bias/gamma/beta (cout) -> z (rows,cout) pre-BN, y (rows,cout) post BN(+ReLU), mean/var (cout)
+// = the batch moments (population variance) the caller feeds to the EMA update.
+F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
+                                      const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
+                                      float *z, float *y, float *mean, float *var, int precision, void *workspace, size_t workspace_bytes,
+                                      void *stream) {
+    if (!y) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: y is NULL");
+    return conv_bn_forward_impl(rows, cin, cout, x, W, bias, group_bias, group_s, gamma, beta, relu, eps, z, y, 0, nullptr, nullptr, mean, var,
+                                precision, workspace, workspace_bytes, stream);
+}
+
+// The same layer when its activation only feeds tf.reduce_max over groups of pool_s consecutive rows (the sample axis): returns
+// pooled (rows/pool_s, cout) and inv_ties = 1 / (number of rows attaining the maximum) instead of y, which is never materialised.
+F3D_API int f3d_conv_bn_train_forward_pooled(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
+                                             const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
+                                             float *z, int pool_s, float *pooled, float *inv_ties, float *mean, float *var, int precision,
+                                             void *workspace, size_t workspace_bytes, void *stream) {
+    if (pool_s <= 0) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward_pooled: pool_s must be positive");
+    return conv_bn_forward_impl(rows, cin, cout, x, W, bias, group_bias, group_s, gamma, beta, relu, eps, z, nullptr, pool_s, pooled, inv_ties,
+                                mean, var, precision, workspace, workspace_bytes, stream);
 }
 
 // gy (rows,cout) = dL/dy.  Outputs: dx (rows,cin; NULL to skip), dW (cin,cout), db, dgamma, dbeta (cout).

@@ -27,7 +27,9 @@ def _native():
     return importlib.import_module(("3dfeatnet_b200." if __name__.split(".")[0] == "3dfeatnet_b200" else "") + "_lib")
 
 
-def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision, gbias=None, gs=0):
+def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision, gbias=None, gs=0, pool_s=0):
+    """-> (x, w, gamma, beta, z, y, mean, var) and, when pool_s > 0, (..., pooled, inv_ties) with y = None: the activation of a
+    pool-only layer is never materialised (f3d_conv_bn_train_forward_pooled)."""
     _lib = _native()
     L = _lib.lib()
     x2, w2 = x.detach().contiguous().float(), w.detach().contiguous().float()
@@ -38,9 +40,20 @@ def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision, gbias=None, gs=0
     nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
     z = torch.empty((rows, cout), dtype=torch.float32, device=x2.device)
-    y = torch.empty_like(z)
     mean = torch.empty(cout, dtype=torch.float32, device=x2.device)
     var = torch.empty_like(mean)
+    if pool_s:
+        if rows % pool_s:
+            raise ValueError("pool_s must divide the number of rows")
+        pooled = torch.empty((rows // pool_s, cout), dtype=torch.float32, device=x2.device)
+        inv = torch.empty_like(pooled)
+        _lib.check(L.f3d_conv_bn_train_forward_pooled(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2),
+                                                      _lib.ptr(gb2) if gb2 is not None else None, int(gs), _lib.ptr(g2), _lib.ptr(be2),
+                                                      int(use_relu), BN_EPS, _lib.ptr(z), int(pool_s), _lib.ptr(pooled), _lib.ptr(inv),
+                                                      _lib.ptr(mean), _lib.ptr(var), precision, _lib.ptr(ws), nbytes, _lib.stream()),
+                   "conv_bn_train_forward_pooled")
+        return x2, w2, g2, be2, z, None, mean, var, pooled, inv
+    y = torch.empty_like(z)
     _lib.check(L.f3d_conv_bn_train_forward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2),
                                            _lib.ptr(gb2) if gb2 is not None else None, int(gs), _lib.ptr(g2), _lib.ptr(be2),
                                            int(use_relu), BN_EPS, _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var),
@@ -84,7 +97,7 @@ def _max_pool_forward(x3):
 class _ConvBnTrain(torch.autograd.Function):
     """conv 1x1 + bias + batch-norm with BATCH statistics + optional ReLU as one differentiable CUDA op
     (csrc/train_layers.cu, contractions in csrc/train_tc.cu).  Returns (out, batch_mean, batch_var); the moments are not
-    differentiable outputs (they only feed the EMA shadows).  Saves x, z (pre-BN) and y for the backward.
+    differentiable outputs (they only feed the EMA shadows).  Saves x and z (pre-BN) for the backward (which recomputes y).
 
     pool_s > 0: the layer is followed by tf.reduce_max over groups of pool_s consecutive rows (the sample axis) and ONLY
     feeds that pool (detector conv2, descriptor conv_mid); out is then the pooled (rows/pool_s, cout) tensor and in the
@@ -96,15 +109,13 @@ class _ConvBnTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, use_relu, pool_s, gbias, gs):
         ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
-        saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision, gbias, gs if gbias is not None else 0)
+        saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision, gbias, gs if gbias is not None else 0, int(pool_s))
         y, mean, var = saved[5], saved[6], saved[7]
         ctx.use_relu, ctx.pool_s, ctx.gs = bool(use_relu), int(pool_s), int(gs) if gbias is not None else 0
         ctx.mark_non_differentiable(mean, var)
-        if pool_s:
-            pooled, inv = _max_pool_forward(y.view(y.shape[0] // pool_s, pool_s, y.shape[1]))
-            ctx.save_for_backward(*saved, pooled, inv)
-            return pooled, mean, var
         ctx.save_for_backward(*saved)
+        if pool_s:  # saved = (..., y = None, mean, var, pooled, inv): BN + ReLU + max-pool in one pass, no (rows, cout) activation
+            return saved[8], mean, var
         return y, mean, var
 
     @staticmethod

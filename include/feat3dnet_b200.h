@@ -185,6 +185,13 @@ int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const float *x,
                               const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
                               float *z, float *y, float *mean, float *var, int precision, void *workspace,
                               size_t workspace_bytes, void *stream);
+/* The same layer when its activation only feeds tf.reduce_max over groups of pool_s consecutive rows (the sample axis;
+ * feat3dnet.py:60,75,130): pooled (rows/pool_s, cout) and inv_ties (1 / number of rows attaining the maximum) come back
+ * instead of y, which is never materialised (bit-identical to the forward above followed by f3d_maxpool_samples_forward). */
+int f3d_conv_bn_train_forward_pooled(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
+                                     const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
+                                     float *z, int pool_s, float *pooled, float *inv_ties, float *mean, float *var, int precision,
+                                     void *workspace, size_t workspace_bytes, void *stream);
 /* The gradient TensorFlow derives for the layer above: gy = dL/dy (rows,cout) -> dx (rows,cin; NULL = not needed),
  * dW (cin,cout), db, dgamma, dbeta (cout), through the batch statistics.  cout a power of two in 16..1024; dx needs
  * cin == 3 or a multiple of 16.  pool_s > 0: the layer's output only feeds the max-pool over groups of pool_s consecutive
