@@ -409,8 +409,7 @@ class Feat3dNet:
             _lib.check(_lib.lib().f3d_adam_step(len(names), _lib.ptr(st["records"]), st["max_n"], float(lr), 0.9, 0.999, 1e-8,
                                                 st["t"], float(grad_scale), _lib.ptr(st["t_dev"]), _lib.stream()), "adam_step")
             if end_points is not None and end_points.get('bn_updates'):
-                for k, v in end_points['bn_updates'].items():
-                    self.weights[k].copy_(v)
+                _layers.apply_ema_updates(self.weights, end_points['bn_updates'])
         self.invalidate()
         return flat
 

@@ -14,6 +14,35 @@ import torch.nn.functional as F
 
 BN_EPS = 1e-3   # layers.py:271
 BN_DECAY = 0.9  # layers.py:251 (bn_decay=None everywhere in the model)
+
+
+class PendingEma(object):
+    """A moving-average update waiting for the optimiser step (layers.py:252-269: shadow <- shadow - (1 - decay)(shadow - batch)).
+    The forward only records (batch statistic, decay); apply_ema_updates() performs all of them in three multi-tensor launches
+    instead of four tiny kernels per statistic (72 per step for the 18 statistics of the model)."""
+    __slots__ = ("stat", "decay")
+
+    def __init__(self, stat, decay):
+        self.stat, self.decay = stat, float(decay)
+
+    def value(self, shadow):
+        """the updated shadow as a new tensor (the op-by-op statement)"""
+        return shadow - (1 - self.decay) * (shadow - self.stat)
+
+
+def apply_ema_updates(weights, updates):
+    """weights[k] <- weights[k] - (1 - decay)(weights[k] - batch statistic) for every k in `updates` ({name: PendingEma}), in
+    place; the arithmetic (sub, mul by the Python scalar, sub) is the op-by-op statement's, so the results are bit-identical."""
+    by_decay = {}
+    for k, u in updates.items():
+        by_decay.setdefault(u.decay, ([], []))
+        by_decay[u.decay][0].append(weights[k])
+        by_decay[u.decay][1].append(u.stat.to(weights[k].dtype))
+    with torch.no_grad():
+        for decay, (dst, src) in by_decay.items():
+            diffs = torch._foreach_sub(dst, src)
+            torch._foreach_mul_(diffs, 1 - decay)
+            torch._foreach_sub_(dst, diffs)
 FUSED_TRAINING = True  # training-mode conv+BN(+ReLU) through csrc/train_layers.cu (False: the op-by-op torch statement)
 TRAIN_PRECISION = "bf16x3"  # contractions of the training layers: "bf16x3" = tcgen05 tensor cores, "fp32" = FFMA kernels
 _PRECISION_CODE = {"fp32": 0, "bf16x3": 2}
@@ -176,8 +205,8 @@ def batch_norm_template(inputs, is_training, scope, moments_dims, bn_decay, para
         if new_stats is not None:
             decay = bn_decay if bn_decay is not None else BN_DECAY
             mm, mv = params[scope + "/moving_mean"], params[scope + "/moving_variance"]
-            new_stats[scope + "/moving_mean"] = (mm - (1 - decay) * (mm - mean)).detach()
-            new_stats[scope + "/moving_variance"] = (mv - (1 - decay) * (mv - var)).detach()
+            new_stats[scope + "/moving_mean"] = PendingEma(mean.detach(), decay)
+            new_stats[scope + "/moving_variance"] = PendingEma(var.detach(), decay)
     else:
         mean, var = params[scope + "/moving_mean"], params[scope + "/moving_variance"]
     inv = torch.rsqrt(var + BN_EPS) * gamma  # tf.nn.batch_normalization
@@ -230,8 +259,8 @@ def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', acti
         if new_stats is not None:
             decay = bn_decay if bn_decay is not None else BN_DECAY
             mm, mv = params[scope + "/bn/moving_mean"], params[scope + "/bn/moving_variance"]
-            new_stats[scope + "/bn/moving_mean"] = (mm - (1 - decay) * (mm - mean)).detach()
-            new_stats[scope + "/bn/moving_variance"] = (mv - (1 - decay) * (mv - var)).detach()
+            new_stats[scope + "/bn/moving_mean"] = PendingEma(mean.detach(), decay)
+            new_stats[scope + "/bn/moving_variance"] = PendingEma(var.detach(), decay)
         if fuse_pool:
             return y.reshape(inputs.shape[0], inputs.shape[1], 1, num_outputs)
         y = y.reshape(*inputs.shape[:-1], num_outputs)
