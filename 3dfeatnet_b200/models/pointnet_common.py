@@ -18,11 +18,23 @@ farthest_point_sample, gather_point = _ts.farthest_point_sample, _ts.gather_poin
 
 
 # ------------------------------------------------------------------------------------------------ private helpers
+_last_query = None  # (xyz, xyz._version, centres, centres._version, nsample, radius, idx, pts_cnt) of the latest ball query
+
+
 def _neighbour_indices(xyz, centres, nsample, radius, knn):
-    """(idx (B,M,S) int32, pts_cnt): ball query, or kNN where the reference sets pts_cnt to nsample ("Hack", :37/:99)."""
+    """(idx (B,M,S) int32, pts_cnt): ball query, or kNN where the reference sets pts_cnt to nsample ("Hack", :37/:99).
+    The reference runs the identical ball query twice per forward (detector :39, descriptor :102, same cloud, same centres);
+    here the second request is answered from the first (same tensor objects, unmodified since: ids and versions checked)."""
+    global _last_query
     if knn:
         return knn_point(nsample, xyz, centres)[1], nsample
-    return query_ball_point(radius, nsample, xyz, centres)
+    q = _last_query
+    if (q is not None and q[0] is xyz and q[1] == xyz._version and q[2] is centres and q[3] == centres._version
+            and q[4] == nsample and q[5] == radius):
+        return q[6], q[7]
+    idx, pts_cnt = query_ball_point(radius, nsample, xyz, centres)
+    _last_query = (xyz, xyz._version, centres, centres._version, nsample, radius, idx, pts_cnt)
+    return idx, pts_cnt
 
 
 def _local_frames(xyz, centres, idx, radius, normalize_radius):
