@@ -56,6 +56,9 @@ SIGNATURES = {
     "f3d_triplet_loss_workspace_bytes": (_sz, [_i, _i]),
     "f3d_triplet_loss": (_i, [_i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_adam_step": (_i, [_i, _vp, _c.c_longlong, _f, _f, _f, _f, _c.c_longlong, _f, _vp, _vp]),
+    "f3d_detector_heads_workspace_bytes": (_sz, [_i]),
+    "f3d_detector_heads_forward": (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "f3d_detector_heads_backward": (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_pack_rows": (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "f3d_match_descriptors": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "f3d_ransac_workspace_bytes": (_sz, [_i, _i]),

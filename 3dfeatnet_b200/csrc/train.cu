@@ -316,3 +316,146 @@ F3D_API int f3d_adam_step(int num_records, const void *records, long long max_n,
     adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
     return check_launch("adam_tick_kernel");
 }
+
+// ---- detector heads (training) --------------------------------------------------------------------------------------
+// feature_detection_module's per-cluster heads (models/feat3dnet.py:142-149): attention = softplus(h w_a + b_a),
+// orientation = atan2 of the l2-normalised (h W_o + b_o).  As torch ops they were ~30 launches per step (two cuBLAS GEMVs with
+// a 9216-long reduction for the weight gradients among them); here: one forward kernel, one backward kernel + a fixed-order
+// reduction of the per-CTA weight-gradient partials (deterministic).  One warp per row of h (k channels, k a multiple of 32).
+namespace f3d {
+constexpr int kHeadWarps = 8;
+
+__device__ __forceinline__ void heads_dots(const float *__restrict__ hrow, const float *__restrict__ wa, const float *__restrict__ wo, int k,
+                                           int lane, float &a, float &ox, float &oy) {
+    float sa = 0.f, sx = 0.f, sy = 0.f;
+    for (int c = lane; c < k; c += 32) {
+        const float v = __ldg(hrow + c);
+        sa = fmaf(v, __ldg(wa + c), sa);
+        sx = fmaf(v, __ldg(wo + 2 * c), sx);
+        sy = fmaf(v, __ldg(wo + 2 * c + 1), sy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(kFull, sa, o);
+        sx += __shfl_xor_sync(kFull, sx, o);
+        sy += __shfl_xor_sync(kFull, sy, o);
+    }
+    a = sa; ox = sx; oy = sy;
+}
+
+__global__ void __launch_bounds__(kHeadWarps * 32)
+heads_fwd_kernel(long long rows, int k, const float *__restrict__ h, const float *__restrict__ wa, const float *__restrict__ ba,
+                 const float *__restrict__ wo, const float *__restrict__ bo, float *__restrict__ attention, float *__restrict__ orientation) {
+    const int lane = threadIdx.x & 31;
+    const long long r = static_cast<long long>(blockIdx.x) * kHeadWarps + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float a, ox, oy;
+    heads_dots(h + r * k, wa, wo, k, lane, a, ox, oy);
+    if (lane == 0) {
+        a += __ldg(ba);
+        ox += __ldg(bo);
+        oy += __ldg(bo + 1);
+        attention[r] = a > 20.0f ? a : log1pf(expf(a));                       // F.softplus (beta 1, threshold 20)
+        const float inv = rsqrtf(fmaxf(ox * ox + oy * oy, 1e-8f));            // tf.nn.l2_normalize(eps = 1e-8)
+        orientation[r] = atan2f(oy * inv, ox * inv);
+    }
+}
+
+// part: [gridDim.x][3 k + 3] = per-CTA sums of {h^T da, h^T dox, h^T doy (interleaved like W_o), sum da, sum dox, sum doy}
+__global__ void __launch_bounds__(kHeadWarps * 32)
+heads_bwd_kernel(long long rows, int k, const float *__restrict__ h, const float *__restrict__ wa, const float *__restrict__ ba,
+                 const float *__restrict__ wo, const float *__restrict__ bo, const float *__restrict__ g_att, const float *__restrict__ g_ori,
+                 float *__restrict__ dh, float *__restrict__ part) {
+    extern __shared__ float hsm[];  // [kHeadWarps][3 k + 3]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = k / 32;         // channels per lane (k <= 128)
+    float aw[4] = {0, 0, 0, 0}, axw[4] = {0, 0, 0, 0}, ayw[4] = {0, 0, 0, 0};
+    float sda = 0.f, sdx = 0.f, sdy = 0.f;
+    const long long stride = static_cast<long long>(gridDim.x) * kHeadWarps;
+    for (long long r = static_cast<long long>(blockIdx.x) * kHeadWarps + warp; r < rows; r += stride) {  // fixed row -> warp map
+        const float *hrow = h + r * k;
+        float a, ox, oy;
+        heads_dots(hrow, wa, wo, k, lane, a, ox, oy);
+        a += __ldg(ba);
+        ox += __ldg(bo);
+        oy += __ldg(bo + 1);
+        const float ga = g_att ? __ldg(g_att + r) : 0.f, go = g_ori ? __ldg(g_ori + r) : 0.f;
+        const float da = ga * (a > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-a)));  // d softplus = sigmoid
+        const float ss = ox * ox + oy * oy;
+        const float is = ss > 0.f ? 1.0f / ss : 0.f;                           // d atan2(oy, ox) = (-oy, ox) / (ox^2 + oy^2)
+        const float dox = -go * oy * is, doy = go * ox * is;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= per) break;
+            const int c = lane + 32 * j;
+            const float v = __ldg(hrow + c);
+            if (dh) dh[r * k + c] = fmaf(da, __ldg(wa + c), fmaf(dox, __ldg(wo + 2 * c), doy * __ldg(wo + 2 * c + 1)));
+            aw[j] = fmaf(v, da, aw[j]);
+            axw[j] = fmaf(v, dox, axw[j]);
+            ayw[j] = fmaf(v, doy, ayw[j]);
+        }
+        sda += da; sdx += dox; sdy += doy;
+    }
+    float *mine = hsm + warp * (3 * k + 3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= per) break;
+        const int c = lane + 32 * j;
+        mine[c] = aw[j];
+        mine[k + 2 * c] = axw[j];
+        mine[k + 2 * c + 1] = ayw[j];
+    }
+    if (lane == 0) { mine[3 * k] = sda; mine[3 * k + 1] = sdx; mine[3 * k + 2] = sdy; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 3 * k + 3; e += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < kHeadWarps; ++w) s += hsm[w * (3 * k + 3) + e];  // fixed order
+        part[static_cast<size_t>(blockIdx.x) * (3 * k + 3) + e] = s;
+    }
+}
+
+__global__ void heads_reduce_kernel(int nparts, int k, const float *__restrict__ part, float *__restrict__ dwa, float *__restrict__ dba,
+                                    float *__restrict__ dwo, float *__restrict__ dbo) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * k + 3) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[static_cast<size_t>(p) * (3 * k + 3) + e];  // fixed order
+    if (e < k) dwa[e] = s;
+    else if (e < 3 * k) dwo[e - k] = s;
+    else if (e == 3 * k) dba[0] = s;
+    else dbo[e - 3 * k - 1] = s;
+}
+constexpr int kHeadParts = 296;
+}  // namespace f3d
+
+F3D_API size_t f3d_detector_heads_workspace_bytes(int k) { return static_cast<size_t>(f3d::kHeadParts) * (3 * (k > 0 ? k : 0) + 3) * sizeof(float); }
+
+F3D_API int f3d_detector_heads_forward(long long rows, int k, const float *h, const float *w_att, const float *b_att, const float *w_ori,
+                                       const float *b_ori, float *attention, float *orientation, void *stream) {
+    if (rows < 0 || k <= 0 || k % 32 || k > 128 || !h || !w_att || !b_att || !w_ori || !b_ori || !attention || !orientation)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "detector_heads_forward: bad arguments (k must be 32, 64, 96 or 128)");
+    if (rows == 0) return 0;
+    heads_fwd_kernel<<<static_cast<unsigned>((rows + kHeadWarps - 1) / kHeadWarps), kHeadWarps * 32, 0, as_stream(stream)>>>(
+        rows, k, h, w_att, b_att, w_ori, b_ori, attention, orientation);
+    return check_launch("heads_fwd_kernel");
+}
+
+// g_att / g_ori: gradients of the loss w.r.t. attention / orientation (either may be NULL = zero).  dh may be NULL.
+F3D_API int f3d_detector_heads_backward(long long rows, int k, const float *h, const float *w_att, const float *b_att, const float *w_ori,
+                                        const float *b_ori, const float *g_att, const float *g_ori, float *dh, float *dw_att, float *db_att,
+                                        float *dw_ori, float *db_ori, void *workspace, size_t workspace_bytes, void *stream) {
+    if (rows <= 0 || k <= 0 || k % 32 || k > 128 || !h || !w_att || !b_att || !w_ori || !b_ori || !dw_att || !db_att || !dw_ori || !db_ori)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "detector_heads_backward: bad arguments (k must be 32, 64, 96 or 128)");
+    if (!workspace || workspace_bytes < f3d_detector_heads_workspace_bytes(k))
+        return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "detector_heads_backward: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const long long want = (rows + kHeadWarps - 1) / kHeadWarps;
+    const int grid = static_cast<int>(want < kHeadParts ? want : kHeadParts);
+    float *part = static_cast<float *>(workspace);
+    const size_t smem = static_cast<size_t>(kHeadWarps) * (3 * k + 3) * sizeof(float);
+    heads_bwd_kernel<<<grid, kHeadWarps * 32, smem, st>>>(rows, k, h, w_att, b_att, w_ori, b_ori, g_att, g_ori, dh, part);
+    int rc = check_launch("heads_bwd_kernel");
+    if (rc) return rc;
+    heads_reduce_kernel<<<(3 * k + 3 + 127) / 128, 128, 0, st>>>(grid, k, part, dw_att, db_att, dw_ori, db_ori);
+    return check_launch("heads_reduce_kernel");
+}

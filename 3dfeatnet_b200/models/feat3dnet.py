@@ -216,6 +216,9 @@ def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp
                             is_training=is_training, scope=scope + '/conv_post_%d' % i, params=params,
                             new_stats=new_stats)
 
+    fused = _layers.detector_heads(new_points, params, scope) if (is_training and not compute_det_gradients) else None
+    if fused is not None:  # both heads, forward and backward, as one CUDA op each (csrc/train.cu)
+        return new_xyz, idx, fused[0], fused[1], end_points
     attention = conv2d(new_points, 1, [1, 1], stride=[1, 1], padding='VALID', activation=_layers.softplus, bn=False,
                        scope=scope + '/attention', params=params)
     attention = attention.squeeze(3).squeeze(2)

@@ -183,6 +183,54 @@ class _MaxPoolSamples(torch.autograd.Function):
         return dx
 
 
+class _DetectorHeads(torch.autograd.Function):
+    """attention = softplus(h w_att + b_att), orientation = atan2(l2_normalize(h w_ori + b_ori)) over the rows of h (R,k):
+    the detector's heads (feat3dnet.py:142-149) as one forward and one backward CUDA op (csrc/train.cu)."""
+
+    @staticmethod
+    def forward(ctx, h, w_att, b_att, w_ori, b_ori):
+        _lib = _native()
+        t = [v.detach().contiguous().float() for v in (h, w_att, b_att, w_ori, b_ori)]
+        _lib.require_cuda(*t)
+        rows, k = t[0].shape
+        att = torch.empty(rows, dtype=torch.float32, device=t[0].device)
+        ori = torch.empty_like(att)
+        _lib.check(_lib.lib().f3d_detector_heads_forward(rows, k, *(_lib.ptr(v) for v in t), _lib.ptr(att), _lib.ptr(ori), _lib.stream()),
+                   "detector_heads_forward")
+        ctx.save_for_backward(*t)
+        return att, ori
+
+    @staticmethod
+    def backward(ctx, g_att, g_ori):
+        _lib = _native()
+        L = _lib.lib()
+        h, w_att, b_att, w_ori, b_ori = ctx.saved_tensors
+        rows, k = h.shape
+        ga = g_att.contiguous().float() if g_att is not None else None
+        go = g_ori.contiguous().float() if g_ori is not None else None
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        dwa, dba, dwo, dbo = torch.empty_like(w_att), torch.empty_like(b_att), torch.empty_like(w_ori), torch.empty_like(b_ori)
+        nbytes = L.f3d_detector_heads_workspace_bytes(k)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+        _lib.check(L.f3d_detector_heads_backward(rows, k, _lib.ptr(h), _lib.ptr(w_att), _lib.ptr(b_att), _lib.ptr(w_ori), _lib.ptr(b_ori),
+                                                 _lib.ptr(ga), _lib.ptr(go), _lib.ptr(dh), _lib.ptr(dwa), _lib.ptr(dba), _lib.ptr(dwo),
+                                                 _lib.ptr(dbo), _lib.ptr(ws), nbytes, _lib.stream()), "detector_heads_backward")
+        return dh, dwa, dba, dwo, dbo
+
+
+def detector_heads(new_points, params, scope):
+    """(B,M,1,k) pooled detector features -> (attention (B,M), orientation (B,M)) through the fused heads op, or None when the
+    shape / device is not covered (the caller then states the heads with conv2d)."""
+    if not (FUSED_TRAINING and new_points.is_cuda and new_points.dim() == 4 and new_points.shape[2] == 1
+            and new_points.shape[3] % 32 == 0 and new_points.shape[3] <= 128):
+        return None
+    b, m, _, k = new_points.shape
+    wa, ba = params[scope + "/attention/conv2d/weights"], params[scope + "/attention/conv2d/biases"]
+    wo, bo = params[scope + "/orientation/conv2d/weights"], params[scope + "/orientation/conv2d/biases"]
+    att, ori = _DetectorHeads.apply(new_points.reshape(b * m, k), wa.reshape(k), ba.reshape(1), wo.reshape(k, 2), bo.reshape(2))
+    return att.view(b, m), ori.view(b, m)
+
+
 def max_pool_samples(x):
     """(B,M,S,C) -> (B,M,1,C): tf.reduce_max(x, axis=[2], keep_dims=True).  CUDA op when x is on the GPU and C % 4 == 0."""
     if x.is_cuda and x.dim() == 4 and x.shape[3] % 4 == 0:

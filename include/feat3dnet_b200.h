@@ -224,6 +224,17 @@ int f3d_triplet_loss(int b, int m, int f, float margin, const float *fa, const f
                      const float *att, float *loss, float *dfa, float *dfp, float *dfn, float *datt, void *workspace,
                      size_t workspace_bytes, void *stream);
 
+/* The detector's per-cluster heads in training (models/feat3dnet.py:142-149): h (rows,k) -> attention = softplus(h w_att + b_att)
+ * (rows), orientation = atan2 of the l2-normalised (h w_ori + b_ori) (rows); w_att (k), w_ori (k,2).  k in {32,64,96,128}.
+ * Backward: g_att / g_ori = dL/d attention, dL/d orientation (either may be NULL) -> dh (rows,k; NULL to skip), dw_att (k),
+ * db_att (1), dw_ori (k,2), db_ori (2); deterministic (fixed-order partial sums).  workspace: f3d_detector_heads_workspace_bytes(k). */
+size_t f3d_detector_heads_workspace_bytes(int k);
+int f3d_detector_heads_forward(long long rows, int k, const float *h, const float *w_att, const float *b_att, const float *w_ori,
+                               const float *b_ori, float *attention, float *orientation, void *stream);
+int f3d_detector_heads_backward(long long rows, int k, const float *h, const float *w_att, const float *b_att, const float *w_ori,
+                                const float *b_ori, const float *g_att, const float *g_ori, float *dh, float *dw_att, float *db_att,
+                                float *dw_ori, float *db_ori, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Feat3dNet.get_train_op  models/feat3dnet.py:359-375: tf.train.AdamOptimizer(lr).minimize over all variables in
  * ONE launch.  records: device array of num_records x {float *param; const float *grad; float *m; float *v;
  * long long n;} (40 bytes each); max_n = the largest n.  step = 1-based update count; grad_scale multiplies every

@@ -345,3 +345,36 @@ def test_train_loop_follows_the_reference_schedule(cuda, tmp_path):
     ck.initialize_model(fresh, hist["checkpoints"][-1])
     for k, v in net.weights.items():
         assert torch.equal(fresh.weights[k].detach().float().cpu(), v.detach().float().cpu()), k
+
+
+@pytest.mark.parametrize("rows,k", [(9216, 64), (777, 32), (50, 128)])
+def test_detector_heads_op_matches_the_torch_statement(cuda, rows, k):
+    """feat3dnet.py:142-149 as one CUDA op: forward values and every gradient against the op-by-op statement in fp64; two runs
+    of the backward give identical bits (fixed-order reductions)"""
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(rows + k)
+    h = torch.relu(torch.randn(rows, k, generator=g, dtype=torch.float64))
+    wa, ba = torch.randn(k, generator=g, dtype=torch.float64) * 0.3, torch.randn(1, generator=g, dtype=torch.float64)
+    wo, bo = torch.randn(k, 2, generator=g, dtype=torch.float64) * 0.3, torch.randn(2, generator=g, dtype=torch.float64) * 0.1
+    ga, go = torch.randn(rows, generator=g, dtype=torch.float64), torch.randn(rows, generator=g, dtype=torch.float64)
+    ref_in = [t.clone().requires_grad_(True) for t in (h, wa, ba, wo, bo)]
+    a = torch.nn.functional.softplus(ref_in[0] @ ref_in[1] + ref_in[2])
+    xy = ref_in[0] @ ref_in[3] + ref_in[4]
+    xy = xy * torch.rsqrt(torch.clamp((xy * xy).sum(1, keepdim=True), min=1e-8))
+    o = torch.atan2(xy[:, 1], xy[:, 0])
+    ref_g = torch.autograd.grad((a * ga).sum() + (o * go).sum(), ref_in)
+    outs = []
+    for _ in range(2):
+        dev_in = [t.float().to(cuda).requires_grad_(True) for t in (h, wa, ba, wo, bo)]
+        att, ori = layers._DetectorHeads.apply(*dev_in)
+        grads = torch.autograd.grad((att * ga.float().to(cuda)).sum() + (ori * go.float().to(cuda)).sum(), dev_in)
+        outs.append((att, ori, grads))
+    att, ori, grads = outs[0]
+    assert torch.allclose(att.cpu().double(), a.detach(), rtol=1e-5, atol=1e-6)
+    d = ori.cpu().double() - o.detach()
+    assert torch.atan2(torch.sin(d), torch.cos(d)).abs().max() < 1e-5
+    for name, got, want in zip(("dh", "dw_att", "db_att", "dw_ori", "db_ori"), grads, ref_g):
+        scale = want.abs().max().item() + 1e-12
+        assert (got.cpu().double() - want).abs().max().item() < 2e-5 * scale + 1e-6, name
+    for x, y in zip(outs[0][2], outs[1][2]):
+        assert torch.equal(x, y)
