@@ -5,7 +5,7 @@ The host side mirrors the reference's module tree so that it drops in for that p
     tf_ops.sampling.tf_sampling   farthest_point_sample, gather_point, prob_sample
     tf_ops.grouping.tf_grouping   query_ball_point, query_ball_point2, select_top_k, group_point, knn_point
     models.pointnet_common        sample_points, query_and_group_points, sample_and_group, sample_and_group_all
-    models.layers                 conv2d, pairwise_dist, batch_norm_for_conv2d
+    models.layers                 conv2d, pairwise_dist, batch_norm_for_{fc,conv1d,conv2d,conv3d}, fully_connected, dropout
     models.feat3dnet              pointnet_sa_module, feature_detection_module, feature_extraction_module, Feat3dNet
     inference                     nms
 

@@ -273,6 +273,42 @@ def batch_norm_for_conv2d(inputs, is_training, bn_decay, scope, params, new_stat
     return batch_norm_template(inputs, is_training, scope, [0, 1, 2], bn_decay, params, new_stats)
 
 
+def batch_norm_for_conv3d(inputs, is_training, bn_decay, scope, params, new_stats=None):
+    return batch_norm_template(inputs, is_training, scope, [0, 1, 2, 3], bn_decay, params, new_stats)
+
+
+def dropout(inputs, is_training, scope=None, keep_prob=0.5, noise_shape=None):
+    """layers.py:107-127 (not called by the model): tf.nn.dropout when training -- kept elements scaled by 1/keep_prob,
+    the mask drawn with `noise_shape` and broadcast -- identity otherwise."""
+    if not is_training:
+        return inputs
+    if not 0.0 < keep_prob <= 1.0:
+        raise ValueError("dropout: keep_prob must be in (0, 1], got %r" % (keep_prob,))
+    shape = list(inputs.shape) if noise_shape is None else list(noise_shape)
+    keep = torch.rand(shape, device=inputs.device, dtype=inputs.dtype) < keep_prob
+    return inputs * keep.to(inputs.dtype) / keep_prob
+
+
+def fully_connected(inputs, num_outputs, scope, use_xavier=True, stddev=1e-3, weight_decay=0.0, activation_fn=relu, bn=False,
+                    bn_decay=None, is_training=None, params=None, new_stats=None):
+    """layers.py:130-171 (not called by the model): (B,Cin) @ <scope>/weights (Cin,num_outputs) + <scope>/biases, then
+    optional BN over the batch axis (<scope>/bn/...) and the activation.  The initialiser arguments are accepted and unused:
+    variables come from `params`."""
+    if params is None or scope is None:
+        raise ValueError("fully_connected needs params= (flat dict keyed by TF scope names) and scope=")
+    if inputs.dim() != 2:
+        raise ValueError("fully_connected: inputs must be (B, Cin), got %s" % (tuple(inputs.shape),))
+    w, b = params[scope + "/weights"], params[scope + "/biases"]
+    if tuple(w.shape) != (inputs.shape[1], num_outputs):
+        raise ValueError("fully_connected: weight shape %s does not match (%d -> %d)" % (tuple(w.shape), inputs.shape[1], num_outputs))
+    outputs = torch.matmul(inputs, w) + b
+    if bn:
+        outputs = batch_norm_for_fc(outputs, bool(is_training), bn_decay, scope + "/bn", params, new_stats)
+    if activation_fn is not None:
+        outputs = activation_fn(outputs)
+    return outputs
+
+
 def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', activation=relu, bn=True, bn_decay=None,
            is_training=None, scope=None, reuse=None, params=None, new_stats=None, pool_samples=False, concat_pooled=None):
     """ 2D convolution with non-linear operation (layers.py:11-46): slim.conv2d WITH bias -> BN -> activation.

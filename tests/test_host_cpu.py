@@ -119,6 +119,48 @@ def test_unfused_layers_match_oracle_net_on_cpu():
     assert torch.allclose(loss, onet.triplet_loss(fa, fp, fn, att, 0.2, True))
 
 
+def test_unused_layer_helpers_follow_the_reference_semantics():
+    """fully_connected / dropout / batch_norm_for_conv3d (layers.py:107-171,213-223): part of `models.layers`, never called
+    by the model; checked against the TF statements written out in fp64."""
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((6, 5), generator=g)
+    P = {"fc/weights": torch.randn((5, 4), generator=g), "fc/biases": torch.randn(4, generator=g),
+         "fc/bn/gamma": torch.rand(4, generator=g) + 0.5, "fc/bn/beta": torch.randn(4, generator=g),
+         "fc/bn/moving_mean": torch.randn(4, generator=g), "fc/bn/moving_variance": torch.rand(4, generator=g) + 0.1}
+    lin = x.double() @ P["fc/weights"].double() + P["fc/biases"].double()
+    assert torch.allclose(layers.fully_connected(x, 4, "fc", params=P).double(), lin.clamp_min(0), atol=1e-5)
+    for training in (False, True):
+        mean = lin.mean(0) if training else P["fc/bn/moving_mean"].double()
+        var = lin.var(0, unbiased=False) if training else P["fc/bn/moving_variance"].double()
+        want = (lin - mean) / torch.sqrt(var + 1e-3) * P["fc/bn/gamma"].double() + P["fc/bn/beta"].double()
+        stats = {}
+        got = layers.fully_connected(x, 4, "fc", activation_fn=None, bn=True, is_training=training, params=P, new_stats=stats)
+        assert torch.allclose(got.double(), want, atol=1e-5)
+        assert (set(stats) == {"fc/bn/moving_mean", "fc/bn/moving_variance"}) == training
+    with pytest.raises(ValueError):
+        layers.fully_connected(x, 3, "fc", params=P)
+    with pytest.raises(ValueError):
+        layers.fully_connected(x.reshape(2, 3, 5), 4, "fc", params=P)
+    # dropout: identity in eval; in training kept entries are x / keep_prob and the mask follows noise_shape
+    y = torch.ones((4, 64, 8))
+    assert layers.dropout(y, False, "dp") is y
+    torch.manual_seed(3)
+    d = layers.dropout(y, True, "dp", keep_prob=0.25, noise_shape=[4, 1, 8])
+    assert set(d.unique().tolist()) <= {0.0, 4.0}
+    assert torch.equal(d, d[:, :1].expand_as(d)) and 0 < (d > 0).float().mean() < 1
+    assert torch.equal(layers.dropout(y, True, "dp", keep_prob=1.0), y)
+    with pytest.raises(ValueError):
+        layers.dropout(y, True, "dp", keep_prob=0.0)
+    # conv3d BN: moments over every axis but the channel one
+    v = torch.randn((2, 3, 4, 5, 4), generator=g)
+    Pb = {"bn/gamma": P["fc/bn/gamma"], "bn/beta": P["fc/bn/beta"]}
+    got = layers.batch_norm_for_conv3d(v, True, None, "bn", Pb)
+    flat = v.double().reshape(-1, 4)
+    want = (flat - flat.mean(0)) / torch.sqrt(flat.var(0, unbiased=False) + 1e-3) * Pb["bn/gamma"].double() + Pb["bn/beta"].double()
+    assert torch.allclose(got.double().reshape(-1, 4), want, atol=1e-5)
+
+
 def test_shard_range_partitions():
     d = pkg("dist")
     for total in (0, 1, 7, 64, 65):
