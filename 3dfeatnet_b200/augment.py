@@ -23,6 +23,14 @@ def rotate_z(xyz, gen=None):
     return torch.stack((x * c - y * s, x * s + y * c, z), dim=2)
 
 
+def rotate_y(xyz, gen=None):
+    """RotateY (:84-98, upright_axis=1 data sets): data @ [[c,0,s],[0,1,0],[-s,0,c]]  ->  x' = x c - z s, z' = x s + z c."""
+    a = _rand(gen, (xyz.shape[0], 1), xyz.device) * (2 * math.pi)
+    c, s = torch.cos(a), torch.sin(a)
+    x, y, z = xyz.unbind(dim=2)
+    return torch.stack((x * c - z * s, y, x * s + z * c), dim=2)
+
+
 def jitter(xyz, sigma=0.01, clip=0.05, gen=None):
     """Jitter (:38-52): N(0, sigma) per coordinate, clipped at +-clip."""
     return xyz + torch.clamp(sigma * _randn(gen, xyz.shape, xyz.device), -clip, clip)
@@ -52,9 +60,14 @@ def shift(xyz, shift_range=0.1, gen=None):
 _ORDER = (("Rotate1D", rotate_z), ("Jitter", jitter), ("Scale", scale), ("RotateSmall", rotate_small), ("Shift", shift))
 
 
-def apply_augmentations(xyz, names=("Jitter", "RotateSmall", "Shift", "Rotate1D"), gen=None):
-    """get_augmentations_from_list + the per-cloud application of data/datagenerator.py, on a (B,N,3) device tensor."""
+def apply_augmentations(xyz, names=("Jitter", "RotateSmall", "Shift", "Rotate1D"), gen=None, upright_axis=2):
+    """get_augmentations_from_list + the per-cloud application of data/datagenerator.py, on a (B,N,3) device tensor.
+    upright_axis=1 turns Rotate1D into the rotation about y (:17-18); any other value but 2 drops it, like the reference."""
     for name, fn in _ORDER:
         if names is not None and name in names:
+            if name == "Rotate1D" and upright_axis != 2:
+                if upright_axis != 1:
+                    continue
+                fn = rotate_y
             xyz = fn(xyz, gen=gen)
     return xyz

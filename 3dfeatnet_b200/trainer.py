@@ -20,8 +20,8 @@ def train(model, train_data, num_epochs=1, batch_size=BATCH_SIZE, num_points=409
           lr=1e-5, checkpoint_dir=None, checkpoint_every_n_steps=500, val_folder=None, val_groundtruths=None,
           validate_every_n_steps=250, data_dim=6, seed=0, grad_hook=None, grad_scale=1.0, max_steps=None, on_step=None):
     """model: Feat3dNet in training mode; train_data: data.datagenerator.DataGenerator.  `augmentation` names follow
-    get_augmentations_from_list (data/augment.py:4-29) and are applied per cloud on the device (augment.py); objects with the
-    reference's `.apply(xyz)` interface may be passed through `train_data.next_triplet` by the caller instead.
+    get_augmentations_from_list (data/augment.py:4-29) and are applied per cloud on the device (augment.py); a list of the
+    objects that function returns (the reference's `.apply(xyz)` interface, data/augment.py here) is applied on the device too.
     Returns {'steps', 'losses', 'fp_rates': [(step, fp_rate)], 'checkpoints': [paths]}."""
     dev = model.device if hasattr(model, "device") else torch.device("cuda")
     gen = torch.Generator(device=dev)
@@ -37,7 +37,10 @@ def train(model, train_data, num_epochs=1, batch_size=BATCH_SIZE, num_points=409
             if anchors is None or anchors.shape[0] != batch_size:  # train.py:148-149: the short last batch ends the epoch
                 break
             clouds = [torch.as_tensor(a[:, :, :3]).to(dev, non_blocking=True) for a in (anchors, positives, negatives)]
-            if augmentation:
+            if augmentation and all(hasattr(a, "apply") for a in augmentation):  # objects of data/augment.py (train.py:45)
+                for a in augmentation:
+                    clouds = [a.apply(c) for c in clouds]
+            elif augmentation:
                 clouds = [_aug.apply_augmentations(c, augmentation, gen=gen) for c in clouds]
             xyz, feats, att, ep = model.get_train_model(clouds[0], clouds[1], clouds[2], True)
             loss, ep = model.get_loss(xyz, feats, att, ep)

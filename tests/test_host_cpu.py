@@ -68,9 +68,12 @@ def test_dropin_import_paths(f3d_lib):
         m = importlib.import_module("models.feat3dnet")
         assert callable(m.feature_detection_module) and callable(m.feature_extraction_module)
         assert importlib.import_module("models.net_factory").get_network("3DFeatNet") is m.Feat3dNet
+        m = importlib.import_module("data.augment")  # train.py:12
+        assert callable(m.get_augmentations_from_list) and issubclass(m.RotateZ, m.Augmentation)
+        assert callable(importlib.import_module("data.datagenerator").DataGenerator)  # train.py:13
     finally:
         sys.path.remove(os.path.dirname(pkg().__file__))
-        for k in [k for k in sys.modules if k.split(".")[0] in ("tf_ops", "models", "_lib")]:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("tf_ops", "models", "_lib", "data", "augment")]:
             del sys.modules[k]
 
 
@@ -297,6 +300,47 @@ def test_augmentations_follow_the_reference_semantics():
     b = aug.apply_augmentations(xyz, gen=torch.Generator().manual_seed(1))
     assert torch.equal(a, b) and not torch.equal(a, xyz)
     assert torch.equal(aug.apply_augmentations(xyz, names=()), xyz)
+    ry = aug.rotate_y(xyz, gen=gen)
+    assert torch.allclose(ry[:, :, 1], xyz[:, :, 1]) and torch.allclose(ry.norm(dim=2), xyz.norm(dim=2), rtol=1e-5, atol=1e-4)
+    up1 = aug.apply_augmentations(xyz, names=("Rotate1D",), gen=gen, upright_axis=1)
+    assert torch.allclose(up1[:, :, 1], xyz[:, :, 1]) and not torch.allclose(up1[:, :, 2], xyz[:, :, 2])
+    assert torch.equal(aug.apply_augmentations(xyz, names=("Rotate1D",), gen=gen, upright_axis=0), xyz)
+
+
+def test_augmentation_objects_keep_the_reference_interface():
+    """data/augment.py:4-137: get_augmentations_from_list order and upright axis, `.apply` on the (N,3) NumPy clouds that
+    DataGenerator.next_triplet passes, constructor parameters, batched torch input with one draw per cloud."""
+    da = pkg("data.augment")
+    assert da.get_augmentations_from_list(None) == []
+    objs = da.get_augmentations_from_list(['Shift', 'RotateSmall', 'Scale', 'Jitter', 'Rotate1D'])
+    assert [type(o) for o in objs] == [da.RotateZ, da.Jitter, da.Scale, da.RotateSmall, da.Shift]
+    assert type(da.get_augmentations_from_list(['Rotate1D'], upright_axis=1)[0]) is da.RotateY
+    assert da.get_augmentations_from_list(['Rotate1D'], upright_axis=0) == []
+    assert all(isinstance(o, da.Augmentation) for o in objs)
+    with pytest.raises(NotImplementedError):
+        da.Augmentation().apply(np.zeros((4, 3), np.float32))
+    rng = np.random.default_rng(0)
+    cloud = (rng.normal(size=(300, 3)) * 8).astype(np.float32)
+    torch.manual_seed(5)
+    for o in objs + [da.RotateY()]:
+        out = o.apply(cloud.copy())
+        assert isinstance(out, np.ndarray) and out.shape == cloud.shape and out.dtype == np.float32
+        assert not np.array_equal(out, cloud)
+    j = da.Jitter(sigma=0.5, clip=0.2).apply(cloud) - cloud
+    assert np.abs(j).max() <= 0.2 + 1e-6 and (np.abs(j) > 0.19).mean() > 0.3
+    s = da.Shift(shift_range=3.0).apply(cloud) - cloud
+    assert np.abs(s).max() <= 3.0 + 1e-5 and np.allclose(s, s[:1], atol=1e-5)
+    sc = da.Scale(scale_low=2.0, scale_high=2.0).apply(cloud, keypoints=None)
+    assert np.allclose(sc, 2 * cloud, rtol=1e-6)
+    assert np.allclose(da.RotateSmall(angle_sigma=0.0).apply(cloud), cloud, atol=1e-5)
+    assert np.allclose(da.RotateZ().apply(cloud)[:, 2], cloud[:, 2]) and np.allclose(da.RotateY().apply(cloud)[:, 1], cloud[:, 1])
+    # batched tensors: one draw per cloud, reproducible through gen=
+    batch = torch.as_tensor(np.stack([cloud, cloud]))
+    out = da.Shift(gen=torch.Generator().manual_seed(2)).apply(batch)
+    assert out.shape == batch.shape and not torch.allclose(out[0], out[1])
+    assert torch.equal(out, da.Shift(gen=torch.Generator().manual_seed(2)).apply(batch))
+    with pytest.raises(ValueError):
+        da.Jitter().apply(np.zeros((5, 6), np.float32))
 
 
 def _write_dataset(tmp_path, n_clouds=6, pts=300, seed=0):
@@ -354,6 +398,12 @@ def test_datagenerator_follows_the_reference_interface(tmp_path):
     gen3 = dg_mod.DataGenerator(meta, num_cols=6, seed=11)
     b1, _, _ = gen3.next_triplet(k=1, num_points=64, augmentation=[Shift1()])
     assert np.allclose(b1[:, :, :3], b0[:, :, :3] + 1.0) and np.array_equal(b1[:, :, 3:], b0[:, :, 3:])
+    # ... and so are the reference-style objects of data/augment.py (train.py:45,146)
+    gen4 = dg_mod.DataGenerator(meta, num_cols=6, seed=11)
+    objs = pkg("data.augment").get_augmentations_from_list(['Jitter', 'Shift'])
+    b2, _, _ = gen4.next_triplet(k=1, num_points=64, augmentation=objs)
+    d = b2[:, :, :3] - b0[:, :, :3]
+    assert b2.dtype == np.float32 and 0 < np.abs(d).max() <= 0.15 + 1e-5 and np.array_equal(b2[:, :, 3:], b0[:, :, 3:])
     with pytest.raises(ValueError):
         (tmp_path / "bad.txt").write_text("c0.bin | 1\n")
         dg_mod.DataGenerator(str(tmp_path / "bad.txt"))
