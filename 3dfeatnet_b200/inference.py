@@ -59,7 +59,8 @@ def detect_and_describe(model, point_cloud, nms_radius=0.5, min_response_ratio=1
 
 # ---------------------------------------------------------------------------------------------- file formats
 def load_point_cloud(path, num_cols=6):
-    """data/datagenerator.py:163-182: a raw float32 file of N x num_cols values (xyz + 3 unused columns) -> (N,num_cols)."""
+    """data/datagenerator.py:163-182: a raw float32 file of N x num_cols values (xyz + 3 unused columns for clouds, 3 for
+    keypoint files) -> (N,num_cols)."""
     import numpy as np
 
     a = np.fromfile(path, dtype=np.float32)
@@ -80,15 +81,46 @@ def save_keypoints_and_descriptors(path, xyz, features):
 
 
 def compute_descriptors_for_file(model, in_path, out_path, randomize_points=False, seed=0, max_keypoints=1024,
-                                 nms_radius=0.5, min_response_ratio=1e-2, device="cuda"):
-    """One iteration of compute_descriptors' file loop (inference.py:99-180): load .bin, (optionally) permute the points,
-    detect at every point, NMS, describe, keep the num_keypoints real rows, write [xyz | descriptor] rows."""
+                                 nms_radius=0.5, min_response_ratio=1e-2, device="cuda", num_points=-1, keypoints_path=None,
+                                 data_dim=6):
+    """One iteration of compute_descriptors' file loop (inference.py:99-180): load .bin, (optionally) permute the points and
+    keep the first `num_points` of them (:108-116), then either detect at every point + NMS (:118-151) or read the keypoints
+    of `keypoints_path` (a float32 file of xyz rows, :153-158), describe, keep the num_keypoints real rows and write
+    [xyz | descriptor] rows.  Returns the (rows, 3 + feature_dim) shape written."""
     import numpy as np
 
-    cloud = load_point_cloud(in_path)
+    cloud = load_point_cloud(in_path, num_cols=data_dim)
     if randomize_points:  # inference.py:108-113
         cloud = cloud[np.random.default_rng(seed).permutation(cloud.shape[0])]
+    if num_points > 0:  # :115-116
+        cloud = cloud[:num_points]
     pc = torch.as_tensor(np.ascontiguousarray(cloud[None])).to(device)
-    xyz_nms, features, _, num = detect_and_describe(model, pc, nms_radius, min_response_ratio, max_keypoints)
-    k = num[0]
+    if keypoints_path is None:
+        xyz_nms, features, _, num = detect_and_describe(model, pc, nms_radius, min_response_ratio, max_keypoints)
+        k = num[0]
+    else:
+        kp = load_point_cloud(keypoints_path, num_cols=3)
+        if kp.shape[0] == 0:
+            raise ValueError("%s holds no keypoints" % keypoints_path)
+        k = kp.shape[0]
+        xyz_nms = torch.as_tensor(np.ascontiguousarray(kp[None])).to(device)
+        xyz_nms, features, _, _ = model.get_inference_model(pc, False, keypoints=xyz_nms)
     return save_keypoints_and_descriptors(out_path, xyz_nms[0, :k], features[0, :k])
+
+
+def compute_descriptors(model, data_dir, output_dir, data_dim=6, num_points=-1, use_keypoints_from=None, randomize_points=False,
+                        nms_radius=0.5, min_response_ratio=1e-2, max_keypoints=1024, seed=0, device="cuda"):
+    """compute_descriptors() of inference.py:67-180 without the TF session / argument parsing: every `<name>.bin` of
+    `data_dir` -> `output_dir/<name>.bin` holding [xyz | descriptor] float32 rows.  The arguments are the CLI's (:26-58);
+    with `use_keypoints_from` the keypoints of `<use_keypoints_from>/<name>_kp.bin` are described instead of detected ones.
+    `model` is a Feat3dNet built the way the reference builds it for inference (num_clusters=-1, Attention=True, :81-83).
+    Returns the processed file names in the order they were processed (sorted; the reference takes os.listdir order)."""
+    import os
+
+    os.makedirs(output_dir, exist_ok=True)
+    bin_files = sorted(f for f in os.listdir(data_dir) if f.endswith(".bin"))
+    for i, f in enumerate(bin_files):
+        kp_path = None if use_keypoints_from is None else os.path.join(use_keypoints_from, "%s_kp.bin" % f[:-4])
+        compute_descriptors_for_file(model, os.path.join(data_dir, f), os.path.join(output_dir, f), randomize_points, seed + i,
+                                     max_keypoints, nms_radius, min_response_ratio, device, num_points, kp_path, data_dim)
+    return bin_files

@@ -221,6 +221,64 @@ def test_bin_formats_roundtrip(tmp_path):
     assert np.array_equal(back[:, :3], xyz.numpy()) and np.array_equal(back[:, 3:], feat.numpy())
 
 
+def test_compute_descriptors_directory_flow(tmp_path, monkeypatch):
+    """The host logic of compute_descriptors (inference.py:67-180) around a stand-in model: the .bin loop, --num_points,
+    --randomize_points, --use_keypoints_from (<name>_kp.bin, 3 columns), data_dim, and the rows written per file.  The device
+    work (attention, NMS, descriptors) is covered by test_nms_gpu.py::test_detect_nms_describe_flow."""
+    inf = pkg("inference")
+    rng = np.random.default_rng(4)
+    data, out, kps = tmp_path / "data", tmp_path / "out", tmp_path / "kp"
+    data.mkdir(); kps.mkdir()
+    clouds = {}
+    for name, n in (("b", 90), ("a", 120)):
+        clouds[name] = rng.random((n, 6)).astype(np.float32)
+        clouds[name].tofile(data / (name + ".bin"))
+        rng.random((7 if name == "a" else 5, 3)).astype(np.float32).tofile(kps / (name + "_kp.bin"))
+    (data / "notes.txt").write_text("not a cloud")
+
+    class Model:
+        calls = []
+
+        def get_inference_model(self, pc, is_training, keypoints=None, fetch_features=True):
+            assert is_training is False and pc.dim() == 3 and pc.shape[0] == 1
+            Model.calls.append((tuple(pc.shape), tuple(keypoints.shape), fetch_features))
+            feats = keypoints.sum(dim=2, keepdim=True).expand(-1, -1, 4) if fetch_features else None
+            att = keypoints[:, :, 0]
+            return keypoints, feats, att, {"attention": att}
+
+    # described at the keypoints of <name>_kp.bin; the first num_points rows of each cloud are fed
+    done = inf.compute_descriptors(Model(), str(data), str(out), num_points=80, use_keypoints_from=str(kps), device="cpu")
+    assert done == ["a.bin", "b.bin"] and sorted(os.listdir(out)) == done
+    assert Model.calls == [((1, 80, 6), (1, 7, 3), True), ((1, 80, 6), (1, 5, 3), True)]
+    rows = np.fromfile(out / "a.bin", dtype=np.float32).reshape(7, 3 + 4)
+    kp = np.fromfile(kps / "a_kp.bin", dtype=np.float32).reshape(7, 3)
+    assert np.array_equal(rows[:, :3], kp) and np.allclose(rows[:, 3:], kp.sum(1, keepdims=True))
+    with pytest.raises(ValueError):
+        (kps / "a_kp.bin").write_bytes(b"")
+        inf.compute_descriptors(Model(), str(data), str(out), use_keypoints_from=str(kps), device="cpu")
+
+    # detected keypoints: attention at every point in MAX_POINTS chunks, NMS (stand-in: the 3 strongest), describe, keep `num` rows
+    def fake_nms(xyz, attention, nms_radius, min_response_ratio, max_keypoints):
+        top = attention.argsort(dim=1, descending=True)[:, :max_keypoints]
+        sel = torch.gather(xyz, 1, top.unsqueeze(2).expand(-1, -1, 3))
+        return sel, torch.gather(attention, 1, top), [3]
+
+    monkeypatch.setattr(inf, "nms", fake_nms)
+    monkeypatch.setattr(inf, "MAX_POINTS", 50)
+    Model.calls = []
+    shape = inf.compute_descriptors_for_file(Model(), str(data / "a.bin"), str(out / "a2.bin"), randomize_points=True, seed=9,
+                                             max_keypoints=6, device="cpu")
+    assert shape == (3, 7)
+    assert [c[1][1] for c in Model.calls] == [50, 50, 20, 6] and [c[2] for c in Model.calls] == [False, False, False, True]
+    rows = np.fromfile(out / "a2.bin", dtype=np.float32).reshape(3, 7)
+    best = clouds["a"][np.argsort(-clouds["a"][:, 0], kind="stable")[:3], :3]
+    assert np.array_equal(rows[:, :3], best)           # the permutation does not change which points win
+    # data_dim: a 3-column cloud file
+    clouds["a"][:, :3].copy().tofile(data / "c3.bin")
+    assert inf.compute_descriptors_for_file(Model(), str(data / "c3.bin"), str(out / "c3.bin"), max_keypoints=6, device="cpu",
+                                            data_dim=3) == (3, 7)
+
+
 def test_checkpoint_round_trips_and_restore_rules(tmp_path):
     """checkpoint.py: npz and TF tensor-bundle round trips, the TF name / layout mapping (1x1 kernels, EMA shadows,
     optimizer slots ignored) and initialize_model's exclude / ignore-missing rules (reference inference.py:183-217)."""
