@@ -5,7 +5,8 @@ TEST INFRASTRUCTURE ONLY (see oracle/ops_oracle.c).  PARITY UNPINNED at this bou
 arithmetic of these layers lives in TensorFlow 1.15 + tf.contrib.slim (requirements.txt:45-47), which
 is neither vendored under /root/reference nor installable here, and the reference holds no test or
 golden vector for any of them.  What is restated is the documented semantics
-of the TF ops at the reference's call sites, cited per function.
+of the TF ops at the reference's call sites, cited per function; tests/test_oracle_net_cpu.py holds it
+against PyTorch's own library modules (an independent statement of the same semantics, not a TF vector).
 
 Parameters are a flat dict keyed by the TF variable scope names:
     <scope>/conv2d/weights  (Cin, Cout)      slim.conv2d 1x1 kernel, layers.py:32-37
