@@ -1,8 +1,11 @@
 """CPU restatement of the keypoint non-maximum suppression of inference.py:226-261.
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED: the neighbour search is scikit-learn's
-NearestNeighbors(n_neighbors=50, algorithm='ball_tree') (reference pin 0.24.2, requirements.txt:39;
-this image has 1.9.0), the reference has no test for it.  The function body follows the reference
+TEST INFRASTRUCTURE ONLY.  Pinned to the reference function: tests/golden/ref_nms.npz holds outputs of
+the reference's own nms() (its FunctionDef taken out of inference.py with `ast` and executed unmodified,
+tests/golden/make_golden_nms.py) and tests/test_oracle_nms_cpu.py holds both statements below to them
+bit for bit.  The neighbour search is scikit-learn's NearestNeighbors(n_neighbors=50,
+algorithm='ball_tree') (reference pin 0.24.2, requirements.txt:39; this image has 1.9.0 -- the one
+remaining gap); the reference has no test of its own for it.  The function body follows the reference
 statement by statement; args.* of the reference become keyword arguments with the CLI defaults
 (inference.py:40-47: nms_radius 0.5, min_response_ratio 1e-2, max_keypoints 1024).
 

@@ -81,6 +81,19 @@ def test_nms_threshold_padding_and_ties(cuda):
         inf.nms(torch.zeros((1, 10, 3), device=cuda), torch.zeros((1, 10), device=cuda))  # fewer points than 50 neighbours
 
 
+def test_nms_matches_reference_golden(cuda):
+    """tests/golden/ref_nms.npz: outputs of the reference's own nms() (taken out of inference.py with `ast` and executed
+    unmodified, tests/golden/make_golden_nms.py) -- 1024-keypoint truncation, the 50-NN rule on dense clouds, padding."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_nms.npz"))
+    for name in sorted({k.split("/")[0] for k in g.files}):
+        radius, ratio, kmax = g[name + "/cli"]
+        got = run_nms(g[name + "/xyz"], g[name + "/attention"], cuda, nms_radius=float(radius), min_response_ratio=float(ratio),
+                      max_keypoints=int(kmax))
+        assert got[2] == g[name + "/num_keypoints"].tolist(), name
+        assert np.array_equal(got[0], g[name + "/xyz_nms"]) and np.array_equal(got[1], g[name + "/attention_nms"]), name
+
+
 def test_cumsum_and_prob_sample_bit_exact(cuda):
     ts = pkg("tf_ops.sampling.tf_sampling")
     lib_mod = pkg("_lib")
