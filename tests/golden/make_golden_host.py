@@ -1,0 +1,153 @@
+"""Regenerates tests/golden/ref_host.npz from the REFERENCE's own host-side Python (needs /root/reference; run in the build
+container, not on the GPU box):
+
+  validate / load_validation_groundtruths   train.py:243-315.  train.py cannot be imported (TensorFlow, argparse at module
+      level), so the two FunctionDefs are taken out of the parsed file with `ast` and executed unmodified in a namespace
+      holding what they read (np, os, NUM_CLUSTERS, the reference's DataGenerator); the TF session is replaced by an object
+      whose run(fetches, feed_dict) returns descriptors from `toy_descriptors` below -- the cluster stacking, keypoint
+      offsets, distance, percentile and FP-rate arithmetic are the reference's.
+  data/augment.py                           imported as it is (NumPy only); its random draws are replaced by fixed values so
+      that the geometric statement of every augmentation (axis, sign, composition order, clipping) is recorded.
+
+Only inputs, draws and outputs are stored; no reference source is written anywhere.
+
+    python tests/golden/make_golden_host.py
+"""
+import ast
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = os.environ.get("F3D_REFERENCE", "/root/reference")
+
+
+def reference_module(relpath, name):
+    """Import a NumPy-only reference file by path (data/augment.py, data/datagenerator.py)."""
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_functions(relpath, names, namespace):
+    """The named top-level functions of a reference file that cannot be imported, compiled unmodified into `namespace`."""
+    path = os.path.join(REFERENCE, relpath)
+    tree = ast.parse(open(path).read(), filename=path)
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert sorted(n.name for n in body) == sorted(names), "missing in %s: %s" % (relpath, names)
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), namespace)
+    return [namespace[n] for n in names]
+
+
+# ------------------------------------------------------------------------------------------- validation
+def toy_descriptors(cloud, keypoints, dim=8):
+    """A deterministic stand-in for the network: descriptor j = moments of the points within 50 m (in x) of keypoint j.
+    cloud (1,N,>=3), keypoints (1,M,3) of any numeric dtype -> (1,M,3), (1,M,dim) float32."""
+    cloud = np.asarray(cloud, np.float64)[0, :, :3]
+    kp = np.asarray(keypoints, np.float64)[0]
+    feats = np.zeros((kp.shape[0], dim), np.float64)
+    for j in range(kp.shape[0]):
+        local = cloud[np.abs(cloud[:, 0] - kp[j, 0]) < 50.0] - kp[j]
+        if local.shape[0]:
+            feats[j, :3], feats[j, 3:6] = local.mean(0), local.std(0)
+            feats[j, 6], feats[j, 7] = np.abs(local).max(), local.shape[0] / 64.0
+    return kp[None].astype(np.float32), feats[None].astype(np.float32)
+
+
+def write_validation_set(folder, num_pairs=600, seed=31):
+    """`<i>_0.bin` / `<i>_1.bin` cluster pairs (6 float32 columns) + groundtruths.txt; matching pairs are noisy copies,
+    non-matching ones independent draws of the same spread, so that the FP rate at 95 % recall is neither 0 nor 1."""
+    rng = np.random.default_rng(seed)
+    lines = ["idx dist overlap match"]
+    for i in range(num_pairs):
+        match = int(rng.random() < 0.5)
+        scale = 1.0 + (i % 5)
+        a = rng.normal(0, scale, (int(rng.integers(20, 40)), 6)).astype(np.float32)
+        b = (a + rng.normal(0, 0.25 * scale, a.shape) if match else rng.normal(0, scale, a.shape)).astype(np.float32)
+        a.tofile(os.path.join(folder, "%d_0.bin" % i))
+        b.tofile(os.path.join(folder, "%d_1.bin" % i))
+        lines.append("%d %.3f %.3f %d" % (i, rng.random(), rng.random(), match))
+    path = os.path.join(folder, "groundtruths.txt")
+    open(path, "w").write("\n".join(lines) + "\n")
+    return path
+
+
+class ToySession(object):
+    """Stands in for tf.Session in the reference's validate(): run(fetches, feed_dict) -> toy_descriptors(cloud, keypoints)."""
+
+    def __init__(self, end_points):
+        self.ep = end_points
+
+    def run(self, fetches, feed_dict):
+        assert fetches == [self.ep['output_xyz'], self.ep['output_features']]
+        return toy_descriptors(feed_dict[self.ep['input_pointclouds']], feed_dict[self.ep['keypoints']])
+
+
+def reference_validate(folder, gt_path, proportion=1):
+    dg = reference_module("data/datagenerator.py", "ref_datagenerator")
+    ns = dict(np=np, os=os, NUM_CLUSTERS=512, DataGenerator=dg.DataGenerator)  # NUM_CLUSTERS: train.py:24
+    validate, load_gt = reference_functions("train.py", ["validate", "load_validation_groundtruths"], ns)
+    gts = load_gt(gt_path, proportion)
+    ep = dict(output_xyz="xyz", output_features="features", input_pointclouds="clouds", keypoints="keypoints")
+    return gts, validate(ToySession(ep), ep, "is_training", folder, gts, 6)
+
+
+# ------------------------------------------------------------------------------------------- augmentations
+AUG_DRAWS = dict(angle01=0.3125, jitter_scale=3.0, scale=1.125, small_angles=(0.5, -2.0, 4.0), shift=(0.05, -0.1, 0.025))
+
+
+def reference_augmentations(cloud):
+    """Every reference augmentation applied to `cloud` (N,3) with its random draws replaced by AUG_DRAWS."""
+    aug = reference_module("data/augment.py", "ref_augment")
+    noise = np.random.default_rng(5).standard_normal(cloud.shape)
+    out = {}
+
+    class Draws(object):  # what the reference reads from np.random, returning the fixed draws
+        def __init__(self, uniform=None, randn=None):
+            self._u, self._n = uniform, randn
+
+        def uniform(self, *a, **k):
+            return self._u
+
+        def randn(self, *shape):
+            return np.asarray(self._n, np.float64).reshape(shape)
+
+    real = aug.np.random
+    try:
+        aug.np.random = Draws(uniform=AUG_DRAWS["angle01"])
+        out["RotateZ"], out["RotateY"] = aug.RotateZ().apply(cloud.copy()), aug.RotateY().apply(cloud.copy())
+        aug.np.random = Draws(randn=noise * AUG_DRAWS["jitter_scale"])
+        out["Jitter"] = aug.Jitter().apply(cloud.copy())
+        aug.np.random = Draws(uniform=AUG_DRAWS["scale"])
+        out["Scale"] = aug.Scale().apply(cloud.copy())
+        aug.np.random = Draws(randn=AUG_DRAWS["small_angles"])
+        out["RotateSmall"] = aug.RotateSmall().apply(cloud.copy())
+        aug.np.random = Draws(uniform=np.asarray(AUG_DRAWS["shift"]))
+        out["Shift"] = aug.Shift().apply(cloud.copy())
+    finally:
+        aug.np.random = real
+    return noise, out
+
+
+if __name__ == "__main__":
+    import tempfile
+
+    store = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        gt_path = write_validation_set(tmp)
+        for prop in (1, 0.25):
+            gts, fp = reference_validate(tmp, gt_path, prop)
+            store["validate/fp_rate_%s" % prop] = np.float64(fp)
+            store["validate/groundtruths_%s" % prop] = np.array(gts, np.int64)
+            print("validate: proportion", prop, "pairs", len(gts), "fp rate", fp)
+    cloud = np.random.default_rng(8).uniform(-20, 20, (64, 3))
+    noise, outs = reference_augmentations(cloud)
+    store["augment/cloud"], store["augment/noise"] = cloud, noise
+    for k, v in outs.items():
+        store["augment/" + k] = np.asarray(v, np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_host.npz"), **store)
+    print("wrote ref_host.npz", os.path.getsize(os.path.join(HERE, "ref_host.npz")), "bytes")
+    sys.exit(0)
