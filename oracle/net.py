@@ -1,12 +1,15 @@
 """CPU restatement (PyTorch-CPU, fp32 or fp64) of the 3DFeat-Net detector/descriptor graph, its
 loss and its TF-1 Adam step.
 
-TEST INFRASTRUCTURE ONLY (see oracle/ops_oracle.c).  PARITY UNPINNED at this boundary: the
-arithmetic of these layers lives in TensorFlow 1.15 + tf.contrib.slim (requirements.txt:45-47), which
-is neither vendored under /root/reference nor installable here, and the reference holds no test or
-golden vector for any of them.  What is restated is the documented semantics
-of the TF ops at the reference's call sites, cited per function; tests/test_oracle_net_cpu.py holds it
-against PyTorch's own library modules (an independent statement of the same semantics, not a TF vector).
+TEST INFRASTRUCTURE ONLY (see oracle/ops_oracle.c).  GRAPH PINNED, PRIMITIVES UNPINNED: the reference's
+own models/{layers,pointnet_common,feat3dnet}.py are imported unmodified and executed on an eager float64
+stand-in for the TensorFlow primitives they call (tests/golden/tf_shim.py, make_golden_net.py ->
+tests/golden/ref_net.npz), and tests/test_oracle_net_cpu.py holds this file to those outputs to 1e-9 --
+layer order, scopes, BN / activation flags, pooling, concat, rotation, heads and loss are the reference's.
+The arithmetic inside the primitives lives in TensorFlow 1.15 + tf.contrib.slim (requirements.txt:45-47),
+which is neither vendored under /root/reference nor installable here, and the reference holds no test or
+golden vector for it: there the documented semantics of the TF ops are restated,
+cited per function, and cross-checked against PyTorch's own library modules (same test file).
 
 Parameters are a flat dict keyed by the TF variable scope names:
     <scope>/conv2d/weights  (Cin, Cout)      slim.conv2d 1x1 kernel, layers.py:32-37

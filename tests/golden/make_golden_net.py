@@ -1,0 +1,125 @@
+"""Regenerates tests/golden/ref_net.npz by EXECUTING THE REFERENCE'S OWN MODEL FILES (models/layers.py,
+models/pointnet_common.py, models/feat3dnet.py, imported unmodified from /root/reference) on the eager TensorFlow stand-in of
+tests/golden/tf_shim.py, in float64 (build container only; needs a fresh interpreter).
+
+Per case: Feat3dNet(param).get_inference_model(cloud, is_training, use_bn=True, compute_det_gradients=False) -> keypoints,
+descriptors, attention, orientation (+ the BN shadow updates in training mode), and for the training case the reference's
+get_loss on the anchor / positive / negative thirds.  get_train_model itself cannot run: it leaves compute_det_gradients at
+True, and feature_detection_module then indexes end_points['gradients'] of an empty dict (feat3dnet.py:104,122).
+"keypoints fed" cases reproduce `feed_dict={end_points['keypoints']: ...}` (inference.py:128-131, train.py:291-298): feeding
+that tensor replaces the output of sample_points for everything downstream, so models.feat3dnet.sample_points is bound to a
+function returning the fed keypoints.
+
+Variables come from oracle.net.init_params(seed, feature_dim, randomize_bn=True) under their TF names (1x1 kernels stored as
+(Cin,Cout)); only inputs, configuration and outputs are written.
+
+    python tests/golden/make_golden_net.py [out.npz]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+CASES = {
+    # name: dict(seed, B, N, param..., mode)
+    "eval_fps": dict(seed=11, clouds=2, points=6000, num_clusters=32, num_samples=64, feature_dim=32, no_regress=False,
+                     attention=True, training=False, keypoints=None, store_grouped=True),
+    "eval_noregress_f128": dict(seed=12, clouds=1, points=2500, num_clusters=40, num_samples=32, feature_dim=128, no_regress=True,
+                                attention=True, training=False, keypoints=None),
+    "eval_all_points": dict(seed=13, clouds=1, points=600, num_clusters=-1, num_samples=64, feature_dim=32, no_regress=False,
+                            attention=True, training=False, keypoints=None),
+    "eval_keypoints_fed": dict(seed=14, clouds=2, points=2000, num_clusters=-1, num_samples=64, feature_dim=32, no_regress=False,
+                               attention=True, training=False, keypoints=37),
+    "train_triplets": dict(seed=15, clouds=6, points=1500, num_clusters=32, num_samples=64, feature_dim=32, no_regress=False,
+                           attention=True, training=True, keypoints=None, margin=0.2),
+    "train_no_attention": dict(seed=16, clouds=3, points=1200, num_clusters=24, num_samples=64, feature_dim=32, no_regress=False,
+                               attention=False, training=True, keypoints=None, margin=0.5),
+}
+
+
+def case_inputs(cfg):
+    """Oxford-shape clouds (6 float32 columns like the .bin files: the model must ignore columns 3..5) and, if asked, keypoints
+    that are partly cloud points and partly off-cloud positions (some with empty balls: the fallback rule of the ball query)."""
+    rng = np.random.default_rng(cfg["seed"])
+    base = np.load(os.path.join(HERE, "oxford_270_xyz.npy")).astype(np.float32)
+    clouds = []
+    for _ in range(cfg["clouds"]):
+        pts = base[rng.permutation(base.shape[0])[:cfg["points"]]]
+        a = rng.uniform(0, 2 * np.pi)
+        rot = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+        pts = (pts @ rot + rng.normal(0, 0.01, pts.shape)).astype(np.float32)
+        clouds.append(np.concatenate([pts, rng.integers(0, 4, pts.shape).astype(np.float32)], axis=1))
+    clouds = np.stack(clouds)
+    kp = None
+    if cfg["keypoints"]:
+        k = cfg["keypoints"]
+        kp = clouds[:, :k, :3].copy()
+        kp[:, k // 2:] += rng.normal(0, 1.0, kp[:, k // 2:].shape).astype(np.float32)
+        kp[:, -3:] += np.float32(500.0)  # far from every point: empty balls
+    return clouds, kp
+
+
+def run_reference(cfg, clouds, kp, params):
+    import tf_shim
+    import models.feat3dnet as ref_f3  # the reference's file (tf_shim.install put /root/reference first on sys.path)
+
+    assert ref_f3.__file__.startswith(tf_shim_root), ref_f3.__file__
+    store = tf_shim.STORE
+    store.params, store.updates, store.touched, store.scope = dict(params), {}, set(), []
+    model = ref_f3.Feat3dNet(dict(NoRegress=cfg["no_regress"], BaseScale=2.0, Attention=cfg["attention"],
+                                  num_clusters=cfg["num_clusters"], num_samples=cfg["num_samples"],
+                                  feature_dim=cfg["feature_dim"], margin=cfg.get("margin", 0.2), freeze_scopes=None))
+    original = ref_f3.sample_points
+    if kp is not None:
+        ref_f3.sample_points = lambda xyz, npoint: tf_shim.t(kp)  # feed_dict={end_points['keypoints']: kp}
+    try:
+        xyz, features, attention, ep = model.get_inference_model(tf_shim.t(clouds), cfg["training"], use_bn=True,
+                                                                 compute_det_gradients=False)
+    finally:
+        ref_f3.sample_points = original
+    out = dict(xyz=xyz.numpy(), features=features.numpy(), attention_end_point=ep["attention"].numpy(),
+               orientation=ep["orientation"].numpy())
+    if cfg.get("store_grouped"):  # the descriptor's clusters before / after the rotation by the detector's orientation
+        out.update(grouped_xyz_before=ep["grouped_xyz_before"].numpy(), grouped_xyz=ep["grouped_xyz"].numpy())
+    assert (attention is None) == (not cfg["attention"])
+    if cfg["training"]:
+        import tensorflow as tf
+        loss, ep2 = model.get_loss(None, tf.split(features, 3, axis=0),
+                                   tf.split(attention, 3, axis=0)[0] if attention is not None else None, {})
+        out["loss"] = np.float64(loss.numpy())
+        out["sum_positive"], out["sum_negative"] = ep2["sum_positive"].numpy(), ep2["sum_negative"].numpy()
+        for k, v in store.updates.items():
+            out["bn_update/" + k] = v
+    unused = set(params) - store.touched
+    assert not unused, "variables the reference graph never read: %s" % sorted(unused)
+    return out
+
+
+if __name__ == "__main__":
+    import tf_shim
+    from oracle import net as onet
+
+    tf_shim_root = os.environ.get("F3D_REFERENCE", "/root/reference")
+    tf_shim.install(tf_shim_root)
+    store = {}
+    for name, cfg in CASES.items():
+        clouds, kp = case_inputs(cfg)
+        params = onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True)
+        out = run_reference(cfg, clouds, kp, params)
+        store[name + "/config"] = np.array(json.dumps(cfg))
+        store[name + "/clouds"] = clouds
+        if kp is not None:
+            store[name + "/keypoints"] = kp
+        for k, v in out.items():
+            store[name + "/out/" + k] = v
+        print(name, {k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items() if not k.startswith("bn_update")},
+              "bn updates:", sum(k.startswith("bn_update") for k in out))
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "ref_net.npz")
+    np.savez_compressed(path, **store)
+    print("wrote", path, os.path.getsize(path), "bytes")

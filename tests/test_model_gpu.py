@@ -81,6 +81,24 @@ def test_fused_forward_shapes_fp32(cuda, B, N, M, S, F, no_regress):
     compare(out, ref, TOL["fp32"], "shape")
 
 
+@pytest.mark.parametrize("case", ["eval_fps", "eval_noregress_f128"])
+def test_fused_forward_matches_reference_graph_golden(cuda, case):
+    """tests/golden/ref_net.npz: outputs of the reference's OWN models/{layers,pointnet_common,feat3dnet}.py executed unmodified
+    on an eager float64 stand-in for the TF primitives (tests/golden/tf_shim.py, make_golden_net.py) -- the CUDA forward
+    against the reference's graph code directly (test_oracle_net_cpu.py holds the oracle to the same file)."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_net.npz"))
+    cfg = json.loads(str(g[case + "/config"]))
+    xyz = np.ascontiguousarray(g[case + "/clouds"][:, :, :3])
+    params = onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True)
+    out, _ = run_pipeline(xyz, params, cfg["num_clusters"], cfg["num_samples"], cfg["feature_dim"], no_regress=cfg["no_regress"])
+    assert np.array_equal(out["xyz"].cpu().numpy().astype(np.float64), g[case + "/out/xyz"])
+    ref = dict(attention=torch.as_tensor(g[case + "/out/attention_end_point"]), orientation=torch.as_tensor(g[case + "/out/orientation"]),
+               features=torch.as_tensor(g[case + "/out/features"]))
+    compare(out, ref, TOL["fp32"], case)
+
+
 def test_model_api_matches_pipeline_and_unfused_path(cuda):
     """Feat3dNet.get_inference_model (reference signature): the fused eval path equals the pipeline, and the unfused
     differentiable layers (models/layers.py) agree with it within the fp32 tolerance; external keypoints are honoured."""

@@ -162,3 +162,93 @@ def test_adam_step_agrees_with_torch_adam_at_epsilon_hat():
         opt.step()
         assert torch.allclose(P["w"], q.detach(), rtol=1e-12, atol=1e-15), t
     assert not torch.allclose(P["w"], theta0)
+
+
+# ------------------------------------------------------------------------- the reference's own graph code
+# tests/golden/ref_net.npz: outputs of the reference's models/{layers,pointnet_common,feat3dnet}.py, imported and executed
+# UNMODIFIED on an eager float64 stand-in for the TensorFlow primitives they call (tests/golden/tf_shim.py,
+# make_golden_net.py).  The wiring of the graph -- layer order, scopes / variable names, BN and activation flags, pooling,
+# tile + concat, rotation, heads, loss -- is the reference's; oracle/net.py must reproduce it.
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _ref_net_cases(path=None):
+    g = np.load(path or os.path.join(GOLD, "ref_net.npz"))
+    for name in sorted({k.split("/")[0] for k in g.files}):
+        cfg = json.loads(str(g[name + "/config"]))
+        out = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(name + "/out/")}
+        yield name, cfg, g[name + "/clouds"], (g[name + "/keypoints"] if name + "/keypoints" in g.files else None), out
+
+
+def _angle_diff(a, b):
+    d = torch.as_tensor(a) - torch.as_tensor(b)
+    return torch.atan2(torch.sin(d), torch.cos(d)).abs().max().item()
+
+
+def test_oracle_net_reproduces_the_reference_graph_golden():
+    names = []
+    for name, cfg, clouds, kp, want in _ref_net_cases():
+        names.append(name)
+        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True), torch.float64)
+        stats = {}
+        got = onet.inference_model(clouds, P, cfg["num_clusters"], 2.0, cfg["num_samples"], cfg["feature_dim"], cfg["no_regress"],
+                                   cfg["training"], kp, stats, torch.float64)
+        assert np.array_equal(np.asarray(got["xyz"], np.float64), want["xyz"]), name          # keypoints: FPS / all points / fed
+        assert torch.allclose(got["features"], torch.as_tensor(want["features"]), rtol=1e-9, atol=1e-11), name
+        assert torch.allclose(got["attention"], torch.as_tensor(want["attention_end_point"]), rtol=1e-9, atol=1e-12), name
+        assert _angle_diff(got["orientation"], want["orientation"]) < 1e-9, name
+        if "grouped_xyz" in want:  # the descriptor's clusters before and after the rotation by the detector's orientation
+            desc = onet.descriptor(clouds, P, got["xyz"], got["orientation"], 2.0, cfg["num_samples"], cfg["feature_dim"],
+                                   dtype=torch.float64)
+            plain = onet.descriptor(clouds, P, got["xyz"], None, 2.0, cfg["num_samples"], cfg["feature_dim"], dtype=torch.float64)
+            assert torch.allclose(desc["rotated_xyz"], torch.as_tensor(want["grouped_xyz"]), rtol=1e-9, atol=1e-12)
+            assert torch.allclose(plain["rotated_xyz"], torch.as_tensor(want["grouped_xyz_before"]), rtol=1e-12, atol=1e-14)
+        if cfg["training"]:
+            fa, fp, fn = torch.chunk(got["features"], 3, dim=0)
+            att_a = torch.chunk(got["attention"], 3, dim=0)[0]
+            loss = onet.triplet_loss(fa, fp, fn, att_a, cfg["margin"], cfg["attention"])
+            assert want["loss"] > 0 and abs(float(loss) - float(want["loss"])) < 1e-10, name
+            updates = {k[len("bn_update/"):]: v for k, v in want.items() if k.startswith("bn_update/")}
+            assert set(updates) == set(stats) and len(updates) == 18, name
+            for k, v in updates.items():
+                assert torch.allclose(stats[k], torch.as_tensor(v), rtol=1e-9, atol=1e-12), (name, k)
+        else:
+            assert stats == {}
+    assert names == sorted(["eval_fps", "eval_noregress_f128", "eval_all_points", "eval_keypoints_fed", "train_triplets",
+                            "train_no_attention"])
+
+
+def test_reference_graph_golden_has_the_interesting_cases():
+    cases = {c[0]: c for c in _ref_net_cases()}
+    kp_case = cases["eval_keypoints_fed"]
+    P = onet.init_params(seed=kp_case[1]["seed"], randomize_bn=True)
+    det = onet.detector(kp_case[2], onet.to_torch(P), -1, 2.0, 64, keypoints_np=kp_case[3])
+    assert (det["pts_cnt"] == 0).any() and ((det["pts_cnt"] > 0) & (det["pts_cnt"] < 64)).any()  # empty balls (fallback), padded ones
+    fps_case = cases["eval_fps"]
+    full = onet.detector(fps_case[2], onet.to_torch(onet.init_params(seed=fps_case[1]["seed"], randomize_bn=True)), 32, 2.0, 64)
+    assert (full["pts_cnt"] == 64).any() and (full["pts_cnt"] < 64).any()                        # truncated at nsample, and padded
+    assert cases["eval_noregress_f128"][4]["features"].shape[-1] == 128       # the 256-channel conv_mid_0 variant
+    assert cases["eval_all_points"][4]["xyz"].shape[1] == cases["eval_all_points"][2].shape[1]  # num_clusters = -1
+    assert not np.allclose(cases["eval_fps"][4]["grouped_xyz"], cases["eval_fps"][4]["grouped_xyz_before"])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/feat3dnet.py"), reason="the reference tree is only in the build container")
+def test_reference_graph_golden_regenerates_from_the_reference(tmp_path):
+    """Re-runs the reference's model files (fresh interpreter) and compares with the committed file."""
+    out = str(tmp_path / "ref_net.npz")
+    r = subprocess.run([sys.executable, os.path.join(GOLD, "make_golden_net.py"), out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    a, b = np.load(out), np.load(os.path.join(GOLD, "ref_net.npz"))
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        if a[k].dtype.kind == "f":
+            assert np.allclose(a[k], b[k], rtol=1e-12, atol=1e-14), k
+        else:
+            assert np.array_equal(a[k], b[k]), k
