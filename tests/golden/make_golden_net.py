@@ -3,8 +3,8 @@ models/pointnet_common.py, models/feat3dnet.py, imported unmodified from /root/r
 tests/golden/tf_shim.py, in float64 (build container only; needs a fresh interpreter).
 
 Per case: Feat3dNet(param).get_inference_model(cloud, is_training, use_bn=True, compute_det_gradients=False) -> keypoints,
-descriptors, attention, orientation (+ the BN shadow updates in training mode), and for the training case the reference's
-get_loss on the anchor / positive / negative thirds.  get_train_model itself cannot run: it leaves compute_det_gradients at
+descriptors, attention, orientation (+ the BN shadow updates in training mode), and for the training cases the reference's
+get_loss on the anchor / positive / negative thirds and its gradient with respect to every trainable variable.  get_train_model itself cannot run: it leaves compute_det_gradients at
 True, and feature_detection_module then indexes end_points['gradients'] of an empty dict (feat3dnet.py:104,122).
 "keypoints fed" cases reproduce `feed_dict={end_points['keypoints']: ...}` (inference.py:128-131, train.py:291-298): feeding
 that tensor replaces the output of sample_points for everything downstream, so models.feat3dnet.sample_points is bound to a
@@ -37,7 +37,7 @@ CASES = {
     "eval_keypoints_fed": dict(seed=14, clouds=2, points=2000, num_clusters=-1, num_samples=64, feature_dim=32, no_regress=False,
                                attention=True, training=False, keypoints=37),
     "train_triplets": dict(seed=15, clouds=6, points=1500, num_clusters=32, num_samples=64, feature_dim=32, no_regress=False,
-                           attention=True, training=True, keypoints=None, margin=0.2),
+                           attention=True, training=True, keypoints=None, margin=0.2, store_gradients=True),
     "train_no_attention": dict(seed=16, clouds=3, points=1200, num_clusters=24, num_samples=64, feature_dim=32, no_regress=False,
                                attention=False, training=True, keypoints=None, margin=0.5),
 }
@@ -72,6 +72,13 @@ def run_reference(cfg, clouds, kp, params):
     assert ref_f3.__file__.startswith(tf_shim_root), ref_f3.__file__
     store = tf_shim.STORE
     store.params, store.updates, store.touched, store.scope = dict(params), {}, set(), []
+    leaves = {}
+    if cfg["training"]:  # trainable variables as autograd leaves: the loss of the reference's graph is differentiated below
+        import torch
+        for k, v in params.items():
+            if not k.endswith(("moving_mean", "moving_variance")):
+                leaves[k] = torch.tensor(v, dtype=torch.float64, requires_grad=True)
+        store.params.update(leaves)
     model = ref_f3.Feat3dNet(dict(NoRegress=cfg["no_regress"], BaseScale=2.0, Attention=cfg["attention"],
                                   num_clusters=cfg["num_clusters"], num_samples=cfg["num_samples"],
                                   feature_dim=cfg["feature_dim"], margin=cfg.get("margin", 0.2), freeze_scopes=None))
@@ -83,8 +90,8 @@ def run_reference(cfg, clouds, kp, params):
                                                                  compute_det_gradients=False)
     finally:
         ref_f3.sample_points = original
-    out = dict(xyz=xyz.numpy(), features=features.numpy(), attention_end_point=ep["attention"].numpy(),
-               orientation=ep["orientation"].numpy())
+    out = dict(xyz=xyz.detach().numpy(), features=features.detach().numpy(), attention_end_point=ep["attention"].detach().numpy(),
+               orientation=ep["orientation"].detach().numpy())
     if cfg.get("store_grouped"):  # the descriptor's clusters before / after the rotation by the detector's orientation
         out.update(grouped_xyz_before=ep["grouped_xyz_before"].numpy(), grouped_xyz=ep["grouped_xyz"].numpy())
     assert (attention is None) == (not cfg["attention"])
@@ -92,10 +99,21 @@ def run_reference(cfg, clouds, kp, params):
         import tensorflow as tf
         loss, ep2 = model.get_loss(None, tf.split(features, 3, axis=0),
                                    tf.split(attention, 3, axis=0)[0] if attention is not None else None, {})
-        out["loss"] = np.float64(loss.numpy())
-        out["sum_positive"], out["sum_negative"] = ep2["sum_positive"].numpy(), ep2["sum_negative"].numpy()
+        out["loss"] = np.float64(loss.detach().numpy())
+        out["sum_positive"], out["sum_negative"] = ep2["sum_positive"].detach().numpy(), ep2["sum_negative"].detach().numpy()
         for k, v in store.updates.items():
             out["bn_update/" + k] = v
+        # d loss / d variable through the reference's graph (autograd over the stand-in's primitives; tf.reduce_max and
+        # torch.amax both share the gradient equally among tied maxima)
+        names = sorted(leaves)
+        grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+        for k, g in zip(names, grads):
+            g = np.zeros_like(params[k], dtype=np.float64) if g is None else g.numpy()
+            # float64: norm and a fixed random projection per variable; the full tensor in float32 for one case (file size)
+            proj = np.random.default_rng(len(k)).standard_normal(g.size)
+            out["gradsum/" + k] = np.array([np.sqrt((g * g).sum()), float(g.ravel() @ proj)])
+            if cfg.get("store_gradients"):
+                out["grad/" + k] = g.astype(np.float32)
     unused = set(params) - store.touched
     assert not unused, "variables the reference graph never read: %s" % sorted(unused)
     return out
@@ -118,8 +136,8 @@ if __name__ == "__main__":
             store[name + "/keypoints"] = kp
         for k, v in out.items():
             store[name + "/out/" + k] = v
-        print(name, {k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items() if not k.startswith("bn_update")},
-              "bn updates:", sum(k.startswith("bn_update") for k in out))
+        print(name, {k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items() if "/" not in k},
+              "bn updates:", sum(k.startswith("bn_update") for k in out), "gradients:", sum(k.startswith("grad") for k in out))
     path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "ref_net.npz")
     np.savez_compressed(path, **store)
     print("wrote", path, os.path.getsize(path), "bytes")

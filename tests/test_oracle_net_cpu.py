@@ -225,6 +225,41 @@ def test_oracle_net_reproduces_the_reference_graph_golden():
                             "train_no_attention"])
 
 
+def test_oracle_gradients_reproduce_the_reference_graph_golden():
+    """d loss / d variable of the reference's own graph + get_loss (autograd through the stand-in's primitives) against the
+    gradients oracle.net.train_step differentiates -- the ones the CUDA backward is checked against (test_train_gpu.py)."""
+    seen = 0
+    for name, cfg, clouds, kp, want in _ref_net_cases():
+        if not cfg["training"]:
+            continue
+        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True), torch.float64,
+                          requires_grad=True)
+        a, p, n = np.split(clouds, 3, axis=0)
+        loss, grads, _ = onet.train_step(a, p, n, P, {}, cfg["num_clusters"], 2.0, cfg["num_samples"], cfg["feature_dim"],
+                                         cfg["margin"], cfg["attention"], cfg["no_regress"], lr=0.0, dtype=torch.float64)
+        assert abs(float(loss) - float(want["loss"])) < 1e-10
+        sums = {k[len("gradsum/"):]: v for k, v in want.items() if k.startswith("gradsum/")}
+        assert set(sums) == set(grads) and len(sums) == 40, name
+        nonzero = 0
+        for k, (norm, proj) in sums.items():
+            g = grads[k].detach().numpy().ravel()
+            r = np.random.default_rng(len(k)).standard_normal(g.size)
+            scale = max(norm, 1e-12)
+            assert abs(np.sqrt((g * g).sum()) - norm) <= 1e-8 * scale + 1e-14, (name, k)
+            assert abs(float(g @ r) - proj) <= 1e-7 * scale * np.sqrt(g.size) + 1e-14, (name, k)
+            nonzero += norm > 1e-9
+            if "grad/" + k in want:
+                full = want["grad/" + k].ravel().astype(np.float64)
+                assert np.abs(g - full).max() <= 1e-6 * max(np.abs(full).max(), 1e-12) + 1e-12, (name, k)
+        # conv biases in front of a training-mode BN have (numerically) zero gradient, and so has the attention head when the
+        # loss does not use it; every other variable must receive one
+        assert nonzero >= (30 if cfg["attention"] else 27), (name, nonzero)
+        if not cfg["attention"]:
+            assert sums["detection/attention/conv2d/weights"][0] == 0.0  # Attention=False: the detector gets no gradient
+        seen += 1
+    assert seen == 2
+
+
 def test_reference_graph_golden_has_the_interesting_cases():
     cases = {c[0]: c for c in _ref_net_cases()}
     kp_case = cases["eval_keypoints_fed"]
