@@ -9,6 +9,8 @@ container, not on the GPU box):
   data/augment.py                           imported as it is (NumPy only); its random draws are replaced by fixed values so
       that the geometric statement of every augmentation (axis, sign, composition order, clipping) is recorded.
 
+  tf_ops/grouping/tf_grouping.py::knn_point  taken out with `ast`, executed in float32 on tests/golden/tf_shim.py.
+
 Only inputs, draws and outputs are stored; no reference source is written anywhere.
 
     python tests/golden/make_golden_host.py
@@ -132,6 +134,42 @@ def reference_augmentations(cloud):
     return noise, out
 
 
+# ------------------------------------------------------------------------------------------- knn_point
+def reference_knn_point(k, xyz1, xyz2):
+    """knn_point of tf_ops/grouping/tf_grouping.py:63-88 (the file loads the op library at import, so the FunctionDef is taken
+    out with `ast`), executed in float32 on the TF stand-in of tf_shim.py; its select_top_k is the C oracle's selection sort,
+    which is pinned to the reference kernel.  What is the reference's: the (b,m,n,c) tiling, the squared distance, the slices."""
+    import contextlib
+    import io
+
+    import torch
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import tf_shim
+    from oracle import ops
+
+    tf, _ = tf_shim.build_tensorflow()
+    tf.slice = lambda x, begin, size: x[tuple(slice(b, None if n == -1 else b + n) for b, n in zip(begin, size))]
+
+    def select_top_k(kk, dist):
+        outi, out = ops.select_top_k(kk, dist.numpy())
+        return tf_shim.t(outi, torch.int32), tf_shim.t(out, torch.float32)
+
+    (knn_point,) = reference_functions("tf_ops/grouping/tf_grouping.py", ["knn_point"], dict(tf=tf, select_top_k=select_top_k))
+    with contextlib.redirect_stdout(io.StringIO()):  # the function prints its shapes
+        val, idx = knn_point(k, tf_shim.t(xyz1, torch.float32), tf_shim.t(xyz2, torch.float32))
+    return val.numpy(), idx.numpy()
+
+
+def knn_inputs(seed=21):
+    rng = np.random.default_rng(seed)
+    xyz1 = rng.uniform(-5, 5, (2, 400, 3)).astype(np.float32)
+    xyz2 = rng.uniform(-5, 5, (2, 48, 3)).astype(np.float32)
+    xyz1[0, 100:110] = xyz1[0, 0:10]  # duplicated points: equal distances, the selection sort's (unstable) tie order shows
+    xyz2[1, :8] = xyz1[1, :8]         # queries that are cloud points: zero distances
+    return xyz1, xyz2
+
+
 if __name__ == "__main__":
     import tempfile
 
@@ -148,6 +186,10 @@ if __name__ == "__main__":
     store["augment/cloud"], store["augment/noise"] = cloud, noise
     for k, v in outs.items():
         store["augment/" + k] = np.asarray(v, np.float64)
+    xyz1, xyz2 = knn_inputs()
+    val, idx = reference_knn_point(16, xyz1, xyz2)
+    store["knn/xyz1"], store["knn/xyz2"], store["knn/val"], store["knn/idx"] = xyz1, xyz2, val, idx
+    print("knn_point:", val.shape, idx.dtype)
     np.savez_compressed(os.path.join(HERE, "ref_host.npz"), **store)
     print("wrote ref_host.npz", os.path.getsize(os.path.join(HERE, "ref_host.npz")), "bytes")
     sys.exit(0)

@@ -137,3 +137,24 @@ def test_augmentations_and_generator_match_reference_live(tmp_path):
     our_dg.shuffle()
     our_dg.reset()
     assert list(our_dg.indices) == list(ref_dg.indices) == list(range(7))
+
+
+def test_knn_point_matches_reference_golden():
+    """the C oracle's knn_point (what the CUDA kNN is checked against) vs the reference's own Python knn_point: same float32
+    squared distances, same k smallest in the selection sort's order (ties included)"""
+    from oracle import ops
+    g = np.load(os.path.join(GOLD, "ref_host.npz"))
+    val, idx = ops.knn_point(16, g["knn/xyz1"], g["knn/xyz2"])
+    assert np.array_equal(idx, g["knn/idx"]) and np.array_equal(val, g["knn/val"])
+    assert (g["knn/val"][1, :8, 0] == 0).all() and (np.diff(g["knn/val"], axis=2) >= 0).all()
+    assert (np.diff(g["knn/val"][0], axis=1) == 0).any()  # the fixture holds exact ties
+
+
+@needs_reference
+def test_knn_point_matches_reference_live():
+    from oracle import ops
+    mk = _mk()
+    xyz1, xyz2 = mk.knn_inputs(seed=99)
+    val, idx = mk.reference_knn_point(5, xyz1, xyz2)
+    oval, oidx = ops.knn_point(5, xyz1, xyz2)
+    assert np.array_equal(idx, oidx) and np.array_equal(val, oval)
