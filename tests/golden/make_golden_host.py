@@ -9,6 +9,9 @@ container, not on the GPU box):
   data/augment.py                           imported as it is (NumPy only); its random draws are replaced by fixed values so
       that the geometric statement of every augmentation (axis, sign, composition order, clipping) is recorded.
 
+  compute_descriptors / nms                 inference.py:67-180,226-261, taken out with `ast`; the network factory and the TF
+      session are stand-ins evaluating `toy_network`, so the file loop, --num_points, the MAX_POINTS chunking of the attention
+      pass, NMS, --use_keypoints_from and the rows written are the reference's.
   tf_ops/grouping/tf_grouping.py::knn_point  taken out with `ast`, executed in float32 on tests/golden/tf_shim.py.
 
 Only inputs, draws and outputs are stored; no reference source is written anywhere.
@@ -170,6 +173,89 @@ def knn_inputs(seed=21):
     return xyz1, xyz2
 
 
+# ------------------------------------------------------------------------------------------- compute_descriptors
+def toy_network(cloud, keypoints, dim=8):
+    """Stand-in for the network in the file flow: attention_j = local density of the cloud around keypoint j (distinct values,
+    permutation invariant), descriptor_j = a few moments.  cloud (1,N,>=3), keypoints (1,M,3) -> xyz (1,M,3) f32,
+    features (1,M,dim) f32, attention (1,M) f32."""
+    pts = np.asarray(cloud, np.float64)[0, :, :3]
+    kp = np.asarray(keypoints, np.float64)[0]
+    d2 = ((kp[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    w = np.exp(-d2 / 4.0)
+    att = w.sum(1) / pts.shape[0] + 1e-3
+    mean = (w[:, :, None] * (pts[None] - kp[:, None])).sum(1) / w.sum(1)[:, None]
+    feats = np.concatenate([mean, att[:, None], np.sin(kp), np.full((kp.shape[0], dim - 7), pts.shape[0] / 1000.0)], axis=1)
+    return kp[None].astype(np.float32), feats[None].astype(np.float32), att[None].astype(np.float32)
+
+
+def write_inference_set(folder, seed=41):
+    """data/<name>.bin clouds (6 columns) and kp/<name>_kp.bin keypoint files (3 columns)."""
+    rng = np.random.default_rng(seed)
+    data, kps = os.path.join(folder, "data"), os.path.join(folder, "kp")
+    os.makedirs(data), os.makedirs(kps)
+    for name, n in (("scan_a", 1500), ("scan_b", 900)):
+        cloud = np.concatenate([rng.uniform(-6, 6, (n, 3)) * [1, 1, 0.2], rng.normal(size=(n, 3))], axis=1).astype(np.float32)
+        cloud.tofile(os.path.join(data, name + ".bin"))
+        (cloud[rng.permutation(n)[:23 if name == "scan_a" else 11], :3] + np.float32(0.25)).tofile(os.path.join(kps, name + "_kp.bin"))
+    return data, kps
+
+
+INFERENCE_CASES = {
+    "detect": dict(num_points=-1, use_keypoints_from=False, max_keypoints=64, max_points=700),
+    "detect_first_800": dict(num_points=800, use_keypoints_from=False, max_keypoints=1024, max_points=30000),
+    "keypoints_from": dict(num_points=-1, use_keypoints_from=True, max_keypoints=1024, max_points=30000),
+}
+
+
+def reference_compute_descriptors(data_dir, kp_dir, output_dir, case):
+    """The reference's compute_descriptors() and nms() (inference.py:67-180,226-261; FunctionDefs taken out with `ast`, the
+    module itself parses the command line and imports TensorFlow) run unmodified: `args` carries the CLI fields (:26-58),
+    the network factory returns a class whose ops are names, and tf.Session().run evaluates `toy_network` on the fed cloud and
+    keypoints.  MAX_POINTS (inference.py:22, 30000) is lowered in one case so that the attention pass is chunked."""
+    import logging
+    import types
+    from sklearn.neighbors import NearestNeighbors
+
+    class Net(object):
+        def __init__(self, param):
+            assert param["num_clusters"] == -1 and param["Attention"] is True  # inference.py:81-83
+            self.param = param
+
+        def get_placeholders(self, data_dim):
+            return "cloud_pl", None, None
+
+        def get_inference_model(self, cloud_pl, is_training, use_bn=True):
+            return "xyz_op", "features_op", "attention_op", {"keypoints": "keypoints_pl"}
+
+    class Session(object):
+        def __init__(self, config=None):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def run(self, fetches, feed_dict):
+            assert feed_dict["is_training_pl"] is False
+            xyz, feats, att = toy_network(feed_dict["cloud_pl"], feed_dict["keypoints_pl"])
+            return [dict(xyz_op=xyz, features_op=feats, attention_op=att)[f] for f in fetches]
+
+    dg = reference_module("data/datagenerator.py", "ref_datagenerator_inf")
+    args = types.SimpleNamespace(
+        gpu=0, model="3DFeatNet", data_dim=6, num_points=case["num_points"], base_scale=2.0, num_samples=64,
+        use_keypoints_from=kp_dir if case["use_keypoints_from"] else None, feature_dim=32, randomize_points=False, nms_radius=0.5,
+        min_response_ratio=1e-2, max_keypoints=case["max_keypoints"], data_dir=data_dir, checkpoint="unused", output_dir=output_dir)
+    ns = dict(np=np, os=os, args=args, logger=logging.getLogger("reference.inference"), MAX_POINTS=case["max_points"],
+              USE_BN=True, config=None, DataGenerator=dg.DataGenerator, NearestNeighbors=NearestNeighbors,
+              get_network=lambda name: Net, initialize_model=lambda sess, ckpt: None, log_arguments=lambda: None,
+              tf=types.SimpleNamespace(placeholder=lambda dtype: "is_training_pl", bool=bool, Session=Session))
+    compute_descriptors, _ = reference_functions("inference.py", ["compute_descriptors", "nms"], ns)
+    compute_descriptors()
+    return {f: np.fromfile(os.path.join(output_dir, f), dtype=np.float32) for f in sorted(os.listdir(output_dir))}
+
+
 if __name__ == "__main__":
     import tempfile
 
@@ -186,6 +272,12 @@ if __name__ == "__main__":
     store["augment/cloud"], store["augment/noise"] = cloud, noise
     for k, v in outs.items():
         store["augment/" + k] = np.asarray(v, np.float64)
+    with tempfile.TemporaryDirectory() as tmp:
+        data_dir, kp_dir = write_inference_set(tmp)
+        for cname, case in INFERENCE_CASES.items():
+            for f, rows in reference_compute_descriptors(data_dir, kp_dir, os.path.join(tmp, "out_" + cname), case).items():
+                store["inference/%s/%s" % (cname, f)] = rows
+                print("compute_descriptors:", cname, f, rows.size // 11, "keypoints")
     xyz1, xyz2 = knn_inputs()
     val, idx = reference_knn_point(16, xyz1, xyz2)
     store["knn/xyz1"], store["knn/xyz2"], store["knn/val"], store["knn/idx"] = xyz1, xyz2, val, idx

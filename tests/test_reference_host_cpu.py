@@ -158,3 +158,59 @@ def test_knn_point_matches_reference_live():
     val, idx = mk.reference_knn_point(5, xyz1, xyz2)
     oval, oidx = ops.knn_point(5, xyz1, xyz2)
     assert np.array_equal(idx, oidx) and np.array_equal(val, oval)
+
+
+class ToyFlowModel(object):
+    """get_inference_model(cloud, False, keypoints=..., fetch_features=...) -> the stand-in network of the golden file"""
+
+    def __init__(self, mk):
+        self.mk = mk
+
+    def get_inference_model(self, pc, is_training, keypoints=None, fetch_features=True):
+        assert is_training is False
+        xyz, feats, att = self.mk.toy_network(pc.numpy(), keypoints.numpy())
+        att = torch.as_tensor(att)
+        return torch.as_tensor(xyz), (torch.as_tensor(feats) if fetch_features else None), att, {"attention": att}
+
+
+def _our_compute_descriptors(mk, monkeypatch, data_dir, kp_dir, out_dir, case):
+    from oracle import nms as onms
+    inf = pkg("inference")
+
+    def cpu_nms(xyz, attention, nms_radius, min_response_ratio, max_keypoints):  # the device NMS refuses CPU tensors
+        x, a, num, _ = onms.nms(xyz.numpy(), attention.numpy(), nms_radius, min_response_ratio, max_keypoints)
+        return torch.as_tensor(x), torch.as_tensor(a), num
+
+    monkeypatch.setattr(inf, "nms", cpu_nms)
+    monkeypatch.setattr(inf, "MAX_POINTS", case["max_points"])
+    done = inf.compute_descriptors(ToyFlowModel(mk), data_dir, out_dir, data_dim=6, num_points=case["num_points"],
+                                   use_keypoints_from=kp_dir if case["use_keypoints_from"] else None,
+                                   max_keypoints=case["max_keypoints"], device="cpu")
+    return {f: np.fromfile(os.path.join(out_dir, f), dtype=np.float32) for f in done}
+
+
+def test_compute_descriptors_matches_reference_golden(tmp_path, monkeypatch):
+    """the reference's compute_descriptors() + nms() run unmodified around a stand-in network (make_golden_host.py): chunked
+    attention pass over every point, NMS, keypoints kept / padded, --num_points, --use_keypoints_from, the rows written"""
+    mk = _mk()
+    g = np.load(os.path.join(GOLD, "ref_host.npz"))
+    data_dir, kp_dir = mk.write_inference_set(str(tmp_path))
+    for cname, case in mk.INFERENCE_CASES.items():
+        ours = _our_compute_descriptors(mk, monkeypatch, data_dir, kp_dir, str(tmp_path / ("out_" + cname)), case)
+        assert sorted(ours) == ["scan_a.bin", "scan_b.bin"]
+        for f, rows in ours.items():
+            want = g["inference/%s/%s" % (cname, f)]
+            assert rows.size == want.size and rows.size % 11 == 0 and rows.size > 0, (cname, f)
+            assert np.array_equal(rows, want), (cname, f)
+
+
+@needs_reference
+def test_compute_descriptors_matches_reference_live(tmp_path, monkeypatch):
+    mk = _mk()
+    data_dir, kp_dir = mk.write_inference_set(str(tmp_path), seed=77)
+    case = dict(num_points=1000, use_keypoints_from=False, max_keypoints=200, max_points=333)
+    want = mk.reference_compute_descriptors(data_dir, kp_dir, str(tmp_path / "ref_out"), case)
+    ours = _our_compute_descriptors(mk, monkeypatch, data_dir, kp_dir, str(tmp_path / "our_out"), case)
+    assert sorted(ours) == sorted(want)
+    for f in want:
+        assert np.array_equal(ours[f], want[f]), f
