@@ -300,11 +300,13 @@ def initialize_model(model, checkpoint, ignore_missing_vars=False, restore_exclu
     if checkpoint is None:
         return []
     ckpt = load_checkpoint(checkpoint)
-    exclude = tuple(e.rstrip("/") + "/" for e in (restore_exclude or []))
+    import re
+    # tf.get_collection(GLOBAL_VARIABLES, scope=e) keeps the variables whose name re.match()es e: a regex PREFIX match
+    excluded = lambda name: any(re.match(e, name) for e in (restore_exclude or []))
     restored, missing = [], []
     with torch.no_grad():
         for name, dst in model.weights.items():
-            if exclude and name.startswith(exclude):
+            if excluded(name):
                 continue
             if name not in ckpt:
                 missing.append(name)

@@ -137,6 +137,45 @@ def reference_augmentations(cloud):
     return noise, out
 
 
+# ------------------------------------------------------------------------------------------- initialize_model
+def reference_restore_plan(model_vars, checkpoint_vars, ignore_missing_vars, restore_exclude):
+    """initialize_model of inference.py:183-217 (same text in train.py:187-232) run unmodified over stand-in TF objects:
+    returns ("restore", [names handed to tf.train.Saver]) or ("error", [names the Saver would not find in the checkpoint]).
+    Restated TF behaviour: get_collection(GLOBAL_VARIABLES, scope) filters with re.match(scope, name); Saver.restore raises
+    NotFoundError when a variable of its var_list is absent from the checkpoint."""
+    import logging
+    import re
+    import types
+
+    class Var(object):
+        def __init__(self, name):
+            self.op = types.SimpleNamespace(name=name)
+
+        def __repr__(self):
+            return self.op.name
+
+    variables = [Var(n) for n in model_vars]
+    result = {}
+
+    class Saver(object):
+        def __init__(self, var_list):
+            self.names = [v.op.name for v in var_list]
+
+        def restore(self, sess, checkpoint):
+            absent = [n for n in self.names if n not in checkpoint_vars]
+            result["plan"] = ("error", absent) if absent else ("restore", self.names)
+
+    tf = types.SimpleNamespace(
+        global_variables_initializer=lambda: "init", GraphKeys=types.SimpleNamespace(GLOBAL_VARIABLES="global_variables"),
+        get_collection=lambda key, scope=None: [v for v in variables if scope is None or re.match(scope, v.op.name)],
+        train=types.SimpleNamespace(Saver=Saver))
+    ns = dict(tf=tf, logger=logging.getLogger("reference.inference"), args=types.SimpleNamespace(checkpoint="ckpt"),
+              get_tensors_in_checkpoint_file=lambda ckpt: list(checkpoint_vars), print=lambda *a, **k: None)
+    (initialize_model,) = reference_functions("inference.py", ["initialize_model"], ns)
+    initialize_model(types.SimpleNamespace(run=lambda op: None), "ckpt", ignore_missing_vars, restore_exclude)
+    return result["plan"]
+
+
 # ------------------------------------------------------------------------------------------- knn_point
 def reference_knn_point(k, xyz1, xyz2):
     """knn_point of tf_ops/grouping/tf_grouping.py:63-88 (the file loads the op library at import, so the FunctionDef is taken

@@ -214,3 +214,32 @@ def test_compute_descriptors_matches_reference_live(tmp_path, monkeypatch):
     assert sorted(ours) == sorted(want)
     for f in want:
         assert np.array_equal(ours[f], want[f]), f
+
+
+@needs_reference
+def test_initialize_model_restore_rules_match_reference_live(tmp_path):
+    """checkpoint.initialize_model vs the reference's initialize_model (inference.py:183-217) run unmodified over stand-in TF
+    objects: which variables are restored, which are excluded (regex prefix match of the scope), and when a missing one is fatal"""
+    import types
+    from oracle import net as onet
+    mk, ck = _mk(), importlib.import_module("3dfeatnet_b200.checkpoint")
+    params = onet.init_params(seed=1, randomize_bn=True)
+    model_vars = sorted(params)
+    partial = {k: v for k, v in params.items() if not k.startswith("detection/conv_post_1") and "orientation" not in k}
+    full_path, part_path = str(tmp_path / "full.npz"), str(tmp_path / "part.npz")
+    ck.save_npz(params, full_path)
+    ck.save_npz(partial, part_path)
+    for path, ckpt_vars in ((full_path, set(params)), (part_path, set(partial))):
+        for ignore in (False, True):
+            for exclude in (None, ["detection"], ["description/layer1/conv_mid", "detection/att"], ["detection/conv_post_1", "detection/orient"]):
+                kind, names = mk.reference_restore_plan(model_vars, ckpt_vars, ignore, exclude)
+                model = types.SimpleNamespace(weights={k: torch.zeros(v.shape) for k, v in params.items()}, invalidate=lambda: None)
+                if kind == "error":
+                    with pytest.raises(KeyError):
+                        ck.initialize_model(model, path, ignore, exclude)
+                else:
+                    restored = ck.initialize_model(model, path, ignore, exclude)
+                    assert sorted(restored) == sorted(names), (path, ignore, exclude)
+                    for k in model_vars:
+                        same = torch.equal(model.weights[k], torch.as_tensor(params[k]))
+                        assert same == (k in names) or not params[k].any(), k
