@@ -119,6 +119,61 @@ def run_reference(cfg, clouds, kp, params):
     return out
 
 
+# ---------------------------------------------------------------------------- models/pointnet_common.py on its own
+def composition_inputs(seed=23):
+    rng = np.random.default_rng(seed)
+    xyz = rng.uniform(-3, 3, (2, 500, 3)).astype(np.float32)
+    points = rng.normal(size=(2, 500, 5)).astype(np.float32)
+    keypoints = xyz[:, :20].copy()
+    keypoints[:, 10:] += rng.normal(0, 0.5, (2, 10, 3)).astype(np.float32)
+    keypoints[:, -2:] += np.float32(100.0)  # empty balls
+    orientations = rng.uniform(-np.pi, np.pi, (2, 20)).astype(np.float32)
+    return xyz, points, keypoints, orientations
+
+
+def composition_cases():
+    """(function name, keyword arguments) for every branch of the four functions: features or not, use_xyz, kNN, radius
+    normalisation, fed keypoints vs FPS, and the two (opposite) rotation conventions."""
+    cases = [("sample_points", dict(npoint=16)), ("sample_points", dict(npoint=0))]
+    for with_points in (False, True):
+        for use_xyz in (True, False):
+            for knn in (False, True):
+                for normalize in (True, False):
+                    for orient in (False, True):
+                        kw = dict(with_points=with_points, use_xyz=use_xyz, knn=knn, normalize_radius=normalize, orient=orient)
+                        cases.append(("query_and_group_points", dict(kw)))
+                        cases.append(("sample_and_group", dict(kw, fed_keypoints=orient or knn)))
+            cases.append(("sample_and_group_all", dict(with_points=with_points, use_xyz=use_xyz)))
+    return cases
+
+
+def digest(a, seed):
+    """shape (padded to 5) followed by four fixed random projections of the flattened tensor, float64"""
+    a = np.asarray(a, np.float64)
+    proj = np.random.default_rng(1000 + seed).standard_normal((4, a.size)) @ a.ravel()
+    return np.concatenate([np.array(a.shape + (0,) * (5 - a.ndim), np.float64), proj])
+
+
+def call_composition(mod, wrap, fn, kw, xyz, points, keypoints, orientations, nsample=16, radius=1.5, npoint=20):
+    """Calls `fn` of a pointnet_common module (the reference's on the stand-in, or the product's) and returns its tensors in a
+    flat, ordered list.  `wrap` turns a NumPy array into the module's tensor type."""
+    X, P, K, O = wrap(xyz), wrap(points), wrap(keypoints), wrap(orientations)
+    if fn == "sample_points":
+        return [mod.sample_points(X, kw["npoint"])]
+    pts = P if kw["with_points"] else None
+    if fn == "sample_and_group_all":
+        return list(mod.sample_and_group_all(X, pts, kw["use_xyz"]))
+    ori = O if kw["orient"] else None
+    if fn == "query_and_group_points":
+        return list(mod.query_and_group_points(X, pts, K, nsample, radius, knn=kw["knn"], use_xyz=kw["use_xyz"],
+                                               normalize_radius=kw["normalize_radius"], orientations=ori))
+    new_xyz, new_points, idx, grouped, ep = mod.sample_and_group(
+        npoint, radius, nsample, X, pts, knn=kw["knn"], use_xyz=kw["use_xyz"], keypoints=K if kw["fed_keypoints"] else None,
+        orientations=ori, normalize_radius=kw["normalize_radius"])
+    out = [new_xyz, new_points, idx, grouped, ep["grouped_xyz_before"], ep["grouped_xyz"]]
+    return out + ([ep["rotation"]] if kw["orient"] else [])
+
+
 if __name__ == "__main__":
     import tf_shim
     from oracle import net as onet
@@ -138,6 +193,19 @@ if __name__ == "__main__":
             store[name + "/out/" + k] = v
         print(name, {k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items() if "/" not in k},
               "bn updates:", sum(k.startswith("bn_update") for k in out), "gradients:", sum(k.startswith("grad") for k in out))
+    import models.pointnet_common as ref_pc  # the reference's file
+    assert ref_pc.__file__.startswith(tf_shim_root), ref_pc.__file__
+    inputs = composition_inputs()
+    for i, (fn, kw) in enumerate(composition_cases()):
+        outs = call_composition(ref_pc, tf_shim.t, fn, kw, *inputs)
+        full = fn == "sample_points" or (kw["with_points"] and kw["use_xyz"] and (fn == "sample_and_group_all" or (
+            not kw["knn"] and kw["normalize_radius"] and kw["orient"])))
+        for j, o in enumerate(outs):
+            a = o.detach().numpy()
+            store["pointnet_common/%03d/%d/digest" % (i, j)] = digest(a, i * 16 + j)
+            if full:  # whole tensors for one call per function; shape + projections for every branch (file size)
+                store["pointnet_common/%03d/%d/full" % (i, j)] = a.astype(np.int32) if a.dtype.kind == "i" else a.astype(np.float32)
+    print("pointnet_common:", len(composition_cases()), "calls")
     path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "ref_net.npz")
     np.savez_compressed(path, **store)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -192,7 +192,8 @@ def build_tensorflow():
         "tensorflow", float32=DTYPE, float16=torch.float16, Tensor=T, AUTO_REUSE="AUTO_REUSE",
         variable_scope=variable_scope, get_variable_scope=get_variable_scope, control_dependencies=control_dependencies,
         expand_dims=lambda x, axis=None, dim=None: torch.unsqueeze(x, axis if axis is not None else dim),
-        tile=lambda x, multiples: x.repeat(*[int(m) for m in multiples]),
+        tile=lambda x, multiples: (x if isinstance(x, torch.Tensor) else t(x, torch.int64)).repeat(*[int(m) for m in multiples]),
+        shape=lambda x: tuple(x.shape),
         concat=lambda values, axis: torch.cat(list(values), dim=axis),
         stack=lambda values, axis=0: torch.movedim(t(list(values)), 0, axis),
         split=lambda x, n, axis=0: list(torch.chunk(x, n, dim=axis)),

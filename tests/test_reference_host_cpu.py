@@ -243,3 +243,64 @@ def test_initialize_model_restore_rules_match_reference_live(tmp_path):
                     for k in model_vars:
                         same = torch.equal(model.weights[k], torch.as_tensor(params[k]))
                         assert same == (k in names) or not params[k].any(), k
+
+
+def _product_pointnet_common_on_cpu(monkeypatch):
+    """The product's models/pointnet_common.py with its five CUDA operators replaced by the C oracle, so that the composition
+    code around them (what the reference's file states in TF) can run without a GPU."""
+    from oracle import ops
+    pc = pkg("models.pointnet_common")
+    f32 = lambda x: np.ascontiguousarray(x.detach().numpy(), np.float32)
+    i32 = lambda x: np.ascontiguousarray(x.detach().numpy(), np.int32)
+    ti = lambda a: torch.as_tensor(np.asarray(a, np.int32))
+
+    def query_ball_point(radius, nsample, xyz1, xyz2):
+        idx, cnt = ops.query_ball_point(radius, nsample, f32(xyz1), f32(xyz2))
+        return ti(idx), ti(cnt)
+
+    def knn_point(k, xyz1, xyz2):
+        val, idx = ops.knn_point(k, f32(xyz1), f32(xyz2))
+        return torch.as_tensor(val), ti(idx)
+
+    monkeypatch.setattr(pc, "query_ball_point", query_ball_point)
+    monkeypatch.setattr(pc, "knn_point", knn_point)
+    monkeypatch.setattr(pc, "group_point", lambda points, idx: torch.as_tensor(ops.group_point(f32(points), i32(idx))))
+    monkeypatch.setattr(pc, "farthest_point_sample", lambda npoint, inp: ti(ops.farthest_point_sample(npoint, f32(inp))))
+    monkeypatch.setattr(pc, "gather_point", lambda inp, idx: torch.as_tensor(ops.gather_point(f32(inp), i32(idx))))
+    monkeypatch.setattr(pc, "_last_query", None)
+    return pc
+
+
+def test_pointnet_common_compositions_match_reference_golden(monkeypatch):
+    """tests/golden/ref_net.npz holds the outputs of the reference's OWN models/pointnet_common.py (executed unmodified on the TF
+    stand-in) for every branch of sample_points / query_and_group_points / sample_and_group / sample_and_group_all: with and
+    without point features, use_xyz, kNN, radius normalisation, fed keypoints vs FPS, and the two opposite rotation conventions
+    (:49-54 vs :112-119).  The product's compositions must return the same tensors in the same order."""
+    spec = importlib.util.spec_from_file_location("make_golden_net", os.path.join(GOLD, "make_golden_net.py"))
+    mkn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mkn)
+    pc = _product_pointnet_common_on_cpu(monkeypatch)
+    g = np.load(os.path.join(GOLD, "ref_net.npz"))
+    inputs = mkn.composition_inputs()
+    cases = mkn.composition_cases()
+    assert len(cases) == 70
+    checked_full = 0
+    for i, (fn, kw) in enumerate(cases):
+        outs = mkn.call_composition(pc, torch.as_tensor, fn, kw, *inputs)
+        keys = [k for k in g.files if k.startswith("pointnet_common/%03d/" % i) and k.endswith("/digest")]
+        assert len(outs) == len(keys), (fn, kw)
+        for j, o in enumerate(outs):
+            a = o.detach().numpy()
+            want = g["pointnet_common/%03d/%d/digest" % (i, j)]
+            got = mkn.digest(a, i * 16 + j)
+            assert tuple(got[:5]) == tuple(want[:5]), (fn, kw, j, "shape")
+            scale = np.sqrt((np.asarray(a, np.float64) ** 2).sum()) + 1e-12
+            assert np.abs(got[5:] - want[5:]).max() <= 2e-5 * scale, (fn, kw, j)
+            fk = "pointnet_common/%03d/%d/full" % (i, j)
+            if fk in g.files:
+                checked_full += 1
+                if g[fk].dtype.kind == "i":
+                    assert np.array_equal(a, g[fk]), (fn, kw, j)
+                else:
+                    assert np.allclose(a, g[fk], rtol=1e-5, atol=1e-5), (fn, kw, j)
+    assert checked_full >= 2 + 2 + 7 + 4
