@@ -181,7 +181,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def _ref_net_cases(path=None):
     g = np.load(path or os.path.join(GOLD, "ref_net.npz"))
-    for name in sorted({k.split("/")[0] for k in g.files}):
+    for name in sorted({k.split("/")[0] for k in g.files if k.endswith("/config")}):  # the model cases ("pointnet_common/..." apart)
         cfg = json.loads(str(g[name + "/config"]))
         out = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(name + "/out/")}
         yield name, cfg, g[name + "/clouds"], (g[name + "/keypoints"] if name + "/keypoints" in g.files else None), out
