@@ -264,9 +264,10 @@ def _product_pointnet_common_on_cpu(monkeypatch):
 
     monkeypatch.setattr(pc, "query_ball_point", query_ball_point)
     monkeypatch.setattr(pc, "knn_point", knn_point)
-    monkeypatch.setattr(pc, "group_point", lambda points, idx: torch.as_tensor(ops.group_point(f32(points), i32(idx))))
+    # gathers return the dtype they were given (float64 callers hold float32-representable coordinates)
+    monkeypatch.setattr(pc, "group_point", lambda points, idx: torch.as_tensor(ops.group_point(f32(points), i32(idx))).to(points.dtype))
     monkeypatch.setattr(pc, "farthest_point_sample", lambda npoint, inp: ti(ops.farthest_point_sample(npoint, f32(inp))))
-    monkeypatch.setattr(pc, "gather_point", lambda inp, idx: torch.as_tensor(ops.gather_point(f32(inp), i32(idx))))
+    monkeypatch.setattr(pc, "gather_point", lambda inp, idx: torch.as_tensor(ops.gather_point(f32(inp), i32(idx))).to(inp.dtype))
     monkeypatch.setattr(pc, "_last_query", None)
     return pc
 
@@ -304,3 +305,62 @@ def test_pointnet_common_compositions_match_reference_golden(monkeypatch):
                 else:
                     assert np.allclose(a, g[fk], rtol=1e-5, atol=1e-5), (fn, kw, j)
     assert checked_full >= 2 + 2 + 7 + 4
+
+
+def test_product_module_graph_matches_reference_graph_golden(monkeypatch):
+    """The product's own differentiable statements -- models.feat3dnet.feature_detection_module / feature_extraction_module /
+    Feat3dNet.get_loss over models.layers and models.pointnet_common -- run on the CPU in float64 (the five CUDA operators
+    replaced by the C oracle) against the outputs of the reference's graph files executed unmodified (tests/golden/ref_net.npz):
+    keypoints exact, attention / orientation / descriptors / BN shadow updates / loss to 1e-9, loss gradients to 1e-8.  The fused CUDA kernels are held
+    to the same semantics by test_model_gpu.py and test_train_gpu.py."""
+    import json
+    from oracle import net as onet
+    _product_pointnet_common_on_cpu(monkeypatch)
+    f3 = pkg("models.feat3dnet")
+    g = np.load(os.path.join(GOLD, "ref_net.npz"))
+    names = sorted({k.split("/")[0] for k in g.files if k.endswith("/config")})
+    assert len(names) == 6
+    for name in names:
+        cfg = json.loads(str(g[name + "/config"]))
+        want = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(name + "/out/")}
+        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True), torch.float64,
+                          requires_grad=cfg["training"])
+        xyz = torch.as_tensor(g[name + "/clouds"][:, :, :3]).double().contiguous()
+        kp = torch.as_tensor(g[name + "/keypoints"]).double() if name + "/keypoints" in g.files else None
+        stats = {}
+        new_xyz, idx, att, ori, _ = f3.feature_detection_module(
+            xyz, None, cfg["num_clusters"], 2.0, cfg["training"], [64, 128, 256], [128, 64], num_samples=cfg["num_samples"],
+            params=P, new_stats=stats, keypoints=kp)
+        _, feats, ep = f3.feature_extraction_module(
+            xyz, None, cfg["training"], [32, 64], [128 if cfg["feature_dim"] <= 64 else 256], [cfg["feature_dim"]],
+            keypoints=new_xyz, orientations=None if cfg["no_regress"] else ori, radius=2.0, num_samples=cfg["num_samples"],
+            params=P, new_stats=stats)
+        assert np.array_equal(new_xyz.numpy(), want["xyz"]), name
+        assert torch.allclose(att, torch.as_tensor(want["attention_end_point"]), rtol=1e-9, atol=1e-12), name
+        d = ori - torch.as_tensor(want["orientation"])
+        assert torch.atan2(torch.sin(d), torch.cos(d)).abs().max() < 1e-9, name
+        assert torch.allclose(feats, torch.as_tensor(want["features"]), rtol=1e-9, atol=1e-11), name
+        if "grouped_xyz" in want:
+            assert torch.allclose(ep["grouped_xyz"], torch.as_tensor(want["grouped_xyz"]), rtol=1e-9, atol=1e-12)
+            assert torch.allclose(ep["grouped_xyz_before"], torch.as_tensor(want["grouped_xyz_before"]), rtol=1e-12, atol=1e-14)
+        if cfg["training"]:
+            net = f3.Feat3dNet.__new__(f3.Feat3dNet)
+            net.param = dict(Attention=cfg["attention"], margin=cfg["margin"])
+            loss, _ = net.get_loss(None, torch.chunk(feats, 3, dim=0), torch.chunk(att, 3, dim=0)[0] if cfg["attention"] else None, {})
+            assert abs(float(loss.detach()) - float(want["loss"])) < 1e-10, name
+            updates = {k[len("bn_update/"):]: v for k, v in want.items() if k.startswith("bn_update/")}
+            assert set(updates) == set(stats) and len(stats) == 18, name
+            for k, v in updates.items():
+                assert torch.allclose(stats[k].value(P[k]), torch.as_tensor(v), rtol=1e-9, atol=1e-12), (name, k)
+            # d loss / d variable through the product's layers (autograd) == through the reference's graph
+            leaves = sorted(k for k, v in P.items() if v.requires_grad)
+            grads = torch.autograd.grad(loss, [P[k] for k in leaves], allow_unused=True)
+            for k, gr in zip(leaves, grads):
+                norm, proj = want["gradsum/" + k]
+                gr = np.zeros(P[k].numel()) if gr is None else gr.numpy().ravel()
+                r = np.random.default_rng(len(k)).standard_normal(gr.size)
+                scale = max(norm, 1e-12)
+                assert abs(np.sqrt((gr * gr).sum()) - norm) <= 1e-8 * scale + 1e-14, (name, k)
+                assert abs(float(gr @ r) - proj) <= 1e-7 * scale * np.sqrt(gr.size) + 1e-14, (name, k)
+        else:
+            assert stats == {}
