@@ -142,7 +142,7 @@ def run_reference(args):
     synth = importlib.import_module("3dfeatnet_b200.synth")
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = max(1, args.cpu_sample)
+    sample = max(1, min(args.cpu_sample, args.batch))
     xyz = synth.make_batch(sample, args.points, seed0=1000)
     params = onet.to_torch(onet.init_params(seed=0))
     for _ in range(min(args.warmup, 1)):
@@ -157,7 +157,7 @@ def run_reference(args):
                 config=dict(workload=workload_name(args.batch, args.points, args.clusters, args.nsample), clouds_per_step=sample,
                             precision="fp32", parallelism="rank 0 only, all host threads"),
                 cpu_baseline=dict(value=value, unit="keypoints/s", cores=max(cores, oops.num_threads()), kind="port",
-                                  sample="%d clouds of %d points per step (of the 64-cloud batch)" % (sample, args.points)),
+                                  sample="%d clouds of %d points per step (of the %d-cloud batch)" % (sample, args.points, args.batch)),
                 e2e=dict(value=value, unit="keypoints/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 

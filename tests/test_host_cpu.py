@@ -486,3 +486,27 @@ def test_validation_metric_and_cluster_stacking(tmp_path):
     assert np.allclose(pc[0, 20:41, 0], clouds[1][:, 0] + 100.0) and np.array_equal(pc[0, 20:41, 1:], clouds[1][:, 1:])
     assert offsets[0, :4, 0].tolist() == [0.0, 100.0, 200.0, 0.0] and not offsets[0, :, 1:].any()
     assert val.validate(None, str(tmp_path), []) == 1  # nothing to validate (train.py:262-263)
+
+
+def test_bench_reference_arm_prints_the_contracted_line_and_product_arm_needs_cuda():
+    """bench.py --impl reference (the CPU statement of the path on the host cores) prints ONE JSON line with the contract's
+    keys; the product arm has no CPU fallback: without a GPU it fails instead of timing anything."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    small = ["--steps", "1", "--warmup", "0", "--batch", "2", "--points", "2048", "--clusters", "64"]
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"] + small, capture_output=True,
+                       text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "keypoints+descriptors/sec" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == dict(value=d["value"], unit=d["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert d["config"]["clouds_per_step"] == 2 and "2 clouds" in d["cpu_baseline"]["sample"] and "workload" in d["config"]
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py")] + small, capture_output=True, text=True, timeout=600,
+                           cwd=root)
+        assert r.returncode != 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
