@@ -6,6 +6,7 @@ import torch
 
 _ROOT = __name__.split(".")[0]
 _lib = importlib.import_module("3dfeatnet_b200._lib" if _ROOT == "3dfeatnet_b200" else "_lib")
+_dist = importlib.import_module("3dfeatnet_b200.dist" if _ROOT == "3dfeatnet_b200" else "dist")
 
 MAX_POINTS = 30000  # inference.py:22: centres per detection pass
 
@@ -109,18 +110,21 @@ def compute_descriptors_for_file(model, in_path, out_path, randomize_points=Fals
 
 
 def compute_descriptors(model, data_dir, output_dir, data_dim=6, num_points=-1, use_keypoints_from=None, randomize_points=False,
-                        nms_radius=0.5, min_response_ratio=1e-2, max_keypoints=1024, seed=0, device="cuda"):
+                        nms_radius=0.5, min_response_ratio=1e-2, max_keypoints=1024, seed=0, device="cuda", rank=0, world=1):
     """compute_descriptors() of inference.py:67-180 without the TF session / argument parsing: every `<name>.bin` of
     `data_dir` -> `output_dir/<name>.bin` holding [xyz | descriptor] float32 rows.  The arguments are the CLI's (:26-58);
     with `use_keypoints_from` the keypoints of `<use_keypoints_from>/<name>_kp.bin` are described instead of detected ones.
     `model` is a Feat3dNet built the way the reference builds it for inference (num_clusters=-1, Attention=True, :81-83).
-    Returns the processed file names in the order they were processed (sorted; the reference takes os.listdir order)."""
+    Scans are independent, so with `world` > 1 processes (one per GPU) rank r takes the r-th contiguous slice of the sorted
+    file list (dist.shard_range) and no collective is needed; the permutation seed of a file does not depend on the split.
+    Returns the file names this rank processed, in order (sorted; the reference takes os.listdir order)."""
     import os
 
     os.makedirs(output_dir, exist_ok=True)
     bin_files = sorted(f for f in os.listdir(data_dir) if f.endswith(".bin"))
-    for i, f in enumerate(bin_files):
+    lo, hi = _dist.shard_range(len(bin_files), rank, world)
+    for i, f in list(enumerate(bin_files))[lo:hi]:
         kp_path = None if use_keypoints_from is None else os.path.join(use_keypoints_from, "%s_kp.bin" % f[:-4])
         compute_descriptors_for_file(model, os.path.join(data_dir, f), os.path.join(output_dir, f), randomize_points, seed + i,
                                      max_keypoints, nms_radius, min_response_ratio, device, num_points, kp_path, data_dim)
-    return bin_files
+    return bin_files[lo:hi]

@@ -273,6 +273,19 @@ def test_compute_descriptors_directory_flow(tmp_path, monkeypatch):
     rows = np.fromfile(out / "a2.bin", dtype=np.float32).reshape(3, 7)
     best = clouds["a"][np.argsort(-clouds["a"][:, 0], kind="stable")[:3], :3]
     assert np.array_equal(rows[:, :3], best)           # the permutation does not change which points win
+    # one process per GPU: the sorted file list is cut into contiguous slices, every file is processed exactly once, and the
+    # rows a rank writes equal the single-process ones
+    for n_files in range(5):
+        clouds["a"].tofile(data / ("shard%d.bin" % n_files))
+    single = tmp_path / "single"
+    all_files = inf.compute_descriptors(Model(), str(data), str(single), max_keypoints=6, device="cpu", randomize_points=True)
+    for world in (2, 3, 8):
+        sharded = tmp_path / ("world%d" % world)
+        parts = [inf.compute_descriptors(Model(), str(data), str(sharded), max_keypoints=6, device="cpu", randomize_points=True,
+                                         rank=r, world=world) for r in range(world)]
+        assert [f for p in parts for f in p] == all_files and max(map(len, parts)) - min(map(len, parts)) <= 1
+        for f in all_files:
+            assert (sharded / f).read_bytes() == (single / f).read_bytes(), (world, f)
     # data_dim: a 3-column cloud file
     clouds["a"][:, :3].copy().tofile(data / "c3.bin")
     assert inf.compute_descriptors_for_file(Model(), str(data / "c3.bin"), str(out / "c3.bin"), max_keypoints=6, device="cpu",
