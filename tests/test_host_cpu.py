@@ -523,3 +523,108 @@ def test_bench_reference_arm_prints_the_contracted_line_and_product_arm_needs_cu
         r = subprocess.run([sys.executable, os.path.join(root, "bench.py")] + small, capture_output=True, text=True, timeout=600,
                            cwd=root)
         assert r.returncode != 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def _tensor_bundle_protos():
+    """BundleHeaderProto / BundleEntryProto / TensorShapeProto (tensorflow/core/protobuf/tensor_bundle.proto,
+    framework/tensor_shape.proto: field numbers as published) built at run time with the protobuf library."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="f3d_test_tensor_bundle.proto", package="f3dtest", syntax="proto3")
+
+    def msg(name, fields, parent=None):
+        m = (parent.nested_type if parent is not None else fd.message_type).add(name=name)
+        for fname, number, ftype, label, type_name in fields:
+            f = m.field.add(name=fname, number=number, type=ftype, label=label)
+            if type_name:
+                f.type_name = type_name
+        return m
+
+    shape = msg("TensorShapeProto", [("dim", 2, F.TYPE_MESSAGE, F.LABEL_REPEATED, ".f3dtest.TensorShapeProto.Dim"),
+                                     ("unknown_rank", 3, F.TYPE_BOOL, F.LABEL_OPTIONAL, None)])
+    msg("Dim", [("size", 1, F.TYPE_INT64, F.LABEL_OPTIONAL, None), ("name", 2, F.TYPE_STRING, F.LABEL_OPTIONAL, None)], parent=shape)
+    msg("VersionDef", [("producer", 1, F.TYPE_INT32, F.LABEL_OPTIONAL, None), ("min_consumer", 2, F.TYPE_INT32, F.LABEL_OPTIONAL, None)])
+    msg("BundleHeaderProto", [("num_shards", 1, F.TYPE_INT32, F.LABEL_OPTIONAL, None), ("endianness", 2, F.TYPE_INT32, F.LABEL_OPTIONAL, None),
+                              ("version", 3, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".f3dtest.VersionDef")])
+    msg("BundleEntryProto", [("dtype", 1, F.TYPE_INT32, F.LABEL_OPTIONAL, None),
+                             ("shape", 2, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".f3dtest.TensorShapeProto"),
+                             ("shard_id", 3, F.TYPE_INT32, F.LABEL_OPTIONAL, None), ("offset", 4, F.TYPE_INT64, F.LABEL_OPTIONAL, None),
+                             ("size", 5, F.TYPE_INT64, F.LABEL_OPTIONAL, None), ("crc32c", 6, F.TYPE_FIXED32, F.LABEL_OPTIONAL, None)])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName("f3dtest." + n))
+    return get("BundleHeaderProto"), get("BundleEntryProto")
+
+
+def test_tf_bundle_reader_on_an_independently_written_index(tmp_path):
+    """checkpoint.read_tf_bundle against an index it did not write: entries serialised by the protobuf LIBRARY, table blocks with
+    leveldb prefix compression (restart interval 3) spread over several data blocks, two shards -- what a real TF Saver emits,
+    where the package's own writer only ever uses shared = 0, one block, one shard.  CRC-32C against the RFC 3720 vectors."""
+    import struct
+    ck = importlib.import_module("3dfeatnet_b200.checkpoint")
+    # CRC-32C (Castagnoli) known answers, and TF's mask ((crc >> 15 | crc << 17) + 0xa282ead8)
+    unmask = lambda m: (lambda r: ((r >> 17) | (r << 15)) & 0xFFFFFFFF)((m - 0xA282EAD8) & 0xFFFFFFFF)
+    for buf, want in ((b"123456789", 0xE3069283), (b"\x00" * 32, 0x8A9136AA), (b"\xff" * 32, 0x62A8AB43), (bytes(range(32)), 0x46DD794E)):
+        assert unmask(ck._masked_crc32c(buf)) == want
+    Header, Entry = _tensor_bundle_protos()
+    rng = np.random.default_rng(12)
+    names = ["detection/conv%d/conv2d/%s" % (i, leaf) for i in range(4) for leaf in ("biases", "weights")] + ["global_step"]
+    arrays = {n: rng.normal(size=(1, 1, 3 + i, 4) if n.endswith("weights") else (4,)).astype(np.float32) for i, n in enumerate(names)}
+    arrays["global_step"] = np.array(1234, np.int64)
+    shard_bytes = [bytearray(), bytearray()]
+    entries = [(b"", Header(num_shards=2, version=dict(producer=1)).SerializeToString())]
+    for i, n in enumerate(sorted(arrays)):
+        a, shard = arrays[n], i % 2
+        e = Entry(dtype=9 if a.dtype == np.int64 else 1, shard_id=shard, offset=len(shard_bytes[shard]), size=a.nbytes,
+                  crc32c=ck._masked_crc32c(a.tobytes()))
+        for s in a.shape:
+            e.shape.dim.add(size=s)
+        got = ck._parse_entry(e.SerializeToString())
+        assert (got["dtype"], got["shape"], got["shard_id"], got["offset"], got["size"]) == (e.dtype, list(a.shape), shard, e.offset, a.nbytes)
+        shard_bytes[shard] += a.tobytes()
+        entries.append((n.encode(), e.SerializeToString()))
+    for s in range(2):
+        (tmp_path / ("model.ckpt-7.data-%05d-of-00002" % s)).write_bytes(bytes(shard_bytes[s]))
+
+    def varint(v):
+        out = bytearray()
+        while v >= 0x80:
+            out.append((v & 0x7F) | 0x80)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+
+    def block(items, interval=3):  # leveldb block: shared-prefix compressed entries, restart array, restart count
+        body, restarts, prev = bytearray(), [], b""
+        for i, (k, v) in enumerate(items):
+            shared = 0
+            if i % interval == 0:
+                restarts.append(len(body))
+            else:
+                while shared < min(len(k), len(prev)) and k[shared] == prev[shared]:
+                    shared += 1
+            body += varint(shared) + varint(len(k) - shared) + varint(len(v)) + k[shared:] + v
+            prev = k
+        return bytes(body) + b"".join(struct.pack("<I", r) for r in (restarts or [0])) + struct.pack("<I", max(len(restarts), 1))
+
+    out = bytearray()
+
+    def emit(blk):
+        handle = varint(len(out)) + varint(len(blk))
+        out.extend(blk + b"\x00" + struct.pack("<I", ck._masked_crc32c(blk + b"\x00")))
+        return handle
+
+    chunks = [entries[:4], entries[4:8], entries[8:]]
+    index_items = [(c[-1][0] + b"\x00", emit(block(c))) for c in chunks]
+    meta = emit(block([]))
+    index = emit(block(index_items, interval=1))
+    footer = meta + index
+    out.extend(footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", 0xdb4775248b80fb57))
+    (tmp_path / "model.ckpt-7.index").write_bytes(bytes(out))
+    back = ck.read_tf_bundle(str(tmp_path / "model.ckpt-7"))
+    assert sorted(back) == sorted(arrays)
+    for n, a in arrays.items():
+        assert back[n].dtype == a.dtype and back[n].shape == a.shape and np.array_equal(back[n], a), n
+    model = ck.load_checkpoint(str(tmp_path / "model.ckpt-7"))  # TF layout -> model layout: (1,1,Cin,Cout) kernels become (Cin,Cout)
+    assert model["detection/conv2/conv2d/weights"].shape == arrays["detection/conv2/conv2d/weights"].shape[2:]
+    assert "global_step" not in model
