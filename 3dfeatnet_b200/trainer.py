@@ -1,7 +1,8 @@
 """The training loop of the reference's train.py (train():93-184) around the hand-written training step: epochs over the
 triplet generator (shuffle, next_triplet, stop at the first short batch), the reference's augmentations applied on the device,
 get_train_model -> get_loss -> get_train_op, a checkpoint every `checkpoint_every_n_steps`, validate() at step 1 and every
-`validate_every_n_steps`.  TF summaries / logging configuration are out of scope; progress comes back as a history dict."""
+`validate_every_n_steps`; train_two_stage() is train.sh (descriptor pretraining, then the full model restored without the
+`detection` scope).  TF summaries / logging configuration are out of scope; progress comes back as a history dict."""
 import importlib
 import os
 
@@ -60,3 +61,40 @@ def train(model, train_data, num_epochs=1, batch_size=BATCH_SIZE, num_points=409
                 return history
     history["steps"] = step
     return history
+
+
+def latest_checkpoint(checkpoint_dir):
+    """The highest-step `checkpoint.ckpt-<step>.npz` that train() wrote into `checkpoint_dir` (the role of
+    tf.train.latest_checkpoint for `--checkpoint <dir>`), or None when there is none."""
+    best, best_step = None, -1
+    if checkpoint_dir and os.path.isdir(checkpoint_dir):
+        for f in os.listdir(checkpoint_dir):
+            if f.startswith("checkpoint.ckpt-") and f.endswith(".npz") and f[len("checkpoint.ckpt-"):-4].isdigit():
+                s = int(f[len("checkpoint.ckpt-"):-4])
+                if s > best_step:
+                    best, best_step = os.path.join(checkpoint_dir, f), s
+    return best
+
+
+def train_two_stage(make_model, train_data, log_dir, param=None, pretrain_epochs=2, num_epochs=70, **train_kwargs):
+    """The reference's two-stage recipe (train.sh): (1) pretrain the descriptor alone -- `--noattention --noregress`, i.e.
+    param NoRegress=True / Attention=False, augmentations Jitter RotateSmall Shift, 2 epochs, checkpoints under
+    <log_dir>/pretrain/ckpt; (2) build the full model (attention + orientation), restore the pretrain checkpoint except the
+    `detection` scope (`--restore_exclude detection`), add the Rotate1D augmentation and train for 70 epochs, checkpoints under
+    <log_dir>/secondstage/ckpt.  `make_model(param)` returns a Feat3dNet; other keywords go to train() for both stages.
+    The final state of stage 1 is always saved, so that the checkpoint stage 2 restores exists even when the run is shorter than
+    checkpoint_every_n_steps.  Returns {'pretrain', 'secondstage': train() histories, 'restored': names, 'model': stage-2 model}."""
+    base = dict(param or {})
+    dirs = {s: os.path.join(log_dir, s, "ckpt") for s in ("pretrain", "secondstage")}
+    model1 = make_model(dict(base, NoRegress=True, Attention=False))
+    h1 = train(model1, train_data, num_epochs=pretrain_epochs, augmentation=("Jitter", "RotateSmall", "Shift"),
+               checkpoint_dir=dirs["pretrain"], **train_kwargs)
+    final = os.path.join(dirs["pretrain"], "checkpoint.ckpt-%d.npz" % h1["steps"])
+    if final not in h1["checkpoints"]:
+        _ck.save_npz(model1.weights, final)
+        h1["checkpoints"].append(final)
+    model2 = make_model(dict(base, NoRegress=False, Attention=True))
+    restored = _ck.initialize_model(model2, latest_checkpoint(dirs["pretrain"]), restore_exclude=["detection"])
+    h2 = train(model2, train_data, num_epochs=num_epochs, augmentation=("Jitter", "RotateSmall", "Shift", "Rotate1D"),
+               checkpoint_dir=dirs["secondstage"], **train_kwargs)
+    return dict(pretrain=h1, secondstage=h2, restored=restored, model=model2)

@@ -628,3 +628,76 @@ def test_tf_bundle_reader_on_an_independently_written_index(tmp_path):
     model = ck.load_checkpoint(str(tmp_path / "model.ckpt-7"))  # TF layout -> model layout: (1,1,Cin,Cout) kernels become (Cin,Cout)
     assert model["detection/conv2/conv2d/weights"].shape == arrays["detection/conv2/conv2d/weights"].shape[2:]
     assert "global_step" not in model
+
+
+class _StubTrainModel(object):
+    """Stands in for Feat3dNet in the trainer's host logic: two 'scopes' of weights, a loss that depends on them, an SGD step."""
+    made = []
+
+    def __init__(self, param):
+        self.param, self.device = dict(param), torch.device("cpu")
+        g = torch.Generator().manual_seed(len(_StubTrainModel.made))
+        self.weights = {"detection/conv0/conv2d/weights": torch.randn(3, 4, generator=g),
+                        "description/layer1/conv0/conv2d/weights": torch.randn(3, 4, generator=g)}
+        self.seen, self.invalidated = [], 0
+        _StubTrainModel.made.append(self)
+
+    def invalidate(self):
+        self.invalidated += 1
+
+    def get_train_model(self, a, p, n, is_training):
+        assert is_training is True and a.shape == p.shape == n.shape and a.shape[2] == 3
+        self.seen.append((a.clone(), p.clone(), n.clone()))
+        return None, (a, p, n), None, {}
+
+    def get_loss(self, xyz, features, att, ep):
+        w = self.weights["description/layer1/conv0/conv2d/weights"]
+        return (features[0].mean() - features[1].mean()) ** 2 + (w ** 2).mean(), ep
+
+    def get_train_op(self, loss, lr=1e-5, end_points=None, grad_hook=None, grad_scale=1.0):
+        self.weights["description/layer1/conv0/conv2d/weights"] *= (1 - lr)
+
+
+def test_trainer_schedule_and_two_stage_recipe_on_a_stand_in_model(tmp_path):
+    """trainer.train (train.py:93-184): epochs, short last batch ends the epoch, checkpoint / validation schedule, augmentation
+    names or objects; trainer.train_two_stage (train.sh): descriptor-only pretraining, then the full model restored from the
+    pretrain checkpoint except the `detection` scope, Rotate1D added.  The real model runs the same loop in test_train_gpu.py."""
+    tr, dg_mod, ck = pkg("trainer"), pkg("data.datagenerator"), importlib.import_module("3dfeatnet_b200.checkpoint")
+    meta = _write_dataset(tmp_path, n_clouds=7, pts=300, seed=2)
+    data = dg_mod.DataGenerator(meta, num_cols=6, seed=1)
+    _StubTrainModel.made = []
+    model = _StubTrainModel({})
+    steps_seen = []
+    h = tr.train(model, data, num_epochs=2, batch_size=3, num_points=64, augmentation=("Shift",), lr=0.1,
+                 checkpoint_dir=str(tmp_path / "ck"), checkpoint_every_n_steps=3, on_step=lambda s, hist: steps_seen.append(s))
+    assert h["steps"] == 4 and steps_seen == [1, 2, 3, 4]          # 7 clouds / batch 3 -> 2 full batches per epoch, the short one dropped
+    assert [os.path.basename(p) for p in h["checkpoints"]] == ["checkpoint.ckpt-3.npz"] and len(h["losses"]) == 4
+    assert tr.latest_checkpoint(str(tmp_path / "ck")) == h["checkpoints"][0] and tr.latest_checkpoint(str(tmp_path / "none")) is None
+    a, p, n = model.seen[0]
+    assert a.shape == (3, 64, 3) and not torch.equal(a, p)
+    # augmentation objects (data/augment.py) are applied on the tensors too; none leaves the generator's clouds untouched
+    plain = _StubTrainModel({})
+    dg_mod.DataGenerator(meta, num_cols=6, seed=5)
+    tr.train(plain, dg_mod.DataGenerator(meta, num_cols=6, seed=5), batch_size=3, num_points=64, augmentation=(), max_steps=1)
+    shifted = _StubTrainModel({})
+    obj = pkg("data.augment").Shift(shift_range=5.0)
+    tr.train(shifted, dg_mod.DataGenerator(meta, num_cols=6, seed=5), batch_size=3, num_points=64, augmentation=[obj], max_steps=1)
+    d = shifted.seen[0][0] - plain.seen[0][0]
+    assert d.abs().max() > 0.1 and torch.allclose(d, d[:, :1].expand_as(d), atol=1e-4)   # one offset per cloud
+    # train.sh
+    _StubTrainModel.made = []
+    out = tr.train_two_stage(_StubTrainModel, dg_mod.DataGenerator(meta, num_cols=6, seed=3), str(tmp_path / "logs"),
+                             param={"feature_dim": 32}, pretrain_epochs=1, num_epochs=2, batch_size=3, num_points=64, lr=0.1)
+    m1, m2 = _StubTrainModel.made
+    assert m1.param == dict(feature_dim=32, NoRegress=True, Attention=False) and m2.param == dict(feature_dim=32, NoRegress=False, Attention=True)
+    assert out["model"] is m2 and out["pretrain"]["steps"] == 2 and out["secondstage"]["steps"] == 4
+    assert os.path.basename(out["pretrain"]["checkpoints"][-1]) == "checkpoint.ckpt-2.npz"    # the final pretrain state is saved
+    assert out["restored"] == ["description/layer1/conv0/conv2d/weights"] and m2.invalidated == 1
+    saved = ck.load_checkpoint(out["pretrain"]["checkpoints"][-1])
+    assert torch.allclose(torch.as_tensor(saved["description/layer1/conv0/conv2d/weights"]),
+                          m1.weights["description/layer1/conv0/conv2d/weights"])
+    # stage 2 started from the pretrained descriptor and its own (fresh) detector, and trained on from there
+    assert torch.allclose(m2.weights["description/layer1/conv0/conv2d/weights"],
+                          m1.weights["description/layer1/conv0/conv2d/weights"] * 0.9 ** 4)
+    assert not torch.equal(m2.weights["detection/conv0/conv2d/weights"], m1.weights["detection/conv0/conv2d/weights"])
+    assert os.path.isdir(tmp_path / "logs" / "secondstage" / "ckpt")
