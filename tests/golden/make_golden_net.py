@@ -40,6 +40,9 @@ CASES = {
                            attention=True, training=True, keypoints=None, margin=0.2, store_gradients=True),
     "train_no_attention": dict(seed=16, clouds=3, points=1200, num_clusters=24, num_samples=64, feature_dim=32, no_regress=False,
                                attention=False, training=True, keypoints=None, margin=0.5),
+    # train.sh's pretraining stage: --noattention --noregress
+    "train_stage1": dict(seed=17, clouds=3, points=1200, num_clusters=24, num_samples=64, feature_dim=32, no_regress=True,
+                         attention=False, training=True, keypoints=None, margin=0.2),
 }
 
 

@@ -319,7 +319,7 @@ def test_product_module_graph_matches_reference_graph_golden(monkeypatch):
     f3 = pkg("models.feat3dnet")
     g = np.load(os.path.join(GOLD, "ref_net.npz"))
     names = sorted({k.split("/")[0] for k in g.files if k.endswith("/config")})
-    assert len(names) == 6
+    assert len(names) == 7
     for name in names:
         cfg = json.loads(str(g[name + "/config"]))
         want = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(name + "/out/")}
