@@ -342,3 +342,57 @@ def test_sample_and_group_matches_oracle_composition(cuda):
     assert torch.equal(new_points, grouped)
     # detector-side helper: identity sampling when npoint <= 0 (pointnet_common.py:24-25)
     assert torch.equal(pc.sample_points(xyz, -1), xyz)
+
+
+# ------------------------------------------------------------------------------------------------ the reference's smoke mains
+def test_reference_grouping_main_shapes(cuda):
+    """tf_ops/grouping/tf_grouping.py:90-118 (`__main__`, no assertion there): np.random.seed(100), points (32,512,64),
+    xyz1 (32,512,3), xyz2 (32,128,3), kNN with k = nsample = 64 then group_point -- and its radius = 0.1 branch -- with the
+    oracle as the check the reference script lacks."""
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    np.random.seed(100)
+    pts = np.random.random((32, 512, 64)).astype('float32')
+    tmp1 = np.random.random((32, 512, 3)).astype('float32')
+    tmp2 = np.random.random((32, 128, 3)).astype('float32')
+    points, xyz1, xyz2 = T(pts, cuda), T(tmp1, cuda), T(tmp2, cuda)
+    val, idx = tg.knn_point(64, xyz1, xyz2)
+    grouped = tg.group_point(points, idx)
+    wval, widx = oops.knn_point(64, tmp1, tmp2)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(val.cpu().numpy(), wval)
+    assert grouped.shape == (32, 128, 64, 64) and grouped.dtype == torch.float32
+    assert np.array_equal(grouped.cpu().numpy(), oops.group_point(pts, widx))
+    idx2, cnt2 = tg.query_ball_point(0.1, 64, xyz1, xyz2)          # the script's knn=False branch
+    widx2, wcnt2 = oops.query_ball_point(0.1, 64, tmp1, tmp2)
+    assert np.array_equal(idx2.cpu().numpy(), widx2) and np.array_equal(cnt2.cpu().numpy(), wcnt2)
+    assert np.array_equal(tg.group_point(points, idx2).cpu().numpy(), oops.group_point(pts, widx2))
+
+
+def test_reference_sampling_main_flow(cuda):
+    """tf_ops/sampling/tf_sampling.py:60-89 (`__main__`, no assertion there): 5 random triangles (seed 100), 8192 surface
+    samples drawn with prob_sample over the triangle areas + gather_point, then farthest_point_sample(1024) + gather_point.
+    The element-wise arithmetic is done once in NumPy; the four operator calls are compared with the oracle bit for bit."""
+    ts = pkg("tf_ops.sampling.tf_sampling")
+    np.random.seed(100)
+    triangles = np.random.rand(1, 5, 3, 3).astype('float32')
+    tria, trib, tric = (np.ascontiguousarray(triangles[:, :, i, :]) for i in range(3))
+    areas = np.sqrt((np.cross(trib - tria, tric - tria) ** 2).sum(2) + 1e-9).astype(np.float32)
+    rng = np.random.default_rng(100)                                  # tf.random_uniform in the script
+    randomnumbers, us, vs = (rng.random((1, 8192), dtype=np.float32) for _ in range(3))
+    triids = ts.prob_sample(T(areas, cuda), T(randomnumbers, cuda))
+    want_ids = oops.prob_sample(areas, randomnumbers)
+    assert np.array_equal(triids.cpu().numpy(), want_ids) and set(np.unique(want_ids)) <= set(range(5))
+    corners = []
+    for tri in (tria, trib, tric):
+        got = ts.gather_point(T(tri, cuda), triids).cpu().numpy()
+        assert np.array_equal(got, oops.gather_point(tri, want_ids))
+        corners.append(got)
+    uplusv, uminusv = 1 - np.abs(us + vs - 1), us - vs
+    us, vs = (uplusv + uminusv) * 0.5, (uplusv - uminusv) * 0.5
+    pt_sample = (corners[0] + (corners[1] - corners[0]) * us[..., None] + (corners[2] - corners[0]) * vs[..., None]).astype(np.float32)
+    pt = T(pt_sample, cuda)
+    fps = ts.farthest_point_sample(1024, pt)
+    want_fps = oops.farthest_point_sample(1024, pt_sample)
+    assert np.array_equal(fps.cpu().numpy(), want_fps)
+    reduced = ts.gather_point(pt, fps).cpu().numpy()
+    assert reduced.shape == (1, 1024, 3) and reduced.dtype == np.float32
+    assert np.array_equal(reduced, oops.gather_point(pt_sample, want_fps))
