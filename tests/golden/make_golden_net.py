@@ -40,6 +40,13 @@ CASES = {
                            attention=True, training=True, keypoints=None, margin=0.2, store_gradients=True),
     "train_no_attention": dict(seed=16, clouds=3, points=1200, num_clusters=24, num_samples=64, feature_dim=32, no_regress=False,
                                attention=False, training=True, keypoints=None, margin=0.5),
+    # BASELINE.json configs[0]: example_data/oxford_270.bin (16384 points), 512 clusters, r = 2.0, nsample = 64, random init -- with
+    # non-trivial BN statistics, and in the TF random-init state (EMA shadows 0); the cloud is the committed fixture, the variables
+    # are those of tests/test_model_gpu.py::test_c1_oxford_270_fp32, which holds the CUDA forward to the oracle on this very input
+    "c1_oxford_270_bn": dict(seed=0, fixture="oxford_270_xyz.npy", clouds=1, points=16384, num_clusters=512, num_samples=64,
+                             feature_dim=32, no_regress=False, attention=True, training=False, keypoints=None, randomize_bn=True),
+    "c1_oxford_270_init": dict(seed=0, fixture="oxford_270_xyz.npy", clouds=1, points=16384, num_clusters=512, num_samples=64,
+                               feature_dim=32, no_regress=False, attention=True, training=False, keypoints=None, randomize_bn=False),
     # train.sh's pretraining stage: --noattention --noregress
     "train_stage1": dict(seed=17, clouds=3, points=1200, num_clusters=24, num_samples=64, feature_dim=32, no_regress=True,
                          attention=False, training=True, keypoints=None, margin=0.2),
@@ -49,6 +56,8 @@ CASES = {
 def case_inputs(cfg):
     """Oxford-shape clouds (6 float32 columns like the .bin files: the model must ignore columns 3..5) and, if asked, keypoints
     that are partly cloud points and partly off-cloud positions (some with empty balls: the fallback rule of the ball query)."""
+    if cfg.get("fixture"):
+        return np.load(os.path.join(HERE, cfg["fixture"])).astype(np.float32)[None], None
     rng = np.random.default_rng(cfg["seed"])
     base = np.load(os.path.join(HERE, "oxford_270_xyz.npy")).astype(np.float32)
     clouds = []
@@ -186,10 +195,11 @@ if __name__ == "__main__":
     store = {}
     for name, cfg in CASES.items():
         clouds, kp = case_inputs(cfg)
-        params = onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True)
+        params = onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=cfg.get("randomize_bn", True))
         out = run_reference(cfg, clouds, kp, params)
         store[name + "/config"] = np.array(json.dumps(cfg))
-        store[name + "/clouds"] = clouds
+        if not cfg.get("fixture"):  # fixture clouds are files of their own
+            store[name + "/clouds"] = clouds
         if kp is not None:
             store[name + "/keypoints"] = kp
         for k, v in out.items():

@@ -184,7 +184,8 @@ def _ref_net_cases(path=None):
     for name in sorted({k.split("/")[0] for k in g.files if k.endswith("/config")}):  # the model cases ("pointnet_common/..." apart)
         cfg = json.loads(str(g[name + "/config"]))
         out = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(name + "/out/")}
-        yield name, cfg, g[name + "/clouds"], (g[name + "/keypoints"] if name + "/keypoints" in g.files else None), out
+        clouds = np.load(os.path.join(GOLD, cfg["fixture"])).astype(np.float32)[None] if cfg.get("fixture") else g[name + "/clouds"]
+        yield name, cfg, clouds, (g[name + "/keypoints"] if name + "/keypoints" in g.files else None), out
 
 
 def _angle_diff(a, b):
@@ -196,7 +197,7 @@ def test_oracle_net_reproduces_the_reference_graph_golden():
     names = []
     for name, cfg, clouds, kp, want in _ref_net_cases():
         names.append(name)
-        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True), torch.float64)
+        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=cfg.get("randomize_bn", True)), torch.float64)
         stats = {}
         got = onet.inference_model(clouds, P, cfg["num_clusters"], 2.0, cfg["num_samples"], cfg["feature_dim"], cfg["no_regress"],
                                    cfg["training"], kp, stats, torch.float64)
@@ -221,7 +222,7 @@ def test_oracle_net_reproduces_the_reference_graph_golden():
                 assert torch.allclose(stats[k], torch.as_tensor(v), rtol=1e-9, atol=1e-12), (name, k)
         else:
             assert stats == {}
-    assert names == sorted(["eval_fps", "eval_noregress_f128", "eval_all_points", "eval_keypoints_fed", "train_triplets",
+    assert names == sorted(["c1_oxford_270_bn", "c1_oxford_270_init", "eval_fps", "eval_noregress_f128", "eval_all_points", "eval_keypoints_fed", "train_triplets",
                             "train_no_attention", "train_stage1"])
 
 
@@ -232,7 +233,7 @@ def test_oracle_gradients_reproduce_the_reference_graph_golden():
     for name, cfg, clouds, kp, want in _ref_net_cases():
         if not cfg["training"]:
             continue
-        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True), torch.float64,
+        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=cfg.get("randomize_bn", True)), torch.float64,
                           requires_grad=True)
         a, p, n = np.split(clouds, 3, axis=0)
         loss, grads, _ = onet.train_step(a, p, n, P, {}, cfg["num_clusters"], 2.0, cfg["num_samples"], cfg["feature_dim"],

@@ -319,13 +319,14 @@ def test_product_module_graph_matches_reference_graph_golden(monkeypatch):
     f3 = pkg("models.feat3dnet")
     g = np.load(os.path.join(GOLD, "ref_net.npz"))
     names = sorted({k.split("/")[0] for k in g.files if k.endswith("/config")})
-    assert len(names) == 7
+    assert len(names) == 9
     for name in names:
         cfg = json.loads(str(g[name + "/config"]))
         want = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(name + "/out/")}
-        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=True), torch.float64,
+        P = onet.to_torch(onet.init_params(seed=cfg["seed"], feature_dim=cfg["feature_dim"], randomize_bn=cfg.get("randomize_bn", True)), torch.float64,
                           requires_grad=cfg["training"])
-        xyz = torch.as_tensor(g[name + "/clouds"][:, :, :3]).double().contiguous()
+        clouds = np.load(os.path.join(GOLD, cfg["fixture"])).astype(np.float32)[None] if cfg.get("fixture") else g[name + "/clouds"]
+        xyz = torch.as_tensor(clouds[:, :, :3]).double().contiguous()
         kp = torch.as_tensor(g[name + "/keypoints"]).double() if name + "/keypoints" in g.files else None
         stats = {}
         new_xyz, idx, att, ori, _ = f3.feature_detection_module(
