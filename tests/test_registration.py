@@ -137,3 +137,29 @@ def test_register_two_clouds_end_to_end(cuda):
     good = np.flatnonzero(~bad)
     assert np.array_equal(matches.cpu().numpy()[good, 1], perm[good])
     assert len(set(good) - set(inl.cpu().numpy().tolist())) == 0 and trials >= 10
+
+
+def test_oracle_rigid_fit_agrees_with_scipy():
+    """The registration oracle restates MATLAB code that cannot run here (parity unpinned); as a second, independent statement
+    of the same mathematics SciPy's Rotation is used: quat2rot (w-first quaternion) == Rotation.from_quat (x,y,z,w), and the
+    quaternion least-squares fit of estimateRigidTransform.m == Rotation.align_vectors (Kabsch) on noisy correspondences."""
+    from scipy.spatial.transform import Rotation
+    from oracle import registration as oreg
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        assert np.allclose(oreg.quat2rot(q), Rotation.from_quat([q[1], q[2], q[3], q[0]]).as_matrix(), atol=1e-12)
+    for n, noise in ((3, 0.0), (10, 0.01), (200, 0.05)):
+        y = rng.normal(size=(3, n)) * 5
+        R = Rotation.from_rotvec(rng.normal(size=3)).as_matrix()
+        t = rng.normal(size=3) * 3
+        x = R @ y + t[:, None] + rng.normal(size=(3, n)) * noise
+        T, eps = oreg.estimate_rigid_transform(x, y)
+        xc, yc = x.mean(1, keepdims=True), y.mean(1, keepdims=True)
+        kabsch, _ = Rotation.align_vectors((x - xc).T, (y - yc).T)       # rotation taking y-centred onto x-centred, least squares
+        assert np.allclose(T[:3, :3], kabsch.as_matrix(), atol=1e-8), (n, noise)
+        assert np.allclose(T[:3, 3], (xc - kabsch.as_matrix() @ yc)[:, 0], atol=1e-8)
+        assert np.allclose(T[3], [0, 0, 0, 1]) and abs(np.linalg.det(T[:3, :3]) - 1) < 1e-10 and eps >= -1e-12
+        if noise == 0.0:
+            assert np.allclose(T[:3, :3], R, atol=1e-9) and np.allclose(T[:3, 3], t, atol=1e-8)
