@@ -184,8 +184,11 @@ def _gloo_worker(rank, world, port, q):
     flat = torch.arange(107619, dtype=torch.float32) * (rank + 1)  # the model's 107 619 trainable floats
     d.allreduce_mean_(flat)
     mx = d.max_over_ranks(float(rank) + 0.5, torch.device("cpu"))
+    # the training step's form: SUM all-reduce of the flat gradient, 1/world applied later inside the Adam kernel (grad_scale)
+    summed = d.allreduce_sum_(torch.full((107619,), float(rank + 1)))
     d.barrier()
-    q.put((rank, lo, hi, float(flat[1000]), mx))
+    q.put((rank, lo, hi, float(flat[1000]), mx, float(summed[5]) * (1.0 / world), d.env_world()))
+    d.shutdown()
 
 
 def test_gloo_world_size_2_gradient_exchange():
@@ -202,6 +205,8 @@ def test_gloo_world_size_2_gradient_exchange():
     assert [(r[1], r[2]) for r in res] == [(0, 5), (5, 10)]
     assert all(abs(r[3] - 1000 * 1.5) < 1e-3 for r in res)  # mean of 1x and 2x
     assert all(r[4] == 1.5 for r in res)
+    assert all(r[5] == 1.5 for r in res)                     # sum (1 + 2) x grad_scale 1/2 == the mean
+    assert [r[6] for r in res] == [(0, 0, 2), (1, 1, 2)]     # RANK / LOCAL_RANK / WORLD_SIZE as torchrun sets them
 
 
 def test_bin_formats_roundtrip(tmp_path):
