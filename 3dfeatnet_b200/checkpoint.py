@@ -280,8 +280,40 @@ def write_tf_bundle(prefix, arrays):
 
 
 # ------------------------------------------------------------------------------------------------ restore
+def latest_checkpoint(checkpoint_dir):
+    """tf.train.latest_checkpoint for `--checkpoint <dir>` (inference.py:189-190, train.py:192-193): the prefix named by the
+    directory's TF `checkpoint` state file (`model_checkpoint_path: "..."`) when there is one, otherwise the highest-step
+    `<name>.ckpt-<step>` found as `.npz` (what train() writes) or as a TF bundle (`.index`); None when there is none."""
+    import re
+
+    if not checkpoint_dir or not os.path.isdir(checkpoint_dir):
+        return None
+    state = os.path.join(checkpoint_dir, "checkpoint")
+    if os.path.isfile(state):
+        with open(state, "r") as f:
+            m = re.search(r'^model_checkpoint_path:\s*"(.*)"\s*$', f.read(), re.M)
+        if m:
+            p = m.group(1)
+            p = p if os.path.isabs(p) else os.path.join(checkpoint_dir, p)
+            if os.path.exists(p + ".index") or os.path.exists(p) or os.path.exists(p + ".npz"):
+                return p
+    best, best_step = None, -1
+    for f in os.listdir(checkpoint_dir):
+        m = re.match(r"^(.*\.ckpt-(\d+))(\.npz|\.index)$", f)
+        if m and int(m.group(2)) > best_step:
+            best_step = int(m.group(2))
+            best = os.path.join(checkpoint_dir, f if m.group(3) == ".npz" else m.group(1))
+    return best
+
+
 def load_checkpoint(path):
-    """`.npz` file, or a TF checkpoint prefix (`<path>.index` exists) -> {parameter name: float32 array}."""
+    """`.npz` file, a TF checkpoint prefix (`<path>.index` exists), or a checkpoint DIRECTORY (resolved like
+    tf.train.latest_checkpoint, as the reference does when os.path.isdir(checkpoint)) -> {parameter name: float32 array}."""
+    if os.path.isdir(path):
+        resolved = latest_checkpoint(path)
+        if resolved is None:
+            raise FileNotFoundError("no checkpoint in directory %s" % path)
+        path = resolved
     if os.path.exists(path + ".index"):
         return to_model_arrays(read_tf_bundle(path))
     if os.path.exists(path):

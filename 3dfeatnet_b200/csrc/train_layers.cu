@@ -114,8 +114,10 @@ conv_fwd_kernel(long long rows, int cin, int cout, const float *__restrict__ x, 
 
 // out[w] = sum over the parts of part[p*width + w] in fp64 and a fixed order: 32 slices (p mod 32) per column, each
 // ascending, then the slices ascending.  Block = 32 columns x 32 slices.
+// OutT = double keeps the total unrounded for a consumer that subtracts two such sums (the BN batch variance below).
+template <typename OutT>
 __global__ void __launch_bounds__(1024)
-partial_reduce_kernel(int nparts, long long width, const float *__restrict__ part, float *__restrict__ out) {
+partial_reduce_kernel(int nparts, long long width, const float *__restrict__ part, OutT *__restrict__ out) {
     __shared__ double red[32][33];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const long long w = static_cast<long long>(blockIdx.x) * 32 + lane;
@@ -127,7 +129,7 @@ partial_reduce_kernel(int nparts, long long width, const float *__restrict__ par
     if (slice == 0 && w < width) {
         double t = 0.0;
         for (int k = 0; k < 32; ++k) t += red[k][lane];
-        out[w] = static_cast<float>(t);
+        out[w] = static_cast<OutT>(t);
     }
 }
 
@@ -139,13 +141,15 @@ __device__ __forceinline__ void bn_scale_shift(float gamma, float beta, float me
     sh = __fmaf_rn(-mean, sc, beta);
 }
 
-// sums[2][c] -> mean, var (population), coef = {scale = gamma*rsqrt(var+eps), shift = beta - mean*scale}
-__global__ void bn_stats_finalize_kernel(int c, double inv_rows, float eps, const float *__restrict__ sums, const float *__restrict__ gamma,
+// sums[2][c] -> mean, var (population), coef = {scale = gamma*rsqrt(var+eps), shift = beta - mean*scale}.  The two sums
+// arrive in fp64 (partial_reduce_kernel<double>): var = E[z^2] - mean^2 cancels when |mean| >> std, and a sum of squares
+// already rounded to fp32 would leave var with a relative error of 2^-24 * mean^2 / var.
+__global__ void bn_stats_finalize_kernel(int c, double inv_rows, float eps, const double *__restrict__ sums, const float *__restrict__ gamma,
                                          const float *__restrict__ beta, float *__restrict__ mean, float *__restrict__ var, float *__restrict__ coef) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= c) return;
-    const double mu = static_cast<double>(sums[ch]) * inv_rows;
-    double v = static_cast<double>(sums[c + ch]) * inv_rows - mu * mu;
+    const double mu = sums[ch] * inv_rows;
+    double v = sums[c + ch] * inv_rows - mu * mu;
     if (v < 0.0) v = 0.0;
     mean[ch] = static_cast<float>(mu);
     var[ch] = static_cast<float>(v);
@@ -695,7 +699,7 @@ F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int co
     const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
     const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit));
     const size_t wimg = lin_tc_weight_bytes(cin, cout) > lin_tc_weight_bytes(cout, cin) ? lin_tc_weight_bytes(cin, cout) : lin_tc_weight_bytes(cout, cin);
-    const size_t fwd = align256(stat_parts * 2 * cout * 4) + align256(2 * cout * 4) + align256(2 * cout * 4) + align256(wimg);
+    const size_t fwd = align256(stat_parts * 2 * cout * 4) + align256(2 * cout * 8) + align256(2 * cout * 4) + align256(wimg);
     const WgradPlan p = plan_wgrad(rows, cin, cout);
     int tcg = 0;
     long long tcper = 0;
@@ -736,15 +740,15 @@ static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *
     char *w = static_cast<char *>(workspace);
     float *part = reinterpret_cast<float *>(w);
     w += align256(stat_parts * 2 * cout * 4);
-    float *sums = reinterpret_cast<float *>(w);
-    w += align256(2 * cout * 4);
+    double *sums = reinterpret_cast<double *>(w);  // fp64 through bn_stats_finalize
+    w += align256(2 * cout * 8);
     float *coef = reinterpret_cast<float *>(w);
     w += align256(2 * cout * 4);
     uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
     int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, kFwdSplit, st)
                 : launch_conv_fwd(rows, cin, cout, x, W, bias, group_bias, group_s, z, part, st);
     if (rc) return rc;
-    partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(nparts), 2 * cout, part, sums);
+    partial_reduce_kernel<double><<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(nparts), 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
     bn_stats_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, beta, mean, var, coef);
@@ -845,7 +849,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
         rc = check_launch("bn_bwd_reduce_kernel");
     }
     if (rc) return rc;
-    partial_reduce_kernel<<<(2 * cout + 31) / 32, 1024, 0, st>>>(nred1, 2 * cout, part, sums);
+    partial_reduce_kernel<float><<<(2 * cout + 31) / 32, 1024, 0, st>>>(nred1, 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
     bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2);
@@ -856,7 +860,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     bn_bwd_apply_kernel<<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;
-    partial_reduce_kernel<<<(cout + 31) / 32, 1024, 0, st>>>(napp, cout, partB, db);
+    partial_reduce_kernel<float><<<(cout + 31) / 32, 1024, 0, st>>>(napp, cout, partB, db);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
 
@@ -868,17 +872,17 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     }
     const long long nw = static_cast<long long>(cin) * cout;
     if (w3) {
-        partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(napp, nw, partW, dW);
+        partial_reduce_kernel<float><<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(napp, nw, partW, dW);
     } else if (precision == 2 && wgrad_tc_supported(cin, cout)) {
         rc = wgrad_tc(rows, cin, cout, x, dz, partW, st);
         if (rc) return rc;
-        partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(tcg, nw, partW, dW);
+        partial_reduce_kernel<float><<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(tcg, nw, partW, dW);
     } else {
         const size_t smem = static_cast<size_t>(kWgKC) * (p.cin_t + p.cout_t) * sizeof(float);
         conv_wgrad_kernel<<<dim3(p.gx, p.ny), 256, smem, st>>>(rows, cin, cout, p.cin_t, p.cout_t, p.rows_per_cta, x, dz, partW, partB_scratch);
         rc = check_launch("conv_wgrad_kernel");
         if (rc) return rc;
-        partial_reduce_kernel<<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(p.nparts, nw, partW, dW);
+        partial_reduce_kernel<float><<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(p.nparts, nw, partW, dW);
     }
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;

@@ -138,7 +138,7 @@ def descriptor_forward_fused(xyz, new_xyz, idx, orientation, radius, packed, fea
 def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is_training, scope, bn=True, bn_decay=None,
                        tnet_spec=None, knn=False, use_xyz=True,
                        keypoints=None, orientations=None, normalize_radius=True, final_relu=True,
-                       params=None, new_stats=None):
+                       params=None, new_stats=None, neighbours=None):
     """ PointNet Set Abstraction (SA) Module (feat3dnet.py:9-87), unfused differentiable statement.
 
     Returns:
@@ -151,7 +151,7 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is
     else:
         new_xyz, new_points, idx, grouped_xyz, end_points = sample_and_group(
             npoint, radius, nsample, xyz, points, tnet_spec, knn, use_xyz, keypoints=keypoints,
-            orientations=orientations, normalize_radius=normalize_radius)
+            orientations=orientations, normalize_radius=normalize_radius, neighbours=neighbours)
 
     for i, num_out_channel in enumerate(mlp):
         new_points = conv2d(new_points, num_out_channel, [1, 1], stride=[1, 1], padding='VALID', bn=bn,
@@ -196,8 +196,7 @@ def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp
         end_points['gradients'] = {'det': {}}
     new_xyz = sample_points(xyz, num_clusters) if keypoints is None else keypoints
     new_points, idx = query_and_group_points(xyz, points, new_xyz, num_samples, radius, knn=False, use_xyz=True,
-                                             normalize_radius=True, orientations=None)
-    end_points['pts_cnt'] = query_and_group_points.last_pts_cnt
+                                             normalize_radius=True, orientations=None, end_points=end_points)
 
     for i, num_out_channel in enumerate(mlp):
         # the last layer's activation only feeds the max-pool: conv2d(pool_samples=True) pools in the same call
@@ -233,13 +232,15 @@ def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp
 
 
 def feature_extraction_module(l0_xyz, l0_points, is_training, mlp, mlp2, mlp3, keypoints, orientations, radius=2.0,
-                              num_samples=64, use_bn=True, params=None, new_stats=None, scope="description"):
+                              num_samples=64, use_bn=True, params=None, new_stats=None, scope="description", neighbours=None):
     """ Extract feature descriptors (feat3dnet.py:154-187), unfused differentiable statement.
+    neighbours: optional (idx, pts_cnt) of the ball query the detector ran on the same (l0_xyz, keypoints, radius, num_samples)
+    -- the reference issues that query twice (pointnet_common.py:39 and :102); handing it over runs it once, with no hidden state.
     Returns: xyz, features, end_points """
     l1_xyz, l1_points, l1_idx, end_points = pointnet_sa_module(
         l0_xyz, l0_points, 512, radius, num_samples, mlp=mlp, mlp2=mlp2, mlp3=mlp3, is_training=is_training,
         scope=scope + '/layer1', bn=use_bn, bn_decay=None, keypoints=keypoints, orientations=orientations,
-        normalize_radius=True, final_relu=False, params=params, new_stats=new_stats)
+        normalize_radius=True, final_relu=False, params=params, new_stats=new_stats, neighbours=neighbours)
     ss = (l1_points * l1_points).sum(2, keepdim=True)
     features = l1_points * torch.rsqrt(torch.clamp(ss, min=1e-8))
     return l1_xyz, features, end_points
@@ -344,7 +345,7 @@ class Feat3dNet:
         mlp, mlp2, mlp3 = [32, 64], ([128] if fdim <= 64 else [256]), [fdim]
         xyz, features, ep2 = feature_extraction_module(
             l0_xyz, None, is_training, mlp, mlp2, mlp3, keypoints=kp, orientations=keypoint_orientation, radius=radius,
-            num_samples=ns, use_bn=use_bn, params=self.weights, new_stats=new_stats)
+            num_samples=ns, use_bn=use_bn, params=self.weights, new_stats=new_stats, neighbours=(idx, ep['pts_cnt']))
         end_points.update(ep2)
         end_points['bn_updates'] = new_stats
         return xyz, features, (attention if self.param['Attention'] else None), end_points
@@ -445,6 +446,7 @@ class Feat3dNet:
                     dst.copy_(src)
             graph.replay()
             self._adam["t"] += 1
+            self.invalidate()  # the replay moved the weights and the BN shadows: the folded eval copy is stale
             return loss
 
         replay.graph = graph

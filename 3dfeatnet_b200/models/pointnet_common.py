@@ -18,23 +18,19 @@ farthest_point_sample, gather_point = _ts.farthest_point_sample, _ts.gather_poin
 
 
 # ------------------------------------------------------------------------------------------------ private helpers
-_last_query = None  # (xyz, xyz._version, centres, centres._version, nsample, radius, idx, pts_cnt) of the latest ball query
-
-
-def _neighbour_indices(xyz, centres, nsample, radius, knn):
+def _neighbour_indices(xyz, centres, nsample, radius, knn, neighbours=None):
     """(idx (B,M,S) int32, pts_cnt): ball query, or kNN where the reference sets pts_cnt to nsample ("Hack", :37/:99).
-    The reference runs the identical ball query twice per forward (detector :39, descriptor :102, same cloud, same centres);
-    here the second request is answered from the first (same tensor objects, unmodified since: ids and versions checked)."""
-    global _last_query
+    The reference runs the identical ball query twice per forward (detector :39, descriptor :102, same cloud, same centres).
+    This module keeps no state between calls: a caller that already holds the answer for exactly these arguments hands it
+    over as `neighbours=(idx, pts_cnt)` (models/feat3dnet.py passes the detector's query to the descriptor)."""
+    if neighbours is not None:
+        idx, pts_cnt = neighbours
+        if tuple(idx.shape) != (xyz.shape[0], centres.shape[1], nsample):
+            raise ValueError("neighbours: idx has shape %s, expected %s" % (tuple(idx.shape), (xyz.shape[0], centres.shape[1], nsample)))
+        return idx, pts_cnt
     if knn:
         return knn_point(nsample, xyz, centres)[1], nsample
-    q = _last_query
-    if (q is not None and q[0] is xyz and q[1] == xyz._version and q[2] is centres and q[3] == centres._version
-            and q[4] == nsample and q[5] == radius):
-        return q[6], q[7]
-    idx, pts_cnt = query_ball_point(radius, nsample, xyz, centres)
-    _last_query = (xyz, xyz._version, centres, centres._version, nsample, radius, idx, pts_cnt)
-    return idx, pts_cnt
+    return query_ball_point(radius, nsample, xyz, centres)
 
 
 def _local_frames(xyz, centres, idx, radius, normalize_radius):
@@ -71,11 +67,13 @@ def sample_points(xyz, npoint):
 
 
 def query_and_group_points(xyz, points, new_xyz, nsample, radius, knn=False,
-                           use_xyz=True, normalize_radius=True, orientations=None):
+                           use_xyz=True, normalize_radius=True, orientations=None, end_points=None, neighbours=None):
     """Detector-side grouping (reference :32-66): returns (new_points (B,M,S,3[+C]), idx).
-    The pts_cnt the reference only logs as a histogram (:41) is kept in `query_and_group_points.last_pts_cnt`."""
-    idx, pts_cnt = _neighbour_indices(xyz, new_xyz, nsample, radius, knn)
-    query_and_group_points.last_pts_cnt = pts_cnt
+    The pts_cnt the reference only logs as a histogram (:41) is stored in the caller's `end_points` dict (when given) as
+    end_points['pts_cnt']; `neighbours=(idx, pts_cnt)` skips the query (see _neighbour_indices)."""
+    idx, pts_cnt = _neighbour_indices(xyz, new_xyz, nsample, radius, knn, neighbours)
+    if end_points is not None:
+        end_points['pts_cnt'] = pts_cnt
     local = _local_frames(xyz, new_xyz, idx, radius, normalize_radius)
     if orientations is not None:
         local = _spin_about_z(local, orientations, clockwise=True)
@@ -83,14 +81,15 @@ def query_and_group_points(xyz, points, new_xyz, nsample, radius, knn=False,
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, tnet_spec=None, knn=False, use_xyz=True,
-                     keypoints=None, orientations=None, normalize_radius=False):
-    """Descriptor-side sampling + grouping (reference :69-135).
+                     keypoints=None, orientations=None, normalize_radius=False, neighbours=None):
+    """Descriptor-side sampling + grouping (reference :69-135).  `neighbours=(idx, pts_cnt)`: the answer of the identical
+    query the detector already ran on (xyz, keypoints, nsample, radius) -- see _neighbour_indices.
     Returns (new_xyz (B,M,3), new_points (B,M,S,3[+C]), idx (B,M,S), grouped_xyz (B,M,S,3), end_points) where end_points
     carries 'grouped_xyz_before', 'rotation' (when orientations are given), 'grouped_xyz' and 'pts_cnt'."""
     if tnet_spec is not None:  # the reference calls an undefined tnet() here (:122-123); unused by 3DFeat-Net
         raise ValueError("tnet_spec is not supported")
     centres = keypoints if keypoints is not None else sample_points(xyz, npoint)
-    idx, pts_cnt = _neighbour_indices(xyz, centres, nsample, radius, knn)
+    idx, pts_cnt = _neighbour_indices(xyz, centres, nsample, radius, knn, neighbours)
     before = _local_frames(xyz, centres, idx, radius, normalize_radius)
     end_points = {'pts_cnt': pts_cnt, 'grouped_xyz_before': before}
     local = before

@@ -63,17 +63,7 @@ def train(model, train_data, num_epochs=1, batch_size=BATCH_SIZE, num_points=409
     return history
 
 
-def latest_checkpoint(checkpoint_dir):
-    """The highest-step `checkpoint.ckpt-<step>.npz` that train() wrote into `checkpoint_dir` (the role of
-    tf.train.latest_checkpoint for `--checkpoint <dir>`), or None when there is none."""
-    best, best_step = None, -1
-    if checkpoint_dir and os.path.isdir(checkpoint_dir):
-        for f in os.listdir(checkpoint_dir):
-            if f.startswith("checkpoint.ckpt-") and f.endswith(".npz") and f[len("checkpoint.ckpt-"):-4].isdigit():
-                s = int(f[len("checkpoint.ckpt-"):-4])
-                if s > best_step:
-                    best, best_step = os.path.join(checkpoint_dir, f), s
-    return best
+latest_checkpoint = _ck.latest_checkpoint  # tf.train.latest_checkpoint's role; lives with the checkpoint readers
 
 
 def train_two_stage(make_model, train_data, log_dir, param=None, pretrain_epochs=2, num_epochs=70, **train_kwargs):

@@ -335,6 +335,25 @@ def test_checkpoint_round_trips_and_restore_rules(tmp_path):
     m, init = fresh()
     names = ck.initialize_model(m, prefix)
     assert len(names) == len(params) and all(np.array_equal(m.weights[k].numpy(), params[k]) for k in params)
+    # --checkpoint <directory> (inference.py:189-190, train.py:192-193: tf.train.latest_checkpoint): the TF state file wins,
+    # otherwise the highest step; load_checkpoint / initialize_model accept the directory itself
+    ckdir = tmp_path / "ckdir"
+    ckdir.mkdir()
+    older = onet.init_params(seed=11, randomize_bn=True)
+    ck.save_npz(older, str(ckdir / "checkpoint.ckpt-500.npz"))
+    ck.write_tf_bundle(str(ckdir / "model.ckpt-1000"), tf_names)
+    assert ck.latest_checkpoint(str(ckdir)) == str(ckdir / "model.ckpt-1000")
+    from_dir = ck.load_checkpoint(str(ckdir))
+    assert all(np.array_equal(from_dir[k], params[k]) for k in params)
+    (ckdir / "checkpoint").write_text('model_checkpoint_path: "checkpoint.ckpt-500"\nall_model_checkpoint_paths: "checkpoint.ckpt-500"\n')
+    assert ck.latest_checkpoint(str(ckdir)) == str(ckdir / "checkpoint.ckpt-500")
+    m, init = fresh()
+    ck.initialize_model(m, str(ckdir))
+    assert all(np.array_equal(m.weights[k].numpy(), older[k]) for k in older)
+    assert ck.latest_checkpoint(str(tmp_path / "nothing-here")) is None
+    with pytest.raises(FileNotFoundError):
+        (tmp_path / "empty").mkdir()
+        ck.load_checkpoint(str(tmp_path / "empty"))
     m, init = fresh()                                   # stage 2 of train.sh: restore everything but the detector
     ck.initialize_model(m, prefix, restore_exclude=["detection"])
     assert all(np.array_equal(m.weights[k].numpy(), init[k] if k.startswith("detection/") else params[k]) for k in params)

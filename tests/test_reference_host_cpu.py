@@ -268,7 +268,6 @@ def _product_pointnet_common_on_cpu(monkeypatch):
     monkeypatch.setattr(pc, "group_point", lambda points, idx: torch.as_tensor(ops.group_point(f32(points), i32(idx))).to(points.dtype))
     monkeypatch.setattr(pc, "farthest_point_sample", lambda npoint, inp: ti(ops.farthest_point_sample(npoint, f32(inp))))
     monkeypatch.setattr(pc, "gather_point", lambda inp, idx: torch.as_tensor(ops.gather_point(f32(inp), i32(idx))).to(inp.dtype))
-    monkeypatch.setattr(pc, "_last_query", None)
     return pc
 
 

@@ -153,6 +153,25 @@ def test_conv_bn_train_forward_backward(cuda, rows, cin, cout, use_relu, precisi
         assert (a.cpu().double() - r).abs().max().item() < 2e-4 * scale + 1e-6, name
 
 
+def test_conv_bn_train_variance_with_a_large_mean(cuda, monkeypatch):
+    """var = E[z^2] - mean^2 with |mean| = 200 std: the channel sums stay in fp64 up to the subtraction (a sum of squares rounded
+    to fp32 first would leave var off by 2^-24 * mean^2 / var = 2e-3 relative); batch statistics of the reference's
+    tf.nn.moments (layers.py:250) in fp64 as the statement."""
+    layers = pkg("models.layers")
+    monkeypatch.setattr(layers, "TRAIN_PRECISION", "fp32")
+    g = torch.Generator().manual_seed(4)
+    rows, cin, cout = 60000, 16, 16
+    x = torch.randn(rows, cin, generator=g) * 0.05
+    w = torch.eye(cin)
+    b = torch.full((cout,), 10.0)
+    gamma, beta = torch.ones(cout), torch.zeros(cout)
+    y, mean, var = layers.conv_bn_train(*(t.to(cuda) for t in (x, w, b, gamma, beta)), False)
+    z = x.double() @ w.double() + b.double()
+    assert torch.allclose(mean.cpu().double(), z.mean(0), rtol=1e-6)
+    rel = ((var.cpu().double() - z.var(0, unbiased=False)).abs() / z.var(0, unbiased=False)).max().item()
+    assert rel < 2e-4, "batch variance relative error %.2e" % rel   # fp32 z itself carries 1e-6 absolute noise at |z| = 10
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_conv_bn_train_is_deterministic_and_skips_dx(cuda, precision, monkeypatch):
     layers = pkg("models.layers")
@@ -311,6 +330,40 @@ def test_captured_train_step_equals_eager_steps(cuda):
     for k in net_e.weights:
         assert torch.equal(net_e.weights[k], net_g.weights[k]), k
     assert torch.equal(net_e._adam["m"], net_g._adam["m"]) and torch.equal(net_e._adam["v"], net_g._adam["v"])
+
+
+def test_eval_forward_between_graph_replays_sees_the_updated_weights(cuda):
+    """replay -> eval -> replay -> eval: the folded eval-mode weight copy is invalidated by every replay (the graph updates the
+    weights and the BN shadows without going through get_train_op's Python), so each eval forward equals the one of the eager
+    sequence at the same step."""
+    f3, synth = pkg("models.feat3dnet"), pkg("synth")
+    B, N, M = 2, 2048, 64
+    a, p, n = (torch.as_tensor(synth.make_batch(B, N, seed0=s)).to(cuda) for s in (31, 32, 33))
+    params = onet.init_params(seed=9, randomize_bn=True)
+    probe = torch.as_tensor(synth.make_batch(1, 2048, seed0=40)).to(cuda)
+
+    def eval_out(net):
+        kp, feat, att, ep = net.get_inference_model(probe, False)
+        return feat.clone(), att.clone(), ep["orientation"].clone()
+
+    net_e = f3.Feat3dNet({'num_clusters': M}, weights=params, device=cuda).train_mode()
+    outs_e = []
+    for step in range(4):
+        xyz, feats, att, ep = net_e.get_train_model(a, p, n, True)
+        loss, ep = net_e.get_loss(xyz, feats, att, ep)
+        net_e.get_train_op(loss, lr=1e-2, end_points=ep)
+        if step >= 2:
+            outs_e.append(eval_out(net_e))
+    net_g = f3.Feat3dNet({'num_clusters': M}, weights=params, device=cuda).train_mode()
+    replay = net_g.capture_train_step(a, p, n, lr=1e-2, warmup=2)
+    outs_g = []
+    for _ in range(2):
+        replay()
+        outs_g.append(eval_out(net_g))
+    assert not torch.equal(outs_g[0][0], outs_g[1][0]), "the weights moved between the two eval forwards"
+    for e, g in zip(outs_e, outs_g):
+        for te, tg in zip(e, g):
+            assert torch.equal(te, tg)
 
 
 def test_train_loop_follows_the_reference_schedule(cuda, tmp_path):
