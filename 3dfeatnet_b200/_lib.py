@@ -65,6 +65,7 @@ SIGNATURES = {
     "f3d_ransac_fit_rt": (_i, [_i, _vp, _vp, _i, _vp, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_rigid_fit": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "f3d_debug_umma_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "f3d_debug_umma_bench": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
     "f3d_debug_wgrad_tc": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "f3d_detector_tc_weight_bytes": (_sz, []),
     "f3d_debug_set_timeline": (None, [_vp]),

@@ -282,6 +282,10 @@ int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int 
  * dbg bit 0 skips the operand staging, bit 1 the MMAs (micro-benchmarking). */
 int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, int dbg, void *stream);
 size_t f3d_detector_tc_weight_bytes(void);
+/* Measurement aid: `groups` x `per_group` back-to-back tcgen05.mma of shape (128 * cta_group) x N x 16 (A from tensor memory, B a
+ * zero-filled bf16 no-swizzle image in shared memory, K- or MN-major), one commit per group, on `ctas` CTAs at once (cta_group 2:
+ * clusters of 2, M = 256 across the pair).  out: 2 int64 per CTA = {clock64 cycles of the loop, instructions}.  */
+int f3d_debug_umma_bench(int cta_group, int N, int groups, int per_group, int b_mn_major, int ctas, void *out, void *stream);
 /* Bring-up: device buffer of (tiles per CTA) x 16 int64 receiving CTA 0's clock64() timeline of the detector tensor
  * kernel (slots: 0/1/2 MMA warp, 4-6 producer, 8-13 epilogue); NULL disables. */
 void f3d_debug_set_timeline(void *buf);
