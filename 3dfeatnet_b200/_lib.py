@@ -8,6 +8,11 @@ LIB_PATH = os.path.join(HERE, "lib3dfeatnet_b200.so")
 
 PRECISION_IMAGES_CACHED = 0x100  # F3D_PRECISION_IMAGES_CACHED
 
+
+def precision_sm_limit(n):
+    """F3D_PRECISION_SM_LIMIT(n): the persistent tensor-core kernels of a forward call launch at most n CTAs (0 = all SMs)."""
+    return (int(n) & 0xff) << 16
+
 _c = ctypes
 _vp, _i, _f, _sz, _ll = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_longlong
 
@@ -19,6 +24,7 @@ SIGNATURES = {
     "f3d_reset_launch_count": (None, []),
     "f3d_farthest_point_sample": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_farthest_point_sample_gather": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "f3d_farthest_point_sample_gather_ctas": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "f3d_gather_point": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_gather_point_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_cumsum": (_i, [_i, _i, _vp, _vp, _vp]),
@@ -70,8 +76,8 @@ SIGNATURES = {
     "f3d_detector_tc_weight_bytes": (_sz, []),
     "f3d_debug_set_timeline": (None, [_vp]),
     "f3d_debug_set_timeline_desc": (None, [_vp]),
-    "f3d_debug_time_detector_rows": (None, [_i]),
-    "f3d_debug_detector_rows_ms": (_c.c_float, []),
+    "f3d_debug_kernel_timer": (None, [_i]),
+    "f3d_debug_kernel_timings": (_i, [_i, _vp, _vp, _vp]),
 }
 
 _LIB = None
@@ -114,6 +120,16 @@ def stream():
     import torch
 
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def kernel_timings(max_records=512):
+    """[(kernel name, ms, algorithmic units)] recorded since f3d_debug_kernel_timer(1) (measurement aid)."""
+    names = ctypes.create_string_buffer(max_records * 48)
+    ms = (ctypes.c_float * max_records)()
+    units = (ctypes.c_double * max_records)()
+    n = lib().f3d_debug_kernel_timings(max_records, ctypes.cast(names, ctypes.c_void_p), ctypes.cast(ms, ctypes.c_void_p),
+                                       ctypes.cast(units, ctypes.c_void_p))
+    return [(names.raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode(), float(ms[i]), float(units[i])) for i in range(n)]
 
 
 def require_cuda(*tensors):

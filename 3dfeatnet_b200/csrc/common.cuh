@@ -17,6 +17,11 @@ extern thread_local char g_err[256];
 int fail(int code, const char *what);
 int check_launch(const char *what);  // cudaPeekAtLastError -> code (0 ok), bumps the launch counter
 
+// measurement aid (runtime.cu): CUDA-event bracket of one named launch on its own stream, recorded only while
+// f3d_debug_kernel_timer(1) is in effect; `units` = the algorithmic bytes / flops of the launch
+void ktimer_begin(const char *name, double units, cudaStream_t st);
+void ktimer_end(cudaStream_t st);
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 constexpr int kWarp = 32;

@@ -9,18 +9,18 @@ int descriptor_forward_fp32(int b, int n, int m, int S, float radius, int featur
                             const float *new_xyz, const int *idx, const float *orientation, const float *packed,
                             float *pooled_ws, float *features, cudaStream_t st);
 int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
-                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, bool build_image, cudaStream_t st);
+                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, bool build_image, int max_ctas, cudaStream_t st);
 int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
                        const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
-                       float *pooled2, bool build_image, cudaStream_t st);
+                       float *pooled2, bool build_image, int max_ctas, cudaStream_t st);
 size_t descriptor_tc_weight_bytes();
 int descriptor_post_fp32(long long nc, const float *pooled2, const float *packed, int feature_dim, float *features,
                          cudaStream_t st);
 size_t post_tc_weight_bytes();
 int detector_post_tc(long long nc, const float *pooled, const float *packed, uint8_t *wimg, float *attention, float *orientation,
-                     bool build_image, cudaStream_t st);
+                     bool build_image, int max_ctas, cudaStream_t st);
 int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, const float *packed, uint8_t *wimg, float *features,
-                       bool build_image, cudaStream_t st);
+                       bool build_image, int max_ctas, cudaStream_t st);
 int detector_post_fp32(long long num_clusters, const float *pooled, const float *packed, float *attention,
                        float *orientation, cudaStream_t st);
 }  // namespace f3d
@@ -67,6 +67,7 @@ F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius,
     if (!workspace || workspace_bytes < f3d_forward_workspace_bytes(b, m, 32))
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "detector_forward: workspace too small");
     const bool build_images = (precision & F3D_PRECISION_IMAGES_CACHED) == 0;
+    const int max_ctas = (precision >> 16) & 0xff;  // F3D_PRECISION_SM_LIMIT(n): SMs granted to the persistent kernels (0 = all)
     precision &= 0xff;
     if (precision == 0)
         return detector_forward_fp32(b, n, m, nsample, radius, xyz, new_xyz, idx, packed, static_cast<float *>(workspace),
@@ -75,10 +76,10 @@ F3D_API int f3d_detector_forward(int b, int n, int m, int nsample, float radius,
         if (nsample != 64) return fail(F3D_ERR_UNSUPPORTED, "detector_forward: the tensor-core path needs nsample == 64");
         float *pooled = static_cast<float *>(workspace);
         int rc = detector_rows_tc(static_cast<long long>(b) * m, n, m, radius, xyz, new_xyz, idx, packed, image_slot(workspace, b, m, 0), pooled,
-                                  build_images, as_stream(stream));
+                                  build_images, max_ctas, as_stream(stream));
         if (rc) return rc;
         return detector_post_tc(static_cast<long long>(b) * m, pooled, packed, image_slot(workspace, b, m, 1), attention, orientation,
-                                build_images, as_stream(stream));
+                                build_images, max_ctas, as_stream(stream));
     }
     return fail(F3D_ERR_UNSUPPORTED, "detector_forward: precision must be 0 (fp32) or 2 (bf16x3 tensor cores)");
 }
@@ -92,6 +93,7 @@ F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radiu
     if (!workspace || workspace_bytes < f3d_forward_workspace_bytes(b, m, feature_dim))
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "descriptor_forward: workspace too small");
     const bool build_images = (precision & F3D_PRECISION_IMAGES_CACHED) == 0;
+    const int max_ctas = (precision >> 16) & 0xff;  // F3D_PRECISION_SM_LIMIT(n)
     precision &= 0xff;
     if (precision == 0)
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
@@ -99,10 +101,10 @@ F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radiu
     if (precision == 2 && nsample == 64 && feature_dim <= 64) {  // tcgen05, bf16x3 split
         float *pooled2 = static_cast<float *>(workspace);
         int rc = descriptor_rows_tc(static_cast<long long>(b) * m, n, m, radius, feature_dim, xyz, new_xyz, idx, orientation,
-                                    packed, image_slot(workspace, b, m, 2), pooled2, build_images, as_stream(stream));
+                                    packed, image_slot(workspace, b, m, 2), pooled2, build_images, max_ctas, as_stream(stream));
         if (rc) return rc;
         return descriptor_post_tc(static_cast<long long>(b) * m, feature_dim, pooled2, packed, image_slot(workspace, b, m, 3), features,
-                                  build_images, as_stream(stream));
+                                  build_images, max_ctas, as_stream(stream));
     }
     if (precision == 2)  // shapes the tensor-core kernel does not cover (nsample != 64, feature_dim 128): exact fp32 kernel
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,

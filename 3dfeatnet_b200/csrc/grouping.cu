@@ -555,8 +555,11 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
     const size_t smem = static_cast<size_t>(wpc) * (nwords + 32 * spl) * sizeof(unsigned);
     cudaError_t e = cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "bq_grid_query: cudaFuncSetAttribute");
+    // algorithmic bytes of the whole ball query: B * (12 N + 12 M + 4 M S + 4 M)
+    ktimer_begin("bq_grid_query_kernel", static_cast<double>(b) * (12.0 * n + 12.0 * m + 4.0 * m * nsample + 4.0 * m), st);
     bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, ws.sorted, ws.cell_start, ws.info, xyz2, idx,
                                                                     pts_cnt);
+    ktimer_end(st);
     int rc = check_launch("bq_grid_query_kernel");
     if (rc) return rc;
     const unsigned fb_blocks = blocks_for(w, kBqWarps);

@@ -469,12 +469,9 @@ __global__ void det_tc_prep_kernel(const float *__restrict__ P, WeightLayout L, 
 }
 
 static long long *g_det_dbg = nullptr;  // set through f3d_debug_set_timeline (bring-up only)
-// optional CUDA-event bracket of the rows kernel on its own launch stream (bench.py's roofline measurement)
-static bool g_det_time = false;
-static cudaEvent_t g_det_ev[2] = {nullptr, nullptr};
 
 int detector_rows_tc(long long num_clusters, int n, int m, float radius, const float *xyz, const float *new_xyz,
-                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, bool build_image, cudaStream_t st) {
+                     const int *idx, const float *packed, uint8_t *wimg, float *pooled, bool build_image, int max_ctas, cudaStream_t st) {
     if (num_clusters == 0) return 0;
     if (build_image) {
         const int total = 128 * 64 + 256 * 128 + 640;
@@ -492,11 +489,13 @@ int detector_rows_tc(long long num_clusters, int n, int m, float radius, const f
     cudaError_t e = cudaFuncSetAttribute(det_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(det::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "det_rows_tc: cudaFuncSetAttribute");
-    const unsigned grid = static_cast<unsigned>(num_clusters < num_sms ? num_clusters : num_sms);
-    if (g_det_time) cudaEventRecord(g_det_ev[0], st);
+    const int ctas = (max_ctas > 0 && max_ctas < num_sms) ? max_ctas : num_sms;  // persistent: one CTA per SM the caller grants
+    const unsigned grid = static_cast<unsigned>(num_clusters < ctas ? num_clusters : ctas);
+    // algorithmic flops: 2 * rows * (3*64 + 64*128 + 128*256), rows = 64 samples per cluster
+    ktimer_begin("det_rows_tc_kernel", 2.0 * 41152.0 * 64.0 * static_cast<double>(num_clusters), st);
     det_rows_tc_kernel<<<grid, det::kThreads, det::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, wimg, pooled,
                                                                      g_det_dbg);
-    if (g_det_time) cudaEventRecord(g_det_ev[1], st);
+    ktimer_end(st);
     return check_launch("det_rows_tc_kernel");
 }
 
@@ -519,22 +518,5 @@ F3D_API int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float 
 namespace f3d { extern long long *g_desc_dbg; }
 F3D_API void f3d_debug_set_timeline(void *buf) { f3d::g_det_dbg = static_cast<long long *>(buf); }
 F3D_API void f3d_debug_set_timeline_desc(void *buf) { f3d::g_desc_dbg = static_cast<long long *>(buf); }
-
-// Measurement aid: when enabled, det_rows_tc_kernel is bracketed by CUDA events on the stream it is launched on;
-// f3d_debug_detector_rows_ms() waits for the last bracket and returns its duration (ms), or -1.
-F3D_API void f3d_debug_time_detector_rows(int enable) {
-    if (enable && !f3d::g_det_ev[0]) {
-        cudaEventCreate(&f3d::g_det_ev[0]);
-        cudaEventCreate(&f3d::g_det_ev[1]);
-    }
-    f3d::g_det_time = enable != 0;
-}
-F3D_API float f3d_debug_detector_rows_ms(void) {
-    if (!f3d::g_det_ev[0]) return -1.0f;
-    float ms = -1.0f;
-    if (cudaEventSynchronize(f3d::g_det_ev[1]) != cudaSuccess) return -1.0f;
-    if (cudaEventElapsedTime(&ms, f3d::g_det_ev[0], f3d::g_det_ev[1]) != cudaSuccess) return -1.0f;
-    return ms;
-}
 
 F3D_API size_t f3d_detector_tc_weight_bytes(void) { return det::kWeightBytes; }

@@ -428,7 +428,7 @@ long long *g_desc_dbg = nullptr;  // bring-up timeline buffer (f3d_debug_set_tim
 
 int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
                        const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
-                       float *pooled2, bool build_image, cudaStream_t st) {
+                       float *pooled2, bool build_image, int max_ctas, cudaStream_t st) {
     if (num_clusters == 0) return 0;
     if (build_image) {
         const int total = 128 * 32 + 2 * 128 * 64 + 320;
@@ -446,9 +446,13 @@ int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int f
     cudaError_t e = cudaFuncSetAttribute(desc_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(dsc::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "desc_rows_tc: cudaFuncSetAttribute");
-    const unsigned grid = static_cast<unsigned>(num_clusters < num_sms ? num_clusters : num_sms);
+    const int ctas = (max_ctas > 0 && max_ctas < num_sms) ? max_ctas : num_sms;
+    const unsigned grid = static_cast<unsigned>(num_clusters < ctas ? num_clusters : ctas);
+    // algorithmic flops (split-weight form): 2 * (rows * 10336 + clusters * 8192)
+    ktimer_begin("desc_rows_tc_kernel", 2.0 * (10336.0 * 64.0 + 8192.0) * static_cast<double>(num_clusters), st);
     desc_rows_tc_kernel<<<grid, dsc::kThreads, dsc::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, orientation, wimg,
                                                                       pooled2, g_desc_dbg);
+    ktimer_end(st);
     return check_launch("desc_rows_tc_kernel");
 }
 

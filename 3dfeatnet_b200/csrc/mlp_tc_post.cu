@@ -394,7 +394,7 @@ static int post_num_sms() {
 size_t post_tc_weight_bytes() { return post::kDetImgBytes; }  // >= kDescImgBytes
 
 int detector_post_tc(long long nc, const float *pooled, const float *packed, uint8_t *wimg, float *attention, float *orientation,
-                     bool build_image, cudaStream_t st) {
+                     bool build_image, int max_ctas, cudaStream_t st) {
     if (nc == 0) return 0;
     int rc = 0;
     if (build_image) {
@@ -406,13 +406,16 @@ int detector_post_tc(long long nc, const float *pooled, const float *packed, uin
     cudaError_t e = cudaFuncSetAttribute(post_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(post::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "post_tc: cudaFuncSetAttribute");
     const long long ntiles = (nc + post::kTile - 1) / post::kTile;
-    const unsigned grid = static_cast<unsigned>(ntiles < post_num_sms() ? ntiles : post_num_sms());
+    const int ctas = (max_ctas > 0 && max_ctas < post_num_sms()) ? max_ctas : post_num_sms();
+    const unsigned grid = static_cast<unsigned>(ntiles < ctas ? ntiles : ctas);
+    ktimer_begin("post_tc_kernel<detector>", 2.0 * (256.0 * 128 + 128 * 64 + 64 * 3) * static_cast<double>(nc), st);
     post_tc_kernel<0><<<grid, post::kThreads, post::kSmemBytes, st>>>(nc, 0, pooled, wimg, attention, orientation);
+    ktimer_end(st);
     return check_launch("post_tc_kernel<detector>");
 }
 
 int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, const float *packed, uint8_t *wimg, float *features,
-                       bool build_image, cudaStream_t st) {
+                       bool build_image, int max_ctas, cudaStream_t st) {
     if (nc == 0) return 0;
     int rc = 0;
     if (build_image) {
@@ -424,8 +427,11 @@ int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, cons
     cudaError_t e = cudaFuncSetAttribute(post_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(post::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "post_tc: cudaFuncSetAttribute");
     const long long ntiles = (nc + post::kTile - 1) / post::kTile;
-    const unsigned grid = static_cast<unsigned>(ntiles < post_num_sms() ? ntiles : post_num_sms());
+    const int ctas = (max_ctas > 0 && max_ctas < post_num_sms()) ? max_ctas : post_num_sms();
+    const unsigned grid = static_cast<unsigned>(ntiles < ctas ? ntiles : ctas);
+    ktimer_begin("post_tc_kernel<descriptor>", 2.0 * 128.0 * feature_dim * static_cast<double>(nc), st);
     post_tc_kernel<1><<<grid, post::kThreads, post::kSmemBytes, st>>>(nc, feature_dim, pooled2, wimg, features, nullptr);
+    ktimer_end(st);
     return check_launch("post_tc_kernel<descriptor>");
 }
 

@@ -126,7 +126,7 @@ struct FpsWin {  // double-buffered per-warp winners: (distance bits, tie code <
 
 template <int W, int G, int CL>
 __global__ void __launch_bounds__(W * 32, 1)
-fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restrict__ out, float *__restrict__ out_xyz) {
+fps_group_kernel(int num_clouds, int n_total, int m, const float *__restrict__ inp, int *__restrict__ out, float *__restrict__ out_xyz) {
     constexpr int T = W * 32;
     constexpr int NP = T * 4 * G;
     constexpr int kGrid = 32, kCells = kGrid * kGrid;
@@ -149,7 +149,9 @@ fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restr
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rank = CL > 1 ? cluster_ctarank() : 0u;
-    const int cloud = blockIdx.x / CL;
+    // A CTA (or cluster) walks the clouds blockIdx.x / CL, + gridDim.x / CL, ...: with fewer CTAs than clouds the sampling of a
+    // batch occupies a chosen number of SMs for longer (the pipeline runs it beside the contractions of the previous batch).
+    for (int cloud = blockIdx.x / CL; cloud < num_clouds; cloud += gridDim.x / CL) {
     const int chunk = CL > 1 ? (n_total + CL - 1) / CL : n_total;
     const int k_first = static_cast<int>(rank) * chunk;
     const int n = max(min(chunk, n_total - k_first), 0);
@@ -381,7 +383,9 @@ fps_group_kernel(int n_total, int m, const float *__restrict__ inp, int *__restr
             }
         }
     }
-    if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still write into its shared memory
+    if (CL > 1) cluster_sync_all();  // no CTA exits (or re-initialises) while a peer may still write into its shared memory
+    else __syncthreads();            // the shared-memory cloud and the winner slots are rebuilt for the next cloud
+    }
 }
 
 // ---- fallback for any n: running distances in a caller-provided (b,n) scratch, points from L2 ------------
@@ -436,13 +440,17 @@ __global__ void gather_point_kernel(int n, int m, long long total, const float *
 }
 
 template <int W, int G, int CL>
-static int launch_fps_group(int b, int n, int m, const float *inp, int *out, float *out_xyz, cudaStream_t st) {
+static int launch_fps_group(int b, int n, int m, const float *inp, int *out, float *out_xyz, int max_ctas, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(W) * 32 * 4 * G * (3 * sizeof(float) + sizeof(unsigned short));
     cudaError_t e = cudaFuncSetAttribute(fps_group_kernel<W, G, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "fps: cudaFuncSetAttribute");
+    // algorithmic bytes: B * (12 N + 4 M) (+ 12 M when the sampled coordinates are written too)
+    ktimer_begin("fps_group_kernel", static_cast<double>(b) * (12.0 * n + 4.0 * m + (out_xyz ? 12.0 * m : 0.0)), st);
     if (CL == 1) {
-        fps_group_kernel<W, G, CL><<<b, W * 32, smem, st>>>(n, m, inp, out, out_xyz);
+        const int grid = (max_ctas > 0 && max_ctas < b) ? max_ctas : b;  // fewer CTAs than clouds: each walks several clouds
+        fps_group_kernel<W, G, CL><<<grid, W * 32, smem, st>>>(b, n, m, inp, out, out_xyz);
+        ktimer_end(st);
         return check_launch("fps_group_kernel");
     }
     cudaLaunchConfig_t cfg = {};
@@ -457,7 +465,8 @@ static int launch_fps_group(int b, int n, int m, const float *inp, int *out, flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, fps_group_kernel<W, G, CL>, n, m, inp, out, out_xyz);
+    e = cudaLaunchKernelEx(&cfg, fps_group_kernel<W, G, CL>, b, n, m, inp, out, out_xyz);
+    ktimer_end(st);
     ++g_launches;
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -470,19 +479,19 @@ static int launch_fps_group(int b, int n, int m, const float *inp, int *out, flo
 
 using namespace f3d;
 
-static int fps_dispatch(int b, int n, int m, const float *inp, float *temp, int *out, float *out_xyz, void *stream) {
+static int fps_dispatch(int b, int n, int m, const float *inp, float *temp, int *out, float *out_xyz, int max_ctas, void *stream) {
     if (b < 0 || n <= 0 || m <= 0 || !inp || !out) return fail(F3D_ERR_INVALID_ARGUMENT, "farthest_point_sample: bad arguments");
     if (b == 0) return 0;
     cudaStream_t st = as_stream(stream);
     // 512 threads (measured: 256 threads x 16 groups 0.308 ms, 1024 threads x 4 groups 0.325 ms, 512 x 8 0.266 ms at n = 16384)
-    if (n <= 2048) return launch_fps_group<16, 1, 1>(b, n, m, inp, out, out_xyz, st);
-    if (n <= 4096) return launch_fps_group<16, 2, 1>(b, n, m, inp, out, out_xyz, st);
-    if (n <= 8192) return launch_fps_group<16, 4, 1>(b, n, m, inp, out, out_xyz, st);
-    if (n <= 16384) return launch_fps_group<16, 8, 1>(b, n, m, inp, out, out_xyz, st);
+    if (n <= 2048) return launch_fps_group<16, 1, 1>(b, n, m, inp, out, out_xyz, max_ctas, st);
+    if (n <= 4096) return launch_fps_group<16, 2, 1>(b, n, m, inp, out, out_xyz, max_ctas, st);
+    if (n <= 8192) return launch_fps_group<16, 4, 1>(b, n, m, inp, out, out_xyz, max_ctas, st);
+    if (n <= 16384) return launch_fps_group<16, 8, 1>(b, n, m, inp, out, out_xyz, max_ctas, st);
     // larger clouds: a cluster of 2 / 4 / 8 CTAs per cloud, 16384 points each (KITTI-shape scans, 131072 points)
-    if (n <= 2 * 16384) return launch_fps_group<16, 8, 2>(b, n, m, inp, out, out_xyz, st);
-    if (n <= 4 * 16384) return launch_fps_group<16, 8, 4>(b, n, m, inp, out, out_xyz, st);
-    if (n <= 8 * 16384) return launch_fps_group<16, 8, 8>(b, n, m, inp, out, out_xyz, st);
+    if (n <= 2 * 16384) return launch_fps_group<16, 8, 2>(b, n, m, inp, out, out_xyz, max_ctas, st);
+    if (n <= 4 * 16384) return launch_fps_group<16, 8, 4>(b, n, m, inp, out, out_xyz, max_ctas, st);
+    if (n <= 8 * 16384) return launch_fps_group<16, 8, 8>(b, n, m, inp, out, out_xyz, max_ctas, st);
     if (!temp) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "farthest_point_sample: n > 131072 needs temp of b*n floats");
     fps_global_kernel<<<b, kFpsThreads, 0, st>>>(n, m, inp, temp, out);
     int rc = check_launch("fps_global_kernel");
@@ -493,14 +502,25 @@ static int fps_dispatch(int b, int n, int m, const float *inp, float *temp, int 
 }
 
 F3D_API int f3d_farthest_point_sample(int b, int n, int m, const float *inp, float *temp, int *out, void *stream) {
-    return fps_dispatch(b, n, m, inp, temp, out, nullptr, stream);
+    return fps_dispatch(b, n, m, inp, temp, out, nullptr, 0, stream);
 }
 
 // farthest_point_sample + gather_point of the samples in one launch (sample_points, models/pointnet_common.py:14-29): the
 // kernel already holds the winner's coordinates each round, so new_xyz costs three more stores and no second kernel.
 F3D_API int f3d_farthest_point_sample_gather(int b, int n, int m, const float *inp, float *temp, int *out, float *new_xyz, void *stream) {
     if (!new_xyz) return fail(F3D_ERR_INVALID_ARGUMENT, "farthest_point_sample_gather: new_xyz is NULL");
-    return fps_dispatch(b, n, m, inp, temp, out, new_xyz, stream);
+    return fps_dispatch(b, n, m, inp, temp, out, new_xyz, 0, stream);
+}
+
+// Same, on at most `max_ctas` CTAs (n <= 16384: one CTA per cloud, each CTA walks ceil(b / max_ctas) clouds one after the other;
+// larger clouds keep their cluster of CTAs per cloud and ignore the limit).  The sampling of a batch is a chain of m dependent
+// rounds per cloud -- latency, not throughput -- so a caller that has other work for the remaining SMs (the contractions of the
+// previous batch, 3dfeatnet_b200/pipeline.py) trades a longer sampling phase for SMs.  Results do not depend on max_ctas.
+F3D_API int f3d_farthest_point_sample_gather_ctas(int b, int n, int m, const float *inp, float *temp, int *out, float *new_xyz, int max_ctas,
+                                                  void *stream) {
+    if (!new_xyz) return fail(F3D_ERR_INVALID_ARGUMENT, "farthest_point_sample_gather: new_xyz is NULL");
+    if (max_ctas < 0) return fail(F3D_ERR_INVALID_ARGUMENT, "farthest_point_sample_gather: max_ctas < 0");
+    return fps_dispatch(b, n, m, inp, temp, out, new_xyz, max_ctas, stream);
 }
 
 F3D_API int f3d_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream) {

@@ -756,11 +756,15 @@ static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *
     if (rc) return rc;
     if (pool_s > 0) {
         const long long groups = rows / pool_s, np = groups * (cout / 4);
+        ktimer_begin("bn_apply_pool_kernel", 4.0 * static_cast<double>(rows) * cout, st);  // z read once; the pooled output is 1/pool_s of it
         bn_apply_pool_kernel<<<static_cast<unsigned>((np + 127) / 128), 128, 0, st>>>(groups, pool_s, cout / 4, z, coef, relu, pooled, inv_ties);
+        ktimer_end(st);
         return check_launch("bn_apply_pool_kernel");
     }
     const long long n4 = rows * cout / 4;
+    ktimer_begin("bn_apply_kernel", 8.0 * static_cast<double>(rows) * cout, st);  // z in, y out
     bn_apply_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(n4, cout, z, coef, relu, y);
+    ktimer_end(st);
     return check_launch("bn_apply_kernel");
 }
 
@@ -845,7 +849,9 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
         bn_bwd_reduce_pooled_kernel<<<nred1, 256, 0, st>>>(groups, cout, gy, pooled, gamma, beta, relu, part);
         rc = check_launch("bn_bwd_reduce_pooled_kernel");
     } else {
+        ktimer_begin("bn_bwd_reduce_kernel", 8.0 * static_cast<double>(rows) * cout, st);  // gy and z in
         bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, relu, part);
+        ktimer_end(st);
         rc = check_launch("bn_bwd_reduce_kernel");
     }
     if (rc) return rc;
@@ -857,7 +863,10 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     if (rc) return rc;
     const bool w3 = cin == 3;  // the xyz layers: dW rides along with the dz pass (partials in the dW-partials area: 3*cout per chunk)
     const int napp = static_cast<int>(rows < kApplyBlocks ? rows : kApplyBlocks);
+    // gy (dense mode only) and z in, dz out
+    ktimer_begin("bn_bwd_apply_kernel", (pool_s > 0 ? 8.0 : 12.0) * static_cast<double>(rows) * cout, st);
     bn_bwd_apply_kernel<<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
+    ktimer_end(st);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;
     partial_reduce_kernel<float><<<(cout + 31) / 32, 1024, 0, st>>>(napp, cout, partB, db);

@@ -822,6 +822,8 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
     const LinPlan P = lin_tc_plan(rows, k_real, nsplit);
     const dim3 grid(mblocks, P.grid);
     cudaError_t e = cudaSuccess;
+    // algorithmic bytes: the fp32 rows in and out (each read / written once), weights negligible
+    ktimer_begin(nsplit == 3 ? "lin_tc (3-way split, forward)" : "lin_tc (2-way split, dgrad)", 4.0 * static_cast<double>(rows) * (k_real + nout), st);
 #define F3D_LAUNCH_PIPE(NS, NT)                                                                                                    \
     e = cudaFuncSetAttribute(lin_tc_pipe_kernel<NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));  \
     if (e == cudaSuccess)                                                                                                          \
@@ -831,6 +833,7 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
         else if (nsplit == 3) { F3D_LAUNCH_PIPE(3, 32) }
         else if (P.nt == 64) { F3D_LAUNCH_PIPE(2, 64) }
         else { F3D_LAUNCH_PIPE(2, 32) }
+        ktimer_end(st);
         if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
         return check_launch("lin_tc_pipe_kernel");
     }
@@ -842,6 +845,7 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
         e = cudaFuncSetAttribute(lin_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));
         if (e == cudaSuccess) lin_tc_kernel<2><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part);
     }
+    ktimer_end(st);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
     return check_launch("lin_tc_kernel");
 }
@@ -867,7 +871,9 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
     const size_t smem = 2 * img + 2 * static_cast<size_t>(wg::kRows) * (cin + cout) * 4 + 64;
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "wgrad_tc: cudaFuncSetAttribute");
+    ktimer_begin("wgrad_tc_kernel", 4.0 * static_cast<double>(rows) * (cin + cout), st);
     wgrad_tc_kernel<<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg);
+    ktimer_end(st);
     return check_launch("wgrad_tc_kernel");
 }
 

@@ -450,6 +450,8 @@ class Feat3dNet:
             return loss
 
         replay.graph = graph
+        replay.static_inputs = static  # (anchors, positives, negatives) buffers the graph reads
+        replay.loss = loss
         return replay
 
     def train_mode(self):

@@ -45,6 +45,11 @@ int f3d_farthest_point_sample(int b, int n, int m, const float *inp, float *temp
 /* The same plus gather_point of the samples (sample_points, models/pointnet_common.py:14-29) in the same launch:
  * new_xyz (b,m,3) = inp[b, out[b,j], :] -- identical values to f3d_gather_point on the returned indices. */
 int f3d_farthest_point_sample_gather(int b, int n, int m, const float *inp, float *temp, int *out, float *new_xyz, void *stream);
+/* The same on at most max_ctas CTAs (0 = one per cloud): for n <= 16384 each CTA then walks ceil(b / max_ctas) clouds one after the
+ * other, so the sampling of a batch holds a chosen number of SMs (for longer) and the rest stay free for other streams.
+ * Identical results for every max_ctas. */
+int f3d_farthest_point_sample_gather_ctas(int b, int n, int m, const float *inp, float *temp, int *out, float *new_xyz, int max_ctas,
+                                          void *stream);
 
 /* gatherpointLauncher(b,n,m,inp,idx,out)  tf_sampling_g.cu:206-208, op tf_sampling.cpp:126-148. */
 int f3d_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream);
@@ -145,6 +150,10 @@ size_t f3d_forward_workspace_bytes(int b, int m, int feature_dim);
  * workspace still holds the images of an earlier call of the SAME function with unchanged `packed` contents and feature_dim,
  * and the image-build kernels are skipped (weights are constants between checkpoints; results are bit-identical). */
 #define F3D_PRECISION_IMAGES_CACHED 0x100
+/* F3D_PRECISION_SM_LIMIT(n) may be OR-ed into `precision` as well (n in 1..255, 0 = no limit): the persistent tensor-core kernels of the
+ * call (one CTA per SM) launch at most n CTAs, leaving the other SMs to work the caller runs beside it on another stream -- the
+ * pipeline samples the next batch (f3d_farthest_point_sample_gather_ctas) there.  Results do not depend on n. */
+#define F3D_PRECISION_SM_LIMIT(n) (((n) & 0xff) << 16)
 int f3d_detector_forward(int b, int n, int m, int nsample, float radius, const float *xyz, const float *new_xyz,
                          const int *idx, const float *packed, float *attention, float *orientation, int precision,
                          void *workspace, size_t workspace_bytes, void *stream);
@@ -290,9 +299,12 @@ int f3d_debug_umma_bench(int cta_group, int N, int groups, int per_group, int b_
  * kernel (slots: 0/1/2 MMA warp, 4-6 producer, 8-13 epilogue); NULL disables. */
 void f3d_debug_set_timeline(void *buf);
 void f3d_debug_set_timeline_desc(void *buf); /* same for the descriptor tensor kernel */
-/* Measurement aid: bracket det_rows_tc_kernel with CUDA events on its launch stream / read the last duration (ms). */
-void f3d_debug_time_detector_rows(int enable);
-float f3d_debug_detector_rows_ms(void);
+/* Measurement aid: while enabled (enable != 0 also clears earlier records) the hot kernels -- fps_group, bq_grid_query, det_rows_tc,
+ * desc_rows_tc, post_tc, lin_tc, wgrad_tc, the BN passes -- are bracketed by CUDA events on the stream they are launched on (eager
+ * launches only, not under graph capture).  f3d_debug_kernel_timings waits for them and returns their count (<= max): names
+ * (max x 48 chars), durations (ms) and the ALGORITHMIC bytes or flops of each launch as its call site states them. */
+void f3d_debug_kernel_timer(int enable);
+int f3d_debug_kernel_timings(int max, char *names, float *ms, double *units);
 
 #ifdef __cplusplus
 }

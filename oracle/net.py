@@ -148,11 +148,12 @@ def detector(xyz_np, P, num_clusters, radius, nsample, is_training=False, keypoi
     for i in range(2):
         h = conv2d(h, P, "detection/conv_post_%d" % i, True, "relu", is_training, new_stats)
     att = conv2d(h, P, "detection/attention", False, "softplus")[:, :, 0, 0]
-    oxy = conv2d(h, P, "detection/orientation", False, None)[:, :, 0, :]
-    oxy = l2_normalize(oxy, 2, 1e-8)
+    oxy_raw = conv2d(h, P, "detection/orientation", False, None)[:, :, 0, :]
+    oxy = l2_normalize(oxy_raw, 2, 1e-8)
     ori = torch.atan2(oxy[:, :, 1], oxy[:, :, 0])
+    # orientation_xy: the head output BEFORE l2_normalize / atan2 -- its norm is the conditioning of the angle (oracle/parity.py)
     return dict(new_xyz=new_xyz, fps_idx=fps_idx, idx=idx, pts_cnt=cnt, attention=att, orientation=ori,
-                grouped_xyz=g)
+                orientation_xy=oxy_raw, grouped_xyz=g)
 
 
 def descriptor(xyz_np, P, keypoints_np, orientation, radius, nsample, feature_dim=32, is_training=False,
@@ -184,7 +185,8 @@ def inference_model(xyz_np, P, num_clusters=512, radius=2.0, nsample=64, feature
     ori = None if no_regress else det["orientation"]
     desc = descriptor(xyz_np, P, det["new_xyz"], ori, radius, nsample, feature_dim, is_training, new_stats, dtype)
     return dict(xyz=det["new_xyz"], features=desc["features"], attention=det["attention"],
-                orientation=det["orientation"], idx=det["idx"], pts_cnt=det["pts_cnt"], fps_idx=det["fps_idx"])
+                orientation=det["orientation"], orientation_xy=det["orientation_xy"], idx=det["idx"], pts_cnt=det["pts_cnt"],
+                fps_idx=det["fps_idx"])
 
 
 def pairwise_dist(A, B):

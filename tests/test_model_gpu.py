@@ -1,42 +1,27 @@
 """GPU parity tests (-m gpu) of the fused detector / descriptor forward and of the model-level API against the
 oracle network (oracle/net.py, PyTorch-CPU).  Index outputs (FPS, ball query) are compared bit-exactly; floating
-point outputs within the tolerances written here:
-
-  fp32 path   (CUDA-core FFMA, BN folded into the weights):  attention 1e-4 relative to the cloud's max attention,
-              orientation 1e-4 rad (wrapped), descriptors 1e-4 absolute on unit-norm vectors.
-  tf32/3xtf32 (tcgen05) paths: see TOL below.
-The oracle itself moves by ~1e-6 between fp32 and fp64 evaluation, so these bounds leave two orders of headroom for
-summation-order differences and none for a wrong layer.
+point outputs within the ONE tolerance table of oracle/parity.py (attention and orientation-head error relative to the
+cloud's largest value, descriptors at the path's own angle and end to end), which smoke() and bench.py apply as well.
+The oracle itself moves by ~1e-6 between fp32 and fp64 evaluation.
 """
 import numpy as np
 import pytest
 import torch
 
 from oracle import net as onet
+from oracle import parity
 from tests.conftest import pkg
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": dict(att=1e-4, ori=1e-4, feat=1e-4),
-       "3xtf32": dict(att=2e-4, ori=2e-4, feat=2e-4),
-       "tf32": dict(att=2e-2, ori=2e-2, feat=2e-2)}
+wrap = parity.wrap
 
 
-def wrap(d):
-    return torch.atan2(torch.sin(d), torch.cos(d))
-
-
-def compare(out, ref, tol, what=""):
-    att, ratt = out["attention"].cpu().double(), ref["attention"].double()
-    e_att = ((att - ratt).abs() / ratt.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)).max().item()
-    e_ori = wrap(out["orientation"].cpu().double() - ref["orientation"].double()).abs().max().item()
-    e_feat = (out["features"].cpu().double() - ref["features"].double()).abs().max().item()
-    assert e_att < tol["att"], "%s attention err %.3e" % (what, e_att)
-    assert e_feat < tol["feat"], "%s descriptor err %.3e" % (what, e_feat)
-    # orientation of a near-zero (x,y) head output is ill-conditioned; require the bound on all but 0.5 % of clusters
-    d = wrap(out["orientation"].cpu().double() - ref["orientation"].double()).abs().reshape(-1)
-    assert (d > tol["ori"]).double().mean().item() < 5e-3, "%s orientation err %.3e" % (what, e_ori)
-    return e_att, e_ori, e_feat
+def compare(out, ref, precision, what="", own=None):
+    """Device result vs a reference under the row of the tolerance table for `precision`; `own` = oracle descriptor at the device
+    path's own angle (parity.oracle_descriptor_at), when the caller has computed it.  Returns the error figures."""
+    dev = dict(attention=out["attention"], orientation=out["orientation"], features=out.get("features"))
+    return parity.check(parity.errors(dev, ref, own), precision, what)
 
 
 def run_pipeline(xyz, params, M, S=64, F=32, precision="fp32", no_regress=False, dev="cuda:0"):
@@ -61,7 +46,7 @@ def test_c1_oxford_270_fp32(cuda, randomize_bn):
     assert np.array_equal(out["idx"].cpu().numpy(), ref["idx"])
     assert np.array_equal(out["pts_cnt"].cpu().numpy(), ref["pts_cnt"])
     assert np.array_equal(out["xyz"].cpu().numpy(), ref["xyz"])
-    compare(out, ref, TOL["fp32"], "C1")
+    compare(out, ref, "fp32", "C1")
     nrm = out["features"].norm(dim=2)  # unit norm, or exactly 0 for a cluster whose MLP output is all zero
     assert ((nrm - 1).abs() < 1e-5).logical_or(nrm == 0).all()
     assert pipe.launches_per_step >= 5
@@ -78,7 +63,7 @@ def test_fused_forward_shapes_fp32(cuda, B, N, M, S, F, no_regress):
     ref = onet.inference_model(xyz, onet.to_torch(params, torch.float64), num_clusters=M, nsample=S, feature_dim=F,
                                no_regress=no_regress, dtype=torch.float64)
     assert np.array_equal(out["idx"].cpu().numpy(), ref["idx"])
-    compare(out, ref, TOL["fp32"], "shape")
+    compare(out, ref, "fp32", "shape")
 
 
 @pytest.mark.parametrize("case", ["eval_fps", "eval_noregress_f128"])
@@ -96,7 +81,7 @@ def test_fused_forward_matches_reference_graph_golden(cuda, case):
     assert np.array_equal(out["xyz"].cpu().numpy().astype(np.float64), g[case + "/out/xyz"])
     ref = dict(attention=torch.as_tensor(g[case + "/out/attention_end_point"]), orientation=torch.as_tensor(g[case + "/out/orientation"]),
                features=torch.as_tensor(g[case + "/out/features"]))
-    compare(out, ref, TOL["fp32"], case)
+    compare(out, ref, "fp32", case)
 
 
 def test_model_api_matches_pipeline_and_unfused_path(cuda):
@@ -120,7 +105,7 @@ def test_model_api_matches_pipeline_and_unfused_path(cuda):
                                                 keypoints=new_xyz, orientations=ori_u, params=net.weights)
     torch.backends.cuda.matmul.allow_tf32 = False
     ref = dict(attention=att_u.cpu(), orientation=ori_u.cpu(), features=feat_u.cpu())
-    compare(dict(attention=att, orientation=ep["orientation"], features=feat), ref, TOL["fp32"], "unfused")
+    compare(dict(attention=att, orientation=ep["orientation"], features=feat), ref, "fp32", "unfused")
 
 
 def test_saliency_gradients_run_through_group_point_grad(cuda):
@@ -230,3 +215,54 @@ def test_cached_weight_images_and_packed_rows(cuda):
     host = pipe.step_host()
     torch.cuda.synchronize()
     assert torch.equal(host, want.cpu())
+
+
+def test_pipelined_step_equals_serial_step_for_every_partition(cuda):
+    """step_pipelined (sampling of batch i+1 beside the contractions of batch i, on a partition of the SMs) returns the bits of the
+    serial step for each batch, whatever the partition; f3d_farthest_point_sample_gather_ctas returns the same samples for every CTA
+    count (each CTA then walks several clouds); the host loop built on it returns the serial rows."""
+    pm, lib_mod = pkg("pipeline"), pkg("_lib")
+    B, N, M = 10, 4096, 96
+    batches = [torch.as_tensor(pkg("synth").make_batch(B, N, seed0=300 + 17 * k)).to(cuda) for k in range(3)]
+    params = onet.init_params(seed=8, randomize_bn=True)
+    pipe = pm.DetectDescribePipeline(B, N, weights=params, num_clusters=M, precision="bf16x3", device=cuda, use_graph=True)
+    want = []
+    for x in batches:
+        out = pipe.run(x)
+        want.append({k: v.clone() for k, v in out.items()})
+    L = lib_mod.lib()
+    for ctas in (1, 3, 7, 10, 0):
+        idx = torch.empty((B, M), dtype=torch.int32, device=cuda)
+        kp = torch.empty((B, M, 3), device=cuda)
+        lib_mod.check(L.f3d_farthest_point_sample_gather_ctas(B, N, M, lib_mod.ptr(batches[0]), None, lib_mod.ptr(idx), lib_mod.ptr(kp), ctas,
+                                                              lib_mod.stream()), "fps ctas")
+        assert torch.equal(idx, want[0]["fps_idx"]) and torch.equal(kp, want[0]["xyz"]), ctas
+    for part in ((5, 100, 0), (10, 0, 0), (3, 120, 60), (5, 143, 143)):
+        pipe.set_partition(*part)
+        pl = pipe._pipelined_state(ring=2)
+        pl["xyz"][0].copy_(batches[0])
+        pl["xyz"][1].copy_(batches[1])
+        pipe.xyz.copy_(batches[0])
+        pipe.prime_pipelined()
+        pl["xyz"][1].copy_(batches[1])           # prime_pipelined(ring=2) mirrors buffer 0: put batch 1 back
+        for i in range(3):                        # step i completes the batch in buffer i % 2: batches 0, 1, 0
+            pipe.step_pipelined()
+            w = want[i % 2]
+            got = dict(xyz=pipe.keypoints, fps_idx=pipe.fps_idx, idx=pipe.idx, pts_cnt=pipe.pts_cnt, attention=pipe.attention,
+                       orientation=pipe.orientation, features=pipe.features)
+            for k, v in got.items():
+                assert torch.equal(v, w[k]), (part, i, k)
+    # host loop: three different batches in, their rows out in order
+    pipe.set_partition(5, 100, 0)
+    pipe.host_pipelined = True
+    pipe.h_xyz.copy_(batches[0].cpu())
+    pipe.warm_host_graphs()
+    hosts = [b.cpu().pin_memory() for b in batches]
+    for steps in (1, 2, 3, 5):
+        ms, rows = pipe.run_host_steps(steps, host_batches=hosts)
+        w = want[(steps - 1) % 3]
+        assert torch.equal(rows, torch.cat([w["xyz"], w["attention"][..., None], w["orientation"][..., None], w["features"]], dim=2).cpu()), steps
+    # the serial step still works afterwards and owns its buffers again
+    out = pipe.run(batches[2])
+    for k in ("xyz", "fps_idx", "features"):
+        assert torch.equal(out[k], want[2][k])
