@@ -76,9 +76,20 @@ def errors(out, ref, desc_at_own_angle=None):
     return e
 
 
+def _report(e, precision, what):
+    """F3D_PARITY_REPORT=<file>: append every set of error figures that goes through check() (how the table above was filled in)."""
+    import json
+    import os
+    path = os.environ.get("F3D_PARITY_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(what=what, precision=precision, **{k: v for k, v in e.items() if not k.startswith("_")})) + "\n")
+
+
 def check(e, precision, what=""):
     """Assert the figures of errors() against TOL[precision]; returns the public (scalar) part of e."""
     tol = TOL[precision]
+    _report(e, precision, what)
     assert e["att"] < tol["att"], "%s attention error %.3e >= %.1e (%s)" % (what, e["att"], tol["att"], precision)
     if "ori_w" in e:
         assert e["ori_w"] < tol["ori_w"], "%s orientation-head error %.3e >= %.1e (%s)" % (what, e["ori_w"], tol["ori_w"], precision)

@@ -322,6 +322,46 @@ def test_knn_point_vs_oracle(cuda, b, n, m, c, k):
     assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(val.cpu().numpy(), wval)
 
 
+# ------------------------------------------------------------------------------------------------ C2 sweep (BASELINE.json configs[1])
+@pytest.mark.parametrize("n", [4096, 8192, 16384, 32768, 65536, 131072])
+def test_c2_sweep_knn_topk_group_point(cuda, n):
+    """configs[1]: uniform clouds U(-30,30)^2 x U(-2,15) of 4k .. 128k points (10 % exact duplicates => distance ties), nsample 64:
+    knn_point / select_top_k (tf_grouping.py:63-88, tf_grouping_g.cu:137-177) and group_point + its gradient (:94-132) against the
+    oracle bit for bit, and against the reference's own CUDA kernels built as-is (selection sort and group exactly, the atomics of
+    the gradient to reassociation tolerance).  Ball query and FPS have their own sweeps above."""
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    k = 64
+    x1 = clouds("dups", 1, n, 900 + n)
+    rng = np.random.default_rng(n)
+    m_knn = 64                                            # centres for kNN: the (m, n) distance matrix is what scales with n
+    x2 = np.ascontiguousarray(x1[:, rng.choice(n, m_knn, replace=False)] + rng.normal(0, 0.3, (1, m_knn, 3)).astype(np.float32))
+    val, idx = tg.knn_point(k, T(x1, cuda), T(x2, cuda))
+    wval, widx = oops.knn_point(k, x1, x2)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(val.cpu().numpy(), wval)
+    # the op alone on a distance matrix with many exact ties (quantised distances): whole (b,m,n) outputs
+    d = np.floor(rng.random((1, 16, n), dtype=np.float32) * 200.0).astype(np.float32)
+    outi, out = tg.select_top_k(k, T(d, cuda))
+    wi, wo = oops.select_top_k(k, d)
+    assert np.array_equal(outi.cpu().numpy(), wi) and np.array_equal(out.cpu().numpy(), wo)
+    if HAVE_REF:
+        ri, ro = oref.gpu_select_top_k(k, T(d, cuda))
+        assert torch.equal(outi, ri) and torch.equal(out, ro)
+    # group_point (+ grad) on M = n / 32 clusters x 64 samples taken from the kNN-shaped index range, with padded (repeated) rows
+    m = n // 32
+    gidx = rng.integers(0, n, (1, m, k)).astype(np.int32)
+    gidx[:, :, k // 2:] = gidx[:, :, :1]
+    for c in (3, 16):
+        pts = rng.random((1, n, c), dtype=np.float32)
+        got = tg.group_point(T(pts, cuda), T(gidx, cuda))
+        assert np.array_equal(got.cpu().numpy(), oops.group_point(pts, gidx))
+        g = rng.standard_normal((1, m, k, c)).astype(np.float32)
+        grad = tg.group_point_grad(n, T(gidx, cuda), T(g, cuda))
+        assert np.array_equal(grad.cpu().numpy(), oops.group_point_grad(pts, gidx, g))
+        if HAVE_REF:
+            assert torch.equal(got, oref.gpu_group_point(T(pts, cuda), T(gidx, cuda)))
+            assert torch.allclose(grad, oref.gpu_group_point_grad(T(pts, cuda), T(gidx, cuda), T(g, cuda)), rtol=1e-5, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------ layer-level composition
 def test_sample_and_group_matches_oracle_composition(cuda):
     pc = pkg("models.pointnet_common")
