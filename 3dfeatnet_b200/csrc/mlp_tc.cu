@@ -21,8 +21,13 @@
 //   warps 1-4   : producers -- gather + normalise + layer 0 (3->64, FFMA) -> operand X1 (bf16 hi/lo, K-major)
 //   warps 5-8   : epilogue of even tiles, warps 9-12: epilogue of odd tiles
 //                 E1: D1 (TMEM) -> +bias, ReLU -> operand X2 ;  E2: D2 (TMEM) -> max over samples, +bias, ReLU -> HBM
-// Tensor-pipe order in steady state:  ... MMA2(t-1) | MMA1(t+1) | MMA2(t) | MMA1(t+2) ...  so E1(t) runs under
-// MMA2(t-1), its X2 stores land under MMA1(t+1), and E2(t-1) runs under MMA2(t).
+// conv2 (97 % of the MMA work) is issued per PAIR of tiles with N = 128: a 128x64x16 instruction holds the tensor pipe for 41.9
+// cycles for 32 of math, a 128x128x16 one for 66.5 for 64 (profiles/r02_a_umma_instruction_shape.md).  The two tiles of a pair sit
+// side by side in one X2 slot (sample-contiguous operand, 16 groups of 8 samples), the slots form a ring of two pairs, and the
+// accumulator of each 128-channel block holds both tiles (128 columns).  Tensor memory: D1 64 + W1 64 + D2 2x128 + W2(hi) 128 = 512
+// columns; the lo split of W2 (third product term) stays in shared memory and feeds its MMAs as an SS-mode A operand.
+// Tensor-pipe order in steady state:  ... MMA2(p-1) | MMA1 of the next tiles | MMA2(p) ...  so E1 of pair p+1 runs under MMA2(p)
+// and E2(p-1) under MMA2(p).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "weights_layout.h"
@@ -106,43 +111,51 @@ constexpr uint32_t kLboX1 = kSamples * 16;   // X1: written 16 B per thread, no 
 // epilogue thread (one channel, 64 samples) writes 8 x 16 B per split instead of 64 x 2 B
 constexpr uint32_t kLboX2 = 128;                 // K groups of 8 channels
 constexpr uint32_t kSboX2 = 16 * 128;            // groups of 8 samples (128 channels)
-// shared-memory image (bytes).  The first kWeightBytes are copied verbatim from the packed global buffer.
-constexpr uint32_t kW1Split = 128 * 64 * 2;            // 16 KB per split
-constexpr uint32_t kW2Blk = 128 * 128 * 2;             // 32 KB per (split, M block)
-constexpr uint32_t kOffW1 = 0;                          // [split 2][chunk 8][row 128][8] bf16
-constexpr uint32_t kOffW2 = kOffW1 + 2 * kW1Split;      // [split 2][mblk 2][chunk 16][row 128][8] bf16
-constexpr uint32_t kOffW0 = kOffW2 + 4 * kW2Blk;        // float4 [64]: (w_x, w_y, w_z, bias) of layer 0 per channel
-constexpr uint32_t kOffB0 = kOffW0 + 3 * 64 * 4;        // (tail of the float4 table)
-constexpr uint32_t kOffB1 = kOffB0 + 64 * 4;            // fp32 [128]
+// Weight image in global memory (det_tc_prep_kernel), bytes:  [W2 lo | W1 | W2 hi | small], bulk-copied to the shared-memory
+// offsets below.  W2 lo stays where it lands (A operand of the SS-mode MMAs); W1 and W2 hi are copied on into tensor memory
+// (tcgen05.cp) and their staging area -- plus 32 KB behind it -- is recycled as the ring of X2 slots.
+constexpr uint32_t kW1Split = 128 * 64 * 2;             // 16 KB per split
+constexpr uint32_t kW2Blk = 128 * 128 * 2;              // 32 KB per (split, M block)
+constexpr uint32_t kOffW2lo = 0;                        // [mblk 2][chunk 16][row 128][8] bf16                     64 KB
+constexpr uint32_t kOffW1 = kOffW2lo + 2 * kW2Blk;      // [split 2][chunk 8][row 128][8] bf16 (staging)           32 KB
+constexpr uint32_t kOffW2hi = kOffW1 + 2 * kW1Split;    // [mblk 2][chunk 16][row 128][8] bf16 (staging)           64 KB
+constexpr uint32_t kImgBulk = kOffW2hi + 2 * kW2Blk;    // 160 KB copied to shared-memory offset 0
+constexpr uint32_t kImgSmall = kImgBulk;                // image offset of the fp32 block: W0 float4[64], b1[128], b2[256]
+constexpr uint32_t kSmallBytes = 64 * 16 + 128 * 4 + 256 * 4;
+constexpr uint32_t kWeightBytes = kImgBulk + kSmallBytes;  // 166 400
+// X2 ring: slot = pair & 1; one slot = [split 2][16 groups of 8 samples][128 channels x 16 B]: tile (pair*2 + g) owns sample groups
+// g*8 .. g*8+7 of both splits, so the N = 128 operand of a pair is one uniform-stride block
+constexpr uint32_t kX2Split = 16 * kSboX2;              // 32 KB
+constexpr uint32_t kX2Slot = 2 * kX2Split;              // 64 KB
+constexpr uint32_t kOffX2 = kOffW1;                     // aliases the W1 / W2 hi staging area (+ 32 KB)
+constexpr uint32_t kOffW0 = kOffX2 + 2 * kX2Slot;       // 192 KB: float4 [64]: (w_x, w_y, w_z, bias) of layer 0 per channel
+constexpr uint32_t kOffB1 = kOffW0 + 64 * 16;           // fp32 [128]
 constexpr uint32_t kOffB2 = kOffB1 + 128 * 4;           // fp32 [256]
-constexpr uint32_t kWeightBytes = kOffB2 + 256 * 4;     // 166 400
 constexpr uint32_t kX1Split = 8 * kLboX1;               // 8 KB
-constexpr uint32_t kOffX1 = kWeightBytes;               // [split 2][chunk 8][row 64][8] bf16
-constexpr uint32_t kX2Split = 8 * kSboX2;               // 16 KB
-constexpr uint32_t kX2Buf = 2 * kX2Split;               // one X2 operand (hi + lo)
-// W2 is copied into TENSOR MEMORY once (tcgen05.cp) and its shared-memory staging area is then recycled as the two X2
-// operand buffers, so MMA2 reads only its 2 KB B operand from shared memory and E1(t+1) overlaps MMA2(t).
-constexpr uint32_t kOffX2 = kOffW2;                     // [buf 2][split 2][chunk 16] stride kLboX2 (aliases the W2 staging)
+constexpr uint32_t kOffX1 = kOffB2 + 256 * 4;           // [split 2][chunk 8][row 64][8] bf16
 constexpr uint32_t kOffBars = kOffX1 + 2 * kX1Split;
 constexpr uint32_t kSmemBytes = kOffBars + 20 * 8 + 16;
-static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffBars % 8 == 0, "alignment");
-static_assert(2 * kX2Buf <= 4 * kW2Blk, "X2 buffers must fit the W2 staging area");
+static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffBars % 8 == 0 && kOffW0 % 16 == 0, "alignment");
+static_assert(kOffX2 + 2 * kX2Slot >= kImgBulk, "the X2 ring covers the staging area");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-// TMEM columns: D1 at 0 (64), W1 at 64 + split*32 (64 K = 32 columns), D2 (two M blocks) at 128 / 192,
-// W2 at 256 + (split*2 + mblk)*64 (128 K = 64 columns): all 512 columns in use, every MMA reads its A operand from TMEM.
+// TMEM columns: D1 at 0 (64), W1 at 64 + split*32 (64 K = 32 columns), D2 of M block mb at 128 + mb*128 (two tiles x 64 samples),
+// W2 hi at 384 + mb*64 (128 K = 64 columns): all 512 columns in use.
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemW1 = 64;
-constexpr uint32_t kTmemW2 = 256;
+constexpr uint32_t kTmemD2 = 128;
+constexpr uint32_t kTmemW2 = 384;
 
-// D2 (256 channels = two 128-lane M blocks A / B) is single-buffered: its FULL / FREE barriers are per M block, so E2 drains
-// block A while the tensor pipe computes block B, and MMA2(t+1) block A starts as soon as block B of tile t has been issued.
+// D2 (256 channels = two 128-lane M blocks A / B, each holding the two tiles of a pair) is single-buffered: its FULL / FREE barriers
+// are per M block, so E2 drains block A while the tensor pipe computes block B, and MMA2(p+1) block A starts as soon as block B of
+// pair p has been issued.  X2_FULL is per tile parity (the epilogue warpgroup that wrote it), X2_FREE per ring slot.
 enum Bar { W_FULL = 0, W2_TMEM, X1_FULL, X1_FREE, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE,
-           D2A_FULL0, D2A_FULL1, D2B_FULL0, D2B_FULL1, D2A_FREE, D2B_FREE, kNumBars };
+           D2A_FULL, D2B_FULL, D2A_FREE, D2B_FREE, kNumBars };
 static_assert(kNumBars <= 20, "barrier area");
 // NOTE on mbarrier parity: a waiter may lag a barrier by at most ONE phase (try_wait.parity(p) is true as soon as the
 // barrier is in the phase after p).  The two epilogue warpgroups alternate tiles, i.e. each sees every SECOND completion of
-// a per-tile event, so every barrier they wait on is per-warpgroup (D1_FULL[2], D2A/B_FULL[2], X2_FREE[2]); only the MMA warps,
-// which consume every completion in order, wait on shared single barriers (D2A/B_FREE, X1_FULL).
+// a per-tile event, so the per-TILE barriers they wait on are per-warpgroup (D1_FULL[2]); per-PAIR events (D2A/B_FULL, X2_FREE of a
+// slot) are seen by both warpgroups at every completion and use one barrier each, like the ones the MMA warps wait on (D2A/B_FREE,
+// X1_FULL, X2_FULL[2]).
 }  // namespace det
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -168,12 +181,10 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         mbar_init(&bars[W2_TMEM], 1);
         mbar_init(&bars[X1_FULL], 128);
         mbar_init(&bars[X1_FREE], 1);
-        mbar_init(&bars[D2A_FULL0], 1);
-        mbar_init(&bars[D2A_FULL1], 1);
-        mbar_init(&bars[D2B_FULL0], 1);
-        mbar_init(&bars[D2B_FULL1], 1);
-        mbar_init(&bars[D2A_FREE], 128);
-        mbar_init(&bars[D2B_FREE], 128);
+        mbar_init(&bars[D2A_FULL], 1);
+        mbar_init(&bars[D2B_FULL], 1);
+        mbar_init(&bars[D2A_FREE], 256);  // both epilogue warpgroups (one tile of the pair each)
+        mbar_init(&bars[D2B_FREE], 256);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars[X2_FULL0 + b], 128);
             mbar_init(&bars[X2_FREE0 + b], 1);
@@ -200,25 +211,23 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             // ---- weights: one bulk-TMA burst, resident for the whole kernel ---------------------------------
             if (lane == 0) {
                 mbar_arrive_expect_tx(&bars[W_FULL], kWeightBytes);
-                for (uint32_t off = 0; off < kWeightBytes; off += 16384) {
-                    const uint32_t sz = min(16384u, kWeightBytes - off);
-                    bulk_g2s(smem + off, wimg + off, sz, &bars[W_FULL]);
-                }
+                for (uint32_t off = 0; off < kImgBulk; off += 16384) bulk_g2s(smem + off, wimg + off, 16384u, &bars[W_FULL]);
+                bulk_g2s(smem + kOffW0, wimg + kImgSmall, kSmallBytes, &bars[W_FULL]);
             }
             __syncwarp();
             mbar_wait(&bars[W_FULL], 0);
             // ---- MMA issue loop: the whole warp walks it (uniform control flow), one elected lane issues --------
             const uint32_t idesc = make_idesc(1, 128, kSamples);
             const uint32_t sbase = smem_u32(smem);
-            // ---- W2 (both splits, both M blocks) -> tensor memory, once; its staging area then becomes the X2 buffers
+            // ---- W2 hi (both M blocks) and W1 -> tensor memory, once; their staging area then becomes the X2 ring
             tcgen05_fence_after();
             if (elect_one()) {
 #pragma unroll
-                for (int blk = 0; blk < 4; ++blk)  // blk = split*2 + mblk, same order as the shared-memory image
+                for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        tmem_cp_128x256b(tmem_base + kTmemW2 + blk * 64 + k * 8,
-                                         make_smem_desc(sbase + kOffW2 + blk * kW2Blk + k * 2 * kLboW, kLboW, kSbo));
+                        tmem_cp_128x256b(tmem_base + kTmemW2 + mb * 64 + k * 8,
+                                         make_smem_desc(sbase + kOffW2hi + mb * kW2Blk + k * 2 * kLboW, kLboW, kSbo));
 #pragma unroll
                 for (int sp = 0; sp < 2; ++sp)
 #pragma unroll
@@ -228,38 +237,48 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 umma_commit(&bars[W2_TMEM]);
             }
             __syncwarp();
-            auto mma2 = [&](int t) {  // A operand (W2) from tensor memory, B operand X2[t & 1] from shared memory
-                mbar_wait(&bars[X2_FULL0 + (t & 1)], (t >> 1) & 1);
+            const uint32_t idesc128 = make_idesc(1, 128, 2 * kSamples) | kIdescBMnMajor;
+            const uint32_t idesc64 = idesc | kIdescBMnMajor;
+            auto mma2 = [&](int pr) {  // pair pr = tiles 2pr, 2pr+1: B operand = X2 slot pr & 1 (both tiles side by side)
+                const bool two = 2 * pr + 1 < T;
+                mbar_wait(&bars[X2_FULL0], pr & 1);
+                if (two) mbar_wait(&bars[X2_FULL1], pr & 1);
                 tcgen05_fence_after();
-                stamp(t, 1);
+                stamp(2 * pr, 1);
+                const uint32_t id = two ? idesc128 : idesc64;
+                const uint32_t xb0 = sbase + kOffX2 + (pr & 1) * kX2Slot;
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
-                    mbar_wait(&bars[D2A_FREE + mb], (t & 1) ^ 1);  // E2(t-1) has moved this M block into registers
+                    mbar_wait(&bars[D2A_FREE + mb], (pr & 1) ^ 1);  // E2(pr-1) has moved this M block into registers
                     tcgen05_fence_after();
                     if (elect_one()) {
-                        const uint32_t d = tmem_base + 128 + mb * 64;
+                        const uint32_t d = tmem_base + kTmemD2 + mb * 128;
+                        const uint32_t wa = tmem_base + kTmemW2 + mb * 64;             // W2 hi, tensor memory
+                        const uint32_t wl = sbase + kOffW2lo + mb * kW2Blk;            // W2 lo, shared memory
                         uint32_t acc = 0;
 #pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint32_t wa = tmem_base + kTmemW2 + ((pass == 2 ? 2 : 0) + mb) * 64;
-                            const uint32_t xb = sbase + kOffX2 + (t & 1) * kX2Buf + (pass == 1 ? kX2Split : 0);
+                        for (int pass = 0; pass < 2; ++pass) {  // (Whi,Xhi) (Whi,Xlo)
+                            const uint32_t xb = xb0 + (pass == 1 ? kX2Split : 0);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSboX2), idesc | kIdescBMnMajor, acc);
+                                umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSboX2), id, acc);
                                 acc = 1;
                             }
                         }
-                        if (mb == 1) umma_commit(&bars[X2_FREE0 + (t & 1)]);
-                        umma_commit(&bars[(mb == 0 ? D2A_FULL0 : D2B_FULL0) + (t & 1)]);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)  // (Wlo,Xhi): both operands from shared memory
+                            umma_f16(d, make_smem_desc(wl + k * 2 * kLboW, kLboW, kSbo), make_smem_desc(xb0 + k * 2 * kLboX2, kLboX2, kSboX2), id, 1u);
+                        if (mb == 1) umma_commit(&bars[X2_FREE0 + (pr & 1)]);
+                        umma_commit(&bars[D2A_FULL + mb]);
                     }
                     __syncwarp();
                 }
-                stamp(t, 2);
+                stamp(2 * pr, 2);
             };
             // MMA1 (conv1) is issued by warp 13: two issuing warps hide each other's mbarrier-wait latency (~90 cycles per
             // try_wait, 4 per tile), which a single issuer left as bubbles in the tensor pipe.  Data dependencies are carried by
             // the barriers alone, so the interleaving of the two instruction streams in the pipe is free.
-            for (int t = 0; t < T; ++t) mma2(t);
+            for (int pr = 0; 2 * pr < T; ++pr) mma2(pr);
         }
     } else if (warp <= 4) {
         // ---- producers: gather + normalise + layer 0 -> X1 ------------------------------------------------------
@@ -369,16 +388,19 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const float b1 = reinterpret_cast<const float *>(smem + kOffB1)[ch];
         const float *B2 = reinterpret_cast<const float *>(smem + kOffB2);
-        uint8_t *x2 = smem + kOffX2 + g * kX2Buf + (ch >> 3) * kLboX2 + (ch & 7) * 16;  // this warpgroup's tiles use X2[g]
+        // this warpgroup's tiles own sample groups g*8 .. g*8+7 of their pair's slot
+        uint8_t *x2g = smem + kOffX2 + g * 8 * kSboX2 + (ch >> 3) * kLboX2 + (ch & 7) * 16;
         mbar_wait(&bars[W2_TMEM], 0);  // the X2 buffers alias the W2 staging area: wait until W2 sits in tensor memory
-        for (int t = g; t < T; t += 2) {
+        uint32_t r0[32], r1[32];
+        // E1(t): D1 -> +bias, ReLU, split -> this tile's half of X2 slot (pair & 1)
+        auto e1 = [&](int t) {
             const int b = t & 1;
-            const uint32_t ph = (t >> 1) & 1;
-            // E1: D1 -> +bias, ReLU, split -> X2[b]
+            const int pr = t >> 1;               // pair
+            const uint32_t ph = pr & 1;          // parity of per-pair events = ring slot of the pair
+            uint8_t *x2 = x2g + ph * kX2Slot;
             mbar_wait(&bars[D1_FULL0 + b], ph);
             tcgen05_fence_after();
             if (q == 1) stamp(t, 8);
-            uint32_t r0[32], r1[32];
             tmem_ld32(tmem_base + lane_addr, r0);
             tmem_ld32(tmem_base + lane_addr + 32, r1);
             tmem_ld_wait();
@@ -395,7 +417,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 rb = *reinterpret_cast<const uint32_t *>(&l2);
             }
             if (q == 1) stamp(t, 9);
-            mbar_wait(&bars[X2_FREE0 + b], ph ^ 1);  // MMA2(t-2) has finished reading this buffer
+            mbar_wait(&bars[X2_FREE0 + ph], ((pr >> 1) & 1) ^ 1);  // MMA2(pr-2) has finished reading this slot
             if (q == 1) stamp(t, 10);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {  // samples 8j .. 8j+7 of this channel: 16 contiguous bytes per split
@@ -406,16 +428,19 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             fence_proxy_async_smem();
             mbar_arrive(&bars[X2_FULL0 + b]);
             if (q == 1) stamp(t, 11);
-            // E2: D2 -> max over the 64 samples, +bias, ReLU -> pooled (ReLU and +bias commute with max); M block A is
-            // released to MMA2(t+1) before block B has even been computed
+        };
+        // E2(t): D2 -> max over the 64 samples, +bias, ReLU -> pooled (ReLU and +bias commute with max); M block A is released to
+        // MMA2(pair+1) before block B has even been computed
+        auto e2 = [&](int t) {
+            const uint32_t ph = (t >> 1) & 1;
             const long long cl = first + static_cast<long long>(t) * gridDim.x;
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
-                mbar_wait(&bars[(mb == 0 ? D2A_FULL0 : D2B_FULL0) + b], ph);
+                mbar_wait(&bars[D2A_FULL + mb], ph);
                 tcgen05_fence_after();
                 if (q == 1 && mb == 0) stamp(t, 12);
-                tmem_ld32(tmem_base + lane_addr + 128 + mb * 64, r0);
-                tmem_ld32(tmem_base + lane_addr + 128 + mb * 64 + 32, r1);
+                tmem_ld32(tmem_base + lane_addr + kTmemD2 + mb * 128 + g * 64, r0);   // this tile's 64 of the pair's 128 columns
+                tmem_ld32(tmem_base + lane_addr + kTmemD2 + mb * 128 + g * 64 + 32, r1);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 mbar_arrive(&bars[D2A_FREE + mb]);
@@ -427,6 +452,13 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 pooled[cl * 256 + mb * 128 + ch] = fmaxf(mv + B2[mb * 128 + ch], 0.0f);
             }
             if (q == 1) stamp(t, 13);
+        };
+        // Both warpgroups work on the SAME pair (one tile each), so the operand of the NEXT pair has to be written before this
+        // pair's accumulator is drained: E1(t+2) runs under MMA2(pair of t), then E2(t) waits for that MMA2 to finish.
+        if (g < T) e1(g);
+        for (int t = g; t < T; t += 2) {
+            if (t + 2 < T) e1(t + 2);
+            e2(t);
         }
     }
     tcgen05_fence_before();
@@ -455,11 +487,11 @@ __global__ void det_tc_prep_kernel(const float *__restrict__ P, WeightLayout L, 
         const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
         const int mb = r >> 7, rr = r & 127;
         const uint32_t o = (k >> 3) * kLboW + rr * 16 + (k & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(wimg + kOffW2 + mb * kW2Blk + o) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(wimg + kOffW2 + (2 + mb) * kW2Blk + o) = lo;
+        *reinterpret_cast<__nv_bfloat16 *>(wimg + kOffW2hi + mb * kW2Blk + o) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(wimg + kOffW2lo + mb * kW2Blk + o) = lo;
     } else {
         const int e = i - 128 * 64 - 256 * 128;
-        float *f = reinterpret_cast<float *>(wimg + kOffW0);
+        float *f = reinterpret_cast<float *>(wimg + kImgSmall);
         if (e < 256) {  // per channel k: (W0[0][k], W0[1][k], W0[2][k], b0[k])
             const int k = e >> 2, c = e & 3;
             f[e] = c < 3 ? P[L.off[W_DET0] + c * 64 + k] : P[L.off[B_DET0] + k];

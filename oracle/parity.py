@@ -20,12 +20,13 @@ What is measured (device result vs. the oracle, per cloud):
                 included), so the bound is loose and stated for all but a 1e-3 fraction of the clusters; the per-cluster statement
                 that holds for every cluster is  |f - f_ref| <= desc_own + desc_per_rad * |theta - theta_ref|.
 
-Measured on a B200 at the bench batch (C3: 64 clouds x 16384 points, 512 clusters), C4 and C5, against the fp64 oracle
-(profiles/r02_a_parity_C{3,4,5}.json; worst of the TF random-init and the randomised-BN weight sets):
+Measured on a B200 over every case the GPU tests run (29 comparisons: the bench batch C3 = 64 clouds x 16384 points x 512 clusters,
+C4, C5, the small ragged shapes, both weight sets, the reference-graph golden files), against the fp64 oracle; worst value of each
+figure (profiles/r02_c_parity_report.jsonl, profiles/r02_a_parity_C{3,4,5}.json):
 
-  precision   attention   orientation (weighted)   descriptor (own angle)   descriptor e2e max / p99.9   raw angle max
-  fp32        1.4e-6      see test output          3.2e-7                   3.2e-5 / 1.2e-5              1.7e-4 rad
-  bf16x3      3.6e-5      see test output          7.4e-6                   6.6e-4 / 2.9e-4              7.7e-3 rad
+  precision   attention   orientation (weighted)   descriptor (own angle)   descriptor e2e max / p99.9   raw angle max / p99.5
+  fp32        1.4e-6      2.3e-6                   3.2e-7                   3.2e-5 / 1.2e-5              1.7e-4 / 1.3e-5 rad
+  bf16x3      1.4e-4      4.9e-5                   7.4e-6                   6.6e-4 / 2.9e-4              7.7e-3 / 3.1e-4 rad
 
 bf16x3 = every fp32 operand of a tensor-core contraction carried as two bf16 terms (16 mantissa bits), products hi*hi + hi*lo +
 lo*hi with fp32 accumulation: ~2^-17 relative per operand, against 2^-24 for fp32 -- hence one to two orders between the rows.
@@ -33,13 +34,13 @@ lo*hi with fp32 accumulation: ~2^-17 relative per operand, against 2^-24 for fp3
 import numpy as np
 import torch
 
-# One table.  Every bound has >= 2.5x headroom over the worst value measured at C3 / C4 / C5 and is far below what a wrong layer,
+# One table.  Every bound has >= 2x headroom over the worst value measured (table above) and is far below what a wrong layer,
 # scale, bias or activation produces (those are O(1e-2 .. 1)).
 # `angle` (rad, all but ANGLE_EXEMPT_FRACTION of the clusters) is only used against references that do not carry the head
 # output |xy| (the golden files of the reference's own graph code, the unfused torch path).
 TOL = {
     "fp32": dict(att=1e-5, ori_w=1e-5, desc_own=2e-6, desc_e2e=1e-4, desc_per_rad=2.0, angle=1e-4),
-    "bf16x3": dict(att=1e-4, ori_w=1e-4, desc_own=2e-5, desc_e2e=1e-3, desc_per_rad=2.0, angle=1e-3),
+    "bf16x3": dict(att=3e-4, ori_w=3e-4, desc_own=2e-5, desc_e2e=1e-3, desc_per_rad=2.0, angle=1e-3),
 }
 ANGLE_EXEMPT_FRACTION = 5e-3
 E2E_EXEMPT_FRACTION = 1e-3  # clusters allowed above desc_e2e (ill-conditioned angle); none may break the per-radian statement
