@@ -5,16 +5,24 @@
 // conv 3->32->64 (+BN+ReLU), reduce_max, tile+concat, conv_mid_0 128->128 (+BN, no ReLU), reduce_max.
 // Same machinery and the same D^T = W^T X^T formulation as mlp_tc.cu (TMEM lane = output channel, column = sample).
 //
-//   MMA1 : D1[128 x 64] = W1^T[128 x 32]  X1^T                   (conv1, 32 -> 64; rows 64..127 of the M axis REPEAT rows
-//                                                                   0..63, so all four epilogue warps of a warpgroup find
+//   MMA1 : D1[128 x 64] = W1^T[128 x 32]  X1^T                   (conv1, 32 -> 64, per tile; rows 64..127 of the M axis REPEAT
+//                                                                   rows 0..63, so all four epilogue warps of a warpgroup find
 //                                                                   the 64 channels in their own 32 TMEM lanes)
 //   E1   : relu(D1 + b1) -> X2 (operand of conv_mid_0, stored SAMPLE-contiguous = MN-major: one 16-byte store per 8 samples)
 //          and, per channel, its max over the 64 samples -> P; warps 0/1 take samples 0..31, warps 2/3 samples 32..63
-//   MMA2 : D2[128 x 64]  = Wa^T[128 x 64]  X2^T                   (conv_mid_0, rows 0..63 of its weight: the per-point part)
+//   MMA2 : D2[128 x 128] = Wa^T[128 x 64]  X2^T                   (conv_mid_0, rows 0..63 of its weight: the per-point part) --
+//                                                                   issued per PAIR of tiles: a 128x128x16 MMA holds the tensor
+//                                                                   pipe 66.5 cycles, two 128x64x16 ones 2 x 41.9
+//                                                                   (profiles/r02_a_umma_instruction_shape.md)
 //   MMA3 : D3[128 x 8]   = Wb^T[128 x 64]  P^T                    (rows 64..127: the tiled max-pool part, ONE column per
-//                                                                   cluster instead of 64 -- the split-weight identity)
-//   E2   : pooled2 = max_s D2[:, s] + D3[:, 0] + b_mid            (no ReLU: final_relu=False, feat3dnet.py:71)
+//                                                                   cluster instead of 64 -- the split-weight identity; the two
+//                                                                   tiles of a pair are rows 0 / 1 of the same 8-row operand)
+//   E2   : pooled2 = max_s D2[:, s] + D3[:, tile] + b_mid         (no ReLU: final_relu=False, feat3dnet.py:71)
 //
+// 18 warps: 0 = MMA2/3 issue, 1-4 and 14-17 = two producer warpgroups (even / odd tiles, one X1 buffer each: with the pair MMAs the
+// tensor pipe needs ~860 cycles per tile and one producer warpgroup ~1060), 5-12 = two epilogue warpgroups (even / odd tiles), 13 = MMA1
+// issue.  The epilogue warpgroups work on the same pair, so each writes the operand of its NEXT tile before draining the current
+// accumulator (see mlp_tc.cu).
 // conv_post_0 + l2-normalise run afterwards over 128 clusters per CTA (desc_post_fp32_kernel).
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -28,7 +36,7 @@ using namespace tc;
 
 namespace dsc {
 constexpr int kSamples = 64;
-constexpr int kThreads = 14 * 32;  // warp 0 MMA2/3 issue, 1-4 producers, 5-12 epilogues, 13 MMA1 issue
+constexpr int kThreads = 18 * 32;  // warp 0 MMA2/3 issue, 1-4 / 14-17 producers (even / odd tiles), 5-12 epilogues, 13 MMA1 issue
 constexpr uint32_t kSbo = 128;
 constexpr uint32_t kLboW = 128 * 16;
 constexpr uint32_t kLboX1 = kSamples * 16;
@@ -46,24 +54,30 @@ constexpr uint32_t kOffB1 = kOffB0 + 32 * 4;             // fp32 [64]
 constexpr uint32_t kOffBm = kOffB1 + 64 * 4;             // fp32 [128]
 constexpr uint32_t kWeightBytes = kOffBm + 128 * 4;      // 83 200
 constexpr uint32_t kX1Split = 4 * kLboX1;                // 4 KB
+constexpr uint32_t kX1Buf = 2 * kX1Split;                // one X1 operand (hi + lo); buffer = tile & 1 (one per producer warpgroup)
 constexpr uint32_t kOffX1 = kWeightBytes;
-constexpr uint32_t kX2Split = 8 * kSboX2;                // 8 KB
-constexpr uint32_t kX2Buf = 2 * kX2Split;                // one X2 operand (hi + lo)
-constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Split;       // [buf 2][split 2][chunk 8] stride kLboX2
+// X2 ring: slot = pair & 1; one slot = [split 2][16 groups of 8 samples][64 channels x 16 B]; tile (pair*2 + g) owns sample groups
+// g*8 .. g*8+7, so the N = 128 operand of a pair is one uniform-stride block
+constexpr uint32_t kX2Split = 16 * kSboX2;               // 16 KB
+constexpr uint32_t kX2Slot = 2 * kX2Split;               // 32 KB
+constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Buf;
 constexpr uint32_t kPSplit = 8 * kLboP;                  // 1 KB
-constexpr uint32_t kPBuf = 2 * kPSplit;
-constexpr uint32_t kOffP = kOffX2 + 2 * kX2Buf;          // [buf 2][split 2][chunk 8][row 8][8]
+constexpr uint32_t kPBuf = 2 * kPSplit;                  // per pair slot; row g of the 8-row group = tile g of the pair
+constexpr uint32_t kOffP = kOffX2 + 2 * kX2Slot;         // [slot 2][split 2][chunk 8][row 8][8]
 constexpr uint32_t kOffPm = kOffP + 2 * kPBuf;            // fp32 [warpgroup 2][128]: partial channel maxima of the sample halves
 constexpr uint32_t kOffBars = kOffPm + 2 * 128 * 4;
 constexpr uint32_t kSmemBytes = kOffBars + 20 * 8 + 16;
 static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffP % 128 == 0 && kOffBars % 8 == 0, "alignment");
-// TMEM columns: D1[2] at 0 / 64, D2[2] at 128 / 192, D3[2] at 256 / 288, then the weights (A operands, copied once with
-// tcgen05.cp): W1 at 320 + split*16 (32 K = 16 columns), Wa at 352 + split*32, Wb at 416 + split*32 (64 K = 32 columns)
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+// TMEM columns: D1 at 0 (64), D2[slot] at 64 + slot*128 (two tiles x 64 samples), D3 at 320 (8 used), then the weights (A operands,
+// copied once with tcgen05.cp): W1 at 352 + split*16 (32 K = 16 columns), Wa at 384 + split*32, Wb at 448 + split*32 (64 K = 32 columns)
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemW1 = 320, kTmemWa = 352, kTmemWb = 416;
-// per-warpgroup barriers wherever the two alternating epilogue warpgroups wait (see the note in mlp_tc.cu)
-enum Bar { W_FULL = 0, W_TMEM, X1_FULL, X1_FREE, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE0, D1_FREE1,
+constexpr uint32_t kTmemD2 = 64, kTmemD3 = 320;
+constexpr uint32_t kTmemW1 = 352, kTmemWa = 384, kTmemWb = 448;
+// per-tile events the alternating epilogue warpgroups wait on are per-warpgroup barriers; per-pair events are per ring slot
+enum Bar { W_FULL = 0, W_TMEM, X1_FULL0, X1_FULL1, X1_FREE0, X1_FREE1, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE,
            D2_FULL0, D2_FULL1, D2_FREE0, D2_FREE1, kNumBars };
+static_assert(kNumBars <= 20, "barrier area");
 }  // namespace dsc
 
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -86,19 +100,19 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
     if (threadIdx.x == 0) {
         mbar_init(&bars[W_FULL], 1);
         mbar_init(&bars[W_TMEM], 1);
-        mbar_init(&bars[X1_FULL], 128);
-        mbar_init(&bars[X1_FREE], 1);
+        mbar_init(&bars[D1_FREE], 128);
         for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars[X1_FULL0 + b], 128);
+            mbar_init(&bars[X1_FREE0 + b], 1);
             mbar_init(&bars[X2_FULL0 + b], 128);
             mbar_init(&bars[X2_FREE0 + b], 1);
             mbar_init(&bars[D1_FULL0 + b], 1);
-            mbar_init(&bars[D1_FREE0 + b], 128);
             mbar_init(&bars[D2_FULL0 + b], 1);
-            mbar_init(&bars[D2_FREE0 + b], 128);
+            mbar_init(&bars[D2_FREE0 + b], 256);  // both epilogue warpgroups (one tile of the pair each)
         }
         fence_barrier_init();
     }
-    // rows 1..7 of the pooled operand P are never written: zero them once (their D3 columns are never read either)
+    // rows 2..7 of the pooled operand P are never written: zero the operand once (their D3 columns are never read either)
     for (uint32_t i = threadIdx.x; i < 2 * kPBuf / 4; i += kThreads) reinterpret_cast<uint32_t *>(smem + kOffP)[i] = 0;
     fence_proxy_async_smem();
     if (warp == 0) {
@@ -124,7 +138,8 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             __syncwarp();
             mbar_wait(&bars[W_FULL], 0);
-            const uint32_t idesc64 = make_idesc(1, 128, kSamples);
+            const uint32_t idesc64 = make_idesc(1, 128, kSamples) | kIdescBMnMajor;
+            const uint32_t idesc128 = make_idesc(1, 128, 2 * kSamples) | kIdescBMnMajor;
             const uint32_t idesc8 = make_idesc(1, 128, 8);
             const uint32_t sbase = smem_u32(smem);
             // ---- all three weight matrices (hi and lo splits) -> tensor memory, once: every MMA reads A from TMEM
@@ -148,102 +163,115 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             __syncwarp();
             mbar_wait(&bars[W_TMEM], 0);
-            auto mma23 = [&](int t) {
-                mbar_wait(&bars[X2_FULL0 + (t & 1)], (t >> 1) & 1);
-                mbar_wait(&bars[D2_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+            auto mma23 = [&](int pr) {  // pair pr = tiles 2pr, 2pr+1: X2 / P slot pr & 1, accumulator D2[pr & 1], the single D3
+                const int sl = pr & 1;
+                const bool two = 2 * pr + 1 < T;
+                mbar_wait(&bars[X2_FULL0], pr & 1);
+                if (two) mbar_wait(&bars[X2_FULL1], pr & 1);
+                mbar_wait(&bars[D2_FREE0 + sl], ((pr >> 1) & 1) ^ 1);  // E2(pr-2) has drained this accumulator
                 tcgen05_fence_after();
-                stamp(t, 1);
+                stamp(2 * pr, 1);
                 if (elect_one()) {
-                const uint32_t d2 = tmem_base + 128 + (t & 1) * 64;
-                const uint32_t d3 = tmem_base + 256 + (t & 1) * 32;
-                uint32_t acc = 0;
+                    const uint32_t d2 = tmem_base + kTmemD2 + sl * 128;
+                    const uint32_t id = two ? idesc128 : idesc64;
+                    uint32_t acc = 0;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t wa = tmem_base + kTmemWa + (pass == 2 ? 32 : 0);
-                    const uint32_t xb = sbase + kOffX2 + (t & 1) * kX2Buf + (pass == 1 ? kX2Split : 0);
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t wa = tmem_base + kTmemWa + (pass == 2 ? 32 : 0);
+                        const uint32_t xb = sbase + kOffX2 + sl * kX2Slot + (pass == 1 ? kX2Split : 0);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_f16_ts(d2, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSboX2), idesc64 | kIdescBMnMajor, acc);
-                        acc = 1;
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16_ts(d2, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX2, kLboX2, kSboX2), id, acc);
+                            acc = 1;
+                        }
                     }
-                }
-                acc = 0;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t wa = tmem_base + kTmemWb + (pass == 2 ? 32 : 0);
-                    const uint32_t xb = sbase + kOffP + (t & 1) * kPBuf + (pass == 1 ? kPSplit : 0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_f16_ts(d3, wa + k * 8, make_smem_desc(xb + k * 2 * kLboP, kLboP, kSbo), idesc8, acc);
-                        acc = 1;
-                    }
-                }
-                umma_commit(&bars[X2_FREE0 + (t & 1)]);
-                umma_commit(&bars[D2_FULL0 + (t & 1)]);
                 }
                 __syncwarp();
-                stamp(t, 2);
+                // D3 is single-buffered: E2(pr-1), which reads it, arrives on the OTHER slot's D2_FREE
+                if (pr > 0) mbar_wait(&bars[D2_FREE0 + (sl ^ 1)], ((pr - 1) >> 1) & 1);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t d3 = tmem_base + kTmemD3;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t wa = tmem_base + kTmemWb + (pass == 2 ? 32 : 0);
+                        const uint32_t xb = sbase + kOffP + sl * kPBuf + (pass == 1 ? kPSplit : 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16_ts(d3, wa + k * 8, make_smem_desc(xb + k * 2 * kLboP, kLboP, kSbo), idesc8, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars[X2_FREE0 + sl]);
+                    umma_commit(&bars[D2_FULL0 + sl]);
+                }
+                __syncwarp();
+                stamp(2 * pr, 2);
             };
             // MMA1 (conv1) is issued by warp 13: two issuing warps hide each other's mbarrier waits (see mlp_tc.cu)
-            for (int t = 0; t < T; ++t) mma23(t);
+            for (int pr = 0; 2 * pr < T; ++pr) mma23(pr);
         }
     } else if (warp == 13) {
-        // ---- second MMA issuer: conv1 (X1 -> D1), A operand W1 from tensor memory ---------------------------------------
+        // ---- second MMA issuer: conv1 (X1[t & 1] -> D1), A operand W1 from tensor memory ---------------------------------
         const uint32_t idesc64 = make_idesc(1, 128, kSamples);
         const uint32_t sbase = smem_u32(smem);
         mbar_wait(&bars[W_TMEM], 0);  // the weights have been copied into tensor memory
         tcgen05_fence_after();
         auto mma1 = [&](int t) {
-            mbar_wait(&bars[X1_FULL], t & 1);
-            mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);
+            mbar_wait(&bars[X1_FULL0 + (t & 1)], (t >> 1) & 1);
+            mbar_wait(&bars[D1_FREE], (t & 1) ^ 1);  // E1(t-1) has moved the single D1 accumulator into registers
             tcgen05_fence_after();
             stamp(t, 0);
             if (elect_one()) {
-            const uint32_t d = tmem_base + (t & 1) * 64;
-            uint32_t acc = 0;
+                const uint32_t d = tmem_base;
+                uint32_t acc = 0;
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t wa = tmem_base + kTmemW1 + (pass == 2 ? 16 : 0);
-                const uint32_t xb = sbase + kOffX1 + (pass == 1 ? kX1Split : 0);
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t wa = tmem_base + kTmemW1 + (pass == 2 ? 16 : 0);
+                    const uint32_t xb = sbase + kOffX1 + (t & 1) * kX1Buf + (pass == 1 ? kX1Split : 0);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc64, acc);
-                    acc = 1;
+                    for (int k = 0; k < 2; ++k) {
+                        umma_f16_ts(d, wa + k * 8, make_smem_desc(xb + k * 2 * kLboX1, kLboX1, kSbo), idesc64, acc);
+                        acc = 1;
+                    }
                 }
-            }
-            umma_commit(&bars[X1_FREE]);
-            umma_commit(&bars[D1_FULL0 + (t & 1)]);
+                umma_commit(&bars[X1_FREE0 + (t & 1)]);
+                umma_commit(&bars[D1_FULL0 + (t & 1)]);
             }
             __syncwarp();
         };
         for (int t = 0; t < T; ++t) mma1(t);
-    } else if (warp <= 4) {
+    } else if (warp <= 4 || warp >= 14) {
         // ---- producers: gather + normalise + rotate + layer 0 (3 -> 32) -> X1 ------------------------------------
-        // Software-pipelined like the detector's: index of tile t+2 and coordinates / orientation of tile t+1 in flight.
+        // Two warpgroups: pg = 0 (warps 1-4) makes the even tiles, pg = 1 (warps 14-17) the odd ones, each into its own X1 buffer.
+        // Software-pipelined over the warpgroup's own tile sequence: index of item i+2D and coordinates / orientation of item i+D
+        // in flight while item i is computed.
         mbar_wait(&bars[W_FULL], 0);
         const float4 *W0 = reinterpret_cast<const float4 *>(smem + kOffW0);  // per channel: (w_x, w_y, w_z, bias)
-        const int pt = threadIdx.x - 32;
+        const int pg = warp >= 14 ? 1 : 0;
+        const int pt = pg ? threadIdx.x - 14 * 32 : threadIdx.x - 32;
         const int s = pt & 63, h = pt >> 6;  // sample, channel half (16 channels = 2 K chunks)
-        uint8_t *x1 = smem + kOffX1 + s * 16;
+        uint8_t *x1 = smem + kOffX1 + pg * kX1Buf + s * 16;
         const unsigned stride = gridDim.x;
+        const int Tg = T > pg ? (T - pg + 1) / 2 : 0;  // items (tiles) of this warpgroup: tile = pg + 2 i
         const float inv_r = 1.0f / radius;  // exact replacement of the division when radius is a power of two (see mlp_tc.cu)
         const bool pow2 = (__float_as_uint(radius) & 0x007fffffu) == 0u && radius > 1e-30f && radius < 1e30f;
-        auto load_idx = [&](int t) -> int {
-            if (t >= T) return 0;
-            const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
-            return __ldg(idx + static_cast<size_t>(cl) * kSamples + s);
+        auto cluster_of = [&](int i) -> unsigned { return static_cast<unsigned>(first) + static_cast<unsigned>(pg + 2 * i) * stride; };
+        auto load_idx = [&](int i) -> int {
+            if (i >= Tg) return 0;
+            return __ldg(idx + static_cast<size_t>(cluster_of(i)) * kSamples + s);
         };
-        // Software pipeline, depth D: at tile t the coordinates of tile t+D (whose index was loaded D tiles earlier) and the
-        // index of tile t+2D are requested.  With D = 1 the kernel was bound by this dependent L2 gather (clock64 timeline:
-        // ~2100 cycles per producer iteration against ~1000 of MMA + epilogue work); the slots are static (loop unrolled by D).
+        // With depth 1 the kernel was bound by this dependent L2 gather (clock64 timeline: ~2100 cycles per producer iteration
+        // against ~1000 of MMA + epilogue work); the slots are static (loop unrolled by D).
         constexpr int D = 3;
         struct Grp { float px, py, pz, qx, qy, qz, th; };
         Grp gq[D];
         int iq[D];
-        auto load_xyz = [&](Grp &g, int t, int ii) {
+        auto load_xyz = [&](Grp &g, int i, int ii) {
             g.px = g.py = g.pz = g.qx = g.qy = g.qz = g.th = 0.f;
-            if (t >= T) return;
-            const unsigned cl = static_cast<unsigned>(first) + static_cast<unsigned>(t) * stride;
+            if (i >= Tg) return;
+            const unsigned cl = cluster_of(i);
             ii = min(max(ii, 0), n - 1);
             const float *p = xyz + (static_cast<size_t>(cl / static_cast<unsigned>(m)) * n + ii) * 3;
             const float *c = new_xyz + static_cast<size_t>(cl) * 3;
@@ -257,12 +285,13 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         for (int d = 0; d < D; ++d) load_xyz(gq[d], d, iq[d]);
 #pragma unroll
         for (int d = 0; d < D; ++d) iq[d] = load_idx(D + d);
-        for (int t0 = 0; t0 < T; t0 += D) {
+        for (int i0 = 0; i0 < Tg; i0 += D) {
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            const int t = t0 + d;
-            if (t >= T) break;
-            if (warp == 1) stamp(t, 4);
+            const int i = i0 + d;
+            if (i >= Tg) break;
+            const int t = pg + 2 * i;
+            if ((warp & 3) == 1) stamp(t, 4);
             const float px = gq[d].px, py = gq[d].py, pz = gq[d].pz, qx = gq[d].qx, qy = gq[d].qy, qz = gq[d].qz, th = gq[d].th;
             float gx = pow2 ? (px - qx) * inv_r : (px - qx) / radius;
             float gy = pow2 ? (py - qy) * inv_r : (py - qy) / radius;
@@ -275,8 +304,8 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 gx = xr;
                 gy = yr;
             }
-            load_xyz(gq[d], t + D, iq[d]);
-            iq[d] = load_idx(t + 2 * D);
+            load_xyz(gq[d], i + D, iq[d]);
+            iq[d] = load_idx(i + 2 * D);
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -295,9 +324,9 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
                 lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
             }
-            if (warp == 1) stamp(t, 5);
-            mbar_wait(&bars[X1_FREE], (t & 1) ^ 1);
-            if (warp == 1) stamp(t, 6);
+            if ((warp & 3) == 1) stamp(t, 5);
+            mbar_wait(&bars[X1_FREE0 + pg], (i & 1) ^ 1);  // MMA1 of this warpgroup's previous tile has read the buffer
+            if ((warp & 3) == 1) stamp(t, 6);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 *reinterpret_cast<uint4 *>(x1 + (h * 2 + q) * kLboX1) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
@@ -305,11 +334,11 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                     make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
             }
             fence_proxy_async_smem();
-            mbar_arrive(&bars[X1_FULL]);
+            mbar_arrive(&bars[X1_FULL0 + pg]);
           }
         }
     } else {
-        // ---- epilogue warpgroups ---------------------------------------------------------------------------------
+        // ---- epilogue warpgroups: g = 0 (warps 5-8) even tiles, g = 1 (warps 9-12) odd tiles -------------------------
         mbar_wait(&bars[W_FULL], 0);
         const int g = (warp - 5) >> 2;
         const int q = warp & 3;
@@ -319,25 +348,26 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         const int c1 = (q & 1) * 32 + lane;      // E1: conv1 channel (TMEM lane q*32+lane holds channel (q*32+lane) mod 64)
         const float b1 = reinterpret_cast<const float *>(smem + kOffB1)[c1];
         const float bm = reinterpret_cast<const float *>(smem + kOffBm)[ch];
-        // this warpgroup's tiles use operand buffer g; 8 consecutive samples of one channel are 16 contiguous bytes
-        uint8_t *x2 = smem + kOffX2 + g * kX2Buf + hsel * 4 * kSboX2 + (c1 >> 3) * kLboX2 + (c1 & 7) * 16;
-        uint8_t *pp = smem + kOffP + g * kPBuf + (c1 >> 3) * kLboP + (c1 & 7) * 2;     // row 0 of the pooled operand
+        // this warpgroup's tiles own sample groups g*8 .. g*8+7 of their pair's slot; 8 consecutive samples of one channel are 16
+        // contiguous bytes; its pooled vector is row g of the pair's P operand
+        uint8_t *x2g = smem + kOffX2 + (g * 8 + hsel * 4) * kSboX2 + (c1 >> 3) * kLboX2 + (c1 & 7) * 16;
+        uint8_t *ppg = smem + kOffP + (c1 >> 3) * kLboP + g * 16 + (c1 & 7) * 2;
         float *pm = reinterpret_cast<float *>(smem + kOffPm) + g * 128;
-        for (int t = g; t < T; t += 2) {
+        uint32_t r0[32], r1[32];
+        auto e1 = [&](int t) {
             const int b = t & 1;
-            const uint32_t ph = (t >> 1) & 1;
-            // E1
-            mbar_wait(&bars[D1_FULL0 + b], ph);
+            const int pr = t >> 1;
+            const uint32_t sl = pr & 1;
+            mbar_wait(&bars[D1_FULL0 + b], pr & 1);
             tcgen05_fence_after();
             if (q == 1) stamp(t, 8);
-            uint32_t r0[32], r1[32];
-            tmem_ld32(tmem_base + lane_addr + b * 64 + hsel * 32, r0);
+            tmem_ld32(tmem_base + lane_addr + hsel * 32, r0);
             tmem_ld_wait();
             tcgen05_fence_before();
-            mbar_arrive(&bars[D1_FREE0 + b]);
+            mbar_arrive(&bars[D1_FREE]);
             float pmax = 0.0f;  // values are post-ReLU (>= 0)
             uint32_t hi[16], lo[16];
-            // bias, ReLU, max-pool and the hi/lo split BEFORE waiting for the operand buffer
+            // bias, ReLU, max-pool and the hi/lo split BEFORE waiting for the operand slot
 #pragma unroll
             for (int sidx = 0; sidx < 32; sidx += 2) {
                 const float va = fmaxf(__uint_as_float(r0[sidx]) + b1, 0.0f), vb = fmaxf(__uint_as_float(r0[sidx + 1]) + b1, 0.0f);
@@ -349,8 +379,9 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             pm[q * 32 + lane] = pmax;
             if (q == 1) stamp(t, 9);
-            mbar_wait(&bars[X2_FREE0 + b], ph ^ 1);  // MMA2/3(t-2) have finished reading this buffer
+            mbar_wait(&bars[X2_FREE0 + sl], ((pr >> 1) & 1) ^ 1);  // MMA2/3(pr-2) have finished reading this slot
             if (q == 1) stamp(t, 10);
+            uint8_t *x2 = x2g + sl * kX2Slot;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 *reinterpret_cast<uint4 *>(x2 + j * kSboX2) = make_uint4(hi[j * 4], hi[j * 4 + 1], hi[j * 4 + 2], hi[j * 4 + 3]);
@@ -358,6 +389,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");  // both sample halves of every channel maximum are in pm
             if (q < 2) {
+                uint8_t *pp = ppg + sl * kPBuf;
                 const float full = fmaxf(pmax, pm[(q + 2) * 32 + lane]);
                 const __nv_bfloat16 hp = __float2bfloat16_rn(full);
                 *reinterpret_cast<__nv_bfloat16 *>(pp) = hp;
@@ -366,26 +398,35 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             fence_proxy_async_smem();
             mbar_arrive(&bars[X2_FULL0 + b]);
             if (q == 1) stamp(t, 11);
-            // E2
-            mbar_wait(&bars[D2_FULL0 + b], ph);
+        };
+        auto e2 = [&](int t) {
+            const int pr = t >> 1;
+            const uint32_t sl = pr & 1;
+            mbar_wait(&bars[D2_FULL0 + sl], (pr >> 1) & 1);
             tcgen05_fence_after();
             if (q == 1) stamp(t, 12);
-            tmem_ld32(tmem_base + lane_addr + 128 + b * 64, r0);
-            tmem_ld32(tmem_base + lane_addr + 128 + b * 64 + 32, r1);
+            tmem_ld32(tmem_base + lane_addr + kTmemD2 + sl * 128 + g * 64, r0);   // this tile's 64 of the pair's 128 columns
+            tmem_ld32(tmem_base + lane_addr + kTmemD2 + sl * 128 + g * 64 + 32, r1);
             tmem_ld_wait();
             float mv = __uint_as_float(r0[0]);
 #pragma unroll
             for (int j = 1; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r0[j]));
 #pragma unroll
             for (int j = 0; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r1[j]));
-            tmem_ld32(tmem_base + lane_addr + 256 + b * 32, r0);  // only column 0 (the pooled row) is meaningful
+            tmem_ld32(tmem_base + lane_addr + kTmemD3, r0);  // column g: the pooled row of this tile
             tmem_ld_wait();
-            const float cterm = __uint_as_float(r0[0]);
+            const float cterm = __uint_as_float(g ? r0[1] : r0[0]);
             tcgen05_fence_before();
-            mbar_arrive(&bars[D2_FREE0 + b]);
+            mbar_arrive(&bars[D2_FREE0 + sl]);
             const long long cl = first + static_cast<long long>(t) * gridDim.x;
             pooled2[cl * 128 + ch] = mv + cterm + bm;
             if (q == 1) stamp(t, 13);
+        };
+        // both warpgroups work on the same pair: the next tile's operand is written before the current accumulator is drained
+        if (g < T) e1(g);
+        for (int t = g; t < T; t += 2) {
+            if (t + 2 < T) e1(t + 2);
+            e2(t);
         }
     }
     tcgen05_fence_before();
