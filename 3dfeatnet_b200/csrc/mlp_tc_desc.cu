@@ -18,6 +18,7 @@
 //                                                                   cluster instead of 64 -- the split-weight identity; the two
 //                                                                   tiles of a pair are rows 0 / 1 of the same 8-row operand)
 //   E2   : pooled2 = max_s D2[:, s] + D3[:, tile] + b_mid         (no ReLU: final_relu=False, feat3dnet.py:71)
+// D1 and D2 are double-buffered; D3 is single (its reader, E2 of the previous pair, is awaited before MMA3).
 //
 // 18 warps: 0 = MMA2/3 issue, 1-4 and 14-17 = two producer warpgroups (even / odd tiles, one X1 buffer each: with the pair MMAs the
 // tensor pipe needs ~860 cycles per tile and one producer warpgroup ~1060), 5-12 = two epilogue warpgroups (even / odd tiles), 13 = MMA1
@@ -69,14 +70,17 @@ constexpr uint32_t kOffBars = kOffPm + 2 * 128 * 4;
 constexpr uint32_t kSmemBytes = kOffBars + 20 * 8 + 16;
 static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffP % 128 == 0 && kOffBars % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-// TMEM columns: D1 at 0 (64), D2[slot] at 64 + slot*128 (two tiles x 64 samples), D3 at 320 (8 used), then the weights (A operands,
-// copied once with tcgen05.cp): W1 at 352 + split*16 (32 K = 16 columns), Wa at 384 + split*32, Wb at 448 + split*32 (64 K = 32 columns)
+// TMEM columns: D1[tile & 1] at 0 / 64, D2[slot] at 128 + slot*128 (two tiles x 64 samples), D3 at 384 (8 used), then the weights
+// that feed MMAs from tensor memory (copied once with tcgen05.cp): W1 at 416 + split*16 (32 K = 16 columns), Wa at 448 + split*32
+// (64 K = 32 columns).  Wb (the N = 8 MMAs of the pooled term) stays in shared memory: an SS-mode 128x8x16 instruction reads its
+// 4 KB A operand in ~33 cycles, the time such an instruction holds the pipe anyway (34 cycles), and the 64 columns it would take
+// are what lets BOTH D1 and D2 be double-buffered.
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemD2 = 64, kTmemD3 = 320;
-constexpr uint32_t kTmemW1 = 352, kTmemWa = 384, kTmemWb = 448;
+constexpr uint32_t kTmemD2 = 128, kTmemD3 = 384;
+constexpr uint32_t kTmemW1 = 416, kTmemWa = 448;
 // per-tile events the alternating epilogue warpgroups wait on are per-warpgroup barriers; per-pair events are per ring slot
-enum Bar { W_FULL = 0, W_TMEM, X1_FULL0, X1_FULL1, X1_FREE0, X1_FREE1, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE,
-           D2_FULL0, D2_FULL1, D2_FREE0, D2_FREE1, kNumBars };
+enum Bar { W_FULL = 0, W_TMEM, X1_FULL0, X1_FULL1, X1_FREE0, X1_FREE1, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE0,
+           D1_FREE1, D2_FULL0, D2_FULL1, D2_FREE0, D2_FREE1, kNumBars };
 static_assert(kNumBars <= 20, "barrier area");
 }  // namespace dsc
 
@@ -100,8 +104,8 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
     if (threadIdx.x == 0) {
         mbar_init(&bars[W_FULL], 1);
         mbar_init(&bars[W_TMEM], 1);
-        mbar_init(&bars[D1_FREE], 128);
         for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars[D1_FREE0 + b], 128);
             mbar_init(&bars[X1_FULL0 + b], 128);
             mbar_init(&bars[X1_FREE0 + b], 1);
             mbar_init(&bars[X2_FULL0 + b], 128);
@@ -142,7 +146,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             const uint32_t idesc128 = make_idesc(1, 128, 2 * kSamples) | kIdescBMnMajor;
             const uint32_t idesc8 = make_idesc(1, 128, 8);
             const uint32_t sbase = smem_u32(smem);
-            // ---- all three weight matrices (hi and lo splits) -> tensor memory, once: every MMA reads A from TMEM
+            // ---- W1 and Wa (hi and lo splits) -> tensor memory, once; Wb feeds its MMAs from shared memory
             tcgen05_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -152,12 +156,9 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                         tmem_cp_128x256b(tmem_base + kTmemW1 + sp * 16 + k * 8,
                                          make_smem_desc(sbase + kOffW1 + sp * kW1Split + k * 2 * kLboW, kLboW, kSbo));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 4; ++k)
                         tmem_cp_128x256b(tmem_base + kTmemWa + sp * 32 + k * 8,
                                          make_smem_desc(sbase + kOffWa + sp * kWmSplit + k * 2 * kLboW, kLboW, kSbo));
-                        tmem_cp_128x256b(tmem_base + kTmemWb + sp * 32 + k * 8,
-                                         make_smem_desc(sbase + kOffWb + sp * kWmSplit + k * 2 * kLboW, kLboW, kSbo));
-                    }
                 }
                 umma_commit(&bars[W_TMEM]);
             }
@@ -195,11 +196,11 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                     uint32_t acc = 0;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t wa = tmem_base + kTmemWb + (pass == 2 ? 32 : 0);
+                        const uint32_t wb = sbase + kOffWb + (pass == 2 ? kWmSplit : 0);
                         const uint32_t xb = sbase + kOffP + sl * kPBuf + (pass == 1 ? kPSplit : 0);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_f16_ts(d3, wa + k * 8, make_smem_desc(xb + k * 2 * kLboP, kLboP, kSbo), idesc8, acc);
+                            umma_f16(d3, make_smem_desc(wb + k * 2 * kLboW, kLboW, kSbo), make_smem_desc(xb + k * 2 * kLboP, kLboP, kSbo), idesc8, acc);
                             acc = 1;
                         }
                     }
@@ -220,11 +221,11 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         tcgen05_fence_after();
         auto mma1 = [&](int t) {
             mbar_wait(&bars[X1_FULL0 + (t & 1)], (t >> 1) & 1);
-            mbar_wait(&bars[D1_FREE], (t & 1) ^ 1);  // E1(t-1) has moved the single D1 accumulator into registers
+            mbar_wait(&bars[D1_FREE0 + (t & 1)], ((t >> 1) & 1) ^ 1);  // E1(t-2) has moved this D1 buffer into registers
             tcgen05_fence_after();
             stamp(t, 0);
             if (elect_one()) {
-                const uint32_t d = tmem_base;
+                const uint32_t d = tmem_base + (t & 1) * 64;
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -361,10 +362,10 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             mbar_wait(&bars[D1_FULL0 + b], pr & 1);
             tcgen05_fence_after();
             if (q == 1) stamp(t, 8);
-            tmem_ld32(tmem_base + lane_addr + hsel * 32, r0);
+            tmem_ld32(tmem_base + lane_addr + b * 64 + hsel * 32, r0);
             tmem_ld_wait();
             tcgen05_fence_before();
-            mbar_arrive(&bars[D1_FREE]);
+            mbar_arrive(&bars[D1_FREE0 + b]);
             float pmax = 0.0f;  // values are post-ReLU (>= 0)
             uint32_t hi[16], lo[16];
             // bias, ReLU, max-pool and the hi/lo split BEFORE waiting for the operand slot
