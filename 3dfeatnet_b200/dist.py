@@ -23,6 +23,20 @@ def init(backend=None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Restrict this process to the CPUs NVML reports as local to its GPU (nvmlDeviceSetCpuAffinity), so that pinned host buffers
+    allocated afterwards are first-touched on the GPU's NUMA node and the H2D / D2H copies of 8 ranks do not all cross one socket.
+    Returns the CPU count of the new affinity mask, or None when NVML / the call is unavailable (nothing changes then)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(int(local_rank)))
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def shard_range(total, rank, world):
     """Contiguous [lo,hi) slice of `total` units owned by `rank` (sizes differ by at most one)."""
     base, rem = divmod(total, world)

@@ -421,7 +421,11 @@ def bench_infer(args, dist, dev, rank, local_rank, world, peaks):
         err = parity.check(parity.errors(out, ref, own), args.precision, "bench")
         line["parity"] = dict(vs="fp64 oracle (oracle/net.py) on the first %d clouds of the timed batch" % npar, indices="FPS and ball query bit-exact",
                               errors=err, tolerance=parity.TOL[args.precision], ok=True)
-        # ---- the CPU statement timed on this box's cores
+    if not args.no_cpu_baseline and world == 1:  # the CPU statement timed on this box's cores (rank 0 at N = 1 only)
+        from oracle import net as onet, ops as oops
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
         sample = min(max(1, args.cpu_sample), B)
         cpu_params = onet.to_torch(onet.init_params(seed=0))
         cpu_xyz = xyz[:sample]
@@ -540,7 +544,7 @@ def bench_train(args, dist, dev, rank, local_rank, world, peaks):
                                  traffic=None, peak_source="%s HBM copy bandwidth (MEASURED_PEAKS.json)" % peaks["source"],
                                  algorithmic_bytes_per_step=hbm_bytes, ms_in_these_kernels=hbm_ms, top_kernel=top["kernel"],
                                  how="algorithmic bytes as stated at each launch site (rows x channels x 4 in and out) / CUDA-event time of the eager launches")
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         from oracle import ops as oops
 
         cores = os.cpu_count() or 1
@@ -567,6 +571,8 @@ def main():
     rank, local_rank, world = dist.init("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:  # pinned host buffers of every rank on its own GPU's NUMA node (the end-to-end path moves 17 MB per step per GPU)
+        dist.bind_to_gpu_numa_node(local_rank)
     peaks = load_peaks()
     line = None
     if args.workload in ("both", "infer"):
