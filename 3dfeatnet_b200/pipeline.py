@@ -192,7 +192,7 @@ class DetectDescribePipeline:
         if pl is None or not pl["primed"]:
             raise _lib.F3DError("call prime_pipelined() first")
         i = pl["i"]
-        key = i % (2 if pl["ring"] == 2 else 4)
+        key = i % pl["ring"]
         if self.use_graph:
             g = pl["graphs"].get(key)
             if g is None:
@@ -374,7 +374,8 @@ class DetectDescribePipeline:
         two buffers step i reads).  The timed region starts at the first H2D and includes the prologue (sampling of batch 0) and the
         sampling of one batch past the end; every batch is copied in from pinned host memory and its rows are copied back."""
         hp = self._host_pipe()
-        pl = self._pipelined_state(ring=4)
+        R = self.host_ring
+        pl = self._pipelined_state(ring=R)
         host_batches = host_batches or [self.h_xyz]
         cur = torch.cuda.current_stream()
         for st in (hp["s_h2d"], hp["s_comp"], hp["s_d2h"]):
@@ -382,11 +383,11 @@ class DetectDescribePipeline:
         ev_h2d, ev_comp, ev_d2h = {}, {}, {}
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-        def h2d(j):  # batch j -> input buffer j % 4 (last read by step j-4 as batch and step j-5 as the next batch)
+        def h2d(j):  # batch j -> input buffer j % R (last read by step j-R as batch and step j-R-1 as the next batch)
             with torch.cuda.stream(hp["s_h2d"]):
-                if j - 4 in ev_comp:
-                    hp["s_h2d"].wait_event(ev_comp[j - 4])
-                pl["xyz"][j % 4].copy_(host_batches[j % len(host_batches)], non_blocking=True)
+                if j - R in ev_comp:
+                    hp["s_h2d"].wait_event(ev_comp[j - R])
+                pl["xyz"][j % R].copy_(host_batches[j % len(host_batches)], non_blocking=True)
                 ev_h2d[j] = torch.cuda.Event()
                 ev_h2d[j].record()
 
@@ -406,7 +407,7 @@ class DetectDescribePipeline:
                 if flush is not None:
                     flush()
                 if self.use_graph:
-                    g = hp["graphs"].get(("pl", i % 4))
+                    g = hp["graphs"].get(("pl", i % R))
                     if g is None:
                         raise _lib.F3DError("call warm_host_graphs() before timing with use_graph=True")
                     g.replay()
@@ -430,16 +431,17 @@ class DetectDescribePipeline:
         """Capture one CUDA graph per input/output buffer parity for run_host_steps (eager first, to set attributes)."""
         hp = self._host_pipe()
         if self.host_pipelined:
-            pl = self._pipelined_state(ring=4)
-            for j in range(4):
+            R = self.host_ring
+            pl = self._pipelined_state(ring=R)
+            for j in range(R):
                 pl["xyz"][j].copy_(self.h_xyz)
             with torch.cuda.stream(hp["s_comp"]):
                 self._enqueue_sample(pl["xyz"][0], pl["fps_idx"][0], pl["kp"][0], pl["bq_ws"][0], 0)
-                for i in range(4):
+                for i in range(R):
                     self._enqueue_pipelined(i, pack_to=hp["d_out"][i & 1])
             torch.cuda.synchronize()
             if self.use_graph:
-                for i in range(4):
+                for i in range(R):
                     if hp["graphs"].get(("pl", i)) is None:
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g, stream=hp["s_comp"]):
