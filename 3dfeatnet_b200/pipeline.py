@@ -52,6 +52,7 @@ class DetectDescribePipeline:
         self.launches_per_step = None
         self._kp0, self._fps0 = self.keypoints, self.fps_idx  # the serial step's own buffers (step_pipelined re-points the public names)
         self.host_pipelined = False  # run_host_steps(): use the software-pipelined step
+        self.host_ring = 4           # input buffers of the pipelined host loop (even, >= 4; bench.py sizes the ring beyond the L2)
         self._graph = None
         self._side = None  # second stream: ball-query grid build under FPS
         # ---- software-pipelined step (step_pipelined): sampling of batch i+1 beside the contractions of batch i ------------------
@@ -159,6 +160,8 @@ class DetectDescribePipeline:
                       kp=[self._kp0, torch.empty_like(self._kp0)], fps_idx=[self._fps0, torch.empty_like(self._fps0)],
                       bq_ws=[self.bq_ws, torch.empty_like(self.bq_ws)], pack=None)
             self._pl = pl
+            if self._hp is not None:  # graphs of the host loop captured over the previous ring's buffers
+                self._hp["graphs"] = {k: g for k, g in self._hp["graphs"].items() if not isinstance(k, tuple)}
         return pl
 
     def prime_pipelined(self, ring=2):
@@ -375,6 +378,8 @@ class DetectDescribePipeline:
         sampling of one batch past the end; every batch is copied in from pinned host memory and its rows are copied back."""
         hp = self._host_pipe()
         R = self.host_ring
+        if R < 4 or R & 1:
+            raise _lib.F3DError("host_ring must be even and >= 4 (keypoints / grids are double-buffered by step parity)")
         pl = self._pipelined_state(ring=R)
         host_batches = host_batches or [self.h_xyz]
         cur = torch.cuda.current_stream()

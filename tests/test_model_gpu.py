@@ -262,6 +262,12 @@ def test_pipelined_step_equals_serial_step_for_every_partition(cuda):
         ms, rows = pipe.run_host_steps(steps, host_batches=hosts)
         w = want[(steps - 1) % 3]
         assert torch.equal(rows, torch.cat([w["xyz"], w["attention"][..., None], w["orientation"][..., None], w["features"]], dim=2).cpu()), steps
+    pipe.host_ring = 6   # a longer ring of input buffers (bench.py sizes it beyond the L2): same rows
+    pipe.warm_host_graphs()
+    for steps in (4, 7, 13):
+        ms, rows = pipe.run_host_steps(steps, host_batches=hosts)
+        w = want[(steps - 1) % 3]
+        assert torch.equal(rows, torch.cat([w["xyz"], w["attention"][..., None], w["orientation"][..., None], w["features"]], dim=2).cpu()), steps
     # the serial step still works afterwards and owns its buffers again
     out = pipe.run(batches[2])
     for k in ("xyz", "fps_idx", "features"):
