@@ -4,14 +4,16 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/feat3dnet_b200.h"
 
 #define F3D_API extern "C" __attribute__((visibility("default")))
 
 namespace f3d {
 
-// per-thread bookkeeping exported through f3d_launch_count() / f3d_last_error_string()
-extern thread_local long long g_launches;
+// bookkeeping exported through f3d_launch_count() (process-wide) / f3d_last_error_string() (per thread)
+extern std::atomic<long long> g_launches;
 extern thread_local char g_err[256];
 
 int fail(int code, const char *what);

@@ -1,0 +1,35 @@
+// dz_source.cuh -- the BN-backward gradient dz of a POOL-ONLY layer (detector conv2, descriptor conv_mid), formed on the fly.
+//
+// For such a layer the upstream gradient lives on the pooled tensor: g[row][ch] = (y == max of the group) ? gpool / ties : 0, and
+//     dz = s (g - k1 - (z - mu) istd k2),   s = gamma istd, k1 = mean(g), k2 = mean(g zhat)          (train_layers.cu)
+// is a function of z[row][ch], seven per-channel coefficients and three per-(group, channel) values.  bn_bwd_apply_kernel writes it
+// to HBM for the two contractions that consume it (dW = x^T dz, dx = dz W^T); the fused path hands this description to the
+// contractions instead, whose operand converters evaluate dz_value() on the z tile they have just fetched: the (rows, c) gradient is
+// then neither written nor read.  One function, explicit roundings: both paths produce the same bits.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace f3d {
+
+struct DzSource {
+    const float *z;       // (rows, c) pre-BN activation
+    const float *coef;    // [7][c]: bsc, bsh (y = z bsc + bsh), s, k1, mu, istd, k2
+    const float *pooled;  // (rows / gs, c) group maxima of y
+    const float *gpool;   // (rows / gs, c) gradient of the pooled tensor
+    const float *inv;     // (rows / gs, c) 1 / number of tied maxima
+    int gs;               // rows per group
+    int relu;
+};
+
+constexpr int kDzCoefs = 7;
+
+__device__ __forceinline__ float dz_value(float z, float bsc, float bsh, float s, float k1, float mu, float is, float k2, float pm, float gsc,
+                                          int relu) {
+    float y = __fmaf_rn(z, bsc, bsh);  // bit-identical to what bn_apply computes
+    if (relu) y = fmaxf(y, 0.f);
+    float g = y == pm ? gsc : 0.f;
+    if (relu) g = y > 0.f ? g : 0.f;
+    return __fmul_rn(s, __fsub_rn(__fsub_rn(g, k1), __fmul_rn(__fmul_rn(__fsub_rn(z, mu), is), k2)));
+}
+
+}  // namespace f3d

@@ -3,9 +3,11 @@
 
 #include <string.h>
 
+#include <atomic>
+
 namespace f3d {
 
-thread_local long long g_launches = 0;
+std::atomic<long long> g_launches{0};  // process-wide: autograd issues the backward launches from its own thread
 thread_local char g_err[256] = "";
 
 int fail(int code, const char *what) {
@@ -93,5 +95,5 @@ F3D_API int f3d_debug_kernel_timings(int max, char *names, float *ms, double *un
 
 F3D_API int f3d_version(void) { return 100; }
 F3D_API const char *f3d_last_error_string(void) { return f3d::g_err; }
-F3D_API long long f3d_launch_count(void) { return f3d::g_launches; }
-F3D_API void f3d_reset_launch_count(void) { f3d::g_launches = 0; }
+F3D_API long long f3d_launch_count(void) { return f3d::g_launches.load(std::memory_order_relaxed); }
+F3D_API void f3d_reset_launch_count(void) { f3d::g_launches.store(0, std::memory_order_relaxed); }

@@ -14,6 +14,7 @@
 //             dx = dz W^T                                           conv_fwd_kernel on the transposed weights / dgrad3
 // Every reduction runs in a fixed order (no atomics): two runs give identical bits.  The three contractions run either as
 // the fp32 FFMA kernels of this file (precision 0) or on the tensor cores (precision 2, train_tc.cu).
+#include "dz_source.cuh"
 #include "mlp_tile.cuh"
 
 namespace f3d {
@@ -196,7 +197,7 @@ __device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, c
         C.pm = __ldg(reinterpret_cast<const float4 *>(G.pooled) + po);
         const float4 gp = __ldg(reinterpret_cast<const float4 *>(G.gy) + po);
         const float4 ic = __ldg(reinterpret_cast<const float4 *>(G.inv) + po);
-        C.gs = make_float4(gp.x * ic.x, gp.y * ic.y, gp.z * ic.z, gp.w * ic.w);
+        C.gs = make_float4(__fmul_rn(gp.x, ic.x), __fmul_rn(gp.y, ic.y), __fmul_rn(gp.z, ic.z), __fmul_rn(gp.w, ic.w));
     }
     return make_float4(yy.x == C.pm.x ? C.gs.x : 0.f, yy.y == C.pm.y ? C.gs.y : 0.f, yy.z == C.pm.z ? C.gs.z : 0.f, yy.w == C.pm.w ? C.gs.w : 0.f);
 }
@@ -301,15 +302,31 @@ bn_bwd_reduce_pooled_kernel(long long groups, int c, const float *__restrict__ g
 }
 
 // sums[2][c] (sum g, sum g*zhat) -> dbeta, dgamma, coef2 = {s = gamma*istd, k1 = mean(g), k2 = mean(g*zhat)}
+// coef7 (optional): the per-channel table of DzSource (dz_source.cuh): bsc, bsh, s, k1, mu, istd, k2
 __global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const float *__restrict__ sums, const float *__restrict__ gamma,
-                                       const float *__restrict__ var, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef2) {
+                                       const float *__restrict__ var, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef2,
+                                       const float *__restrict__ beta, const float *__restrict__ mean, float *__restrict__ coef7) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= c) return;
     dbeta[ch] = sums[ch];
     dgamma[ch] = sums[c + ch];
-    coef2[ch] = gamma[ch] * rsqrtf(var[ch] + eps);
-    coef2[c + ch] = static_cast<float>(static_cast<double>(sums[ch]) * inv_rows);
-    coef2[2 * c + ch] = static_cast<float>(static_cast<double>(sums[c + ch]) * inv_rows);
+    const float s = gamma[ch] * rsqrtf(var[ch] + eps);
+    const float k1 = static_cast<float>(static_cast<double>(sums[ch]) * inv_rows);
+    const float k2 = static_cast<float>(static_cast<double>(sums[c + ch]) * inv_rows);
+    coef2[ch] = s;
+    coef2[c + ch] = k1;
+    coef2[2 * c + ch] = k2;
+    if (coef7) {
+        float bsc, bsh;
+        bn_scale_shift(gamma[ch], beta[ch], mean[ch], var[ch], eps, bsc, bsh);
+        coef7[ch] = bsc;
+        coef7[c + ch] = bsh;
+        coef7[2 * c + ch] = s;
+        coef7[3 * c + ch] = k1;
+        coef7[4 * c + ch] = mean[ch];
+        coef7[5 * c + ch] = rsqrtf(var[ch] + eps);
+        coef7[6 * c + ch] = k2;
+    }
 }
 
 // dz = s (g - k1 - zhat k2) and, per row chunk, the column sums of dz (= the bias gradient): partB[blk*c + ch]
@@ -365,10 +382,11 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
             float4 d;
-            d.x = s.x * (g.x - k1.x - (zz.x - mu.x) * is.x * k2.x);
-            d.y = s.y * (g.y - k1.y - (zz.y - mu.y) * is.y * k2.y);
-            d.z = s.z * (g.z - k1.z - (zz.z - mu.z) * is.z * k2.z);
-            d.w = s.w * (g.w - k1.w - (zz.w - mu.w) * is.w * k2.w);
+            // explicit roundings, the same expression as dz_value() (dz_source.cuh): the fused contractions reproduce these bits
+            d.x = __fmul_rn(s.x, __fsub_rn(__fsub_rn(g.x, k1.x), __fmul_rn(__fmul_rn(__fsub_rn(zz.x, mu.x), is.x), k2.x)));
+            d.y = __fmul_rn(s.y, __fsub_rn(__fsub_rn(g.y, k1.y), __fmul_rn(__fmul_rn(__fsub_rn(zz.y, mu.y), is.y), k2.y)));
+            d.z = __fmul_rn(s.z, __fsub_rn(__fsub_rn(g.z, k1.z), __fmul_rn(__fmul_rn(__fsub_rn(zz.z, mu.z), is.z), k2.z)));
+            d.w = __fmul_rn(s.w, __fsub_rn(__fsub_rn(g.w, k1.w), __fmul_rn(__fmul_rn(__fsub_rn(zz.w, mu.w), is.w), k2.w)));
             reinterpret_cast<float4 *>(dz)[o] = d;
             sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
             if (x3) {
@@ -634,10 +652,18 @@ bool lin_tc_supported(int k_real, int nout);
 size_t lin_tc_weight_bytes(int k_real, int nout);
 int lin_tc_grid(long long rows, int k_real, int nsplit);
 int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
-           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st);
+           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st, const DzSource *S = nullptr,
+           float *dgb = nullptr);
+bool lin_tc_dz_supported(long long rows, int k_real, int gs, bool need_group_sums);
 bool wgrad_tc_supported(int cin, int cout);
+bool wgrad_tc_dz_supported(long long rows, int cin, int cout, int gs);
 void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta);
-int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg = 0);
+int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg = 0,
+             const DzSource *S = nullptr, float *partB = nullptr);
+
+// Pool-only layers on the tensor-core path: dz is formed inside the two contractions that consume it instead of being written by
+// bn_bwd_apply_kernel and read back twice (f3d_debug_set_fuse_dz(0) restores the three-kernel path; same bits in dW and dx).
+static int g_fuse_dz = 1;
 
 static int pick_ct(int cout) { return cout % 128 == 0 ? 8 : cout % 64 == 0 ? 4 : cout % 32 == 0 ? 2 : cout % 16 == 0 ? 1 : 0; }
 
@@ -709,6 +735,7 @@ F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int co
     const size_t bwd = align256(static_cast<size_t>(rows) * cout * 4)                       // dz
                        + align256(static_cast<size_t>(kRedBlocks) * 2 * cout * 4)           // BN reduction partials
                        + align256(2 * cout * 4) + align256(3 * cout * 4)                    // sums, coef2
+                       + align256(kDzCoefs * cout * 4)                                      // coefficient table of the fused dz source
                        + align256(wparts * cin * cout * 4)                                  // dW partials
                        + align256(static_cast<size_t>(p.nparts) * cout * 4)                 // db partials (FFMA wgrad scratch)
                        + align256(static_cast<size_t>(kRedBlocks) * cout * 4)               // db partials
@@ -830,6 +857,8 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     w += align256(2 * cout * 4);
     float *coef2 = reinterpret_cast<float *>(w);
     w += align256(3 * cout * 4);
+    float *coef7 = reinterpret_cast<float *>(w);
+    w += align256(kDzCoefs * cout * 4);
     float *partW = reinterpret_cast<float *>(w);
     w += align256(wparts * cin * cout * 4);
     float *partB_scratch = reinterpret_cast<float *>(w);
@@ -858,10 +887,27 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     partial_reduce_kernel<float><<<(2 * cout + 31) / 32, 1024, 0, st>>>(nred1, 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
     if (rc) return rc;
-    bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2);
+    const bool w3 = cin == 3;  // the xyz layers: dW rides along with the dz pass (partials in the dW-partials area: 3*cout per chunk)
+    // pool-only layer on the tensor-core path: dz is formed inside wgrad / dgrad from z and the pooled tensors, never stored
+    const bool fuse_dz = g_fuse_dz && pool_s > 0 && precision == 2 && !w3 && dx && tc_dgrad && wgrad_tc_dz_supported(rows, cin, cout, pool_s) &&
+                         lin_tc_dz_supported(rows, cout, pool_s, dgroup_bias != nullptr) && (!dgroup_bias || group_s == pool_s) && cin <= 128;
+    bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2, beta,
+                                                               mean, fuse_dz ? coef7 : nullptr);
     rc = check_launch("bn_bwd_finalize_kernel");
     if (rc) return rc;
-    const bool w3 = cin == 3;  // the xyz layers: dW rides along with the dz pass (partials in the dW-partials area: 3*cout per chunk)
+    if (fuse_dz) {
+        const DzSource S{z, coef7, pooled, gy, inv_ties, pool_s, relu};
+        rc = wgrad_tc(rows, cin, cout, x, nullptr, partW, st, 0, &S, partB);
+        if (rc) return rc;
+        const long long nw = static_cast<long long>(cin) * cout;
+        partial_reduce_kernel<float><<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(tcg, nw, partW, dW);
+        rc = check_launch("partial_reduce_kernel");
+        if (rc) return rc;
+        partial_reduce_kernel<float><<<(cout + 31) / 32, 1024, 0, st>>>(tcg, cout, partB, db);
+        rc = check_launch("partial_reduce_kernel");
+        if (rc) return rc;
+        return lin_tc(rows, cout, cin, nullptr, W, cout, 1, nullptr, nullptr, 0, dx, nullptr, wimg, 2, st, &S, dgroup_bias);
+    }
     const int napp = static_cast<int>(rows < kApplyBlocks ? rows : kApplyBlocks);
     // gy (dense mode only) and z in, dz out
     ktimer_begin("bn_bwd_apply_kernel", (pool_s > 0 ? 8.0 : 12.0) * static_cast<double>(rows) * cout, st);
@@ -909,6 +955,14 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
         }
     }
     return rc;
+}
+
+// Measurement / test aid: 0 = pool-only layers write dz with bn_bwd_apply_kernel and read it back in wgrad and dgrad (the path the fused
+// one is checked against, bit for bit); 1 (default) = dz formed inside the contractions.  Returns the previous setting.
+F3D_API int f3d_debug_set_fuse_dz(int on) {
+    const int prev = g_fuse_dz;
+    g_fuse_dz = on ? 1 : 0;
+    return prev;
 }
 
 // tf.reduce_max(x, axis=[2]) of models/feat3dnet.py:138,147,182 on a channels-last (groups, s, c) tensor, c % 4 == 0.

@@ -18,6 +18,7 @@
 //   per stage (TMA ring, double-buffered operand images; see the kernel).  Per-CTA partials are reduced in a fixed order
 //   afterwards (deterministic).
 #include "common.cuh"
+#include "dz_source.cuh"
 #include "tc_ptx.cuh"
 
 #include <cuda_bf16.h>
@@ -313,20 +314,30 @@ constexpr int kMaxRing = 3;
 __host__ __device__ constexpr uint32_t lbo(int nsplit, int nt) { return static_cast<uint32_t>(nt) * 16 + (nsplit == 3 ? 16 : 32); }
 }  // namespace lp
 
-template <int nsplit, int NT>
+// FUSED: the input rows are not read from x but formed on the fly as the BN-backward gradient dz of a pool-only layer (DzSource,
+// dz_source.cuh): the ring fetches the z tile plus the three pooled rows of the tile's group (S.gs % NT == 0), the converters evaluate
+// dz_value() before the bf16 split.  dgb != NULL (S.gs == NT): the per-group column sums of dz -- the gradient of the layer's per-group
+// additive term -- are reduced by the converter warps and written once per tile.
+template <int nsplit, int NT, bool FUSED>
 __global__ void __launch_bounds__(lp::kThreads, 1)
 lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint32_t tmem_cols, const float *__restrict__ x,
                    const uint8_t *__restrict__ wimg, const float *__restrict__ bias, const float *__restrict__ gbias, int gs,
-                   float *__restrict__ out, float *__restrict__ part) {
+                   float *__restrict__ out, float *__restrict__ part, DzSource S, float *__restrict__ dgb) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t kLbo = lp::lbo(nsplit, NT);
     const uint32_t wbytes = 256u * kp;
     const uint32_t split = static_cast<uint32_t>(kp / 8) * kLbo;
     const uint32_t img_bytes = static_cast<uint32_t>(nsplit) * split;
-    const uint32_t slot_bytes = NT * static_cast<uint32_t>(k_real) * 4;
+    const uint32_t pool_bytes = FUSED ? 3u * static_cast<uint32_t>(k_real) * 4 : 0u;  // pooled max | pooled gradient | 1 / ties of the tile's group
+    const uint32_t slot_bytes = NT * static_cast<uint32_t>(k_real) * 4 + pool_bytes;
     uint8_t *ringbuf = smem + 2 * img_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * img_bytes + nring * slot_bytes);
+    float *coef_s = reinterpret_cast<float *>(smem + 2 * img_bytes + nring * slot_bytes + 128);  // FUSED: [7][k_real], then gred [4][k_real]
+    float *gred = coef_s + kDzCoefs * k_real;
+    if (FUSED) {
+        for (int i = threadIdx.x; i < kDzCoefs * k_real; i += lp::kThreads) coef_s[i] = __ldg(S.coef + i);
+    }
     uint64_t *bar_w = bars, *bar_wm = bars + 1, *ring_full = bars + 2, *img_full = bars + 2 + lp::kMaxRing, *mma_done = img_full + 2,
              *d_free = mma_done + 2;
     uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(d_free + 2);
@@ -393,10 +404,18 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
             const uint32_t valid = static_cast<uint32_t>(rows - r0 < NT ? rows - r0 : NT);
             const uint32_t bytes = valid * static_cast<uint32_t>(k_real) * 4;
             if (lane == 0) {
-                mbar_arrive_expect_tx(ring_full + slot, bytes);
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(x + r0 * k_real);
+                mbar_arrive_expect_tx(ring_full + slot, bytes + pool_bytes);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>((FUSED ? S.z : x) + r0 * k_real);
                 for (uint32_t off = 0; off < bytes; off += 16384)
                     bulk_g2s(ringbuf + slot * slot_bytes + off, src + off, bytes - off < 16384u ? bytes - off : 16384u, ring_full + slot);
+                if (FUSED) {
+                    const size_t go = static_cast<size_t>(r0 / S.gs) * k_real;
+                    uint8_t *pd = ringbuf + slot * slot_bytes + NT * static_cast<uint32_t>(k_real) * 4;
+                    const uint32_t kb = static_cast<uint32_t>(k_real) * 4;
+                    bulk_g2s(pd, S.pooled + go, kb, ring_full + slot);
+                    bulk_g2s(pd + kb, S.gpool + go, kb, ring_full + slot);
+                    bulk_g2s(pd + 2 * kb, S.inv + go, kb, ring_full + slot);
+                }
             }
             __syncwarp();
         };
@@ -441,26 +460,77 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
             mbar_wait(ring_full + slot, static_cast<uint32_t>((it / nring) & 1));
             if (it >= 2) mbar_wait(mma_done + b, static_cast<uint32_t>(((it >> 1) - 1) & 1));  // MMAs of tile it-2 have read image b
             uint8_t *img = smem + b * img_bytes;
+            if constexpr (!FUSED) {
 #pragma unroll
-            for (int p = 0; p < NT / 16; ++p) {
-                const int r = p * 16 + wc * 4 + rsub;
-                const bool valid = r0 + r < rows;
-                const uint8_t *src = ringbuf + slot * slot_bytes + r * row_bytes + h * 16;
+                for (int p = 0; p < NT / 16; ++p) {
+                    const int r = p * 16 + wc * 4 + rsub;
+                    const bool valid = r0 + r < rows;
+                    const uint8_t *src = ringbuf + slot * slot_bytes + r * row_bytes + h * 16;
+                    for (int c = c4; c < kp / 8; c += 4) {
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid && c * 8 < k_real) a = *reinterpret_cast<const float4 *>(src + c * 32);
+                        uint8_t *dst = img + c * kLbo + r * 16 + h * 8;
+#pragma unroll
+                        for (int sp = 0; sp < nsplit; ++sp) {
+                            const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                            *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                            a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
+                        }
+                    }
+                }
+            } else {
+                // channel chunk outside, rows inside: the ten coefficient quads of a chunk are loaded once per NT / 16 rows
+                const float *pool = reinterpret_cast<const float *>(ringbuf + slot * slot_bytes + NT * row_bytes);
                 for (int c = c4; c < kp / 8; c += 4) {
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid && c * 8 < k_real) a = *reinterpret_cast<const float4 *>(src + c * 32);
-                    uint8_t *dst = img + c * kLbo + r * 16 + h * 8;
+                    const int ch = c * 8 + h * 4;
+                    const bool chok = ch < k_real;
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    auto ld = [&](const float *base) { return chok ? *reinterpret_cast<const float4 *>(base + ch) : z4; };
+                    const float4 bsc = ld(coef_s), bsh = ld(coef_s + k_real), ss = ld(coef_s + 2 * k_real), k1 = ld(coef_s + 3 * k_real),
+                                 mu = ld(coef_s + 4 * k_real), is = ld(coef_s + 5 * k_real), k2 = ld(coef_s + 6 * k_real);
+                    const float4 pm = ld(pool), gp = ld(pool + k_real), iv = ld(pool + 2 * k_real);
+                    const float4 gsc = make_float4(__fmul_rn(gp.x, iv.x), __fmul_rn(gp.y, iv.y), __fmul_rn(gp.z, iv.z), __fmul_rn(gp.w, iv.w));
+                    float4 acc = z4;
 #pragma unroll
-                    for (int sp = 0; sp < nsplit; ++sp) {
-                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-                        *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                        a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
+                    for (int p = 0; p < NT / 16; ++p) {
+                        const int r = p * 16 + wc * 4 + rsub;
+                        float4 a = z4;
+                        if (r0 + r < rows && chok) {
+                            const float4 zz = *reinterpret_cast<const float4 *>(ringbuf + slot * slot_bytes + r * row_bytes + h * 16 + c * 32);
+                            a.x = dz_value(zz.x, bsc.x, bsh.x, ss.x, k1.x, mu.x, is.x, k2.x, pm.x, gsc.x, S.relu);
+                            a.y = dz_value(zz.y, bsc.y, bsh.y, ss.y, k1.y, mu.y, is.y, k2.y, pm.y, gsc.y, S.relu);
+                            a.z = dz_value(zz.z, bsc.z, bsh.z, ss.z, k1.z, mu.z, is.z, k2.z, pm.z, gsc.z, S.relu);
+                            a.w = dz_value(zz.w, bsc.w, bsh.w, ss.w, k1.w, mu.w, is.w, k2.w, pm.w, gsc.w, S.relu);
+                        }
+                        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+                        uint8_t *dst = img + c * kLbo + r * 16 + h * 8;
+#pragma unroll
+                        for (int sp = 0; sp < nsplit; ++sp) {
+                            const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                            *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                            a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
+                        }
+                    }
+                    if (dgb) {  // column sums of the tile (= one group): over the 4 row lanes of the warp here, over the 4 warps below
+#pragma unroll
+                        for (int m = 8; m <= 16; m <<= 1) {
+                            acc.x += __shfl_xor_sync(kFull, acc.x, m); acc.y += __shfl_xor_sync(kFull, acc.y, m);
+                            acc.z += __shfl_xor_sync(kFull, acc.z, m); acc.w += __shfl_xor_sync(kFull, acc.w, m);
+                        }
+                        if (rsub == 0 && chok) *reinterpret_cast<float4 *>(gred + wc * k_real + ch) = acc;
                     }
                 }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(img_full + b);
+            if (FUSED && dgb) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // the four converter warps
+                float *dst = dgb + static_cast<size_t>(r0 / S.gs) * k_real;
+                for (int ch = wc * 32 + lane; ch < k_real; ch += 128)
+                    dst[ch] = (gred[ch] + gred[k_real + ch]) + (gred[2 * k_real + ch] + gred[3 * k_real + ch]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // gred is rewritten by the next tile
+            }
         }
     } else {
         // ------------------------------------------------------------------ epilogue: accumulator -> global, BN statistics
@@ -548,6 +618,35 @@ constexpr int kChunks = kRows / 8;   // K chunks per stage
 constexpr int kThreads = 512;        // 16 warps: the conversion is the long phase of a stage
 }  // namespace wg
 
+// 8 rows x 4 channels of fp32 -> four 16-byte chunks (8 rows of one channel each) of the hi and the lo image
+__device__ __forceinline__ void wgrad_store_unit(uint8_t *dst, uint32_t split, const float4 (&v)[8]) {
+    uint4 hi, lo;
+    {
+        const float col[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
+        split8(col, hi, lo);
+        *reinterpret_cast<uint4 *>(dst) = hi;
+        *reinterpret_cast<uint4 *>(dst + split) = lo;
+    }
+    {
+        const float col[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
+        split8(col, hi, lo);
+        *reinterpret_cast<uint4 *>(dst + 16) = hi;
+        *reinterpret_cast<uint4 *>(dst + split + 16) = lo;
+    }
+    {
+        const float col[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
+        split8(col, hi, lo);
+        *reinterpret_cast<uint4 *>(dst + 32) = hi;
+        *reinterpret_cast<uint4 *>(dst + split + 32) = lo;
+    }
+    {
+        const float col[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
+        split8(col, hi, lo);
+        *reinterpret_cast<uint4 *>(dst + 48) = hi;
+        *reinterpret_cast<uint4 *>(dst + split + 48) = lo;
+    }
+}
+
 __device__ __forceinline__ void wgrad_convert(uint8_t *img, uint32_t lbo, uint32_t split, const uint8_t *__restrict__ stage, int c, int valid_rows) {
     // unit u -> (row chunk rc, channel quad c4); a warp handles 32 consecutive quads of one row chunk; converter threads only
     const int quads = c >> 2;
@@ -559,53 +658,68 @@ __device__ __forceinline__ void wgrad_convert(uint8_t *img, uint32_t lbo, uint32
             const int r = rc * 8 + i;
             v[i] = r < valid_rows ? *reinterpret_cast<const float4 *>(stage + (static_cast<size_t>(r) * c + c4 * 4) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        uint8_t *dst = img + rc * lbo + (c4 >> 1) * wg::kSboP + (c4 & 1) * 64;
-        uint4 hi, lo;
-        {
-            const float col[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
-            split8(col, hi, lo);
-            *reinterpret_cast<uint4 *>(dst) = hi;
-            *reinterpret_cast<uint4 *>(dst + split) = lo;
-        }
-        {
-            const float col[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
-            split8(col, hi, lo);
-            *reinterpret_cast<uint4 *>(dst + 16) = hi;
-            *reinterpret_cast<uint4 *>(dst + split + 16) = lo;
-        }
-        {
-            const float col[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
-            split8(col, hi, lo);
-            *reinterpret_cast<uint4 *>(dst + 32) = hi;
-            *reinterpret_cast<uint4 *>(dst + split + 32) = lo;
-        }
-        {
-            const float col[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
-            split8(col, hi, lo);
-            *reinterpret_cast<uint4 *>(dst + 48) = hi;
-            *reinterpret_cast<uint4 *>(dst + split + 48) = lo;
-        }
+        wgrad_store_unit(img + rc * lbo + (c4 >> 1) * wg::kSboP + (c4 & 1) * 64, split, v);
     }
 }
 
+// The dz operand of a pool-only layer, formed on the fly (DzSource): `stage` holds the z rows of the stage, `pool` the pooled maximum /
+// pooled gradient / 1 / ties rows of the stage's group, `coef` the per-channel table.  One unit per thread (4 * c / 4 <= 480 converter
+// threads), so a thread keeps the same channel quad for the whole kernel and `dbsum` is its share of db = column sums of dz.
+__device__ __forceinline__ void wgrad_convert_dz(uint8_t *img, uint32_t lbo, uint32_t split, const uint8_t *__restrict__ stage, int c, int valid_rows,
+                                                 const float *__restrict__ coef, const float *__restrict__ pool, int relu, float4 &dbsum) {
+    const int quads = c >> 2;
+    const int u = threadIdx.x - 32;
+    if (u >= wg::kChunks * quads) return;
+    const int rc = u / quads, c4 = u - rc * quads;
+    auto ld = [&](const float *base) { return *reinterpret_cast<const float4 *>(base + c4 * 4); };
+    const float4 bsc = ld(coef), bsh = ld(coef + c), ss = ld(coef + 2 * c), k1 = ld(coef + 3 * c), mu = ld(coef + 4 * c), is = ld(coef + 5 * c),
+                 k2 = ld(coef + 6 * c);
+    const float4 pm = ld(pool), gp = ld(pool + c), iv = ld(pool + 2 * c);
+    const float4 gsc = make_float4(__fmul_rn(gp.x, iv.x), __fmul_rn(gp.y, iv.y), __fmul_rn(gp.z, iv.z), __fmul_rn(gp.w, iv.w));
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rc * 8 + i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < valid_rows) {
+            const float4 zz = *reinterpret_cast<const float4 *>(stage + (static_cast<size_t>(r) * c + c4 * 4) * 4);
+            v[i].x = dz_value(zz.x, bsc.x, bsh.x, ss.x, k1.x, mu.x, is.x, k2.x, pm.x, gsc.x, relu);
+            v[i].y = dz_value(zz.y, bsc.y, bsh.y, ss.y, k1.y, mu.y, is.y, k2.y, pm.y, gsc.y, relu);
+            v[i].z = dz_value(zz.z, bsc.z, bsh.z, ss.z, k1.z, mu.z, is.z, k2.z, pm.z, gsc.z, relu);
+            v[i].w = dz_value(zz.w, bsc.w, bsh.w, ss.w, k1.w, mu.w, is.w, k2.w, pm.w, gsc.w, relu);
+            dbsum.x += v[i].x; dbsum.y += v[i].y; dbsum.z += v[i].z; dbsum.w += v[i].w;
+        }
+    }
+    wgrad_store_unit(img + rc * lbo + (c4 >> 1) * wg::kSboP + (c4 & 1) * 64, split, v);
+}
+
 // cin % 8 == 0, cin <= 128, cout % 16 == 0, cout <= 256.  One CTA per SM.
+// FUSED: dz is not read but formed on the fly from z (DzSource, S.gs % 32 == 0 so that a stage lies inside one group); the column sums
+// of dz (= db) come out as per-CTA partials partB[cta][cout].
+template <bool FUSED>
 __global__ void __launch_bounds__(wg::kThreads, 1)
 wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint32_t tmem_cols, const float *__restrict__ x,
-                const float *__restrict__ dz, float *__restrict__ partW, int dbg) {
+                const float *__restrict__ dz, float *__restrict__ partW, int dbg, DzSource S, float *__restrict__ partB) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lbo_a = 16 * wg::kSboP, lbo_b = static_cast<uint32_t>(cout / 8) * wg::kSboP;
     const uint32_t split_a = wg::kChunks * lbo_a, split_b = wg::kChunks * lbo_b;
     const uint32_t img_bytes = 2 * split_a + 2 * split_b;                 // one image buffer: [A hi | A lo | B hi | B lo]
     const uint32_t xs_bytes = wg::kRows * static_cast<uint32_t>(cin) * 4, ds_bytes = wg::kRows * static_cast<uint32_t>(cout) * 4;
-    const uint32_t stage_bytes = xs_bytes + ds_bytes;
+    const uint32_t pool_bytes = FUSED ? 3u * static_cast<uint32_t>(cout) * 4 : 0u;  // pooled max | pooled gradient | 1 / ties of the stage's group
+    const uint32_t stage_bytes = xs_bytes + ds_bytes + pool_bytes;
     uint8_t *ring = smem + 2 * img_bytes;
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + 2 * img_bytes + 2 * stage_bytes);  // [2] ring stage filled
     uint64_t *bar_mma = bar_full + 2;                                                          // [2] MMAs of an image buffer done
     uint64_t *bar_img = bar_full + 4;                                                          // [2] image buffer converted
     uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_full + 6);
+    float *coef_s = reinterpret_cast<float *>(smem + 2 * img_bytes + 2 * stage_bytes + 64);   // FUSED: [7][cout], then dbred [4][cout]
+    float *dbred = coef_s + kDzCoefs * cout;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
+    if (FUSED) {
+        for (int i = threadIdx.x; i < kDzCoefs * cout; i += wg::kThreads) coef_s[i] = __ldg(S.coef + i);
+    }
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -638,12 +752,19 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
             if (lane == 0) {
                 uint8_t *dst = ring + (s & 1) * stage_bytes;
                 const uint32_t xb = valid * static_cast<uint32_t>(cin) * 4, db = valid * static_cast<uint32_t>(cout) * 4;
-                mbar_arrive_expect_tx(bar_full + (s & 1), xb + db);
+                mbar_arrive_expect_tx(bar_full + (s & 1), xb + db + pool_bytes);
                 const uint8_t *xsrc = reinterpret_cast<const uint8_t *>(x + r0 * cin);
-                const uint8_t *dsrc = reinterpret_cast<const uint8_t *>(dz + r0 * cout);
+                const uint8_t *dsrc = reinterpret_cast<const uint8_t *>((FUSED ? S.z : dz) + r0 * cout);
                 for (uint32_t off = 0; off < xb; off += 16384) bulk_g2s(dst + off, xsrc + off, xb - off < 16384u ? xb - off : 16384u, bar_full + (s & 1));
                 for (uint32_t off = 0; off < db; off += 16384)
                     bulk_g2s(dst + xs_bytes + off, dsrc + off, db - off < 16384u ? db - off : 16384u, bar_full + (s & 1));
+                if (FUSED) {
+                    const size_t go = static_cast<size_t>(r0 / S.gs) * cout;
+                    const uint32_t cb = static_cast<uint32_t>(cout) * 4;
+                    bulk_g2s(dst + xs_bytes + ds_bytes, S.pooled + go, cb, bar_full + (s & 1));
+                    bulk_g2s(dst + xs_bytes + ds_bytes + cb, S.gpool + go, cb, bar_full + (s & 1));
+                    bulk_g2s(dst + xs_bytes + ds_bytes + 2 * cb, S.inv + go, cb, bar_full + (s & 1));
+                }
             }
             __syncwarp();
         };
@@ -673,6 +794,7 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
         }
     } else {
         // ---- converter warps: ring slot (fp32, row-major) -> operand image (bf16 hi/lo, K = row major)
+        float4 dbsum = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < nstages; ++s) {
             const int b = s & 1;
             uint8_t *img = smem + b * img_bytes;
@@ -683,12 +805,25 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
                 const int valid = static_cast<int>(rend - r0 < wg::kRows ? rend - r0 : wg::kRows);
                 const uint8_t *stage = ring + b * stage_bytes;
                 wgrad_convert(img, lbo_a, split_a, stage, cin, valid);
-                wgrad_convert(img + 2 * split_a, lbo_b, split_b, stage + xs_bytes, cout, valid);
+                if constexpr (FUSED)
+                    wgrad_convert_dz(img + 2 * split_a, lbo_b, split_b, stage + xs_bytes, cout, valid, coef_s,
+                                     reinterpret_cast<const float *>(stage + xs_bytes + ds_bytes), S.relu, dbsum);
+                else
+                    wgrad_convert(img + 2 * split_a, lbo_b, split_b, stage + xs_bytes, cout, valid);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_img + b);
         }
+        if (FUSED) {  // this thread's share of db: rows chunk rc of every stage, channel quad c4
+            const int quads = cout >> 2, u = threadIdx.x - 32;
+            if (u < wg::kChunks * quads) *reinterpret_cast<float4 *>(dbred + (u / quads) * cout + (u % quads) * 4) = dbsum;
+        }
+    }
+    if (FUSED) {
+        __syncthreads();
+        for (int ch = threadIdx.x; ch < cout; ch += wg::kThreads)
+            partB[static_cast<size_t>(blockIdx.x) * cout + ch] = (dbred[ch] + dbred[cout + ch]) + (dbred[2 * cout + ch] + dbred[3 * cout + ch]);
     }
     // drain: the last MMAs of both image buffers
     if (nstages >= 1) mbar_wait(bar_mma + ((nstages - 1) & 1), static_cast<uint32_t>(((nstages - 1) >> 1) & 1));
@@ -758,17 +893,19 @@ struct LinPlan {
     int grid;      // row CTAs (the stats partials are 2 per CTA)
 };
 
-static LinPlan lin_tc_plan(long long rows, int k_real, int nsplit) {
+static LinPlan lin_tc_plan(long long rows, int k_real, int nsplit, bool fused = false) {
     LinPlan P{};
     const int kp = lin_tc_kp(k_real);
+    // fused dz source: three pooled rows ride in every ring slot, the coefficient table and the group-sum scratch follow the barriers
+    const size_t slot_extra = fused ? static_cast<size_t>(3) * k_real * 4 : 0, tail_extra = fused ? static_cast<size_t>(kDzCoefs + 4) * k_real * 4 : 0;
     // the warp-specialised kernel pays off when the operand conversion + MMAs are the long phases (K >= 128); for narrow
     // inputs the tile is store-bound and the all-warps epilogue of lin_tc_kernel at 3-4 CTAs/SM is faster (measured)
     if (k_real % 8 == 0 && kp >= 128) {
         for (int nt = 64; nt >= 32 && !P.pipe; nt -= 32) {
             const size_t img = static_cast<size_t>(nsplit) * (kp / 8) * lp::lbo(nsplit, nt);
-            const size_t slot = static_cast<size_t>(nt) * k_real * 4;
+            const size_t slot = static_cast<size_t>(nt) * k_real * 4 + slot_extra;
             for (int nring = lp::kMaxRing; nring >= 2; --nring) {
-                const size_t smem = 2 * img + nring * slot + 128;
+                const size_t smem = 2 * img + nring * slot + 128 + tail_extra;
                 if (smem <= 226 * 1024 && static_cast<size_t>(256) * kp <= 2 * img + nring * slot) {
                     P.pipe = true;
                     P.nt = nt;
@@ -811,28 +948,45 @@ int lin_tc_grid(long long rows, int k_real, int nsplit) { return lin_tc_plan(row
 // out (rows, nout) = x (rows, k_real) * A^T (+ bias) (+ gbias[row / gs]) with A[m][k] = src[m*sm + k*sk]; nsplit = 2 (bf16x3)
 // or 3 (six product terms, fp32-grade);  part: 2*lin_tc_grid() partials of
 // {sum, sum of squares} per channel, or NULL.  wimg: lin_tc_weight_bytes() of scratch.
+// fused dz source (S != NULL, nsplit 2): can the contraction read z and form dz itself?  Needs the warp-specialised kernel, tiles inside
+// one group, and -- when the per-group sums of dz are wanted -- tiles that ARE groups.
+bool lin_tc_dz_supported(long long rows, int k_real, int gs, bool need_group_sums) {
+    if (k_real % 8 != 0 || gs <= 0 || rows % gs != 0) return false;
+    const LinPlan P = lin_tc_plan(rows, k_real, 2, true);
+    if (!P.pipe || gs % P.nt != 0) return false;
+    return !need_group_sums || gs == P.nt;
+}
+
 int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
-           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st) {
+           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st, const DzSource *S, float *dgb) {
     const int kp = lin_tc_kp(k_real);
     const int mblocks = (nout + 127) / 128;
     const long long total = 128LL * kp * mblocks;
+    const bool fused = S != nullptr;
+    if (fused && (nsplit != 2 || !lin_tc_dz_supported(rows, k_real, S->gs, dgb != nullptr) || mblocks != 1))
+        return fail(F3D_ERR_UNSUPPORTED, "lin_tc: fused dz source not supported for this shape");
     lin_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, sm, sk, nout, k_real, kp, mblocks, nsplit, wimg);
     int rc = check_launch("lin_prep_kernel");
     if (rc) return rc;
-    const LinPlan P = lin_tc_plan(rows, k_real, nsplit);
+    const LinPlan P = lin_tc_plan(rows, k_real, nsplit, fused);
     const dim3 grid(mblocks, P.grid);
     cudaError_t e = cudaSuccess;
+    const DzSource S0 = fused ? *S : DzSource{};
     // algorithmic bytes: the fp32 rows in and out (each read / written once), weights negligible
-    ktimer_begin(nsplit == 3 ? "lin_tc (3-way split, forward)" : "lin_tc (2-way split, dgrad)", 4.0 * static_cast<double>(rows) * (k_real + nout), st);
-#define F3D_LAUNCH_PIPE(NS, NT)                                                                                                    \
-    e = cudaFuncSetAttribute(lin_tc_pipe_kernel<NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));  \
-    if (e == cudaSuccess)                                                                                                          \
-        lin_tc_pipe_kernel<NS, NT><<<grid, lp::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part);
+    ktimer_begin(nsplit == 3 ? "lin_tc (3-way split, forward)" : fused ? "lin_tc (2-way split, dgrad, dz formed from z)" : "lin_tc (2-way split, dgrad)",
+                 4.0 * static_cast<double>(rows) * (k_real + nout), st);
+#define F3D_LAUNCH_PIPE(NS, NT, FU)                                                                                                      \
+    e = cudaFuncSetAttribute(lin_tc_pipe_kernel<NS, NT, FU>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));    \
+    if (e == cudaSuccess)                                                                                                                \
+        lin_tc_pipe_kernel<NS, NT, FU><<<grid, lp::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, \
+                                                                           part, S0, dgb);
     if (P.pipe) {
-        if (nsplit == 3 && P.nt == 64) { F3D_LAUNCH_PIPE(3, 64) }
-        else if (nsplit == 3) { F3D_LAUNCH_PIPE(3, 32) }
-        else if (P.nt == 64) { F3D_LAUNCH_PIPE(2, 64) }
-        else { F3D_LAUNCH_PIPE(2, 32) }
+        if (fused && P.nt == 64) { F3D_LAUNCH_PIPE(2, 64, true) }
+        else if (fused) { F3D_LAUNCH_PIPE(2, 32, true) }
+        else if (nsplit == 3 && P.nt == 64) { F3D_LAUNCH_PIPE(3, 64, false) }
+        else if (nsplit == 3) { F3D_LAUNCH_PIPE(3, 32, false) }
+        else if (P.nt == 64) { F3D_LAUNCH_PIPE(2, 64, false) }
+        else { F3D_LAUNCH_PIPE(2, 32, false) }
         ktimer_end(st);
         if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
         return check_launch("lin_tc_pipe_kernel");
@@ -861,18 +1015,36 @@ void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta) {
     *grid = static_cast<int>((nst + per - 1) / per);
 }
 
-// partW: grid x cin x cout floats
-int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg) {
+static size_t wgrad_tc_smem(int cin, int cout, bool fused) {
+    const size_t img = 2 * static_cast<size_t>(wg::kChunks) * 16 * wg::kSboP + 2 * static_cast<size_t>(wg::kChunks) * (cout / 8) * wg::kSboP;
+    return 2 * img + 2 * (static_cast<size_t>(wg::kRows) * (cin + cout) * 4 + (fused ? static_cast<size_t>(3) * cout * 4 : 0)) + 64 +
+           (fused ? static_cast<size_t>(kDzCoefs + 4) * cout * 4 : 0);
+}
+
+// fused dz source: a 32-row stage must lie inside one group, one converter unit per thread, and everything must fit in shared memory
+bool wgrad_tc_dz_supported(long long rows, int cin, int cout, int gs) {
+    return wgrad_tc_supported(cin, cout) && gs > 0 && gs % wg::kRows == 0 && rows % gs == 0 && wg::kChunks * (cout / 4) <= wg::kThreads - 32 &&
+           wgrad_tc_smem(cin, cout, true) <= 227 * 1024;
+}
+
+// partW: grid x cin x cout floats.  S != NULL: dz formed on the fly from z (see the kernel), partB: grid x cout column sums of dz.
+int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg, const DzSource *S,
+             float *partB) {
     int grid = 0;
     long long per = 0;
     wgrad_tc_plan(rows, &grid, &per);
     const uint32_t cols = pow2_cols(static_cast<uint32_t>(cout));
-    const size_t img = 2 * static_cast<size_t>(wg::kChunks) * 16 * wg::kSboP + 2 * static_cast<size_t>(wg::kChunks) * (cout / 8) * wg::kSboP;
-    const size_t smem = 2 * img + 2 * static_cast<size_t>(wg::kRows) * (cin + cout) * 4 + 64;
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const bool fused = S != nullptr;
+    if (fused && (!wgrad_tc_dz_supported(rows, cin, cout, S->gs) || !partB)) return fail(F3D_ERR_UNSUPPORTED, "wgrad_tc: fused dz source not supported for this shape");
+    const size_t smem = wgrad_tc_smem(cin, cout, fused);
+    cudaError_t e = fused ? cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                          : cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "wgrad_tc: cudaFuncSetAttribute");
-    ktimer_begin("wgrad_tc_kernel", 4.0 * static_cast<double>(rows) * (cin + cout), st);
-    wgrad_tc_kernel<<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg);
+    ktimer_begin(fused ? "wgrad_tc_kernel (dz formed from z)" : "wgrad_tc_kernel", 4.0 * static_cast<double>(rows) * (cin + cout), st);
+    if (fused)
+        wgrad_tc_kernel<true><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, nullptr, partW, dbg, *S, partB);
+    else
+        wgrad_tc_kernel<false><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg, DzSource{}, nullptr);
     ktimer_end(st);
     return check_launch("wgrad_tc_kernel");
 }
@@ -882,5 +1054,5 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
 // Bring-up / micro-benchmark entry: the wgrad contraction alone.  dbg bit 0 skips the operand staging, bit 1 the MMAs.
 F3D_API int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, int dbg, void *stream) {
     if (!f3d::wgrad_tc_supported(cin, cout)) return f3d::fail(F3D_ERR_UNSUPPORTED, "debug_wgrad_tc: unsupported shape");
-    return f3d::wgrad_tc(rows, cin, cout, x, dz, partW, f3d::as_stream(stream), dbg);
+    return f3d::wgrad_tc(rows, cin, cout, x, dz, partW, f3d::as_stream(stream), dbg, nullptr, nullptr);
 }

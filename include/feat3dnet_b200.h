@@ -31,7 +31,7 @@ extern "C" {
 /* library / device introspection */
 int f3d_version(void);
 const char *f3d_last_error_string(void);
-/* number of kernel launches issued through this library by the calling thread since the last reset */
+/* number of kernel launches issued through this library (all threads of the process) since the last reset */
 long long f3d_launch_count(void);
 void f3d_reset_launch_count(void);
 
@@ -290,6 +290,9 @@ int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int 
 /* Bring-up: the tensor-core weight-gradient contraction alone (partW: 2*SMs x cin x cout floats of per-CTA partials);
  * dbg bit 0 skips the operand staging, bit 1 the MMAs (micro-benchmarking). */
 int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, int dbg, void *stream);
+/* Test / measurement aid: 0 = pool-only training layers materialise dz (bn_bwd_apply) for wgrad and dgrad, 1 (default) = dz is formed
+ * inside the two contractions from z and the pooled tensors.  Both paths give the same dW / dx bits.  Returns the previous value. */
+int f3d_debug_set_fuse_dz(int on);
 size_t f3d_detector_tc_weight_bytes(void);
 /* Measurement aid: `groups` x `per_group` back-to-back tcgen05.mma of shape (128 * cta_group) x N x 16 (A from tensor memory, B a
  * zero-filled bf16 no-swizzle image in shared memory, K- or MN-major), one commit per group, on `ctas` CTAs at once (cta_group 2:

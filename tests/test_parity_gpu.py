@@ -85,7 +85,7 @@ def test_c4_training_step_vs_fp64_oracle(cuda):
             worst = min(worst, torch.nn.functional.cosine_similarity(gk, ok, dim=0).item())
     print("C4 train vs fp64 oracle: loss %.6f / %.6f, grad cos %.6f, |g|/|g_ref| %.5f, worst per-variable cos %.5f, forward %s"
           % (loss.item(), oloss.item(), cos, scale, worst, {k: "%.1e" % v for k, v in e.items() if not k.startswith("_")}))
-    assert cos > 0.9995 and abs(scale - 1.0) < 1e-2 and worst > 0.99
+    assert cos > 0.9999 and abs(scale - 1.0) < 2e-3 and worst > 0.999  # measured on a B200: 0.999986, 0.99953, 0.99997
     for k in ("detection/conv0/bn/moving_mean", "detection/conv2/bn/moving_variance", "description/layer1/conv_mid_0/bn/moving_variance"):
         assert torch.allclose(net.weights[k].cpu().double(), oP[k].detach(), rtol=1e-4, atol=1e-6), k
     # Adam (TF-1 form): the first step moves every trainable entry by lr * sign(g) up to eps

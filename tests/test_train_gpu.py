@@ -272,6 +272,51 @@ def test_conv_mid_without_concat_matches_the_concatenated_statement(cuda, precis
         assert (a.cpu().double() - r).abs().max().item() < 3e-4 * (r.abs().max().item() + 1e-9) + 1e-6, name
 
 
+@pytest.mark.parametrize("cin,cout,use_relu,mid", [(128, 256, True, False), (64, 128, False, True), (64, 128, True, False), (128, 128, True, True)])
+def test_pool_only_layer_dz_formed_inside_the_contractions(cuda, cin, cout, use_relu, mid):
+    """Pool-only layers (detector conv2, descriptor conv_mid) on the tensor-core path: wgrad and dgrad form dz = BN-backward gradient
+    from z + the pooled tensors in their operand converters (csrc/dz_source.cuh) instead of reading the (rows, cout) tensor
+    bn_bwd_apply_kernel would write.  Same arithmetic, so dW / dx / dgamma / dbeta carry the SAME BITS as the three-kernel path; db and the
+    gradient of the per-group term (sums of dz in a different order) agree to rounding."""
+    layers, lib_mod = pkg("models.layers"), pkg("_lib")
+    g = torch.Generator().manual_seed(5)
+    B, M, S = 2, 77, 64
+    x = torch.relu(torch.randn(B, M, S, cin, generator=g))
+    x[:, :, 1::2] = x[:, :, 0::2]          # duplicated samples => tied maxima everywhere
+    params = {"l/conv2d/weights": torch.randn(cin * (2 if mid else 1), cout, generator=g) * 0.2, "l/conv2d/biases": torch.randn(cout, generator=g) * 0.1,
+              "l/bn/gamma": torch.rand(cout, generator=g) + 0.5, "l/bn/beta": torch.randn(cout, generator=g) * 0.1,
+              "l/bn/moving_mean": torch.zeros(cout), "l/bn/moving_variance": torch.ones(cout)}
+    go = torch.randn(B, M, 1, cout, generator=g).to(cuda)
+    res = []
+    L = lib_mod.lib()
+    for fuse in (1, 0):
+        prev = L.f3d_debug_set_fuse_dz(fuse)
+        try:
+            P = {k: v.to(cuda).requires_grad_(k.split("/")[-1] in ("weights", "biases", "gamma", "beta")) for k, v in params.items()}
+            xc = x.to(cuda).requires_grad_(True)
+            pooled_in = layers.max_pool_samples(xc) if mid else None
+            L.f3d_reset_launch_count()
+            out = layers.conv2d(xc, cout, [1, 1], scope="l", is_training=True, activation=layers.relu if use_relu else None, params=P,
+                                pool_samples=True, concat_pooled=pooled_in)
+            leaves = [xc] + [P[k] for k in ("l/conv2d/weights", "l/bn/gamma", "l/bn/beta", "l/conv2d/biases")]
+            res.append((out.detach(), torch.autograd.grad((out * go).sum(), leaves), L.f3d_launch_count()))
+        finally:
+            L.f3d_debug_set_fuse_dz(prev)
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[0][2] < res[1][2], "the fused path must launch fewer kernels (no bn_bwd_apply, no group_sum)"
+    names = ("dx", "dW", "dgamma", "dbeta", "db")
+    for name, a, b in zip(names, res[0][1], res[1][1]):
+        if name == "db":
+            # db = column sums of dz, which the BN backward makes ZERO in exact arithmetic: both paths return rounding noise of the
+            # order eps * sum|dz| (measured 5e-6), summed in a different order
+            assert a.abs().max().item() < 5e-5 and b.abs().max().item() < 5e-5, name
+        elif mid and name in ("dx", "dW"):
+            # with the per-group term, dx and the lower half of dW receive d(per-group term) = group sums of dz (different order)
+            assert torch.allclose(a, b, rtol=1e-4, atol=2e-6 * (b.abs().max().item() + 1e-9)), name
+        else:
+            assert torch.equal(a, b), name
+
+
 def test_c4_training_step_fused_vs_torch_layers_and_deterministic(cuda):
     """BASELINE configs[3] size (6 triplets x 4096 points, 512 clusters x 64 samples): the CUDA training layers against the
     op-by-op torch fp32 statement of the same graph (loss, gradient direction), and bit-reproducibility of the CUDA path."""
