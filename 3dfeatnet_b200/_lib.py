@@ -57,6 +57,10 @@ SIGNATURES = {
                                               _vp, _sz, _vp]),
     "f3d_conv_bn_train_backward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "f3d_conv_bn_train_forward_chain": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _i, _vp, _vp, _vp,
+                                             _vp, _vp, _i, _vp, _sz, _vp]),
+    "f3d_conv_bn_train_backward_chain": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _vp, _vp, _vp,
+                                              _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "f3d_maxpool_samples_forward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_maxpool_samples_backward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "f3d_triplet_loss_workspace_bytes": (_sz, [_i, _i]),

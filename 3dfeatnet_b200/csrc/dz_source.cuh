@@ -1,4 +1,6 @@
-// dz_source.cuh -- the BN-backward gradient dz of a POOL-ONLY layer (detector conv2, descriptor conv_mid), formed on the fly.
+// dz_source.cuh -- operands formed on the fly inside the contractions.
+//
+// (1) DzSource: the BN-backward gradient dz of a POOL-ONLY layer (detector conv2, descriptor conv_mid), formed on the fly.
 //
 // For such a layer the upstream gradient lives on the pooled tensor: g[row][ch] = (y == max of the group) ? gpool / ties : 0, and
 //     dz = s (g - k1 - (z - mu) istd k2),   s = gamma istd, k1 = mean(g), k2 = mean(g zhat)          (train_layers.cu)
@@ -22,6 +24,20 @@ struct DzSource {
 };
 
 constexpr int kDzCoefs = 7;
+
+// The INPUT rows of a contraction when they are the activation of the previous layer, y = act(z * scale + shift) (bn_apply): the
+// consumers (forward lin_tc, wgrad) fetch the previous layer's pre-BN tensor z and evaluate the activation in their operand converters
+// with bn_apply's own rounding, so y is neither written by the producer nor read by the consumers: the tensor never exists in HBM.
+struct XSource {
+    const float *coef;  // NULL: the rows are read as they are.  Else [2][k]: scale, shift of the producing layer (bn_stats_finalize)
+    int relu;
+};
+
+__device__ __forceinline__ float4 x_value(const float4 &z, const float4 &sc, const float4 &sh, int relu) {
+    float4 y = make_float4(__fmaf_rn(z.x, sc.x, sh.x), __fmaf_rn(z.y, sc.y, sh.y), __fmaf_rn(z.z, sc.z, sh.z), __fmaf_rn(z.w, sc.w, sh.w));
+    if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+    return y;
+}
 
 __device__ __forceinline__ float dz_value(float z, float bsc, float bsh, float s, float k1, float mu, float is, float k2, float pm, float gsc,
                                           int relu) {

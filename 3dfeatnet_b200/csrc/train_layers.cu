@@ -180,7 +180,11 @@ struct GradSource {
     const float *pooled;  // (rows / s, c) or NULL
     const float *inv;     // (rows / s, c) 1 / ties
     int s;                // samples per group, 0 = dense
+    const float *dense2;  // pooled mode only: an additional dense (rows, c) gradient (the activation feeds the pool AND a dense consumer), or NULL
 };
+
+// the dense gradient tensor a BN-backward pass has to stream next to z (NULL: none, pooled-only layer)
+__device__ __forceinline__ const float *dense_grad(const GradSource &G) { return G.s == 0 ? G.gy : G.dense2; }
 
 // per-thread cache of the pooled maximum and the scaled pooled gradient of the group the thread is walking through
 struct PoolCache {
@@ -188,9 +192,20 @@ struct PoolCache {
     float4 pm, gs;
 };
 
-__device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, const float4 &dense, long long r, int cv, int cvec, const float4 &yy) {
+// row cursor of a thread that walks rows r, r + step, ...: the group index advances without a 64-bit division per row
+struct GroupCursor {
+    long long grp = 0;
+    int rem = 0;
+    __device__ __forceinline__ void init(long long r, int s) {
+        if (s > 0) { grp = r / s; rem = static_cast<int>(r - grp * s); }
+    }
+    __device__ __forceinline__ void advance(int step, int s) {
+        if (s > 0) { rem += step; while (rem >= s) { rem -= s; ++grp; } }
+    }
+};
+
+__device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, const float4 &dense, long long grp, int cv, int cvec, const float4 &yy) {
     if (G.s == 0) return dense;  // dense mode: the caller has already loaded gy[row] (one iteration ahead)
-    const long long grp = r / G.s;
     if (grp != C.grp) {
         const size_t po = static_cast<size_t>(grp) * cvec + cv;
         C.grp = grp;
@@ -199,7 +214,9 @@ __device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, c
         const float4 ic = __ldg(reinterpret_cast<const float4 *>(G.inv) + po);
         C.gs = make_float4(__fmul_rn(gp.x, ic.x), __fmul_rn(gp.y, ic.y), __fmul_rn(gp.z, ic.z), __fmul_rn(gp.w, ic.w));
     }
-    return make_float4(yy.x == C.pm.x ? C.gs.x : 0.f, yy.y == C.pm.y ? C.gs.y : 0.f, yy.z == C.pm.z ? C.gs.z : 0.f, yy.w == C.pm.w ? C.gs.w : 0.f);
+    float4 g = make_float4(yy.x == C.pm.x ? C.gs.x : 0.f, yy.y == C.pm.y ? C.gs.y : 0.f, yy.z == C.pm.z ? C.gs.z : 0.f, yy.w == C.pm.w ? C.gs.w : 0.f);
+    if (G.dense2) { g.x += dense.x; g.y += dense.y; g.z += dense.z; g.w += dense.w; }  // same order as maxpool_bwd followed by the add of the two gradients
+    return g;
 }
 
 // per row-chunk partial sums of g and g*zhat, g = gy * [y > 0] (ReLU) or gy.  part[(blk*2+{0,1})*c + ch]
@@ -224,14 +241,17 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
     float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sz = sg;
     PoolCache pc;
     if (rlane < rl) {
-        for (long long r = rbeg + rlane; r < rend; r += rl) {
+        GroupCursor gc;
+        gc.init(rbeg + rlane, G.s);
+        for (long long r = rbeg + rlane; r < rend; r += rl, gc.advance(rl, G.s)) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
             // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
             float4 yy = make_float4(__fmaf_rn(zz.x, bsc.x, bsh.x), __fmaf_rn(zz.y, bsc.y, bsh.y), __fmaf_rn(zz.z, bsc.z, bsh.z), __fmaf_rn(zz.w, bsc.w, bsh.w));
             if (relu) yy = make_float4(fmaxf(yy.x, 0.f), fmaxf(yy.y, 0.f), fmaxf(yy.z, 0.f), fmaxf(yy.w, 0.f));
-            const float4 gd = G.s == 0 ? __ldg(reinterpret_cast<const float4 *>(G.gy) + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 g = load_grad(G, pc, gd, r, cv, cvec, yy);
+            const float *gdn = dense_grad(G);
+            const float4 gd = gdn ? __ldg(reinterpret_cast<const float4 *>(gdn) + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g = load_grad(G, pc, gd, gc.grp, cv, cvec, yy);
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
@@ -361,23 +381,26 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         long long r = rbeg + rlane;
         float4 zz_n = zero4, gd_n = zero4;
+        const float *gdn = dense_grad(G);
+        GroupCursor gc;
+        gc.init(r, G.s);
         if (r < rend) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             zz_n = __ldg(reinterpret_cast<const float4 *>(z) + o);
-            if (G.s == 0) gd_n = __ldg(reinterpret_cast<const float4 *>(G.gy) + o);
+            if (gdn) gd_n = __ldg(reinterpret_cast<const float4 *>(gdn) + o);
         }
-        for (; r < rend; r += rl) {
+        for (; r < rend; r += rl, gc.advance(rl, G.s)) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = zz_n, gd = gd_n;
             if (r + rl < rend) {
                 const size_t on = static_cast<size_t>(r + rl) * cvec + cv;
                 zz_n = __ldg(reinterpret_cast<const float4 *>(z) + on);
-                if (G.s == 0) gd_n = __ldg(reinterpret_cast<const float4 *>(G.gy) + on);
+                if (gdn) gd_n = __ldg(reinterpret_cast<const float4 *>(gdn) + on);
             }
             // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
             float4 yy = make_float4(__fmaf_rn(zz.x, bsc.x, bsh.x), __fmaf_rn(zz.y, bsc.y, bsh.y), __fmaf_rn(zz.z, bsc.z, bsh.z), __fmaf_rn(zz.w, bsc.w, bsh.w));
             if (relu) yy = make_float4(fmaxf(yy.x, 0.f), fmaxf(yy.y, 0.f), fmaxf(yy.z, 0.f), fmaxf(yy.w, 0.f));
-            float4 g = load_grad(G, pc, gd, r, cv, cvec, yy);
+            float4 g = load_grad(G, pc, gd, gc.grp, cv, cvec, yy);
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
@@ -653,13 +676,13 @@ size_t lin_tc_weight_bytes(int k_real, int nout);
 int lin_tc_grid(long long rows, int k_real, int nsplit);
 int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
            const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st, const DzSource *S = nullptr,
-           float *dgb = nullptr);
+           float *dgb = nullptr, const float *xcoef = nullptr, int xrelu = 0);
 bool lin_tc_dz_supported(long long rows, int k_real, int gs, bool need_group_sums);
 bool wgrad_tc_supported(int cin, int cout);
 bool wgrad_tc_dz_supported(long long rows, int cin, int cout, int gs);
 void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta);
 int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg = 0,
-             const DzSource *S = nullptr, float *partB = nullptr);
+             const DzSource *S = nullptr, float *partB = nullptr, const float *xcoef = nullptr, int xrelu = 0);
 
 // Pool-only layers on the tensor-core path: dz is formed inside the two contractions that consume it instead of being written by
 // bn_bwd_apply_kernel and read back twice (f3d_debug_set_fuse_dz(0) restores the three-kernel path; same bits in dW and dx).
@@ -744,17 +767,26 @@ F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int co
     return (fwd > bwd ? fwd : bwd) + 256;
 }
 
-// y != NULL: the (rows, cout) activation is written.  pool_s > 0 (y == NULL): only its max over groups of pool_s rows is (pooled, inv_ties).
-static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *x, const float *W, const float *bias,
+// Any of three results of the layer on top of z and the batch moments:
+//   y != NULL        the (rows, cout) activation is written;
+//   pool_s > 0       its max over groups of pool_s rows is (pooled, inv_ties);
+//   coef_out != NULL the BN scale / shift [2][cout] is, for a consumer that forms the activation from z itself (XSource).
+// xcoef != NULL: x holds the PREVIOUS layer's z and xcoef its scale / shift: the input rows are act(x * scale + shift), formed inside
+// the contraction (tensor-core path only).
+static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *x, const float *xcoef, int xrelu, const float *W, const float *bias,
                                 const float *group_bias, int group_s, const float *gamma, const float *beta, int relu, float eps,
-                                float *z, float *y, int pool_s, float *pooled, float *inv_ties, float *mean, float *var, int precision,
-                                void *workspace, size_t workspace_bytes, void *stream) {
+                                float *z, float *y, int pool_s, float *pooled, float *inv_ties, float *coef_out, float *mean, float *var,
+                                int precision, void *workspace, size_t workspace_bytes, void *stream) {
     if (group_bias && (group_s <= 0 || rows % group_s != 0))
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: group_bias needs group_s > 0 dividing rows");
     if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !mean || !var)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: bad arguments");
-    if (pool_s > 0 ? (rows % pool_s != 0 || !pooled || !inv_ties) : !y)
-        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: needs y, or pool_s dividing rows with pooled / inv_ties");
+    if (pool_s < 0 || (pool_s > 0 && (rows % pool_s != 0 || !pooled || !inv_ties)))
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: pool_s must divide rows and comes with pooled / inv_ties");
+    if (!y && pool_s == 0 && !coef_out)
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: nothing to produce (y, pooled or coef_out)");
+    if (xcoef && !(precision == 2 && lin_tc_supported(cin, cout) && cin % 8 == 0))
+        return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_forward: an activation source needs the tensor-core path and cin % 8 == 0");
     if (precision != 0 && precision != 2) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: precision must be 0 (fp32) or 2 (bf16x3)");
     if (cout % 4 != 0) return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_forward: output channels must be a multiple of 4");
     if (!workspace || workspace_bytes < f3d_conv_bn_train_workspace_bytes(rows, cin, cout))
@@ -769,10 +801,10 @@ static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *
     w += align256(stat_parts * 2 * cout * 4);
     double *sums = reinterpret_cast<double *>(w);  // fp64 through bn_stats_finalize
     w += align256(2 * cout * 8);
-    float *coef = reinterpret_cast<float *>(w);
+    float *coef = coef_out ? coef_out : reinterpret_cast<float *>(w);
     w += align256(2 * cout * 4);
     uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
-    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, kFwdSplit, st)
+    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, kFwdSplit, st, nullptr, nullptr, xcoef, xrelu)
                 : launch_conv_fwd(rows, cin, cout, x, W, bias, group_bias, group_s, z, part, st);
     if (rc) return rc;
     partial_reduce_kernel<double><<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(nparts), 2 * cout, part, sums);
@@ -786,8 +818,10 @@ static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *
         ktimer_begin("bn_apply_pool_kernel", 4.0 * static_cast<double>(rows) * cout, st);  // z read once; the pooled output is 1/pool_s of it
         bn_apply_pool_kernel<<<static_cast<unsigned>((np + 127) / 128), 128, 0, st>>>(groups, pool_s, cout / 4, z, coef, relu, pooled, inv_ties);
         ktimer_end(st);
-        return check_launch("bn_apply_pool_kernel");
+        rc = check_launch("bn_apply_pool_kernel");
+        if (rc) return rc;
     }
+    if (!y) return 0;
     const long long n4 = rows * cout / 4;
     ktimer_begin("bn_apply_kernel", 8.0 * static_cast<double>(rows) * cout, st);  // z in, y out
     bn_apply_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(n4, cout, z, coef, relu, y);
@@ -802,8 +836,8 @@ F3D_API int f3d_conv_bn_train_forward(long long rows, int cin, int cout, const f
                                       float *z, float *y, float *mean, float *var, int precision, void *workspace, size_t workspace_bytes,
                                       void *stream) {
     if (!y) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward: y is NULL");
-    return conv_bn_forward_impl(rows, cin, cout, x, W, bias, group_bias, group_s, gamma, beta, relu, eps, z, y, 0, nullptr, nullptr, mean, var,
-                                precision, workspace, workspace_bytes, stream);
+    return conv_bn_forward_impl(rows, cin, cout, x, nullptr, 0, W, bias, group_bias, group_s, gamma, beta, relu, eps, z, y, 0, nullptr, nullptr, nullptr,
+                                mean, var, precision, workspace, workspace_bytes, stream);
 }
 
 // The same layer when its activation only feeds tf.reduce_max over groups of pool_s consecutive rows (the sample axis): returns
@@ -813,24 +847,41 @@ F3D_API int f3d_conv_bn_train_forward_pooled(long long rows, int cin, int cout, 
                                              float *z, int pool_s, float *pooled, float *inv_ties, float *mean, float *var, int precision,
                                              void *workspace, size_t workspace_bytes, void *stream) {
     if (pool_s <= 0) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_forward_pooled: pool_s must be positive");
-    return conv_bn_forward_impl(rows, cin, cout, x, W, bias, group_bias, group_s, gamma, beta, relu, eps, z, nullptr, pool_s, pooled, inv_ties,
-                                mean, var, precision, workspace, workspace_bytes, stream);
+    return conv_bn_forward_impl(rows, cin, cout, x, nullptr, 0, W, bias, group_bias, group_s, gamma, beta, relu, eps, z, nullptr, pool_s, pooled, inv_ties,
+                                nullptr, mean, var, precision, workspace, workspace_bytes, stream);
 }
 
-// gy (rows,cout) = dL/dy.  Outputs: dx (rows,cin; NULL to skip), dW (cin,cout), db, dgamma, dbeta (cout).
-F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
-                                       const float *beta, const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
-                                       const float *gy, int pool_s, const float *pooled, const float *inv_ties, float *dx, float *dW,
-                                       float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s, int precision,
-                                       void *workspace, size_t workspace_bytes, void *stream) {
+// The layer inside a CHAIN of layers whose activations are never materialised.  Inputs: x_coef != NULL says that x is the previous
+// layer's pre-BN tensor z and x_coef [2][cin] its BN scale / shift (that layer's coef_out): the rows act(x * scale + shift) (ReLU when
+// x_relu) are formed inside the contraction.  Results, any subset (at least one): y (rows, cout) written; pool_s > 0: pooled / inv_ties
+// (rows / pool_s, cout); coef_out [2][cout]: scale / shift of THIS layer for the next one in the chain.
+F3D_API int f3d_conv_bn_train_forward_chain(long long rows, int cin, int cout, const float *x, const float *x_coef, int x_relu, const float *W,
+                                            const float *bias, const float *group_bias, int group_s, const float *gamma, const float *beta, int relu,
+                                            float eps, float *z, float *y, int pool_s, float *pooled, float *inv_ties, float *coef_out, float *mean,
+                                            float *var, int precision, void *workspace, size_t workspace_bytes, void *stream) {
+    return conv_bn_forward_impl(rows, cin, cout, x, x_coef, x_relu, W, bias, group_bias, group_s, gamma, beta, relu, eps, z, y, pool_s, pooled, inv_ties,
+                                coef_out, mean, var, precision, workspace, workspace_bytes, stream);
+}
+
+// gy (rows, cout) = dL/dy (dense, may be NULL when the pooled gradient is given); pool_s > 0: gpool (rows / pool_s, cout) = gradient of the
+// pooled tensor, with pooled / inv_ties of the forward.  Both may be present (the activation feeds the pool and a dense consumer).
+// xcoef != NULL: x holds the previous layer's z (see conv_bn_forward_impl).  Outputs: dx (rows,cin; NULL to skip), dW, db, dgamma, dbeta.
+static int conv_bn_backward_impl(long long rows, int cin, int cout, const float *x, const float *xcoef, int xrelu, const float *W, const float *gamma,
+                                 const float *beta, const float *z, const float *mean, const float *var, int relu, float eps,
+                                 const float *gy, int pool_s, const float *pooled, const float *gpool, const float *inv_ties, float *dx, float *dW,
+                                 float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s, int precision,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
     if (dgroup_bias && (group_s <= 0 || rows % group_s != 0))
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: dgroup_bias needs group_s > 0 dividing rows");
-    if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !mean || !var || !gy || !dW || !db || !dgamma || !dbeta)
+    if (rows <= 0 || cin <= 0 || cout <= 0 || !x || !W || !gamma || !beta || !z || !mean || !var || !dW || !db || !dgamma || !dbeta)
         return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: bad arguments");
-    (void)y;  // the activation is recomputed from z (bit-identical), not read back
-    if (pool_s < 0 || (pool_s > 0 && (!pooled || !inv_ties || rows % pool_s != 0)))
-        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: pooled gradient needs pooled, inv_ties and rows % pool_s == 0");
-    const GradSource G{gy, pool_s > 0 ? pooled : nullptr, pool_s > 0 ? inv_ties : nullptr, pool_s};
+    if (pool_s < 0 || (pool_s > 0 && (!pooled || !gpool || !inv_ties || rows % pool_s != 0)))
+        return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: pooled gradient needs pooled, gpool, inv_ties and rows % pool_s == 0");
+    if (pool_s == 0 && !gy) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: no gradient given (gy or the pooled set)");
+    const bool mixed = pool_s > 0 && gy != nullptr;  // pooled + dense gradient
+    const GradSource G{pool_s > 0 ? gpool : gy, pool_s > 0 ? pooled : nullptr, pool_s > 0 ? inv_ties : nullptr, pool_s, mixed ? gy : nullptr};
+    if (xcoef && !(precision == 2 && cin % 8 == 0 && wgrad_tc_supported(cin, cout)))
+        return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_backward: an activation source needs the tensor-core weight gradient (cin % 8 == 0, <= 128)");
     if (precision != 0 && precision != 2) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: precision must be 0 (fp32) or 2 (bf16x3)");
     if (cout % 16 != 0 || 256 % (cout / 4) != 0)
         return fail(F3D_ERR_UNSUPPORTED, "conv_bn_train_backward: output channels must be 16, 32, 64, 128, 256, 512 or 1024");
@@ -872,10 +923,10 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     const int nred = static_cast<int>(rows < kRedBlocks ? rows : kRedBlocks);
     int rc = 0;
     int nred1 = nred;
-    if (pool_s > 0) {
+    if (pool_s > 0 && !mixed) {
         const long long groups = rows / pool_s;
         nred1 = static_cast<int>(groups < kRedBlocks ? groups : kRedBlocks);
-        bn_bwd_reduce_pooled_kernel<<<nred1, 256, 0, st>>>(groups, cout, gy, pooled, gamma, beta, relu, part);
+        bn_bwd_reduce_pooled_kernel<<<nred1, 256, 0, st>>>(groups, cout, gpool, pooled, gamma, beta, relu, part);
         rc = check_launch("bn_bwd_reduce_pooled_kernel");
     } else {
         ktimer_begin("bn_bwd_reduce_kernel", 8.0 * static_cast<double>(rows) * cout, st);  // gy and z in
@@ -889,15 +940,15 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     if (rc) return rc;
     const bool w3 = cin == 3;  // the xyz layers: dW rides along with the dz pass (partials in the dW-partials area: 3*cout per chunk)
     // pool-only layer on the tensor-core path: dz is formed inside wgrad / dgrad from z and the pooled tensors, never stored
-    const bool fuse_dz = g_fuse_dz && pool_s > 0 && precision == 2 && !w3 && dx && tc_dgrad && wgrad_tc_dz_supported(rows, cin, cout, pool_s) &&
+    const bool fuse_dz = g_fuse_dz && pool_s > 0 && !mixed && precision == 2 && !w3 && dx && tc_dgrad && wgrad_tc_dz_supported(rows, cin, cout, pool_s) &&
                          lin_tc_dz_supported(rows, cout, pool_s, dgroup_bias != nullptr) && (!dgroup_bias || group_s == pool_s) && cin <= 128;
     bn_bwd_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, var, dgamma, dbeta, coef2, beta,
                                                                mean, fuse_dz ? coef7 : nullptr);
     rc = check_launch("bn_bwd_finalize_kernel");
     if (rc) return rc;
     if (fuse_dz) {
-        const DzSource S{z, coef7, pooled, gy, inv_ties, pool_s, relu};
-        rc = wgrad_tc(rows, cin, cout, x, nullptr, partW, st, 0, &S, partB);
+        const DzSource S{z, coef7, pooled, gpool, inv_ties, pool_s, relu};
+        rc = wgrad_tc(rows, cin, cout, x, nullptr, partW, st, 0, &S, partB, xcoef, xrelu);
         if (rc) return rc;
         const long long nw = static_cast<long long>(cin) * cout;
         partial_reduce_kernel<float><<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(tcg, nw, partW, dW);
@@ -910,7 +961,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     }
     const int napp = static_cast<int>(rows < kApplyBlocks ? rows : kApplyBlocks);
     // gy (dense mode only) and z in, dz out
-    ktimer_begin("bn_bwd_apply_kernel", (pool_s > 0 ? 8.0 : 12.0) * static_cast<double>(rows) * cout, st);
+    ktimer_begin("bn_bwd_apply_kernel", (pool_s > 0 && !mixed ? 8.0 : 12.0) * static_cast<double>(rows) * cout, st);
     bn_bwd_apply_kernel<<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     ktimer_end(st);
     rc = check_launch("bn_bwd_apply_kernel");
@@ -929,7 +980,7 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
     if (w3) {
         partial_reduce_kernel<float><<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(napp, nw, partW, dW);
     } else if (precision == 2 && wgrad_tc_supported(cin, cout)) {
-        rc = wgrad_tc(rows, cin, cout, x, dz, partW, st);
+        rc = wgrad_tc(rows, cin, cout, x, dz, partW, st, 0, nullptr, nullptr, xcoef, xrelu);
         if (rc) return rc;
         partial_reduce_kernel<float><<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(tcg, nw, partW, dW);
     } else {
@@ -955,6 +1006,31 @@ F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const 
         }
     }
     return rc;
+}
+
+F3D_API int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x, const float *W, const float *gamma,
+                                       const float *beta, const float *z, const float *y, const float *mean, const float *var, int relu, float eps,
+                                       const float *gy, int pool_s, const float *pooled, const float *inv_ties, float *dx, float *dW,
+                                       float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s, int precision,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
+    (void)y;  // the activation is recomputed from z (bit-identical), not read back
+    if (!gy) return fail(F3D_ERR_INVALID_ARGUMENT, "conv_bn_train_backward: gy is NULL");
+    // gy is the dense gradient, or -- pool_s > 0 -- the gradient of the pooled tensor
+    return conv_bn_backward_impl(rows, cin, cout, x, nullptr, 0, W, gamma, beta, z, mean, var, relu, eps, pool_s > 0 ? nullptr : gy, pool_s, pooled,
+                                 pool_s > 0 ? gy : nullptr, inv_ties, dx, dW, db, dgamma, dbeta, dgroup_bias, group_s, precision, workspace,
+                                 workspace_bytes, stream);
+}
+
+// Backward of a layer of a chain (f3d_conv_bn_train_forward_chain): x_coef as there; gy (dense, rows x cout) and / or the pooled set
+// (pool_s, pooled, gpool, inv_ties): when both are given the layer's activation fed the pool and a dense consumer and the two gradients
+// are summed on the fly (no maxpool backward pass, no add).
+F3D_API int f3d_conv_bn_train_backward_chain(long long rows, int cin, int cout, const float *x, const float *x_coef, int x_relu, const float *W,
+                                             const float *gamma, const float *beta, const float *z, const float *mean, const float *var, int relu,
+                                             float eps, const float *gy, int pool_s, const float *pooled, const float *gpool, const float *inv_ties,
+                                             float *dx, float *dW, float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s,
+                                             int precision, void *workspace, size_t workspace_bytes, void *stream) {
+    return conv_bn_backward_impl(rows, cin, cout, x, x_coef, x_relu, W, gamma, beta, z, mean, var, relu, eps, gy, pool_s, pooled, gpool, inv_ties, dx,
+                                 dW, db, dgamma, dbeta, dgroup_bias, group_s, precision, workspace, workspace_bytes, stream);
 }
 
 // Measurement / test aid: 0 = pool-only layers write dz with bn_bwd_apply_kernel and read it back in wgrad and dgrad (the path the fused

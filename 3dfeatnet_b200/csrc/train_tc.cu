@@ -84,7 +84,8 @@ constexpr int kRingMax = 2;  // ring depth (1 when shared memory cannot hold two
 template <int nsplit>
 __global__ void __launch_bounds__(ttc::kThreads, 4)
 lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
-              const float *__restrict__ bias, const float *__restrict__ gbias, int gs, float *__restrict__ out, float *__restrict__ part) {
+              const float *__restrict__ bias, const float *__restrict__ gbias, int gs, float *__restrict__ out, float *__restrict__ part,
+              XSource X) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const bool ring = (k_real & 7) == 0;
@@ -184,14 +185,22 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
             // bytes of one row, a half-warp writes 16 distinct 8-byte slots of the operand image (no bank conflicts)
             const int rsub = lane >> 3, c4 = (lane >> 1) & 3, h = lane & 1;
             const uint32_t row_bytes = static_cast<uint32_t>(k_real) * 4;
+            for (int c = c4; c < kp / 8; c += 4) {
+                // X.coef: the rows in the ring are the previous layer's z; its BN + ReLU is applied here (XSource, dz_source.cuh)
+                float4 xsc = make_float4(1.f, 1.f, 1.f, 1.f), xsh = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool chok = c * 8 + h * 4 < k_real;
+                if (X.coef && chok) {
+                    xsc = __ldg(reinterpret_cast<const float4 *>(X.coef + c * 8 + h * 4));
+                    xsh = __ldg(reinterpret_cast<const float4 *>(X.coef + k_real + c * 8 + h * 4));
+                }
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const int r = p * 32 + warp * 4 + rsub;
-                const bool valid = r0 + r < rows;
-                const uint8_t *src = ringbuf + stage * stage_bytes + r * row_bytes + h * 16;
-                for (int c = c4; c < kp / 8; c += 4) {
+                for (int p = 0; p < 2; ++p) {
+                    const int r = p * 32 + warp * 4 + rsub;
                     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) a = *reinterpret_cast<const float4 *>(src + c * 32);
+                    if (r0 + r < rows && chok) {
+                        a = *reinterpret_cast<const float4 *>(ringbuf + stage * stage_bytes + r * row_bytes + h * 16 + c * 32);
+                        if (X.coef) a = x_value(a, xsc, xsh, X.relu);
+                    }
                     uint8_t *dst = smem + c * kLboXp + r * 16 + h * 8;
 #pragma unroll
                     for (int sp = 0; sp < nsplit; ++sp) {  // a = hi (+ mid) + lo, each a bf16
@@ -322,7 +331,7 @@ template <int nsplit, int NT, bool FUSED>
 __global__ void __launch_bounds__(lp::kThreads, 1)
 lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint32_t tmem_cols, const float *__restrict__ x,
                    const uint8_t *__restrict__ wimg, const float *__restrict__ bias, const float *__restrict__ gbias, int gs,
-                   float *__restrict__ out, float *__restrict__ part, DzSource S, float *__restrict__ dgb) {
+                   float *__restrict__ out, float *__restrict__ part, DzSource S, float *__restrict__ dgb, XSource X) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t kLbo = lp::lbo(nsplit, NT);
@@ -461,14 +470,22 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
             if (it >= 2) mbar_wait(mma_done + b, static_cast<uint32_t>(((it >> 1) - 1) & 1));  // MMAs of tile it-2 have read image b
             uint8_t *img = smem + b * img_bytes;
             if constexpr (!FUSED) {
+                for (int c = c4; c < kp / 8; c += 4) {
+                    // X.coef: the rows in the ring are the previous layer's z; its BN + ReLU is applied here (XSource, dz_source.cuh)
+                    float4 xsc = make_float4(1.f, 1.f, 1.f, 1.f), xsh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool chok = c * 8 + h * 4 < k_real;
+                    if (X.coef && chok) {
+                        xsc = __ldg(reinterpret_cast<const float4 *>(X.coef + c * 8 + h * 4));
+                        xsh = __ldg(reinterpret_cast<const float4 *>(X.coef + k_real + c * 8 + h * 4));
+                    }
 #pragma unroll
-                for (int p = 0; p < NT / 16; ++p) {
-                    const int r = p * 16 + wc * 4 + rsub;
-                    const bool valid = r0 + r < rows;
-                    const uint8_t *src = ringbuf + slot * slot_bytes + r * row_bytes + h * 16;
-                    for (int c = c4; c < kp / 8; c += 4) {
+                    for (int p = 0; p < NT / 16; ++p) {
+                        const int r = p * 16 + wc * 4 + rsub;
                         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid && c * 8 < k_real) a = *reinterpret_cast<const float4 *>(src + c * 32);
+                        if (r0 + r < rows && chok) {
+                            a = *reinterpret_cast<const float4 *>(ringbuf + slot * slot_bytes + r * row_bytes + h * 16 + c * 32);
+                            if (X.coef) a = x_value(a, xsc, xsh, X.relu);
+                        }
                         uint8_t *dst = img + c * kLbo + r * 16 + h * 8;
 #pragma unroll
                         for (int sp = 0; sp < nsplit; ++sp) {
@@ -647,7 +664,8 @@ __device__ __forceinline__ void wgrad_store_unit(uint8_t *dst, uint32_t split, c
     }
 }
 
-__device__ __forceinline__ void wgrad_convert(uint8_t *img, uint32_t lbo, uint32_t split, const uint8_t *__restrict__ stage, int c, int valid_rows) {
+__device__ __forceinline__ void wgrad_convert(uint8_t *img, uint32_t lbo, uint32_t split, const uint8_t *__restrict__ stage, int c, int valid_rows,
+                                              const XSource X = XSource{nullptr, 0}) {
     // unit u -> (row chunk rc, channel quad c4); a warp handles 32 consecutive quads of one row chunk; converter threads only
     const int quads = c >> 2;
     for (int u = threadIdx.x - 32; u < wg::kChunks * quads; u += wg::kThreads - 32) {
@@ -657,6 +675,12 @@ __device__ __forceinline__ void wgrad_convert(uint8_t *img, uint32_t lbo, uint32
         for (int i = 0; i < 8; ++i) {
             const int r = rc * 8 + i;
             v[i] = r < valid_rows ? *reinterpret_cast<const float4 *>(stage + (static_cast<size_t>(r) * c + c4 * 4) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (X.coef) {  // the staged rows are the previous layer's z: its BN + ReLU is applied here (XSource, dz_source.cuh)
+            const float4 xsc = __ldg(reinterpret_cast<const float4 *>(X.coef + c4 * 4)), xsh = __ldg(reinterpret_cast<const float4 *>(X.coef + c + c4 * 4));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (rc * 8 + i < valid_rows) v[i] = x_value(v[i], xsc, xsh, X.relu);
         }
         wgrad_store_unit(img + rc * lbo + (c4 >> 1) * wg::kSboP + (c4 & 1) * 64, split, v);
     }
@@ -699,7 +723,7 @@ __device__ __forceinline__ void wgrad_convert_dz(uint8_t *img, uint32_t lbo, uin
 template <bool FUSED>
 __global__ void __launch_bounds__(wg::kThreads, 1)
 wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint32_t tmem_cols, const float *__restrict__ x,
-                const float *__restrict__ dz, float *__restrict__ partW, int dbg, DzSource S, float *__restrict__ partB) {
+                const float *__restrict__ dz, float *__restrict__ partW, int dbg, DzSource S, float *__restrict__ partB, XSource X) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lbo_a = 16 * wg::kSboP, lbo_b = static_cast<uint32_t>(cout / 8) * wg::kSboP;
@@ -804,7 +828,7 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
                 const long long r0 = rbeg + static_cast<long long>(s) * wg::kRows;
                 const int valid = static_cast<int>(rend - r0 < wg::kRows ? rend - r0 : wg::kRows);
                 const uint8_t *stage = ring + b * stage_bytes;
-                wgrad_convert(img, lbo_a, split_a, stage, cin, valid);
+                wgrad_convert(img, lbo_a, split_a, stage, cin, valid, X);
                 if constexpr (FUSED)
                     wgrad_convert_dz(img + 2 * split_a, lbo_b, split_b, stage + xs_bytes, cout, valid, coef_s,
                                      reinterpret_cast<const float *>(stage + xs_bytes + ds_bytes), S.relu, dbsum);
@@ -958,8 +982,11 @@ bool lin_tc_dz_supported(long long rows, int k_real, int gs, bool need_group_sum
 }
 
 int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
-           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st, const DzSource *S, float *dgb) {
+           const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st, const DzSource *S, float *dgb,
+           const float *xcoef, int xrelu) {
     const int kp = lin_tc_kp(k_real);
+    const XSource X{xcoef, xrelu};
+    if (xcoef && (S != nullptr || k_real % 8 != 0)) return fail(F3D_ERR_UNSUPPORTED, "lin_tc: activation source needs k % 8 == 0 and no dz source");
     const int mblocks = (nout + 127) / 128;
     const long long total = 128LL * kp * mblocks;
     const bool fused = S != nullptr;
@@ -979,7 +1006,7 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
     e = cudaFuncSetAttribute(lin_tc_pipe_kernel<NS, NT, FU>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));    \
     if (e == cudaSuccess)                                                                                                                \
         lin_tc_pipe_kernel<NS, NT, FU><<<grid, lp::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, \
-                                                                           part, S0, dgb);
+                                                                           part, S0, dgb, X);
     if (P.pipe) {
         if (fused && P.nt == 64) { F3D_LAUNCH_PIPE(2, 64, true) }
         else if (fused) { F3D_LAUNCH_PIPE(2, 32, true) }
@@ -994,10 +1021,10 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
 #undef F3D_LAUNCH_PIPE
     if (nsplit == 3) {
         e = cudaFuncSetAttribute(lin_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));
-        if (e == cudaSuccess) lin_tc_kernel<3><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part);
+        if (e == cudaSuccess) lin_tc_kernel<3><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part, X);
     } else {
         e = cudaFuncSetAttribute(lin_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));
-        if (e == cudaSuccess) lin_tc_kernel<2><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part);
+        if (e == cudaSuccess) lin_tc_kernel<2><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part, X);
     }
     ktimer_end(st);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
@@ -1029,7 +1056,8 @@ bool wgrad_tc_dz_supported(long long rows, int cin, int cout, int gs) {
 
 // partW: grid x cin x cout floats.  S != NULL: dz formed on the fly from z (see the kernel), partB: grid x cout column sums of dz.
 int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, cudaStream_t st, int dbg, const DzSource *S,
-             float *partB) {
+             float *partB, const float *xcoef, int xrelu) {
+    const XSource X{xcoef, xrelu};
     int grid = 0;
     long long per = 0;
     wgrad_tc_plan(rows, &grid, &per);
@@ -1042,9 +1070,9 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
     if (e != cudaSuccess) return fail(static_cast<int>(e), "wgrad_tc: cudaFuncSetAttribute");
     ktimer_begin(fused ? "wgrad_tc_kernel (dz formed from z)" : "wgrad_tc_kernel", 4.0 * static_cast<double>(rows) * (cin + cout), st);
     if (fused)
-        wgrad_tc_kernel<true><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, nullptr, partW, dbg, *S, partB);
+        wgrad_tc_kernel<true><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, nullptr, partW, dbg, *S, partB, X);
     else
-        wgrad_tc_kernel<false><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg, DzSource{}, nullptr);
+        wgrad_tc_kernel<false><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg, DzSource{}, nullptr, X);
     ktimer_end(st);
     return check_launch("wgrad_tc_kernel");
 }
@@ -1054,5 +1082,5 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
 // Bring-up / micro-benchmark entry: the wgrad contraction alone.  dbg bit 0 skips the operand staging, bit 1 the MMAs.
 F3D_API int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, int dbg, void *stream) {
     if (!f3d::wgrad_tc_supported(cin, cout)) return f3d::fail(F3D_ERR_UNSUPPORTED, "debug_wgrad_tc: unsupported shape");
-    return f3d::wgrad_tc(rows, cin, cout, x, dz, partW, f3d::as_stream(stream), dbg, nullptr, nullptr);
+    return f3d::wgrad_tc(rows, cin, cout, x, dz, partW, f3d::as_stream(stream), dbg, nullptr, nullptr, nullptr, 0);
 }

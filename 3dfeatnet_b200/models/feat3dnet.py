@@ -153,11 +153,21 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is
             npoint, radius, nsample, xyz, points, tnet_spec, knn, use_xyz, keypoints=keypoints,
             orientations=orientations, normalize_radius=normalize_radius, neighbours=neighbours)
 
+    # training on the tensor cores: the activations of the chain conv0 -> conv1 -> conv_mid stay unmaterialised (layers.DeferredActivation);
+    # the last layer of `mlp` feeds the pool AND conv_mid, so it hands back its pooled maximum next to the deferred activation
+    chain = bool(is_training) and bn and mlp and mlp2 and new_points.is_cuda and new_points.shape[-1] == 3 and _layers.chain_supported() \
+        and all(c % 16 == 0 and c & (c - 1) == 0 and c <= 128 for c in mlp)
+    pooled = None
     for i, num_out_channel in enumerate(mlp):
+        last = i == len(mlp) - 1
         new_points = conv2d(new_points, num_out_channel, [1, 1], stride=[1, 1], padding='VALID', bn=bn,
-                            is_training=is_training, scope=scope + '/conv%d' % i, params=params, new_stats=new_stats)
+                            is_training=is_training, scope=scope + '/conv%d' % i, params=params, new_stats=new_stats,
+                            defer=chain, also_pool=chain and last)
+        if chain and last:
+            new_points, pooled = new_points
 
-    pooled = _layers.max_pool_samples(new_points)  # tf.reduce_max; the gradient is shared among ties like TF
+    if pooled is None:
+        pooled = _layers.max_pool_samples(new_points)  # tf.reduce_max; the gradient is shared among ties like TF
     # the reference tiles `pooled` over the samples and concatenates it to new_points (:60-66); conv2d(concat_pooled=) states
     # the same layer without building the (B,M,S,2C) tensor
     for i, num_out_channel in enumerate(mlp2 or []):
@@ -198,12 +208,15 @@ def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp
     new_points, idx = query_and_group_points(xyz, points, new_xyz, num_samples, radius, knn=False, use_xyz=True,
                                              normalize_radius=True, orientations=None, end_points=end_points)
 
+    # training on the tensor cores: the activations between the layers of the chain stay unmaterialised (layers.DeferredActivation)
+    chain = bool(is_training) and use_bn and not compute_det_gradients and new_points.is_cuda and new_points.shape[-1] == 3 \
+        and _layers.chain_supported() and all(c % 16 == 0 and c & (c - 1) == 0 for c in mlp) and all(c <= 128 for c in mlp[:-1])
     for i, num_out_channel in enumerate(mlp):
         # the last layer's activation only feeds the max-pool: conv2d(pool_samples=True) pools in the same call
         pool_here = (i == len(mlp) - 1) and not compute_det_gradients
         new_points = conv2d(new_points, num_out_channel, [1, 1], stride=[1, 1], padding='VALID', bn=use_bn,
                             is_training=is_training, scope=scope + '/conv%d' % i, params=params, new_stats=new_stats,
-                            pool_samples=pool_here)
+                            pool_samples=pool_here, defer=chain and not pool_here)
         if compute_det_gradients:
             (g,) = torch.autograd.grad(new_points, xyz, grad_outputs=new_points.detach(), retain_graph=True)
             end_points['gradients']['det']['mlp_{}'.format(i)] = g

@@ -44,6 +44,7 @@ def apply_ema_updates(weights, updates):
             torch._foreach_mul_(diffs, 1 - decay)
             torch._foreach_sub_(dst, diffs)
 FUSED_TRAINING = True  # training-mode conv+BN(+ReLU) through csrc/train_layers.cu (False: the op-by-op torch statement)
+CHAIN_ACTIVATIONS = True  # the per-point MLP chains leave their intermediate activations unmaterialised (DeferredActivation)
 TRAIN_PRECISION = "bf16x3"  # contractions of the training layers: "bf16x3" = tcgen05 tensor cores, "fp32" = FFMA kernels
 _PRECISION_CODE = {"fp32": 0, "bf16x3": 2}
 
@@ -56,9 +57,38 @@ def _native():
     return importlib.import_module(("3dfeatnet_b200." if __name__.split(".")[0] == "3dfeatnet_b200" else "") + "_lib")
 
 
-def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision, gbias=None, gs=0, pool_s=0):
-    """-> (x, w, gamma, beta, z, y, mean, var) and, when pool_s > 0, (..., pooled, inv_ties) with y = None: the activation of a
-    pool-only layer is never materialised (f3d_conv_bn_train_forward_pooled)."""
+class DeferredActivation(object):
+    """The output of a training-mode conv2d whose activation is NOT materialised: y = act(z * scale + shift) with z the layer's pre-BN
+    tensor (B,M,S,C), coef = [scale | shift] (2C,) and relu the activation flag.  The next conv2d of the chain takes it as its input
+    and forms y inside its contractions (csrc/dz_source.cuh, XSource).  `z` is the autograd handle of y: the gradient that flows into
+    it is dL/dy (the producing layer's backward recomputes y from z)."""
+    __slots__ = ("z", "coef", "relu")
+
+    def __init__(self, z, coef, relu):
+        self.z, self.coef, self.relu = z, coef, bool(relu)
+
+    @property
+    def shape(self):
+        return self.z.shape
+
+    @property
+    def is_cuda(self):
+        return self.z.is_cuda
+
+    def dim(self):
+        return self.z.dim()
+
+    def materialize(self):
+        """the activation as an ordinary tensor (op-by-op statement; differentiable through z)"""
+        c = self.z.shape[-1]
+        y = self.z * self.coef[:c] + self.coef[c:]
+        return torch.relu(y) if self.relu else y
+
+
+def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision, gbias=None, gs=0, pool_s=0, x_coef=None, x_relu=False, want_y=True,
+                     want_coef=False):
+    """-> dict(x, w, gamma, beta, z, y, mean, var, pooled, inv, coef): y when want_y; pooled / inv (max over groups of pool_s rows and
+    1 / ties) when pool_s > 0; coef = this layer's BN scale / shift when want_coef.  x_coef: x holds the previous layer's z (chain)."""
     _lib = _native()
     L = _lib.lib()
     x2, w2 = x.detach().contiguous().float(), w.detach().contiguous().float()
@@ -71,44 +101,50 @@ def _conv_bn_forward(x, w, b, gamma, beta, use_relu, precision, gbias=None, gs=0
     z = torch.empty((rows, cout), dtype=torch.float32, device=x2.device)
     mean = torch.empty(cout, dtype=torch.float32, device=x2.device)
     var = torch.empty_like(mean)
+    pooled = inv = y = coef = None
     if pool_s:
         if rows % pool_s:
             raise ValueError("pool_s must divide the number of rows")
         pooled = torch.empty((rows // pool_s, cout), dtype=torch.float32, device=x2.device)
         inv = torch.empty_like(pooled)
-        _lib.check(L.f3d_conv_bn_train_forward_pooled(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2),
-                                                      _lib.ptr(gb2) if gb2 is not None else None, int(gs), _lib.ptr(g2), _lib.ptr(be2),
-                                                      int(use_relu), BN_EPS, _lib.ptr(z), int(pool_s), _lib.ptr(pooled), _lib.ptr(inv),
-                                                      _lib.ptr(mean), _lib.ptr(var), precision, _lib.ptr(ws), nbytes, _lib.stream()),
-                   "conv_bn_train_forward_pooled")
-        return x2, w2, g2, be2, z, None, mean, var, pooled, inv
-    y = torch.empty_like(z)
-    _lib.check(L.f3d_conv_bn_train_forward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2),
-                                           _lib.ptr(gb2) if gb2 is not None else None, int(gs), _lib.ptr(g2), _lib.ptr(be2),
-                                           int(use_relu), BN_EPS, _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var),
-                                           precision, _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_forward")
-    return x2, w2, g2, be2, z, y, mean, var
+    if want_y:
+        y = torch.empty_like(z)
+    if want_coef:
+        coef = torch.empty(2 * cout, dtype=torch.float32, device=x2.device)
+    xc = x_coef.detach().contiguous().float() if x_coef is not None else None
+    p = _lib.ptr
+    _lib.check(L.f3d_conv_bn_train_forward_chain(rows, cin, cout, p(x2), p(xc) if xc is not None else None, int(bool(x_relu)), p(w2), p(b2),
+                                                 p(gb2) if gb2 is not None else None, int(gs), p(g2), p(be2), int(use_relu), BN_EPS, p(z),
+                                                 p(y) if y is not None else None, int(pool_s), p(pooled) if pooled is not None else None,
+                                                 p(inv) if inv is not None else None, p(coef) if coef is not None else None, p(mean), p(var),
+                                                 precision, p(ws), nbytes, _lib.stream()), "conv_bn_train_forward_chain")
+    return dict(x=x2, w=w2, gamma=g2, beta=be2, z=z, y=y, mean=mean, var=var, pooled=pooled, inv=inv, coef=coef, x_coef=xc)
 
 
-def _conv_bn_backward(saved, use_relu, precision, gy, need_dx, pool_s=0, pooled=None, inv=None, gs=0):
-    """-> (dx, dW, db, dgamma, dbeta, dgroup_bias); dgroup_bias only when gs > 0."""
+def _conv_bn_backward(saved, use_relu, precision, gy, need_dx, pool_s=0, gpool=None, gs=0, x_relu=False):
+    """saved: the dict of _conv_bn_forward.  gy: dense gradient or None; gpool: gradient of the pooled tensor or None.
+    -> (dx, dW, db, dgamma, dbeta, dgroup_bias); dgroup_bias only when gs > 0."""
     _lib = _native()
     L = _lib.lib()
-    x2, w2, g2, be2, z, y, mean, var = saved
+    x2, w2, g2, be2, z, mean, var = (saved[k] for k in ("x", "w", "gamma", "beta", "z", "mean", "var"))
+    pooled, inv, xc = saved["pooled"], saved["inv"], saved["x_coef"]
     rows, cin, cout = x2.shape[0], x2.shape[1], w2.shape[1]
-    gy = gy.contiguous().float()
+    gy = gy.contiguous().float() if gy is not None else None
+    gpool = gpool.contiguous().float() if gpool is not None else None
+    if gpool is None:
+        pool_s = 0
     nbytes = L.f3d_conv_bn_train_workspace_bytes(rows, cin, cout)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
     dx = torch.empty_like(x2) if need_dx else None
     dw = torch.empty_like(w2)
     db, dg, dbe = (torch.empty(cout, dtype=torch.float32, device=x2.device) for _ in range(3))
     dgb = torch.empty((rows // gs, cout), dtype=torch.float32, device=x2.device) if gs > 0 else None
-    _lib.check(L.f3d_conv_bn_train_backward(rows, cin, cout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(be2), _lib.ptr(z), _lib.ptr(y),
-                                            _lib.ptr(mean), _lib.ptr(var), int(use_relu), BN_EPS, _lib.ptr(gy), int(pool_s),
-                                            _lib.ptr(pooled) if pooled is not None else None, _lib.ptr(inv) if inv is not None else None,
-                                            _lib.ptr(dx) if dx is not None else None, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dg),
-                                            _lib.ptr(dbe), _lib.ptr(dgb) if dgb is not None else None, int(gs), precision,
-                                            _lib.ptr(ws), nbytes, _lib.stream()), "conv_bn_train_backward")
+    p = _lib.ptr
+    opt = lambda t: p(t) if t is not None else None
+    _lib.check(L.f3d_conv_bn_train_backward_chain(rows, cin, cout, p(x2), opt(xc), int(bool(x_relu)), p(w2), p(g2), p(be2), p(z), p(mean), p(var),
+                                                  int(use_relu), BN_EPS, opt(gy), int(pool_s), opt(pooled) if pool_s else None, opt(gpool),
+                                                  opt(inv) if pool_s else None, opt(dx), p(dw), p(db), p(dg), p(dbe), opt(dgb), int(gs), precision,
+                                                  p(ws), nbytes, _lib.stream()), "conv_bn_train_backward_chain")
     return dx, dw, db, dg, dbe, dgb
 
 
@@ -125,37 +161,49 @@ def _max_pool_forward(x3):
 
 class _ConvBnTrain(torch.autograd.Function):
     """conv 1x1 + bias + batch-norm with BATCH statistics + optional ReLU as one differentiable CUDA op
-    (csrc/train_layers.cu, contractions in csrc/train_tc.cu).  Returns (out, batch_mean, batch_var); the moments are not
-    differentiable outputs (they only feed the EMA shadows).  Saves x and z (pre-BN) for the backward (which recomputes y).
+    (csrc/train_layers.cu, contractions in csrc/train_tc.cu).  Returns (out, pooled, coef, batch_mean, batch_var); coef and the
+    moments are not differentiable (the moments only feed the EMA shadows).  Saves x and z (pre-BN); the backward recomputes y.
 
-    pool_s > 0: the layer is followed by tf.reduce_max over groups of pool_s consecutive rows (the sample axis) and ONLY
-    feeds that pool (detector conv2, descriptor conv_mid); out is then the pooled (rows/pool_s, cout) tensor and in the
-    backward the dense (rows, cout) gradient is never materialised: the BN-backward kernels rebuild it on the fly from
-    the pooled maxima, the pooled gradient and the tie counts.
+    mode "y":      out = the activation (rows, cout).
+    mode "pool":   the layer is followed by tf.reduce_max over groups of pool_s consecutive rows (the sample axis) and ONLY feeds that
+                   pool (detector conv2, descriptor conv_mid): out = pooled (rows/pool_s, cout); in the backward the dense (rows, cout)
+                   gradient is never materialised: it is rebuilt on the fly from the pooled maxima, the pooled gradient and the tie counts.
+    mode "defer":  the activation is not materialised: out = z, standing for y in the autograd graph (see DeferredActivation), and
+                   coef = the BN scale / shift the consumer needs.  With pool_s > 0 `pooled` = max of the activation over the groups is
+                   returned as well (descriptor conv1 feeds the pool and conv_mid); the backward then sums both gradients on the fly.
+    x_coef:        x is itself a deferred activation (the previous layer's z) with this scale / shift and x_relu.
     gbias (rows/gs, cout) or None: a per-group additive term of the pre-BN activation (the pooled half of a
-    concat([x, tile(pooled)]) input, see conv2d_concat_pooled); its gradient is the per-group row sum of dz."""
+    concat([x, tile(pooled)]) input, see conv2d(concat_pooled=)); its gradient is the per-group row sum of dz."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, use_relu, pool_s, gbias, gs):
+    def forward(ctx, x, w, b, gamma, beta, use_relu, pool_s, gbias, gs, mode, x_coef, x_relu):
         ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
-        saved = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision, gbias, gs if gbias is not None else 0, int(pool_s))
-        y, mean, var = saved[5], saved[6], saved[7]
-        ctx.use_relu, ctx.pool_s, ctx.gs = bool(use_relu), int(pool_s), int(gs) if gbias is not None else 0
-        ctx.mark_non_differentiable(mean, var)
-        ctx.save_for_backward(*saved)
-        if pool_s:  # saved = (..., y = None, mean, var, pooled, inv): BN + ReLU + max-pool in one pass, no (rows, cout) activation
-            return saved[8], mean, var
-        return y, mean, var
+        sv = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision, gbias, gs if gbias is not None else 0, int(pool_s),
+                              x_coef=x_coef, x_relu=x_relu, want_y=(mode == "y"), want_coef=(mode == "defer"))
+        ctx.use_relu, ctx.pool_s, ctx.gs, ctx.mode, ctx.x_relu = bool(use_relu), int(pool_s), int(gs) if gbias is not None else 0, mode, bool(x_relu)
+        ctx.keys = [k for k in ("x", "w", "gamma", "beta", "z", "mean", "var", "pooled", "inv", "x_coef") if sv[k] is not None]
+        ctx.save_for_backward(*[sv[k] for k in ctx.keys])
+        mean, var, coef, pooled = sv["mean"], sv["var"], sv["coef"], sv["pooled"]
+        ctx.mark_non_differentiable(*[t for t in (mean, var, coef) if t is not None])
+        if mode == "y":
+            return sv["y"], None, None, mean, var
+        if mode == "pool":
+            return pooled, None, None, mean, var
+        return sv["z"], pooled, coef, mean, var
 
     @staticmethod
-    def backward(ctx, gout, _gm, _gv):
-        if ctx.pool_s:
-            *saved, pooled, inv = ctx.saved_tensors
+    def backward(ctx, gout, gpooled, _gc, _gm, _gv):
+        saved = dict.fromkeys(("x", "w", "gamma", "beta", "z", "mean", "var", "pooled", "inv", "x_coef"))
+        saved.update(zip(ctx.keys, ctx.saved_tensors))
+        if ctx.mode == "pool":
+            gy, gpool = None, gout
         else:
-            saved, pooled, inv = ctx.saved_tensors, None, None
-        dx, dw, db, dg, dbe, dgb = _conv_bn_backward(saved, ctx.use_relu, ctx.precision, gout, ctx.needs_input_grad[0], ctx.pool_s,
-                                                     pooled, inv, ctx.gs)
-        return dx, dw, db, dg, dbe, None, None, dgb, None
+            gy, gpool = gout, (gpooled if ctx.pool_s else None)
+            if gy is None and gpool is None:
+                gy = torch.zeros_like(saved["z"])
+        dx, dw, db, dg, dbe, dgb = _conv_bn_backward(saved, ctx.use_relu, ctx.precision, gy, ctx.needs_input_grad[0], ctx.pool_s, gpool, ctx.gs,
+                                                     ctx.x_relu)
+        return dx, dw, db, dg, dbe, None, None, dgb, None, None, None, None
 
 
 class _MaxPoolSamples(torch.autograd.Function):
@@ -240,7 +288,13 @@ def max_pool_samples(x):
 
 def conv_bn_train(x, w, b, gamma, beta, use_relu=True, pool_s=0, gbias=None, gs=0):
     """(rows,cin) x (cin,cout) -> (out, batch_mean, batch_var): the training-mode layer as one CUDA op (see _ConvBnTrain)."""
-    return _ConvBnTrain.apply(x, w, b, gamma, beta, use_relu, pool_s, gbias, gs)
+    out, _, _, mean, var = _ConvBnTrain.apply(x, w, b, gamma, beta, use_relu, pool_s, gbias, gs, "pool" if pool_s else "y", None, False)
+    return out, mean, var
+
+
+def conv_bn_train_chain(x, w, b, gamma, beta, use_relu=True, pool_s=0, gbias=None, gs=0, mode="y", x_coef=None, x_relu=False):
+    """The layer inside a chain of unmaterialised activations -> (out, pooled, coef, batch_mean, batch_var); see _ConvBnTrain."""
+    return _ConvBnTrain.apply(x, w, b, gamma, beta, use_relu, pool_s, gbias, gs, mode, x_coef, x_relu)
 
 
 def batch_norm_template(inputs, is_training, scope, moments_dims, bn_decay, params, new_stats=None):
@@ -309,15 +363,25 @@ def fully_connected(inputs, num_outputs, scope, use_xavier=True, stddev=1e-3, we
     return outputs
 
 
+def chain_supported():
+    """True when the training layers may leave their activations unmaterialised (DeferredActivation): the tensor-core contractions form
+    them on the fly; the fp32 FFMA path (TRAIN_PRECISION = "fp32") and the op-by-op statement read a stored tensor."""
+    return FUSED_TRAINING and CHAIN_ACTIVATIONS and TRAIN_PRECISION == "bf16x3"
+
+
 def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', activation=relu, bn=True, bn_decay=None,
-           is_training=None, scope=None, reuse=None, params=None, new_stats=None, pool_samples=False, concat_pooled=None):
+           is_training=None, scope=None, reuse=None, params=None, new_stats=None, pool_samples=False, concat_pooled=None,
+           defer=False, also_pool=False):
     """ 2D convolution with non-linear operation (layers.py:11-46): slim.conv2d WITH bias -> BN -> activation.
 
     inputs: (B,H,W,C).  Only the 1x1 / stride-1 kernels the model uses are implemented.
     pool_samples=True additionally applies tf.reduce_max(axis=[2], keep_dims=True) to the result -- the callers that pool
     right after the layer say so here, which lets the training path fuse the pool's gradient into the layer's backward.
     concat_pooled (B,H,1,C2) or None: the layer's input is concat([inputs, tile(concat_pooled, W)], -1) (the reference's
-    feat3dnet.py:60-66); weights are (C+C2, Cout).  The training path never materialises the concatenation."""
+    feat3dnet.py:60-66); weights are (C+C2, Cout).  The training path never materialises the concatenation.
+    Chains (training mode on the GPU, chain_supported()): `inputs` may be a DeferredActivation (the previous layer's output, not
+    materialised); defer=True returns one instead of a tensor -- for the next conv2d of the chain only; also_pool=True (with defer)
+    returns (DeferredActivation, tf.reduce_max(activation, axis=[2], keep_dims=True)) for a layer that feeds the pool and a conv2d."""
     if list(kernel_size) != [1, 1] or list(stride) != [1, 1]:
         raise ValueError("conv2d: only kernel_size=[1,1], stride=[1,1] is supported (all the model uses)")
     if params is None or scope is None:
@@ -326,25 +390,38 @@ def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', acti
     cin_total = inputs.shape[-1] + (concat_pooled.shape[-1] if concat_pooled is not None else 0)
     if w.shape[-1] != num_outputs or w.shape[-2] != cin_total:
         raise ValueError("conv2d: weight shape %s does not match (%d -> %d)" % (tuple(w.shape), cin_total, num_outputs))
-    if (bn and is_training and inputs.is_cuda and FUSED_TRAINING and (activation is relu or activation is None)
-            and num_outputs % 16 == 0 and num_outputs & (num_outputs - 1) == 0):
+    fused = (bn and is_training and inputs.is_cuda and FUSED_TRAINING and (activation is relu or activation is None)
+             and num_outputs % 16 == 0 and num_outputs & (num_outputs - 1) == 0)
+    deferred_in = isinstance(inputs, DeferredActivation)
+    if (deferred_in or defer) and not (fused and chain_supported() and inputs.dim() == 4):
+        raise ValueError("conv2d: deferred activations need the fused tensor-core training path (see chain_supported())")
+    if also_pool and not defer:
+        raise ValueError("conv2d: also_pool comes with defer=True (use pool_samples=True for a layer that only feeds the pool)")
+    if fused:
         # training mode on the GPU: conv + bias + batch-statistics BN + ReLU, forward and backward, in csrc/train_layers.cu
         fuse_pool = pool_samples and inputs.dim() == 4
         w2 = w.reshape(w.shape[-2], w.shape[-1])
-        gbias, gs, x_rows = None, 0, inputs
+        gbias, gs = None, 0
+        x_rows = inputs.z if deferred_in else inputs
         if concat_pooled is not None:
             # input = concat([inputs, tile(concat_pooled)], -1) without building it: the pooled half contributes
             # concat_pooled @ W_bottom once per cluster (the split-weight identity)
             c1 = inputs.shape[-1]
             gbias = torch.matmul(concat_pooled.reshape(-1, concat_pooled.shape[-1]), w2[c1:])
             gs, w2 = inputs.shape[2], w2[:c1]
-        y, mean, var = conv_bn_train(x_rows.reshape(-1, x_rows.shape[-1]), w2, b, params[scope + "/bn/gamma"],
-                                     params[scope + "/bn/beta"], activation is relu, inputs.shape[2] if fuse_pool else 0, gbias, gs)
+        mode = "defer" if defer else "pool" if fuse_pool else "y"
+        pool_s = inputs.shape[2] if (fuse_pool or also_pool) else 0
+        y, pooled, coef, mean, var = conv_bn_train_chain(
+            x_rows.reshape(-1, x_rows.shape[-1]), w2, b, params[scope + "/bn/gamma"], params[scope + "/bn/beta"], activation is relu, pool_s,
+            gbias, gs, mode, inputs.coef if deferred_in else None, inputs.relu if deferred_in else False)
         if new_stats is not None:
             decay = bn_decay if bn_decay is not None else BN_DECAY
             mm, mv = params[scope + "/bn/moving_mean"], params[scope + "/bn/moving_variance"]
             new_stats[scope + "/bn/moving_mean"] = PendingEma(mean.detach(), decay)
             new_stats[scope + "/bn/moving_variance"] = PendingEma(var.detach(), decay)
+        if defer:
+            out = DeferredActivation(y.reshape(*inputs.shape[:-1], num_outputs), coef, activation is relu)
+            return (out, pooled.reshape(inputs.shape[0], inputs.shape[1], 1, num_outputs)) if also_pool else out
         if fuse_pool:
             return y.reshape(inputs.shape[0], inputs.shape[1], 1, num_outputs)
         y = y.reshape(*inputs.shape[:-1], num_outputs)

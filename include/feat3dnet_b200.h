@@ -215,6 +215,26 @@ int f3d_conv_bn_train_backward(long long rows, int cin, int cout, const float *x
                                float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s, int precision,
                                void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same layer inside a CHAIN of conv2d layers (the per-point MLPs of feat3dnet.py:43-47,119-123: conv0 -> conv1 -> conv2) whose
+ * intermediate activations are never written to HBM.
+ *   x_coef != NULL: x is the PREVIOUS layer's pre-BN tensor z and x_coef [2][cin] its BN scale / shift (that layer's coef_out); the input
+ *   rows [relu](x * scale + shift) are formed inside the contractions with the forward's exact roundings (tensor-core path, cin % 8 == 0,
+ *   cin <= 128 for the weight gradient).
+ *   Forward results, any subset (at least one): y (rows, cout); pool_s > 0: pooled / inv_ties (rows / pool_s, cout); coef_out [2][cout].
+ *   Backward gradients: gy (dense, rows x cout; NULL = none) and / or the pooled set (pool_s, pooled, gpool = gradient of the pooled
+ *   tensor, inv_ties).  With both, the activation fed the pool and a dense consumer (descriptor conv1, feat3dnet.py:47,60-66) and the two
+ *   gradients are summed on the fly: neither a max-pool backward pass nor an add over (rows, cout) is run.
+ * Results carry the same bits as the unchained calls on a materialised activation. */
+int f3d_conv_bn_train_forward_chain(long long rows, int cin, int cout, const float *x, const float *x_coef, int x_relu, const float *W,
+                                    const float *bias, const float *group_bias, int group_s, const float *gamma, const float *beta, int relu,
+                                    float eps, float *z, float *y, int pool_s, float *pooled, float *inv_ties, float *coef_out, float *mean,
+                                    float *var, int precision, void *workspace, size_t workspace_bytes, void *stream);
+int f3d_conv_bn_train_backward_chain(long long rows, int cin, int cout, const float *x, const float *x_coef, int x_relu, const float *W,
+                                     const float *gamma, const float *beta, const float *z, const float *mean, const float *var, int relu,
+                                     float eps, const float *gy, int pool_s, const float *pooled, const float *gpool, const float *inv_ties,
+                                     float *dx, float *dW, float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s,
+                                     int precision, void *workspace, size_t workspace_bytes, void *stream);
+
 /* tf.reduce_max(new_points, axis=[2])  models/feat3dnet.py:138,147,182 on a channels-last (groups, s, c) tensor
  * (c % 4 == 0) -> out (groups, c) and inv_ties (groups, c; NULL = not wanted) = 1 / (number of samples attaining the
  * maximum); and its gradient: samples attaining the maximum share gout equally (TF _MinOrMaxGrad). */

@@ -317,6 +317,43 @@ def test_pool_only_layer_dz_formed_inside_the_contractions(cuda, cin, cout, use_
             assert torch.equal(a, b), name
 
 
+@pytest.mark.parametrize("B,N,M,fdim", [(2, 2048, 77, 32), (3, 4096, 128, 128)])
+def test_chained_layers_carry_the_bits_of_the_materialised_path(cuda, B, N, M, fdim):
+    """The per-point MLP chains (detector conv0 -> conv1 -> conv2, descriptor conv0 -> conv1 -> conv_mid) with their intermediate
+    activations left unmaterialised (layers.DeferredActivation: the consumers form relu(z * scale + shift) in their operand converters,
+    the layer that feeds the pool and conv_mid sums its two gradients on the fly) against the same step with every activation written
+    by bn_apply and read back: same arithmetic, so the loss, the gradient of all trainable variables and the BN moments carry the SAME
+    BITS -- while the chained step launches fewer kernels (no bn_apply of the four chained layers, no max-pool forward / backward,
+    no gradient add)."""
+    f3, layers, synth, lib_mod = pkg("models.feat3dnet"), pkg("models.layers"), pkg("synth"), pkg("_lib")
+    a, p, n = (torch.as_tensor(synth.make_batch(B, N, seed0=s)).to(cuda) for s in (31, 32, 33))
+    params = onet.init_params(seed=4, randomize_bn=True, feature_dim=fdim)
+    L = lib_mod.lib()
+
+    def run(chain):
+        layers.CHAIN_ACTIVATIONS = chain
+        try:
+            net = f3.Feat3dNet({'num_clusters': M, 'feature_dim': fdim}, weights=params, device=cuda).train_mode()
+            torch.cuda.synchronize()
+            L.f3d_reset_launch_count()
+            xyz, feats, att, ep = net.get_train_model(a, p, n, True)
+            loss, ep = net.get_loss(xyz, feats, att, ep)
+            flat = net.get_train_op(loss, lr=1e-5, end_points=ep)
+            torch.cuda.synchronize()
+            launches = L.f3d_launch_count()
+            stats = {k: v.stat.clone() for k, v in ep['bn_updates'].items()}
+            return loss.detach().item(), flat.detach().clone(), stats, launches
+        finally:
+            layers.CHAIN_ACTIVATIONS = True
+
+    l1, g1, s1, n1 = run(True)
+    l0, g0, s0, n0 = run(False)
+    assert l1 == l0
+    assert torch.equal(g1, g0)
+    assert s1.keys() == s0.keys() and all(torch.equal(s1[k], s0[k]) for k in s1)
+    assert n1 < n0, (n1, n0)
+
+
 def test_c4_training_step_fused_vs_torch_layers_and_deterministic(cuda):
     """BASELINE configs[3] size (6 triplets x 4096 points, 512 clusters x 64 samples): the CUDA training layers against the
     op-by-op torch fp32 statement of the same graph (loss, gradient direction), and bit-reproducibility of the CUDA path."""
