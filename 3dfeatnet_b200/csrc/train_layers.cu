@@ -220,7 +220,9 @@ __device__ __forceinline__ float4 load_grad(const GradSource &G, PoolCache &C, c
 }
 
 // per row-chunk partial sums of g and g*zhat, g = gy * [y > 0] (ReLU) or gy.  part[(blk*2+{0,1})*c + ch]
-__global__ void __launch_bounds__(256)
+// POOL = false: dense gradient only (G.s == 0), no group bookkeeping in registers.
+template <bool POOL>
+__global__ void __launch_bounds__(256, 4)  // 592 blocks = one wave at 4 blocks per SM: keep the kernel at 64 registers
 bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ gamma, const float *__restrict__ beta,
                      const float *__restrict__ z, const float *__restrict__ mean, const float *__restrict__ var, int relu,
                      float *__restrict__ part) {
@@ -242,16 +244,21 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
     PoolCache pc;
     if (rlane < rl) {
         GroupCursor gc;
-        gc.init(rbeg + rlane, G.s);
-        for (long long r = rbeg + rlane; r < rend; r += rl, gc.advance(rl, G.s)) {
+        if (POOL) gc.init(rbeg + rlane, G.s);
+        for (long long r = rbeg + rlane; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
             // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
             float4 yy = make_float4(__fmaf_rn(zz.x, bsc.x, bsh.x), __fmaf_rn(zz.y, bsc.y, bsh.y), __fmaf_rn(zz.z, bsc.z, bsh.z), __fmaf_rn(zz.w, bsc.w, bsh.w));
             if (relu) yy = make_float4(fmaxf(yy.x, 0.f), fmaxf(yy.y, 0.f), fmaxf(yy.z, 0.f), fmaxf(yy.w, 0.f));
-            const float *gdn = dense_grad(G);
-            const float4 gd = gdn ? __ldg(reinterpret_cast<const float4 *>(gdn) + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 g = load_grad(G, pc, gd, gc.grp, cv, cvec, yy);
+            float4 g;
+            if (POOL) {
+                const float4 gd = G.dense2 ? __ldg(reinterpret_cast<const float4 *>(G.dense2) + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                g = load_grad(G, pc, gd, gc.grp, cv, cvec, yy);
+                gc.advance(rl, G.s);
+            } else {
+                g = __ldg(reinterpret_cast<const float4 *>(G.gy) + o);
+            }
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
@@ -350,6 +357,7 @@ __global__ void bn_bwd_finalize_kernel(int c, double inv_rows, float eps, const 
 }
 
 // dz = s (g - k1 - zhat k2) and, per row chunk, the column sums of dz (= the bias gradient): partB[blk*c + ch]
+template <bool POOL>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ z,
@@ -381,15 +389,15 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         long long r = rbeg + rlane;
         float4 zz_n = zero4, gd_n = zero4;
-        const float *gdn = dense_grad(G);
+        const float *gdn = POOL ? G.dense2 : G.gy;
         GroupCursor gc;
-        gc.init(r, G.s);
+        if (POOL) gc.init(r, G.s);
         if (r < rend) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             zz_n = __ldg(reinterpret_cast<const float4 *>(z) + o);
             if (gdn) gd_n = __ldg(reinterpret_cast<const float4 *>(gdn) + o);
         }
-        for (; r < rend; r += rl, gc.advance(rl, G.s)) {
+        for (; r < rend; r += rl) {
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = zz_n, gd = gd_n;
             if (r + rl < rend) {
@@ -400,7 +408,11 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
             // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
             float4 yy = make_float4(__fmaf_rn(zz.x, bsc.x, bsh.x), __fmaf_rn(zz.y, bsc.y, bsh.y), __fmaf_rn(zz.z, bsc.z, bsh.z), __fmaf_rn(zz.w, bsc.w, bsh.w));
             if (relu) yy = make_float4(fmaxf(yy.x, 0.f), fmaxf(yy.y, 0.f), fmaxf(yy.z, 0.f), fmaxf(yy.w, 0.f));
-            float4 g = load_grad(G, pc, gd, gc.grp, cv, cvec, yy);
+            float4 g = gd;
+            if (POOL) {
+                g = load_grad(G, pc, gd, gc.grp, cv, cvec, yy);
+                gc.advance(rl, G.s);
+            }
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
@@ -930,7 +942,10 @@ static int conv_bn_backward_impl(long long rows, int cin, int cout, const float 
         rc = check_launch("bn_bwd_reduce_pooled_kernel");
     } else {
         ktimer_begin("bn_bwd_reduce_kernel", 8.0 * static_cast<double>(rows) * cout, st);  // gy and z in
-        bn_bwd_reduce_kernel<<<nred, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, relu, part);
+        if (pool_s > 0)
+            bn_bwd_reduce_kernel<true><<<nred, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, relu, part);
+        else
+            bn_bwd_reduce_kernel<false><<<nred, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, relu, part);
         ktimer_end(st);
         rc = check_launch("bn_bwd_reduce_kernel");
     }
@@ -962,7 +977,10 @@ static int conv_bn_backward_impl(long long rows, int cin, int cout, const float 
     const int napp = static_cast<int>(rows < kApplyBlocks ? rows : kApplyBlocks);
     // gy (dense mode only) and z in, dz out
     ktimer_begin("bn_bwd_apply_kernel", (pool_s > 0 && !mixed ? 8.0 : 12.0) * static_cast<double>(rows) * cout, st);
-    bn_bwd_apply_kernel<<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
+    if (pool_s > 0)
+        bn_bwd_apply_kernel<true><<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
+    else
+        bn_bwd_apply_kernel<false><<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     ktimer_end(st);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;

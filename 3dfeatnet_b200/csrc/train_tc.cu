@@ -79,6 +79,40 @@ __global__ void lin_prep_kernel(const float *__restrict__ src, long long sm, lon
 // engine (bulk copies of up to 16 KB into a ring, kRing tiles ahead, mbarrier completion) so the loads of the next tiles
 // are in flight during the conversion / MMA / epilogue of the current one; the conversion reads the ring with
 // conflict-free LDS.128 and writes the bf16 hi/lo operand image (chunk stride padded by 32 B against bank conflicts).
+// Measurement aid (f3d_debug_set_lin_tc_phases): phases of the lin_tc kernels that are SKIPPED -- bit 0 the operand conversion, bit 1 the
+// MMAs, bit 2 the epilogue's global stores, bit 3 the TMA fetches.  Results are garbage with any bit set; the pipeline still runs.
+__device__ int g_lin_dbg = 0;
+
+// Epilogue of the lin_tc kernels: the N accumulator values of this thread's channel (rows r .. r + N - 1 of the tile) + bias -> global
+// memory (row stride nout), optionally with the BN statistics.  Instruction count matters here (the epilogue warps are issue-bound):
+// one pointer bump per row instead of a 64-bit row * nout product, no per-row bounds test on full tiles.
+template <int N, bool STATS>
+__device__ __forceinline__ void store_channel_rows(float *__restrict__ o, int nout, int nvalid, const uint32_t (&r)[N], float bb, float &s1, float &s2) {
+    if (nvalid >= N) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float v = __uint_as_float(r[j]) + bb;
+            *o = v;
+            o += nout;
+            if (STATS) { s1 += v; s2 = fmaf(v, v, s2); }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (j < nvalid) {
+                const float v = __uint_as_float(r[j]) + bb;
+                *o = v;
+                o += nout;
+                if (STATS) { s1 += v; s2 = fmaf(v, v, s2); }
+            }
+        }
+    }
+}
+
+// Measurement aid (f3d_debug_lin_tc_trace): clock64() stamps of CTA (0, 0) of lin_tc_kernel, 16 slots per tile for threads 0 and 255
+__device__ long long *g_lin_trace = nullptr;
+constexpr int kTraceTiles = 64;
+
 constexpr int kRingMax = 2;  // ring depth (1 when shared memory cannot hold two stages next to a 3-split operand image)
 
 template <int nsplit>
@@ -106,6 +140,10 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
     const uint32_t sbase = smem_u32(smem);
     const int mb = blockIdx.x;
     const long long cta = blockIdx.y, ncta = gridDim.y;
+    const int dbg = g_lin_dbg;
+    long long *tr = nullptr;
+    if (g_lin_trace && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 0 || threadIdx.x == 255)) tr = g_lin_trace + (threadIdx.x ? kTraceTiles * 16 : 0);
+#define F3D_LT(i) if (tr && it < kTraceTiles) tr[it * 16 + (i)] = clock64();
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
@@ -155,7 +193,9 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
         const long long r0 = tile * kTile;
         const uint32_t valid = static_cast<uint32_t>(rows - r0 < kTile ? rows - r0 : kTile);
         const uint32_t bytes = valid * static_cast<uint32_t>(k_real) * 4;  // the tile's rows are one contiguous block
-        if (lane == 0) {
+        if (lane == 0 && (dbg & 8)) {
+            mbar_arrive_expect_tx(bar_full + s, 0);
+        } else if (lane == 0) {
             mbar_arrive_expect_tx(bar_full + s, bytes);
             const uint8_t *src = reinterpret_cast<const uint8_t *>(x + r0 * k_real);
             for (uint32_t off = 0; off < bytes; off += 16384) {
@@ -179,13 +219,15 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
     for (long long tile = cta; tile < ntiles; tile += ncta, ++it) {
         const long long r0 = tile * kTile;
         const int stage = static_cast<int>(it % kRing);
+        F3D_LT(0)
         if (ring) {
             mbar_wait(bar_full + stage, static_cast<uint32_t>((it / kRing) & 1));
+            F3D_LT(1)
             // lane -> (row within a group of 4, chunk c mod 4, 16-byte half of the chunk): a quarter-warp reads 128 contiguous
             // bytes of one row, a half-warp writes 16 distinct 8-byte slots of the operand image (no bank conflicts)
             const int rsub = lane >> 3, c4 = (lane >> 1) & 3, h = lane & 1;
             const uint32_t row_bytes = static_cast<uint32_t>(k_real) * 4;
-            for (int c = c4; c < kp / 8; c += 4) {
+            for (int c = c4; c < ((dbg & 1) ? 0 : kp / 8); c += 4) {
                 // X.coef: the rows in the ring are the previous layer's z; its BN + ReLU is applied here (XSource, dz_source.cuh)
                 float4 xsc = make_float4(1.f, 1.f, 1.f, 1.f), xsh = make_float4(0.f, 0.f, 0.f, 0.f);
                 const bool chok = c * 8 + h * 4 < k_real;
@@ -236,8 +278,10 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
                 }
             }
         }
+        F3D_LT(2)
         fence_proxy_async_smem();
         __syncthreads();  // operand image complete; ring stage `stage` fully read
+        F3D_LT(3)
         if (warp == 0) {
             tcgen05_fence_after();
             if (elect_one()) {
@@ -247,7 +291,7 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
                 constexpr int nterms = nsplit == 3 ? 6 : 3;
                 uint32_t acc = 0;
 #pragma unroll
-                for (int term = 0; term < nterms; ++term) {
+                for (int term = 0; term < ((dbg & 2) ? 0 : nterms); ++term) {
                     const int ws = term == 2 ? 1 : term == 4 ? 2 : term == 5 ? 1 : 0;
                     const int xs = term == 1 ? 1 : term == 3 ? 2 : term == 5 ? 1 : 0;
                     const uint32_t wa = tmem_base + ws * (kp / 2);
@@ -262,12 +306,15 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
             __syncwarp();
             if (ring && tile + kRing * ncta < ntiles) fetch(tile + kRing * ncta, stage);  // refill the stage just consumed
         }
+        F3D_LT(4)
         mbar_wait(bar_m, mpar);
         mpar ^= 1;
         tcgen05_fence_after();
+        F3D_LT(5)
         uint32_t r[32];
         tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0, r);
         tmem_ld_wait();
+        F3D_LT(6)
         if (ch_ok) {
             if (gbias) {
                 // optional per-group additive term (rows of a group of gs consecutive rows share it): the pooled half of a
@@ -288,19 +335,19 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
                 }
             }
             float *o = out + (r0 + col0) * nout + gch;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (r0 + col0 + j < rows) {
-                    const float v = __uint_as_float(r[j]) + bb;
-                    o[static_cast<size_t>(j) * nout] = v;
-                    s1 += v;
-                    s2 = fmaf(v, v, s2);
-                }
-            }
+            const long long left = rows - (r0 + col0);
+            const int nvalid = (dbg & 4) ? 0 : left < 32 ? static_cast<int>(left) : 32;
+            if (part)
+                store_channel_rows<32, true>(o, nout, nvalid, r, bb, s1, s2);
+            else
+                store_channel_rows<32, false>(o, nout, nvalid, r, bb, s1, s2);
         }
+        F3D_LT(7)
         tcgen05_fence_before();
         __syncthreads();  // the operand image and the accumulator are reused by the next tile
+        F3D_LT(8)
     }
+#undef F3D_LT
     if (part && ch_ok) {
         float *p = part + (static_cast<size_t>(cta) * 2 + half) * 2 * nout;
         p[gch] = s1;
@@ -313,12 +360,15 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // lin_tc_pipe_kernel: the same contraction as lin_tc_kernel with the three phases of a tile running CONCURRENTLY on
-// different warps (k_real % 8 == 0): warp 0 issues the TMA fetches (ring, up to 3 tiles ahead) and the MMAs, warps 1-4
-// convert ring slot -> operand image (double-buffered), warps 5-8 drain the accumulator (double-buffered in TMEM) to
-// global memory and keep the BN statistics.  mbarriers: ring_full (TMA bytes), img_full (4 converter warps), mma_done
-// (tcgen05.commit: frees the image AND publishes the accumulator), d_free (4 epilogue warps).
+// different warps (k_real % 8 == 0): warp 0 issues the TMA fetches (ring, up to 3 tiles ahead) and the MMAs, warps 1-8
+// convert ring slot -> operand image (double-buffered), warps 9-16 drain the accumulator (double-buffered in TMEM) to
+// global memory and keep the BN statistics.  mbarriers: ring_full (TMA bytes), img_full (the converter warps), mma_done
+// (tcgen05.commit: frees the image AND publishes the accumulator), d_free (the epilogue warps).  Converters and epilogue are
+// latency / issue-bound per warp (measured with tools/lin_tc_phases.py), hence eight warps each.
 namespace lp {
-constexpr int kThreads = 288;
+constexpr int kConvWarps = 8;  // converter warps (rows of a tile split among them)
+constexpr int kEpiWarps = 8;   // epilogue warps: two per TMEM lane quarter, each draining half of the tile's rows
+constexpr int kThreads = 32 * (1 + kConvWarps + kEpiWarps);
 constexpr int kMaxRing = 3;
 __host__ __device__ constexpr uint32_t lbo(int nsplit, int nt) { return static_cast<uint32_t>(nt) * 16 + (nsplit == 3 ? 16 : 32); }
 }  // namespace lp
@@ -354,15 +404,16 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
     const uint32_t sbase = smem_u32(smem);
     const int mb = blockIdx.x;
     const long long cta = blockIdx.y, ncta = gridDim.y;
+    const int dbg = g_lin_dbg;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_wm, 1);
         for (int i = 0; i < lp::kMaxRing; ++i) mbar_init(ring_full + i, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(img_full + i, 4);
+            mbar_init(img_full + i, lp::kConvWarps);
             mbar_init(mma_done + i, 1);
-            mbar_init(d_free + i, 4);
+            mbar_init(d_free + i, lp::kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -412,7 +463,9 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
             const long long r0 = tile * NT;
             const uint32_t valid = static_cast<uint32_t>(rows - r0 < NT ? rows - r0 : NT);
             const uint32_t bytes = valid * static_cast<uint32_t>(k_real) * 4;
-            if (lane == 0) {
+            if (lane == 0 && (dbg & 8)) {
+                mbar_arrive_expect_tx(ring_full + slot, 0);
+            } else if (lane == 0) {
                 mbar_arrive_expect_tx(ring_full + slot, bytes + pool_bytes);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>((FUSED ? S.z : x) + r0 * k_real);
                 for (uint32_t off = 0; off < bytes; off += 16384)
@@ -443,7 +496,7 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                 const uint32_t d = tmem_d + b * NT;
                 uint32_t acc = 0;
 #pragma unroll
-                for (int term = 0; term < nterms; ++term) {
+                for (int term = 0; term < ((dbg & 2) ? 0 : nterms); ++term) {
                     const int ws = term == 2 ? 1 : term == 4 ? 2 : term == 5 ? 1 : 0;
                     const int xs = term == 1 ? 1 : term == 3 ? 2 : term == 5 ? 1 : 0;
                     const uint32_t wa = tmem_base + ws * (kp / 2);
@@ -457,8 +510,10 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
             }
             __syncwarp();
         }
-    } else if (warp <= 4) {
+    } else if (warp <= lp::kConvWarps) {
         // ------------------------------------------------------------------ converters: ring slot -> operand image
+        constexpr int kRowsPass = lp::kConvWarps * 4;  // rows converted per pass of the converter warps
+        static_assert(NT % kRowsPass == 0, "tile rows must be a multiple of the converters' rows per pass");
         const int wc = warp - 1;
         const int rsub = lane >> 3, c4 = (lane >> 1) & 3, h = lane & 1;
         const uint32_t row_bytes = static_cast<uint32_t>(k_real) * 4;
@@ -469,7 +524,8 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
             mbar_wait(ring_full + slot, static_cast<uint32_t>((it / nring) & 1));
             if (it >= 2) mbar_wait(mma_done + b, static_cast<uint32_t>(((it >> 1) - 1) & 1));  // MMAs of tile it-2 have read image b
             uint8_t *img = smem + b * img_bytes;
-            if constexpr (!FUSED) {
+            if (dbg & 1) {
+            } else if constexpr (!FUSED) {
                 for (int c = c4; c < kp / 8; c += 4) {
                     // X.coef: the rows in the ring are the previous layer's z; its BN + ReLU is applied here (XSource, dz_source.cuh)
                     float4 xsc = make_float4(1.f, 1.f, 1.f, 1.f), xsh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -479,8 +535,8 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                         xsh = __ldg(reinterpret_cast<const float4 *>(X.coef + k_real + c * 8 + h * 4));
                     }
 #pragma unroll
-                    for (int p = 0; p < NT / 16; ++p) {
-                        const int r = p * 16 + wc * 4 + rsub;
+                    for (int p = 0; p < NT / kRowsPass; ++p) {
+                        const int r = p * kRowsPass + wc * 4 + rsub;
                         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (r0 + r < rows && chok) {
                             a = *reinterpret_cast<const float4 *>(ringbuf + slot * slot_bytes + r * row_bytes + h * 16 + c * 32);
@@ -496,7 +552,7 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                     }
                 }
             } else {
-                // channel chunk outside, rows inside: the ten coefficient quads of a chunk are loaded once per NT / 16 rows
+                // channel chunk outside, rows inside: the ten coefficient quads of a chunk are loaded once per NT / kRowsPass rows
                 const float *pool = reinterpret_cast<const float *>(ringbuf + slot * slot_bytes + NT * row_bytes);
                 for (int c = c4; c < kp / 8; c += 4) {
                     const int ch = c * 8 + h * 4;
@@ -509,8 +565,8 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                     const float4 gsc = make_float4(__fmul_rn(gp.x, iv.x), __fmul_rn(gp.y, iv.y), __fmul_rn(gp.z, iv.z), __fmul_rn(gp.w, iv.w));
                     float4 acc = z4;
 #pragma unroll
-                    for (int p = 0; p < NT / 16; ++p) {
-                        const int r = p * 16 + wc * 4 + rsub;
+                    for (int p = 0; p < NT / kRowsPass; ++p) {
+                        const int r = p * kRowsPass + wc * 4 + rsub;
                         float4 a = z4;
                         if (r0 + r < rows && chok) {
                             const float4 zz = *reinterpret_cast<const float4 *>(ringbuf + slot * slot_bytes + r * row_bytes + h * 16 + c * 32);
@@ -528,7 +584,7 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                             a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
                         }
                     }
-                    if (dgb) {  // column sums of the tile (= one group): over the 4 row lanes of the warp here, over the 4 warps below
+                    if (dgb) {  // column sums of the tile (= one group): over the 4 row lanes of the warp here, over the converter warps below
 #pragma unroll
                         for (int m = 8; m <= 16; m <<= 1) {
                             acc.x += __shfl_xor_sync(kFull, acc.x, m); acc.y += __shfl_xor_sync(kFull, acc.y, m);
@@ -542,16 +598,19 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
             __syncwarp();
             if (lane == 0) mbar_arrive(img_full + b);
             if (FUSED && dgb) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // the four converter warps
+                static_assert(lp::kConvWarps == 8, "the fixed-order sum below is written for eight converter warps");
+                asm volatile("bar.sync 1, %0;" ::"n"(lp::kConvWarps * 32) : "memory");  // the converter warps
                 float *dst = dgb + static_cast<size_t>(r0 / S.gs) * k_real;
-                for (int ch = wc * 32 + lane; ch < k_real; ch += 128)
-                    dst[ch] = (gred[ch] + gred[k_real + ch]) + (gred[2 * k_real + ch] + gred[3 * k_real + ch]);
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // gred is rewritten by the next tile
+                for (int ch = wc * 32 + lane; ch < k_real; ch += lp::kConvWarps * 32)
+                    dst[ch] = ((gred[ch] + gred[k_real + ch]) + (gred[2 * k_real + ch] + gred[3 * k_real + ch])) +
+                              ((gred[4 * k_real + ch] + gred[5 * k_real + ch]) + (gred[6 * k_real + ch] + gred[7 * k_real + ch]));
+                asm volatile("bar.sync 1, %0;" ::"n"(lp::kConvWarps * 32) : "memory");  // gred is rewritten by the next tile
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue: accumulator -> global, BN statistics
-        const int q = warp & 3;
+        constexpr int NH = NT / 2;  // rows (accumulator columns) per epilogue warp: the two warps of a lane quarter split the tile
+        const int q = warp & 3, half = (warp - 1 - lp::kConvWarps) >> 2;
         const int ch = q * 32 + lane;
         const int gch = mb * 128 + ch;
         const bool ch_ok = gch < nout;
@@ -560,33 +619,30 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
         long long it = 0;
         for (long long tile = cta; tile < ntiles; tile += ncta, ++it) {
             const int b = static_cast<int>(it & 1);
-            const long long r0 = tile * NT;
+            const long long r0 = tile * NT + half * NH;
             mbar_wait(mma_done + b, static_cast<uint32_t>((it >> 1) & 1));
             tcgen05_fence_after();
-            uint32_t r[NT];
-#pragma unroll
-            for (int hh = 0; hh < NT / 32; ++hh) {
-                uint32_t t[32];
-                tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + b * NT + hh * 32, t);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[hh * 32 + j] = t[j];
-            }
+            uint32_t r[NH];
+            if constexpr (NH == 32)
+                tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + b * NT + half * NH, r);
+            else
+                tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + b * NT + half * NH, r);
+            tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d_free + b);
-            if (ch_ok) {
+            if (ch_ok && r0 < rows) {
                 if (gbias) {
                     const long long g0 = r0 / gs;
                     const int rem0 = static_cast<int>(r0 - g0 * gs);
                     const long long gmax = (rows - 1) / gs;
-                    if (rem0 + NT - 1 < gs) {
+                    if (rem0 + NH - 1 < gs) {
                         const float gb = __ldg(gbias + g0 * nout + gch);
 #pragma unroll
-                        for (int j = 0; j < NT; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + gb);
+                        for (int j = 0; j < NH; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + gb);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < NT; ++j) {
+                        for (int j = 0; j < NH; ++j) {
                             long long grp = g0 + (rem0 + j) / gs;
                             grp = grp < gmax ? grp : gmax;
                             r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(gbias + grp * nout + gch));
@@ -594,23 +650,18 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                     }
                 }
                 float *o = out + r0 * nout + gch;
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    if (r0 + j < rows) {
-                        const float v = __uint_as_float(r[j]) + bb;
-                        o[static_cast<size_t>(j) * nout] = v;
-                        s1 += v;
-                        s2 = fmaf(v, v, s2);
-                    }
-                }
+                const long long left = rows - r0;
+                const int nvalid = (dbg & 4) ? 0 : left < NH ? static_cast<int>(left) : NH;
+                if (part)
+                    store_channel_rows<NH, true>(o, nout, nvalid, r, bb, s1, s2);
+                else
+                    store_channel_rows<NH, false>(o, nout, nvalid, r, bb, s1, s2);
             }
         }
-        if (part && ch_ok) {  // two partial slots per CTA like lin_tc_kernel: this thread owns all rows, the second slot is zero
-            float *p = part + static_cast<size_t>(cta) * 2 * 2 * nout;
+        if (part && ch_ok) {  // two partial slots per CTA like lin_tc_kernel: one per half of the tiles' rows
+            float *p = part + (static_cast<size_t>(cta) * 2 + half) * 2 * nout;
             p[gch] = s1;
             p[nout + gch] = s2;
-            p[2 * nout + gch] = 0.0f;
-            p[3 * nout + gch] = 0.0f;
         }
     }
     tcgen05_fence_before();
@@ -921,7 +972,7 @@ static LinPlan lin_tc_plan(long long rows, int k_real, int nsplit, bool fused = 
     LinPlan P{};
     const int kp = lin_tc_kp(k_real);
     // fused dz source: three pooled rows ride in every ring slot, the coefficient table and the group-sum scratch follow the barriers
-    const size_t slot_extra = fused ? static_cast<size_t>(3) * k_real * 4 : 0, tail_extra = fused ? static_cast<size_t>(kDzCoefs + 4) * k_real * 4 : 0;
+    const size_t slot_extra = fused ? static_cast<size_t>(3) * k_real * 4 : 0, tail_extra = fused ? static_cast<size_t>(kDzCoefs + lp::kConvWarps) * k_real * 4 : 0;
     // the warp-specialised kernel pays off when the operand conversion + MMAs are the long phases (K >= 128); for narrow
     // inputs the tile is store-bound and the all-warps epilogue of lin_tc_kernel at 3-4 CTAs/SM is faster (measured)
     if (k_real % 8 == 0 && kp >= 128) {
@@ -1078,6 +1129,25 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
 }
 
 }  // namespace f3d
+
+// Measurement aids: which phases of the lin_tc kernels run (see g_lin_dbg; 0 = all), and the contraction alone:
+// out (rows, nout) = x (rows, k) * A^T with A[m][k] = W[m * k + kk]; wimg: f3d_debug_lin_tc_weight_bytes(k, nout) of scratch.
+F3D_API int f3d_debug_set_lin_tc_phases(int skip_mask) {
+    const cudaError_t e = cudaMemcpyToSymbol(f3d::g_lin_dbg, &skip_mask, sizeof(int));
+    return e == cudaSuccess ? 0 : f3d::fail(static_cast<int>(e), "debug_set_lin_tc_phases");
+}
+// buf: device memory of 2 * 64 * 16 long long (threads 0 and 255 of CTA (0,0) of lin_tc_kernel: 16 clock64() slots per tile), NULL = off
+F3D_API int f3d_debug_lin_tc_trace(void *buf) {
+    const cudaError_t e = cudaMemcpyToSymbol(f3d::g_lin_trace, &buf, sizeof(void *));
+    return e == cudaSuccess ? 0 : f3d::fail(static_cast<int>(e), "debug_lin_tc_trace");
+}
+F3D_API size_t f3d_debug_lin_tc_weight_bytes(int k, int nout) { return f3d::lin_tc_weight_bytes(k, nout); }
+F3D_API int f3d_debug_lin_tc(long long rows, int k, int nout, const float *x, const float *W, float *out, float *part, void *wimg, int nsplit,
+                             void *stream) {
+    if (!f3d::lin_tc_supported(k, nout) || (nsplit != 2 && nsplit != 3)) return f3d::fail(F3D_ERR_UNSUPPORTED, "debug_lin_tc: unsupported shape");
+    return f3d::lin_tc(rows, k, nout, x, W, k, 1, nullptr, nullptr, 0, out, part, static_cast<uint8_t *>(wimg), nsplit, f3d::as_stream(stream), nullptr,
+                       nullptr, nullptr, 0);
+}
 
 // Bring-up / micro-benchmark entry: the wgrad contraction alone.  dbg bit 0 skips the operand staging, bit 1 the MMAs.
 F3D_API int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, int dbg, void *stream) {

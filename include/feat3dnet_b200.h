@@ -313,6 +313,15 @@ int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const 
 /* Test / measurement aid: 0 = pool-only training layers materialise dz (bn_bwd_apply) for wgrad and dgrad, 1 (default) = dz is formed
  * inside the two contractions from z and the pooled tensors.  Both paths give the same dW / dx bits.  Returns the previous value. */
 int f3d_debug_set_fuse_dz(int on);
+/* Measurement aids: skip phases of the lin_tc kernels (bit 0 operand conversion, 1 MMAs, 2 epilogue stores, 3 TMA fetches; 0 = run all;
+ * results are garbage with a bit set), and the contraction alone: out (rows, nout) = x (rows, k) W^T, W (nout, k) row-major, nsplit 2 | 3,
+ * part = NULL or 2 * 2 * nout floats per row CTA of column-sum partials, wimg = f3d_debug_lin_tc_weight_bytes(k, nout) of scratch. */
+int f3d_debug_set_lin_tc_phases(int skip_mask);
+/* buf: device memory of 2 * 64 * 16 long long receiving clock64() stamps of threads 0 and 255 of CTA (0,0) of lin_tc_kernel (16 slots per
+ * tile, first 64 tiles); NULL switches the trace off. */
+int f3d_debug_lin_tc_trace(void *buf);
+size_t f3d_debug_lin_tc_weight_bytes(int k, int nout);
+int f3d_debug_lin_tc(long long rows, int k, int nout, const float *x, const float *W, float *out, float *part, void *wimg, int nsplit, void *stream);
 size_t f3d_detector_tc_weight_bytes(void);
 /* Measurement aid: `groups` x `per_group` back-to-back tcgen05.mma of shape (128 * cta_group) x N x 16 (A from tensor memory, B a
  * zero-filled bf16 no-swizzle image in shared memory, K- or MN-major), one commit per group, on `ctas` CTAs at once (cta_group 2:
