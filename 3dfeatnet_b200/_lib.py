@@ -50,6 +50,8 @@ SIGNATURES = {
     "f3d_descriptor_forward": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "f3d_nms_workspace_bytes": (_sz, [_i, _i]),
     "f3d_nms": (_i, [_i, _i, _vp, _vp, _c.c_double, _c.c_double, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "f3d_group_local_frames": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp, _vp, _vp]),
+    "f3d_group_local_frames_angle_grad": (_i, [_i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "f3d_conv_bn_train_workspace_bytes": (_sz, [_c.c_longlong, _i, _i]),
     "f3d_conv_bn_train_forward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _vp, _sz,
                                        _vp]),

@@ -422,7 +422,7 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
             d.y = __fmul_rn(s.y, __fsub_rn(__fsub_rn(g.y, k1.y), __fmul_rn(__fmul_rn(__fsub_rn(zz.y, mu.y), is.y), k2.y)));
             d.z = __fmul_rn(s.z, __fsub_rn(__fsub_rn(g.z, k1.z), __fmul_rn(__fmul_rn(__fsub_rn(zz.z, mu.z), is.z), k2.z)));
             d.w = __fmul_rn(s.w, __fsub_rn(__fsub_rn(g.w, k1.w), __fmul_rn(__fmul_rn(__fsub_rn(zz.w, mu.w), is.w), k2.w)));
-            reinterpret_cast<float4 *>(dz)[o] = d;
+            if (dz) reinterpret_cast<float4 *>(dz)[o] = d;
             sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
             if (x3) {
                 const float x0 = __ldg(x3 + r * 3), x1 = __ldg(x3 + r * 3 + 1), x2 = __ldg(x3 + r * 3 + 2);
@@ -976,11 +976,14 @@ static int conv_bn_backward_impl(long long rows, int cin, int cout, const float 
     }
     const int napp = static_cast<int>(rows < kApplyBlocks ? rows : kApplyBlocks);
     // gy (dense mode only) and z in, dz out
-    ktimer_begin("bn_bwd_apply_kernel", (pool_s > 0 && !mixed ? 8.0 : 12.0) * static_cast<double>(rows) * cout, st);
+    ktimer_begin("bn_bwd_apply_kernel", (pool_s > 0 && !mixed ? 8.0 : 12.0) * static_cast<double>(rows) * cout -
+                                            ((w3 && !dx && !dgroup_bias) ? 4.0 * static_cast<double>(rows) * cout : 0.0), st);
+    // an xyz layer whose input needs no gradient (the detector's conv0): dW and db come out of this pass, nobody reads dz
+    float *dz_out = (w3 && !dx && !dgroup_bias) ? nullptr : dz;
     if (pool_s > 0)
-        bn_bwd_apply_kernel<true><<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
+        bn_bwd_apply_kernel<true><<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz_out, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     else
-        bn_bwd_apply_kernel<false><<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
+        bn_bwd_apply_kernel<false><<<napp, 256, 0, st>>>(rows, cout, eps, G, gamma, beta, z, mean, var, coef2, relu, dz_out, partB, w3 ? x : nullptr, w3 ? partW : nullptr);
     ktimer_end(st);
     rc = check_launch("bn_bwd_apply_kernel");
     if (rc) return rc;

@@ -178,6 +178,7 @@ class _ConvBnTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, use_relu, pool_s, gbias, gs, mode, x_coef, x_relu):
         ctx.precision = _PRECISION_CODE[TRAIN_PRECISION]
+        ctx.set_materialize_grads(False)  # no zero tensors for the outputs nobody differentiates (moments, coef, unused pooled)
         sv = _conv_bn_forward(x, w, b, gamma, beta, use_relu, ctx.precision, gbias, gs if gbias is not None else 0, int(pool_s),
                               x_coef=x_coef, x_relu=x_relu, want_y=(mode == "y"), want_coef=(mode == "defer"))
         ctx.use_relu, ctx.pool_s, ctx.gs, ctx.mode, ctx.x_relu = bool(use_relu), int(pool_s), int(gs) if gbias is not None else 0, mode, bool(x_relu)
@@ -196,7 +197,7 @@ class _ConvBnTrain(torch.autograd.Function):
         saved = dict.fromkeys(("x", "w", "gamma", "beta", "z", "mean", "var", "pooled", "inv", "x_coef"))
         saved.update(zip(ctx.keys, ctx.saved_tensors))
         if ctx.mode == "pool":
-            gy, gpool = None, gout
+            gy, gpool = None, (gout if gout is not None else torch.zeros_like(saved["pooled"]))
         else:
             gy, gpool = gout, (gpooled if ctx.pool_s else None)
             if gy is None and gpool is None:

@@ -33,6 +33,56 @@ def _neighbour_indices(xyz, centres, nsample, radius, knn, neighbours=None):
     return query_ball_point(radius, nsample, xyz, centres)
 
 
+class _LocalFrames(torch.autograd.Function):
+    """group_point - centre, / radius, rotation about z by the cluster's angle: one CUDA launch (csrc/frames.cu) instead of a gather
+    and a dozen element-wise passes; differentiable with respect to the angles (what the training step needs).  Returns
+    (rotated, before, R): `before` = the rows ahead of the rotation, R (B,M,3,3) the rotation matrices (None unless want_before)."""
+
+    @staticmethod
+    def forward(ctx, xyz, centres, idx, angles, radius, normalize_radius, clockwise, want_before):
+        _lib = importlib.import_module(_pfx + "_lib")
+        x, c, i = xyz.detach().contiguous().float(), centres.detach().contiguous().float(), idx.contiguous()
+        a = angles.detach().contiguous().float() if angles is not None else None
+        _lib.require_cuda(x, c, i)
+        b, n, m, s = x.shape[0], x.shape[1], c.shape[1], i.shape[2]
+        out = torch.empty((b, m, s, 3), dtype=torch.float32, device=x.device)
+        before = torch.empty_like(out) if want_before else None
+        rot = torch.empty((b, m, 3, 3), dtype=torch.float32, device=x.device) if (want_before and a is not None) else None
+        _lib.check(_lib.lib().f3d_group_local_frames(b, n, m, s, _lib.ptr(x), _lib.ptr(c), _lib.ptr(i), _lib.ptr(a) if a is not None else None,
+                                                     int(bool(clockwise)), float(radius), int(bool(normalize_radius)),
+                                                     _lib.ptr(before) if before is not None else None, _lib.ptr(rot) if rot is not None else None,
+                                                     _lib.ptr(out), _lib.stream()), "group_local_frames")
+        ctx.clockwise = bool(clockwise)
+        ctx.has_angles = a is not None
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(out)
+        ctx.mark_non_differentiable(*[t for t in (before, rot) if t is not None])
+        return out, before, rot
+
+    @staticmethod
+    def backward(ctx, gout, _gbefore, _grot):
+        if not ctx.has_angles or gout is None or not ctx.needs_input_grad[3]:
+            return None, None, None, None, None, None, None, None
+        _lib = importlib.import_module(_pfx + "_lib")
+        (out,) = ctx.saved_tensors
+        b, m, s, _ = out.shape
+        g = gout.contiguous().float()
+        dangle = torch.empty((b, m), dtype=torch.float32, device=out.device)
+        _lib.check(_lib.lib().f3d_group_local_frames_angle_grad(b, m, s, _lib.ptr(out), _lib.ptr(g), int(ctx.clockwise), _lib.ptr(dangle), _lib.stream()),
+                   "group_local_frames_angle_grad")
+        return None, None, None, dangle, None, None, None, None
+
+
+FUSED_FRAMES = True  # False: the op-by-op statement below also where the fused op applies
+
+
+def _fused_frames_ok(xyz, centres, idx):
+    """The fused op carries no gradient to xyz / centres: it serves the forwards where neither needs one (training and inference of the
+    model; the saliency gradients of compute_det_gradients differentiate with respect to xyz and take the op-by-op statement)."""
+    needs = torch.is_grad_enabled() and (xyz.requires_grad or centres.requires_grad)
+    return FUSED_FRAMES and xyz.is_cuda and xyz.dim() == 3 and xyz.shape[2] == 3 and idx.dtype == torch.int32 and not needs
+
+
 def _local_frames(xyz, centres, idx, radius, normalize_radius):
     """Gather the neighbourhoods and express them relative to their centre, optionally in units of the radius."""
     local = group_point(xyz, idx) - centres.unsqueeze(2)
@@ -74,9 +124,12 @@ def query_and_group_points(xyz, points, new_xyz, nsample, radius, knn=False,
     idx, pts_cnt = _neighbour_indices(xyz, new_xyz, nsample, radius, knn, neighbours)
     if end_points is not None:
         end_points['pts_cnt'] = pts_cnt
-    local = _local_frames(xyz, new_xyz, idx, radius, normalize_radius)
-    if orientations is not None:
-        local = _spin_about_z(local, orientations, clockwise=True)
+    if _fused_frames_ok(xyz, new_xyz, idx):
+        local = _LocalFrames.apply(xyz, new_xyz, idx, orientations, radius, normalize_radius, True, False)[0]
+    else:
+        local = _local_frames(xyz, new_xyz, idx, radius, normalize_radius)
+        if orientations is not None:
+            local = _spin_about_z(local, orientations, clockwise=True)
     return _with_features(local, points, idx, use_xyz), idx
 
 
@@ -90,9 +143,15 @@ def sample_and_group(npoint, radius, nsample, xyz, points, tnet_spec=None, knn=F
         raise ValueError("tnet_spec is not supported")
     centres = keypoints if keypoints is not None else sample_points(xyz, npoint)
     idx, pts_cnt = _neighbour_indices(xyz, centres, nsample, radius, knn, neighbours)
+    if _fused_frames_ok(xyz, centres, idx):
+        local, before, rot = _LocalFrames.apply(xyz, centres, idx, orientations, radius, normalize_radius, False, orientations is not None)
+        end_points = {'pts_cnt': pts_cnt, 'grouped_xyz_before': local if before is None else before, 'grouped_xyz': local}
+        if rot is not None:
+            end_points['rotation'] = rot  # (B,M,3,3), the reference's R
+        return centres, _with_features(local, points, idx, use_xyz), idx, local, end_points
     before = _local_frames(xyz, centres, idx, radius, normalize_radius)
-    end_points = {'pts_cnt': pts_cnt, 'grouped_xyz_before': before}
     local = before
+    end_points = {'pts_cnt': pts_cnt, 'grouped_xyz_before': before}
     if orientations is not None:
         local = _spin_about_z(before, orientations, clockwise=False)
         c, s = torch.cos(orientations), torch.sin(orientations)

@@ -107,6 +107,18 @@ size_t f3d_knn_workspace_bytes(int b, int n, int m, int c, int k);
 int f3d_knn_point(int b, int n, int m, int c, int k, const float *xyz1, const float *xyz2, float *val, int *idx,
                   void *workspace, size_t workspace_bytes, void *stream);
 
+/* The neighbourhoods in their local frames, models/pointnet_common.py:42-54 (query_and_group_points: clockwise = 1) and :104-119
+ * (sample_and_group: clockwise = 0), one launch instead of group_point + tile + sub + div + cos / sin / stack (or matmul with R):
+ * out (b,m,s,3) = rotate_z((xyz[idx] - centre) [/ radius when normalize_radius], angles[b,m]); angles NULL = no rotation;
+ * before (b,m,s,3) or NULL receives the rows before the rotation (end_points['grouped_xyz_before']), rotation (b,m,3,3) or NULL the
+ * matrices R = ((c, s, 0), (-s, c, 0), (0, 0, 1)) of :112-117 (end_points['rotation']).  Same roundings as the op chain.
+ * ..._angle_grad: dangle (b,m) = gradient with respect to the angles given out (the forward's result) and gout = dL/dout -- what the
+ * training step needs (the descriptor's clusters turn with the detector's orientation, models/feat3dnet.py:301-305); the gradients
+ * with respect to xyz / centres go through f3d_group_point_grad on the op-by-op statement. */
+int f3d_group_local_frames(int b, int n, int m, int s, const float *xyz, const float *centres, const int *idx, const float *angles,
+                           int clockwise, float radius, int normalize_radius, float *before, float *rotation, float *out, void *stream);
+int f3d_group_local_frames_angle_grad(int b, int m, int s, const float *out, const float *gout, int clockwise, float *dangle, void *stream);
+
 /* groupPointLauncher(b,n,c,m,nsample,points,idx,out)  tf_grouping_g.cu:191-194, op tf_grouping.cpp:209-237. */
 int f3d_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
                     void *stream);

@@ -384,6 +384,48 @@ def test_sample_and_group_matches_oracle_composition(cuda):
     assert torch.equal(pc.sample_points(xyz, -1), xyz)
 
 
+@pytest.mark.parametrize("radius,normalize", [(2.0, True), (1.7, True), (2.0, False)])
+def test_fused_local_frames_carry_the_bits_of_the_op_chain(cuda, radius, normalize):
+    """csrc/frames.cu (group_point - centre, / radius, rotation in ONE launch) against the op-by-op statement of
+    pointnet_common.py:42-54 / :104-119 on torch ops: same rows bit for bit at the model's radius (both conventions of the rotation,
+    with and without angles), same 'grouped_xyz_before' / 'rotation' end points, and the gradient with respect to the angles to rounding."""
+    pc = pkg("models.pointnet_common")
+    x = clouds("oxford", 3, 4096, 7)
+    xyz = T(x, cuda)
+    g = torch.Generator().manual_seed(3)
+    ori = ((torch.rand(3, 96, generator=g) - 0.5) * 7.0).to(cuda)
+    kp = pc.sample_points(xyz, 96)
+    res = {}
+    for fused in (True, False):
+        pc.FUSED_FRAMES = fused
+        try:
+            o = ori.clone().requires_grad_(True)
+            c, npts, idx, grouped, ep = pc.sample_and_group(96, radius, 64, xyz, None, keypoints=kp, orientations=o, normalize_radius=normalize)
+            w = torch.randn(grouped.shape, generator=torch.Generator().manual_seed(9)).to(cuda)
+            (go,) = torch.autograd.grad((grouped * w).sum(), o)
+            o2 = ori.clone().requires_grad_(True)
+            q, qidx = pc.query_and_group_points(xyz, None, kp, 64, radius, normalize_radius=normalize, orientations=o2)
+            (go2,) = torch.autograd.grad((q * w).sum(), o2)
+            plain, _ = pc.query_and_group_points(xyz, None, kp, 64, radius, normalize_radius=normalize, orientations=None)
+            res[fused] = (grouped.detach(), ep['grouped_xyz_before'].detach(), ep['rotation'].detach(), go, q.detach(), go2, plain.detach(), idx, qidx)
+        finally:
+            pc.FUSED_FRAMES = True
+    a, b = res[True], res[False]
+    # the kernel divides by the radius like TensorFlow's RealDiv; torch multiplies by the rounded reciprocal of a Python scalar: the same
+    # bits when the radius is a power of two (the model's 2.0), one unit in the last place apart otherwise
+    exact = (not normalize) or radius == 2.0
+    for i in (0, 1, 2, 4, 6, 7, 8):
+        assert torch.equal(a[i], b[i]) if (exact or i in (2, 7, 8)) else torch.allclose(a[i], b[i], rtol=3e-7, atol=1e-7), i
+    assert torch.equal(a[6], a[1])  # no angles: the rows before the rotation
+    for i in (3, 5):
+        assert torch.allclose(a[i], b[i], rtol=1e-4, atol=1e-4 * b[i].abs().max().item()), i
+    # a cloud that needs a gradient takes the op-by-op statement (the fused op carries none to xyz)
+    xg = xyz.clone().requires_grad_(True)
+    q, _ = pc.query_and_group_points(xg, None, kp, 64, radius, normalize_radius=normalize, orientations=ori)
+    (gx,) = torch.autograd.grad(q.sum(), xg)
+    assert gx.abs().sum().item() > 0
+
+
 # ------------------------------------------------------------------------------------------------ the reference's smoke mains
 def test_reference_grouping_main_shapes(cuda):
     """tf_ops/grouping/tf_grouping.py:90-118 (`__main__`, no assertion there): np.random.seed(100), points (32,512,64),
