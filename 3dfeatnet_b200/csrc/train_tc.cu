@@ -684,6 +684,8 @@ constexpr int kRows = 32;            // rows per stage
 constexpr uint32_t kSboP = 144;      // stride between 8-channel core matrices (128 B + 16 B padding)
 constexpr int kChunks = kRows / 8;   // K chunks per stage
 constexpr int kThreads = 512;        // 16 warps: the conversion is the long phase of a stage
+constexpr int kMaxRing = 4;          // ring slots of fp32 stages (as many as fit next to the operand images: the fetch of stage s + ring
+                                     // is issued when stage s has been converted, so a 2-deep ring leaves the copy one stage of cover)
 }  // namespace wg
 
 // 8 rows x 4 channels of fp32 -> four 16-byte chunks (8 rows of one channel each) of the hi and the lo image
@@ -737,35 +739,93 @@ __device__ __forceinline__ void wgrad_convert(uint8_t *img, uint32_t lbo, uint32
     }
 }
 
-// The dz operand of a pool-only layer, formed on the fly (DzSource): `stage` holds the z rows of the stage, `pool` the pooled maximum /
-// pooled gradient / 1 / ties rows of the stage's group, `coef` the per-channel table.  One unit per thread (4 * c / 4 <= 480 converter
-// threads), so a thread keeps the same channel quad for the whole kernel and `dbsum` is its share of db = column sums of dz.
-__device__ __forceinline__ void wgrad_convert_dz(uint8_t *img, uint32_t lbo, uint32_t split, const uint8_t *__restrict__ stage, int c, int valid_rows,
-                                                 const float *__restrict__ coef, const float *__restrict__ pool, int relu, float4 &dbsum) {
-    const int quads = c >> 2;
-    const int u = threadIdx.x - 32;
-    if (u >= wg::kChunks * quads) return;
-    const int rc = u / quads, c4 = u - rc * quads;
-    auto ld = [&](const float *base) { return *reinterpret_cast<const float4 *>(base + c4 * 4); };
-    const float4 bsc = ld(coef), bsh = ld(coef + c), ss = ld(coef + 2 * c), k1 = ld(coef + 3 * c), mu = ld(coef + 4 * c), is = ld(coef + 5 * c),
-                 k2 = ld(coef + 6 * c);
-    const float4 pm = ld(pool), gp = ld(pool + c), iv = ld(pool + 2 * c);
-    const float4 gsc = make_float4(__fmul_rn(gp.x, iv.x), __fmul_rn(gp.y, iv.y), __fmul_rn(gp.z, iv.z), __fmul_rn(gp.w, iv.w));
-    float4 v[8];
+// Both operands of a stage in ONE pass over a combined unit index, with units of 8 rows x W channels (W = 4, 2 or 1): narrow layers
+// have few 4-channel units (96 for 32 + 64 channels) and converting A and then B left the same three warps with two dependent units
+// each while twelve warps idled -- the stage time was that latency (tools/wgrad_tc_phases.py).  W is chosen by the launcher so that
+// about 384 units exist per stage.
+template <int W>
+__device__ __forceinline__ void wgrad_convert_both(uint8_t *img_a, uint32_t lbo_a, uint32_t split_a, uint8_t *img_b, uint32_t lbo_b, uint32_t split_b,
+                                                   const uint8_t *__restrict__ stage_a, const uint8_t *__restrict__ stage_b, int cin, int cout,
+                                                   int valid_rows, const XSource X) {
+    const int ga = cin / W, gb = cout / W;
+    const int ua = wg::kChunks * ga, ut = ua + wg::kChunks * gb;
+    for (int u = threadIdx.x - 32; u < ut; u += wg::kThreads - 32) {
+        const bool is_a = u < ua;
+        const int uu = is_a ? u : u - ua, g = is_a ? ga : gb, c = is_a ? cin : cout;
+        const int rc = uu / g, cg = uu - rc * g;
+        const uint8_t *src = (is_a ? stage_a : stage_b) + static_cast<size_t>(cg) * W * 4;
+        float v[8][W];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = rc * 8 + i;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < valid_rows) {
-            const float4 zz = *reinterpret_cast<const float4 *>(stage + (static_cast<size_t>(r) * c + c4 * 4) * 4);
-            v[i].x = dz_value(zz.x, bsc.x, bsh.x, ss.x, k1.x, mu.x, is.x, k2.x, pm.x, gsc.x, relu);
-            v[i].y = dz_value(zz.y, bsc.y, bsh.y, ss.y, k1.y, mu.y, is.y, k2.y, pm.y, gsc.y, relu);
-            v[i].z = dz_value(zz.z, bsc.z, bsh.z, ss.z, k1.z, mu.z, is.z, k2.z, pm.z, gsc.z, relu);
-            v[i].w = dz_value(zz.w, bsc.w, bsh.w, ss.w, k1.w, mu.w, is.w, k2.w, pm.w, gsc.w, relu);
-            dbsum.x += v[i].x; dbsum.y += v[i].y; dbsum.z += v[i].z; dbsum.w += v[i].w;
+        for (int i = 0; i < 8; ++i) {
+            const int r = rc * 8 + i;
+            const uint8_t *p = src + static_cast<size_t>(r) * c * 4;
+            if (r < valid_rows) {
+                if constexpr (W == 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(p);
+                    v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+                } else if constexpr (W == 2) {
+                    const float2 t = *reinterpret_cast<const float2 *>(p);
+                    v[i][0] = t.x; v[i][1] = t.y;
+                } else {
+                    v[i][0] = *reinterpret_cast<const float *>(p);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < W; ++j) v[i][j] = 0.f;
+            }
+        }
+        if (is_a && X.coef) {  // the staged rows are the previous layer's z: its BN + ReLU is applied here (XSource, dz_source.cuh)
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const float sc = __ldg(X.coef + cg * W + j), sh = __ldg(X.coef + cin + cg * W + j);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (rc * 8 + i < valid_rows) {
+                        const float y = __fmaf_rn(v[i][j], sc, sh);
+                        v[i][j] = X.relu ? fmaxf(y, 0.f) : y;
+                    }
+            }
+        }
+        uint8_t *img = is_a ? img_a : img_b;
+        const uint32_t lbo = is_a ? lbo_a : lbo_b, split = is_a ? split_a : split_b;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const int ch = cg * W + j;
+            const float col[8] = {v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]};
+            uint4 hi, lo;
+            split8(col, hi, lo);
+            uint8_t *dst = img + rc * lbo + (ch >> 3) * wg::kSboP + (ch & 7) * 16;
+            *reinterpret_cast<uint4 *>(dst) = hi;
+            *reinterpret_cast<uint4 *>(dst + split) = lo;
         }
     }
-    wgrad_store_unit(img + rc * lbo + (c4 >> 1) * wg::kSboP + (c4 & 1) * 64, split, v);
+}
+
+// The dz operand of a pool-only layer, formed on the fly (DzSource): `stage` holds the z rows of the stage, `pool` the pooled maximum /
+// pooled gradient / 1 / ties rows of the stage's group, `coef` the per-channel table.  ALL converter threads take part: thread t owns the
+// channel quad t % quads for the whole kernel (its seven coefficient quads live in registers) and rows t / quads, + rows_pass, ... of the
+// stage; z is overwritten IN PLACE by dz = dz_value(z), after which the ordinary transposing conversion (wgrad_convert) runs on the slot.
+// (One 8-row x 4-channel unit per thread, as the conversion itself is organised, left 128-256 of the 480 threads with ~400 dependent
+// instructions each: the stage time was that thread's latency.)  `dbsum` is the thread's share of db = column sums of dz.
+struct DzCoefRegs {
+    float4 bsc, bsh, ss, k1, mu, is, k2;
+};
+__device__ __forceinline__ void wgrad_dz_in_place(uint8_t *__restrict__ stage, int c, int valid_rows, const DzCoefRegs &K, const float *__restrict__ pool,
+                                                  int relu, int q, int row0, int rows_pass, float4 &dbsum) {
+    const float4 pm = *reinterpret_cast<const float4 *>(pool + q * 4), gp = *reinterpret_cast<const float4 *>(pool + c + q * 4),
+                 iv = *reinterpret_cast<const float4 *>(pool + 2 * c + q * 4);
+    const float4 gsc = make_float4(__fmul_rn(gp.x, iv.x), __fmul_rn(gp.y, iv.y), __fmul_rn(gp.z, iv.z), __fmul_rn(gp.w, iv.w));
+    for (int r = row0; r < valid_rows; r += rows_pass) {
+        float4 *p = reinterpret_cast<float4 *>(stage + (static_cast<size_t>(r) * c + q * 4) * 4);
+        const float4 zz = *p;
+        float4 d;
+        d.x = dz_value(zz.x, K.bsc.x, K.bsh.x, K.ss.x, K.k1.x, K.mu.x, K.is.x, K.k2.x, pm.x, gsc.x, relu);
+        d.y = dz_value(zz.y, K.bsc.y, K.bsh.y, K.ss.y, K.k1.y, K.mu.y, K.is.y, K.k2.y, pm.y, gsc.y, relu);
+        d.z = dz_value(zz.z, K.bsc.z, K.bsh.z, K.ss.z, K.k1.z, K.mu.z, K.is.z, K.k2.z, pm.z, gsc.z, relu);
+        d.w = dz_value(zz.w, K.bsc.w, K.bsh.w, K.ss.w, K.k1.w, K.mu.w, K.is.w, K.k2.w, pm.w, gsc.w, relu);
+        *p = d;
+        dbsum.x += d.x; dbsum.y += d.y; dbsum.z += d.z; dbsum.w += d.w;
+    }
 }
 
 // cin % 8 == 0, cin <= 128, cout % 16 == 0, cout <= 256.  One CTA per SM.
@@ -774,7 +834,8 @@ __device__ __forceinline__ void wgrad_convert_dz(uint8_t *img, uint32_t lbo, uin
 template <bool FUSED>
 __global__ void __launch_bounds__(wg::kThreads, 1)
 wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint32_t tmem_cols, const float *__restrict__ x,
-                const float *__restrict__ dz, float *__restrict__ partW, int dbg, DzSource S, float *__restrict__ partB, XSource X) {
+                const float *__restrict__ dz, float *__restrict__ partW, int dbg, DzSource S, float *__restrict__ partB, XSource X, int nring,
+                int wunit) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lbo_a = 16 * wg::kSboP, lbo_b = static_cast<uint32_t>(cout / 8) * wg::kSboP;
@@ -784,11 +845,11 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
     const uint32_t pool_bytes = FUSED ? 3u * static_cast<uint32_t>(cout) * 4 : 0u;  // pooled max | pooled gradient | 1 / ties of the stage's group
     const uint32_t stage_bytes = xs_bytes + ds_bytes + pool_bytes;
     uint8_t *ring = smem + 2 * img_bytes;
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + 2 * img_bytes + 2 * stage_bytes);  // [2] ring stage filled
-    uint64_t *bar_mma = bar_full + 2;                                                          // [2] MMAs of an image buffer done
-    uint64_t *bar_img = bar_full + 4;                                                          // [2] image buffer converted
-    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_full + 6);
-    float *coef_s = reinterpret_cast<float *>(smem + 2 * img_bytes + 2 * stage_bytes + 64);   // FUSED: [7][cout], then dbred [4][cout]
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + 2 * img_bytes + nring * stage_bytes);  // [kMaxRing] ring stage filled
+    uint64_t *bar_mma = bar_full + wg::kMaxRing;                                                   // [2] MMAs of an image buffer done
+    uint64_t *bar_img = bar_mma + 2;                                                               // [2] image buffer converted
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bar_img + 2);
+    float *coef_s = reinterpret_cast<float *>(smem + 2 * img_bytes + nring * stage_bytes + 128);  // FUSED: [7][cout], then dbred [(480 / (cout / 4))][cout]
     float *dbred = coef_s + kDzCoefs * cout;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
@@ -797,8 +858,8 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
     }
 
     if (threadIdx.x == 0) {
+        for (int i = 0; i < wg::kMaxRing; ++i) mbar_init(bar_full + i, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_full + i, 1);
             mbar_init(bar_mma + i, 1);
             mbar_init(bar_img + i, wg::kThreads / 32 - 1);  // one arrival per converter warp
         }
@@ -821,38 +882,38 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
 
     if (warp == 0) {
         // ---- issuer warp: TMA fetches (one stage ahead) and the MMAs; never touches the data itself
-        auto fetch = [&](int s) {  // the fp32 rows of stage s -> ring slot s & 1
+        auto fetch = [&](int s) {  // the fp32 rows of stage s -> ring slot s % nring
             const long long r0 = rbeg + static_cast<long long>(s) * wg::kRows;
             const uint32_t valid = static_cast<uint32_t>(rend - r0 < wg::kRows ? rend - r0 : wg::kRows);
             if (lane == 0) {
-                uint8_t *dst = ring + (s & 1) * stage_bytes;
+                const int slot = s % nring;
+                uint8_t *dst = ring + slot * stage_bytes;
                 const uint32_t xb = valid * static_cast<uint32_t>(cin) * 4, db = valid * static_cast<uint32_t>(cout) * 4;
-                mbar_arrive_expect_tx(bar_full + (s & 1), xb + db + pool_bytes);
+                mbar_arrive_expect_tx(bar_full + slot, xb + db + pool_bytes);
                 const uint8_t *xsrc = reinterpret_cast<const uint8_t *>(x + r0 * cin);
                 const uint8_t *dsrc = reinterpret_cast<const uint8_t *>((FUSED ? S.z : dz) + r0 * cout);
-                for (uint32_t off = 0; off < xb; off += 16384) bulk_g2s(dst + off, xsrc + off, xb - off < 16384u ? xb - off : 16384u, bar_full + (s & 1));
+                for (uint32_t off = 0; off < xb; off += 16384) bulk_g2s(dst + off, xsrc + off, xb - off < 16384u ? xb - off : 16384u, bar_full + slot);
                 for (uint32_t off = 0; off < db; off += 16384)
-                    bulk_g2s(dst + xs_bytes + off, dsrc + off, db - off < 16384u ? db - off : 16384u, bar_full + (s & 1));
+                    bulk_g2s(dst + xs_bytes + off, dsrc + off, db - off < 16384u ? db - off : 16384u, bar_full + slot);
                 if (FUSED) {
                     const size_t go = static_cast<size_t>(r0 / S.gs) * cout;
                     const uint32_t cb = static_cast<uint32_t>(cout) * 4;
-                    bulk_g2s(dst + xs_bytes + ds_bytes, S.pooled + go, cb, bar_full + (s & 1));
-                    bulk_g2s(dst + xs_bytes + ds_bytes + cb, S.gpool + go, cb, bar_full + (s & 1));
-                    bulk_g2s(dst + xs_bytes + ds_bytes + 2 * cb, S.inv + go, cb, bar_full + (s & 1));
+                    bulk_g2s(dst + xs_bytes + ds_bytes, S.pooled + go, cb, bar_full + slot);
+                    bulk_g2s(dst + xs_bytes + ds_bytes + cb, S.gpool + go, cb, bar_full + slot);
+                    bulk_g2s(dst + xs_bytes + ds_bytes + 2 * cb, S.inv + go, cb, bar_full + slot);
                 }
             }
             __syncwarp();
         };
         if (!(dbg & 1)) {
-            if (nstages > 0) fetch(0);
-            if (nstages > 1) fetch(1);
+            for (int s = 0; s < nring && s < nstages; ++s) fetch(s);
         }
         uint32_t acc = 0;
         for (int s = 0; s < nstages; ++s) {
             const int b = s & 1;
             mbar_wait(bar_img + b, static_cast<uint32_t>((s >> 1) & 1));  // image b converted, ring slot b consumed
             tcgen05_fence_after();
-            if (!(dbg & 1) && s + 2 < nstages) fetch(s + 2);
+            if (!(dbg & 1) && s + nring < nstages) fetch(s + nring);  // image b converted <=> ring slot s % nring consumed
             if (elect_one()) {
                 const uint32_t a0 = sbase + b * img_bytes, b0 = a0 + 2 * split_a;
                 for (int pass = 0; pass < ((dbg & 2) ? 0 : 3); ++pass) {
@@ -870,35 +931,53 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
     } else {
         // ---- converter warps: ring slot (fp32, row-major) -> operand image (bf16 hi/lo, K = row major)
         float4 dbsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        // FUSED: channel quad and first row of this thread in the dz pass (threads beyond rows_pass * quads sit it out)
+        const int quads = cout >> 2, ct = threadIdx.x - 32;
+        const int rows_pass = (wg::kThreads - 32) / quads;
+        const int dq = ct % quads, drow = ct / quads;
+        DzCoefRegs K{};
+        if (FUSED && drow < rows_pass) {
+            auto ld = [&](int i) { return *reinterpret_cast<const float4 *>(coef_s + i * cout + dq * 4); };
+            K = DzCoefRegs{ld(0), ld(1), ld(2), ld(3), ld(4), ld(5), ld(6)};
+        }
         for (int s = 0; s < nstages; ++s) {
             const int b = s & 1;
             uint8_t *img = smem + b * img_bytes;
             if (s >= 2) mbar_wait(bar_mma + b, static_cast<uint32_t>(((s >> 1) - 1) & 1));  // MMAs of stage s-2 have read this image
             if (!(dbg & 1)) {
-                mbar_wait(bar_full + b, static_cast<uint32_t>((s >> 1) & 1));
+                const int slot = s % nring;
+                mbar_wait(bar_full + slot, static_cast<uint32_t>((s / nring) & 1));
                 const long long r0 = rbeg + static_cast<long long>(s) * wg::kRows;
                 const int valid = static_cast<int>(rend - r0 < wg::kRows ? rend - r0 : wg::kRows);
-                const uint8_t *stage = ring + b * stage_bytes;
-                wgrad_convert(img, lbo_a, split_a, stage, cin, valid, X);
-                if constexpr (FUSED)
-                    wgrad_convert_dz(img + 2 * split_a, lbo_b, split_b, stage + xs_bytes, cout, valid, coef_s,
-                                     reinterpret_cast<const float *>(stage + xs_bytes + ds_bytes), S.relu, dbsum);
+                uint8_t *stage = ring + slot * stage_bytes;
+                if constexpr (FUSED) {
+                    if (drow < rows_pass)
+                        wgrad_dz_in_place(stage + xs_bytes, cout, valid, K, reinterpret_cast<const float *>(stage + xs_bytes + ds_bytes), S.relu, dq, drow,
+                                          rows_pass, dbsum);
+                }
+                if constexpr (FUSED) asm volatile("bar.sync 2, %0;" ::"n"(wg::kThreads - 32) : "memory");  // dz of the whole stage is in place
+                if (wunit == 4)
+                    wgrad_convert_both<4>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X);
+                else if (wunit == 2)
+                    wgrad_convert_both<2>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X);
                 else
-                    wgrad_convert(img + 2 * split_a, lbo_b, split_b, stage + xs_bytes, cout, valid);
+                    wgrad_convert_both<1>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_img + b);
         }
-        if (FUSED) {  // this thread's share of db: rows chunk rc of every stage, channel quad c4
-            const int quads = cout >> 2, u = threadIdx.x - 32;
-            if (u < wg::kChunks * quads) *reinterpret_cast<float4 *>(dbred + (u / quads) * cout + (u % quads) * 4) = dbsum;
-        }
+        if (FUSED && drow < rows_pass)  // this thread's share of db: rows drow, drow + rows_pass, ... of every stage, channel quad dq
+            *reinterpret_cast<float4 *>(dbred + drow * cout + dq * 4) = dbsum;
     }
     if (FUSED) {
         __syncthreads();
-        for (int ch = threadIdx.x; ch < cout; ch += wg::kThreads)
-            partB[static_cast<size_t>(blockIdx.x) * cout + ch] = (dbred[ch] + dbred[cout + ch]) + (dbred[2 * cout + ch] + dbred[3 * cout + ch]);
+        const int rows_pass = (wg::kThreads - 32) / (cout >> 2);
+        for (int ch = threadIdx.x; ch < cout; ch += wg::kThreads) {
+            float t = 0.f;
+            for (int r = 0; r < rows_pass; ++r) t += dbred[r * cout + ch];  // fixed order
+            partB[static_cast<size_t>(blockIdx.x) * cout + ch] = t;
+        }
     }
     // drain: the last MMAs of both image buffers
     if (nstages >= 1) mbar_wait(bar_mma + ((nstages - 1) & 1), static_cast<uint32_t>(((nstages - 1) >> 1) & 1));
@@ -1093,16 +1172,22 @@ void wgrad_tc_plan(long long rows, int *grid, long long *rows_per_cta) {
     *grid = static_cast<int>((nst + per - 1) / per);
 }
 
-static size_t wgrad_tc_smem(int cin, int cout, bool fused) {
+static size_t wgrad_tc_smem(int cin, int cout, bool fused, int nring) {
     const size_t img = 2 * static_cast<size_t>(wg::kChunks) * 16 * wg::kSboP + 2 * static_cast<size_t>(wg::kChunks) * (cout / 8) * wg::kSboP;
-    return 2 * img + 2 * (static_cast<size_t>(wg::kRows) * (cin + cout) * 4 + (fused ? static_cast<size_t>(3) * cout * 4 : 0)) + 64 +
-           (fused ? static_cast<size_t>(kDzCoefs + 4) * cout * 4 : 0);
+    return 2 * img + nring * (static_cast<size_t>(wg::kRows) * (cin + cout) * 4 + (fused ? static_cast<size_t>(3) * cout * 4 : 0)) + 128 +
+           (fused ? static_cast<size_t>(kDzCoefs) * cout * 4 + static_cast<size_t>(wg::kThreads - 32) * 16 : 0);
 }
 
-// fused dz source: a 32-row stage must lie inside one group, one converter unit per thread, and everything must fit in shared memory
+// as many ring slots (2 .. kMaxRing) as fit into shared memory
+static int wgrad_tc_ring(int cin, int cout, bool fused) {
+    int nring = wg::kMaxRing;
+    while (nring > 2 && wgrad_tc_smem(cin, cout, fused, nring) > 227 * 1024) --nring;
+    return nring;
+}
+
+// fused dz source: a 32-row stage must lie inside one group and everything must fit in shared memory
 bool wgrad_tc_dz_supported(long long rows, int cin, int cout, int gs) {
-    return wgrad_tc_supported(cin, cout) && gs > 0 && gs % wg::kRows == 0 && rows % gs == 0 && wg::kChunks * (cout / 4) <= wg::kThreads - 32 &&
-           wgrad_tc_smem(cin, cout, true) <= 227 * 1024;
+    return wgrad_tc_supported(cin, cout) && gs > 0 && gs % wg::kRows == 0 && rows % gs == 0 && wgrad_tc_smem(cin, cout, true, 2) <= 227 * 1024;
 }
 
 // partW: grid x cin x cout floats.  S != NULL: dz formed on the fly from z (see the kernel), partB: grid x cout column sums of dz.
@@ -1115,15 +1200,18 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
     const uint32_t cols = pow2_cols(static_cast<uint32_t>(cout));
     const bool fused = S != nullptr;
     if (fused && (!wgrad_tc_dz_supported(rows, cin, cout, S->gs) || !partB)) return fail(F3D_ERR_UNSUPPORTED, "wgrad_tc: fused dz source not supported for this shape");
-    const size_t smem = wgrad_tc_smem(cin, cout, fused);
+    const int nring = wgrad_tc_ring(cin, cout, fused);
+    const int units4 = wg::kChunks * (cin + cout) / 4;  // 8-row x 4-channel units per stage; about 384 units keep the 480 converter threads busy
+    const int wunit = units4 >= 360 ? 4 : 2 * units4 >= 360 ? 2 : 1;
+    const size_t smem = wgrad_tc_smem(cin, cout, fused, nring);
     cudaError_t e = fused ? cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
                           : cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "wgrad_tc: cudaFuncSetAttribute");
     ktimer_begin(fused ? "wgrad_tc_kernel (dz formed from z)" : "wgrad_tc_kernel", 4.0 * static_cast<double>(rows) * (cin + cout), st);
     if (fused)
-        wgrad_tc_kernel<true><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, nullptr, partW, dbg, *S, partB, X);
+        wgrad_tc_kernel<true><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, nullptr, partW, dbg, *S, partB, X, nring, wunit);
     else
-        wgrad_tc_kernel<false><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg, DzSource{}, nullptr, X);
+        wgrad_tc_kernel<false><<<grid, wg::kThreads, smem, st>>>(rows, cin, cout, per, cols, x, dz, partW, dbg, DzSource{}, nullptr, X, nring, wunit);
     ktimer_end(st);
     return check_launch("wgrad_tc_kernel");
 }
