@@ -33,6 +33,16 @@ struct XSource {
     int relu;
 };
 
+// Max-pool statistics taken in the forward contraction's epilogue (pool-only layers): per HALF group of 32 consecutive rows and per
+// channel, in "key" space key = z for gamma >= 0, -z otherwise (the BN scale has gamma's sign, so the activation is non-decreasing in the
+// key): zext[(half_group * 3 + {0,1,2}) * c + ch] = {largest key m1, number of rows attaining it, largest key below m1 (or -inf)}.
+// After the batch statistics are known, pool_from_extremes_kernel turns them into the pooled maximum and the tie count of the ACTIVATION
+// -- exactly: ties among activations are the rows at m1 unless the second key rounds to the same activation, which it checks.
+struct PoolEpilogue {
+    float *zext;         // NULL: off
+    const float *gamma;  // (c) BN scale parameter (its sign selects max or min of z)
+};
+
 __device__ __forceinline__ float4 x_value(const float4 &z, const float4 &sc, const float4 &sh, int relu) {
     float4 y = make_float4(__fmaf_rn(z.x, sc.x, sh.x), __fmaf_rn(z.y, sc.y, sh.y), __fmaf_rn(z.z, sc.z, sh.z), __fmaf_rn(z.w, sc.w, sh.w));
     if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));

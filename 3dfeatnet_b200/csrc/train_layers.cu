@@ -639,6 +639,49 @@ __global__ void bn_apply_pool_kernel(long long groups, int s, int c4, const floa
     reinterpret_cast<float4 *>(inv)[e] = make_float4(1.0f / nx, 1.0f / ny, 1.0f / nz, 1.0f / nw);
 }
 
+// The pooled maximum and the tie count of a pool-only layer from the statistics its forward contraction took in the epilogue
+// (PoolEpilogue, dz_source.cuh), once the BN scale / shift exist: no pass over the (rows, c) tensor z.  Per (group of 64 rows, channel)
+// the two half groups' {largest key m1, multiplicity c1, second largest distinct key m2} are merged; the activation
+// y = act(z * scale + shift) is non-decreasing in the key, so max y = y(m1) and the rows with y == max are exactly the c1 rows at m1
+// UNLESS y(m2) == y(m1) (two distinct z round to one activation: a handful of (group, channel) pairs per step) -- then the 64 values of
+// the group are re-read and counted like bn_apply_pool_kernel does.  Same pooled bits as that kernel, same inv_ties bits wherever the
+// pooled value is not a ReLU-clamped zero (there the gradient is masked and the count unused).
+__global__ void pool_from_extremes_kernel(long long groups, int c, const float *__restrict__ zext, const float *__restrict__ coef, int relu,
+                                          const float *__restrict__ z, float *__restrict__ out, float *__restrict__ inv) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= groups * c) return;
+    const long long g = e / c;
+    const int ch = static_cast<int>(e - g * c);
+    const float sc = __ldg(coef + ch), sh = __ldg(coef + c + ch);
+    const float *a = zext + (2 * g) * 3 * c + ch, *b = a + 3 * c;
+    const float am1 = __ldg(a), ac1 = __ldg(a + c), am2 = __ldg(a + 2 * c), bm1 = __ldg(b), bc1 = __ldg(b + c), bm2 = __ldg(b + 2 * c);
+    float m1, c1, m2;
+    if (am1 > bm1) { m1 = am1; c1 = ac1; m2 = fmaxf(am2, bm1); }
+    else if (bm1 > am1) { m1 = bm1; c1 = bc1; m2 = fmaxf(bm2, am1); }
+    else { m1 = am1; c1 = ac1 + bc1; m2 = fmaxf(am2, bm2); }
+    // key -> z: the epilogue negated z where gamma < 0; scale has gamma's sign (scale == 0: every row has y = shift, handled below)
+    const bool neg = sc < 0.f || (sc == 0.f && __float_as_uint(sc) != 0u);
+    auto act = [&](float key) {
+        const float zz = neg ? -key : key;
+        const float y = __fmaf_rn(zz, sc, sh);
+        return relu ? fmaxf(y, 0.f) : y;
+    };
+    const float y1 = act(m1);
+    float n = c1;
+    // rounding ties rows below m1 with the maximum: count them all.  (A maximum clamped to 0 by the ReLU ties every inactive row, but its
+    // gradient is masked by y > 0 everywhere it is used, so the count is never read: no recount for it.)
+    if (m2 != -INFINITY && !(relu && y1 == 0.f) && act(m2) == y1) {
+        const float *p = z + g * 64 * c + ch;
+        n = 0.f;
+        for (int k = 0; k < 64; ++k) {
+            const float y = __fmaf_rn(__ldg(p + static_cast<size_t>(k) * c), sc, sh);
+            n += ((relu ? fmaxf(y, 0.f) : y) == y1) ? 1.f : 0.f;
+        }
+    }
+    out[e] = y1;
+    inv[e] = 1.0f / n;
+}
+
 // its gradient: dx = gout / (number of samples attaining the maximum) where x == max, else 0 (TensorFlow's _MinOrMaxGrad)
 __global__ void maxpool_bwd_kernel(long long groups, int s, int c4, const float *__restrict__ x, const float *__restrict__ mx,
                                    const float *__restrict__ inv, const float *__restrict__ gout, float *__restrict__ dx) {
@@ -688,7 +731,8 @@ size_t lin_tc_weight_bytes(int k_real, int nout);
 int lin_tc_grid(long long rows, int k_real, int nsplit);
 int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
            const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st, const DzSource *S = nullptr,
-           float *dgb = nullptr, const float *xcoef = nullptr, int xrelu = 0);
+           float *dgb = nullptr, const float *xcoef = nullptr, int xrelu = 0, float *zext = nullptr, const float *gamma = nullptr);
+int lin_tc_tile(long long rows, int k_real, int nsplit);
 bool lin_tc_dz_supported(long long rows, int k_real, int gs, bool need_group_sums);
 bool wgrad_tc_supported(int cin, int cout);
 bool wgrad_tc_dz_supported(long long rows, int cin, int cout, int gs);
@@ -699,6 +743,9 @@ int wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz,
 // Pool-only layers on the tensor-core path: dz is formed inside the two contractions that consume it instead of being written by
 // bn_bwd_apply_kernel and read back twice (f3d_debug_set_fuse_dz(0) restores the three-kernel path; same bits in dW and dx).
 static int g_fuse_dz = 1;
+// Pool-only layers on the tensor-core path: the max-pool statistics ride in the forward contraction's epilogue (pool_from_extremes_kernel)
+// instead of a second pass over z (bn_apply_pool_kernel); f3d_debug_set_epilogue_pool(0) restores that pass.  Same pooled / inv_ties bits.
+static int g_epilogue_pool = 1;
 
 static int pick_ct(int cout) { return cout % 128 == 0 ? 8 : cout % 64 == 0 ? 4 : cout % 32 == 0 ? 2 : cout % 16 == 0 ? 1 : 0; }
 
@@ -760,7 +807,8 @@ F3D_API size_t f3d_conv_bn_train_workspace_bytes(long long rows, int cin, int co
     const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
     const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit));
     const size_t wimg = lin_tc_weight_bytes(cin, cout) > lin_tc_weight_bytes(cout, cin) ? lin_tc_weight_bytes(cin, cout) : lin_tc_weight_bytes(cout, cin);
-    const size_t fwd = align256(stat_parts * 2 * cout * 4) + align256(2 * cout * 8) + align256(2 * cout * 4) + align256(wimg);
+    const size_t fwd = align256(stat_parts * 2 * cout * 4) + align256(2 * cout * 8) + align256(2 * cout * 4) + align256(wimg) +
+                       align256(static_cast<size_t>((rows + 31) / 32) * 3 * cout * 4);  // pooling statistics of the epilogue (per half group)
     const WgradPlan p = plan_wgrad(rows, cin, cout);
     int tcg = 0;
     long long tcper = 0;
@@ -816,7 +864,15 @@ static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *
     float *coef = coef_out ? coef_out : reinterpret_cast<float *>(w);
     w += align256(2 * cout * 4);
     uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
-    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, kFwdSplit, st, nullptr, nullptr, xcoef, xrelu)
+    {
+        const size_t wimg_b = lin_tc_weight_bytes(cin, cout) > lin_tc_weight_bytes(cout, cin) ? lin_tc_weight_bytes(cin, cout) : lin_tc_weight_bytes(cout, cin);
+        w += align256(wimg_b);
+    }
+    float *zext = reinterpret_cast<float *>(w);
+    // pool-only layer on the tensor cores with 64-row tiles = groups: the pool's statistics are taken in the contraction's epilogue
+    const bool epi_pool = g_epilogue_pool && tc && pool_s == 64 && rows % 64 == 0 && cin % 8 == 0 && lin_tc_tile(rows, cin, kFwdSplit) == 64;
+    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, kFwdSplit, st, nullptr, nullptr, xcoef, xrelu,
+                         epi_pool ? zext : nullptr, gamma)
                 : launch_conv_fwd(rows, cin, cout, x, W, bias, group_bias, group_s, z, part, st);
     if (rc) return rc;
     partial_reduce_kernel<double><<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(nparts), 2 * cout, part, sums);
@@ -825,7 +881,12 @@ static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *
     bn_stats_finalize_kernel<<<(cout + 127) / 128, 128, 0, st>>>(cout, 1.0 / static_cast<double>(rows), eps, sums, gamma, beta, mean, var, coef);
     rc = check_launch("bn_stats_finalize_kernel");
     if (rc) return rc;
-    if (pool_s > 0) {
+    if (pool_s > 0 && epi_pool) {
+        const long long np = (rows / pool_s) * cout;
+        pool_from_extremes_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, st>>>(rows / pool_s, cout, zext, coef, relu, z, pooled, inv_ties);
+        rc = check_launch("pool_from_extremes_kernel");
+        if (rc) return rc;
+    } else if (pool_s > 0) {
         const long long groups = rows / pool_s, np = groups * (cout / 4);
         ktimer_begin("bn_apply_pool_kernel", 4.0 * static_cast<double>(rows) * cout, st);  // z read once; the pooled output is 1/pool_s of it
         bn_apply_pool_kernel<<<static_cast<unsigned>((np + 127) / 128), 128, 0, st>>>(groups, pool_s, cout / 4, z, coef, relu, pooled, inv_ties);
@@ -1059,6 +1120,14 @@ F3D_API int f3d_conv_bn_train_backward_chain(long long rows, int cin, int cout, 
 F3D_API int f3d_debug_set_fuse_dz(int on) {
     const int prev = g_fuse_dz;
     g_fuse_dz = on ? 1 : 0;
+    return prev;
+}
+
+// Measurement / test aid: 0 = pool-only layers take the pooled maximum and the tie counts with a pass over z (bn_apply_pool_kernel),
+// 1 (default) = from the statistics of the forward contraction's epilogue.  Both give the same bits.  Returns the previous setting.
+F3D_API int f3d_debug_set_epilogue_pool(int on) {
+    const int prev = g_epilogue_pool;
+    g_epilogue_pool = on ? 1 : 0;
     return prev;
 }
 

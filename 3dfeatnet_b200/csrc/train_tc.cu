@@ -86,8 +86,11 @@ __device__ int g_lin_dbg = 0;
 // Epilogue of the lin_tc kernels: the N accumulator values of this thread's channel (rows r .. r + N - 1 of the tile) + bias -> global
 // memory (row stride nout), optionally with the BN statistics.  Instruction count matters here (the epilogue warps are issue-bound):
 // one pointer bump per row instead of a 64-bit row * nout product, no per-row bounds test on full tiles.
-template <int N, bool STATS>
-__device__ __forceinline__ void store_channel_rows(float *__restrict__ o, int nout, int nvalid, const uint32_t (&r)[N], float bb, float &s1, float &s2) {
+// POOL: the thread also tracks {largest key, its multiplicity, second largest distinct key} of its N rows (PoolEpilogue, dz_source.cuh);
+// sgn = 0 or 0x80000000 flips z into key space.
+template <int N, bool STATS, bool POOL>
+__device__ __forceinline__ void store_channel_rows(float *__restrict__ o, int nout, int nvalid, const uint32_t (&r)[N], float bb, float &s1, float &s2,
+                                                   uint32_t sgn, float &m1, float &c1, float &m2) {
     if (nvalid >= N) {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -95,6 +98,13 @@ __device__ __forceinline__ void store_channel_rows(float *__restrict__ o, int no
             *o = v;
             o += nout;
             if (STATS) { s1 += v; s2 = fmaf(v, v, s2); }
+            if (POOL) {
+                const float key = __uint_as_float(__float_as_uint(v) ^ sgn);
+                const bool gt = key > m1, eq = key == m1;
+                m2 = gt ? m1 : (!eq && key > m2) ? key : m2;
+                c1 = gt ? 1.0f : eq ? c1 + 1.0f : c1;
+                m1 = gt ? key : m1;
+            }
         }
     } else {
 #pragma unroll
@@ -119,7 +129,7 @@ template <int nsplit>
 __global__ void __launch_bounds__(ttc::kThreads, 4)
 lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t tmem_cols, const float *__restrict__ x, const uint8_t *__restrict__ wimg,
               const float *__restrict__ bias, const float *__restrict__ gbias, int gs, float *__restrict__ out, float *__restrict__ part,
-              XSource X) {
+              XSource X, PoolEpilogue PE) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const bool ring = (k_real & 7) == 0;
@@ -337,10 +347,19 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
             float *o = out + (r0 + col0) * nout + gch;
             const long long left = rows - (r0 + col0);
             const int nvalid = (dbg & 4) ? 0 : left < 32 ? static_cast<int>(left) : 32;
-            if (part)
-                store_channel_rows<32, true>(o, nout, nvalid, r, bb, s1, s2);
-            else
-                store_channel_rows<32, false>(o, nout, nvalid, r, bb, s1, s2);
+            float m1 = -INFINITY, c1 = 0.f, m2 = -INFINITY;
+            if (PE.zext) {  // forward of a pool-only layer (full tiles only: rows % 64 == 0)
+                const uint32_t sgn = __ldg(PE.gamma + gch) >= 0.f ? 0u : 0x80000000u;
+                store_channel_rows<32, true, true>(o, nout, nvalid, r, bb, s1, s2, sgn, m1, c1, m2);
+                float *ze = PE.zext + static_cast<size_t>((r0 + col0) >> 5) * 3 * nout + gch;
+                ze[0] = m1;
+                ze[nout] = c1;
+                ze[2 * nout] = m2;
+            } else if (part) {
+                store_channel_rows<32, true, false>(o, nout, nvalid, r, bb, s1, s2, 0u, m1, c1, m2);
+            } else {
+                store_channel_rows<32, false, false>(o, nout, nvalid, r, bb, s1, s2, 0u, m1, c1, m2);
+            }
         }
         F3D_LT(7)
         tcgen05_fence_before();
@@ -381,7 +400,7 @@ template <int nsplit, int NT, bool FUSED>
 __global__ void __launch_bounds__(lp::kThreads, 1)
 lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint32_t tmem_cols, const float *__restrict__ x,
                    const uint8_t *__restrict__ wimg, const float *__restrict__ bias, const float *__restrict__ gbias, int gs,
-                   float *__restrict__ out, float *__restrict__ part, DzSource S, float *__restrict__ dgb, XSource X) {
+                   float *__restrict__ out, float *__restrict__ part, DzSource S, float *__restrict__ dgb, XSource X, PoolEpilogue PE) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t kLbo = lp::lbo(nsplit, NT);
@@ -652,10 +671,19 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                 float *o = out + r0 * nout + gch;
                 const long long left = rows - r0;
                 const int nvalid = (dbg & 4) ? 0 : left < NH ? static_cast<int>(left) : NH;
-                if (part)
-                    store_channel_rows<NH, true>(o, nout, nvalid, r, bb, s1, s2);
-                else
-                    store_channel_rows<NH, false>(o, nout, nvalid, r, bb, s1, s2);
+                float m1 = -INFINITY, c1 = 0.f, m2 = -INFINITY;
+                if (NH == 32 && PE.zext) {  // forward of a pool-only layer (full tiles only: rows % 64 == 0)
+                    const uint32_t sgn = __ldg(PE.gamma + gch) >= 0.f ? 0u : 0x80000000u;
+                    store_channel_rows<NH, true, true>(o, nout, nvalid, r, bb, s1, s2, sgn, m1, c1, m2);
+                    float *ze = PE.zext + static_cast<size_t>(r0 >> 5) * 3 * nout + gch;
+                    ze[0] = m1;
+                    ze[nout] = c1;
+                    ze[2 * nout] = m2;
+                } else if (part) {
+                    store_channel_rows<NH, true, false>(o, nout, nvalid, r, bb, s1, s2, 0u, m1, c1, m2);
+                } else {
+                    store_channel_rows<NH, false, false>(o, nout, nvalid, r, bb, s1, s2, 0u, m1, c1, m2);
+                }
             }
         }
         if (part && ch_ok) {  // two partial slots per CTA like lin_tc_kernel: one per half of the tiles' rows
@@ -1098,6 +1126,11 @@ static LinPlan lin_tc_plan(long long rows, int k_real, int nsplit, bool fused = 
 }
 
 int lin_tc_grid(long long rows, int k_real, int nsplit) { return lin_tc_plan(rows, k_real, nsplit).grid; }
+// rows per tile of the kernel lin_tc() launches for this shape (the pooling epilogue needs 64 = two half groups of 32)
+int lin_tc_tile(long long rows, int k_real, int nsplit) {
+    const LinPlan P = lin_tc_plan(rows, k_real, nsplit);
+    return P.pipe ? P.nt : ttc::kTile;
+}
 
 // out (rows, nout) = x (rows, k_real) * A^T (+ bias) (+ gbias[row / gs]) with A[m][k] = src[m*sm + k*sk]; nsplit = 2 (bf16x3)
 // or 3 (six product terms, fp32-grade);  part: 2*lin_tc_grid() partials of
@@ -1113,9 +1146,12 @@ bool lin_tc_dz_supported(long long rows, int k_real, int gs, bool need_group_sum
 
 int lin_tc(long long rows, int k_real, int nout, const float *x, const float *src, long long sm, long long sk, const float *bias,
            const float *gbias, int gs, float *out, float *part, uint8_t *wimg, int nsplit, cudaStream_t st, const DzSource *S, float *dgb,
-           const float *xcoef, int xrelu) {
+           const float *xcoef, int xrelu, float *zext, const float *gamma) {
     const int kp = lin_tc_kp(k_real);
     const XSource X{xcoef, xrelu};
+    const PoolEpilogue PE{zext, gamma};
+    if (zext && (S != nullptr || rows % 64 != 0 || !gamma || lin_tc_tile(rows, k_real, nsplit) != 64))
+        return fail(F3D_ERR_UNSUPPORTED, "lin_tc: the pooling epilogue needs 64-row tiles and rows % 64 == 0");
     if (xcoef && (S != nullptr || k_real % 8 != 0)) return fail(F3D_ERR_UNSUPPORTED, "lin_tc: activation source needs k % 8 == 0 and no dz source");
     const int mblocks = (nout + 127) / 128;
     const long long total = 128LL * kp * mblocks;
@@ -1136,7 +1172,7 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
     e = cudaFuncSetAttribute(lin_tc_pipe_kernel<NS, NT, FU>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));    \
     if (e == cudaSuccess)                                                                                                                \
         lin_tc_pipe_kernel<NS, NT, FU><<<grid, lp::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, \
-                                                                           part, S0, dgb, X);
+                                                                           part, S0, dgb, X, PE);
     if (P.pipe) {
         if (fused && P.nt == 64) { F3D_LAUNCH_PIPE(2, 64, true) }
         else if (fused) { F3D_LAUNCH_PIPE(2, 32, true) }
@@ -1151,10 +1187,10 @@ int lin_tc(long long rows, int k_real, int nout, const float *x, const float *sr
 #undef F3D_LAUNCH_PIPE
     if (nsplit == 3) {
         e = cudaFuncSetAttribute(lin_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));
-        if (e == cudaSuccess) lin_tc_kernel<3><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part, X);
+        if (e == cudaSuccess) lin_tc_kernel<3><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part, X, PE);
     } else {
         e = cudaFuncSetAttribute(lin_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P.smem));
-        if (e == cudaSuccess) lin_tc_kernel<2><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part, X);
+        if (e == cudaSuccess) lin_tc_kernel<2><<<grid, ttc::kThreads, P.smem, st>>>(rows, k_real, kp, nout, P.nring, P.cols, x, wimg, bias, gbias, gs, out, part, X, PE);
     }
     ktimer_end(st);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "lin_tc: cudaFuncSetAttribute");
@@ -1234,7 +1270,7 @@ F3D_API int f3d_debug_lin_tc(long long rows, int k, int nout, const float *x, co
                              void *stream) {
     if (!f3d::lin_tc_supported(k, nout) || (nsplit != 2 && nsplit != 3)) return f3d::fail(F3D_ERR_UNSUPPORTED, "debug_lin_tc: unsupported shape");
     return f3d::lin_tc(rows, k, nout, x, W, k, 1, nullptr, nullptr, 0, out, part, static_cast<uint8_t *>(wimg), nsplit, f3d::as_stream(stream), nullptr,
-                       nullptr, nullptr, 0);
+                       nullptr, nullptr, 0, nullptr, nullptr);
 }
 
 // Bring-up / micro-benchmark entry: the wgrad contraction alone.  dbg bit 0 skips the operand staging, bit 1 the MMAs.

@@ -317,6 +317,49 @@ def test_pool_only_layer_dz_formed_inside_the_contractions(cuda, cin, cout, use_
             assert torch.equal(a, b), name
 
 
+@pytest.mark.parametrize("cin,cout,use_relu,mid,neg_gamma", [(128, 256, True, False, False), (64, 128, False, True, True), (64, 128, True, False, True),
+                                                             (128, 128, False, False, False)])
+def test_pool_statistics_taken_in_the_contraction_epilogue(cuda, cin, cout, use_relu, mid, neg_gamma):
+    """Pool-only layers on the tensor-core path: the forward contraction's epilogue records, per half group and channel, the largest z (the
+    smallest where gamma < 0), its multiplicity and the runner-up; pool_from_extremes_kernel turns them into the pooled maximum and the tie
+    counts once the BN statistics exist (re-counting the rare groups where two distinct z round to one activation) -- against the pass over z
+    of bn_apply_pool_kernel: same pooled output, same gradients, bit for bit, on inputs full of exact ties and with channels that the ReLU
+    switches off."""
+    layers, lib_mod = pkg("models.layers"), pkg("_lib")
+    g = torch.Generator().manual_seed(17)
+    B, M, S = 2, 90, 64
+    x = torch.relu(torch.randn(B, M, S, cin, generator=g))
+    x[:, :, 1::2] = x[:, :, 0::2]          # duplicated samples => tied maxima everywhere
+    x[:, 10:20] = x[:, 10:20, :1]          # whole groups of identical rows
+    gamma = torch.rand(cout, generator=g) + 0.5
+    if neg_gamma:
+        gamma[::3] = -gamma[::3]
+        gamma[5] = 0.0
+    beta = torch.randn(cout, generator=g) * 0.5
+    beta[::4] -= 3.0                        # channels whose activation is (almost) always clamped by the ReLU
+    params = {"l/conv2d/weights": torch.randn(cin * (2 if mid else 1), cout, generator=g) * 0.2, "l/conv2d/biases": torch.randn(cout, generator=g) * 0.1,
+              "l/bn/gamma": gamma, "l/bn/beta": beta, "l/bn/moving_mean": torch.zeros(cout), "l/bn/moving_variance": torch.ones(cout)}
+    go = torch.randn(B, M, 1, cout, generator=g).to(cuda)
+    res = []
+    L = lib_mod.lib()
+    for epi in (1, 0):
+        prev = L.f3d_debug_set_epilogue_pool(epi)
+        try:
+            P = {k: v.to(cuda).requires_grad_(k.split("/")[-1] in ("weights", "biases", "gamma", "beta")) for k, v in params.items()}
+            xc = x.to(cuda).requires_grad_(True)
+            pooled_in = layers.max_pool_samples(xc) if mid else None
+            L.f3d_reset_launch_count()
+            out = layers.conv2d(xc, cout, [1, 1], scope="l", is_training=True, activation=layers.relu if use_relu else None, params=P,
+                                pool_samples=True, concat_pooled=pooled_in)
+            leaves = [xc] + [P[k] for k in ("l/conv2d/weights", "l/bn/gamma", "l/bn/beta", "l/conv2d/biases")]
+            res.append((out.detach(), torch.autograd.grad((out * go).sum(), leaves)))
+        finally:
+            L.f3d_debug_set_epilogue_pool(prev)
+    assert torch.equal(res[0][0], res[1][0])
+    for name, a, b in zip(("dx", "dW", "dgamma", "dbeta", "db"), res[0][1], res[1][1]):
+        assert torch.equal(a, b), name
+
+
 @pytest.mark.parametrize("B,N,M,fdim", [(2, 2048, 77, 32), (3, 4096, 128, 128)])
 def test_chained_layers_carry_the_bits_of_the_materialised_path(cuda, B, N, M, fdim):
     """The per-point MLP chains (detector conv0 -> conv1 -> conv2, descriptor conv0 -> conv1 -> conv_mid) with their intermediate
