@@ -25,6 +25,11 @@ struct DzSource {
 
 constexpr int kDzCoefs = 7;
 
+// the seven coefficient quads of one channel quad, kept in registers by a converter thread that owns that quad for the whole kernel
+struct DzCoefRegs {
+    float4 bsc, bsh, ss, k1, mu, is, k2;
+};
+
 // The INPUT rows of a contraction when they are the activation of the previous layer, y = act(z * scale + shift) (bn_apply): the
 // consumers (forward lin_tc, wgrad) fetch the previous layer's pre-BN tensor z and evaluate the activation in their operand converters
 // with bn_apply's own rounding, so y is neither written by the producer nor read by the consumers: the tensor never exists in HBM.

@@ -20,6 +20,22 @@ namespace f3d {
 
 constexpr int kLossThreads = 256;
 
+// (m, f) row-major global -> shared memory with row stride f + 1 (conflict-free column walks): a warp copies a row, no index division
+__device__ __forceinline__ void stage_rows_padded(float *__restrict__ so, const float *__restrict__ o, int m, int f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int c = lane; c < f; c += 32) {
+        int r = warp;
+        for (; r + 7 * nw < m; r += 8 * nw) {  // eight independent loads in flight per thread
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(o + static_cast<size_t>(r + u * nw) * f + c);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) so[(r + u * nw) * (f + 1) + c] = v[u];
+        }
+        for (; r < m; r += nw) so[r * (f + 1) + c] = __ldg(o + static_cast<size_t>(r) * f + c);
+    }
+}
+
 // best[b,i] = min_k |fa[b,i]-fo[b,k]|^2 (squared_difference summed over F, layers.py:60), arg[b,i] = first arg-min,
 // ties[b,i] = number of columns attaining the minimum.  One warp per anchor; `other` staged in shared memory.
 __global__ void __launch_bounds__(kLossThreads)
@@ -28,7 +44,7 @@ loss_min_kernel(int m, int f, const float *__restrict__ fa, const float *__restr
     extern __shared__ float so[];  // [m][f+1]
     const int b = blockIdx.y;
     const float *o = fo + static_cast<size_t>(b) * m * f;
-    for (int e = threadIdx.x; e < m * f; e += blockDim.x) so[(e / f) * (f + 1) + e % f] = o[e];
+    stage_rows_padded(so, o, m, f);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -113,7 +129,7 @@ loss_grad_anchor_kernel(int m, int f, float sgn, int accumulate, const float *__
     extern __shared__ float so[];  // [m][f+1]
     const int b = blockIdx.y;
     const float *o = fo + static_cast<size_t>(b) * m * f;
-    for (int e = threadIdx.x; e < m * f; e += blockDim.x) so[(e / f) * (f + 1) + e % f] = o[e];
+    stage_rows_padded(so, o, m, f);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

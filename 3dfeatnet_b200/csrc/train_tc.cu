@@ -389,7 +389,11 @@ constexpr int kConvWarps = 8;  // converter warps (rows of a tile split among th
 constexpr int kEpiWarps = 8;   // epilogue warps: two per TMEM lane quarter, each draining half of the tile's rows
 constexpr int kThreads = 32 * (1 + kConvWarps + kEpiWarps);
 constexpr int kMaxRing = 3;
-__host__ __device__ constexpr uint32_t lbo(int nsplit, int nt) { return static_cast<uint32_t>(nt) * 16 + (nsplit == 3 ? 16 : 32); }
+// operand-image stride between 8-wide K chunks.  The fused dz converter writes a ROW of the tile per warp (32 channel quads -> 16 chunks
+// x 2 halves): +16 puts consecutive chunks 4 banks apart, so its 8-byte stores take the minimum of two wavefronts.
+__host__ __device__ constexpr uint32_t lbo(int nsplit, int nt, bool fused = false) {
+    return static_cast<uint32_t>(nt) * 16 + ((nsplit == 3 || fused) ? 16 : 32);
+}
 }  // namespace lp
 
 // FUSED: the input rows are not read from x but formed on the fly as the BN-backward gradient dz of a pool-only layer (DzSource,
@@ -403,7 +407,7 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                    float *__restrict__ out, float *__restrict__ part, DzSource S, float *__restrict__ dgb, XSource X, PoolEpilogue PE) {
     using namespace ttc;
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr uint32_t kLbo = lp::lbo(nsplit, NT);
+    constexpr uint32_t kLbo = lp::lbo(nsplit, NT, FUSED);
     const uint32_t wbytes = 256u * kp;
     const uint32_t split = static_cast<uint32_t>(kp / 8) * kLbo;
     const uint32_t img_bytes = static_cast<uint32_t>(nsplit) * split;
@@ -536,6 +540,14 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
         const int wc = warp - 1;
         const int rsub = lane >> 3, c4 = (lane >> 1) & 3, h = lane & 1;
         const uint32_t row_bytes = static_cast<uint32_t>(k_real) * 4;
+        // FUSED: channel quad / first row / row step of this thread (k_real a multiple of 16 with (converter threads) % (k_real / 4) == 0)
+        const int fquads = k_real >> 2, ft = threadIdx.x - 32;
+        const int fq = ft % fquads, frow = ft / fquads, frows_pass = (lp::kConvWarps * 32) / fquads;
+        DzCoefRegs KF{};
+        if (FUSED) {
+            auto ld = [&](int i) { return *reinterpret_cast<const float4 *>(coef_s + i * k_real + fq * 4); };
+            KF = DzCoefRegs{ld(0), ld(1), ld(2), ld(3), ld(4), ld(5), ld(6)};
+        }
         long long it = 0;
         for (long long tile = cta; tile < ntiles; tile += ncta, ++it) {
             const int b = static_cast<int>(it & 1), slot = static_cast<int>(it % nring);
@@ -571,58 +583,47 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                     }
                 }
             } else {
-                // channel chunk outside, rows inside: the ten coefficient quads of a chunk are loaded once per NT / kRowsPass rows
+                // thread t of the converters owns channel quad t % quads for the whole kernel (its seven coefficient quads stay in
+                // registers, KF below) and rows t / quads, + rows_pass, ... of every tile: one LDS.128 per four values instead of fourteen
+                // (the coefficient and pooled rows used to be re-read for every row: the converters were shared-memory-bound)
                 const float *pool = reinterpret_cast<const float *>(ringbuf + slot * slot_bytes + NT * row_bytes);
-                for (int c = c4; c < kp / 8; c += 4) {
-                    const int ch = c * 8 + h * 4;
-                    const bool chok = ch < k_real;
-                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    auto ld = [&](const float *base) { return chok ? *reinterpret_cast<const float4 *>(base + ch) : z4; };
-                    const float4 bsc = ld(coef_s), bsh = ld(coef_s + k_real), ss = ld(coef_s + 2 * k_real), k1 = ld(coef_s + 3 * k_real),
-                                 mu = ld(coef_s + 4 * k_real), is = ld(coef_s + 5 * k_real), k2 = ld(coef_s + 6 * k_real);
-                    const float4 pm = ld(pool), gp = ld(pool + k_real), iv = ld(pool + 2 * k_real);
-                    const float4 gsc = make_float4(__fmul_rn(gp.x, iv.x), __fmul_rn(gp.y, iv.y), __fmul_rn(gp.z, iv.z), __fmul_rn(gp.w, iv.w));
-                    float4 acc = z4;
-#pragma unroll
-                    for (int p = 0; p < NT / kRowsPass; ++p) {
-                        const int r = p * kRowsPass + wc * 4 + rsub;
-                        float4 a = z4;
-                        if (r0 + r < rows && chok) {
-                            const float4 zz = *reinterpret_cast<const float4 *>(ringbuf + slot * slot_bytes + r * row_bytes + h * 16 + c * 32);
-                            a.x = dz_value(zz.x, bsc.x, bsh.x, ss.x, k1.x, mu.x, is.x, k2.x, pm.x, gsc.x, S.relu);
-                            a.y = dz_value(zz.y, bsc.y, bsh.y, ss.y, k1.y, mu.y, is.y, k2.y, pm.y, gsc.y, S.relu);
-                            a.z = dz_value(zz.z, bsc.z, bsh.z, ss.z, k1.z, mu.z, is.z, k2.z, pm.z, gsc.z, S.relu);
-                            a.w = dz_value(zz.w, bsc.w, bsh.w, ss.w, k1.w, mu.w, is.w, k2.w, pm.w, gsc.w, S.relu);
-                        }
-                        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-                        uint8_t *dst = img + c * kLbo + r * 16 + h * 8;
-#pragma unroll
-                        for (int sp = 0; sp < nsplit; ++sp) {
-                            const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-                            *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                            a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
-                        }
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 pm = *reinterpret_cast<const float4 *>(pool + fq * 4), gp = *reinterpret_cast<const float4 *>(pool + k_real + fq * 4),
+                             iv = *reinterpret_cast<const float4 *>(pool + 2 * k_real + fq * 4);
+                const float4 gsc = make_float4(__fmul_rn(gp.x, iv.x), __fmul_rn(gp.y, iv.y), __fmul_rn(gp.z, iv.z), __fmul_rn(gp.w, iv.w));
+                float4 acc = z4;
+                uint8_t *dst0 = img + (fq >> 1) * kLbo + (fq & 1) * 8;
+                for (int r = frow; r < NT; r += frows_pass) {
+                    float4 a = z4;
+                    if (r0 + r < rows) {
+                        const float4 zz = *reinterpret_cast<const float4 *>(ringbuf + slot * slot_bytes + r * row_bytes + fq * 16);
+                        a.x = dz_value(zz.x, KF.bsc.x, KF.bsh.x, KF.ss.x, KF.k1.x, KF.mu.x, KF.is.x, KF.k2.x, pm.x, gsc.x, S.relu);
+                        a.y = dz_value(zz.y, KF.bsc.y, KF.bsh.y, KF.ss.y, KF.k1.y, KF.mu.y, KF.is.y, KF.k2.y, pm.y, gsc.y, S.relu);
+                        a.z = dz_value(zz.z, KF.bsc.z, KF.bsh.z, KF.ss.z, KF.k1.z, KF.mu.z, KF.is.z, KF.k2.z, pm.z, gsc.z, S.relu);
+                        a.w = dz_value(zz.w, KF.bsc.w, KF.bsh.w, KF.ss.w, KF.k1.w, KF.mu.w, KF.is.w, KF.k2.w, pm.w, gsc.w, S.relu);
                     }
-                    if (dgb) {  // column sums of the tile (= one group): over the 4 row lanes of the warp here, over the converter warps below
+                    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+                    uint8_t *dst = dst0 + r * 16;
 #pragma unroll
-                        for (int m = 8; m <= 16; m <<= 1) {
-                            acc.x += __shfl_xor_sync(kFull, acc.x, m); acc.y += __shfl_xor_sync(kFull, acc.y, m);
-                            acc.z += __shfl_xor_sync(kFull, acc.z, m); acc.w += __shfl_xor_sync(kFull, acc.w, m);
-                        }
-                        if (rsub == 0 && chok) *reinterpret_cast<float4 *>(gred + wc * k_real + ch) = acc;
+                    for (int sp = 0; sp < nsplit; ++sp) {
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                        *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                        a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
                     }
                 }
+                if (dgb) *reinterpret_cast<float4 *>(gred + frow * k_real + fq * 4) = acc;  // this thread's rows of the tile (= one group)
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(img_full + b);
             if (FUSED && dgb) {
-                static_assert(lp::kConvWarps == 8, "the fixed-order sum below is written for eight converter warps");
                 asm volatile("bar.sync 1, %0;" ::"n"(lp::kConvWarps * 32) : "memory");  // the converter warps
                 float *dst = dgb + static_cast<size_t>(r0 / S.gs) * k_real;
-                for (int ch = wc * 32 + lane; ch < k_real; ch += lp::kConvWarps * 32)
-                    dst[ch] = ((gred[ch] + gred[k_real + ch]) + (gred[2 * k_real + ch] + gred[3 * k_real + ch])) +
-                              ((gred[4 * k_real + ch] + gred[5 * k_real + ch]) + (gred[6 * k_real + ch] + gred[7 * k_real + ch]));
+                for (int ch = wc * 32 + lane; ch < k_real; ch += lp::kConvWarps * 32) {
+                    float t = 0.f;
+                    for (int g = 0; g < frows_pass; ++g) t += gred[g * k_real + ch];  // fixed order
+                    dst[ch] = t;
+                }
                 asm volatile("bar.sync 1, %0;" ::"n"(lp::kConvWarps * 32) : "memory");  // gred is rewritten by the next tile
             }
         }
@@ -835,9 +836,6 @@ __device__ __forceinline__ void wgrad_convert_both(uint8_t *img_a, uint32_t lbo_
 // stage; z is overwritten IN PLACE by dz = dz_value(z), after which the ordinary transposing conversion (wgrad_convert) runs on the slot.
 // (One 8-row x 4-channel unit per thread, as the conversion itself is organised, left 128-256 of the 480 threads with ~400 dependent
 // instructions each: the stage time was that thread's latency.)  `dbsum` is the thread's share of db = column sums of dz.
-struct DzCoefRegs {
-    float4 bsc, bsh, ss, k1, mu, is, k2;
-};
 __device__ __forceinline__ void wgrad_dz_in_place(uint8_t *__restrict__ stage, int c, int valid_rows, const DzCoefRegs &K, const float *__restrict__ pool,
                                                   int relu, int q, int row0, int rows_pass, float4 &dbsum) {
     const float4 pm = *reinterpret_cast<const float4 *>(pool + q * 4), gp = *reinterpret_cast<const float4 *>(pool + c + q * 4),
@@ -1079,12 +1077,12 @@ static LinPlan lin_tc_plan(long long rows, int k_real, int nsplit, bool fused = 
     LinPlan P{};
     const int kp = lin_tc_kp(k_real);
     // fused dz source: three pooled rows ride in every ring slot, the coefficient table and the group-sum scratch follow the barriers
-    const size_t slot_extra = fused ? static_cast<size_t>(3) * k_real * 4 : 0, tail_extra = fused ? static_cast<size_t>(kDzCoefs + lp::kConvWarps) * k_real * 4 : 0;
+    const size_t slot_extra = fused ? static_cast<size_t>(3) * k_real * 4 : 0, tail_extra = fused ? static_cast<size_t>(kDzCoefs) * k_real * 4 + lp::kConvWarps * 32 * 16 : 0;  // coefficient table + one float4 per converter thread
     // the warp-specialised kernel pays off when the operand conversion + MMAs are the long phases (K >= 128); for narrow
     // inputs the tile is store-bound and the all-warps epilogue of lin_tc_kernel at 3-4 CTAs/SM is faster (measured)
     if (k_real % 8 == 0 && kp >= 128) {
         for (int nt = 64; nt >= 32 && !P.pipe; nt -= 32) {
-            const size_t img = static_cast<size_t>(nsplit) * (kp / 8) * lp::lbo(nsplit, nt);
+            const size_t img = static_cast<size_t>(nsplit) * (kp / 8) * lp::lbo(nsplit, nt, fused);
             const size_t slot = static_cast<size_t>(nt) * k_real * 4 + slot_extra;
             for (int nring = lp::kMaxRing; nring >= 2; --nring) {
                 const size_t smem = 2 * img + nring * slot + 128 + tail_extra;
@@ -1138,7 +1136,8 @@ int lin_tc_tile(long long rows, int k_real, int nsplit) {
 // fused dz source (S != NULL, nsplit 2): can the contraction read z and form dz itself?  Needs the warp-specialised kernel, tiles inside
 // one group, and -- when the per-group sums of dz are wanted -- tiles that ARE groups.
 bool lin_tc_dz_supported(long long rows, int k_real, int gs, bool need_group_sums) {
-    if (k_real % 8 != 0 || gs <= 0 || rows % gs != 0) return false;
+    // the converters give every thread one channel quad: 16 | k_real and (k_real / 4) | 256 threads
+    if (k_real % 16 != 0 || (lp::kConvWarps * 32) % (k_real / 4) != 0 || gs <= 0 || rows % gs != 0) return false;
     const LinPlan P = lin_tc_plan(rows, k_real, 2, true);
     if (!P.pipe || gs % P.nt != 0) return false;
     return !need_group_sums || gs == P.nt;
