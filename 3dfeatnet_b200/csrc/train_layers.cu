@@ -113,6 +113,49 @@ conv_fwd_kernel(long long rows, int cin, int cout, const float *__restrict__ x, 
     }
 }
 
+// The xyz layers (3 input channels: detector / descriptor conv0, models/feat3dnet.py:43,119 on the grouped coordinates): z = x W + b in
+// plain fp32 FMAs.  A streaming kernel bound by the write of z: 3 of 16 K-slots of an MMA would be used, and the tensor-core kernel spent
+// its time converting and draining for nothing.  Thread = (channel quad, row lane); per-block column sums of z and z^2 for the BN
+// statistics in the layout of the other forward kernels: part[(blk*2 + {0,1})*c + ch].
+__global__ void __launch_bounds__(256)
+conv3_fwd_kernel(long long rows, int c, const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ bias,
+                 float *__restrict__ z, float *__restrict__ part) {
+    __shared__ float4 red[2][256];
+    const int cvec = c >> 2, rl = 256 / cvec;
+    const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
+    const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const long long rbeg = blockIdx.x * chunk, rend = min(rows, rbeg + chunk);
+    const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W) + cv), w1 = __ldg(reinterpret_cast<const float4 *>(W + c) + cv),
+                 w2 = __ldg(reinterpret_cast<const float4 *>(W + 2 * c) + cv);
+    const float4 bb = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    if (rlane < rl) {
+        for (long long r = rbeg + rlane; r < rend; r += rl) {
+            const float x0 = __ldg(x + r * 3), x1 = __ldg(x + r * 3 + 1), x2 = __ldg(x + r * 3 + 2);
+            float4 v;
+            v.x = __fmaf_rn(x2, w2.x, __fmaf_rn(x1, w1.x, __fmaf_rn(x0, w0.x, bb.x)));
+            v.y = __fmaf_rn(x2, w2.y, __fmaf_rn(x1, w1.y, __fmaf_rn(x0, w0.y, bb.y)));
+            v.z = __fmaf_rn(x2, w2.z, __fmaf_rn(x1, w1.z, __fmaf_rn(x0, w0.z, bb.z)));
+            v.w = __fmaf_rn(x2, w2.w, __fmaf_rn(x1, w1.w, __fmaf_rn(x0, w0.w, bb.w)));
+            reinterpret_cast<float4 *>(z)[static_cast<size_t>(r) * cvec + cv] = v;
+            s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+            s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+        }
+    }
+    red[0][threadIdx.x] = s1;
+    red[1][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < 2 * cvec) {
+        const int which = threadIdx.x / cvec, v = threadIdx.x - which * cvec;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < rl; ++l) {
+            const float4 u = red[which][l * cvec + v];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        reinterpret_cast<float4 *>(part + (static_cast<size_t>(blockIdx.x) * 2 + which) * c)[v] = t;
+    }
+}
+
 // out[w] = sum over the parts of part[p*width + w] in fp64 and a fixed order: 32 slices (p mod 32) per column, each
 // ascending, then the slices ascending.  Block = 32 columns x 32 slices.
 // OutT = double keeps the total unrounded for a consumer that subtracts two such sums (the BN batch variance below).
@@ -853,8 +896,11 @@ static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "conv_bn_train_forward: workspace too small");
     cudaStream_t st = as_stream(stream);
     const size_t tiles = static_cast<size_t>((rows + kTileRows - 1) / kTileRows);
-    const bool tc = precision == 2 && lin_tc_supported(cin, cout);
-    const size_t nparts = tc ? static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit)) : tiles;
+    // the xyz layers on either precision: plain fp32 FMAs (exact fp32, and faster than padding K = 3 to an MMA)
+    const bool xyz3 = cin == 3 && !group_bias && cout % 4 == 0 && 256 % (cout / 4) == 0;
+    const int grid3 = static_cast<int>(tiles < static_cast<size_t>(kRedBlocks) ? tiles : static_cast<size_t>(kRedBlocks));
+    const bool tc = !xyz3 && precision == 2 && lin_tc_supported(cin, cout);
+    const size_t nparts = xyz3 ? static_cast<size_t>(grid3) : tc ? static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit)) : tiles;
     const size_t stat_parts = tiles > static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit)) ? tiles : static_cast<size_t>(2 * lin_tc_grid(rows, cin, kFwdSplit));
     char *w = static_cast<char *>(workspace);
     float *part = reinterpret_cast<float *>(w);
@@ -871,9 +917,17 @@ static int conv_bn_forward_impl(long long rows, int cin, int cout, const float *
     float *zext = reinterpret_cast<float *>(w);
     // pool-only layer on the tensor cores with 64-row tiles = groups: the pool's statistics are taken in the contraction's epilogue
     const bool epi_pool = g_epilogue_pool && tc && pool_s == 64 && rows % 64 == 0 && cin % 8 == 0 && lin_tc_tile(rows, cin, kFwdSplit) == 64;
-    int rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, kFwdSplit, st, nullptr, nullptr, xcoef, xrelu,
+    int rc = 0;
+    if (xyz3) {
+        ktimer_begin("conv3_fwd_kernel", 4.0 * static_cast<double>(rows) * (3 + cout), st);
+        conv3_fwd_kernel<<<grid3, 256, 0, st>>>(rows, cout, x, W, bias, z, part);
+        ktimer_end(st);
+        rc = check_launch("conv3_fwd_kernel");
+    } else {
+        rc = tc ? lin_tc(rows, cin, cout, x, W, 1, cout, bias, group_bias, group_s, z, part, wimg, kFwdSplit, st, nullptr, nullptr, xcoef, xrelu,
                          epi_pool ? zext : nullptr, gamma)
                 : launch_conv_fwd(rows, cin, cout, x, W, bias, group_bias, group_s, z, part, st);
+    }
     if (rc) return rc;
     partial_reduce_kernel<double><<<(2 * cout + 31) / 32, 1024, 0, st>>>(static_cast<int>(nparts), 2 * cout, part, sums);
     rc = check_launch("partial_reduce_kernel");
