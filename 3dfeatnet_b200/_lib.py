@@ -63,6 +63,9 @@ SIGNATURES = {
                                              _vp, _vp, _i, _vp, _sz, _vp]),
     "f3d_conv_bn_train_backward_chain": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _vp, _vp, _vp,
                                               _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "f3d_linear_workspace_bytes": (_sz, [_c.c_longlong, _i, _i]),
+    "f3d_linear_forward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "f3d_linear_backward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "f3d_maxpool_samples_forward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp]),
     "f3d_maxpool_samples_backward": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "f3d_triplet_loss_workspace_bytes": (_sz, [_i, _i]),

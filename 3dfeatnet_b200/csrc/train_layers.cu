@@ -1169,6 +1169,58 @@ F3D_API int f3d_conv_bn_train_backward_chain(long long rows, int cin, int cout, 
                                  dW, db, dgamma, dbeta, dgroup_bias, group_s, precision, workspace, workspace_bytes, stream);
 }
 
+// out (rows, nout) = x (rows, k) W, W (k, nout) row-major, and its gradients, on the tensor-core contractions of the training layers: the
+// per-cluster term of conv_mid -- pooled (B*M, C) times the lower rows of the layer's weights, the pooled half of concat([h, tile(max h)])
+// (models/feat3dnet.py:60-69) -- and anything else that is a plain matrix product of row-major fp32 tensors.  Forward with the 3-way split
+// (fp32-grade), gradients with the 2-way split, like the layers.  k % 8 == 0, k <= 128, nout % 16 == 0, nout <= 256 for dW.
+F3D_API size_t f3d_linear_workspace_bytes(long long rows, int k, int nout) {
+    if (rows <= 0 || k <= 0 || nout <= 0) return 256;
+    const size_t wimg = lin_tc_weight_bytes(k, nout) > lin_tc_weight_bytes(nout, k) ? lin_tc_weight_bytes(k, nout) : lin_tc_weight_bytes(nout, k);
+    int tcg = 0;
+    long long per = 0;
+    wgrad_tc_plan(rows, &tcg, &per);
+    return align256(wimg) + align256(static_cast<size_t>(tcg) * k * nout * 4) + 256;
+}
+
+F3D_API int f3d_linear_forward(long long rows, int k, int nout, const float *x, const float *W, float *out, void *workspace, size_t workspace_bytes,
+                               void *stream) {
+    if (rows <= 0 || k <= 0 || nout <= 0 || !x || !W || !out) return fail(F3D_ERR_INVALID_ARGUMENT, "linear_forward: bad arguments");
+    if (!lin_tc_supported(k, nout)) return fail(F3D_ERR_UNSUPPORTED, "linear_forward: k must be <= 256");
+    if (!workspace || workspace_bytes < f3d_linear_workspace_bytes(rows, k, nout)) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "linear_forward: workspace too small");
+    // A[m = output channel][kk] = W[kk * nout + m]
+    return lin_tc(rows, k, nout, x, W, 1, nout, nullptr, nullptr, 0, out, nullptr, static_cast<uint8_t *>(workspace), kFwdSplit, as_stream(stream));
+}
+
+// g (rows, nout) = dL/dout -> dx (rows, k; NULL to skip) = g W^T, dW (k, nout; NULL to skip) = x^T g
+F3D_API int f3d_linear_backward(long long rows, int k, int nout, const float *x, const float *W, const float *g, float *dx, float *dW, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+    if (rows <= 0 || k <= 0 || nout <= 0 || !x || !W || !g) return fail(F3D_ERR_INVALID_ARGUMENT, "linear_backward: bad arguments");
+    if (!workspace || workspace_bytes < f3d_linear_workspace_bytes(rows, k, nout)) return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "linear_backward: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    char *w = static_cast<char *>(workspace);
+    uint8_t *wimg = reinterpret_cast<uint8_t *>(w);
+    const size_t wimg_b = lin_tc_weight_bytes(k, nout) > lin_tc_weight_bytes(nout, k) ? lin_tc_weight_bytes(k, nout) : lin_tc_weight_bytes(nout, k);
+    float *partW = reinterpret_cast<float *>(w + align256(wimg_b));
+    int rc = 0;
+    if (dW) {
+        if (!wgrad_tc_supported(k, nout)) return fail(F3D_ERR_UNSUPPORTED, "linear_backward: dW needs k % 8 == 0, k <= 128, nout % 16 == 0, nout <= 256");
+        int tcg = 0;
+        long long per = 0;
+        wgrad_tc_plan(rows, &tcg, &per);
+        rc = wgrad_tc(rows, k, nout, x, g, partW, st);
+        if (rc) return rc;
+        const long long nw = static_cast<long long>(k) * nout;
+        partial_reduce_kernel<float><<<static_cast<unsigned>((nw + 31) / 32), 1024, 0, st>>>(tcg, nw, partW, dW);
+        rc = check_launch("partial_reduce_kernel");
+        if (rc) return rc;
+    }
+    if (dx) {
+        if (!lin_tc_supported(nout, k)) return fail(F3D_ERR_UNSUPPORTED, "linear_backward: nout must be <= 256 for dx");
+        rc = lin_tc(rows, nout, k, g, W, nout, 1, nullptr, nullptr, 0, dx, nullptr, wimg, 2, st);  // A[m = kk][co] = W[kk * nout + co]
+    }
+    return rc;
+}
+
 // Measurement / test aid: 0 = pool-only layers write dz with bn_bwd_apply_kernel and read it back in wgrad and dgrad (the path the fused
 // one is checked against, bit for bit); 1 (default) = dz formed inside the contractions.  Returns the previous setting.
 F3D_API int f3d_debug_set_fuse_dz(int on) {

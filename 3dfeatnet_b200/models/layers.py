@@ -207,6 +207,49 @@ class _ConvBnTrain(torch.autograd.Function):
         return dx, dw, db, dg, dbe, None, None, dgb, None, None, None, None
 
 
+class _LinearTC(torch.autograd.Function):
+    """out = x @ W for row-major fp32 (rows, k) x (k, nout) on the tensor-core contractions of the training layers (csrc/train_tc.cu through
+    f3d_linear_forward / _backward): the per-cluster term of conv_mid, which used to be the one cuBLAS call of the training step."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        _lib = _native()
+        L = _lib.lib()
+        x2, w2 = x.detach().contiguous().float(), w.detach().contiguous().float()
+        _lib.require_cuda(x2, w2)
+        rows, k, nout = x2.shape[0], x2.shape[1], w2.shape[1]
+        nbytes = L.f3d_linear_workspace_bytes(rows, k, nout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
+        out = torch.empty((rows, nout), dtype=torch.float32, device=x2.device)
+        _lib.check(L.f3d_linear_forward(rows, k, nout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(out), _lib.ptr(ws), nbytes, _lib.stream()), "linear_forward")
+        ctx.save_for_backward(x2, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        _lib = _native()
+        L = _lib.lib()
+        x2, w2 = ctx.saved_tensors
+        rows, k, nout = x2.shape[0], x2.shape[1], w2.shape[1]
+        g2 = g.contiguous().float()
+        nbytes = L.f3d_linear_workspace_bytes(rows, k, nout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w2) if ctx.needs_input_grad[1] else None
+        _lib.check(L.f3d_linear_backward(rows, k, nout, _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(g2), _lib.ptr(dx) if dx is not None else None,
+                                         _lib.ptr(dw) if dw is not None else None, _lib.ptr(ws), nbytes, _lib.stream()), "linear_backward")
+        return dx, dw
+
+
+def linear_rows(x, w):
+    """(rows, k) @ (k, nout): the tensor-core contraction where its shapes are covered (training on the GPU with TRAIN_PRECISION "bf16x3"),
+    torch.matmul otherwise."""
+    k, nout = w.shape
+    if (FUSED_TRAINING and TRAIN_PRECISION == "bf16x3" and x.is_cuda and x.dim() == 2 and k % 8 == 0 and k <= 128 and nout % 16 == 0 and nout <= 256):
+        return _LinearTC.apply(x, w)
+    return torch.matmul(x, w)
+
+
 class _MaxPoolSamples(torch.autograd.Function):
     """tf.reduce_max over the sample axis of a (B,M,S,C) tensor with TensorFlow's tie-sharing gradient (csrc/train_layers.cu)."""
 
@@ -408,7 +451,7 @@ def conv2d(inputs, num_outputs, kernel_size, stride=[1, 1], padding='SAME', acti
             # input = concat([inputs, tile(concat_pooled)], -1) without building it: the pooled half contributes
             # concat_pooled @ W_bottom once per cluster (the split-weight identity)
             c1 = inputs.shape[-1]
-            gbias = torch.matmul(concat_pooled.reshape(-1, concat_pooled.shape[-1]), w2[c1:])
+            gbias = linear_rows(concat_pooled.reshape(-1, concat_pooled.shape[-1]), w2[c1:])
             gs, w2 = inputs.shape[2], w2[:c1]
         mode = "defer" if defer else "pool" if fuse_pool else "y"
         pool_s = inputs.shape[2] if (fuse_pool or also_pool) else 0

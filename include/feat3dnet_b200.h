@@ -247,6 +247,15 @@ int f3d_conv_bn_train_backward_chain(long long rows, int cin, int cout, const fl
                                      float *dx, float *dW, float *db, float *dgamma, float *dbeta, float *dgroup_bias, int group_s,
                                      int precision, void *workspace, size_t workspace_bytes, void *stream);
 
+/* out (rows, nout) = x (rows, k) W with W (k, nout) row-major, and its gradients dx = g W^T, dW = x^T g, on the tensor-core contractions of the
+ * training layers (forward: 3-way bf16 split, fp32-grade; gradients: 2-way split).  Used for the per-cluster term of conv_mid: the pooled half of
+ * concat([h, tile(max h)]) (models/feat3dnet.py:60-69) contributes pooled W_bottom once per cluster.  k <= 256; dW needs k % 8 == 0, k <= 128,
+ * nout % 16 == 0, nout <= 256.  dx / dW may be NULL.  workspace: f3d_linear_workspace_bytes(rows, k, nout). */
+size_t f3d_linear_workspace_bytes(long long rows, int k, int nout);
+int f3d_linear_forward(long long rows, int k, int nout, const float *x, const float *W, float *out, void *workspace, size_t workspace_bytes, void *stream);
+int f3d_linear_backward(long long rows, int k, int nout, const float *x, const float *W, const float *g, float *dx, float *dW, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 /* tf.reduce_max(new_points, axis=[2])  models/feat3dnet.py:138,147,182 on a channels-last (groups, s, c) tensor
  * (c % 4 == 0) -> out (groups, c) and inv_ties (groups, c; NULL = not wanted) = 1 / (number of samples attaining the
  * maximum); and its gradient: samples attaining the maximum share gout equally (TF _MinOrMaxGrad). */

@@ -317,6 +317,26 @@ def test_pool_only_layer_dz_formed_inside_the_contractions(cuda, cin, cout, use_
             assert torch.equal(a, b), name
 
 
+@pytest.mark.parametrize("rows,k,nout", [(9216, 64, 128), (1000, 64, 256), (77, 8, 16), (4096, 128, 128)])
+def test_linear_rows_on_the_tensor_cores(cuda, rows, k, nout):
+    """layers.linear_rows (f3d_linear_forward / _backward: the per-cluster term of conv_mid, formerly a cuBLAS call) against fp64:
+    forward to fp32 rounding (3-way split), gradients to the 2-way split's 1e-5."""
+    layers = pkg("models.layers")
+    g = torch.Generator().manual_seed(rows + k)
+    x = torch.randn(rows, k, generator=g).to(cuda).requires_grad_(True)
+    w = (torch.randn(k, nout, generator=g) * 0.2).to(cuda).requires_grad_(True)
+    go = torch.randn(rows, nout, generator=g).to(cuda)
+    out = layers.linear_rows(x, w)
+    assert out.grad_fn is not None and type(out.grad_fn).__name__.startswith("_LinearTC")
+    dx, dw = torch.autograd.grad((out * go).sum(), (x, w))
+    xd, wd = x.detach().double(), w.detach().double()
+    ref = xd @ wd
+    assert (out.detach().double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    rdx, rdw = go.double() @ wd.t(), xd.t() @ go.double()
+    assert (dx.double() - rdx).abs().max().item() < 3e-5 * rdx.abs().max().item()
+    assert (dw.double() - rdw).abs().max().item() < 3e-5 * rdw.abs().max().item()
+
+
 @pytest.mark.parametrize("cin,cout,use_relu,mid,neg_gamma", [(128, 256, True, False, False), (64, 128, False, True, True), (64, 128, True, False, True),
                                                              (128, 128, False, False, False)])
 def test_pool_statistics_taken_in_the_contraction_epilogue(cuda, cin, cout, use_relu, mid, neg_gamma):
