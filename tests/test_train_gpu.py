@@ -311,8 +311,9 @@ def test_pool_only_layer_dz_formed_inside_the_contractions(cuda, cin, cout, use_
             # order eps * sum|dz| (measured 5e-6), summed in a different order
             assert a.abs().max().item() < 5e-5 and b.abs().max().item() < 5e-5, name
         elif mid and name in ("dx", "dW"):
-            # with the per-group term, dx and the lower half of dW receive d(per-group term) = group sums of dz (different order)
-            assert torch.allclose(a, b, rtol=1e-4, atol=2e-6 * (b.abs().max().item() + 1e-9)), name
+            # with the per-group term, dx and the lower half of dW receive d(per-group term) = group sums of dz (different order), and those
+            # pass through the 2-way split contractions of layers.linear_rows: rounding-level input differences come out at the split's 1e-5
+            assert torch.allclose(a, b, rtol=1e-4, atol=2e-5 * (b.abs().max().item() + 1e-9)), name
         else:
             assert torch.equal(a, b), name
 
@@ -331,7 +332,7 @@ def test_linear_rows_on_the_tensor_cores(cuda, rows, k, nout):
     dx, dw = torch.autograd.grad((out * go).sum(), (x, w))
     xd, wd = x.detach().double(), w.detach().double()
     ref = xd @ wd
-    assert (out.detach().double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    assert (out.detach().double() - ref).abs().max().item() < 5e-6 * ref.abs().max().item()  # fp32 accumulation over k terms
     rdx, rdw = go.double() @ wd.t(), xd.t() @ go.double()
     assert (dx.double() - rdx).abs().max().item() < 3e-5 * rdx.abs().max().item()
     assert (dw.double() - rdw).abs().max().item() < 3e-5 * rdw.abs().max().item()
