@@ -372,6 +372,29 @@ def bench_infer(args, dist, dev, rank, local_rank, world, peaks):
                           serial_out["features"]], dim=2).cpu()
     assert torch.equal(h_out, ref_rows), "end-to-end output differs from the device-resident pass"
 
+    # the same host<->device traffic with NO compute, all ranks at once: what the box's host links deliver to this rank when every GPU
+    # copies (a step cannot be shorter than this; at N = 8 this, not the kernels, is what bounds the end-to-end number)
+    hp = pipe._host_pipe()
+    dbuf = torch.empty_like(pipe.xyz)
+    hbuf = pipe.h_xyz
+    dout, hout = hp["d_out"][0], hp["h_out"][0]
+    sc, ec = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for timed in (False, True):
+        torch.cuda.synchronize()
+        dist.barrier()
+        with torch.cuda.stream(hp["s_h2d"]):
+            sc.record()
+            for _ in range(args.steps):
+                dbuf.copy_(hbuf, non_blocking=True)
+        with torch.cuda.stream(hp["s_d2h"]):
+            for _ in range(args.steps):
+                hout.copy_(dout, non_blocking=True)
+            hp["s_d2h"].wait_stream(hp["s_h2d"])
+            ec.record()
+        torch.cuda.synchronize()
+    copies_ms = dist.max_over_ranks(sc.elapsed_time(ec), dev) / args.steps
+    dist.barrier()
+
     clocks = sampler.finish()
     if rank != 0:
         return None
@@ -407,6 +430,10 @@ def bench_infer(args, dist, dev, rank, local_rank, world, peaks):
                                   "bit-identical to the serial step" if pipelined else "serial: FPS -> ball query -> detector -> descriptor")),
                 e2e=dict(value=e2e_value, unit="keypoints/s", h2d_bytes_per_step=pipe.h2d_bytes, d2h_bytes_per_step=pipe.d2h_bytes,
                          ms_per_step=e2e_ms / args.steps,
+                         copies_alone_ms_per_step=copies_ms,
+                         copies_alone_GBps_per_gpu=(pipe.h2d_bytes + pipe.d2h_bytes) / (copies_ms * 1e-3) / 1e9,
+                         copies_alone_note="the step's H2D + D2H with no compute, every rank copying at once (max over ranks): the floor the "
+                                           "box's host links put under an end-to-end step at this N",
                          how="pinned host xyz -> H2D -> pipeline -> D2H of [xyz|att|ori|desc] rows, every step; copies of "
                              "neighbouring steps overlap compute on 3 streams; " + e2e_l2),
                 gpu_launches=launches, stage_ms=stage_ms, roofline=roofline, kernels=kernels, clocks=clocks)
