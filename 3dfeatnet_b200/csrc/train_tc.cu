@@ -882,6 +882,10 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
     if (FUSED) {
         for (int i = threadIdx.x; i < kDzCoefs * cout; i += wg::kThreads) coef_s[i] = __ldg(S.coef + i);
     }
+    // measurement aid (f3d_debug_lin_tc_trace): clock64() stamps of CTA 0, thread 0 (issuer) and thread 32 (a converter), 16 slots per stage
+    long long *tr = nullptr;
+    if (g_lin_trace && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32)) tr = g_lin_trace + (threadIdx.x ? kTraceTiles * 16 : 0);
+#define F3D_WT(i) if (tr && s < kTraceTiles) tr[s * 16 + (i)] = clock64();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < wg::kMaxRing; ++i) mbar_init(bar_full + i, 1);
@@ -937,9 +941,12 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
         uint32_t acc = 0;
         for (int s = 0; s < nstages; ++s) {
             const int b = s & 1;
+            F3D_WT(0)
             mbar_wait(bar_img + b, static_cast<uint32_t>((s >> 1) & 1));  // image b converted, ring slot b consumed
             tcgen05_fence_after();
+            F3D_WT(1)
             if (!(dbg & 1) && s + nring < nstages) fetch(s + nring);  // image b converted <=> ring slot s % nring consumed
+            F3D_WT(3)
             if (elect_one()) {
                 const uint32_t a0 = sbase + b * img_bytes, b0 = a0 + 2 * split_a;
                 for (int pass = 0; pass < ((dbg & 2) ? 0 : 3); ++pass) {
@@ -953,6 +960,7 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
                 umma_commit(bar_mma + b);
             }
             __syncwarp();
+            F3D_WT(2)
         }
     } else {
         // ---- converter warps: ring slot (fp32, row-major) -> operand image (bf16 hi/lo, K = row major)
@@ -969,10 +977,13 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
         for (int s = 0; s < nstages; ++s) {
             const int b = s & 1;
             uint8_t *img = smem + b * img_bytes;
+            F3D_WT(0)
             if (s >= 2) mbar_wait(bar_mma + b, static_cast<uint32_t>(((s >> 1) - 1) & 1));  // MMAs of stage s-2 have read this image
+            F3D_WT(1)
             if (!(dbg & 1)) {
                 const int slot = s % nring;
                 mbar_wait(bar_full + slot, static_cast<uint32_t>((s / nring) & 1));
+                F3D_WT(2)
                 const long long r0 = rbeg + static_cast<long long>(s) * wg::kRows;
                 const int valid = static_cast<int>(rend - r0 < wg::kRows ? rend - r0 : wg::kRows);
                 uint8_t *stage = ring + slot * stage_bytes;
@@ -989,9 +1000,11 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
                 else
                     wgrad_convert_both<1>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X);
             }
+            F3D_WT(3)
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_img + b);
+            F3D_WT(4)
         }
         if (FUSED && drow < rows_pass)  // this thread's share of db: rows drow, drow + rows_pass, ... of every stage, channel quad dq
             *reinterpret_cast<float4 *>(dbred + drow * cout + dq * 4) = dbsum;
