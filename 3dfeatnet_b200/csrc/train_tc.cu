@@ -1086,6 +1086,7 @@ struct LinPlan {
     int grid;      // row CTAs (the stats partials are 2 per CTA)
 };
 
+static int kPipeMinK = 128;  // (f3d_debug_set_lin_tc_pipe_min_k: measurement aid)
 static LinPlan lin_tc_plan(long long rows, int k_real, int nsplit, bool fused = false) {
     LinPlan P{};
     const int kp = lin_tc_kp(k_real);
@@ -1093,7 +1094,7 @@ static LinPlan lin_tc_plan(long long rows, int k_real, int nsplit, bool fused = 
     const size_t slot_extra = fused ? static_cast<size_t>(3) * k_real * 4 : 0, tail_extra = fused ? static_cast<size_t>(kDzCoefs) * k_real * 4 + lp::kConvWarps * 32 * 16 : 0;  // coefficient table + one float4 per converter thread
     // the warp-specialised kernel pays off when the operand conversion + MMAs are the long phases (K >= 128); for narrow
     // inputs the tile is store-bound and the all-warps epilogue of lin_tc_kernel at 3-4 CTAs/SM is faster (measured)
-    if (k_real % 8 == 0 && kp >= 128) {
+    if (k_real % 8 == 0 && kp >= kPipeMinK) {
         for (int nt = 64; nt >= 32 && !P.pipe; nt -= 32) {
             const size_t img = static_cast<size_t>(nsplit) * (kp / 8) * lp::lbo(nsplit, nt, fused);
             const size_t slot = static_cast<size_t>(nt) * k_real * 4 + slot_extra;
@@ -1276,6 +1277,11 @@ F3D_API int f3d_debug_set_lin_tc_phases(int skip_mask) {
 F3D_API int f3d_debug_lin_tc_trace(void *buf) {
     const cudaError_t e = cudaMemcpyToSymbol(f3d::g_lin_trace, &buf, sizeof(void *));
     return e == cudaSuccess ? 0 : f3d::fail(static_cast<int>(e), "debug_lin_tc_trace");
+}
+F3D_API int f3d_debug_set_lin_tc_pipe_min_k(int k) {
+    const int prev = f3d::kPipeMinK;
+    f3d::kPipeMinK = k;
+    return prev;
 }
 F3D_API size_t f3d_debug_lin_tc_weight_bytes(int k, int nout) { return f3d::lin_tc_weight_bytes(k, nout); }
 F3D_API int f3d_debug_lin_tc(long long rows, int k, int nout, const float *x, const float *W, float *out, float *part, void *wimg, int nsplit,

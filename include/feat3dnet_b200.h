@@ -341,6 +341,8 @@ int f3d_debug_set_epilogue_pool(int on);
  * results are garbage with a bit set), and the contraction alone: out (rows, nout) = x (rows, k) W^T, W (nout, k) row-major, nsplit 2 | 3,
  * part = NULL or 2 * 2 * nout floats per row CTA of column-sum partials, wimg = f3d_debug_lin_tc_weight_bytes(k, nout) of scratch. */
 int f3d_debug_set_lin_tc_phases(int skip_mask);
+/* Measurement aid: the smallest (padded) K for which lin_tc launches its warp-specialised kernel (default 128).  Returns the previous value. */
+int f3d_debug_set_lin_tc_pipe_min_k(int k);
 /* buf: device memory of 2 * 64 * 16 long long receiving clock64() stamps of threads 0 and 255 of CTA (0,0) of lin_tc_kernel (16 slots per
  * tile, first 64 tiles); NULL switches the trace off. */
 int f3d_debug_lin_tc_trace(void *buf);
