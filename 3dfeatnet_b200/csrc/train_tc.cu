@@ -775,7 +775,7 @@ __device__ __forceinline__ void wgrad_convert(uint8_t *img, uint32_t lbo, uint32
 template <int W>
 __device__ __forceinline__ void wgrad_convert_both(uint8_t *img_a, uint32_t lbo_a, uint32_t split_a, uint8_t *img_b, uint32_t lbo_b, uint32_t split_b,
                                                    const uint8_t *__restrict__ stage_a, const uint8_t *__restrict__ stage_b, int cin, int cout,
-                                                   int valid_rows, const XSource X) {
+                                                   int valid_rows, const XSource X, int dbg = 0) {
     const int ga = cin / W, gb = cout / W;
     const int ua = wg::kChunks * ga, ut = ua + wg::kChunks * gb;
     for (int u = threadIdx.x - 32; u < ut; u += wg::kThreads - 32) {
@@ -788,7 +788,7 @@ __device__ __forceinline__ void wgrad_convert_both(uint8_t *img_a, uint32_t lbo_
         for (int i = 0; i < 8; ++i) {
             const int r = rc * 8 + i;
             const uint8_t *p = src + static_cast<size_t>(r) * c * 4;
-            if (r < valid_rows) {
+            if (r < valid_rows && !(dbg & 4)) {
                 if constexpr (W == 4) {
                     const float4 t = *reinterpret_cast<const float4 *>(p);
                     v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
@@ -824,8 +824,10 @@ __device__ __forceinline__ void wgrad_convert_both(uint8_t *img_a, uint32_t lbo_
             uint4 hi, lo;
             split8(col, hi, lo);
             uint8_t *dst = img + rc * lbo + (ch >> 3) * wg::kSboP + (ch & 7) * 16;
-            *reinterpret_cast<uint4 *>(dst) = hi;
-            *reinterpret_cast<uint4 *>(dst + split) = lo;
+            if (!(dbg & 8)) {
+                *reinterpret_cast<uint4 *>(dst) = hi;
+                *reinterpret_cast<uint4 *>(dst + split) = lo;
+            }
         }
     }
 }
@@ -993,12 +995,13 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
                                           rows_pass, dbsum);
                 }
                 if constexpr (FUSED) asm volatile("bar.sync 2, %0;" ::"n"(wg::kThreads - 32) : "memory");  // dz of the whole stage is in place
-                if (wunit == 4)
-                    wgrad_convert_both<4>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X);
+                if (dbg & 16) {
+                } else if (wunit == 4)
+                    wgrad_convert_both<4>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X, dbg);
                 else if (wunit == 2)
-                    wgrad_convert_both<2>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X);
+                    wgrad_convert_both<2>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X, dbg);
                 else
-                    wgrad_convert_both<1>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X);
+                    wgrad_convert_both<1>(img, lbo_a, split_a, img + 2 * split_a, lbo_b, split_b, stage, stage + xs_bytes, cin, cout, valid, X, dbg);
             }
             F3D_WT(3)
             fence_proxy_async_smem();

@@ -329,7 +329,8 @@ int f3d_rigid_fit(int npts, const float *pts1, const float *pts2, const unsigned
 int f3d_debug_umma_selftest(const void *a_img, const void *b_img, float *D, int N, int K, int lbo_a, int sbo_a, int lbo_b,
                             int sbo_b, int a_bytes, int b_bytes, int a_in_tmem, void *stream);
 /* Bring-up: the tensor-core weight-gradient contraction alone (partW: 2*SMs x cin x cout floats of per-CTA partials);
- * dbg bit 0 skips the operand staging, bit 1 the MMAs (micro-benchmarking). */
+ * dbg bit 0 skips the operand staging (TMA + conversion), bit 1 the MMAs, bit 2 the conversion's shared-memory loads, bit 3 its stores,
+ * bit 4 the conversion altogether (micro-benchmarking: tools/wgrad_tc_phases.py). */
 int f3d_debug_wgrad_tc(long long rows, int cin, int cout, const float *x, const float *dz, float *partW, int dbg, void *stream);
 /* Test / measurement aid: 0 = pool-only training layers materialise dz (bn_bwd_apply) for wgrad and dgrad, 1 (default) = dz is formed
  * inside the two contractions from z and the pooled tensors.  Both paths give the same dW / dx bits.  Returns the previous value. */

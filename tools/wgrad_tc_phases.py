@@ -16,7 +16,7 @@ for cin, cout in ((32, 64), (64, 128), (128, 256)):
     dz = torch.randn(rows, cout, device=dev)
     partW = torch.empty(2 * 148 * cin * cout, device=dev)
     line = "wgrad %3d x %3d (%4.0f MB, floor %.3f ms):" % (cin, cout, 4e-6 * rows * (cin + cout), 4.0 * rows * (cin + cout) / 6.5e9)
-    for dbg, name in ((0, "all"), (1, "no TMA/convert"), (2, "no MMAs"), (3, "skeleton")):
+    for dbg, name in ((0, "all"), (1, "no TMA/convert"), (2, "no MMAs"), (3, "skeleton"), (4, "convert w/o LDS"), (8, "convert w/o STS"), (12, "convert w/o LDS+STS"), (16, "TMA but no convert")):
         ts = []
         for it in range(4):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
