@@ -119,6 +119,13 @@ __device__ __forceinline__ void store_channel_rows(float *__restrict__ o, int no
     }
 }
 
+// contiguous global block -> shared memory through the TMA engine in as few bulk copies as possible: the issue of one cp.async.bulk costs
+// the issuing thread ~450 cycles (clock64 trace, tools/wgrad_tc_trace.py), and that thread is the MMA issuer
+constexpr uint32_t kBulkMax = 65536;
+__device__ __forceinline__ void bulk_g2s_block(uint8_t *dst, const uint8_t *src, uint32_t bytes, uint64_t *bar) {
+    for (uint32_t off = 0; off < bytes; off += kBulkMax) bulk_g2s(dst + off, src + off, bytes - off < kBulkMax ? bytes - off : kBulkMax, bar);
+}
+
 // Measurement aid (f3d_debug_lin_tc_trace): clock64() stamps of CTA (0, 0) of lin_tc_kernel, 16 slots per tile for threads 0 and 255
 __device__ long long *g_lin_trace = nullptr;
 constexpr int kTraceTiles = 64;
@@ -208,10 +215,7 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
         } else if (lane == 0) {
             mbar_arrive_expect_tx(bar_full + s, bytes);
             const uint8_t *src = reinterpret_cast<const uint8_t *>(x + r0 * k_real);
-            for (uint32_t off = 0; off < bytes; off += 16384) {
-                const uint32_t n = bytes - off < 16384u ? bytes - off : 16384u;
-                bulk_g2s(ringbuf + s * stage_bytes + off, src + off, n, bar_full + s);
-            }
+            bulk_g2s_block(ringbuf + s * stage_bytes, src, bytes, bar_full + s);
         }
         __syncwarp();
     };
@@ -491,8 +495,7 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
             } else if (lane == 0) {
                 mbar_arrive_expect_tx(ring_full + slot, bytes + pool_bytes);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>((FUSED ? S.z : x) + r0 * k_real);
-                for (uint32_t off = 0; off < bytes; off += 16384)
-                    bulk_g2s(ringbuf + slot * slot_bytes + off, src + off, bytes - off < 16384u ? bytes - off : 16384u, ring_full + slot);
+                bulk_g2s_block(ringbuf + slot * slot_bytes, src, bytes, ring_full + slot);
                 if (FUSED) {
                     const size_t go = static_cast<size_t>(r0 / S.gs) * k_real;
                     uint8_t *pd = ringbuf + slot * slot_bytes + NT * static_cast<uint32_t>(k_real) * 4;
@@ -924,9 +927,8 @@ wgrad_tc_kernel(long long rows, int cin, int cout, long long rows_per_cta, uint3
                 mbar_arrive_expect_tx(bar_full + slot, xb + db + pool_bytes);
                 const uint8_t *xsrc = reinterpret_cast<const uint8_t *>(x + r0 * cin);
                 const uint8_t *dsrc = reinterpret_cast<const uint8_t *>((FUSED ? S.z : dz) + r0 * cout);
-                for (uint32_t off = 0; off < xb; off += 16384) bulk_g2s(dst + off, xsrc + off, xb - off < 16384u ? xb - off : 16384u, bar_full + slot);
-                for (uint32_t off = 0; off < db; off += 16384)
-                    bulk_g2s(dst + xs_bytes + off, dsrc + off, db - off < 16384u ? db - off : 16384u, bar_full + slot);
+                bulk_g2s_block(dst, xsrc, xb, bar_full + slot);
+                bulk_g2s_block(dst + xs_bytes, dsrc, db, bar_full + slot);
                 if (FUSED) {
                     const size_t go = static_cast<size_t>(r0 / S.gs) * cout;
                     const uint32_t cb = static_cast<uint32_t>(cout) * 4;
