@@ -211,7 +211,8 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
             // ---- weights: one bulk-TMA burst, resident for the whole kernel ---------------------------------
             if (lane == 0) {
                 mbar_arrive_expect_tx(&bars[W_FULL], kWeightBytes);
-                for (uint32_t off = 0; off < kImgBulk; off += 16384) bulk_g2s(smem + off, wimg + off, 16384u, &bars[W_FULL]);
+                // few large copies: the issue of one cp.async.bulk costs this thread ~450 cycles (tools/wgrad_tc_trace.py)
+                for (uint32_t off = 0; off < kImgBulk; off += 65536) bulk_g2s(smem + off, wimg + off, min(65536u, kImgBulk - off), &bars[W_FULL]);
                 bulk_g2s(smem + kOffW0, wimg + kImgSmall, kSmallBytes, &bars[W_FULL]);
             }
             __syncwarp();

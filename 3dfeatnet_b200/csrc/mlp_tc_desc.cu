@@ -135,8 +135,8 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         {
             if (lane == 0) {
                 mbar_arrive_expect_tx(&bars[W_FULL], kWeightBytes);
-                for (uint32_t off = 0; off < kWeightBytes; off += 16384) {
-                    const uint32_t sz = min(16384u, kWeightBytes - off);
+                for (uint32_t off = 0; off < kWeightBytes; off += 65536) {  // few large copies (each issue costs this thread ~450 cycles)
+                    const uint32_t sz = min(65536u, kWeightBytes - off);
                     bulk_g2s(smem + off, wimg + off, sz, &bars[W_FULL]);
                 }
             }

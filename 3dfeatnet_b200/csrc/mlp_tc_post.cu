@@ -190,7 +190,7 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
         const uint32_t bytes = MODE == 0 ? (piece < 3 ? 65536u : 32768u) : 65536u;
         if (threadIdx.x == 0) {
             mbar_arrive_expect_tx(bar_w, bytes);
-            for (uint32_t off = 0; off < bytes; off += 16384) bulk_g2s(smem + kOffStage + off, wimg + goff + off, 16384, bar_w);
+            bulk_g2s(smem + kOffStage, wimg + goff, bytes, bar_w);  // one copy per piece: every cp.async.bulk costs its issuer ~450 cycles
         }
         mbar_wait(bar_w, wpar);
         wpar ^= 1;
