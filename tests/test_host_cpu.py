@@ -122,6 +122,31 @@ def test_unfused_layers_match_oracle_net_on_cpu():
     assert torch.allclose(loss, onet.triplet_loss(fa, fp, fn, att, 0.2, True))
 
 
+def test_chain_and_fused_helpers_have_no_cpu_side_door():
+    """The training-path fusions of round 2 are device paths: on CPU tensors conv2d refuses a deferred activation (there is no kernel to
+    form it), linear_rows / the local frames take the op-by-op torch statement, and a DeferredActivation can be materialised as the
+    plain tensor it stands for."""
+    from oracle import net as onet
+
+    layers, pc = pkg("models.layers"), pkg("models.pointnet_common")
+    P = {k: torch.as_tensor(v) for k, v in onet.init_params(seed=3, randomize_bn=True).items()}
+    x = torch.randn((2, 5, 64, 3))
+    with pytest.raises(ValueError, match="deferred activations"):
+        layers.conv2d(x, 64, [1, 1], padding='VALID', bn=True, is_training=True, scope="detection/conv0", params=P, defer=True)
+    with pytest.raises(ValueError, match="also_pool"):
+        layers.conv2d(x, 64, [1, 1], padding='VALID', bn=True, is_training=True, scope="detection/conv0", params=P, also_pool=True)
+    z = torch.randn(2, 5, 64, 8)
+    coef = torch.cat((torch.rand(8) + 0.5, torch.randn(8)))
+    d = layers.DeferredActivation(z, coef, True)
+    assert d.shape == z.shape and d.dim() == 4 and not d.is_cuda
+    assert torch.equal(d.materialize(), torch.relu(z * coef[:8] + coef[8:]))
+    a, w = torch.randn(40, 64), torch.randn(64, 128)
+    assert torch.equal(layers.linear_rows(a, w), a @ w)
+    xyz, kp = torch.randn(2, 50, 3), torch.randn(2, 4, 3)
+    idx = torch.randint(0, 50, (2, 4, 8), dtype=torch.int32)
+    assert not pc._fused_frames_ok(xyz, kp, idx)
+
+
 def test_unused_layer_helpers_follow_the_reference_semantics():
     """fully_connected / dropout / batch_norm_for_conv3d (layers.py:107-171,213-223): part of `models.layers`, never called
     by the model; checked against the TF statements written out in fp64."""
