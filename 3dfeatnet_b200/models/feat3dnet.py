@@ -138,7 +138,7 @@ def descriptor_forward_fused(xyz, new_xyz, idx, orientation, radius, packed, fea
 def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is_training, scope, bn=True, bn_decay=None,
                        tnet_spec=None, knn=False, use_xyz=True,
                        keypoints=None, orientations=None, normalize_radius=True, final_relu=True,
-                       params=None, new_stats=None, neighbours=None):
+                       params=None, new_stats=None, neighbours=None, after_mid_hook=None):
     """ PointNet Set Abstraction (SA) Module (feat3dnet.py:9-87), unfused differentiable statement.
 
     Returns:
@@ -179,6 +179,8 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is
     if not mlp2:
         new_points = torch.cat((new_points, pooled.expand(-1, -1, new_points.shape[2], -1)), dim=3)
         new_points = _layers.max_pool_samples(new_points)
+    if after_mid_hook is not None:
+        after_mid_hook()  # the last per-point layer has been launched: only per-cluster work follows until the backward returns to it
 
     for i, num_out_channel in enumerate(mlp3 or []):
         act = _layers.relu if (final_relu or i < len(mlp3) - 1) else None
@@ -191,7 +193,7 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, mlp3, is
 
 def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp, mlp2, num_samples=64, use_bn=True,
                              compute_det_gradients=False, params=None, new_stats=None, scope="detection",
-                             keypoints=None):
+                             keypoints=None, neighbours=None):
     """ Detect features in point cloud (feat3dnet.py:90-151), unfused differentiable statement.
 
     compute_det_gradients: the reference's default (True) raises KeyError while building its graph
@@ -206,7 +208,7 @@ def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp
         end_points['gradients'] = {'det': {}}
     new_xyz = sample_points(xyz, num_clusters) if keypoints is None else keypoints
     new_points, idx = query_and_group_points(xyz, points, new_xyz, num_samples, radius, knn=False, use_xyz=True,
-                                             normalize_radius=True, orientations=None, end_points=end_points)
+                                             normalize_radius=True, orientations=None, end_points=end_points, neighbours=neighbours)
 
     # training on the tensor cores: the activations between the layers of the chain stay unmaterialised (layers.DeferredActivation)
     chain = bool(is_training) and use_bn and not compute_det_gradients and new_points.is_cuda and new_points.shape[-1] == 3 \
@@ -245,7 +247,8 @@ def feature_detection_module(xyz, points, num_clusters, radius, is_training, mlp
 
 
 def feature_extraction_module(l0_xyz, l0_points, is_training, mlp, mlp2, mlp3, keypoints, orientations, radius=2.0,
-                              num_samples=64, use_bn=True, params=None, new_stats=None, scope="description", neighbours=None):
+                              num_samples=64, use_bn=True, params=None, new_stats=None, scope="description", neighbours=None,
+                              after_mid_hook=None):
     """ Extract feature descriptors (feat3dnet.py:154-187), unfused differentiable statement.
     neighbours: optional (idx, pts_cnt) of the ball query the detector ran on the same (l0_xyz, keypoints, radius, num_samples)
     -- the reference issues that query twice (pointnet_common.py:39 and :102); handing it over runs it once, with no hidden state.
@@ -253,7 +256,7 @@ def feature_extraction_module(l0_xyz, l0_points, is_training, mlp, mlp2, mlp3, k
     l1_xyz, l1_points, l1_idx, end_points = pointnet_sa_module(
         l0_xyz, l0_points, 512, radius, num_samples, mlp=mlp, mlp2=mlp2, mlp3=mlp3, is_training=is_training,
         scope=scope + '/layer1', bn=use_bn, bn_decay=None, keypoints=keypoints, orientations=orientations,
-        normalize_radius=True, final_relu=False, params=params, new_stats=new_stats, neighbours=neighbours)
+        normalize_radius=True, final_relu=False, params=params, new_stats=new_stats, neighbours=neighbours, after_mid_hook=after_mid_hook)
     ss = (l1_points * l1_points).sum(2, keepdim=True)
     features = l1_points * torch.rsqrt(torch.clamp(ss, min=1e-8))
     return l1_xyz, features, end_points
@@ -307,12 +310,24 @@ class Feat3dNet:
         return None, None, None
 
     # -- graphs ------------------------------------------------------------------------------------
-    def get_train_model(self, anchors, positives, negatives, is_training, use_bn=True):
-        """feat3dnet.py:227-256: concatenates the triplet on the batch axis and calls get_inference_model."""
+    def sample_clusters(self, point_clouds):
+        """(keypoints, idx, pts_cnt) of the model's clusters for a batch of clouds: farthest point sampling + ball query, exactly what
+        get_inference_model computes at its start.  Handing the result back as `presampled=` skips that part of the forward (the pipelined
+        training step computes it for the next batch beside the backward pass of the current one)."""
+        with torch.no_grad():
+            l0_xyz = point_clouds[:, :, :3].contiguous()
+            kp = sample_points(l0_xyz, self.param['num_clusters'])
+            idx, pts_cnt = _pc.query_ball_point(self.param['BaseScale'], self.param['num_samples'], l0_xyz, kp)
+        return kp, idx, pts_cnt
+
+    def get_train_model(self, anchors, positives, negatives, is_training, use_bn=True, presampled=None, after_mid_hook=None):
+        """feat3dnet.py:227-256: concatenates the triplet on the batch axis and calls get_inference_model.
+        presampled: sample_clusters() of the concatenated batch (optional); after_mid_hook: see capture_train_step(pipelined=True)."""
         end_points = {}
         point_clouds = torch.cat([anchors, positives, negatives], dim=0)
         end_points['input_pointclouds'] = point_clouds
-        xyz, features, attention, endpoints_temp = self.get_inference_model(point_clouds, is_training, use_bn)
+        xyz, features, attention, endpoints_temp = self.get_inference_model(point_clouds, is_training, use_bn, presampled=presampled,
+                                                                            after_mid_hook=after_mid_hook)
         end_points['output_xyz'] = xyz
         end_points['output_features'] = features
         end_points.update(endpoints_temp)
@@ -322,7 +337,7 @@ class Feat3dNet:
         return xyz, features, anchor_attention, end_points
 
     def get_inference_model(self, point_cloud, is_training, use_bn=True, compute_det_gradients=False, keypoints=None,
-                            fetch_features=True):
+                            fetch_features=True, presampled=None, after_mid_hook=None):
         """ The core 3DFeat-Net model (feat3dnet.py:258-313).
 
         point_cloud: (B,N,>=3) CUDA float32.  keypoints: optional (B,M,3) cluster centres (what inference.py feeds
@@ -348,17 +363,21 @@ class Feat3dNet:
             return kp, features, (attention if self.param['Attention'] else None), end_points
 
         new_stats = {} if is_training else None
+        neighbours = None
+        if presampled is not None:  # (keypoints, idx, pts_cnt) of sample_clusters() on this batch
+            keypoints, neighbours = presampled[0], (presampled[1], presampled[2])
         kp, idx, attention, orientation, ep = feature_detection_module(
             l0_xyz, None, self.param['num_clusters'], radius, is_training, [64, 128, 256], [128, 64], num_samples=ns,
             use_bn=use_bn, compute_det_gradients=compute_det_gradients, params=self.weights, new_stats=new_stats,
-            keypoints=keypoints)
+            keypoints=keypoints, neighbours=neighbours)
         end_points.update(ep)
         end_points.update(keypoints=kp, attention=attention, orientation=orientation, idx=idx)
         keypoint_orientation = None if self.param['NoRegress'] else orientation
         mlp, mlp2, mlp3 = [32, 64], ([128] if fdim <= 64 else [256]), [fdim]
         xyz, features, ep2 = feature_extraction_module(
             l0_xyz, None, is_training, mlp, mlp2, mlp3, keypoints=kp, orientations=keypoint_orientation, radius=radius,
-            num_samples=ns, use_bn=use_bn, params=self.weights, new_stats=new_stats, neighbours=(idx, ep['pts_cnt']))
+            num_samples=ns, use_bn=use_bn, params=self.weights, new_stats=new_stats, neighbours=(idx, ep['pts_cnt']),
+            after_mid_hook=after_mid_hook)
         end_points.update(ep2)
         end_points['bn_updates'] = new_stats
         return xyz, features, (attention if self.param['Attention'] else None), end_points
@@ -430,41 +449,119 @@ class Feat3dNet:
         self.invalidate()
         return flat
 
-    def capture_train_step(self, anchors, positives, negatives, lr=1e-5, grad_hook=None, grad_scale=1.0, warmup=3):
-        """Capture one whole training step (get_train_model -> get_loss -> get_train_op: ~340 launches) into a CUDA graph.
+    def capture_train_step(self, anchors, positives, negatives, lr=1e-5, grad_hook=None, grad_scale=1.0, warmup=3, pipelined=False):
+        """Capture one whole training step (get_train_model -> get_loss -> get_train_op: ~180 launches) into a CUDA graph.
         Returns replay(anchors=None, positives=None, negatives=None) -> loss tensor (device, updated by every replay); new
         triplets are copied into the static input buffers first.  The Adam step count lives on the device, so a replay is
-        a real optimiser step.  `warmup` eager steps run first (they are real steps too)."""
-        static = [t.detach().clone() for t in (anchors, positives, negatives)]
+        a real optimiser step.  `warmup` eager steps run first (they are real steps too).
 
-        def step():
-            xyz, feats, att, ep = self.get_train_model(static[0], static[1], static[2], True)
+        pipelined=True: the SOFTWARE-PIPELINED step.  Farthest point sampling + ball query (0.2 ms at C4: 18 CTAs busy, 130 SMs idle)
+        depend on the input clouds only, so the clusters of the NEXT batch are computed on a side stream beside the per-cluster part of
+        the current step (forked after the forward's last per-point layer, where tails, loss and their gradients leave most SMs idle;
+        joined at the end of the step).
+        replay(a, p, n) then takes the triplets of the step AFTER the one it runs: it runs the step on the batch staged by the previous
+        call (the first one: the batch given here) and stages (a, p, n) -- copies them in and samples their clusters -- for the next call;
+        None re-stages the same batch.  Same arithmetic, same bits as the serial step on the same sequence of batches."""
+        if not pipelined:
+            static = [t.detach().clone() for t in (anchors, positives, negatives)]
+
+            def step():
+                xyz, feats, att, ep = self.get_train_model(static[0], static[1], static[2], True)
+                loss, ep = self.get_loss(xyz, feats, att, ep)
+                self.get_train_op(loss, lr=lr, end_points=ep, grad_hook=grad_hook, grad_scale=grad_scale)
+                return loss.detach()
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = step()
+
+            def replay(anchors=None, positives=None, negatives=None):
+                for dst, src in zip(static, (anchors, positives, negatives)):
+                    if src is not None:
+                        dst.copy_(src, non_blocking=True)
+                graph.replay()
+                self._adam["t"] += 1
+                self.invalidate()  # the replay moved the weights and the BN shadows: the folded eval copy is stale
+                return loss
+
+            replay.graph = graph
+            replay.static_inputs = static  # (anchors, positives, negatives) buffers the graph reads
+            replay.loss = loss
+            return replay
+
+        # two input sets and two sets of sampled clusters, used alternately: step k runs on set k & 1 and samples set (k + 1) & 1
+        inputs = [[t.detach().clone() for t in (anchors, positives, negatives)] for _ in range(2)]
+        sampler = torch.cuda.Stream(priority=-1)  # high priority: its few CTAs take SMs as soon as blocks of the BN passes retire
+
+        def sample_into(dst, src_inputs):
+            kp, idx, cnt = self.sample_clusters(torch.cat(src_inputs, dim=0))
+            if dst is None:
+                return [kp, idx, cnt]
+            for d, v in zip(dst, (kp, idx, cnt)):
+                d.copy_(v)
+            return dst
+
+        def step(cur, samples, fork):
+            hook = None
+            if fork:
+                main = torch.cuda.current_stream()
+
+                def hook():
+                    # the forward has launched its last per-point kernel (descriptor conv_mid): until the backward pass returns to that
+                    # layer only per-cluster kernels run (tails, loss, their gradients: ~0.25 ms in which most SMs idle).  The sampling
+                    # kernels of the next batch (whole-SM CTAs, 0.2 ms) go beside them on a high-priority stream.
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream())
+                    sampler.wait_event(ev)
+                    with torch.cuda.stream(sampler):
+                        sample_into(samples[1 - cur], inputs[1 - cur])
+            xyz, feats, att, ep = self.get_train_model(inputs[cur][0], inputs[cur][1], inputs[cur][2], True, presampled=samples[cur],
+                                                       after_mid_hook=hook)
             loss, ep = self.get_loss(xyz, feats, att, ep)
             self.get_train_op(loss, lr=lr, end_points=ep, grad_hook=grad_hook, grad_scale=grad_scale)
+            if fork:
+                torch.cuda.current_stream().wait_stream(sampler)  # join: the next batch's clusters are part of this step
             return loss.detach()
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
+            samples = [sample_into(None, inputs[0]), sample_into(None, inputs[1])]
             for _ in range(max(1, warmup)):
-                step()
+                step(0, samples, False)
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss = step()
+        graphs, losses = [], []
+        for cur in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                losses.append(step(cur, samples, True))
+            graphs.append(g)
+        state = {"cur": 0}
+        loss = torch.zeros_like(losses[0])
 
         def replay(anchors=None, positives=None, negatives=None):
-            for dst, src in zip(static, (anchors, positives, negatives)):
-                if src is not None:
-                    dst.copy_(src)
-            graph.replay()
+            cur = state["cur"]
+            # stage the batch of the NEXT step: the graph about to run samples its clusters beside its own backward pass
+            for dst, src, same in zip(inputs[1 - cur], (anchors, positives, negatives), inputs[cur]):
+                dst.copy_(src if src is not None else same, non_blocking=True)
+            graphs[cur].replay()
+            loss.copy_(losses[cur])
+            state["cur"] = 1 - cur
             self._adam["t"] += 1
-            self.invalidate()  # the replay moved the weights and the BN shadows: the folded eval copy is stale
+            self.invalidate()
             return loss
 
-        replay.graph = graph
-        replay.static_inputs = static  # (anchors, positives, negatives) buffers the graph reads
+        replay.graph = graphs
+        replay.static_inputs = inputs[0]
+        replay.next_inputs = lambda: inputs[1 - state["cur"]]  # where replay() stages the next batch
         replay.loss = loss
+        replay.pipelined = True
         return replay
 
     def train_mode(self):

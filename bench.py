@@ -519,34 +519,45 @@ def bench_train(args, dist, dev, rank, local_rank, world, peaks):
     own_launches = int(L.f3d_launch_count())
     kernels = kernel_table(timings, peaks)
 
-    replay = net.capture_train_step(a, p, n, lr=1e-5, grad_hook=dist.allreduce_sum_, grad_scale=scale, warmup=1)
-    for _ in range(max(args.warmup, 3)):
-        replay()
-    torch.cuda.synchronize()
+    def time_replays(replay):
+        for _ in range(max(args.warmup, 3)):
+            replay()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            loss = replay()
+        e.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return dist.max_over_ranks(s.elapsed_time(e), dev) / args.steps, loss
+
+    # the serial step (sampling -> forward -> loss -> backward -> all-reduce -> Adam, one graph) on a model of its own, for the record;
+    # the timed step is the software-pipelined one unless --pipelined 0: the clusters of the NEXT batch (FPS + ball query: 18 CTAs, serial
+    # rounds) are computed on a side stream beside the backward pass of the current step; K steps do K samplings and K optimiser steps,
+    # the first batch's sampling is a prologue outside the timed region; same bits as the serial step (tests/test_train_gpu.py)
+    pipelined = bool(args.pipelined)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    dist.barrier()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(args.steps):
-        loss = replay()
-    e.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = dist.max_over_ranks(s.elapsed_time(e), dev) / args.steps
+    serial_ms = None
+    if pipelined:
+        net_s = f3.Feat3dNet({'num_clusters': M}, device=dev, seed=0).train_mode()
+        serial_ms, _ = time_replays(net_s.capture_train_step(a, p, n, lr=1e-5, grad_hook=dist.allreduce_sum_, grad_scale=scale, warmup=1))
+        del net_s
+        torch.cuda.empty_cache()
+    replay = net.capture_train_step(a, p, n, lr=1e-5, grad_hook=dist.allreduce_sum_, grad_scale=scale, warmup=1, pipelined=pipelined)
+    ms, loss = time_replays(replay)
 
     # end to end: the triplet batch comes from pinned host memory every step and the loss goes back to the host
     h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
-    static = replay.static_inputs
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
     s2.record()
     for _ in range(args.steps):
-        for dst, src in zip(static, host):
-            dst.copy_(src, non_blocking=True)
-        loss = replay()
+        loss = replay(*host)  # H2D of the pinned triplets into the graph's input buffers (pipelined: the batch of the NEXT step), then the step
         h_loss.copy_(loss.reshape(1), non_blocking=True)
     e2.record()
     torch.cuda.synchronize()
@@ -580,6 +591,10 @@ def bench_train(args, dist, dev, rank, local_rank, world, peaks):
                  dtype="f32 (forward contractions: 3-way bf16 split on tcgen05; dgrad / wgrad: 2-way split; everything else fp32)",
                  data="synthetic", loss=float(loss),
                  config=dict(workload=TRAIN_WORKLOAD, cuda_graph=True, l2="per-step working set (>2 GB of activations) exceeds the 126 MB L2",
+                             step=("software-pipelined: FPS + ball query of batch i+1 on a side stream beside the backward pass of batch i; K steps do K "
+                                   "samplings and K optimiser steps, the first batch's sampling is a prologue outside the timed region; same bits "
+                                   "as the serial step" if pipelined else "serial: sampling -> forward -> loss -> backward -> all-reduce -> Adam"),
+                             serial_ms_per_step=serial_ms,
                              parallelism="data-parallel dp%d: triplets sharded, BN statistics per GPU, one SUM all-reduce + 1/world in Adam" % world),
                  e2e=dict(value=clouds * 1e3 / e2e_ms, unit="clouds/s", ms_per_step=e2e_ms, h2d_bytes_per_step=sum(t.numel() * 4 for t in host),
                           d2h_bytes_per_step=4, how="pinned host triplets -> H2D -> graph replay -> loss D2H, every step"),

@@ -480,6 +480,36 @@ def test_captured_train_step_equals_eager_steps(cuda):
     assert torch.equal(net_e._adam["m"], net_g._adam["m"]) and torch.equal(net_e._adam["v"], net_g._adam["v"])
 
 
+def test_pipelined_train_step_equals_the_serial_step_on_a_sequence_of_batches(cuda):
+    """capture_train_step(pipelined=True): farthest point sampling + ball query of the NEXT batch run on a side stream beside the backward
+    pass of the current step.  replay(b_{k+1}) runs step k on the batch staged by the previous call and stages b_{k+1}.  On a sequence of
+    DIFFERENT batches the losses, the weights, the Adam moments and the BN shadows equal those of the serial graph fed the same sequence,
+    bit for bit."""
+    f3, synth = pkg("models.feat3dnet"), pkg("synth")
+    B, N, M = 2, 2048, 64
+    batches = [[torch.as_tensor(synth.make_batch(B, N, seed0=50 + 10 * k + s)).to(cuda) for s in range(3)] for k in range(4)]
+    params = onet.init_params(seed=12, randomize_bn=True)
+
+    net_s = f3.Feat3dNet({'num_clusters': M}, weights=params, device=cuda).train_mode()
+    rs = net_s.capture_train_step(*batches[0], lr=1e-3, warmup=1)      # the warm-up step runs on batch 0
+    losses_s = [rs(*batches[k]).clone() for k in range(4)]
+
+    net_p = f3.Feat3dNet({'num_clusters': M}, weights=params, device=cuda).train_mode()
+    rp = net_p.capture_train_step(*batches[0], lr=1e-3, warmup=1, pipelined=True)
+    assert rp.pipelined
+    losses_p = []
+    for k in range(4):
+        nxt = batches[k + 1] if k + 1 < 4 else (None, None, None)
+        losses_p.append(rp(*nxt).clone())                               # runs batch k, stages batch k + 1
+    torch.cuda.synchronize()
+    for k in range(4):
+        assert torch.equal(losses_p[k], losses_s[k]), k
+    assert int(net_p._adam["t_dev"].item()) == int(net_s._adam["t_dev"].item()) == 5
+    for k in net_s.weights:
+        assert torch.equal(net_s.weights[k], net_p.weights[k]), k
+    assert torch.equal(net_s._adam["m"], net_p._adam["m"]) and torch.equal(net_s._adam["v"], net_p._adam["v"])
+
+
 def test_eval_forward_between_graph_replays_sees_the_updated_weights(cuda):
     """replay -> eval -> replay -> eval: the folded eval-mode weight copy is invalidated by every replay (the graph updates the
     weights and the BN shadows without going through get_train_op's Python), so each eval forward equals the one of the eager

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--chain", type=int, default=1)
+    ap.add_argument("--pipelined", type=int, default=0, help="1: the software-pipelined step (next batch's sampling beside the backward pass)")
     args = ap.parse_args()
     pkg = lambda n: importlib.import_module("3dfeatnet_b200." + n)
     f3, layers, synth = pkg("models.feat3dnet"), pkg("models.layers"), pkg("synth")
@@ -28,7 +29,7 @@ def main():
     B, N, M = 6, 4096, 512
     a, p, n = (torch.as_tensor(synth.make_batch(B, N, seed0=s)).to(dev) for s in (1, 2, 3))
     net = f3.Feat3dNet({'num_clusters': M}, device=dev, seed=0).train_mode()
-    replay = net.capture_train_step(a, p, n, lr=1e-5, warmup=2)
+    replay = net.capture_train_step(a, p, n, lr=1e-5, warmup=2, pipelined=bool(args.pipelined))
     for _ in range(3):
         replay()
     torch.cuda.synchronize()
