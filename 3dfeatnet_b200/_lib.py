@@ -84,6 +84,7 @@ SIGNATURES = {
     "f3d_debug_wgrad_tc": (_i, [_c.c_longlong, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "f3d_debug_set_fuse_dz": (_i, [_i]),
     "f3d_debug_set_epilogue_pool": (_i, [_i]),
+    "f3d_debug_set_row_walk": (_i, [_i]),
     "f3d_debug_set_lin_tc_phases": (_i, [_i]),
     "f3d_debug_set_lin_tc_pipe_min_k": (_i, [_i]),
     "f3d_debug_lin_tc_trace": (_i, [_vp]),

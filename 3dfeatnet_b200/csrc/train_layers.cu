@@ -113,6 +113,35 @@ conv_fwd_kernel(long long rows, int cin, int cout, const float *__restrict__ x, 
     }
 }
 
+// The rows a thread of a chunk-owning streaming kernel visits.  A block does NOT own one contiguous 1/grid of the rows: with 592 blocks
+// streaming equal contiguous chunks in lockstep the kernels ran at 4.4 TB/s (every stream at the same relative offset: the same few
+// DRAM channels at a time); walking SMALL chunks of kWalk * rl rows round-robin over the grid they run at 5.4 TB/s.  The order in which a
+// thread meets its rows is fixed by (grid, rl), so the partial sums stay deterministic.
+constexpr int kWalk = 8;
+__device__ int g_row_walk = 1;  // f3d_debug_set_row_walk(0): one contiguous chunk per block (the round-1 walk), for A/B measurements
+struct RowWalk {
+    long long r, c0, cend, rows, cstep;
+    int rl, rlane;
+    long long sr;
+    __device__ __forceinline__ RowWalk(long long rows_, int rl_, int rlane_) : rows(rows_), rl(rl_), rlane(rlane_) {
+        sr = g_row_walk ? static_cast<long long>(kWalk) * rl : (rows + gridDim.x - 1) / gridDim.x;
+        c0 = static_cast<long long>(blockIdx.x) * sr;
+        cstep = static_cast<long long>(gridDim.x) * sr;
+        r = c0 + rlane;
+        cend = min(rows, c0 + sr);
+    }
+    __device__ __forceinline__ bool valid() const { return r < cend; }
+    // -> true when the walk jumped to another chunk (group bookkeeping has to be re-derived)
+    __device__ __forceinline__ bool next() {
+        r += rl;
+        if (r < cend) return false;
+        c0 += cstep;
+        r = c0 + rlane;
+        cend = min(rows, c0 + sr);
+        return true;
+    }
+};
+
 // The xyz layers (3 input channels: detector / descriptor conv0, models/feat3dnet.py:43,119 on the grouped coordinates): z = x W + b in
 // plain fp32 FMAs.  A streaming kernel bound by the write of z: 3 of 16 K-slots of an MMA would be used, and the tensor-core kernel spent
 // its time converting and draining for nothing.  Thread = (channel quad, row lane); per-block column sums of z and z^2 for the BN
@@ -123,14 +152,13 @@ conv3_fwd_kernel(long long rows, int c, const float *__restrict__ x, const float
     __shared__ float4 red[2][256];
     const int cvec = c >> 2, rl = 256 / cvec;
     const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
-    const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
-    const long long rbeg = blockIdx.x * chunk, rend = min(rows, rbeg + chunk);
     const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W) + cv), w1 = __ldg(reinterpret_cast<const float4 *>(W + c) + cv),
                  w2 = __ldg(reinterpret_cast<const float4 *>(W + 2 * c) + cv);
     const float4 bb = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
     if (rlane < rl) {
-        for (long long r = rbeg + rlane; r < rend; r += rl) {
+        for (RowWalk wk(rows, rl, rlane); wk.valid(); wk.next()) {
+            const long long r = wk.r;
             const float x0 = __ldg(x + r * 3), x1 = __ldg(x + r * 3 + 1), x2 = __ldg(x + r * 3 + 2);
             float4 v;
             v.x = __fmaf_rn(x2, w2.x, __fmaf_rn(x1, w1.x, __fmaf_rn(x0, w0.x, bb.x)));
@@ -272,8 +300,6 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
     __shared__ float4 red[2][256];
     const int cvec = c >> 2, rl = 256 / cvec;
     const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
-    const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
-    const long long rbeg = blockIdx.x * chunk, rend = min(rows, rbeg + chunk);
     const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean) + cv);
     const float4 vv = __ldg(reinterpret_cast<const float4 *>(var) + cv);
     const float4 is = make_float4(rsqrtf(vv.x + eps), rsqrtf(vv.y + eps), rsqrtf(vv.z + eps), rsqrtf(vv.w + eps));
@@ -286,9 +312,11 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
     float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sz = sg;
     PoolCache pc;
     if (rlane < rl) {
+        RowWalk wk(rows, rl, rlane);
         GroupCursor gc;
-        if (POOL) gc.init(rbeg + rlane, G.s);
-        for (long long r = rbeg + rlane; r < rend; r += rl) {
+        if (POOL) gc.init(wk.r, G.s);
+        for (; wk.valid();) {
+            const long long r = wk.r;
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = __ldg(reinterpret_cast<const float4 *>(z) + o);
             // the layer's activation is recomputed from z (bit-identical to what bn_apply stored) instead of read back
@@ -298,9 +326,13 @@ bn_bwd_reduce_kernel(long long rows, int c, float eps, GradSource G, const float
             if (POOL) {
                 const float4 gd = G.dense2 ? __ldg(reinterpret_cast<const float4 *>(G.dense2) + o) : make_float4(0.f, 0.f, 0.f, 0.f);
                 g = load_grad(G, pc, gd, gc.grp, cv, cvec, yy);
-                gc.advance(rl, G.s);
             } else {
                 g = __ldg(reinterpret_cast<const float4 *>(G.gy) + o);
+            }
+            if (wk.next()) {
+                if (POOL) gc.init(wk.r, G.s);
+            } else if (POOL) {
+                gc.advance(rl, G.s);
             }
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
@@ -411,8 +443,6 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
     __shared__ float4 red[256];
     const int cvec = c >> 2, rl = 256 / cvec;
     const int cv = threadIdx.x % cvec, rlane = threadIdx.x / cvec;
-    const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
-    const long long rbeg = blockIdx.x * chunk, rend = min(rows, rbeg + chunk);
     const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean) + cv);
     const float4 vv = __ldg(reinterpret_cast<const float4 *>(var) + cv);
     const float4 is = make_float4(rsqrtf(vv.x + eps), rsqrtf(vv.y + eps), rsqrtf(vv.z + eps), rsqrtf(vv.w + eps));
@@ -430,21 +460,23 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
     if (rlane < rl) {
         // the loads of row r + rl are issued before row r is processed (twice the bytes in flight per thread)
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        long long r = rbeg + rlane;
+        RowWalk wk(rows, rl, rlane);
         float4 zz_n = zero4, gd_n = zero4;
         const float *gdn = POOL ? G.dense2 : G.gy;
         GroupCursor gc;
-        if (POOL) gc.init(r, G.s);
-        if (r < rend) {
-            const size_t o = static_cast<size_t>(r) * cvec + cv;
+        if (POOL) gc.init(wk.r, G.s);
+        if (wk.valid()) {
+            const size_t o = static_cast<size_t>(wk.r) * cvec + cv;
             zz_n = __ldg(reinterpret_cast<const float4 *>(z) + o);
             if (gdn) gd_n = __ldg(reinterpret_cast<const float4 *>(gdn) + o);
         }
-        for (; r < rend; r += rl) {
+        while (wk.valid()) {
+            const long long r = wk.r;
             const size_t o = static_cast<size_t>(r) * cvec + cv;
             const float4 zz = zz_n, gd = gd_n;
-            if (r + rl < rend) {
-                const size_t on = static_cast<size_t>(r + rl) * cvec + cv;
+            const bool jumped = wk.next();  // wk: the row after r in this thread's walk
+            if (wk.valid()) {
+                const size_t on = static_cast<size_t>(wk.r) * cvec + cv;
                 zz_n = __ldg(reinterpret_cast<const float4 *>(z) + on);
                 if (gdn) gd_n = __ldg(reinterpret_cast<const float4 *>(gdn) + on);
             }
@@ -454,7 +486,7 @@ bn_bwd_apply_kernel(long long rows, int c, float eps, GradSource G, const float 
             float4 g = gd;
             if (POOL) {
                 g = load_grad(G, pc, gd, gc.grp, cv, cvec, yy);
-                gc.advance(rl, G.s);
+                if (jumped) gc.init(wk.r, G.s); else gc.advance(rl, G.s);
             }
             if (relu) {
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
@@ -1227,6 +1259,14 @@ F3D_API int f3d_debug_set_fuse_dz(int on) {
     const int prev = g_fuse_dz;
     g_fuse_dz = on ? 1 : 0;
     return prev;
+}
+
+// Measurement aid: 0 = the chunk-owning streaming kernels give every block one contiguous 1/grid of the rows (round 1), 1 (default) =
+// small chunks round-robin over the grid.  Different summation order, same determinism.  Returns 0.
+F3D_API int f3d_debug_set_row_walk(int on) {
+    const int v = on ? 1 : 0;
+    const cudaError_t e = cudaMemcpyToSymbol(f3d::g_row_walk, &v, sizeof(int));
+    return e == cudaSuccess ? 0 : fail(static_cast<int>(e), "debug_set_row_walk");
 }
 
 // Measurement / test aid: 0 = pool-only layers take the pooled maximum and the tie counts with a pass over z (bn_apply_pool_kernel),

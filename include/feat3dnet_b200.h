@@ -338,6 +338,10 @@ int f3d_debug_set_fuse_dz(int on);
 /* Test / measurement aid: 0 = pool-only training layers take the pooled maximum / tie counts with a pass over z (bn_apply_pool), 1 (default) =
  * from statistics gathered in the forward contraction's epilogue.  Same bits.  Returns the previous value. */
 int f3d_debug_set_epilogue_pool(int on);
+/* Measurement aid: 0 = the chunk-owning streaming kernels of the training layers (BN-backward passes, xyz-layer forward) give every block one
+ * contiguous 1/grid of the rows, 1 (default) = small chunks round-robin over the grid (4.4 -> 5.4 TB/s: 592 equal streams in lockstep hit the
+ * same DRAM channels).  The summation order differs between the two; each is deterministic. */
+int f3d_debug_set_row_walk(int on);
 /* Measurement aids: skip phases of the lin_tc kernels (bit 0 operand conversion, 1 MMAs, 2 epilogue stores, 3 TMA fetches; 0 = run all;
  * results are garbage with a bit set), and the contraction alone: out (rows, nout) = x (rows, k) W^T, W (nout, k) row-major, nsplit 2 | 3,
  * part = NULL or 2 * 2 * nout floats per row CTA of column-sum partials, wimg = f3d_debug_lin_tc_weight_bytes(k, nout) of scratch. */
