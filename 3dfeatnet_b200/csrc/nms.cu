@@ -152,8 +152,12 @@ nms_cell_scan_kernel(int max_cells, int *__restrict__ cell_start, int *__restric
     }
 }
 
-__global__ void nms_cell_fill_kernel(int n, double radius, int max_cells, const float *__restrict__ xyz, const float *__restrict__ bbox,
-                                     int *__restrict__ cursor, int *__restrict__ sorted) {
+// sorted[pos] = index of the point at position pos of the cell-sorted order, sorted_pts[pos] = (x, y, z, attention) of that point: the
+// query kernel walks the cloud in this order, so that the threads of a warp share their candidate cells (same loop bounds, broadcast loads)
+// and read a candidate's record with one 16-byte load instead of index -> three coordinates -> attention
+__global__ void nms_cell_fill_kernel(int n, double radius, int max_cells, const float *__restrict__ xyz, const float *__restrict__ attention,
+                                     const float *__restrict__ bbox, int *__restrict__ cursor, int *__restrict__ sorted,
+                                     float4 *__restrict__ sorted_pts) {
     const int batch = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -162,6 +166,7 @@ __global__ void nms_cell_fill_kernel(int n, double radius, int max_cells, const 
     const int cell = nms_cell_coord(p[1], g.y0, g.inv_h, g.ny) * g.nx + nms_cell_coord(p[0], g.x0, g.inv_h, g.nx);
     const int pos = atomicAdd(cursor + static_cast<size_t>(batch) * (max_cells + 1) + cell, 1);
     sorted[static_cast<size_t>(batch) * n + pos] = k;
+    sorted_pts[static_cast<size_t>(batch) * n + pos] = make_float4(p[0], p[1], p[2], attention[static_cast<size_t>(batch) * n + k]);
 }
 
 // keep[b,p] = 1 iff p is a local attention maximum among its (at most num_neighbors-1) nearest in-radius neighbours.
@@ -171,35 +176,39 @@ __global__ void nms_cell_fill_kernel(int n, double radius, int max_cells, const 
 // Otherwise the tree only returns the num_neighbors-1 nearest: the point dies iff fewer than num_neighbors-1 neighbours
 // precede the nearest threat -- a second scan that counts them (instead of materialising the sorted neighbour list).
 __global__ void __launch_bounds__(128)
-nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const float *__restrict__ xyz, const float *__restrict__ attention,
-                const float *__restrict__ bbox, const int *__restrict__ cell_start, const int *__restrict__ sorted,
-                unsigned char *__restrict__ keep) {
+nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const float *__restrict__ bbox, const int *__restrict__ cell_start,
+                const int *__restrict__ sorted, const float4 *__restrict__ sorted_pts, unsigned char *__restrict__ keep) {
     const int batch = blockIdx.y;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const float *p = xyz + static_cast<size_t>(batch) * n * 3;
-    const float *att = attention + static_cast<size_t>(batch) * n;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // position in the cell-sorted order: neighbouring threads, neighbouring cells
+    if (t >= n) return;
     const int *cs = cell_start + static_cast<size_t>(batch) * (max_cells + 1);
     const int *srt = sorted + static_cast<size_t>(batch) * n;
+    const float4 *pts = sorted_pts + static_cast<size_t>(batch) * n;
     const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
     const double T = nms_threshold(radius);
-    const double qx = p[3 * q], qy = p[3 * q + 1], qz = p[3 * q + 2];
-    const float qa = att[q];
+    const float4 me = __ldg(pts + t);
+    const int q = __ldg(srt + t);
+    const double qx = me.x, qy = me.y, qz = me.z;
+    const float qa = me.w;
     const int cx = nms_cell_coord(qx, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(qy, g.y0, g.inv_h, g.ny);
     const int y_lo = max(cy - 1, 0), y_hi = min(cy + 1, g.ny - 1), x_lo = max(cx - 1, 0), x_hi = min(cx + 1, g.nx - 1);
     int cnt = 0;
     double td = 1.0e300;  // nearest threat
     int tk = 0x7fffffff;
     for (int yy = y_lo; yy <= y_hi; ++yy) {
-        for (int e = cs[yy * g.nx + x_lo]; e < cs[yy * g.nx + x_hi + 1]; ++e) {  // the cells of one grid row are contiguous
-            const int k = srt[e];
-            if (k == q) continue;
-            const double d = nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+        const int e1 = cs[yy * g.nx + x_hi + 1];
+        for (int e = cs[yy * g.nx + x_lo]; e < e1; ++e) {  // the cells of one grid row are contiguous
+            if (e == t) continue;
+            const float4 c = __ldg(pts + e);
+            const double d = nms_d2(qx, qy, qz, c.x, c.y, c.z);
             if (d > T) continue;
             ++cnt;
-            if (att[k] > qa && (d < td || (d == td && k < tk))) {  // ties in attention: position 0 (self) wins the argmax
-                td = d;
-                tk = k;
+            if (c.w > qa && d <= td) {  // ties in attention: position 0 (self) wins the argmax
+                const int k = __ldg(srt + e);
+                if (d < td || k < tk) {
+                    td = d;
+                    tk = k;
+                }
             }
         }
     }
@@ -209,12 +218,13 @@ nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const fl
         if (cnt > num_neighbors - 1) {
             int before = 0;
             for (int yy = y_lo; yy <= y_hi; ++yy) {
-                for (int e = cs[yy * g.nx + x_lo]; e < cs[yy * g.nx + x_hi + 1]; ++e) {
-                    const int k = srt[e];
-                    if (k == q) continue;
-                    const double d = nms_d2(qx, qy, qz, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+                const int e1 = cs[yy * g.nx + x_hi + 1];
+                for (int e = cs[yy * g.nx + x_lo]; e < e1; ++e) {
+                    if (e == t) continue;
+                    const float4 c = __ldg(pts + e);
+                    const double d = nms_d2(qx, qy, qz, c.x, c.y, c.z);
                     if (d > T) continue;
-                    before += (d < td || (d == td && k < tk)) ? 1 : 0;
+                    before += (d < td || (d == td && __ldg(srt + e) < tk)) ? 1 : 0;
                 }
             }
             if (before >= num_neighbors - 1) kp = 1;  // the threat is not among the neighbours the tree returns
@@ -315,7 +325,7 @@ F3D_API size_t f3d_nms_workspace_bytes(int b, int n) {
     if (b <= 0 || n <= 0) return 256;
     const size_t bn = static_cast<size_t>(b) * n;
     const size_t cells = static_cast<size_t>(nms_max_cells(n)) + 1;
-    return bn * (1 + 4 + 4 + 4) + static_cast<size_t>(b) * cells * 8 + static_cast<size_t>(b) * 32 + 2048;
+    return bn * (1 + 4 + 4 + 4 + 16) + static_cast<size_t>(b) * cells * 8 + static_cast<size_t>(b) * 32 + 2048;
 }
 
 F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_radius, double min_response_ratio,
@@ -333,7 +343,7 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     const int max_cells = nms_max_cells(n);
     const size_t cells = static_cast<size_t>(max_cells) + 1;
     // layout: [counts: 2b ints][maxatt: b floats][bbox: 4b floats][pad] [cell_start: b*cells ints][cursor: b*cells ints]
-    //         [list: bn ints][dense_list: bn ints][sorted: bn ints][keep: bn bytes]
+    //         [list: bn ints][dense_list: bn ints][sorted: bn ints][sorted_pts: bn float4][keep: bn bytes]
     char *base = static_cast<char *>(workspace);
     int *count = reinterpret_cast<int *>(base);
     int *dense_count = count + b;
@@ -345,7 +355,8 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     int *list = cursor + static_cast<size_t>(b) * cells;
     int *dense_list = list + bn;
     int *sorted = dense_list + bn;
-    unsigned char *keep = reinterpret_cast<unsigned char *>(sorted + bn);
+    float4 *sorted_pts = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(sorted + bn) + 15) & ~static_cast<uintptr_t>(15));
+    unsigned char *keep = reinterpret_cast<unsigned char *>(sorted_pts + bn);
     cudaError_t e = cudaMemsetAsync(base, 0, head + static_cast<size_t>(b) * cells * sizeof(int), st);  // counters + cell counts
     if (e != cudaSuccess) return fail(static_cast<int>(e), "nms: memset");
     const double grid_radius = nms_radius;
@@ -358,11 +369,10 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     nms_cell_scan_kernel<<<b, 1024, 0, st>>>(max_cells, cell_start, cursor);
     rc = check_launch("nms_cell_scan_kernel");
     if (rc) return rc;
-    nms_cell_fill_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, grid_radius, max_cells, xyz, bbox, cursor, sorted);
+    nms_cell_fill_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, grid_radius, max_cells, xyz, attention, bbox, cursor, sorted, sorted_pts);
     rc = check_launch("nms_cell_fill_kernel");
     if (rc) return rc;
-    nms_keep_kernel<<<dim3((n + 127) / 128, b), 128, 0, st>>>(n, nms_radius, num_neighbors, max_cells, xyz, attention, bbox, cell_start, sorted,
-                                                              keep);
+    nms_keep_kernel<<<dim3((n + 127) / 128, b), 128, 0, st>>>(n, nms_radius, num_neighbors, max_cells, bbox, cell_start, sorted, sorted_pts, keep);
     rc = check_launch("nms_keep_kernel");
     if (rc) return rc;
     nms_max_kernel<<<b, 1024, 0, st>>>(n, attention, maxatt);
