@@ -18,6 +18,7 @@ namespace f3d {
 
 constexpr int kCentresPerWarp = 4;
 constexpr int kBqWarps = 8;  // warps per CTA
+constexpr int kBqSortCentres = 4096;  // centres per cloud from which the grid query walks them in spatially binned order
 constexpr int kRefStride = 256;  // blockDim.x of the reference launch (tf_grouping_g.cu:180): centre j belongs to thread j % 256
 
 // per-cloud header of the grid path's workspace (bq_grid_build_kernel)
@@ -284,7 +285,7 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
 __global__ void __launch_bounds__(256)
 bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float4 *__restrict__ sorted,
                      const int *__restrict__ cell_start, BqGridInfo *info,
-                     const float *__restrict__ xyz2, int *__restrict__ idx, int *__restrict__ pts_cnt) {
+                     const float *__restrict__ xyz2, int *__restrict__ idx, int *__restrict__ pts_cnt, const float4 *__restrict__ centres_sorted) {
     extern __shared__ unsigned bq_bitmap[];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int nwords = (n + 31) >> 5;
@@ -295,9 +296,19 @@ bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float
     const long long w = static_cast<long long>(blockIdx.x) * wpc + wl;
     if (w >= static_cast<long long>(b) * m) return;
     const int batch = static_cast<int>(w / m);
-    const int j = static_cast<int>(w - static_cast<long long>(batch) * m);
-    const float *c = xyz2 + (static_cast<size_t>(batch) * m + j) * 3;
-    const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+    int j = static_cast<int>(w - static_cast<long long>(batch) * m);
+    float cx, cy, cz;
+    if (centres_sorted) {
+        // many centres per cloud (attention at every point, inference.py:99-131): the warps take the centres in the order of a spatial
+        // binning of the centres themselves, so that the warps of a CTA (and of the CTAs that share its SM) walk the same candidate
+        // cells and find them in L1 instead of each gathering its own 3 x 3 cells from L2.  .w = the centre's index (row of idx).
+        const float4 rec = __ldg(centres_sorted + static_cast<size_t>(batch) * m + j);
+        cx = rec.x; cy = rec.y; cz = rec.z;
+        j = __float_as_int(rec.w);
+    } else {
+        const float *c = xyz2 + (static_cast<size_t>(batch) * m + j) * 3;
+        cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
+    }
     const float T = ball_threshold(radius);
     const BqGridInfo gi = info[batch];
     const float4 *pts = sorted + static_cast<size_t>(batch) * n;
@@ -557,8 +568,18 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
     if (e != cudaSuccess) return fail(static_cast<int>(e), "bq_grid_query: cudaFuncSetAttribute");
     // algorithmic bytes of the whole ball query: B * (12 N + 12 M + 4 M S + 4 M)
     ktimer_begin("bq_grid_query_kernel", static_cast<double>(b) * (12.0 * n + 12.0 * m + 4.0 * m * nsample + 4.0 * m), st);
+    // with at least kBqSortCentres centres per cloud and room for a second binning in the workspace, the centres are binned too
+    const float4 *centres_sorted = nullptr;
+    const size_t off2 = (f3d_query_ball_point_workspace_bytes(b, n) + 255) & ~static_cast<size_t>(255);
+    if (m >= kBqSortCentres && m <= 262144 && workspace_bytes >= off2 + f3d_query_ball_point_workspace_bytes(b, m)) {
+        const BqWorkspace w2 = bq_workspace(b, m, static_cast<char *>(workspace) + off2);
+        bq_grid_build_kernel<<<b, kBqBuildThreads, 0, st>>>(m, radius, xyz2, w2.sorted, w2.cell_start, w2.info);
+        const int rc2 = check_launch("bq_grid_build_kernel");
+        if (rc2) return rc2;
+        centres_sorted = w2.sorted;
+    }
     bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, ws.sorted, ws.cell_start, ws.info, xyz2, idx,
-                                                                    pts_cnt);
+                                                                    pts_cnt, centres_sorted);
     ktimer_end(st);
     int rc = check_launch("bq_grid_query_kernel");
     if (rc) return rc;

@@ -7,6 +7,7 @@ import torch
 _ROOT = __name__.split(".")[0]
 _lib = importlib.import_module("3dfeatnet_b200._lib" if _ROOT == "3dfeatnet_b200" else "_lib")
 _dist = importlib.import_module("3dfeatnet_b200.dist" if _ROOT == "3dfeatnet_b200" else "dist")
+_tg = importlib.import_module(("3dfeatnet_b200." if _ROOT == "3dfeatnet_b200" else "") + "tf_ops.grouping.tf_grouping")
 
 MAX_POINTS = 30000  # inference.py:22: centres per detection pass
 
@@ -47,14 +48,18 @@ def detect_and_describe(model, point_cloud, nms_radius=0.5, min_response_ratio=1
     point_cloud: (1,N,>=3) CUDA float32.  Returns (xyz_nms (1,K,3), features (1,K,F), attention_nms (1,K), num_keypoints)."""
     xyz = point_cloud[:, :, :3].contiguous()
     n = xyz.shape[1]
+    # the cloud is binned once for the ball queries of all chunks and of the descriptor pass (the model sees the same xyz tensor)
+    reuse = xyz.is_cuda and hasattr(model, "packed_weights")  # (stand-in models of the CPU tests take the plain call)
+    extra = {"ball_grid": _tg.BallGrid(model.param['BaseScale'], xyz, max_centres=min(n, MAX_POINTS))} if reuse else {}
+    cloud = xyz if reuse else point_cloud  # the model reads columns 0..2 only; handing it xyz itself keeps the grid's tensor identity
     atts = []
     for s in range(0, n, MAX_POINTS):
         kp = xyz[:, s:s + MAX_POINTS, :].contiguous()
-        _, _, att, ep = model.get_inference_model(point_cloud, False, keypoints=kp, fetch_features=False)
+        _, _, att, ep = model.get_inference_model(cloud, False, keypoints=kp, fetch_features=False, **extra)
         atts.append(ep["attention"])
     attention = torch.cat(atts, dim=1)
     xyz_nms, att_nms, num = nms(xyz, attention, nms_radius, min_response_ratio, max_keypoints)
-    _, features, _, _ = model.get_inference_model(point_cloud, False, keypoints=xyz_nms)
+    _, features, _, _ = model.get_inference_model(cloud, False, keypoints=xyz_nms, **extra)
     return xyz_nms, features, att_nms, num
 
 

@@ -337,7 +337,7 @@ class Feat3dNet:
         return xyz, features, anchor_attention, end_points
 
     def get_inference_model(self, point_cloud, is_training, use_bn=True, compute_det_gradients=False, keypoints=None,
-                            fetch_features=True, presampled=None, after_mid_hook=None):
+                            fetch_features=True, presampled=None, after_mid_hook=None, ball_grid=None):
         """ The core 3DFeat-Net model (feat3dnet.py:258-313).
 
         point_cloud: (B,N,>=3) CUDA float32.  keypoints: optional (B,M,3) cluster centres (what inference.py feeds
@@ -354,7 +354,9 @@ class Feat3dNet:
         if not is_training and use_bn and not compute_det_gradients:
             with torch.no_grad():
                 kp = sample_points(l0_xyz, self.param['num_clusters']) if keypoints is None else keypoints.contiguous()
-                idx, pts_cnt = _pc.query_ball_point(radius, ns, l0_xyz, kp)
+                # ball_grid: a tf_grouping.BallGrid of l0_xyz (same tensor, same radius), for callers that query one cloud repeatedly
+                idx, pts_cnt = _pc.query_ball_point(radius, ns, l0_xyz, kp, grid=ball_grid) if ball_grid is not None else \
+                    _pc.query_ball_point(radius, ns, l0_xyz, kp)
                 packed = self.packed_weights()
                 attention, orientation = detector_forward_fused(l0_xyz, kp, idx, radius, packed, self.precision)
                 ori = None if self.param['NoRegress'] else orientation

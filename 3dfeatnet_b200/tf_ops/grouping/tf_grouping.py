@@ -33,7 +33,25 @@ def _check_xyz_pair(op, xyz1, xyz2):
         raise ValueError("%s expects (batch_size, npoint, 3) xyz2 shape." % op)
 
 
-def query_ball_point(radius, nsample, xyz1, xyz2, use_grid=True):
+class BallGrid(object):
+    """The spatial binning of a cloud for query_ball_point (f3d_ball_grid_build): build it once, hand it to every query on the same
+    (radius, xyz1) as `grid=` -- the attention pass of the file flow queries one cloud five times (inference.py:118-131)."""
+    __slots__ = ("ws", "ws_bytes", "b", "n", "radius", "xyz1")
+
+    def __init__(self, radius, xyz1, max_centres=0):
+        xyz1 = _f32(xyz1.detach(), "xyz1")
+        _lib.require_cuda(xyz1)
+        L = _lib.lib()
+        self.b, self.n, self.radius, self.xyz1 = xyz1.shape[0], xyz1.shape[1], float(radius), xyz1
+        nbytes = L.f3d_query_ball_point_workspace_bytes(self.b, self.n)
+        if max_centres >= 4096:  # room for the spatial binning of the centres of a many-centre query
+            nbytes = ((nbytes + 255) // 256) * 256 + L.f3d_query_ball_point_workspace_bytes(self.b, int(max_centres))
+        self.ws_bytes = nbytes
+        self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=xyz1.device)
+        _lib.check(L.f3d_ball_grid_build(self.b, self.n, self.radius, _lib.ptr(xyz1), _lib.ptr(self.ws), nbytes, _lib.stream()), "ball_grid_build")
+
+
+def query_ball_point(radius, nsample, xyz1, xyz2, use_grid=True, grid=None):
     '''
     Input:
         radius: float32, ball search radius
@@ -56,8 +74,16 @@ def query_ball_point(radius, nsample, xyz1, xyz2, use_grid=True):
     idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
     L = _lib.lib()
+    if grid is not None:  # a BallGrid of this cloud and radius: only the query runs
+        if (grid.b, grid.n, grid.radius) != (b, n, float(radius)) or grid.xyz1.data_ptr() != xyz1.data_ptr():
+            raise ValueError("query_ball_point: grid was built for another cloud or radius")
+        _lib.check(L.f3d_ball_grid_query(b, n, m, float(radius), nsample, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx), _lib.ptr(cnt),
+                                         _lib.ptr(grid.ws), grid.ws_bytes, _lib.stream()), "ball_grid_query")
+        return idx, cnt
     if use_grid:  # grid-accelerated kernel (identical results); use_grid=False forces the plain scan
         ws_bytes = L.f3d_query_ball_point_workspace_bytes(b, n)
+        if m >= 4096:  # room for the spatial binning of the centres (many centres per cloud: the attention pass of inference.py)
+            ws_bytes = ((ws_bytes + 255) // 256) * 256 + L.f3d_query_ball_point_workspace_bytes(b, m)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=xyz1.device)
         _lib.check(L.f3d_query_ball_point_ws(b, n, m, float(radius), nsample, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx),
                                              _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream()), "query_ball_point")

@@ -78,7 +78,9 @@ int f3d_query_ball_point(int b, int n, int m, float radius, int nsample, const f
 /* Same operator with a caller-provided workspace of f3d_query_ball_point_workspace_bytes(b,n) bytes: the cloud is
  * binned into an xy grid of cell size ~radius and each centre only tests its 3x3 cell neighbourhood; identical
  * results (hits are re-ordered by index through a shared-memory bitmap).  Falls back to the scan above when the
- * workspace is NULL / too small. */
+ * workspace is NULL / too small.  With m >= 4096 centres per cloud (the attention pass of inference.py:99-131 scores every point) and a
+ * workspace of align256(..._workspace_bytes(b,n)) + ..._workspace_bytes(b,m) bytes the centres are binned too and visited in that
+ * order, so that the warps of a CTA share their candidate cells (same rows, each written at its centre's own index). */
 size_t f3d_query_ball_point_workspace_bytes(int b, int n);
 int f3d_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
                             int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream);

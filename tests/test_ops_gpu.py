@@ -143,6 +143,8 @@ def _centres(x, m, mode, seed):
     ("oxford", 1, 32768, 1024, 2.0, 64, "subset"), ("uniform", 1, 65536, 2048, 2.0, 64, "subset"),
     ("uniform", 1, 131072, 4096, 2.0, 64, "subset"), ("uniform", 2, 600, 70, 0.05, 8, "external"),
     ("uniform", 1, 50, 9, 100.0, 64, "subset"),
+    # >= 4096 centres per cloud: the grid query walks the centres in spatially binned order (same rows, written at the centre's own index)
+    ("oxford", 2, 16384, 8192, 2.0, 64, "subset"), ("uniform", 1, 20000, 6000, 2.0, 32, "external"),
 ])
 def test_ball_query_bit_exact_vs_oracle(cuda, kind, b, n, m, radius, ns, mode):
     tg = pkg("tf_ops.grouping.tf_grouping")
