@@ -12,14 +12,14 @@ int detector_rows_tc(long long num_clusters, int n, int m, float radius, const f
                      const int *idx, const float *packed, uint8_t *wimg, float *pooled, bool build_image, int max_ctas, cudaStream_t st);
 int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
                        const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
-                       float *pooled2, bool build_image, int max_ctas, cudaStream_t st);
+                       float *pooledA, float *pmaxh, bool build_image, int max_ctas, cudaStream_t st);
 size_t descriptor_tc_weight_bytes();
 int descriptor_post_fp32(long long nc, const float *pooled2, const float *packed, int feature_dim, float *features,
                          cudaStream_t st);
 size_t post_tc_weight_bytes();
 int detector_post_tc(long long nc, const float *pooled, const float *packed, uint8_t *wimg, float *attention, float *orientation,
                      bool build_image, int max_ctas, cudaStream_t st);
-int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, const float *packed, uint8_t *wimg, float *features,
+int descriptor_post_tc(long long nc, int feature_dim, const float *pooledA, const float *pmaxh, const float *packed, uint8_t *wimg, float *features,
                        bool build_image, int max_ctas, cudaStream_t st);
 int detector_post_fp32(long long num_clusters, const float *pooled, const float *packed, float *attention,
                        float *orientation, cudaStream_t st);
@@ -99,12 +99,16 @@ F3D_API int f3d_descriptor_forward(int b, int n, int m, int nsample, float radiu
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,
                                        static_cast<float *>(workspace), features, as_stream(stream));
     if (precision == 2 && nsample == 64 && feature_dim <= 64) {  // tcgen05, bf16x3 split
-        float *pooled2 = static_cast<float *>(workspace);
-        int rc = descriptor_rows_tc(static_cast<long long>(b) * m, n, m, radius, feature_dim, xyz, new_xyz, idx, orientation,
-                                    packed, image_slot(workspace, b, m, 2), pooled2, build_images, max_ctas, as_stream(stream));
+        // the row kernel leaves, per cluster, the per-point half of conv_mid_0 max-pooled (128 floats) and the two sample-half maxima of
+        // the 64 conv1 channels (2 x 64 floats); the tail adds the pooled half of conv_mid_0 (the workspace holds 256 floats per cluster)
+        const long long nc = static_cast<long long>(b) * m;
+        float *pooledA = static_cast<float *>(workspace);
+        float *pmaxh = pooledA + nc * 128;
+        int rc = descriptor_rows_tc(nc, n, m, radius, feature_dim, xyz, new_xyz, idx, orientation, packed, image_slot(workspace, b, m, 2),
+                                    pooledA, pmaxh, build_images, max_ctas, as_stream(stream));
         if (rc) return rc;
-        return descriptor_post_tc(static_cast<long long>(b) * m, feature_dim, pooled2, packed, image_slot(workspace, b, m, 3), features,
-                                  build_images, max_ctas, as_stream(stream));
+        return descriptor_post_tc(nc, feature_dim, pooledA, pmaxh, packed, image_slot(workspace, b, m, 3), features, build_images, max_ctas,
+                                  as_stream(stream));
     }
     if (precision == 2)  // shapes the tensor-core kernel does not cover (nsample != 64, feature_dim 128): exact fp32 kernel
         return descriptor_forward_fp32(b, n, m, nsample, radius, feature_dim, xyz, new_xyz, idx, orientation, packed,

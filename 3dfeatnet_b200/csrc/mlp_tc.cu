@@ -334,10 +334,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                     a = fmaf(gz, w.z, a);
                     v[e] = fmaxf(a, 0.0f);
                 }
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[0] - __low2float(h2), v[1] - __high2float(h2));
-                hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
-                lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
+                split_bf16x2(v[0], v[1], hi[j], lo[j]);
             }
             if (warp == 1) stamp(t, 5);
             mbar_wait(&bars[X1_FREE], (t & 1) ^ 1);
@@ -412,10 +409,7 @@ det_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const flo
                 uint32_t &ra = sidx < 32 ? r0[sidx & 31] : r1[sidx & 31];
                 uint32_t &rb = sidx < 32 ? r0[(sidx + 1) & 31] : r1[(sidx + 1) & 31];
                 const float va = fmaxf(__uint_as_float(ra) + b1, 0.0f), vb = fmaxf(__uint_as_float(rb) + b1, 0.0f);
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
-                ra = *reinterpret_cast<const uint32_t *>(&h2);
-                rb = *reinterpret_cast<const uint32_t *>(&l2);
+                split_bf16x2(va, vb, ra, rb);
             }
             if (q == 1) stamp(t, 9);
             mbar_wait(&bars[X2_FREE0 + ph], ((pr >> 1) & 1) ^ 1);  // MMA2(pr-2) has finished reading this slot

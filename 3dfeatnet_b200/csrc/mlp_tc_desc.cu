@@ -14,22 +14,28 @@
 //                                                                   issued per PAIR of tiles: a 128x128x16 MMA holds the tensor
 //                                                                   pipe 66.5 cycles, two 128x64x16 ones 2 x 41.9
 //                                                                   (profiles/r02_a_umma_instruction_shape.md)
-//   MMA3 : D3[128 x 8]   = Wb^T[128 x 64]  P^T                    (rows 64..127: the tiled max-pool part, ONE column per
-//                                                                   cluster instead of 64 -- the split-weight identity; the two
-//                                                                   tiles of a pair are rows 0 / 1 of the same 8-row operand)
-//   E2   : pooled2 = max_s D2[:, s] + D3[:, tile] + b_mid         (no ReLU: final_relu=False, feat3dnet.py:71)
-// D1 and D2 are double-buffered; D3 is single (its reader, E2 of the previous pair, is awaited before MMA3).
+//   E2   : pooledA = max_s D2[:, s] + b_mid                         (no ReLU: final_relu=False, feat3dnet.py:71)
+// The OTHER half of conv_mid_0 -- rows 64..127 of its weight times the tiled max-pool vector P, one column per cluster by the
+// split-weight identity -- rides the tail kernel (post_tc_kernel<1>, one N = 64 MMA group per 64 clusters): as an N = 8 MMA per
+// pair of tiles inside this kernel it held the tensor pipe 413 of a pair's 1714 cycles for 48 cycles of math (an instruction
+// never takes less than ~34 cycles, profiles/r02_a_umma_instruction_shape.md), and its single accumulator serialised the pairs.
+// This kernel writes pooledA and the two sample-half maxima of every conv1 channel (pmaxh); the tail forms
+// pooled2 = pooledA + Wb^T max(pmaxh[0], pmaxh[1]).
+// D1 and D2 are double-buffered.
 //
-// 18 warps: 0 = MMA2/3 issue, 1-4 and 14-17 = two producer warpgroups (even / odd tiles, one X1 buffer each: with the pair MMAs the
-// tensor pipe needs ~860 cycles per tile and one producer warpgroup ~1060), 5-12 = two epilogue warpgroups (even / odd tiles), 13 = MMA1
-// issue.  The epilogue warpgroups work on the same pair, so each writes the operand of its NEXT tile before draining the current
-// accumulator (see mlp_tc.cu).
-// conv_post_0 + l2-normalise run afterwards over 128 clusters per CTA (desc_post_fp32_kernel).
+// 22 warps: 0 = MMA2/3 issue, 1-4 and 14-17 = two producer warpgroups (even / odd tiles, one X1 buffer each: with the pair MMAs the
+// tensor pipe needs ~860 cycles per tile and one producer warpgroup ~1060), 5-12 = two E1 warpgroups (even / odd tiles), 13 = MMA1
+// issue, 18-21 = the E2 warpgroup (both tiles of every pair).  E1 (~1400 cycles per tile: accumulator -> bias / ReLU / hi-lo split ->
+// operand stores -> proxy fence) was the longest stage when the same warpgroup also drained D2 (clock64 timeline
+// profiles/r02_e_desc_tc_timeline.txt: an epilogue warpgroup was busy 2130 of the 2130 cycles of a pair period); with E2 on warps of its
+// own the pair period is E1's alone.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "weights_layout.h"
 
 #include <cuda_bf16.h>
+
+#include <type_traits>
 
 namespace f3d {
 
@@ -37,23 +43,21 @@ using namespace tc;
 
 namespace dsc {
 constexpr int kSamples = 64;
-constexpr int kThreads = 18 * 32;  // warp 0 MMA2/3 issue, 1-4 / 14-17 producers (even / odd tiles), 5-12 epilogues, 13 MMA1 issue
+constexpr int kThreads = 22 * 32;  // warp 0 MMA2 issue, 1-4 / 14-17 producers (even / odd tiles), 5-12 E1, 13 MMA1 issue, 18-21 E2
 constexpr uint32_t kSbo = 128;
 constexpr uint32_t kLboW = 128 * 16;
 constexpr uint32_t kLboX1 = kSamples * 16;
 constexpr uint32_t kLboX2 = 128;                        // X2 is MN-major: K groups of 8 channels 128 B apart,
 constexpr uint32_t kSboX2 = 8 * 128;                    // groups of 8 samples 1 KB apart (64 channels)
-constexpr uint32_t kLboP = 8 * 16;                      // P: one 8-row group per K chunk
 constexpr uint32_t kW1Split = 128 * 32 * 2;             // 8 KB
 constexpr uint32_t kWmSplit = 128 * 64 * 2;             // 16 KB
 constexpr uint32_t kOffW1 = 0;                           // [split 2][chunk 4][row 128][8]
 constexpr uint32_t kOffWa = kOffW1 + 2 * kW1Split;       // [split 2][chunk 8][row 128][8]
-constexpr uint32_t kOffWb = kOffWa + 2 * kWmSplit;
-constexpr uint32_t kOffW0 = kOffWb + 2 * kWmSplit;       // float4 [32]: (w_x, w_y, w_z, bias) of layer 0 per channel
+constexpr uint32_t kOffW0 = kOffWa + 2 * kWmSplit;       // fp32 [16][8]: (w_x, w_y, w_z, bias) of layer 0, interleaved per channel pair
 constexpr uint32_t kOffB0 = kOffW0 + 3 * 32 * 4;         // (tail of the float4 table)
 constexpr uint32_t kOffB1 = kOffB0 + 32 * 4;             // fp32 [64]
 constexpr uint32_t kOffBm = kOffB1 + 64 * 4;             // fp32 [128]
-constexpr uint32_t kWeightBytes = kOffBm + 128 * 4;      // 83 200
+constexpr uint32_t kWeightBytes = kOffBm + 128 * 4;      // 50 432
 constexpr uint32_t kX1Split = 4 * kLboX1;                // 4 KB
 constexpr uint32_t kX1Buf = 2 * kX1Split;                // one X1 operand (hi + lo); buffer = tile & 1 (one per producer warpgroup)
 constexpr uint32_t kOffX1 = kWeightBytes;
@@ -62,21 +66,14 @@ constexpr uint32_t kOffX1 = kWeightBytes;
 constexpr uint32_t kX2Split = 16 * kSboX2;               // 16 KB
 constexpr uint32_t kX2Slot = 2 * kX2Split;               // 32 KB
 constexpr uint32_t kOffX2 = kOffX1 + 2 * kX1Buf;
-constexpr uint32_t kPSplit = 8 * kLboP;                  // 1 KB
-constexpr uint32_t kPBuf = 2 * kPSplit;                  // per pair slot; row g of the 8-row group = tile g of the pair
-constexpr uint32_t kOffP = kOffX2 + 2 * kX2Slot;         // [slot 2][split 2][chunk 8][row 8][8]
-constexpr uint32_t kOffPm = kOffP + 2 * kPBuf;            // fp32 [warpgroup 2][128]: partial channel maxima of the sample halves
-constexpr uint32_t kOffBars = kOffPm + 2 * 128 * 4;
+constexpr uint32_t kOffBars = kOffX2 + 2 * kX2Slot;
 constexpr uint32_t kSmemBytes = kOffBars + 20 * 8 + 16;
-static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffP % 128 == 0 && kOffBars % 8 == 0, "alignment");
+static_assert(kWeightBytes % 16 == 0 && kOffX1 % 128 == 0 && kOffX2 % 128 == 0 && kOffBars % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-// TMEM columns: D1[tile & 1] at 0 / 64, D2[slot] at 128 + slot*128 (two tiles x 64 samples), D3 at 384 (8 used), then the weights
-// that feed MMAs from tensor memory (copied once with tcgen05.cp): W1 at 416 + split*16 (32 K = 16 columns), Wa at 448 + split*32
-// (64 K = 32 columns).  Wb (the N = 8 MMAs of the pooled term) stays in shared memory: an SS-mode 128x8x16 instruction reads its
-// 4 KB A operand in ~33 cycles, the time such an instruction holds the pipe anyway (34 cycles), and the 64 columns it would take
-// are what lets BOTH D1 and D2 be double-buffered.
+// TMEM columns: D1[tile & 1] at 0 / 64, D2[slot] at 128 + slot*128 (two tiles x 64 samples), then the weights, which feed their
+// MMAs from tensor memory (copied once with tcgen05.cp): W1 at 416 + split*16 (32 K = 16 columns), Wa at 448 + split*32 (64 K = 32).
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemD2 = 128, kTmemD3 = 384;
+constexpr uint32_t kTmemD2 = 128;
 constexpr uint32_t kTmemW1 = 416, kTmemWa = 448;
 // per-tile events the alternating epilogue warpgroups wait on are per-warpgroup barriers; per-pair events are per ring slot
 enum Bar { W_FULL = 0, W_TMEM, X1_FULL0, X1_FULL1, X1_FREE0, X1_FREE1, X2_FULL0, X2_FULL1, X2_FREE0, X2_FREE1, D1_FULL0, D1_FULL1, D1_FREE0,
@@ -88,13 +85,16 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }
 
-__global__ void __launch_bounds__(dsc::kThreads, 1)
+template <bool kTrace>  // kTrace: clock64() stamps of CTA 0 (tools/tc_timeline.py); the production instantiation carries none
+__global__ void __launch_bounds__(dsc::kThreads, 1)  // 80 registers: 6 of the 22 warps share a scheduler's 16 384
 desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const float *__restrict__ xyz,
                     const float *__restrict__ new_xyz, const int *__restrict__ idx, const float *__restrict__ orientation,
-                    const uint8_t *__restrict__ wimg, float *__restrict__ pooled2, long long *__restrict__ dbg) {
+                    const uint8_t *__restrict__ wimg, float *__restrict__ pooledA, float *__restrict__ pmaxh, long long *__restrict__ dbg) {
     using namespace dsc;
     auto stamp = [&](int t, int slot) {  // optional clock64() timeline of CTA 0 (bring-up)
-        if (dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) dbg[t * 16 + slot] = clock64();
+        if constexpr (kTrace) {
+            if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) dbg[t * 16 + slot] = clock64();
+        }
     };
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBars);
@@ -112,13 +112,10 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             mbar_init(&bars[X2_FREE0 + b], 1);
             mbar_init(&bars[D1_FULL0 + b], 1);
             mbar_init(&bars[D2_FULL0 + b], 1);
-            mbar_init(&bars[D2_FREE0 + b], 256);  // both epilogue warpgroups (one tile of the pair each)
+            mbar_init(&bars[D2_FREE0 + b], 128);  // the E2 warpgroup (both tiles of the pair)
         }
         fence_barrier_init();
     }
-    // rows 2..7 of the pooled operand P are never written: zero the operand once (their D3 columns are never read either)
-    for (uint32_t i = threadIdx.x; i < 2 * kPBuf / 4; i += kThreads) reinterpret_cast<uint32_t *>(smem + kOffP)[i] = 0;
-    fence_proxy_async_smem();
     if (warp == 0) {
         tmem_alloc(tmem_base_s, kTmemCols);
         tmem_relinquish();
@@ -144,9 +141,8 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             mbar_wait(&bars[W_FULL], 0);
             const uint32_t idesc64 = make_idesc(1, 128, kSamples) | kIdescBMnMajor;
             const uint32_t idesc128 = make_idesc(1, 128, 2 * kSamples) | kIdescBMnMajor;
-            const uint32_t idesc8 = make_idesc(1, 128, 8);
             const uint32_t sbase = smem_u32(smem);
-            // ---- W1 and Wa (hi and lo splits) -> tensor memory, once; Wb feeds its MMAs from shared memory
+            // ---- W1 and Wa (hi and lo splits) -> tensor memory, once
             tcgen05_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -164,7 +160,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             }
             __syncwarp();
             mbar_wait(&bars[W_TMEM], 0);
-            auto mma23 = [&](int pr) {  // pair pr = tiles 2pr, 2pr+1: X2 / P slot pr & 1, accumulator D2[pr & 1], the single D3
+            auto mma2 = [&](int pr) {  // pair pr = tiles 2pr, 2pr+1: X2 slot pr & 1, accumulator D2[pr & 1]
                 const int sl = pr & 1;
                 const bool two = 2 * pr + 1 < T;
                 mbar_wait(&bars[X2_FULL0], pr & 1);
@@ -186,24 +182,6 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                             acc = 1;
                         }
                     }
-                }
-                __syncwarp();
-                // D3 is single-buffered: E2(pr-1), which reads it, arrives on the OTHER slot's D2_FREE
-                if (pr > 0) mbar_wait(&bars[D2_FREE0 + (sl ^ 1)], ((pr - 1) >> 1) & 1);
-                tcgen05_fence_after();
-                if (elect_one()) {
-                    const uint32_t d3 = tmem_base + kTmemD3;
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t wb = sbase + kOffWb + (pass == 2 ? kWmSplit : 0);
-                        const uint32_t xb = sbase + kOffP + sl * kPBuf + (pass == 1 ? kPSplit : 0);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_f16(d3, make_smem_desc(wb + k * 2 * kLboW, kLboW, kSbo), make_smem_desc(xb + k * 2 * kLboP, kLboP, kSbo), idesc8, acc);
-                            acc = 1;
-                        }
-                    }
                     umma_commit(&bars[X2_FREE0 + sl]);
                     umma_commit(&bars[D2_FULL0 + sl]);
                 }
@@ -211,7 +189,7 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 stamp(2 * pr, 2);
             };
             // MMA1 (conv1) is issued by warp 13: two issuing warps hide each other's mbarrier waits (see mlp_tc.cu)
-            for (int pr = 0; 2 * pr < T; ++pr) mma23(pr);
+            for (int pr = 0; 2 * pr < T; ++pr) mma2(pr);
         }
     } else if (warp == 13) {
         // ---- second MMA issuer: conv1 (X1[t & 1] -> D1), A operand W1 from tensor memory ---------------------------------
@@ -243,13 +221,19 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             __syncwarp();
         };
         for (int t = 0; t < T; ++t) mma1(t);
-    } else if (warp <= 4 || warp >= 14) {
+    } else if (warp <= 4 || (warp >= 14 && warp < 18)) {
         // ---- producers: gather + normalise + rotate + layer 0 (3 -> 32) -> X1 ------------------------------------
         // Two warpgroups: pg = 0 (warps 1-4) makes the even tiles, pg = 1 (warps 14-17) the odd ones, each into its own X1 buffer.
-        // Software-pipelined over the warpgroup's own tile sequence: index of item i+2D and coordinates / orientation of item i+D
-        // in flight while item i is computed.
+        // Software-pipelined over the warpgroup's own tile sequence: index of item i+2D and coordinates of item i+D in flight
+        // while item i is computed.  The kernel's pace is the instruction count of its warps (six warps per scheduler, each a
+        // serial chain: profiles/r02_ba_desc_tc_timeline.txt), so the per-item bookkeeping is kept off the issue slots: both
+        // prefetch streams advance running pointers (no cluster / m division per item), the rotation's (cos, sin) of 32 items are
+        // computed at once -- lane l of a warp takes item 32 k + l -- and handed out by shuffle, layer 0 and the hi/lo split run on
+        // packed fp32 pairs (FFMA2 / FADD2), and the exact division by a radius that is not a power of two is a separate
+        // instantiation of the loop instead of a select per coordinate.
         mbar_wait(&bars[W_FULL], 0);
-        const float4 *W0 = reinterpret_cast<const float4 *>(smem + kOffW0);  // per channel: (w_x, w_y, w_z, bias)
+        // per channel PAIR (a, b): {(wx_a, wx_b), (wy_a, wy_b)}, {(wz_a, wz_b), (bias_a, bias_b)}
+        const ulonglong2 *W0 = reinterpret_cast<const ulonglong2 *>(smem + kOffW0);
         const int pg = warp >= 14 ? 1 : 0;
         const int pt = pg ? threadIdx.x - 14 * 32 : threadIdx.x - 32;
         const int s = pt & 63, h = pt >> 6;  // sample, channel half (16 channels = 2 K chunks)
@@ -258,103 +242,157 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
         const int Tg = T > pg ? (T - pg + 1) / 2 : 0;  // items (tiles) of this warpgroup: tile = pg + 2 i
         const float inv_r = 1.0f / radius;  // exact replacement of the division when radius is a power of two (see mlp_tc.cu)
         const bool pow2 = (__float_as_uint(radius) & 0x007fffffu) == 0u && radius > 1e-30f && radius < 1e30f;
-        auto cluster_of = [&](int i) -> unsigned { return static_cast<unsigned>(first) + static_cast<unsigned>(pg + 2 * i) * stride; };
-        auto load_idx = [&](int i) -> int {
-            if (i >= Tg) return 0;
-            return __ldg(idx + static_cast<size_t>(cluster_of(i)) * kSamples + s);
+        const unsigned cl0 = static_cast<unsigned>(first) + static_cast<unsigned>(pg) * stride, step = 2u * stride;  // cluster of item i = cl0 + i step
+        // stream 1: ball-query index of this thread's sample, items 0, 1, 2, ...
+        const int *ip = idx + static_cast<size_t>(cl0) * kSamples + s;
+        const size_t ip_step = static_cast<size_t>(step) * kSamples;
+        int i_idx = 0;
+        auto next_idx = [&]() -> int {
+            int v = 0;
+            if (i_idx < Tg) v = __ldg(ip);
+            ip += ip_step;
+            ++i_idx;
+            return v;
         };
-        // With depth 1 the kernel was bound by this dependent L2 gather (clock64 timeline: ~2100 cycles per producer iteration
+        // stream 2: the sample's point and the cluster centre; cloud of the cluster = cluster / m, advanced without dividing
+        struct Grp { float px, py, pz, qx, qy, qz; };
+        const unsigned um = static_cast<unsigned>(m), qstep = step / um, rstep = step % um;
+        unsigned cl_x = cl0, bat_x = cl0 / um, rem_x = cl0 % um;
+        int i_x = 0;
+        auto next_xyz = [&](Grp &g, int ii) {
+            g.px = g.py = g.pz = g.qx = g.qy = g.qz = 0.f;
+            if (i_x < Tg) {
+                ii = min(max(ii, 0), n - 1);
+                const float *p = xyz + (static_cast<size_t>(bat_x) * n + ii) * 3;
+                const float *c = new_xyz + static_cast<size_t>(cl_x) * 3;
+                g.px = __ldg(p); g.py = __ldg(p + 1); g.pz = __ldg(p + 2);
+                g.qx = __ldg(c); g.qy = __ldg(c + 1); g.qz = __ldg(c + 2);
+            }
+            cl_x += step; bat_x += qstep; rem_x += rstep;
+            if (rem_x >= um) { rem_x -= um; ++bat_x; }
+            ++i_x;
+        };
+        // stream 3: orientation of item 32 k + lane, one block of 32 items ahead
+        auto load_th = [&](int i) -> float {
+            return (orientation && i < Tg) ? __ldg(orientation + (cl0 + static_cast<unsigned>(i) * step)) : 0.0f;
+        };
+        float th_pref = load_th(lane), cs_l = 1.0f, sn_l = 0.0f;
+        // With depth 1 the kernel was bound by the dependent L2 gather (clock64 timeline: ~2100 cycles per producer iteration
         // against ~1000 of MMA + epilogue work); the slots are static (loop unrolled by D).
         constexpr int D = 3;
-        struct Grp { float px, py, pz, qx, qy, qz, th; };
         Grp gq[D];
         int iq[D];
-        auto load_xyz = [&](Grp &g, int i, int ii) {
-            g.px = g.py = g.pz = g.qx = g.qy = g.qz = g.th = 0.f;
-            if (i >= Tg) return;
-            const unsigned cl = cluster_of(i);
-            ii = min(max(ii, 0), n - 1);
-            const float *p = xyz + (static_cast<size_t>(cl / static_cast<unsigned>(m)) * n + ii) * 3;
-            const float *c = new_xyz + static_cast<size_t>(cl) * 3;
-            g.px = __ldg(p); g.py = __ldg(p + 1); g.pz = __ldg(p + 2);
-            g.qx = __ldg(c); g.qy = __ldg(c + 1); g.qz = __ldg(c + 2);
-            if (orientation) g.th = __ldg(orientation + cl);
-        };
 #pragma unroll
-        for (int d = 0; d < D; ++d) iq[d] = load_idx(d);
+        for (int d = 0; d < D; ++d) iq[d] = next_idx();
 #pragma unroll
-        for (int d = 0; d < D; ++d) load_xyz(gq[d], d, iq[d]);
+        for (int d = 0; d < D; ++d) next_xyz(gq[d], iq[d]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) iq[d] = load_idx(D + d);
-        for (int i0 = 0; i0 < Tg; i0 += D) {
+        for (int d = 0; d < D; ++d) iq[d] = next_idx();
+        auto produce = [&](auto pow2_c) {
+          constexpr bool kPow2 = decltype(pow2_c)::value;
+          for (int i0 = 0; i0 < Tg; i0 += D) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) {
-            const int i = i0 + d;
-            if (i >= Tg) break;
-            const int t = pg + 2 * i;
-            if ((warp & 3) == 1) stamp(t, 4);
-            const float px = gq[d].px, py = gq[d].py, pz = gq[d].pz, qx = gq[d].qx, qy = gq[d].qy, qz = gq[d].qz, th = gq[d].th;
-            float gx = pow2 ? (px - qx) * inv_r : (px - qx) / radius;
-            float gy = pow2 ? (py - qy) * inv_r : (py - qy) / radius;
-            const float gz = pow2 ? (pz - qz) * inv_r : (pz - qz) / radius;
-            if (orientation) {  // pointnet_common.py:110-120: x' = x c - y s ; y' = x s + y c
-                float cs, sn;
-                sincosf(th, &sn, &cs);
-                const float xr = gx * cs - gy * sn;
-                const float yr = gx * sn + gy * cs;
-                gx = xr;
-                gy = yr;
+            for (int d = 0; d < D; ++d) {
+              const int i = i0 + d;
+              if (i >= Tg) break;
+              const int t = pg + 2 * i;
+              if ((warp & 3) == 1) stamp(t, 4);
+              if (orientation && (i & 31) == 0) {  // (warp-uniform) the next 32 items' rotations
+                  sincosf(th_pref, &sn_l, &cs_l);
+                  th_pref = load_th(i + 32 + lane);
+              }
+              const float px = gq[d].px, py = gq[d].py, pz = gq[d].pz, qx = gq[d].qx, qy = gq[d].qy, qz = gq[d].qz;
+              float gx = kPow2 ? (px - qx) * inv_r : (px - qx) / radius;
+              float gy = kPow2 ? (py - qy) * inv_r : (py - qy) / radius;
+              const float gz = kPow2 ? (pz - qz) * inv_r : (pz - qz) / radius;
+              if (orientation) {  // pointnet_common.py:110-120: x' = x c - y s ; y' = x s + y c
+                  const float cs = __shfl_sync(0xffffffffu, cs_l, i & 31), sn = __shfl_sync(0xffffffffu, sn_l, i & 31);
+                  const float xr = gx * cs - gy * sn;
+                  const float yr = gx * sn + gy * cs;
+                  gx = xr;
+                  gy = yr;
+              }
+              next_xyz(gq[d], iq[d]);
+              iq[d] = next_idx();
+              const uint64_t gx2 = pk2(gx, gx), gy2 = pk2(gy, gy), gz2 = pk2(gz, gz);
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                  const ulonglong2 wa = W0[(h * 8 + j) * 2], wb = W0[(h * 8 + j) * 2 + 1];
+                  uint64_t a = fma2(gx2, wa.x, wb.y);
+                  a = fma2(gy2, wa.y, a);
+                  a = fma2(gz2, wb.x, a);
+                  float v0, v1;
+                  upk2(a, v0, v1);
+                  split_bf16x2(fmaxf(v0, 0.0f), fmaxf(v1, 0.0f), hi[j], lo[j]);
+              }
+              if ((warp & 3) == 1) stamp(t, 5);
+              mbar_wait(&bars[X1_FREE0 + pg], (i & 1) ^ 1);  // MMA1 of this warpgroup's previous tile has read the buffer
+              if ((warp & 3) == 1) stamp(t, 6);
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                  *reinterpret_cast<uint4 *>(x1 + (h * 2 + q) * kLboX1) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+                  *reinterpret_cast<uint4 *>(x1 + kX1Split + (h * 2 + q) * kLboX1) =
+                      make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+              }
+              fence_proxy_async_smem();
+              mbar_arrive(&bars[X1_FULL0 + pg]);
             }
-            load_xyz(gq[d], i + D, iq[d]);
-            iq[d] = load_idx(i + 2 * D);
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float v[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float4 w = W0[h * 16 + j * 2 + e];
-                    float a = w.w;
-                    a = fmaf(gx, w.x, a);
-                    a = fmaf(gy, w.y, a);
-                    a = fmaf(gz, w.z, a);
-                    v[e] = fmaxf(a, 0.0f);
-                }
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[0] - __low2float(h2), v[1] - __high2float(h2));
-                hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
-                lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
-            }
-            if ((warp & 3) == 1) stamp(t, 5);
-            mbar_wait(&bars[X1_FREE0 + pg], (i & 1) ^ 1);  // MMA1 of this warpgroup's previous tile has read the buffer
-            if ((warp & 3) == 1) stamp(t, 6);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                *reinterpret_cast<uint4 *>(x1 + (h * 2 + q) * kLboX1) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
-                *reinterpret_cast<uint4 *>(x1 + kX1Split + (h * 2 + q) * kLboX1) =
-                    make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(&bars[X1_FULL0 + pg]);
           }
+        };
+        if (pow2) produce(std::true_type{});
+        else produce(std::false_type{});
+    } else if (warp >= 18) {
+        // ---- E2 warpgroup: pooledA = max over the samples of D2 + b_mid, both tiles of every pair --------------------
+        mbar_wait(&bars[W_FULL], 0);
+        const int q = warp & 3;
+        const int ch = q * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const float bm = reinterpret_cast<const float *>(smem + kOffBm)[ch];
+        uint32_t r0[32];
+        for (int pr = 0; 2 * pr < T; ++pr) {
+            const uint32_t sl = pr & 1;
+            const bool two = 2 * pr + 1 < T;
+            mbar_wait(&bars[D2_FULL0 + sl], (pr >> 1) & 1);
+            tcgen05_fence_after();
+            if (q == 1) stamp(2 * pr, 12);
+            float mv[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (g == 1 && !two) break;  // (the N = 64 MMA of a last single tile leaves columns 64..127 unwritten)
+                tmem_ld32(tmem_base + lane_addr + kTmemD2 + sl * 128 + g * 64, r0);
+                tmem_ld_wait();
+                float a = __uint_as_float(r0[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) a = fmaxf(a, __uint_as_float(r0[j]));
+                tmem_ld32(tmem_base + lane_addr + kTmemD2 + sl * 128 + g * 64 + 32, r0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a = fmaxf(a, __uint_as_float(r0[j]));
+                mv[g] = a;
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&bars[D2_FREE0 + sl]);
+            const long long cl = first + static_cast<long long>(2 * pr) * gridDim.x;
+            pooledA[cl * 128 + ch] = mv[0] + bm;
+            if (two) pooledA[(cl + gridDim.x) * 128 + ch] = mv[1] + bm;
+            if (q == 1) stamp(2 * pr, 13);
         }
     } else {
-        // ---- epilogue warpgroups: g = 0 (warps 5-8) even tiles, g = 1 (warps 9-12) odd tiles -------------------------
+        // ---- E1 warpgroups: g = 0 (warps 5-8) even tiles, g = 1 (warps 9-12) odd tiles --------------------------------
         mbar_wait(&bars[W_FULL], 0);
         const int g = (warp - 5) >> 2;
         const int q = warp & 3;
-        const int ch = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const int hsel = q >> 1;                 // E1: which half of the 64 samples this warp handles
         const int c1 = (q & 1) * 32 + lane;      // E1: conv1 channel (TMEM lane q*32+lane holds channel (q*32+lane) mod 64)
         const float b1 = reinterpret_cast<const float *>(smem + kOffB1)[c1];
-        const float bm = reinterpret_cast<const float *>(smem + kOffBm)[ch];
+        const uint64_t b1p = pk2(b1, b1);
         // this warpgroup's tiles own sample groups g*8 .. g*8+7 of their pair's slot; 8 consecutive samples of one channel are 16
-        // contiguous bytes; its pooled vector is row g of the pair's P operand
+        // contiguous bytes
         uint8_t *x2g = smem + kOffX2 + (g * 8 + hsel * 4) * kSboX2 + (c1 >> 3) * kLboX2 + (c1 & 7) * 16;
-        uint8_t *ppg = smem + kOffP + (c1 >> 3) * kLboP + g * 16 + (c1 & 7) * 2;
-        float *pm = reinterpret_cast<float *>(smem + kOffPm) + g * 128;
-        uint32_t r0[32], r1[32];
+        float *pmx = pmaxh + hsel * 64 + c1;  // this thread's channel maximum over its half of the samples, per cluster
+        uint32_t r0[32];
         auto e1 = [&](int t) {
             const int b = t & 1;
             const int pr = t >> 1;
@@ -370,15 +408,15 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
             uint32_t hi[16], lo[16];
             // bias, ReLU, max-pool and the hi/lo split BEFORE waiting for the operand slot
 #pragma unroll
-            for (int sidx = 0; sidx < 32; sidx += 2) {
-                const float va = fmaxf(__uint_as_float(r0[sidx]) + b1, 0.0f), vb = fmaxf(__uint_as_float(r0[sidx + 1]) + b1, 0.0f);
+            for (int sidx = 0; sidx < 32; sidx += 2) {  // packed fp32 pairs: one FADD2 for the two bias additions, one for the two residuals
+                float va, vb;
+                upk2(add2(pk2(__uint_as_float(r0[sidx]), __uint_as_float(r0[sidx + 1])), b1p), va, vb);
+                va = fmaxf(va, 0.0f);
+                vb = fmaxf(vb, 0.0f);
                 pmax = fmaxf(pmax, fmaxf(va, vb));
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
-                hi[sidx >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
-                lo[sidx >> 1] = *reinterpret_cast<const uint32_t *>(&l2);
+                split_bf16x2(va, vb, hi[sidx >> 1], lo[sidx >> 1]);
             }
-            pm[q * 32 + lane] = pmax;
+            pmx[(first + static_cast<long long>(t) * gridDim.x) * 128] = pmax;
             if (q == 1) stamp(t, 9);
             mbar_wait(&bars[X2_FREE0 + sl], ((pr >> 1) & 1) ^ 1);  // MMA2/3(pr-2) have finished reading this slot
             if (q == 1) stamp(t, 10);
@@ -388,47 +426,11 @@ desc_rows_tc_kernel(long long num_clusters, int n, int m, float radius, const fl
                 *reinterpret_cast<uint4 *>(x2 + j * kSboX2) = make_uint4(hi[j * 4], hi[j * 4 + 1], hi[j * 4 + 2], hi[j * 4 + 3]);
                 *reinterpret_cast<uint4 *>(x2 + kX2Split + j * kSboX2) = make_uint4(lo[j * 4], lo[j * 4 + 1], lo[j * 4 + 2], lo[j * 4 + 3]);
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");  // both sample halves of every channel maximum are in pm
-            if (q < 2) {
-                uint8_t *pp = ppg + sl * kPBuf;
-                const float full = fmaxf(pmax, pm[(q + 2) * 32 + lane]);
-                const __nv_bfloat16 hp = __float2bfloat16_rn(full);
-                *reinterpret_cast<__nv_bfloat16 *>(pp) = hp;
-                *reinterpret_cast<__nv_bfloat16 *>(pp + kPSplit) = __float2bfloat16_rn(full - __bfloat162float(hp));
-            }
             fence_proxy_async_smem();
             mbar_arrive(&bars[X2_FULL0 + b]);
             if (q == 1) stamp(t, 11);
         };
-        auto e2 = [&](int t) {
-            const int pr = t >> 1;
-            const uint32_t sl = pr & 1;
-            mbar_wait(&bars[D2_FULL0 + sl], (pr >> 1) & 1);
-            tcgen05_fence_after();
-            if (q == 1) stamp(t, 12);
-            tmem_ld32(tmem_base + lane_addr + kTmemD2 + sl * 128 + g * 64, r0);   // this tile's 64 of the pair's 128 columns
-            tmem_ld32(tmem_base + lane_addr + kTmemD2 + sl * 128 + g * 64 + 32, r1);
-            tmem_ld_wait();
-            float mv = __uint_as_float(r0[0]);
-#pragma unroll
-            for (int j = 1; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r0[j]));
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(r1[j]));
-            tmem_ld32(tmem_base + lane_addr + kTmemD3, r0);  // column g: the pooled row of this tile
-            tmem_ld_wait();
-            const float cterm = __uint_as_float(g ? r0[1] : r0[0]);
-            tcgen05_fence_before();
-            mbar_arrive(&bars[D2_FREE0 + sl]);
-            const long long cl = first + static_cast<long long>(t) * gridDim.x;
-            pooled2[cl * 128 + ch] = mv + cterm + bm;
-            if (q == 1) stamp(t, 13);
-        };
-        // both warpgroups work on the same pair: the next tile's operand is written before the current accumulator is drained
-        if (g < T) e1(g);
-        for (int t = g; t < T; t += 2) {
-            if (t + 2 < T) e1(t + 2);
-            e2(t);
-        }
+        for (int t = g; t < T; t += 2) e1(t);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -451,15 +453,11 @@ __global__ void desc_tc_prep_kernel(const float *__restrict__ P, WeightLayout L,
         const int e = i - 128 * 32;
         const int r = e & 127, k = e >> 7;
         put(kOffWa, kWmSplit, (k >> 3) * kLboW + r * 16 + (k & 7) * 2, P[L.off[W_MID] + k * 128 + r]);
-    } else if (i < 128 * 32 + 2 * 128 * 64) {  // Wb^T = W_mid[64:128, :]^T
-        const int e = i - 128 * 32 - 128 * 64;
-        const int r = e & 127, k = e >> 7;
-        put(kOffWb, kWmSplit, (k >> 3) * kLboW + r * 16 + (k & 7) * 2, P[L.off[W_MID] + (64 + k) * 128 + r]);
     } else {
-        const int e = i - 128 * 32 - 2 * 128 * 64;
+        const int e = i - 128 * 32 - 128 * 64;
         float *f = reinterpret_cast<float *>(wimg + kOffW0);
-        if (e < 128) {  // per channel k: (W0[0][k], W0[1][k], W0[2][k], b0[k])
-            const int k = e >> 2, c = e & 3;
+        if (e < 128) {  // per channel pair (2p, 2p+1): (wx, wx', wy, wy', wz, wz', b, b') -- the producers' packed fp32 pairs
+            const int pr = e >> 3, c = (e >> 1) & 3, k = 2 * pr + (e & 1);
             f[e] = c < 3 ? P[L.off[W_DESC0] + c * 32 + k] : P[L.off[B_DESC0] + k];
         } else if (e < 192) f[e] = P[L.off[B_DESC1] + e - 128];
         else if (e < 320) f[e] = P[L.off[B_MID] + e - 192];
@@ -470,10 +468,10 @@ long long *g_desc_dbg = nullptr;  // bring-up timeline buffer (f3d_debug_set_tim
 
 int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int feature_dim, const float *xyz,
                        const float *new_xyz, const int *idx, const float *orientation, const float *packed, uint8_t *wimg,
-                       float *pooled2, bool build_image, int max_ctas, cudaStream_t st) {
+                       float *pooledA, float *pmaxh, bool build_image, int max_ctas, cudaStream_t st) {
     if (num_clusters == 0) return 0;
     if (build_image) {
-        const int total = 128 * 32 + 2 * 128 * 64 + 320;
+        const int total = 128 * 32 + 128 * 64 + 320;
         desc_tc_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(feature_dim), wimg);
         const int rc = check_launch("desc_tc_prep_kernel");
         if (rc) return rc;
@@ -485,15 +483,15 @@ int descriptor_rows_tc(long long num_clusters, int n, int m, float radius, int f
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
     }
-    cudaError_t e = cudaFuncSetAttribute(desc_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(dsc::kSmemBytes));
+    auto kernel = g_desc_dbg ? desc_rows_tc_kernel<true> : desc_rows_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dsc::kSmemBytes));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "desc_rows_tc: cudaFuncSetAttribute");
     const int ctas = (max_ctas > 0 && max_ctas < num_sms) ? max_ctas : num_sms;
     const unsigned grid = static_cast<unsigned>(num_clusters < ctas ? num_clusters : ctas);
-    // algorithmic flops (split-weight form): 2 * (rows * 10336 + clusters * 8192)
-    ktimer_begin("desc_rows_tc_kernel", 2.0 * (10336.0 * 64.0 + 8192.0) * static_cast<double>(num_clusters), st);
-    desc_rows_tc_kernel<<<grid, dsc::kThreads, dsc::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, orientation, wimg,
-                                                                      pooled2, g_desc_dbg);
+    // algorithmic flops (split-weight form): 2 * (rows * 10336 + clusters * 8192); the per-cluster term runs in the tail
+    ktimer_begin("desc_rows_tc_kernel", 2.0 * (10336.0 * 64.0) * static_cast<double>(num_clusters), st);
+    kernel<<<grid, dsc::kThreads, dsc::kSmemBytes, st>>>(num_clusters, n, m, radius, xyz, new_xyz, idx, orientation, wimg, pooledA, pmaxh,
+                                                         g_desc_dbg);
     ktimer_end(st);
     return check_launch("desc_rows_tc_kernel");
 }

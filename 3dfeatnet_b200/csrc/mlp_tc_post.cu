@@ -2,7 +2,9 @@
 //
 // Detector (models/feat3dnet.py:134-149): pooled (256) -> conv_post_0 (128, BN, ReLU) -> conv_post_1 (64, BN, ReLU) ->
 //   attention = softplus(64 -> 1), orientation = atan2 of the l2-normalised (64 -> 2) output.
-// Descriptor (models/feat3dnet.py:79-84,185): pooled (128) -> conv_post_0 (F, BN, no ReLU) -> l2-normalise.
+// Descriptor (models/feat3dnet.py:71-84,185): the per-cluster half of conv_mid_0 -- rows 64..127 of its weight times the max-pooled conv1
+//   vector, which the reference tiles over the 64 samples and concatenates (feat3dnet.py:66-70); by the split-weight identity it is one
+//   column per cluster and is added here to the row kernel's max-pooled per-point half -- -> conv_post_0 (F, BN, no ReLU) -> l2-normalise.
 //
 // These layers are 1.6 % of the flops but ran at 140 + 55 us as fp32 FFMA kernels (one 128-cluster tile per SM, weights
 // streamed through a 28 KB L1).  Here a tile is 64 clusters = the N axis of every MMA; the weights (bf16 hi/lo) are copied
@@ -46,13 +48,13 @@ constexpr uint32_t kOffBars = kOffBias + 512 * 4;
 constexpr uint32_t kSmemBytes = kOffBars + 64;
 static_assert(kOffX2 % 128 == 0 && kOffX3 % 128 == 0 && kOffOut % 16 == 0 && kOffBars % 8 == 0, "alignment");
 // tensor memory map (columns): detector W3 0..255 (2 splits x 128), W4 256..383 (2 x 64), Wh 384..447 (2 x 32), D 448..511
-//                               descriptor Wp 0..127 (2 x 64), D 448..511
+//                               descriptor Wp 0..127 (2 x 64), Wb 128..191 (2 x 32), D 448..511
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemD = 448;
 // global weight image (bytes): detector [W3 hi 64K][W3 lo 64K][W4 hi 32K][W4 lo 32K][Wh hi 16K][Wh lo 16K][bias fp32 512]
 constexpr uint32_t kDetImgBytes = 2 * 65536 + 2 * 32768 + 2 * 16384 + 2048;
-// descriptor [Wp hi 32K][Wp lo 32K][bias fp32 512]
-constexpr uint32_t kDescImgBytes = 2 * 32768 + 2048;
+// descriptor [Wp hi 32K][Wp lo 32K][Wb hi 16K][Wb lo 16K][bias fp32 512]
+constexpr uint32_t kDescImgBytes = 2 * 32768 + 2 * 16384 + 2048;
 }  // namespace post
 
 // One elected lane copies `nsteps` K-steps (16 bf16 = 8 TMEM columns each) of a staged weight piece into tensor memory.
@@ -80,6 +82,28 @@ struct PostRows {
             }
         }
     }
+    // rows of 2 x K floats (the two sample-half maxima of a cluster's conv1 channels, written by desc_rows_tc_kernel): their maximum
+    __device__ __forceinline__ void load_max(const float *__restrict__ src, long long c0, long long num_clusters) {
+        const int r = threadIdx.x & 63, cq = threadIdx.x >> 6;
+        const bool valid = c0 + r < num_clusters;
+        const float *row = src + (c0 + r) * (2 * K);
+        float4 ua[kIter], ub[kIter];
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            va[i] = vb[i] = ua[i] = ub[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                va[i] = __ldg(reinterpret_cast<const float4 *>(row + (cq + 4 * i) * 8));
+                vb[i] = __ldg(reinterpret_cast<const float4 *>(row + (cq + 4 * i) * 8 + 4));
+                ua[i] = __ldg(reinterpret_cast<const float4 *>(row + K + (cq + 4 * i) * 8));
+                ub[i] = __ldg(reinterpret_cast<const float4 *>(row + K + (cq + 4 * i) * 8 + 4));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            va[i] = make_float4(fmaxf(va[i].x, ua[i].x), fmaxf(va[i].y, ua[i].y), fmaxf(va[i].z, ua[i].z), fmaxf(va[i].w, ua[i].w));
+            vb[i] = make_float4(fmaxf(vb[i].x, ub[i].x), fmaxf(vb[i].y, ub[i].y), fmaxf(vb[i].z, ub[i].z), fmaxf(vb[i].w, ub[i].w));
+        }
+    }
     __device__ __forceinline__ void store(uint8_t *img, uint32_t split_bytes) const {
         const int r = threadIdx.x & 63, cq = threadIdx.x >> 6;
 #pragma unroll
@@ -90,10 +114,7 @@ struct PostRows {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
-                hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
-                lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
+                split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
             }
             uint8_t *dst = img + c * post::kLboIn + r * 16;
             *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -138,10 +159,7 @@ __device__ __forceinline__ void post_store_operand(uint8_t *x, uint32_t split_by
                 va = fmaxf(va, 0.0f);
                 vb = fmaxf(vb, 0.0f);
             }
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
-            const __nv_bfloat162 l2 = __floats2bfloat162_rn(va - __low2float(h2), vb - __high2float(h2));
-            hi[j] = *reinterpret_cast<const uint32_t *>(&h2);
-            lo[j] = *reinterpret_cast<const uint32_t *>(&l2);
+            split_bf16x2(va, vb, hi[j], lo[j]);
         }
         *reinterpret_cast<uint4 *>(base + g * sbo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4 *>(base + split_bytes + g * sbo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -149,11 +167,13 @@ __device__ __forceinline__ void post_store_operand(uint8_t *x, uint32_t split_by
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// MODE 0: detector tail (256 -> 128 -> 64 -> {attention, orientation});  MODE 1: descriptor tail (128 -> F -> l2norm)
+// MODE 0: detector tail (256 -> 128 -> 64 -> {attention, orientation}), `pooled` = the row kernel's max-pooled 256 channels.
+// MODE 1: descriptor tail (pooled conv1 vector 64 -> + per-point half = conv_mid_0 128 -> F -> l2norm), `pooled` = the row kernel's
+//         max-pooled per-point half of conv_mid_0 incl. bias (128 per cluster), `aux` = its two sample-half maxima of conv1 (2 x 64)
 template <int MODE>
 __global__ void __launch_bounds__(post::kThreads, 1)
-post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict__ pooled, const uint8_t *__restrict__ wimg,
-               float *__restrict__ out0, float *__restrict__ out1) {
+post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict__ pooled, const float *__restrict__ aux,
+               const uint8_t *__restrict__ wimg, float *__restrict__ out0, float *__restrict__ out1) {
     using namespace post;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + kOffBars);
@@ -183,11 +203,11 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
     uint32_t wpar = 0, mpar = 0;
 
     // ---- weights -> tensor memory, piece by piece through the staging buffer (bulk TMA, then tcgen05.cp) -------------
-    constexpr int kPieces = MODE == 0 ? 4 : 1;
+    constexpr int kPieces = MODE == 0 ? 4 : 2;
     for (int piece = 0; piece < kPieces; ++piece) {
-        // piece -> (global offset, bytes); detector: W3 hi | W3 lo | W4 hi+lo | Wh hi+lo ; descriptor: Wp hi+lo
-        const uint32_t goff = MODE == 0 ? (piece < 2 ? piece * 65536u : (piece == 2 ? 131072u : 196608u)) : 0u;
-        const uint32_t bytes = MODE == 0 ? (piece < 3 ? 65536u : 32768u) : 65536u;
+        // piece -> (global offset, bytes); detector: W3 hi | W3 lo | W4 hi+lo | Wh hi+lo ; descriptor: Wp hi+lo | Wb hi+lo
+        const uint32_t goff = MODE == 0 ? (piece < 2 ? piece * 65536u : (piece == 2 ? 131072u : 196608u)) : piece * 65536u;
+        const uint32_t bytes = MODE == 0 ? (piece < 3 ? 65536u : 32768u) : (piece == 0 ? 65536u : 32768u);
         if (threadIdx.x == 0) {
             mbar_arrive_expect_tx(bar_w, bytes);
             bulk_g2s(smem + kOffStage, wimg + goff, bytes, bar_w);  // one copy per piece: every cp.async.bulk costs its issuer ~450 cycles
@@ -206,9 +226,12 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
                         post_cp_weights(tmem_base + 384, sbase + kOffStage, 4);                             // Wh hi, K = 64
                         post_cp_weights(tmem_base + 416, sbase + kOffStage + 16384, 4);                     // Wh lo
                     }
-                } else {
+                } else if (piece == 0) {
                     post_cp_weights(tmem_base + 0, sbase + kOffStage, 8);                                   // Wp hi, K = 128
                     post_cp_weights(tmem_base + 64, sbase + kOffStage + 32768, 8);                          // Wp lo
+                } else {
+                    post_cp_weights(tmem_base + 128, sbase + kOffStage, 4);                                 // Wb hi, K = 64
+                    post_cp_weights(tmem_base + 160, sbase + kOffStage + 16384, 4);                         // Wb lo
                 }
                 umma_commit(bar_m);
             }
@@ -226,11 +249,15 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
     const long long ntiles = (num_clusters + kTile - 1) / kTile;
     // ---- first operand from HBM/L2: pooled rows -> bf16 hi/lo, K-major.  The rows of tile t+1 are requested right after layer 1 of
     // tile t has been issued and converted into the staging buffer as soon as that MMA group has completed (its only reader).
-    constexpr int K1 = MODE == 0 ? 256 : 128;
+    constexpr int K1 = MODE == 0 ? 256 : 64;
     constexpr uint32_t kSplit1 = (K1 / 8) * kLboIn;
     PostRows<K1> rows;
+    auto load_rows = [&](long long c0) {
+        if (MODE == 0) rows.load(pooled, K1, c0, num_clusters);
+        else rows.load_max(aux, c0, num_clusters);
+    };
     if (static_cast<long long>(blockIdx.x) < ntiles) {
-        rows.load(pooled, K1, static_cast<long long>(blockIdx.x) * kTile, num_clusters);
+        load_rows(static_cast<long long>(blockIdx.x) * kTile);
         rows.store(smem + kOffStage, kSplit1);
     }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -241,14 +268,19 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
         if (warp == 0) {
             tcgen05_fence_after();
             if (elect_one()) {
-                post_mma(tmem_base + kTmemD, tmem_base + 0, tmem_base + (MODE == 0 ? 128 : 64), sbase + kOffStage, sbase + kOffStage + kSplit1,
-                         kLboIn, kSbo, K1 / 16, idesc);
+                post_mma(tmem_base + kTmemD, tmem_base + (MODE == 0 ? 0 : 128), tmem_base + (MODE == 0 ? 128 : 160), sbase + kOffStage,
+                         sbase + kOffStage + kSplit1, kLboIn, kSbo, K1 / 16, idesc);
                 umma_commit(bar_m);
             }
             __syncwarp();
         }
         const long long next = tile + gridDim.x;
-        if (next < ntiles) rows.load(pooled, K1, next * kTile, num_clusters);
+        if (next < ntiles) load_rows(next * kTile);
+        float pa[MODE == 0 ? 1 : 32];  // descriptor: the per-point half of conv_mid_0 of this thread's channel, 32 clusters (in flight during the MMA)
+        if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pa[j] = c0 + col0 + j < num_clusters ? __ldg(pooled + (c0 + col0 + j) * 128 + ch) : 0.0f;
+        }
         mbar_wait(bar_m, mpar);
         mpar ^= 1;
         tcgen05_fence_after();
@@ -309,7 +341,28 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             }
             __syncthreads();  // outT and the operand buffers are reused by the next tile
         } else {
-            // descriptor: conv_post_0 (no ReLU) -> l2-normalise over the F channels of each cluster
+            // descriptor: conv_mid_0 = per-point half (max-pooled by the row kernel, bias included) + pooled half (this accumulator); no ReLU
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + pa[j]);
+            post_store_operand<false>(smem + kOffX2, kX2Split, kSboX2, ch, col0, r, 0.0f);
+            tcgen05_fence_before();
+            fence_proxy_async_smem();
+            __syncthreads();
+            // ---- conv_post_0, 128 -> F (rows F..127 of the weight are zero padding)
+            if (warp == 0) {
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    post_mma(tmem_base + kTmemD, tmem_base + 0, tmem_base + 64, sbase + kOffX2, sbase + kOffX2 + kX2Split, kLboX, kSboX2, 8,
+                             idesc | kIdescBMnMajor);
+                    umma_commit(bar_m);
+                }
+                __syncwarp();
+            }
+            mbar_wait(bar_m, mpar);
+            mpar ^= 1;
+            tcgen05_fence_after();
+            post_load_acc(tmem_base, q, col0, r);
+            // conv_post_0 (no ReLU) -> l2-normalise over the F channels of each cluster
             if (ch < feature_dim) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) outT[ch * (kTile + 1) + col0 + j] = __uint_as_float(r[j]) + bias[ch];
@@ -373,8 +426,12 @@ __global__ void post_prep_kernel(const float *__restrict__ P, WeightLayout L, in
         if (i < 128 * 128) {  // conv_post_0 of the descriptor: W (128,F), rows F..127 zero
             const int r = i & 127, k = i >> 7;
             put(0, 32768, r, k, r < F ? P[L.off[W_POST] + k * F + r] : 0.0f);
-        } else if (i < 128 * 128 + 512) {
+        } else if (i < 128 * 128 + 128 * 64) {  // Wb^T = W_mid[64:128, :]^T: the half of conv_mid_0 that sees the pooled conv1 vector
             const int e = i - 128 * 128;
+            const int r = e & 127, k = e >> 7;
+            put(65536, 65536 + 16384, r, k, P[L.off[W_MID] + (64 + k) * 128 + r]);
+        } else if (i < 128 * 128 + 128 * 64 + 512) {
+            const int e = i - 128 * 128 - 128 * 64;
             reinterpret_cast<float *>(img + kDescImgBytes - 2048)[e] = e < F ? P[L.off[B_POST] + e] : 0.0f;
         }
     }
@@ -409,17 +466,17 @@ int detector_post_tc(long long nc, const float *pooled, const float *packed, uin
     const int ctas = (max_ctas > 0 && max_ctas < post_num_sms()) ? max_ctas : post_num_sms();
     const unsigned grid = static_cast<unsigned>(ntiles < ctas ? ntiles : ctas);
     ktimer_begin("post_tc_kernel<detector>", 2.0 * (256.0 * 128 + 128 * 64 + 64 * 3) * static_cast<double>(nc), st);
-    post_tc_kernel<0><<<grid, post::kThreads, post::kSmemBytes, st>>>(nc, 0, pooled, wimg, attention, orientation);
+    post_tc_kernel<0><<<grid, post::kThreads, post::kSmemBytes, st>>>(nc, 0, pooled, nullptr, wimg, attention, orientation);
     ktimer_end(st);
     return check_launch("post_tc_kernel<detector>");
 }
 
-int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, const float *packed, uint8_t *wimg, float *features,
-                       bool build_image, int max_ctas, cudaStream_t st) {
+int descriptor_post_tc(long long nc, int feature_dim, const float *pooledA, const float *pmaxh, const float *packed, uint8_t *wimg,
+                       float *features, bool build_image, int max_ctas, cudaStream_t st) {
     if (nc == 0) return 0;
     int rc = 0;
     if (build_image) {
-        const int total = 128 * 128 + 512;
+        const int total = 128 * 128 + 128 * 64 + 512;
         post_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(feature_dim), 1, wimg);
         rc = check_launch("post_prep_kernel");
         if (rc) return rc;
@@ -429,8 +486,8 @@ int descriptor_post_tc(long long nc, int feature_dim, const float *pooled2, cons
     const long long ntiles = (nc + post::kTile - 1) / post::kTile;
     const int ctas = (max_ctas > 0 && max_ctas < post_num_sms()) ? max_ctas : post_num_sms();
     const unsigned grid = static_cast<unsigned>(ntiles < ctas ? ntiles : ctas);
-    ktimer_begin("post_tc_kernel<descriptor>", 2.0 * 128.0 * feature_dim * static_cast<double>(nc), st);
-    post_tc_kernel<1><<<grid, post::kThreads, post::kSmemBytes, st>>>(nc, feature_dim, pooled2, wimg, features, nullptr);
+    ktimer_begin("post_tc_kernel<descriptor>", 2.0 * (64.0 * 128.0 + 128.0 * feature_dim) * static_cast<double>(nc), st);
+    post_tc_kernel<1><<<grid, post::kThreads, post::kSmemBytes, st>>>(nc, feature_dim, pooledA, pmaxh, wimg, features, nullptr);
     ktimer_end(st);
     return check_launch("post_tc_kernel<descriptor>");
 }

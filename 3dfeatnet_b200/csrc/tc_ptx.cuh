@@ -155,5 +155,46 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 pairs (FFMA2 / FADD2 of sm_100): two IEEE fp32 operations per issued instruction, same bits as the scalar forms
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// ---- bf16 hi/lo split of fp32 pairs (the "bf16x3" operand format): x = hi + lo up to 2^-17 |x|, hi = bf16(x), lo = bf16(x - hi).
+// The residual is formed against the BITS of the packed hi pair (one shift, one mask, one FADD2); __low2float / __high2float cost two
+// byte permutes and two shifts per pair.
+__device__ __forceinline__ void bf16x2_residual(float a, float b, uint32_t hbits, float &ra, float &rb) {
+    upk2(sub2(pk2(a, b), pk2(__uint_as_float(hbits << 16), __uint_as_float(hbits & 0xffff0000u))), ra, rb);
+}
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    hi = bf16x2_bits(a, b);
+    float ra, rb;
+    bf16x2_residual(a, b, hi, ra, rb);
+    lo = bf16x2_bits(ra, rb);
+}
+
 }  // namespace tc
 }  // namespace f3d

@@ -42,10 +42,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
-        h[j] = *reinterpret_cast<const uint32_t *>(&h2);
-        l[j] = *reinterpret_cast<const uint32_t *>(&l2);
+        split_bf16x2(v[2 * j], v[2 * j + 1], h[j], l[j]);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
