@@ -14,6 +14,8 @@
 // "nearest" state for exactly those centres (see bq_fallback_kernel).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace f3d {
 
 constexpr int kCentresPerWarp = 4;
@@ -174,6 +176,18 @@ bq_fallback_kernel(int b, int n, int m, int nsample, const float *__restrict__ x
 // order with popc prefix sums, which also yields the first hit for padding.  Empty balls go to bq_fallback_kernel.
 constexpr int kBqMaxCells = 4096;
 constexpr int kBqBuildThreads = 1024;
+// Large clouds (n >= kBqWindowedFrom) are binned per INDEX WINDOW: the point indices are cut into <= 32 windows of `win` consecutive
+// indices and every window gets its own cell table over the common grid -- sorted order = [window][cell].  The reference's contract is
+// the first nsample hits in ascending index order, and a KITTI-shape scan has thousands of points in the 3 x 3 cells of a centre
+// (inference.py scores every point of a 131 072-point scan): a centre walks its windows in ascending order and stops at nsample hits,
+// i.e. after ~1/30 of its candidates, and the hits of a window are ordered through 4 bitmap words per lane.
+constexpr int kBqWindowedFrom = 32768;
+constexpr int kBqSparse = 1024;  // centres with at most this many candidates in all windows together take them in one pass
+__host__ __device__ inline int bq_window(int n) {  // indices per window: a multiple of 1024 (= 32 lanes x 32 bits), at most 32 windows
+    if (n < kBqWindowedFrom) return n;
+    return ((((n + 31) >> 5) + 1023) >> 10) << 10;
+}
+__host__ __device__ inline int bq_num_windows(int n) { return n < kBqWindowedFrom ? 1 : (n + bq_window(n) - 1) / bq_window(n); }
 
 
 __device__ __forceinline__ int bq_cell_coord(float v, float v0, float inv_c, int nc) {
@@ -181,8 +195,11 @@ __device__ __forceinline__ int bq_cell_coord(float v, float v0, float inv_c, int
     return static_cast<int>(fminf(fmaxf(t, -2.0f), static_cast<float>(nc + 1)));
 }
 
+// grid (clouds, windows): CTA (cloud, w) sorts the points with indices [w win, (w+1) win) into sorted[w win ...] by cell and writes the
+// cell table of its window; every CTA of a cloud derives the same grid from the whole cloud's bounding box.  One window = the whole cloud
+// for n < kBqWindowedFrom and for the spatial binning of the centres.
 __global__ void __launch_bounds__(kBqBuildThreads, 1)
-bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4 *__restrict__ sorted,
+bq_grid_build_kernel(int n, int win, float radius, const float *__restrict__ xyz1, float4 *__restrict__ sorted,
                      int *__restrict__ cell_start, BqGridInfo *__restrict__ info) {
     __shared__ int cursor[kBqMaxCells];
     __shared__ float red[4][32];
@@ -191,7 +208,8 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *p = xyz1 + static_cast<size_t>(blockIdx.x) * n * 3;
     float4 *out = sorted + static_cast<size_t>(blockIdx.x) * n;
-    int *cs = cell_start + static_cast<size_t>(blockIdx.x) * (kBqMaxCells + 1);
+    int *cs = cell_start + (static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * (kBqMaxCells + 1);
+    const int k0 = blockIdx.y * win, k1 = min(n, k0 + win);  // this CTA's index window
 
     float mnx = 3.0e38f, mxx = -3.0e38f, mny = 3.0e38f, mxy = -3.0e38f;
     for (int k = tid; k < n; k += kBqBuildThreads) {
@@ -229,7 +247,7 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
             }
             if (!(ncx * ncy <= kBqMaxCells)) { ncx = 1; ncy = 1; c = 3.0e38f; }  // non-finite extents: a single cell
             gi.x0 = mnx; gi.y0 = mny; gi.inv_c = 1.0f / c; gi.ncx = ncx; gi.ncy = ncy; gi.has_empty = 0; gi.pad[0] = gi.pad[1] = 0;
-            info[blockIdx.x] = gi;
+            if (blockIdx.y == 0) info[blockIdx.x] = gi;
         }
     }
     __syncthreads();
@@ -240,7 +258,7 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
         const int cy = min(max(bq_cell_coord(y, y0, inv_c, ncy), 0), ncy - 1);
         return cy * ncx + cx;
     };
-    for (int k = tid; k < n; k += kBqBuildThreads) atomicAdd(&cursor[cell_of(__ldg(p + 3 * k), __ldg(p + 3 * k + 1))], 1);
+    for (int k = k0 + tid; k < k1; k += kBqBuildThreads) atomicAdd(&cursor[cell_of(__ldg(p + 3 * k), __ldg(p + 3 * k + 1))], 1);
     __syncthreads();
     {  // exclusive scan of kBqMaxCells counters: 4 per thread, warp shuffle scan, 32 warp totals
         constexpr int PER = kBqMaxCells / kBqBuildThreads;
@@ -260,7 +278,7 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
             wsum[lane] = winc - w;
         }
         __syncthreads();
-        int run = wsum[warp] + inc - tot;
+        int run = k0 + wsum[warp] + inc - tot;  // positions are absolute: window w owns sorted[w win, ...)
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             cursor[tid * PER + i] = run;
@@ -270,7 +288,7 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz1, float4
         if (tid == kBqBuildThreads - 1 && ncells == kBqMaxCells) cs[kBqMaxCells] = run;
     }
     __syncthreads();
-    for (int k = tid; k < n; k += kBqBuildThreads) {
+    for (int k = k0 + tid; k < k1; k += kBqBuildThreads) {
         const float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1), z = __ldg(p + 3 * k + 2);
         const int pos = atomicAdd(&cursor[cell_of(x, y)], 1);
         out[pos] = make_float4(x, y, z, __int_as_float(k));
@@ -376,6 +394,167 @@ bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float
     if (lane == 0) {
         pts_cnt[static_cast<size_t>(batch) * m + j] = cc;
         if (cc == 0) info[batch].has_empty = 1;  // every writer stores the same value
+    }
+}
+
+// Windowed form of the grid query for n >= kBqWindowedFrom (see bq_window).  Persistent warps: warp g takes centres g, g + G, ...;
+// its bitmap is zeroed once and every centre clears the words it set.  Lane w holds the three row ranges of window w.
+//  * at most kBqSparse candidates over all windows: lane w tests the candidates of window w, the hits are ordered by the
+//    summary walk of bq_grid_query_kernel;
+//  * more: the windows are visited in ascending order with the whole warp striding over each row range, the hits of a window sit
+//    in the window's own bitmap words (win / 1024 per lane, ascending lane order = ascending index order) and are emitted
+//    before the next window is touched; the walk stops at nsample hits -- exactly the reference's break at cnt == nsample.
+__global__ void __launch_bounds__(256)
+bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, int nsample, const float4 *__restrict__ sorted,
+                         const int *__restrict__ cell_start, BqGridInfo *info, const float *__restrict__ xyz2, int *__restrict__ idx,
+                         int *__restrict__ pts_cnt, const float4 *__restrict__ centres_sorted) {
+    extern __shared__ unsigned bq_bitmap[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int nwords = (n + 31) >> 5;
+    const int spl = (((nwords + 31) >> 5) + 31) >> 5;  // summary words per lane
+    const int per_warp = nwords + 32 * spl;
+    unsigned *bm = bq_bitmap + static_cast<size_t>(wl) * per_warp;
+    unsigned *sm = bm + nwords;                        // summary word s covers bitmap words [32 s, 32 s + 32)
+    for (int i = lane; i < per_warp; i += 32) bm[i] = 0;
+    __syncwarp();
+    const float T = ball_threshold(radius);
+    const int wpl = win >> 10;                         // bitmap words of one window per lane
+    const long long total_warps = static_cast<long long>(gridDim.x) * wpc, centres = static_cast<long long>(b) * m;
+    for (long long w = static_cast<long long>(blockIdx.x) * wpc + wl; w < centres; w += total_warps) {
+        const int batch = static_cast<int>(w / m);
+        int j = static_cast<int>(w - static_cast<long long>(batch) * m);
+        float cx, cy, cz;
+        if (centres_sorted) {  // the centres in the order of their own spatial binning (.w = the centre's index)
+            const float4 rec = __ldg(centres_sorted + static_cast<size_t>(batch) * m + j);
+            cx = rec.x; cy = rec.y; cz = rec.z;
+            j = __float_as_int(rec.w);
+        } else {
+            const float *c = xyz2 + (static_cast<size_t>(batch) * m + j) * 3;
+            cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
+        }
+        const BqGridInfo gi = info[batch];
+        const float4 *pts = sorted + static_cast<size_t>(batch) * n;
+        int *row = idx + (static_cast<size_t>(batch) * m + j) * nsample;
+        const int gx = bq_cell_coord(cx, gi.x0, gi.inv_c, gi.ncx), gy = bq_cell_coord(cy, gi.y0, gi.inv_c, gi.ncy);
+        const int c0 = max(gx - 1, 0), c1 = min(gx + 1, gi.ncx - 1);
+        const int r0 = max(gy - 1, 0), r1 = min(gy + 1, gi.ncy - 1);
+        // lane w: the (up to three) row ranges of window w
+        int rs[3] = {0, 0, 0}, re[3] = {0, 0, 0};
+        if (lane < nwin && c0 <= c1 && T > 0.0f) {
+            const int *cs = cell_start + (static_cast<size_t>(batch) * nwin + lane) * (kBqMaxCells + 1);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (r0 + k <= r1) {
+                    rs[k] = __ldg(cs + (r0 + k) * gi.ncx + c0);
+                    re[k] = __ldg(cs + (r0 + k) * gi.ncx + c1 + 1);
+                }
+        }
+        const int cw = (re[0] - rs[0]) + (re[1] - rs[1]) + (re[2] - rs[2]);
+        int C = cw;
+#pragma unroll
+        for (int s2 = 16; s2 > 0; s2 >>= 1) C += __shfl_xor_sync(kFull, C, s2);
+        int H = 0, first = -1;  // hits found (all of them below nsample, at least nsample otherwise), lowest hit
+        if (C > 0 && C <= kBqSparse) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                for (int i = rs[k]; i < re[k]; ++i) {
+                    const float4 q = __ldg(pts + i);
+                    if (!(sqdist_ref(cx - q.x, cy - q.y, cz - q.z) >= T)) {
+                        const int kk = __float_as_int(q.w);
+                        atomicOr(&bm[kk >> 5], 1u << (kk & 31));
+                        atomicOr(&sm[kk >> 10], 1u << ((kk >> 5) & 31));
+                    }
+                }
+            __syncwarp();
+            int mine = 0, low = 0x7fffffff;
+            for (int sp = 0; sp < spl; ++sp) {
+                const int s2 = lane * spl + sp;
+                unsigned sw = sm[s2];
+                while (sw) {
+                    const int wi = s2 * 32 + __ffs(sw) - 1;
+                    sw &= sw - 1;
+                    const unsigned word = bm[wi];
+                    mine += __popc(word);
+                    low = min(low, wi * 32 + __ffs(word) - 1);
+                }
+            }
+            int inc = mine;
+#pragma unroll
+            for (int s2 = 1; s2 < 32; s2 <<= 1) { const int v = __shfl_up_sync(kFull, inc, s2); if (lane >= s2) inc += v; }
+            H = __shfl_sync(kFull, inc, 31);
+            const unsigned owners = __ballot_sync(kFull, mine > 0);
+            if (owners) first = __shfl_sync(kFull, low, __ffs(owners) - 1);
+            int pos = inc - mine;
+            for (int sp = 0; sp < spl; ++sp) {  // emit in ascending order up to nsample, clear every touched word
+                const int s2 = lane * spl + sp;
+                unsigned sw = sm[s2];
+                if (!sw) continue;
+                sm[s2] = 0;
+                while (sw) {
+                    const int wi = s2 * 32 + __ffs(sw) - 1;
+                    sw &= sw - 1;
+                    unsigned word = bm[wi];
+                    bm[wi] = 0;
+                    while (word && pos < nsample) {
+                        row[pos++] = wi * 32 + __ffs(word) - 1;
+                        word &= word - 1;
+                    }
+                }
+            }
+        } else if (C > 0) {
+            unsigned todo = __ballot_sync(kFull, cw > 0);
+            while (todo && H < nsample) {
+                const int wn = __ffs(todo) - 1;
+                todo &= todo - 1;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int s2 = __shfl_sync(kFull, rs[k], wn), e2 = __shfl_sync(kFull, re[k], wn);
+                    for (int i = s2 + lane; i < e2; i += 32) {
+                        const float4 q = __ldg(pts + i);
+                        if (!(sqdist_ref(cx - q.x, cy - q.y, cz - q.z) >= T)) {
+                            const int kk = __float_as_int(q.w);
+                            atomicOr(&bm[kk >> 5], 1u << (kk & 31));
+                        }
+                    }
+                }
+                __syncwarp();
+                unsigned *wb = bm + static_cast<size_t>(wn) * (win >> 5) + lane * wpl;  // this lane's words of the window
+                const int wbase = wn * win + lane * wpl * 32;
+                int mine = 0, low = 0x7fffffff;
+                for (int t = 0; t < wpl; ++t) {
+                    const unsigned word = (wbase + t * 32 < n) ? wb[t] : 0u;
+                    mine += __popc(word);
+                    if (word && low == 0x7fffffff) low = wbase + t * 32 + __ffs(word) - 1;
+                }
+                int inc = mine;
+#pragma unroll
+                for (int s2 = 1; s2 < 32; s2 <<= 1) { const int v = __shfl_up_sync(kFull, inc, s2); if (lane >= s2) inc += v; }
+                const int Hw = __shfl_sync(kFull, inc, 31);
+                const unsigned owners = __ballot_sync(kFull, mine > 0);
+                if (first < 0 && owners) first = __shfl_sync(kFull, low, __ffs(owners) - 1);
+                int pos = H + inc - mine;
+                for (int t = 0; t < wpl; ++t) {
+                    if (wbase + t * 32 >= n) break;
+                    unsigned word = wb[t];
+                    if (!word) continue;
+                    wb[t] = 0;
+                    while (word && pos < nsample) {
+                        row[pos++] = wbase + t * 32 + __ffs(word) - 1;
+                        word &= word - 1;
+                    }
+                }
+                H += Hw;
+                __syncwarp();
+            }
+        }
+        const int cc = min(H, nsample);
+        if (cc > 0)
+            for (int s2 = cc + lane; s2 < nsample; s2 += 32) row[s2] = first;
+        if (lane == 0) {
+            pts_cnt[static_cast<size_t>(batch) * m + j] = cc;
+            if (cc == 0) info[batch].has_empty = 1;  // every writer stores the same value
+        }
+        __syncwarp();
     }
 }
 
@@ -515,7 +694,7 @@ F3D_API int f3d_query_ball_point(int b, int n, int m, float radius, int nsample,
 
 F3D_API size_t f3d_query_ball_point_workspace_bytes(int b, int n) {
     if (b <= 0 || n <= 0) return 256;
-    return static_cast<size_t>(b) * n * sizeof(float4) + static_cast<size_t>(b) * (kBqMaxCells + 1) * sizeof(int) +
+    return static_cast<size_t>(b) * n * sizeof(float4) + static_cast<size_t>(b) * bq_num_windows(n) * (kBqMaxCells + 1) * sizeof(int) +
            static_cast<size_t>(b) * sizeof(BqGridInfo) + 512;
 }
 
@@ -533,7 +712,7 @@ static BqWorkspace bq_workspace(int b, int n, void *workspace) {
     BqWorkspace w;
     w.sorted = static_cast<float4 *>(workspace);
     w.cell_start = reinterpret_cast<int *>(w.sorted + static_cast<size_t>(b) * n);
-    w.info = reinterpret_cast<BqGridInfo *>(w.cell_start + static_cast<size_t>(b) * (kBqMaxCells + 1));
+    w.info = reinterpret_cast<BqGridInfo *>(w.cell_start + static_cast<size_t>(b) * bq_num_windows(n) * (kBqMaxCells + 1));
     return w;
 }
 
@@ -545,7 +724,8 @@ F3D_API int f3d_ball_grid_build(int b, int n, float radius, const float *xyz1, v
         return fail(F3D_ERR_WORKSPACE_TOO_SMALL, "ball_grid_build: workspace missing, too small or misaligned (or n > 262144)");
     if (b == 0) return 0;
     const BqWorkspace w = bq_workspace(b, n, workspace);
-    bq_grid_build_kernel<<<b, kBqBuildThreads, 0, as_stream(stream)>>>(n, radius, xyz1, w.sorted, w.cell_start, w.info);
+    bq_grid_build_kernel<<<dim3(b, bq_num_windows(n)), kBqBuildThreads, 0, as_stream(stream)>>>(n, bq_window(n), radius, xyz1, w.sorted,
+                                                                                              w.cell_start, w.info);
     return check_launch("bq_grid_build_kernel");
 }
 
@@ -573,13 +753,30 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
     const size_t off2 = (f3d_query_ball_point_workspace_bytes(b, n) + 255) & ~static_cast<size_t>(255);
     if (m >= kBqSortCentres && m <= 262144 && workspace_bytes >= off2 + f3d_query_ball_point_workspace_bytes(b, m)) {
         const BqWorkspace w2 = bq_workspace(b, m, static_cast<char *>(workspace) + off2);
-        bq_grid_build_kernel<<<b, kBqBuildThreads, 0, st>>>(m, radius, xyz2, w2.sorted, w2.cell_start, w2.info);
+        bq_grid_build_kernel<<<b, kBqBuildThreads, 0, st>>>(m, m, radius, xyz2, w2.sorted, w2.cell_start, w2.info);  // one window: a spatial order
         const int rc2 = check_launch("bq_grid_build_kernel");
         if (rc2) return rc2;
         centres_sorted = w2.sorted;
     }
-    bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, ws.sorted, ws.cell_start, ws.info, xyz2, idx,
-                                                                    pts_cnt, centres_sorted);
+    if (n >= kBqWindowedFrom) {
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            if (num_sms <= 0) num_sms = 148;
+        }
+        e = cudaFuncSetAttribute(bq_grid_query_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "bq_grid_query_win: cudaFuncSetAttribute");
+        const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024))));
+        const unsigned need = blocks_for(w, wpc), cap = static_cast<unsigned>(num_sms) * per_sm;
+        bq_grid_query_win_kernel<<<need < cap ? need : cap, wpc * 32, smem, st>>>(b, n, m, bq_window(n), bq_num_windows(n), radius, nsample,
+                                                                               ws.sorted, ws.cell_start, ws.info, xyz2, idx, pts_cnt,
+                                                                               centres_sorted);
+    } else {
+        bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, ws.sorted, ws.cell_start, ws.info, xyz2,
+                                                                        idx, pts_cnt, centres_sorted);
+    }
     ktimer_end(st);
     int rc = check_launch("bq_grid_query_kernel");
     if (rc) return rc;

@@ -110,45 +110,88 @@ __global__ void nms_cell_count_kernel(int n, double radius, int max_cells, const
     atomicAdd(cell_count + static_cast<size_t>(batch) * (max_cells + 1) + cell, 1);
 }
 
-// exclusive scan of the cell counts (in place -> cell starts, entry [cells] = n) and a copy as the fill cursors
-__global__ void __launch_bounds__(1024)
-nms_cell_scan_kernel(int max_cells, int *__restrict__ cell_start, int *__restrict__ cursor) {
-    __shared__ int warp_sum[32];
-    __shared__ int carry;
-    int *cs = cell_start + static_cast<size_t>(blockIdx.x) * (max_cells + 1);
-    int *cu = cursor + static_cast<size_t>(blockIdx.x) * (max_cells + 1);
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
+// exclusive scan of the cell counts (in place -> cell starts, entry [cells] = n) and a copy as the fill cursors, over the cells the
+// cloud's grid really has (nx * ny + 1 entries of the max_cells + 1 the table is sized for).  Two launches over chunks of kScanChunk
+// cells: chunk sums, then every CTA adds up the sums in front of its chunk and scans its own cells -- a 131 072-point scan has
+// up to 524 289 cells, which took 356 us as a loop of one CTA.
+constexpr int kScanChunk = 4096;  // 1024 threads x 4 consecutive cells
+__device__ __forceinline__ int nms_block_sum(int v, int *warp_sum) {  // 1024 threads; result in every thread
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base <= max_cells; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i <= max_cells ? cs[i] : 0;
-        int incl = v;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
+    __syncthreads();
+    if (lane == 0) warp_sum[warp] = v;
+    __syncthreads();
+    int w = warp_sum[lane];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) w += __shfl_xor_sync(kFull, w, s);
+    return w;
+}
+__global__ void __launch_bounds__(1024)
+nms_cell_partial_kernel(double radius, int max_cells, const float *__restrict__ bbox, const int *__restrict__ cell_count,
+                        int *__restrict__ partial) {
+    __shared__ int warp_sum[32];
+    const int batch = blockIdx.y;
+    const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
+    const int last = g.nx * g.ny;  // entries 0 .. last
+    const int i0 = blockIdx.x * kScanChunk + threadIdx.x * 4;
+    if (blockIdx.x * kScanChunk > last) return;
+    const int *cs = cell_count + static_cast<size_t>(batch) * (max_cells + 1);
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (i0 + k <= last) v += cs[i0 + k];
+    v = nms_block_sum(v, warp_sum);
+    if (threadIdx.x == 0) partial[batch * gridDim.x + blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(1024)
+nms_cell_scan_kernel(double radius, int max_cells, const float *__restrict__ bbox, const int *__restrict__ partial,
+                     int *__restrict__ cell_start, int *__restrict__ cursor) {
+    __shared__ int warp_sum[32];
+    const int batch = blockIdx.y;
+    const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
+    const int last = g.nx * g.ny;
+    if (blockIdx.x * kScanChunk > last) return;
+    int *cs = cell_start + static_cast<size_t>(batch) * (max_cells + 1);
+    int *cu = cursor + static_cast<size_t>(batch) * (max_cells + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int before = 0;  // cells of the chunks in front of this one
+    for (int c = threadIdx.x; c < static_cast<int>(blockIdx.x); c += 1024) before += partial[batch * gridDim.x + c];
+    before = nms_block_sum(before, warp_sum);
+    const int i0 = blockIdx.x * kScanChunk + threadIdx.x * 4;
+    int v[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = i0 + k <= last ? cs[i0 + k] : 0;
+        tot += v[k];
+    }
+    int incl = tot;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, s);
+        if (lane >= s) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sum[lane];
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
-            const int t = __shfl_up_sync(kFull, incl, s);
-            if (lane >= s) incl += t;
+            const int t = __shfl_up_sync(kFull, w, s);
+            if (lane >= s) w += t;
         }
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = warp_sum[lane];
+        warp_sum[lane] = w;
+    }
+    __syncthreads();
+    int run = before + (warp ? warp_sum[warp - 1] : 0) + incl - tot;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const int t = __shfl_up_sync(kFull, w, s);
-                if (lane >= s) w += t;
-            }
-            warp_sum[lane] = w;
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k <= last) {
+            cs[i0 + k] = run;
+            cu[i0 + k] = run;
         }
-        __syncthreads();
-        const int excl = carry + (warp ? warp_sum[warp - 1] : 0) + incl - v;
-        if (i <= max_cells) {
-            cs[i] = excl;
-            cu[i] = excl;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
+        run += v[k];
     }
 }
 
@@ -325,7 +368,8 @@ F3D_API size_t f3d_nms_workspace_bytes(int b, int n) {
     if (b <= 0 || n <= 0) return 256;
     const size_t bn = static_cast<size_t>(b) * n;
     const size_t cells = static_cast<size_t>(nms_max_cells(n)) + 1;
-    return bn * (1 + 4 + 4 + 4 + 16) + static_cast<size_t>(b) * cells * 8 + static_cast<size_t>(b) * 32 + 2048;
+    return bn * (1 + 4 + 4 + 4 + 16) + static_cast<size_t>(b) * cells * 8 + static_cast<size_t>(b) * 32 + 2048 +
+           static_cast<size_t>(b) * ((cells + kScanChunk - 1) / kScanChunk) * 4 + 64;
 }
 
 F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, double nms_radius, double min_response_ratio,
@@ -357,6 +401,7 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     int *sorted = dense_list + bn;
     float4 *sorted_pts = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(sorted + bn) + 15) & ~static_cast<uintptr_t>(15));
     unsigned char *keep = reinterpret_cast<unsigned char *>(sorted_pts + bn);
+    int *partial = reinterpret_cast<int *>((reinterpret_cast<uintptr_t>(keep + bn) + 15) & ~static_cast<uintptr_t>(15));  // chunk sums of the cell scan
     cudaError_t e = cudaMemsetAsync(base, 0, head + static_cast<size_t>(b) * cells * sizeof(int), st);  // counters + cell counts
     if (e != cudaSuccess) return fail(static_cast<int>(e), "nms: memset");
     const double grid_radius = nms_radius;
@@ -366,7 +411,11 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     nms_cell_count_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, grid_radius, max_cells, xyz, bbox, cell_start);
     rc = check_launch("nms_cell_count_kernel");
     if (rc) return rc;
-    nms_cell_scan_kernel<<<b, 1024, 0, st>>>(max_cells, cell_start, cursor);
+    const int nchunks = (max_cells + 1 + kScanChunk - 1) / kScanChunk;
+    nms_cell_partial_kernel<<<dim3(nchunks, b), 1024, 0, st>>>(grid_radius, max_cells, bbox, cell_start, partial);
+    rc = check_launch("nms_cell_partial_kernel");
+    if (rc) return rc;
+    nms_cell_scan_kernel<<<dim3(nchunks, b), 1024, 0, st>>>(grid_radius, max_cells, bbox, partial, cell_start, cursor);
     rc = check_launch("nms_cell_scan_kernel");
     if (rc) return rc;
     nms_cell_fill_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, grid_radius, max_cells, xyz, attention, bbox, cursor, sorted, sorted_pts);

@@ -24,6 +24,8 @@ def clouds(kind, b, n, seed):
         return synth.uniform_cloud(b, n, seed)
     if kind == "oxford":
         return synth.make_batch(b, n, seed0=seed)
+    if kind == "kitti":
+        return synth.make_batch(b, n, seed0=seed, kind="kitti")
     rng = np.random.default_rng(seed)
     if kind == "dups":  # 10 % exact duplicates (datagenerator.py:148-157 pads clouds this way)
         x = synth.uniform_cloud(b, n, seed)
@@ -145,6 +147,11 @@ def _centres(x, m, mode, seed):
     ("uniform", 1, 50, 9, 100.0, 64, "subset"),
     # >= 4096 centres per cloud: the grid query walks the centres in spatially binned order (same rows, written at the centre's own index)
     ("oxford", 2, 16384, 8192, 2.0, 64, "subset"), ("uniform", 1, 20000, 6000, 2.0, 32, "external"),
+    # >= 32768 points: the cloud is binned per index window and a centre stops at nsample hits (dense KITTI-shape neighbourhoods: thousands of
+    # candidates per centre; sparse ones take all windows in one pass); ragged n, empty balls, nsample 16 / 128, duplicates
+    ("kitti", 1, 131072, 6000, 2.0, 64, "subset"), ("kitti", 2, 50001, 5000, 2.0, 64, "external"),
+    ("uniform", 1, 40000, 300, 6.0, 128, "subset"), ("dups", 1, 33000, 4200, 3.0, 16, "subset"),
+    ("kitti", 1, 262144, 500, 1.0, 64, "external"),
 ])
 def test_ball_query_bit_exact_vs_oracle(cuda, kind, b, n, m, radius, ns, mode):
     tg = pkg("tf_ops.grouping.tf_grouping")
