@@ -420,18 +420,20 @@ bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, i
     const float T = ball_threshold(radius);
     const int wpl = win >> 10;                         // bitmap words of one window per lane
     const long long total_warps = static_cast<long long>(gridDim.x) * wpc, centres = static_cast<long long>(b) * m;
+    // centre record (x, y, z, row): from the centres' own spatial binning when there is one (.w = the centre's index), else in order
+    auto load_centre = [&](long long w) -> float4 {
+        if (w >= centres) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (centres_sorted) return __ldg(centres_sorted + w);
+        const float *c = xyz2 + w * 3;
+        return make_float4(__ldg(c), __ldg(c + 1), __ldg(c + 2), __int_as_float(static_cast<int>(w % m)));
+    };
+    float4 rec_next = load_centre(static_cast<long long>(blockIdx.x) * wpc + wl);
     for (long long w = static_cast<long long>(blockIdx.x) * wpc + wl; w < centres; w += total_warps) {
         const int batch = static_cast<int>(w / m);
-        int j = static_cast<int>(w - static_cast<long long>(batch) * m);
-        float cx, cy, cz;
-        if (centres_sorted) {  // the centres in the order of their own spatial binning (.w = the centre's index)
-            const float4 rec = __ldg(centres_sorted + static_cast<size_t>(batch) * m + j);
-            cx = rec.x; cy = rec.y; cz = rec.z;
-            j = __float_as_int(rec.w);
-        } else {
-            const float *c = xyz2 + (static_cast<size_t>(batch) * m + j) * 3;
-            cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
-        }
+        const float4 rec = rec_next;
+        rec_next = load_centre(w + total_warps);  // in flight under this centre's walk
+        const float cx = rec.x, cy = rec.y, cz = rec.z;
+        const int j = __float_as_int(rec.w);
         const BqGridInfo gi = info[batch];
         const float4 *pts = sorted + static_cast<size_t>(batch) * n;
         int *row = idx + (static_cast<size_t>(batch) * m + j) * nsample;
@@ -506,16 +508,23 @@ bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, i
             while (todo && H < nsample) {
                 const int wn = __ffs(todo) - 1;
                 todo &= todo - 1;
+                // the window's three row ranges as ONE candidate list, four candidates per lane in flight (each step of the walk is a
+                // round trip to L2: the per-warp bitmaps leave the SM little L1)
+                const int s0 = __shfl_sync(kFull, rs[0], wn), s1 = __shfl_sync(kFull, rs[1], wn), s2 = __shfl_sync(kFull, rs[2], wn);
+                const int l0 = __shfl_sync(kFull, re[0], wn) - s0, l1 = __shfl_sync(kFull, re[1], wn) - s1;
+                const int lt = l0 + l1 + __shfl_sync(kFull, re[2], wn) - s2;
+                auto at = [&](int i) { return i < l0 ? s0 + i : (i < l0 + l1 ? s1 + (i - l0) : s2 + (i - l0 - l1)); };
+                for (int i0 = lane; i0 < lt; i0 += 128) {
+                    float4 q[4];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int s2 = __shfl_sync(kFull, rs[k], wn), e2 = __shfl_sync(kFull, re[k], wn);
-                    for (int i = s2 + lane; i < e2; i += 32) {
-                        const float4 q = __ldg(pts + i);
-                        if (!(sqdist_ref(cx - q.x, cy - q.y, cz - q.z) >= T)) {
-                            const int kk = __float_as_int(q.w);
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + 32 * u < lt) q[u] = __ldg(pts + at(i0 + 32 * u));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + 32 * u < lt && !(sqdist_ref(cx - q[u].x, cy - q[u].y, cz - q[u].z) >= T)) {
+                            const int kk = __float_as_int(q[u].w);
                             atomicOr(&bm[kk >> 5], 1u << (kk & 31));
                         }
-                    }
                 }
                 __syncwarp();
                 unsigned *wb = bm + static_cast<size_t>(wn) * (win >> 5) + lane * wpl;  // this lane's words of the window
