@@ -369,15 +369,28 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             }
             tcgen05_fence_before();
             __syncthreads();
-            if (threadIdx.x < kTile && c0 + threadIdx.x < num_clusters) {
-                const int c = threadIdx.x;
+            {  // four threads per cluster, a contiguous quarter of the channels each: 4 x 32 contiguous bytes per cluster row at F = 32
+                const int c = threadIdx.x >> 2, qd = threadIdx.x & 3;
+                const int kb = (feature_dim + 3) >> 2, k0 = qd * kb, k1 = min(feature_dim, k0 + kb);
                 float ss = 0.0f;
-                for (int k = 0; k < feature_dim; ++k) {
+                for (int k = k0; k < k1; ++k) {
                     const float v = outT[k * (kTile + 1) + c];
                     ss = fmaf(v, v, ss);
                 }
+                ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 2);
                 const float inv = 1.0f / sqrtf(fmaxf(ss, 1e-8f));
-                for (int k = 0; k < feature_dim; ++k) out0[(c0 + c) * feature_dim + k] = outT[k * (kTile + 1) + c] * inv;
+                if (c0 + c < num_clusters) {
+                    float *dst = out0 + (c0 + c) * feature_dim;
+                    if ((kb & 3) == 0 && (feature_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(out0) & 15) == 0) {
+                        for (int k = k0; k < k1; k += 4)
+                            *reinterpret_cast<float4 *>(dst + k) =
+                                make_float4(outT[k * (kTile + 1) + c] * inv, outT[(k + 1) * (kTile + 1) + c] * inv,
+                                            outT[(k + 2) * (kTile + 1) + c] * inv, outT[(k + 3) * (kTile + 1) + c] * inv);
+                    } else {
+                        for (int k = k0; k < k1; ++k) dst[k] = outT[k * (kTile + 1) + c] * inv;
+                    }
+                }
             }
             __syncthreads();
         }
