@@ -1,7 +1,9 @@
 // mlp_tc_post.cu -- the per-cluster tails of the detector and the descriptor on the tensor cores ("bf16x3").
 //
 // Detector (models/feat3dnet.py:134-149): pooled (256) -> conv_post_0 (128, BN, ReLU) -> conv_post_1 (64, BN, ReLU) ->
-//   attention = softplus(64 -> 1), orientation = atan2 of the l2-normalised (64 -> 2) output.
+//   attention = softplus(64 -> 1), orientation = atan2 of the l2-normalised (64 -> 2) output.  The two heads (3 outputs per cluster,
+//   12 288 multiply-adds per 64-cluster tile) run on the CUDA cores in exact fp32 straight from conv_post_1's activations: as a padded
+//   128-row MMA they cost 504 cycles of tensor pipe, an operand conversion, a proxy fence and a commit / wait round trip per tile.
 // Descriptor (models/feat3dnet.py:71-84,185): the per-cluster half of conv_mid_0 -- rows 64..127 of its weight times the max-pooled conv1
 //   vector, which the reference tiles over the 64 samples and concatenates (feat3dnet.py:66-70); by the split-weight identity it is one
 //   column per cluster and is added here to the row kernel's max-pooled per-point half -- -> conv_post_0 (F, BN, no ReLU) -> l2-normalise.
@@ -47,12 +49,12 @@ constexpr uint32_t kOffBias = kOffOut + 128 * (kTile + 1) * 4;  // fp32 [512]
 constexpr uint32_t kOffBars = kOffBias + 512 * 4;
 constexpr uint32_t kSmemBytes = kOffBars + 64;
 static_assert(kOffX2 % 128 == 0 && kOffX3 % 128 == 0 && kOffOut % 16 == 0 && kOffBars % 8 == 0, "alignment");
-// tensor memory map (columns): detector W3 0..255 (2 splits x 128), W4 256..383 (2 x 64), Wh 384..447 (2 x 32), D 448..511
+// tensor memory map (columns): detector W3 0..255 (2 splits x 128), W4 256..383 (2 x 64), D 448..511
 //                               descriptor Wp 0..127 (2 x 64), Wb 128..191 (2 x 32), D 448..511
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemD = 448;
-// global weight image (bytes): detector [W3 hi 64K][W3 lo 64K][W4 hi 32K][W4 lo 32K][Wh hi 16K][Wh lo 16K][bias fp32 512]
-constexpr uint32_t kDetImgBytes = 2 * 65536 + 2 * 32768 + 2 * 16384 + 2048;
+// global weight image (bytes): detector [W3 hi 64K][W3 lo 64K][W4 hi 32K][W4 lo 32K][fp32 512: biases 0..194, head weights 256..447]
+constexpr uint32_t kDetImgBytes = 2 * 65536 + 2 * 32768 + 2048;
 // descriptor [Wp hi 32K][Wp lo 32K][Wb hi 16K][Wb lo 16K][bias fp32 512]
 constexpr uint32_t kDescImgBytes = 2 * 32768 + 2 * 16384 + 2048;
 }  // namespace post
@@ -203,11 +205,11 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
     uint32_t wpar = 0, mpar = 0;
 
     // ---- weights -> tensor memory, piece by piece through the staging buffer (bulk TMA, then tcgen05.cp) -------------
-    constexpr int kPieces = MODE == 0 ? 4 : 2;
+    constexpr int kPieces = MODE == 0 ? 3 : 2;
     for (int piece = 0; piece < kPieces; ++piece) {
-        // piece -> (global offset, bytes); detector: W3 hi | W3 lo | W4 hi+lo | Wh hi+lo ; descriptor: Wp hi+lo | Wb hi+lo
-        const uint32_t goff = MODE == 0 ? (piece < 2 ? piece * 65536u : (piece == 2 ? 131072u : 196608u)) : piece * 65536u;
-        const uint32_t bytes = MODE == 0 ? (piece < 3 ? 65536u : 32768u) : (piece == 0 ? 65536u : 32768u);
+        // piece -> (global offset, bytes); detector: W3 hi | W3 lo | W4 hi+lo ; descriptor: Wp hi+lo | Wb hi+lo
+        const uint32_t goff = piece * 65536u;
+        const uint32_t bytes = MODE == 0 ? 65536u : (piece == 0 ? 65536u : 32768u);
         if (threadIdx.x == 0) {
             mbar_arrive_expect_tx(bar_w, bytes);
             bulk_g2s(smem + kOffStage, wimg + goff, bytes, bar_w);  // one copy per piece: every cp.async.bulk costs its issuer ~450 cycles
@@ -219,12 +221,9 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             if (elect_one()) {
                 if (MODE == 0) {
                     if (piece < 2) post_cp_weights(tmem_base + piece * 128, sbase + kOffStage, 16);       // W3 split `piece`, K = 256
-                    else if (piece == 2) {
+                    else {
                         post_cp_weights(tmem_base + 256, sbase + kOffStage, 8);                             // W4 hi, K = 128
                         post_cp_weights(tmem_base + 320, sbase + kOffStage + 32768, 8);                     // W4 lo
-                    } else {
-                        post_cp_weights(tmem_base + 384, sbase + kOffStage, 4);                             // Wh hi, K = 64
-                        post_cp_weights(tmem_base + 416, sbase + kOffStage + 16384, 4);                     // Wh lo
                     }
                 } else if (piece == 0) {
                     post_cp_weights(tmem_base + 0, sbase + kOffStage, 8);                                   // Wp hi, K = 128
@@ -305,36 +304,39 @@ post_tc_kernel(long long num_clusters, int feature_dim, const float *__restrict_
             mbar_wait(bar_m, mpar);
             mpar ^= 1;
             tcgen05_fence_after();
-            post_load_acc(tmem_base, q, col0, r);
-            if (q < 2) post_store_operand<true>(smem + kOffX3, kX3Split, kSboX3, ch, col0, r, bias[128 + ch]);
-            tcgen05_fence_before();
-            fence_proxy_async_smem();
-            __syncthreads();
-            // ---- heads: rows 0 (attention), 1 and 2 (orientation x, y) of a zero-padded 128 x 64 weight
-            if (warp == 0) {
-                tcgen05_fence_after();
-                if (elect_one()) {
-                    post_mma(tmem_base + kTmemD, tmem_base + 384, tmem_base + 416, sbase + kOffX3, sbase + kOffX3 + kX3Split, kLboX, kSboX3, 4,
-                             idesc | kIdescBMnMajor);
-                    umma_commit(bar_m);
-                }
-                __syncwarp();
-            }
-            mbar_wait(bar_m, mpar);
-            mpar ^= 1;
-            tcgen05_fence_after();
-            if (q == 0) {  // warps 0 and 4 hold rows 0..31; only rows 0..2 matter
+            // conv_post_1's 64 activations (bias, ReLU) in fp32, channel-major with the clusters contiguous
+            if (q < 2) {
                 post_load_acc(tmem_base, q, col0, r);
-                if (lane < 3) {
+                const float b2 = bias[128 + ch];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) outT[lane * (kTile + 1) + col0 + j] = __uint_as_float(r[j]) + bias[192 + lane];
-                }
+                for (int j = 0; j < 32; ++j) outT[ch * (kTile + 1) + col0 + j] = fmaxf(__uint_as_float(r[j]) + b2, 0.0f);
             }
             tcgen05_fence_before();
+            __syncthreads();
+            {  // heads on the CUDA cores: thread = (cluster, quarter of the 64 channels); partial sums into rows 64.. of outT
+                const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int kc = part * 16 + k;
+                    const float v = outT[kc * (kTile + 1) + c];
+                    a0 = fmaf(v, bias[256 + kc], a0);          // attention (64 -> 1)
+                    a1 = fmaf(v, bias[320 + 2 * kc], a1);      // orientation (64 -> 2)
+                    a2 = fmaf(v, bias[320 + 2 * kc + 1], a2);
+                }
+                outT[(64 + part * 3 + 0) * (kTile + 1) + c] = a0;
+                outT[(64 + part * 3 + 1) * (kTile + 1) + c] = a1;
+                outT[(64 + part * 3 + 2) * (kTile + 1) + c] = a2;
+            }
             __syncthreads();
             if (threadIdx.x < kTile && c0 + threadIdx.x < num_clusters) {
                 const int c = threadIdx.x;
-                const float att = outT[c], ox = outT[(kTile + 1) + c], oy = outT[2 * (kTile + 1) + c];
+                float h[3];
+#pragma unroll
+                for (int o = 0; o < 3; ++o)
+                    h[o] = ((outT[(64 + o) * (kTile + 1) + c] + outT[(67 + o) * (kTile + 1) + c]) + outT[(70 + o) * (kTile + 1) + c]) +
+                           outT[(73 + o) * (kTile + 1) + c] + bias[192 + o];
+                const float att = h[0], ox = h[1], oy = h[2];
                 out0[c0 + c] = att > 20.0f ? att : log1pf(expf(att));                     // softplus
                 const float inv = 1.0f / sqrtf(fmaxf(ox * ox + oy * oy, 1e-8f));          // tf.nn.l2_normalize(eps=1e-8)
                 out1[c0 + c] = atan2f(oy * inv, ox * inv);
@@ -418,20 +420,15 @@ __global__ void post_prep_kernel(const float *__restrict__ P, WeightLayout L, in
             const int e = i - 128 * 256;
             const int r = e & 127, k = e >> 7;
             put(131072, 131072 + 32768, r, k, r < 64 ? P[L.off[W_DETP1] + k * 64 + r] : 0.0f);
-        } else if (i < 128 * 256 + 128 * 128 + 128 * 64) {  // heads: row 0 attention, rows 1-2 orientation
+        } else if (i < 128 * 256 + 128 * 128 + 512) {  // biases, then the heads' fp32 weights (attention 64, orientation 64 x 2)
             const int e = i - 128 * 256 - 128 * 128;
-            const int r = e & 127, k = e >> 7;
-            float w = 0.0f;
-            if (r == 0) w = P[L.off[W_ATT] + k];
-            else if (r < 3) w = P[L.off[W_ORI] + 2 * k + (r - 1)];
-            put(196608, 196608 + 16384, r, k, w);
-        } else if (i < 128 * 256 + 128 * 128 + 128 * 64 + 512) {
-            const int e = i - 128 * 256 - 128 * 128 - 128 * 64;
             float b = 0.0f;
             if (e < 128) b = P[L.off[B_DETP0] + e];
             else if (e < 192) b = P[L.off[B_DETP1] + e - 128];
             else if (e == 192) b = P[L.off[B_ATT]];
             else if (e < 195) b = P[L.off[B_ORI] + e - 193];
+            else if (e >= 256 && e < 320) b = P[L.off[W_ATT] + e - 256];
+            else if (e >= 320 && e < 448) b = P[L.off[W_ORI] + e - 320];
             reinterpret_cast<float *>(img + kDetImgBytes - 2048)[e] = b;
         }
     } else {
@@ -468,7 +465,7 @@ int detector_post_tc(long long nc, const float *pooled, const float *packed, uin
     if (nc == 0) return 0;
     int rc = 0;
     if (build_image) {
-        const int total = 128 * 256 + 128 * 128 + 128 * 64 + 512;
+        const int total = 128 * 256 + 128 * 128 + 512;
         post_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(packed, make_weight_layout(32), 0, wimg);
         rc = check_launch("post_prep_kernel");
         if (rc) return rc;
