@@ -259,13 +259,13 @@ def kernel_table(timings, peaks):
     return rows
 
 
-# the resource that limits each inference kernel according to profiles/r02_g_kernels_ncu_summary.md (ncu --set full, C3)
+# the resource that limits each inference kernel according to profiles/r02_be_kernels_ncu_summary.md (ncu --set full, C3)
 LIMITERS = {
     "fps_group_kernel": "serial latency: 511 dependent rounds per cloud, 0.53 us per round (one barrier + two redux trees); issue slots 21 %, DRAM 0.6 %",
     "bq_grid_query_kernel": "instruction issue 58 % (IPC 2.3) + L2 gather latency (long_scoreboard); DRAM 3.5 %, L2 hit 76 %",
     "bq_grid_build_kernel": "shared-memory counting sort (mio / lg throttle); DRAM 7 %",
     "det_rows_tc_kernel": "tensor pipe 81 % active; 3 MMAs per algorithmic MAC (bf16x3), DRAM traffic = algorithmic bytes",
-    "desc_rows_tc_kernel": "dependency chain E1 -> pair MMA -> E2 per tile: tensor pipe 48 %, issue slots 54 %, shared memory 57 %",
+    "desc_rows_tc_kernel": "instruction streams of its 22 warps (producers ~200 instructions per 64-sample tile): tensor pipe 59 %, issue slots 53 %, L1/shared 69 %",
     "post_tc_kernel": "latency: weight staging + three dependent MMA groups per 64-cluster tile; every unit below 30 %",
 }
 
