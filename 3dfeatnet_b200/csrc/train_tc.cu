@@ -259,7 +259,8 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
                     for (int sp = 0; sp < nsplit; ++sp) {  // a = hi (+ mid) + lo, each a bf16
                         const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
                         *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                        a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
+                        bf16x2_residual(a.x, a.y, *reinterpret_cast<const uint32_t *>(&h0), a.x, a.y);
+                            bf16x2_residual(a.z, a.w, *reinterpret_cast<const uint32_t *>(&h1), a.z, a.w);
                     }
                 }
             }
@@ -282,8 +283,7 @@ lin_tc_kernel(long long rows, int k_real, int kp, int nout, int kRing, uint32_t 
                     for (int j = 0; j < 4; ++j) {
                         const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
                         hw[j] = *reinterpret_cast<const uint32_t *>(&h2);
-                        v[2 * j] -= __low2float(h2);
-                        v[2 * j + 1] -= __high2float(h2);
+                        bf16x2_residual(v[2 * j], v[2 * j + 1], hw[j], v[2 * j], v[2 * j + 1]);
                     }
                     *reinterpret_cast<uint4 *>(dst + sp * split) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                 }
@@ -578,7 +578,8 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                         for (int sp = 0; sp < nsplit; ++sp) {
                             const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
                             *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                            a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
+                            bf16x2_residual(a.x, a.y, *reinterpret_cast<const uint32_t *>(&h0), a.x, a.y);
+                            bf16x2_residual(a.z, a.w, *reinterpret_cast<const uint32_t *>(&h1), a.z, a.w);
                         }
                     }
                 }
@@ -608,7 +609,8 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                     for (int sp = 0; sp < nsplit; ++sp) {
                         const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
                         *reinterpret_cast<uint2 *>(dst + sp * split) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                        a.x -= __low2float(h0); a.y -= __high2float(h0); a.z -= __low2float(h1); a.w -= __high2float(h1);
+                        bf16x2_residual(a.x, a.y, *reinterpret_cast<const uint32_t *>(&h0), a.x, a.y);
+                            bf16x2_residual(a.z, a.w, *reinterpret_cast<const uint32_t *>(&h1), a.z, a.w);
                     }
                 }
                 if (dgb) *reinterpret_cast<float4 *>(gred + frow * k_real + fq * 4) = acc;  // this thread's rows of the tile (= one group)
