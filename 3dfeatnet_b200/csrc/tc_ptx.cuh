@@ -155,7 +155,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- packed fp32 pairs (FFMA2 / FADD2 of sm_100): two IEEE fp32 operations per issued instruction, same bits as the scalar forms
+// ---- packed fp32 pairs (FFMA2 / FADD2 / FMUL2 of sm_100): two IEEE fp32 operations per issued instruction.  Each instruction gives the bits of
+// its scalar form (tools/f32x2_bits.cu: 8.4 M random pairs incl. subnormals and zeros, no mismatch), BUT ptxas contracts a packed multiply that
+// feeds a packed add / sub into one FFMA2 even when both carry an explicit .rn (tools/dz_bits.cu) -- where the scalar code relies on the separate
+// roundings of __fmul_rn / __fadd_rn, the add that consumes a product must stay scalar.
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -170,6 +173,11 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {

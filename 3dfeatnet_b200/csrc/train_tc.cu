@@ -598,10 +598,7 @@ lin_tc_pipe_kernel(long long rows, int k_real, int kp, int nout, int nring, uint
                     float4 a = z4;
                     if (r0 + r < rows) {
                         const float4 zz = *reinterpret_cast<const float4 *>(ringbuf + slot * slot_bytes + r * row_bytes + fq * 16);
-                        a.x = dz_value(zz.x, KF.bsc.x, KF.bsh.x, KF.ss.x, KF.k1.x, KF.mu.x, KF.is.x, KF.k2.x, pm.x, gsc.x, S.relu);
-                        a.y = dz_value(zz.y, KF.bsc.y, KF.bsh.y, KF.ss.y, KF.k1.y, KF.mu.y, KF.is.y, KF.k2.y, pm.y, gsc.y, S.relu);
-                        a.z = dz_value(zz.z, KF.bsc.z, KF.bsh.z, KF.ss.z, KF.k1.z, KF.mu.z, KF.is.z, KF.k2.z, pm.z, gsc.z, S.relu);
-                        a.w = dz_value(zz.w, KF.bsc.w, KF.bsh.w, KF.ss.w, KF.k1.w, KF.mu.w, KF.is.w, KF.k2.w, pm.w, gsc.w, S.relu);
+                        a = dz_value4(zz, KF, pm, gsc, S.relu);
                     }
                     acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
                     uint8_t *dst = dst0 + r * 16;
@@ -849,10 +846,7 @@ __device__ __forceinline__ void wgrad_dz_in_place(uint8_t *__restrict__ stage, i
         float4 *p = reinterpret_cast<float4 *>(stage + (static_cast<size_t>(r) * c + q * 4) * 4);
         const float4 zz = *p;
         float4 d;
-        d.x = dz_value(zz.x, K.bsc.x, K.bsh.x, K.ss.x, K.k1.x, K.mu.x, K.is.x, K.k2.x, pm.x, gsc.x, relu);
-        d.y = dz_value(zz.y, K.bsc.y, K.bsh.y, K.ss.y, K.k1.y, K.mu.y, K.is.y, K.k2.y, pm.y, gsc.y, relu);
-        d.z = dz_value(zz.z, K.bsc.z, K.bsh.z, K.ss.z, K.k1.z, K.mu.z, K.is.z, K.k2.z, pm.z, gsc.z, relu);
-        d.w = dz_value(zz.w, K.bsc.w, K.bsh.w, K.ss.w, K.k1.w, K.mu.w, K.is.w, K.k2.w, pm.w, gsc.w, relu);
+        d = dz_value4(zz, K, pm, gsc, relu);
         *p = d;
         dbsum.x += d.x; dbsum.y += d.y; dbsum.z += d.z; dbsum.w += d.w;
     }
