@@ -80,7 +80,10 @@ int f3d_query_ball_point(int b, int n, int m, float radius, int nsample, const f
  * results (hits are re-ordered by index through a shared-memory bitmap).  Falls back to the scan above when the
  * workspace is NULL / too small.  With m >= 4096 centres per cloud (the attention pass of inference.py:99-131 scores every point) and a
  * workspace of align256(..._workspace_bytes(b,n)) + ..._workspace_bytes(b,m) bytes the centres are binned too and visited in that
- * order, so that the warps of a CTA share their candidate cells (same rows, each written at its centre's own index). */
+ * order, so that the warps of a CTA share their candidate cells (same rows, each written at its centre's own index).
+ * Clouds of n >= 32768 points are binned per index window (<= 32 windows of consecutive indices, one cell table each; the workspace size
+ * accounts for it): a centre walks its windows in ascending order and stops at nsample hits -- the reference's break at cnt == nsample,
+ * tf_grouping_g.cu:31-46 -- instead of testing every point of its 3x3 cells (thousands in a KITTI-shape scan). */
 size_t f3d_query_ball_point_workspace_bytes(int b, int n);
 int f3d_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
                             int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream);
