@@ -306,33 +306,99 @@ __global__ void nms_compact_kernel(int n, double ratio, const float *__restrict_
     }
 }
 
-// rank of a survivor = number of survivors that sort before it in (attention, index) DESCENDING order
-__global__ void __launch_bounds__(256)
-nms_rank_kernel(int n, int max_keypoints, const float *__restrict__ attention, const int *__restrict__ list,
-                const int *__restrict__ count, int *__restrict__ out_idx) {
-    __shared__ float ta[256];
-    __shared__ int ti[256];
-    const int batch = blockIdx.y;
+// The max_keypoints best survivors in (attention, index) DESCENDING order -- out_idx[rank] = point index -- without ranking every survivor
+// against every other one (a KITTI-shape scan leaves tens of thousands; the all-pairs count took 146 us): one CTA per cloud finds the
+// K-th best by an MSB-first radix select over the 64-bit value (order-preserving attention key, point index) -- passes of 8 bits with
+// warp-aggregated histogram updates, stopping as soon as the bucket of the K-th holds exactly what is still needed (a handful of passes
+// when the attentions differ; ties of the K-th go on into the index bits, so that a cloud of equal attentions keeps exactly K too) --
+// and ranks the K kept survivors among themselves with the reference's order.
+__device__ __forceinline__ unsigned nms_okey(float a) {  // a < b  <=>  okey(a) < okey(b);  -0 counts as +0 like the float comparison
+    const unsigned u = __float_as_uint(a + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(1024)
+nms_topk_kernel(int n, int max_keypoints, const float *__restrict__ attention, const int *__restrict__ list, const int *__restrict__ count,
+                unsigned *__restrict__ keys, int *__restrict__ cand, int *__restrict__ out_idx) {
+    constexpr int kStage = 2048;
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_r, s_m, s_done;
+    __shared__ unsigned tk[kStage];
+    __shared__ int ti[kStage];
+    const int batch = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int cnt = count[batch];
-    if (static_cast<int>(blockIdx.x) * 256 >= cnt) return;
+    if (cnt == 0) return;
     const int *lst = list + static_cast<size_t>(batch) * n;
     const float *att = attention + static_cast<size_t>(batch) * n;
-    const int e = blockIdx.x * 256 + threadIdx.x;
-    const int me = e < cnt ? lst[e] : -1;
-    const float ma = e < cnt ? att[me] : 0.0f;
-    int rank = 0;
-    for (int base = 0; base < cnt; base += 256) {
-        __syncthreads();
-        const int j = base + threadIdx.x;
-        if (j < cnt) {
-            ti[threadIdx.x] = lst[j];
-            ta[threadIdx.x] = att[lst[j]];
+    unsigned *ky = keys + static_cast<size_t>(batch) * n;
+    int *cd = cand + static_cast<size_t>(batch) * n;
+    int *out = out_idx + static_cast<size_t>(batch) * max_keypoints;
+    for (int e = tid; e < cnt; e += 1024) ky[e] = nms_okey(att[lst[e]]);
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    unsigned long long thr = 0;  // the kept survivors: (key, index) >= thr
+    if (cnt > max_keypoints) {
+        unsigned long long prefix = 0, mask = 0;
+        int r = max_keypoints;  // the r-th largest value among those that match the prefix
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            for (int d = tid; d < 256; d += 1024) hist[d] = 0;
+            __syncthreads();
+            for (int e0 = 0; e0 < cnt; e0 += 1024) {  // (whole warps take part in the match)
+                const int e = e0 + tid;
+                unsigned long long v = e < cnt ? static_cast<unsigned long long>(ky[e]) << 32 : 0ull;
+                if (shift < 32 && e < cnt) v |= static_cast<unsigned>(lst[e]);
+                const bool in = e < cnt && (v & mask) == prefix;
+                const unsigned d = in ? static_cast<unsigned>(v >> shift) & 255u : 256u;
+                const unsigned same = __match_any_sync(kFull, d);
+                if (in && lane == __ffs(same) - 1) atomicAdd(&hist[d], __popc(same));
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int cum = 0;
+                for (int d = 255; d >= 0; --d) {
+                    const int c = hist[d];
+                    if (cum + c >= r) {
+                        s_prefix = prefix | (static_cast<unsigned long long>(d) << shift);
+                        s_r = r - cum;
+                        s_done = c == r - cum;  // the whole bucket is wanted: its lower bits need no look
+                        break;
+                    }
+                    cum += c;
+                }
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            r = s_r;
+            mask |= 0xffull << shift;
+            const bool done = s_done != 0;
+            __syncthreads();
+            if (done) break;
         }
-        __syncthreads();
-        const int lim = min(256, cnt - base);
-        for (int i = 0; i < lim; ++i) rank += (ta[i] > ma || (ta[i] == ma && ti[i] > me)) ? 1 : 0;
+        thr = prefix;
     }
-    if (e < cnt && rank < max_keypoints) out_idx[static_cast<size_t>(batch) * max_keypoints + rank] = me;
+    for (int e = tid; e < cnt; e += 1024)
+        if (((static_cast<unsigned long long>(ky[e]) << 32) | static_cast<unsigned>(lst[e])) >= thr) cd[atomicAdd(&s_m, 1)] = e;
+    __syncthreads();
+    const int M = s_m;  // = min(cnt, max_keypoints)
+    for (int c0 = 0; c0 < M; c0 += 1024) {  // (all threads walk the staging loop)
+        const int c = c0 + tid;
+        const int e = c < M ? cd[c] : 0;
+        const unsigned kc = c < M ? ky[e] : 0u;
+        const int ic = c < M ? lst[e] : 0;
+        int rank = 0;
+        for (int base = 0; base < M; base += kStage) {
+            __syncthreads();
+            for (int j = tid; j < kStage && base + j < M; j += 1024) {
+                const int ej = cd[base + j];
+                tk[j] = ky[ej];
+                ti[j] = lst[ej];
+            }
+            __syncthreads();
+            const int lim = min(kStage, M - base);
+            for (int j = 0; j < lim; ++j) rank += (tk[j] > kc || (tk[j] == kc && ti[j] > ic)) ? 1 : 0;
+        }
+        if (c < M && rank < max_keypoints) out[rank] = ic;
+    }
 }
 
 __global__ void nms_finalize_kernel(int n, int max_keypoints, const float *__restrict__ xyz, const float *__restrict__ attention,
@@ -430,8 +496,9 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     nms_compact_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, min_response_ratio, attention, keep, maxatt, list, count);
     rc = check_launch("nms_compact_kernel");
     if (rc) return rc;
-    nms_rank_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, max_keypoints, attention, list, count, out_idx);
-    rc = check_launch("nms_rank_kernel");
+    // (dense_list and, once nms_keep has run, sorted are free: keys and kept positions of the selection)
+    nms_topk_kernel<<<b, 1024, 0, st>>>(n, max_keypoints, attention, list, count, reinterpret_cast<unsigned *>(dense_list), sorted, out_idx);
+    rc = check_launch("nms_topk_kernel");
     if (rc) return rc;
     nms_finalize_kernel<<<dim3((max_keypoints + 1023) / 1024, b), min(1024, ((max_keypoints + 31) / 32) * 32), 0, st>>>(
         n, max_keypoints, xyz, attention, count, out_idx, out_xyz, out_attention, num_keypoints);

@@ -81,6 +81,21 @@ def test_nms_threshold_padding_and_ties(cuda):
         inf.nms(torch.zeros((1, 10, 3), device=cuda), torch.zeros((1, 10), device=cuda))  # fewer points than 50 neighbours
 
 
+@pytest.mark.parametrize("levels,kmax", [(4, 1024), (1, 1024), (4, 100), (64, 3000), (3, 6000)])
+def test_nms_top_k_cut_inside_a_tie_group(cuda, levels, kmax):
+    """thousands of survivors whose attentions take a few values only: the cut at max_keypoints falls inside a group of equal attentions
+    and is decided by the point index (the reference sorts (attention, index) tuples in reverse, inference.py:249-251) -- the radix select
+    of nms_topk_kernel runs on into the index bits; kmax > survivors: everything kept, padded with the best"""
+    rng = np.random.default_rng(levels * 7 + kmax)
+    xyz = (rng.random((2, 5000, 3)) * 400).astype(np.float32)  # sparse: every point is its own maximum
+    att = (0.5 + rng.integers(0, levels, (2, 5000)) / 8.0).astype(np.float32)
+    want = onms.nms(xyz, att, max_keypoints=kmax)
+    got = run_nms(xyz, att, cuda, max_keypoints=kmax)
+    assert got[2] == want[2]
+    assert np.array_equal(got[3], want[3])
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
 def test_nms_matches_reference_golden(cuda):
     """tests/golden/ref_nms.npz: outputs of the reference's own nms() (taken out of inference.py with `ast` and executed
     unmodified, tests/golden/make_golden_nms.py) -- 1024-keypoint truncation, the 50-NN rule on dense clouds, padding."""
