@@ -235,22 +235,36 @@ nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const fl
     const float qa = me.w;
     const int cx = nms_cell_coord(qx, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(qy, g.y0, g.inv_h, g.ny);
     const int y_lo = max(cy - 1, 0), y_hi = min(cy + 1, g.ny - 1), x_lo = max(cx - 1, 0), x_hi = min(cx + 1, g.nx - 1);
+    // A float32 look at every candidate first (relative error of d2f < 3e-7): the float64 distance -- three conversions and seven
+    // double-precision operations per candidate -- is only evaluated where the float32 one cannot decide, i.e. within 1e-5 of the radius
+    // or for a larger-attention candidate that may be nearer than the nearest threat so far (a handful per query: the bound shrinks).
+    const float t_hi = __double2float_ru(T * 1.00001), t_lo = __double2float_rd(T * 0.99999);
     int cnt = 0;
     double td = 1.0e300;  // nearest threat
+    float td_hi = 3.4e38f;  // d2f > td_hi  =>  d > td
     int tk = 0x7fffffff;
     for (int yy = y_lo; yy <= y_hi; ++yy) {
         const int e1 = cs[yy * g.nx + x_hi + 1];
         for (int e = cs[yy * g.nx + x_lo]; e < e1; ++e) {  // the cells of one grid row are contiguous
             if (e == t) continue;
             const float4 c = __ldg(pts + e);
+            const float fx = me.x - c.x, fy = me.y - c.y, fz = me.z - c.z;
+            const float d2f = fx * fx + fy * fy + fz * fz;
+            if (d2f > t_hi) continue;  // outside for sure
+            const bool larger = c.w > qa;
+            if (d2f < t_lo && !(larger && d2f <= td_hi)) {  // inside for sure, and not the nearest threat for sure
+                ++cnt;
+                continue;
+            }
             const double d = nms_d2(qx, qy, qz, c.x, c.y, c.z);
             if (d > T) continue;
             ++cnt;
-            if (c.w > qa && d <= td) {  // ties in attention: position 0 (self) wins the argmax
+            if (larger && d <= td) {  // ties in attention: position 0 (self) wins the argmax
                 const int k = __ldg(srt + e);
                 if (d < td || k < tk) {
                     td = d;
                     tk = k;
+                    td_hi = __double2float_ru(d) * 1.00002f;
                 }
             }
         }
@@ -260,11 +274,19 @@ nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const fl
         kp = 0;
         if (cnt > num_neighbors - 1) {
             int before = 0;
+            const float td_lo = __double2float_rd(td) * 0.99998f;  // d2f < td_lo  =>  d < td
             for (int yy = y_lo; yy <= y_hi; ++yy) {
                 const int e1 = cs[yy * g.nx + x_hi + 1];
                 for (int e = cs[yy * g.nx + x_lo]; e < e1; ++e) {
                     if (e == t) continue;
                     const float4 c = __ldg(pts + e);
+                    const float fx = me.x - c.x, fy = me.y - c.y, fz = me.z - c.z;
+                    const float d2f = fx * fx + fy * fy + fz * fz;
+                    if (d2f > t_hi || d2f > td_hi) continue;  // outside, or behind the threat, for sure
+                    if (d2f < t_lo && d2f < td_lo) {          // inside and in front of the threat for sure
+                        ++before;
+                        continue;
+                    }
                     const double d = nms_d2(qx, qy, qz, c.x, c.y, c.z);
                     if (d > T) continue;
                     before += (d < td || (d == td && __ldg(srt + e) < tk)) ? 1 : 0;
