@@ -71,31 +71,63 @@ __device__ __forceinline__ int nms_cell_coord(double v, double v0, double inv_h,
     return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
-// bbox[b] = {min x, min y, max x, max y}
+// bbox[b] = {min x, min y, max x, max y} and maxatt[b] = max attention of cloud b in ONE launch of gridDim.x CTAs per cloud (two launches of
+// one CTA per cloud took 25 us each at 131 072 points): every CTA reduces a stripe, the last one to finish (a ticket per cloud in `done`,
+// zeroed by the caller) folds the stripes' results.  min / max are order-independent: same bits whatever the finishing order.
 __global__ void __launch_bounds__(1024)
-nms_bbox_kernel(int n, const float *__restrict__ xyz, float *__restrict__ bbox) {
-    __shared__ float red[4][32];
-    const float *p = xyz + static_cast<size_t>(blockIdx.x) * n * 3;
-    float lx = 3.0e38f, ly = 3.0e38f, hx = -3.0e38f, hy = -3.0e38f;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+nms_bbox_max_kernel(int n, const float *__restrict__ xyz, const float *__restrict__ attention, float *__restrict__ stripes,
+                    int *__restrict__ done, float *__restrict__ bbox, float *__restrict__ maxatt) {
+    __shared__ float red[5][32];
+    __shared__ int s_last;
+    const int batch = blockIdx.y, G = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *p = xyz + static_cast<size_t>(batch) * n * 3;
+    const float *att = attention + static_cast<size_t>(batch) * n;
+    float v[5] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.4e38f};  // min x, min y, max x, max y, max attention
+    for (int k = blockIdx.x * 1024 + threadIdx.x; k < n; k += G * 1024) {
         const float x = p[3 * k], y = p[3 * k + 1];
-        lx = fminf(lx, x); ly = fminf(ly, y); hx = fmaxf(hx, x); hy = fmaxf(hy, y);
+        v[0] = fminf(v[0], x); v[1] = fminf(v[1], y); v[2] = fmaxf(v[2], x); v[3] = fmaxf(v[3], y);
+        v[4] = fmaxf(v[4], att[k]);
     }
+    auto fold = [&](int s) {
+        v[0] = fminf(v[0], __shfl_xor_sync(kFull, v[0], s)); v[1] = fminf(v[1], __shfl_xor_sync(kFull, v[1], s));
+        v[2] = fmaxf(v[2], __shfl_xor_sync(kFull, v[2], s)); v[3] = fmaxf(v[3], __shfl_xor_sync(kFull, v[3], s));
+        v[4] = fmaxf(v[4], __shfl_xor_sync(kFull, v[4], s));
+    };
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        lx = fminf(lx, __shfl_xor_sync(kFull, lx, s)); ly = fminf(ly, __shfl_xor_sync(kFull, ly, s));
-        hx = fmaxf(hx, __shfl_xor_sync(kFull, hx, s)); hy = fmaxf(hy, __shfl_xor_sync(kFull, hy, s));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        red[0][threadIdx.x >> 5] = lx; red[1][threadIdx.x >> 5] = ly; red[2][threadIdx.x >> 5] = hx; red[3][threadIdx.x >> 5] = hy;
+    for (int s = 16; s > 0; s >>= 1) fold(s);
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) red[c][warp] = v[c];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 32; ++w) {
-            lx = fminf(lx, red[0][w]); ly = fminf(ly, red[1][w]); hx = fmaxf(hx, red[2][w]); hy = fmaxf(hy, red[3][w]);
+    if (warp != 0) return;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) v[c] = red[c][lane];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) fold(s);
+    if (G > 1) {
+        float *mine = stripes + (static_cast<size_t>(batch) * G + blockIdx.x) * 5;
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) __stcg(mine + c, v[c]);
+            __threadfence();
+            s_last = atomicAdd(done + batch, 1) == G - 1;
         }
-        float *o = bbox + blockIdx.x * 4;
-        o[0] = lx; o[1] = ly; o[2] = hx; o[3] = hy;
+        __syncwarp();
+        if (!s_last) return;
+        __threadfence();
+        for (int c = lane; c < G; c += 32) {  // (the last CTA's own stripe is in v already; folding it again changes nothing)
+            const float *o = stripes + (static_cast<size_t>(batch) * G + c) * 5;
+            v[0] = fminf(v[0], __ldcg(o)); v[1] = fminf(v[1], __ldcg(o + 1)); v[2] = fmaxf(v[2], __ldcg(o + 2));
+            v[3] = fmaxf(v[3], __ldcg(o + 3)); v[4] = fmaxf(v[4], __ldcg(o + 4));
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) fold(s);
+    }
+    if (lane == 0) {
+        float *o = bbox + batch * 4;
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
+        maxatt[batch] = v[4];
     }
 }
 
@@ -218,102 +250,141 @@ __global__ void nms_cell_fill_kernel(int n, double radius, int max_cells, const 
 // No threat: the point survives.  A threat and at most num_neighbors-1 neighbours: it is consulted, the point dies.
 // Otherwise the tree only returns the num_neighbors-1 nearest: the point dies iff fewer than num_neighbors-1 neighbours
 // precede the nearest threat -- a second scan that counts them (instead of materialising the sorted neighbour list).
+//
+// A float32 look at every candidate first (relative error of d2f < 3e-7): the float64 distance -- three conversions and seven
+// double-precision operations per candidate -- is only evaluated where the float32 one cannot decide, i.e. within 1e-5 of the radius
+// or for a larger-attention candidate that may be nearer than the nearest threat so far (a handful per query: the bound shrinks).
+//
+// The 32 queries of a warp are neighbours in the cell-sorted order.  When they sit in one grid row and span at most three cells (always
+// the case where the cloud is dense, which is where the time goes: thousands of candidates per query near the sensor of a KITTI-shape
+// scan) the warp walks the UNION of their candidate ranges together: 32 records per coalesced load into a shared-memory tile (the next
+// tile's load in flight), every lane reading the tile by broadcast -- candidates outside a lane's own 3 x 3 cells are farther than the
+// radius (cells are >= radius wide) and drop out at the float32 test, so the union changes nothing.  Other warps (row ends, sparse
+// regions) keep the per-lane walk.
+struct NmsQuery {
+    float x, y, z, a;
+    int t;
+    float t_hi, t_lo;
+    double T;
+};
+struct NmsThreat {
+    int cnt;
+    double td;    // nearest threat so far, (d2, index) order
+    float td_hi;  // d2f > td_hi  =>  d > td
+    int tk;
+};
+__device__ __forceinline__ void nms_visit_first(const NmsQuery &q, NmsThreat &s, const float4 c, int e, const int *__restrict__ srt) {
+    const float fx = q.x - c.x, fy = q.y - c.y, fz = q.z - c.z;
+    const float d2f = fx * fx + fy * fy + fz * fz;
+    if (d2f > q.t_hi || e == q.t) return;  // outside for sure / the query itself
+    const bool larger = c.w > q.a;
+    if (d2f < q.t_lo && !(larger && d2f <= s.td_hi)) {  // inside for sure, and not the nearest threat for sure
+        ++s.cnt;
+        return;
+    }
+    const double d = nms_d2(q.x, q.y, q.z, c.x, c.y, c.z);
+    if (d > q.T) return;
+    ++s.cnt;
+    if (larger && d <= s.td) {  // ties in attention: position 0 (self) wins the argmax
+        const int k = __ldg(srt + e);
+        if (d < s.td || k < s.tk) {
+            s.td = d;
+            s.tk = k;
+            s.td_hi = __double2float_ru(d) * 1.00002f;
+        }
+    }
+}
+// second scan: the in-radius neighbours that precede the threat in (d2, index) order
+__device__ __forceinline__ void nms_visit_second(const NmsQuery &q, const NmsThreat &s, float td_lo, int &before, const float4 c, int e,
+                                                 const int *__restrict__ srt) {
+    const float fx = q.x - c.x, fy = q.y - c.y, fz = q.z - c.z;
+    const float d2f = fx * fx + fy * fy + fz * fz;
+    if (d2f > q.t_hi || d2f > s.td_hi || e == q.t) return;  // outside, or behind the threat, for sure
+    if (d2f < q.t_lo && d2f < td_lo) {                      // inside and in front of the threat for sure
+        ++before;
+        return;
+    }
+    const double d = nms_d2(q.x, q.y, q.z, c.x, c.y, c.z);
+    if (d > q.T) return;
+    before += (d < s.td || (d == s.td && __ldg(srt + e) < s.tk)) ? 1 : 0;
+}
+template <bool kSecond>
+__device__ __forceinline__ void nms_walk_lane(const NmsQuery &q, NmsThreat &s, float td_lo, int &before, const int *__restrict__ cs, int nx,
+                                              int y_lo, int y_hi, int x_lo, int x_hi, const float4 *__restrict__ pts,
+                                              const int *__restrict__ srt) {
+    for (int yy = y_lo; yy <= y_hi; ++yy) {
+        const int e1 = cs[yy * nx + x_hi + 1];
+        for (int e = cs[yy * nx + x_lo]; e < e1; ++e) {  // the cells of one grid row are contiguous
+            const float4 c = __ldg(pts + e);
+            if (kSecond) nms_visit_second(q, s, td_lo, before, c, e, srt);
+            else nms_visit_first(q, s, c, e, srt);
+        }
+    }
+}
+template <bool kSecond>
+__device__ __forceinline__ void nms_walk_warp(const NmsQuery &q, NmsThreat &s, float td_lo, int &before, const int *__restrict__ cs, int nx,
+                                              int y_lo, int y_hi, int x_lo, int x_hi, const float4 *__restrict__ pts,
+                                              const int *__restrict__ srt, float4 *tile, int lane) {
+    for (int yy = y_lo; yy <= y_hi; ++yy) {  // (bounds are the warp's: every lane walks the same candidates)
+        const int e0 = cs[yy * nx + x_lo], e1 = cs[yy * nx + x_hi + 1];
+        float4 next = e0 + lane < e1 ? __ldg(pts + e0 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = e0; base < e1; base += 32) {
+            __syncwarp();
+            tile[lane] = next;
+            __syncwarp();
+            if (base + 32 + lane < e1) next = __ldg(pts + base + 32 + lane);
+            const int lim = min(32, e1 - base);
+#pragma unroll 4
+            for (int j = 0; j < lim; ++j) {
+                const float4 c = tile[j];
+                if (kSecond) nms_visit_second(q, s, td_lo, before, c, base + j, srt);
+                else nms_visit_first(q, s, c, base + j, srt);
+            }
+        }
+    }
+}
 __global__ void __launch_bounds__(128)
 nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const float *__restrict__ bbox, const int *__restrict__ cell_start,
                 const int *__restrict__ sorted, const float4 *__restrict__ sorted_pts, unsigned char *__restrict__ keep) {
-    const int batch = blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // position in the cell-sorted order: neighbouring threads, neighbouring cells
-    if (t >= n) return;
+    __shared__ float4 tiles[4][32];
+    const int batch = blockIdx.y, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;  // position in the cell-sorted order: neighbouring threads, neighbouring cells
+    if ((t0 & ~31) >= n) return;                            // (whole warps only: the lanes of a warp walk together)
+    const int t = min(t0, n - 1);
     const int *cs = cell_start + static_cast<size_t>(batch) * (max_cells + 1);
     const int *srt = sorted + static_cast<size_t>(batch) * n;
     const float4 *pts = sorted_pts + static_cast<size_t>(batch) * n;
     const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
-    const double T = nms_threshold(radius);
     const float4 me = __ldg(pts + t);
-    const int q = __ldg(srt + t);
-    const double qx = me.x, qy = me.y, qz = me.z;
-    const float qa = me.w;
-    const int cx = nms_cell_coord(qx, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(qy, g.y0, g.inv_h, g.ny);
+    const int qi = __ldg(srt + t);
+    NmsQuery q;
+    q.x = me.x; q.y = me.y; q.z = me.z; q.a = me.w; q.t = t;
+    q.T = nms_threshold(radius);
+    q.t_hi = __double2float_ru(q.T * 1.00001);
+    q.t_lo = __double2float_rd(q.T * 0.99999);
+    const int cx = nms_cell_coord(me.x, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(me.y, g.y0, g.inv_h, g.ny);
     const int y_lo = max(cy - 1, 0), y_hi = min(cy + 1, g.ny - 1), x_lo = max(cx - 1, 0), x_hi = min(cx + 1, g.nx - 1);
-    // A float32 look at every candidate first (relative error of d2f < 3e-7): the float64 distance -- three conversions and seven
-    // double-precision operations per candidate -- is only evaluated where the float32 one cannot decide, i.e. within 1e-5 of the radius
-    // or for a larger-attention candidate that may be nearer than the nearest threat so far (a handful per query: the bound shrinks).
-    const float t_hi = __double2float_ru(T * 1.00001), t_lo = __double2float_rd(T * 0.99999);
-    int cnt = 0;
-    double td = 1.0e300;  // nearest threat
-    float td_hi = 3.4e38f;  // d2f > td_hi  =>  d > td
-    int tk = 0x7fffffff;
-    for (int yy = y_lo; yy <= y_hi; ++yy) {
-        const int e1 = cs[yy * g.nx + x_hi + 1];
-        for (int e = cs[yy * g.nx + x_lo]; e < e1; ++e) {  // the cells of one grid row are contiguous
-            if (e == t) continue;
-            const float4 c = __ldg(pts + e);
-            const float fx = me.x - c.x, fy = me.y - c.y, fz = me.z - c.z;
-            const float d2f = fx * fx + fy * fy + fz * fz;
-            if (d2f > t_hi) continue;  // outside for sure
-            const bool larger = c.w > qa;
-            if (d2f < t_lo && !(larger && d2f <= td_hi)) {  // inside for sure, and not the nearest threat for sure
-                ++cnt;
-                continue;
-            }
-            const double d = nms_d2(qx, qy, qz, c.x, c.y, c.z);
-            if (d > T) continue;
-            ++cnt;
-            if (larger && d <= td) {  // ties in attention: position 0 (self) wins the argmax
-                const int k = __ldg(srt + e);
-                if (d < td || k < tk) {
-                    td = d;
-                    tk = k;
-                    td_hi = __double2float_ru(d) * 1.00002f;
-                }
-            }
-        }
-    }
+    // the warp's cells: one row, at most three cells wide -> walk the union together
+    const int cx_min = __reduce_min_sync(kFull, cx), cx_max = __reduce_max_sync(kFull, cx);
+    const bool together = __all_sync(kFull, cy == __shfl_sync(kFull, cy, 0)) && cx_max - cx_min <= 2;
+    const int wx_lo = max(cx_min - 1, 0), wx_hi = min(cx_max + 1, g.nx - 1);
+    float4 *tile = tiles[threadIdx.x >> 5];
+    NmsThreat s;
+    s.cnt = 0; s.td = 1.0e300; s.td_hi = 3.4e38f; s.tk = 0x7fffffff;
+    int before = 0;
+    if (together) nms_walk_warp<false>(q, s, 0.f, before, cs, g.nx, y_lo, y_hi, wx_lo, wx_hi, pts, srt, tile, lane);
+    else nms_walk_lane<false>(q, s, 0.f, before, cs, g.nx, y_lo, y_hi, x_lo, x_hi, pts, srt);
     unsigned char kp = 1;
-    if (tk != 0x7fffffff) {
-        kp = 0;
-        if (cnt > num_neighbors - 1) {
-            int before = 0;
-            const float td_lo = __double2float_rd(td) * 0.99998f;  // d2f < td_lo  =>  d < td
-            for (int yy = y_lo; yy <= y_hi; ++yy) {
-                const int e1 = cs[yy * g.nx + x_hi + 1];
-                for (int e = cs[yy * g.nx + x_lo]; e < e1; ++e) {
-                    if (e == t) continue;
-                    const float4 c = __ldg(pts + e);
-                    const float fx = me.x - c.x, fy = me.y - c.y, fz = me.z - c.z;
-                    const float d2f = fx * fx + fy * fy + fz * fz;
-                    if (d2f > t_hi || d2f > td_hi) continue;  // outside, or behind the threat, for sure
-                    if (d2f < t_lo && d2f < td_lo) {          // inside and in front of the threat for sure
-                        ++before;
-                        continue;
-                    }
-                    const double d = nms_d2(qx, qy, qz, c.x, c.y, c.z);
-                    if (d > T) continue;
-                    before += (d < td || (d == td && __ldg(srt + e) < tk)) ? 1 : 0;
-                }
-            }
-            if (before >= num_neighbors - 1) kp = 1;  // the threat is not among the neighbours the tree returns
-        }
+    const bool again = s.tk != 0x7fffffff && s.cnt > num_neighbors - 1;  // the tree only returns the num_neighbors-1 nearest
+    if (s.tk != 0x7fffffff) kp = 0;
+    const float td_lo = again ? __double2float_rd(s.td) * 0.99998f : 0.f;  // d2f < td_lo  =>  d < td
+    if (together) {
+        if (__any_sync(kFull, again)) nms_walk_warp<true>(q, s, td_lo, before, cs, g.nx, y_lo, y_hi, wx_lo, wx_hi, pts, srt, tile, lane);
+    } else if (again) {
+        nms_walk_lane<true>(q, s, td_lo, before, cs, g.nx, y_lo, y_hi, x_lo, x_hi, pts, srt);
     }
-    keep[static_cast<size_t>(batch) * n + q] = kp;
-}
-
-__global__ void __launch_bounds__(1024)
-nms_max_kernel(int n, const float *__restrict__ attention, float *__restrict__ maxatt) {
-    __shared__ float red[32];
-    const float *att = attention + static_cast<size_t>(blockIdx.x) * n;
-    float m = -3.4e38f;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) m = fmaxf(m, att[k]);
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, s));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        m = red[threadIdx.x];
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, s));
-        if (threadIdx.x == 0) maxatt[blockIdx.x] = m;
-    }
+    if (again && before >= num_neighbors - 1) kp = 1;  // the threat is not among the neighbours the tree returns
+    if (t0 < n) keep[static_cast<size_t>(batch) * n + qi] = kp;
 }
 
 __global__ void nms_compact_kernel(int n, double ratio, const float *__restrict__ attention, const unsigned char *__restrict__ keep,
@@ -493,8 +564,10 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     cudaError_t e = cudaMemsetAsync(base, 0, head + static_cast<size_t>(b) * cells * sizeof(int), st);  // counters + cell counts
     if (e != cudaSuccess) return fail(static_cast<int>(e), "nms: memset");
     const double grid_radius = nms_radius;
-    nms_bbox_kernel<<<b, 1024, 0, st>>>(n, xyz, bbox);
-    int rc = check_launch("nms_bbox_kernel");
+    // (the stripes' results sit in `list` until nms_compact fills it; the tickets in the zeroed dense_count)
+    const int stripes = n >= 8192 ? min(64, n / 2048) : 1;
+    nms_bbox_max_kernel<<<dim3(stripes, b), 1024, 0, st>>>(n, xyz, attention, reinterpret_cast<float *>(list), dense_count, bbox, maxatt);
+    int rc = check_launch("nms_bbox_max_kernel");
     if (rc) return rc;
     nms_cell_count_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, grid_radius, max_cells, xyz, bbox, cell_start);
     rc = check_launch("nms_cell_count_kernel");
@@ -511,9 +584,6 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     if (rc) return rc;
     nms_keep_kernel<<<dim3((n + 127) / 128, b), 128, 0, st>>>(n, nms_radius, num_neighbors, max_cells, bbox, cell_start, sorted, sorted_pts, keep);
     rc = check_launch("nms_keep_kernel");
-    if (rc) return rc;
-    nms_max_kernel<<<b, 1024, 0, st>>>(n, attention, maxatt);
-    rc = check_launch("nms_max_kernel");
     if (rc) return rc;
     nms_compact_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, min_response_ratio, attention, keep, maxatt, list, count);
     rc = check_launch("nms_compact_kernel");

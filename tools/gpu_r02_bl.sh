@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU session bl: NMS top-K by radix select over (attention key, index); nms_keep with a float32 look before the float64 distance -- NMS tests, W4 flow, kernel list
+# round 2, GPU session bl: NMS top-K by radix select; nms_keep: float32 look first, warps walk the union of their candidates through a shared tile; bbox + max in one launch -- NMS tests, W4 flow, kernel list
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_nms_gpu.py -m gpu -x -q > gpurun_out/r02bl_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -15 gpurun_out/r02bl_pytest.log
 if [ $rc -ne 0 ]; then exit 0; fi
