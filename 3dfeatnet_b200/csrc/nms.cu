@@ -426,7 +426,17 @@ nms_topk_kernel(int n, int max_keypoints, const float *__restrict__ attention, c
     unsigned *ky = keys + static_cast<size_t>(batch) * n;
     int *cd = cand + static_cast<size_t>(batch) * n;
     int *out = out_idx + static_cast<size_t>(batch) * max_keypoints;
-    for (int e = tid; e < cnt; e += 1024) ky[e] = nms_okey(att[lst[e]]);
+    for (int e0 = tid; e0 < cnt; e0 += 4096) {  // (four independent index -> attention chains in flight)
+        int id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) id[u] = e0 + u * 1024 < cnt ? lst[e0 + u * 1024] : 0;
+        float a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = att[id[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (e0 + u * 1024 < cnt) ky[e0 + u * 1024] = nms_okey(a[u]);
+    }
     if (tid == 0) s_m = 0;
     __syncthreads();
     unsigned long long thr = 0;  // the kept survivors: (key, index) >= thr
@@ -436,14 +446,23 @@ nms_topk_kernel(int n, int max_keypoints, const float *__restrict__ attention, c
         for (int shift = 56; shift >= 0; shift -= 8) {
             for (int d = tid; d < 256; d += 1024) hist[d] = 0;
             __syncthreads();
-            for (int e0 = 0; e0 < cnt; e0 += 1024) {  // (whole warps take part in the match)
-                const int e = e0 + tid;
-                unsigned long long v = e < cnt ? static_cast<unsigned long long>(ky[e]) << 32 : 0ull;
-                if (shift < 32 && e < cnt) v |= static_cast<unsigned>(lst[e]);
-                const bool in = e < cnt && (v & mask) == prefix;
-                const unsigned d = in ? static_cast<unsigned>(v >> shift) & 255u : 256u;
-                const unsigned same = __match_any_sync(kFull, d);
-                if (in && lane == __ffs(same) - 1) atomicAdd(&hist[d], __popc(same));
+            for (int e0 = 0; e0 < cnt; e0 += 4096) {  // (whole warps take part in the match; four loads per thread in flight)
+                unsigned kk[4], ii[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * 1024 + tid;
+                    kk[u] = e < cnt ? ky[e] : 0u;
+                    ii[u] = shift < 32 && e < cnt ? static_cast<unsigned>(lst[e]) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * 1024 + tid;
+                    const unsigned long long v = static_cast<unsigned long long>(kk[u]) << 32 | ii[u];
+                    const bool in = e < cnt && (v & mask) == prefix;
+                    const unsigned d = in ? static_cast<unsigned>(v >> shift) & 255u : 256u;
+                    const unsigned same = __match_any_sync(kFull, d);
+                    if (in && lane == __ffs(same) - 1) atomicAdd(&hist[d], __popc(same));
+                }
             }
             __syncthreads();
             if (tid == 0) {
@@ -469,8 +488,18 @@ nms_topk_kernel(int n, int max_keypoints, const float *__restrict__ attention, c
         }
         thr = prefix;
     }
-    for (int e = tid; e < cnt; e += 1024)
-        if (((static_cast<unsigned long long>(ky[e]) << 32) | static_cast<unsigned>(lst[e])) >= thr) cd[atomicAdd(&s_m, 1)] = e;
+    for (int e0 = tid; e0 < cnt; e0 += 4096) {
+        unsigned kk[4], ii[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 1024;
+            kk[u] = e < cnt ? ky[e] : 0u;
+            ii[u] = e < cnt ? static_cast<unsigned>(lst[e]) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (e0 + u * 1024 < cnt && (static_cast<unsigned long long>(kk[u]) << 32 | ii[u]) >= thr) cd[atomicAdd(&s_m, 1)] = e0 + u * 1024;
+    }
     __syncthreads();
     const int M = s_m;  // = min(cnt, max_keypoints)
     for (int c0 = 0; c0 < M; c0 += 1024) {  // (all threads walk the staging loop)

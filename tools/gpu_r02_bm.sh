@@ -1,0 +1,8 @@
+#!/bin/bash
+# round 2, GPU session bm: NMS pass (top-K loops with four loads in flight) -- NMS tests, W4 flow, kernel list, C5 file flow on one GPU
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_nms_gpu.py -m gpu -x -q > gpurun_out/r02bm_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -5 gpurun_out/r02bm_pytest.log
+if [ $rc -ne 0 ]; then exit 0; fi
+timeout 300 python tools/w4_kitti.py > gpurun_out/r02bm_w4.jsonl 2> gpurun_out/r02bm_w4.err; echo "w4 rc=$?"; cut -c1-330 gpurun_out/r02bm_w4.jsonl; tail -3 gpurun_out/r02bm_w4.err
+timeout 300 python tools/w4_profile.py 2>&1 | grep "f3d::" | cut -c1-60,140-200 | head -16
+timeout 300 python tools/c5_kitti_multi.py --scans 128 --check 4 > gpurun_out/r02bm_c5_1gpu.json 2> gpurun_out/r02bm_c5_1gpu.err; echo "c5 rc=$?"; cut -c1-700 gpurun_out/r02bm_c5_1gpu.json; tail -2 gpurun_out/r02bm_c5_1gpu.err
