@@ -387,139 +387,182 @@ nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const fl
     if (t0 < n) keep[static_cast<size_t>(batch) * n + qi] = kp;
 }
 
+// Survivors' attentions lie in (threshold, max]: a monotone map of that interval onto kNmsBuckets buckets (float subtraction, product and
+// truncation are all monotone) lets the compaction histogram them on the side -- the top-K selection then reads which bucket the K-th best
+// falls into instead of searching for it.
+constexpr int kNmsBuckets = 2048;
+__device__ __forceinline__ int nms_bucket(float a, float lo, float scale) {
+    const int v = static_cast<int>((a - lo) * scale);
+    return v < 0 ? 0 : (v >= kNmsBuckets ? kNmsBuckets - 1 : v);
+}
 __global__ void nms_compact_kernel(int n, double ratio, const float *__restrict__ attention, const unsigned char *__restrict__ keep,
-                                   const float *__restrict__ maxatt, int *__restrict__ list, int *__restrict__ count) {
+                                   const float *__restrict__ maxatt, int *__restrict__ list, int *__restrict__ bucket, int *__restrict__ count,
+                                   int *__restrict__ hist) {
     const int batch = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const double thresh = static_cast<double>(maxatt[batch]) * ratio;  // float32 scalar * python float -> float64 (NumPy 1.19)
-    if (keep[static_cast<size_t>(batch) * n + k] == 1 && static_cast<double>(attention[static_cast<size_t>(batch) * n + k]) > thresh) {
+    const float mx = maxatt[batch];
+    const double thresh = static_cast<double>(mx) * ratio;  // float32 scalar * python float -> float64 (NumPy 1.19)
+    const float a = attention[static_cast<size_t>(batch) * n + k];
+    if (keep[static_cast<size_t>(batch) * n + k] == 1 && static_cast<double>(a) > thresh) {
+        const float lo = __double2float_rd(thresh);
+        float scale = static_cast<float>(kNmsBuckets) / (mx - lo);
+        if (!(scale > 0.0f && scale < 3.0e38f)) scale = 0.0f;  // (max == threshold, infinities: one bucket)
+        const int bk = nms_bucket(a, lo, scale);
         const int pos = atomicAdd(count + batch, 1);
         list[static_cast<size_t>(batch) * n + pos] = k;
+        bucket[static_cast<size_t>(batch) * n + pos] = bk;
+        atomicAdd(hist + batch * kNmsBuckets + bk, 1);
     }
 }
 
 // The max_keypoints best survivors in (attention, index) DESCENDING order -- out_idx[rank] = point index -- without ranking every survivor
-// against every other one (a KITTI-shape scan leaves tens of thousands; the all-pairs count took 146 us): one CTA per cloud finds the
-// K-th best by an MSB-first radix select over the 64-bit value (order-preserving attention key, point index) -- passes of 8 bits with
-// warp-aggregated histogram updates, stopping as soon as the bucket of the K-th holds exactly what is still needed (a handful of passes
-// when the attentions differ; ties of the K-th go on into the index bits, so that a cloud of equal attentions keeps exactly K too) --
-// and ranks the K kept survivors among themselves with the reference's order.
+// against every other one (a KITTI-shape scan leaves tens of thousands; the all-pairs count took 146 us).  One CTA per cloud:
+//  1. the bucket histogram of nms_compact_kernel, summed from the top, names the bucket the K-th best falls into; survivors of higher
+//     buckets are kept outright, those of that bucket (a few dozen when the attentions differ) are the candidates for the places left;
+//  2. among the candidates, the r-th best is found by an MSB-first radix select over the 64-bit value (order-preserving attention key,
+//     point index) -- passes of 8 bits with warp-aggregated histogram updates, stopping as soon as the digit of the r-th holds exactly
+//     what is still needed; ties of the K-th go on into the index bits, so that a cloud of equal attentions keeps exactly K too;
+//  3. the K kept survivors are ranked among themselves with the reference's order.
 __device__ __forceinline__ unsigned nms_okey(float a) {  // a < b  <=>  okey(a) < okey(b);  -0 counts as +0 like the float comparison
     const unsigned u = __float_as_uint(a + 0.0f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __global__ void __launch_bounds__(1024)
-nms_topk_kernel(int n, int max_keypoints, const float *__restrict__ attention, const int *__restrict__ list, const int *__restrict__ count,
-                unsigned *__restrict__ keys, int *__restrict__ cand, int *__restrict__ out_idx) {
+nms_topk_kernel(int n, int max_keypoints, const float *__restrict__ attention, const int *__restrict__ list, const int *__restrict__ bucket,
+                const int *__restrict__ count, const int *__restrict__ bucket_hist, int *__restrict__ cand, unsigned *__restrict__ tie_key,
+                int *__restrict__ tie_pos, int *__restrict__ out_idx) {
     constexpr int kStage = 2048;
     __shared__ int hist[256];
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_r, s_m, s_done;
-    __shared__ unsigned tk[kStage];
-    __shared__ int ti[kStage];
+    __shared__ int s_r, s_m, s_t, s_done, s_cut, s_above;
+    __shared__ __align__(16) unsigned long long tv[kStage];
     const int batch = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int cnt = count[batch];
     if (cnt == 0) return;
     const int *lst = list + static_cast<size_t>(batch) * n;
+    const int *bkt = bucket + static_cast<size_t>(batch) * n;
     const float *att = attention + static_cast<size_t>(batch) * n;
-    unsigned *ky = keys + static_cast<size_t>(batch) * n;
-    int *cd = cand + static_cast<size_t>(batch) * n;
+    int *cd = cand + static_cast<size_t>(batch) * n;         // positions (in the survivor list) of the kept ones
+    unsigned *ky = tie_key + static_cast<size_t>(batch) * n;  // candidates of the cut bucket: key ...
+    int *tp = tie_pos + static_cast<size_t>(batch) * n;       // ... and position in the survivor list
     int *out = out_idx + static_cast<size_t>(batch) * max_keypoints;
-    for (int e0 = tid; e0 < cnt; e0 += 4096) {  // (four independent index -> attention chains in flight)
-        int id[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) id[u] = e0 + u * 1024 < cnt ? lst[e0 + u * 1024] : 0;
-        float a[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) a[u] = att[id[u]];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (e0 + u * 1024 < cnt) ky[e0 + u * 1024] = nms_okey(a[u]);
+    if (tid == 0) {
+        s_m = 0;
+        s_t = 0;
+        s_cut = -1;  // cnt <= max_keypoints: every survivor is kept
+        s_above = 0;
     }
-    if (tid == 0) s_m = 0;
     __syncthreads();
-    unsigned long long thr = 0;  // the kept survivors: (key, index) >= thr
-    if (cnt > max_keypoints) {
-        unsigned long long prefix = 0, mask = 0;
-        int r = max_keypoints;  // the r-th largest value among those that match the prefix
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            for (int d = tid; d < 256; d += 1024) hist[d] = 0;
-            __syncthreads();
-            for (int e0 = 0; e0 < cnt; e0 += 4096) {  // (whole warps take part in the match; four loads per thread in flight)
-                unsigned kk[4], ii[4];
+    if (cnt > max_keypoints && tid < 32) {  // 1. the bucket of the K-th best: lane l sums buckets [B - 64 (l + 1), B - 64 l) from the top
+        const int *h = bucket_hist + batch * kNmsBuckets;
+        constexpr int kPer = kNmsBuckets / 32;
+        const int top = kNmsBuckets - 1 - lane * kPer;
+        int tot = 0;
+        for (int i = 0; i < kPer; ++i) tot += h[top - i];
+        int inc = tot;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = e0 + u * 1024 + tid;
-                    kk[u] = e < cnt ? ky[e] : 0u;
-                    ii[u] = shift < 32 && e < cnt ? static_cast<unsigned>(lst[e]) : 0u;
+        for (int s = 1; s < 32; s <<= 1) {
+            const int v = __shfl_up_sync(kFull, inc, s);
+            if (lane >= s) inc += v;
+        }
+        if (inc >= max_keypoints && inc - tot < max_keypoints) {  // exactly one lane: the sum crosses K inside its buckets
+            int cum = inc - tot;
+            for (int i = 0; i < kPer; ++i) {
+                const int c = h[top - i];
+                if (cum + c >= max_keypoints) {
+                    s_cut = top - i;
+                    s_above = cum;
+                    break;
                 }
+                cum += c;
+            }
+        }
+    }
+    __syncthreads();
+    const int cut = s_cut, r0 = max_keypoints - s_above;  // r0 places left for the candidates of bucket `cut`
+    for (int e0 = tid; e0 < cnt; e0 += 4096) {
+        int bb[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = e0 + u * 1024 + tid;
-                    const unsigned long long v = static_cast<unsigned long long>(kk[u]) << 32 | ii[u];
-                    const bool in = e < cnt && (v & mask) == prefix;
+        for (int u = 0; u < 4; ++u) bb[u] = e0 + u * 1024 < cnt ? bkt[e0 + u * 1024] : -2;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (bb[u] > cut) cd[atomicAdd(&s_m, 1)] = e0 + u * 1024;
+            else if (bb[u] == cut) tp[atomicAdd(&s_t, 1)] = e0 + u * 1024;
+        }
+    }
+    __syncthreads();
+    const int T = s_t;
+    if (T > 0) {  // 2. the r0 best of the T candidates (T >= r0 by the choice of the bucket)
+        for (int c = tid; c < T; c += 1024) ky[c] = nms_okey(att[lst[tp[c]]]);
+        __syncthreads();
+        unsigned long long prefix = 0, mask = 0, thr = 0;
+        int r = r0;  // the r-th largest value among those that match the prefix
+        if (T > r0) {
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                for (int d = tid; d < 256; d += 1024) hist[d] = 0;
+                __syncthreads();
+                for (int c0 = 0; c0 < T; c0 += 1024) {  // (whole warps take part in the match)
+                    const int c = c0 + tid;
+                    unsigned long long v = c < T ? static_cast<unsigned long long>(ky[c]) << 32 : 0ull;
+                    if (shift < 32 && c < T) v |= static_cast<unsigned>(lst[tp[c]]);
+                    const bool in = c < T && (v & mask) == prefix;
                     const unsigned d = in ? static_cast<unsigned>(v >> shift) & 255u : 256u;
                     const unsigned same = __match_any_sync(kFull, d);
                     if (in && lane == __ffs(same) - 1) atomicAdd(&hist[d], __popc(same));
                 }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int cum = 0;
-                for (int d = 255; d >= 0; --d) {
-                    const int c = hist[d];
-                    if (cum + c >= r) {
-                        s_prefix = prefix | (static_cast<unsigned long long>(d) << shift);
-                        s_r = r - cum;
-                        s_done = c == r - cum;  // the whole bucket is wanted: its lower bits need no look
-                        break;
+                __syncthreads();
+                if (tid == 0) {
+                    int cum = 0;
+                    for (int d = 255; d >= 0; --d) {
+                        const int c = hist[d];
+                        if (cum + c >= r) {
+                            s_prefix = prefix | (static_cast<unsigned long long>(d) << shift);
+                            s_r = r - cum;
+                            s_done = c == r - cum;  // the whole digit is wanted: its lower bits need no look
+                            break;
+                        }
+                        cum += c;
                     }
-                    cum += c;
                 }
+                __syncthreads();
+                prefix = s_prefix;
+                r = s_r;
+                mask |= 0xffull << shift;
+                const bool done = s_done != 0;
+                __syncthreads();
+                if (done) break;
             }
-            __syncthreads();
-            prefix = s_prefix;
-            r = s_r;
-            mask |= 0xffull << shift;
-            const bool done = s_done != 0;
-            __syncthreads();
-            if (done) break;
+            thr = prefix;
         }
-        thr = prefix;
+        for (int c = tid; c < T; c += 1024)
+            if ((static_cast<unsigned long long>(ky[c]) << 32 | static_cast<unsigned>(lst[tp[c]])) >= thr) cd[atomicAdd(&s_m, 1)] = tp[c];
+        __syncthreads();
     }
-    for (int e0 = tid; e0 < cnt; e0 += 4096) {
-        unsigned kk[4], ii[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = e0 + u * 1024;
-            kk[u] = e < cnt ? ky[e] : 0u;
-            ii[u] = e < cnt ? static_cast<unsigned>(lst[e]) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (e0 + u * 1024 < cnt && (static_cast<unsigned long long>(kk[u]) << 32 | ii[u]) >= thr) cd[atomicAdd(&s_m, 1)] = e0 + u * 1024;
-    }
-    __syncthreads();
     const int M = s_m;  // = min(cnt, max_keypoints)
+    // 3. rank of a kept survivor = how many kept (key, index) values are larger than its own (the values are distinct).  The values are
+    // staged in shared memory and read two per 16-byte broadcast load: with one 4-byte load per key and per index the 1024 x 1024
+    // comparisons of a KITTI-shape scan spent 34 us on the shared-memory pipe alone.
+    auto value_at = [&](int c) {
+        const int i = lst[cd[c]];
+        return static_cast<unsigned long long>(nms_okey(att[i])) << 32 | static_cast<unsigned>(i);
+    };
     for (int c0 = 0; c0 < M; c0 += 1024) {  // (all threads walk the staging loop)
         const int c = c0 + tid;
-        const int e = c < M ? cd[c] : 0;
-        const unsigned kc = c < M ? ky[e] : 0u;
-        const int ic = c < M ? lst[e] : 0;
+        const unsigned long long vc = c < M ? value_at(c) : ~0ull;
         int rank = 0;
         for (int base = 0; base < M; base += kStage) {
-            __syncthreads();
-            for (int j = tid; j < kStage && base + j < M; j += 1024) {
-                const int ej = cd[base + j];
-                tk[j] = ky[ej];
-                ti[j] = lst[ej];
-            }
-            __syncthreads();
             const int lim = min(kStage, M - base);
-            for (int j = 0; j < lim; ++j) rank += (tk[j] > kc || (tk[j] == kc && ti[j] > ic)) ? 1 : 0;
+            __syncthreads();
+            for (int j = tid; j < ((lim + 7) & ~7); j += 1024) tv[j] = j < lim ? value_at(base + j) : 0ull;  // (0 is larger than nothing)
+            __syncthreads();
+            const ulonglong2 *t2 = reinterpret_cast<const ulonglong2 *>(tv);
+            for (int j = 0; j < (lim + 7) / 8 * 4; j += 4) {
+                const ulonglong2 a0 = t2[j], a1 = t2[j + 1], a2 = t2[j + 2], a3 = t2[j + 3];
+                rank += (a0.x > vc) + (a0.y > vc) + (a1.x > vc) + (a1.y > vc) + (a2.x > vc) + (a2.y > vc) + (a3.x > vc) + (a3.y > vc);
+            }
         }
-        if (c < M && rank < max_keypoints) out[rank] = ic;
+        if (c < M && rank < max_keypoints) out[rank] = static_cast<int>(vc & 0xffffffffu);
     }
 }
 
@@ -556,7 +599,7 @@ F3D_API size_t f3d_nms_workspace_bytes(int b, int n) {
     if (b <= 0 || n <= 0) return 256;
     const size_t bn = static_cast<size_t>(b) * n;
     const size_t cells = static_cast<size_t>(nms_max_cells(n)) + 1;
-    return bn * (1 + 4 + 4 + 4 + 16) + static_cast<size_t>(b) * cells * 8 + static_cast<size_t>(b) * 32 + 2048 +
+    return bn * (1 + 4 + 4 + 4 + 16) + static_cast<size_t>(b) * cells * 8 + static_cast<size_t>(b) * (32 + kNmsBuckets * 4) + 2048 +
            static_cast<size_t>(b) * ((cells + kScanChunk - 1) / kScanChunk) * 4 + 64;
 }
 
@@ -574,14 +617,15 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     const size_t bn = static_cast<size_t>(b) * n;
     const int max_cells = nms_max_cells(n);
     const size_t cells = static_cast<size_t>(max_cells) + 1;
-    // layout: [counts: 2b ints][maxatt: b floats][bbox: 4b floats][pad] [cell_start: b*cells ints][cursor: b*cells ints]
+    // layout: [counts: 2b ints][maxatt: b floats][bbox: 4b floats][bucket histogram: b*kNmsBuckets ints][pad] [cell_start: b*cells ints][cursor: b*cells ints]
     //         [list: bn ints][dense_list: bn ints][sorted: bn ints][sorted_pts: bn float4][keep: bn bytes]
     char *base = static_cast<char *>(workspace);
     int *count = reinterpret_cast<int *>(base);
     int *dense_count = count + b;
     float *maxatt = reinterpret_cast<float *>(dense_count + b);
     float *bbox = maxatt + b;
-    const size_t head = (static_cast<size_t>(b) * 28 + 255) & ~static_cast<size_t>(255);
+    int *bucket_hist = reinterpret_cast<int *>(bbox + 4 * b);
+    const size_t head = (static_cast<size_t>(b) * (28 + kNmsBuckets * 4) + 255) & ~static_cast<size_t>(255);
     int *cell_start = reinterpret_cast<int *>(base + head);
     int *cursor = cell_start + static_cast<size_t>(b) * cells;
     int *list = cursor + static_cast<size_t>(b) * cells;
@@ -614,11 +658,14 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     nms_keep_kernel<<<dim3((n + 127) / 128, b), 128, 0, st>>>(n, nms_radius, num_neighbors, max_cells, bbox, cell_start, sorted, sorted_pts, keep);
     rc = check_launch("nms_keep_kernel");
     if (rc) return rc;
-    nms_compact_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, min_response_ratio, attention, keep, maxatt, list, count);
+    nms_compact_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, min_response_ratio, attention, keep, maxatt, list, dense_list, count,
+                                                                 bucket_hist);
     rc = check_launch("nms_compact_kernel");
     if (rc) return rc;
-    // (dense_list and, once nms_keep has run, sorted are free: keys and kept positions of the selection)
-    nms_topk_kernel<<<b, 1024, 0, st>>>(n, max_keypoints, attention, list, count, reinterpret_cast<unsigned *>(dense_list), sorted, out_idx);
+    // (dense_list holds the survivors' buckets; once nms_keep has run, sorted and sorted_pts are free: kept positions, and keys /
+    // positions of the cut bucket's candidates)
+    nms_topk_kernel<<<b, 1024, 0, st>>>(n, max_keypoints, attention, list, dense_list, count, bucket_hist, sorted,
+                                        reinterpret_cast<unsigned *>(sorted_pts) + bn, reinterpret_cast<int *>(sorted_pts), out_idx);
     rc = check_launch("nms_topk_kernel");
     if (rc) return rc;
     nms_finalize_kernel<<<dim3((max_keypoints + 1023) / 1024, b), min(1024, ((max_keypoints + 31) / 32) * 32), 0, st>>>(
