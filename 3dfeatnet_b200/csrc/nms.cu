@@ -308,13 +308,14 @@ __device__ __forceinline__ void nms_visit_second(const NmsQuery &q, const NmsThr
     if (d > q.T) return;
     before += (d < s.td || (d == s.td && __ldg(srt + e) < s.tk)) ? 1 : 0;
 }
+// (slice, slices): this warp's share of the candidates -- every slices-th candidate of a per-lane walk, every slices-th tile of a warp walk
 template <bool kSecond>
 __device__ __forceinline__ void nms_walk_lane(const NmsQuery &q, NmsThreat &s, float td_lo, int &before, const int *__restrict__ cs, int nx,
                                               int y_lo, int y_hi, int x_lo, int x_hi, const float4 *__restrict__ pts,
-                                              const int *__restrict__ srt) {
+                                              const int *__restrict__ srt, int slice, int slices) {
     for (int yy = y_lo; yy <= y_hi; ++yy) {
         const int e1 = cs[yy * nx + x_hi + 1];
-        for (int e = cs[yy * nx + x_lo]; e < e1; ++e) {  // the cells of one grid row are contiguous
+        for (int e = cs[yy * nx + x_lo] + slice; e < e1; e += slices) {  // the cells of one grid row are contiguous
             const float4 c = __ldg(pts + e);
             if (kSecond) nms_visit_second(q, s, td_lo, before, c, e, srt);
             else nms_visit_first(q, s, c, e, srt);
@@ -324,15 +325,15 @@ __device__ __forceinline__ void nms_walk_lane(const NmsQuery &q, NmsThreat &s, f
 template <bool kSecond>
 __device__ __forceinline__ void nms_walk_warp(const NmsQuery &q, NmsThreat &s, float td_lo, int &before, const int *__restrict__ cs, int nx,
                                               int y_lo, int y_hi, int x_lo, int x_hi, const float4 *__restrict__ pts,
-                                              const int *__restrict__ srt, float4 *tile, int lane) {
+                                              const int *__restrict__ srt, float4 *tile, int lane, int slice, int slices) {
     for (int yy = y_lo; yy <= y_hi; ++yy) {  // (bounds are the warp's: every lane walks the same candidates)
-        const int e0 = cs[yy * nx + x_lo], e1 = cs[yy * nx + x_hi + 1];
+        const int e0 = cs[yy * nx + x_lo] + 32 * slice, e1 = cs[yy * nx + x_hi + 1];
         float4 next = e0 + lane < e1 ? __ldg(pts + e0 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int base = e0; base < e1; base += 32) {
+        for (int base = e0; base < e1; base += 32 * slices) {
             __syncwarp();
             tile[lane] = next;
             __syncwarp();
-            if (base + 32 + lane < e1) next = __ldg(pts + base + 32 + lane);
+            if (base + 32 * slices + lane < e1) next = __ldg(pts + base + 32 * slices + lane);
             const int lim = min(32, e1 - base);
 #pragma unroll 4
             for (int j = 0; j < lim; ++j) {
@@ -343,23 +344,35 @@ __device__ __forceinline__ void nms_walk_warp(const NmsQuery &q, NmsThreat &s, f
         }
     }
 }
-__global__ void __launch_bounds__(128)
+// One CTA of kNmsSlices warps per 32 queries (lane = query in every warp): warp w takes every kNmsSlices-th tile of the candidates, the
+// partial (count, nearest threat) and `before` counts are folded through shared memory.  The kernel's time is the walk of the densest
+// group of queries (a single warp spent ~250 us on the thousands of candidates around the sensor of a KITTI-shape scan, twice when the
+// 50-NN rule asks for the second scan, while most of the device had long finished).
+constexpr int kNmsSlices = 4;
+__global__ void __launch_bounds__(32 * kNmsSlices)
 nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const float *__restrict__ bbox, const int *__restrict__ cell_start,
                 const int *__restrict__ sorted, const float4 *__restrict__ sorted_pts, unsigned char *__restrict__ keep) {
-    __shared__ float4 tiles[4][32];
-    const int batch = blockIdx.y, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;  // position in the cell-sorted order: neighbouring threads, neighbouring cells
-    if ((t0 & ~31) >= n) return;                            // (whole warps only: the lanes of a warp walk together)
+    __shared__ float4 tiles[kNmsSlices][32];
+    __shared__ NmsGrid s_grid;
+    __shared__ double s_T;
+    __shared__ double p_td[kNmsSlices][32];
+    __shared__ int p_tk[kNmsSlices][32], p_cnt[kNmsSlices][32];
+    const int batch = blockIdx.y, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_grid = nms_grid(bbox + batch * 4, radius, max_cells);
+        s_T = nms_threshold(radius);
+    }
+    __syncthreads();
+    const int t0 = blockIdx.x * 32 + lane;  // position in the cell-sorted order: neighbouring lanes, neighbouring cells
     const int t = min(t0, n - 1);
     const int *cs = cell_start + static_cast<size_t>(batch) * (max_cells + 1);
     const int *srt = sorted + static_cast<size_t>(batch) * n;
     const float4 *pts = sorted_pts + static_cast<size_t>(batch) * n;
-    const NmsGrid g = nms_grid(bbox + batch * 4, radius, max_cells);
+    const NmsGrid g = s_grid;
     const float4 me = __ldg(pts + t);
-    const int qi = __ldg(srt + t);
     NmsQuery q;
     q.x = me.x; q.y = me.y; q.z = me.z; q.a = me.w; q.t = t;
-    q.T = nms_threshold(radius);
+    q.T = s_T;
     q.t_hi = __double2float_ru(q.T * 1.00001);
     q.t_lo = __double2float_rd(q.T * 0.99999);
     const int cx = nms_cell_coord(me.x, g.x0, g.inv_h, g.nx), cy = nms_cell_coord(me.y, g.y0, g.inv_h, g.ny);
@@ -368,23 +381,44 @@ nms_keep_kernel(int n, double radius, int num_neighbors, int max_cells, const fl
     const int cx_min = __reduce_min_sync(kFull, cx), cx_max = __reduce_max_sync(kFull, cx);
     const bool together = __all_sync(kFull, cy == __shfl_sync(kFull, cy, 0)) && cx_max - cx_min <= 2;
     const int wx_lo = max(cx_min - 1, 0), wx_hi = min(cx_max + 1, g.nx - 1);
-    float4 *tile = tiles[threadIdx.x >> 5];
+    float4 *tile = tiles[wl];
     NmsThreat s;
     s.cnt = 0; s.td = 1.0e300; s.td_hi = 3.4e38f; s.tk = 0x7fffffff;
     int before = 0;
-    if (together) nms_walk_warp<false>(q, s, 0.f, before, cs, g.nx, y_lo, y_hi, wx_lo, wx_hi, pts, srt, tile, lane);
-    else nms_walk_lane<false>(q, s, 0.f, before, cs, g.nx, y_lo, y_hi, x_lo, x_hi, pts, srt);
+    if (together) nms_walk_warp<false>(q, s, 0.f, before, cs, g.nx, y_lo, y_hi, wx_lo, wx_hi, pts, srt, tile, lane, wl, kNmsSlices);
+    else nms_walk_lane<false>(q, s, 0.f, before, cs, g.nx, y_lo, y_hi, x_lo, x_hi, pts, srt, wl, kNmsSlices);
+    p_cnt[wl][lane] = s.cnt; p_td[wl][lane] = s.td; p_tk[wl][lane] = s.tk;
+    __syncthreads();
+    s.cnt = 0; s.td = 1.0e300; s.tk = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < kNmsSlices; ++w) {  // every warp folds the same partials in the same order
+        s.cnt += p_cnt[w][lane];
+        const double d = p_td[w][lane];
+        const int k = p_tk[w][lane];
+        if (d < s.td || (d == s.td && k < s.tk)) { s.td = d; s.tk = k; }
+    }
     unsigned char kp = 1;
     const bool again = s.tk != 0x7fffffff && s.cnt > num_neighbors - 1;  // the tree only returns the num_neighbors-1 nearest
     if (s.tk != 0x7fffffff) kp = 0;
+    if (!__syncthreads_or(again)) {  // (uniform over the CTA)
+        if (wl == 0 && t0 < n) keep[static_cast<size_t>(batch) * n + __ldg(srt + t)] = kp;
+        return;
+    }
+    s.td_hi = again ? __double2float_ru(s.td) * 1.00002f : 0.f;
     const float td_lo = again ? __double2float_rd(s.td) * 0.99998f : 0.f;  // d2f < td_lo  =>  d < td
     if (together) {
-        if (__any_sync(kFull, again)) nms_walk_warp<true>(q, s, td_lo, before, cs, g.nx, y_lo, y_hi, wx_lo, wx_hi, pts, srt, tile, lane);
+        nms_walk_warp<true>(q, s, td_lo, before, cs, g.nx, y_lo, y_hi, wx_lo, wx_hi, pts, srt, tile, lane, wl, kNmsSlices);
     } else if (again) {
-        nms_walk_lane<true>(q, s, td_lo, before, cs, g.nx, y_lo, y_hi, x_lo, x_hi, pts, srt);
+        nms_walk_lane<true>(q, s, td_lo, before, cs, g.nx, y_lo, y_hi, x_lo, x_hi, pts, srt, wl, kNmsSlices);
     }
+    p_cnt[wl][lane] = before;  // (the first fold's reads are behind the barrier of __syncthreads_or)
+    __syncthreads();
+    if (wl != 0) return;
+    before = 0;
+#pragma unroll
+    for (int w = 0; w < kNmsSlices; ++w) before += p_cnt[w][lane];
     if (again && before >= num_neighbors - 1) kp = 1;  // the threat is not among the neighbours the tree returns
-    if (t0 < n) keep[static_cast<size_t>(batch) * n + qi] = kp;
+    if (t0 < n) keep[static_cast<size_t>(batch) * n + __ldg(srt + t)] = kp;
 }
 
 // Survivors' attentions lie in (threshold, max]: a monotone map of that interval onto kNmsBuckets buckets (float subtraction, product and
@@ -655,7 +689,7 @@ F3D_API int f3d_nms(int b, int n, const float *xyz, const float *attention, doub
     nms_cell_fill_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, grid_radius, max_cells, xyz, attention, bbox, cursor, sorted, sorted_pts);
     rc = check_launch("nms_cell_fill_kernel");
     if (rc) return rc;
-    nms_keep_kernel<<<dim3((n + 127) / 128, b), 128, 0, st>>>(n, nms_radius, num_neighbors, max_cells, bbox, cell_start, sorted, sorted_pts, keep);
+    nms_keep_kernel<<<dim3((n + 31) / 32, b), 32 * kNmsSlices, 0, st>>>(n, nms_radius, num_neighbors, max_cells, bbox, cell_start, sorted, sorted_pts, keep);
     rc = check_launch("nms_keep_kernel");
     if (rc) return rc;
     nms_compact_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, min_response_ratio, attention, keep, maxatt, list, dense_list, count,

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU session bm: NMS top-K through the bucket histogram of the compaction -- NMS tests, W4 flow, kernel list, C5 file flow on one GPU
+# round 2, GPU session bm: nms_keep with the candidates of a query group split over the warps of a CTA -- NMS tests, W4 flow, kernel list, C5 file flow on one GPU
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_nms_gpu.py -m gpu -x -q > gpurun_out/r02bm_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -5 gpurun_out/r02bm_pytest.log
 if [ $rc -ne 0 ]; then exit 0; fi
