@@ -182,6 +182,7 @@ constexpr int kBqBuildThreads = 1024;
 // (inference.py scores every point of a 131 072-point scan): a centre walks its windows in ascending order and stops at nsample hits,
 // i.e. after ~1/30 of its candidates, and the hits of a window are ordered through 4 bitmap words per lane.
 constexpr int kBqWindowedFrom = 32768;
+constexpr int kBqMaxWpl = 8;  // bitmap words of one window per lane: window <= 8192 indices (n <= 262144, the grid path's limit)
 constexpr int kBqSparse = 1024;  // centres with at most this many candidates in all windows together take them in one pass
 __host__ __device__ inline int bq_window(int n) {  // indices per window: a multiple of 1024 (= 32 lanes x 32 bits), at most 32 windows
     if (n < kBqWindowedFrom) return n;
@@ -457,16 +458,23 @@ bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, i
         for (int s2 = 16; s2 > 0; s2 >>= 1) C += __shfl_xor_sync(kFull, C, s2);
         int H = 0, first = -1;  // hits found (all of them below nsample, at least nsample otherwise), lowest hit
         if (C > 0 && C <= kBqSparse) {
+            {  // the lane's three row ranges as one list, four loads in flight (a lone dependent load per step left the lane waiting on L2)
+                const int l0 = re[0] - rs[0], l1 = re[1] - rs[1];
+                auto at = [&](int i) { return i < l0 ? rs[0] + i : (i < l0 + l1 ? rs[1] + (i - l0) : rs[2] + (i - l0 - l1)); };
+                for (int i0 = 0; i0 < cw; i0 += 4) {
+                    float4 q[4];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                for (int i = rs[k]; i < re[k]; ++i) {
-                    const float4 q = __ldg(pts + i);
-                    if (!(sqdist_ref(cx - q.x, cy - q.y, cz - q.z) >= T)) {
-                        const int kk = __float_as_int(q.w);
-                        atomicOr(&bm[kk >> 5], 1u << (kk & 31));
-                        atomicOr(&sm[kk >> 10], 1u << ((kk >> 5) & 31));
-                    }
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u < cw) q[u] = __ldg(pts + at(i0 + u));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u < cw && !(sqdist_ref(cx - q[u].x, cy - q[u].y, cz - q[u].z) >= T)) {
+                            const int kk = __float_as_int(q[u].w);
+                            atomicOr(&bm[kk >> 5], 1u << (kk & 31));
+                            atomicOr(&sm[kk >> 10], 1u << ((kk >> 5) & 31));
+                        }
                 }
+            }
             __syncwarp();
             int mine = 0, low = 0x7fffffff;
             for (int sp = 0; sp < spl; ++sp) {
@@ -508,19 +516,19 @@ bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, i
             while (todo && H < nsample) {
                 const int wn = __ffs(todo) - 1;
                 todo &= todo - 1;
-                // the window's three row ranges as ONE candidate list, four candidates per lane in flight (each step of the walk is a
+                // the window's three row ranges as ONE candidate list, eight candidates per lane in flight (each step of the walk is a
                 // round trip to L2: the per-warp bitmaps leave the SM little L1)
                 const int s0 = __shfl_sync(kFull, rs[0], wn), s1 = __shfl_sync(kFull, rs[1], wn), s2 = __shfl_sync(kFull, rs[2], wn);
                 const int l0 = __shfl_sync(kFull, re[0], wn) - s0, l1 = __shfl_sync(kFull, re[1], wn) - s1;
                 const int lt = l0 + l1 + __shfl_sync(kFull, re[2], wn) - s2;
                 auto at = [&](int i) { return i < l0 ? s0 + i : (i < l0 + l1 ? s1 + (i - l0) : s2 + (i - l0 - l1)); };
-                for (int i0 = lane; i0 < lt; i0 += 128) {
-                    float4 q[4];
+                for (int i0 = lane; i0 < lt; i0 += 256) {
+                    float4 q[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < 8; ++u)
                         if (i0 + 32 * u < lt) q[u] = __ldg(pts + at(i0 + 32 * u));
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < 8; ++u)
                         if (i0 + 32 * u < lt && !(sqdist_ref(cx - q[u].x, cy - q[u].y, cz - q[u].z) >= T)) {
                             const int kk = __float_as_int(q[u].w);
                             atomicOr(&bm[kk >> 5], 1u << (kk & 31));
@@ -530,10 +538,12 @@ bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, i
                 unsigned *wb = bm + static_cast<size_t>(wn) * (win >> 5) + lane * wpl;  // this lane's words of the window
                 const int wbase = wn * win + lane * wpl * 32;
                 int mine = 0, low = 0x7fffffff;
-                for (int t = 0; t < wpl; ++t) {
-                    const unsigned word = (wbase + t * 32 < n) ? wb[t] : 0u;
-                    mine += __popc(word);
-                    if (word && low == 0x7fffffff) low = wbase + t * 32 + __ffs(word) - 1;
+                unsigned wd[kBqMaxWpl];  // the lane's words of the window, in registers for the count and the emission
+#pragma unroll
+                for (int t = 0; t < kBqMaxWpl; ++t) {
+                    wd[t] = (t < wpl && wbase + t * 32 < n) ? wb[t] : 0u;
+                    mine += __popc(wd[t]);
+                    if (wd[t] && low == 0x7fffffff) low = wbase + t * 32 + __ffs(wd[t]) - 1;
                 }
                 int inc = mine;
 #pragma unroll
@@ -542,9 +552,9 @@ bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, i
                 const unsigned owners = __ballot_sync(kFull, mine > 0);
                 if (first < 0 && owners) first = __shfl_sync(kFull, low, __ffs(owners) - 1);
                 int pos = H + inc - mine;
-                for (int t = 0; t < wpl; ++t) {
-                    if (wbase + t * 32 >= n) break;
-                    unsigned word = wb[t];
+#pragma unroll
+                for (int t = 0; t < kBqMaxWpl; ++t) {
+                    unsigned word = wd[t];
                     if (!word) continue;
                     wb[t] = 0;
                     while (word && pos < nsample) {

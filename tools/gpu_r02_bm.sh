@@ -1,7 +1,7 @@
 #!/bin/bash
-# round 2, GPU session bm: nms_keep with the candidates of a query group split over the warps of a CTA -- NMS tests, W4 flow, kernel list, C5 file flow on one GPU
+# round 2, GPU session bm: windowed ball query -- window words in registers, four loads in flight in the sparse pass, eight in the dense one -- op + NMS tests, W4 flow, kernel list, C5 file flow on one GPU
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_nms_gpu.py -m gpu -x -q > gpurun_out/r02bm_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -5 gpurun_out/r02bm_pytest.log
+timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_nms_gpu.py -m gpu -x -q > gpurun_out/r02bm_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -5 gpurun_out/r02bm_pytest.log
 if [ $rc -ne 0 ]; then exit 0; fi
 timeout 300 python tools/w4_kitti.py > gpurun_out/r02bm_w4.jsonl 2> gpurun_out/r02bm_w4.err; echo "w4 rc=$?"; cut -c1-330 gpurun_out/r02bm_w4.jsonl; tail -3 gpurun_out/r02bm_w4.err
 timeout 300 python tools/w4_profile.py 2>&1 | grep "f3d::" | cut -c1-60,140-200 | head -16
