@@ -408,7 +408,7 @@ bq_grid_query_kernel(int b, int n, int m, float radius, int nsample, const float
 __global__ void __launch_bounds__(256)
 bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, int nsample, const float4 *__restrict__ sorted,
                          const int *__restrict__ cell_start, BqGridInfo *info, const float *__restrict__ xyz2, int *__restrict__ idx,
-                         int *__restrict__ pts_cnt, const float4 *__restrict__ centres_sorted) {
+                         int *__restrict__ pts_cnt, const float4 *__restrict__ centres_sorted, int alias_off, int alias_span) {
     extern __shared__ unsigned bq_bitmap[];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int nwords = (n + 31) >> 5;
@@ -420,7 +420,10 @@ bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, i
     __syncwarp();
     const float T = ball_threshold(radius);
     const int wpl = win >> 10;                         // bitmap words of one window per lane
-    const long long total_warps = static_cast<long long>(gridDim.x) * wpc, centres = static_cast<long long>(b) * m;
+    // alias_off >= 0 (one cloud): the centres ARE points alias_off .. alias_off + m - 1 of the cloud (same memory), centres_sorted is the
+    // cloud's own binning from the first window that holds one of them on, alias_span records long: records of other points are skipped
+    const long long total_warps = static_cast<long long>(gridDim.x) * wpc,
+                    centres = alias_off >= 0 ? static_cast<long long>(alias_span) : static_cast<long long>(b) * m;
     // centre record (x, y, z, row): from the centres' own spatial binning when there is one (.w = the centre's index), else in order
     auto load_centre = [&](long long w) -> float4 {
         if (w >= centres) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -430,11 +433,15 @@ bq_grid_query_win_kernel(int b, int n, int m, int win, int nwin, float radius, i
     };
     float4 rec_next = load_centre(static_cast<long long>(blockIdx.x) * wpc + wl);
     for (long long w = static_cast<long long>(blockIdx.x) * wpc + wl; w < centres; w += total_warps) {
-        const int batch = static_cast<int>(w / m);
+        const int batch = alias_off >= 0 ? 0 : static_cast<int>(w / m);
         const float4 rec = rec_next;
         rec_next = load_centre(w + total_warps);  // in flight under this centre's walk
         const float cx = rec.x, cy = rec.y, cz = rec.z;
-        const int j = __float_as_int(rec.w);
+        int j = __float_as_int(rec.w);
+        if (alias_off >= 0) {
+            j -= alias_off;
+            if (j < 0 || j >= m) continue;  // (the whole warp: one centre per warp)
+        }
         const BqGridInfo gi = info[batch];
         const float4 *pts = sorted + static_cast<size_t>(batch) * n;
         int *row = idx + (static_cast<size_t>(batch) * m + j) * nsample;
@@ -770,7 +777,20 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
     // with at least kBqSortCentres centres per cloud and room for a second binning in the workspace, the centres are binned too
     const float4 *centres_sorted = nullptr;
     const size_t off2 = (f3d_query_ball_point_workspace_bytes(b, n) + 255) & ~static_cast<size_t>(255);
-    if (m >= kBqSortCentres && m <= 262144 && workspace_bytes >= off2 + f3d_query_ball_point_workspace_bytes(b, m)) {
+    // centres that are a slice of the cloud itself (inference.py:118-131 scores every point of a scan, MAX_POINTS centres at a time): the
+    // cloud's binning already holds them in a spatial order, window by window -- no second binning (26 us per chunk of a KITTI-shape scan)
+    int alias_off = -1, alias_span = 0;
+    if (b == 1 && n >= kBqWindowedFrom && m >= kBqSortCentres) {
+        const uintptr_t p1 = reinterpret_cast<uintptr_t>(xyz1), p2 = reinterpret_cast<uintptr_t>(xyz2);
+        if (p2 >= p1 && (p2 - p1) % 12 == 0 && (p2 - p1) / 12 + static_cast<uintptr_t>(m) <= static_cast<uintptr_t>(n)) {
+            alias_off = static_cast<int>((p2 - p1) / 12);
+            const int win = bq_window(n), first = alias_off / win * win;
+            const long long last = (static_cast<long long>(alias_off) + m - 1) / win * win + win;
+            alias_span = static_cast<int>((last < n ? last : n) - first);
+            centres_sorted = ws.sorted + first;
+        }
+    }
+    if (alias_off < 0 && m >= kBqSortCentres && m <= 262144 && workspace_bytes >= off2 + f3d_query_ball_point_workspace_bytes(b, m)) {
         const BqWorkspace w2 = bq_workspace(b, m, static_cast<char *>(workspace) + off2);
         bq_grid_build_kernel<<<b, kBqBuildThreads, 0, st>>>(m, m, radius, xyz2, w2.sorted, w2.cell_start, w2.info);  // one window: a spatial order
         const int rc2 = check_launch("bq_grid_build_kernel");
@@ -788,10 +808,10 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
         e = cudaFuncSetAttribute(bq_grid_query_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return fail(static_cast<int>(e), "bq_grid_query_win: cudaFuncSetAttribute");
         const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024))));
-        const unsigned need = blocks_for(w, wpc), cap = static_cast<unsigned>(num_sms) * per_sm;
+        const unsigned need = blocks_for(alias_off >= 0 ? alias_span : w, wpc), cap = static_cast<unsigned>(num_sms) * per_sm;
         bq_grid_query_win_kernel<<<need < cap ? need : cap, wpc * 32, smem, st>>>(b, n, m, bq_window(n), bq_num_windows(n), radius, nsample,
                                                                                ws.sorted, ws.cell_start, ws.info, xyz2, idx, pts_cnt,
-                                                                               centres_sorted);
+                                                                               centres_sorted, alias_off, alias_span);
     } else {
         bq_grid_query_kernel<<<blocks_for(w, wpc), wpc * 32, smem, st>>>(b, n, m, radius, nsample, ws.sorted, ws.cell_start, ws.info, xyz2,
                                                                         idx, pts_cnt, centres_sorted);

@@ -167,6 +167,29 @@ def test_ball_query_bit_exact_vs_oracle(cuda, kind, b, n, m, radius, ns, mode):
         assert (wcnt == 0).any()  # the fallback path was exercised
 
 
+@pytest.mark.parametrize("kind,n,start,m,ns", [("kitti", 131072, 0, 30000, 64), ("kitti", 131072, 30000, 30000, 64),
+                                               ("kitti", 131072, 120000, 11072, 64), ("dups", 40000, 4097, 5000, 16),
+                                               ("uniform", 33000, 28000, 5000, 32), ("kitti", 262144, 250000, 8000, 64)])
+def test_ball_query_centres_that_are_a_slice_of_the_cloud(cuda, kind, n, start, m, ns):
+    """inference.py:118-131 scores every point of a scan, MAX_POINTS centres at a time: the centres are points start .. start + m - 1 of the
+    cloud, handed over as a view of the same memory -- the windowed kernel then takes them in the order of the cloud's own binning (no
+    second binning), rows still at the centre's own index; chunk borders fall inside index windows"""
+    tg = pkg("tf_ops.grouping.tf_grouping")
+    x = clouds(kind, 1, n, 11 + n)
+    radius = 2.0
+    widx, wcnt = oops.query_ball_point(radius, ns, x, np.ascontiguousarray(x[:, start:start + m]))
+    xd = T(x, cuda)
+    view = xd[:, start:start + m, :]
+    assert view.is_contiguous() and view.data_ptr() == xd.data_ptr() + 12 * start
+    idx, cnt = tg.query_ball_point(radius, ns, xd, view)
+    assert np.array_equal(cnt.cpu().numpy(), wcnt) and np.array_equal(idx.cpu().numpy(), widx)
+    grid = tg.BallGrid(radius, xd, max_centres=m)   # the file flow's form: one binning, a query per chunk
+    idx2, cnt2 = tg.query_ball_point(radius, ns, xd, view, grid=grid)
+    assert torch.equal(idx2, idx) and torch.equal(cnt2, cnt)
+    idx3, cnt3 = tg.query_ball_point(radius, ns, xd, view.clone(), grid=grid)  # a copy of the centres: the binned-centres path, same rows
+    assert torch.equal(idx3, idx) and torch.equal(cnt3, cnt)
+
+
 def test_ball_query_radius_on_representable_boundaries(cuda):
     """points at exactly d == r (not a hit: strict '<'), one ulp inside, one ulp outside; radii 0.5, 2.0, sqrt-inexact 0.3"""
     tg = pkg("tf_ops.grouping.tf_grouping")

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU session bm: windowed ball query -- window words in registers, four loads in flight in the sparse pass, eight in the dense one -- op + NMS tests, W4 flow, kernel list, C5 file flow on one GPU
+# round 2, GPU session bm: windowed ball query takes centres that are a slice of the cloud in the order of the cloud's own binning -- op + NMS tests, W4 flow, kernel list, C5 file flow on one GPU
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_nms_gpu.py -m gpu -x -q > gpurun_out/r02bm_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -5 gpurun_out/r02bm_pytest.log
 if [ $rc -ne 0 ]; then exit 0; fi
