@@ -83,7 +83,9 @@ int f3d_query_ball_point(int b, int n, int m, float radius, int nsample, const f
  * order, so that the warps of a CTA share their candidate cells (same rows, each written at its centre's own index).
  * Clouds of n >= 32768 points are binned per index window (<= 32 windows of consecutive indices, one cell table each; the workspace size
  * accounts for it): a centre walks its windows in ascending order and stops at nsample hits -- the reference's break at cnt == nsample,
- * tf_grouping_g.cu:31-46 -- instead of testing every point of its 3x3 cells (thousands in a KITTI-shape scan). */
+ * tf_grouping_g.cu:31-46 -- instead of testing every point of its 3x3 cells (thousands in a KITTI-shape scan).  When xyz2 points INTO
+ * xyz1 (one cloud, the centres are points of the cloud itself, as in inference.py:118-131) the centres are visited in the order of the
+ * cloud's binning; the rows written are the same. */
 size_t f3d_query_ball_point_workspace_bytes(int b, int n);
 int f3d_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
                             int *pts_cnt, void *workspace, size_t workspace_bytes, void *stream);
