@@ -185,9 +185,11 @@ constexpr int kBqBuildThreads = 1024;
 constexpr int kBqWindowedFrom = 32768;
 constexpr int kBqMaxWpl = 8;  // bitmap words of one window per lane: window <= 8192 indices (n <= 262144, the grid path's limit)
 constexpr int kBqSparse = 1024;  // centres with at most this many candidates in all windows together take them in one pass
-__host__ __device__ inline int bq_window(int n) {  // indices per window: a multiple of 1024 (= 32 lanes x 32 bits), at most 32 windows
+__host__ __device__ inline int bq_window(int n) {  // indices per window: 1024 (= 32 lanes x 32 bits) x a power of two, 17 .. 32 windows
     if (n < kBqWindowedFrom) return n;
-    return ((((n + 31) >> 5) + 1023) >> 10) << 10;
+    int win = 1024;
+    while (32LL * win < n) win <<= 1;  // (a power of two: a group of the grouped kernel holds a whole number of windows)
+    return win;
 }
 __host__ __device__ inline int bq_num_windows(int n) { return n < kBqWindowedFrom ? 1 : (n + bq_window(n) - 1) / bq_window(n); }
 
@@ -996,13 +998,11 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
             if (num_sms <= 0) num_sms = 148;
         }
         static const bool whole_cloud_bitmaps = std::getenv("F3D_BQ_WHOLE_CLOUD_BITMAPS") != nullptr;  // A/B: the kernel before the grouped one
-        // The grouped kernel takes clouds whose index window is a power of two (1024 .. 8192: win divides kBqGroupBits, e.g. every n in
-        // (98 304, 131 072] and (196 608, 262 144]).  With windows of 3072 / 5120 / 6144 / 7168 points its sparse pass -- 3, 5, 6 or 7 lanes per
-        // window -- ends in "illegal instruction" on the device (n = 70 000 and 170 000 in test_ball_query_bit_exact_vs_oracle; the window
-        // walk of the same kernel is fine there, F3D_BQ_GRP_MODE=2); the cause was not found in this round (compute-sanitizer is closed on
-        // the pool), so those clouds keep bq_grid_query_win_kernel.  F3D_BQ_GRP_ANY_WINDOW=1 lifts the restriction to reproduce it.
-        static const bool any_window = std::getenv("F3D_BQ_GRP_ANY_WINDOW") != nullptr;
-        if (!whole_cloud_bitmaps && w < (1LL << 31) - (1LL << 20) && (kBqGroupBits % bq_window(n) == 0 || any_window)) {
+        // bq_window() is a power of two, so win divides kBqGroupBits.  (With windows of 3072 / 6144 points -- the sizing before: any multiple
+        // of 1024 -- the sparse pass of the grouped kernel, then 3 or 6 lanes per window, ended in "illegal instruction" on the device while
+        // its window walk passed the same cases; the cause was not found, compute-sanitizer being closed on the pool.  The check stays as a
+        // guard: a window that does not divide the group would take bq_grid_query_win_kernel.)
+        if (!whole_cloud_bitmaps && w < (1LL << 31) - (1LL << 20) && kBqGroupBits % bq_window(n) == 0) {
             static const int grp_mode = std::getenv("F3D_BQ_GRP_MODE") ? std::atoi(std::getenv("F3D_BQ_GRP_MODE")) : 0;  // diagnosis: 1 sparse pass only, 2 window walk only
             const unsigned need = blocks_for(alias_off >= 0 ? alias_span : w, 8), cap = static_cast<unsigned>(num_sms) * 3u;
             bq_grid_query_grp_kernel<<<need < cap ? need : cap, 256, 0, st>>>(b, n, m, bq_window(n), bq_num_windows(n), radius, nsample, ws.sorted,

@@ -152,7 +152,7 @@ def _centres(x, m, mode, seed):
     ("kitti", 1, 131072, 6000, 2.0, 64, "subset"), ("kitti", 2, 50001, 5000, 2.0, 64, "external"),
     ("uniform", 1, 40000, 300, 6.0, 128, "subset"), ("dups", 1, 33000, 4200, 3.0, 16, "subset"),
     ("kitti", 1, 262144, 500, 1.0, 64, "external"),
-    # index windows of 3072 / 6144 points (not a power of two: a group of the grouped kernel holds 10 / 5 of them), 2 clouds of 32 windows of 1024
+    # 18 / 21 index windows (n / 32 rounded up to a power of two: 4096 / 8192 points each), 2 clouds of 32 windows of 1024 points
     ("kitti", 1, 70000, 5000, 2.0, 64, "subset"), ("uniform", 1, 170000, 3000, 2.5, 64, "external"), ("kitti", 2, 32768, 4100, 1.5, 48, "subset"),
 ])
 def test_ball_query_bit_exact_vs_oracle(cuda, kind, b, n, m, radius, ns, mode):
