@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2, GPU session bt: grouped windowed ball query (power-of-two index windows; other windows keep the whole-cloud-bitmap kernel) -- op + NMS
 # tests, the grouped kernel forced onto windows of 3072 / 6144 points (diagnosis), W4 flow, kernel list with both kernels, C5 on one GPU
+# (F3D_BQ_GRP_ANY_WINDOW existed at that commit only)
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_nms_gpu.py -m gpu -x -q > gpurun_out/r02bt_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -3 gpurun_out/r02bt_pytest.log
 echo "== any window:"; F3D_BQ_GRP_ANY_WINDOW=1 timeout 120 python -m pytest tests/test_ops_gpu.py -m gpu -x -q -k "70000 and not 170000" 2>&1 | tail -1
