@@ -665,7 +665,8 @@ bq_grid_query_grp_kernel(int b, int n, int m, int win, int nwin, float radius, i
                 const int wsrc = serves ? w0 + lane_win : 0, sub = lane_sub;
                 const int a0 = __shfl_sync(kFull, rs[0], wsrc), a1 = __shfl_sync(kFull, rs[1], wsrc), a2 = __shfl_sync(kFull, rs[2], wsrc);
                 const int l0 = __shfl_sync(kFull, re[0], wsrc) - a0, l1 = __shfl_sync(kFull, re[1], wsrc) - a1;
-                const int lt = serves ? l0 + l1 + __shfl_sync(kFull, re[2], wsrc) - a2 : 0;
+                const int e2 = __shfl_sync(kFull, re[2], wsrc);  // (by every lane: inside `serves ? ... : 0` the lanes that sit out skipped
+                const int lt = serves ? l0 + l1 + e2 - a2 : 0;   //  a full-mask shuffle -- the fault of the 3072 / 6144-point windows)
                 auto at = [&](int i) { return i < l0 ? a0 + i : (i < l0 + l1 ? a1 + (i - l0) : a2 + (i - l0 - l1)); };
                 for (int i0 = sub; i0 < lt; i0 += 4 * wpl) {
                     float4 q[4];
@@ -999,9 +1000,10 @@ F3D_API int f3d_ball_grid_query(int b, int n, int m, float radius, int nsample, 
         }
         static const bool whole_cloud_bitmaps = std::getenv("F3D_BQ_WHOLE_CLOUD_BITMAPS") != nullptr;  // A/B: the kernel before the grouped one
         // bq_window() is a power of two, so win divides kBqGroupBits.  (With windows of 3072 / 6144 points -- the sizing before: any multiple
-        // of 1024 -- the sparse pass of the grouped kernel, then 3 or 6 lanes per window, ended in "illegal instruction" on the device while
-        // its window walk passed the same cases; the cause was not found, compute-sanitizer being closed on the pool.  The check stays as a
-        // guard: a window that does not divide the group would take bq_grid_query_win_kernel.)
+        // of 1024 -- the sparse pass of the grouped kernel, then 3 or 6 lanes per window, ended in "illegal instruction": one of its full-mask
+        // shuffles sat inside `serves ? ... : 0` and the two lanes that serve no window skipped it -- found with progress markers in
+        // host-mapped memory, tools/bq_fault_core.py, and hoisted.  The check stays as a guard: a window that does not divide the group
+        // would take bq_grid_query_win_kernel.)
         if (!whole_cloud_bitmaps && w < (1LL << 31) - (1LL << 20) && kBqGroupBits % bq_window(n) == 0) {
             static const int grp_mode = std::getenv("F3D_BQ_GRP_MODE") ? std::atoi(std::getenv("F3D_BQ_GRP_MODE")) : 0;  // diagnosis: 1 sparse pass only, 2 window walk only
             const unsigned need = blocks_for(alias_off >= 0 ? alias_span : w, 8), cap = static_cast<unsigned>(num_sms) * 3u;
