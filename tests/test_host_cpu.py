@@ -55,6 +55,29 @@ def test_product_does_not_import_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
 
 
+def test_no_warp_collective_inside_a_conditional_expression():
+    """A full-mask warp collective in one arm of `c ? a : b`, or behind `&&` / `||`, is skipped by the lanes whose condition differs.
+    One such shuffle (`lt = serves ? ... __shfl_sync(kFull, re[2], wsrc) ... : 0` in bq_grid_query_grp_kernel) ended in "illegal
+    instruction" on the device with 3072 / 6144-point index windows.  The arms that remain are guarded by warp-uniform values
+    only (a ballot result, a value broadcast by a shuffle); anything new has to be hoisted or added here with its reason."""
+    import re
+
+    uniform_guards = (  # (file, guard as written): the condition is the same in every lane
+        ("grouping.cu", "owners ?"), ("grouping.cu", "first < 0 && owners"),
+    )
+    root = os.path.join(os.path.dirname(pkg().__file__), "csrc")
+    pat = re.compile(r"(\?|&&|\|\|)[^;]*(__shfl\w*_sync|__ballot_sync|__reduce_\w+_sync|__any_sync|__all_sync|__match_\w+_sync)\s*\(")
+    found = []
+    for f in sorted(os.listdir(root)):
+        if not f.endswith((".cu", ".cuh")):
+            continue
+        for i, line in enumerate(open(os.path.join(root, f)).read().split("\n"), 1):
+            code = line.split("//")[0]
+            if pat.search(code) and not any(f == g[0] and g[1] in code for g in uniform_guards):
+                found.append("%s:%d: %s" % (f, i, code.strip()))
+    assert not found, found
+
+
 def test_dropin_import_paths(f3d_lib):
     """The reference's own import lines resolve once the package directory is on sys.path."""
     pkg().install_dropin()
